@@ -1,0 +1,200 @@
+/*
+ * pfcu.h - the thin C-ABI between the C99 host state machine (pixelforge.h front end) and the
+ * hand-written sm_100a rasteriser.  Plain pointers and sizes only: no C++, no torch types.
+ *
+ * What it replaces in the reference (Bigfoot71/PixelForge):
+ *   - the internal seam  pfiProcessRasterize_TRIANGLE* -> static Rasterize_Triangle(face, is3D, v1, v2, v3, viewPos)
+ *     (src/internal/primitives/primitives.h:31-33, src/internal/primitives/triangles.c:53-55,287-558),
+ *     whose implicit inputs are read from the global context (triangles.c:373-396);
+ *   - the surface side effects of pfClear (src/context.c:680-787) and the framebuffer / texture
+ *     storage of src/framebuffer.c:29-64 and src/texture.c:30-69.
+ *
+ * Instead of one synchronous call per triangle the host appends screen-space triangles (the output
+ * of the reference's Process_ProjectAndClipTriangle, triangles.c:246-280) to an ordered batch, tags
+ * each with the index of a state snapshot, and hands the batch to pfcu_submit().  Submission order
+ * is preserved per pixel, so blending and depth results equal the reference's sequential execution.
+ *
+ * Two implementations of this ABI exist:
+ *   - pixelforge_b200/csrc/pfcu.cu          the product (CUDA, sm_100a) -> libpfcu.so / libpixelforge.so
+ *   - oracle/pfcu_oracle.c                  TEST ONLY scalar C restatement of the reference algorithm
+ */
+#ifndef PFCU_H
+#define PFCU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef PFCU_API
+#  define PFCU_API __attribute__((visibility("default")))
+#endif
+
+/* ---- status codes --------------------------------------------------------------------------- */
+enum {
+    PFCU_OK            = 0,
+    PFCU_ERR_NO_DEVICE = 1,   /* no CUDA device / driver: the product never falls back to the CPU */
+    PFCU_ERR_OOM       = 2,
+    PFCU_ERR_INVALID   = 3,
+    PFCU_ERR_CUDA      = 4
+};
+
+/* ---- state snapshot flags (what selects the per-fragment program, triangles.c:390-396) ------ */
+enum {
+    PFCU_ST_BLEND      = 1u << 0,   /* PF_BLEND enabled                                  */
+    PFCU_ST_DEPTH_TEST = 1u << 1,   /* PF_DEPTH_TEST enabled                             */
+    PFCU_ST_TEXTURE    = 1u << 2,   /* PF_TEXTURE_2D enabled and a texture is bound      */
+    PFCU_ST_PHONG      = 1u << 3,   /* PF_LIGHTING && lightModel == PF_PHONG && lights   */
+    PFCU_ST_SMOOTH     = 1u << 4    /* shade model PF_SMOOTH (else PF_FLAT)              */
+};
+
+/* texel formats understood by the sampler (reference getters: src/internal/pixel.h:2604-2632,2909-2920) */
+enum {
+    PFCU_TEX_RGBA8 = 0,   /* PF_RGBA / PF_UNSIGNED_BYTE */
+    PFCU_TEX_BGRA8 = 1,   /* PF_BGRA / PF_UNSIGNED_BYTE */
+    PFCU_TEX_RGB8  = 2,   /* PF_RGB  / PF_UNSIGNED_BYTE  (3 bytes per texel, alpha reads 255) */
+    PFCU_TEX_BGR8  = 3    /* PF_BGR  / PF_UNSIGNED_BYTE */
+};
+
+typedef struct pfcu_surface pfcu_surface;   /* colour RGBA8 + depth f32, row-major [y*W+x], in HBM   */
+typedef struct pfcu_texture pfcu_texture;   /* texel array in HBM                                    */
+typedef struct pfcu_batch   pfcu_batch;     /* triangles + states already resident in HBM            */
+
+/* One projected vertex: the fields of PFIvertex (src/internal/context/context.h:203-210) that
+ * Rasterize_Triangle reads.  48 bytes. */
+typedef struct {
+    float    sx, sy;        /* screen[0..1], +0.5 biased (internal/context/context.c:63-64)          */
+    float    zinv;          /* homogeneous[2]: 1/z_clip for 3D, z_clip for "2D" (triangles.c:257-267) */
+    float    u, v;          /* texcoord, pre-multiplied by zinv for 3D (triangles.c:269)             */
+    float    px, py, pz;    /* object-space position (Phong only)                                    */
+    float    nx, ny, nz;    /* normal (Phong only)                                                   */
+    uint32_t rgba;          /* PFcolor as a little-endian dword: r | g<<8 | b<<16 | a<<24            */
+} pfcu_vertex;
+
+/* One Rasterize_Triangle invocation.  152 bytes. */
+typedef struct {
+    pfcu_vertex v[3];
+    uint32_t    state;      /* index into the batch's state table                                    */
+    uint8_t     face;       /* PF_FRONT (0) or PF_BACK (1): the faceToRender argument                */
+    uint8_t     is3d;       /* the is3D argument (perspective uv, no viewport clamp of the bbox)     */
+    uint16_t    pad;
+} pfcu_triangle;
+
+typedef struct {            /* PFIlight (internal/context/context.h:216-228) minus the list link     */
+    float    position[3];
+    float    direction[3];
+    float    inner_cutoff, outer_cutoff;
+    float    att_constant, att_linear, att_quadratic;
+    uint32_t ambient, diffuse, specular;    /* PFcolor dwords                                         */
+} pfcu_light;
+
+typedef struct {            /* PFImaterial (internal/context/context.h:233-239)                       */
+    uint32_t ambient, diffuse, specular, emission;
+    float    shininess;
+} pfcu_material;
+
+/* Everything Rasterize_Triangle reads from G_currentCtx (triangles.c:318-321,373-396,520). */
+typedef struct {
+    uint32_t            flags;          /* PFCU_ST_*                                                  */
+    uint8_t             blend_mode;     /* PFblendmode                                                */
+    uint8_t             depth_func;     /* PFdepthmode                                                */
+    uint8_t             tex_filter;     /* PFtexturefilter                                            */
+    uint8_t             tex_wrap;       /* PFtexturewrap                                              */
+    int32_t             vp_min[2];      /* ctx->vpMin, bbox clamp for "2D" triangles                  */
+    int32_t             vp_max[2];      /* ctx->vpMax                                                 */
+    const pfcu_texture *texture;        /* NULL when PFCU_ST_TEXTURE is clear                         */
+    uint32_t            n_lights;       /* active lights in enable order (Phong only)                 */
+    pfcu_light          lights[8];
+    pfcu_material       material[2];    /* faceMaterial[PF_FRONT], faceMaterial[PF_BACK]              */
+    float               view_pos[3];    /* translation row of inverse(matView) (triangles.c:84-86)    */
+    uint32_t            pad;
+} pfcu_state;
+
+typedef struct {
+    uint64_t triangles_submitted;   /* Rasterize_Triangle invocations                                 */
+    uint64_t triangles_rasterised;  /* ... that survive the face / zero-area test (triangles.c:303)   */
+    uint64_t pixels_shaded;         /* fragments whose final mask lane is set: colour+depth written   */
+    uint64_t pixels_depth_failed;   /* covered fragments rejected by the depth test                   */
+    uint64_t kernel_launches;       /* kernels launched by this library                               */
+} pfcu_counters;
+
+/* ---- runtime -------------------------------------------------------------------------------- */
+
+/* Bind to CUDA device `device` (-1: $PF_CUDA_DEVICE, else $LOCAL_RANK, else 0) and create the stream.
+ * Idempotent.  Returns PFCU_ERR_NO_DEVICE when no GPU is usable. */
+PFCU_API int  pfcu_init(int device);
+PFCU_API void pfcu_shutdown(void);
+PFCU_API const char *pfcu_last_error(void);
+PFCU_API const char *pfcu_backend_name(void);          /* "cuda-sm_100a" or "oracle-c" (tests)      */
+
+/* Use an externally owned CUDA stream (cudaStream_t passed as void*) for all later work. */
+PFCU_API int  pfcu_set_stream(void *cuda_stream);
+PFCU_API void *pfcu_get_stream(void);
+
+/* Page-locked host memory for batches: pfcu_submit() from such a block is a single asynchronous
+ * DMA with no staging copy.  pfcu_host_wait(p) blocks until the last submit that read from the
+ * block starting at p has finished reading it (so the host may overwrite it). */
+PFCU_API void *pfcu_host_alloc(size_t bytes);
+PFCU_API void  pfcu_host_free(void *p);
+PFCU_API int   pfcu_host_wait(const void *p);
+
+/* Tables that reproduce the host's RCPPS / RSQRTPS (reference: src/internal/simd.h:1217-1245).
+ * rcp[i], i = top `rcp_bits` mantissa bits: float bits of rcp(1.m);  rsqrt[(odd<<rsqrt_bits)|i]:
+ * float bits of rsqrt(1.m * 2^odd).  Harvested by the host library from the CPU it runs on. */
+PFCU_API int  pfcu_set_approx_tables(const uint32_t *rcp, int rcp_bits, const uint32_t *rsqrt, int rsqrt_bits);
+
+/* ---- surfaces (framebuffer.c:29-64, context.c:126-138) -------------------------------------- */
+PFCU_API pfcu_surface *pfcu_surface_create(uint32_t width, uint32_t height);
+/* Wrap caller-owned device memory (e.g. a torch tensor): colour u32[w*h], depth f32[w*h]. */
+PFCU_API pfcu_surface *pfcu_surface_wrap(void *dev_color, void *dev_depth, uint32_t width, uint32_t height);
+PFCU_API void     pfcu_surface_destroy(pfcu_surface *s);
+PFCU_API uint32_t pfcu_surface_width(const pfcu_surface *s);
+PFCU_API uint32_t pfcu_surface_height(const pfcu_surface *s);
+PFCU_API void    *pfcu_surface_color_ptr(const pfcu_surface *s);    /* device pointers */
+PFCU_API void    *pfcu_surface_depth_ptr(const pfcu_surface *s);
+/* Host <-> device copies of whole rows [y0, y0+rows); either pointer may be NULL.  Host pointers
+ * address the full surface (row-major, row y at offset y*W).  Asynchronous on the stream for
+ * uploads; downloads return after the data is on the host. */
+PFCU_API int pfcu_surface_upload(pfcu_surface *s, const void *host_color, const float *host_depth, uint32_t y0, uint32_t rows);
+PFCU_API int pfcu_surface_download(pfcu_surface *s, void *host_color, float *host_depth, uint32_t y0, uint32_t rows);
+/* Plain fill of every pixel (pfClearFramebuffer, framebuffer.c:89-102). */
+PFCU_API int pfcu_surface_fill(pfcu_surface *s, int do_color, uint32_t rgba, int do_depth, float depth);
+/* pfClear with the reference's exact SIMD behaviour (context.c:696-713): pixels
+ * [8, size - size%8) receive the value, pixels 0..7 are left alone, the tail copies pixel 0. */
+PFCU_API int pfcu_surface_clear_ref(pfcu_surface *s, int do_color, uint32_t rgba, int do_depth, float depth);
+/* Multi-GPU screen-tile split: this process only rasterises tiles whose owner == rank
+ * (owner(tile) = (tile_x + tile_y * tiles_x) % world).  world <= 1 disables the split. */
+PFCU_API int pfcu_surface_set_tile_owner(pfcu_surface *s, uint32_t rank, uint32_t world);
+/* Pack this rank's tiles into / unpack rank r's tiles from a contiguous device staging buffer
+ * (colour then depth per tile), for the NCCL gather to the presenting rank. */
+PFCU_API size_t pfcu_surface_owned_bytes(const pfcu_surface *s, uint32_t rank, uint32_t world, int with_depth);
+PFCU_API int pfcu_surface_pack_tiles(pfcu_surface *s, uint32_t rank, uint32_t world, int with_depth, void *dev_staging);
+PFCU_API int pfcu_surface_unpack_tiles(pfcu_surface *s, uint32_t rank, uint32_t world, int with_depth, const void *dev_staging);
+
+/* ---- textures (texture.c:30-69) -------------------------------------------------------------- */
+PFCU_API pfcu_texture *pfcu_texture_create(const void *host_pixels, uint32_t width, uint32_t height, int pfcu_tex_format);
+PFCU_API pfcu_texture *pfcu_texture_from_surface(pfcu_surface *s);   /* render-to-texture alias, RGBA8 */
+PFCU_API int  pfcu_texture_update(pfcu_texture *t, const void *host_pixels);
+PFCU_API void pfcu_texture_destroy(pfcu_texture *t);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* Rasterise `n_tris` triangles, in order, into `s`.  Host pointers; the call copies them to the
+ * device (pinned staging + cudaMemcpyAsync) and launches setup -> bin -> tile raster.  Asynchronous. */
+PFCU_API int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states,
+                         const pfcu_triangle *tris, uint32_t n_tris);
+/* Same, split in two so that a batch can stay resident in HBM and be replayed (benchmarks, lists). */
+PFCU_API pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states,
+                                       const pfcu_triangle *tris, uint32_t n_tris);
+PFCU_API int  pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b);
+PFCU_API void pfcu_batch_destroy(pfcu_batch *b);
+
+PFCU_API int  pfcu_finish(void);                       /* wait for everything queued so far          */
+PFCU_API int  pfcu_get_counters(pfcu_counters *out);   /* implies pfcu_finish()                      */
+PFCU_API void pfcu_reset_counters(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFCU_H */

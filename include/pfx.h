@@ -1,0 +1,47 @@
+/*
+ * pfx.h - OPTIONAL extension entry points of pixelforge-b200.  Nothing here exists in the
+ * reference; programs that only include pixelforge.h never need it.  The reference has no flush
+ * call because every pfVertex* rasterises synchronously; a batching GPU back end
+ * needs one for throughput-oriented callers.
+ */
+#ifndef PIXEL_FORGE_X_H
+#define PIXEL_FORGE_X_H
+
+#include "pixelforge.h"
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+typedef struct {
+    PFuint64 triangles_submitted;    /* Rasterize_Triangle-equivalent invocations sent to the GPU */
+    PFuint64 triangles_rasterised;   /* ... surviving the face / zero-area test                   */
+    PFuint64 pixels_shaded;          /* colour+depth writes                                       */
+    PFuint64 pixels_depth_failed;
+    PFuint64 kernel_launches;
+} PFXcounters;
+
+/* PF_CUDA_SYNC=end (default): the caller's buffers are refreshed at every pfEnd / pfCallList /
+ * pfDraw* / pfClear, as with the reference.  explicit: only at the API's read-back points and at
+ * pfxFinish().  pfxSetSyncMode overrides the environment variable. */
+PF_API void pfxSetSyncMode(PFboolean explicitSync);
+/* Submit everything batched so far on the current context (asynchronous). */
+PF_API void pfxFlush(void);
+/* pfxFlush + wait + bring the current target's host buffer (and visible z-buffer) up to date. */
+PF_API void pfxFinish(void);
+PF_API void pfxGetCounters(PFXcounters *out);
+PF_API void pfxResetCounters(void);
+/* Multi-GPU screen-tile split of the current target: this process renders tiles t with
+ * t % world == rank (tile = 64x64 pixels, t = tx + ty*tilesX). */
+PF_API void pfxSetTileOwner(PFuint rank, PFuint world);
+/* Device pointers of the current target (colour RGBA8 [y*W+x], depth f32) for zero-copy interop. */
+PF_API void *pfxGetDeviceColor(void);
+PF_API void *pfxGetDeviceDepth(void);
+/* Copy of the current target's depth buffer into `out` (width*height floats). */
+PF_API void pfxReadDepth(PFfloat *out);
+PF_API const char *pfxBackendName(void);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif

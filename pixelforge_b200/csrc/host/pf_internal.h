@@ -1,0 +1,179 @@
+/*
+ * pf_internal.h - private state of the C99 front end (not installed).
+ *
+ * The front end keeps the OpenGL-1.x style state machine of the reference
+ * (src/internal/context/context.h:322-401) but, instead of rasterising inside pfVertex*, it runs the
+ * per-vertex stage on the host and appends screen-space triangles to an ordered batch that the
+ * pfcu C-ABI (include/pfcu.h) consumes.
+ */
+#ifndef PF_INTERNAL_H
+#define PF_INTERNAL_H
+
+#include "pixelforge.h"
+#include "pfcu.h"
+
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* constants that change results (reference: src/internal/config.h:25-55) */
+#define PFH_PROJECTION_STACK   2
+#define PFH_MODELVIEW_STACK    8
+#define PFH_TEXTURE_STACK      4
+#define PFH_MAX_LIGHTS         8
+#define PFH_MAX_POLY_VERTS     12
+#define PFH_CLIP_EPSILON       1e-5f
+#define PFH_PI                 3.14159265358979323846
+#define PFH_DEG2RAD            (PFH_PI / 180.0)
+
+typedef float pf_mat4[16];
+
+/* texture object behind a PFtexture handle (reference: struct PFItex, context.h:160-178) */
+typedef struct pf_tex {
+    void           *pixels;         /* caller-owned host texels (or calloc'ed by pfGenFramebuffer)   */
+    PFsizei         w, h;
+    PFpixelformat   format;
+    PFdatatype      type;
+    PFtexturewrap   wrap;
+    PFtexturefilter filter;
+    pfcu_texture   *dev;            /* device copy, created on first use in a draw                   */
+    struct pf_surf *surf;           /* non-NULL when this texture is a render target                 */
+} pf_tex;
+
+/* a render target: colour texture + depth, with its device surface and host-mirror bookkeeping */
+typedef struct pf_surf {
+    pfcu_surface *dev;
+    pf_tex       *tex;              /* colour; tex->pixels is the host mirror                        */
+    PFfloat      *zhost;            /* host depth mirror (NULL: none kept)                           */
+    int           z_public;         /* zbuffer pointer is visible to the user (PFframebuffer)        */
+    int           host_newer;       /* host mirror modified since the last upload                    */
+    int           dev_newer;        /* device modified since the last download                       */
+    PFuint        dirty_y0, dirty_y1; /* rows [y0, y1) touched on the device since last download     */
+    pfcu_texture *as_texture;       /* alias used when the colour buffer is sampled                  */
+    struct pf_surf *next;           /* registry link (lookup from a PFframebuffer copy)              */
+} pf_surf;
+
+typedef struct {
+    float   homogeneous[4];
+    float   screen[2];
+    float   position[4];
+    float   normal[3];
+    float   texcoord[2];
+    PFcolor color;
+} pf_vertex;
+
+typedef struct {
+    float   position[3], direction[3];
+    float   innerCutOff, outerCutOff;
+    float   attConstant, attLinear, attQuadratic;
+    PFcolor ambient, diffuse, specular;
+    int     next;                   /* index of next active light, -1 = end                         */
+} pf_light;
+
+typedef struct { PFcolor ambient, diffuse, specular, emission; float shininess; } pf_material;
+
+typedef struct { const void *buffer; PFsizei stride; PFint size; PFdatatype type; } pf_attrib;
+
+typedef struct { PFfogmode mode; float density, start, end; PFcolor color; } pf_fog;
+
+typedef struct {
+    float *data; size_t size, cap, elem;    /* elem = floats (or dwords) per entry */
+} pf_fvec;
+
+typedef struct {
+    pf_material material[2];
+    pf_fvec positions, texcoords, normals, colors;
+    PFtexture texture;
+    PFdrawmode mode;
+} pf_call;
+
+typedef struct { pf_call *calls; size_t size, cap; } pf_list;
+
+typedef struct {
+    pf_material material[2];
+    float texcoord[2], normal[3];
+    PFcolor color;
+    PFtexture texture;
+    PFuint state;
+} pf_backup;
+
+typedef struct pf_ctx {
+    /* targets */
+    pf_surf       *main_surf;
+    PFframebuffer  mainFramebuffer;        /* {texture handle, NULL}                                 */
+    PFframebuffer *bindedFramebuffer;
+    pf_surf       *cur_surf;               /* surface current draws go to                            */
+    void          *auxFramebuffer;
+    pf_tex        *currentTexture;
+
+    /* viewport */
+    PFint   vpPos[2]; PFsizei vpDim[2]; PFint vpMin[2], vpMax[2];
+
+    /* immediate mode */
+    pf_vertex  vertexBuffer[6];
+    PFsizei    vertexCounter;
+    float      currentNormal[3], currentTexcoord[2];
+    PFcolor    currentColor;
+    PFdrawmode currentDrawMode;
+    pf_attrib  apos, anrm, acol, atex;
+
+    /* fixed-function state */
+    PFcolor clearColor; float clearDepth, pointSize, lineWidth;
+    float rasterPos[4], pixelZoom[2];
+    PFpolygonmode polygonMode[2];
+    pf_material   material[2];
+    PFface cmFace; PFenum cmMode;
+    pf_light lights[PFH_MAX_LIGHTS]; int activeHead;
+    pf_fog fog;
+    PFblendmode blendMode; PFdepthmode depthMode;
+    PFshademode shadingMode; PFlightmode lightingMode; PFface cullFace;
+    PFerrcode errCode; PFuint state;
+
+    /* matrices */
+    pf_mat4 matProjection, matTexture, matModel, matView, matMVP, matNormal;
+    pf_mat4 stackProjection[PFH_PROJECTION_STACK], stackModelview[PFH_MODELVIEW_STACK], stackTexture[PFH_TEXTURE_STACK];
+    PFsizei nProjection, nModelview, nTexture;
+    PFmatrixmode matrixMode; float *currentMatrix; int modelMatrixUsed;
+    float viewPos[3]; int viewPosValid;
+
+    /* render lists */
+    pf_list  *recording;
+    pf_backup backup;
+    int       replaying;
+
+    /* batching */
+    pfcu_triangle *tris[2];     /* pinned double buffer */
+    int            cur_buf;
+    uint32_t       n_tris, tri_cap;
+    pfcu_state    *states; uint32_t n_states, state_cap;
+    int            state_dirty;
+    uint64_t       tris_emitted;
+} pf_ctx;
+
+extern PF_CTX_DECL pf_ctx *pf_cur;
+
+/* pf_pipeline.c */
+void pfh_process_primitive(pf_ctx *c);                 /* vertexBuffer full -> triangles -> batch       */
+void pfh_flush(pf_ctx *c);                             /* submit the pending batch (asynchronous)       */
+void pfh_sync_surface(pf_ctx *c, pf_surf *s);          /* flush + bring the host mirror up to date      */
+void pfh_upload_if_needed(pf_ctx *c, pf_surf *s);      /* host mirror -> device when host is newer      */
+void pfh_end_of_draw(pf_ctx *c);                       /* PF_CUDA_SYNC=end policy hook                  */
+int  pfh_sync_mode_explicit(void);
+void pfh_set_sync_mode(int explicit_mode);
+void pfh_update_matrices(pf_ctx *c, int with_normal);
+
+/* pf_objects.c */
+pf_surf *pfh_surf_create(pf_tex *tex, PFfloat *zhost, int z_public);
+void     pfh_surf_destroy(pf_surf *s);
+pf_surf *pfh_surf_lookup(PFtexture tex);
+int      pfh_tex_format_code(PFpixelformat f, PFdatatype t);   /* PFCU_TEX_* or -1 */
+PFsizei  pfh_pixel_bytes(PFpixelformat f, PFdatatype t);
+PFcolor  pfh_pixel_get(const pf_tex *t, size_t i);            /* host mirror access (RGBA8 family)     */
+void     pfh_pixel_set(pf_tex *t, size_t i, PFcolor c);
+int      pfh_runtime_init(void);                               /* pfcu_init + approx tables, once      */
+
+/* pf_x86approx.c */
+int pfh_harvest_rcp(uint32_t **table, int *bits);
+int pfh_harvest_rsqrt(uint32_t **table, int *bits);
+
+#endif

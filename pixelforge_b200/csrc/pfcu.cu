@@ -1,0 +1,1462 @@
+/*
+ * pfcu.cu - sm_100a implementation of the pfcu C-ABI (include/pfcu.h): the per-fragment triangle
+ * path of PixelForge on a B200.
+ *
+ * Pipeline per submitted batch (all on one stream, order preserving):
+ *   k_setup   one thread per triangle: integer snap, signed area / face cull, bbox, int32 edge
+ *             constants, 1/sum (reference: triangles.c:294-349); writes bbox[], TriSetup[], TriData[];
+ *   k_bin_*   coarse binning (512x512 px bins) with warp-ballot compaction; per-bin triangle lists
+ *             keep submission order (count -> scan -> ordered fill);
+ *   k_raster  one CTA per 64x64 screen tile: colour + depth tile staged in shared memory, the
+ *             bin's list is filtered against the tile (bbox + edge-function reject) by ballot
+ *             compaction into a shared queue, and every warp walks the queue IN ORDER over the
+ *             8x4-pixel blocks it owns (fixed pixel ownership => blending/depth order equals
+ *             submission order without atomics).  Coverage, depth, colour interpolation,
+ *             texturing, per-fragment Blinn-Phong and blending restate the reference's AVX2 lane
+ *             arithmetic bit for bit (triangles.c:400-529, color.h, sampler.h, blend.h, depth.h,
+ *             lighting.c:148-258, simd.h cephes log/exp); RCPPS/RSQRTPS come from host-harvested
+ *             tables.  Tile load/store is 128-bit vectorised and coalesced.
+ * No tensor cores: nothing on this path is a dense contraction.  Compile with -fmad=false.
+ */
+#include "pfcu.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <limits.h>
+
+#include <vector>
+#include <mutex>
+
+/* ------------------------------------------------------------------------------------------------ */
+/* configuration                                                                                    */
+/* ------------------------------------------------------------------------------------------------ */
+
+#define TILE        64              /* screen tile edge in pixels                                    */
+#define TILE_PIX    (TILE * TILE)
+#define BIN_TILES   8               /* a bin is 8x8 tiles = 512x512 pixels                           */
+#define BIN_PIX     (TILE * BIN_TILES)
+#define RASTER_THREADS 256
+#define QUEUE_CAP   768             /* triangle indices buffered per tile between raster passes      */
+#define SETUP_THREADS 256
+#define BIN_BATCH   1024            /* triangles per binning CTA                                     */
+#define MAX_BINS    1024            /* 32x32 bins = 16384^2 pixels                                   */
+
+#define TF_VALID    1u              /* survived cull and has a non-empty bbox on the surface         */
+#define TF_SAFE     2u              /* int32 edge functions cannot wrap inside the bbox              */
+
+struct __align__(16) TriSetup {     /* 48 B */
+    int   w1R, w2R, w3R; float invSum;
+    int   w1X, w1Y, w2X, w2Y;
+    int   w3X, w3Y; unsigned flags; unsigned pad;
+};
+
+struct __align__(16) TriData {      /* 160 B, grouped by what each fragment program reads */
+    float z1, z2, z3; unsigned meta;            /* meta: state | face<<24 | is3d<<25               */
+    unsigned c1, c2, c3, pad0;
+    float u1, u2, u3, pad1;
+    float v1, v2, v3, pad2;
+    float px[4], py[4], pz[4];
+    float nx[4], ny[4], nz[4];
+};
+
+struct DevLight { float pos[3], dir[3], inner, outer, attc, attl, attq; unsigned ambient, diffuse, specular; };
+struct DevMaterial { unsigned ambient, diffuse, specular, emission; float shininess; };
+
+struct __align__(16) DevState {
+    unsigned flags;
+    unsigned char blend_mode, depth_func, tex_filter, tex_wrap;
+    int vp_min[2], vp_max[2];
+    const unsigned char *tex; unsigned tw, th; int tfmt;
+    unsigned n_lights;
+    DevLight lights[8];
+    DevMaterial material[2];
+    float view_pos[3];
+};
+
+struct pfcu_surface {
+    uint32_t w, h; uint32_t *color; float *depth; bool owned;
+    uint32_t rank, world; uint32_t tiles_x, tiles_y;
+};
+struct pfcu_texture { uint32_t w, h; int fmt; unsigned char *pixels; bool owned; pfcu_surface *alias; };
+struct pfcu_batch {
+    DevState *states; uint32_t n_states; pfcu_triangle *tris; uint32_t n_tris; unsigned feature_mask;
+};
+
+/* ------------------------------------------------------------------------------------------------ */
+/* runtime state                                                                                    */
+/* ------------------------------------------------------------------------------------------------ */
+
+struct PinnedBlock { void *p; size_t bytes; cudaEvent_t done; bool pending; };
+
+struct Runtime {
+    bool ok = false; int device = 0; int sms = 148;
+    cudaStream_t stream = nullptr; bool own_stream = false;
+    /* growable device scratch, reused batch after batch (single stream => no hazards) */
+    pfcu_triangle *d_tris = nullptr; size_t cap_tris = 0;
+    DevState *d_states = nullptr; size_t cap_states = 0;
+    int4 *d_bbox = nullptr; TriSetup *d_setup = nullptr; TriData *d_data = nullptr; size_t cap_setup = 0;
+    unsigned *d_bin_counts = nullptr; size_t cap_bin_counts = 0;     /* [batches+1][bins] */
+    unsigned *d_bin_list = nullptr; size_t cap_bin_list = 0;
+    unsigned *d_bin_start = nullptr;                                  /* [MAX_BINS+1] */
+    unsigned long long *d_counters = nullptr;                         /* rasterised, shaded, depth-failed */
+    uint32_t *d_rcp = nullptr, *d_rsq = nullptr; int rcp_bits = 0, rsq_bits = 0;
+    /* pinned staging for pageable sources */
+    void *h_stage = nullptr; size_t cap_stage = 0; cudaEvent_t stage_done = nullptr;
+    DevState *h_states = nullptr; size_t cap_hstates = 0; cudaEvent_t states_done = nullptr;
+    std::vector<PinnedBlock> pinned;
+    uint64_t submitted = 0, launches = 0;
+    std::mutex mu;
+    char err[512] = { 0 };
+};
+
+static Runtime g;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    snprintf(g.err, sizeof g.err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    return PFCU_ERR_CUDA; } } while (0)
+
+#define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    snprintf(g.err, sizeof g.err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    return nullptr; } } while (0)
+
+__constant__ const uint32_t *c_rcp_tab;
+__constant__ const uint32_t *c_rsq_tab;
+__constant__ int c_rcp_shift, c_rsq_shift, c_rsq_bits;
+
+/* ------------------------------------------------------------------------------------------------ */
+/* device: x86 lane semantics                                                                       */
+/* ------------------------------------------------------------------------------------------------ */
+
+#define FM(a, b) __fmul_rn((a), (b))
+#define FA(a, b) __fadd_rn((a), (b))
+#define FS(a, b) __fsub_rn((a), (b))
+#define FD(a, b) __fdiv_rn((a), (b))
+
+/* MINPS / MAXPS: second operand when either is NaN */
+__device__ __forceinline__ float min_x86(float a, float b) { return (a < b) ? a : b; }
+__device__ __forceinline__ float max_x86(float a, float b) { return (a > b) ? a : b; }
+__device__ __forceinline__ float clamp_x86(float x, float lo, float hi) { return min_x86(max_x86(x, lo), hi); }
+
+/* CVTPS2DQ (round to nearest even; 0x80000000 when out of range / NaN) */
+__device__ __forceinline__ int cvt_rne_x86(float x)
+{
+    int r = __float2int_rn(x);
+    return (fabsf(x) < 2147483648.0f) ? r : INT_MIN;
+}
+__device__ __forceinline__ int cvt_trunc_x86(float x)
+{
+    int r = __float2int_rz(x);
+    return (fabsf(x) < 2147483648.0f) ? r : INT_MIN;
+}
+
+/* RCPPS via the host-harvested table (simd.h:1217-1225; see host/pf_x86approx.c) */
+__device__ __forceinline__ float rcp_x86(float x)
+{
+    const unsigned u = __float_as_uint(x), s = u & 0x80000000u, e = (u >> 23) & 255u, m = u & 0x7fffffu;
+    const unsigned tv = __ldg(c_rcp_tab + (m >> c_rcp_shift));
+    const int ex = (int)(tv >> 23) + 127 - (int)e;
+    unsigned r = s | ((unsigned)ex << 23) | (tv & 0x7fffffu);
+    if (ex <= 0) r = s;
+    if (e == 0u) r = s | 0x7f800000u;
+    if (e == 255u) r = m ? (u | 0x00400000u) : s;
+    return __uint_as_float(r);
+}
+
+/* RSQRTPS (simd.h:1237-1245) */
+__device__ __forceinline__ float rsqrt_x86(float x)
+{
+    const unsigned u = __float_as_uint(x), s = u & 0x80000000u, e = (u >> 23) & 255u, m = u & 0x7fffffu;
+    const unsigned odd = (e & 1u) ^ 1u;
+    const int half = ((int)e - 127 - (int)odd) / 2;
+    const unsigned tv = __ldg(c_rsq_tab + ((odd << c_rsq_bits) | (m >> c_rsq_shift)));
+    unsigned r = ((unsigned)((int)(tv >> 23) - half) << 23) | (tv & 0x7fffffu);
+    if (e == 255u) r = 0u;
+    if (s) r = 0xffc00000u;
+    if (e == 0u) r = s | 0x7f800000u;
+    if (e == 255u && m) r = u | 0x00400000u;
+    return __uint_as_float(r);
+}
+
+/* _mm256_log_ps (simd.h:183-252) */
+__device__ __forceinline__ float log_cephes(float x)
+{
+    const bool invalid = (x <= 0.0f);
+    x = max_x86(x, __uint_as_float(0x00800000u));
+    int imm0 = (int)(__float_as_uint(x) >> 23);
+    x = __uint_as_float((__float_as_uint(x) & ~0x7f800000u) | 0x3f000000u);
+    imm0 -= 0x7f;
+    float e = __int2float_rn(imm0);
+    e = FA(e, 1.0f);
+    const bool lt = (x < 0.707106781186547524f);
+    float tmp = lt ? x : 0.0f;
+    x = FS(x, 1.0f);
+    e = FS(e, lt ? 1.0f : 0.0f);
+    x = FA(x, tmp);
+    const float z = FM(x, x);
+    float y = 7.0376836292E-2f;
+    y = FM(y, x); y = FA(y, -1.1514610310E-1f);
+    y = FM(y, x); y = FA(y, 1.1676998740E-1f);
+    y = FM(y, x); y = FA(y, -1.2420140846E-1f);
+    y = FM(y, x); y = FA(y, 1.4249322787E-1f);
+    y = FM(y, x); y = FA(y, -1.6668057665E-1f);
+    y = FM(y, x); y = FA(y, 2.0000714765E-1f);
+    y = FM(y, x); y = FA(y, -2.4999993993E-1f);
+    y = FM(y, x); y = FA(y, 3.3333331174E-1f);
+    y = FM(y, x);
+    y = FM(y, z);
+    tmp = FM(e, -2.12194440e-4f);
+    y = FA(y, tmp);
+    tmp = FM(z, 0.5f);
+    y = FS(y, tmp);
+    tmp = FM(e, 0.693359375f);
+    x = FA(x, y);
+    x = FA(x, tmp);
+    return invalid ? __uint_as_float(0xffffffffu) : x;
+}
+
+/* _mm256_exp_ps (simd.h:254-304) */
+__device__ __forceinline__ float exp_cephes(float x)
+{
+    x = min_x86(x, 88.3762626647949f);
+    x = max_x86(x, -88.3762626647949f);
+    float fx = FM(x, 1.44269504088896341f);
+    fx = FA(fx, 0.5f);
+    float tmp = floorf(fx);
+    const float mask = (tmp > fx) ? 1.0f : 0.0f;
+    fx = FS(tmp, mask);
+    tmp = FM(fx, 0.693359375f);
+    float z = FM(fx, -2.12194440e-4f);
+    x = FS(x, tmp);
+    x = FS(x, z);
+    z = FM(x, x);
+    float y = 1.9875691500E-4f;
+    y = FM(y, x); y = FA(y, 1.3981999507E-3f);
+    y = FM(y, x); y = FA(y, 8.3334519073E-3f);
+    y = FM(y, x); y = FA(y, 4.1665795894E-2f);
+    y = FM(y, x); y = FA(y, 1.6666665459E-1f);
+    y = FM(y, x); y = FA(y, 5.0000001201E-1f);
+    y = FM(y, z);
+    y = FA(y, x);
+    y = FA(y, 1.0f);
+    int imm0 = cvt_trunc_x86(fx);
+    imm0 = (int)((unsigned)imm0 + 0x7fu);
+    return FM(y, __uint_as_float((unsigned)imm0 << 23));
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* device: colour arithmetic                                                                        */
+/* ------------------------------------------------------------------------------------------------ */
+
+#define CHN(c, i) ((int)(((c) >> (8 * (i))) & 255u))
+#define INV255 (1.0f / 255.0f)
+
+__device__ __forceinline__ unsigned pack4(int r, int g, int b, int a)   /* OR of shifted lanes, no masking (color.h:112-122) */
+{
+    return (unsigned)r | ((unsigned)g << 8) | ((unsigned)b << 16) | ((unsigned)a << 24);
+}
+
+__device__ __forceinline__ unsigned quant(float v)                      /* color.h:124-135 */
+{
+    return (unsigned)cvt_rne_x86(FM(clamp_x86(v, 0.0f, 1.0f), 255.0f));
+}
+
+/* (texel * frag) >> 8 per channel (blend.h:199-212) */
+__device__ __forceinline__ unsigned mul_color(unsigned a, unsigned b)
+{
+    return pack4((CHN(a, 0) * CHN(b, 0)) >> 8, (CHN(a, 1) * CHN(b, 1)) >> 8,
+                 (CHN(a, 2) * CHN(b, 2)) >> 8, (CHN(a, 3) * CHN(b, 3)) >> 8);
+}
+
+__device__ __forceinline__ unsigned color_lerp(unsigned a, unsigned b, float t)   /* color.h:137-144 (Q7 fixed) */
+{
+    unsigned p = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float A = FM(__int2float_rn(CHN(a, i)), INV255), B = FM(__int2float_rn(CHN(b, i)), INV255);
+        p |= quant(FA(A, FM(t, FS(B, A)))) << (8 * i);
+    }
+    return p;
+}
+
+__device__ __forceinline__ unsigned blend_px(int mode, unsigned s, unsigned d)   /* blend.h:137-274 */
+{
+    int o[4];
+    switch (mode) {
+    case 0:
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = (CHN(s, i) + CHN(d, i)) >> 1;
+        break;
+    case 1: {
+        const int alpha = CHN(s, 3) + 1, inv = 256 - alpha;
+#pragma unroll
+        for (int i = 0; i < 3; i++) o[i] = (CHN(s, i) * alpha + CHN(d, i) * inv) >> 8;
+        o[3] = (255 * alpha + CHN(d, 3) * inv) >> 8;
+    } break;
+    case 2:
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = min(CHN(s, i) + CHN(d, i), 255);
+        break;
+    case 3:                                 /* "subtractive" adds (Q6) and may carry into the next channel */
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = max(CHN(s, i) + CHN(d, i), 0);
+        break;
+    case 4:
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = (CHN(s, i) * CHN(d, i)) >> 8;
+        break;
+    case 5:
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = min(((CHN(d, i) * (255 - CHN(s, i))) >> 8) + CHN(s, i), 255);
+        break;
+    case 6:
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = max(CHN(s, i), CHN(d, i));
+        break;
+    default:
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = min(CHN(s, i), CHN(d, i));
+        break;
+    }
+    return pack4(o[0], o[1], o[2], o[3]);
+}
+
+__device__ __forceinline__ bool depth_pass(int func, float z, float zb)   /* depth.h:80-114; NOTEQUAL == EQUAL (Q5) */
+{
+    switch (func) {
+    case 0: case 1: return z == zb;
+    case 2: return z < zb;
+    case 3: return z <= zb;
+    case 4: return z > zb;
+    default: return z >= zb;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* device: texturing (sampler.h:202-410)                                                            */
+/* ------------------------------------------------------------------------------------------------ */
+
+__device__ __forceinline__ int tex_coord(int wrap, float t, unsigned size)
+{
+    const float sm1 = __uint2float_rn(size - 1u);
+    if (wrap == 0) {                    /* REPEAT: |RNE((t - trunc t) * (size-1))| */
+        const float f = FM(FS(t, truncf(t)), sm1);
+        const int i = cvt_rne_x86(f);
+        return (i < 0) ? (int)(0u - (unsigned)i) : i;
+    } else if (wrap == 1) {             /* MIRRORED_REPEAT */
+        const float a = fabsf(t);
+        float m = FS(a, FM(floorf(FD(a, 2.0f)), 2.0f));
+        const float r = FS(1.0f, FS(m, 1.0f));
+        if (m > 1.0f) m = r;
+        return cvt_rne_x86(FA(FM(m, sm1), 0.5f));
+    } else {                            /* CLAMP_TO_EDGE */
+        return cvt_rne_x86(FA(FM(clamp_x86(t, 0.0f, 1.0f), sm1), 0.5f));
+    }
+}
+
+__device__ __forceinline__ unsigned tex_fetch(const DevState *st, int x, int y)
+{
+    const int off = (int)((unsigned)y * st->tw + (unsigned)x);
+    if (off < 0 || (unsigned)off >= st->tw * st->th) return 0u;     /* the reference would read out of bounds */
+    const unsigned char *base = st->tex;
+    switch (st->tfmt) {
+    case PFCU_TEX_RGBA8: return __ldg((const unsigned *)base + off);
+    case PFCU_TEX_BGRA8: { const unsigned r = __ldg((const unsigned *)base + off);
+        return (r & 0xff00ff00u) | ((r & 0xffu) << 16) | ((r >> 16) & 0xffu); }
+    case PFCU_TEX_RGB8: { const unsigned char *p = base + 3 * (size_t)off;
+        return (unsigned)__ldg(p) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p + 2) << 16) | 0xff000000u; }
+    default: { const unsigned char *p = base + 3 * (size_t)off;
+        return (unsigned)__ldg(p + 2) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p) << 16) | 0xff000000u; }
+    }
+}
+
+__device__ __forceinline__ unsigned tex_sample(const DevState *st, float u, float v)
+{
+    const int wrap = st->tex_wrap;
+    const int x0 = tex_coord(wrap, u, st->tw), y0 = tex_coord(wrap, v, st->th);
+    if (st->tex_filter == 0) return tex_fetch(st, x0, y0);
+    const float fw = __uint2float_rn(st->tw), fh = __uint2float_rn(st->th);
+    const float tx = FD(1.0f, fw), ty = FD(1.0f, fh);
+    const int x1 = tex_coord(wrap, FA(u, tx), st->tw), y1 = tex_coord(wrap, FA(v, ty), st->th);
+    const float fx = clamp_x86(FS(FM(u, fw), __int2float_rn(x0)), 0.0f, 1.0f);
+    const float fy = clamp_x86(FS(FM(v, fh), __int2float_rn(y0)), 0.0f, 1.0f);
+    const unsigned c00 = tex_fetch(st, x0, y0), c10 = tex_fetch(st, x1, y0);
+    const unsigned c01 = tex_fetch(st, x0, y1), c11 = tex_fetch(st, x1, y1);
+    return color_lerp(color_lerp(c00, c10, fx), color_lerp(c01, c11, fx), fy);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* device: per-fragment Blinn-Phong (lighting.c:148-258)                                            */
+/* ------------------------------------------------------------------------------------------------ */
+
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return FA(FA(FM(ax, bx), FM(ay, by)), FM(az, bz));
+}
+
+__device__ __noinline__ unsigned phong(unsigned frag, const DevState *st, int face,
+                                       float Px, float Py, float Pz, float Nx, float Ny, float Nz)
+{
+    const DevMaterial *m = &st->material[face];
+    float D[3], A[3], S[3], acc[3] = { 0.0f, 0.0f, 0.0f };
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        D[i] = FM(__int2float_rn(CHN(frag, i)), INV255);
+        A[i] = FM(FM(__int2float_rn(CHN(m->ambient, i)), INV255), D[i]);
+        S[i] = FM(__int2float_rn(CHN(m->specular, i)), INV255);
+    }
+    float Vx = FS(st->view_pos[0], Px), Vy = FS(st->view_pos[1], Py), Vz = FS(st->view_pos[2], Pz);
+    {
+        const float inv = rsqrt_x86(max_x86(dot3(Vx, Vy, Vz, Vx, Vy, Vz), 1e-5f));
+        Vx = FM(Vx, inv); Vy = FM(Vy, inv); Vz = FM(Vz, inv);
+    }
+    const float shininess = m->shininess;
+    for (unsigned li = 0; li < st->n_lights; li++) {
+        const DevLight *l = &st->lights[li];
+        float Lx = FS(l->pos[0], Px), Ly = FS(l->pos[1], Py), Lz = FS(l->pos[2], Pz);
+        {
+            const float inv = rsqrt_x86(max_x86(dot3(Lx, Ly, Lz, Lx, Ly, Lz), 1e-5f));
+            Lx = FM(Lx, inv); Ly = FM(Ly, inv); Lz = FM(Lz, inv);
+        }
+        const float diff = max_x86(dot3(Nx, Ny, Nz, Lx, Ly, Lz), 0.0f);
+        float Hx = FA(Lx, Vx), Hy = FA(Ly, Vy), Hz = FA(Lz, Vz);
+        {
+            const float inv = rsqrt_x86(dot3(Hx, Hy, Hz, Hx, Hy, Hz));      /* no epsilon here */
+            Hx = FM(Hx, inv); Hy = FM(Hy, inv); Hz = FM(Hz, inv);
+        }
+        float spec = max_x86(dot3(Nx, Ny, Nz, Hx, Hy, Hz), 0.0f);
+        spec = exp_cephes(FM(log_cephes(spec), shininess));                 /* pow(0) -> e^88 (Q9) */
+        float inten = 1.0f; bool spot = false;
+        if (l->inner < 3.14159265358979323846f) {
+            spot = true;
+            const float theta = dot3(Lx, Ly, Lz, FS(0.0f, l->dir[0]), FS(0.0f, l->dir[1]), FS(0.0f, l->dir[2]));
+            inten = clamp_x86(FD(FS(theta, l->outer), FS(l->inner, l->outer)), 0.0f, 1.0f);
+        }
+        float att = 1.0f; bool atten = false;
+        if (l->attl != 0.0f || l->attq != 0.0f) {
+            atten = true;
+            const float d0 = FS(l->pos[0], Px), d1 = FS(l->pos[1], Py);     /* y twice, z dropped (Q10) */
+            const float dsq = FA(FM(d0, d0), FA(FM(d1, d1), FM(d1, d1)));
+            const float dist = __fsqrt_rn(dsq);
+            att = rcp_x86(FA(l->attc, FA(FM(l->attl, dist), FM(l->attq, dsq))));
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            float amb = FM(FM(__int2float_rn(CHN(l->ambient, i)), INV255), A[i]);
+            float dif = FM(FM(FM(__int2float_rn(CHN(l->diffuse, i)), INV255), diff), D[i]);
+            float spc = FM(FM(FM(__int2float_rn(CHN(l->specular, i)), INV255), spec), S[i]);
+            if (spot) { dif = FM(dif, inten); spc = FM(spc, inten); }
+            if (atten) { amb = FM(amb, att); dif = FM(dif, att); spc = FM(spc, att); }
+            acc[i] = FA(acc[i], amb); acc[i] = FA(acc[i], dif); acc[i] = FA(acc[i], spc);
+        }
+    }
+    return quant(acc[0]) | (quant(acc[1]) << 8) | (quant(acc[2]) << 16);   /* alpha = 0 (Q9) */
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* kernels: setup                                                                                   */
+/* ------------------------------------------------------------------------------------------------ */
+
+__device__ __forceinline__ int to_int_x86(float f) { return cvt_trunc_x86(f); }   /* (PFint)f == CVTTSS2SI */
+__device__ __forceinline__ int wmul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
+__device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+__device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+__device__ __forceinline__ long long labs64(long long v) { return v < 0 ? -v : v; }
+
+__global__ void __launch_bounds__(SETUP_THREADS)
+k_setup(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ states, unsigned n,
+        int surfW, int surfH, int4 *__restrict__ bbox, TriSetup *__restrict__ setup, TriData *__restrict__ data,
+        unsigned long long *__restrict__ counters)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    if (i < n) {
+        const pfcu_triangle *t = tris + i;
+        const pfcu_vertex *v1 = &t->v[0], *v2 = &t->v[1], *v3 = &t->v[2];
+        const int face = t->face, is3d = t->is3d;
+        const DevState *st = states + t->state;
+
+        const int x1 = to_int_x86(v1->sx), y1 = to_int_x86(v1->sy);
+        const int x2 = to_int_x86(v2->sx), y2 = to_int_x86(v2->sy);
+        const int x3 = to_int_x86(v3->sx), y3 = to_int_x86(v3->sy);
+
+        /* signed area in wrapping int32, compared as float like the reference (triangles.c:303-308) */
+        const float area = __int2float_rn(wsub(wmul(wsub(x2, x1), wsub(y3, y1)), wmul(wsub(x3, x1), wsub(y2, y1))));
+        const bool culled = (face == 0 && area >= 0.0f) || (face == 1 && area <= 0.0f);
+
+        int xMin = min(x1, min(x2, x3)), yMin = min(y1, min(y2, y3));
+        int xMax = max(x1, max(x2, x3)), yMax = max(y1, max(y2, y3));
+        if (!is3d) {
+            xMin = min(max(xMin, st->vp_min[0]), st->vp_max[0]); yMin = min(max(yMin, st->vp_min[1]), st->vp_max[1]);
+            xMax = min(max(xMax, st->vp_min[0]), st->vp_max[0]); yMax = min(max(yMax, st->vp_min[1]), st->vp_max[1]);
+        }
+        int w1X = wsub(y3, y2), w1Y = wsub(x2, x3);
+        int w2X = wsub(y1, y3), w2Y = wsub(x3, x1);
+        int w3X = wsub(y2, y1), w3Y = wsub(x1, x2);
+        if (face == 1) { w1X = wsub(0, w1X); w1Y = wsub(0, w1Y); w2X = wsub(0, w2X); w2Y = wsub(0, w2Y); w3X = wsub(0, w3X); w3Y = wsub(0, w3Y); }
+        const int w1R = wadd(wmul(wsub(xMin, x2), w1X), wmul(w1Y, wsub(yMin, y2)));
+        const int w2R = wadd(wmul(wsub(xMin, x3), w2X), wmul(w2Y, wsub(yMin, y3)));
+        const int w3R = wadd(wmul(wsub(xMin, x1), w3X), wmul(w3Y, wsub(yMin, y1)));
+        const float invSum = FD(1.0f, __int2float_rn(wadd(wadd(w1R, w2R), w3R)));
+
+        /* can any edge function leave int32 inside the bbox?  (exact 64-bit bound) */
+        const long long bw = (long long)xMax - xMin, bh = (long long)yMax - yMin;
+        const long long r1 = ((long long)xMin - x2) * w1X + (long long)w1Y * ((long long)yMin - y2);
+        const long long r2 = ((long long)xMin - x3) * w2X + (long long)w2Y * ((long long)yMin - y3);
+        const long long r3 = ((long long)xMin - x1) * w3X + (long long)w3Y * ((long long)yMin - y1);
+        const long long lim = 0x7fffffffLL;
+        const bool coords_ok = labs64(x1) < (1 << 24) && labs64(y1) < (1 << 24) && labs64(x2) < (1 << 24) &&
+                               labs64(y2) < (1 << 24) && labs64(x3) < (1 << 24) && labs64(y3) < (1 << 24);
+        const bool safe = coords_ok &&
+            labs64(r1) + labs64(w1X) * bw + labs64(w1Y) * bh < lim &&
+            labs64(r2) + labs64(w2X) * bw + labs64(w2Y) * bh < lim &&
+            labs64(r3) + labs64(w3X) * bw + labs64(w3Y) * bh < lim;
+
+        /* clip the visited rectangle to the surface: x in [xMin, xMax-1], y in [yMin, yMax] */
+        const bool nonempty = !culled && xMin < xMax && yMin <= yMax && xMax > 0 && yMax >= 0 && xMin < surfW && yMin < surfH;
+        valid = nonempty;
+
+        bbox[i] = valid ? make_int4(xMin, yMin, xMax, yMax) : make_int4(1, 1, 0, 0);
+        TriSetup s;
+        s.w1R = w1R; s.w2R = w2R; s.w3R = w3R; s.invSum = invSum;
+        s.w1X = w1X; s.w1Y = w1Y; s.w2X = w2X; s.w2Y = w2Y; s.w3X = w3X; s.w3Y = w3Y;
+        s.flags = (valid ? TF_VALID : 0u) | (safe ? TF_SAFE : 0u); s.pad = 0;
+        setup[i] = s;
+        if (valid) {
+            TriData d;
+            d.z1 = v1->zinv; d.z2 = v2->zinv; d.z3 = v3->zinv;
+            d.meta = (t->state & 0xffffffu) | ((unsigned)face << 24) | ((unsigned)(is3d ? 1 : 0) << 25);
+            d.c1 = v1->rgba; d.c2 = v2->rgba; d.c3 = v3->rgba; d.pad0 = 0;
+            d.u1 = v1->u; d.u2 = v2->u; d.u3 = v3->u; d.pad1 = 0;
+            d.v1 = v1->v; d.v2 = v2->v; d.v3 = v3->v; d.pad2 = 0;
+            d.px[0] = v1->px; d.px[1] = v2->px; d.px[2] = v3->px; d.px[3] = 0;
+            d.py[0] = v1->py; d.py[1] = v2->py; d.py[2] = v3->py; d.py[3] = 0;
+            d.pz[0] = v1->pz; d.pz[1] = v2->pz; d.pz[2] = v3->pz; d.pz[3] = 0;
+            d.nx[0] = v1->nx; d.nx[1] = v2->nx; d.nx[2] = v3->nx; d.nx[3] = 0;
+            d.ny[0] = v1->ny; d.ny[1] = v2->ny; d.ny[2] = v3->ny; d.ny[3] = 0;
+            d.nz[0] = v1->nz; d.nz[1] = v2->nz; d.nz[2] = v3->nz; d.nz[3] = 0;
+            data[i] = d;
+        }
+        /* "rasterised" = survives the face / zero-area test */
+        valid = !culled;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(counters + 0, (unsigned long long)__popc(b));
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* kernels: order-preserving coarse binning                                                         */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* pass 1: counts[batch][bin] = number of triangles of this batch whose bbox touches the bin */
+__global__ void __launch_bounds__(256)
+k_bin_count(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, unsigned *__restrict__ counts)
+{
+    extern __shared__ unsigned s_cnt[];
+    const int nb = binsX * binsY;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) s_cnt[k] = 0;
+    __syncthreads();
+    const unsigned base = blockIdx.x * BIN_BATCH;
+    for (unsigned k = threadIdx.x; k < BIN_BATCH; k += blockDim.x) {
+        const unsigned i = base + k;
+        if (i >= n) break;
+        const int4 b = __ldg(bbox + i);
+        if (b.x >= b.z) continue;
+        const int bx0 = max(b.x, 0) / BIN_PIX, bx1 = min((b.z - 1) / BIN_PIX, binsX - 1);
+        const int by0 = max(b.y, 0) / BIN_PIX, by1 = min(b.w / BIN_PIX, binsY - 1);
+        for (int by = by0; by <= by1; by++)
+            for (int bx = bx0; bx <= bx1; bx++) atomicAdd(&s_cnt[by * binsX + bx], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) counts[(size_t)blockIdx.x * nb + k] = s_cnt[k];
+}
+
+/* pass 2: per bin, exclusive scan of counts over batches (in place) + bin totals; one CTA per bin */
+__global__ void __launch_bounds__(256)
+k_bin_scan(unsigned *__restrict__ counts, int nBatches, int nb, unsigned *__restrict__ totals)
+{
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned s_carry;
+    const int bin = blockIdx.x;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nBatches; base += 256) {
+        const int k = base + threadIdx.x;
+        const unsigned v = (k < nBatches) ? counts[(size_t)k * nb + bin] : 0u;
+        unsigned x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        unsigned woff = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += s_warp[w];
+        const unsigned carry = s_carry;
+        if (k < nBatches) counts[(size_t)k * nb + bin] = carry + woff + x - v;
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = carry + woff + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[bin] = s_carry;
+}
+
+/* pass 3: bin start offsets (exclusive scan over <= MAX_BINS totals); single CTA */
+__global__ void k_bin_starts(const unsigned *__restrict__ totals, int nb, unsigned *__restrict__ starts)
+{
+    if (threadIdx.x == 0) {
+        unsigned acc = 0;
+        for (int k = 0; k < nb; k++) { starts[k] = acc; acc += totals[k]; }
+        starts[nb] = acc;
+    }
+}
+
+/* pass 4: ordered fill.  Within a batch, triangle order per bin is recovered with ballots:
+ * the CTA walks its triangles 256 at a time; for every bin touched by the CTA it ranks the
+ * touching triangles by index (warp ballot + cross-warp prefix). */
+__global__ void __launch_bounds__(256)
+k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY,
+           const unsigned *__restrict__ offsets /* scanned counts */, const unsigned *__restrict__ starts,
+           unsigned *__restrict__ list)
+{
+    extern __shared__ unsigned s_mem[];
+    unsigned *s_pos = s_mem;                    /* [nb] running write position of this batch per bin */
+    __shared__ unsigned s_warp[8];
+    __shared__ int s_box[4];
+    const int nb = binsX * binsY;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) s_pos[k] = starts[k] + offsets[(size_t)blockIdx.x * nb + k];
+    __syncthreads();
+    const unsigned base = blockIdx.x * BIN_BATCH;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned k0 = 0; k0 < BIN_BATCH; k0 += 256) {
+        const unsigned i = base + k0 + threadIdx.x;
+        int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
+        if (i < n) {
+            const int4 b = __ldg(bbox + i);
+            if (b.x < b.z) {
+                bx0 = max(b.x, 0) / BIN_PIX; bx1 = min((b.z - 1) / BIN_PIX, binsX - 1);
+                by0 = max(b.y, 0) / BIN_PIX; by1 = min(b.w / BIN_PIX, binsY - 1);
+            }
+        }
+        /* union bin rectangle of these 256 triangles */
+        if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = -1; s_box[3] = -1; }
+        __syncthreads();
+        if (bx0 <= bx1 && by0 <= by1) {
+            atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0); atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1);
+        }
+        __syncthreads();
+        const int ux0 = s_box[0], uy0 = s_box[1], ux1 = s_box[2], uy1 = s_box[3];
+        for (int by = uy0; by <= uy1; by++) {
+            for (int bx = ux0; bx <= ux1; bx++) {
+                const bool hit = bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1;
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) s_warp[warp] = __popc(bal);
+                __syncthreads();
+                unsigned woff = 0, total = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) { const unsigned c = s_warp[w]; if (w < warp) woff += c; total += c; }
+                const int bin = by * binsX + bx;
+                const unsigned pos = s_pos[bin];
+                if (hit) list[pos + woff + __popc(bal & ((1u << lane) - 1u))] = i;
+                __syncthreads();
+                if (threadIdx.x == 0) s_pos[bin] = pos + total;
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* kernel: tile rasteriser                                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+
+struct RasterParams {
+    const int4 *bbox; const TriSetup *setup; const TriData *data; const DevState *states;
+    const unsigned *bin_list; const unsigned *bin_starts; int binsX;
+    uint32_t *color; float *depth; int W, H; int tilesX, tilesY;
+    unsigned rank, world; unsigned nTiles;
+    unsigned long long *counters;
+};
+
+/* swizzled tile address: rows are 64 words; XOR-ing bits 3..4 of x with (y & 3) makes both the
+ * 8x4-block access of the shading loop and the 128-bit row access of load/store conflict-free */
+__device__ __forceinline__ int tile_addr(int lx, int ly) { return ly * TILE + (lx ^ ((ly & 3) << 3)); }
+
+template <bool HAS_TEX, bool HAS_PHONG>
+__global__ void __launch_bounds__(RASTER_THREADS, 2)
+k_raster(const RasterParams p)
+{
+    __shared__ __align__(16) unsigned s_color[TILE_PIX];
+    __shared__ __align__(16) float s_depth[TILE_PIX];
+    __shared__ unsigned s_queue[QUEUE_CAP];
+    __shared__ unsigned s_wcount[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned tile = (p.world > 1) ? (p.rank + blockIdx.x * p.world) : blockIdx.x;
+    if (tile >= p.nTiles) return;
+    const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+    const int X0 = tx * TILE, Y0 = ty * TILE;
+    const int X1 = min(X0 + TILE, p.W) - 1, Y1 = min(Y0 + TILE, p.H) - 1;      /* inclusive */
+    const bool full_tile = (X0 + TILE <= p.W) && (Y0 + TILE <= p.H) && ((p.W & 3) == 0);
+
+    const int bin = (ty / BIN_TILES) * p.binsX + (tx / BIN_TILES);
+    const unsigned lbeg = p.bin_starts[bin], lend = p.bin_starts[bin + 1];
+
+    bool loaded = false;
+    unsigned long long shaded = 0, zfailed = 0;
+    for (unsigned base = lbeg; base < lend; ) {
+        /* ---- fill the queue: ordered compaction of the bin list against this tile ---- */
+        unsigned qn = 0;
+        while (base < lend && qn + RASTER_THREADS <= QUEUE_CAP) {
+            const unsigned k = base + tid;
+            bool hit = false; unsigned ti = 0;
+            if (k < lend) {
+                ti = __ldg(p.bin_list + k);
+                const int4 b = __ldg(p.bbox + ti);
+                hit = b.x <= X1 && b.z - 1 >= X0 && b.y <= Y1 && b.w >= Y0 && b.x < b.z;
+                if (hit) {
+                    /* edge-function reject of the whole tile (only when int32 cannot wrap) */
+                    const TriSetup s = p.setup[ti];
+                    if (s.flags & TF_SAFE) {
+                        const int rx0 = max(b.x, X0) - b.x, rx1 = min(b.z - 1, X1) - b.x;
+                        const int ry0 = max(b.y, Y0) - b.y, ry1 = min(b.w, Y1) - b.y;
+                        const int m1 = s.w1R + (s.w1X > 0 ? rx1 : rx0) * s.w1X + (s.w1Y > 0 ? ry1 : ry0) * s.w1Y;
+                        const int m2 = s.w2R + (s.w2X > 0 ? rx1 : rx0) * s.w2X + (s.w2Y > 0 ? ry1 : ry0) * s.w2Y;
+                        const int m3 = s.w3R + (s.w3X > 0 ? rx1 : rx0) * s.w3X + (s.w3Y > 0 ? ry1 : ry0) * s.w3Y;
+                        if ((m1 | m2 | m3) < 0) hit = false;
+                    }
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_wcount[warp] = __popc(bal);
+            __syncthreads();
+            unsigned woff = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { const unsigned c = s_wcount[w]; if (w < warp) woff += c; total += c; }
+            if (hit) s_queue[qn + woff + __popc(bal & ((1u << lane) - 1u))] = ti;
+            qn += total;
+            base += RASTER_THREADS;
+            __syncthreads();
+        }
+        if (qn == 0) continue;
+
+        /* ---- lazy tile load: 128-bit coalesced rows into the swizzled shared tile ---- */
+        if (!loaded) {
+            loaded = true;
+            if (full_tile) {
+                for (int r = tid >> 4; r < TILE; r += RASTER_THREADS / 16) {
+                    const int c4 = (tid & 15) << 2;
+                    const size_t gi = (size_t)(Y0 + r) * p.W + X0 + c4;
+                    const uint4 cv = __ldcs(reinterpret_cast<const uint4 *>(p.color + gi));
+                    const float4 dv = __ldcs(reinterpret_cast<const float4 *>(p.depth + gi));
+                    const int sa = tile_addr(c4, r);
+                    *reinterpret_cast<uint4 *>(s_color + sa) = cv;
+                    *reinterpret_cast<float4 *>(s_depth + sa) = dv;
+                }
+            } else {
+                for (int k = tid; k < TILE_PIX; k += RASTER_THREADS) {
+                    const int lx = k & (TILE - 1), ly = k >> 6;
+                    if (X0 + lx <= X1 && Y0 + ly <= Y1) {
+                        const size_t gi = (size_t)(Y0 + ly) * p.W + X0 + lx;
+                        s_color[tile_addr(lx, ly)] = p.color[gi];
+                        s_depth[tile_addr(lx, ly)] = p.depth[gi];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        /* ---- every warp walks the queue in order over the 8x4 blocks it owns ---- */
+        const int lx8 = lane & 7, ly4 = lane >> 3;
+        for (unsigned q = 0; q < qn; q++) {
+            const unsigned ti = s_queue[q];
+            const int4 b = __ldg(p.bbox + ti);
+            const int cx0 = max(b.x, X0) - X0, cx1 = min(b.z - 1, X1) - X0;     /* tile-local, inclusive */
+            const int cy0 = max(b.y, Y0) - Y0, cy1 = min(b.w, Y1) - Y0;
+            const int bx0 = cx0 >> 3, bx1 = cx1 >> 3, by0 = cy0 >> 2, by1 = cy1 >> 2;
+            /* does this warp own a block in range?  one block per block-row: bx = (warp - 3*by) & 7 */
+            bool any_block = false;
+            for (int by = by0; by <= by1; by++) { const int bx = (warp - 3 * by) & 7; if (bx >= bx0 && bx <= bx1) { any_block = true; break; } }
+            if (!any_block) continue;
+
+            const TriSetup s = p.setup[ti];
+            bool have_attr = false;
+            float z1 = 0, z2 = 0, z3 = 0; unsigned meta = 0, c1 = 0, c2 = 0, c3 = 0;
+            const DevState *st = nullptr;
+            unsigned flags = 0;
+
+            for (int by = by0; by <= by1; by++) {
+                const int bx = (warp - 3 * by) & 7;
+                if (bx < bx0 || bx > bx1) continue;
+                const int lx = (bx << 3) + lx8, ly = (by << 2) + ly4;
+                const int x = X0 + lx, y = Y0 + ly;
+                const int dx = x - b.x, dy = y - b.y;
+                const int w1 = wadd(wadd(s.w1R, wmul(dy, s.w1Y)), wmul(dx, s.w1X));
+                const int w2 = wadd(wadd(s.w2R, wmul(dy, s.w2Y)), wmul(dx, s.w2X));
+                const int w3 = wadd(wadd(s.w3R, wmul(dy, s.w3Y)), wmul(dx, s.w3X));
+                bool m = ((w1 | w2 | w3) > 0) && lx >= cx0 && lx <= cx1 && ly >= cy0 && ly <= cy1;
+                if (!__any_sync(0xffffffffu, m)) continue;
+
+                if (!have_attr) {
+                    have_attr = true;
+                    const uint4 a0 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti));
+                    const uint4 a1 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti) + 1);
+                    z1 = __uint_as_float(a0.x); z2 = __uint_as_float(a0.y); z3 = __uint_as_float(a0.z); meta = a0.w;
+                    c1 = a1.x; c2 = a1.y; c3 = a1.z;
+                    st = p.states + (meta & 0xffffffu);
+                    flags = st->flags;
+                }
+                const float W1 = FM(__int2float_rn(w1), s.invSum);
+                const float W2 = FM(__int2float_rn(w2), s.invSum);
+                const float W3 = FM(__int2float_rn(w3), s.invSum);
+                const float z = rcp_x86(FA(FA(FM(z1, W1), FM(z2, W2)), FM(z3, W3)));
+                const int sa = tile_addr(lx, ly);
+                if (flags & PFCU_ST_DEPTH_TEST) {
+                    const bool pass = depth_pass(st->depth_func, z, s_depth[sa]);
+                    if (m && !pass) zfailed++;
+                    m = m && pass;
+                    if (!__any_sync(0xffffffffu, m)) continue;
+                }
+
+                /* colour (color.h:153-203) */
+                unsigned frag;
+                if (flags & PFCU_ST_SMOOTH) {
+                    const int u1 = cvt_rne_x86(FM(W1, 255.0f)), u2 = cvt_rne_x86(FM(W2, 255.0f)), u3 = cvt_rne_x86(FM(W3, 255.0f));
+                    unsigned o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const unsigned sum = (unsigned)u1 * (unsigned)CHN(c1, i) + (unsigned)u2 * (unsigned)CHN(c2, i) + (unsigned)u3 * (unsigned)CHN(c3, i);
+                        o[i] = (sum * 257u) >> 16;
+                    }
+                    frag = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+                } else {
+                    const float mx = max_x86(W1, max_x86(W2, W3));
+                    frag = ((mx == W1) ? c1 : 0u) | ((mx == W2) ? c2 : 0u) | ((mx == W3) ? c3 : 0u);
+                }
+
+                if (HAS_TEX && (flags & PFCU_ST_TEXTURE)) {
+                    const uint4 a2 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti) + 2);
+                    const uint4 a3 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti) + 3);
+                    float u = FA(FA(FM(__uint_as_float(a2.x), W1), FM(__uint_as_float(a2.y), W2)), FM(__uint_as_float(a2.z), W3));
+                    float v = FA(FA(FM(__uint_as_float(a3.x), W1), FM(__uint_as_float(a3.y), W2)), FM(__uint_as_float(a3.z), W3));
+                    if (meta & (1u << 25)) { u = FM(u, z); v = FM(v, z); }
+                    if (m) frag = mul_color(tex_sample(st, u, v), frag);   /* masked-off lanes sample (0,0) upstream and are discarded */
+                }
+
+                if (HAS_PHONG && (flags & PFCU_ST_PHONG)) {
+                    const float4 *a = reinterpret_cast<const float4 *>(p.data + ti) + 4;
+                    const float4 px = __ldg(a), py = __ldg(a + 1), pz = __ldg(a + 2);
+                    const float4 nx = __ldg(a + 3), ny = __ldg(a + 4), nz = __ldg(a + 5);
+                    const float Nx = FA(FA(FM(nx.x, W1), FM(nx.y, W2)), FM(nx.z, W3));
+                    const float Ny = FA(FA(FM(ny.x, W1), FM(ny.y, W2)), FM(ny.z, W3));
+                    const float Nz = FA(FA(FM(nz.x, W1), FM(nz.y, W2)), FM(nz.z, W3));
+                    const float Px = FA(FA(FM(px.x, W1), FM(px.y, W2)), FM(px.z, W3));
+                    const float Py = FA(FA(FM(py.x, W1), FM(py.y, W2)), FM(py.z, W3));
+                    const float Pz = FA(FA(FM(pz.x, W1), FM(pz.y, W2)), FM(pz.z, W3));
+                    if (m) frag = phong(frag, st, (meta >> 24) & 1u, Px, Py, Pz, Nx, Ny, Nz);
+                }
+
+                if (m) {
+                    if (flags & PFCU_ST_BLEND) frag = blend_px(st->blend_mode, frag, s_color[sa]);
+                    s_color[sa] = frag;
+                    s_depth[sa] = z;            /* written even with the depth test off (Q11) */
+                    shaded++;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    /* ---- write the tile back ---- */
+    if (loaded) {
+        if (full_tile) {
+            for (int r = tid >> 4; r < TILE; r += RASTER_THREADS / 16) {
+                const int c4 = (tid & 15) << 2;
+                const size_t gi = (size_t)(Y0 + r) * p.W + X0 + c4;
+                const int sa = tile_addr(c4, r);
+                __stcs(reinterpret_cast<uint4 *>(p.color + gi), *reinterpret_cast<const uint4 *>(s_color + sa));
+                __stcs(reinterpret_cast<float4 *>(p.depth + gi), *reinterpret_cast<const float4 *>(s_depth + sa));
+            }
+        } else {
+            for (int k = tid; k < TILE_PIX; k += RASTER_THREADS) {
+                const int lx = k & (TILE - 1), ly = k >> 6;
+                if (X0 + lx <= X1 && Y0 + ly <= Y1) {
+                    const size_t gi = (size_t)(Y0 + ly) * p.W + X0 + lx;
+                    p.color[gi] = s_color[tile_addr(lx, ly)];
+                    p.depth[gi] = s_depth[tile_addr(lx, ly)];
+                }
+            }
+        }
+    }
+    /* counters: warp reduce, one atomic per warp */
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        shaded += __shfl_down_sync(0xffffffffu, shaded, o);
+        zfailed += __shfl_down_sync(0xffffffffu, zfailed, o);
+    }
+    if (lane == 0) {
+        if (shaded) atomicAdd(p.counters + 1, shaded);
+        if (zfailed) atomicAdd(p.counters + 2, zfailed);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* kernels: surface utilities                                                                       */
+/* ------------------------------------------------------------------------------------------------ */
+
+__global__ void k_fill(uint32_t *color, float *depth, size_t first, size_t n, int do_color, uint32_t rgba, int do_depth, float z)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < first + n; i += stride) {
+        if (do_color) color[i] = rgba;
+        if (do_depth) depth[i] = z;
+    }
+}
+
+/* vectorised body of a fill: [first4*4, (first4+n4)*4) */
+__global__ void k_fill4(uint4 *color, float4 *depth, size_t first4, size_t n4, int do_color, uint32_t rgba, int do_depth, float z)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const uint4 cv = make_uint4(rgba, rgba, rgba, rgba);
+    const float4 dv = make_float4(z, z, z, z);
+    for (size_t i = first4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < first4 + n4; i += stride) {
+        if (do_color) color[i] = cv;
+        if (do_depth) depth[i] = dv;
+    }
+}
+
+/* tail of the reference's pfClear: pixels [aligned, size) copy pixel 0 (context.c:710-713) */
+__global__ void k_clear_tail(uint32_t *color, float *depth, unsigned aligned, unsigned size, int do_color, int do_depth)
+{
+    const unsigned i = aligned + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < size) { if (do_color) color[i] = color[0]; if (do_depth) depth[i] = depth[0]; }
+}
+
+__global__ void k_pack_tiles(uint32_t *color, float *depth, int W, int H, int tilesX, unsigned nTiles,
+                             unsigned rank, unsigned world, int with_depth, uint32_t *staging, int unpack)
+{
+    const unsigned tile = rank + blockIdx.x * world;
+    if (tile >= nTiles) return;
+    const int X0 = (tile % tilesX) * TILE, Y0 = (tile / tilesX) * TILE;
+    uint32_t *sc = staging + (size_t)blockIdx.x * TILE_PIX * (with_depth ? 2 : 1);
+    uint32_t *sd = sc + TILE_PIX;
+    for (int k = threadIdx.x; k < TILE_PIX; k += blockDim.x) {
+        const int x = X0 + (k & (TILE - 1)), y = Y0 + (k >> 6);
+        if (x >= W || y >= H) continue;
+        const size_t gi = (size_t)y * W + x;
+        if (unpack) { color[gi] = sc[k]; if (with_depth) depth[gi] = __uint_as_float(sd[k]); }
+        else { sc[k] = color[gi]; if (with_depth) sd[k] = __float_as_uint(depth[gi]); }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* host: runtime                                                                                    */
+/* ------------------------------------------------------------------------------------------------ */
+
+template <typename T> static int grow(T **p, size_t *cap, size_t need)
+{
+    if (need <= *cap) return PFCU_OK;
+    size_t ncap = *cap ? *cap : 1024;
+    while (ncap < need) ncap *= 2;
+    CK(cudaStreamSynchronize(g.stream));
+    cudaFree(*p); *p = nullptr; *cap = 0;
+    if (cudaMalloc(p, ncap * sizeof(T)) != cudaSuccess) { snprintf(g.err, sizeof g.err, "out of device memory growing scratch to %zu elements", ncap); return PFCU_ERR_OOM; }
+    *cap = ncap;
+    return PFCU_OK;
+}
+
+extern "C" {
+
+const char *pfcu_last_error(void) { return g.err; }
+const char *pfcu_backend_name(void) { return "cuda-sm_100a"; }
+
+int pfcu_init(int device)
+{
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (g.ok) return PFCU_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        snprintf(g.err, sizeof g.err, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return PFCU_ERR_NO_DEVICE;
+    }
+    if (device < 0) {
+        const char *env = getenv("PF_CUDA_DEVICE");
+        if (!env) env = getenv("LOCAL_RANK");
+        device = env ? atoi(env) : 0;
+        if (device < 0 || device >= count) device = 0;
+    }
+    if (device >= count) { snprintf(g.err, sizeof g.err, "device %d out of range (%d devices)", device, count); return PFCU_ERR_NO_DEVICE; }
+    CK(cudaSetDevice(device));
+    g.device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    g.sms = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        snprintf(g.err, sizeof g.err, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return PFCU_ERR_NO_DEVICE;
+    }
+    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    g.own_stream = true;
+    CK(cudaMalloc(&g.d_counters, 4 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(g.d_counters, 0, 4 * sizeof(unsigned long long), g.stream));
+    CK(cudaMalloc(&g.d_bin_start, (MAX_BINS + 2) * 2 * sizeof(unsigned)));
+    CK(cudaEventCreateWithFlags(&g.stage_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.states_done, cudaEventDisableTiming));
+    g.ok = true;
+    return PFCU_OK;
+}
+
+void pfcu_shutdown(void)
+{
+    if (!g.ok) return;
+    cudaStreamSynchronize(g.stream);
+    cudaFree(g.d_tris); cudaFree(g.d_states); cudaFree(g.d_bbox); cudaFree(g.d_setup); cudaFree(g.d_data);
+    cudaFree(g.d_bin_counts); cudaFree(g.d_bin_list); cudaFree(g.d_bin_start); cudaFree(g.d_counters);
+    cudaFree(g.d_rcp); cudaFree(g.d_rsq);
+    if (g.h_stage) cudaFreeHost(g.h_stage);
+    if (g.h_states) cudaFreeHost(g.h_states);
+    if (g.own_stream) cudaStreamDestroy(g.stream);
+    g.ok = false; g.stream = nullptr; g.own_stream = false;
+    g.d_tris = nullptr; g.cap_tris = 0; g.d_states = nullptr; g.cap_states = 0;
+    g.d_bbox = nullptr; g.d_setup = nullptr; g.d_data = nullptr; g.cap_setup = 0;
+    g.d_bin_counts = nullptr; g.cap_bin_counts = 0; g.d_bin_list = nullptr; g.cap_bin_list = 0;
+    g.d_bin_start = nullptr; g.d_counters = nullptr; g.d_rcp = nullptr; g.d_rsq = nullptr;
+    g.h_stage = nullptr; g.cap_stage = 0; g.h_states = nullptr; g.cap_hstates = 0; g.pinned.clear();
+}
+
+int pfcu_set_stream(void *cuda_stream)
+{
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    CK(cudaStreamSynchronize(g.stream));
+    if (g.own_stream) { cudaStreamDestroy(g.stream); g.own_stream = false; }
+    g.stream = (cudaStream_t)cuda_stream;
+    return PFCU_OK;
+}
+
+void *pfcu_get_stream(void) { return (void *)g.stream; }
+
+void *pfcu_host_alloc(size_t bytes)
+{
+    if (!g.ok && pfcu_init(-1) != PFCU_OK) return nullptr;
+    PinnedBlock b; b.bytes = bytes; b.pending = false;
+    if (cudaHostAlloc(&b.p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming) != cudaSuccess) { cudaFreeHost(b.p); return nullptr; }
+    std::lock_guard<std::mutex> lk(g.mu);
+    g.pinned.push_back(b);
+    return b.p;
+}
+
+static PinnedBlock *find_pinned(const void *p)
+{
+    for (auto &b : g.pinned) if ((const char *)p >= (const char *)b.p && (const char *)p < (const char *)b.p + b.bytes) return &b;
+    return nullptr;
+}
+
+void pfcu_host_free(void *p)
+{
+    std::lock_guard<std::mutex> lk(g.mu);
+    for (size_t i = 0; i < g.pinned.size(); i++) if (g.pinned[i].p == p) {
+        if (g.pinned[i].pending) cudaEventSynchronize(g.pinned[i].done);
+        cudaEventDestroy(g.pinned[i].done); cudaFreeHost(p);
+        g.pinned.erase(g.pinned.begin() + i);
+        return;
+    }
+}
+
+int pfcu_host_wait(const void *p)
+{
+    PinnedBlock *b = find_pinned(p);
+    if (b && b->pending) { CK(cudaEventSynchronize(b->done)); b->pending = false; }
+    return PFCU_OK;
+}
+
+int pfcu_set_approx_tables(const uint32_t *rcp, int rcp_bits, const uint32_t *rsqrt, int rsqrt_bits)
+{
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (rcp_bits < 1 || rcp_bits > 23 || rsqrt_bits < 1 || rsqrt_bits > 23) return PFCU_ERR_INVALID;
+    CK(cudaStreamSynchronize(g.stream));
+    cudaFree(g.d_rcp); cudaFree(g.d_rsq);
+    CK(cudaMalloc(&g.d_rcp, sizeof(uint32_t) << rcp_bits));
+    CK(cudaMalloc(&g.d_rsq, sizeof(uint32_t) << (rsqrt_bits + 1)));
+    CK(cudaMemcpy(g.d_rcp, rcp, sizeof(uint32_t) << rcp_bits, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(g.d_rsq, rsqrt, sizeof(uint32_t) << (rsqrt_bits + 1), cudaMemcpyHostToDevice));
+    const int rshift = 23 - rcp_bits, sshift = 23 - rsqrt_bits;
+    CK(cudaMemcpyToSymbol(c_rcp_tab, &g.d_rcp, sizeof(void *)));
+    CK(cudaMemcpyToSymbol(c_rsq_tab, &g.d_rsq, sizeof(void *)));
+    CK(cudaMemcpyToSymbol(c_rcp_shift, &rshift, sizeof(int)));
+    CK(cudaMemcpyToSymbol(c_rsq_shift, &sshift, sizeof(int)));
+    CK(cudaMemcpyToSymbol(c_rsq_bits, &rsqrt_bits, sizeof(int)));
+    g.rcp_bits = rcp_bits; g.rsq_bits = rsqrt_bits;
+    return PFCU_OK;
+}
+
+/* ---- surfaces ---- */
+
+static void surface_dims(pfcu_surface *s) { s->tiles_x = (s->w + TILE - 1) / TILE; s->tiles_y = (s->h + TILE - 1) / TILE; }
+
+pfcu_surface *pfcu_surface_create(uint32_t w, uint32_t h)
+{
+    if (!g.ok || w == 0 || h == 0) { snprintf(g.err, sizeof g.err, "surface_create: runtime not initialised or empty surface"); return nullptr; }
+    pfcu_surface *s = (pfcu_surface *)calloc(1, sizeof *s);
+    if (!s) return nullptr;
+    s->w = w; s->h = h; s->owned = true; s->world = 1;
+    surface_dims(s);
+    const size_t bytes = ((size_t)w * h + 64) * 4;
+    if (cudaMalloc(&s->color, bytes) != cudaSuccess || cudaMalloc(&s->depth, bytes) != cudaSuccess) {
+        snprintf(g.err, sizeof g.err, "surface_create: out of device memory (%ux%u)", w, h);
+        cudaFree(s->color); free(s); return nullptr;
+    }
+    cudaMemsetAsync(s->color, 0, bytes, g.stream);
+    cudaMemsetAsync(s->depth, 0, bytes, g.stream);
+    return s;
+}
+
+pfcu_surface *pfcu_surface_wrap(void *dev_color, void *dev_depth, uint32_t w, uint32_t h)
+{
+    if (!g.ok || !dev_color || !dev_depth) return nullptr;
+    pfcu_surface *s = (pfcu_surface *)calloc(1, sizeof *s);
+    if (!s) return nullptr;
+    s->w = w; s->h = h; s->color = (uint32_t *)dev_color; s->depth = (float *)dev_depth; s->owned = false; s->world = 1;
+    surface_dims(s);
+    return s;
+}
+
+void pfcu_surface_destroy(pfcu_surface *s)
+{
+    if (!s) return;
+    if (g.ok) cudaStreamSynchronize(g.stream);
+    if (s->owned) { cudaFree(s->color); cudaFree(s->depth); }
+    free(s);
+}
+
+uint32_t pfcu_surface_width(const pfcu_surface *s) { return s->w; }
+uint32_t pfcu_surface_height(const pfcu_surface *s) { return s->h; }
+void *pfcu_surface_color_ptr(const pfcu_surface *s) { return s->color; }
+void *pfcu_surface_depth_ptr(const pfcu_surface *s) { return s->depth; }
+
+int pfcu_surface_upload(pfcu_surface *s, const void *hc, const float *hd, uint32_t y0, uint32_t rows)
+{
+    if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
+    const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;
+    if (hc) CK(cudaMemcpyAsync(s->color + off, (const uint32_t *)hc + off, n, cudaMemcpyHostToDevice, g.stream));
+    if (hd) CK(cudaMemcpyAsync(s->depth + off, hd + off, n, cudaMemcpyHostToDevice, g.stream));
+    /* pageable sources are staged by the driver before the call returns; pinned ones are not */
+    CK(cudaStreamSynchronize(g.stream));
+    return PFCU_OK;
+}
+
+int pfcu_surface_download(pfcu_surface *s, void *hc, float *hd, uint32_t y0, uint32_t rows)
+{
+    if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
+    const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;
+    if (hc) CK(cudaMemcpyAsync((uint32_t *)hc + off, s->color + off, n, cudaMemcpyDeviceToHost, g.stream));
+    if (hd) CK(cudaMemcpyAsync(hd + off, s->depth + off, n, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return PFCU_OK;
+}
+
+static int fill_range(pfcu_surface *s, size_t first, size_t n, int dc, uint32_t rgba, int dd, float z)
+{
+    if (n == 0) return PFCU_OK;
+    /* head (to 4-pixel alignment), vector body, tail */
+    size_t head = (4 - (first & 3)) & 3; if (head > n) head = n;
+    const size_t body4 = (n - head) / 4, tail = n - head - body4 * 4;
+    const int blocks = g.sms * 8;
+    if (head) { k_fill<<<1, 32, 0, g.stream>>>(s->color, s->depth, first, head, dc, rgba, dd, z); g.launches++; }
+    if (body4) {
+        k_fill4<<<blocks, 256, 0, g.stream>>>((uint4 *)s->color, (float4 *)s->depth, (first + head) / 4, body4, dc, rgba, dd, z);
+        g.launches++;
+    }
+    if (tail) { k_fill<<<1, 32, 0, g.stream>>>(s->color, s->depth, first + head + body4 * 4, tail, dc, rgba, dd, z); g.launches++; }
+    CK(cudaGetLastError());
+    return PFCU_OK;
+}
+
+int pfcu_surface_fill(pfcu_surface *s, int dc, uint32_t rgba, int dd, float z)
+{
+    return fill_range(s, 0, (size_t)s->w * s->h, dc, rgba, dd, z);
+}
+
+int pfcu_surface_clear_ref(pfcu_surface *s, int dc, uint32_t rgba, int dd, float z)
+{
+    const unsigned size = s->w * s->h, aligned = size - (size % 8u);
+    if (aligned > 8) { int rc = fill_range(s, 8, aligned - 8, dc, rgba, dd, z); if (rc) return rc; }
+    if (aligned < size) { k_clear_tail<<<1, 32, 0, g.stream>>>(s->color, s->depth, aligned, size, dc, dd); g.launches++; }
+    CK(cudaGetLastError());
+    return PFCU_OK;
+}
+
+int pfcu_surface_set_tile_owner(pfcu_surface *s, uint32_t rank, uint32_t world)
+{
+    if (world == 0) world = 1;
+    if (rank >= world) return PFCU_ERR_INVALID;
+    s->rank = rank; s->world = world;
+    return PFCU_OK;
+}
+
+static uint32_t owned_tiles(const pfcu_surface *s, uint32_t rank, uint32_t world)
+{
+    const uint32_t nt = s->tiles_x * s->tiles_y;
+    if (world <= 1) return nt;
+    return nt / world + ((nt % world) > rank ? 1u : 0u);
+}
+
+size_t pfcu_surface_owned_bytes(const pfcu_surface *s, uint32_t rank, uint32_t world, int with_depth)
+{
+    return (size_t)owned_tiles(s, rank, world) * TILE_PIX * 4u * (with_depth ? 2u : 1u);
+}
+
+static int pack_unpack(pfcu_surface *s, uint32_t rank, uint32_t world, int with_depth, void *staging, int unpack)
+{
+    if (world == 0) world = 1;
+    const uint32_t n = owned_tiles(s, rank, world);
+    if (n == 0) return PFCU_OK;
+    k_pack_tiles<<<n, 256, 0, g.stream>>>(s->color, s->depth, (int)s->w, (int)s->h, (int)s->tiles_x, s->tiles_x * s->tiles_y,
+                                          rank, world, with_depth, (uint32_t *)staging, unpack);
+    g.launches++;
+    CK(cudaGetLastError());
+    return PFCU_OK;
+}
+
+int pfcu_surface_pack_tiles(pfcu_surface *s, uint32_t r, uint32_t w, int wd, void *st) { return pack_unpack(s, r, w, wd, st, 0); }
+int pfcu_surface_unpack_tiles(pfcu_surface *s, uint32_t r, uint32_t w, int wd, const void *st) { return pack_unpack(s, r, w, wd, (void *)st, 1); }
+
+/* ---- textures ---- */
+
+static size_t tex_bytes(uint32_t w, uint32_t h, int fmt) { return (size_t)w * h * ((fmt == PFCU_TEX_RGBA8 || fmt == PFCU_TEX_BGRA8) ? 4u : 3u); }
+
+pfcu_texture *pfcu_texture_create(const void *host_pixels, uint32_t w, uint32_t h, int fmt)
+{
+    if (!g.ok || fmt < PFCU_TEX_RGBA8 || fmt > PFCU_TEX_BGR8 || w == 0 || h == 0) return nullptr;
+    pfcu_texture *t = (pfcu_texture *)calloc(1, sizeof *t);
+    if (!t) return nullptr;
+    t->w = w; t->h = h; t->fmt = fmt; t->owned = true;
+    const size_t bytes = tex_bytes(w, h, fmt);
+    if (cudaMalloc(&t->pixels, bytes + 16) != cudaSuccess) { snprintf(g.err, sizeof g.err, "texture_create: out of device memory"); free(t); return nullptr; }
+    cudaMemsetAsync(t->pixels, 0, bytes + 16, g.stream);
+    if (host_pixels && pfcu_texture_update(t, host_pixels) != PFCU_OK) { cudaFree(t->pixels); free(t); return nullptr; }
+    return t;
+}
+
+pfcu_texture *pfcu_texture_from_surface(pfcu_surface *s)
+{
+    pfcu_texture *t = (pfcu_texture *)calloc(1, sizeof *t);
+    if (!t) return nullptr;
+    t->w = s->w; t->h = s->h; t->fmt = PFCU_TEX_RGBA8; t->pixels = (unsigned char *)s->color; t->owned = false; t->alias = s;
+    return t;
+}
+
+int pfcu_texture_update(pfcu_texture *t, const void *host_pixels)
+{
+    if (!t || !t->owned || !host_pixels) return PFCU_ERR_INVALID;
+    CK(cudaMemcpyAsync(t->pixels, host_pixels, tex_bytes(t->w, t->h, t->fmt), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return PFCU_OK;
+}
+
+void pfcu_texture_destroy(pfcu_texture *t)
+{
+    if (!t) return;
+    if (g.ok) cudaStreamSynchronize(g.stream);
+    if (t->owned) cudaFree(t->pixels);
+    free(t);
+}
+
+/* ---- the hot path ---- */
+
+static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
+{
+    unsigned mask = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const pfcu_state *s = in + i; DevState *d = out + i;
+        memset(d, 0, sizeof *d);
+        d->flags = s->flags;
+        if (!(s->texture) ) d->flags &= ~PFCU_ST_TEXTURE;
+        if (s->n_lights == 0) d->flags &= ~PFCU_ST_PHONG;
+        d->blend_mode = s->blend_mode; d->depth_func = s->depth_func; d->tex_filter = s->tex_filter; d->tex_wrap = s->tex_wrap;
+        d->vp_min[0] = s->vp_min[0]; d->vp_min[1] = s->vp_min[1]; d->vp_max[0] = s->vp_max[0]; d->vp_max[1] = s->vp_max[1];
+        if (d->flags & PFCU_ST_TEXTURE) { d->tex = s->texture->pixels; d->tw = s->texture->w; d->th = s->texture->h; d->tfmt = s->texture->fmt; }
+        d->n_lights = s->n_lights > 8 ? 8 : s->n_lights;
+        for (unsigned l = 0; l < d->n_lights; l++) {
+            const pfcu_light *a = &s->lights[l]; DevLight *b = &d->lights[l];
+            memcpy(b->pos, a->position, 12); memcpy(b->dir, a->direction, 12);
+            b->inner = a->inner_cutoff; b->outer = a->outer_cutoff;
+            b->attc = a->att_constant; b->attl = a->att_linear; b->attq = a->att_quadratic;
+            b->ambient = a->ambient; b->diffuse = a->diffuse; b->specular = a->specular;
+        }
+        for (int f = 0; f < 2; f++) {
+            d->material[f].ambient = s->material[f].ambient; d->material[f].diffuse = s->material[f].diffuse;
+            d->material[f].specular = s->material[f].specular; d->material[f].emission = s->material[f].emission;
+            d->material[f].shininess = s->material[f].shininess;
+        }
+        memcpy(d->view_pos, s->view_pos, 12);
+        mask |= d->flags;
+    }
+    return mask;
+}
+
+static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const DevState *d_states, uint32_t n, unsigned feature_mask)
+{
+    if (n == 0) return PFCU_OK;
+    if (!g.d_rcp) { snprintf(g.err, sizeof g.err, "pfcu_set_approx_tables() has not been called"); return PFCU_ERR_INVALID; }
+    int rc;
+    if (n > g.cap_setup) {
+        size_t c1 = g.cap_setup, c2 = g.cap_setup, c3 = g.cap_setup;
+        if ((rc = grow(&g.d_bbox, &c1, n))) return rc;
+        if ((rc = grow(&g.d_setup, &c2, n))) return rc;
+        if ((rc = grow(&g.d_data, &c3, n))) return rc;
+        g.cap_setup = c1;
+    }
+    const int binsX = (int)((s->w + BIN_PIX - 1) / BIN_PIX), binsY = (int)((s->h + BIN_PIX - 1) / BIN_PIX);
+    const int nb = binsX * binsY;
+    if (nb > MAX_BINS) { snprintf(g.err, sizeof g.err, "surface too large for the binner (%d bins)", nb); return PFCU_ERR_INVALID; }
+    const unsigned nBatches = (n + BIN_BATCH - 1) / BIN_BATCH;
+    if ((rc = grow(&g.d_bin_counts, &g.cap_bin_counts, (size_t)nBatches * nb))) return rc;
+
+    k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, g.stream>>>(
+        d_tris, d_states, n, (int)s->w, (int)s->h, g.d_bbox, g.d_setup, g.d_data, g.d_counters);
+    k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), g.stream>>>(g.d_bbox, n, binsX, binsY, g.d_bin_counts);
+    unsigned *d_totals = g.d_bin_start + (MAX_BINS + 2);
+    k_bin_scan<<<nb, 256, 0, g.stream>>>(g.d_bin_counts, (int)nBatches, nb, d_totals);
+    k_bin_starts<<<1, 32, 0, g.stream>>>(d_totals, nb, g.d_bin_start);
+    /* Per-bin lists hold (triangle, bin) overlaps.  The exact total is only known on the device;
+       n*nb bounds it.  Small cases are sized by the bound, large ones read the total back. */
+    {
+        const size_t bound = (size_t)n * (size_t)nb;
+        size_t want = bound <= ((size_t)n * 4 > 65536 ? (size_t)n * 4 : 65536) ? bound : 0;
+        if (!want && bound <= g.cap_bin_list) want = bound;
+        if (!want) {
+            unsigned total = 0;
+            CK(cudaMemcpyAsync(&total, g.d_bin_start + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, g.stream));
+            CK(cudaStreamSynchronize(g.stream));
+            want = total;
+        }
+        if ((rc = grow(&g.d_bin_list, &g.cap_bin_list, want ? want : 1))) return rc;
+    }
+    k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), g.stream>>>(g.d_bbox, n, binsX, binsY, g.d_bin_counts, g.d_bin_start, g.d_bin_list);
+    g.launches += 5;
+
+    RasterParams p;
+    p.bbox = g.d_bbox; p.setup = g.d_setup; p.data = g.d_data; p.states = d_states;
+    p.bin_list = g.d_bin_list; p.bin_starts = g.d_bin_start; p.binsX = binsX;
+    p.color = s->color; p.depth = s->depth; p.W = (int)s->w; p.H = (int)s->h;
+    p.tilesX = (int)s->tiles_x; p.tilesY = (int)s->tiles_y;
+    p.rank = s->rank; p.world = s->world ? s->world : 1; p.nTiles = s->tiles_x * s->tiles_y;
+    p.counters = g.d_counters;
+    const unsigned grid = owned_tiles(s, p.rank, p.world);
+    if (grid) {
+        const bool tex = (feature_mask & PFCU_ST_TEXTURE) != 0, ph = (feature_mask & PFCU_ST_PHONG) != 0;
+        if (tex && ph)       k_raster<true, true><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
+        else if (tex)        k_raster<true, false><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
+        else if (ph)         k_raster<false, true><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
+        else                 k_raster<false, false><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
+        g.launches++;
+    }
+    CK(cudaGetLastError());
+    g.submitted += n;
+    return PFCU_OK;
+}
+
+int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, const pfcu_triangle *tris, uint32_t n_tris)
+{
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!s || (n_tris && (!states || !tris || n_states == 0))) return PFCU_ERR_INVALID;
+    if (n_tris == 0) return PFCU_OK;
+    int rc;
+    if ((rc = grow(&g.d_tris, &g.cap_tris, n_tris))) return rc;
+    if ((rc = grow(&g.d_states, &g.cap_states, n_states))) return rc;
+
+    /* states: convert handles to device pointers in pinned staging */
+    if (n_states > g.cap_hstates) {
+        CK(cudaEventSynchronize(g.states_done));
+        if (g.h_states) cudaFreeHost(g.h_states);
+        size_t c = g.cap_hstates ? g.cap_hstates : 64; while (c < n_states) c *= 2;
+        CK(cudaHostAlloc(&g.h_states, c * sizeof(DevState), cudaHostAllocDefault));
+        g.cap_hstates = c;
+    } else CK(cudaEventSynchronize(g.states_done));
+    const unsigned mask = convert_states(states, n_states, g.h_states);
+    CK(cudaMemcpyAsync(g.d_states, g.h_states, n_states * sizeof(DevState), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaEventRecord(g.states_done, g.stream));
+
+    /* triangles: one DMA from pinned memory, or staged through our own pinned buffer */
+    const size_t bytes = (size_t)n_tris * sizeof(pfcu_triangle);
+    PinnedBlock *pb = find_pinned(tris);
+    if (pb) {
+        CK(cudaMemcpyAsync(g.d_tris, tris, bytes, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaEventRecord(pb->done, g.stream));
+        pb->pending = true;
+    } else {
+        if (bytes > g.cap_stage) {
+            CK(cudaEventSynchronize(g.stage_done));
+            if (g.h_stage) cudaFreeHost(g.h_stage);
+            size_t c = g.cap_stage ? g.cap_stage : (1u << 20); while (c < bytes) c *= 2;
+            CK(cudaHostAlloc(&g.h_stage, c, cudaHostAllocDefault));
+            g.cap_stage = c;
+        } else CK(cudaEventSynchronize(g.stage_done));
+        memcpy(g.h_stage, tris, bytes);
+        CK(cudaMemcpyAsync(g.d_tris, g.h_stage, bytes, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaEventRecord(g.stage_done, g.stream));
+    }
+    return launch_pipeline(s, g.d_tris, g.d_states, n_tris, mask);
+}
+
+pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const pfcu_triangle *tris, uint32_t n_tris)
+{
+    if (!g.ok || !states || !tris || n_states == 0 || n_tris == 0) return nullptr;
+    pfcu_batch *b = (pfcu_batch *)calloc(1, sizeof *b);
+    if (!b) return nullptr;
+    std::vector<DevState> tmp(n_states);
+    b->feature_mask = convert_states(states, n_states, tmp.data());
+    b->n_states = n_states; b->n_tris = n_tris;
+    CKP(cudaMalloc(&b->states, n_states * sizeof(DevState)));
+    CKP(cudaMalloc(&b->tris, (size_t)n_tris * sizeof(pfcu_triangle)));
+    CKP(cudaMemcpyAsync(b->states, tmp.data(), n_states * sizeof(DevState), cudaMemcpyHostToDevice, g.stream));
+    CKP(cudaMemcpyAsync(b->tris, tris, (size_t)n_tris * sizeof(pfcu_triangle), cudaMemcpyHostToDevice, g.stream));
+    CKP(cudaStreamSynchronize(g.stream));
+    return b;
+}
+
+int pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b)
+{
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!s || !b) return PFCU_ERR_INVALID;
+    return launch_pipeline(s, b->tris, b->states, b->n_tris, b->feature_mask);
+}
+
+void pfcu_batch_destroy(pfcu_batch *b)
+{
+    if (!b) return;
+    if (g.ok) cudaStreamSynchronize(g.stream);
+    cudaFree(b->states); cudaFree(b->tris); free(b);
+}
+
+int pfcu_finish(void)
+{
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    CK(cudaStreamSynchronize(g.stream));
+    return PFCU_OK;
+}
+
+int pfcu_get_counters(pfcu_counters *out)
+{
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    unsigned long long h[4] = { 0, 0, 0, 0 };
+    CK(cudaMemcpyAsync(h, g.d_counters, sizeof h, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    out->triangles_submitted = g.submitted;
+    out->triangles_rasterised = h[0];
+    out->pixels_shaded = h[1];
+    out->pixels_depth_failed = h[2];
+    out->kernel_launches = g.launches;
+    return PFCU_OK;
+}
+
+void pfcu_reset_counters(void)
+{
+    if (!g.ok) return;
+    cudaMemsetAsync(g.d_counters, 0, 4 * sizeof(unsigned long long), g.stream);
+    g.submitted = 0; g.launches = 0;
+}
+
+} /* extern "C" */

@@ -1,0 +1,620 @@
+/*
+ * scenes.c - synthetic scenes for parity tests and benchmarks, written against pixelforge.h ONLY,
+ * so the very same translation unit is compiled three times:
+ *   - against the product            (libpfscenes_cuda.so,   -DPFSCENE_HAVE_PFX)
+ *   - against front end + C oracle   (libpfscenes_oracle.so, -DPFSCENE_HAVE_PFX)   tests only
+ *   - against the unmodified reference library and header (libpfscenes_ref*.so)    tests / CPU baseline
+ * Scene definitions follow BASELINE.json configs C1..C5 and SURVEY.md 8-d; all inputs are
+ * generated from an LCG (s <- 1664525 s + 1013904223), no files are read.
+ */
+#include "pixelforge.h"
+#ifdef PFSCENE_HAVE_PFX
+#include "pfx.h"
+#endif
+
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#define SCN_PI 3.14159265358979323846
+
+#if defined(__GNUC__)
+#define SCN_API __attribute__((visibility("default")))
+#else
+#define SCN_API
+#endif
+
+typedef struct {
+    int width, height;
+    int frames;         /* timed frames                                                           */
+    int warmup;         /* untimed frames before them                                             */
+    int variant;        /* scene specific bit field                                               */
+    int size;           /* scene specific size (grid resolution, layers, contexts ...)            */
+    int seed;
+    int explicit_sync;  /* product only: 1 = PF_CUDA_SYNC=explicit + pfxFinish per frame          */
+    int first_frame;    /* animation frame index of the first rendered frame                      */
+} pfscene_cfg;
+
+typedef struct {
+    double ms_total, ms_min, ms_median;
+    unsigned long long triangles_submitted, triangles_rasterised, pixels_shaded, pixels_depth_failed, kernel_launches;
+    unsigned long long api_triangles;   /* triangles the scene asked for (per frame)              */
+} pfscene_result;
+
+/* ---- helpers ---------------------------------------------------------------------------------- */
+
+static uint32_t lcg_state;
+static uint32_t lcg(void) { lcg_state = 1664525u * lcg_state + 1013904223u; return lcg_state; }
+static float lcgf(void) { return (float)(lcg() >> 8) * (1.0f / 16777216.0f); }
+
+static double now_ms(void)
+{
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+static void finish(void)
+{
+#ifdef PFSCENE_HAVE_PFX
+    pfxFinish();
+#endif
+}
+
+static float *g_depth_dst; static int g_depth_w;
+static PFcolor grab_depth(PFint x, PFint y, PFfloat depth, PFcolor c) { g_depth_dst[(size_t)y * g_depth_w + x] = depth; return c; }
+
+static void read_depth(float *dst, int w)
+{
+    if (!dst) return;
+#ifdef PFSCENE_HAVE_PFX
+    (void)w; pfxReadDepth(dst);
+#else
+    g_depth_dst = dst; g_depth_w = w; pfPostProcess(grab_depth);
+#endif
+}
+
+static void cam_perspective(double fovy_deg, double aspect, double zn, double zf)
+{
+    double top = zn * tan(fovy_deg * 0.5 * SCN_PI / 180.0), right = top * aspect;
+    pfMatrixMode(PF_PROJECTION); pfLoadIdentity();
+    pfFrustum((PFfloat)-right, (PFfloat)right, (PFfloat)-top, (PFfloat)top, (PFfloat)zn, (PFfloat)zf);
+    pfMatrixMode(PF_MODELVIEW); pfLoadIdentity();
+}
+
+static void cam_lookat(const float eye[3], const float at[3])
+{
+    float f[3] = { eye[0] - at[0], eye[1] - at[1], eye[2] - at[2] };
+    float l = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]); f[0] /= l; f[1] /= l; f[2] /= l;
+    float up[3] = { 0, 1, 0 };
+    float r[3] = { up[1] * f[2] - up[2] * f[1], up[2] * f[0] - up[0] * f[2], up[0] * f[1] - up[1] * f[0] };
+    l = sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]); r[0] /= l; r[1] /= l; r[2] /= l;
+    float u[3] = { f[1] * r[2] - f[2] * r[1], f[2] * r[0] - f[0] * r[2], f[0] * r[1] - f[1] * r[0] };
+    float m[16] = { r[0], u[0], f[0], 0, r[1], u[1], f[1], 0, r[2], u[2], f[2], 0,
+                    -(r[0] * eye[0] + r[1] * eye[1] + r[2] * eye[2]), -(u[0] * eye[0] + u[1] * eye[1] + u[2] * eye[2]),
+                    -(f[0] * eye[0] + f[1] * eye[1] + f[2] * eye[2]), 1 };
+    pfMatrixMode(PF_MODELVIEW); pfLoadIdentity(); pfMultMatrixf(m);
+}
+
+static void ortho2d(int w, int h)
+{
+    pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
+    pfMatrixMode(PF_PROJECTION); pfLoadIdentity();
+    pfOrtho(0.0f, (PFfloat)w, (PFfloat)h, 0.0f, 0.0f, 1.0f);
+    pfMatrixMode(PF_MODELVIEW); pfLoadIdentity();
+}
+
+static uint8_t *make_texture(int w, int h, int comps, uint32_t seed, int lo, int hi, int alo, int ahi)
+{
+    uint8_t *t = (uint8_t *)malloc((size_t)w * h * comps + 16);
+    lcg_state = seed;
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        uint32_t r = lcg();
+        for (int c = 0; c < comps; c++) {
+            int v = (int)((r >> (8 * c)) & 255u);
+            if (c < 3) v = lo + v % (hi - lo + 1); else v = alo + v % (ahi - alo + 1);
+            t[i * comps + c] = (uint8_t)v;
+        }
+    }
+    return t;
+}
+
+/* ---- C1: gears (call sequence of the reference's Gears demo, examples/SDL2/SDL2_Gears.c:4-194) --- */
+
+static unsigned long long g_api_tris;
+
+static void ring_vertex(double r, double a, double z) { pfVertex3f((PFfloat)(r * cos(a)), (PFfloat)(r * sin(a)), (PFfloat)z); }
+
+static void gear(double inner, double outer, double width, int teeth, double tooth_depth)
+{
+    const double r0 = inner, r1 = outer - tooth_depth / 2.0, r2 = outer + tooth_depth / 2.0;
+    const double da = 2.0 * SCN_PI / teeth / 4.0, hz = width * 0.5;
+    const double step = 2.0 * SCN_PI / teeth;
+
+    pfShadeModel(PF_FLAT);
+    for (int side = 0; side < 2; side++) {                  /* front (+z) then back (-z) */
+        const double z = side ? -hz : hz;
+        pfNormal3f(0.0f, 0.0f, side ? -1.0f : 1.0f);
+        pfBegin(PF_QUAD_STRIP);                             /* the face disc */
+        for (int i = 0; i <= teeth; i++) {
+            const double a = i * step;
+            if (!side) { ring_vertex(r0, a, z); ring_vertex(r1, a, z); ring_vertex(r0, a, z); ring_vertex(r1, a + 3 * da, z); }
+            else       { ring_vertex(r1, a, z); ring_vertex(r0, a, z); ring_vertex(r1, a + 3 * da, z); ring_vertex(r0, a, z); }
+        }
+        pfEnd();
+        pfBegin(PF_QUADS);                                  /* the tooth faces */
+        for (int i = 0; i < teeth; i++) {
+            const double a = i * step;
+            if (!side) { ring_vertex(r1, a, z); ring_vertex(r2, a + da, z); ring_vertex(r2, a + 2 * da, z); ring_vertex(r1, a + 3 * da, z); }
+            else       { ring_vertex(r1, a + 3 * da, z); ring_vertex(r2, a + 2 * da, z); ring_vertex(r2, a + da, z); ring_vertex(r1, a, z); }
+        }
+        pfEnd();
+        g_api_tris += (unsigned long long)(teeth + 1) * 2 + (unsigned long long)teeth * 2;
+    }
+    pfBegin(PF_QUAD_STRIP);                                 /* outward faces of the teeth */
+    for (int i = 0; i < teeth; i++) {
+        const double a = i * step;
+        ring_vertex(r1, a, hz); ring_vertex(r1, a, -hz);
+        double u = r2 * cos(a + da) - r1 * cos(a), v = r2 * sin(a + da) - r1 * sin(a), len = sqrt(u * u + v * v);
+        u /= len; v /= len;
+        pfNormal3f((PFfloat)v, (PFfloat)-u, 0.0f);
+        ring_vertex(r2, a + da, hz); ring_vertex(r2, a + da, -hz);
+        pfNormal3f((PFfloat)cos(a), (PFfloat)sin(a), 0.0f);
+        ring_vertex(r2, a + 2 * da, hz); ring_vertex(r2, a + 2 * da, -hz);
+        u = r1 * cos(a + 3 * da) - r2 * cos(a + 2 * da); v = r1 * sin(a + 3 * da) - r2 * sin(a + 2 * da);
+        pfNormal3f((PFfloat)v, (PFfloat)-u, 0.0f);
+        ring_vertex(r1, a + 3 * da, hz); ring_vertex(r1, a + 3 * da, -hz);
+        pfNormal3f((PFfloat)cos(a), (PFfloat)sin(a), 0.0f);
+    }
+    ring_vertex(r1, 0.0, hz); ring_vertex(r1, 0.0, -hz);
+    pfEnd();
+    g_api_tris += (unsigned long long)teeth * 8;
+
+    pfShadeModel(PF_SMOOTH);
+    pfBegin(PF_QUAD_STRIP);                                 /* bore */
+    for (int i = 0; i <= teeth; i++) {
+        const double a = i * step;
+        pfNormal3f((PFfloat)-cos(a), (PFfloat)-sin(a), 0.0f);
+        ring_vertex(r0, a, -hz); ring_vertex(r0, a, hz);
+    }
+    pfEnd();
+    g_api_tris += (unsigned long long)teeth * 2;
+}
+
+static void gears_setup(int w, int h)
+{
+    float pos[3] = { 5.0f, 5.0f, 10.0f }, dir[3];
+    float l = sqrtf(150.0f);
+    dir[0] = -pos[0] / l; dir[1] = -pos[1] / l; dir[2] = -pos[2] / l;
+    pfLightfv(PF_LIGHT0, PF_POSITION, pos);
+    pfLightfv(PF_LIGHT0, PF_SPOT_DIRECTION, dir);
+    pfEnable(PF_CULL_FACE); pfEnable(PF_LIGHTING); pfEnableLight(PF_LIGHT0); pfEnable(PF_DEPTH_TEST);
+    float aspect = (float)h / (float)w;
+    pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
+    pfMatrixMode(PF_PROJECTION); pfLoadIdentity();
+    pfFrustum(-1.0f, 1.0f, -aspect, aspect, 5.0f, 60.0f);
+    pfMatrixMode(PF_MODELVIEW); pfLoadIdentity();
+    pfTranslatef(0.0f, 0.0f, -40.0f);
+}
+
+static void gears_frame(float angle)
+{
+    pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+    pfEnable(PF_COLOR_MATERIAL);
+    pfColorMaterial(PF_FRONT_AND_BACK, PF_AMBIENT_AND_DIFFUSE);
+    pfPushMatrix();
+    pfRotatef(20.0f, 1.0f, 0.0f, 0.0f); pfRotatef(30.0f, 0.0f, 1.0f, 0.0f); pfRotatef(0.0f, 0.0f, 0.0f, 1.0f);
+    pfPushMatrix(); pfTranslatef(-3.0f, -2.0f, 0.0f); pfRotatef(angle, 0.0f, 0.0f, 1.0f);
+    pfColor3ub(255, 0, 0); gear(1.0, 4.0, 1.0, 20, 0.7); pfPopMatrix();
+    pfPushMatrix(); pfTranslatef(3.1f, -2.0f, 0.0f); pfRotatef(-2.0f * angle - 9.0f, 0.0f, 0.0f, 1.0f);
+    pfColor3ub(0, 255, 0); gear(0.5, 2.0, 2.0, 10, 0.7); pfPopMatrix();
+    pfPushMatrix(); pfTranslatef(-3.1f, 4.2f, 0.0f); pfRotatef(-2.0f * angle - 25.0f, 0.0f, 0.0f, 1.0f);
+    pfColor3ub(0, 0, 255); gear(1.3, 2.0, 0.5, 10, 0.7); pfPopMatrix();
+    pfPopMatrix();
+    pfDisable(PF_COLOR_MATERIAL);
+}
+
+/* ---- C2: textured torus, bilinear/nearest, repeat/clamp/mirror, alpha blend + depth ------------- */
+/* variant: bit0 bilinear, bits1-2 wrap mode, bit3 RGB8 texture instead of RGBA8, bit4 no blending */
+
+typedef struct { float *pos, *nrm, *uv; uint32_t *idx; int nverts, nidx; } mesh_t;
+
+static mesh_t make_torus(int nu, int nv, float R, float r, float uvscale)
+{
+    mesh_t m; m.nverts = (nu + 1) * (nv + 1); m.nidx = nu * nv * 6;
+    m.pos = (float *)malloc(sizeof(float) * 3 * m.nverts); m.nrm = (float *)malloc(sizeof(float) * 3 * m.nverts);
+    m.uv = (float *)malloc(sizeof(float) * 2 * m.nverts); m.idx = (uint32_t *)malloc(sizeof(uint32_t) * m.nidx);
+    for (int i = 0; i <= nu; i++) for (int j = 0; j <= nv; j++) {
+        double a = 2.0 * SCN_PI * i / nu, b = 2.0 * SCN_PI * j / nv;
+        int k = i * (nv + 1) + j;
+        m.pos[3 * k] = (float)((R + r * cos(b)) * cos(a)); m.pos[3 * k + 1] = (float)(r * sin(b)); m.pos[3 * k + 2] = (float)((R + r * cos(b)) * sin(a));
+        m.nrm[3 * k] = (float)(cos(b) * cos(a)); m.nrm[3 * k + 1] = (float)sin(b); m.nrm[3 * k + 2] = (float)(cos(b) * sin(a));
+        m.uv[2 * k] = uvscale * (float)i / nu * 4.0f - 0.5f * (uvscale - 1.0f); m.uv[2 * k + 1] = uvscale * (float)j / nv - 0.5f * (uvscale - 1.0f);
+    }
+    int n = 0;
+    for (int i = 0; i < nu; i++) for (int j = 0; j < nv; j++) {
+        uint32_t a = (uint32_t)(i * (nv + 1) + j), b = a + 1, c = a + (uint32_t)(nv + 1), d = c + 1;
+        m.idx[n++] = a; m.idx[n++] = b; m.idx[n++] = c; m.idx[n++] = b; m.idx[n++] = d; m.idx[n++] = c;
+    }
+    return m;
+}
+
+static void free_mesh(mesh_t *m) { free(m->pos); free(m->nrm); free(m->uv); free(m->idx); }
+
+static void draw_mesh_immediate(const mesh_t *m)
+{
+    pfBegin(PF_TRIANGLES);
+    for (int k = 0; k < m->nidx; k++) {
+        uint32_t i = m->idx[k];
+        pfNormal3fv(m->nrm + 3 * i); pfTexCoordfv(m->uv + 2 * i); pfVertex3fv(m->pos + 3 * i);
+    }
+    pfEnd();
+    g_api_tris += (unsigned long long)m->nidx / 3;
+}
+
+static void draw_mesh_arrays(const mesh_t *m)
+{
+    pfEnable(PF_VERTEX_ARRAY); pfEnable(PF_NORMAL_ARRAY); pfEnable(PF_TEXTURE_COORD_ARRAY);
+    pfVertexPointer(3, PF_FLOAT, 0, m->pos); pfNormalPointer(PF_FLOAT, 0, m->nrm); pfTexCoordPointer(PF_FLOAT, 0, m->uv);
+    pfDrawElements(PF_TRIANGLES, (PFsizei)m->nidx, PF_UNSIGNED_INT, m->idx);
+    pfDisable(PF_VERTEX_ARRAY); pfDisable(PF_NORMAL_ARRAY); pfDisable(PF_TEXTURE_COORD_ARRAY);
+    g_api_tris += (unsigned long long)m->nidx / 3;
+}
+
+/* ---- C3: height field, per-pixel Blinn-Phong ----------------------------------------------------- */
+
+static mesh_t make_heightfield(int n)
+{
+    mesh_t m; m.nverts = (n + 1) * (n + 1); m.nidx = n * n * 6;
+    m.pos = (float *)malloc(sizeof(float) * 3 * m.nverts); m.nrm = (float *)malloc(sizeof(float) * 3 * m.nverts);
+    m.uv = (float *)malloc(sizeof(float) * 2 * m.nverts); m.idx = (uint32_t *)malloc(sizeof(uint32_t) * m.nidx);
+    for (int j = 0; j <= n; j++) for (int i = 0; i <= n; i++) {
+        double x = -2.0 + 4.0 * i / n, y = -1.2 + 2.4 * j / n;
+        double z = 0.3 * sin(3 * x) * cos(3 * y);
+        double dzdx = 0.9 * cos(3 * x) * cos(3 * y), dzdy = -0.9 * sin(3 * x) * sin(3 * y);
+        double l = sqrt(dzdx * dzdx + dzdy * dzdy + 1.0);
+        int k = j * (n + 1) + i;
+        m.pos[3 * k] = (float)x; m.pos[3 * k + 1] = (float)y; m.pos[3 * k + 2] = (float)z;
+        m.nrm[3 * k] = (float)(-dzdx / l); m.nrm[3 * k + 1] = (float)(-dzdy / l); m.nrm[3 * k + 2] = (float)(1.0 / l);
+        m.uv[2 * k] = (float)i / n; m.uv[2 * k + 1] = (float)j / n;
+    }
+    int c = 0;
+    for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) {
+        uint32_t a = (uint32_t)(j * (n + 1) + i), b = a + 1, d = a + (uint32_t)(n + 1), e = d + 1;
+        m.idx[c++] = a; m.idx[c++] = b; m.idx[c++] = e; m.idx[c++] = a; m.idx[c++] = e; m.idx[c++] = d;
+    }
+    return m;
+}
+
+/* ---- C4: overdraw -------------------------------------------------------------------------------- */
+
+static void draw_textured_quad(PFtexture tex, float x, float y, float w, float h, float urep, float vrep)
+{
+    pfBindTexture(tex);
+    pfBegin(PF_QUADS);
+    pfTexCoord2f(0.0f, 0.0f); pfVertex2f(x, y);
+    pfTexCoord2f(0.0f, vrep); pfVertex2f(x, y + h);
+    pfTexCoord2f(urep, vrep); pfVertex2f(x + w, y + h);
+    pfTexCoord2f(urep, 0.0f); pfVertex2f(x + w, y);
+    pfEnd();
+    pfBindTexture(0);
+    g_api_tris += 2;
+}
+
+/* ---- micro scenes for parity ---------------------------------------------------------------------- */
+
+static void random_vertex(int w, int h, int with_uv, float zlo, float zhi)
+{
+    PFcolor c = { (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(64 + ((lcg() >> 24) % 192)) };
+    pfColor(c);
+    if (with_uv) pfTexCoord2f(lcgf() * 6.0f - 3.0f, lcgf() * 6.0f - 3.0f);
+    pfNormal3f(lcgf() - 0.5f, lcgf() - 0.5f, lcgf() + 0.2f);
+    pfVertex3f(lcgf() * (w * 1.2f) - 0.1f * w, lcgf() * (h * 1.2f) - 0.1f * h, zlo + lcgf() * (zhi - zlo));
+}
+
+/* variant bits: 0-2 blend mode (with bit3: blending on), 4-6 depth func (bit7: depth test on),
+   8 flat shading, 9 texture on, 10 bilinear, 11-12 wrap, 13 cull off, 14-16 draw mode selector,
+   17 RGB8 texture, 18 perspective camera instead of 2D ortho, 19 Phong lights, 20 render into an FBO
+   and composite it, 21 spotlight+attenuation, 22 BGRA texture */
+static void micro_scene(const pfscene_cfg *cfg, PFtexture tex)
+{
+    const int v = cfg->variant, w = cfg->width, h = cfg->height;
+    pfClearColor(10, 20, 30, 255);
+    pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+    if (v & (1 << 18)) {
+        cam_perspective(60.0, (double)w / h, 0.1, 100.0);
+        pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
+        float eye[3] = { 0.3f, 0.4f, 3.0f }, at[3] = { 0, 0, 0 };
+        cam_lookat(eye, at);
+    } else ortho2d(w, h);
+    if (v & 8) { pfEnable(PF_BLEND); pfBlendFunc((PFblendmode)(v & 7)); } else pfDisable(PF_BLEND);
+    if (v & 128) { pfEnable(PF_DEPTH_TEST); pfDepthFunc((PFdepthmode)((v >> 4) & 7) > PF_GEQUAL ? PF_LESS : (PFdepthmode)((v >> 4) & 7)); } else pfDisable(PF_DEPTH_TEST);
+    pfShadeModel((v & 256) ? PF_FLAT : PF_SMOOTH);
+    if (v & 512) {
+        pfEnable(PF_TEXTURE_2D);
+        pfTextureParameter(tex, (PFtexturewrap)(((v >> 11) & 3) % 3), (v & 1024) ? PF_BILINEAR : PF_NEAREST);
+        pfBindTexture(tex);
+    } else pfDisable(PF_TEXTURE_2D);
+    if (v & (1 << 13)) pfDisable(PF_CULL_FACE); else pfEnable(PF_CULL_FACE);
+    if (v & (1 << 19)) {
+        float lp[3] = { 1.5f, 2.0f, 2.5f }, lp2[3] = { -2.0f, 0.5f, 1.0f }, ld[3] = { 0.5f, -0.3f, -0.8f };
+        float amb[3] = { 0.8f, 0.3f, 0.2f }, spec[3] = { 1.0f, 1.0f, 1.0f };
+        pfEnable(PF_LIGHTING); pfLightModel(PF_PHONG);
+        pfLightfv(PF_LIGHT0, PF_POSITION, lp); pfEnableLight(PF_LIGHT0);
+        pfLightfv(PF_LIGHT1, PF_POSITION, lp2);
+        if (v & (1 << 21)) {
+            pfLightfv(PF_LIGHT1, PF_SPOT_DIRECTION, ld);
+            pfLightf(PF_LIGHT1, PF_SPOT_INNER_CUTOFF, 25.0f); pfLightf(PF_LIGHT1, PF_SPOT_OUTER_CUTOFF, 40.0f);
+            pfLightf(PF_LIGHT1, PF_LINEAR_ATTENUATION, 0.05f); pfLightf(PF_LIGHT1, PF_QUADRATIC_ATTENUATION, 0.02f);
+        }
+        pfEnableLight(PF_LIGHT1);
+        pfMaterialfv(PF_FRONT_AND_BACK, PF_AMBIENT_AND_DIFFUSE, amb); pfMaterialfv(PF_FRONT_AND_BACK, PF_SPECULAR, spec);
+        pfMaterialf(PF_FRONT_AND_BACK, PF_SHININESS, 32.0f);
+    }
+    lcg_state = (uint32_t)cfg->seed * 2654435761u + 12345u;
+    const int n = cfg->size > 0 ? cfg->size : 64;
+    static const PFdrawmode modes[6] = { PF_TRIANGLES, PF_QUADS, PF_TRIANGLE_FAN, PF_TRIANGLE_STRIP, PF_QUAD_FAN, PF_QUAD_STRIP };
+    const PFdrawmode mode = modes[((v >> 14) & 7) % 6];
+    const int persp = (v >> 18) & 1;
+    pfBegin(mode);
+    for (int i = 0; i < n * 3; i++) {
+        if (persp) {
+            PFcolor c = { (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(64 + ((lcg() >> 24) % 192)) };
+            pfColor(c);
+            pfTexCoord2f(lcgf() * 4.0f - 2.0f, lcgf() * 4.0f - 2.0f);
+            pfNormal3f(lcgf() - 0.5f, lcgf() - 0.5f, lcgf() + 0.2f);
+            pfVertex3f(lcgf() * 5.0f - 2.5f, lcgf() * 4.0f - 2.0f, lcgf() * 6.0f - 2.0f);     /* some cross the near plane */
+        } else random_vertex(w, h, 1, -0.9f, -0.1f);
+    }
+    pfEnd();
+    pfDisable(PF_LIGHTING); pfDisableLight(PF_LIGHT0); pfDisableLight(PF_LIGHT1); pfLightModel(PF_GOURAUD);
+    pfBindTexture(0);
+}
+
+/* ---- the runner ------------------------------------------------------------------------------------ */
+
+static int cmp_double(const void *a, const void *b) { double x = *(const double *)a, y = *(const double *)b; return (x > y) - (x < y); }
+
+static void collect(pfscene_result *res, double *times, int n)
+{
+    res->ms_total = 0; res->ms_min = 1e300;
+    for (int i = 0; i < n; i++) { res->ms_total += times[i]; if (times[i] < res->ms_min) res->ms_min = times[i]; }
+    if (n > 0) { qsort(times, (size_t)n, sizeof(double), cmp_double); res->ms_median = times[n / 2]; } else res->ms_min = 0;
+#ifdef PFSCENE_HAVE_PFX
+    PFXcounters k; pfxGetCounters(&k);
+    res->triangles_submitted = k.triangles_submitted; res->triangles_rasterised = k.triangles_rasterised;
+    res->pixels_shaded = k.pixels_shaded; res->pixels_depth_failed = k.pixels_depth_failed; res->kernel_launches = k.kernel_launches;
+#endif
+}
+
+static void reset_counters(void)
+{
+#ifdef PFSCENE_HAVE_PFX
+    pfxResetCounters();
+#endif
+}
+
+SCN_API const char *pfscene_backend(void)
+{
+#ifdef PFSCENE_HAVE_PFX
+    return pfxBackendName();
+#else
+    return "reference";
+#endif
+}
+
+/* Renders `cfg->warmup + cfg->frames` frames of scene `name`; the colour buffer (w*h*4 bytes) and,
+ * when depth_out != NULL, the depth buffer of the LAST frame are returned.  Counters cover the timed
+ * frames only.  Returns 0 on success. */
+SCN_API int pfscene_render(const char *name, const pfscene_cfg *cfg, uint8_t *color_out, float *depth_out, pfscene_result *res)
+{
+    const int w = cfg->width, h = cfg->height;
+    const int total = cfg->warmup + cfg->frames;
+    double *times = (double *)calloc((size_t)(cfg->frames > 0 ? cfg->frames : 1), sizeof(double));
+    memset(res, 0, sizeof *res);
+#ifdef PFSCENE_HAVE_PFX
+    pfxSetSyncMode(cfg->explicit_sync ? PF_TRUE : PF_FALSE);
+#endif
+
+    if (strcmp(name, "batch") == 0) {
+        /* C5: `size` independent 512x512-style contexts, each with its own target, texture and the
+           three gear render lists; replayed with a per-context angle.  Textured + lit + depth. */
+        const int n = cfg->size > 0 ? cfg->size : 4;
+        PFcontext *ctx = (PFcontext *)calloc((size_t)n, sizeof(PFcontext));
+        uint8_t **buf = (uint8_t **)calloc((size_t)n, sizeof(uint8_t *));
+        uint8_t **texpx = (uint8_t **)calloc((size_t)n, sizeof(uint8_t *));
+        PFtexture *tex = (PFtexture *)calloc((size_t)n, sizeof(PFtexture));
+        PFrenderlist (*lists)[3] = (PFrenderlist (*)[3])calloc((size_t)n, sizeof(PFrenderlist[3]));
+        for (int c = 0; c < n; c++) {
+            buf[c] = (uint8_t *)calloc((size_t)w * h * 4 + 64, 1);
+            ctx[c] = pfCreateContext(buf[c], (PFsizei)w, (PFsizei)h, PF_RGBA, PF_UNSIGNED_BYTE);
+            if (!ctx[c]) { fprintf(stderr, "pfscene: pfCreateContext failed\n"); return 2; }
+            pfMakeCurrent(ctx[c]);
+            texpx[c] = make_texture(256, 256, 4, (uint32_t)(cfg->seed + c), 96, 255, 255, 255);
+            tex[c] = pfGenTexture(texpx[c], 256, 256, PF_RGBA, PF_UNSIGNED_BYTE);
+            gears_setup(w, h);
+            pfEnable(PF_TEXTURE_2D);
+            static const double gp[3][5] = { { 1.0, 4.0, 1.0, 20, 0.7 }, { 0.5, 2.0, 2.0, 10, 0.7 }, { 1.3, 2.0, 0.5, 10, 0.7 } };
+            for (int g = 0; g < 3; g++) {
+                lists[c][g] = pfGenList();
+                pfBindTexture(tex[c]);
+                pfNewList(lists[c][g]);
+                pfTexCoord2f(0.25f * (float)g, 0.5f);
+                gear(gp[g][0], gp[g][1], gp[g][2], (int)gp[g][3], gp[g][4]);
+                pfEndList();
+            }
+        }
+        for (int f = 0; f < total; f++) {
+            if (f == cfg->warmup) { reset_counters(); g_api_tris = 0; }
+            double t0 = now_ms();
+            for (int c = 0; c < n; c++) {
+                pfMakeCurrent(ctx[c]);
+                float angle = 7.0f * (float)c + 1.44f * (float)(cfg->first_frame + f);
+                pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+                pfEnable(PF_COLOR_MATERIAL); pfColorMaterial(PF_FRONT_AND_BACK, PF_AMBIENT_AND_DIFFUSE);
+                pfPushMatrix();
+                pfRotatef(20.0f, 1.0f, 0.0f, 0.0f); pfRotatef(30.0f, 0.0f, 1.0f, 0.0f);
+                static const float tr[3][2] = { { -3.0f, -2.0f }, { 3.1f, -2.0f }, { -3.1f, 4.2f } };
+                static const PFubyte col[3][3] = { { 255, 64, 64 }, { 64, 255, 64 }, { 64, 64, 255 } };
+                for (int g = 0; g < 3; g++) {
+                    pfPushMatrix();
+                    pfTranslatef(tr[g][0], tr[g][1], 0.0f);
+                    pfRotatef(g == 0 ? angle : (g == 1 ? -2.0f * angle - 9.0f : -2.0f * angle - 25.0f), 0.0f, 0.0f, 1.0f);
+                    pfColor3ub(col[g][0], col[g][1], col[g][2]);
+                    pfCallList(lists[c][g]);
+                    pfPopMatrix();
+                }
+                pfPopMatrix();
+                pfDisable(PF_COLOR_MATERIAL);
+            }
+            for (int c = 0; c < n; c++) { pfMakeCurrent(ctx[c]); finish(); }
+            if (f >= cfg->warmup) times[f - cfg->warmup] = now_ms() - t0;
+        }
+        res->api_triangles = g_api_tris;
+        collect(res, times, cfg->frames);
+        /* output: context 0 followed by the XOR of all contexts' pixels in the depth slot is not needed;
+           return context (size-1) so that per-context parameters matter */
+        pfMakeCurrent(ctx[n - 1]);
+        if (color_out) memcpy(color_out, buf[n - 1], (size_t)w * h * 4);
+        read_depth(depth_out, w);
+        for (int c = 0; c < n; c++) {
+            pfMakeCurrent(ctx[c]);
+            for (int g = 0; g < 3; g++) pfDeleteList(&lists[c][g]);
+            pfDeleteTexture(&tex[c], PF_FALSE);
+            pfMakeCurrent(NULL);
+            pfDeleteContext(ctx[c]);
+            free(buf[c]); free(texpx[c]);
+        }
+        free(ctx); free(buf); free(texpx); free(tex); free(lists); free(times);
+        return 0;
+    }
+
+    uint8_t *target = (uint8_t *)calloc((size_t)w * h * 4 + 64, 1);
+    PFcontext ctx = pfCreateContext(target, (PFsizei)w, (PFsizei)h, PF_RGBA, PF_UNSIGNED_BYTE);
+    if (!ctx) { fprintf(stderr, "pfscene: pfCreateContext failed\n"); free(target); free(times); return 2; }
+    pfMakeCurrent(ctx);
+    int rc = 0;
+    uint8_t *texpx = NULL; PFtexture tex = NULL; mesh_t mesh; memset(&mesh, 0, sizeof mesh);
+    PFframebuffer fbo; memset(&fbo, 0, sizeof fbo);
+
+    if (strcmp(name, "gears") == 0) {
+        gears_setup(w, h);
+    } else if (strcmp(name, "textured") == 0) {
+        const int rgb = (cfg->variant >> 3) & 1;
+        texpx = make_texture(1024, 1024, rgb ? 3 : 4, (uint32_t)cfg->seed, 0, 255, 128, 255);
+        tex = pfGenTexture(texpx, 1024, 1024, rgb ? PF_RGB : PF_RGBA, PF_UNSIGNED_BYTE);
+        pfTextureParameter(tex, (PFtexturewrap)(((cfg->variant >> 1) & 3) % 3), (cfg->variant & 1) ? PF_BILINEAR : PF_NEAREST);
+        const int nu = cfg->size > 0 ? cfg->size : 256;
+        mesh = make_torus(nu, nu / 2, 12.0f, 5.0f, ((cfg->variant >> 1) & 3) ? 1.6f : 1.0f);
+        pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
+        cam_perspective(60.0, (double)w / h, 0.01, 1000.0);
+        pfEnable(PF_TEXTURE_2D); pfEnable(PF_DEPTH_TEST);
+        if (!(cfg->variant & 16)) { pfEnable(PF_BLEND); pfBlendFunc(PF_BLEND_ALPHA); }
+        pfDisable(PF_CULL_FACE);
+    } else if (strcmp(name, "phong") == 0) {
+        const int n = cfg->size > 0 ? cfg->size : 708;
+        mesh = make_heightfield(n);
+        pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
+        cam_perspective(60.0, (double)w / h, 0.01, 1000.0);
+        float eye[3] = { 0.0f, 0.0f, 2.6f }, at[3] = { 0, 0, 0 };
+        cam_lookat(eye, at);
+        float lp[3] = { 2.0f, 3.0f, 4.0f }, amb[3] = { 0.8f, 0.3f, 0.2f }, spec[3] = { 1.0f, 1.0f, 1.0f };
+        pfEnable(PF_LIGHTING); pfLightModel(PF_PHONG);
+        pfLightfv(PF_LIGHT0, PF_POSITION, lp); pfEnableLight(PF_LIGHT0);
+        pfMaterialfv(PF_FRONT_AND_BACK, PF_AMBIENT_AND_DIFFUSE, amb); pfMaterialfv(PF_FRONT_AND_BACK, PF_SPECULAR, spec);
+        pfMaterialf(PF_FRONT_AND_BACK, PF_SHININESS, 32.0f);
+        pfEnable(PF_DEPTH_TEST); pfEnable(PF_CULL_FACE);
+    } else if (strcmp(name, "overdraw") == 0) {
+        /* variant: bit0 alpha-blend + depth test (4K target scene) instead of additive / no depth;
+           bit1 bilinear */
+        texpx = make_texture(512, 512, 4, (uint32_t)cfg->seed, 0, 3, (cfg->variant & 1) ? 96 : 0, (cfg->variant & 1) ? 200 : 3);
+        if (cfg->variant & 1) { lcg_state = 7u; for (size_t i = 0; i < 512u * 512u; i++) for (int c = 0; c < 3; c++) texpx[i * 4 + c] = (uint8_t)(lcg() >> 24); }
+        tex = pfGenTexture(texpx, 512, 512, PF_RGBA, PF_UNSIGNED_BYTE);
+        pfTextureParameter(tex, PF_REPEAT, (cfg->variant & 2) ? PF_BILINEAR : PF_NEAREST);
+        ortho2d(w, h);
+        pfEnable(PF_TEXTURE_2D); pfEnable(PF_BLEND);
+        if (cfg->variant & 1) { pfBlendFunc(PF_BLEND_ALPHA); pfEnable(PF_DEPTH_TEST); pfDepthFunc(PF_LEQUAL); }
+        else pfBlendFunc(PF_BLEND_ADD);
+    } else if (strcmp(name, "micro") == 0) {
+        const int rgb = (cfg->variant >> 17) & 1, bgra = (cfg->variant >> 22) & 1;
+        texpx = make_texture(61, 37, rgb ? 3 : 4, (uint32_t)cfg->seed ^ 0xabcdu, 0, 255, 0, 255);
+        tex = pfGenTexture(texpx, 61, 37, rgb ? PF_RGB : (bgra ? PF_BGRA : PF_RGBA), PF_UNSIGNED_BYTE);
+        if (cfg->variant & (1 << 20)) fbo = pfGenFramebuffer(96, 80, PF_RGBA, PF_UNSIGNED_BYTE);
+    } else {
+        fprintf(stderr, "pfscene: unknown scene '%s'\n", name);
+        rc = 1;
+    }
+
+    for (int f = 0; rc == 0 && f < total; f++) {
+        if (f == cfg->warmup) { reset_counters(); g_api_tris = 0; }
+        const int frame = cfg->first_frame + f;
+        double t0 = now_ms();
+        if (strcmp(name, "gears") == 0) {
+            gears_frame(1.44f * (float)frame);
+        } else if (strcmp(name, "textured") == 0) {
+            double t = 0.35 + 0.05 * frame;
+            float eye[3] = { (float)(35.0 * cos(t)), 30.0f, (float)(35.0 * sin(t)) }, at[3] = { 0.0f, 0.0f, 0.0f };
+            cam_lookat(eye, at);
+            pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+            pfBindTexture(tex);
+            pfColor4ub(255, 255, 255, 200);
+            if (cfg->variant & 32) draw_mesh_arrays(&mesh); else draw_mesh_immediate(&mesh);
+        } else if (strcmp(name, "phong") == 0) {
+            pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+            pfColor4ub(255, 255, 255, 255);
+            if (cfg->variant & 32) {
+                pfEnable(PF_VERTEX_ARRAY); pfEnable(PF_NORMAL_ARRAY);
+                pfVertexPointer(3, PF_FLOAT, 0, mesh.pos); pfNormalPointer(PF_FLOAT, 0, mesh.nrm);
+                pfDrawElements(PF_TRIANGLES, (PFsizei)mesh.nidx, PF_UNSIGNED_INT, mesh.idx);
+                pfDisable(PF_VERTEX_ARRAY); pfDisable(PF_NORMAL_ARRAY);
+                g_api_tris += (unsigned long long)mesh.nidx / 3;
+            } else {
+                pfBegin(PF_TRIANGLES);
+                for (int k = 0; k < mesh.nidx; k++) { uint32_t i = mesh.idx[k]; pfNormal3fv(mesh.nrm + 3 * i); pfVertex3fv(mesh.pos + 3 * i); }
+                pfEnd();
+                g_api_tris += (unsigned long long)mesh.nidx / 3;
+            }
+        } else if (strcmp(name, "overdraw") == 0) {
+            const int layers = cfg->size > 0 ? cfg->size : 64;
+            pfClearColor(0, 0, 0, 255);
+            pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+            pfColor4ub(255, 255, 255, 255);
+            for (int l = 0; l < layers; l++)
+                draw_textured_quad(tex, 0.0f, 0.0f, (float)w, (float)h, (float)w / 512.0f, (float)h / 512.0f);
+        } else if (strcmp(name, "micro") == 0) {
+            if (cfg->variant & (1 << 20)) {
+                /* pass 1: render into the FBO; pass 2: draw it as a texture over the main buffer */
+                pfscene_cfg sub = *cfg; sub.width = 96; sub.height = 80; sub.variant &= ~(1 << 20);
+                pfBindFramebuffer(&fbo); pfEnable(PF_FRAMEBUFFER);
+                micro_scene(&sub, tex);
+                pfDisable(PF_FRAMEBUFFER);
+                sub = *cfg; sub.variant &= ~(1 << 20); sub.seed += 17;
+                micro_scene(&sub, tex);
+                ortho2d(w, h);
+                pfDisable(PF_LIGHTING); pfDisable(PF_DEPTH_TEST); pfEnable(PF_TEXTURE_2D); pfEnable(PF_BLEND); pfBlendFunc(PF_BLEND_ALPHA);
+                pfTextureParameter(fbo.texture, PF_CLAMP_TO_EDGE, PF_NEAREST);
+                pfColor4ub(255, 255, 255, 255);
+                draw_textured_quad(fbo.texture, 8.0f, 6.0f, 0.7f * w, 0.6f * h, 1.0f, 1.0f);
+            } else micro_scene(cfg, tex);
+        }
+        finish();
+        if (f >= cfg->warmup) times[f - cfg->warmup] = now_ms() - t0;
+    }
+
+    if (rc == 0) {
+        res->api_triangles = g_api_tris;
+        collect(res, times, cfg->frames);
+        if (color_out) memcpy(color_out, target, (size_t)w * h * 4);
+        read_depth(depth_out, w);
+    }
+    if (fbo.texture) pfDeleteFramebuffer(&fbo);
+    if (tex) pfDeleteTexture(&tex, PF_FALSE);
+    free(texpx);
+    if (mesh.pos) free_mesh(&mesh);
+    pfMakeCurrent(NULL);
+    pfDeleteContext(ctx);
+    free(target); free(times);
+    return rc;
+}

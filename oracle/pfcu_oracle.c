@@ -252,7 +252,9 @@ static uint32_t tex_fetch(const pfcu_texture *t, int32_t x, int32_t y)
     int32_t off = (int32_t)((uint32_t)y * t->w + (uint32_t)x);
     const uint8_t *base = t->alias ? (const uint8_t *)t->alias->color : t->pixels;
     size_t n = (size_t)t->w * t->h;
-    if (off < 0 || (size_t)off >= n) return 0;     /* reference would read out of bounds */
+    /* the reference would read out of bounds here (e.g. CLAMP_TO_EDGE rounds v*(h-1)+0.5 up to row h);
+       defined as "memory after the texture reads as zero": RGBA 0, and alpha 255 for 3-byte formats */
+    if (off < 0 || (size_t)off >= n) return (t->fmt == PFCU_TEX_RGB8 || t->fmt == PFCU_TEX_BGR8) ? 0xff000000u : 0u;
     uint32_t raw;
     switch (t->fmt) {
     case PFCU_TEX_RGBA8: memcpy(&raw, base + 4 * (size_t)off, 4); return raw;                 /* pixel.h:2909-2913 */

@@ -358,7 +358,9 @@ __device__ __forceinline__ int tex_coord(int wrap, float t, unsigned size)
 __device__ __forceinline__ unsigned tex_fetch(const DevState *st, int x, int y)
 {
     const int off = (int)((unsigned)y * st->tw + (unsigned)x);
-    if (off < 0 || (unsigned)off >= st->tw * st->th) return 0u;     /* the reference would read out of bounds */
+    /* the reference reads out of bounds here (CLAMP/MIRROR round v*(h-1)+0.5 up to row h); defined as
+       "memory after the texture reads as zero": RGBA 0, and alpha 255 for the 3-byte formats */
+    if (off < 0 || (unsigned)off >= st->tw * st->th) return (st->tfmt >= PFCU_TEX_RGB8) ? 0xff000000u : 0u;
     const unsigned char *base = st->tex;
     switch (st->tfmt) {
     case PFCU_TEX_RGBA8: return __ldg((const unsigned *)base + off);

@@ -108,7 +108,11 @@ static void ortho2d(int w, int h)
 
 static uint8_t *make_texture(int w, int h, int comps, uint32_t seed, int lo, int hi, int alo, int ahi)
 {
-    uint8_t *t = (uint8_t *)malloc((size_t)w * h * comps + 16);
+    /* Two zeroed guard rows: with CLAMP_TO_EDGE / MIRRORED_REPEAT the reference rounds
+       v*(h-1)+0.5 half-to-even and can address row h (sampler.h:220-255), i.e. it reads past the
+       texture.  The guard rows make that read deterministic (0) for the reference; the product and
+       the oracle return 0 for any out-of-range texel index. */
+    uint8_t *t = (uint8_t *)calloc((size_t)w * (h + 2) * comps + 16, 1);
     lcg_state = seed;
     for (size_t i = 0; i < (size_t)w * h; i++) {
         uint32_t r = lcg();
@@ -541,7 +545,10 @@ SCN_API int pfscene_render(const char *name, const pfscene_cfg *cfg, uint8_t *co
         const int rgb = (cfg->variant >> 17) & 1, bgra = (cfg->variant >> 22) & 1;
         texpx = make_texture(61, 37, rgb ? 3 : 4, (uint32_t)cfg->seed ^ 0xabcdu, 0, 255, 0, 255);
         tex = pfGenTexture(texpx, 61, 37, rgb ? PF_RGB : (bgra ? PF_BGRA : PF_RGBA), PF_UNSIGNED_BYTE);
-        if (cfg->variant & (1 << 20)) fbo = pfGenFramebuffer(96, 80, PF_RGBA, PF_UNSIGNED_BYTE);
+        /* the FBO is larger than the 96x80 viewport used to draw into it: for a viewport smaller than the
+           MAIN buffer the reference computes vpMax = x+width (one past the last column/row,
+           context.c:567-570), so "2D" triangles may touch column 96 / row 80 */
+        if (cfg->variant & (1 << 20)) fbo = pfGenFramebuffer(104, 88, PF_RGBA, PF_UNSIGNED_BYTE);
     } else {
         fprintf(stderr, "pfscene: unknown scene '%s'\n", name);
         rc = 1;
@@ -594,7 +601,7 @@ SCN_API int pfscene_render(const char *name, const pfscene_cfg *cfg, uint8_t *co
                 micro_scene(&sub, tex);
                 ortho2d(w, h);
                 pfDisable(PF_LIGHTING); pfDisable(PF_DEPTH_TEST); pfEnable(PF_TEXTURE_2D); pfEnable(PF_BLEND); pfBlendFunc(PF_BLEND_ALPHA);
-                pfTextureParameter(fbo.texture, PF_CLAMP_TO_EDGE, PF_NEAREST);
+                pfTextureParameter(fbo.texture, PF_REPEAT, PF_NEAREST);   /* CLAMP would index row h of the FBO at v == 1 (reads past the reference's own allocation) */
                 pfColor4ub(255, 255, 255, 255);
                 draw_textured_quad(fbo.texture, 8.0f, 6.0f, 0.7f * w, 0.6f * h, 1.0f, 1.0f);
             } else micro_scene(cfg, tex);

@@ -1,0 +1,257 @@
+"""GPU tests (-m gpu): the CUDA product (libpixelforge.so, sm_100a) against
+  (1) the golden hashes generated from the unmodified reference,
+  (2) the live reference library (oracle/_ref travels to the GPU box as a prebuilt .so),
+  (3) the scalar C oracle through the pfcu C-ABI on random triangle streams,
+and size-independent properties at BASELINE.json's full sizes.
+Bar: bit-exact colour and depth (the reference's requirement is identical coverage / depth masks and
+colour within 1 LSB; we hold the stricter one)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from cases import CASES, CASE_IDS
+
+pytestmark = pytest.mark.gpu
+FLT_MAX = np.finfo(np.float32).max
+
+
+def _loaded_native_library():
+    with open("/proc/self/maps") as f:
+        return any("libpixelforge.so" in line for line in f)
+
+
+@pytest.mark.parametrize("case", CASES, ids=CASE_IDS)
+def test_product_matches_golden(case, product_scenes, golden, host_matches_golden):
+    if not host_matches_golden:
+        pytest.skip("golden hashes were generated on a CPU with different RCPPS/RSQRTPS tables")
+    cid, scene, w, h, kw, _ = case
+    assert product_scenes.backend == "cuda-sm_100a"
+    color, depth, res = product_scenes.render(scene, w, h, **kw)
+    g = golden["cases"][cid]
+    assert int(((color & 0xFFFFFF) != 0).sum()) == g["nonzero_rgb"]
+    assert hashlib.sha256(color.tobytes()).hexdigest() == g["color_sha256"], "colour differs from the reference"
+    assert hashlib.sha256(depth.tobytes()).hexdigest() == g["depth_sha256"], "depth differs from the reference"
+    assert _loaded_native_library()
+
+
+@pytest.mark.parametrize("case", CASES, ids=CASE_IDS)
+def test_product_matches_live_reference(case, product_scenes, ref_scenes, ref_bfix_scenes):
+    cid, scene, w, h, kw, needs_fix = case
+    ref = ref_bfix_scenes if needs_fix else ref_scenes
+    cp, dp, _ = product_scenes.render(scene, w, h, **kw)
+    cr, dr, _ = ref.render(scene, w, h, **kw)
+    assert int((cp != cr).sum()) == 0
+    assert int((dp.view(np.uint32) != dr.view(np.uint32)).sum()) == 0
+
+
+@pytest.mark.parametrize("sync_mode", [0, 1], ids=["sync-end", "sync-explicit"])
+def test_sync_modes_agree(product_scenes, sync_mode):
+    """PF_CUDA_SYNC=end (reference semantics: pixels visible after every pfEnd) and explicit give the same image."""
+    a, da, _ = product_scenes.render("gears", 400, 300, explicit_sync=sync_mode)
+    b, db, _ = product_scenes.render("gears", 400, 300, explicit_sync=1)
+    assert np.array_equal(a, b) and np.array_equal(da.view(np.uint32), db.view(np.uint32))
+
+
+# ---- pfcu level: random triangle streams, CUDA vs oracle -----------------------------------------------
+
+@pytest.fixture(scope="module")
+def pfcu_pair():
+    from pixelforge_b200 import load_pfcu
+    prod, orc = load_pfcu("product"), load_pfcu("oracle")
+    prod.init(); orc.init()
+    assert prod.backend == "cuda-sm_100a" and orc.backend == "oracle-c"
+    return prod, orc
+
+
+def random_stream(rng, w, h, n, flags, blend=1, depth=2, big=False, is3d=0, n_states=1, tex=None, phong=False):
+    from pixelforge_b200.binding import STATE_DTYPE, TRIANGLE_DTYPE, ST_PHONG, ST_TEXTURE
+    states = np.zeros(n_states, STATE_DTYPE)
+    for i in range(n_states):
+        st = states[i]
+        st["flags"] = flags if i == 0 else (flags ^ 16)
+        st["blend_mode"] = (blend + i) % 8; st["depth_func"] = depth
+        st["vp_min"] = (0, 0); st["vp_max"] = (w - 1, h - 1)
+        if tex is not None:
+            st["flags"] |= ST_TEXTURE; st["texture"] = tex[0]; st["tex_filter"] = tex[1]; st["tex_wrap"] = (tex[2] + i) % 3
+        if phong:
+            st["flags"] |= ST_PHONG; st["n_lights"] = 2
+            for l in range(2):
+                L = st["lights"][l]
+                L["position"] = rng.uniform(-3, 3, 3); L["direction"] = rng.uniform(-1, 1, 3)
+                L["inner_cutoff"] = np.pi if l == 0 else np.cos(np.radians(20)); L["outer_cutoff"] = np.pi if l == 0 else np.cos(np.radians(35))
+                L["att_constant"] = 1.0; L["att_linear"] = 0.0 if l == 0 else 0.1; L["att_quadratic"] = 0.0 if l == 0 else 0.02
+                L["ambient"] = 0xFF333333; L["diffuse"] = 0xFFFFFFFF; L["specular"] = 0xFFFFFFFF
+            for f in range(2):
+                M = st["material"][f]
+                M["ambient"] = 0xFF3050C0; M["diffuse"] = 0xFF3050C0; M["specular"] = 0xFFFFFFFF; M["emission"] = 0xFF000000
+                M["shininess"] = 16.0 * (f + 1)
+            st["view_pos"] = (0.2, 0.1, 3.0)
+    tris = np.zeros(n, TRIANGLE_DTYPE)
+    span = max(w, h) if big else 40
+    cx = rng.uniform(-10, w + 10, n); cy = rng.uniform(-10, h + 10, n)
+    for k in range(3):
+        v = tris["v"][:, k]
+        v["sx"] = cx + rng.uniform(-span, span, n); v["sy"] = cy + rng.uniform(-span, span, n)
+        v["zinv"] = rng.uniform(0.2, 5.0, n)
+        v["u"] = rng.uniform(-2, 2, n); v["v"] = rng.uniform(-2, 2, n)
+        for c in ("px", "py", "pz"): v[c] = rng.uniform(-2, 2, n)
+        for c in ("nx", "ny", "nz"): v[c] = rng.uniform(-1, 1, n)
+        v["rgba"] = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    tris["state"] = rng.integers(0, n_states, n); tris["face"] = rng.integers(0, 2, n); tris["is3d"] = is3d
+    return states, tris
+
+
+def make_textures(prod, orc, rng, w, h, fmt):
+    comps = 4 if fmt < 2 else 3
+    px = rng.integers(0, 256, (h + 2) * w * comps, dtype=np.uint8); px[h * w * comps:] = 0
+    tp = prod.lib.pfcu_texture_create(px.ctypes.data, w, h, fmt)
+    to = orc.lib.pfcu_texture_create(px.ctypes.data, w, h, fmt)
+    assert tp and to
+    return tp, to
+
+
+STREAM_CASES = [
+    # id, w, h, n, flags, kwargs
+    ("small-flat-noblend", 200, 150, 3000, 0, {}),
+    ("small-smooth-alpha-less", 200, 150, 3000, 1 | 2 | 16, {}),
+    ("big-smooth-add-lequal", 333, 211, 300, 1 | 2 | 16, dict(blend=2, depth=3, big=True)),
+    ("big-multi-state", 515, 389, 400, 1 | 2, dict(big=True, n_states=5)),
+    ("edge-1px-surface", 1, 1, 50, 16, dict(big=True)),
+    ("ragged-7x5", 7, 5, 100, 1 | 16, dict(big=True)),
+    ("wide-4099x3", 4099, 3, 200, 1 | 16, dict(big=True)),
+    ("many-65k", 1024, 512, 70000, 2 | 16, {}),
+    ("3d-persp-uv", 300, 200, 2000, 2 | 16, dict(is3d=1)),
+]
+
+
+@pytest.mark.parametrize("case", STREAM_CASES, ids=[c[0] for c in STREAM_CASES])
+def test_stream_cuda_vs_oracle(case, pfcu_pair):
+    prod, orc = pfcu_pair
+    cid, w, h, n, flags, kw = case
+    rng = np.random.default_rng(hash(cid) & 0xFFFF)
+    states, tris = random_stream(rng, w, h, n, flags, **kw)
+    color0 = rng.integers(0, 2**32, (h, w), dtype=np.uint64).astype(np.uint32)
+    cp, dp = prod.render_stream(w, h, states, tris, color0=color0)
+    co, do = orc.render_stream(w, h, states, tris, color0=color0)
+    assert int((cp != co).sum()) == 0
+    assert int((dp.view(np.uint32) != do.view(np.uint32)).sum()) == 0
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3], ids=["rgba8", "bgra8", "rgb8", "bgr8"])
+@pytest.mark.parametrize("filt", [0, 1], ids=["nearest", "bilinear"])
+def test_stream_textured(pfcu_pair, fmt, filt):
+    prod, orc = pfcu_pair
+    rng = np.random.default_rng(100 + fmt * 2 + filt)
+    tp, to = make_textures(prod, orc, rng, 37, 29, fmt)
+    for is3d in (0, 1):
+        sp, tris = random_stream(rng, 256, 192, 1500, 1 | 2 | 16, n_states=3, tex=(tp, filt, 0), is3d=is3d, big=bool(is3d))
+        so = sp.copy(); so["texture"] = to
+        cp, dp = prod.render_stream(256, 192, sp, tris)
+        co, do = orc.render_stream(256, 192, so, tris)
+        assert int((cp != co).sum()) == 0 and int((dp.view(np.uint32) != do.view(np.uint32)).sum()) == 0
+    prod.lib.pfcu_texture_destroy(tp); orc.lib.pfcu_texture_destroy(to)
+
+
+def test_stream_phong(pfcu_pair):
+    prod, orc = pfcu_pair
+    rng = np.random.default_rng(7)
+    tp, to = make_textures(prod, orc, rng, 64, 64, 0)
+    sp, tris = random_stream(rng, 320, 240, 1200, 2 | 16, n_states=2, tex=(tp, 0, 1), phong=True, is3d=1)
+    so = sp.copy(); so["texture"] = to
+    cp, dp = prod.render_stream(320, 240, sp, tris)
+    co, do = orc.render_stream(320, 240, so, tris)
+    assert int((cp != co).sum()) == 0 and int((dp.view(np.uint32) != do.view(np.uint32)).sum()) == 0
+    assert (cp[dp != FLT_MAX] >> 24 == 0).all()         # Q9: Phong forces alpha to 0
+
+
+def test_empty_and_degenerate(pfcu_pair):
+    prod, orc = pfcu_pair
+    from pixelforge_b200.binding import STATE_DTYPE, TRIANGLE_DTYPE
+    rng = np.random.default_rng(3)
+    states, tris = random_stream(rng, 64, 64, 10, 16)
+    tris["v"]["sx"][:, 1] = tris["v"]["sx"][:, 0]; tris["v"]["sy"][:, 1] = tris["v"]["sy"][:, 0]    # zero area
+    cp, dp = prod.render_stream(64, 64, states, tris)
+    assert (cp == 0).all() and (dp == FLT_MAX).all()
+    # n_tris == 0 is a no-op
+    s = prod.lib.pfcu_surface_create(8, 8)
+    assert prod.lib.pfcu_submit(s, states.ctypes.data, 1, tris.ctypes.data, 0) == 0
+    prod.lib.pfcu_surface_destroy(s)
+    # NaN / inf / huge coordinates must neither crash nor diverge from the oracle
+    states, tris = random_stream(rng, 128, 96, 64, 1 | 16, big=True)
+    tris["v"]["sx"][:8, 0] = np.nan; tris["v"]["sy"][8:16, 1] = np.inf; tris["v"]["sx"][16:24, 2] = 3e9
+    tris["v"]["sx"][24:32, 0] = -70000.0; tris["v"]["sy"][24:32, 1] = 90000.0; tris["v"]["zinv"][32:40, 0] = 0.0
+    cp, dp = prod.render_stream(128, 96, states, tris)
+    co, do = orc.render_stream(128, 96, states, tris)
+    assert int((cp != co).sum()) == 0 and int((dp.view(np.uint32) != do.view(np.uint32)).sum()) == 0
+
+
+def test_clear_quirk_and_fill(pfcu_pair):
+    prod, orc = pfcu_pair
+    for lib in (prod, orc):
+        for (w, h) in ((64, 64), (13, 7), (3, 2)):
+            s = lib.lib.pfcu_surface_create(w, h)
+            c0 = np.arange(w * h, dtype=np.uint32).reshape(h, w) + 5; d0 = np.full((h, w), 0.25, np.float32)
+            lib.check(lib.lib.pfcu_surface_upload(s, c0.ctypes.data, d0.ctypes.data, 0, h))
+            lib.check(lib.lib.pfcu_surface_clear_ref(s, 1, 0xAABBCCDD, 1, 9.0))
+            c = np.zeros((h, w), np.uint32); d = np.zeros((h, w), np.float32)
+            lib.check(lib.lib.pfcu_surface_download(s, c.ctypes.data, d.ctypes.data, 0, h))
+            n = w * h; al = n - n % 8
+            exp = c0.reshape(-1).copy(); exp[8:al] = 0xAABBCCDD; exp[al:] = exp[0] if al < n else exp[al:]
+            if al <= 8: exp[al:] = c0.reshape(-1)[0]
+            assert np.array_equal(c.reshape(-1), exp), (lib.backend, w, h)
+            lib.lib.pfcu_surface_destroy(s)
+
+
+def test_tile_split_reassembles(pfcu_pair):
+    """Screen-tile split: N ranks each rasterise the tiles they own; packing and unpacking
+    the owned tiles reproduces the single-GPU image byte for byte."""
+    prod, _ = pfcu_pair
+    rng = np.random.default_rng(11)
+    w, h = 600, 333
+    states, tris = random_stream(rng, w, h, 500, 1 | 2 | 16, big=True)
+    full_c, full_d = prod.render_stream(w, h, states, tris)
+    for world in (2, 3, 8):
+        acc_c = np.zeros((h, w), np.uint32); acc_d = np.full((h, w), FLT_MAX, np.float32)
+        for rank in range(world):
+            c, d = prod.render_stream(w, h, states, tris, tile_owner=(rank, world))
+            tiles_x = (w + 63) // 64
+            ys, xs = np.mgrid[0:h, 0:w]
+            own = ((xs // 64 + (ys // 64) * tiles_x) % world) == rank
+            assert (c[~own] == 0).all(), "a rank wrote outside its tiles"
+            acc_c[own] = c[own]; acc_d[own] = d[own]
+        assert np.array_equal(acc_c, full_c) and np.array_equal(acc_d.view(np.uint32), full_d.view(np.uint32))
+
+
+# ---- full-size properties (BASELINE.json sizes; the oracle is too slow here) ----------------------------
+
+def test_fullsize_overdraw_properties(product_scenes):
+    """C4 at 7680x4320: additive blend of L identical layers of a texture with channels 0..3 gives
+    exactly L * texel on every covered pixel; idempotent across runs; shaded count = closed form."""
+    w, h, layers = 7680, 4320, 16
+    color, depth, res = product_scenes.render("overdraw", w, h, size=layers, want_depth=False)
+    c2, _, _ = product_scenes.render("overdraw", w, h, size=layers, want_depth=False)
+    assert np.array_equal(color, c2)
+    assert (color[:, -1] & 0xFFFFFF == 0).all()                     # right column never drawn (Q4)
+    one, _, r1 = product_scenes.render("overdraw", w, h, size=1, want_depth=False)
+    ch1 = one.view(np.uint8).reshape(h, w, 4).astype(np.int32); chL = color.view(np.uint8).reshape(h, w, 4).astype(np.int32)
+    body = (slice(1, None), slice(0, w - 1))
+    # pixels on the shared diagonal are hit twice per layer; everything else exactly once
+    dbl = (ch1[body][..., :3] > 3).any(axis=-1)
+    assert dbl.sum() < 2 * (w + h)
+    assert np.array_equal(chL[body][~dbl][..., :3], np.minimum(ch1[body][~dbl][..., :3] * layers, 255))
+    assert res.pixels_shaded == r1.pixels_shaded * layers
+
+
+def test_fullsize_phong_properties(product_scenes):
+    """C3 at 3840x2160 with the 1,002,528-triangle height field: idempotence, alpha == 0 on every lit
+    pixel (Q9), depth monotone under a second identical pass (LESS rejects everything)."""
+    w, h = 3840, 2160
+    c1, d1, r1 = product_scenes.render("phong", w, h, size=708, variant=32)
+    c2, d2, r2 = product_scenes.render("phong", w, h, size=708, variant=32, frames=2)
+    assert r1.triangles_submitted == 1002528
+    assert np.array_equal(c1, c2) and np.array_equal(d1.view(np.uint32), d2.view(np.uint32))
+    lit = d1 != FLT_MAX
+    assert lit.sum() > 0.4 * w * h
+    assert ((c1[lit] >> 24) == 0).all()
+    assert r2.pixels_shaded == 2 * r1.pixels_shaded          # each frame clears first, so both frames shade alike

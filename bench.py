@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of pixelforge-b200 (contract: see the task's bench.py section).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one frame of the workload: pfClear + the scene's draw calls (the per-fragment hot path
+over one batch of synthetic triangles).  Headline workload = BASELINE.json configs[1]: a textured
+model at 1920x1080 with bilinear filtering, alpha blending and depth test.
+
+Legs of the default (ours) arm, all printed in ONE JSON line by rank 0:
+  value      shaded Gpix/s with the frame's triangle stream already resident in HBM: CUDA events on
+             the launching stream around {clear, setup, bin, raster}; L2 flushed between iterations.
+  e2e        the same metric through the public pixelforge.h API with HOST buffers: host vertex stage,
+             H2D of the triangle batch from pinned memory, kernels, D2H of the framebuffer into the
+             caller's buffer - wall clock around pfClear..pfxFinish.
+  roofline   k_raster (the dominant kernel): algorithmic bytes / its CUDA-event time.
+  cpu_baseline  the reference's own OpenMP+AVX2 code (oracle/_ref, compiled from /root/reference)
+             on this box's host cores, bounded sample, in a subprocess.
+  extra      the other BASELINE.json configs (C1, C3, C4, the 4K textured+blended target scene, C5).
+`--impl reference` times the UNMODIFIED reference library on the same workload (rank 0 only).
+With --gpus N > 1 (torchrun) every rank renders its own context (independent contexts, one per GPU,
+no data-path collective: weak scaling); the C4 overdraw scene is additionally run screen-tile split
+with an NCCL gather of the tiles to rank 0 and reported under extra.tile_split.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# workload table: scene, size, variant, resolution, algorithmic bytes per shaded pixel (SURVEY 8-d:
+# 4[depth test] + 4 (z write) + 4[blend] + 4 (colour write) + 4*taps[texture])
+WORKLOADS = {
+    "c2_textured_1080p": dict(scene="textured", w=1920, h=1080, size=256, variant=1 | 32 | 64, bytes_px=32,
+                              desc="C2: textured torus (65,536 quads*2 faces), 1920x1080, bilinear REPEAT, alpha blend, depth LESS, vertex arrays"),
+    "c1_gears_800x600": dict(scene="gears", w=800, h=600, size=0, variant=0, bytes_px=12,
+                             desc="C1: Gears, 800x600, immediate mode, Gouraud, depth LESS"),
+    "c3_phong_4k": dict(scene="phong", w=3840, h=2160, size=708, variant=32, bytes_px=12,
+                        desc="C3: 1,002,528-triangle height field, 3840x2160, per-pixel Blinn-Phong, depth LESS"),
+    "c4_overdraw_8k": dict(scene="overdraw", w=7680, h=4320, size=64, variant=0, bytes_px=16,
+                           desc="C4: 64 layers of additive-blended textured full-screen quads, 7680x4320, nearest REPEAT"),
+    "ns_textured_blend_4k": dict(scene="overdraw", w=3840, h=2160, size=64, variant=1, bytes_px=20,
+                                 desc="north-star scene: 64 layers textured + alpha-blended + depth-tested quads, 3840x2160, nearest"),
+    "c5_batch_512": dict(scene="batch", w=512, h=512, size=32, variant=0, bytes_px=16,
+                         desc="C5: independent 512x512 contexts (render-list replay, textured + Gouraud lit, depth), 32 per GPU"),
+}
+HEADLINE = "c2_textured_1080p"
+METRIC = "shaded_gpix_per_s"
+UNIT = "Gpix/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---- clocks sampling ------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- the reference arm / cpu baseline ---------------------------------------------------------------
+
+def shaded_pixels_table():
+    """Shaded pixels / triangles per frame of each workload (frame 0), measured by the product's device
+    counters and asserted equal to the oracle's in tests/test_bench_counts.py.  The reference library
+    has no counters, so its arm uses this table (identical coverage is the parity gate)."""
+    with open(os.path.join(ROOT, "tests", "golden", "workload_counts.json")) as f:
+        return json.load(f)
+
+
+def run_reference(args, wl_name, bounded_frames=None, bilinear_fix=False):
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
+    os.environ.setdefault("OMP_WAIT_POLICY", "active")
+    from pixelforge_b200 import load_reference_scenes
+    wl = WORKLOADS[wl_name]
+    lib = load_reference_scenes(bilinear_fix)
+    steps = bounded_frames if bounded_frames else args.steps
+    warm = 1 if bounded_frames else args.warmup
+    size = wl["size"]
+    sample = f"{steps} full frames after {warm} warm-up"
+    if wl["scene"] == "batch":
+        size = min(size, 8)
+        sample += f", {size} contexts"
+    _, _, res = lib.render(wl["scene"], wl["w"], wl["h"], frames=steps, warmup=warm, variant=wl["variant"], size=size, want_depth=False)
+    counts = shaded_pixels_table().get(wl_name, {})
+    px = counts.get("pixels_shaded", 0) * (size / wl["size"] if wl["scene"] == "batch" else 1)
+    tris = counts.get("triangles_submitted", 0) * (size / wl["size"] if wl["scene"] == "batch" else 1)
+    ms = res.ms_total / max(steps, 1)
+    return {"ms_per_step": ms, "gpix": px / (ms * 1e-3) / 1e9 if ms > 0 else 0.0, "mtri": tris / (ms * 1e-3) / 1e6 if ms > 0 else 0.0,
+            "ms_median": res.ms_median, "cores": int(os.environ["OMP_NUM_THREADS"]), "sample": sample,
+            "kind": "reference", "library": "oracle/_ref/" + ("libpf_ref_bfix.so (Q7 one-token bilinear fix)" if bilinear_fix else "libpf_ref.so (unmodified)")}
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl_name = args.workload
+    wl = WORKLOADS[wl_name]
+    try:
+        r = run_reference(args, wl_name, bounded_frames=args.baseline_frames if args.as_baseline else None,
+                          bilinear_fix=args.as_baseline and bool(wl["variant"] & 1) and wl["scene"] == "textured")
+    except FileNotFoundError as e:
+        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref not built: {e}"}))
+        return 0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["gpix"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/i32/f32", "data": "synthetic",
+        "config": {"workload": wl_name, "description": wl["desc"], "l2_policy": "n/a (CPU)"},
+        "mtri_per_s": r["mtri"],
+        "cpu_baseline": {"value": r["gpix"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": r["sample"], "library": r["library"]},
+        "e2e": {"value": r["gpix"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---- our arm ---------------------------------------------------------------------------------------
+
+def measure_workload(wl_name, steps, warmup, torch, scenes, pfcu, stream, flush_buf, want_e2e=True, tile_owner=None):
+    """Returns a dict with device-resident (`value`) and end-to-end numbers for one workload."""
+    from pixelforge_b200.binding import Counters, Profile, STATE_DTYPE, TRIANGLE_DTYPE
+    wl = WORKLOADS[wl_name]
+    L = pfcu.lib
+    out = {"workload": wl_name}
+    with scenes.open(wl["scene"], wl["w"], wl["h"], variant=wl["variant"], size=wl["size"], explicit_sync=1) as sc:
+        L.pfcu_set_stream(stream.cuda_stream)
+        n_ctx = wl["size"] if wl["scene"] == "batch" else 1
+
+        # ---- end to end through the public API (host buffers) ----
+        if want_e2e:
+            for i in range(max(warmup, 1)):
+                sc.frame(0); sc.finish()
+            L.pfxResetCounters()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                sc.frame(0); sc.finish()
+            torch.cuda.synchronize()
+            e2e_s = (time.perf_counter() - t0) / steps
+            k = Counters(); L.pfcu_get_counters(k)
+            out.update(e2e_ms=e2e_s * 1e3, px_per_step=k.pixels_shaded / steps, tris_per_step=k.triangles_submitted / steps,
+                       tris_rasterised_per_step=k.triangles_rasterised / steps, zfail_per_step=k.pixels_depth_failed / steps,
+                       h2d_bytes=int(k.triangles_submitted / steps * TRIANGLE_DTYPE.itemsize), d2h_bytes=wl["w"] * wl["h"] * 4 * n_ctx)
+
+        # ---- device-resident replay: capture one frame per context, keep it in HBM ----
+        batches = []
+        for c in range(n_ctx):
+            sc.make_current(c)
+            L.pfxCaptureBegin()
+        sc.frame(0)
+        for c in range(n_ctx):
+            sc.make_current(c)
+            states, tris = pfcu.capture_end()
+            surf = L.pfxGetSurfaceHandle()
+            if tile_owner:
+                L.pfcu_surface_set_tile_owner(surf, tile_owner[0], tile_owner[1])
+            b = L.pfcu_batch_upload(states.ctypes.data, len(states), tris.ctypes.data, len(tris))
+            if not b:
+                raise RuntimeError("pfcu_batch_upload failed: " + pfcu.error())
+            batches.append((surf, b, len(tris)))
+        sc.finish()
+        clear_rgba, clear_z = 0xFF000000, 3.4028234663852886e38
+
+        def step():
+            for surf, b, _ in batches:
+                L.pfcu_surface_clear_ref(surf, 1, clear_rgba, 1, clear_z)
+                L.pfcu_batch_submit(surf, b)
+
+        for i in range(max(warmup, 3)):
+            step()
+        L.pfcu_finish()
+        L.pfxResetCounters()
+        L.pfcu_profile_enable(1)
+        prof = Profile(); L.pfcu_profile_read(prof)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        with torch.cuda.stream(stream):
+            for i in range(steps):
+                flush_buf.fill_(i & 0xFF)          # L2 flush: write a buffer larger than L2 (untimed)
+                ev[i][0].record(stream)
+                step()
+                ev[i][1].record(stream)
+        stream.synchronize()
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+        L.pfcu_profile_read(prof)
+        L.pfcu_profile_enable(0)
+        k = Counters(); L.pfcu_get_counters(k)
+        out.update(dev_ms=dev_ms, dev_px_per_step=k.pixels_shaded / steps, dev_tris_per_step=k.triangles_submitted / steps,
+                   raster_ms=prof.raster_ms / steps, frontend_ms=prof.frontend_ms / steps,
+                   raster_launches_per_step=prof.raster_launches / steps, launches_per_step=k.kernel_launches / steps)
+        for surf, b, _ in batches:
+            L.pfcu_batch_destroy(b)
+    return out
+
+
+def ours_main(args):
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("PF_CUDA_DEVICE", str(local))
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from pixelforge_b200 import load_product_scenes, load_pfcu
+    scenes = load_product_scenes(); pfcu = load_pfcu("product")
+    stream = torch.cuda.Stream()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # 256 MiB > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t.item())
+
+    wl_name = args.workload; wl = WORKLOADS[wl_name]
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    m = measure_workload(wl_name, args.steps, args.warmup, torch, scenes, pfcu, stream, flush_buf)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    dev_ms = max_over_ranks(m["dev_ms"]); e2e_ms = max_over_ranks(m["e2e_ms"])
+    px_all = sum_over_ranks(m["dev_px_per_step"]); tris_all = sum_over_ranks(m["dev_tris_per_step"])
+    value = px_all / (dev_ms * 1e-3) / 1e9
+    e2e_value = sum_over_ranks(m["px_per_step"]) / (e2e_ms * 1e-3) / 1e9
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    alg_bytes = m["dev_px_per_step"] * wl["bytes_px"]
+    achieved = alg_bytes / (m["raster_ms"] * 1e-3) / 1e9 if m["raster_ms"] > 0 else 0.0
+
+    extra = {}
+    if rank == 0 or world > 1:
+        names = [] if args.no_extra else [n for n in WORKLOADS if n != wl_name]
+        for n in names:
+            try:
+                steps = max(2, min(args.steps, 5)) if n in ("c3_phong_4k", "c4_overdraw_8k", "ns_textured_blend_4k", "c5_batch_512") else args.steps
+                x = measure_workload(n, steps, 3, torch, scenes, pfcu, stream, flush_buf)
+                w2 = WORKLOADS[n]
+                a2 = x["dev_px_per_step"] * w2["bytes_px"] / (x["raster_ms"] * 1e-3) / 1e9 if x["raster_ms"] > 0 else 0.0
+                extra[n] = {"desc": w2["desc"], "gpix_per_s": x["dev_px_per_step"] / (x["dev_ms"] * 1e-3) / 1e9,
+                            "mtri_per_s": x["dev_tris_per_step"] / (x["dev_ms"] * 1e-3) / 1e6, "ms_per_step": x["dev_ms"],
+                            "e2e_gpix_per_s": x["px_per_step"] / (x["e2e_ms"] * 1e-3) / 1e9, "e2e_mtri_per_s": x["tris_per_step"] / (x["e2e_ms"] * 1e-3) / 1e6,
+                            "e2e_ms_per_step": x["e2e_ms"], "shaded_px_per_step": x["dev_px_per_step"], "triangles_per_step": x["dev_tris_per_step"],
+                            "roofline": {"bound": "hbm", "achieved": a2, "peak": peak, "unit": "GB/s", "frac": a2 / peak, "bytes_per_px": w2["bytes_px"],
+                                         "raster_ms": x["raster_ms"], "frontend_ms": x["frontend_ms"]}}
+            except Exception as e:   # an extra must never take the headline down
+                extra[n] = {"error": repr(e)}
+        if world > 1 and not args.no_extra:
+            try:
+                from pixelforge_b200.multigpu import tile_split_benchmark
+                extra["tile_split_c4"] = tile_split_benchmark(torch, dist, scenes, pfcu, stream, WORKLOADS["c4_overdraw_8k"], rank, world, steps=3)
+            except Exception as e:
+                extra["tile_split_c4"] = {"error": repr(e)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--as-baseline", "--workload", wl_name,
+                                "--baseline-frames", "3"], capture_output=True, text=True, timeout=600)
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            cpu = j.get("cpu_baseline") or {"unavailable": j.get("unavailable")}
+            if "value" in (cpu or {}):
+                cpu["ms_per_frame"] = j["ms_per_step"]
+        except Exception as e:
+            cpu = {"unavailable": repr(e)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32", "data": "synthetic",
+        "config": {"workload": wl_name, "description": wl["desc"], "width": wl["w"], "height": wl["h"],
+                   "triangles_per_step": tris_all / world, "shaded_px_per_step": px_all / world, "parallelism": f"independent contexts x{world}",
+                   "l2_policy": "256 MiB buffer written between timed iterations (untimed)"},
+        "mtri_per_s": tris_all / (dev_ms * 1e-3) / 1e6,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": m["d2h_bytes"],
+                "ms_per_step": e2e_ms, "mtri_per_s": sum_over_ranks(m["tris_per_step"]) / (e2e_ms * 1e-3) / 1e6 if world == 1 else None},
+        "gpu_launches": int(round(m["launches_per_step"] * args.steps)),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "k_raster", "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_shaded_px": wl["bytes_px"],
+                     "kernel_ms": m["raster_ms"], "frontend_kernels_ms": m["frontend_ms"], "peak_source": peak_src},
+        "cpu_baseline": cpu, "clocks": clocks, "extra": extra,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=HEADLINE, choices=list(WORKLOADS))
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--as-baseline", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--baseline-frames", type=int, default=3, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    return reference_main(args) if args.impl == "reference" else ours_main(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -190,6 +190,15 @@ PFCU_API pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_stat
 PFCU_API int  pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b);
 PFCU_API void pfcu_batch_destroy(pfcu_batch *b);
 
+/* Optional device-side timing of the pipeline stages (CUDA events on the launching stream). */
+typedef struct {
+    double   raster_ms;         /* sum of k_raster launch durations since the last read            */
+    double   frontend_ms;       /* sum of setup + binning durations                                 */
+    uint64_t raster_launches;
+} pfcu_profile;
+PFCU_API void pfcu_profile_enable(int on);
+PFCU_API int  pfcu_profile_read(pfcu_profile *out);    /* implies pfcu_finish(); resets the sums      */
+
 PFCU_API int  pfcu_finish(void);                       /* wait for everything queued so far          */
 PFCU_API int  pfcu_get_counters(pfcu_counters *out);   /* implies pfcu_finish()                      */
 PFCU_API void pfcu_reset_counters(void);

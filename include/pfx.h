@@ -39,6 +39,13 @@ PF_API void *pfxGetDeviceColor(void);
 PF_API void *pfxGetDeviceDepth(void);
 /* Copy of the current target's depth buffer into `out` (width*height floats). */
 PF_API void pfxReadDepth(PFfloat *out);
+/* Record the triangle/state stream the current context hands to the pfcu C-ABI (it is still
+ * rendered).  pfxCaptureEnd flushes and returns pointers to arrays of pfcu_state / pfcu_triangle
+ * (include/pfcu.h) that stay valid until the next pfxCaptureBegin or pfDeleteContext. */
+PF_API void pfxCaptureBegin(void);
+PF_API void pfxCaptureEnd(const void **states, PFuint *nStates, const void **triangles, PFuint *nTriangles);
+/* The pfcu_surface* behind the current target. */
+PF_API void *pfxGetSurfaceHandle(void);
 PF_API const char *pfxBackendName(void);
 
 #if defined(__cplusplus)

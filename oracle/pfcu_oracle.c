@@ -598,6 +598,8 @@ pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const
 }
 int  pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b) { return pfcu_submit(s, b->states, b->n_states, b->tris, b->n_tris); }
 void pfcu_batch_destroy(pfcu_batch *b) { if (b) { free(b->states); free(b->tris); free(b); } }
+void pfcu_profile_enable(int on) { (void)on; }
+int  pfcu_profile_read(pfcu_profile *out) { memset(out, 0, sizeof *out); return PFCU_OK; }
 int  pfcu_finish(void) { return PFCU_OK; }
 int  pfcu_get_counters(pfcu_counters *out) { *out = g_cnt; return PFCU_OK; }
 void pfcu_reset_counters(void) { memset(&g_cnt, 0, sizeof g_cnt); }

@@ -46,6 +46,18 @@ class SceneLib:
         self.lib.pfscene_render.restype = C.c_int
         self.lib.pfscene_render.argtypes = [C.c_char_p, C.POINTER(SceneCfg), C.c_void_p, C.c_void_p, C.POINTER(SceneResult)]
         self.lib.pfscene_backend.restype = C.c_char_p
+        self.lib.pfscene_open.restype = C.c_void_p
+        self.lib.pfscene_open.argtypes = [C.c_char_p, C.POINTER(SceneCfg)]
+        self.lib.pfscene_frame.restype = None
+        self.lib.pfscene_frame.argtypes = [C.c_void_p, C.c_int]
+        self.lib.pfscene_finish.restype = None
+        self.lib.pfscene_finish.argtypes = [C.c_void_p]
+        self.lib.pfscene_make_current.restype = None
+        self.lib.pfscene_make_current.argtypes = [C.c_void_p, C.c_int]
+        self.lib.pfscene_read.restype = None
+        self.lib.pfscene_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.pfscene_close.restype = None
+        self.lib.pfscene_close.argtypes = [C.c_void_p]
 
     @property
     def backend(self):
@@ -62,6 +74,45 @@ class SceneLib:
         if rc != 0:
             raise RuntimeError(f"pfscene_render({name}) failed with {rc} on backend {self.path}")
         return color, depth, res
+
+
+    def open(self, name, width, height, variant=0, size=0, seed=1, explicit_sync=1):
+        """Keep a scene (context, textures, meshes) alive across frames; see Scene."""
+        return Scene(self, name, SceneCfg(width, height, 1, 0, variant, size, seed, explicit_sync, 0))
+
+
+class Scene:
+    def __init__(self, lib, name, cfg):
+        self.lib, self.cfg, self.name = lib, cfg, name
+        self.handle = lib.lib.pfscene_open(name.encode(), C.byref(cfg))
+        if not self.handle:
+            raise RuntimeError(f"pfscene_open({name}) failed on {lib.path}")
+
+    def frame(self, index=0):
+        self.lib.lib.pfscene_frame(self.handle, index)
+
+    def finish(self):
+        self.lib.lib.pfscene_finish(self.handle)
+
+    def make_current(self, index=0):
+        self.lib.lib.pfscene_make_current(self.handle, index)
+
+    def read(self, want_depth=False):
+        color = np.zeros((self.cfg.height, self.cfg.width), dtype=np.uint32)
+        depth = np.zeros((self.cfg.height, self.cfg.width), dtype=np.float32) if want_depth else None
+        self.lib.lib.pfscene_read(self.handle, color.ctypes.data, depth.ctypes.data if want_depth else None)
+        return color, depth
+
+    def close(self):
+        if self.handle:
+            self.lib.lib.pfscene_close(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def load_product_scenes():
@@ -100,6 +151,10 @@ ST_BLEND, ST_DEPTH_TEST, ST_TEXTURE, ST_PHONG, ST_SMOOTH = 1, 2, 4, 8, 16
 TEX_RGBA8, TEX_BGRA8, TEX_RGB8, TEX_BGR8 = 0, 1, 2, 3
 
 
+class Profile(C.Structure):
+    _fields_ = [("raster_ms", C.c_double), ("frontend_ms", C.c_double), ("raster_launches", C.c_uint64)]
+
+
 class Counters(C.Structure):
     _fields_ = [("triangles_submitted", C.c_uint64), ("triangles_rasterised", C.c_uint64),
                 ("pixels_shaded", C.c_uint64), ("pixels_depth_failed", C.c_uint64), ("kernel_launches", C.c_uint64)]
@@ -114,8 +169,12 @@ PFCU_SYMBOLS = [
     "pfcu_surface_pack_tiles", "pfcu_surface_unpack_tiles",
     "pfcu_texture_create", "pfcu_texture_from_surface", "pfcu_texture_update", "pfcu_texture_destroy",
     "pfcu_submit", "pfcu_batch_upload", "pfcu_batch_submit", "pfcu_batch_destroy",
-    "pfcu_finish", "pfcu_get_counters", "pfcu_reset_counters",
+    "pfcu_finish", "pfcu_get_counters", "pfcu_reset_counters", "pfcu_profile_enable", "pfcu_profile_read",
 ]
+
+PFX_SYMBOLS = ["pfxSetSyncMode", "pfxFlush", "pfxFinish", "pfxGetCounters", "pfxResetCounters", "pfxSetTileOwner",
+               "pfxGetDeviceColor", "pfxGetDeviceDepth", "pfxReadDepth", "pfxCaptureBegin", "pfxCaptureEnd",
+               "pfxGetSurfaceHandle", "pfxBackendName"]
 
 
 class PfcuLib:
@@ -149,6 +208,13 @@ class PfcuLib:
             "pfcu_batch_submit": (C.c_int, [vp, vp]), "pfcu_batch_destroy": (None, [vp]),
             "pfcu_finish": (C.c_int, []), "pfcu_get_counters": (C.c_int, [C.POINTER(Counters)]),
             "pfcu_reset_counters": (None, []),
+            "pfcu_profile_enable": (None, [C.c_int]), "pfcu_profile_read": (C.c_int, [C.POINTER(Profile)]),
+            # pfx extensions of the front end (operate on the calling thread's current context)
+            "pfxFlush": (None, []), "pfxFinish": (None, []), "pfxSetTileOwner": (None, [u32, u32]),
+            "pfxGetDeviceColor": (vp, []), "pfxGetDeviceDepth": (vp, []), "pfxGetSurfaceHandle": (vp, []),
+            "pfxCaptureBegin": (None, []),
+            "pfxCaptureEnd": (None, [C.POINTER(vp), C.POINTER(u32), C.POINTER(vp), C.POINTER(u32)]),
+            "pfxResetCounters": (None, []),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -190,6 +256,14 @@ class PfcuLib:
         rcp, rb, rsq, sb = self.harvest_tables()
         self.check(self.lib.pfcu_set_approx_tables(rcp, rb, rsq, sb), "pfcu_set_approx_tables")
         self._tables = (rcp, rb, rsq, sb)
+
+    def capture_end(self):
+        """-> (states ndarray[STATE_DTYPE], tris ndarray[TRIANGLE_DTYPE]) copied out of the front end."""
+        ps, pt, ns, nt = C.c_void_p(), C.c_void_p(), C.c_uint32(), C.c_uint32()
+        self.lib.pfxCaptureEnd(C.byref(ps), C.byref(ns), C.byref(pt), C.byref(nt))
+        states = np.frombuffer((C.c_char * (ns.value * STATE_DTYPE.itemsize)).from_address(ps.value), dtype=STATE_DTYPE).copy() if ns.value else np.zeros(0, STATE_DTYPE)
+        tris = np.frombuffer((C.c_char * (nt.value * TRIANGLE_DTYPE.itemsize)).from_address(pt.value), dtype=TRIANGLE_DTYPE).copy() if nt.value else np.zeros(0, TRIANGLE_DTYPE)
+        return states, tris
 
     def render_stream(self, width, height, states, tris, color0=None, depth0=None, clear=None, tile_owner=None):
         """Rasterise a triangle stream into a fresh surface; returns (color u32[h,w], depth f32[h,w])."""

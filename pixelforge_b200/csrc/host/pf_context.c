@@ -90,7 +90,7 @@ void pfDeleteContext(PFcontext ctx)
     if (c->cur_surf != c->main_surf) pfh_sync_surface(c, c->cur_surf);
     pfcu_finish();
     for (int i = 0; i < 2; i++) if (c->tris[i]) pfcu_host_free(c->tris[i]);
-    free(c->states);
+    free(c->states); free(c->cap_tris); free(c->cap_states);
     pf_tex *tex = (pf_tex *)c->mainFramebuffer.texture;
     pfh_surf_destroy(c->main_surf);
     PF_FREE(tex);
@@ -1092,5 +1092,25 @@ void pfxReadDepth(PFfloat *out)
     pfh_upload_if_needed(c, c->cur_surf);
     pfcu_surface_download(c->cur_surf->dev, NULL, out, 0, c->cur_surf->tex->h);
 }
+
+void pfxCaptureBegin(void)
+{
+    CTX; if (!c) return;
+    pfh_flush(c);
+    c->capturing = 1; c->cap_ntris = 0; c->cap_nstates = 0;
+}
+
+void pfxCaptureEnd(const void **states, PFuint *nStates, const void **triangles, PFuint *nTriangles)
+{
+    CTX; if (!c) return;
+    pfh_flush(c);
+    c->capturing = 0;
+    if (states) *states = c->cap_states;
+    if (nStates) *nStates = (PFuint)c->cap_nstates;
+    if (triangles) *triangles = c->cap_tris;
+    if (nTriangles) *nTriangles = (PFuint)c->cap_ntris;
+}
+
+void *pfxGetSurfaceHandle(void) { return pf_cur ? pf_cur->cur_surf->dev : NULL; }
 
 const char *pfxBackendName(void) { return pfcu_backend_name(); }

@@ -148,6 +148,10 @@ typedef struct pf_ctx {
     pfcu_state    *states; uint32_t n_states, state_cap;
     int            state_dirty;
     uint64_t       tris_emitted;
+    /* optional capture of the submitted stream (pfxCaptureBegin/End) */
+    int            capturing;
+    pfcu_triangle *cap_tris; size_t cap_ntris, cap_tris_cap;
+    pfcu_state    *cap_states; size_t cap_nstates, cap_states_cap;
 } pf_ctx;
 
 extern PF_CTX_DECL pf_ctx *pf_cur;

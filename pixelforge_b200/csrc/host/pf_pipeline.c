@@ -166,10 +166,34 @@ void pfh_upload_if_needed(pf_ctx *c, pf_surf *s)
     }
 }
 
+static void capture_append(pf_ctx *c)
+{
+    if (c->cap_ntris + c->n_tris > c->cap_tris_cap) {
+        size_t nc = c->cap_tris_cap ? c->cap_tris_cap * 2 : 4096;
+        while (nc < c->cap_ntris + c->n_tris) nc *= 2;
+        pfcu_triangle *p = (pfcu_triangle *)realloc(c->cap_tris, nc * sizeof *p);
+        if (!p) { c->errCode = PF_ERROR_OUT_OF_MEMORY; return; }
+        c->cap_tris = p; c->cap_tris_cap = nc;
+    }
+    if (c->cap_nstates + c->n_states > c->cap_states_cap) {
+        size_t nc = c->cap_states_cap ? c->cap_states_cap * 2 : 16;
+        while (nc < c->cap_nstates + c->n_states) nc *= 2;
+        pfcu_state *p = (pfcu_state *)realloc(c->cap_states, nc * sizeof *p);
+        if (!p) { c->errCode = PF_ERROR_OUT_OF_MEMORY; return; }
+        c->cap_states = p; c->cap_states_cap = nc;
+    }
+    memcpy(c->cap_states + c->cap_nstates, c->states, c->n_states * sizeof(pfcu_state));
+    const pfcu_triangle *src = c->tris[c->cur_buf];
+    pfcu_triangle *dst = c->cap_tris + c->cap_ntris;
+    for (uint32_t i = 0; i < c->n_tris; i++) { dst[i] = src[i]; dst[i].state += (uint32_t)c->cap_nstates; }
+    c->cap_ntris += c->n_tris; c->cap_nstates += c->n_states;
+}
+
 void pfh_flush(pf_ctx *c)
 {
     if (!c || c->n_tris == 0) { if (c) { c->n_states = 0; c->state_dirty = 1; } return; }
     pf_surf *s = c->cur_surf;
+    if (c->capturing) capture_append(c);
     pfh_upload_if_needed(c, s);
     int rc = pfcu_submit(s->dev, c->states, c->n_states, c->tris[c->cur_buf], c->n_tris);
     if (rc != PFCU_OK) {

@@ -107,6 +107,9 @@ struct Runtime {
     DevState *h_states = nullptr; size_t cap_hstates = 0; cudaEvent_t states_done = nullptr;
     std::vector<PinnedBlock> pinned;
     uint64_t submitted = 0, launches = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;       /* triples: before setup, before raster, after raster */
+    std::vector<cudaEvent_t> prof_pool;
     std::mutex mu;
     char err[512] = { 0 };
 };
@@ -1316,6 +1319,14 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     const unsigned nBatches = (n + BIN_BATCH - 1) / BIN_BATCH;
     if ((rc = grow(&g.d_bin_counts, &g.cap_bin_counts, (size_t)nBatches * nb))) return rc;
 
+    cudaEvent_t pe[3] = { nullptr, nullptr, nullptr };
+    if (g.profiling) {
+        for (int i = 0; i < 3; i++) {
+            if (!g.prof_pool.empty()) { pe[i] = g.prof_pool.back(); g.prof_pool.pop_back(); }
+            else CK(cudaEventCreate(&pe[i]));
+        }
+        CK(cudaEventRecord(pe[0], g.stream));
+    }
     k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, g.stream>>>(
         d_tris, d_states, n, (int)s->w, (int)s->h, g.d_bbox, g.d_setup, g.d_data, g.d_counters);
     k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), g.stream>>>(g.d_bbox, n, binsX, binsY, g.d_bin_counts);
@@ -1347,6 +1358,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     p.rank = s->rank; p.world = s->world ? s->world : 1; p.nTiles = s->tiles_x * s->tiles_y;
     p.counters = g.d_counters;
     const unsigned grid = owned_tiles(s, p.rank, p.world);
+    if (g.profiling) CK(cudaEventRecord(pe[1], g.stream));
     if (grid) {
         const bool tex = (feature_mask & PFCU_ST_TEXTURE) != 0, ph = (feature_mask & PFCU_ST_PHONG) != 0;
         if (tex && ph)       k_raster<true, true><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
@@ -1355,6 +1367,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         else                 k_raster<false, false><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
         g.launches++;
     }
+    if (g.profiling) { CK(cudaEventRecord(pe[2], g.stream)); for (int i = 0; i < 3; i++) g.prof_events.push_back(pe[i]); }
     CK(cudaGetLastError());
     g.submitted += n;
     return PFCU_OK;
@@ -1431,6 +1444,24 @@ void pfcu_batch_destroy(pfcu_batch *b)
     if (!b) return;
     if (g.ok) cudaStreamSynchronize(g.stream);
     cudaFree(b->states); cudaFree(b->tris); free(b);
+}
+
+void pfcu_profile_enable(int on) { g.profiling = on != 0; }
+
+int pfcu_profile_read(pfcu_profile *out)
+{
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    CK(cudaStreamSynchronize(g.stream));
+    out->raster_ms = 0; out->frontend_ms = 0; out->raster_launches = 0;
+    for (size_t i = 0; i + 2 < g.prof_events.size(); i += 3) {
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, g.prof_events[i], g.prof_events[i + 1]));
+        CK(cudaEventElapsedTime(&b, g.prof_events[i + 1], g.prof_events[i + 2]));
+        out->frontend_ms += a; out->raster_ms += b; out->raster_launches++;
+    }
+    for (auto e : g.prof_events) g.prof_pool.push_back(e);
+    g.prof_events.clear();
+    return PFCU_OK;
 }
 
 int pfcu_finish(void)

@@ -1,0 +1,85 @@
+"""Multi-GPU plumbing for the screen-tile split (BASELINE.json config C4).
+
+One process per GPU (torch.distributed).  Every rank receives the same ordered triangle batch and
+rasterises only the 64x64 tiles it owns (owner(tile) = tile % world, enforced inside k_raster), so the
+per-pixel result is byte-identical to a single-GPU render.  The only exchange step is the gather of
+the finished tiles to the presenting rank: each rank packs its tiles into a contiguous staging
+buffer (k_pack_tiles), the buffers are gathered with NCCL over NVLink (or gloo in CPU tests, where
+the "device" is the oracle build), and the presenter unpacks them into its surface.
+"""
+import numpy as np
+
+
+def owned_tiles(width, height, rank, world, tile=64):
+    nt = ((width + tile - 1) // tile) * ((height + tile - 1) // tile)
+    return nt // world + (1 if (nt % world) > rank else 0)
+
+
+def gather_tiles(torch, dist, pfcu, surface, width, height, rank, world, with_depth=False, device="cuda", dst=0):
+    """Pack this rank's tiles, gather all ranks' tiles on `dst`, unpack there.  Returns bytes moved to dst."""
+    L = pfcu.lib
+    per_tile = 64 * 64 * 4 * (2 if with_depth else 1)
+    max_tiles = owned_tiles(width, height, 0, world)            # rank 0 owns the most
+    staging = torch.zeros(max_tiles * per_tile, dtype=torch.uint8, device=device)
+    pfcu.check(L.pfcu_surface_pack_tiles(surface, rank, world, int(with_depth), staging.data_ptr()), "pack_tiles")
+    if device == "cuda":
+        # pack ran on the pfcu stream; make the collective wait for it
+        pfcu.check(L.pfcu_finish(), "finish")
+    if world == 1:
+        return 0
+    if rank == dst:
+        bufs = [torch.empty_like(staging) for _ in range(world)]
+        dist.gather(staging, bufs, dst=dst)
+        moved = 0
+        for r in range(world):
+            if r == dst:
+                continue
+            pfcu.check(L.pfcu_surface_unpack_tiles(surface, r, world, int(with_depth), bufs[r].data_ptr()), "unpack_tiles")
+            moved += owned_tiles(width, height, r, world) * per_tile
+        if device == "cuda":
+            pfcu.check(L.pfcu_finish(), "finish")
+        return moved
+    dist.gather(staging, None, dst=dst)
+    return 0
+
+
+def tile_split_benchmark(torch, dist, scenes, pfcu, stream, wl, rank, world, steps=3):
+    """Strong-scaling run of one big surface split by screen tiles across `world` GPUs."""
+    from .binding import Counters
+    L = pfcu.lib
+    with scenes.open(wl["scene"], wl["w"], wl["h"], variant=wl["variant"], size=wl["size"], explicit_sync=1) as sc:
+        L.pfcu_set_stream(stream.cuda_stream)
+        L.pfxCaptureBegin()
+        sc.frame(0)
+        states, tris = pfcu.capture_end()
+        surf = L.pfxGetSurfaceHandle()
+        L.pfcu_surface_set_tile_owner(surf, rank, world)
+        b = L.pfcu_batch_upload(states.ctypes.data, len(states), tris.ctypes.data, len(tris))
+        times, gather_ms = [], []
+        L.pfxResetCounters()
+        for i in range(steps + 1):
+            torch.cuda.synchronize(); dist.barrier()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                L.pfcu_surface_clear_ref(surf, 1, 0xFF000000, 1, 3.4028234663852886e38)
+                L.pfcu_batch_submit(surf, b)
+                e1.record(stream)
+                gather_tiles(torch, dist, pfcu, surf, wl["w"], wl["h"], rank, world)
+                e2.record(stream)
+            torch.cuda.synchronize()
+            if i > 0:
+                times.append(e0.elapsed_time(e1)); gather_ms.append(e1.elapsed_time(e2))
+        k = Counters(); L.pfcu_get_counters(k)
+        t = torch.tensor([sum(times) / len(times), sum(gather_ms) / len(gather_ms)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        px = torch.tensor([k.pixels_shaded / (steps + 1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(px, op=dist.ReduceOp.SUM)
+        L.pfcu_surface_set_tile_owner(surf, 0, 1)
+        L.pfcu_batch_destroy(b)
+        sc.finish()
+    render_ms, gat_ms = float(t[0]), float(t[1])
+    return {"desc": wl["desc"] + f", screen-tile split over {world} GPUs + NCCL gather to rank 0", "scaling": "strong",
+            "render_ms": render_ms, "gather_ms": gat_ms, "shaded_px": float(px[0]),
+            "gpix_per_s_render": float(px[0]) / (render_ms * 1e-3) / 1e9,
+            "gpix_per_s_with_gather": float(px[0]) / ((render_ms + gat_ms) * 1e-3) / 1e9}

@@ -379,19 +379,18 @@ static void micro_scene(const pfscene_cfg *cfg, PFtexture tex)
 
 /* ---- the runner ------------------------------------------------------------------------------------ */
 
-static int cmp_double(const void *a, const void *b) { double x = *(const double *)a, y = *(const double *)b; return (x > y) - (x < y); }
+#define MAX_BATCH_CTX 1024
 
-static void collect(pfscene_result *res, double *times, int n)
-{
-    res->ms_total = 0; res->ms_min = 1e300;
-    for (int i = 0; i < n; i++) { res->ms_total += times[i]; if (times[i] < res->ms_min) res->ms_min = times[i]; }
-    if (n > 0) { qsort(times, (size_t)n, sizeof(double), cmp_double); res->ms_median = times[n / 2]; } else res->ms_min = 0;
-#ifdef PFSCENE_HAVE_PFX
-    PFXcounters k; pfxGetCounters(&k);
-    res->triangles_submitted = k.triangles_submitted; res->triangles_rasterised = k.triangles_rasterised;
-    res->pixels_shaded = k.pixels_shaded; res->pixels_depth_failed = k.pixels_depth_failed; res->kernel_launches = k.kernel_launches;
-#endif
-}
+typedef struct {
+    char name[32];
+    pfscene_cfg cfg;
+    /* single-context scenes */
+    PFcontext ctx; uint8_t *target; uint8_t *texpx; PFtexture tex; mesh_t mesh; PFframebuffer fbo;
+    /* "batch": n contexts */
+    int n; PFcontext *ctxs; uint8_t **bufs; uint8_t **texpxs; PFtexture *texs; PFrenderlist (*lists)[3];
+} scene_t;
+
+static int cmp_double(const void *a, const void *b) { double x = *(const double *)a, y = *(const double *)b; return (x > y) - (x < y); }
 
 static void reset_counters(void)
 {
@@ -409,109 +408,66 @@ SCN_API const char *pfscene_backend(void)
 #endif
 }
 
-/* Renders `cfg->warmup + cfg->frames` frames of scene `name`; the colour buffer (w*h*4 bytes) and,
- * when depth_out != NULL, the depth buffer of the LAST frame are returned.  Counters cover the timed
- * frames only.  Returns 0 on success. */
-SCN_API int pfscene_render(const char *name, const pfscene_cfg *cfg, uint8_t *color_out, float *depth_out, pfscene_result *res)
+SCN_API void pfscene_close(void *handle);
+
+/* Creates the context(s), textures, meshes and fixed state of scene `name`.  Returns NULL on failure. */
+SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
 {
+    scene_t *s = (scene_t *)calloc(1, sizeof *s);
+    if (!s) return NULL;
+    strncpy(s->name, name, sizeof s->name - 1);
+    s->cfg = *cfg;
     const int w = cfg->width, h = cfg->height;
-    const int total = cfg->warmup + cfg->frames;
-    double *times = (double *)calloc((size_t)(cfg->frames > 0 ? cfg->frames : 1), sizeof(double));
-    memset(res, 0, sizeof *res);
 #ifdef PFSCENE_HAVE_PFX
     pfxSetSyncMode(cfg->explicit_sync ? PF_TRUE : PF_FALSE);
 #endif
 
     if (strcmp(name, "batch") == 0) {
-        /* C5: `size` independent 512x512-style contexts, each with its own target, texture and the
-           three gear render lists; replayed with a per-context angle.  Textured + lit + depth. */
+        /* C5: `size` independent contexts, each with its own target, texture and the three gear render
+           lists; replayed every frame with a per-context angle.  Textured + Gouraud-lit + depth. */
         const int n = cfg->size > 0 ? cfg->size : 4;
-        PFcontext *ctx = (PFcontext *)calloc((size_t)n, sizeof(PFcontext));
-        uint8_t **buf = (uint8_t **)calloc((size_t)n, sizeof(uint8_t *));
-        uint8_t **texpx = (uint8_t **)calloc((size_t)n, sizeof(uint8_t *));
-        PFtexture *tex = (PFtexture *)calloc((size_t)n, sizeof(PFtexture));
-        PFrenderlist (*lists)[3] = (PFrenderlist (*)[3])calloc((size_t)n, sizeof(PFrenderlist[3]));
+        s->n = n;
+        s->ctxs = (PFcontext *)calloc((size_t)n, sizeof(PFcontext));
+        s->bufs = (uint8_t **)calloc((size_t)n, sizeof(uint8_t *));
+        s->texpxs = (uint8_t **)calloc((size_t)n, sizeof(uint8_t *));
+        s->texs = (PFtexture *)calloc((size_t)n, sizeof(PFtexture));
+        s->lists = (PFrenderlist (*)[3])calloc((size_t)n, sizeof(PFrenderlist[3]));
         for (int c = 0; c < n; c++) {
-            buf[c] = (uint8_t *)calloc((size_t)w * h * 4 + 64, 1);
-            ctx[c] = pfCreateContext(buf[c], (PFsizei)w, (PFsizei)h, PF_RGBA, PF_UNSIGNED_BYTE);
-            if (!ctx[c]) { fprintf(stderr, "pfscene: pfCreateContext failed\n"); return 2; }
-            pfMakeCurrent(ctx[c]);
-            texpx[c] = make_texture(256, 256, 4, (uint32_t)(cfg->seed + c), 96, 255, 255, 255);
-            tex[c] = pfGenTexture(texpx[c], 256, 256, PF_RGBA, PF_UNSIGNED_BYTE);
+            s->bufs[c] = (uint8_t *)calloc((size_t)w * h * 4 + 64, 1);
+            s->ctxs[c] = pfCreateContext(s->bufs[c], (PFsizei)w, (PFsizei)h, PF_RGBA, PF_UNSIGNED_BYTE);
+            if (!s->ctxs[c]) { fprintf(stderr, "pfscene: pfCreateContext failed\n"); s->n = c; pfscene_close(s); return NULL; }
+            pfMakeCurrent(s->ctxs[c]);
+            s->texpxs[c] = make_texture(256, 256, 4, (uint32_t)(cfg->seed + c), 96, 255, 255, 255);
+            s->texs[c] = pfGenTexture(s->texpxs[c], 256, 256, PF_RGBA, PF_UNSIGNED_BYTE);
             gears_setup(w, h);
             pfEnable(PF_TEXTURE_2D);
             static const double gp[3][5] = { { 1.0, 4.0, 1.0, 20, 0.7 }, { 0.5, 2.0, 2.0, 10, 0.7 }, { 1.3, 2.0, 0.5, 10, 0.7 } };
             for (int g = 0; g < 3; g++) {
-                lists[c][g] = pfGenList();
-                pfBindTexture(tex[c]);
-                pfNewList(lists[c][g]);
+                s->lists[c][g] = pfGenList();
+                pfBindTexture(s->texs[c]);
+                pfNewList(s->lists[c][g]);
                 pfTexCoord2f(0.25f * (float)g, 0.5f);
                 gear(gp[g][0], gp[g][1], gp[g][2], (int)gp[g][3], gp[g][4]);
                 pfEndList();
             }
         }
-        for (int f = 0; f < total; f++) {
-            if (f == cfg->warmup) { reset_counters(); g_api_tris = 0; }
-            double t0 = now_ms();
-            for (int c = 0; c < n; c++) {
-                pfMakeCurrent(ctx[c]);
-                float angle = 7.0f * (float)c + 1.44f * (float)(cfg->first_frame + f);
-                pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
-                pfEnable(PF_COLOR_MATERIAL); pfColorMaterial(PF_FRONT_AND_BACK, PF_AMBIENT_AND_DIFFUSE);
-                pfPushMatrix();
-                pfRotatef(20.0f, 1.0f, 0.0f, 0.0f); pfRotatef(30.0f, 0.0f, 1.0f, 0.0f);
-                static const float tr[3][2] = { { -3.0f, -2.0f }, { 3.1f, -2.0f }, { -3.1f, 4.2f } };
-                static const PFubyte col[3][3] = { { 255, 64, 64 }, { 64, 255, 64 }, { 64, 64, 255 } };
-                for (int g = 0; g < 3; g++) {
-                    pfPushMatrix();
-                    pfTranslatef(tr[g][0], tr[g][1], 0.0f);
-                    pfRotatef(g == 0 ? angle : (g == 1 ? -2.0f * angle - 9.0f : -2.0f * angle - 25.0f), 0.0f, 0.0f, 1.0f);
-                    pfColor3ub(col[g][0], col[g][1], col[g][2]);
-                    pfCallList(lists[c][g]);
-                    pfPopMatrix();
-                }
-                pfPopMatrix();
-                pfDisable(PF_COLOR_MATERIAL);
-            }
-            for (int c = 0; c < n; c++) { pfMakeCurrent(ctx[c]); finish(); }
-            if (f >= cfg->warmup) times[f - cfg->warmup] = now_ms() - t0;
-        }
-        res->api_triangles = g_api_tris;
-        collect(res, times, cfg->frames);
-        /* output: context 0 followed by the XOR of all contexts' pixels in the depth slot is not needed;
-           return context (size-1) so that per-context parameters matter */
-        pfMakeCurrent(ctx[n - 1]);
-        if (color_out) memcpy(color_out, buf[n - 1], (size_t)w * h * 4);
-        read_depth(depth_out, w);
-        for (int c = 0; c < n; c++) {
-            pfMakeCurrent(ctx[c]);
-            for (int g = 0; g < 3; g++) pfDeleteList(&lists[c][g]);
-            pfDeleteTexture(&tex[c], PF_FALSE);
-            pfMakeCurrent(NULL);
-            pfDeleteContext(ctx[c]);
-            free(buf[c]); free(texpx[c]);
-        }
-        free(ctx); free(buf); free(texpx); free(tex); free(lists); free(times);
-        return 0;
+        return s;
     }
 
-    uint8_t *target = (uint8_t *)calloc((size_t)w * h * 4 + 64, 1);
-    PFcontext ctx = pfCreateContext(target, (PFsizei)w, (PFsizei)h, PF_RGBA, PF_UNSIGNED_BYTE);
-    if (!ctx) { fprintf(stderr, "pfscene: pfCreateContext failed\n"); free(target); free(times); return 2; }
-    pfMakeCurrent(ctx);
-    int rc = 0;
-    uint8_t *texpx = NULL; PFtexture tex = NULL; mesh_t mesh; memset(&mesh, 0, sizeof mesh);
-    PFframebuffer fbo; memset(&fbo, 0, sizeof fbo);
+    s->target = (uint8_t *)calloc((size_t)w * h * 4 + 64, 1);
+    s->ctx = pfCreateContext(s->target, (PFsizei)w, (PFsizei)h, PF_RGBA, PF_UNSIGNED_BYTE);
+    if (!s->ctx) { fprintf(stderr, "pfscene: pfCreateContext failed\n"); free(s->target); free(s); return NULL; }
+    pfMakeCurrent(s->ctx);
 
     if (strcmp(name, "gears") == 0) {
         gears_setup(w, h);
     } else if (strcmp(name, "textured") == 0) {
         const int rgb = (cfg->variant >> 3) & 1;
-        texpx = make_texture(1024, 1024, rgb ? 3 : 4, (uint32_t)cfg->seed, 0, 255, 128, 255);
-        tex = pfGenTexture(texpx, 1024, 1024, rgb ? PF_RGB : PF_RGBA, PF_UNSIGNED_BYTE);
-        pfTextureParameter(tex, (PFtexturewrap)(((cfg->variant >> 1) & 3) % 3), (cfg->variant & 1) ? PF_BILINEAR : PF_NEAREST);
+        s->texpx = make_texture(1024, 1024, rgb ? 3 : 4, (uint32_t)cfg->seed, 0, 255, 128, 255);
+        s->tex = pfGenTexture(s->texpx, 1024, 1024, rgb ? PF_RGB : PF_RGBA, PF_UNSIGNED_BYTE);
+        pfTextureParameter(s->tex, (PFtexturewrap)(((cfg->variant >> 1) & 3) % 3), (cfg->variant & 1) ? PF_BILINEAR : PF_NEAREST);
         const int nu = cfg->size > 0 ? cfg->size : 256;
-        mesh = make_torus(nu, nu / 2, 12.0f, 5.0f, ((cfg->variant >> 1) & 3) ? 1.6f : 1.0f);
+        s->mesh = make_torus(nu, nu / 2, 12.0f, 5.0f, ((cfg->variant >> 1) & 3) ? 1.6f : 1.0f);
         pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
         cam_perspective(60.0, (double)w / h, 0.01, 1000.0);
         pfEnable(PF_TEXTURE_2D); pfEnable(PF_DEPTH_TEST);
@@ -519,7 +475,7 @@ SCN_API int pfscene_render(const char *name, const pfscene_cfg *cfg, uint8_t *co
         pfDisable(PF_CULL_FACE);
     } else if (strcmp(name, "phong") == 0) {
         const int n = cfg->size > 0 ? cfg->size : 708;
-        mesh = make_heightfield(n);
+        s->mesh = make_heightfield(n);
         pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
         cam_perspective(60.0, (double)w / h, 0.01, 1000.0);
         float eye[3] = { 0.0f, 0.0f, 2.6f }, at[3] = { 0, 0, 0 };
@@ -531,97 +487,195 @@ SCN_API int pfscene_render(const char *name, const pfscene_cfg *cfg, uint8_t *co
         pfMaterialf(PF_FRONT_AND_BACK, PF_SHININESS, 32.0f);
         pfEnable(PF_DEPTH_TEST); pfEnable(PF_CULL_FACE);
     } else if (strcmp(name, "overdraw") == 0) {
-        /* variant: bit0 alpha-blend + depth test (4K target scene) instead of additive / no depth;
-           bit1 bilinear */
-        texpx = make_texture(512, 512, 4, (uint32_t)cfg->seed, 0, 3, (cfg->variant & 1) ? 96 : 0, (cfg->variant & 1) ? 200 : 3);
-        if (cfg->variant & 1) { lcg_state = 7u; for (size_t i = 0; i < 512u * 512u; i++) for (int c = 0; c < 3; c++) texpx[i * 4 + c] = (uint8_t)(lcg() >> 24); }
-        tex = pfGenTexture(texpx, 512, 512, PF_RGBA, PF_UNSIGNED_BYTE);
-        pfTextureParameter(tex, PF_REPEAT, (cfg->variant & 2) ? PF_BILINEAR : PF_NEAREST);
+        /* variant: bit0 alpha-blend + depth test (the "4K textured+blended" target scene) instead of
+           additive / no depth test; bit1 bilinear */
+        s->texpx = make_texture(512, 512, 4, (uint32_t)cfg->seed, 0, 3, (cfg->variant & 1) ? 96 : 0, (cfg->variant & 1) ? 200 : 3);
+        if (cfg->variant & 1) { lcg_state = 7u; for (size_t i = 0; i < 512u * 512u; i++) for (int c = 0; c < 3; c++) s->texpx[i * 4 + c] = (uint8_t)(lcg() >> 24); }
+        s->tex = pfGenTexture(s->texpx, 512, 512, PF_RGBA, PF_UNSIGNED_BYTE);
+        pfTextureParameter(s->tex, PF_REPEAT, (cfg->variant & 2) ? PF_BILINEAR : PF_NEAREST);
         ortho2d(w, h);
         pfEnable(PF_TEXTURE_2D); pfEnable(PF_BLEND);
         if (cfg->variant & 1) { pfBlendFunc(PF_BLEND_ALPHA); pfEnable(PF_DEPTH_TEST); pfDepthFunc(PF_LEQUAL); }
         else pfBlendFunc(PF_BLEND_ADD);
     } else if (strcmp(name, "micro") == 0) {
         const int rgb = (cfg->variant >> 17) & 1, bgra = (cfg->variant >> 22) & 1;
-        texpx = make_texture(61, 37, rgb ? 3 : 4, (uint32_t)cfg->seed ^ 0xabcdu, 0, 255, 0, 255);
-        tex = pfGenTexture(texpx, 61, 37, rgb ? PF_RGB : (bgra ? PF_BGRA : PF_RGBA), PF_UNSIGNED_BYTE);
+        s->texpx = make_texture(61, 37, rgb ? 3 : 4, (uint32_t)cfg->seed ^ 0xabcdu, 0, 255, 0, 255);
+        s->tex = pfGenTexture(s->texpx, 61, 37, rgb ? PF_RGB : (bgra ? PF_BGRA : PF_RGBA), PF_UNSIGNED_BYTE);
         /* the FBO is larger than the 96x80 viewport used to draw into it: for a viewport smaller than the
            MAIN buffer the reference computes vpMax = x+width (one past the last column/row,
            context.c:567-570), so "2D" triangles may touch column 96 / row 80 */
-        if (cfg->variant & (1 << 20)) fbo = pfGenFramebuffer(104, 88, PF_RGBA, PF_UNSIGNED_BYTE);
+        if (cfg->variant & (1 << 20)) s->fbo = pfGenFramebuffer(104, 88, PF_RGBA, PF_UNSIGNED_BYTE);
     } else {
         fprintf(stderr, "pfscene: unknown scene '%s'\n", name);
-        rc = 1;
+        pfscene_close(s);
+        return NULL;
     }
+    return s;
+}
 
-    for (int f = 0; rc == 0 && f < total; f++) {
-        if (f == cfg->warmup) { reset_counters(); g_api_tris = 0; }
-        const int frame = cfg->first_frame + f;
-        double t0 = now_ms();
-        if (strcmp(name, "gears") == 0) {
-            gears_frame(1.44f * (float)frame);
-        } else if (strcmp(name, "textured") == 0) {
-            double t = 0.35 + 0.05 * frame;
-            float eye[3] = { (float)(35.0 * cos(t)), 30.0f, (float)(35.0 * sin(t)) }, at[3] = { 0.0f, 0.0f, 0.0f };
-            cam_lookat(eye, at);
+/* Issues the API calls of one frame (clear + draw).  Does NOT wait for the GPU. */
+SCN_API void pfscene_frame(void *handle, int frame)
+{
+    scene_t *s = (scene_t *)handle;
+    const pfscene_cfg *cfg = &s->cfg;
+    const int w = cfg->width, h = cfg->height;
+    const char *name = s->name;
+    if (strcmp(name, "batch") == 0) {
+        for (int c = 0; c < s->n; c++) {
+            pfMakeCurrent(s->ctxs[c]);
+            float angle = 7.0f * (float)c + 1.44f * (float)frame;
             pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
-            pfBindTexture(tex);
-            pfColor4ub(255, 255, 255, 200);
-            if (cfg->variant & 32) draw_mesh_arrays(&mesh); else draw_mesh_immediate(&mesh);
-        } else if (strcmp(name, "phong") == 0) {
-            pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
-            pfColor4ub(255, 255, 255, 255);
-            if (cfg->variant & 32) {
-                pfEnable(PF_VERTEX_ARRAY); pfEnable(PF_NORMAL_ARRAY);
-                pfVertexPointer(3, PF_FLOAT, 0, mesh.pos); pfNormalPointer(PF_FLOAT, 0, mesh.nrm);
-                pfDrawElements(PF_TRIANGLES, (PFsizei)mesh.nidx, PF_UNSIGNED_INT, mesh.idx);
-                pfDisable(PF_VERTEX_ARRAY); pfDisable(PF_NORMAL_ARRAY);
-                g_api_tris += (unsigned long long)mesh.nidx / 3;
-            } else {
-                pfBegin(PF_TRIANGLES);
-                for (int k = 0; k < mesh.nidx; k++) { uint32_t i = mesh.idx[k]; pfNormal3fv(mesh.nrm + 3 * i); pfVertex3fv(mesh.pos + 3 * i); }
-                pfEnd();
-                g_api_tris += (unsigned long long)mesh.nidx / 3;
+            pfEnable(PF_COLOR_MATERIAL); pfColorMaterial(PF_FRONT_AND_BACK, PF_AMBIENT_AND_DIFFUSE);
+            pfPushMatrix();
+            pfRotatef(20.0f, 1.0f, 0.0f, 0.0f); pfRotatef(30.0f, 0.0f, 1.0f, 0.0f);
+            static const float tr[3][2] = { { -3.0f, -2.0f }, { 3.1f, -2.0f }, { -3.1f, 4.2f } };
+            static const PFubyte col[3][3] = { { 255, 64, 64 }, { 64, 255, 64 }, { 64, 64, 255 } };
+            for (int g = 0; g < 3; g++) {
+                pfPushMatrix();
+                pfTranslatef(tr[g][0], tr[g][1], 0.0f);
+                pfRotatef(g == 0 ? angle : (g == 1 ? -2.0f * angle - 9.0f : -2.0f * angle - 25.0f), 0.0f, 0.0f, 1.0f);
+                pfColor3ub(col[g][0], col[g][1], col[g][2]);
+                pfCallList(s->lists[c][g]);
+                pfPopMatrix();
             }
-        } else if (strcmp(name, "overdraw") == 0) {
-            const int layers = cfg->size > 0 ? cfg->size : 64;
-            pfClearColor(0, 0, 0, 255);
-            pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
-            pfColor4ub(255, 255, 255, 255);
-            for (int l = 0; l < layers; l++)
-                draw_textured_quad(tex, 0.0f, 0.0f, (float)w, (float)h, (float)w / 512.0f, (float)h / 512.0f);
-        } else if (strcmp(name, "micro") == 0) {
-            if (cfg->variant & (1 << 20)) {
-                /* pass 1: render into the FBO; pass 2: draw it as a texture over the main buffer */
-                pfscene_cfg sub = *cfg; sub.width = 96; sub.height = 80; sub.variant &= ~(1 << 20);
-                pfBindFramebuffer(&fbo); pfEnable(PF_FRAMEBUFFER);
-                micro_scene(&sub, tex);
-                pfDisable(PF_FRAMEBUFFER);
-                sub = *cfg; sub.variant &= ~(1 << 20); sub.seed += 17;
-                micro_scene(&sub, tex);
-                ortho2d(w, h);
-                pfDisable(PF_LIGHTING); pfDisable(PF_DEPTH_TEST); pfEnable(PF_TEXTURE_2D); pfEnable(PF_BLEND); pfBlendFunc(PF_BLEND_ALPHA);
-                pfTextureParameter(fbo.texture, PF_REPEAT, PF_NEAREST);   /* CLAMP would index row h of the FBO at v == 1 (reads past the reference's own allocation) */
-                pfColor4ub(255, 255, 255, 255);
-                draw_textured_quad(fbo.texture, 8.0f, 6.0f, 0.7f * w, 0.6f * h, 1.0f, 1.0f);
-            } else micro_scene(cfg, tex);
+            pfPopMatrix();
+            pfDisable(PF_COLOR_MATERIAL);
         }
-        finish();
+        return;
+    }
+    pfMakeCurrent(s->ctx);
+    if (strcmp(name, "gears") == 0) {
+        gears_frame(1.44f * (float)frame);
+    } else if (strcmp(name, "textured") == 0) {
+        double t = 0.35 + 0.05 * frame;
+        float eye[3] = { (float)(35.0 * cos(t)), 30.0f, (float)(35.0 * sin(t)) }, at[3] = { 0.0f, 0.0f, 0.0f };
+        if (cfg->variant & 64) { eye[0] = (float)(19.0 * cos(t)); eye[1] = 9.0f; eye[2] = (float)(19.0 * sin(t)); }   /* close-up: fills the screen */
+        cam_lookat(eye, at);
+        pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+        pfBindTexture(s->tex);
+        pfColor4ub(255, 255, 255, 200);
+        if (cfg->variant & 32) draw_mesh_arrays(&s->mesh); else draw_mesh_immediate(&s->mesh);
+    } else if (strcmp(name, "phong") == 0) {
+        pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+        pfColor4ub(255, 255, 255, 255);
+        if (cfg->variant & 32) {
+            pfEnable(PF_VERTEX_ARRAY); pfEnable(PF_NORMAL_ARRAY);
+            pfVertexPointer(3, PF_FLOAT, 0, s->mesh.pos); pfNormalPointer(PF_FLOAT, 0, s->mesh.nrm);
+            pfDrawElements(PF_TRIANGLES, (PFsizei)s->mesh.nidx, PF_UNSIGNED_INT, s->mesh.idx);
+            pfDisable(PF_VERTEX_ARRAY); pfDisable(PF_NORMAL_ARRAY);
+            g_api_tris += (unsigned long long)s->mesh.nidx / 3;
+        } else {
+            pfBegin(PF_TRIANGLES);
+            for (int k = 0; k < s->mesh.nidx; k++) { uint32_t i = s->mesh.idx[k]; pfNormal3fv(s->mesh.nrm + 3 * i); pfVertex3fv(s->mesh.pos + 3 * i); }
+            pfEnd();
+            g_api_tris += (unsigned long long)s->mesh.nidx / 3;
+        }
+    } else if (strcmp(name, "overdraw") == 0) {
+        const int layers = cfg->size > 0 ? cfg->size : 64;
+        pfClearColor(0, 0, 0, 255);
+        pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+        pfColor4ub(255, 255, 255, 255);
+        for (int l = 0; l < layers; l++)
+            draw_textured_quad(s->tex, 0.0f, 0.0f, (float)w, (float)h, (float)w / 512.0f, (float)h / 512.0f);
+    } else if (strcmp(name, "micro") == 0) {
+        if (cfg->variant & (1 << 20)) {
+            /* pass 1: render into the FBO; pass 2: draw it as a texture over the main buffer */
+            pfscene_cfg sub = *cfg; sub.width = 96; sub.height = 80; sub.variant &= ~(1 << 20);
+            pfBindFramebuffer(&s->fbo); pfEnable(PF_FRAMEBUFFER);
+            micro_scene(&sub, s->tex);
+            pfDisable(PF_FRAMEBUFFER);
+            sub = *cfg; sub.variant &= ~(1 << 20); sub.seed += 17;
+            micro_scene(&sub, s->tex);
+            ortho2d(w, h);
+            pfDisable(PF_LIGHTING); pfDisable(PF_DEPTH_TEST); pfEnable(PF_TEXTURE_2D); pfEnable(PF_BLEND); pfBlendFunc(PF_BLEND_ALPHA);
+            pfTextureParameter(s->fbo.texture, PF_REPEAT, PF_NEAREST);   /* CLAMP would index row h of the FBO at v == 1 (reads past the reference's own allocation) */
+            pfColor4ub(255, 255, 255, 255);
+            draw_textured_quad(s->fbo.texture, 8.0f, 6.0f, 0.7f * w, 0.6f * h, 1.0f, 1.0f);
+        } else micro_scene(cfg, s->tex);
+    }
+}
+
+/* Waits for the frame and brings the caller-visible buffers up to date (no-op for the reference,
+ * which is synchronous). */
+SCN_API void pfscene_finish(void *handle)
+{
+    scene_t *s = (scene_t *)handle;
+    if (s->n) { for (int c = 0; c < s->n; c++) { pfMakeCurrent(s->ctxs[c]); finish(); } }
+    else { pfMakeCurrent(s->ctx); finish(); }
+}
+
+SCN_API void pfscene_make_current(void *handle, int index)
+{
+    scene_t *s = (scene_t *)handle;
+    pfMakeCurrent(s->n ? s->ctxs[index % s->n] : s->ctx);
+}
+
+/* Copies out the colour (w*h*4 bytes) and optionally the depth buffer (context size-1 for "batch"). */
+SCN_API void pfscene_read(void *handle, uint8_t *color_out, float *depth_out)
+{
+    scene_t *s = (scene_t *)handle;
+    const size_t bytes = (size_t)s->cfg.width * s->cfg.height * 4;
+    if (s->n) { pfMakeCurrent(s->ctxs[s->n - 1]); if (color_out) memcpy(color_out, s->bufs[s->n - 1], bytes); }
+    else { pfMakeCurrent(s->ctx); if (color_out) memcpy(color_out, s->target, bytes); }
+    read_depth(depth_out, s->cfg.width);
+}
+
+SCN_API void pfscene_close(void *handle)
+{
+    scene_t *s = (scene_t *)handle;
+    if (!s) return;
+    if (s->ctxs) {
+        for (int c = 0; c < s->n; c++) {
+            pfMakeCurrent(s->ctxs[c]);
+            for (int g = 0; g < 3; g++) if (s->lists[c][g]) pfDeleteList(&s->lists[c][g]);
+            if (s->texs[c]) pfDeleteTexture(&s->texs[c], PF_FALSE);
+            pfMakeCurrent(NULL);
+            pfDeleteContext(s->ctxs[c]);
+            free(s->bufs[c]); free(s->texpxs[c]);
+        }
+        free(s->ctxs); free(s->bufs); free(s->texpxs); free(s->texs); free(s->lists);
+    } else if (s->ctx) {
+        pfMakeCurrent(s->ctx);
+        if (s->fbo.texture) pfDeleteFramebuffer(&s->fbo);
+        if (s->tex) pfDeleteTexture(&s->tex, PF_FALSE);
+        free(s->texpx);
+        if (s->mesh.pos) free_mesh(&s->mesh);
+        pfMakeCurrent(NULL);
+        pfDeleteContext(s->ctx);
+        free(s->target);
+    }
+    free(s);
+}
+
+/* Renders `cfg->warmup + cfg->frames` frames of scene `name` and times each frame with the wall clock
+ * (API calls + wait + host buffers up to date).  The colour buffer and, when depth_out != NULL, the
+ * depth buffer of the LAST frame are returned.  Counters cover the timed frames only. */
+SCN_API int pfscene_render(const char *name, const pfscene_cfg *cfg, uint8_t *color_out, float *depth_out, pfscene_result *res)
+{
+    memset(res, 0, sizeof *res);
+    void *s = pfscene_open(name, cfg);
+    if (!s) return 2;
+    const int total = cfg->warmup + cfg->frames;
+    double *times = (double *)calloc((size_t)(cfg->frames > 0 ? cfg->frames : 1), sizeof(double));
+    for (int f = 0; f < total; f++) {
+        if (f == cfg->warmup) { reset_counters(); g_api_tris = 0; }
+        double t0 = now_ms();
+        pfscene_frame(s, cfg->first_frame + f);
+        pfscene_finish(s);
         if (f >= cfg->warmup) times[f - cfg->warmup] = now_ms() - t0;
     }
-
-    if (rc == 0) {
-        res->api_triangles = g_api_tris;
-        collect(res, times, cfg->frames);
-        if (color_out) memcpy(color_out, target, (size_t)w * h * 4);
-        read_depth(depth_out, w);
-    }
-    if (fbo.texture) pfDeleteFramebuffer(&fbo);
-    if (tex) pfDeleteTexture(&tex, PF_FALSE);
-    free(texpx);
-    if (mesh.pos) free_mesh(&mesh);
-    pfMakeCurrent(NULL);
-    pfDeleteContext(ctx);
-    free(target); free(times);
-    return rc;
+    const int n = cfg->frames;
+    res->api_triangles = g_api_tris;
+    res->ms_total = 0; res->ms_min = n > 0 ? 1e300 : 0;
+    for (int i = 0; i < n; i++) { res->ms_total += times[i]; if (times[i] < res->ms_min) res->ms_min = times[i]; }
+    if (n > 0) { qsort(times, (size_t)n, sizeof(double), cmp_double); res->ms_median = times[n / 2]; }
+#ifdef PFSCENE_HAVE_PFX
+    { PFXcounters k; pfxGetCounters(&k);
+      res->triangles_submitted = k.triangles_submitted; res->triangles_rasterised = k.triangles_rasterised;
+      res->pixels_shaded = k.pixels_shaded; res->pixels_depth_failed = k.pixels_depth_failed; res->kernel_launches = k.kernel_launches; }
+#endif
+    pfscene_read(s, color_out, depth_out);
+    pfscene_close(s);
+    free(times);
+    return 0;
 }

@@ -197,8 +197,10 @@ def test_clear_quirk_and_fill(pfcu_pair):
             c = np.zeros((h, w), np.uint32); d = np.zeros((h, w), np.float32)
             lib.check(lib.lib.pfcu_surface_download(s, c.ctypes.data, d.ctypes.data, 0, h))
             n = w * h; al = n - n % 8
-            exp = c0.reshape(-1).copy(); exp[8:al] = 0xAABBCCDD; exp[al:] = exp[0] if al < n else exp[al:]
-            if al <= 8: exp[al:] = c0.reshape(-1)[0]
+            exp = c0.reshape(-1).copy()
+            if al > 8:
+                exp[8:al] = 0xAABBCCDD
+            exp[al:] = c0.reshape(-1)[0]            # the tail copies pixel 0, which is never cleared
             assert np.array_equal(c.reshape(-1), exp), (lib.backend, w, h)
             lib.lib.pfcu_surface_destroy(s)
 

@@ -35,7 +35,7 @@
 
 #define TILE        64              /* screen tile edge in pixels                                    */
 #define TILE_PIX    (TILE * TILE)
-#define BIN_TILES   8               /* a bin is 8x8 tiles = 512x512 pixels                           */
+#define BIN_TILES   4               /* a bin is 4x4 tiles = 256x256 pixels                           */
 #define BIN_PIX     (TILE * BIN_TILES)
 #define RASTER_THREADS 256
 #define QUEUE_CAP   768             /* triangle indices buffered per tile between raster passes      */
@@ -340,9 +340,12 @@ __device__ __forceinline__ bool depth_pass(int func, float z, float zb)   /* dep
 /* device: texturing (sampler.h:202-410)                                                            */
 /* ------------------------------------------------------------------------------------------------ */
 
-__device__ __forceinline__ int tex_coord(int wrap, float t, unsigned size)
+struct TexRegs {            /* texture state kept in registers while a warp stays in one state */
+    const unsigned char *base; unsigned tw, th, total; float wm1, hm1; int fmt, wrap, filter;
+};
+
+__device__ __forceinline__ int tex_coord(int wrap, float t, float sm1)
 {
-    const float sm1 = __uint2float_rn(size - 1u);
     if (wrap == 0) {                    /* REPEAT: |RNE((t - trunc t) * (size-1))| */
         const float f = FM(FS(t, truncf(t)), sm1);
         const int i = cvt_rne_x86(f);
@@ -358,36 +361,30 @@ __device__ __forceinline__ int tex_coord(int wrap, float t, unsigned size)
     }
 }
 
-__device__ __forceinline__ unsigned tex_fetch(const DevState *st, int x, int y)
+__device__ __forceinline__ unsigned tex_fetch(const TexRegs &t, int x, int y)
 {
-    const int off = (int)((unsigned)y * st->tw + (unsigned)x);
+    const int off = (int)((unsigned)y * t.tw + (unsigned)x);
     /* the reference reads out of bounds here (CLAMP/MIRROR round v*(h-1)+0.5 up to row h); defined as
        "memory after the texture reads as zero": RGBA 0, and alpha 255 for the 3-byte formats */
-    if (off < 0 || (unsigned)off >= st->tw * st->th) return (st->tfmt >= PFCU_TEX_RGB8) ? 0xff000000u : 0u;
-    const unsigned char *base = st->tex;
-    switch (st->tfmt) {
-    case PFCU_TEX_RGBA8: return __ldg((const unsigned *)base + off);
-    case PFCU_TEX_BGRA8: { const unsigned r = __ldg((const unsigned *)base + off);
-        return (r & 0xff00ff00u) | ((r & 0xffu) << 16) | ((r >> 16) & 0xffu); }
-    case PFCU_TEX_RGB8: { const unsigned char *p = base + 3 * (size_t)off;
-        return (unsigned)__ldg(p) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p + 2) << 16) | 0xff000000u; }
-    default: { const unsigned char *p = base + 3 * (size_t)off;
-        return (unsigned)__ldg(p + 2) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p) << 16) | 0xff000000u; }
-    }
+    if ((unsigned)off >= t.total) return (t.fmt >= PFCU_TEX_RGB8) ? 0xff000000u : 0u;
+    if (t.fmt == PFCU_TEX_RGBA8) return __ldg((const unsigned *)t.base + off);
+    if (t.fmt == PFCU_TEX_BGRA8) { const unsigned r = __ldg((const unsigned *)t.base + off); return __byte_perm(r, 0, 0x3012); }
+    const unsigned char *p = t.base + 3 * (size_t)off;
+    const unsigned b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2);
+    return (t.fmt == PFCU_TEX_RGB8) ? (b0 | (b1 << 8) | (b2 << 16) | 0xff000000u) : (b2 | (b1 << 8) | (b0 << 16) | 0xff000000u);
 }
 
-__device__ __forceinline__ unsigned tex_sample(const DevState *st, float u, float v)
+__device__ __forceinline__ unsigned tex_sample(const TexRegs &t, float u, float v)
 {
-    const int wrap = st->tex_wrap;
-    const int x0 = tex_coord(wrap, u, st->tw), y0 = tex_coord(wrap, v, st->th);
-    if (st->tex_filter == 0) return tex_fetch(st, x0, y0);
-    const float fw = __uint2float_rn(st->tw), fh = __uint2float_rn(st->th);
+    const int x0 = tex_coord(t.wrap, u, t.wm1), y0 = tex_coord(t.wrap, v, t.hm1);
+    if (t.filter == 0) return tex_fetch(t, x0, y0);
+    const float fw = __uint2float_rn(t.tw), fh = __uint2float_rn(t.th);
     const float tx = FD(1.0f, fw), ty = FD(1.0f, fh);
-    const int x1 = tex_coord(wrap, FA(u, tx), st->tw), y1 = tex_coord(wrap, FA(v, ty), st->th);
+    const int x1 = tex_coord(t.wrap, FA(u, tx), t.wm1), y1 = tex_coord(t.wrap, FA(v, ty), t.hm1);
     const float fx = clamp_x86(FS(FM(u, fw), __int2float_rn(x0)), 0.0f, 1.0f);
     const float fy = clamp_x86(FS(FM(v, fh), __int2float_rn(y0)), 0.0f, 1.0f);
-    const unsigned c00 = tex_fetch(st, x0, y0), c10 = tex_fetch(st, x1, y0);
-    const unsigned c01 = tex_fetch(st, x0, y1), c11 = tex_fetch(st, x1, y1);
+    const unsigned c00 = tex_fetch(t, x0, y0), c10 = tex_fetch(t, x1, y0);
+    const unsigned c01 = tex_fetch(t, x0, y1), c11 = tex_fetch(t, x1, y1);
     return color_lerp(color_lerp(c00, c10, fx), color_lerp(c01, c11, fx), fy);
 }
 
@@ -687,13 +684,99 @@ struct RasterParams {
  * 8x4-block access of the shading loop and the 128-bit row access of load/store conflict-free */
 __device__ __forceinline__ int tile_addr(int lx, int ly) { return ly * TILE + (lx ^ ((ly & 3) << 3)); }
 
+/* ---- packed colour arithmetic ------------------------------------------------------------------
+ * A colour is carried as two words with one channel per 16-bit lane: rb = r | b<<16, ga = g | a<<16.
+ * Every per-channel formula of the reference keeps its intermediate below 2^16 (proofs inline), so
+ * both lanes are computed by one 32-bit instruction with no cross-lane carry. */
+struct Px2 { unsigned rb, ga; };
+
+__device__ __forceinline__ Px2 px_split(unsigned c) { Px2 p; p.rb = c & 0x00ff00ffu; p.ga = (c >> 8) & 0x00ff00ffu; return p; }
+/* the reference packs by OR-ing channel<<8i WITHOUT masking (color.h:112-122); lanes here may hold up
+ * to 9 bits (blend "subtractive"), and OR-ing rb with ga<<8 reproduces exactly that carry-over */
+__device__ __forceinline__ unsigned px_join(Px2 p) { return p.rb | (p.ga << 8); }
+
+/* pfiColorBarySmooth_simd (color.h:153-181): ((u1*c1 + u2*c2 + u3*c3) * 257) >> 16 per channel.
+ * u1+u2+u3 <= 256 for covered pixels, so a lane's sum x <= 65280; (x*257)>>16 == (x + (x>>8)) >> 8. */
+__device__ __forceinline__ unsigned smooth_lanes(unsigned a, unsigned b, unsigned c, int u1, int u2, int u3)
+{
+    unsigned x = (unsigned)u1 * a + (unsigned)u2 * b + (unsigned)u3 * c;
+    x = x + ((x >> 8) & 0x00ff00ffu);
+    return (x >> 8) & 0x00ff00ffu;
+}
+
+/* (texel * frag) >> 8 per channel (blend.h:199-212) */
+__device__ __forceinline__ Px2 px_mul(unsigned texel, Px2 f)
+{
+    const unsigned r = (texel & 0xffu) * (f.rb & 0xffffu);
+    const unsigned g = ((texel >> 8) & 0xffu) * (f.ga & 0xffffu);
+    const unsigned b = ((texel >> 16) & 0xffu) * (f.rb >> 16);
+    const unsigned a = (texel >> 24) * (f.ga >> 16);
+    Px2 o;
+    o.rb = __byte_perm(r, b, 0x7531);      /* byte1 of each product; bytes 3 are zero */
+    o.ga = __byte_perm(g, a, 0x7531);
+    return o;
+}
+
+__device__ __noinline__ Px2 blend_slow(int mode, Px2 s, unsigned dst)
+{
+    const unsigned c = blend_px(mode, px_join(s) , dst);     /* only reached with lanes <= 255 */
+    return px_split(c);
+}
+
+/* blend.h:137-274 on packed lanes */
+__device__ __forceinline__ Px2 px_blend(int mode, Px2 s, unsigned dst)
+{
+    const Px2 d = px_split(dst);
+    Px2 o;
+    if (mode == 1) {                        /* ALPHA: (s*a + d*(256-a)) >> 8, a = s.a + 1; sums <= 255*256 */
+        const unsigned alpha = (s.ga >> 16) + 1u, inv = 256u - alpha;
+        o.rb = ((s.rb * alpha + d.rb * inv) >> 8) & 0x00ff00ffu;
+        o.ga = ((((s.ga & 0xffffu) | 0x00ff0000u) * alpha + d.ga * inv) >> 8) & 0x00ff00ffu;
+    } else if (mode == 2) {                 /* ADD: min(s + d, 255) */
+        const unsigned rb = s.rb + d.rb, ga = s.ga + d.ga;
+        o.rb = __vminu2(rb, 0x00ff00ffu); o.ga = __vminu2(ga, 0x00ff00ffu);
+    } else if (mode == 0) {                 /* AVERAGE */
+        o.rb = ((s.rb + d.rb) >> 1) & 0x00ff00ffu; o.ga = ((s.ga + d.ga) >> 1) & 0x00ff00ffu;
+    } else if (mode == 3) {                 /* "SUB" adds without an upper clamp (Q6): lanes reach 510 */
+        o.rb = s.rb + d.rb; o.ga = s.ga + d.ga;
+    } else if (mode == 6) {
+        o.rb = __vmaxu2(s.rb, d.rb); o.ga = __vmaxu2(s.ga, d.ga);
+    } else if (mode == 7) {
+        o.rb = __vminu2(s.rb, d.rb); o.ga = __vminu2(s.ga, d.ga);
+    } else o = blend_slow(mode, s, dst);    /* MUL, SCREEN */
+    return o;
+}
+
+/* depth.h:80-114 as a 3-bit mask over {less, equal, greater}; false on NaN like the ordered compares */
+__device__ __forceinline__ unsigned depth_mask(int func)
+{
+    return (0x643122u >> (4 * func)) & 7u;   /* nibbles, low first: EQ 2, NEQ 2 (Q5), LT 1, LE 3, GT 4, GE 6 */
+}
+
+/* RCPPS from the shared-memory copy of the table (fast path: normal input, normal result) */
+__device__ __forceinline__ float rcp_fast(const unsigned *tab, int shift, float x)
+{
+    const unsigned u = __float_as_uint(x), E = u & 0x7f800000u;
+    if (E - 0x00800000u >= 0x7e000000u) return rcp_x86(x);              /* zero/denormal/huge/inf/NaN */
+    const unsigned tv = tab[(u & 0x007fffffu) >> shift];
+    return __uint_as_float((tv + 0x3f800000u - E) | (u & 0x80000000u));
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* kernel: tile rasteriser                                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+
+#define RCP_SMEM_BITS 11
+
 template <bool HAS_TEX, bool HAS_PHONG>
-__global__ void __launch_bounds__(RASTER_THREADS, 2)
+__global__ void __launch_bounds__(RASTER_THREADS, 3)
 k_raster(const RasterParams p)
 {
     __shared__ __align__(16) unsigned s_color[TILE_PIX];
     __shared__ __align__(16) float s_depth[TILE_PIX];
+    __shared__ unsigned s_rcp[1 << RCP_SMEM_BITS];
     __shared__ unsigned s_queue[QUEUE_CAP];
+    __shared__ unsigned char s_qmask[QUEUE_CAP];
     __shared__ unsigned s_wcount[8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -706,29 +789,48 @@ k_raster(const RasterParams p)
 
     const int bin = (ty / BIN_TILES) * p.binsX + (tx / BIN_TILES);
     const unsigned lbeg = p.bin_starts[bin], lend = p.bin_starts[bin + 1];
+    if (lbeg == lend) return;
+
+    /* RCPPS table: shared copy when it has <= 2^11 entries (every CPU we met), else the global one */
+    const int rcp_shift = c_rcp_shift;
+    const bool rcp_shared = rcp_shift >= 23 - RCP_SMEM_BITS;
+    if (rcp_shared) for (int k = tid; k < (1 << (23 - rcp_shift)); k += RASTER_THREADS) s_rcp[k] = c_rcp_tab[k];
 
     bool loaded = false;
-    unsigned long long shaded = 0, zfailed = 0;
+    unsigned shaded = 0, zfailed = 0;
+    const int lx8 = lane & 7, ly4 = lane >> 3;
+
     for (unsigned base = lbeg; base < lend; ) {
         /* ---- fill the queue: ordered compaction of the bin list against this tile ---- */
         unsigned qn = 0;
         while (base < lend && qn + RASTER_THREADS <= QUEUE_CAP) {
             const unsigned k = base + tid;
-            bool hit = false; unsigned ti = 0;
+            bool hit = false; unsigned ti = 0, wmask = 0;
             if (k < lend) {
                 ti = __ldg(p.bin_list + k);
                 const int4 b = __ldg(p.bbox + ti);
                 hit = b.x <= X1 && b.z - 1 >= X0 && b.y <= Y1 && b.w >= Y0 && b.x < b.z;
                 if (hit) {
+                    const int rx0 = max(b.x, X0), rx1 = min(b.z - 1, X1), ry0 = max(b.y, Y0), ry1 = min(b.w, Y1);
                     /* edge-function reject of the whole tile (only when int32 cannot wrap) */
                     const TriSetup s = p.setup[ti];
                     if (s.flags & TF_SAFE) {
-                        const int rx0 = max(b.x, X0) - b.x, rx1 = min(b.z - 1, X1) - b.x;
-                        const int ry0 = max(b.y, Y0) - b.y, ry1 = min(b.w, Y1) - b.y;
-                        const int m1 = s.w1R + (s.w1X > 0 ? rx1 : rx0) * s.w1X + (s.w1Y > 0 ? ry1 : ry0) * s.w1Y;
-                        const int m2 = s.w2R + (s.w2X > 0 ? rx1 : rx0) * s.w2X + (s.w2Y > 0 ? ry1 : ry0) * s.w2Y;
-                        const int m3 = s.w3R + (s.w3X > 0 ? rx1 : rx0) * s.w3X + (s.w3Y > 0 ? ry1 : ry0) * s.w3Y;
+                        const int ax0 = rx0 - b.x, ax1 = rx1 - b.x, ay0 = ry0 - b.y, ay1 = ry1 - b.y;
+                        const int m1 = s.w1R + (s.w1X > 0 ? ax1 : ax0) * s.w1X + (s.w1Y > 0 ? ay1 : ay0) * s.w1Y;
+                        const int m2 = s.w2R + (s.w2X > 0 ? ax1 : ax0) * s.w2X + (s.w2Y > 0 ? ay1 : ay0) * s.w2Y;
+                        const int m3 = s.w3R + (s.w3X > 0 ? ax1 : ax0) * s.w3X + (s.w3Y > 0 ? ay1 : ay0) * s.w3Y;
                         if ((m1 | m2 | m3) < 0) hit = false;
+                    }
+                    /* which warps own an 8x4 block inside the clipped bbox?  warp = (bx + 3*by) & 7 */
+                    const int bx0 = (rx0 - X0) >> 3, nbx = ((rx1 - X0) >> 3) - bx0 + 1;
+                    const int by0 = (ry0 - Y0) >> 2, nby = ((ry1 - Y0) >> 2) - by0 + 1;
+                    if (nbx >= 8) wmask = 0xffu;
+                    else {
+                        const unsigned run = (1u << nbx) - 1u;
+                        for (int j = 0; j < min(nby, 8); j++) {
+                            const int sh = (bx0 + 3 * (by0 + j)) & 7;
+                            wmask |= ((run << sh) | (run >> (8 - sh))) & 0xffu;
+                        }
                     }
                 }
             }
@@ -738,7 +840,7 @@ k_raster(const RasterParams p)
             unsigned woff = 0, total = 0;
 #pragma unroll
             for (int w = 0; w < 8; w++) { const unsigned c = s_wcount[w]; if (w < warp) woff += c; total += c; }
-            if (hit) s_queue[qn + woff + __popc(bal & ((1u << lane) - 1u))] = ti;
+            if (hit) { const unsigned pos = qn + woff + __popc(bal & ((1u << lane) - 1u)); s_queue[pos] = ti; s_qmask[pos] = (unsigned char)wmask; }
             qn += total;
             base += RASTER_THREADS;
             __syncthreads();
@@ -768,104 +870,112 @@ k_raster(const RasterParams p)
                     }
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
 
         /* ---- every warp walks the queue in order over the 8x4 blocks it owns ---- */
-        const int lx8 = lane & 7, ly4 = lane >> 3;
-        for (unsigned q = 0; q < qn; q++) {
-            const unsigned ti = s_queue[q];
-            const int4 b = __ldg(p.bbox + ti);
-            const int cx0 = max(b.x, X0) - X0, cx1 = min(b.z - 1, X1) - X0;     /* tile-local, inclusive */
-            const int cy0 = max(b.y, Y0) - Y0, cy1 = min(b.w, Y1) - Y0;
-            const int bx0 = cx0 >> 3, bx1 = cx1 >> 3, by0 = cy0 >> 2, by1 = cy1 >> 2;
-            /* does this warp own a block in range?  one block per block-row: bx = (warp - 3*by) & 7 */
-            bool any_block = false;
-            for (int by = by0; by <= by1; by++) { const int bx = (warp - 3 * by) & 7; if (bx >= bx0 && bx <= bx1) { any_block = true; break; } }
-            if (!any_block) continue;
+        unsigned cur_state = 0xffffffffu;
+        const DevState *st = nullptr;
+        unsigned flags = 0, zmask = 0; int blend_mode = 0;
+        TexRegs tex; tex.base = nullptr; tex.tw = tex.th = tex.total = 0; tex.wm1 = tex.hm1 = 0.0f; tex.fmt = tex.wrap = tex.filter = 0;
+        for (unsigned q0 = 0; q0 < qn; q0 += 32) {
+            const unsigned mk = (q0 + lane < qn) ? s_qmask[q0 + lane] : 0u;
+            unsigned rel = __ballot_sync(0xffffffffu, (mk >> warp) & 1u);
+            while (rel) {
+                const int j = __ffs(rel) - 1; rel &= rel - 1u;
+                const unsigned ti = s_queue[q0 + j];
+                const int4 b = __ldg(p.bbox + ti);
+                const TriSetup s = p.setup[ti];
+                const int cx0 = max(b.x, X0) - X0, cx1 = min(b.z - 1, X1) - X0;     /* tile-local, inclusive */
+                const int cy0 = max(b.y, Y0) - Y0, cy1 = min(b.w, Y1) - Y0;
+                const int bx0 = cx0 >> 3, bx1 = cx1 >> 3, by0 = cy0 >> 2, by1 = cy1 >> 2;
 
-            const TriSetup s = p.setup[ti];
-            bool have_attr = false;
-            float z1 = 0, z2 = 0, z3 = 0; unsigned meta = 0, c1 = 0, c2 = 0, c3 = 0;
-            const DevState *st = nullptr;
-            unsigned flags = 0;
-
-            for (int by = by0; by <= by1; by++) {
-                const int bx = (warp - 3 * by) & 7;
-                if (bx < bx0 || bx > bx1) continue;
-                const int lx = (bx << 3) + lx8, ly = (by << 2) + ly4;
-                const int x = X0 + lx, y = Y0 + ly;
-                const int dx = x - b.x, dy = y - b.y;
-                const int w1 = wadd(wadd(s.w1R, wmul(dy, s.w1Y)), wmul(dx, s.w1X));
-                const int w2 = wadd(wadd(s.w2R, wmul(dy, s.w2Y)), wmul(dx, s.w2X));
-                const int w3 = wadd(wadd(s.w3R, wmul(dy, s.w3Y)), wmul(dx, s.w3X));
-                bool m = ((w1 | w2 | w3) > 0) && lx >= cx0 && lx <= cx1 && ly >= cy0 && ly <= cy1;
-                if (!__any_sync(0xffffffffu, m)) continue;
-
-                if (!have_attr) {
-                    have_attr = true;
-                    const uint4 a0 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti));
-                    const uint4 a1 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti) + 1);
-                    z1 = __uint_as_float(a0.x); z2 = __uint_as_float(a0.y); z3 = __uint_as_float(a0.z); meta = a0.w;
-                    c1 = a1.x; c2 = a1.y; c3 = a1.z;
-                    st = p.states + (meta & 0xffffffu);
-                    flags = st->flags;
-                }
-                const float W1 = FM(__int2float_rn(w1), s.invSum);
-                const float W2 = FM(__int2float_rn(w2), s.invSum);
-                const float W3 = FM(__int2float_rn(w3), s.invSum);
-                const float z = rcp_x86(FA(FA(FM(z1, W1), FM(z2, W2)), FM(z3, W3)));
-                const int sa = tile_addr(lx, ly);
-                if (flags & PFCU_ST_DEPTH_TEST) {
-                    const bool pass = depth_pass(st->depth_func, z, s_depth[sa]);
-                    if (m && !pass) zfailed++;
-                    m = m && pass;
-                    if (!__any_sync(0xffffffffu, m)) continue;
-                }
-
-                /* colour (color.h:153-203) */
-                unsigned frag;
-                if (flags & PFCU_ST_SMOOTH) {
-                    const int u1 = cvt_rne_x86(FM(W1, 255.0f)), u2 = cvt_rne_x86(FM(W2, 255.0f)), u3 = cvt_rne_x86(FM(W3, 255.0f));
-                    unsigned o[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const unsigned sum = (unsigned)u1 * (unsigned)CHN(c1, i) + (unsigned)u2 * (unsigned)CHN(c2, i) + (unsigned)u3 * (unsigned)CHN(c3, i);
-                        o[i] = (sum * 257u) >> 16;
+                const uint4 a0 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti));
+                const uint4 a1 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti) + 1);
+                const float z1 = __uint_as_float(a0.x), z2 = __uint_as_float(a0.y), z3 = __uint_as_float(a0.z);
+                const unsigned meta = a0.w;
+                if ((meta & 0xffffffu) != cur_state) {
+                    cur_state = meta & 0xffffffu;
+                    st = p.states + cur_state;
+                    flags = st->flags; blend_mode = st->blend_mode;
+                    zmask = (flags & PFCU_ST_DEPTH_TEST) ? depth_mask(st->depth_func) : 8u;   /* 8: no test */
+                    if (HAS_TEX && (flags & PFCU_ST_TEXTURE)) {
+                        tex.base = st->tex; tex.tw = st->tw; tex.th = st->th; tex.total = st->tw * st->th;
+                        tex.wm1 = __uint2float_rn(st->tw - 1u); tex.hm1 = __uint2float_rn(st->th - 1u);
+                        tex.fmt = st->tfmt; tex.wrap = st->tex_wrap; tex.filter = st->tex_filter;
                     }
-                    frag = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
-                } else {
-                    const float mx = max_x86(W1, max_x86(W2, W3));
-                    frag = ((mx == W1) ? c1 : 0u) | ((mx == W2) ? c2 : 0u) | ((mx == W3) ? c3 : 0u);
                 }
+                const Px2 c1 = px_split(a1.x), c2 = px_split(a1.y), c3 = px_split(a1.z);
+                /* per-lane edge values at this lane's pixel of block (0,0) */
+                const int dx0 = X0 + lx8 - b.x, dy0 = Y0 + ly4 - b.y;
+                const int e1 = wadd(wadd(s.w1R, wmul(dy0, s.w1Y)), wmul(dx0, s.w1X));
+                const int e2 = wadd(wadd(s.w2R, wmul(dy0, s.w2Y)), wmul(dx0, s.w2X));
+                const int e3 = wadd(wadd(s.w3R, wmul(dy0, s.w3Y)), wmul(dx0, s.w3X));
 
-                if (HAS_TEX && (flags & PFCU_ST_TEXTURE)) {
-                    const uint4 a2 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti) + 2);
-                    const uint4 a3 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti) + 3);
-                    float u = FA(FA(FM(__uint_as_float(a2.x), W1), FM(__uint_as_float(a2.y), W2)), FM(__uint_as_float(a2.z), W3));
-                    float v = FA(FA(FM(__uint_as_float(a3.x), W1), FM(__uint_as_float(a3.y), W2)), FM(__uint_as_float(a3.z), W3));
-                    if (meta & (1u << 25)) { u = FM(u, z); v = FM(v, z); }
-                    if (m) frag = mul_color(tex_sample(st, u, v), frag);   /* masked-off lanes sample (0,0) upstream and are discarded */
-                }
+                for (int by = by0; by <= by1; by++) {
+                    const int bx = (warp - 3 * by) & 7;
+                    if (bx < bx0 || bx > bx1) continue;
+                    const int lx = (bx << 3) + lx8, ly = (by << 2) + ly4;
+                    const int w1 = wadd(e1, wadd(wmul(bx << 3, s.w1X), wmul(by << 2, s.w1Y)));
+                    const int w2 = wadd(e2, wadd(wmul(bx << 3, s.w2X), wmul(by << 2, s.w2Y)));
+                    const int w3 = wadd(e3, wadd(wmul(bx << 3, s.w3X), wmul(by << 2, s.w3Y)));
+                    bool m = ((w1 | w2 | w3) > 0) && (unsigned)(lx - cx0) <= (unsigned)(cx1 - cx0) && (unsigned)(ly - cy0) <= (unsigned)(cy1 - cy0);
+                    if (!__any_sync(0xffffffffu, m)) continue;
 
-                if (HAS_PHONG && (flags & PFCU_ST_PHONG)) {
-                    const float4 *a = reinterpret_cast<const float4 *>(p.data + ti) + 4;
-                    const float4 px = __ldg(a), py = __ldg(a + 1), pz = __ldg(a + 2);
-                    const float4 nx = __ldg(a + 3), ny = __ldg(a + 4), nz = __ldg(a + 5);
-                    const float Nx = FA(FA(FM(nx.x, W1), FM(nx.y, W2)), FM(nx.z, W3));
-                    const float Ny = FA(FA(FM(ny.x, W1), FM(ny.y, W2)), FM(ny.z, W3));
-                    const float Nz = FA(FA(FM(nz.x, W1), FM(nz.y, W2)), FM(nz.z, W3));
-                    const float Px = FA(FA(FM(px.x, W1), FM(px.y, W2)), FM(px.z, W3));
-                    const float Py = FA(FA(FM(py.x, W1), FM(py.y, W2)), FM(py.z, W3));
-                    const float Pz = FA(FA(FM(pz.x, W1), FM(pz.y, W2)), FM(pz.z, W3));
-                    if (m) frag = phong(frag, st, (meta >> 24) & 1u, Px, Py, Pz, Nx, Ny, Nz);
-                }
+                    const float W1 = FM(__int2float_rn(w1), s.invSum);
+                    const float W2 = FM(__int2float_rn(w2), s.invSum);
+                    const float W3 = FM(__int2float_rn(w3), s.invSum);
+                    const float zsum = FA(FA(FM(z1, W1), FM(z2, W2)), FM(z3, W3));
+                    const float z = rcp_shared ? rcp_fast(s_rcp, rcp_shift, zsum) : rcp_x86(zsum);
+                    const int sa = tile_addr(lx, ly);
+                    if (zmask != 8u) {
+                        const float zb = s_depth[sa];
+                        const unsigned rel3 = (z < zb ? 1u : 0u) | (z == zb ? 2u : 0u) | (z > zb ? 4u : 0u);
+                        const bool pass = (rel3 & zmask) != 0u;
+                        if (m && !pass) zfailed++;
+                        m = m && pass;
+                        if (!__any_sync(0xffffffffu, m)) continue;
+                    }
 
-                if (m) {
-                    if (flags & PFCU_ST_BLEND) frag = blend_px(st->blend_mode, frag, s_color[sa]);
-                    s_color[sa] = frag;
-                    s_depth[sa] = z;            /* written even with the depth test off (Q11) */
-                    shaded++;
+                    /* colour (color.h:153-203) */
+                    Px2 frag;
+                    if (flags & PFCU_ST_SMOOTH) {
+                        const int u1 = __float2int_rn(FM(W1, 255.0f)), u2 = __float2int_rn(FM(W2, 255.0f)), u3 = __float2int_rn(FM(W3, 255.0f));
+                        frag.rb = smooth_lanes(c1.rb, c2.rb, c3.rb, u1, u2, u3);
+                        frag.ga = smooth_lanes(c1.ga, c2.ga, c3.ga, u1, u2, u3);
+                    } else {
+                        const float mx = max_x86(W1, max_x86(W2, W3));
+                        frag = px_split(((mx == W1) ? a1.x : 0u) | ((mx == W2) ? a1.y : 0u) | ((mx == W3) ? a1.z : 0u));
+                    }
+
+                    if (HAS_TEX && (flags & PFCU_ST_TEXTURE)) {
+                        const uint4 a2 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti) + 2);
+                        const uint4 a3 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti) + 3);
+                        float u = FA(FA(FM(__uint_as_float(a2.x), W1), FM(__uint_as_float(a2.y), W2)), FM(__uint_as_float(a2.z), W3));
+                        float v = FA(FA(FM(__uint_as_float(a3.x), W1), FM(__uint_as_float(a3.y), W2)), FM(__uint_as_float(a3.z), W3));
+                        if (meta & (1u << 25)) { u = FM(u, z); v = FM(v, z); }
+                        if (m) frag = px_mul(tex_sample(tex, u, v), frag);   /* masked-off lanes sample (0,0) upstream and are discarded */
+                    }
+
+                    if (HAS_PHONG && (flags & PFCU_ST_PHONG)) {
+                        const float4 *a = reinterpret_cast<const float4 *>(p.data + ti) + 4;
+                        const float4 px = __ldg(a), py = __ldg(a + 1), pz = __ldg(a + 2);
+                        const float4 nx = __ldg(a + 3), ny = __ldg(a + 4), nz = __ldg(a + 5);
+                        const float Nx = FA(FA(FM(nx.x, W1), FM(nx.y, W2)), FM(nx.z, W3));
+                        const float Ny = FA(FA(FM(ny.x, W1), FM(ny.y, W2)), FM(ny.z, W3));
+                        const float Nz = FA(FA(FM(nz.x, W1), FM(nz.y, W2)), FM(nz.z, W3));
+                        const float Px = FA(FA(FM(px.x, W1), FM(px.y, W2)), FM(px.z, W3));
+                        const float Py = FA(FA(FM(py.x, W1), FM(py.y, W2)), FM(py.z, W3));
+                        const float Pz = FA(FA(FM(pz.x, W1), FM(pz.y, W2)), FM(pz.z, W3));
+                        if (m) frag = px_split(phong(px_join(frag), st, (meta >> 24) & 1u, Px, Py, Pz, Nx, Ny, Nz));
+                    }
+
+                    if (m) {
+                        if (flags & PFCU_ST_BLEND) frag = px_blend(blend_mode, frag, s_color[sa]);
+                        s_color[sa] = px_join(frag);
+                        s_depth[sa] = z;            /* written even with the depth test off (Q11) */
+                        shaded++;
+                    }
                 }
             }
         }
@@ -900,11 +1010,12 @@ k_raster(const RasterParams p)
         zfailed += __shfl_down_sync(0xffffffffu, zfailed, o);
     }
     if (lane == 0) {
-        if (shaded) atomicAdd(p.counters + 1, shaded);
-        if (zfailed) atomicAdd(p.counters + 2, zfailed);
+        if (shaded) atomicAdd(p.counters + 1, (unsigned long long)shaded);
+        if (zfailed) atomicAdd(p.counters + 2, (unsigned long long)zfailed);
     }
 }
 
+/* ------------------------------------------------------------------------------------------------ */
 /* ------------------------------------------------------------------------------------------------ */
 /* kernels: surface utilities                                                                       */
 /* ------------------------------------------------------------------------------------------------ */

@@ -753,12 +753,19 @@ __device__ __forceinline__ unsigned depth_mask(int func)
     return (0x643122u >> (4 * func)) & 7u;   /* nibbles, low first: EQ 2, NEQ 2 (Q5), LT 1, LE 3, GT 4, GE 6 */
 }
 
+/* shared-memory access through 32-bit window addresses computed once per CTA (the compiler otherwise
+ * rebuilds the cluster-window base of every __shared__ array at each access) */
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ float lds_f32(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts_u32(unsigned addr, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
+
 /* RCPPS from the shared-memory copy of the table (fast path: normal input, normal result) */
-__device__ __forceinline__ float rcp_fast(const unsigned *tab, int shift, float x)
+__device__ __forceinline__ float rcp_fast(unsigned tab_addr, int shift, float x)
 {
     const unsigned u = __float_as_uint(x), E = u & 0x7f800000u;
     if (E - 0x00800000u >= 0x7e000000u) return rcp_x86(x);              /* zero/denormal/huge/inf/NaN */
-    const unsigned tv = tab[(u & 0x007fffffu) >> shift];
+    const unsigned tv = lds_u32(tab_addr + (((u & 0x007fffffu) >> shift) << 2));
     return __uint_as_float((tv + 0x3f800000u - E) | (u & 0x80000000u));
 }
 
@@ -768,8 +775,129 @@ __device__ __forceinline__ float rcp_fast(const unsigned *tab, int shift, float 
 
 #define RCP_SMEM_BITS 11
 
-template <bool HAS_TEX, bool HAS_PHONG>
-__global__ void __launch_bounds__(RASTER_THREADS, 3)
+struct TileCtx {
+    int X0, Y0, X1, Y1;                 /* tile rectangle on the surface, inclusive               */
+    unsigned sm_color, sm_depth, sm_rcp; /* shared-window byte addresses                           */
+    int rcp_shift; bool rcp_shared;
+    int lx8, ly4, warp;
+    unsigned shaded, zfailed;
+    const TriData *data;
+};
+
+/* One triangle over the 8x4 blocks this warp owns.  TEXM: 0 no texture, 1 nearest+REPEAT+RGBA8,
+ * 2 any sampler.  BLENDM: 0 off, 1 ALPHA, 2 ADD, 3 any mode.  Everything is computed for all 32 lanes
+ * (no divergent regions); only the final stores are predicated by the coverage/depth mask. */
+template <int TEXM, int BLENDM, bool PHONG>
+__device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const int4 b, const TriSetup &s, const uint4 a0, const uint4 a1,
+                                          const DevState *st, const unsigned flags, const unsigned zmask, const int blend_mode, const TexRegs &tex)
+{
+    const int cx0 = max(b.x, t.X0) - t.X0, cx1 = min(b.z - 1, t.X1) - t.X0;     /* tile-local, inclusive */
+    const int cy0 = max(b.y, t.Y0) - t.Y0, cy1 = min(b.w, t.Y1) - t.Y0;
+    const int bx0 = cx0 >> 3, bx1 = cx1 >> 3, by0 = cy0 >> 2, by1 = cy1 >> 2;
+    const unsigned xspan = (unsigned)(cx1 - cx0), yspan = (unsigned)(cy1 - cy0);
+    const float z1 = __uint_as_float(a0.x), z2 = __uint_as_float(a0.y), z3 = __uint_as_float(a0.z);
+    const unsigned meta = a0.w;
+    const bool is3d = (meta >> 25) & 1u;
+    const bool smooth = (flags & PFCU_ST_SMOOTH) != 0;
+    const bool ztest = zmask != 8u, zlt = (zmask & 1u) != 0, zeq = (zmask & 2u) != 0, zgt = (zmask & 4u) != 0;
+    const unsigned c1rb = a1.x & 0x00ff00ffu, c1ga = (a1.x >> 8) & 0x00ff00ffu;
+    const unsigned c2rb = a1.y & 0x00ff00ffu, c2ga = (a1.y >> 8) & 0x00ff00ffu;
+    const unsigned c3rb = a1.z & 0x00ff00ffu, c3ga = (a1.z >> 8) & 0x00ff00ffu;
+    float tu1 = 0, tu2 = 0, tu3 = 0, tv1 = 0, tv2 = 0, tv3 = 0;
+    const bool texturing = TEXM != 0 && (!PHONG || (flags & PFCU_ST_TEXTURE));     /* the Phong variant checks at run time */
+    const bool blending = BLENDM != 0 && (!PHONG || (flags & PFCU_ST_BLEND));
+    if (texturing) {
+        const uint4 a2 = __ldg(reinterpret_cast<const uint4 *>(t.data + ti) + 2);
+        const uint4 a3 = __ldg(reinterpret_cast<const uint4 *>(t.data + ti) + 3);
+        tu1 = __uint_as_float(a2.x); tu2 = __uint_as_float(a2.y); tu3 = __uint_as_float(a2.z);
+        tv1 = __uint_as_float(a3.x); tv2 = __uint_as_float(a3.y); tv3 = __uint_as_float(a3.z);
+    }
+    /* edge values at this lane's pixel of block (0,0) */
+    const int dx0 = t.X0 + t.lx8 - b.x, dy0 = t.Y0 + t.ly4 - b.y;
+    const int e1 = wadd(wadd(s.w1R, wmul(dy0, s.w1Y)), wmul(dx0, s.w1X));
+    const int e2 = wadd(wadd(s.w2R, wmul(dy0, s.w2Y)), wmul(dx0, s.w2X));
+    const int e3 = wadd(wadd(s.w3R, wmul(dy0, s.w3Y)), wmul(dx0, s.w3X));
+
+    for (int by = by0; by <= by1; by++) {
+        const int bx = (t.warp - 3 * by) & 7;
+        if (bx < bx0 || bx > bx1) continue;
+        const int lx = (bx << 3) + t.lx8, ly = (by << 2) + t.ly4;
+        const int w1 = wadd(e1, wadd(wmul(bx << 3, s.w1X), wmul(by << 2, s.w1Y)));
+        const int w2 = wadd(e2, wadd(wmul(bx << 3, s.w2X), wmul(by << 2, s.w2Y)));
+        const int w3 = wadd(e3, wadd(wmul(bx << 3, s.w3X), wmul(by << 2, s.w3Y)));
+        bool m = ((w1 | w2 | w3) > 0) && (unsigned)(lx - cx0) <= xspan && (unsigned)(ly - cy0) <= yspan;
+        if (!__any_sync(0xffffffffu, m)) continue;
+
+        const float W1 = FM(__int2float_rn(w1), s.invSum);
+        const float W2 = FM(__int2float_rn(w2), s.invSum);
+        const float W3 = FM(__int2float_rn(w3), s.invSum);
+        const float zsum = FA(FA(FM(z1, W1), FM(z2, W2)), FM(z3, W3));
+        const float z = t.rcp_shared ? rcp_fast(t.sm_rcp, t.rcp_shift, zsum) : rcp_x86(zsum);
+        const unsigned sa = (unsigned)tile_addr(lx, ly) << 2;
+        if (ztest) {
+            const float zb = lds_f32(t.sm_depth + sa);
+            const bool pass = (zlt && z < zb) || (zeq && z == zb) || (zgt && z > zb);
+            t.zfailed += (m && !pass) ? 1u : 0u;
+            m = m && pass;
+            if (!__any_sync(0xffffffffu, m)) continue;
+        }
+
+        /* colour (color.h:153-203) */
+        Px2 frag;
+        if (smooth) {
+            const int u1 = __float2int_rn(FM(W1, 255.0f)), u2 = __float2int_rn(FM(W2, 255.0f)), u3 = __float2int_rn(FM(W3, 255.0f));
+            frag.rb = smooth_lanes(c1rb, c2rb, c3rb, u1, u2, u3);
+            frag.ga = smooth_lanes(c1ga, c2ga, c3ga, u1, u2, u3);
+        } else {
+            const float mx = max_x86(W1, max_x86(W2, W3));
+            frag = px_split(((mx == W1) ? a1.x : 0u) | ((mx == W2) ? a1.y : 0u) | ((mx == W3) ? a1.z : 0u));
+        }
+
+        if (texturing) {
+            float u = FA(FA(FM(tu1, W1), FM(tu2, W2)), FM(tu3, W3));
+            float v = FA(FA(FM(tv1, W1), FM(tv2, W2)), FM(tv3, W3));
+            if (is3d) { u = FM(u, z); v = FM(v, z); }
+            if (!m) { u = 0.0f; v = 0.0f; }                 /* triangles.c:510: masked-off lanes sample (0,0) */
+            unsigned texel;
+            if (TEXM == 1) {
+                const float fu = FM(FS(u, truncf(u)), tex.wm1), fv = FM(FS(v, truncf(v)), tex.hm1);
+                const int xi = cvt_rne_x86(fu), yi = cvt_rne_x86(fv);
+                const unsigned off = (unsigned)abs(yi) * tex.tw + (unsigned)abs(xi);
+                texel = 0u;
+                if (off < tex.total) texel = __ldg((const unsigned *)tex.base + off);
+            } else texel = tex_sample(tex, u, v);
+            frag = px_mul(texel, frag);
+        }
+
+        if (PHONG) {
+            if (flags & PFCU_ST_PHONG) {
+                const float4 *a = reinterpret_cast<const float4 *>(t.data + ti) + 4;
+                const float4 px = __ldg(a), py = __ldg(a + 1), pz = __ldg(a + 2);
+                const float4 nx = __ldg(a + 3), ny = __ldg(a + 4), nz = __ldg(a + 5);
+                const float Nx = FA(FA(FM(nx.x, W1), FM(nx.y, W2)), FM(nx.z, W3));
+                const float Ny = FA(FA(FM(ny.x, W1), FM(ny.y, W2)), FM(ny.z, W3));
+                const float Nz = FA(FA(FM(nz.x, W1), FM(nz.y, W2)), FM(nz.z, W3));
+                const float Px = FA(FA(FM(px.x, W1), FM(px.y, W2)), FM(px.z, W3));
+                const float Py = FA(FA(FM(py.x, W1), FM(py.y, W2)), FM(py.z, W3));
+                const float Pz = FA(FA(FM(pz.x, W1), FM(pz.y, W2)), FM(pz.z, W3));
+                frag = px_split(phong(px_join(frag), st, (meta >> 24) & 1u, Px, Py, Pz, Nx, Ny, Nz));
+            }
+        }
+
+        if (blending) {
+            const unsigned dst = lds_u32(t.sm_color + sa);
+            frag = px_blend(BLENDM == 3 ? blend_mode : BLENDM, frag, dst);
+        }
+        if (m) {
+            sts_u32(t.sm_color + sa, px_join(frag));
+            sts_f32(t.sm_depth + sa, z);            /* written even with the depth test off (Q11) */
+            t.shaded++;
+        }
+    }
+}
+
+template <bool HAS_PHONG>
+__global__ void __launch_bounds__(RASTER_THREADS, HAS_PHONG ? 2 : 3)
 k_raster(const RasterParams p)
 {
     __shared__ __align__(16) unsigned s_color[TILE_PIX];
@@ -783,8 +911,10 @@ k_raster(const RasterParams p)
     const unsigned tile = (p.world > 1) ? (p.rank + blockIdx.x * p.world) : blockIdx.x;
     if (tile >= p.nTiles) return;
     const int tx = tile % p.tilesX, ty = tile / p.tilesX;
-    const int X0 = tx * TILE, Y0 = ty * TILE;
-    const int X1 = min(X0 + TILE, p.W) - 1, Y1 = min(Y0 + TILE, p.H) - 1;      /* inclusive */
+    TileCtx t;
+    t.X0 = tx * TILE; t.Y0 = ty * TILE;
+    t.X1 = min(t.X0 + TILE, p.W) - 1; t.Y1 = min(t.Y0 + TILE, p.H) - 1;
+    const int X0 = t.X0, Y0 = t.Y0, X1 = t.X1, Y1 = t.Y1;
     const bool full_tile = (X0 + TILE <= p.W) && (Y0 + TILE <= p.H) && ((p.W & 3) == 0);
 
     const int bin = (ty / BIN_TILES) * p.binsX + (tx / BIN_TILES);
@@ -792,13 +922,16 @@ k_raster(const RasterParams p)
     if (lbeg == lend) return;
 
     /* RCPPS table: shared copy when it has <= 2^11 entries (every CPU we met), else the global one */
-    const int rcp_shift = c_rcp_shift;
-    const bool rcp_shared = rcp_shift >= 23 - RCP_SMEM_BITS;
-    if (rcp_shared) for (int k = tid; k < (1 << (23 - rcp_shift)); k += RASTER_THREADS) s_rcp[k] = c_rcp_tab[k];
+    t.rcp_shift = c_rcp_shift;
+    t.rcp_shared = t.rcp_shift >= 23 - RCP_SMEM_BITS;
+    if (t.rcp_shared) for (int k = tid; k < (1 << (23 - t.rcp_shift)); k += RASTER_THREADS) s_rcp[k] = c_rcp_tab[k];
+    t.sm_color = (unsigned)__cvta_generic_to_shared(s_color);
+    t.sm_depth = (unsigned)__cvta_generic_to_shared(s_depth);
+    t.sm_rcp = (unsigned)__cvta_generic_to_shared(s_rcp);
+    t.lx8 = lane & 7; t.ly4 = lane >> 3; t.warp = warp;
+    t.shaded = 0; t.zfailed = 0; t.data = p.data;
 
     bool loaded = false;
-    unsigned shaded = 0, zfailed = 0;
-    const int lx8 = lane & 7, ly4 = lane >> 3;
 
     for (unsigned base = lbeg; base < lend; ) {
         /* ---- fill the queue: ordered compaction of the bin list against this tile ---- */
@@ -876,7 +1009,7 @@ k_raster(const RasterParams p)
         /* ---- every warp walks the queue in order over the 8x4 blocks it owns ---- */
         unsigned cur_state = 0xffffffffu;
         const DevState *st = nullptr;
-        unsigned flags = 0, zmask = 0; int blend_mode = 0;
+        unsigned flags = 0, zmask = 8u; int blend_mode = 0, prog = 0;
         TexRegs tex; tex.base = nullptr; tex.tw = tex.th = tex.total = 0; tex.wm1 = tex.hm1 = 0.0f; tex.fmt = tex.wrap = tex.filter = 0;
         for (unsigned q0 = 0; q0 < qn; q0 += 32) {
             const unsigned mk = (q0 + lane < qn) ? s_qmask[q0 + lane] : 0u;
@@ -886,96 +1019,38 @@ k_raster(const RasterParams p)
                 const unsigned ti = s_queue[q0 + j];
                 const int4 b = __ldg(p.bbox + ti);
                 const TriSetup s = p.setup[ti];
-                const int cx0 = max(b.x, X0) - X0, cx1 = min(b.z - 1, X1) - X0;     /* tile-local, inclusive */
-                const int cy0 = max(b.y, Y0) - Y0, cy1 = min(b.w, Y1) - Y0;
-                const int bx0 = cx0 >> 3, bx1 = cx1 >> 3, by0 = cy0 >> 2, by1 = cy1 >> 2;
-
                 const uint4 a0 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti));
                 const uint4 a1 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti) + 1);
-                const float z1 = __uint_as_float(a0.x), z2 = __uint_as_float(a0.y), z3 = __uint_as_float(a0.z);
-                const unsigned meta = a0.w;
-                if ((meta & 0xffffffu) != cur_state) {
-                    cur_state = meta & 0xffffffu;
+                if ((a0.w & 0xffffffu) != cur_state) {
+                    cur_state = a0.w & 0xffffffu;
                     st = p.states + cur_state;
                     flags = st->flags; blend_mode = st->blend_mode;
                     zmask = (flags & PFCU_ST_DEPTH_TEST) ? depth_mask(st->depth_func) : 8u;   /* 8: no test */
-                    if (HAS_TEX && (flags & PFCU_ST_TEXTURE)) {
+                    int texm = 0;
+                    if (flags & PFCU_ST_TEXTURE) {
                         tex.base = st->tex; tex.tw = st->tw; tex.th = st->th; tex.total = st->tw * st->th;
                         tex.wm1 = __uint2float_rn(st->tw - 1u); tex.hm1 = __uint2float_rn(st->th - 1u);
                         tex.fmt = st->tfmt; tex.wrap = st->tex_wrap; tex.filter = st->tex_filter;
+                        texm = (tex.fmt == PFCU_TEX_RGBA8 && tex.wrap == 0 && tex.filter == 0) ? 1 : 2;
                     }
+                    const int blendm = !(flags & PFCU_ST_BLEND) ? 0 : (blend_mode == 1 ? 1 : (blend_mode == 2 ? 2 : 3));
+                    prog = texm * 4 + blendm;
+                    if (HAS_PHONG && (flags & PFCU_ST_PHONG)) prog = 12;
                 }
-                const Px2 c1 = px_split(a1.x), c2 = px_split(a1.y), c3 = px_split(a1.z);
-                /* per-lane edge values at this lane's pixel of block (0,0) */
-                const int dx0 = X0 + lx8 - b.x, dy0 = Y0 + ly4 - b.y;
-                const int e1 = wadd(wadd(s.w1R, wmul(dy0, s.w1Y)), wmul(dx0, s.w1X));
-                const int e2 = wadd(wadd(s.w2R, wmul(dy0, s.w2Y)), wmul(dx0, s.w2X));
-                const int e3 = wadd(wadd(s.w3R, wmul(dy0, s.w3Y)), wmul(dx0, s.w3X));
-
-                for (int by = by0; by <= by1; by++) {
-                    const int bx = (warp - 3 * by) & 7;
-                    if (bx < bx0 || bx > bx1) continue;
-                    const int lx = (bx << 3) + lx8, ly = (by << 2) + ly4;
-                    const int w1 = wadd(e1, wadd(wmul(bx << 3, s.w1X), wmul(by << 2, s.w1Y)));
-                    const int w2 = wadd(e2, wadd(wmul(bx << 3, s.w2X), wmul(by << 2, s.w2Y)));
-                    const int w3 = wadd(e3, wadd(wmul(bx << 3, s.w3X), wmul(by << 2, s.w3Y)));
-                    bool m = ((w1 | w2 | w3) > 0) && (unsigned)(lx - cx0) <= (unsigned)(cx1 - cx0) && (unsigned)(ly - cy0) <= (unsigned)(cy1 - cy0);
-                    if (!__any_sync(0xffffffffu, m)) continue;
-
-                    const float W1 = FM(__int2float_rn(w1), s.invSum);
-                    const float W2 = FM(__int2float_rn(w2), s.invSum);
-                    const float W3 = FM(__int2float_rn(w3), s.invSum);
-                    const float zsum = FA(FA(FM(z1, W1), FM(z2, W2)), FM(z3, W3));
-                    const float z = rcp_shared ? rcp_fast(s_rcp, rcp_shift, zsum) : rcp_x86(zsum);
-                    const int sa = tile_addr(lx, ly);
-                    if (zmask != 8u) {
-                        const float zb = s_depth[sa];
-                        const unsigned rel3 = (z < zb ? 1u : 0u) | (z == zb ? 2u : 0u) | (z > zb ? 4u : 0u);
-                        const bool pass = (rel3 & zmask) != 0u;
-                        if (m && !pass) zfailed++;
-                        m = m && pass;
-                        if (!__any_sync(0xffffffffu, m)) continue;
-                    }
-
-                    /* colour (color.h:153-203) */
-                    Px2 frag;
-                    if (flags & PFCU_ST_SMOOTH) {
-                        const int u1 = __float2int_rn(FM(W1, 255.0f)), u2 = __float2int_rn(FM(W2, 255.0f)), u3 = __float2int_rn(FM(W3, 255.0f));
-                        frag.rb = smooth_lanes(c1.rb, c2.rb, c3.rb, u1, u2, u3);
-                        frag.ga = smooth_lanes(c1.ga, c2.ga, c3.ga, u1, u2, u3);
-                    } else {
-                        const float mx = max_x86(W1, max_x86(W2, W3));
-                        frag = px_split(((mx == W1) ? a1.x : 0u) | ((mx == W2) ? a1.y : 0u) | ((mx == W3) ? a1.z : 0u));
-                    }
-
-                    if (HAS_TEX && (flags & PFCU_ST_TEXTURE)) {
-                        const uint4 a2 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti) + 2);
-                        const uint4 a3 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti) + 3);
-                        float u = FA(FA(FM(__uint_as_float(a2.x), W1), FM(__uint_as_float(a2.y), W2)), FM(__uint_as_float(a2.z), W3));
-                        float v = FA(FA(FM(__uint_as_float(a3.x), W1), FM(__uint_as_float(a3.y), W2)), FM(__uint_as_float(a3.z), W3));
-                        if (meta & (1u << 25)) { u = FM(u, z); v = FM(v, z); }
-                        if (m) frag = px_mul(tex_sample(tex, u, v), frag);   /* masked-off lanes sample (0,0) upstream and are discarded */
-                    }
-
-                    if (HAS_PHONG && (flags & PFCU_ST_PHONG)) {
-                        const float4 *a = reinterpret_cast<const float4 *>(p.data + ti) + 4;
-                        const float4 px = __ldg(a), py = __ldg(a + 1), pz = __ldg(a + 2);
-                        const float4 nx = __ldg(a + 3), ny = __ldg(a + 4), nz = __ldg(a + 5);
-                        const float Nx = FA(FA(FM(nx.x, W1), FM(nx.y, W2)), FM(nx.z, W3));
-                        const float Ny = FA(FA(FM(ny.x, W1), FM(ny.y, W2)), FM(ny.z, W3));
-                        const float Nz = FA(FA(FM(nz.x, W1), FM(nz.y, W2)), FM(nz.z, W3));
-                        const float Px = FA(FA(FM(px.x, W1), FM(px.y, W2)), FM(px.z, W3));
-                        const float Py = FA(FA(FM(py.x, W1), FM(py.y, W2)), FM(py.z, W3));
-                        const float Pz = FA(FA(FM(pz.x, W1), FM(pz.y, W2)), FM(pz.z, W3));
-                        if (m) frag = px_split(phong(px_join(frag), st, (meta >> 24) & 1u, Px, Py, Pz, Nx, Ny, Nz));
-                    }
-
-                    if (m) {
-                        if (flags & PFCU_ST_BLEND) frag = px_blend(blend_mode, frag, s_color[sa]);
-                        s_color[sa] = px_join(frag);
-                        s_depth[sa] = z;            /* written even with the depth test off (Q11) */
-                        shaded++;
-                    }
+                switch (prog) {
+                case 0:  shade_tri<0, 0, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 1:  shade_tri<0, 1, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 2:  shade_tri<0, 2, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 3:  shade_tri<0, 3, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 4:  shade_tri<1, 0, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 5:  shade_tri<1, 1, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 6:  shade_tri<1, 2, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 7:  shade_tri<1, 3, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 8:  shade_tri<2, 0, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 9:  shade_tri<2, 1, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 10: shade_tri<2, 2, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 11: shade_tri<2, 3, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                default: if (HAS_PHONG) shade_tri<2, 3, true>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
                 }
             }
         }
@@ -1004,6 +1079,7 @@ k_raster(const RasterParams p)
         }
     }
     /* counters: warp reduce, one atomic per warp */
+    unsigned shaded = t.shaded, zfailed = t.zfailed;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         shaded += __shfl_down_sync(0xffffffffu, shaded, o);
@@ -1471,11 +1547,8 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     const unsigned grid = owned_tiles(s, p.rank, p.world);
     if (g.profiling) CK(cudaEventRecord(pe[1], g.stream));
     if (grid) {
-        const bool tex = (feature_mask & PFCU_ST_TEXTURE) != 0, ph = (feature_mask & PFCU_ST_PHONG) != 0;
-        if (tex && ph)       k_raster<true, true><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
-        else if (tex)        k_raster<true, false><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
-        else if (ph)         k_raster<false, true><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
-        else                 k_raster<false, false><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
+        if (feature_mask & PFCU_ST_PHONG) k_raster<true><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
+        else                              k_raster<false><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
         g.launches++;
     }
     if (g.profiling) { CK(cudaEventRecord(pe[2], g.stream)); for (int i = 0; i < 3; i++) g.prof_events.push_back(pe[i]); }

@@ -647,6 +647,7 @@ void pfColorPointer(PFint size, PFenum type, PFsizei stride, const void *pointer
 
 static int fetch_float(const pf_attrib *a, size_t idx, float *out, int n)
 {
+    if (a->type == PF_FLOAT) { memcpy(out, (const PFfloat *)a->buffer + idx * (size_t)n, (size_t)n * sizeof(float)); return 1; }
     for (int k = 0; k < n; k++) {
         size_t e = idx * (size_t)n + (size_t)k;
         switch (a->type) {

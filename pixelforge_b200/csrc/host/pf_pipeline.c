@@ -429,7 +429,15 @@ static int project_and_clip(const pf_ctx *c, pf_vertex *poly, int *n)
         for (int i = 0; i < *n; i++) to_screen(c, &poly[i]);
         return 0;
     }
-    if (clip_w(poly, n) && clip_xyz(poly, n)) {
+    /* Trivial accept: when all three vertices are inside every clip plane, Sutherland-Hodgman returns
+       the polygon unchanged (same vertices, same order), so the seven clipping passes are skipped.
+       Comparisons are written exactly as the clippers test them; NaNs fall through to the full path. */
+    int inside = (*n == 3);
+    for (int i = 0; inside && i < 3; i++) {
+        const float *hv = poly[i].homogeneous; const float w = hv[3];
+        inside = !(w < PFH_CLIP_EPSILON) && hv[0] <= w && -hv[0] <= w && hv[1] <= w && -hv[1] <= w && hv[2] <= w && -hv[2] <= w;
+    }
+    if (inside || (clip_w(poly, n) && clip_xyz(poly, n))) {
         for (int i = 0; i < *n; i++) {
             pf_vertex *v = &poly[i];
             v->homogeneous[2] = 1.0f / v->homogeneous[2];

@@ -12,7 +12,7 @@ CC        := gcc
 # multiply-add anywhere in the vertex or fragment arithmetic would change pixels.
 HOST_CFLAGS = -std=gnu99 -O2 -fPIC -ffp-contract=off -fno-fast-math -fvisibility=hidden -DPF_BUILD_SHARED -DNDEBUG \
               -Iinclude -Wall -Wextra -Wno-unused-parameter -Wno-missing-field-initializers
-NVCC_FLAGS  = -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -std=c++17 \
+NVCC_FLAGS  = -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -std=c++17 -Ipixelforge_b200/csrc \
               -Xcompiler -fPIC,-fvisibility=hidden -Iinclude
 
 HOST_SRC = pixelforge_b200/csrc/host/pf_context.c pixelforge_b200/csrc/host/pf_pipeline.c \
@@ -36,7 +36,7 @@ build/host/%.o: pixelforge_b200/csrc/host/%.c $(HOST_HDR)
 	@mkdir -p build/host
 	$(CC) $(HOST_CFLAGS) -c $< -o $@
 
-build/pfcu.o: pixelforge_b200/csrc/pfcu.cu include/pfcu.h
+build/pfcu.o: pixelforge_b200/csrc/pfcu.cu include/pfcu.h pixelforge_b200/csrc/pf_vstage.h
 	@mkdir -p build
 	$(NVCC) $(NVCC_FLAGS) -Xptxas -v -c $< -o $@ 2> build/pfcu.ptxas.log || (cat build/pfcu.ptxas.log; false)
 

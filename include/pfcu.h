@@ -179,6 +179,41 @@ PFCU_API pfcu_texture *pfcu_texture_from_surface(pfcu_surface *s);   /* render-t
 PFCU_API int  pfcu_texture_update(pfcu_texture *t, const void *host_pixels);
 PFCU_API void pfcu_texture_destroy(pfcu_texture *t);
 
+/* ---- optional device vertex stage (SURVEY 8-f "next" row 1) ---------------------------------- */
+/* Parameters of the per-vertex stage: what the reference latches at pfBegin (context.c:96-111) and reads in
+ * triangles.c:62-116,246-280 / internal/context/context.c:51-65. */
+typedef struct {
+    float    mvp[16];           /* model-view-projection, row-vector convention (v' = v * M)             */
+    float    normal_mat[16];
+    int32_t  vp_pos[2];
+    uint32_t vp_dim[2];         /* viewport size - 1                                                     */
+    uint32_t lighting;          /* PF_LIGHTING with active lights: normal transform + colour * diffuse   */
+    uint32_t diffuse[2];        /* faceMaterial[PF_FRONT/PF_BACK].diffuse                                */
+} pfcu_vparams;
+
+/* One pfDrawElements / pfDrawArrays call in PF_TRIANGLES mode over tightly packed float arrays
+ * (context.c:1231-1575).  Host pointers; copied to the device by the call. */
+typedef struct {
+    const float   *positions;  uint32_t pos_size;      /* 2..4 floats per vertex                          */
+    const float   *normals;                            /* 3 floats per vertex, or NULL (normal = 0)       */
+    const float   *texcoords;                          /* 2 floats per vertex, or NULL (texcoord = 0)     */
+    const uint8_t *colors;     uint32_t color_size;    /* 3 or 4 ubytes per vertex, or NULL               */
+    uint32_t       n_vertices;                         /* vertices referenced (max index + 1)             */
+    const void    *indices;    uint32_t index_bytes;   /* 1, 2 or 4; NULL = sequential from `first`       */
+    uint32_t       first, count;                       /* number of indices / vertices to draw            */
+    uint32_t       current_color;                      /* colour when there is no colour array            */
+    uint32_t       n_faces;    uint8_t faces[2];       /* faceToRender passes per triangle, in order      */
+    uint16_t       pad;
+} pfcu_draw;
+
+enum { PFCU_CAP_DEVICE_VERTEX = 1u };
+PFCU_API unsigned pfcu_capabilities(void);
+/* Vertex stage + rasterisation of one draw call, entirely on the device; ordered after everything
+ * submitted before it.  `state` is the single state snapshot in force.  *n_out receives the number of
+ * Rasterize_Triangle-equivalent triangles produced (after clipping). */
+PFCU_API int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vparams *vp,
+                                 const pfcu_draw *draw, uint32_t *n_out);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* Rasterise `n_tris` triangles, in order, into `s`.  Host pointers; the call copies them to the
  * device (pinned staging + cudaMemcpyAsync) and launches setup -> bin -> tile raster.  Asynchronous. */

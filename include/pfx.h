@@ -44,6 +44,9 @@ PF_API void pfxReadDepth(PFfloat *out);
  * (include/pfcu.h) that stay valid until the next pfxCaptureBegin or pfDeleteContext. */
 PF_API void pfxCaptureBegin(void);
 PF_API void pfxCaptureEnd(const void **states, PFuint *nStates, const void **triangles, PFuint *nTriangles);
+/* Large PF_TRIANGLES vertex-array draws run their vertex stage (transform, clip, project) on the GPU
+ * (default on; PF_CUDA_DEVICE_VERTEX=0 or this call turn it off for the current context). */
+PF_API void pfxEnableDeviceVertexStage(PFboolean on);
 /* The pfcu_surface* behind the current target. */
 PF_API void *pfxGetSurfaceHandle(void);
 PF_API const char *pfxBackendName(void);

@@ -598,6 +598,9 @@ pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const
 }
 int  pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b) { return pfcu_submit(s, b->states, b->n_states, b->tris, b->n_tris); }
 void pfcu_batch_destroy(pfcu_batch *b) { if (b) { free(b->states); free(b->tris); free(b); } }
+unsigned pfcu_capabilities(void) { return 0u; }     /* the oracle has no device vertex stage: the front end keeps it on the host */
+int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *st, const pfcu_vparams *vp, const pfcu_draw *d, uint32_t *n)
+{ (void)s; (void)st; (void)vp; (void)d; (void)n; return PFCU_ERR_INVALID; }
 void pfcu_profile_enable(int on) { (void)on; }
 int  pfcu_profile_read(pfcu_profile *out) { memset(out, 0, sizeof *out); return PFCU_OK; }
 int  pfcu_finish(void) { return PFCU_OK; }

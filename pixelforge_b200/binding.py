@@ -174,7 +174,7 @@ PFCU_SYMBOLS = [
 
 PFX_SYMBOLS = ["pfxSetSyncMode", "pfxFlush", "pfxFinish", "pfxGetCounters", "pfxResetCounters", "pfxSetTileOwner",
                "pfxGetDeviceColor", "pfxGetDeviceDepth", "pfxReadDepth", "pfxCaptureBegin", "pfxCaptureEnd",
-               "pfxGetSurfaceHandle", "pfxBackendName"]
+               "pfxGetSurfaceHandle", "pfxBackendName", "pfxEnableDeviceVertexStage"]
 
 
 class PfcuLib:

@@ -79,6 +79,7 @@ PFcontext pfCreateContext(void *targetBuffer, PFsizei width, PFsizei height, PFp
     c->shadingMode = PF_SMOOTH; c->lightingMode = PF_GOURAUD; c->cullFace = PF_BACK;
     c->errCode = PF_NO_ERROR;
     c->state_dirty = 1;
+    { const char *e = getenv("PF_CUDA_DEVICE_VERTEX"); c->device_vertex = !(e && e[0] == '0'); }
     return c;
 }
 
@@ -544,7 +545,7 @@ void pfVertex4fv(const PFfloat *v)
     memcpy(vx->position, v, 16);
     memcpy(vx->normal, c->currentNormal, 12);
     memcpy(vx->texcoord, c->currentTexcoord, 8);
-    vx->color = c->currentColor;
+    memcpy(&vx->color, &c->currentColor, 4);
     if (c->vertexCounter == verts_per_primitive(c->currentDrawMode)) {
         pfh_process_primitive(c);
         carry_over(c);
@@ -688,9 +689,13 @@ static void draw_indexed(PFdrawmode mode, PFsizei count, PFint first, int indexe
     int useCol = (c->state & PF_COLOR_ARRAY) && c->acol.buffer;
     PFsizei per = verts_per_primitive(mode);
 
+    if (mode == PF_TRIANGLES && pfh_device_draw(c, count, first, indexed, itype, indices, useNrm, useTex, useCol)) {
+        pfh_end_of_draw(c);
+        return;
+    }
     for (PFsizei i = 0; i < per; i++) {
         memset(&c->vertexBuffer[i], 0, sizeof(pf_vertex));
-        c->vertexBuffer[i].color = c->currentColor;
+        memcpy(&c->vertexBuffer[i].color, &c->currentColor, 4);
     }
     pfBegin(mode);
     for (PFsizei i = 0; i < count; i++) {
@@ -707,7 +712,7 @@ static void draw_indexed(PFdrawmode mode, PFsizei count, PFint first, int indexe
         if (!fetch_float(&c->apos, j, vx->position, c->apos.size)) { c->errCode = PF_INVALID_ENUM; if (indexed) return; }
         if (useNrm && !fetch_float(&c->anrm, j, vx->normal, 3)) { c->errCode = PF_INVALID_ENUM; if (indexed) return; }
         if (useTex && !fetch_float(&c->atex, j, vx->texcoord, 2)) { c->errCode = PF_INVALID_ENUM; if (indexed) return; }
-        if (useCol && !fetch_color(&c->acol, j, &vx->color)) { c->errCode = PF_INVALID_ENUM; if (indexed) return; }
+        if (useCol && !fetch_color(&c->acol, j, (PFcolor *)&vx->color)) { c->errCode = PF_INVALID_ENUM; if (indexed) return; }
         if (c->vertexCounter == per) {
             pfh_process_primitive(c);
             carry_over(c);
@@ -1093,6 +1098,8 @@ void pfxReadDepth(PFfloat *out)
     pfh_upload_if_needed(c, c->cur_surf);
     pfcu_surface_download(c->cur_surf->dev, NULL, out, 0, c->cur_surf->tex->h);
 }
+
+void pfxEnableDeviceVertexStage(PFboolean on) { if (pf_cur) pf_cur->device_vertex = on ? 1 : 0; }
 
 void pfxCaptureBegin(void)
 {

@@ -11,6 +11,7 @@
 
 #include "pixelforge.h"
 #include "pfcu.h"
+#include "../pf_vstage.h"
 
 #include <stddef.h>
 #include <stdlib.h>
@@ -53,14 +54,7 @@ typedef struct pf_surf {
     struct pf_surf *next;           /* registry link (lookup from a PFframebuffer copy)              */
 } pf_surf;
 
-typedef struct {
-    float   homogeneous[4];
-    float   screen[2];
-    float   position[4];
-    float   normal[3];
-    float   texcoord[2];
-    PFcolor color;
-} pf_vertex;
+typedef pfv_vertex pf_vertex;         /* shared with the device vertex stage (pf_vstage.h); colour as a dword */
 
 typedef struct {
     float   position[3], direction[3];
@@ -149,6 +143,7 @@ typedef struct pf_ctx {
     int            state_dirty;
     uint64_t       tris_emitted;
     /* optional capture of the submitted stream (pfxCaptureBegin/End) */
+    int            device_vertex;   /* large vertex-array draws run the vertex stage on the GPU (default on) */
     int            capturing;
     pfcu_triangle *cap_tris; size_t cap_ntris, cap_tris_cap;
     pfcu_state    *cap_states; size_t cap_nstates, cap_states_cap;
@@ -165,6 +160,11 @@ void pfh_end_of_draw(pf_ctx *c);                       /* PF_CUDA_SYNC=end polic
 int  pfh_sync_mode_explicit(void);
 void pfh_set_sync_mode(int explicit_mode);
 void pfh_update_matrices(pf_ctx *c, int with_normal);
+void pfh_vstage_params(const pf_ctx *c, pfv_params *p);
+void pfh_update_view_pos(pf_ctx *c);
+void pfh_snapshot_state(pf_ctx *c, pfcu_state *st);
+int  pfh_device_draw(pf_ctx *c, PFsizei count, PFint first, int indexed, PFdatatype itype, const void *indices,
+                     int useNrm, int useTex, int useCol);    /* 1 = drawn on the device vertex path */   /* the state the next primitive would use */
 
 /* pf_objects.c */
 pf_surf *pfh_surf_create(pf_tex *tex, PFfloat *zhost, int z_public);

@@ -122,6 +122,8 @@ static void build_state(pf_ctx *c, pfcu_state *st)
     }
 }
 
+void pfh_snapshot_state(pf_ctx *c, pfcu_state *st) { build_state(c, st); }
+
 static uint32_t current_state_index(pf_ctx *c)
 {
     if (!c->state_dirty && c->n_states > 0) return c->n_states - 1;
@@ -233,23 +235,14 @@ static inline void emit_triangle(pf_ctx *c, int face, int is3d, const pf_vertex 
     if (!ensure_batch(c)) return;
     uint32_t sidx = current_state_index(c);
     pfcu_triangle *t = &c->tris[c->cur_buf][c->n_tris];
-    const pf_vertex *vs[3] = { a, b, d };
-    float ymin = 1e30f, ymax = -1e30f;
-    for (int i = 0; i < 3; i++) {
-        const pf_vertex *v = vs[i];
-        pfcu_vertex *o = &t->v[i];
-        o->sx = v->screen[0]; o->sy = v->screen[1];
-        o->zinv = v->homogeneous[2];
-        o->u = v->texcoord[0]; o->v = v->texcoord[1];
-        o->px = v->position[0]; o->py = v->position[1]; o->pz = v->position[2];
-        o->nx = v->normal[0]; o->ny = v->normal[1]; o->nz = v->normal[2];
-        memcpy(&o->rgba, &v->color, 4);
-        if (v->screen[1] < ymin) ymin = v->screen[1];
-        if (v->screen[1] > ymax) ymax = v->screen[1];
-    }
-    t->state = sidx; t->face = (uint8_t)face; t->is3d = (uint8_t)is3d; t->pad = 0;
+    pfv_emit(t, a, b, d, sidx, face, is3d);
 
     /* dirty rows for the next host-mirror refresh */
+    float ymin = a->screen[1], ymax = a->screen[1];
+    if (b->screen[1] < ymin) ymin = b->screen[1];
+    if (d->screen[1] < ymin) ymin = d->screen[1];
+    if (b->screen[1] > ymax) ymax = b->screen[1];
+    if (d->screen[1] > ymax) ymax = d->screen[1];
     pf_surf *s = c->cur_surf;
     float h = (float)s->tex->h;
     if (!(ymin > 0.0f)) ymin = 0.0f;            /* also catches NaN */
@@ -335,120 +328,91 @@ static PFcolor light_vertex(const pf_ctx *c, const pf_material *m, PFcolor diffu
     return out;
 }
 
-/* ---- clipping and projection (triangles.c:157-280, internal/context/context.c:51-90) --------- */
+/* ---- parameters of the shared vertex stage (pf_vstage.h) ------------------------------------------ */
 
-static void to_screen(const pf_ctx *c, pf_vertex *v)
+void pfh_vstage_params(const pf_ctx *c, pfv_params *p)
 {
-    v->screen[0] = (c->vpPos[0] + (v->homogeneous[0] + 1.0f) * 0.5f * c->vpDim[0]) + 0.5f;
-    v->screen[1] = (c->vpPos[1] + (1.0f - v->homogeneous[1]) * 0.5f * c->vpDim[1]) + 0.5f;
+    memcpy(p->mvp, c->matMVP, sizeof p->mvp);
+    memcpy(p->normal_mat, c->matNormal, sizeof p->normal_mat);
+    p->vp_pos[0] = c->vpPos[0]; p->vp_pos[1] = c->vpPos[1];
+    p->vp_dim[0] = c->vpDim[0]; p->vp_dim[1] = c->vpDim[1];
+    p->lighting = ((c->state & PF_LIGHTING) && lights_active(c)) ? 1u : 0u;
+    p->diffuse[0] = color_dword(c->material[0].diffuse);
+    p->diffuse[1] = color_dword(c->material[1].diffuse);
 }
 
-static pf_vertex lerp_vertex(const pf_vertex *a, const pf_vertex *b, float t)
+void pfh_update_view_pos(pf_ctx *c)
 {
-    pf_vertex r;
-    memset(&r, 0, sizeof r);
-    const PFubyte *ca = (const PFubyte *)&a->color, *cb = (const PFubyte *)&b->color;
-    PFubyte *cr = (PFubyte *)&r.color;
-    PFubyte ut = (PFubyte)(255 * t);
-    for (int i = 0; i < 4; i++) {
-        r.homogeneous[i] = a->homogeneous[i] + t * (b->homogeneous[i] - a->homogeneous[i]);
-        r.position[i] = a->position[i] + t * (b->position[i] - a->position[i]);
-        cr[i] = (PFubyte)(ca[i] + (ut * ((int)cb[i] - ca[i])) / 255);
-        if (i < 2) r.texcoord[i] = a->texcoord[i] + t * (b->texcoord[i] - a->texcoord[i]);
-        if (i < 3) r.normal[i] = a->normal[i] + t * (b->normal[i] - a->normal[i]);
-    }
-    return r;
+    if (c->viewPosValid) return;
+    pf_mat4 inv;
+    m4_invert(inv, c->matView);
+    c->viewPos[0] = inv[12]; c->viewPos[1] = inv[13]; c->viewPos[2] = inv[14];
+    c->viewPosValid = 1;
+    if (c->lightingMode == PF_PHONG) c->state_dirty = 1;
 }
 
-static int clip_w(pf_vertex *poly, int *n)
-{
-    pf_vertex in[PFH_MAX_POLY_VERTS];
-    int nin = *n;
-    memcpy(in, poly, (size_t)nin * sizeof(pf_vertex));
-    *n = 0;
-    const pf_vertex *prev = &in[nin - 1];
-    int pd = (prev->homogeneous[3] < PFH_CLIP_EPSILON) ? -1 : 1;
-    for (int i = 0; i < nin; i++) {
-        int cd = (in[i].homogeneous[3] < PFH_CLIP_EPSILON) ? -1 : 1;
-        if (pd * cd < 0)
-            poly[(*n)++] = lerp_vertex(prev, &in[i],
-                (PFH_CLIP_EPSILON - prev->homogeneous[3]) / (in[i].homogeneous[3] - prev->homogeneous[3]));
-        if (cd > 0) poly[(*n)++] = in[i];
-        pd = cd; prev = &in[i];
-    }
-    return *n > 0;
-}
+/* ---- large vertex-array draws: the vertex stage runs on the device ---------------------------------
+ * Eligible: PF_TRIANGLES over tightly packed PF_FLOAT positions (+ optional float normals / texcoords,
+ * ubyte colours), filled polygons, no Gouraud lighting (its powf/sqrtf come from the host libm and stay
+ * on the host).  Same functions (pf_vstage.h), same order of operations, same triangle order. */
+#define PFH_DEVICE_DRAW_MIN_TRIS 1024u
 
-static int clip_xyz(pf_vertex *poly, int *n)
+int pfh_device_draw(pf_ctx *c, PFsizei count, PFint first, int indexed, PFdatatype itype, const void *indices,
+                    int useNrm, int useTex, int useCol)
 {
-    for (int ax = 0; ax < 3; ax++) {
-        if (*n == 0) return 0;
-        for (int side = 0; side < 2; side++) {          /* +axis plane, then -axis plane */
-            pf_vertex in[PFH_MAX_POLY_VERTS];
-            int nin = *n;
-            memcpy(in, poly, (size_t)nin * sizeof(pf_vertex));
-            *n = 0;
-            const float sg = side ? -1.0f : 1.0f;
-            const pf_vertex *prev = &in[nin - 1];
-            int pd = ((side ? -prev->homogeneous[ax] : prev->homogeneous[ax]) <= prev->homogeneous[3]) ? 1 : -1;
-            for (int i = 0; i < nin; i++) {
-                const pf_vertex *cur = &in[i];
-                int cd = ((side ? -cur->homogeneous[ax] : cur->homogeneous[ax]) <= cur->homogeneous[3]) ? 1 : -1;
-                if (pd * cd <= 0) {
-                    float t;
-                    if (!side) {
-                        float pn = prev->homogeneous[3] - prev->homogeneous[ax];
-                        t = pn / (pn - (cur->homogeneous[3] - cur->homogeneous[ax]));
-                    } else {
-                        float pn = prev->homogeneous[3] + prev->homogeneous[ax];
-                        t = pn / (pn - (cur->homogeneous[3] + cur->homogeneous[ax]));
-                    }
-                    if (*n < PFH_MAX_POLY_VERTS) poly[(*n)++] = lerp_vertex(prev, cur, t);
-                }
-                if (cd > 0 && *n < PFH_MAX_POLY_VERTS) poly[(*n)++] = *cur;
-                pd = cd; prev = cur;
-            }
-            (void)sg;
-            if (*n == 0) return 0;
+    static int caps = -1;
+    if (caps < 0) caps = (int)pfcu_capabilities();
+    if (!(caps & PFCU_CAP_DEVICE_VERTEX) || !c->device_vertex || c->recording || c->capturing) return 0;
+    if (count / 3u < PFH_DEVICE_DRAW_MIN_TRIS) return 0;
+    if (c->apos.type != PF_FLOAT || !c->apos.buffer) return 0;
+    if (useNrm && c->anrm.type != PF_FLOAT) return 0;
+    if (useTex && c->atex.type != PF_FLOAT) return 0;
+    if (useCol && c->acol.type != PF_UNSIGNED_BYTE) return 0;
+    const int lighting = (c->state & PF_LIGHTING) && lights_active(c);
+    if (lighting && c->lightingMode == PF_GOURAUD) return 0;
+
+    pfcu_draw d; memset(&d, 0, sizeof d);
+    if (c->state & PF_CULL_FACE) { d.n_faces = 1; d.faces[0] = (uint8_t)!c->cullFace; }
+    else { d.n_faces = 2; d.faces[0] = PF_FRONT; d.faces[1] = PF_BACK; }
+    for (uint32_t f = 0; f < d.n_faces; f++) if (c->polygonMode[d.faces[f]] != PF_FILL) return 0;
+
+    /* vertices referenced by the draw */
+    size_t nverts;
+    if (indexed) {
+        size_t mx = 0;
+        switch (itype) {
+        case PF_UNSIGNED_BYTE:  { const PFubyte *p = (const PFubyte *)indices; for (PFsizei i = 0; i < count; i++) if (p[i] > mx) mx = p[i]; d.index_bytes = 1; } break;
+        case PF_UNSIGNED_SHORT: { const PFushort *p = (const PFushort *)indices; for (PFsizei i = 0; i < count; i++) if (p[i] > mx) mx = p[i]; d.index_bytes = 2; } break;
+        default:                { const PFuint *p = (const PFuint *)indices; for (PFsizei i = 0; i < count; i++) if (p[i] > mx) mx = p[i]; d.index_bytes = 4; } break;
         }
-    }
-    return *n > 0;
-}
+        nverts = mx + 1; d.indices = indices; d.first = 0;
+    } else { nverts = (size_t)first + count; d.indices = NULL; d.first = (uint32_t)first; }
+    if (nverts > 0x7fffffffu) return 0;
 
-/* returns is3D; *n < 3 means nothing to draw */
-static int project_and_clip(const pf_ctx *c, pf_vertex *poly, int *n)
-{
-    float wsum = 0.0f;
-    for (int i = 0; i < *n; i++) {
-        pf_vertex *v = &poly[i];
-        memcpy(v->homogeneous, v->position, 16);
-        v4_transform(v->homogeneous, v->homogeneous, c->matMVP);
-        wsum += v->homogeneous[3];
+    d.positions = (const float *)c->apos.buffer; d.pos_size = (uint32_t)c->apos.size;
+    d.normals = useNrm ? (const float *)c->anrm.buffer : NULL;
+    d.texcoords = useTex ? (const float *)c->atex.buffer : NULL;
+    d.colors = useCol ? (const uint8_t *)c->acol.buffer : NULL; d.color_size = useCol ? (uint32_t)c->acol.size : 0;
+    d.n_vertices = (uint32_t)nverts; d.count = count - count % 3u;
+    d.current_color = color_dword(c->currentColor);
+
+    pfh_flush(c);                               /* everything submitted before this draw comes first */
+    pfh_update_matrices(c, 1);                  /* what pfBegin latches */
+    pfv_params vp; pfh_vstage_params(c, &vp);
+    if (vp.lighting) pfh_update_view_pos(c);
+    pfcu_state st; build_state(c, &st);
+    pf_surf *s = c->cur_surf;
+    pfh_upload_if_needed(c, s);
+    uint32_t produced = 0;
+    int rc = pfcu_draw_triangles(s->dev, &st, &vp, &d, &produced);
+    if (rc != PFCU_OK) {
+        fprintf(stderr, "pixelforge-b200: pfcu_draw_triangles failed (%d): %s\n", rc, pfcu_last_error());
+        c->errCode = (rc == PFCU_ERR_OOM) ? PF_ERROR_OUT_OF_MEMORY : PF_INVALID_OPERATION;
     }
-    if (fabsf(wsum - 3.0f) < PFH_CLIP_EPSILON) {
-        for (int i = 0; i < *n; i++) to_screen(c, &poly[i]);
-        return 0;
-    }
-    /* Trivial accept: when all three vertices are inside every clip plane, Sutherland-Hodgman returns
-       the polygon unchanged (same vertices, same order), so the seven clipping passes are skipped.
-       Comparisons are written exactly as the clippers test them; NaNs fall through to the full path. */
-    int inside = (*n == 3);
-    for (int i = 0; inside && i < 3; i++) {
-        const float *hv = poly[i].homogeneous; const float w = hv[3];
-        inside = !(w < PFH_CLIP_EPSILON) && hv[0] <= w && -hv[0] <= w && hv[1] <= w && -hv[1] <= w && hv[2] <= w && -hv[2] <= w;
-    }
-    if (inside || (clip_w(poly, n) && clip_xyz(poly, n))) {
-        for (int i = 0; i < *n; i++) {
-            pf_vertex *v = &poly[i];
-            v->homogeneous[2] = 1.0f / v->homogeneous[2];
-            v->texcoord[0] = v->texcoord[0] * v->homogeneous[2];
-            v->texcoord[1] = v->texcoord[1] * v->homogeneous[2];
-            float iw = 1.0f / v->homogeneous[3];
-            v->homogeneous[0] *= iw;
-            v->homogeneous[1] *= iw;
-            to_screen(c, v);
-        }
-    }
+    s->dev_newer = 1; s->dirty_y0 = 0; s->dirty_y1 = s->tex->h;
+    c->tris_emitted += produced;
+    c->state_dirty = 1;
+    c->currentDrawMode = PF_TRIANGLES; c->vertexCounter = 0;
     return 1;
 }
 
@@ -456,35 +420,25 @@ static int project_and_clip(const pf_ctx *c, pf_vertex *poly, int *n)
 
 static void process_triangle(pf_ctx *c, int face, pf_vertex poly[PFH_MAX_POLY_VERTS])
 {
-    int lighting = (c->state & PF_LIGHTING) && lights_active(c);
+    pfv_params vp;
+    pfh_vstage_params(c, &vp);
     int n = 3;
 
-    if (lighting) {
-        if (!c->viewPosValid) {
-            pf_mat4 inv;
-            m4_invert(inv, c->matView);
-            c->viewPos[0] = inv[12]; c->viewPos[1] = inv[13]; c->viewPos[2] = inv[14];
-            c->viewPosValid = 1;
-            if (c->lightingMode == PF_PHONG) c->state_dirty = 1;
-        }
+    if (vp.lighting) {
+        pfh_update_view_pos(c);
         for (int i = 0; i < 3; i++) {
             pf_vertex *v = &poly[i];
-            v3_transform(v->normal, v->normal, c->matNormal);
-            v3_normalize(v->normal, v->normal);
-            const PFcolor d = c->material[face].diffuse;
-            v->color.r = (PFubyte)((v->color.r * d.r) / 255);
-            v->color.g = (PFubyte)((v->color.g * d.g) / 255);
-            v->color.b = (PFubyte)((v->color.b * d.b) / 255);
-            v->color.a = (PFubyte)((v->color.a * d.a) / 255);
+            pfv_prologue(&vp, face, v);
             if (c->lightingMode == PF_GOURAUD) {
                 float ndv = v3_dot(v->normal, c->matView + 8);
-                v->color = light_vertex(c, &c->material[(ndv < 0) ? PF_FRONT : PF_BACK], v->color,
-                                        c->viewPos, v->position, v->normal);
+                PFcolor in, out; memcpy(&in, &v->color, 4);
+                out = light_vertex(c, &c->material[(ndv < 0) ? PF_FRONT : PF_BACK], in, c->viewPos, v->position, v->normal);
+                memcpy(&v->color, &out, 4);
             }
         }
     }
 
-    int is3d = project_and_clip(c, poly, &n);
+    int is3d = pfv_project_and_clip(&vp, poly, &n);
     if (n < 3) return;
     for (int i = 0; i < n - 2; i++) emit_triangle(c, face, is3d, &poly[0], &poly[i + 1], &poly[i + 2]);
 }

@@ -19,6 +19,7 @@
  * No tensor cores: nothing on this path is a dense contraction.  Compile with -fmad=false.
  */
 #include "pfcu.h"
+#include "pf_vstage.h"
 
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -100,6 +101,8 @@ struct Runtime {
     unsigned *d_bin_counts = nullptr; size_t cap_bin_counts = 0;     /* [batches+1][bins] */
     unsigned *d_bin_list = nullptr; size_t cap_bin_list = 0;
     unsigned *d_bin_start = nullptr;                                  /* [MAX_BINS+1] */
+    unsigned char *d_varrays = nullptr; size_t cap_varrays = 0;        /* vertex arrays of the current draw */
+    unsigned *d_vcounts = nullptr; size_t cap_vcounts = 0;
     unsigned long long *d_counters = nullptr;                         /* rasterised, shaded, depth-failed */
     uint32_t *d_rcp = nullptr, *d_rsq = nullptr; int rcp_bits = 0, rsq_bits = 0;
     /* pinned staging for pageable sources */
@@ -1093,6 +1096,106 @@ k_raster(const RasterParams p)
 
 /* ------------------------------------------------------------------------------------------------ */
 /* ------------------------------------------------------------------------------------------------ */
+/* kernels: device vertex stage (pf_vstage.h compiled as device code)                               */
+/* ------------------------------------------------------------------------------------------------ */
+
+struct VtxArgs {
+    const float *pos; int pos_size; const float *nrm; const float *uv; const unsigned char *col; int col_size;
+    const void *idx; int idx_bytes; unsigned first, n_tri; unsigned cur_color; int n_faces; int face[2];
+    unsigned state;
+};
+
+__device__ __forceinline__ unsigned vtx_index(const VtxArgs &a, unsigned k)
+{
+    if (!a.idx) return a.first + k;
+    if (a.idx_bytes == 4) return __ldg((const unsigned *)a.idx + k);
+    if (a.idx_bytes == 2) return __ldg((const unsigned short *)a.idx + k);
+    return __ldg((const unsigned char *)a.idx + k);
+}
+
+/* vertex fetch with the reference's defaults for absent arrays (context.c:1253-1395) */
+__device__ __forceinline__ void vtx_load(const VtxArgs &a, unsigned vi, pfv_vertex *v)
+{
+    v->position[0] = 0.0f; v->position[1] = 0.0f; v->position[2] = 0.0f; v->position[3] = 1.0f;
+    for (int k = 0; k < a.pos_size; k++) v->position[k] = __ldg(a.pos + (size_t)vi * a.pos_size + k);
+    for (int k = 0; k < 3; k++) v->normal[k] = a.nrm ? __ldg(a.nrm + (size_t)vi * 3 + k) : 0.0f;
+    for (int k = 0; k < 2; k++) v->texcoord[k] = a.uv ? __ldg(a.uv + (size_t)vi * 2 + k) : 0.0f;
+    unsigned c = a.cur_color;
+    if (a.col) {
+        c = 0xffffffffu;
+        for (int k = 0; k < a.col_size; k++) c = (c & ~(255u << (8 * k))) | ((unsigned)__ldg(a.col + (size_t)vi * a.col_size + k) << (8 * k));
+    }
+    v->color = c;
+    v->screen[0] = 0.0f; v->screen[1] = 0.0f;
+}
+
+/* runs the whole vertex stage for item (triangle, face pass); returns the number of output triangles */
+__device__ __forceinline__ int vtx_process(const VtxArgs &a, const pfv_params &vp, unsigned item, pfv_vertex *poly, int *is3d, int *face_out)
+{
+    const unsigned tri = item / (unsigned)a.n_faces;
+    const int face = a.face[item % (unsigned)a.n_faces];
+    *face_out = face;
+    for (int k = 0; k < 3; k++) {
+        vtx_load(a, vtx_index(a, tri * 3u + k), &poly[k]);
+        if (vp.lighting) pfv_prologue(&vp, face, &poly[k]);
+    }
+    int n = 3;
+    *is3d = pfv_project_and_clip(&vp, poly, &n);
+    return n >= 3 ? n - 2 : 0;
+}
+
+__global__ void __launch_bounds__(128)
+k_vertex_count(const VtxArgs a, const pfv_params vp, unsigned n_items, unsigned *__restrict__ counts)
+{
+    const unsigned item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_items) return;
+    pfv_vertex poly[PFV_MAX_POLY];
+    int is3d, face;
+    counts[item] = (unsigned)vtx_process(a, vp, item, poly, &is3d, &face);
+}
+
+__global__ void __launch_bounds__(128)
+k_vertex_emit(const VtxArgs a, const pfv_params vp, unsigned n_items, const unsigned *__restrict__ offsets, pfcu_triangle *__restrict__ out)
+{
+    const unsigned item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= n_items) return;
+    pfv_vertex poly[PFV_MAX_POLY];
+    int is3d, face;
+    const int n = vtx_process(a, vp, item, poly, &is3d, &face);
+    pfcu_triangle *dst = out + offsets[item];
+    for (int i = 0; i < n; i++) pfv_emit(dst + i, &poly[0], &poly[i + 1], &poly[i + 2], a.state, face, is3d);
+}
+
+/* exclusive scan of up to 1024 items per CTA; sums[blockIdx] = CTA total */
+__global__ void __launch_bounds__(256)
+k_scan_block(const unsigned *__restrict__ in, unsigned *__restrict__ out, unsigned n, unsigned *__restrict__ sums)
+{
+    __shared__ unsigned s_warp[8];
+    const unsigned base = blockIdx.x * 1024u + threadIdx.x * 4u;
+    unsigned v[4], t = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = (base + k < n) ? in[base + k] : 0u; t += v[k]; }
+    unsigned x = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+    __syncthreads();
+    unsigned woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const unsigned c = s_warp[w]; if (w < (int)(threadIdx.x >> 5)) woff += c; total += c; }
+    unsigned run = woff + x - t;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (base + k < n) out[base + k] = run; run += v[k]; }
+    if (threadIdx.x == 0 && sums) sums[blockIdx.x] = total;
+}
+
+__global__ void k_scan_add(unsigned *__restrict__ data, unsigned n, const unsigned *__restrict__ block_offsets)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) data[i] += block_offsets[i / 1024u];
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* kernels: surface utilities                                                                       */
 /* ------------------------------------------------------------------------------------------------ */
 
@@ -1555,6 +1658,79 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     CK(cudaGetLastError());
     g.submitted += n;
     return PFCU_OK;
+}
+
+/* ---- device vertex stage ---- */
+
+static int scan_exclusive(const unsigned *d_in, unsigned *d_out, unsigned n, unsigned *d_tmp /* >= n/1024 + n/1048576 + 4 */)
+{
+    const unsigned nb = (n + 1023u) / 1024u;
+    k_scan_block<<<nb, 256, 0, g.stream>>>(d_in, d_out, n, d_tmp);
+    g.launches++;
+    if (nb > 1) {
+        unsigned *d_tmp2 = d_tmp + nb;
+        int rc = scan_exclusive(d_tmp, d_tmp, nb, d_tmp2);
+        if (rc) return rc;
+        k_scan_add<<<(n + 255u) / 256u, 256, 0, g.stream>>>(d_out, n, d_tmp);
+        g.launches++;
+    }
+    CK(cudaGetLastError());
+    return PFCU_OK;
+}
+
+unsigned pfcu_capabilities(void) { return PFCU_CAP_DEVICE_VERTEX; }
+
+int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vparams *vp, const pfcu_draw *d, uint32_t *n_out)
+{
+    if (n_out) *n_out = 0;
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!s || !state || !vp || !d || !d->positions || d->pos_size < 2 || d->pos_size > 4 || d->n_faces < 1 || d->n_faces > 2) return PFCU_ERR_INVALID;
+    const unsigned n_tri = d->count / 3u;
+    if (n_tri == 0) return PFCU_OK;
+    const unsigned n_items = n_tri * d->n_faces;
+    int rc;
+    /* arrays -> device (pageable sources are staged by the driver; ordered on the stream) */
+    const size_t nv = d->n_vertices;
+    const size_t b_pos = nv * d->pos_size * 4, b_nrm = d->normals ? nv * 12 : 0, b_uv = d->texcoords ? nv * 8 : 0;
+    const size_t b_col = d->colors ? nv * d->color_size : 0, b_idx = d->indices ? (size_t)d->count * d->index_bytes : 0;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t total_bytes = al(b_pos) + al(b_nrm) + al(b_uv) + al(b_col) + al(b_idx);
+    if ((rc = grow(&g.d_varrays, &g.cap_varrays, total_bytes))) return rc;
+    unsigned char *p = g.d_varrays;
+    VtxArgs a; memset(&a, 0, sizeof a);
+    a.pos = (const float *)p; CK(cudaMemcpyAsync(p, d->positions, b_pos, cudaMemcpyHostToDevice, g.stream)); p += al(b_pos);
+    if (b_nrm) { a.nrm = (const float *)p; CK(cudaMemcpyAsync(p, d->normals, b_nrm, cudaMemcpyHostToDevice, g.stream)); p += al(b_nrm); }
+    if (b_uv) { a.uv = (const float *)p; CK(cudaMemcpyAsync(p, d->texcoords, b_uv, cudaMemcpyHostToDevice, g.stream)); p += al(b_uv); }
+    if (b_col) { a.col = p; CK(cudaMemcpyAsync(p, d->colors, b_col, cudaMemcpyHostToDevice, g.stream)); p += al(b_col); }
+    if (b_idx) { a.idx = p; CK(cudaMemcpyAsync(p, d->indices, b_idx, cudaMemcpyHostToDevice, g.stream)); p += al(b_idx); }
+    a.pos_size = (int)d->pos_size; a.col_size = (int)d->color_size; a.idx_bytes = (int)d->index_bytes;
+    a.first = d->first; a.n_tri = n_tri; a.cur_color = d->current_color; a.n_faces = (int)d->n_faces;
+    a.face[0] = d->faces[0]; a.face[1] = d->faces[1]; a.state = 0;
+
+    /* pass A: output triangles per (triangle, face) item; scan; total */
+    if ((rc = grow(&g.d_vcounts, &g.cap_vcounts, (size_t)n_items * 2 + n_items / 512 + 64))) return rc;
+    unsigned *d_counts = g.d_vcounts, *d_offsets = g.d_vcounts + n_items, *d_tmp = g.d_vcounts + 2 * (size_t)n_items;
+    k_vertex_count<<<(n_items + 127u) / 128u, 128, 0, g.stream>>>(a, *vp, n_items, d_counts);
+    g.launches++;
+    if ((rc = scan_exclusive(d_counts, d_offsets, n_items, d_tmp))) return rc;
+    unsigned last[2] = { 0, 0 };
+    CK(cudaMemcpyAsync(&last[0], d_offsets + (n_items - 1), 4, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(&last[1], d_counts + (n_items - 1), 4, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    const unsigned total = last[0] + last[1];
+    if (n_out) *n_out = total;
+    if (total == 0) return PFCU_OK;
+
+    /* pass B: emit in order, then the usual setup -> bin -> raster pipeline */
+    if ((rc = grow(&g.d_tris, &g.cap_tris, total))) return rc;
+    if ((rc = grow(&g.d_states, &g.cap_states, 1))) return rc;
+    DevState hs;
+    const unsigned mask = convert_states(state, 1, &hs);
+    CK(cudaMemcpyAsync(g.d_states, &hs, sizeof hs, cudaMemcpyHostToDevice, g.stream));
+    k_vertex_emit<<<(n_items + 127u) / 128u, 128, 0, g.stream>>>(a, *vp, n_items, d_offsets, g.d_tris);
+    g.launches++;
+    CK(cudaGetLastError());
+    return launch_pipeline(s, g.d_tris, g.d_states, total, mask);
 }
 
 int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, const pfcu_triangle *tris, uint32_t n_tris)

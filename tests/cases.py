@@ -31,6 +31,10 @@ CASES = [
     ("c2-textured-nearest-clamp-arrays", "textured", 640, 360, dict(size=64, variant=4 | 32), False),
     ("c2-textured-bilinear-repeat", "textured", 640, 360, dict(size=64, variant=1), True),
     ("c2-textured-bilinear-clamp-rgb8", "textured", 640, 360, dict(size=64, variant=1 | 4 | 8), True),
+    # close-up camera inside the torus: heavy near-plane / frustum clipping; vertex arrays -> device vertex stage
+    ("c2-textured-closeup-clipped-arrays", "textured", 640, 360, dict(size=96, variant=32 | 64), False),
+    ("c2-textured-closeup-clipped-bilinear-arrays", "textured", 640, 360, dict(size=96, variant=1 | 32 | 64), True),
+    ("c2-textured-closeup-clipped-immediate", "textured", 640, 360, dict(size=96, variant=64), False),
     ("c3-phong", "phong", 640, 360, dict(size=96), False),
     ("c3-phong-arrays", "phong", 320, 200, dict(size=48, variant=32), False),
     ("c4-overdraw-add", "overdraw", 512, 256, dict(size=8), False),

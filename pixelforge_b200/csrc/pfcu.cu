@@ -758,17 +758,21 @@ __device__ __forceinline__ unsigned depth_mask(int func)
 
 /* shared-memory access through 32-bit window addresses computed once per CTA (the compiler otherwise
  * rebuilds the cluster-window base of every __shared__ array at each access) */
+#define SM_COLOR 0          /* byte offsets inside the CTA's shared block */
+#define SM_DEPTH 16384
+#define SM_RCP   32768
 __device__ __forceinline__ unsigned lds_u32(unsigned addr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ float lds_f32(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ void sts_u32(unsigned addr, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_f32(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ unsigned lds_color(unsigned addr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ float lds_depth(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1+16384];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ void sts_color(unsigned addr, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_depth(unsigned addr, float v) { asm volatile("st.shared.f32 [%0+16384], %1;" :: "r"(addr), "f"(v) : "memory"); }
 
 /* RCPPS from the shared-memory copy of the table (fast path: normal input, normal result) */
 __device__ __forceinline__ float rcp_fast(unsigned tab_addr, int shift, float x)
 {
     const unsigned u = __float_as_uint(x), E = u & 0x7f800000u;
     if (E - 0x00800000u >= 0x7e000000u) return rcp_x86(x);              /* zero/denormal/huge/inf/NaN */
-    const unsigned tv = lds_u32(tab_addr + (((u & 0x007fffffu) >> shift) << 2));
+    unsigned tv; asm volatile("ld.shared.u32 %0, [%1+32768];" : "=r"(tv) : "r"(tab_addr + (((u & 0x007fffffu) >> shift) << 2)));
     return __uint_as_float((tv + 0x3f800000u - E) | (u & 0x80000000u));
 }
 
@@ -780,7 +784,7 @@ __device__ __forceinline__ float rcp_fast(unsigned tab_addr, int shift, float x)
 
 struct TileCtx {
     int X0, Y0, X1, Y1;                 /* tile rectangle on the surface, inclusive               */
-    unsigned sm_color, sm_depth, sm_rcp; /* shared-window byte addresses                           */
+    unsigned sm_base;                   /* shared-window byte address of the CTA's block (opaque)  */
     int rcp_shift; bool rcp_shared;
     int lx8, ly4, warp;
     unsigned shaded, zfailed;
@@ -802,10 +806,11 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
     const unsigned meta = a0.w;
     const bool is3d = (meta >> 25) & 1u;
     const bool smooth = (flags & PFCU_ST_SMOOTH) != 0;
-    const bool ztest = zmask != 8u, zlt = (zmask & 1u) != 0, zeq = (zmask & 2u) != 0, zgt = (zmask & 4u) != 0;
+    const bool ztest = zmask != 8u;
     const unsigned c1rb = a1.x & 0x00ff00ffu, c1ga = (a1.x >> 8) & 0x00ff00ffu;
     const unsigned c2rb = a1.y & 0x00ff00ffu, c2ga = (a1.y >> 8) & 0x00ff00ffu;
     const unsigned c3rb = a1.z & 0x00ff00ffu, c3ga = (a1.z >> 8) & 0x00ff00ffu;
+    const bool same_color = (a1.x == a1.y) && (a1.y == a1.z);
     float tu1 = 0, tu2 = 0, tu3 = 0, tv1 = 0, tv2 = 0, tv3 = 0;
     const bool texturing = TEXM != 0 && (!PHONG || (flags & PFCU_ST_TEXTURE));     /* the Phong variant checks at run time */
     const bool blending = BLENDM != 0 && (!PHONG || (flags & PFCU_ST_BLEND));
@@ -835,11 +840,18 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
         const float W2 = FM(__int2float_rn(w2), s.invSum);
         const float W3 = FM(__int2float_rn(w3), s.invSum);
         const float zsum = FA(FA(FM(z1, W1), FM(z2, W2)), FM(z3, W3));
-        const float z = t.rcp_shared ? rcp_fast(t.sm_rcp, t.rcp_shift, zsum) : rcp_x86(zsum);
-        const unsigned sa = (unsigned)tile_addr(lx, ly) << 2;
+        const float z = t.rcp_shared ? rcp_fast(t.sm_base, t.rcp_shift, zsum) : rcp_x86(zsum);
+        const unsigned sa = t.sm_base + ((unsigned)tile_addr(lx, ly) << 2);
         if (ztest) {
-            const float zb = lds_f32(t.sm_depth + sa);
-            const bool pass = (zlt && z < zb) || (zeq && z == zb) || (zgt && z > zb);
+            const float zb = lds_depth(sa);
+            bool pass;
+            switch (zmask) {                        /* warp-uniform */
+            case 1u: pass = z < zb; break;
+            case 3u: pass = z <= zb; break;
+            case 2u: pass = z == zb; break;
+            case 4u: pass = z > zb; break;
+            default: pass = z >= zb; break;
+            }
             t.zfailed += (m && !pass) ? 1u : 0u;
             m = m && pass;
             if (!__any_sync(0xffffffffu, m)) continue;
@@ -849,8 +861,15 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
         Px2 frag;
         if (smooth) {
             const int u1 = __float2int_rn(FM(W1, 255.0f)), u2 = __float2int_rn(FM(W2, 255.0f)), u3 = __float2int_rn(FM(W3, 255.0f));
-            frag.rb = smooth_lanes(c1rb, c2rb, c3rb, u1, u2, u3);
-            frag.ga = smooth_lanes(c1ga, c2ga, c3ga, u1, u2, u3);
+            if (same_color) {                       /* warp-uniform: (u1+u2+u3)*c has the same lanes as u1*c+u2*c+u3*c */
+                const unsigned us = (unsigned)(u1 + u2 + u3);
+                unsigned x = us * c1rb, y = us * c1ga;
+                x = x + ((x >> 8) & 0x00ff00ffu); y = y + ((y >> 8) & 0x00ff00ffu);
+                frag.rb = (x >> 8) & 0x00ff00ffu; frag.ga = (y >> 8) & 0x00ff00ffu;
+            } else {
+                frag.rb = smooth_lanes(c1rb, c2rb, c3rb, u1, u2, u3);
+                frag.ga = smooth_lanes(c1ga, c2ga, c3ga, u1, u2, u3);
+            }
         } else {
             const float mx = max_x86(W1, max_x86(W2, W3));
             frag = px_split(((mx == W1) ? a1.x : 0u) | ((mx == W2) ? a1.y : 0u) | ((mx == W3) ? a1.z : 0u));
@@ -888,12 +907,12 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
         }
 
         if (blending) {
-            const unsigned dst = lds_u32(t.sm_color + sa);
+            const unsigned dst = lds_color(sa);
             frag = px_blend(BLENDM == 3 ? blend_mode : BLENDM, frag, dst);
         }
         if (m) {
-            sts_u32(t.sm_color + sa, px_join(frag));
-            sts_f32(t.sm_depth + sa, z);            /* written even with the depth test off (Q11) */
+            sts_color(sa, px_join(frag));
+            sts_depth(sa, z);                       /* written even with the depth test off (Q11) */
             t.shaded++;
         }
     }
@@ -903,9 +922,10 @@ template <bool HAS_PHONG>
 __global__ void __launch_bounds__(RASTER_THREADS, HAS_PHONG ? 2 : 3)
 k_raster(const RasterParams p)
 {
-    __shared__ __align__(16) unsigned s_color[TILE_PIX];
-    __shared__ __align__(16) float s_depth[TILE_PIX];
-    __shared__ unsigned s_rcp[1 << RCP_SMEM_BITS];
+    __shared__ __align__(16) unsigned s_mem[2 * TILE_PIX + (1 << RCP_SMEM_BITS)];   /* colour | depth | RCP table */
+    unsigned *const s_color = s_mem;
+    float *const s_depth = reinterpret_cast<float *>(s_mem + TILE_PIX);
+    unsigned *const s_rcp = s_mem + 2 * TILE_PIX;
     __shared__ unsigned s_queue[QUEUE_CAP];
     __shared__ unsigned char s_qmask[QUEUE_CAP];
     __shared__ unsigned s_wcount[8];
@@ -928,9 +948,10 @@ k_raster(const RasterParams p)
     t.rcp_shift = c_rcp_shift;
     t.rcp_shared = t.rcp_shift >= 23 - RCP_SMEM_BITS;
     if (t.rcp_shared) for (int k = tid; k < (1 << (23 - t.rcp_shift)); k += RASTER_THREADS) s_rcp[k] = c_rcp_tab[k];
-    t.sm_color = (unsigned)__cvta_generic_to_shared(s_color);
-    t.sm_depth = (unsigned)__cvta_generic_to_shared(s_depth);
-    t.sm_rcp = (unsigned)__cvta_generic_to_shared(s_rcp);
+    {   /* one opaque register holds the shared-window address; offsets are immediates in the ld/st */
+        unsigned base = (unsigned)__cvta_generic_to_shared(s_mem);
+        asm volatile("mov.u32 %0, %1;" : "=r"(t.sm_base) : "r"(base));
+    }
     t.lx8 = lane & 7; t.ly4 = lane >> 3; t.warp = warp;
     t.shaded = 0; t.zfailed = 0; t.data = p.data;
 

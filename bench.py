@@ -118,7 +118,8 @@ def shaded_pixels_table():
 
 
 def run_reference(args, wl_name, bounded_frames=None, bilinear_fix=False):
-    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
+    # all host threads (torchrun exports OMP_NUM_THREADS=1 to its children; only rank 0 runs this arm)
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("PF_REF_THREADS", str(os.cpu_count()))
     os.environ.setdefault("OMP_WAIT_POLICY", "active")
     from pixelforge_b200 import load_reference_scenes
     wl = WORKLOADS[wl_name]
@@ -150,7 +151,7 @@ def reference_main(args):
         r = run_reference(args, wl_name, bounded_frames=args.baseline_frames if args.as_baseline else None,
                           bilinear_fix=args.as_baseline and bool(wl["variant"] & 1) and wl["scene"] == "textured")
     except FileNotFoundError as e:
-        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref not built: {e}"}))
+        emit_json({"impl": "reference", "unavailable": f"oracle/_ref not built: {e}"})
         return 0
     line = {
         "impl": "reference", "metric": METRIC, "value": r["gpix"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -162,7 +163,7 @@ def reference_main(args):
         "e2e": {"value": r["gpix"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_json(line)
     return 0
 
 
@@ -192,7 +193,7 @@ def measure_workload(wl_name, steps, warmup, torch, scenes, pfcu, stream, flush_
             k = Counters(); L.pfcu_get_counters(k)
             out.update(e2e_ms=e2e_s * 1e3, px_per_step=k.pixels_shaded / steps, tris_per_step=k.triangles_submitted / steps,
                        tris_rasterised_per_step=k.triangles_rasterised / steps, zfail_per_step=k.pixels_depth_failed / steps,
-                       h2d_bytes=int(k.triangles_submitted / steps * TRIANGLE_DTYPE.itemsize), d2h_bytes=wl["w"] * wl["h"] * 4 * n_ctx)
+                       h2d_bytes=int(k.bytes_h2d / steps), d2h_bytes=int(k.bytes_d2h / steps))
 
         # ---- device-resident replay: capture one frame per context, keep it in HBM ----
         batches = []
@@ -294,6 +295,12 @@ def ours_main(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    traffic = None
+    try:    # dram__bytes_read+write of k_raster per launch, from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic = json.load(f).get(wl_name, {}).get("traffic_bytes_per_launch")
+    except Exception:
+        pass
     alg_bytes = m["dev_px_per_step"] * wl["bytes_px"]
     achieved = alg_bytes / (m["raster_ms"] * 1e-3) / 1e9 if m["raster_ms"] > 0 else 0.0
 
@@ -329,8 +336,9 @@ def ours_main(args):
     cpu = None
     if not args.no_cpu_baseline:
         try:
+            env = dict(os.environ); env.pop("OMP_NUM_THREADS", None)      # torchrun pins it to 1; the baseline uses every core
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--as-baseline", "--workload", wl_name,
-                                "--baseline-frames", "3"], capture_output=True, text=True, timeout=600)
+                                "--baseline-frames", "3"], capture_output=True, text=True, timeout=600, env=env)
             j = json.loads(r.stdout.strip().splitlines()[-1])
             cpu = j.get("cpu_baseline") or {"unavailable": j.get("unavailable")}
             if "value" in (cpu or {}):
@@ -348,18 +356,32 @@ def ours_main(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": m["d2h_bytes"],
                 "ms_per_step": e2e_ms, "mtri_per_s": sum_over_ranks(m["tris_per_step"]) / (e2e_ms * 1e-3) / 1e6 if world == 1 else None},
         "gpu_launches": int(round(m["launches_per_step"] * args.steps)),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "k_raster", "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_shaded_px": wl["bytes_px"],
                      "kernel_ms": m["raster_ms"], "frontend_kernels_ms": m["frontend_ms"], "peak_source": peak_src},
         "cpu_baseline": cpu, "clocks": clocks, "extra": extra,
     }
-    print(json.dumps(line))
+    emit_json(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit_json(obj):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version
+    banner, for one) was redirected to stderr at start-up."""
+    data = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -118,6 +118,8 @@ typedef struct {
     uint64_t pixels_shaded;         /* fragments whose final mask lane is set: colour+depth written   */
     uint64_t pixels_depth_failed;   /* covered fragments rejected by the depth test                   */
     uint64_t kernel_launches;       /* kernels launched by this library                               */
+    uint64_t bytes_h2d;             /* host -> device bytes copied (batches, vertex arrays, surfaces, textures) */
+    uint64_t bytes_d2h;             /* device -> host bytes copied (surface downloads)                */
 } pfcu_counters;
 
 /* ---- runtime -------------------------------------------------------------------------------- */

@@ -19,6 +19,7 @@ typedef struct {
     PFuint64 pixels_shaded;          /* colour+depth writes                                       */
     PFuint64 pixels_depth_failed;
     PFuint64 kernel_launches;
+    PFuint64 bytes_h2d, bytes_d2h;   /* PCIe traffic caused by this library                          */
 } PFXcounters;
 
 /* PF_CUDA_SYNC=end (default): the caller's buffers are refreshed at every pfEnd / pfCallList /

@@ -157,7 +157,8 @@ class Profile(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("triangles_submitted", C.c_uint64), ("triangles_rasterised", C.c_uint64),
-                ("pixels_shaded", C.c_uint64), ("pixels_depth_failed", C.c_uint64), ("kernel_launches", C.c_uint64)]
+                ("pixels_shaded", C.c_uint64), ("pixels_depth_failed", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64)]
 
 
 PFCU_SYMBOLS = [

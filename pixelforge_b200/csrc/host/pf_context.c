@@ -1076,7 +1076,7 @@ void pfxGetCounters(PFXcounters *out)
     pfcu_get_counters(&k);
     out->triangles_submitted = k.triangles_submitted; out->triangles_rasterised = k.triangles_rasterised;
     out->pixels_shaded = k.pixels_shaded; out->pixels_depth_failed = k.pixels_depth_failed;
-    out->kernel_launches = k.kernel_launches;
+    out->kernel_launches = k.kernel_launches; out->bytes_h2d = k.bytes_h2d; out->bytes_d2h = k.bytes_d2h;
 }
 
 void pfxResetCounters(void) { if (pf_cur) pfh_flush(pf_cur); pfcu_finish(); pfcu_reset_counters(); }

@@ -109,7 +109,7 @@ struct Runtime {
     void *h_stage = nullptr; size_t cap_stage = 0; cudaEvent_t stage_done = nullptr;
     DevState *h_states = nullptr; size_t cap_hstates = 0; cudaEvent_t states_done = nullptr;
     std::vector<PinnedBlock> pinned;
-    uint64_t submitted = 0, launches = 0;
+    uint64_t submitted = 0, launches = 0, bytes_h2d = 0, bytes_d2h = 0;
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;       /* triples: before setup, before raster, after raster */
     std::vector<cudaEvent_t> prof_pool;
@@ -997,7 +997,12 @@ k_raster(const RasterParams p)
             unsigned woff = 0, total = 0;
 #pragma unroll
             for (int w = 0; w < 8; w++) { const unsigned c = s_wcount[w]; if (w < warp) woff += c; total += c; }
-            if (hit) { const unsigned pos = qn + woff + __popc(bal & ((1u << lane) - 1u)); s_queue[pos] = ti; s_qmask[pos] = (unsigned char)wmask; }
+            if (hit) {
+                const unsigned pos = qn + woff + __popc(bal & ((1u << lane) - 1u)); s_queue[pos] = ti; s_qmask[pos] = (unsigned char)wmask;
+                /* pull the triangle's attribute block towards L1 now: the warps that shade it later would
+                   otherwise each pay a dependent L2 round trip per queue entry */
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(p.data + ti));
+            }
             qn += total;
             base += RASTER_THREADS;
             __syncthreads();
@@ -1041,6 +1046,12 @@ k_raster(const RasterParams p)
             while (rel) {
                 const int j = __ffs(rel) - 1; rel &= rel - 1u;
                 const unsigned ti = s_queue[q0 + j];
+                if (rel) {                          /* software prefetch of this warp's next entry */
+                    const unsigned tn = s_queue[q0 + __ffs(rel) - 1];
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(p.bbox + tn));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(p.setup + tn));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(p.data + tn));
+                }
                 const int4 b = __ldg(p.bbox + ti);
                 const TriSetup s = p.setup[ti];
                 const uint4 a0 = __ldg(reinterpret_cast<const uint4 *>(p.data + ti));
@@ -1455,8 +1466,8 @@ int pfcu_surface_upload(pfcu_surface *s, const void *hc, const float *hd, uint32
 {
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
     const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;
-    if (hc) CK(cudaMemcpyAsync(s->color + off, (const uint32_t *)hc + off, n, cudaMemcpyHostToDevice, g.stream));
-    if (hd) CK(cudaMemcpyAsync(s->depth + off, hd + off, n, cudaMemcpyHostToDevice, g.stream));
+    if (hc) { CK(cudaMemcpyAsync(s->color + off, (const uint32_t *)hc + off, n, cudaMemcpyHostToDevice, g.stream)); g.bytes_h2d += n; }
+    if (hd) { CK(cudaMemcpyAsync(s->depth + off, hd + off, n, cudaMemcpyHostToDevice, g.stream)); g.bytes_h2d += n; }
     /* pageable sources are staged by the driver before the call returns; pinned ones are not */
     CK(cudaStreamSynchronize(g.stream));
     return PFCU_OK;
@@ -1466,8 +1477,8 @@ int pfcu_surface_download(pfcu_surface *s, void *hc, float *hd, uint32_t y0, uin
 {
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
     const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;
-    if (hc) CK(cudaMemcpyAsync((uint32_t *)hc + off, s->color + off, n, cudaMemcpyDeviceToHost, g.stream));
-    if (hd) CK(cudaMemcpyAsync(hd + off, s->depth + off, n, cudaMemcpyDeviceToHost, g.stream));
+    if (hc) { CK(cudaMemcpyAsync((uint32_t *)hc + off, s->color + off, n, cudaMemcpyDeviceToHost, g.stream)); g.bytes_d2h += n; }
+    if (hd) { CK(cudaMemcpyAsync(hd + off, s->depth + off, n, cudaMemcpyDeviceToHost, g.stream)); g.bytes_d2h += n; }
     CK(cudaStreamSynchronize(g.stream));
     return PFCU_OK;
 }
@@ -1567,6 +1578,7 @@ int pfcu_texture_update(pfcu_texture *t, const void *host_pixels)
 {
     if (!t || !t->owned || !host_pixels) return PFCU_ERR_INVALID;
     CK(cudaMemcpyAsync(t->pixels, host_pixels, tex_bytes(t->w, t->h, t->fmt), cudaMemcpyHostToDevice, g.stream));
+    g.bytes_h2d += tex_bytes(t->w, t->h, t->fmt);
     CK(cudaStreamSynchronize(g.stream));
     return PFCU_OK;
 }
@@ -1716,6 +1728,7 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     const size_t b_col = d->colors ? nv * d->color_size : 0, b_idx = d->indices ? (size_t)d->count * d->index_bytes : 0;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t total_bytes = al(b_pos) + al(b_nrm) + al(b_uv) + al(b_col) + al(b_idx);
+    g.bytes_h2d += b_pos + b_nrm + b_uv + b_col + b_idx + sizeof(DevState);
     if ((rc = grow(&g.d_varrays, &g.cap_varrays, total_bytes))) return rc;
     unsigned char *p = g.d_varrays;
     VtxArgs a; memset(&a, 0, sizeof a);
@@ -1774,6 +1787,7 @@ int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, co
     const unsigned mask = convert_states(states, n_states, g.h_states);
     CK(cudaMemcpyAsync(g.d_states, g.h_states, n_states * sizeof(DevState), cudaMemcpyHostToDevice, g.stream));
     CK(cudaEventRecord(g.states_done, g.stream));
+    g.bytes_h2d += n_states * sizeof(DevState) + (size_t)n_tris * sizeof(pfcu_triangle);
 
     /* triangles: one DMA from pinned memory, or staged through our own pinned buffer */
     const size_t bytes = (size_t)n_tris * sizeof(pfcu_triangle);
@@ -1863,6 +1877,7 @@ int pfcu_get_counters(pfcu_counters *out)
     out->pixels_shaded = h[1];
     out->pixels_depth_failed = h[2];
     out->kernel_launches = g.launches;
+    out->bytes_h2d = g.bytes_h2d; out->bytes_d2h = g.bytes_d2h;
     return PFCU_OK;
 }
 
@@ -1870,7 +1885,7 @@ void pfcu_reset_counters(void)
 {
     if (!g.ok) return;
     cudaMemsetAsync(g.d_counters, 0, 4 * sizeof(unsigned long long), g.stream);
-    g.submitted = 0; g.launches = 0;
+    g.submitted = 0; g.launches = 0; g.bytes_h2d = 0; g.bytes_d2h = 0;
 }
 
 } /* extern "C" */

@@ -26,6 +26,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <limits.h>
+#include <math.h>
 
 #include <vector>
 #include <mutex>
@@ -39,7 +40,7 @@
 #define BIN_TILES   4               /* a bin is 4x4 tiles = 256x256 pixels                           */
 #define BIN_PIX     (TILE * BIN_TILES)
 #define RASTER_THREADS 256
-#define QUEUE_CAP   768             /* triangle indices buffered per tile between raster passes      */
+#define QUEUE_CAP   1024            /* triangle indices buffered per tile between raster passes      */
 #define SETUP_THREADS 256
 #define BIN_BATCH   1024            /* triangles per binning CTA                                     */
 #define MAX_BINS    1024            /* 32x32 bins = 16384^2 pixels                                   */
@@ -82,7 +83,7 @@ struct pfcu_surface {
 };
 struct pfcu_texture { uint32_t w, h; int fmt; unsigned char *pixels; bool owned; pfcu_surface *alias; };
 struct pfcu_batch {
-    DevState *states; uint32_t n_states; pfcu_triangle *tris; uint32_t n_tris; unsigned feature_mask;
+    DevState *states; uint32_t n_states; pfcu_triangle *tris; uint32_t n_tris; unsigned feature_mask; int single_prog;
 };
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -794,7 +795,7 @@ struct TileCtx {
 /* One triangle over the 8x4 blocks this warp owns.  TEXM: 0 no texture, 1 nearest+REPEAT+RGBA8,
  * 2 any sampler.  BLENDM: 0 off, 1 ALPHA, 2 ADD, 3 any mode.  Everything is computed for all 32 lanes
  * (no divergent regions); only the final stores are predicated by the coverage/depth mask. */
-template <int TEXM, int BLENDM, bool PHONG>
+template <int TEXM, int BLENDM, bool PHONG, int NW>
 __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const int4 b, const TriSetup &s, const uint4 a0, const uint4 a1,
                                           const DevState *st, const unsigned flags, const unsigned zmask, const int blend_mode, const TexRegs &tex)
 {
@@ -826,8 +827,11 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
     const int e2 = wadd(wadd(s.w2R, wmul(dy0, s.w2Y)), wmul(dx0, s.w2X));
     const int e3 = wadd(wadd(s.w3R, wmul(dy0, s.w3Y)), wmul(dx0, s.w3X));
 
+    /* block ownership: 8 warps -> warp w owns block (bx,by) iff (bx + 3*by) & 7 == w;
+       16 warps -> additionally even block rows belong to warps 0..7, odd rows to warps 8..15 */
     for (int by = by0; by <= by1; by++) {
-        const int bx = (t.warp - 3 * by) & 7;
+        if (NW == 16 && (by & 1) != (t.warp >> 3)) continue;
+        const int bx = ((t.warp & 7) - 3 * by) & 7;
         if (bx < bx0 || bx > bx1) continue;
         const int lx = (bx << 3) + t.lx8, ly = (by << 2) + t.ly4;
         const int w1 = wadd(e1, wadd(wmul(bx << 3, s.w1X), wmul(by << 2, s.w1Y)));
@@ -918,27 +922,34 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
     }
 }
 
-template <bool HAS_PHONG>
-__global__ void __launch_bounds__(RASTER_THREADS, HAS_PHONG ? 2 : 3)
+/* FIXED_PROG >= 0: the whole batch runs one state program (texm*4 + blendm), known at launch; only that
+ * variant is instantiated, which lets the register allocator fit 4 CTAs per SM.  -1: per-triangle dispatch. */
+template <bool HAS_PHONG, int NW, int FIXED_PROG, int TH>
+__global__ void __launch_bounds__(NW * 32, FIXED_PROG >= 0 ? 4 : (NW == 16 ? (HAS_PHONG ? 1 : 2) : (HAS_PHONG ? 2 : 3)))
 k_raster(const RasterParams p)
 {
+    constexpr int NT = NW * 32;
     __shared__ __align__(16) unsigned s_mem[2 * TILE_PIX + (1 << RCP_SMEM_BITS)];   /* colour | depth | RCP table */
     unsigned *const s_color = s_mem;
     float *const s_depth = reinterpret_cast<float *>(s_mem + TILE_PIX);
     unsigned *const s_rcp = s_mem + 2 * TILE_PIX;
     __shared__ unsigned s_queue[QUEUE_CAP];
-    __shared__ unsigned char s_qmask[QUEUE_CAP];
-    __shared__ unsigned s_wcount[8];
+    __shared__ unsigned short s_qmask[QUEUE_CAP];
+    __shared__ unsigned s_wcount[NW];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned tile = (p.world > 1) ? (p.rank + blockIdx.x * p.world) : blockIdx.x;
+    /* a CTA handles a 64 x TH slice of a 64x64 tile (TH = 32 halves the work quantum when the grid would
+       otherwise be only a few waves deep); ownership for the multi-GPU split stays per 64x64 tile */
+    constexpr int SUB = TILE / TH;
+    const unsigned tile = (p.world > 1) ? (p.rank + (blockIdx.x / SUB) * p.world) : (blockIdx.x / SUB);
     if (tile >= p.nTiles) return;
     const int tx = tile % p.tilesX, ty = tile / p.tilesX;
     TileCtx t;
-    t.X0 = tx * TILE; t.Y0 = ty * TILE;
-    t.X1 = min(t.X0 + TILE, p.W) - 1; t.Y1 = min(t.Y0 + TILE, p.H) - 1;
+    t.X0 = tx * TILE; t.Y0 = ty * TILE + (int)(blockIdx.x % SUB) * TH;
+    if (t.Y0 >= p.H) return;
+    t.X1 = min(t.X0 + TILE, p.W) - 1; t.Y1 = min(t.Y0 + TH, p.H) - 1;
     const int X0 = t.X0, Y0 = t.Y0, X1 = t.X1, Y1 = t.Y1;
-    const bool full_tile = (X0 + TILE <= p.W) && (Y0 + TILE <= p.H) && ((p.W & 3) == 0);
+    const bool full_tile = (X0 + TILE <= p.W) && (Y0 + TH <= p.H) && ((p.W & 3) == 0);
 
     const int bin = (ty / BIN_TILES) * p.binsX + (tx / BIN_TILES);
     const unsigned lbeg = p.bin_starts[bin], lend = p.bin_starts[bin + 1];
@@ -947,7 +958,7 @@ k_raster(const RasterParams p)
     /* RCPPS table: shared copy when it has <= 2^11 entries (every CPU we met), else the global one */
     t.rcp_shift = c_rcp_shift;
     t.rcp_shared = t.rcp_shift >= 23 - RCP_SMEM_BITS;
-    if (t.rcp_shared) for (int k = tid; k < (1 << (23 - t.rcp_shift)); k += RASTER_THREADS) s_rcp[k] = c_rcp_tab[k];
+    if (t.rcp_shared) for (int k = tid; k < (1 << (23 - t.rcp_shift)); k += NT) s_rcp[k] = c_rcp_tab[k];
     {   /* one opaque register holds the shared-window address; offsets are immediates in the ld/st */
         unsigned base = (unsigned)__cvta_generic_to_shared(s_mem);
         asm volatile("mov.u32 %0, %1;" : "=r"(t.sm_base) : "r"(base));
@@ -960,7 +971,7 @@ k_raster(const RasterParams p)
     for (unsigned base = lbeg; base < lend; ) {
         /* ---- fill the queue: ordered compaction of the bin list against this tile ---- */
         unsigned qn = 0;
-        while (base < lend && qn + RASTER_THREADS <= QUEUE_CAP) {
+        while (base < lend && qn + NT <= QUEUE_CAP) {
             const unsigned k = base + tid;
             bool hit = false; unsigned ti = 0, wmask = 0;
             if (k < lend) {
@@ -978,16 +989,14 @@ k_raster(const RasterParams p)
                         const int m3 = s.w3R + (s.w3X > 0 ? ax1 : ax0) * s.w3X + (s.w3Y > 0 ? ay1 : ay0) * s.w3Y;
                         if ((m1 | m2 | m3) < 0) hit = false;
                     }
-                    /* which warps own an 8x4 block inside the clipped bbox?  warp = (bx + 3*by) & 7 */
+                    /* which warps own an 8x4 block inside the clipped bbox?  (see shade_tri) */
                     const int bx0 = (rx0 - X0) >> 3, nbx = ((rx1 - X0) >> 3) - bx0 + 1;
                     const int by0 = (ry0 - Y0) >> 2, nby = ((ry1 - Y0) >> 2) - by0 + 1;
-                    if (nbx >= 8) wmask = 0xffu;
-                    else {
-                        const unsigned run = (1u << nbx) - 1u;
-                        for (int j = 0; j < min(nby, 8); j++) {
-                            const int sh = (bx0 + 3 * (by0 + j)) & 7;
-                            wmask |= ((run << sh) | (run >> (8 - sh))) & 0xffu;
-                        }
+                    const unsigned run = nbx >= 8 ? 0xffu : ((1u << nbx) - 1u);
+                    for (int j = 0; j < min(nby, 8); j++) {
+                        const int sh = (bx0 + 3 * (by0 + j)) & 7;
+                        const unsigned bits = ((run << sh) | (run >> (8 - sh))) & 0xffu;
+                        wmask |= (NW == 16 && ((by0 + j) & 1)) ? (bits << 8) : bits;
                     }
                 }
             }
@@ -996,15 +1005,15 @@ k_raster(const RasterParams p)
             __syncthreads();
             unsigned woff = 0, total = 0;
 #pragma unroll
-            for (int w = 0; w < 8; w++) { const unsigned c = s_wcount[w]; if (w < warp) woff += c; total += c; }
+            for (int w = 0; w < NW; w++) { const unsigned c = s_wcount[w]; if (w < warp) woff += c; total += c; }
             if (hit) {
-                const unsigned pos = qn + woff + __popc(bal & ((1u << lane) - 1u)); s_queue[pos] = ti; s_qmask[pos] = (unsigned char)wmask;
+                const unsigned pos = qn + woff + __popc(bal & ((1u << lane) - 1u)); s_queue[pos] = ti; s_qmask[pos] = (unsigned short)wmask;
                 /* pull the triangle's attribute block towards L1 now: the warps that shade it later would
                    otherwise each pay a dependent L2 round trip per queue entry */
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(p.data + ti));
             }
             qn += total;
-            base += RASTER_THREADS;
+            base += NT;
             __syncthreads();
         }
         if (qn == 0) continue;
@@ -1013,7 +1022,7 @@ k_raster(const RasterParams p)
         if (!loaded) {
             loaded = true;
             if (full_tile) {
-                for (int r = tid >> 4; r < TILE; r += RASTER_THREADS / 16) {
+                for (int r = tid >> 4; r < TH; r += NT / 16) {
                     const int c4 = (tid & 15) << 2;
                     const size_t gi = (size_t)(Y0 + r) * p.W + X0 + c4;
                     const uint4 cv = __ldcs(reinterpret_cast<const uint4 *>(p.color + gi));
@@ -1023,7 +1032,7 @@ k_raster(const RasterParams p)
                     *reinterpret_cast<float4 *>(s_depth + sa) = dv;
                 }
             } else {
-                for (int k = tid; k < TILE_PIX; k += RASTER_THREADS) {
+                for (int k = tid; k < TILE * TH; k += NT) {
                     const int lx = k & (TILE - 1), ly = k >> 6;
                     if (X0 + lx <= X1 && Y0 + ly <= Y1) {
                         const size_t gi = (size_t)(Y0 + ly) * p.W + X0 + lx;
@@ -1072,20 +1081,24 @@ k_raster(const RasterParams p)
                     prog = texm * 4 + blendm;
                     if (HAS_PHONG && (flags & PFCU_ST_PHONG)) prog = 12;
                 }
+                if (FIXED_PROG >= 0) {
+                    shade_tri<FIXED_PROG / 4, FIXED_PROG % 4, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex);
+                    continue;
+                }
                 switch (prog) {
-                case 0:  shade_tri<0, 0, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 1:  shade_tri<0, 1, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 2:  shade_tri<0, 2, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 3:  shade_tri<0, 3, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 4:  shade_tri<1, 0, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 5:  shade_tri<1, 1, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 6:  shade_tri<1, 2, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 7:  shade_tri<1, 3, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 8:  shade_tri<2, 0, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 9:  shade_tri<2, 1, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 10: shade_tri<2, 2, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 11: shade_tri<2, 3, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                default: if (HAS_PHONG) shade_tri<2, 3, true>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 0:  shade_tri<0, 0, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 1:  shade_tri<0, 1, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 2:  shade_tri<0, 2, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 3:  shade_tri<0, 3, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 4:  shade_tri<1, 0, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 5:  shade_tri<1, 1, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 6:  shade_tri<1, 2, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 7:  shade_tri<1, 3, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 8:  shade_tri<2, 0, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 9:  shade_tri<2, 1, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 10: shade_tri<2, 2, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 11: shade_tri<2, 3, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                default: if (HAS_PHONG) shade_tri<2, 3, true, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
                 }
             }
         }
@@ -1095,7 +1108,7 @@ k_raster(const RasterParams p)
     /* ---- write the tile back ---- */
     if (loaded) {
         if (full_tile) {
-            for (int r = tid >> 4; r < TILE; r += RASTER_THREADS / 16) {
+            for (int r = tid >> 4; r < TH; r += NT / 16) {
                 const int c4 = (tid & 15) << 2;
                 const size_t gi = (size_t)(Y0 + r) * p.W + X0 + c4;
                 const int sa = tile_addr(c4, r);
@@ -1103,7 +1116,7 @@ k_raster(const RasterParams p)
                 __stcs(reinterpret_cast<float4 *>(p.depth + gi), *reinterpret_cast<const float4 *>(s_depth + sa));
             }
         } else {
-            for (int k = tid; k < TILE_PIX; k += RASTER_THREADS) {
+            for (int k = tid; k < TILE * TH; k += NT) {
                 const int lx = k & (TILE - 1), ly = k >> 6;
                 if (X0 + lx <= X1 && Y0 + ly <= Y1) {
                     const size_t gi = (size_t)(Y0 + ly) * p.W + X0 + lx;
@@ -1593,6 +1606,18 @@ void pfcu_texture_destroy(pfcu_texture *t)
 
 /* ---- the hot path ---- */
 
+/* state program of a DevState, same numbering as k_raster's per-triangle dispatch */
+static int state_program(const DevState *d)
+{
+    if (d->flags & PFCU_ST_PHONG) return 12;
+    int texm = 0;
+    if (d->flags & PFCU_ST_TEXTURE) texm = (d->tfmt == PFCU_TEX_RGBA8 && d->tex_wrap == 0 && d->tex_filter == 0) ? 1 : 2;
+    const int blendm = !(d->flags & PFCU_ST_BLEND) ? 0 : (d->blend_mode == 1 ? 1 : (d->blend_mode == 2 ? 2 : 3));
+    return texm * 4 + blendm;
+}
+
+static int g_last_single_prog = -1;      /* set by convert_states: the common program of all states, or -1 */
+
 static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
 {
     unsigned mask = 0;
@@ -1620,11 +1645,13 @@ static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
         }
         memcpy(d->view_pos, s->view_pos, 12);
         mask |= d->flags;
+        const int prog = state_program(d);
+        if (i == 0) g_last_single_prog = prog; else if (g_last_single_prog != prog) g_last_single_prog = -1;
     }
     return mask;
 }
 
-static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const DevState *d_states, uint32_t n, unsigned feature_mask)
+static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const DevState *d_states, uint32_t n, unsigned feature_mask, int single_prog = -1)
 {
     if (n == 0) return PFCU_OK;
     if (!g.d_rcp) { snprintf(g.err, sizeof g.err, "pfcu_set_approx_tables() has not been called"); return PFCU_ERR_INVALID; }
@@ -1683,8 +1710,19 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     const unsigned grid = owned_tiles(s, p.rank, p.world);
     if (g.profiling) CK(cudaEventRecord(pe[1], g.stream));
     if (grid) {
-        if (feature_mask & PFCU_ST_PHONG) k_raster<true><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
-        else                              k_raster<false><<<grid, RASTER_THREADS, 0, g.stream>>>(p);
+        /* many small triangles per tile: 16 warps per tile halve the serial work of the busiest tiles;
+           few large ones: 8 warps with more registers each issue faster */
+        const bool small_tris = (size_t)n > (size_t)4 * p.nTiles;
+        const bool ph = (feature_mask & PFCU_ST_PHONG) != 0;
+        /* half-height slices when the 64x64 grid would be only a few waves deep with a ragged last wave */
+        const int per_sm = (single_prog == 5 || single_prog == 6) ? 4 : 3;
+        const double waves = (double)grid / ((double)g.sms * per_sm);
+        const bool half = !small_tris && !ph && waves < 8.0 && (ceil(waves) / waves) > 1.06 && (ceil(2 * waves) / (2 * waves)) < (ceil(waves) / waves);
+        if (small_tris) { if (ph) k_raster<true, 16, -1, 64><<<grid, 512, 0, g.stream>>>(p); else k_raster<false, 16, -1, 64><<<grid, 512, 0, g.stream>>>(p); }
+        else if (ph)          k_raster<true, 8, -1, 64><<<grid, 256, 0, g.stream>>>(p);
+        else if (single_prog == 5) { if (half) k_raster<false, 8, 5, 32><<<grid * 2, 256, 0, g.stream>>>(p); else k_raster<false, 8, 5, 64><<<grid, 256, 0, g.stream>>>(p); }   /* nearest REPEAT RGBA8 texture + ALPHA blend */
+        else if (single_prog == 6) { if (half) k_raster<false, 8, 6, 32><<<grid * 2, 256, 0, g.stream>>>(p); else k_raster<false, 8, 6, 64><<<grid, 256, 0, g.stream>>>(p); }   /* nearest REPEAT RGBA8 texture + ADD blend   */
+        else { if (half) k_raster<false, 8, -1, 32><<<grid * 2, 256, 0, g.stream>>>(p); else k_raster<false, 8, -1, 64><<<grid, 256, 0, g.stream>>>(p); }
         g.launches++;
     }
     if (g.profiling) { CK(cudaEventRecord(pe[2], g.stream)); for (int i = 0; i < 3; i++) g.prof_events.push_back(pe[i]); }
@@ -1764,7 +1802,7 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     k_vertex_emit<<<(n_items + 127u) / 128u, 128, 0, g.stream>>>(a, *vp, n_items, d_offsets, g.d_tris);
     g.launches++;
     CK(cudaGetLastError());
-    return launch_pipeline(s, g.d_tris, g.d_states, total, mask);
+    return launch_pipeline(s, g.d_tris, g.d_states, total, mask, g_last_single_prog);
 }
 
 int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, const pfcu_triangle *tris, uint32_t n_tris)
@@ -1808,7 +1846,7 @@ int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, co
         CK(cudaMemcpyAsync(g.d_tris, g.h_stage, bytes, cudaMemcpyHostToDevice, g.stream));
         CK(cudaEventRecord(g.stage_done, g.stream));
     }
-    return launch_pipeline(s, g.d_tris, g.d_states, n_tris, mask);
+    return launch_pipeline(s, g.d_tris, g.d_states, n_tris, mask, g_last_single_prog);
 }
 
 pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const pfcu_triangle *tris, uint32_t n_tris)
@@ -1818,6 +1856,7 @@ pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const
     if (!b) return nullptr;
     std::vector<DevState> tmp(n_states);
     b->feature_mask = convert_states(states, n_states, tmp.data());
+    b->single_prog = g_last_single_prog;
     b->n_states = n_states; b->n_tris = n_tris;
     CKP(cudaMalloc(&b->states, n_states * sizeof(DevState)));
     CKP(cudaMalloc(&b->tris, (size_t)n_tris * sizeof(pfcu_triangle)));
@@ -1831,7 +1870,7 @@ int pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b)
 {
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || !b) return PFCU_ERR_INVALID;
-    return launch_pipeline(s, b->tris, b->states, b->n_tris, b->feature_mask);
+    return launch_pipeline(s, b->tris, b->states, b->n_tris, b->feature_mask, b->single_prog);
 }
 
 void pfcu_batch_destroy(pfcu_batch *b)

@@ -230,7 +230,9 @@ def measure_workload(wl_name, steps, warmup, torch, scenes, pfcu, stream, flush_
             for i in range(steps):
                 flush_buf.fill_(i & 0xFF)          # L2 flush: write a buffer larger than L2 (untimed)
                 ev[i][0].record(stream)
+                L.pfcu_fence()                      # surfaces may live on other internal streams (lanes)
                 step()
+                L.pfcu_fence()
                 ev[i][1].record(stream)
         stream.synchronize()
         dev_ms = sum(a.elapsed_time(b) for a, b in ev) / steps

@@ -141,6 +141,10 @@ PFCU_API void *pfcu_get_stream(void);
 PFCU_API void *pfcu_host_alloc(size_t bytes);
 PFCU_API void  pfcu_host_free(void *p);
 PFCU_API int   pfcu_host_wait(const void *p);
+/* Page-lock caller-owned memory in place (the application's target buffer) so that surface downloads are
+ * direct DMA instead of staged copies.  Best effort: returns non-zero when the range cannot be pinned. */
+PFCU_API int   pfcu_host_register(void *p, size_t bytes);
+PFCU_API void  pfcu_host_unregister(void *p);
 
 /* Tables that reproduce the host's RCPPS / RSQRTPS (reference: src/internal/simd.h:1217-1245).
  * rcp[i], i = top `rcp_bits` mantissa bits: float bits of rcp(1.m);  rsqrt[(odd<<rsqrt_bits)|i]:
@@ -236,6 +240,11 @@ typedef struct {
 PFCU_API void pfcu_profile_enable(int on);
 PFCU_API int  pfcu_profile_read(pfcu_profile *out);    /* implies pfcu_finish(); resets the sums      */
 
+/* Work on different surfaces may run on different internal streams ("lanes", $PF_CUDA_LANES, default 4) so
+ * that independent contexts overlap.  pfcu_fence() orders everything enqueued so far, on every lane, before
+ * everything enqueued later, without blocking the host; callers that time multi-surface work with events
+ * on pfcu_get_stream() call it after recording the start event and before recording the end event. */
+PFCU_API int  pfcu_fence(void);
 PFCU_API int  pfcu_finish(void);                       /* wait for everything queued so far          */
 PFCU_API int  pfcu_get_counters(pfcu_counters *out);   /* implies pfcu_finish()                      */
 PFCU_API void pfcu_reset_counters(void);

@@ -459,6 +459,8 @@ void *pfcu_get_stream(void) { return NULL; }
 void *pfcu_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void  pfcu_host_free(void *p) { free(p); }
 int   pfcu_host_wait(const void *p) { (void)p; return PFCU_OK; }
+int   pfcu_host_register(void *p, size_t bytes) { (void)p; (void)bytes; return PFCU_OK; }
+void  pfcu_host_unregister(void *p) { (void)p; }
 int  pfcu_set_approx_tables(const uint32_t *rcp, int rb, const uint32_t *rs, int sb)
 { (void)rcp; (void)rb; (void)rs; (void)sb; return PFCU_OK; }   /* native RCPSS/RSQRTSS are used */
 
@@ -603,6 +605,7 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *st, const pfcu_vparam
 { (void)s; (void)st; (void)vp; (void)d; (void)n; return PFCU_ERR_INVALID; }
 void pfcu_profile_enable(int on) { (void)on; }
 int  pfcu_profile_read(pfcu_profile *out) { memset(out, 0, sizeof *out); return PFCU_OK; }
+int  pfcu_fence(void) { return PFCU_OK; }
 int  pfcu_finish(void) { return PFCU_OK; }
 int  pfcu_get_counters(pfcu_counters *out) { *out = g_cnt; return PFCU_OK; }
 void pfcu_reset_counters(void) { memset(&g_cnt, 0, sizeof g_cnt); }

@@ -163,14 +163,14 @@ class Counters(C.Structure):
 
 PFCU_SYMBOLS = [
     "pfcu_init", "pfcu_shutdown", "pfcu_last_error", "pfcu_backend_name", "pfcu_set_stream", "pfcu_get_stream",
-    "pfcu_host_alloc", "pfcu_host_free", "pfcu_host_wait", "pfcu_set_approx_tables",
+    "pfcu_host_alloc", "pfcu_host_free", "pfcu_host_wait", "pfcu_host_register", "pfcu_host_unregister", "pfcu_set_approx_tables",
     "pfcu_surface_create", "pfcu_surface_wrap", "pfcu_surface_destroy", "pfcu_surface_width", "pfcu_surface_height",
     "pfcu_surface_color_ptr", "pfcu_surface_depth_ptr", "pfcu_surface_upload", "pfcu_surface_download",
     "pfcu_surface_fill", "pfcu_surface_clear_ref", "pfcu_surface_set_tile_owner", "pfcu_surface_owned_bytes",
     "pfcu_surface_pack_tiles", "pfcu_surface_unpack_tiles",
     "pfcu_texture_create", "pfcu_texture_from_surface", "pfcu_texture_update", "pfcu_texture_destroy",
     "pfcu_submit", "pfcu_batch_upload", "pfcu_batch_submit", "pfcu_batch_destroy",
-    "pfcu_finish", "pfcu_get_counters", "pfcu_reset_counters", "pfcu_profile_enable", "pfcu_profile_read",
+    "pfcu_fence", "pfcu_finish", "pfcu_get_counters", "pfcu_reset_counters", "pfcu_profile_enable", "pfcu_profile_read",
 ]
 
 PFX_SYMBOLS = ["pfxSetSyncMode", "pfxFlush", "pfxFinish", "pfxGetCounters", "pfxResetCounters", "pfxSetTileOwner",
@@ -207,7 +207,7 @@ class PfcuLib:
             "pfcu_texture_update": (C.c_int, [vp, vp]), "pfcu_texture_destroy": (None, [vp]),
             "pfcu_submit": (C.c_int, [vp, vp, u32, vp, u32]), "pfcu_batch_upload": (vp, [vp, u32, vp, u32]),
             "pfcu_batch_submit": (C.c_int, [vp, vp]), "pfcu_batch_destroy": (None, [vp]),
-            "pfcu_finish": (C.c_int, []), "pfcu_get_counters": (C.c_int, [C.POINTER(Counters)]),
+            "pfcu_fence": (C.c_int, []), "pfcu_finish": (C.c_int, []), "pfcu_get_counters": (C.c_int, [C.POINTER(Counters)]),
             "pfcu_reset_counters": (None, []),
             "pfcu_profile_enable": (None, [C.c_int]), "pfcu_profile_read": (C.c_int, [C.POINTER(Profile)]),
             # pfx extensions of the front end (operate on the calling thread's current context)

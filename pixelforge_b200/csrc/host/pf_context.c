@@ -106,6 +106,7 @@ void pfSetMainBuffer(void *targetBuffer, PFsizei width, PFsizei height, PFpixelf
     pf_tex *old = (pf_tex *)c->mainFramebuffer.texture;
     pfh_sync_surface(c, c->main_surf);
     if (old->w == width && old->h == height && old->format == format && old->type == type) {
+        if (c->main_surf->pinned_color) { pfcu_host_unregister(c->main_surf->pinned_color); c->main_surf->pinned_color = NULL; }
         old->pixels = targetBuffer;             /* same geometry: retarget the host mirror, keep depth */
         c->main_surf->host_newer = 1;
         pfcu_surface_upload(c->main_surf->dev, targetBuffer, NULL, 0, height);
@@ -136,6 +137,7 @@ void pfSwapBuffers(void)
     if (!c->auxFramebuffer) { c->errCode = PF_INVALID_OPERATION; return; }
     pf_surf *s = c->cur_surf;
     pfh_sync_surface(c, s);                 /* finished frame -> old front buffer */
+    if (s->pinned_color) { pfcu_host_unregister(s->pinned_color); s->pinned_color = NULL; }
     void *tmp = s->tex->pixels;
     s->tex->pixels = c->auxFramebuffer;
     c->auxFramebuffer = tmp;

@@ -51,6 +51,8 @@ typedef struct pf_surf {
     int           dev_newer;        /* device modified since the last download                       */
     PFuint        dirty_y0, dirty_y1; /* rows [y0, y1) touched on the device since last download     */
     pfcu_texture *as_texture;       /* alias used when the colour buffer is sampled                  */
+    void         *pinned_color;     /* host mirror ranges page-locked in place (NULL: not pinned)    */
+    void         *pinned_depth;
     struct pf_surf *next;           /* registry link (lookup from a PFframebuffer copy)              */
 } pf_surf;
 

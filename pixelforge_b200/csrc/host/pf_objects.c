@@ -119,6 +119,15 @@ pf_surf *pfh_surf_create(pf_tex *tex, PFfloat *zhost, int z_public)
     /* device depth starts at FLT_MAX (context.c:136-138, framebuffer.c:57-59); colour = host content */
     pfcu_surface_fill(s->dev, 0, 0, 1, FLT_MAX);
     if (tex->pixels) pfcu_surface_upload(s->dev, tex->pixels, NULL, 0, tex->h);
+    /* large mirrors: pin in place so that read-backs are direct DMA (PF_CUDA_PIN_HOST=0 disables) */
+    {
+        const char *e = getenv("PF_CUDA_PIN_HOST");
+        const size_t bytes = (size_t)tex->w * tex->h * 4;
+        if (!(e && e[0] == '0') && bytes >= ((size_t)1 << 20)) {
+            if (tex->pixels && pfcu_host_register(tex->pixels, bytes) == PFCU_OK) s->pinned_color = tex->pixels;
+            if (zhost && pfcu_host_register(zhost, bytes) == PFCU_OK) s->pinned_depth = zhost;
+        }
+    }
     s->next = g_surfs; g_surfs = s;
     return s;
 }
@@ -128,6 +137,8 @@ void pfh_surf_destroy(pf_surf *s)
     if (!s) return;
     for (pf_surf **p = &g_surfs; *p; p = &(*p)->next) if (*p == s) { *p = s->next; break; }
     pfcu_finish();
+    if (s->pinned_color) pfcu_host_unregister(s->pinned_color);
+    if (s->pinned_depth) pfcu_host_unregister(s->pinned_depth);
     if (s->as_texture) pfcu_texture_destroy(s->as_texture);
     pfcu_surface_destroy(s->dev);
     if (s->tex) s->tex->surf = NULL;

@@ -80,10 +80,12 @@ struct __align__(16) DevState {
 struct pfcu_surface {
     uint32_t w, h; uint32_t *color; float *depth; bool owned;
     uint32_t rank, world; uint32_t tiles_x, tiles_y;
+    int lane; cudaEvent_t done; bool has_done;      /* last work enqueued on this surface */
 };
 struct pfcu_texture { uint32_t w, h; int fmt; unsigned char *pixels; bool owned; pfcu_surface *alias; };
 struct pfcu_batch {
     DevState *states; uint32_t n_states; pfcu_triangle *tris; uint32_t n_tris; unsigned feature_mask; int single_prog;
+    std::vector<pfcu_surface *> deps;
 };
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -92,33 +94,45 @@ struct pfcu_batch {
 
 struct PinnedBlock { void *p; size_t bytes; cudaEvent_t done; bool pending; };
 
-struct Runtime {
-    bool ok = false; int device = 0; int sms = 148;
+/* A lane = one CUDA stream plus the scratch buffers of the batches in flight on it.  Surfaces are spread
+ * round-robin over the lanes so that independent contexts (BASELINE config C5) overlap on the GPU; work on
+ * one surface always stays on its lane, which keeps it ordered. */
+struct Lane {
     cudaStream_t stream = nullptr; bool own_stream = false;
-    /* growable device scratch, reused batch after batch (single stream => no hazards) */
     pfcu_triangle *d_tris = nullptr; size_t cap_tris = 0;
     DevState *d_states = nullptr; size_t cap_states = 0;
     int4 *d_bbox = nullptr; TriSetup *d_setup = nullptr; TriData *d_data = nullptr; size_t cap_setup = 0;
-    unsigned *d_bin_counts = nullptr; size_t cap_bin_counts = 0;     /* [batches+1][bins] */
+    unsigned *d_bin_counts = nullptr; size_t cap_bin_counts = 0;     /* [batches][bins] */
     unsigned *d_bin_list = nullptr; size_t cap_bin_list = 0;
-    unsigned *d_bin_start = nullptr;                                  /* [MAX_BINS+1] */
+    unsigned *d_bin_start = nullptr;                                  /* [MAX_BINS+2] starts, then totals */
     unsigned char *d_varrays = nullptr; size_t cap_varrays = 0;        /* vertex arrays of the current draw */
     unsigned *d_vcounts = nullptr; size_t cap_vcounts = 0;
-    unsigned long long *d_counters = nullptr;                         /* rasterised, shaded, depth-failed */
-    uint32_t *d_rcp = nullptr, *d_rsq = nullptr; int rcp_bits = 0, rsq_bits = 0;
     /* pinned staging for pageable sources */
     void *h_stage = nullptr; size_t cap_stage = 0; cudaEvent_t stage_done = nullptr;
     DevState *h_states = nullptr; size_t cap_hstates = 0; cudaEvent_t states_done = nullptr;
+    cudaEvent_t fence = nullptr;
+};
+
+#define MAX_LANES 8
+
+struct Runtime {
+    bool ok = false; int device = 0; int sms = 148;
+    Lane lanes[MAX_LANES]; int n_lanes = 1; unsigned next_lane = 0;
+    Lane *cur = nullptr;                                              /* lane of the surface being worked on */
+    unsigned long long *d_counters = nullptr;                         /* rasterised, shaded, depth-failed */
+    uint32_t *d_rcp = nullptr, *d_rsq = nullptr; int rcp_bits = 0, rsq_bits = 0;
     std::vector<PinnedBlock> pinned;
     uint64_t submitted = 0, launches = 0, bytes_h2d = 0, bytes_d2h = 0;
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;       /* triples: before setup, before raster, after raster */
     std::vector<cudaEvent_t> prof_pool;
+    std::vector<pfcu_surface *> deps;           /* surfaces sampled as textures by the states being submitted */
     std::mutex mu;
     char err[512] = { 0 };
 };
 
 static Runtime g;
+#define LN (*g.cur)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     snprintf(g.err, sizeof g.err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
@@ -1298,7 +1312,7 @@ template <typename T> static int grow(T **p, size_t *cap, size_t need)
     if (need <= *cap) return PFCU_OK;
     size_t ncap = *cap ? *cap : 1024;
     while (ncap < need) ncap *= 2;
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaStreamSynchronize(LN.stream));
     cudaFree(*p); *p = nullptr; *cap = 0;
     if (cudaMalloc(p, ncap * sizeof(T)) != cudaSuccess) { snprintf(g.err, sizeof g.err, "out of device memory growing scratch to %zu elements", ncap); return PFCU_ERR_OOM; }
     *cap = ncap;
@@ -1336,45 +1350,74 @@ int pfcu_init(int device)
         snprintf(g.err, sizeof g.err, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         return PFCU_ERR_NO_DEVICE;
     }
-    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    g.own_stream = true;
+    {
+        const char *env = getenv("PF_CUDA_LANES");
+        g.n_lanes = env ? atoi(env) : 4;
+        if (g.n_lanes < 1) g.n_lanes = 1;
+        if (g.n_lanes > MAX_LANES) g.n_lanes = MAX_LANES;
+    }
+    for (int i = 0; i < g.n_lanes; i++) {
+        g.cur = &g.lanes[i];
+        CK(cudaStreamCreateWithFlags(&LN.stream, cudaStreamNonBlocking));
+        LN.own_stream = true;
+        CK(cudaMalloc(&LN.d_bin_start, (MAX_BINS + 2) * 2 * sizeof(unsigned)));
+        CK(cudaEventCreateWithFlags(&LN.stage_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&LN.states_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&LN.fence, cudaEventDisableTiming));
+    }
+    g.cur = &g.lanes[0];
     CK(cudaMalloc(&g.d_counters, 4 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(g.d_counters, 0, 4 * sizeof(unsigned long long), g.stream));
-    CK(cudaMalloc(&g.d_bin_start, (MAX_BINS + 2) * 2 * sizeof(unsigned)));
-    CK(cudaEventCreateWithFlags(&g.stage_done, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&g.states_done, cudaEventDisableTiming));
+    CK(cudaMemset(g.d_counters, 0, 4 * sizeof(unsigned long long)));
     g.ok = true;
     return PFCU_OK;
 }
 
+static void sync_all_lanes(void) { for (int i = 0; i < g.n_lanes; i++) cudaStreamSynchronize(g.lanes[i].stream); }
+static void use_lane(const pfcu_surface *s) { g.cur = &g.lanes[s ? s->lane % g.n_lanes : 0]; }
+
 void pfcu_shutdown(void)
 {
     if (!g.ok) return;
-    cudaStreamSynchronize(g.stream);
-    cudaFree(g.d_tris); cudaFree(g.d_states); cudaFree(g.d_bbox); cudaFree(g.d_setup); cudaFree(g.d_data);
-    cudaFree(g.d_bin_counts); cudaFree(g.d_bin_list); cudaFree(g.d_bin_start); cudaFree(g.d_counters);
-    cudaFree(g.d_rcp); cudaFree(g.d_rsq);
-    if (g.h_stage) cudaFreeHost(g.h_stage);
-    if (g.h_states) cudaFreeHost(g.h_states);
-    if (g.own_stream) cudaStreamDestroy(g.stream);
-    g.ok = false; g.stream = nullptr; g.own_stream = false;
-    g.d_tris = nullptr; g.cap_tris = 0; g.d_states = nullptr; g.cap_states = 0;
-    g.d_bbox = nullptr; g.d_setup = nullptr; g.d_data = nullptr; g.cap_setup = 0;
-    g.d_bin_counts = nullptr; g.cap_bin_counts = 0; g.d_bin_list = nullptr; g.cap_bin_list = 0;
-    g.d_bin_start = nullptr; g.d_counters = nullptr; g.d_rcp = nullptr; g.d_rsq = nullptr;
-    g.h_stage = nullptr; g.cap_stage = 0; g.h_states = nullptr; g.cap_hstates = 0; g.pinned.clear();
+    sync_all_lanes();
+    for (int i = 0; i < g.n_lanes; i++) {
+        g.cur = &g.lanes[i];
+        cudaFree(LN.d_tris); cudaFree(LN.d_states); cudaFree(LN.d_bbox); cudaFree(LN.d_setup); cudaFree(LN.d_data);
+        cudaFree(LN.d_bin_counts); cudaFree(LN.d_bin_list); cudaFree(LN.d_bin_start); cudaFree(LN.d_varrays); cudaFree(LN.d_vcounts);
+        if (LN.h_stage) cudaFreeHost(LN.h_stage);
+        if (LN.h_states) cudaFreeHost(LN.h_states);
+        if (LN.own_stream) cudaStreamDestroy(LN.stream);
+        g.lanes[i] = Lane();
+    }
+    cudaFree(g.d_counters); cudaFree(g.d_rcp); cudaFree(g.d_rsq);
+    g.d_counters = nullptr; g.d_rcp = nullptr; g.d_rsq = nullptr;
+    g.pinned.clear(); g.cur = nullptr; g.ok = false;
+}
+
+/* Order everything enqueued so far on every lane before everything enqueued afterwards on every lane, without
+ * blocking the host: used by callers that bracket multi-surface work with events on lane 0's stream. */
+int pfcu_fence(void)
+{
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    for (int i = 1; i < g.n_lanes; i++) {
+        CK(cudaEventRecord(g.lanes[i].fence, g.lanes[i].stream));
+        CK(cudaStreamWaitEvent(g.lanes[0].stream, g.lanes[i].fence, 0));
+    }
+    CK(cudaEventRecord(g.lanes[0].fence, g.lanes[0].stream));
+    for (int i = 1; i < g.n_lanes; i++) CK(cudaStreamWaitEvent(g.lanes[i].stream, g.lanes[0].fence, 0));
+    return PFCU_OK;
 }
 
 int pfcu_set_stream(void *cuda_stream)
 {
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
-    CK(cudaStreamSynchronize(g.stream));
-    if (g.own_stream) { cudaStreamDestroy(g.stream); g.own_stream = false; }
-    g.stream = (cudaStream_t)cuda_stream;
+    sync_all_lanes();
+    Lane &l0 = g.lanes[0];
+    if (l0.own_stream) { cudaStreamDestroy(l0.stream); l0.own_stream = false; }
+    l0.stream = (cudaStream_t)cuda_stream;       /* lane 0 adopts the caller's stream; see pfcu_fence() */
     return PFCU_OK;
 }
 
-void *pfcu_get_stream(void) { return (void *)g.stream; }
+void *pfcu_get_stream(void) { return g.ok ? (void *)g.lanes[0].stream : nullptr; }
 
 void *pfcu_host_alloc(size_t bytes)
 {
@@ -1404,6 +1447,22 @@ void pfcu_host_free(void *p)
     }
 }
 
+int pfcu_host_register(void *p, size_t bytes)
+{
+    if (!g.ok || !p || bytes == 0) return PFCU_ERR_INVALID;
+    /* page-aligned sub-range; the partial first/last pages stay pageable (cudaMemcpy handles mixed ranges) */
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return PFCU_ERR_CUDA; }
+    return PFCU_OK;
+}
+
+void pfcu_host_unregister(void *p)
+{
+    if (!g.ok || !p) return;
+    sync_all_lanes();
+    if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+}
+
 int pfcu_host_wait(const void *p)
 {
     PinnedBlock *b = find_pinned(p);
@@ -1415,7 +1474,7 @@ int pfcu_set_approx_tables(const uint32_t *rcp, int rcp_bits, const uint32_t *rs
 {
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     if (rcp_bits < 1 || rcp_bits > 23 || rsqrt_bits < 1 || rsqrt_bits > 23) return PFCU_ERR_INVALID;
-    CK(cudaStreamSynchronize(g.stream));
+    sync_all_lanes();
     cudaFree(g.d_rcp); cudaFree(g.d_rsq);
     CK(cudaMalloc(&g.d_rcp, sizeof(uint32_t) << rcp_bits));
     CK(cudaMalloc(&g.d_rsq, sizeof(uint32_t) << (rsqrt_bits + 1)));
@@ -1441,14 +1500,17 @@ pfcu_surface *pfcu_surface_create(uint32_t w, uint32_t h)
     pfcu_surface *s = (pfcu_surface *)calloc(1, sizeof *s);
     if (!s) return nullptr;
     s->w = w; s->h = h; s->owned = true; s->world = 1;
+    s->lane = (int)(g.next_lane++ % (unsigned)g.n_lanes);
+    cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
+    use_lane(s);
     surface_dims(s);
     const size_t bytes = ((size_t)w * h + 64) * 4;
     if (cudaMalloc(&s->color, bytes) != cudaSuccess || cudaMalloc(&s->depth, bytes) != cudaSuccess) {
         snprintf(g.err, sizeof g.err, "surface_create: out of device memory (%ux%u)", w, h);
         cudaFree(s->color); free(s); return nullptr;
     }
-    cudaMemsetAsync(s->color, 0, bytes, g.stream);
-    cudaMemsetAsync(s->depth, 0, bytes, g.stream);
+    cudaMemsetAsync(s->color, 0, bytes, LN.stream);
+    cudaMemsetAsync(s->depth, 0, bytes, LN.stream);
     return s;
 }
 
@@ -1458,6 +1520,8 @@ pfcu_surface *pfcu_surface_wrap(void *dev_color, void *dev_depth, uint32_t w, ui
     pfcu_surface *s = (pfcu_surface *)calloc(1, sizeof *s);
     if (!s) return nullptr;
     s->w = w; s->h = h; s->color = (uint32_t *)dev_color; s->depth = (float *)dev_depth; s->owned = false; s->world = 1;
+    s->lane = 0;                                  /* caller-owned memory: stay on the caller-visible stream */
+    cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
     surface_dims(s);
     return s;
 }
@@ -1465,8 +1529,9 @@ pfcu_surface *pfcu_surface_wrap(void *dev_color, void *dev_depth, uint32_t w, ui
 void pfcu_surface_destroy(pfcu_surface *s)
 {
     if (!s) return;
-    if (g.ok) cudaStreamSynchronize(g.stream);
+    if (g.ok) sync_all_lanes();
     if (s->owned) { cudaFree(s->color); cudaFree(s->depth); }
+    if (s->done) cudaEventDestroy(s->done);
     free(s);
 }
 
@@ -1475,24 +1540,28 @@ uint32_t pfcu_surface_height(const pfcu_surface *s) { return s->h; }
 void *pfcu_surface_color_ptr(const pfcu_surface *s) { return s->color; }
 void *pfcu_surface_depth_ptr(const pfcu_surface *s) { return s->depth; }
 
+static void mark_done(pfcu_surface *s) { if (cudaEventRecord(s->done, LN.stream) == cudaSuccess) s->has_done = true; }
+
 int pfcu_surface_upload(pfcu_surface *s, const void *hc, const float *hd, uint32_t y0, uint32_t rows)
 {
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
+    use_lane(s);
     const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;
-    if (hc) { CK(cudaMemcpyAsync(s->color + off, (const uint32_t *)hc + off, n, cudaMemcpyHostToDevice, g.stream)); g.bytes_h2d += n; }
-    if (hd) { CK(cudaMemcpyAsync(s->depth + off, hd + off, n, cudaMemcpyHostToDevice, g.stream)); g.bytes_h2d += n; }
+    if (hc) { CK(cudaMemcpyAsync(s->color + off, (const uint32_t *)hc + off, n, cudaMemcpyHostToDevice, LN.stream)); g.bytes_h2d += n; }
+    if (hd) { CK(cudaMemcpyAsync(s->depth + off, hd + off, n, cudaMemcpyHostToDevice, LN.stream)); g.bytes_h2d += n; }
     /* pageable sources are staged by the driver before the call returns; pinned ones are not */
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaStreamSynchronize(LN.stream));
     return PFCU_OK;
 }
 
 int pfcu_surface_download(pfcu_surface *s, void *hc, float *hd, uint32_t y0, uint32_t rows)
 {
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
+    use_lane(s);
     const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;
-    if (hc) { CK(cudaMemcpyAsync((uint32_t *)hc + off, s->color + off, n, cudaMemcpyDeviceToHost, g.stream)); g.bytes_d2h += n; }
-    if (hd) { CK(cudaMemcpyAsync(hd + off, s->depth + off, n, cudaMemcpyDeviceToHost, g.stream)); g.bytes_d2h += n; }
-    CK(cudaStreamSynchronize(g.stream));
+    if (hc) { CK(cudaMemcpyAsync((uint32_t *)hc + off, s->color + off, n, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += n; }
+    if (hd) { CK(cudaMemcpyAsync(hd + off, s->depth + off, n, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += n; }
+    CK(cudaStreamSynchronize(LN.stream));
     return PFCU_OK;
 }
 
@@ -1503,27 +1572,32 @@ static int fill_range(pfcu_surface *s, size_t first, size_t n, int dc, uint32_t 
     size_t head = (4 - (first & 3)) & 3; if (head > n) head = n;
     const size_t body4 = (n - head) / 4, tail = n - head - body4 * 4;
     const int blocks = g.sms * 8;
-    if (head) { k_fill<<<1, 32, 0, g.stream>>>(s->color, s->depth, first, head, dc, rgba, dd, z); g.launches++; }
+    if (head) { k_fill<<<1, 32, 0, LN.stream>>>(s->color, s->depth, first, head, dc, rgba, dd, z); g.launches++; }
     if (body4) {
-        k_fill4<<<blocks, 256, 0, g.stream>>>((uint4 *)s->color, (float4 *)s->depth, (first + head) / 4, body4, dc, rgba, dd, z);
+        k_fill4<<<blocks, 256, 0, LN.stream>>>((uint4 *)s->color, (float4 *)s->depth, (first + head) / 4, body4, dc, rgba, dd, z);
         g.launches++;
     }
-    if (tail) { k_fill<<<1, 32, 0, g.stream>>>(s->color, s->depth, first + head + body4 * 4, tail, dc, rgba, dd, z); g.launches++; }
+    if (tail) { k_fill<<<1, 32, 0, LN.stream>>>(s->color, s->depth, first + head + body4 * 4, tail, dc, rgba, dd, z); g.launches++; }
     CK(cudaGetLastError());
     return PFCU_OK;
 }
 
 int pfcu_surface_fill(pfcu_surface *s, int dc, uint32_t rgba, int dd, float z)
 {
-    return fill_range(s, 0, (size_t)s->w * s->h, dc, rgba, dd, z);
+    use_lane(s);
+    const int rc = fill_range(s, 0, (size_t)s->w * s->h, dc, rgba, dd, z);
+    mark_done(s);
+    return rc;
 }
 
 int pfcu_surface_clear_ref(pfcu_surface *s, int dc, uint32_t rgba, int dd, float z)
 {
+    use_lane(s);
     const unsigned size = s->w * s->h, aligned = size - (size % 8u);
     if (aligned > 8) { int rc = fill_range(s, 8, aligned - 8, dc, rgba, dd, z); if (rc) return rc; }
-    if (aligned < size) { k_clear_tail<<<1, 32, 0, g.stream>>>(s->color, s->depth, aligned, size, dc, dd); g.launches++; }
+    if (aligned < size) { k_clear_tail<<<1, 32, 0, LN.stream>>>(s->color, s->depth, aligned, size, dc, dd); g.launches++; }
     CK(cudaGetLastError());
+    mark_done(s);
     return PFCU_OK;
 }
 
@@ -1550,9 +1624,10 @@ size_t pfcu_surface_owned_bytes(const pfcu_surface *s, uint32_t rank, uint32_t w
 static int pack_unpack(pfcu_surface *s, uint32_t rank, uint32_t world, int with_depth, void *staging, int unpack)
 {
     if (world == 0) world = 1;
+    use_lane(s);
     const uint32_t n = owned_tiles(s, rank, world);
     if (n == 0) return PFCU_OK;
-    k_pack_tiles<<<n, 256, 0, g.stream>>>(s->color, s->depth, (int)s->w, (int)s->h, (int)s->tiles_x, s->tiles_x * s->tiles_y,
+    k_pack_tiles<<<n, 256, 0, LN.stream>>>(s->color, s->depth, (int)s->w, (int)s->h, (int)s->tiles_x, s->tiles_x * s->tiles_y,
                                           rank, world, with_depth, (uint32_t *)staging, unpack);
     g.launches++;
     CK(cudaGetLastError());
@@ -1572,9 +1647,10 @@ pfcu_texture *pfcu_texture_create(const void *host_pixels, uint32_t w, uint32_t 
     pfcu_texture *t = (pfcu_texture *)calloc(1, sizeof *t);
     if (!t) return nullptr;
     t->w = w; t->h = h; t->fmt = fmt; t->owned = true;
+    g.cur = &g.lanes[0];
     const size_t bytes = tex_bytes(w, h, fmt);
     if (cudaMalloc(&t->pixels, bytes + 16) != cudaSuccess) { snprintf(g.err, sizeof g.err, "texture_create: out of device memory"); free(t); return nullptr; }
-    cudaMemsetAsync(t->pixels, 0, bytes + 16, g.stream);
+    cudaMemsetAsync(t->pixels, 0, bytes + 16, LN.stream);
     if (host_pixels && pfcu_texture_update(t, host_pixels) != PFCU_OK) { cudaFree(t->pixels); free(t); return nullptr; }
     return t;
 }
@@ -1590,16 +1666,18 @@ pfcu_texture *pfcu_texture_from_surface(pfcu_surface *s)
 int pfcu_texture_update(pfcu_texture *t, const void *host_pixels)
 {
     if (!t || !t->owned || !host_pixels) return PFCU_ERR_INVALID;
-    CK(cudaMemcpyAsync(t->pixels, host_pixels, tex_bytes(t->w, t->h, t->fmt), cudaMemcpyHostToDevice, g.stream));
+    sync_all_lanes();                           /* nobody may still be sampling the old texels */
+    g.cur = &g.lanes[0];
+    CK(cudaMemcpyAsync(t->pixels, host_pixels, tex_bytes(t->w, t->h, t->fmt), cudaMemcpyHostToDevice, LN.stream));
     g.bytes_h2d += tex_bytes(t->w, t->h, t->fmt);
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaStreamSynchronize(LN.stream));
     return PFCU_OK;
 }
 
 void pfcu_texture_destroy(pfcu_texture *t)
 {
     if (!t) return;
-    if (g.ok) cudaStreamSynchronize(g.stream);
+    if (g.ok) sync_all_lanes();
     if (t->owned) cudaFree(t->pixels);
     free(t);
 }
@@ -1621,6 +1699,7 @@ static int g_last_single_prog = -1;      /* set by convert_states: the common pr
 static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
 {
     unsigned mask = 0;
+    g.deps.clear();
     for (uint32_t i = 0; i < n; i++) {
         const pfcu_state *s = in + i; DevState *d = out + i;
         memset(d, 0, sizeof *d);
@@ -1629,7 +1708,10 @@ static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
         if (s->n_lights == 0) d->flags &= ~PFCU_ST_PHONG;
         d->blend_mode = s->blend_mode; d->depth_func = s->depth_func; d->tex_filter = s->tex_filter; d->tex_wrap = s->tex_wrap;
         d->vp_min[0] = s->vp_min[0]; d->vp_min[1] = s->vp_min[1]; d->vp_max[0] = s->vp_max[0]; d->vp_max[1] = s->vp_max[1];
-        if (d->flags & PFCU_ST_TEXTURE) { d->tex = s->texture->pixels; d->tw = s->texture->w; d->th = s->texture->h; d->tfmt = s->texture->fmt; }
+        if (d->flags & PFCU_ST_TEXTURE) {
+            d->tex = s->texture->pixels; d->tw = s->texture->w; d->th = s->texture->h; d->tfmt = s->texture->fmt;
+            if (s->texture->alias) g.deps.push_back(s->texture->alias);      /* render-to-texture: order across lanes */
+        }
         d->n_lights = s->n_lights > 8 ? 8 : s->n_lights;
         for (unsigned l = 0; l < d->n_lights; l++) {
             const pfcu_light *a = &s->lights[l]; DevLight *b = &d->lights[l];
@@ -1656,18 +1738,21 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     if (n == 0) return PFCU_OK;
     if (!g.d_rcp) { snprintf(g.err, sizeof g.err, "pfcu_set_approx_tables() has not been called"); return PFCU_ERR_INVALID; }
     int rc;
-    if (n > g.cap_setup) {
-        size_t c1 = g.cap_setup, c2 = g.cap_setup, c3 = g.cap_setup;
-        if ((rc = grow(&g.d_bbox, &c1, n))) return rc;
-        if ((rc = grow(&g.d_setup, &c2, n))) return rc;
-        if ((rc = grow(&g.d_data, &c3, n))) return rc;
-        g.cap_setup = c1;
+    /* surfaces sampled as textures that live on another lane: wait for their last write */
+    for (pfcu_surface *dep : g.deps)
+        if (dep != s && dep->lane != s->lane && dep->has_done) CK(cudaStreamWaitEvent(LN.stream, dep->done, 0));
+    if (n > LN.cap_setup) {
+        size_t c1 = LN.cap_setup, c2 = LN.cap_setup, c3 = LN.cap_setup;
+        if ((rc = grow(&LN.d_bbox, &c1, n))) return rc;
+        if ((rc = grow(&LN.d_setup, &c2, n))) return rc;
+        if ((rc = grow(&LN.d_data, &c3, n))) return rc;
+        LN.cap_setup = c1;
     }
     const int binsX = (int)((s->w + BIN_PIX - 1) / BIN_PIX), binsY = (int)((s->h + BIN_PIX - 1) / BIN_PIX);
     const int nb = binsX * binsY;
     if (nb > MAX_BINS) { snprintf(g.err, sizeof g.err, "surface too large for the binner (%d bins)", nb); return PFCU_ERR_INVALID; }
     const unsigned nBatches = (n + BIN_BATCH - 1) / BIN_BATCH;
-    if ((rc = grow(&g.d_bin_counts, &g.cap_bin_counts, (size_t)nBatches * nb))) return rc;
+    if ((rc = grow(&LN.d_bin_counts, &LN.cap_bin_counts, (size_t)nBatches * nb))) return rc;
 
     cudaEvent_t pe[3] = { nullptr, nullptr, nullptr };
     if (g.profiling) {
@@ -1675,40 +1760,40 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
             if (!g.prof_pool.empty()) { pe[i] = g.prof_pool.back(); g.prof_pool.pop_back(); }
             else CK(cudaEventCreate(&pe[i]));
         }
-        CK(cudaEventRecord(pe[0], g.stream));
+        CK(cudaEventRecord(pe[0], LN.stream));
     }
-    k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, g.stream>>>(
-        d_tris, d_states, n, (int)s->w, (int)s->h, g.d_bbox, g.d_setup, g.d_data, g.d_counters);
-    k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), g.stream>>>(g.d_bbox, n, binsX, binsY, g.d_bin_counts);
-    unsigned *d_totals = g.d_bin_start + (MAX_BINS + 2);
-    k_bin_scan<<<nb, 256, 0, g.stream>>>(g.d_bin_counts, (int)nBatches, nb, d_totals);
-    k_bin_starts<<<1, 32, 0, g.stream>>>(d_totals, nb, g.d_bin_start);
+    k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, LN.stream>>>(
+        d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data, g.d_counters);
+    k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, binsX, binsY, LN.d_bin_counts);
+    unsigned *d_totals = LN.d_bin_start + (MAX_BINS + 2);
+    k_bin_scan<<<nb, 256, 0, LN.stream>>>(LN.d_bin_counts, (int)nBatches, nb, d_totals);
+    k_bin_starts<<<1, 32, 0, LN.stream>>>(d_totals, nb, LN.d_bin_start);
     /* Per-bin lists hold (triangle, bin) overlaps.  The exact total is only known on the device;
        n*nb bounds it.  Small cases are sized by the bound, large ones read the total back. */
     {
         const size_t bound = (size_t)n * (size_t)nb;
         size_t want = bound <= ((size_t)n * 4 > 65536 ? (size_t)n * 4 : 65536) ? bound : 0;
-        if (!want && bound <= g.cap_bin_list) want = bound;
+        if (!want && bound <= LN.cap_bin_list) want = bound;
         if (!want) {
             unsigned total = 0;
-            CK(cudaMemcpyAsync(&total, g.d_bin_start + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, g.stream));
-            CK(cudaStreamSynchronize(g.stream));
+            CK(cudaMemcpyAsync(&total, LN.d_bin_start + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, LN.stream));
+            CK(cudaStreamSynchronize(LN.stream));
             want = total;
         }
-        if ((rc = grow(&g.d_bin_list, &g.cap_bin_list, want ? want : 1))) return rc;
+        if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, want ? want : 1))) return rc;
     }
-    k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), g.stream>>>(g.d_bbox, n, binsX, binsY, g.d_bin_counts, g.d_bin_start, g.d_bin_list);
+    k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, binsX, binsY, LN.d_bin_counts, LN.d_bin_start, LN.d_bin_list);
     g.launches += 5;
 
     RasterParams p;
-    p.bbox = g.d_bbox; p.setup = g.d_setup; p.data = g.d_data; p.states = d_states;
-    p.bin_list = g.d_bin_list; p.bin_starts = g.d_bin_start; p.binsX = binsX;
+    p.bbox = LN.d_bbox; p.setup = LN.d_setup; p.data = LN.d_data; p.states = d_states;
+    p.bin_list = LN.d_bin_list; p.bin_starts = LN.d_bin_start; p.binsX = binsX;
     p.color = s->color; p.depth = s->depth; p.W = (int)s->w; p.H = (int)s->h;
     p.tilesX = (int)s->tiles_x; p.tilesY = (int)s->tiles_y;
     p.rank = s->rank; p.world = s->world ? s->world : 1; p.nTiles = s->tiles_x * s->tiles_y;
     p.counters = g.d_counters;
     const unsigned grid = owned_tiles(s, p.rank, p.world);
-    if (g.profiling) CK(cudaEventRecord(pe[1], g.stream));
+    if (g.profiling) CK(cudaEventRecord(pe[1], LN.stream));
     if (grid) {
         /* many small triangles per tile: 16 warps per tile halve the serial work of the busiest tiles;
            few large ones: 8 warps with more registers each issue faster */
@@ -1718,15 +1803,20 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         const int per_sm = (single_prog == 5 || single_prog == 6) ? 4 : 3;
         const double waves = (double)grid / ((double)g.sms * per_sm);
         const bool half = !small_tris && !ph && waves < 8.0 && (ceil(waves) / waves) > 1.06 && (ceil(2 * waves) / (2 * waves)) < (ceil(waves) / waves);
-        if (small_tris) { if (ph) k_raster<true, 16, -1, 64><<<grid, 512, 0, g.stream>>>(p); else k_raster<false, 16, -1, 64><<<grid, 512, 0, g.stream>>>(p); }
-        else if (ph)          k_raster<true, 8, -1, 64><<<grid, 256, 0, g.stream>>>(p);
-        else if (single_prog == 5) { if (half) k_raster<false, 8, 5, 32><<<grid * 2, 256, 0, g.stream>>>(p); else k_raster<false, 8, 5, 64><<<grid, 256, 0, g.stream>>>(p); }   /* nearest REPEAT RGBA8 texture + ALPHA blend */
-        else if (single_prog == 6) { if (half) k_raster<false, 8, 6, 32><<<grid * 2, 256, 0, g.stream>>>(p); else k_raster<false, 8, 6, 64><<<grid, 256, 0, g.stream>>>(p); }   /* nearest REPEAT RGBA8 texture + ADD blend   */
-        else { if (half) k_raster<false, 8, -1, 32><<<grid * 2, 256, 0, g.stream>>>(p); else k_raster<false, 8, -1, 64><<<grid, 256, 0, g.stream>>>(p); }
+        if (small_tris) { if (ph) k_raster<true, 16, -1, 64><<<grid, 512, 0, LN.stream>>>(p); else k_raster<false, 16, -1, 64><<<grid, 512, 0, LN.stream>>>(p); }
+        else if (ph)          k_raster<true, 8, -1, 64><<<grid, 256, 0, LN.stream>>>(p);
+        else if (single_prog == 5) { if (half) k_raster<false, 8, 5, 32><<<grid * 2, 256, 0, LN.stream>>>(p); else k_raster<false, 8, 5, 64><<<grid, 256, 0, LN.stream>>>(p); }   /* nearest REPEAT RGBA8 texture + ALPHA blend */
+        else if (single_prog == 6) { if (half) k_raster<false, 8, 6, 32><<<grid * 2, 256, 0, LN.stream>>>(p); else k_raster<false, 8, 6, 64><<<grid, 256, 0, LN.stream>>>(p); }   /* nearest REPEAT RGBA8 texture + ADD blend   */
+        else { if (half) k_raster<false, 8, -1, 32><<<grid * 2, 256, 0, LN.stream>>>(p); else k_raster<false, 8, -1, 64><<<grid, 256, 0, LN.stream>>>(p); }
         g.launches++;
     }
-    if (g.profiling) { CK(cudaEventRecord(pe[2], g.stream)); for (int i = 0; i < 3; i++) g.prof_events.push_back(pe[i]); }
+    if (g.profiling) { CK(cudaEventRecord(pe[2], LN.stream)); for (int i = 0; i < 3; i++) g.prof_events.push_back(pe[i]); }
     CK(cudaGetLastError());
+    mark_done(s);
+    /* write-after-read: a sampled surface on another lane must not be overwritten before this batch read it */
+    for (pfcu_surface *dep : g.deps)
+        if (dep != s && dep->lane != s->lane) CK(cudaStreamWaitEvent(g.lanes[dep->lane % g.n_lanes].stream, s->done, 0));
+    g.deps.clear();
     g.submitted += n;
     return PFCU_OK;
 }
@@ -1736,13 +1826,13 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
 static int scan_exclusive(const unsigned *d_in, unsigned *d_out, unsigned n, unsigned *d_tmp /* >= n/1024 + n/1048576 + 4 */)
 {
     const unsigned nb = (n + 1023u) / 1024u;
-    k_scan_block<<<nb, 256, 0, g.stream>>>(d_in, d_out, n, d_tmp);
+    k_scan_block<<<nb, 256, 0, LN.stream>>>(d_in, d_out, n, d_tmp);
     g.launches++;
     if (nb > 1) {
         unsigned *d_tmp2 = d_tmp + nb;
         int rc = scan_exclusive(d_tmp, d_tmp, nb, d_tmp2);
         if (rc) return rc;
-        k_scan_add<<<(n + 255u) / 256u, 256, 0, g.stream>>>(d_out, n, d_tmp);
+        k_scan_add<<<(n + 255u) / 256u, 256, 0, LN.stream>>>(d_out, n, d_tmp);
         g.launches++;
     }
     CK(cudaGetLastError());
@@ -1758,6 +1848,7 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     if (!s || !state || !vp || !d || !d->positions || d->pos_size < 2 || d->pos_size > 4 || d->n_faces < 1 || d->n_faces > 2) return PFCU_ERR_INVALID;
     const unsigned n_tri = d->count / 3u;
     if (n_tri == 0) return PFCU_OK;
+    use_lane(s);
     const unsigned n_items = n_tri * d->n_faces;
     int rc;
     /* arrays -> device (pageable sources are staged by the driver; ordered on the stream) */
@@ -1767,42 +1858,42 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t total_bytes = al(b_pos) + al(b_nrm) + al(b_uv) + al(b_col) + al(b_idx);
     g.bytes_h2d += b_pos + b_nrm + b_uv + b_col + b_idx + sizeof(DevState);
-    if ((rc = grow(&g.d_varrays, &g.cap_varrays, total_bytes))) return rc;
-    unsigned char *p = g.d_varrays;
+    if ((rc = grow(&LN.d_varrays, &LN.cap_varrays, total_bytes))) return rc;
+    unsigned char *p = LN.d_varrays;
     VtxArgs a; memset(&a, 0, sizeof a);
-    a.pos = (const float *)p; CK(cudaMemcpyAsync(p, d->positions, b_pos, cudaMemcpyHostToDevice, g.stream)); p += al(b_pos);
-    if (b_nrm) { a.nrm = (const float *)p; CK(cudaMemcpyAsync(p, d->normals, b_nrm, cudaMemcpyHostToDevice, g.stream)); p += al(b_nrm); }
-    if (b_uv) { a.uv = (const float *)p; CK(cudaMemcpyAsync(p, d->texcoords, b_uv, cudaMemcpyHostToDevice, g.stream)); p += al(b_uv); }
-    if (b_col) { a.col = p; CK(cudaMemcpyAsync(p, d->colors, b_col, cudaMemcpyHostToDevice, g.stream)); p += al(b_col); }
-    if (b_idx) { a.idx = p; CK(cudaMemcpyAsync(p, d->indices, b_idx, cudaMemcpyHostToDevice, g.stream)); p += al(b_idx); }
+    a.pos = (const float *)p; CK(cudaMemcpyAsync(p, d->positions, b_pos, cudaMemcpyHostToDevice, LN.stream)); p += al(b_pos);
+    if (b_nrm) { a.nrm = (const float *)p; CK(cudaMemcpyAsync(p, d->normals, b_nrm, cudaMemcpyHostToDevice, LN.stream)); p += al(b_nrm); }
+    if (b_uv) { a.uv = (const float *)p; CK(cudaMemcpyAsync(p, d->texcoords, b_uv, cudaMemcpyHostToDevice, LN.stream)); p += al(b_uv); }
+    if (b_col) { a.col = p; CK(cudaMemcpyAsync(p, d->colors, b_col, cudaMemcpyHostToDevice, LN.stream)); p += al(b_col); }
+    if (b_idx) { a.idx = p; CK(cudaMemcpyAsync(p, d->indices, b_idx, cudaMemcpyHostToDevice, LN.stream)); p += al(b_idx); }
     a.pos_size = (int)d->pos_size; a.col_size = (int)d->color_size; a.idx_bytes = (int)d->index_bytes;
     a.first = d->first; a.n_tri = n_tri; a.cur_color = d->current_color; a.n_faces = (int)d->n_faces;
     a.face[0] = d->faces[0]; a.face[1] = d->faces[1]; a.state = 0;
 
     /* pass A: output triangles per (triangle, face) item; scan; total */
-    if ((rc = grow(&g.d_vcounts, &g.cap_vcounts, (size_t)n_items * 2 + n_items / 512 + 64))) return rc;
-    unsigned *d_counts = g.d_vcounts, *d_offsets = g.d_vcounts + n_items, *d_tmp = g.d_vcounts + 2 * (size_t)n_items;
-    k_vertex_count<<<(n_items + 127u) / 128u, 128, 0, g.stream>>>(a, *vp, n_items, d_counts);
+    if ((rc = grow(&LN.d_vcounts, &LN.cap_vcounts, (size_t)n_items * 2 + n_items / 512 + 64))) return rc;
+    unsigned *d_counts = LN.d_vcounts, *d_offsets = LN.d_vcounts + n_items, *d_tmp = LN.d_vcounts + 2 * (size_t)n_items;
+    k_vertex_count<<<(n_items + 127u) / 128u, 128, 0, LN.stream>>>(a, *vp, n_items, d_counts);
     g.launches++;
     if ((rc = scan_exclusive(d_counts, d_offsets, n_items, d_tmp))) return rc;
     unsigned last[2] = { 0, 0 };
-    CK(cudaMemcpyAsync(&last[0], d_offsets + (n_items - 1), 4, cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaMemcpyAsync(&last[1], d_counts + (n_items - 1), 4, cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaMemcpyAsync(&last[0], d_offsets + (n_items - 1), 4, cudaMemcpyDeviceToHost, LN.stream));
+    CK(cudaMemcpyAsync(&last[1], d_counts + (n_items - 1), 4, cudaMemcpyDeviceToHost, LN.stream));
+    CK(cudaStreamSynchronize(LN.stream));
     const unsigned total = last[0] + last[1];
     if (n_out) *n_out = total;
     if (total == 0) return PFCU_OK;
 
     /* pass B: emit in order, then the usual setup -> bin -> raster pipeline */
-    if ((rc = grow(&g.d_tris, &g.cap_tris, total))) return rc;
-    if ((rc = grow(&g.d_states, &g.cap_states, 1))) return rc;
+    if ((rc = grow(&LN.d_tris, &LN.cap_tris, total))) return rc;
+    if ((rc = grow(&LN.d_states, &LN.cap_states, 1))) return rc;
     DevState hs;
     const unsigned mask = convert_states(state, 1, &hs);
-    CK(cudaMemcpyAsync(g.d_states, &hs, sizeof hs, cudaMemcpyHostToDevice, g.stream));
-    k_vertex_emit<<<(n_items + 127u) / 128u, 128, 0, g.stream>>>(a, *vp, n_items, d_offsets, g.d_tris);
+    CK(cudaMemcpyAsync(LN.d_states, &hs, sizeof hs, cudaMemcpyHostToDevice, LN.stream));
+    k_vertex_emit<<<(n_items + 127u) / 128u, 128, 0, LN.stream>>>(a, *vp, n_items, d_offsets, LN.d_tris);
     g.launches++;
     CK(cudaGetLastError());
-    return launch_pipeline(s, g.d_tris, g.d_states, total, mask, g_last_single_prog);
+    return launch_pipeline(s, LN.d_tris, LN.d_states, total, mask, g_last_single_prog);
 }
 
 int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, const pfcu_triangle *tris, uint32_t n_tris)
@@ -1810,43 +1901,44 @@ int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, co
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || (n_tris && (!states || !tris || n_states == 0))) return PFCU_ERR_INVALID;
     if (n_tris == 0) return PFCU_OK;
+    use_lane(s);
     int rc;
-    if ((rc = grow(&g.d_tris, &g.cap_tris, n_tris))) return rc;
-    if ((rc = grow(&g.d_states, &g.cap_states, n_states))) return rc;
+    if ((rc = grow(&LN.d_tris, &LN.cap_tris, n_tris))) return rc;
+    if ((rc = grow(&LN.d_states, &LN.cap_states, n_states))) return rc;
 
     /* states: convert handles to device pointers in pinned staging */
-    if (n_states > g.cap_hstates) {
-        CK(cudaEventSynchronize(g.states_done));
-        if (g.h_states) cudaFreeHost(g.h_states);
-        size_t c = g.cap_hstates ? g.cap_hstates : 64; while (c < n_states) c *= 2;
-        CK(cudaHostAlloc(&g.h_states, c * sizeof(DevState), cudaHostAllocDefault));
-        g.cap_hstates = c;
-    } else CK(cudaEventSynchronize(g.states_done));
-    const unsigned mask = convert_states(states, n_states, g.h_states);
-    CK(cudaMemcpyAsync(g.d_states, g.h_states, n_states * sizeof(DevState), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaEventRecord(g.states_done, g.stream));
+    if (n_states > LN.cap_hstates) {
+        CK(cudaEventSynchronize(LN.states_done));
+        if (LN.h_states) cudaFreeHost(LN.h_states);
+        size_t c = LN.cap_hstates ? LN.cap_hstates : 64; while (c < n_states) c *= 2;
+        CK(cudaHostAlloc(&LN.h_states, c * sizeof(DevState), cudaHostAllocDefault));
+        LN.cap_hstates = c;
+    } else CK(cudaEventSynchronize(LN.states_done));
+    const unsigned mask = convert_states(states, n_states, LN.h_states);
+    CK(cudaMemcpyAsync(LN.d_states, LN.h_states, n_states * sizeof(DevState), cudaMemcpyHostToDevice, LN.stream));
+    CK(cudaEventRecord(LN.states_done, LN.stream));
     g.bytes_h2d += n_states * sizeof(DevState) + (size_t)n_tris * sizeof(pfcu_triangle);
 
     /* triangles: one DMA from pinned memory, or staged through our own pinned buffer */
     const size_t bytes = (size_t)n_tris * sizeof(pfcu_triangle);
     PinnedBlock *pb = find_pinned(tris);
     if (pb) {
-        CK(cudaMemcpyAsync(g.d_tris, tris, bytes, cudaMemcpyHostToDevice, g.stream));
-        CK(cudaEventRecord(pb->done, g.stream));
+        CK(cudaMemcpyAsync(LN.d_tris, tris, bytes, cudaMemcpyHostToDevice, LN.stream));
+        CK(cudaEventRecord(pb->done, LN.stream));
         pb->pending = true;
     } else {
-        if (bytes > g.cap_stage) {
-            CK(cudaEventSynchronize(g.stage_done));
-            if (g.h_stage) cudaFreeHost(g.h_stage);
-            size_t c = g.cap_stage ? g.cap_stage : (1u << 20); while (c < bytes) c *= 2;
-            CK(cudaHostAlloc(&g.h_stage, c, cudaHostAllocDefault));
-            g.cap_stage = c;
-        } else CK(cudaEventSynchronize(g.stage_done));
-        memcpy(g.h_stage, tris, bytes);
-        CK(cudaMemcpyAsync(g.d_tris, g.h_stage, bytes, cudaMemcpyHostToDevice, g.stream));
-        CK(cudaEventRecord(g.stage_done, g.stream));
+        if (bytes > LN.cap_stage) {
+            CK(cudaEventSynchronize(LN.stage_done));
+            if (LN.h_stage) cudaFreeHost(LN.h_stage);
+            size_t c = LN.cap_stage ? LN.cap_stage : (1u << 20); while (c < bytes) c *= 2;
+            CK(cudaHostAlloc(&LN.h_stage, c, cudaHostAllocDefault));
+            LN.cap_stage = c;
+        } else CK(cudaEventSynchronize(LN.stage_done));
+        memcpy(LN.h_stage, tris, bytes);
+        CK(cudaMemcpyAsync(LN.d_tris, LN.h_stage, bytes, cudaMemcpyHostToDevice, LN.stream));
+        CK(cudaEventRecord(LN.stage_done, LN.stream));
     }
-    return launch_pipeline(s, g.d_tris, g.d_states, n_tris, mask, g_last_single_prog);
+    return launch_pipeline(s, LN.d_tris, LN.d_states, n_tris, mask, g_last_single_prog);
 }
 
 pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const pfcu_triangle *tris, uint32_t n_tris)
@@ -1854,15 +1946,17 @@ pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const
     if (!g.ok || !states || !tris || n_states == 0 || n_tris == 0) return nullptr;
     pfcu_batch *b = (pfcu_batch *)calloc(1, sizeof *b);
     if (!b) return nullptr;
+    g.cur = &g.lanes[0];
     std::vector<DevState> tmp(n_states);
     b->feature_mask = convert_states(states, n_states, tmp.data());
     b->single_prog = g_last_single_prog;
+    new (&b->deps) std::vector<pfcu_surface *>(g.deps);
     b->n_states = n_states; b->n_tris = n_tris;
     CKP(cudaMalloc(&b->states, n_states * sizeof(DevState)));
     CKP(cudaMalloc(&b->tris, (size_t)n_tris * sizeof(pfcu_triangle)));
-    CKP(cudaMemcpyAsync(b->states, tmp.data(), n_states * sizeof(DevState), cudaMemcpyHostToDevice, g.stream));
-    CKP(cudaMemcpyAsync(b->tris, tris, (size_t)n_tris * sizeof(pfcu_triangle), cudaMemcpyHostToDevice, g.stream));
-    CKP(cudaStreamSynchronize(g.stream));
+    CKP(cudaMemcpyAsync(b->states, tmp.data(), n_states * sizeof(DevState), cudaMemcpyHostToDevice, LN.stream));
+    CKP(cudaMemcpyAsync(b->tris, tris, (size_t)n_tris * sizeof(pfcu_triangle), cudaMemcpyHostToDevice, LN.stream));
+    CKP(cudaStreamSynchronize(LN.stream));
     return b;
 }
 
@@ -1870,14 +1964,17 @@ int pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b)
 {
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || !b) return PFCU_ERR_INVALID;
+    use_lane(s);
+    g.deps.clear();
+    for (pfcu_surface *dep : b->deps) g.deps.push_back(dep);
     return launch_pipeline(s, b->tris, b->states, b->n_tris, b->feature_mask, b->single_prog);
 }
 
 void pfcu_batch_destroy(pfcu_batch *b)
 {
     if (!b) return;
-    if (g.ok) cudaStreamSynchronize(g.stream);
-    cudaFree(b->states); cudaFree(b->tris); free(b);
+    if (g.ok) sync_all_lanes();
+    cudaFree(b->states); cudaFree(b->tris); b->deps.~vector(); free(b);
 }
 
 void pfcu_profile_enable(int on) { g.profiling = on != 0; }
@@ -1885,7 +1982,7 @@ void pfcu_profile_enable(int on) { g.profiling = on != 0; }
 int pfcu_profile_read(pfcu_profile *out)
 {
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
-    CK(cudaStreamSynchronize(g.stream));
+    sync_all_lanes();
     out->raster_ms = 0; out->frontend_ms = 0; out->raster_launches = 0;
     for (size_t i = 0; i + 2 < g.prof_events.size(); i += 3) {
         float a = 0, b = 0;
@@ -1901,7 +1998,7 @@ int pfcu_profile_read(pfcu_profile *out)
 int pfcu_finish(void)
 {
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
-    CK(cudaStreamSynchronize(g.stream));
+    for (int i = 0; i < g.n_lanes; i++) CK(cudaStreamSynchronize(g.lanes[i].stream));
     return PFCU_OK;
 }
 
@@ -1909,8 +2006,8 @@ int pfcu_get_counters(pfcu_counters *out)
 {
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     unsigned long long h[4] = { 0, 0, 0, 0 };
-    CK(cudaMemcpyAsync(h, g.d_counters, sizeof h, cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
+    sync_all_lanes();
+    CK(cudaMemcpy(h, g.d_counters, sizeof h, cudaMemcpyDeviceToHost));
     out->triangles_submitted = g.submitted;
     out->triangles_rasterised = h[0];
     out->pixels_shaded = h[1];
@@ -1923,7 +2020,8 @@ int pfcu_get_counters(pfcu_counters *out)
 void pfcu_reset_counters(void)
 {
     if (!g.ok) return;
-    cudaMemsetAsync(g.d_counters, 0, 4 * sizeof(unsigned long long), g.stream);
+    sync_all_lanes();
+    cudaMemset(g.d_counters, 0, 4 * sizeof(unsigned long long));
     g.submitted = 0; g.launches = 0; g.bytes_h2d = 0; g.bytes_d2h = 0;
 }
 

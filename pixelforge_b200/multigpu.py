@@ -62,8 +62,10 @@ def tile_split_benchmark(torch, dist, scenes, pfcu, stream, wl, rank, world, ste
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             with torch.cuda.stream(stream):
                 e0.record(stream)
+                L.pfcu_fence()
                 L.pfcu_surface_clear_ref(surf, 1, 0xFF000000, 1, 3.4028234663852886e38)
                 L.pfcu_batch_submit(surf, b)
+                L.pfcu_fence()
                 e1.record(stream)
                 gather_tiles(torch, dist, pfcu, surf, wl["w"], wl["h"], rank, world)
                 e2.record(stream)

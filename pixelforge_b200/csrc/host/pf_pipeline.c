@@ -145,18 +145,43 @@ static uint32_t current_state_index(pf_ctx *c)
 
 #define PFH_BATCH_TRIS (1u << 18)       /* 262,144 triangles = 38 MiB per pinned buffer */
 
+/* Pinned double buffer for the triangle batch.  It starts small (a context that draws a few hundred
+ * triangles per frame should not hold 80 MB of page-locked memory - BASELINE config C5 runs 256 contexts)
+ * and grows 4x each time a batch fills up, to PFH_BATCH_TRIS at most. */
+#define PFH_BATCH_TRIS_MIN 4096u
+
+static uint32_t batch_limit(void)
+{
+    static uint32_t lim = 0;
+    if (!lim) {
+        lim = PFH_BATCH_TRIS;
+        const char *e = getenv("PF_CUDA_BATCH_TRIS");
+        if (e && atoi(e) > 0) lim = (uint32_t)atoi(e);
+    }
+    return lim;
+}
+
+static int alloc_batch(pf_ctx *c, uint32_t cap)
+{
+    pfcu_triangle *nb[2];
+    for (int i = 0; i < 2; i++) {
+        nb[i] = (pfcu_triangle *)pfcu_host_alloc((size_t)cap * sizeof(pfcu_triangle));
+        if (!nb[i]) { if (i) pfcu_host_free(nb[0]); c->errCode = PF_ERROR_OUT_OF_MEMORY; return 0; }
+    }
+    for (int i = 0; i < 2; i++) {
+        if (c->tris[i]) { pfcu_host_wait(c->tris[i]); pfcu_host_free(c->tris[i]); }
+        c->tris[i] = nb[i];
+    }
+    c->tri_cap = cap; c->cur_buf = 0; c->n_tris = 0;
+    return 1;
+}
+
 static int ensure_batch(pf_ctx *c)
 {
     if (c->tris[0]) return 1;
-    c->tri_cap = PFH_BATCH_TRIS;
-    const char *e = getenv("PF_CUDA_BATCH_TRIS");
-    if (e && atoi(e) > 0) c->tri_cap = (uint32_t)atoi(e);
-    for (int i = 0; i < 2; i++) {
-        c->tris[i] = (pfcu_triangle *)pfcu_host_alloc((size_t)c->tri_cap * sizeof(pfcu_triangle));
-        if (!c->tris[i]) { c->errCode = PF_ERROR_OUT_OF_MEMORY; return 0; }
-    }
-    c->cur_buf = 0; c->n_tris = 0;
-    return 1;
+    uint32_t cap = PFH_BATCH_TRIS_MIN;
+    if (cap > batch_limit()) cap = batch_limit();
+    return alloc_batch(c, cap);
 }
 
 void pfh_upload_if_needed(pf_ctx *c, pf_surf *s)
@@ -253,7 +278,13 @@ static inline void emit_triangle(pf_ctx *c, int face, int is3d, const pf_vertex 
         if (y1 > s->dirty_y1) s->dirty_y1 = y1;
     }
     c->tris_emitted++;
-    if (++c->n_tris == c->tri_cap) pfh_flush(c);
+    if (++c->n_tris == c->tri_cap) {
+        pfh_flush(c);
+        if (c->tri_cap < batch_limit()) {           /* the batch filled up: this context draws a lot, grow */
+            uint32_t cap = c->tri_cap * 4u;
+            alloc_batch(c, cap > batch_limit() ? batch_limit() : cap);
+        }
+    }
 }
 
 /* ---- Gouraud vertex lighting: integer Blinn-Phong (lighting.c:23-144) ------------------------ */

@@ -127,12 +127,13 @@ struct Runtime {
     std::vector<cudaEvent_t> prof_events;       /* triples: before setup, before raster, after raster */
     std::vector<cudaEvent_t> prof_pool;
     std::vector<pfcu_surface *> deps;           /* surfaces sampled as textures by the states being submitted */
-    std::mutex mu;
+    std::recursive_mutex mu;                    /* the C-ABI is serialised: contexts on several threads share one runtime */
     char err[512] = { 0 };
 };
 
 static Runtime g;
 #define LN (*g.cur)
+#define API_LOCK std::lock_guard<std::recursive_mutex> api_lock_(g.mu)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     snprintf(g.err, sizeof g.err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
@@ -862,14 +863,12 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
         const unsigned sa = t.sm_base + ((unsigned)tile_addr(lx, ly) << 2);
         if (ztest) {
             const float zb = lds_depth(sa);
-            bool pass;
-            switch (zmask) {                        /* warp-uniform */
-            case 1u: pass = z < zb; break;
-            case 3u: pass = z <= zb; break;
-            case 2u: pass = z == zb; break;
-            case 4u: pass = z > zb; break;
-            default: pass = z >= zb; break;
-            }
+            bool pass;                              /* zmask is warp-uniform; an if-chain (most common first) */
+            if (zmask == 1u) pass = z < zb;         /* avoids the jump table a switch compiles to           */
+            else if (zmask == 3u) pass = z <= zb;
+            else if (zmask == 2u) pass = z == zb;
+            else if (zmask == 4u) pass = z > zb;
+            else pass = z >= zb;
             t.zfailed += (m && !pass) ? 1u : 0u;
             m = m && pass;
             if (!__any_sync(0xffffffffu, m)) continue;
@@ -1326,7 +1325,7 @@ const char *pfcu_backend_name(void) { return "cuda-sm_100a"; }
 
 int pfcu_init(int device)
 {
-    std::lock_guard<std::mutex> lk(g.mu);
+    API_LOCK;
     if (g.ok) return PFCU_OK;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -1377,6 +1376,7 @@ static void use_lane(const pfcu_surface *s) { g.cur = &g.lanes[s ? s->lane % g.n
 
 void pfcu_shutdown(void)
 {
+    API_LOCK;
     if (!g.ok) return;
     sync_all_lanes();
     for (int i = 0; i < g.n_lanes; i++) {
@@ -1397,6 +1397,7 @@ void pfcu_shutdown(void)
  * blocking the host: used by callers that bracket multi-surface work with events on lane 0's stream. */
 int pfcu_fence(void)
 {
+    API_LOCK;
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     for (int i = 1; i < g.n_lanes; i++) {
         CK(cudaEventRecord(g.lanes[i].fence, g.lanes[i].stream));
@@ -1409,6 +1410,7 @@ int pfcu_fence(void)
 
 int pfcu_set_stream(void *cuda_stream)
 {
+    API_LOCK;
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     sync_all_lanes();
     Lane &l0 = g.lanes[0];
@@ -1425,7 +1427,7 @@ void *pfcu_host_alloc(size_t bytes)
     PinnedBlock b; b.bytes = bytes; b.pending = false;
     if (cudaHostAlloc(&b.p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming) != cudaSuccess) { cudaFreeHost(b.p); return nullptr; }
-    std::lock_guard<std::mutex> lk(g.mu);
+    API_LOCK;
     g.pinned.push_back(b);
     return b.p;
 }
@@ -1438,7 +1440,7 @@ static PinnedBlock *find_pinned(const void *p)
 
 void pfcu_host_free(void *p)
 {
-    std::lock_guard<std::mutex> lk(g.mu);
+    API_LOCK;
     for (size_t i = 0; i < g.pinned.size(); i++) if (g.pinned[i].p == p) {
         if (g.pinned[i].pending) cudaEventSynchronize(g.pinned[i].done);
         cudaEventDestroy(g.pinned[i].done); cudaFreeHost(p);
@@ -1449,6 +1451,7 @@ void pfcu_host_free(void *p)
 
 int pfcu_host_register(void *p, size_t bytes)
 {
+    API_LOCK;
     if (!g.ok || !p || bytes == 0) return PFCU_ERR_INVALID;
     /* page-aligned sub-range; the partial first/last pages stay pageable (cudaMemcpy handles mixed ranges) */
     cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
@@ -1458,6 +1461,7 @@ int pfcu_host_register(void *p, size_t bytes)
 
 void pfcu_host_unregister(void *p)
 {
+    API_LOCK;
     if (!g.ok || !p) return;
     sync_all_lanes();
     if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
@@ -1465,6 +1469,7 @@ void pfcu_host_unregister(void *p)
 
 int pfcu_host_wait(const void *p)
 {
+    API_LOCK;
     PinnedBlock *b = find_pinned(p);
     if (b && b->pending) { CK(cudaEventSynchronize(b->done)); b->pending = false; }
     return PFCU_OK;
@@ -1472,6 +1477,7 @@ int pfcu_host_wait(const void *p)
 
 int pfcu_set_approx_tables(const uint32_t *rcp, int rcp_bits, const uint32_t *rsqrt, int rsqrt_bits)
 {
+    API_LOCK;
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     if (rcp_bits < 1 || rcp_bits > 23 || rsqrt_bits < 1 || rsqrt_bits > 23) return PFCU_ERR_INVALID;
     sync_all_lanes();
@@ -1496,6 +1502,7 @@ static void surface_dims(pfcu_surface *s) { s->tiles_x = (s->w + TILE - 1) / TIL
 
 pfcu_surface *pfcu_surface_create(uint32_t w, uint32_t h)
 {
+    API_LOCK;
     if (!g.ok || w == 0 || h == 0) { snprintf(g.err, sizeof g.err, "surface_create: runtime not initialised or empty surface"); return nullptr; }
     pfcu_surface *s = (pfcu_surface *)calloc(1, sizeof *s);
     if (!s) return nullptr;
@@ -1516,6 +1523,7 @@ pfcu_surface *pfcu_surface_create(uint32_t w, uint32_t h)
 
 pfcu_surface *pfcu_surface_wrap(void *dev_color, void *dev_depth, uint32_t w, uint32_t h)
 {
+    API_LOCK;
     if (!g.ok || !dev_color || !dev_depth) return nullptr;
     pfcu_surface *s = (pfcu_surface *)calloc(1, sizeof *s);
     if (!s) return nullptr;
@@ -1528,6 +1536,7 @@ pfcu_surface *pfcu_surface_wrap(void *dev_color, void *dev_depth, uint32_t w, ui
 
 void pfcu_surface_destroy(pfcu_surface *s)
 {
+    API_LOCK;
     if (!s) return;
     if (g.ok) sync_all_lanes();
     if (s->owned) { cudaFree(s->color); cudaFree(s->depth); }
@@ -1544,6 +1553,7 @@ static void mark_done(pfcu_surface *s) { if (cudaEventRecord(s->done, LN.stream)
 
 int pfcu_surface_upload(pfcu_surface *s, const void *hc, const float *hd, uint32_t y0, uint32_t rows)
 {
+    API_LOCK;
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
     use_lane(s);
     const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;
@@ -1556,6 +1566,7 @@ int pfcu_surface_upload(pfcu_surface *s, const void *hc, const float *hd, uint32
 
 int pfcu_surface_download(pfcu_surface *s, void *hc, float *hd, uint32_t y0, uint32_t rows)
 {
+    API_LOCK;
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
     use_lane(s);
     const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;
@@ -1584,6 +1595,7 @@ static int fill_range(pfcu_surface *s, size_t first, size_t n, int dc, uint32_t 
 
 int pfcu_surface_fill(pfcu_surface *s, int dc, uint32_t rgba, int dd, float z)
 {
+    API_LOCK;
     use_lane(s);
     const int rc = fill_range(s, 0, (size_t)s->w * s->h, dc, rgba, dd, z);
     mark_done(s);
@@ -1592,6 +1604,7 @@ int pfcu_surface_fill(pfcu_surface *s, int dc, uint32_t rgba, int dd, float z)
 
 int pfcu_surface_clear_ref(pfcu_surface *s, int dc, uint32_t rgba, int dd, float z)
 {
+    API_LOCK;
     use_lane(s);
     const unsigned size = s->w * s->h, aligned = size - (size % 8u);
     if (aligned > 8) { int rc = fill_range(s, 8, aligned - 8, dc, rgba, dd, z); if (rc) return rc; }
@@ -1623,6 +1636,7 @@ size_t pfcu_surface_owned_bytes(const pfcu_surface *s, uint32_t rank, uint32_t w
 
 static int pack_unpack(pfcu_surface *s, uint32_t rank, uint32_t world, int with_depth, void *staging, int unpack)
 {
+    API_LOCK;
     if (world == 0) world = 1;
     use_lane(s);
     const uint32_t n = owned_tiles(s, rank, world);
@@ -1643,6 +1657,7 @@ static size_t tex_bytes(uint32_t w, uint32_t h, int fmt) { return (size_t)w * h 
 
 pfcu_texture *pfcu_texture_create(const void *host_pixels, uint32_t w, uint32_t h, int fmt)
 {
+    API_LOCK;
     if (!g.ok || fmt < PFCU_TEX_RGBA8 || fmt > PFCU_TEX_BGR8 || w == 0 || h == 0) return nullptr;
     pfcu_texture *t = (pfcu_texture *)calloc(1, sizeof *t);
     if (!t) return nullptr;
@@ -1657,6 +1672,7 @@ pfcu_texture *pfcu_texture_create(const void *host_pixels, uint32_t w, uint32_t 
 
 pfcu_texture *pfcu_texture_from_surface(pfcu_surface *s)
 {
+    API_LOCK;
     pfcu_texture *t = (pfcu_texture *)calloc(1, sizeof *t);
     if (!t) return nullptr;
     t->w = s->w; t->h = s->h; t->fmt = PFCU_TEX_RGBA8; t->pixels = (unsigned char *)s->color; t->owned = false; t->alias = s;
@@ -1665,6 +1681,7 @@ pfcu_texture *pfcu_texture_from_surface(pfcu_surface *s)
 
 int pfcu_texture_update(pfcu_texture *t, const void *host_pixels)
 {
+    API_LOCK;
     if (!t || !t->owned || !host_pixels) return PFCU_ERR_INVALID;
     sync_all_lanes();                           /* nobody may still be sampling the old texels */
     g.cur = &g.lanes[0];
@@ -1676,6 +1693,7 @@ int pfcu_texture_update(pfcu_texture *t, const void *host_pixels)
 
 void pfcu_texture_destroy(pfcu_texture *t)
 {
+    API_LOCK;
     if (!t) return;
     if (g.ok) sync_all_lanes();
     if (t->owned) cudaFree(t->pixels);
@@ -1852,6 +1870,7 @@ unsigned pfcu_capabilities(void) { return PFCU_CAP_DEVICE_VERTEX; }
 
 int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vparams *vp, const pfcu_draw *d, uint32_t *n_out)
 {
+    API_LOCK;
     if (n_out) *n_out = 0;
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || !state || !vp || !d || !d->positions || d->pos_size < 2 || d->pos_size > 4 || d->n_faces < 1 || d->n_faces > 2) return PFCU_ERR_INVALID;
@@ -1907,6 +1926,7 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
 
 int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, const pfcu_triangle *tris, uint32_t n_tris)
 {
+    API_LOCK;
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || (n_tris && (!states || !tris || n_states == 0))) return PFCU_ERR_INVALID;
     if (n_tris == 0) return PFCU_OK;
@@ -1952,6 +1972,7 @@ int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, co
 
 pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const pfcu_triangle *tris, uint32_t n_tris)
 {
+    API_LOCK;
     if (!g.ok || !states || !tris || n_states == 0 || n_tris == 0) return nullptr;
     pfcu_batch *b = (pfcu_batch *)calloc(1, sizeof *b);
     if (!b) return nullptr;
@@ -1971,6 +1992,7 @@ pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const
 
 int pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b)
 {
+    API_LOCK;
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || !b) return PFCU_ERR_INVALID;
     use_lane(s);
@@ -1981,6 +2003,7 @@ int pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b)
 
 void pfcu_batch_destroy(pfcu_batch *b)
 {
+    API_LOCK;
     if (!b) return;
     if (g.ok) sync_all_lanes();
     cudaFree(b->states); cudaFree(b->tris); b->deps.~vector(); free(b);
@@ -1990,6 +2013,7 @@ void pfcu_profile_enable(int on) { g.profiling = on != 0; }
 
 int pfcu_profile_read(pfcu_profile *out)
 {
+    API_LOCK;
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     sync_all_lanes();
     out->raster_ms = 0; out->frontend_ms = 0; out->raster_launches = 0;
@@ -2006,6 +2030,7 @@ int pfcu_profile_read(pfcu_profile *out)
 
 int pfcu_finish(void)
 {
+    API_LOCK;
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     for (int i = 0; i < g.n_lanes; i++) CK(cudaStreamSynchronize(g.lanes[i].stream));
     return PFCU_OK;
@@ -2013,6 +2038,7 @@ int pfcu_finish(void)
 
 int pfcu_get_counters(pfcu_counters *out)
 {
+    API_LOCK;
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
     unsigned long long h[4] = { 0, 0, 0, 0 };
     sync_all_lanes();
@@ -2028,6 +2054,7 @@ int pfcu_get_counters(pfcu_counters *out)
 
 void pfcu_reset_counters(void)
 {
+    API_LOCK;
     if (!g.ok) return;
     sync_all_lanes();
     cudaMemset(g.d_counters, 0, 4 * sizeof(unsigned long long));

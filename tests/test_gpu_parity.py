@@ -257,3 +257,59 @@ def test_fullsize_phong_properties(product_scenes):
     assert lit.sum() > 0.4 * w * h
     assert ((c1[lit] >> 24) == 0).all()
     assert r2.pixels_shaded == 2 * r1.pixels_shaded          # each frame clears first, so both frames shade alike
+
+
+# ---- device vertex stage, lanes, batch growth ------------------------------------------------------------
+
+def _render_with_env(scene, w, h, env, **kw):
+    """Render in a fresh process so that environment knobs read at start-up take effect."""
+    import json, os, subprocess, sys, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "o.npz")
+        code = ("import sys, numpy as np; sys.path.insert(0, %r)\n"
+                "from pixelforge_b200 import load_product_scenes\n"
+                "c, d, r = load_product_scenes().render(%r, %d, %d, **%r)\n"
+                "np.savez(%r, color=c, depth=d, tris=r.triangles_submitted, px=r.pixels_shaded)\n") % (root, scene, w, h, kw, out)
+        e = dict(os.environ); e.update(env)
+        subprocess.run([sys.executable, "-c", code], check=True, env=e)
+        z = np.load(out)
+        return z["color"], z["depth"], int(z["tris"]), int(z["px"])
+
+
+@pytest.mark.parametrize("scene,kw", [("textured", dict(size=96, variant=1 | 32 | 64)), ("phong", dict(size=64, variant=32))],
+                         ids=["textured-closeup-clipped", "phong"])
+def test_device_vertex_stage_equals_host_stage(scene, kw):
+    """Large vertex-array draws run transform/clip/project on the GPU (pf_vstage.h compiled as device code);
+    the result must be bit-identical to the host vertex stage, including the triangle count after clipping."""
+    a = _render_with_env(scene, 640, 360, {"PF_CUDA_DEVICE_VERTEX": "1"}, **kw)
+    b = _render_with_env(scene, 640, 360, {"PF_CUDA_DEVICE_VERTEX": "0"}, **kw)
+    assert a[2] == b[2] and a[3] == b[3]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("env", [{"PF_CUDA_LANES": "1"}, {"PF_CUDA_LANES": "8"}, {"PF_CUDA_BATCH_TRIS": "300"},
+                                 {"PF_CUDA_SLICE": "64"}, {"PF_CUDA_SLICE": "32"}, {"PF_CUDA_PIN_HOST": "0"}],
+                         ids=["1-lane", "8-lanes", "tiny-batches", "slice64", "slice32", "no-pin"])
+def test_runtime_knobs_do_not_change_pixels(env, product_scenes):
+    """Stream lanes, batch splitting, slice height and host pinning are performance knobs only."""
+    for scene, w, h, kw in (("batch", 256, 256, dict(size=5)), ("micro", 160, 120, dict(variant=0x1022a0 | 8 | 1, seed=18, size=40)),
+                            ("gears", 400, 300, dict())):
+        ref_c, ref_d, _ = product_scenes.render(scene, w, h, **kw)
+        c, d, _, _ = _render_with_env(scene, w, h, env, **kw)
+        assert np.array_equal(c, ref_c) and np.array_equal(d.view(np.uint32), ref_d.view(np.uint32)), (scene, env)
+
+
+def test_two_threads_two_contexts(product_scenes):
+    """One current context per thread (PF_CTX_DECL); the shared device runtime is serialised internally."""
+    import threading
+    results = {}
+
+    def work(name, first):
+        results[name] = product_scenes.render("gears", 320, 240, first_frame=first, frames=3)[0]
+
+    ts = [threading.Thread(target=work, args=(i, 2 * i)) for i in range(2)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    for i in range(2):
+        ref = product_scenes.render("gears", 320, 240, first_frame=2 * i, frames=3)[0]
+        assert np.array_equal(results[i], ref)

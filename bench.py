@@ -128,13 +128,21 @@ def run_reference(args, wl_name, bounded_frames=None, bilinear_fix=False):
     warm = 1 if bounded_frames else args.warmup
     size = wl["size"]
     sample = f"{steps} full frames after {warm} warm-up"
+    # bounded samples of the big workloads so that the CPU arm ends within minutes (work scales linearly)
     if wl["scene"] == "batch":
         size = min(size, 8)
-        sample += f", {size} contexts"
+        sample += f", {size} of {wl['size']} contexts"
+    elif wl["scene"] == "overdraw":
+        size = min(size, 4)
+        sample += f", {size} of {wl['size']} layers"
+    if wl["scene"] in ("overdraw", "phong") and not bounded_frames:
+        steps, warm = min(steps, 3), min(warm, 1)
+        sample = f"{steps} frames after {warm} warm-up" + (f", {size} of {wl['size']} layers" if wl["scene"] == "overdraw" else "")
     _, _, res = lib.render(wl["scene"], wl["w"], wl["h"], frames=steps, warmup=warm, variant=wl["variant"], size=size, want_depth=False)
     counts = shaded_pixels_table().get(wl_name, {})
-    px = counts.get("pixels_shaded", 0) * (size / wl["size"] if wl["scene"] == "batch" else 1)
-    tris = counts.get("triangles_submitted", 0) * (size / wl["size"] if wl["scene"] == "batch" else 1)
+    scale = (size / wl["size"]) if wl["scene"] in ("batch", "overdraw") else 1
+    px = counts.get("pixels_shaded", 0) * scale
+    tris = counts.get("triangles_submitted", 0) * scale
     ms = res.ms_total / max(steps, 1)
     return {"ms_per_step": ms, "gpix": px / (ms * 1e-3) / 1e9 if ms > 0 else 0.0, "mtri": tris / (ms * 1e-3) / 1e6 if ms > 0 else 0.0,
             "ms_median": res.ms_median, "cores": int(os.environ["OMP_NUM_THREADS"]), "sample": sample,
@@ -334,6 +342,24 @@ def ours_main(args):
         if world > 1:
             dist.destroy_process_group()
         return 0
+
+    def cpu_run(name, frames):
+        env = dict(os.environ); env.pop("OMP_NUM_THREADS", None)      # torchrun pins it to 1; the baseline uses every core
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--as-baseline", "--workload", name,
+                            "--baseline-frames", str(frames)], capture_output=True, text=True, timeout=900, env=env)
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        c = j.get("cpu_baseline") or {"unavailable": j.get("unavailable")}
+        if "value" in c:
+            c["ms_per_frame_of_sample"] = j["ms_per_step"]; c["mtri_per_s"] = j.get("mtri_per_s")
+        return c
+
+    if not args.no_cpu_baseline and not args.no_extra:
+        for n in extra:
+            if n in WORKLOADS and "error" not in extra[n]:
+                try:
+                    extra[n]["cpu_baseline"] = cpu_run(n, 2)
+                except Exception as e:
+                    extra[n]["cpu_baseline"] = {"unavailable": repr(e)}
 
     cpu = None
     if not args.no_cpu_baseline:

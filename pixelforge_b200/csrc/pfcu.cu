@@ -2,14 +2,16 @@
  * pfcu.cu - sm_100a implementation of the pfcu C-ABI (include/pfcu.h): the per-fragment triangle
  * path of PixelForge on a B200.
  *
- * Pipeline per submitted batch (all on one stream, order preserving):
+ * Pipeline per submitted batch (each surface's work stays on one stream "lane", order preserving):
+ *   k_vertex_* (optional) device vertex stage for large vertex-array draws: pf_vstage.h compiled as device
+ *             code (transform, Phong prologue, clipping, projection), count -> scan -> emit keeps order;
  *   k_setup   one thread per triangle: integer snap, signed area / face cull, bbox, int32 edge
  *             constants, 1/sum (reference: triangles.c:294-349); writes bbox[], TriSetup[], TriData[];
- *   k_bin_*   coarse binning (512x512 px bins) with warp-ballot compaction; per-bin triangle lists
+ *   k_bin_*   coarse binning (256x256 px bins) with warp-ballot compaction; per-bin triangle lists
  *             keep submission order (count -> scan -> ordered fill);
- *   k_raster  one CTA per 64x64 screen tile: colour + depth tile staged in shared memory, the
- *             bin's list is filtered against the tile (bbox + edge-function reject) by ballot
- *             compaction into a shared queue, and every warp walks the queue IN ORDER over the
+ *   k_raster  one CTA per 64x64 screen tile (or a 64x32 / 64x16 slice of it): colour + depth tile staged in
+ *             shared memory, the bin's list is filtered against the tile (bbox + edge-function reject) by
+ *             ballot compaction into a shared queue, and every warp walks the queue IN ORDER over the
  *             8x4-pixel blocks it owns (fixed pixel ownership => blending/depth order equals
  *             submission order without atomics).  Coverage, depth, colour interpolation,
  *             texturing, per-fragment Blinn-Phong and blending restate the reference's AVX2 lane
@@ -688,7 +690,7 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY,
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-/* kernel: tile rasteriser                                                                          */
+/* tile rasteriser: parameters, shared-tile addressing, packed colour arithmetic                    */
 /* ------------------------------------------------------------------------------------------------ */
 
 struct RasterParams {

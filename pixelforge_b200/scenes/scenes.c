@@ -377,6 +377,154 @@ static void micro_scene(const pfscene_cfg *cfg, PFtexture tex)
     pfBindTexture(0);
 }
 
+
+/* ---- "api": breadth of the public API around the triangle path ------------------------------------ */
+/* variant bits: 0 viewport sub-rectangle, 1 texture matrix, 2 Gouraud lighting with two lights (one spot
+   with attenuation), 3 separate back material + no culling, 4 pfRect*, 5 pfDrawPixels with zoom,
+   6 fog, 7 pfPostProcess, 8 pfReadPixels -> pfDrawPixels, 9 pfClearDepth(0.9), 10 cull front faces,
+   11 PF_NORMALIZE with unnormalised normals, 12 colour material (front, diffuse), 13 vertex arrays with a
+   colour pointer (pfDrawArrays, quads), 14 aux buffer + pfSwapBuffers, 15-16 fog mode, 17 blend on */
+
+static PFcolor api_postprocess(PFint x, PFint y, PFfloat depth, PFcolor c)
+{
+    PFcolor o = c;
+    if (((x >> 3) ^ (y >> 3)) & 1) { o.r = (PFubyte)(255 - c.r); o.b = (PFubyte)((c.b + c.g) >> 1); }
+    if (depth < 0.5f) o.g = (PFubyte)(c.g >> 1);
+    return o;
+}
+
+static void api_scene(const pfscene_cfg *cfg, PFtexture tex, uint8_t *aux)
+{
+    const int v = cfg->variant, w = cfg->width, h = cfg->height;
+    lcg_state = (uint32_t)cfg->seed * 747796405u + 2891336453u;
+    if (v & (1 << 14)) pfSetAuxBuffer(aux);
+    pfClearColor(40, 30, 20, 255);
+    pfClearDepth((v & (1 << 9)) ? 0.9f : 3.4028234663852886e38f);
+    pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
+    pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+    cam_perspective(55.0, (double)w / h, 0.1, 50.0);
+    if (v & 1) pfViewport(w / 8, h / 8, (PFsizei)(w * 3 / 4), (PFsizei)(h * 3 / 4));
+    float eye[3] = { 0.5f, 0.8f, 4.0f }, at[3] = { 0, 0, 0 };
+    cam_lookat(eye, at);
+    pfEnable(PF_DEPTH_TEST); pfDepthFunc(PF_LESS);
+    pfEnable(PF_TEXTURE_2D); pfBindTexture(tex);
+    if (v & (1 << 17)) { pfEnable(PF_BLEND); pfBlendFunc(PF_BLEND_ALPHA); } else pfDisable(PF_BLEND);
+    if (v & 2) {
+        pfMatrixMode(PF_TEXTURE); pfLoadIdentity();
+        pfTranslatef(0.25f, 0.1f, 0.0f); pfScalef(2.0f, 0.5f, 1.0f); pfRotatef(30.0f, 0.0f, 0.0f, 1.0f);
+        pfMatrixMode(PF_MODELVIEW);
+    }
+    if (v & 8) pfDisable(PF_CULL_FACE); else { pfEnable(PF_CULL_FACE); pfCullFace((v & (1 << 10)) ? PF_FRONT : PF_BACK); }
+    if (v & 4) {
+        float p0[3] = { 1.0f, 2.0f, 3.0f }, p1[3] = { -2.0f, 1.0f, 2.0f }, d1[3] = { 0.6f, -0.3f, -0.7f };
+        float dif[3] = { 0.9f, 0.8f, 0.6f }, spec[3] = { 0.5f, 0.6f, 0.7f }, amb[3] = { 0.15f, 0.1f, 0.2f };
+        float mdif[3] = { 0.7f, 0.9f, 0.5f }, mspec[3] = { 0.9f, 0.9f, 0.9f }, memi[3] = { 0.05f, 0.0f, 0.1f }, bdif[3] = { 0.2f, 0.3f, 0.9f };
+        pfEnable(PF_LIGHTING); pfLightModel(PF_GOURAUD);
+        pfLightfv(PF_LIGHT0, PF_POSITION, p0); pfLightfv(PF_LIGHT0, PF_DIFFUSE, dif); pfLightfv(PF_LIGHT0, PF_AMBIENT, amb);
+        pfLightf(PF_LIGHT0, PF_LINEAR_ATTENUATION, 0.08f); pfLightf(PF_LIGHT0, PF_CONSTANT_ATTENUATION, 0.9f);
+        pfEnableLight(PF_LIGHT0);
+        pfLightfv(PF_LIGHT2, PF_POSITION, p1); pfLightfv(PF_LIGHT2, PF_SPOT_DIRECTION, d1); pfLightfv(PF_LIGHT2, PF_SPECULAR, spec);
+        pfLightf(PF_LIGHT2, PF_SPOT_INNER_CUTOFF, 20.0f); pfLightf(PF_LIGHT2, PF_SPOT_OUTER_CUTOFF, 35.0f);
+        pfLightf(PF_LIGHT2, PF_QUADRATIC_ATTENUATION, 0.03f);
+        pfEnableLight(PF_LIGHT2);
+        pfMaterialfv(PF_FRONT, PF_DIFFUSE, mdif); pfMaterialfv(PF_FRONT, PF_SPECULAR, mspec); pfMaterialfv(PF_FRONT, PF_EMISSION, memi);
+        pfMaterialf(PF_FRONT, PF_SHININESS, 12.0f);
+        if (v & 8) { pfMaterialfv(PF_BACK, PF_AMBIENT_AND_DIFFUSE, bdif); pfMaterialf(PF_BACK, PF_SHININESS, 40.0f); }
+        if (v & (1 << 12)) { pfEnable(PF_COLOR_MATERIAL); pfColorMaterial(PF_FRONT, PF_DIFFUSE); }
+    }
+    if (v & (1 << 11)) pfEnable(PF_NORMALIZE);
+    const int n = cfg->size > 0 ? cfg->size : 48;
+    if (v & (1 << 13)) {
+        static float pos[4 * 64 * 3], nrm[4 * 64 * 3], uv[4 * 64 * 2]; static PFubyte col[4 * 64 * 4];
+        const int q = n > 64 ? 64 : n;
+        for (int i = 0; i < q; i++) {
+            float cx = lcgf() * 4.0f - 2.0f, cy = lcgf() * 3.0f - 1.5f, cz = lcgf() * 3.0f - 1.5f, sz = 0.2f + lcgf() * 0.8f;
+            static const float ox[4] = { -1, -1, 1, 1 }, oy[4] = { 1, -1, -1, 1 };
+            for (int k = 0; k < 4; k++) {
+                int j = i * 4 + k;
+                pos[3 * j] = cx + ox[k] * sz; pos[3 * j + 1] = cy + oy[k] * sz; pos[3 * j + 2] = cz + 0.3f * ox[k] * oy[k];
+                nrm[3 * j] = 0.3f * ox[k]; nrm[3 * j + 1] = 0.2f * oy[k]; nrm[3 * j + 2] = (v & (1 << 11)) ? 2.5f : 0.93f;
+                uv[2 * j] = 0.5f * (ox[k] + 1.0f) * 1.5f; uv[2 * j + 1] = 0.5f * (oy[k] + 1.0f) * 1.5f;
+                for (int c = 0; c < 4; c++) col[4 * j + c] = (PFubyte)(c == 3 ? 128 + (lcg() >> 25) : lcg() >> 24);
+            }
+        }
+        pfEnable(PF_VERTEX_ARRAY); pfEnable(PF_NORMAL_ARRAY); pfEnable(PF_TEXTURE_COORD_ARRAY); pfEnable(PF_COLOR_ARRAY);
+        pfVertexPointer(3, PF_FLOAT, 0, pos); pfNormalPointer(PF_FLOAT, 0, nrm); pfTexCoordPointer(PF_FLOAT, 0, uv);
+        pfColorPointer(4, PF_UNSIGNED_BYTE, 0, col);
+        pfDrawArrays(PF_QUADS, 0, (PFsizei)(q * 4));
+        pfDisable(PF_VERTEX_ARRAY); pfDisable(PF_NORMAL_ARRAY); pfDisable(PF_TEXTURE_COORD_ARRAY); pfDisable(PF_COLOR_ARRAY);
+    } else {
+        pfBegin(PF_TRIANGLES);
+        for (int i = 0; i < n * 3; i++) {
+            PFcolor c = { (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(128 + (lcg() >> 25)) };
+            pfColor(c);
+            pfTexCoord2f(lcgf() * 3.0f - 1.0f, lcgf() * 3.0f - 1.0f);
+            float nz = (v & (1 << 11)) ? 2.5f : 0.93f;
+            pfNormal3f(0.6f * (lcgf() - 0.5f), 0.6f * (lcgf() - 0.5f), nz);
+            pfVertex3f(lcgf() * 5.0f - 2.5f, lcgf() * 4.0f - 2.0f, lcgf() * 5.0f - 2.0f);
+        }
+        pfEnd();
+    }
+    pfDisable(PF_LIGHTING); pfDisableLight(PF_LIGHT0); pfDisableLight(PF_LIGHT2); pfDisable(PF_COLOR_MATERIAL); pfDisable(PF_NORMALIZE);
+    pfMatrixMode(PF_TEXTURE); pfLoadIdentity(); pfMatrixMode(PF_MODELVIEW);
+    pfBindTexture(0); pfDisable(PF_TEXTURE_2D);
+
+    if (v & (1 << 4)) {
+        ortho2d(w, h);
+        pfColor4ub(250, 200, 10, 255); pfRectf(10.5f, 12.25f, 0.4f * w, 0.3f * h);
+        pfColor4ub(10, 200, 250, 255); pfRects((PFshort)(w - 30), (PFshort)(h - 20), (PFshort)(w + 50), (PFshort)(h / 2));
+        float a[2] = { 0.5f * w, 0.6f * h }, b[2] = { 0.45f * w, 0.9f * h };
+        pfColor4ub(200, 20, 220, 255); pfRectfv(a, b);
+    }
+    static uint32_t sprite[24 * 16];
+    if (v & ((1 << 5) | (1 << 8))) {
+        ortho2d(w, h);
+        for (int i = 0; i < 24 * 16; i++) sprite[i] = lcg() | ((i & 4) ? 0xFF000000u : 0x60000000u);
+    }
+    if (v & (1 << 5)) {
+        pfEnable(PF_BLEND); pfBlendFunc(PF_BLEND_ALPHA);
+        pfPixelZoom(2.5f, 1.75f); pfRasterPos3f(0.3f * w, 0.35f * h, -0.25f);
+        pfDrawPixels(24, 16, PF_RGBA, PF_UNSIGNED_BYTE, sprite);
+        pfDisable(PF_DEPTH_TEST); pfDisable(PF_BLEND);
+        pfPixelZoom(1.0f, 1.0f); pfRasterPos2i(w - 12, h - 9);                   /* clipped by the viewport */
+        pfDrawPixels(24, 16, PF_RGBA, PF_UNSIGNED_BYTE, sprite);
+        pfEnable(PF_DEPTH_TEST);
+    }
+    if (v & (1 << 8)) {
+        static uint32_t grab[40 * 30];
+        memset(grab, 0, sizeof grab);
+        pfReadPixels(w / 3, h / 3, 40, 30, PF_RGBA, PF_UNSIGNED_BYTE, grab);
+        pfDisable(PF_DEPTH_TEST); pfDisable(PF_BLEND);
+        pfPixelZoom(1.0f, 1.0f); pfRasterPos2f(4.0f, (float)h - 40.0f);
+        pfDrawPixels(40, 30, PF_RGBA, PF_UNSIGNED_BYTE, grab);
+        pfEnable(PF_DEPTH_TEST);
+    }
+    if (v & (1 << 6)) {
+        PFint fc[4] = { 180, 190, 220, (v & (1 << 16)) ? 255 : 200 };
+        pfFogi(PF_FOG_MODE, (PFint)(PF_LINEAR + ((v >> 15) & 1) * 1));
+        pfFogf(PF_FOG_DENSITY, 0.8f); pfFogf(PF_FOG_START, 0.93f); pfFogf(PF_FOG_END, 0.985f);
+        pfFogiv(PF_FOG_COLOR, fc);
+        pfFogProcess();
+    }
+    if (v & (1 << 7)) pfPostProcess(api_postprocess);
+    if (v & (1 << 14)) {
+        /* present: the finished frame moves to the aux buffer, drawing continues in the other one */
+        pfSwapBuffers();
+        pfClearColor(1, 2, 3, 255); pfClear(PF_COLOR_BUFFER_BIT);
+        ortho2d(w, h);
+        pfDisable(PF_DEPTH_TEST);
+        pfColor4ub(255, 255, 255, 255);
+        pfBegin(PF_TRIANGLES); pfVertex2f(5.0f, 5.0f); pfVertex2f(5.0f, 0.8f * h); pfVertex2f(0.7f * w, 0.5f * h); pfEnd();
+        pfSwapBuffers();
+        /* thumbnail of what was drawn into the other buffer, so that it is part of the compared output */
+        pfDisable(PF_BLEND);
+        pfPixelZoom(0.25f, 0.25f); pfRasterPos2f(0.7f * w, 4.0f);
+        pfDrawPixels((PFsizei)w, (PFsizei)h, PF_RGBA, PF_UNSIGNED_BYTE, aux);
+        pfPixelZoom(1.0f, 1.0f);
+    }
+    pfDisable(PF_BLEND);
+}
+
 /* ---- the runner ------------------------------------------------------------------------------------ */
 
 #define MAX_BATCH_CTX 1024
@@ -385,7 +533,7 @@ typedef struct {
     char name[32];
     pfscene_cfg cfg;
     /* single-context scenes */
-    PFcontext ctx; uint8_t *target; uint8_t *texpx; PFtexture tex; mesh_t mesh; PFframebuffer fbo;
+    PFcontext ctx; uint8_t *target; uint8_t *aux; uint8_t *texpx; PFtexture tex; mesh_t mesh; PFframebuffer fbo;
     /* "batch": n contexts */
     int n; PFcontext *ctxs; uint8_t **bufs; uint8_t **texpxs; PFtexture *texs; PFrenderlist (*lists)[3];
 } scene_t;
@@ -505,6 +653,11 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
            MAIN buffer the reference computes vpMax = x+width (one past the last column/row,
            context.c:567-570), so "2D" triangles may touch column 96 / row 80 */
         if (cfg->variant & (1 << 20)) s->fbo = pfGenFramebuffer(104, 88, PF_RGBA, PF_UNSIGNED_BYTE);
+    } else if (strcmp(name, "api") == 0) {
+        s->texpx = make_texture(64, 48, 4, (uint32_t)cfg->seed ^ 0x5151u, 0, 255, 64, 255);
+        s->tex = pfGenTexture(s->texpx, 64, 48, PF_RGBA, PF_UNSIGNED_BYTE);
+        pfTextureParameter(s->tex, PF_REPEAT, (cfg->variant & (1 << 18)) ? PF_BILINEAR : PF_NEAREST);
+        s->aux = (uint8_t *)calloc((size_t)w * h * 4 + 64, 1);
     } else {
         fprintf(stderr, "pfscene: unknown scene '%s'\n", name);
         pfscene_close(s);
@@ -592,6 +745,8 @@ SCN_API void pfscene_frame(void *handle, int frame)
             pfColor4ub(255, 255, 255, 255);
             draw_textured_quad(s->fbo.texture, 8.0f, 6.0f, 0.7f * w, 0.6f * h, 1.0f, 1.0f);
         } else micro_scene(cfg, s->tex);
+    } else if (strcmp(name, "api") == 0) {
+        api_scene(cfg, s->tex, s->aux);
     }
 }
 
@@ -642,7 +797,7 @@ SCN_API void pfscene_close(void *handle)
         if (s->mesh.pos) free_mesh(&s->mesh);
         pfMakeCurrent(NULL);
         pfDeleteContext(s->ctx);
-        free(s->target);
+        free(s->target); free(s->aux);
     }
     free(s);
 }

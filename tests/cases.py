@@ -58,5 +58,25 @@ CASES += [_micro("fbo", 18, fbo=1, tex=1, cull_off=1, depth=2), _micro("fbo-pers
 CASES += [_micro(f"random{s}", s, size=60, blend=s % 8, depth=s % 6, tex=s & 1, wrap=s % 3, cull_off=(s >> 1) & 1,
                  mode=s % 6, persp=(s >> 2) & 1, flat=(s >> 3) & 1) for s in range(20, 40)]
 
+
+
+# breadth of the public API around the triangle path (scene "api", see scenes.c for the variant bits):
+# viewport offsets, texture matrix, Gouraud with spot/attenuation/back materials/colour material/normalize,
+# colour arrays, pfRect*, pfDrawPixels + zoom, fog, post-processing, pfReadPixels, pfClearDepth, aux buffer
+def _api(desc, variant, seed=1, ref_bfix=False):
+    return (f"api-{desc}", "api", 200, 150, dict(variant=variant, seed=seed), ref_bfix)
+
+
+_B = lambda *bits: sum(1 << b for b in bits)
+CASES += [_api("plain", 0), _api("viewport", _B(0)), _api("texmatrix", _B(1)), _api("gouraud", _B(2)),
+          _api("gouraud-backmat", _B(2, 3)), _api("gouraud-backmat-colormat", _B(2, 3, 12)),
+          _api("gouraud-normalize", _B(2, 11)), _api("arrays-colorptr", _B(13)),
+          _api("gouraud-arrays-normalize-colormat", _B(2, 11, 12, 13)), _api("cullfront", _B(10)),
+          _api("rects", _B(4)), _api("rects-viewport", _B(0, 4)), _api("drawpixels", _B(5)),
+          _api("drawpixels-viewport-blend", _B(0, 5, 17)), _api("readpixels", _B(8)),
+          _api("fog-linear", _B(6)), _api("fog-exp-opaque", _B(6, 15, 16)), _api("fog-cleardepth", _B(6, 9)),
+          _api("postprocess", _B(7)), _api("swapbuffers", _B(14, 7)),
+          _api("everything", 0x3ffff & ~_B(13), seed=2), _api("everything-bilinear", 0x7ffff & ~_B(13), seed=3, ref_bfix=True)]
+
 CASE_IDS = [c[0] for c in CASES]
 assert len(set(CASE_IDS)) == len(CASE_IDS)

@@ -725,13 +725,14 @@ __device__ __forceinline__ unsigned smooth_lanes(unsigned a, unsigned b, unsigne
     return (x >> 8) & 0x00ff00ffu;
 }
 
-/* (texel * frag) >> 8 per channel (blend.h:199-212) */
+/* (texel * frag) >> 8 per channel (blend.h:199-212).  dp2a multiplies one 16-bit lane of the fragment by
+ * one byte of the texel without extracting the byte first (the other 16-bit lane is zero). */
 __device__ __forceinline__ Px2 px_mul(unsigned texel, Px2 f)
 {
-    const unsigned r = (texel & 0xffu) * (f.rb & 0xffffu);
-    const unsigned g = ((texel >> 8) & 0xffu) * (f.ga & 0xffffu);
-    const unsigned b = ((texel >> 16) & 0xffu) * (f.rb >> 16);
-    const unsigned a = (texel >> 24) * (f.ga >> 16);
+    const unsigned r = __dp2a_lo(f.rb & 0xffffu, texel, 0u);          /* fr * texel.byte0 */
+    const unsigned g = __dp2a_lo(f.ga << 16, texel, 0u);              /* fg * texel.byte1 */
+    const unsigned b = __dp2a_hi(f.rb >> 16, texel, 0u);              /* fb * texel.byte2 */
+    const unsigned a = __dp2a_hi(f.ga & 0xffff0000u, texel, 0u);      /* fa * texel.byte3 */
     Px2 o;
     o.rb = __byte_perm(r, b, 0x7531);      /* byte1 of each product; bytes 3 are zero */
     o.ga = __byte_perm(g, a, 0x7531);
@@ -774,6 +775,21 @@ __device__ __forceinline__ unsigned depth_mask(int func)
     return (0x643122u >> (4 * func)) & 7u;   /* nibbles, low first: EQ 2, NEQ 2 (Q5), LT 1, LE 3, GT 4, GE 6 */
 }
 
+/* The compare selected by the warp-uniform zmask as three predicated compares (a switch or an if-chain
+ * over the function both compile to a jump table inside the block loop). */
+__device__ __forceinline__ bool depth_pass_mask(float z, float zb, unsigned zmask)
+{
+    unsigned r;
+    asm("{\n\t.reg .pred pl, pe, pg;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %3, 1;\n\tsetp.ne.u32 pl, t, 0;\n\t"
+        "and.b32 t, %3, 2;\n\tsetp.ne.u32 pe, t, 0;\n\t"
+        "and.b32 t, %3, 4;\n\tsetp.ne.u32 pg, t, 0;\n\t"
+        "setp.lt.and.f32 pl, %1, %2, pl;\n\tsetp.eq.and.f32 pe, %1, %2, pe;\n\tsetp.gt.and.f32 pg, %1, %2, pg;\n\t"
+        "or.pred pl, pl, pe;\n\tor.pred pl, pl, pg;\n\tselp.u32 %0, 1, 0, pl;\n\t}"
+        : "=r"(r) : "f"(z), "f"(zb), "r"(zmask));
+    return r != 0u;
+}
+
 /* shared-memory access through 32-bit window addresses computed once per CTA (the compiler otherwise
  * rebuilds the cluster-window base of every __shared__ array at each access) */
 #define SM_COLOR 0          /* byte offsets inside the CTA's shared block */
@@ -805,14 +821,17 @@ struct TileCtx {
     unsigned sm_base;                   /* shared-window byte address of the CTA's block (opaque)  */
     int rcp_shift; bool rcp_shared;
     int lx8, ly4, warp;
-    unsigned shaded, zfailed;
+    unsigned lane_rel;                  /* byte offset of this lane's pixel in block (0,0), XOR term folded in (opaque) */
+    unsigned shaded, covered;
     const TriData *data;
 };
 
 /* One triangle over the 8x4 blocks this warp owns.  TEXM: 0 no texture, 1 nearest+REPEAT+RGBA8,
  * 2 any sampler.  BLENDM: 0 off, 1 ALPHA, 2 ADD, 3 any mode.  Everything is computed for all 32 lanes
- * (no divergent regions); only the final stores are predicated by the coverage/depth mask. */
-template <int TEXM, int BLENDM, bool PHONG, int NW>
+ * (no divergent regions); only the final stores are predicated by the coverage/depth mask.
+ * BIG: the launch is a batch of large triangles in ONE state program with the RCPPS table in shared memory
+ * (launch_pipeline checks both), so some per-block early-outs and run-time checks are dropped. */
+template <int TEXM, int BLENDM, bool PHONG, int NW, bool BIG>
 __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const int4 b, const TriSetup &s, const uint4 a0, const uint4 a1,
                                           const DevState *st, const unsigned flags, const unsigned zmask, const int blend_mode, const TexRegs &tex)
 {
@@ -843,35 +862,36 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
     const int e1 = wadd(wadd(s.w1R, wmul(dy0, s.w1Y)), wmul(dx0, s.w1X));
     const int e2 = wadd(wadd(s.w2R, wmul(dy0, s.w2Y)), wmul(dx0, s.w2X));
     const int e3 = wadd(wadd(s.w3R, wmul(dy0, s.w3Y)), wmul(dx0, s.w3X));
+    const int rxc = t.lx8 - cx0, ryc = t.ly4 - cy0;            /* lane offset from the clipped bbox corner */
 
     /* block ownership: 8 warps -> warp w owns block (bx,by) iff (bx + 3*by) & 7 == w;
        16 warps -> additionally even block rows belong to warps 0..7, odd rows to warps 8..15 */
     for (int by = by0; by <= by1; by++) {
         if (NW == 16 && (by & 1) != (t.warp >> 3)) continue;
         const int bx = ((t.warp & 7) - 3 * by) & 7;
-        if (bx < bx0 || bx > bx1) continue;
-        const int lx = (bx << 3) + t.lx8, ly = (by << 2) + t.ly4;
-        const int w1 = wadd(e1, wadd(wmul(bx << 3, s.w1X), wmul(by << 2, s.w1Y)));
-        const int w2 = wadd(e2, wadd(wmul(bx << 3, s.w2X), wmul(by << 2, s.w2Y)));
-        const int w3 = wadd(e3, wadd(wmul(bx << 3, s.w3X), wmul(by << 2, s.w3Y)));
-        bool m = ((w1 | w2 | w3) > 0) && (unsigned)(lx - cx0) <= xspan && (unsigned)(ly - cy0) <= yspan;
+        /* skipping blocks left/right of the bbox early pays for small triangles only; the per-lane
+           x-range test below rejects them anyway */
+        if (!BIG && (bx < bx0 || bx > bx1)) continue;
+        const int bx8 = bx << 3, by4 = by << 2;
+        const int w1 = wadd(wmul(bx8, s.w1X), wadd(wmul(by4, s.w1Y), e1));
+        const int w2 = wadd(wmul(bx8, s.w2X), wadd(wmul(by4, s.w2Y), e2));
+        const int w3 = wadd(wmul(bx8, s.w3X), wadd(wmul(by4, s.w3Y), e3));
+        bool m = ((w1 | w2 | w3) > 0) && (unsigned)(bx8 + rxc) <= xspan && (unsigned)(by4 + ryc) <= yspan;
         if (!__any_sync(0xffffffffu, m)) continue;
+        /* depth-failed = covered - shaded, taken at the end; a predicated add (the compiler turns the C
+           form into a three-instruction select when a branch follows) */
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(t.covered) : "r"((unsigned)m));
 
         const float W1 = FM(__int2float_rn(w1), s.invSum);
         const float W2 = FM(__int2float_rn(w2), s.invSum);
         const float W3 = FM(__int2float_rn(w3), s.invSum);
         const float zsum = FA(FA(FM(z1, W1), FM(z2, W2)), FM(z3, W3));
-        const float z = t.rcp_shared ? rcp_fast(t.sm_base, t.rcp_shift, zsum) : rcp_x86(zsum);
-        const unsigned sa = t.sm_base + ((unsigned)tile_addr(lx, ly) << 2);
+        const float z = (BIG || t.rcp_shared) ? rcp_fast(t.sm_base, t.rcp_shift, zsum) : rcp_x86(zsum);
+        /* byte address of tile_addr(bx8 + lx8, by4 + ly4) */
+        const unsigned sa = t.sm_base + ((unsigned)by << 10) + (t.lane_rel ^ ((unsigned)bx8 << 2));
         if (ztest) {
             const float zb = lds_depth(sa);
-            bool pass;                              /* zmask is warp-uniform; an if-chain (most common first) */
-            if (zmask == 1u) pass = z < zb;         /* avoids the jump table a switch compiles to           */
-            else if (zmask == 3u) pass = z <= zb;
-            else if (zmask == 2u) pass = z == zb;
-            else if (zmask == 4u) pass = z > zb;
-            else pass = z >= zb;
-            t.zfailed += (m && !pass) ? 1u : 0u;
+            const bool pass = depth_pass_mask(z, zb, zmask);
             m = m && pass;
             if (!__any_sync(0xffffffffu, m)) continue;
         }
@@ -898,7 +918,8 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
             float u = FA(FA(FM(tu1, W1), FM(tu2, W2)), FM(tu3, W3));
             float v = FA(FA(FM(tv1, W1), FM(tv2, W2)), FM(tv3, W3));
             if (is3d) { u = FM(u, z); v = FM(v, z); }
-            if (!m) { u = 0.0f; v = 0.0f; }                 /* triangles.c:510: masked-off lanes sample (0,0) */
+            /* masked-off lanes: the reference samples (0,0) for them (triangles.c:510) only to stay inside
+               the texture; here every fetch is bounds-checked and their result is never stored */
             unsigned texel;
             if (TEXM == 1) {
                 const float fu = FM(FS(u, truncf(u)), tex.wm1), fv = FM(FS(v, truncf(v)), tex.hm1);
@@ -978,8 +999,15 @@ k_raster(const RasterParams p)
         unsigned base = (unsigned)__cvta_generic_to_shared(s_mem);
         asm volatile("mov.u32 %0, %1;" : "=r"(t.sm_base) : "r"(base));
     }
-    t.lx8 = lane & 7; t.ly4 = lane >> 3; t.warp = warp;
-    t.shaded = 0; t.zfailed = 0; t.data = p.data;
+    t.lx8 = lane & 7; t.ly4 = lane >> 3;
+    asm volatile("mov.u32 %0, %1;" : "=r"(t.warp) : "r"(warp));      /* opaque: not re-derived from %tid in the block loop */
+    {   /* tile_addr(bx*8 + lx8, by*4 + ly4)*4 == by*1024 + (lane_rel ^ (bx << 5)): the swizzle (ly4 << 5) and the
+           pixel offset occupy disjoint bits.  Opaque so that it stays in a register instead of being rebuilt
+           from %tid in every block iteration. */
+        unsigned rel = (unsigned)(t.ly4 * (TILE * 4 + 32) + t.lx8 * 4);
+        asm volatile("mov.u32 %0, %1;" : "=r"(t.lane_rel) : "r"(rel));
+    }
+    t.shaded = 0; t.covered = 0; t.data = p.data;
 
     bool loaded = false;
 
@@ -1097,23 +1125,23 @@ k_raster(const RasterParams p)
                     if (HAS_PHONG && (flags & PFCU_ST_PHONG)) prog = 12;
                 }
                 if (FIXED_PROG >= 0) {
-                    shade_tri<FIXED_PROG / 4, FIXED_PROG % 4, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex);
+                    shade_tri<FIXED_PROG / 4, FIXED_PROG % 4, false, NW, true>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex);
                     continue;
                 }
                 switch (prog) {
-                case 0:  shade_tri<0, 0, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 1:  shade_tri<0, 1, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 2:  shade_tri<0, 2, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 3:  shade_tri<0, 3, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 4:  shade_tri<1, 0, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 5:  shade_tri<1, 1, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 6:  shade_tri<1, 2, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 7:  shade_tri<1, 3, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 8:  shade_tri<2, 0, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 9:  shade_tri<2, 1, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 10: shade_tri<2, 2, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                case 11: shade_tri<2, 3, false, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
-                default: if (HAS_PHONG) shade_tri<2, 3, true, NW>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 0:  shade_tri<0, 0, false, NW, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 1:  shade_tri<0, 1, false, NW, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 2:  shade_tri<0, 2, false, NW, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 3:  shade_tri<0, 3, false, NW, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 4:  shade_tri<1, 0, false, NW, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 5:  shade_tri<1, 1, false, NW, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 6:  shade_tri<1, 2, false, NW, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 7:  shade_tri<1, 3, false, NW, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 8:  shade_tri<2, 0, false, NW, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 9:  shade_tri<2, 1, false, NW, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 10: shade_tri<2, 2, false, NW, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                case 11: shade_tri<2, 3, false, NW, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
+                default: if (HAS_PHONG) shade_tri<2, 3, true, NW, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex); break;
                 }
             }
         }
@@ -1142,7 +1170,7 @@ k_raster(const RasterParams p)
         }
     }
     /* counters: warp reduce, one atomic per warp */
-    unsigned shaded = t.shaded, zfailed = t.zfailed;
+    unsigned shaded = t.shaded, zfailed = t.covered - t.shaded;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         shaded += __shfl_down_sync(0xffffffffu, shaded, o);
@@ -1819,6 +1847,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
            few large ones: 8 warps with more registers each issue faster */
         const bool small_tris = (size_t)n > (size_t)4 * p.nTiles;
         const bool ph = (feature_mask & PFCU_ST_PHONG) != 0;
+        if (g.rcp_bits > RCP_SMEM_BITS) single_prog = -1;      /* the fixed-program kernels assume the shared RCPPS table */
         /* half-height slices when the 64x64 grid would be only a few waves deep with a ragged last wave */
         const int per_sm = (single_prog == 5 || single_prog == 6) ? 4 : 3;
         const double waves = (double)grid / ((double)g.sms * per_sm);

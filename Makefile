@@ -38,7 +38,7 @@ build/host/%.o: pixelforge_b200/csrc/host/%.c $(HOST_HDR)
 
 build/pfcu.o: pixelforge_b200/csrc/pfcu.cu include/pfcu.h pixelforge_b200/csrc/pf_vstage.h
 	@mkdir -p build
-	$(NVCC) $(NVCC_FLAGS) -Xptxas -v -c $< -o $@ 2> build/pfcu.ptxas.log || (cat build/pfcu.ptxas.log; false)
+	$(NVCC) $(NVCC_FLAGS) $(NVCC_EXTRA) -Xptxas -v -c $< -o $@ 2> build/pfcu.ptxas.log || (cat build/pfcu.ptxas.log; false)
 
 $(LIBDIR)/libpixelforge.so: $(HOST_OBJ) build/pfcu.o
 	@mkdir -p $(LIBDIR)

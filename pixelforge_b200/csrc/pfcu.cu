@@ -369,8 +369,7 @@ __device__ __forceinline__ int tex_coord(int wrap, float t, float sm1)
 {
     if (wrap == 0) {                    /* REPEAT: |RNE((t - trunc t) * (size-1))| */
         const float f = FM(FS(t, truncf(t)), sm1);
-        const int i = cvt_rne_x86(f);
-        return (i < 0) ? (int)(0u - (unsigned)i) : i;
+        return cvt_rne_x86(fabsf(f));   /* == |RNE(f)|: RNE is symmetric, 0x80000000 stays 0x80000000 */
     } else if (wrap == 1) {             /* MIRRORED_REPEAT */
         const float a = fabsf(t);
         float m = FS(a, FM(floorf(FD(a, 2.0f)), 2.0f));
@@ -848,6 +847,9 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
     const unsigned c2rb = a1.y & 0x00ff00ffu, c2ga = (a1.y >> 8) & 0x00ff00ffu;
     const unsigned c3rb = a1.z & 0x00ff00ffu, c3ga = (a1.z >> 8) & 0x00ff00ffu;
     const bool same_color = (a1.x == a1.y) && (a1.y == a1.z);
+    /* untinted (white / grey, alpha included) smooth-shaded textured triangles: the interpolated colour is one
+       scalar, see the grey_tex branches below */
+    const bool grey_tex = BIG && !PHONG && TEXM != 0 && same_color && smooth && a1.x == (a1.x & 0xffu) * 0x01010101u;
     float tu1 = 0, tu2 = 0, tu3 = 0, tv1 = 0, tv2 = 0, tv3 = 0;
     const bool texturing = TEXM != 0 && (!PHONG || (flags & PFCU_ST_TEXTURE));     /* the Phong variant checks at run time */
     const bool blending = BLENDM != 0 && (!PHONG || (flags & PFCU_ST_BLEND));
@@ -873,6 +875,8 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
            x-range test below rejects them anyway */
         if (!BIG && (bx < bx0 || bx > bx1)) continue;
         const int bx8 = bx << 3, by4 = by << 2;
+        /* byte address of tile_addr(bx8 + lx8, by4 + ly4) */
+        const unsigned sa = t.sm_base + ((unsigned)by << 10) + (t.lane_rel ^ ((unsigned)bx8 << 2));
         const int w1 = wadd(wmul(bx8, s.w1X), wadd(wmul(by4, s.w1Y), e1));
         const int w2 = wadd(wmul(bx8, s.w2X), wadd(wmul(by4, s.w2Y), e2));
         const int w3 = wadd(wmul(bx8, s.w3X), wadd(wmul(by4, s.w3Y), e3));
@@ -887,8 +891,6 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
         const float W3 = FM(__int2float_rn(w3), s.invSum);
         const float zsum = FA(FA(FM(z1, W1), FM(z2, W2)), FM(z3, W3));
         const float z = (BIG || t.rcp_shared) ? rcp_fast(t.sm_base, t.rcp_shift, zsum) : rcp_x86(zsum);
-        /* byte address of tile_addr(bx8 + lx8, by4 + ly4) */
-        const unsigned sa = t.sm_base + ((unsigned)by << 10) + (t.lane_rel ^ ((unsigned)bx8 << 2));
         if (ztest) {
             const float zb = lds_depth(sa);
             const bool pass = depth_pass_mask(z, zb, zmask);
@@ -898,9 +900,14 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
 
         /* colour (color.h:153-203) */
         Px2 frag;
+        unsigned kgrey = 0;
         if (smooth) {
             const int u1 = __float2int_rn(FM(W1, 255.0f)), u2 = __float2int_rn(FM(W2, 255.0f)), u3 = __float2int_rn(FM(W3, 255.0f));
-            if (same_color) {                       /* warp-uniform: (u1+u2+u3)*c has the same lanes as u1*c+u2*c+u3*c */
+            if (grey_tex) {                         /* all four channels equal: one scalar instead of two packed words */
+                const unsigned x = (unsigned)(u1 + u2 + u3) * (a1.x & 0xffu);
+                kgrey = (x + (x >> 8)) >> 8;        /* x <= 65280, so this is ((x*257)>>16) <= 255 */
+                frag.rb = frag.ga = 0;
+            } else if (same_color) {                       /* warp-uniform: (u1+u2+u3)*c has the same lanes as u1*c+u2*c+u3*c */
                 const unsigned us = (unsigned)(u1 + u2 + u3);
                 unsigned x = us * c1rb, y = us * c1ga;
                 x = x + ((x >> 8) & 0x00ff00ffu); y = y + ((y >> 8) & 0x00ff00ffu);
@@ -922,13 +929,18 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
                the texture; here every fetch is bounds-checked and their result is never stored */
             unsigned texel;
             if (TEXM == 1) {
+                /* |RNE(x)| == RNE(|x|) (round-to-nearest-even is symmetric; out-of-range and NaN give
+                   0x80000000 either way), and |x| is a free source modifier */
                 const float fu = FM(FS(u, truncf(u)), tex.wm1), fv = FM(FS(v, truncf(v)), tex.hm1);
-                const int xi = cvt_rne_x86(fu), yi = cvt_rne_x86(fv);
-                const unsigned off = (unsigned)abs(yi) * tex.tw + (unsigned)abs(xi);
+                const int xi = cvt_rne_x86(fabsf(fu)), yi = cvt_rne_x86(fabsf(fv));
+                const unsigned off = (unsigned)yi * tex.tw + (unsigned)xi;
                 texel = 0u;
                 if (off < tex.total) texel = __ldg((const unsigned *)tex.base + off);
             } else texel = tex_sample(tex, u, v);
-            frag = px_mul(texel, frag);
+            if (grey_tex) {                         /* (texel_c * k) >> 8 on packed lanes: products stay below 2^16 */
+                frag.rb = (((texel & 0x00ff00ffu) * kgrey) >> 8) & 0x00ff00ffu;
+                frag.ga = ((((texel >> 8) & 0x00ff00ffu) * kgrey) >> 8) & 0x00ff00ffu;
+            } else frag = px_mul(texel, frag);
         }
 
         if (PHONG) {

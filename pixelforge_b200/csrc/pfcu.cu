@@ -74,10 +74,13 @@ struct __align__(16) DevState {
     int vp_min[2], vp_max[2];
     const unsigned char *tex; unsigned tw, th; int tfmt;
     unsigned n_lights;
+    float tex_fw, tex_fh, tex_tx, tex_ty;       /* (float)tw, (float)th, 1/tw, 1/th: bilinear constants (sampler.h:290-300) */
     DevLight lights[8];
     DevMaterial material[2];
     float view_pos[3];
 };
+
+static_assert(offsetof(DevState, tex_fw) % 16 == 0, "tex_fw..tex_ty are fetched as one float4");
 
 struct pfcu_surface {
     uint32_t w, h; uint32_t *color; float *depth; bool owned;
@@ -283,7 +286,9 @@ __device__ __forceinline__ unsigned pack4(int r, int g, int b, int a)   /* OR of
 
 __device__ __forceinline__ unsigned quant(float v)                      /* color.h:124-135 */
 {
-    return (unsigned)cvt_rne_x86(FM(clamp_x86(v, 0.0f, 1.0f), 255.0f));
+    /* clamp_x86 maps NaN to 0 (MAXPS returns its second operand), so the product is always in [0, 255] and
+       CVTPS2DQ's out-of-range result cannot occur */
+    return (unsigned)__float2int_rn(FM(clamp_x86(v, 0.0f, 1.0f), 255.0f));
 }
 
 /* (texel * frag) >> 8 per channel (blend.h:199-212) */
@@ -394,12 +399,12 @@ __device__ __forceinline__ unsigned tex_fetch(const TexRegs &t, int x, int y)
     return (t.fmt == PFCU_TEX_RGB8) ? (b0 | (b1 << 8) | (b2 << 16) | 0xff000000u) : (b2 | (b1 << 8) | (b0 << 16) | 0xff000000u);
 }
 
-__device__ __forceinline__ unsigned tex_sample(const TexRegs &t, float u, float v)
+__device__ __forceinline__ unsigned tex_sample(const TexRegs &t, const DevState *st, float u, float v)
 {
     const int x0 = tex_coord(t.wrap, u, t.wm1), y0 = tex_coord(t.wrap, v, t.hm1);
     if (t.filter == 0) return tex_fetch(t, x0, y0);
-    const float fw = __uint2float_rn(t.tw), fh = __uint2float_rn(t.th);
-    const float tx = FD(1.0f, fw), ty = FD(1.0f, fh);
+    const float4 k = __ldg(reinterpret_cast<const float4 *>(&st->tex_fw));       /* fw, fh, 1/fw, 1/fh */
+    const float fw = k.x, fh = k.y, tx = k.z, ty = k.w;
     const int x1 = tex_coord(t.wrap, FA(u, tx), t.wm1), y1 = tex_coord(t.wrap, FA(v, ty), t.hm1);
     const float fx = clamp_x86(FS(FM(u, fw), __int2float_rn(x0)), 0.0f, 1.0f);
     const float fy = clamp_x86(FS(FM(v, fh), __int2float_rn(y0)), 0.0f, 1.0f);
@@ -868,8 +873,7 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
 
     /* block ownership: 8 warps -> warp w owns block (bx,by) iff (bx + 3*by) & 7 == w;
        16 warps -> additionally even block rows belong to warps 0..7, odd rows to warps 8..15 */
-    for (int by = by0; by <= by1; by++) {
-        if (NW == 16 && (by & 1) != (t.warp >> 3)) continue;
+    for (int by = (NW == 16) ? by0 + ((by0 ^ (t.warp >> 3)) & 1) : by0; by <= by1; by += (NW == 16) ? 2 : 1) {
         const int bx = ((t.warp & 7) - 3 * by) & 7;
         /* skipping blocks left/right of the bbox early pays for small triangles only; the per-lane
            x-range test below rejects them anyway */
@@ -936,7 +940,7 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
                 const unsigned off = (unsigned)yi * tex.tw + (unsigned)xi;
                 texel = 0u;
                 if (off < tex.total) texel = __ldg((const unsigned *)tex.base + off);
-            } else texel = tex_sample(tex, u, v);
+            } else texel = tex_sample(tex, st, u, v);
             if (grey_tex) {                         /* (texel_c * k) >> 8 on packed lanes: products stay below 2^16 */
                 frag.rb = (((texel & 0x00ff00ffu) * kgrey) >> 8) & 0x00ff00ffu;
                 frag.ga = ((((texel >> 8) & 0x00ff00ffu) * kgrey) >> 8) & 0x00ff00ffu;
@@ -1770,6 +1774,8 @@ static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
         d->vp_min[0] = s->vp_min[0]; d->vp_min[1] = s->vp_min[1]; d->vp_max[0] = s->vp_max[0]; d->vp_max[1] = s->vp_max[1];
         if (d->flags & PFCU_ST_TEXTURE) {
             d->tex = s->texture->pixels; d->tw = s->texture->w; d->th = s->texture->h; d->tfmt = s->texture->fmt;
+            d->tex_fw = (float)d->tw; d->tex_fh = (float)d->th;
+            { volatile float one = 1.0f; d->tex_tx = one / d->tex_fw; d->tex_ty = one / d->tex_fh; }   /* IEEE single division, as DIVPS */
             if (s->texture->alias) g.deps.push_back(s->texture->alias);      /* render-to-texture: order across lanes */
         }
         d->n_lights = s->n_lights > 8 ? 8 : s->n_lights;

@@ -1,0 +1,34 @@
+"""Fold the key raw metrics of one kernel launch of an .ncu-rep into profiles/<name>.json under a label.
+
+    python tools/ncu_summary.py gpurun_out/c2_full.ncu-rep profiles/r01_k_raster_summary.json c2_textured_1080p/final
+"""
+import csv, io, json, os, subprocess, sys
+
+KEEP = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor", "sm__cycles_active.avg",
+        "sm__cycles_elapsed.avg", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed"]
+
+
+def main():
+    rep, out, label = sys.argv[1:4]
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    h, units, r = rows[0], rows[1], rows[2]
+    d = {}
+    for k in KEEP:
+        if k in h:
+            i = h.index(k)
+            d[k] = (r[i] + " " + units[i]).strip()
+    allj = json.load(open(out)) if os.path.exists(out) else {}
+    allj[label] = d
+    json.dump(allj, open(out, "w"), indent=1)
+    print(json.dumps(d, indent=1))
+
+
+if __name__ == "__main__":
+    main()

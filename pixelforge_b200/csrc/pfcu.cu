@@ -1199,6 +1199,401 @@ k_raster(const RasterParams p)
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* kernel: fragment-compacting tile rasteriser (batches of many small triangles)                    */
+/* ------------------------------------------------------------------------------------------------ */
+/*
+ * k_raster walks ONE triangle at a time per warp over 8x4-pixel blocks; with triangles of a dozen pixels
+ * most lanes of a block are uncovered and the per-triangle prologue is paid by every warp the triangle
+ * touches.  k_raster_frag turns the work around: a CTA owns a 64 x (NW) slice cut into 8x8-pixel REGIONS, one
+ * region per warp (fixed pixel ownership, so submission order per pixel is kept without atomics).  Each warp
+ *   1. gathers, in order, up to 32 queued triangles that touch its region (lane = triangle),
+ *   2. every lane clips its triangle's bbox to the region: n = candidate pixels; a warp scan of n lays all
+ *      candidates of the 32 triangles out as one ordered fragment stream,
+ *   3. the stream is consumed 32 fragments at a time (lane = fragment, usually of several triangles): owner
+ *      lookup by binary search over the scan, per-lane triangle constants from L1, then exactly the same
+ *      coverage / depth / colour / texture / Phong / blend arithmetic as shade_tri,
+ *   4. fragments of one chunk that hit the same pixel (shared edges and vertices are drawn by every
+ *      triangle that owns them, Q4) are ranked by __match_any_sync and written in rank order.
+ * The region tiles live in shared memory as [region][8][8] with a stride of 72 words so that the 128-bit row
+ * load/store of the slice is bank-conflict free.
+ */
+#define FRAG_RSTRIDE 72
+
+struct FragCtx {
+    unsigned col_base;                  /* shared-window byte address of this warp's colour region     */
+    unsigned rcp_base;                  /* ... of the shared RCPPS table                                */
+    int rcp_shift; bool rcp_shared;
+    int RX0, RY0, RX1, RY1;             /* the region on the surface, inclusive                         */
+    unsigned shaded, covered;
+    const int4 *bbox; const TriSetup *setup; const TriData *data;
+};
+
+template <int OFF> __device__ __forceinline__ float lds_f32_off(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF)); return v; }
+template <int OFF> __device__ __forceinline__ void sts_f32_off(unsigned addr, float v) { asm volatile("st.shared.f32 [%0+%1], %2;" :: "r"(addr), "n"(OFF), "f"(v) : "memory"); }
+
+__device__ __forceinline__ float rcp_tab(const FragCtx &t, float x)
+{
+    const unsigned u = __float_as_uint(x), E = u & 0x7f800000u;
+    if (!t.rcp_shared || E - 0x00800000u >= 0x7e000000u) return rcp_x86(x);
+    const unsigned tv = lds_u32(t.rcp_base + (((u & 0x007fffffu) >> t.rcp_shift) << 2));
+    return __uint_as_float((tv + 0x3f800000u - E) | (u & 0x80000000u));
+}
+
+/* One group of <= 32 triangles in one state (lane l holds triangle ti with nn candidate pixels in this warp's
+ * region; nn == 0 for lanes outside the group).  pk = cx0 | cy0<<4 | cw<<8 | ceil(1024/cw)<<12 describes the
+ * clipped rectangle (region-local).  lo is a lane that is known to hold a valid triangle. */
+template <int TEXM, int BLENDM, bool PHONG, int NW>
+__device__ __forceinline__ void frag_run(FragCtx &t, const unsigned ti, const unsigned nn, const unsigned pk, const int lo,
+                                         const DevState *st, const unsigned flags, const unsigned zmask, const int blend_mode, const TexRegs &tex)
+{
+    constexpr int DEPTH_OFF = NW * FRAG_RSTRIDE * 4;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    unsigned I = nn;                                                /* inclusive scan of the candidate counts */
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(FULL, I, o); if ((int)lane >= o) I += y; }
+    const unsigned total = __shfl_sync(FULL, I, 31);
+    const unsigned Ex = I - nn;
+    const bool smooth = (flags & PFCU_ST_SMOOTH) != 0;
+    const bool ztest = zmask != 8u;
+    const bool texturing = TEXM != 0 && (!PHONG || (flags & PFCU_ST_TEXTURE));
+    const bool blending = BLENDM != 0 && (!PHONG || (flags & PFCU_ST_BLEND));
+
+    for (unsigned base = 0; base < total; base += 32) {
+        const unsigned f = base + lane;
+        const bool valid = f < total;
+        unsigned pos = 0;                                           /* owner = number of lanes whose scan value is <= f */
+#pragma unroll
+        for (int step = 16; step; step >>= 1) { const unsigned v = __shfl_sync(FULL, I, pos + step - 1); if (v <= f) pos += step; }
+        const int j = valid ? (int)pos : lo;
+        const unsigned tj = __shfl_sync(FULL, ti, j), Ej = __shfl_sync(FULL, Ex, j), pkj = __shfl_sync(FULL, pk, j);
+        const unsigned r = valid ? f - Ej : 0u;
+        const unsigned cw = (pkj >> 8) & 15u;
+        const unsigned ry = (r * (pkj >> 12)) >> 10, rx = r - ry * cw;          /* r / cw, r % cw (r < 64, cw <= 8: exact) */
+        const int px = (int)((pkj & 15u) + rx), py = (int)(((pkj >> 4) & 15u) + ry);
+
+        const int4 b = __ldg(t.bbox + tj);
+        const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(t.setup + tj));
+        const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(t.setup + tj) + 1);
+        const uint4 s2 = __ldg(reinterpret_cast<const uint4 *>(t.setup + tj) + 2);
+        const int dx = wsub(t.RX0 + px, b.x), dy = wsub(t.RY0 + py, b.y);
+        const int w1 = wadd(wadd((int)s0.x, wmul(dy, (int)s1.y)), wmul(dx, (int)s1.x));
+        const int w2 = wadd(wadd((int)s0.y, wmul(dy, (int)s1.w)), wmul(dx, (int)s1.z));
+        const int w3 = wadd(wadd((int)s0.z, wmul(dy, (int)s2.y)), wmul(dx, (int)s2.x));
+        bool m = valid && ((w1 | w2 | w3) > 0);
+        if (!__any_sync(FULL, m)) continue;
+        t.covered += m ? 1u : 0u;
+
+        const uint4 a0 = __ldg(reinterpret_cast<const uint4 *>(t.data + tj));
+        const float invSum = __uint_as_float(s0.w);
+        const float W1 = FM(__int2float_rn(w1), invSum);
+        const float W2 = FM(__int2float_rn(w2), invSum);
+        const float W3 = FM(__int2float_rn(w3), invSum);
+        const float zsum = FA(FA(FM(__uint_as_float(a0.x), W1), FM(__uint_as_float(a0.y), W2)), FM(__uint_as_float(a0.z), W3));
+        const float z = rcp_tab(t, zsum);
+
+        /* same-pixel fragments of this chunk (different triangles) must be applied in triangle order */
+        const unsigned sa = t.col_base + (unsigned)(((py << 3) + px) << 2);
+        const unsigned peers = __match_any_sync(FULL, m ? sa : (0x80000000u | lane));
+        const unsigned rank = __popc(peers & lt);
+        const unsigned nr = __reduce_max_sync(FULL, m ? rank : 0u);
+        if (ztest && nr == 0u) {                        /* no conflicts: test before shading, like the reference's early mask */
+            const float zb = lds_f32_off<DEPTH_OFF>(sa);
+            m = m && depth_pass_mask(z, zb, zmask);
+            if (!__any_sync(FULL, m)) continue;
+        }
+
+        /* colour (color.h:153-203) */
+        const uint4 a1 = __ldg(reinterpret_cast<const uint4 *>(t.data + tj) + 1);
+        Px2 frag;
+        if (smooth) {
+            const int u1 = __float2int_rn(FM(W1, 255.0f)), u2 = __float2int_rn(FM(W2, 255.0f)), u3 = __float2int_rn(FM(W3, 255.0f));
+            frag.rb = smooth_lanes(a1.x & 0x00ff00ffu, a1.y & 0x00ff00ffu, a1.z & 0x00ff00ffu, u1, u2, u3);
+            frag.ga = smooth_lanes((a1.x >> 8) & 0x00ff00ffu, (a1.y >> 8) & 0x00ff00ffu, (a1.z >> 8) & 0x00ff00ffu, u1, u2, u3);
+        } else {
+            const float mx = max_x86(W1, max_x86(W2, W3));
+            frag = px_split(((mx == W1) ? a1.x : 0u) | ((mx == W2) ? a1.y : 0u) | ((mx == W3) ? a1.z : 0u));
+        }
+
+        if (texturing) {
+            const uint4 a2 = __ldg(reinterpret_cast<const uint4 *>(t.data + tj) + 2);
+            const uint4 a3 = __ldg(reinterpret_cast<const uint4 *>(t.data + tj) + 3);
+            float u = FA(FA(FM(__uint_as_float(a2.x), W1), FM(__uint_as_float(a2.y), W2)), FM(__uint_as_float(a2.z), W3));
+            float v = FA(FA(FM(__uint_as_float(a3.x), W1), FM(__uint_as_float(a3.y), W2)), FM(__uint_as_float(a3.z), W3));
+            if ((a0.w >> 25) & 1u) { u = FM(u, z); v = FM(v, z); }
+            unsigned texel;
+            if (TEXM == 1) {
+                const float fu = FM(FS(u, truncf(u)), tex.wm1), fv = FM(FS(v, truncf(v)), tex.hm1);
+                const int xi = cvt_rne_x86(fabsf(fu)), yi = cvt_rne_x86(fabsf(fv));
+                const unsigned off = (unsigned)yi * tex.tw + (unsigned)xi;
+                texel = 0u;
+                if (off < tex.total) texel = __ldg((const unsigned *)tex.base + off);
+            } else texel = tex_sample(tex, st, u, v);
+            frag = px_mul(texel, frag);
+        }
+
+        if (PHONG) {
+            if (flags & PFCU_ST_PHONG) {
+                const float4 *a = reinterpret_cast<const float4 *>(t.data + tj) + 4;
+                const float4 qx = __ldg(a), qy = __ldg(a + 1), qz = __ldg(a + 2);
+                const float4 nx = __ldg(a + 3), ny = __ldg(a + 4), nz = __ldg(a + 5);
+                const float Nx = FA(FA(FM(nx.x, W1), FM(nx.y, W2)), FM(nx.z, W3));
+                const float Ny = FA(FA(FM(ny.x, W1), FM(ny.y, W2)), FM(ny.z, W3));
+                const float Nz = FA(FA(FM(nz.x, W1), FM(nz.y, W2)), FM(nz.z, W3));
+                const float Qx = FA(FA(FM(qx.x, W1), FM(qx.y, W2)), FM(qx.z, W3));
+                const float Qy = FA(FA(FM(qy.x, W1), FM(qy.y, W2)), FM(qy.z, W3));
+                const float Qz = FA(FA(FM(qz.x, W1), FM(qz.y, W2)), FM(qz.z, W3));
+                frag = px_split(phong(px_join(frag), st, (a0.w >> 24) & 1u, Qx, Qy, Qz, Nx, Ny, Nz));
+            }
+        }
+
+        /* ordered read-modify-write: round k applies the k-th fragment of every pixel */
+        for (unsigned k = 0; k <= nr; k++) {
+            if (m && rank == k) {
+                bool ok = true;
+                if (ztest && nr != 0u) ok = depth_pass_mask(z, lds_f32_off<DEPTH_OFF>(sa), zmask);
+                if (ok) {
+                    Px2 o = frag;
+                    if (blending) o = px_blend(BLENDM == 3 ? blend_mode : BLENDM, frag, lds_color(sa));
+                    sts_color(sa, px_join(o));
+                    sts_f32_off<DEPTH_OFF>(sa, z);          /* written even with the depth test off (Q11) */
+                    t.shaded++;
+                }
+            }
+            if (nr != 0u) __syncwarp();
+        }
+    }
+}
+
+template <bool HAS_PHONG, int NW>
+__global__ void __launch_bounds__(NW * 32, HAS_PHONG ? (NW == 16 ? 1 : 2) : (NW == 16 ? 2 : 4))
+k_raster_frag(const RasterParams p)
+{
+    constexpr int NT = NW * 32, TH = NW, SUB = TILE / TH;
+    __shared__ __align__(16) unsigned s_tile[2 * NW * FRAG_RSTRIDE];     /* colour regions, then depth regions */
+    unsigned *const s_col = s_tile;
+    float *const s_dep = reinterpret_cast<float *>(s_tile + NW * FRAG_RSTRIDE);
+    __shared__ unsigned s_rcp[1 << RCP_SMEM_BITS];
+    __shared__ unsigned s_queue[QUEUE_CAP];
+    __shared__ unsigned short s_qmask[QUEUE_CAP];
+    __shared__ unsigned s_wcount[NW];
+    __shared__ unsigned s_group[NW][32];
+    static_assert(NW == 8 || NW == 16, "one 8x8 region per warp, 8 regions per row");
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned tile = (p.world > 1) ? (p.rank + (blockIdx.x / SUB) * p.world) : (blockIdx.x / SUB);
+    if (tile >= p.nTiles) return;
+    const int tx = tile % p.tilesX, ty = tile / p.tilesX;
+    const int X0 = tx * TILE, Y0 = ty * TILE + (int)(blockIdx.x % SUB) * TH;
+    if (Y0 >= p.H) return;
+    const int X1 = min(X0 + TILE, p.W) - 1, Y1 = min(Y0 + TH, p.H) - 1;
+    const bool full_tile = (X0 + TILE <= p.W) && (Y0 + TH <= p.H) && ((p.W & 3) == 0);
+
+    const int bin = (ty / BIN_TILES) * p.binsX + (tx / BIN_TILES);
+    const unsigned lbeg = p.bin_starts[bin], lend = p.bin_starts[bin + 1];
+    if (lbeg == lend) return;
+
+    FragCtx t;
+    t.rcp_shift = c_rcp_shift;
+    t.rcp_shared = t.rcp_shift >= 23 - RCP_SMEM_BITS;
+    if (t.rcp_shared) for (int k = tid; k < (1 << (23 - t.rcp_shift)); k += NT) s_rcp[k] = c_rcp_tab[k];
+    t.col_base = (unsigned)__cvta_generic_to_shared(s_col + warp * FRAG_RSTRIDE);
+    t.rcp_base = (unsigned)__cvta_generic_to_shared(s_rcp);
+    t.RX0 = X0 + (warp & 7) * 8; t.RY0 = Y0 + (warp >> 3) * 8;
+    t.RX1 = min(t.RX0 + 7, X1); t.RY1 = min(t.RY0 + 7, Y1);
+    t.shaded = 0; t.covered = 0; t.bbox = p.bbox; t.setup = p.setup; t.data = p.data;
+
+    bool loaded = false;
+
+    for (unsigned base = lbeg; base < lend; ) {
+        /* ---- fill the queue: ordered compaction of the bin list against this slice ---- */
+        unsigned qn = 0;
+        while (base < lend && qn + NT <= QUEUE_CAP) {
+            const unsigned k = base + tid;
+            bool hit = false; unsigned ti = 0, wmask = 0;
+            if (k < lend) {
+                ti = __ldg(p.bin_list + k);
+                const int4 b = __ldg(p.bbox + ti);
+                hit = b.x <= X1 && b.z - 1 >= X0 && b.y <= Y1 && b.w >= Y0 && b.x < b.z;
+                if (hit) {
+                    const int rx0 = max(b.x, X0), rx1 = min(b.z - 1, X1), ry0 = max(b.y, Y0), ry1 = min(b.w, Y1);
+                    const TriSetup s = p.setup[ti];
+                    if (s.flags & TF_SAFE) {        /* edge-function reject of the whole slice (only when int32 cannot wrap) */
+                        const int ax0 = rx0 - b.x, ax1 = rx1 - b.x, ay0 = ry0 - b.y, ay1 = ry1 - b.y;
+                        const int m1 = s.w1R + (s.w1X > 0 ? ax1 : ax0) * s.w1X + (s.w1Y > 0 ? ay1 : ay0) * s.w1Y;
+                        const int m2 = s.w2R + (s.w2X > 0 ? ax1 : ax0) * s.w2X + (s.w2Y > 0 ? ay1 : ay0) * s.w2Y;
+                        const int m3 = s.w3R + (s.w3X > 0 ? ax1 : ax0) * s.w3X + (s.w3Y > 0 ? ay1 : ay0) * s.w3Y;
+                        if ((m1 | m2 | m3) < 0) hit = false;
+                    }
+                    /* regions (= warps) touched by the clipped bbox */
+                    const int gx0 = (rx0 - X0) >> 3, gx1 = (rx1 - X0) >> 3, gy0 = (ry0 - Y0) >> 3, gy1 = (ry1 - Y0) >> 3;
+                    const unsigned run = ((2u << gx1) - 1u) & ~((1u << gx0) - 1u);
+                    wmask = (gy0 == 0 ? run : 0u) | ((NW == 16 && gy1 == 1) ? (run << 8) : 0u);
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_wcount[warp] = __popc(bal);
+            __syncthreads();
+            unsigned woff = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) { const unsigned c = s_wcount[w]; if (w < warp) woff += c; total += c; }
+            if (hit) {
+                const unsigned pos = qn + woff + __popc(bal & ((1u << lane) - 1u)); s_queue[pos] = ti; s_qmask[pos] = (unsigned short)wmask;
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(p.setup + ti));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(p.data + ti));
+            }
+            qn += total;
+            base += NT;
+            __syncthreads();
+        }
+        if (qn == 0) continue;
+
+        /* ---- lazy slice load: 128-bit coalesced rows into the region-major shared tile ---- */
+        if (!loaded) {
+            loaded = true;
+            if (full_tile) {
+                for (int k = tid; k < TH * 16; k += NT) {
+                    const int r = k >> 4, c4 = (k & 15) << 2;
+                    const size_t gi = (size_t)(Y0 + r) * p.W + X0 + c4;
+                    const uint4 cv = __ldcs(reinterpret_cast<const uint4 *>(p.color + gi));
+                    const float4 dv = __ldcs(reinterpret_cast<const float4 *>(p.depth + gi));
+                    const int sa = ((r >> 3) * 8 + (c4 >> 3)) * FRAG_RSTRIDE + (r & 7) * 8 + (c4 & 7);
+                    *reinterpret_cast<uint4 *>(s_col + sa) = cv;
+                    *reinterpret_cast<float4 *>(s_dep + sa) = dv;
+                }
+            } else {
+                for (int k = tid; k < TILE * TH; k += NT) {
+                    const int lx = k & (TILE - 1), ly = k >> 6;
+                    if (X0 + lx <= X1 && Y0 + ly <= Y1) {
+                        const size_t gi = (size_t)(Y0 + ly) * p.W + X0 + lx;
+                        const int sa = ((ly >> 3) * 8 + (lx >> 3)) * FRAG_RSTRIDE + (ly & 7) * 8 + (lx & 7);
+                        s_col[sa] = p.color[gi];
+                        s_dep[sa] = p.depth[gi];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        /* ---- every warp gathers the queue entries of its region, 32 at a time, and runs them ---- */
+        unsigned cur_state = 0xffffffffu;
+        const DevState *st = nullptr;
+        unsigned flags = 0, zmask = 8u; int blend_mode = 0, prog = 0;
+        TexRegs tex; tex.base = nullptr; tex.tw = tex.th = tex.total = 0; tex.wm1 = tex.hm1 = 0.0f; tex.fmt = tex.wrap = tex.filter = 0;
+        unsigned cnt = 0;
+        const unsigned ltm = (1u << lane) - 1u;
+        for (unsigned q0 = 0; q0 < qn; q0 += 32) {
+            bool mine = false; unsigned qti = 0;
+            if (q0 + lane < qn) { mine = (s_qmask[q0 + lane] >> warp) & 1u; qti = s_queue[q0 + lane]; }
+            unsigned rel = __ballot_sync(0xffffffffu, mine);
+            const bool last = q0 + 32 >= qn;
+            do {
+                if (rel) {
+                    const unsigned slot = cnt + __popc(rel & ltm);
+                    const bool take = mine && slot < 32u;
+                    if (take) { s_group[warp][slot] = qti; mine = false; }
+                    const unsigned tk = __ballot_sync(0xffffffffu, take);
+                    cnt += __popc(tk); rel &= ~tk;
+                }
+                if (cnt == 32u || (last && rel == 0u && cnt)) {
+                    /* ---- run one group ---- */
+                    __syncwarp();
+                    const bool have = (unsigned)lane < cnt;
+                    const unsigned ti = have ? s_group[warp][lane] : 0u;
+                    __syncwarp();
+                    unsigned state = 0xffffffffu, nn0 = 0, pk = 0;
+                    if (have) {
+                        const int4 b = __ldg(p.bbox + ti);
+                        state = __ldg(&p.data[ti].meta) & 0xffffffu;
+                        const int cx0 = max(b.x, t.RX0) - t.RX0, cx1 = min(b.z - 1, t.RX1) - t.RX0;
+                        const int cy0 = max(b.y, t.RY0) - t.RY0, cy1 = min(b.w, t.RY1) - t.RY0;
+                        const int cw = cx1 - cx0 + 1, ch = cy1 - cy0 + 1;
+                        if (cw > 0 && ch > 0) {
+                            nn0 = (unsigned)(cw * ch);
+                            pk = (unsigned)cx0 | ((unsigned)cy0 << 4) | ((unsigned)cw << 8) | (((1024u + (unsigned)cw - 1u) / (unsigned)cw) << 12);
+                        }
+                    }
+                    unsigned lo = 0;
+                    while (lo < cnt) {
+                        const unsigned sid = __shfl_sync(0xffffffffu, state, (int)lo);
+                        const unsigned diff = __ballot_sync(0xffffffffu, have && (unsigned)lane >= lo && state != sid);
+                        const unsigned hi = diff ? (unsigned)(__ffs(diff) - 1) : cnt;
+                        const unsigned nn = ((unsigned)lane >= lo && (unsigned)lane < hi) ? nn0 : 0u;
+                        if (sid != cur_state) {
+                            cur_state = sid;
+                            st = p.states + cur_state;
+                            flags = st->flags; blend_mode = st->blend_mode;
+                            zmask = (flags & PFCU_ST_DEPTH_TEST) ? depth_mask(st->depth_func) : 8u;
+                            int texm = 0;
+                            if (flags & PFCU_ST_TEXTURE) {
+                                tex.base = st->tex; tex.tw = st->tw; tex.th = st->th; tex.total = st->tw * st->th;
+                                tex.wm1 = __uint2float_rn(st->tw - 1u); tex.hm1 = __uint2float_rn(st->th - 1u);
+                                tex.fmt = st->tfmt; tex.wrap = st->tex_wrap; tex.filter = st->tex_filter;
+                                texm = (tex.fmt == PFCU_TEX_RGBA8 && tex.wrap == 0 && tex.filter == 0) ? 1 : 2;
+                            }
+                            const int blendm = !(flags & PFCU_ST_BLEND) ? 0 : (blend_mode == 1 ? 1 : (blend_mode == 2 ? 2 : 3));
+                            prog = texm * 4 + blendm;
+                            if (HAS_PHONG && (flags & PFCU_ST_PHONG)) prog = 12;
+                        }
+                        switch (prog) {
+                        case 0:  frag_run<0, 0, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 1:  frag_run<0, 1, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 2:  frag_run<0, 2, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 3:  frag_run<0, 3, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 4:  frag_run<1, 0, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 5:  frag_run<1, 1, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 6:  frag_run<1, 2, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 7:  frag_run<1, 3, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 8:  frag_run<2, 0, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 9:  frag_run<2, 1, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 10: frag_run<2, 2, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 11: frag_run<2, 3, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        default: if (HAS_PHONG) frag_run<2, 3, true, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        }
+                        lo = hi;
+                    }
+                    cnt = 0;
+                }
+            } while (rel);
+        }
+        __syncthreads();
+    }
+
+    /* ---- write the slice back ---- */
+    if (loaded) {
+        if (full_tile) {
+            for (int k = tid; k < TH * 16; k += NT) {
+                const int r = k >> 4, c4 = (k & 15) << 2;
+                const size_t gi = (size_t)(Y0 + r) * p.W + X0 + c4;
+                const int sa = ((r >> 3) * 8 + (c4 >> 3)) * FRAG_RSTRIDE + (r & 7) * 8 + (c4 & 7);
+                __stcs(reinterpret_cast<uint4 *>(p.color + gi), *reinterpret_cast<const uint4 *>(s_col + sa));
+                __stcs(reinterpret_cast<float4 *>(p.depth + gi), *reinterpret_cast<const float4 *>(s_dep + sa));
+            }
+        } else {
+            for (int k = tid; k < TILE * TH; k += NT) {
+                const int lx = k & (TILE - 1), ly = k >> 6;
+                if (X0 + lx <= X1 && Y0 + ly <= Y1) {
+                    const size_t gi = (size_t)(Y0 + ly) * p.W + X0 + lx;
+                    const int sa = ((ly >> 3) * 8 + (lx >> 3)) * FRAG_RSTRIDE + (ly & 7) * 8 + (lx & 7);
+                    p.color[gi] = s_col[sa];
+                    p.depth[gi] = s_dep[sa];
+                }
+            }
+        }
+    }
+    unsigned shaded = t.shaded, zfailed = t.covered - t.shaded;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        shaded += __shfl_down_sync(0xffffffffu, shaded, o);
+        zfailed += __shfl_down_sync(0xffffffffu, zfailed, o);
+    }
+    if (lane == 0) {
+        if (shaded) atomicAdd(p.counters + 1, (unsigned long long)shaded);
+        if (zfailed) atomicAdd(p.counters + 2, (unsigned long long)zfailed);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* ------------------------------------------------------------------------------------------------ */
 /* kernels: device vertex stage (pf_vstage.h compiled as device code)                               */
 /* ------------------------------------------------------------------------------------------------ */
@@ -1873,7 +2268,13 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         /* small triangles: slices of 64x16 (64x32 with Phong) shorten the serial work of the busiest tiles and
            even out the SMs (C2: 0.51 -> 0.30 ms); PF_CUDA_SLICE=64|32|16 overrides for experiments */
         static const int force_slice = getenv("PF_CUDA_SLICE") ? atoi(getenv("PF_CUDA_SLICE")) : 0;
-        if (small_tris) {
+        static const int use_frag = getenv("PF_CUDA_FRAG") ? atoi(getenv("PF_CUDA_FRAG")) : 1;
+        if (small_tris && use_frag && !force_slice) {
+            /* fragment-compacting kernel: 64x16 slices of 16 regions (Phong: 64x8 slices, 8 warps, 128 registers) */
+            if (ph) k_raster_frag<true, 8><<<grid * 8, 256, 0, LN.stream>>>(p);
+            else    k_raster_frag<false, 16><<<grid * 4, 512, 0, LN.stream>>>(p);
+        }
+        else if (small_tris) {
             const int th = force_slice ? force_slice : (ph ? 32 : 16);
             if (ph) { if (th <= 32) k_raster<true, 16, -1, 32><<<grid * 2, 512, 0, LN.stream>>>(p); else k_raster<true, 16, -1, 64><<<grid, 512, 0, LN.stream>>>(p); }
             else if (th <= 16) k_raster<false, 16, -1, 16><<<grid * 4, 512, 0, LN.stream>>>(p);

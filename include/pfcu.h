@@ -238,6 +238,15 @@ typedef struct {
     uint64_t raster_launches;
 } pfcu_profile;
 PFCU_API void pfcu_profile_enable(int on);
+/* Which tile rasteriser a batch runs on: PFCU_RASTER_AUTO (default; by triangles per tile), PFCU_RASTER_TILES
+ * (k_raster: one triangle per warp step over 8x4 blocks, for large triangles) or PFCU_RASTER_FRAGMENTS
+ * (k_raster_frag: fragment compaction, for many small triangles).  A performance knob only: both produce
+ * identical pixels (tests run every parity case under both).  $PF_CUDA_FRAG=0|1|2 sets the start-up value
+ * (0 tiles, 1 auto, 2 fragments). */
+#define PFCU_RASTER_AUTO      0
+#define PFCU_RASTER_TILES     1
+#define PFCU_RASTER_FRAGMENTS 2
+PFCU_API void pfcu_set_raster_path(int path);
 PFCU_API int  pfcu_profile_read(pfcu_profile *out);    /* implies pfcu_finish(); resets the sums      */
 
 /* Work on different surfaces may run on different internal streams ("lanes", $PF_CUDA_LANES, default 4) so

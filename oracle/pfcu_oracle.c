@@ -604,6 +604,7 @@ unsigned pfcu_capabilities(void) { return 0u; }     /* the oracle has no device 
 int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *st, const pfcu_vparams *vp, const pfcu_draw *d, uint32_t *n)
 { (void)s; (void)st; (void)vp; (void)d; (void)n; return PFCU_ERR_INVALID; }
 void pfcu_profile_enable(int on) { (void)on; }
+void pfcu_set_raster_path(int path) { (void)path; }    /* one scalar path here */
 int  pfcu_profile_read(pfcu_profile *out) { memset(out, 0, sizeof *out); return PFCU_OK; }
 int  pfcu_fence(void) { return PFCU_OK; }
 int  pfcu_finish(void) { return PFCU_OK; }

@@ -171,6 +171,7 @@ PFCU_SYMBOLS = [
     "pfcu_texture_create", "pfcu_texture_from_surface", "pfcu_texture_update", "pfcu_texture_destroy",
     "pfcu_submit", "pfcu_batch_upload", "pfcu_batch_submit", "pfcu_batch_destroy",
     "pfcu_fence", "pfcu_finish", "pfcu_get_counters", "pfcu_reset_counters", "pfcu_profile_enable", "pfcu_profile_read",
+    "pfcu_set_raster_path",
 ]
 
 PFX_SYMBOLS = ["pfxSetSyncMode", "pfxFlush", "pfxFinish", "pfxGetCounters", "pfxResetCounters", "pfxSetTileOwner",
@@ -209,7 +210,7 @@ class PfcuLib:
             "pfcu_batch_submit": (C.c_int, [vp, vp]), "pfcu_batch_destroy": (None, [vp]),
             "pfcu_fence": (C.c_int, []), "pfcu_finish": (C.c_int, []), "pfcu_get_counters": (C.c_int, [C.POINTER(Counters)]),
             "pfcu_reset_counters": (None, []),
-            "pfcu_profile_enable": (None, [C.c_int]), "pfcu_profile_read": (C.c_int, [C.POINTER(Profile)]),
+            "pfcu_profile_enable": (None, [C.c_int]), "pfcu_set_raster_path": (None, [C.c_int]), "pfcu_profile_read": (C.c_int, [C.POINTER(Profile)]),
             # pfx extensions of the front end (operate on the calling thread's current context)
             "pfxFlush": (None, []), "pfxFinish": (None, []), "pfxSetTileOwner": (None, [u32, u32]),
             "pfxGetDeviceColor": (vp, []), "pfxGetDeviceDepth": (vp, []), "pfxGetSurfaceHandle": (vp, []),

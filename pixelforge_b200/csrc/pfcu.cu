@@ -129,6 +129,7 @@ struct Runtime {
     std::vector<PinnedBlock> pinned;
     uint64_t submitted = 0, launches = 0, bytes_h2d = 0, bytes_d2h = 0;
     bool profiling = false;
+    int raster_path = PFCU_RASTER_AUTO;
     std::vector<cudaEvent_t> prof_events;       /* triples: before setup, before raster, after raster */
     std::vector<cudaEvent_t> prof_pool;
     std::vector<pfcu_surface *> deps;           /* surfaces sampled as textures by the states being submitted */
@@ -2268,8 +2269,13 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         /* small triangles: slices of 64x16 (64x32 with Phong) shorten the serial work of the busiest tiles and
            even out the SMs (C2: 0.51 -> 0.30 ms); PF_CUDA_SLICE=64|32|16 overrides for experiments */
         static const int force_slice = getenv("PF_CUDA_SLICE") ? atoi(getenv("PF_CUDA_SLICE")) : 0;
-        static const int use_frag = getenv("PF_CUDA_FRAG") ? atoi(getenv("PF_CUDA_FRAG")) : 1;
-        if (small_tris && use_frag && !force_slice) {
+        static const bool env_once = [] {
+            const char *e = getenv("PF_CUDA_FRAG");
+            if (e) g.raster_path = atoi(e) == 0 ? PFCU_RASTER_TILES : (atoi(e) == 2 ? PFCU_RASTER_FRAGMENTS : PFCU_RASTER_AUTO);
+            return true; }();
+        (void)env_once;
+        const bool use_frag = g.raster_path == PFCU_RASTER_FRAGMENTS || (g.raster_path == PFCU_RASTER_AUTO && small_tris && !force_slice);
+        if (use_frag) {
             /* fragment-compacting kernel: 64x16 slices of 16 regions (Phong: 64x8 slices, 8 warps, 128 registers) */
             if (ph) k_raster_frag<true, 8><<<grid * 8, 256, 0, LN.stream>>>(p);
             else    k_raster_frag<false, 16><<<grid * 4, 512, 0, LN.stream>>>(p);
@@ -2460,6 +2466,7 @@ void pfcu_batch_destroy(pfcu_batch *b)
 }
 
 void pfcu_profile_enable(int on) { g.profiling = on != 0; }
+void pfcu_set_raster_path(int path) { API_LOCK; g.raster_path = (path == PFCU_RASTER_TILES || path == PFCU_RASTER_FRAGMENTS) ? path : PFCU_RASTER_AUTO; }
 
 int pfcu_profile_read(pfcu_profile *out)
 {

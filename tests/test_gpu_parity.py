@@ -165,6 +165,63 @@ def test_stream_phong(pfcu_pair):
     assert (cp[dp != FLT_MAX] >> 24 == 0).all()         # Q9: Phong forces alpha to 0
 
 
+# ---- both tile rasterisers (k_raster: triangle per warp step; k_raster_frag: fragment compaction) ------------
+
+@pytest.fixture(params=[1, 2], ids=["tiles", "fragments"])
+def forced_path(request, pfcu_pair):
+    """Force every batch through one of the two rasterisers (pfcu_set_raster_path); AUTO picks by batch shape."""
+    prod, _ = pfcu_pair
+    prod.lib.pfcu_set_raster_path(request.param)
+    yield request.param
+    prod.lib.pfcu_set_raster_path(0)
+
+
+@pytest.mark.parametrize("case", CASES, ids=CASE_IDS)
+def test_forced_path_matches_golden(case, forced_path, product_scenes, golden, host_matches_golden):
+    if not host_matches_golden:
+        pytest.skip("golden hashes were generated on a CPU with different RCPPS/RSQRTPS tables")
+    cid, scene, w, h, kw, _ = case
+    color, depth, res = product_scenes.render(scene, w, h, **kw)
+    g = golden["cases"][cid]
+    assert hashlib.sha256(color.tobytes()).hexdigest() == g["color_sha256"], "colour differs from the reference"
+    assert hashlib.sha256(depth.tobytes()).hexdigest() == g["depth_sha256"], "depth differs from the reference"
+
+
+@pytest.mark.parametrize("case", STREAM_CASES, ids=[c[0] for c in STREAM_CASES])
+def test_forced_path_streams(case, forced_path, pfcu_pair):
+    test_stream_cuda_vs_oracle(case, pfcu_pair)
+
+
+def test_forced_path_textured_phong_degenerate(forced_path, pfcu_pair):
+    for fmt in range(4):
+        for filt in (0, 1):
+            test_stream_textured(pfcu_pair, fmt, filt)
+    test_stream_phong(pfcu_pair)
+    test_empty_and_degenerate(pfcu_pair)
+    test_tile_split_reassembles(pfcu_pair)
+
+
+def test_fragment_path_dense_overlap(pfcu_pair):
+    """Many tiny triangles piled on the same pixels with every blend mode and depth function: the fragment
+    path must apply same-pixel fragments of one chunk in submission order."""
+    prod, orc = pfcu_pair
+    prod.lib.pfcu_set_raster_path(2)
+    try:
+        for seed, (blend, depth, flags) in enumerate([(1, 2, 1 | 2 | 16), (3, 0, 1 | 2), (0, 5, 1 | 2 | 16), (2, 3, 1 | 16), (5, 1, 1 | 2), (4, 4, 1 | 2 | 16), (6, 2, 1), (7, 3, 1 | 2)]):
+            rng = np.random.default_rng(900 + seed)
+            states, tris = random_stream(rng, 24, 17, 4000, flags, blend=blend, depth=depth, n_states=2)
+            for k in range(3):      # squeeze the stream onto a few pixels, quantised depth so that EQUAL hits
+                tris["v"]["sx"][:, k] = rng.integers(0, 24, 4000) + rng.uniform(0, 3, 4000)
+                tris["v"]["sy"][:, k] = rng.integers(0, 17, 4000) + rng.uniform(0, 3, 4000)
+                tris["v"]["zinv"][:, k] = rng.integers(1, 4, 4000).astype(np.float32)
+            color0 = rng.integers(0, 2**32, (17, 24), dtype=np.uint64).astype(np.uint32)
+            cp, dp = prod.render_stream(24, 17, states, tris, color0=color0)
+            co, do = orc.render_stream(24, 17, states, tris, color0=color0)
+            assert int((cp != co).sum()) == 0 and int((dp.view(np.uint32) != do.view(np.uint32)).sum()) == 0, (blend, depth)
+    finally:
+        prod.lib.pfcu_set_raster_path(0)
+
+
 def test_empty_and_degenerate(pfcu_pair):
     prod, orc = pfcu_pair
     from pixelforge_b200.binding import STATE_DTYPE, TRIANGLE_DTYPE

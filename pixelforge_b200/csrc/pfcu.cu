@@ -39,13 +39,16 @@
 
 #define TILE        64              /* screen tile edge in pixels                                    */
 #define TILE_PIX    (TILE * TILE)
-#define BIN_TILES   4               /* a bin is 4x4 tiles = 256x256 pixels                           */
-#define BIN_PIX     (TILE * BIN_TILES)
+/* A bin is 2^k x 2^k pixels, chosen per batch: 256 (4x4 tiles) for batches of large triangles, where a
+ * triangle would otherwise be listed in thousands of bins; 64 (= one tile) for batches of many small ones,
+ * where every slice CTA of the rasteriser would otherwise scan a 16 times longer list. */
+#define BIN_SHIFT_COARSE 8
+#define BIN_SHIFT_FINE   6
 #define RASTER_THREADS 256
 #define QUEUE_CAP   1024            /* triangle indices buffered per tile between raster passes      */
 #define SETUP_THREADS 256
 #define BIN_BATCH   1024            /* triangles per binning CTA                                     */
-#define MAX_BINS    1024            /* 32x32 bins = 16384^2 pixels                                   */
+#define MAX_BINS    12000           /* bin counters live in dynamic shared memory (48 KB); 7680x4320 in 64 px bins = 8160 */
 
 #define TF_VALID    1u              /* survived cull and has a non-empty bbox on the surface         */
 #define TF_SAFE     2u              /* int32 edge functions cannot wrap inside the bbox              */
@@ -579,7 +582,7 @@ k_setup(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ sta
 
 /* pass 1: counts[batch][bin] = number of triangles of this batch whose bbox touches the bin */
 __global__ void __launch_bounds__(256)
-k_bin_count(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, unsigned *__restrict__ counts)
+k_bin_count(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, int bshift, unsigned *__restrict__ counts)
 {
     extern __shared__ unsigned s_cnt[];
     const int nb = binsX * binsY;
@@ -591,8 +594,8 @@ k_bin_count(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, uns
         if (i >= n) break;
         const int4 b = __ldg(bbox + i);
         if (b.x >= b.z) continue;
-        const int bx0 = max(b.x, 0) / BIN_PIX, bx1 = min((b.z - 1) / BIN_PIX, binsX - 1);
-        const int by0 = max(b.y, 0) / BIN_PIX, by1 = min(b.w / BIN_PIX, binsY - 1);
+        const int bx0 = max(b.x, 0) >> bshift, bx1 = min((b.z - 1) >> bshift, binsX - 1);
+        const int by0 = max(b.y, 0) >> bshift, by1 = min(b.w >> bshift, binsY - 1);
         for (int by = by0; by <= by1; by++)
             for (int bx = bx0; bx <= bx1; bx++) atomicAdd(&s_cnt[by * binsX + bx], 1u);
     }
@@ -600,97 +603,147 @@ k_bin_count(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, uns
     for (int k = threadIdx.x; k < nb; k += blockDim.x) counts[(size_t)blockIdx.x * nb + k] = s_cnt[k];
 }
 
-/* pass 2: per bin, exclusive scan of counts over batches (in place) + bin totals; one CTA per bin */
-__global__ void __launch_bounds__(256)
+/* pass 2: per bin, exclusive scan of counts over batches (in place) + bin totals.  A CTA of 32 warps owns 32
+ * consecutive bins (one 128-byte row segment per batch); warp w owns a contiguous range of batches: it sums its
+ * range, the 32 partial sums are scanned across warps, and it walks its range again writing the prefixes. */
+__global__ void __launch_bounds__(1024)
 k_bin_scan(unsigned *__restrict__ counts, int nBatches, int nb, unsigned *__restrict__ totals)
 {
-    __shared__ unsigned s_warp[8];
+    __shared__ unsigned s_part[32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bin = blockIdx.x * 32 + lane;
+    const bool live = bin < nb;
+    const int per = (nBatches + 31) / 32;
+    const int k0 = warp * per, k1 = min(k0 + per, nBatches);
+    unsigned sum = 0;
+    if (live) {
+#pragma unroll 8
+        for (int k = k0; k < k1; k++) sum += counts[(size_t)k * nb + bin];
+    }
+    s_part[warp][lane] = sum;
+    __syncthreads();
+    unsigned run = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 32; w++) { const unsigned c = s_part[w][lane]; if (w < warp) run += c; total += c; }
+    if (live) {
+        for (int k = k0; k < k1; k++) {
+            unsigned *pc = counts + (size_t)k * nb + bin;
+            const unsigned v = *pc; *pc = run; run += v;
+        }
+        if (warp == 0) totals[bin] = total;
+    }
+}
+
+/* pass 3: bin start offsets (exclusive scan over the bin totals); single CTA of 1024 threads */
+__global__ void __launch_bounds__(1024)
+k_bin_starts(const unsigned *__restrict__ totals, int nb, unsigned *__restrict__ starts)
+{
+    __shared__ unsigned s_warp[32];
     __shared__ unsigned s_carry;
-    const int bin = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    for (int base = 0; base < nBatches; base += 256) {
+    for (int base = 0; base < nb; base += 1024) {
         const int k = base + threadIdx.x;
-        const unsigned v = (k < nBatches) ? counts[(size_t)k * nb + bin] : 0u;
+        const unsigned v = (k < nb) ? totals[k] : 0u;
         unsigned x = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
-        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[warp] = x;
         __syncthreads();
-        unsigned woff = 0;
-        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) woff += s_warp[w];
-        const unsigned carry = s_carry;
-        if (k < nBatches) counts[(size_t)k * nb + bin] = carry + woff + x - v;
+        if (warp == 0) {
+            unsigned w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+            s_warp[lane] = w;                   /* inclusive over warps */
+        }
         __syncthreads();
-        if (threadIdx.x == 255) s_carry = carry + woff + x;
+        const unsigned carry = s_carry, woff = warp ? s_warp[warp - 1] : 0u;
+        if (k < nb) starts[k] = carry + woff + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + woff + x;
         __syncthreads();
     }
-    if (threadIdx.x == 0) totals[bin] = s_carry;
+    if (threadIdx.x == 0) starts[nb] = s_carry;
 }
 
-/* pass 3: bin start offsets (exclusive scan over <= MAX_BINS totals); single CTA */
-__global__ void k_bin_starts(const unsigned *__restrict__ totals, int nb, unsigned *__restrict__ starts)
-{
-    if (threadIdx.x == 0) {
-        unsigned acc = 0;
-        for (int k = 0; k < nb; k++) { starts[k] = acc; acc += totals[k]; }
-        starts[nb] = acc;
-    }
-}
-
-/* pass 4: ordered fill.  Within a batch, triangle order per bin is recovered with ballots:
- * the CTA walks its triangles 256 at a time; for every bin touched by the CTA it ranks the
- * touching triangles by index (warp ballot + cross-warp prefix). */
+/* pass 4: ordered fill.  The CTA walks its triangles 256 at a time.  Every bin COLUMN belongs to one warp
+ * (bx & 7); each warp visits, in triangle order, the triangles whose bin rectangle has a column of its own and
+ * appends them to those bins.  A bin is therefore written by one warp only, in submission order, with no
+ * CTA barrier inside a group and no dependence on how the 256 triangles are spread over the screen. */
 __global__ void __launch_bounds__(256)
-k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY,
+k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, int bshift,
            const unsigned *__restrict__ offsets /* scanned counts */, const unsigned *__restrict__ starts,
            unsigned *__restrict__ list)
 {
     extern __shared__ unsigned s_mem[];
     unsigned *s_pos = s_mem;                    /* [nb] running write position of this batch per bin */
-    __shared__ unsigned s_warp[8];
-    __shared__ int s_box[4];
+    __shared__ int4 s_rect[256];
     const int nb = binsX * binsY;
     for (int k = threadIdx.x; k < nb; k += blockDim.x) s_pos[k] = starts[k] + offsets[(size_t)blockIdx.x * nb + k];
-    __syncthreads();
     const unsigned base = blockIdx.x * BIN_BATCH;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned k0 = 0; k0 < BIN_BATCH; k0 += 256) {
+    for (unsigned k0 = 0; k0 < BIN_BATCH && base + k0 < n; k0 += 256) {
         const unsigned i = base + k0 + threadIdx.x;
-        int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
+        int4 r = make_int4(1, 1, 0, 0);
         if (i < n) {
             const int4 b = __ldg(bbox + i);
             if (b.x < b.z) {
-                bx0 = max(b.x, 0) / BIN_PIX; bx1 = min((b.z - 1) / BIN_PIX, binsX - 1);
-                by0 = max(b.y, 0) / BIN_PIX; by1 = min(b.w / BIN_PIX, binsY - 1);
+                r.x = max(b.x, 0) >> bshift; r.z = min((b.z - 1) >> bshift, binsX - 1);
+                r.y = max(b.y, 0) >> bshift; r.w = min(b.w >> bshift, binsY - 1);
             }
         }
-        /* union bin rectangle of these 256 triangles */
-        if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = -1; s_box[3] = -1; }
+        __syncthreads();                        /* previous group done with s_rect (and s_pos initialised) */
+        s_rect[threadIdx.x] = r;
         __syncthreads();
-        if (bx0 <= bx1 && by0 <= by1) {
-            atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0); atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1);
-        }
-        __syncthreads();
-        const int ux0 = s_box[0], uy0 = s_box[1], ux1 = s_box[2], uy1 = s_box[3];
-        for (int by = uy0; by <= uy1; by++) {
-            for (int bx = ux0; bx <= ux1; bx++) {
-                const bool hit = bx >= bx0 && bx <= bx1 && by >= by0 && by <= by1;
-                const unsigned bal = __ballot_sync(0xffffffffu, hit);
-                if (lane == 0) s_warp[warp] = __popc(bal);
-                __syncthreads();
-                unsigned woff = 0, total = 0;
-#pragma unroll
-                for (int w = 0; w < 8; w++) { const unsigned c = s_warp[w]; if (w < warp) woff += c; total += c; }
-                const int bin = by * binsX + bx;
-                const unsigned pos = s_pos[bin];
-                if (hit) list[pos + woff + __popc(bal & ((1u << lane) - 1u))] = i;
-                __syncthreads();
-                if (threadIdx.x == 0) s_pos[bin] = pos + total;
-                __syncthreads();
+        for (int g8 = 0; g8 < 8; g8++) {
+            const int4 q = s_rect[g8 * 32 + lane];
+            /* first column of the rectangle that this warp owns */
+            const int first = q.x + ((warp - q.x) & 7);
+            const bool mine = q.x <= q.z && q.y <= q.w && first <= q.z;
+            const bool one = mine && first + 8 > q.z;                    /* exactly one owned column */
+            unsigned mask = __ballot_sync(0xffffffffu, mine);
+            const unsigned single = __ballot_sync(0xffffffffu, one);
+            const unsigned my_idx = base + k0 + (unsigned)(g8 * 32 + lane);
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                if ((single >> j) & 1u) {
+                    /* a run of consecutive one-column triangles: bin row by bin row (a bin has one row, so all of
+                       its entries are ranked in the same step), ranked per bin with one match */
+                    const unsigned multi = mask & ~single;
+                    const unsigned run = multi ? (mask & ((1u << (__ffs(multi) - 1)) - 1u)) : mask;
+                    const bool in_run = (run >> lane) & 1u;
+                    const int ylo = __reduce_min_sync(0xffffffffu, in_run ? q.y : INT_MAX);
+                    const int yhi = __reduce_max_sync(0xffffffffu, in_run ? q.w : INT_MIN);
+                    for (int by = ylo; by <= yhi; by++) {
+                        const bool act = in_run && q.y <= by && by <= q.w;
+                        const unsigned am = __ballot_sync(0xffffffffu, act);
+                        if (act) {
+                            const int bin = by * binsX + first;
+                            const unsigned peers = __match_any_sync(am, bin);
+                            const unsigned pos = s_pos[bin] + __popc(peers & ((1u << lane) - 1u));
+                            list[pos] = my_idx;
+                            __syncwarp(peers);
+                            if ((peers >> lane) == 1u) s_pos[bin] = pos + 1;   /* highest lane of the group */
+                        }
+                        __syncwarp();
+                    }
+                    mask &= ~run;
+                } else {
+                    mask &= mask - 1u;
+                    const int4 t = s_rect[g8 * 32 + j];
+                    const int f0 = t.x + ((warp - t.x) & 7);
+                    const int ncols = ((t.z - f0) >> 3) + 1, rows = t.w - t.y + 1;
+                    const unsigned idx = base + k0 + (unsigned)(g8 * 32 + j);
+                    for (int e = lane; e < ncols * rows; e += 32) {
+                        const int cy = e / ncols, cx = e - cy * ncols;
+                        const int bin = (t.y + cy) * binsX + f0 + (cx << 3);
+                        const unsigned pos = s_pos[bin]; list[pos] = idx; s_pos[bin] = pos + 1;
+                    }
+                }
+                __syncwarp();
             }
         }
-        __syncthreads();
     }
 }
 
@@ -700,7 +753,7 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY,
 
 struct RasterParams {
     const int4 *bbox; const TriSetup *setup; const TriData *data; const DevState *states;
-    const unsigned *bin_list; const unsigned *bin_starts; int binsX;
+    const unsigned *bin_list; const unsigned *bin_starts; int binsX; int bin_tshift;   /* a bin is 2^bin_tshift tiles wide */
     uint32_t *color; float *depth; int W, H; int tilesX, tilesY;
     unsigned rank, world; unsigned nTiles;
     unsigned long long *counters;
@@ -1004,7 +1057,7 @@ k_raster(const RasterParams p)
     const int X0 = t.X0, Y0 = t.Y0, X1 = t.X1, Y1 = t.Y1;
     const bool full_tile = (X0 + TILE <= p.W) && (Y0 + TH <= p.H) && ((p.W & 3) == 0);
 
-    const int bin = (ty / BIN_TILES) * p.binsX + (tx / BIN_TILES);
+    const int bin = (ty >> p.bin_tshift) * p.binsX + (tx >> p.bin_tshift);
     const unsigned lbeg = p.bin_starts[bin], lend = p.bin_starts[bin + 1];
     if (lbeg == lend) return;
 
@@ -1390,7 +1443,7 @@ k_raster_frag(const RasterParams p)
     const int X1 = min(X0 + TILE, p.W) - 1, Y1 = min(Y0 + TH, p.H) - 1;
     const bool full_tile = (X0 + TILE <= p.W) && (Y0 + TH <= p.H) && ((p.W & 3) == 0);
 
-    const int bin = (ty / BIN_TILES) * p.binsX + (tx / BIN_TILES);
+    const int bin = (ty >> p.bin_tshift) * p.binsX + (tx >> p.bin_tshift);
     const unsigned lbeg = p.bin_starts[bin], lend = p.bin_starts[bin + 1];
     if (lbeg == lend) return;
 
@@ -2210,9 +2263,18 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         if ((rc = grow(&LN.d_data, &c3, n))) return rc;
         LN.cap_setup = c1;
     }
-    const int binsX = (int)((s->w + BIN_PIX - 1) / BIN_PIX), binsY = (int)((s->h + BIN_PIX - 1) / BIN_PIX);
-    const int nb = binsX * binsY;
-    if (nb > MAX_BINS) { snprintf(g.err, sizeof g.err, "surface too large for the binner (%d bins)", nb); return PFCU_ERR_INVALID; }
+    /* many small triangles per tile: fine bins (one per tile) and the fragment-compacting rasteriser;
+       few large ones: coarse bins and the triangle-per-warp-step rasteriser */
+    const unsigned nTilesAll = s->tiles_x * s->tiles_y;
+    const bool small_tris = (size_t)n > (size_t)4 * nTilesAll;
+    static const int force_bshift = getenv("PF_CUDA_BIN_SHIFT") ? atoi(getenv("PF_CUDA_BIN_SHIFT")) : 0;
+    int bshift = force_bshift >= 6 ? force_bshift : (small_tris ? BIN_SHIFT_FINE : BIN_SHIFT_COARSE);
+    int binsX, binsY, nb;
+    for (;; bshift++) {
+        binsX = (int)((s->w + (1u << bshift) - 1) >> bshift); binsY = (int)((s->h + (1u << bshift) - 1) >> bshift);
+        nb = binsX * binsY;
+        if (nb <= MAX_BINS) break;
+    }
     const unsigned nBatches = (n + BIN_BATCH - 1) / BIN_BATCH;
     if ((rc = grow(&LN.d_bin_counts, &LN.cap_bin_counts, (size_t)nBatches * nb))) return rc;
 
@@ -2226,10 +2288,10 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     }
     k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, LN.stream>>>(
         d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data, g.d_counters);
-    k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, binsX, binsY, LN.d_bin_counts);
+    k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, binsX, binsY, bshift, LN.d_bin_counts);
     unsigned *d_totals = LN.d_bin_start + (MAX_BINS + 2);
-    k_bin_scan<<<nb, 256, 0, LN.stream>>>(LN.d_bin_counts, (int)nBatches, nb, d_totals);
-    k_bin_starts<<<1, 32, 0, LN.stream>>>(d_totals, nb, LN.d_bin_start);
+    k_bin_scan<<<(nb + 31) / 32, 1024, 0, LN.stream>>>(LN.d_bin_counts, (int)nBatches, nb, d_totals);
+    k_bin_starts<<<1, 1024, 0, LN.stream>>>(d_totals, nb, LN.d_bin_start);
     /* Per-bin lists hold (triangle, bin) overlaps.  The exact total is only known on the device;
        n*nb bounds it.  Small cases are sized by the bound, large ones read the total back. */
     {
@@ -2244,12 +2306,12 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         }
         if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, want ? want : 1))) return rc;
     }
-    k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, binsX, binsY, LN.d_bin_counts, LN.d_bin_start, LN.d_bin_list);
+    k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, binsX, binsY, bshift, LN.d_bin_counts, LN.d_bin_start, LN.d_bin_list);
     g.launches += 5;
 
     RasterParams p;
     p.bbox = LN.d_bbox; p.setup = LN.d_setup; p.data = LN.d_data; p.states = d_states;
-    p.bin_list = LN.d_bin_list; p.bin_starts = LN.d_bin_start; p.binsX = binsX;
+    p.bin_list = LN.d_bin_list; p.bin_starts = LN.d_bin_start; p.binsX = binsX; p.bin_tshift = bshift - 6;
     p.color = s->color; p.depth = s->depth; p.W = (int)s->w; p.H = (int)s->h;
     p.tilesX = (int)s->tiles_x; p.tilesY = (int)s->tiles_y;
     p.rank = s->rank; p.world = s->world ? s->world : 1; p.nTiles = s->tiles_x * s->tiles_y;
@@ -2259,7 +2321,6 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     if (grid) {
         /* many small triangles per tile: 16 warps per tile halve the serial work of the busiest tiles;
            few large ones: 8 warps with more registers each issue faster */
-        const bool small_tris = (size_t)n > (size_t)4 * p.nTiles;
         const bool ph = (feature_mask & PFCU_ST_PHONG) != 0;
         if (g.rcp_bits > RCP_SMEM_BITS) single_prog = -1;      /* the fixed-program kernels assume the shared RCPPS table */
         /* half-height slices when the 64x64 grid would be only a few waves deep with a ragged last wave */

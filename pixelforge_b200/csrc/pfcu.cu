@@ -1279,8 +1279,26 @@ struct FragCtx {
     int rcp_shift; bool rcp_shared;
     int RX0, RY0, RX1, RY1;             /* the region on the surface, inclusive                         */
     unsigned shaded, covered;
-    const int4 *bbox; const TriSetup *setup; const TriData *data;
+    unsigned tri_base;                  /* shared-window byte address of this warp's triangle staging   */
 };
+
+/* Per-warp staging of a group's triangle constants: field F of the triangle held by lane l is the 16-byte slot
+ * [F][l], so lanes that fetch different triangles hit different banks and lanes on the same triangle broadcast.
+ *   F0 E1 E2 E3 invSum      (edge functions at the region's pixel (0,0), wrapping int32)
+ *   F1 w1X w1Y w2X w2Y      F2 w3X w3Y z1 z2      F3 z3 meta c1 c2      F4 c3 u1 u2 u3      F5 v1 v2 v3 -
+ *   Phong only: F6 px1..3 py1   F7 py2 py3 pz1 pz2   F8 pz3 nx1..3   F9 ny1..3 nz1   F10 nz2 nz3 - -          */
+#define FRAG_NF        6
+#define FRAG_NF_PHONG  11
+__device__ __forceinline__ uint4 lds_tri(unsigned base, int field, int j)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base + (unsigned)((field * 32 + j) << 4)));
+    return v;
+}
+__device__ __forceinline__ void sts_tri(unsigned base, int field, int j, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(base + (unsigned)((field * 32 + j) << 4)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 template <int OFF> __device__ __forceinline__ float lds_f32_off(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF)); return v; }
 template <int OFF> __device__ __forceinline__ void sts_f32_off(unsigned addr, float v) { asm volatile("st.shared.f32 [%0+%1], %2;" :: "r"(addr), "n"(OFF), "f"(v) : "memory"); }
@@ -1297,7 +1315,7 @@ __device__ __forceinline__ float rcp_tab(const FragCtx &t, float x)
  * region; nn == 0 for lanes outside the group).  pk = cx0 | cy0<<4 | cw<<8 | ceil(1024/cw)<<12 describes the
  * clipped rectangle (region-local).  lo is a lane that is known to hold a valid triangle. */
 template <int TEXM, int BLENDM, bool PHONG, int NW>
-__device__ __forceinline__ void frag_run(FragCtx &t, const unsigned ti, const unsigned nn, const unsigned pk, const int lo,
+__device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const unsigned pk, const int lo,
                                          const DevState *st, const unsigned flags, const unsigned zmask, const int blend_mode, const TexRegs &tex)
 {
     constexpr int DEPTH_OFF = NW * FRAG_RSTRIDE * 4;
@@ -1320,30 +1338,27 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned ti, const un
 #pragma unroll
         for (int step = 16; step; step >>= 1) { const unsigned v = __shfl_sync(FULL, I, pos + step - 1); if (v <= f) pos += step; }
         const int j = valid ? (int)pos : lo;
-        const unsigned tj = __shfl_sync(FULL, ti, j), Ej = __shfl_sync(FULL, Ex, j), pkj = __shfl_sync(FULL, pk, j);
+        const unsigned Ej = __shfl_sync(FULL, Ex, j), pkj = __shfl_sync(FULL, pk, j);
         const unsigned r = valid ? f - Ej : 0u;
         const unsigned cw = (pkj >> 8) & 15u;
         const unsigned ry = (r * (pkj >> 12)) >> 10, rx = r - ry * cw;          /* r / cw, r % cw (r < 64, cw <= 8: exact) */
         const int px = (int)((pkj & 15u) + rx), py = (int)(((pkj >> 4) & 15u) + ry);
 
-        const int4 b = __ldg(t.bbox + tj);
-        const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(t.setup + tj));
-        const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(t.setup + tj) + 1);
-        const uint4 s2 = __ldg(reinterpret_cast<const uint4 *>(t.setup + tj) + 2);
-        const int dx = wsub(t.RX0 + px, b.x), dy = wsub(t.RY0 + py, b.y);
-        const int w1 = wadd(wadd((int)s0.x, wmul(dy, (int)s1.y)), wmul(dx, (int)s1.x));
-        const int w2 = wadd(wadd((int)s0.y, wmul(dy, (int)s1.w)), wmul(dx, (int)s1.z));
-        const int w3 = wadd(wadd((int)s0.z, wmul(dy, (int)s2.y)), wmul(dx, (int)s2.x));
+        const uint4 f0 = lds_tri(t.tri_base, 0, j), f1 = lds_tri(t.tri_base, 1, j), f2 = lds_tri(t.tri_base, 2, j);
+        const int w1 = wadd(wadd((int)f0.x, wmul(py, (int)f1.y)), wmul(px, (int)f1.x));
+        const int w2 = wadd(wadd((int)f0.y, wmul(py, (int)f1.w)), wmul(px, (int)f1.z));
+        const int w3 = wadd(wadd((int)f0.z, wmul(py, (int)f2.y)), wmul(px, (int)f2.x));
         bool m = valid && ((w1 | w2 | w3) > 0);
         if (!__any_sync(FULL, m)) continue;
         t.covered += m ? 1u : 0u;
 
-        const uint4 a0 = __ldg(reinterpret_cast<const uint4 *>(t.data + tj));
-        const float invSum = __uint_as_float(s0.w);
+        const uint4 f3 = lds_tri(t.tri_base, 3, j);
+        const unsigned meta = f3.y;
+        const float invSum = __uint_as_float(f0.w);
         const float W1 = FM(__int2float_rn(w1), invSum);
         const float W2 = FM(__int2float_rn(w2), invSum);
         const float W3 = FM(__int2float_rn(w3), invSum);
-        const float zsum = FA(FA(FM(__uint_as_float(a0.x), W1), FM(__uint_as_float(a0.y), W2)), FM(__uint_as_float(a0.z), W3));
+        const float zsum = FA(FA(FM(__uint_as_float(f2.z), W1), FM(__uint_as_float(f2.w), W2)), FM(__uint_as_float(f3.x), W3));
         const float z = rcp_tab(t, zsum);
 
         /* same-pixel fragments of this chunk (different triangles) must be applied in triangle order */
@@ -1358,23 +1373,23 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned ti, const un
         }
 
         /* colour (color.h:153-203) */
-        const uint4 a1 = __ldg(reinterpret_cast<const uint4 *>(t.data + tj) + 1);
+        const uint4 f4 = lds_tri(t.tri_base, 4, j);
+        const unsigned c1 = f3.z, c2 = f3.w, c3 = f4.x;
         Px2 frag;
         if (smooth) {
             const int u1 = __float2int_rn(FM(W1, 255.0f)), u2 = __float2int_rn(FM(W2, 255.0f)), u3 = __float2int_rn(FM(W3, 255.0f));
-            frag.rb = smooth_lanes(a1.x & 0x00ff00ffu, a1.y & 0x00ff00ffu, a1.z & 0x00ff00ffu, u1, u2, u3);
-            frag.ga = smooth_lanes((a1.x >> 8) & 0x00ff00ffu, (a1.y >> 8) & 0x00ff00ffu, (a1.z >> 8) & 0x00ff00ffu, u1, u2, u3);
+            frag.rb = smooth_lanes(c1 & 0x00ff00ffu, c2 & 0x00ff00ffu, c3 & 0x00ff00ffu, u1, u2, u3);
+            frag.ga = smooth_lanes((c1 >> 8) & 0x00ff00ffu, (c2 >> 8) & 0x00ff00ffu, (c3 >> 8) & 0x00ff00ffu, u1, u2, u3);
         } else {
             const float mx = max_x86(W1, max_x86(W2, W3));
-            frag = px_split(((mx == W1) ? a1.x : 0u) | ((mx == W2) ? a1.y : 0u) | ((mx == W3) ? a1.z : 0u));
+            frag = px_split(((mx == W1) ? c1 : 0u) | ((mx == W2) ? c2 : 0u) | ((mx == W3) ? c3 : 0u));
         }
 
         if (texturing) {
-            const uint4 a2 = __ldg(reinterpret_cast<const uint4 *>(t.data + tj) + 2);
-            const uint4 a3 = __ldg(reinterpret_cast<const uint4 *>(t.data + tj) + 3);
-            float u = FA(FA(FM(__uint_as_float(a2.x), W1), FM(__uint_as_float(a2.y), W2)), FM(__uint_as_float(a2.z), W3));
-            float v = FA(FA(FM(__uint_as_float(a3.x), W1), FM(__uint_as_float(a3.y), W2)), FM(__uint_as_float(a3.z), W3));
-            if ((a0.w >> 25) & 1u) { u = FM(u, z); v = FM(v, z); }
+            const uint4 f5 = lds_tri(t.tri_base, 5, j);
+            float u = FA(FA(FM(__uint_as_float(f4.y), W1), FM(__uint_as_float(f4.z), W2)), FM(__uint_as_float(f4.w), W3));
+            float v = FA(FA(FM(__uint_as_float(f5.x), W1), FM(__uint_as_float(f5.y), W2)), FM(__uint_as_float(f5.z), W3));
+            if ((meta >> 25) & 1u) { u = FM(u, z); v = FM(v, z); }
             unsigned texel;
             if (TEXM == 1) {
                 const float fu = FM(FS(u, truncf(u)), tex.wm1), fv = FM(FS(v, truncf(v)), tex.hm1);
@@ -1388,16 +1403,17 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned ti, const un
 
         if (PHONG) {
             if (flags & PFCU_ST_PHONG) {
-                const float4 *a = reinterpret_cast<const float4 *>(t.data + tj) + 4;
-                const float4 qx = __ldg(a), qy = __ldg(a + 1), qz = __ldg(a + 2);
-                const float4 nx = __ldg(a + 3), ny = __ldg(a + 4), nz = __ldg(a + 5);
-                const float Nx = FA(FA(FM(nx.x, W1), FM(nx.y, W2)), FM(nx.z, W3));
-                const float Ny = FA(FA(FM(ny.x, W1), FM(ny.y, W2)), FM(ny.z, W3));
-                const float Nz = FA(FA(FM(nz.x, W1), FM(nz.y, W2)), FM(nz.z, W3));
-                const float Qx = FA(FA(FM(qx.x, W1), FM(qx.y, W2)), FM(qx.z, W3));
-                const float Qy = FA(FA(FM(qy.x, W1), FM(qy.y, W2)), FM(qy.z, W3));
-                const float Qz = FA(FA(FM(qz.x, W1), FM(qz.y, W2)), FM(qz.z, W3));
-                frag = px_split(phong(px_join(frag), st, (a0.w >> 24) & 1u, Qx, Qy, Qz, Nx, Ny, Nz));
+#define UF(x) __uint_as_float(x)
+                const uint4 g6 = lds_tri(t.tri_base, 6, j), g7 = lds_tri(t.tri_base, 7, j), g8 = lds_tri(t.tri_base, 8, j);
+                const uint4 g9 = lds_tri(t.tri_base, 9, j), g10 = lds_tri(t.tri_base, 10, j);
+                const float Qx = FA(FA(FM(UF(g6.x), W1), FM(UF(g6.y), W2)), FM(UF(g6.z), W3));
+                const float Qy = FA(FA(FM(UF(g6.w), W1), FM(UF(g7.x), W2)), FM(UF(g7.y), W3));
+                const float Qz = FA(FA(FM(UF(g7.z), W1), FM(UF(g7.w), W2)), FM(UF(g8.x), W3));
+                const float Nx = FA(FA(FM(UF(g8.y), W1), FM(UF(g8.z), W2)), FM(UF(g8.w), W3));
+                const float Ny = FA(FA(FM(UF(g9.x), W1), FM(UF(g9.y), W2)), FM(UF(g9.z), W3));
+                const float Nz = FA(FA(FM(UF(g9.w), W1), FM(UF(g10.x), W2)), FM(UF(g10.y), W3));
+#undef UF
+                frag = px_split(phong(px_join(frag), st, (meta >> 24) & 1u, Qx, Qy, Qz, Nx, Ny, Nz));
             }
         }
 
@@ -1432,6 +1448,8 @@ k_raster_frag(const RasterParams p)
     __shared__ unsigned short s_qmask[QUEUE_CAP];
     __shared__ unsigned s_wcount[NW];
     __shared__ unsigned s_group[NW][32];
+    extern __shared__ __align__(16) uint4 s_tri[];          /* [NW][NF][32] triangle staging, see FRAG_NF */
+    constexpr int NF = HAS_PHONG ? FRAG_NF_PHONG : FRAG_NF;
     static_assert(NW == 8 || NW == 16, "one 8x8 region per warp, 8 regions per row");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1455,7 +1473,8 @@ k_raster_frag(const RasterParams p)
     t.rcp_base = (unsigned)__cvta_generic_to_shared(s_rcp);
     t.RX0 = X0 + (warp & 7) * 8; t.RY0 = Y0 + (warp >> 3) * 8;
     t.RX1 = min(t.RX0 + 7, X1); t.RY1 = min(t.RY0 + 7, Y1);
-    t.shaded = 0; t.covered = 0; t.bbox = p.bbox; t.setup = p.setup; t.data = p.data;
+    t.shaded = 0; t.covered = 0;
+    t.tri_base = (unsigned)__cvta_generic_to_shared(s_tri + warp * NF * 32);
 
     bool loaded = false;
 
@@ -1493,8 +1512,7 @@ k_raster_frag(const RasterParams p)
             for (int w = 0; w < NW; w++) { const unsigned c = s_wcount[w]; if (w < warp) woff += c; total += c; }
             if (hit) {
                 const unsigned pos = qn + woff + __popc(bal & ((1u << lane) - 1u)); s_queue[pos] = ti; s_qmask[pos] = (unsigned short)wmask;
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(p.setup + ti));
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(p.data + ti));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(p.data + ti));
             }
             qn += total;
             base += NT;
@@ -1557,8 +1575,33 @@ k_raster_frag(const RasterParams p)
                     __syncwarp();
                     unsigned state = 0xffffffffu, nn0 = 0, pk = 0;
                     if (have) {
+                        /* stage this triangle's constants (every load is independent: one memory round trip per group) */
                         const int4 b = __ldg(p.bbox + ti);
-                        state = __ldg(&p.data[ti].meta) & 0xffffffu;
+                        const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(p.setup + ti));
+                        const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(p.setup + ti) + 1);
+                        const uint4 s2 = __ldg(reinterpret_cast<const uint4 *>(p.setup + ti) + 2);
+                        const uint4 *da = reinterpret_cast<const uint4 *>(p.data + ti);
+                        const uint4 a0 = __ldg(da), a1 = __ldg(da + 1), a2 = __ldg(da + 2), a3 = __ldg(da + 3);
+                        state = a0.w & 0xffffffu;
+                        const int ox = wsub(t.RX0, b.x), oy = wsub(t.RY0, b.y);
+                        const unsigned E1 = (unsigned)wadd(wadd((int)s0.x, wmul(oy, (int)s1.y)), wmul(ox, (int)s1.x));
+                        const unsigned E2 = (unsigned)wadd(wadd((int)s0.y, wmul(oy, (int)s1.w)), wmul(ox, (int)s1.z));
+                        const unsigned E3 = (unsigned)wadd(wadd((int)s0.z, wmul(oy, (int)s2.y)), wmul(ox, (int)s2.x));
+                        sts_tri(t.tri_base, 0, lane, make_uint4(E1, E2, E3, s0.w));
+                        sts_tri(t.tri_base, 1, lane, s1);
+                        sts_tri(t.tri_base, 2, lane, make_uint4(s2.x, s2.y, a0.x, a0.y));
+                        sts_tri(t.tri_base, 3, lane, make_uint4(a0.z, a0.w, a1.x, a1.y));
+                        sts_tri(t.tri_base, 4, lane, make_uint4(a1.z, a2.x, a2.y, a2.z));
+                        sts_tri(t.tri_base, 5, lane, make_uint4(a3.x, a3.y, a3.z, 0u));
+                        if (HAS_PHONG) {
+                            const uint4 qx = __ldg(da + 4), qy = __ldg(da + 5), qz = __ldg(da + 6);
+                            const uint4 nx = __ldg(da + 7), ny = __ldg(da + 8), nz = __ldg(da + 9);
+                            sts_tri(t.tri_base, 6, lane, make_uint4(qx.x, qx.y, qx.z, qy.x));
+                            sts_tri(t.tri_base, 7, lane, make_uint4(qy.y, qy.z, qz.x, qz.y));
+                            sts_tri(t.tri_base, 8, lane, make_uint4(qz.z, nx.x, nx.y, nx.z));
+                            sts_tri(t.tri_base, 9, lane, make_uint4(ny.x, ny.y, ny.z, nz.x));
+                            sts_tri(t.tri_base, 10, lane, make_uint4(nz.y, nz.z, 0u, 0u));
+                        }
                         const int cx0 = max(b.x, t.RX0) - t.RX0, cx1 = min(b.z - 1, t.RX1) - t.RX0;
                         const int cy0 = max(b.y, t.RY0) - t.RY0, cy1 = min(b.w, t.RY1) - t.RY0;
                         const int cw = cx1 - cx0 + 1, ch = cy1 - cy0 + 1;
@@ -1567,6 +1610,7 @@ k_raster_frag(const RasterParams p)
                             pk = (unsigned)cx0 | ((unsigned)cy0 << 4) | ((unsigned)cw << 8) | (((1024u + (unsigned)cw - 1u) / (unsigned)cw) << 12);
                         }
                     }
+                    __syncwarp();
                     unsigned lo = 0;
                     while (lo < cnt) {
                         const unsigned sid = __shfl_sync(0xffffffffu, state, (int)lo);
@@ -1590,19 +1634,19 @@ k_raster_frag(const RasterParams p)
                             if (HAS_PHONG && (flags & PFCU_ST_PHONG)) prog = 12;
                         }
                         switch (prog) {
-                        case 0:  frag_run<0, 0, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 1:  frag_run<0, 1, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 2:  frag_run<0, 2, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 3:  frag_run<0, 3, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 4:  frag_run<1, 0, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 5:  frag_run<1, 1, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 6:  frag_run<1, 2, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 7:  frag_run<1, 3, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 8:  frag_run<2, 0, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 9:  frag_run<2, 1, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 10: frag_run<2, 2, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 11: frag_run<2, 3, false, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        default: if (HAS_PHONG) frag_run<2, 3, true, NW>(t, ti, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 0:  frag_run<0, 0, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 1:  frag_run<0, 1, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 2:  frag_run<0, 2, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 3:  frag_run<0, 3, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 4:  frag_run<1, 0, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 5:  frag_run<1, 1, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 6:  frag_run<1, 2, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 7:  frag_run<1, 3, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 8:  frag_run<2, 0, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 9:  frag_run<2, 1, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 10: frag_run<2, 2, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        case 11: frag_run<2, 3, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+                        default: if (HAS_PHONG) frag_run<2, 3, true, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
                         }
                         lo = hi;
                     }
@@ -2338,8 +2382,13 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         const bool use_frag = g.raster_path == PFCU_RASTER_FRAGMENTS || (g.raster_path == PFCU_RASTER_AUTO && small_tris && !force_slice);
         if (use_frag) {
             /* fragment-compacting kernel: 64x16 slices of 16 regions (Phong: 64x8 slices, 8 warps, 128 registers) */
-            if (ph) k_raster_frag<true, 8><<<grid * 8, 256, 0, LN.stream>>>(p);
-            else    k_raster_frag<false, 16><<<grid * 4, 512, 0, LN.stream>>>(p);
+            static const bool attr_once = [] {
+                cudaFuncSetAttribute(k_raster_frag<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * FRAG_NF_PHONG * 512);
+                cudaFuncSetAttribute(k_raster_frag<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * FRAG_NF * 512);
+                return true; }();
+            (void)attr_once;
+            if (ph) k_raster_frag<true, 8><<<grid * 8, 256, 8 * FRAG_NF_PHONG * 512, LN.stream>>>(p);
+            else    k_raster_frag<false, 16><<<grid * 4, 512, 16 * FRAG_NF * 512, LN.stream>>>(p);
         }
         else if (small_tris) {
             const int th = force_slice ? force_slice : (ph ? 32 : 16);

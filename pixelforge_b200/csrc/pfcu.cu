@@ -111,7 +111,7 @@ struct Lane {
     DevState *d_states = nullptr; size_t cap_states = 0;
     int4 *d_bbox = nullptr; TriSetup *d_setup = nullptr; TriData *d_data = nullptr; size_t cap_setup = 0;
     unsigned *d_bin_counts = nullptr; size_t cap_bin_counts = 0;     /* [batches][bins] */
-    unsigned *d_bin_list = nullptr; size_t cap_bin_list = 0;
+    uint2 *d_bin_list = nullptr; size_t cap_bin_list = 0;       /* {triangle, bbox relative to the bin} */
     unsigned *d_bin_start = nullptr;                                  /* [MAX_BINS+2] starts, then totals */
     unsigned char *d_varrays = nullptr; size_t cap_varrays = 0;        /* vertex arrays of the current draw */
     unsigned *d_vcounts = nullptr; size_t cap_vcounts = 0;
@@ -667,6 +667,17 @@ k_bin_starts(const unsigned *__restrict__ totals, int nb, unsigned *__restrict__
     if (threadIdx.x == 0) starts[nb] = s_carry;
 }
 
+/* A bin-list entry carries the triangle's visited rectangle [x0, x1] x [y0, y1] (inclusive) clipped to the bin and
+ * relative to the bin's origin, 8 bits per coordinate (bins are at most 256 pixels wide): the rasteriser's
+ * queue filter then needs no dependent load. */
+__device__ __forceinline__ unsigned bin_rel_bbox(const int4 b, int bx, int by, int bshift)
+{
+    const int ox = bx << bshift, oy = by << bshift, hi = (1 << bshift) - 1;
+    const int x0 = min(max(b.x - ox, 0), hi), x1 = min(max(b.z - 1 - ox, 0), hi);
+    const int y0 = min(max(b.y - oy, 0), hi), y1 = min(max(b.w - oy, 0), hi);
+    return (unsigned)x0 | ((unsigned)y0 << 8) | ((unsigned)x1 << 16) | ((unsigned)y1 << 24);
+}
+
 /* pass 4: ordered fill.  The CTA walks its triangles 256 at a time.  Every bin COLUMN belongs to one warp
  * (bx & 7); each warp visits, in triangle order, the triangles whose bin rectangle has a column of its own and
  * appends them to those bins.  A bin is therefore written by one warp only, in submission order, with no
@@ -674,11 +685,12 @@ k_bin_starts(const unsigned *__restrict__ totals, int nb, unsigned *__restrict__
 __global__ void __launch_bounds__(256)
 k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, int bshift,
            const unsigned *__restrict__ offsets /* scanned counts */, const unsigned *__restrict__ starts,
-           unsigned *__restrict__ list)
+           uint2 *__restrict__ list)
 {
     extern __shared__ unsigned s_mem[];
     unsigned *s_pos = s_mem;                    /* [nb] running write position of this batch per bin */
     __shared__ int4 s_rect[256];
+    __shared__ int4 s_bbox[256];
     const int nb = binsX * binsY;
     for (int k = threadIdx.x; k < nb; k += blockDim.x) s_pos[k] = starts[k] + offsets[(size_t)blockIdx.x * nb + k];
     const unsigned base = blockIdx.x * BIN_BATCH;
@@ -686,8 +698,9 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, int 
     for (unsigned k0 = 0; k0 < BIN_BATCH && base + k0 < n; k0 += 256) {
         const unsigned i = base + k0 + threadIdx.x;
         int4 r = make_int4(1, 1, 0, 0);
+        int4 b = make_int4(1, 1, 0, 0);
         if (i < n) {
-            const int4 b = __ldg(bbox + i);
+            b = __ldg(bbox + i);
             if (b.x < b.z) {
                 r.x = max(b.x, 0) >> bshift; r.z = min((b.z - 1) >> bshift, binsX - 1);
                 r.y = max(b.y, 0) >> bshift; r.w = min(b.w >> bshift, binsY - 1);
@@ -695,9 +708,11 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, int 
         }
         __syncthreads();                        /* previous group done with s_rect (and s_pos initialised) */
         s_rect[threadIdx.x] = r;
+        s_bbox[threadIdx.x] = b;
         __syncthreads();
         for (int g8 = 0; g8 < 8; g8++) {
             const int4 q = s_rect[g8 * 32 + lane];
+            const int4 qb = s_bbox[g8 * 32 + lane];
             /* first column of the rectangle that this warp owns */
             const int first = q.x + ((warp - q.x) & 7);
             const bool mine = q.x <= q.z && q.y <= q.w && first <= q.z;
@@ -722,7 +737,7 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, int 
                             const int bin = by * binsX + first;
                             const unsigned peers = __match_any_sync(am, bin);
                             const unsigned pos = s_pos[bin] + __popc(peers & ((1u << lane) - 1u));
-                            list[pos] = my_idx;
+                            list[pos] = make_uint2(my_idx, bin_rel_bbox(qb, first, by, bshift));
                             __syncwarp(peers);
                             if ((peers >> lane) == 1u) s_pos[bin] = pos + 1;   /* highest lane of the group */
                         }
@@ -732,13 +747,16 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, int 
                 } else {
                     mask &= mask - 1u;
                     const int4 t = s_rect[g8 * 32 + j];
+                    const int4 tb = s_bbox[g8 * 32 + j];
                     const int f0 = t.x + ((warp - t.x) & 7);
                     const int ncols = ((t.z - f0) >> 3) + 1, rows = t.w - t.y + 1;
                     const unsigned idx = base + k0 + (unsigned)(g8 * 32 + j);
                     for (int e = lane; e < ncols * rows; e += 32) {
                         const int cy = e / ncols, cx = e - cy * ncols;
                         const int bin = (t.y + cy) * binsX + f0 + (cx << 3);
-                        const unsigned pos = s_pos[bin]; list[pos] = idx; s_pos[bin] = pos + 1;
+                        const unsigned pos = s_pos[bin];
+                        list[pos] = make_uint2(idx, bin_rel_bbox(tb, f0 + (cx << 3), t.y + cy, bshift));
+                        s_pos[bin] = pos + 1;
                     }
                 }
                 __syncwarp();
@@ -753,7 +771,7 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, int 
 
 struct RasterParams {
     const int4 *bbox; const TriSetup *setup; const TriData *data; const DevState *states;
-    const unsigned *bin_list; const unsigned *bin_starts; int binsX; int bin_tshift;   /* a bin is 2^bin_tshift tiles wide */
+    const uint2 *bin_list; const unsigned *bin_starts; int binsX; int bin_tshift;   /* a bin is 2^bin_tshift tiles wide */
     uint32_t *color; float *depth; int W, H; int tilesX, tilesY;
     unsigned rank, world; unsigned nTiles;
     unsigned long long *counters;
@@ -1088,7 +1106,7 @@ k_raster(const RasterParams p)
             const unsigned k = base + tid;
             bool hit = false; unsigned ti = 0, wmask = 0;
             if (k < lend) {
-                ti = __ldg(p.bin_list + k);
+                ti = __ldg(&p.bin_list[k].x);
                 const int4 b = __ldg(p.bbox + ti);
                 hit = b.x <= X1 && b.z - 1 >= X0 && b.y <= Y1 && b.w >= Y0 && b.x < b.z;
                 if (hit) {
@@ -1468,7 +1486,23 @@ k_raster_frag(const RasterParams p)
     FragCtx t;
     t.rcp_shift = c_rcp_shift;
     t.rcp_shared = t.rcp_shift >= 23 - RCP_SMEM_BITS;
-    if (t.rcp_shared) for (int k = tid; k < (1 << (23 - t.rcp_shift)); k += NT) s_rcp[k] = c_rcp_tab[k];
+    /* the RCPPS table and (full slices) the colour/depth slice arrive asynchronously while the queue is filled */
+    if (t.rcp_shared) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_rcp);
+        for (int k = tid; k < (1 << (21 - t.rcp_shift)); k += NT)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst + (unsigned)(k << 4)), "l"(c_rcp_tab + 4 * k) : "memory");
+    }
+    if (full_tile) {
+        const unsigned dcol = (unsigned)__cvta_generic_to_shared(s_col);
+        for (int k = tid; k < TH * 16; k += NT) {
+            const int r = k >> 4, c4 = (k & 15) << 2;
+            const size_t gi = (size_t)(Y0 + r) * p.W + X0 + c4;
+            const unsigned sa = (unsigned)((((r >> 3) * 8 + (c4 >> 3)) * FRAG_RSTRIDE + (r & 7) * 8 + (c4 & 7)) << 2);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dcol + sa), "l"(p.color + gi) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dcol + sa + NW * FRAG_RSTRIDE * 4), "l"(p.depth + gi) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     t.col_base = (unsigned)__cvta_generic_to_shared(s_col + warp * FRAG_RSTRIDE);
     t.rcp_base = (unsigned)__cvta_generic_to_shared(s_rcp);
     t.RX0 = X0 + (warp & 7) * 8; t.RY0 = Y0 + (warp >> 3) * 8;
@@ -1477,6 +1511,9 @@ k_raster_frag(const RasterParams p)
     t.tri_base = (unsigned)__cvta_generic_to_shared(s_tri + warp * NF * 32);
 
     bool loaded = false;
+    /* the slice relative to its bin, as the bin-list entries store their rectangles */
+    const int bx0 = X0 - (((tx >> p.bin_tshift) << p.bin_tshift) * TILE), by0 = Y0 - (((ty >> p.bin_tshift) << p.bin_tshift) * TILE);
+    const int bx1 = bx0 + (X1 - X0), by1 = by0 + (Y1 - Y0);
 
     for (unsigned base = lbeg; base < lend; ) {
         /* ---- fill the queue: ordered compaction of the bin list against this slice ---- */
@@ -1485,21 +1522,15 @@ k_raster_frag(const RasterParams p)
             const unsigned k = base + tid;
             bool hit = false; unsigned ti = 0, wmask = 0;
             if (k < lend) {
-                ti = __ldg(p.bin_list + k);
-                const int4 b = __ldg(p.bbox + ti);
-                hit = b.x <= X1 && b.z - 1 >= X0 && b.y <= Y1 && b.w >= Y0 && b.x < b.z;
+                const uint2 e = __ldg(p.bin_list + k);
+                ti = e.x;
+                const int ex0 = (int)(e.y & 255u), ey0 = (int)((e.y >> 8) & 255u), ex1 = (int)((e.y >> 16) & 255u), ey1 = (int)(e.y >> 24);
+                hit = ex0 <= bx1 && ex1 >= bx0 && ey0 <= by1 && ey1 >= by0;
                 if (hit) {
-                    const int rx0 = max(b.x, X0), rx1 = min(b.z - 1, X1), ry0 = max(b.y, Y0), ry1 = min(b.w, Y1);
-                    const TriSetup s = p.setup[ti];
-                    if (s.flags & TF_SAFE) {        /* edge-function reject of the whole slice (only when int32 cannot wrap) */
-                        const int ax0 = rx0 - b.x, ax1 = rx1 - b.x, ay0 = ry0 - b.y, ay1 = ry1 - b.y;
-                        const int m1 = s.w1R + (s.w1X > 0 ? ax1 : ax0) * s.w1X + (s.w1Y > 0 ? ay1 : ay0) * s.w1Y;
-                        const int m2 = s.w2R + (s.w2X > 0 ? ax1 : ax0) * s.w2X + (s.w2Y > 0 ? ay1 : ay0) * s.w2Y;
-                        const int m3 = s.w3R + (s.w3X > 0 ? ax1 : ax0) * s.w3X + (s.w3Y > 0 ? ay1 : ay0) * s.w3Y;
-                        if ((m1 | m2 | m3) < 0) hit = false;
-                    }
-                    /* regions (= warps) touched by the clipped bbox */
-                    const int gx0 = (rx0 - X0) >> 3, gx1 = (rx1 - X0) >> 3, gy0 = (ry0 - Y0) >> 3, gy1 = (ry1 - Y0) >> 3;
+                    /* regions (= warps) touched by the clipped rectangle; the edge-function reject is done per
+                       region when the group is staged */
+                    const int gx0 = (max(ex0, bx0) - bx0) >> 3, gx1 = (min(ex1, bx1) - bx0) >> 3;
+                    const int gy0 = (max(ey0, by0) - by0) >> 3, gy1 = (min(ey1, by1) - by0) >> 3;
                     const unsigned run = ((2u << gx1) - 1u) & ~((1u << gx0) - 1u);
                     wmask = (gy0 == 0 ? run : 0u) | ((NW == 16 && gy1 == 1) ? (run << 8) : 0u);
                 }
@@ -1520,20 +1551,10 @@ k_raster_frag(const RasterParams p)
         }
         if (qn == 0) continue;
 
-        /* ---- lazy slice load: 128-bit coalesced rows into the region-major shared tile ---- */
+        /* ---- the slice: cp.async issued at kernel start (full slices), or a bounds-checked load now ---- */
         if (!loaded) {
             loaded = true;
-            if (full_tile) {
-                for (int k = tid; k < TH * 16; k += NT) {
-                    const int r = k >> 4, c4 = (k & 15) << 2;
-                    const size_t gi = (size_t)(Y0 + r) * p.W + X0 + c4;
-                    const uint4 cv = __ldcs(reinterpret_cast<const uint4 *>(p.color + gi));
-                    const float4 dv = __ldcs(reinterpret_cast<const float4 *>(p.depth + gi));
-                    const int sa = ((r >> 3) * 8 + (c4 >> 3)) * FRAG_RSTRIDE + (r & 7) * 8 + (c4 & 7);
-                    *reinterpret_cast<uint4 *>(s_col + sa) = cv;
-                    *reinterpret_cast<float4 *>(s_dep + sa) = dv;
-                }
-            } else {
+            if (!full_tile) {
                 for (int k = tid; k < TILE * TH; k += NT) {
                     const int lx = k & (TILE - 1), ly = k >> 6;
                     if (X0 + lx <= X1 && Y0 + ly <= Y1) {
@@ -1544,6 +1565,7 @@ k_raster_frag(const RasterParams p)
                     }
                 }
             }
+            asm volatile("cp.async.wait_all;" ::: "memory");
             __syncthreads();
         }
 
@@ -1608,6 +1630,14 @@ k_raster_frag(const RasterParams p)
                         if (cw > 0 && ch > 0) {
                             nn0 = (unsigned)(cw * ch);
                             pk = (unsigned)cx0 | ((unsigned)cy0 << 4) | ((unsigned)cw << 8) | (((1024u + (unsigned)cw - 1u) / (unsigned)cw) << 12);
+                            if (s2.z & TF_SAFE) {       /* an edge function negative over the whole clipped rectangle: nothing to shade */
+                                /* evaluated mod 2^32 from the region origin; the corner itself lies inside the bbox, where
+                                   TF_SAFE guarantees the true value fits */
+                                const int m1 = wadd((int)E1, wadd(wmul(((int)s1.x > 0) ? cx1 : cx0, (int)s1.x), wmul(((int)s1.y > 0) ? cy1 : cy0, (int)s1.y)));
+                                const int m2 = wadd((int)E2, wadd(wmul(((int)s1.z > 0) ? cx1 : cx0, (int)s1.z), wmul(((int)s1.w > 0) ? cy1 : cy0, (int)s1.w)));
+                                const int m3 = wadd((int)E3, wadd(wmul(((int)s2.x > 0) ? cx1 : cx0, (int)s2.x), wmul(((int)s2.y > 0) ? cy1 : cy0, (int)s2.y)));
+                                if ((m1 | m2 | m3) < 0) nn0 = 0;
+                            }
                         }
                     }
                     __syncwarp();
@@ -1657,6 +1687,7 @@ k_raster_frag(const RasterParams p)
         __syncthreads();
     }
 
+    asm volatile("cp.async.wait_all;" ::: "memory");        /* nothing may be in flight when the CTA retires */
     /* ---- write the slice back ---- */
     if (loaded) {
         if (full_tile) {
@@ -2319,6 +2350,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         nb = binsX * binsY;
         if (nb <= MAX_BINS) break;
     }
+    if (bshift > 8) { snprintf(g.err, sizeof g.err, "surface too large for the binner (%u x %u)", s->w, s->h); return PFCU_ERR_INVALID; }
     const unsigned nBatches = (n + BIN_BATCH - 1) / BIN_BATCH;
     if ((rc = grow(&LN.d_bin_counts, &LN.cap_bin_counts, (size_t)nBatches * nb))) return rc;
 

@@ -1279,15 +1279,19 @@ k_raster(const RasterParams p)
  * touches.  k_raster_frag turns the work around: a CTA owns a 64 x (NW) slice cut into 8x8-pixel REGIONS, one
  * region per warp (fixed pixel ownership, so submission order per pixel is kept without atomics).  Each warp
  *   1. gathers, in order, up to 32 queued triangles that touch its region (lane = triangle),
- *   2. every lane clips its triangle's bbox to the region: n = candidate pixels; a warp scan of n lays all
- *      candidates of the 32 triangles out as one ordered fragment stream,
+ *   2. every lane loads its triangle's constants (independent loads, one memory round trip per group), moves the
+ *      edge functions to the region's origin, stages everything in shared memory (FRAG_NF fields), clips the
+ *      bbox to the region (n = candidate pixels; 0 when an edge function is negative over the whole clipped
+ *      rectangle) and a warp scan of n lays all candidates of the 32 triangles out as one ordered fragment stream,
  *   3. the stream is consumed 32 fragments at a time (lane = fragment, usually of several triangles): owner
- *      lookup by binary search over the scan, per-lane triangle constants from L1, then exactly the same
+ *      lookup by binary search over the scan, triangle constants from the staging area, then exactly the same
  *      coverage / depth / colour / texture / Phong / blend arithmetic as shade_tri,
  *   4. fragments of one chunk that hit the same pixel (shared edges and vertices are drawn by every
  *      triangle that owns them, Q4) are ranked by __match_any_sync and written in rank order.
  * The region tiles live in shared memory as [region][8][8] with a stride of 72 words so that the 128-bit row
- * load/store of the slice is bank-conflict free.
+ * load/store of the slice is bank-conflict free.  The slice and the RCPPS table arrive by cp.async while the
+ * queue is filtered; the filter reads only the packed bin-list entries (no dependent loads).
+ * Launched as 64x8 slices, 8 warps: 4 CTAs per SM (64 registers), 3 with Phong (80 registers).
  */
 #define FRAG_RSTRIDE 72
 
@@ -1453,8 +1457,8 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const un
     }
 }
 
-template <bool HAS_PHONG, int NW>
-__global__ void __launch_bounds__(NW * 32, HAS_PHONG ? (NW == 16 ? 1 : 2) : (NW == 16 ? 2 : 4))
+template <bool HAS_PHONG, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 k_raster_frag(const RasterParams p)
 {
     constexpr int NT = NW * 32, TH = NW, SUB = TILE / TH;
@@ -2413,14 +2417,14 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         (void)env_once;
         const bool use_frag = g.raster_path == PFCU_RASTER_FRAGMENTS || (g.raster_path == PFCU_RASTER_AUTO && small_tris && !force_slice);
         if (use_frag) {
-            /* fragment-compacting kernel: 64x16 slices of 16 regions (Phong: 64x8 slices, 8 warps, 128 registers) */
+            /* 64x8 slices of eight 8x8 regions, 8 warps; 4 CTAs per SM (Phong: 3, 80 registers) */
             static const bool attr_once = [] {
-                cudaFuncSetAttribute(k_raster_frag<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * FRAG_NF_PHONG * 512);
-                cudaFuncSetAttribute(k_raster_frag<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * FRAG_NF * 512);
+                cudaFuncSetAttribute(k_raster_frag<true, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * FRAG_NF_PHONG * 512);
+                cudaFuncSetAttribute(k_raster_frag<false, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * FRAG_NF * 512);
                 return true; }();
             (void)attr_once;
-            if (ph) k_raster_frag<true, 8><<<grid * 8, 256, 8 * FRAG_NF_PHONG * 512, LN.stream>>>(p);
-            else    k_raster_frag<false, 16><<<grid * 4, 512, 16 * FRAG_NF * 512, LN.stream>>>(p);
+            if (ph) k_raster_frag<true, 8, 3><<<grid * 8, 256, 8 * FRAG_NF_PHONG * 512, LN.stream>>>(p);
+            else    k_raster_frag<false, 8, 4><<<grid * 8, 256, 8 * FRAG_NF * 512, LN.stream>>>(p);
         }
         else if (small_tris) {
             const int th = force_slice ? force_slice : (ph ? 32 : 16);

@@ -495,14 +495,14 @@ __device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (
 __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
 __device__ __forceinline__ long long labs64(long long v) { return v < 0 ? -v : v; }
 
-__global__ void __launch_bounds__(SETUP_THREADS)
-k_setup(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ states, unsigned n,
-        int surfW, int surfH, int4 *__restrict__ bbox, TriSetup *__restrict__ setup, TriData *__restrict__ data,
-        unsigned long long *__restrict__ counters)
+/* setup of triangle i; returns its bbox (empty = (1,1,0,0)) and whether it counts as rasterised */
+__device__ __forceinline__ int4 setup_one(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ states, unsigned i,
+                                          int surfW, int surfH, int4 *__restrict__ bbox, TriSetup *__restrict__ setup,
+                                          TriData *__restrict__ data, bool *rasterised)
 {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = false;
-    if (i < n) {
+    int4 out_box = make_int4(1, 1, 0, 0);
+    {
         const pfcu_triangle *t = tris + i;
         const pfcu_vertex *v1 = &t->v[0], *v2 = &t->v[1], *v3 = &t->v[2];
         const int face = t->face, is3d = t->is3d;
@@ -548,7 +548,8 @@ k_setup(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ sta
         const bool nonempty = !culled && xMin < xMax && yMin <= yMax && xMax > 0 && yMax >= 0 && xMin < surfW && yMin < surfH;
         valid = nonempty;
 
-        bbox[i] = valid ? make_int4(xMin, yMin, xMax, yMax) : make_int4(1, 1, 0, 0);
+        if (valid) out_box = make_int4(xMin, yMin, xMax, yMax);
+        bbox[i] = out_box;
         TriSetup s;
         s.w1R = w1R; s.w2R = w2R; s.w3R = w3R; s.invSum = invSum;
         s.w1X = w1X; s.w1Y = w1Y; s.w2X = w2X; s.w2Y = w2Y; s.w3X = w3X; s.w3Y = w3Y;
@@ -572,6 +573,18 @@ k_setup(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ sta
         /* "rasterised" = survives the face / zero-area test */
         valid = !culled;
     }
+    *rasterised = valid;
+    return out_box;
+}
+
+__global__ void __launch_bounds__(SETUP_THREADS)
+k_setup(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ states, unsigned n,
+        int surfW, int surfH, int4 *__restrict__ bbox, TriSetup *__restrict__ setup, TriData *__restrict__ data,
+        unsigned long long *__restrict__ counters)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    if (i < n) setup_one(tris, states, i, surfW, surfH, bbox, setup, data, &valid);
     const unsigned b = __ballot_sync(0xffffffffu, valid);
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(counters + 0, (unsigned long long)__popc(b));
 }
@@ -761,6 +774,121 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, int 
                 }
                 __syncwarp();
             }
+        }
+    }
+}
+
+/* Batches of at most 1024 triangles (a Gears frame, one context of a many-context batch): setup, bin count,
+ * bin starts and the ordered fill in ONE single-CTA kernel instead of five launches; thread = triangle, warp w
+ * owns the bin columns bx & 31 == w (see k_bin_fill). */
+#define FRONT_SMALL_MAX 1024
+__global__ void __launch_bounds__(1024)
+k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ states, unsigned n, int surfW, int surfH,
+              int4 *__restrict__ bbox, TriSetup *__restrict__ setup, TriData *__restrict__ data, unsigned long long *__restrict__ counters,
+              int binsX, int binsY, int bshift, unsigned *__restrict__ starts, uint2 *__restrict__ list)
+{
+    extern __shared__ unsigned s_mem[];
+    unsigned *s_pos = s_mem;                    /* [nb] counts, then running write positions */
+    __shared__ int4 s_rect[FRONT_SMALL_MAX];
+    __shared__ int4 s_bbox[FRONT_SMALL_MAX];
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_carry;
+    const int nb = binsX * binsY;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < nb; k += 1024) s_pos[k] = 0;
+    if (threadIdx.x == 0) s_carry = 0;
+
+    const unsigned i = threadIdx.x;
+    bool rasterised = false;
+    int4 b = make_int4(1, 1, 0, 0), r = make_int4(1, 1, 0, 0);
+    if (i < n) b = setup_one(tris, states, i, surfW, surfH, bbox, setup, data, &rasterised);
+    if (b.x < b.z) {
+        r.x = max(b.x, 0) >> bshift; r.z = min((b.z - 1) >> bshift, binsX - 1);
+        r.y = max(b.y, 0) >> bshift; r.w = min(b.w >> bshift, binsY - 1);
+    }
+    s_rect[i] = r; s_bbox[i] = b;
+    {
+        const unsigned bal = __ballot_sync(0xffffffffu, rasterised);
+        if (lane == 0 && bal) atomicAdd(counters + 0, (unsigned long long)__popc(bal));
+    }
+    __syncthreads();
+    for (int by = r.y; by <= r.w; by++)
+        for (int bx = r.x; bx <= r.z; bx++) atomicAdd(&s_pos[by * binsX + bx], 1u);
+    __syncthreads();
+
+    /* exclusive scan of the bin counts -> starts[] (global, for the rasteriser) and s_pos */
+    for (int base = 0; base < nb; base += 1024) {
+        const int k = base + threadIdx.x;
+        const unsigned v = (k < nb) ? s_pos[k] : 0u;
+        unsigned x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const unsigned carry = s_carry, woff = warp ? s_warp[warp - 1] : 0u;
+        if (k < nb) { const unsigned e = carry + woff + x - v; s_pos[k] = e; starts[k] = e; }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + woff + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) starts[nb] = s_carry;
+
+    /* ordered fill: every warp walks all triangles, 32 at a time, and appends those with a bin column of its own */
+    const unsigned groups = (n + 31u) / 32u;
+    for (unsigned g8 = 0; g8 < groups; g8++) {
+        const int4 q = s_rect[g8 * 32 + lane];
+        const int4 qb = s_bbox[g8 * 32 + lane];
+        const int first = q.x + ((warp - q.x) & 31);
+        const bool mine = q.x <= q.z && q.y <= q.w && first <= q.z;
+        const bool one = mine && first + 32 > q.z;
+        unsigned mask = __ballot_sync(0xffffffffu, mine);
+        const unsigned single = __ballot_sync(0xffffffffu, one);
+        const unsigned my_idx = g8 * 32 + (unsigned)lane;
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            if ((single >> j) & 1u) {
+                const unsigned multi = mask & ~single;
+                const unsigned run = multi ? (mask & ((1u << (__ffs(multi) - 1)) - 1u)) : mask;
+                const bool in_run = (run >> lane) & 1u;
+                const int ylo = __reduce_min_sync(0xffffffffu, in_run ? q.y : INT_MAX);
+                const int yhi = __reduce_max_sync(0xffffffffu, in_run ? q.w : INT_MIN);
+                for (int by = ylo; by <= yhi; by++) {
+                    const bool act = in_run && q.y <= by && by <= q.w;
+                    const unsigned am = __ballot_sync(0xffffffffu, act);
+                    if (act) {
+                        const int bin = by * binsX + first;
+                        const unsigned peers = __match_any_sync(am, bin);
+                        const unsigned pos = s_pos[bin] + __popc(peers & ((1u << lane) - 1u));
+                        list[pos] = make_uint2(my_idx, bin_rel_bbox(qb, first, by, bshift));
+                        __syncwarp(peers);
+                        if ((peers >> lane) == 1u) s_pos[bin] = pos + 1;
+                    }
+                    __syncwarp();
+                }
+                mask &= ~run;
+            } else {
+                mask &= mask - 1u;
+                const int4 t = s_rect[g8 * 32 + j];
+                const int4 tb = s_bbox[g8 * 32 + j];
+                const int f0 = t.x + ((warp - t.x) & 31);
+                const int ncols = ((t.z - f0) >> 5) + 1, rows = t.w - t.y + 1;
+                const unsigned idx = g8 * 32 + (unsigned)j;
+                for (int e = lane; e < ncols * rows; e += 32) {
+                    const int cy = e / ncols, cx = e - cy * ncols;
+                    const int bin = (t.y + cy) * binsX + f0 + (cx << 5);
+                    const unsigned pos = s_pos[bin];
+                    list[pos] = make_uint2(idx, bin_rel_bbox(tb, f0 + (cx << 5), t.y + cy, bshift));
+                    s_pos[bin] = pos + 1;
+                }
+            }
+            __syncwarp();
         }
     }
 }
@@ -2366,29 +2494,36 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         }
         CK(cudaEventRecord(pe[0], LN.stream));
     }
-    k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, LN.stream>>>(
-        d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data, g.d_counters);
-    k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, binsX, binsY, bshift, LN.d_bin_counts);
-    unsigned *d_totals = LN.d_bin_start + (MAX_BINS + 2);
-    k_bin_scan<<<(nb + 31) / 32, 1024, 0, LN.stream>>>(LN.d_bin_counts, (int)nBatches, nb, d_totals);
-    k_bin_starts<<<1, 1024, 0, LN.stream>>>(d_totals, nb, LN.d_bin_start);
-    /* Per-bin lists hold (triangle, bin) overlaps.  The exact total is only known on the device;
-       n*nb bounds it.  Small cases are sized by the bound, large ones read the total back. */
-    {
-        const size_t bound = (size_t)n * (size_t)nb;
-        size_t want = bound <= ((size_t)n * 4 > 65536 ? (size_t)n * 4 : 65536) ? bound : 0;
-        if (!want && bound <= LN.cap_bin_list) want = bound;
-        if (!want) {
-            unsigned total = 0;
-            CK(cudaMemcpyAsync(&total, LN.d_bin_start + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, LN.stream));
-            CK(cudaStreamSynchronize(LN.stream));
-            want = total;
+    if (n <= FRONT_SMALL_MAX && nb <= 3072) {       /* 3072 bin counters + the rectangles fit the 48 KB of static + dynamic shared memory */
+        /* small batch: the (triangle, bin) overlap count is bounded by n * nb, no read-back needed */
+        if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, (size_t)n * nb))) return rc;
+        k_front_small<<<1, 1024, nb * sizeof(unsigned), LN.stream>>>(d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data,
+                                                                      g.d_counters, binsX, binsY, bshift, LN.d_bin_start, LN.d_bin_list);
+        g.launches += 1;
+    } else {
+        k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, LN.stream>>>(
+            d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data, g.d_counters);
+        k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, binsX, binsY, bshift, LN.d_bin_counts);
+        unsigned *d_totals = LN.d_bin_start + (MAX_BINS + 2);
+        k_bin_scan<<<(nb + 31) / 32, 1024, 0, LN.stream>>>(LN.d_bin_counts, (int)nBatches, nb, d_totals);
+        k_bin_starts<<<1, 1024, 0, LN.stream>>>(d_totals, nb, LN.d_bin_start);
+        /* Per-bin lists hold (triangle, bin) overlaps.  The exact total is only known on the device;
+           n*nb bounds it.  Small cases are sized by the bound, large ones read the total back. */
+        {
+            const size_t bound = (size_t)n * (size_t)nb;
+            size_t want = bound <= ((size_t)n * 4 > 65536 ? (size_t)n * 4 : 65536) ? bound : 0;
+            if (!want && bound <= LN.cap_bin_list) want = bound;
+            if (!want) {
+                unsigned total = 0;
+                CK(cudaMemcpyAsync(&total, LN.d_bin_start + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, LN.stream));
+                CK(cudaStreamSynchronize(LN.stream));
+                want = total;
+            }
+            if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, want ? want : 1))) return rc;
         }
-        if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, want ? want : 1))) return rc;
+        k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, binsX, binsY, bshift, LN.d_bin_counts, LN.d_bin_start, LN.d_bin_list);
+        g.launches += 5;
     }
-    k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, binsX, binsY, bshift, LN.d_bin_counts, LN.d_bin_start, LN.d_bin_list);
-    g.launches += 5;
-
     RasterParams p;
     p.bbox = LN.d_bbox; p.setup = LN.d_setup; p.data = LN.d_data; p.states = d_states;
     p.bin_list = LN.d_bin_list; p.bin_starts = LN.d_bin_start; p.binsX = binsX; p.bin_tshift = bshift - 6;

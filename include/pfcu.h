@@ -212,13 +212,48 @@ typedef struct {
     uint16_t       pad;
 } pfcu_draw;
 
-enum { PFCU_CAP_DEVICE_VERTEX = 1u };
+enum { PFCU_CAP_DEVICE_VERTEX = 1u, PFCU_CAP_RAW_TRIANGLES = 2u };
 PFCU_API unsigned pfcu_capabilities(void);
 /* Vertex stage + rasterisation of one draw call, entirely on the device; ordered after everything
  * submitted before it.  `state` is the single state snapshot in force.  *n_out receives the number of
  * Rasterize_Triangle-equivalent triangles produced (after clipping). */
 PFCU_API int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vparams *vp,
                                  const pfcu_draw *draw, uint32_t *n_out);
+
+/* ---- device vertex stage for immediate mode and render lists ------------------------------------ */
+/* The front end assembles triangles (draw modes, face passes: context.c:41-74, internal/context/context.c:94-244)
+ * and ships them UNPROCESSED: object-space vertices as pfVertex* latched them.  The device runs the reference's
+ * whole per-triangle prologue: normal transform, colour * material diffuse, Gouraud vertex lighting
+ * (lighting.c:23-144), MVP transform, clipping, perspective preparation and viewport mapping (triangles.c:62-116,
+ * 157-280), then the usual setup -> bin -> raster pipeline, in submission order. */
+typedef struct { float pos[4]; float normal[3]; float uv[2]; uint32_t rgba; } pfcu_rawvertex;      /* 40 B */
+typedef struct {
+    pfcu_rawvertex v[3];
+    uint32_t state;             /* index into states[]                                                    */
+    uint32_t vparams;           /* index into vparams[]                                                   */
+    uint8_t  face;              /* faceToRender of this pass                                              */
+    uint8_t  pad[3];
+} pfcu_rawtri;                  /* 132 B */
+/* Everything the per-triangle prologue reads from G_currentCtx besides the fragment state. */
+typedef struct {
+    pfcu_vparams  base;
+    uint32_t      gouraud;      /* PF_LIGHTING with active lights and lightingMode == PF_GOURAUD          */
+    uint32_t      n_lights;     /* active lights in list order                                            */
+    float         view_z[3];    /* matView[8..10]: the sign of N . view_z selects the material (triangles.c:95-101) */
+    float         view_pos[3];  /* translation row of inverse(matView)                                    */
+    pfcu_light    lights[8];
+    pfcu_material material[2];
+    uint32_t      pow_table[2]; /* per face material: index of its specular table in pow_tables[]         */
+} pfcu_vparams_lit;
+/* Gouraud specular = (PFubyte)(255 * powf(max(N.H, 0), shininess)) with the HOST libm's powf (lighting.c:117).
+ * powf is not correctly rounded, so the device cannot recompute it; the front end tabulates, per shininess value,
+ * the 256 smallest inputs x_k with (int)(255 * powf(x_k, shininess)) >= k, k = 1..256 (found by bisection over
+ * float bit patterns with the host's own powf), and the device counts thresholds <= x. */
+#define PFCU_POW_TABLE_SIZE 256
+PFCU_API int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states,
+                             const pfcu_vparams_lit *vparams, uint32_t n_vparams,
+                             const float *pow_tables, uint32_t n_pow_tables,
+                             const pfcu_rawtri *tris, uint32_t n_tris, uint32_t *n_out);
 
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* Rasterise `n_tris` triangles, in order, into `s`.  Host pointers; the call copies them to the

@@ -600,6 +600,13 @@ pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const
 }
 int  pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b) { return pfcu_submit(s, b->states, b->n_states, b->tris, b->n_tris); }
 void pfcu_batch_destroy(pfcu_batch *b) { if (b) { free(b->states); free(b->tris); free(b); } }
+int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, const pfcu_vparams_lit *vparams, uint32_t n_vparams,
+                    const float *pow_tables, uint32_t n_pow_tables, const pfcu_rawtri *tris, uint32_t n_tris, uint32_t *n_out)
+{   /* never advertised (pfcu_capabilities): with this library the front end runs the vertex stage itself */
+    (void)s; (void)states; (void)n_states; (void)vparams; (void)n_vparams; (void)pow_tables; (void)n_pow_tables; (void)tris; (void)n_tris;
+    if (n_out) *n_out = 0;
+    return PFCU_ERR_INVALID;
+}
 unsigned pfcu_capabilities(void) { return 0u; }     /* the oracle has no device vertex stage: the front end keeps it on the host */
 int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *st, const pfcu_vparams *vp, const pfcu_draw *d, uint32_t *n)
 { (void)s; (void)st; (void)vp; (void)d; (void)n; return PFCU_ERR_INVALID; }

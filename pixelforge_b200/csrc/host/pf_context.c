@@ -92,6 +92,7 @@ void pfDeleteContext(PFcontext ctx)
     pfcu_finish();
     for (int i = 0; i < 2; i++) if (c->tris[i]) pfcu_host_free(c->tris[i]);
     free(c->states); free(c->cap_tris); free(c->cap_states);
+    free(c->vparams); free(c->pow_tables); free(c->pow_shininess);
     pf_tex *tex = (pf_tex *)c->mainFramebuffer.texture;
     pfh_surf_destroy(c->main_surf);
     PF_FREE(tex);
@@ -173,14 +174,14 @@ static pf_surf *bound_surface(pf_ctx *c)
 void pfEnable(PFstate state)
 {
     CTX;
-    c->state |= state; c->state_dirty = 1;
+    c->state |= state; c->state_dirty = 1; PFH_VP_TOUCH(c);
     if (state & PF_FRAMEBUFFER) retarget(c, bound_surface(c));
 }
 
 void pfDisable(PFstate state)
 {
     CTX;
-    c->state &= ~state; c->state_dirty = 1;
+    c->state &= ~state; c->state_dirty = 1; PFH_VP_TOUCH(c);
     if (state & PF_FRAMEBUFFER) retarget(c, c->main_surf);
 }
 
@@ -188,7 +189,7 @@ PFerrcode pfGetError(void) { CTX; PFerrcode e = c->errCode; c->errCode = PF_NO_E
 
 /* ---- matrices (context.c:395-548) -------------------------------------------------------------- */
 
-static void matrix_touched(pf_ctx *c) { c->viewPosValid = 0; }
+static void matrix_touched(pf_ctx *c) { c->viewPosValid = 0; PFH_VP_TOUCH(c); }
 
 void pfMatrixMode(PFmatrixmode mode)
 {
@@ -288,7 +289,7 @@ void pfOrtho(PFfloat l, PFfloat r, PFfloat b, PFfloat t, PFfloat n, PFfloat f)
 /* ---- render state (context.c:553-797) ----------------------------------------------------------- */
 
 void pfViewport(PFint x, PFint y, PFsizei width, PFsizei height)
-{
+{ if (pf_cur) PFH_VP_TOUCH(pf_cur);
     CTX;
     if (x <= -(PFint)width || y <= -(PFint)height) { c->errCode = PF_INVALID_OPERATION; return; }
     const pf_tex *mt = (const pf_tex *)c->mainFramebuffer.texture;
@@ -314,7 +315,7 @@ void pfPolygonMode(PFface face, PFpolygonmode mode)
 }
 
 void pfShadeModel(PFshademode mode) { CTX; c->shadingMode = mode; c->state_dirty = 1; }
-void pfLightModel(PFlightmode mode) { CTX; c->lightingMode = mode; c->state_dirty = 1; }
+void pfLightModel(PFlightmode mode) { if (pf_cur) PFH_VP_TOUCH(pf_cur); CTX; c->lightingMode = mode; c->state_dirty = 1; }
 void pfLineWidth(PFfloat w) { CTX; if (w <= 0.0f) { c->errCode = PF_INVALID_VALUE; return; } c->lineWidth = w; }
 void pfPointSize(PFfloat s) { CTX; if (s <= 0.0f) { c->errCode = PF_INVALID_VALUE; return; } c->pointSize = s; }
 void pfCullFace(PFface face) { CTX; if (face > PF_BACK) { c->errCode = PF_INVALID_ENUM; return; } c->cullFace = face; }
@@ -372,7 +373,7 @@ void pfClearColor(PFubyte r, PFubyte g, PFubyte b, PFubyte a) { pf_cur->clearCol
 /* ---- lights and materials (context.c:802-1156) -------------------------------------------------- */
 
 void pfEnableLight(PFsizei light)
-{
+{ if (pf_cur) PFH_VP_TOUCH(pf_cur);
     CTX;
     if (light >= PFH_MAX_LIGHTS) { c->errCode = PF_INVALID_VALUE; return; }
     int *link = &c->activeHead;
@@ -386,7 +387,7 @@ void pfEnableLight(PFsizei light)
 }
 
 void pfDisableLight(PFsizei light)
-{
+{ if (pf_cur) PFH_VP_TOUCH(pf_cur);
     CTX;
     if (light >= PFH_MAX_LIGHTS) { c->errCode = PF_INVALID_VALUE; return; }
     for (int *link = &c->activeHead; *link >= 0; link = &c->lights[*link].next) {
@@ -411,7 +412,7 @@ PFboolean pfIsEnabledLight(PFsizei light)
 static int cutoff_ok(float v) { return (v >= 0 && v <= 90) || v == 180; }
 
 void pfLightf(PFsizei light, PFenum param, PFfloat value)
-{
+{ if (pf_cur) PFH_VP_TOUCH(pf_cur);
     CTX;
     if (light >= PFH_MAX_LIGHTS) { c->errCode = PF_STACK_OVERFLOW; return; }
     pf_light *l = &c->lights[light];
@@ -433,7 +434,7 @@ static PFcolor color_from_f3(const PFfloat *v)
 }
 
 void pfLightfv(PFsizei light, PFenum param, const void *value)
-{
+{ if (pf_cur) PFH_VP_TOUCH(pf_cur);
     CTX;
     if (light >= PFH_MAX_LIGHTS) { c->errCode = PF_STACK_OVERFLOW; return; }
     pf_light *l = &c->lights[light];

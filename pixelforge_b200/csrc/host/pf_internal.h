@@ -144,6 +144,13 @@ typedef struct pf_ctx {
     pfcu_state    *states; uint32_t n_states, state_cap;
     int            state_dirty;
     uint64_t       tris_emitted;
+    /* per-triangle prologue environments of the pending batch (pfcu_vparams_lit) and the raw-triangle mode:
+       a batch holds either processed pfcu_triangle records or unprocessed pfcu_rawtri records (same buffer) */
+    pfcu_vparams_lit *vparams; uint32_t n_vparams, vparams_cap;
+    uint32_t       vp_epoch, vp_epoch_built;    /* bumped by every call that changes what the prologue reads */
+    pf_material    vp_material[2];              /* materials of the newest entry (may change per vertex with PF_COLOR_MATERIAL) */
+    int            batch_raw;
+    float         *pow_tables; float *pow_shininess; uint32_t n_pow, pow_cap;   /* specular tables by shininess */
     /* optional capture of the submitted stream (pfxCaptureBegin/End) */
     int            device_vertex;   /* large vertex-array draws run the vertex stage on the GPU (default on) */
     int            capturing;
@@ -164,6 +171,7 @@ void pfh_set_sync_mode(int explicit_mode);
 void pfh_update_matrices(pf_ctx *c, int with_normal);
 void pfh_vstage_params(const pf_ctx *c, pfv_params *p);
 void pfh_update_view_pos(pf_ctx *c);
+#define PFH_VP_TOUCH(c) ((c)->vp_epoch++)
 void pfh_snapshot_state(pf_ctx *c, pfcu_state *st);
 int  pfh_device_draw(pf_ctx *c, PFsizei count, PFint first, int indexed, PFdatatype itype, const void *indices,
                      int useNrm, int useTex, int useCol);    /* 1 = drawn on the device vertex path */   /* the state the next primitive would use */

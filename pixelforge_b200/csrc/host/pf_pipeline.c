@@ -35,6 +35,7 @@ void pfh_set_sync_mode(int explicit_mode) { g_sync_explicit = explicit_mode ? 1 
 
 void pfh_update_matrices(pf_ctx *c, int with_normal)
 {
+    PFH_VP_TOUCH(c);
     if (c->modelMatrixUsed) {
         m4_mul(c->matMVP, c->matModel, c->matView);
         m4_mul(c->matMVP, c->matMVP, c->matProjection);
@@ -218,11 +219,18 @@ static void capture_append(pf_ctx *c)
 
 void pfh_flush(pf_ctx *c)
 {
-    if (!c || c->n_tris == 0) { if (c) { c->n_states = 0; c->state_dirty = 1; } return; }
+    if (!c || c->n_tris == 0) { if (c) { c->n_states = 0; c->state_dirty = 1; c->n_vparams = 0; } return; }
     pf_surf *s = c->cur_surf;
     if (c->capturing) capture_append(c);
     pfh_upload_if_needed(c, s);
-    int rc = pfcu_submit(s->dev, c->states, c->n_states, c->tris[c->cur_buf], c->n_tris);
+    int rc;
+    if (c->batch_raw) {
+        uint32_t produced = 0;
+        rc = pfcu_submit_raw(s->dev, c->states, c->n_states, c->vparams, c->n_vparams, c->pow_tables, c->n_pow,
+                             (const pfcu_rawtri *)c->tris[c->cur_buf], c->n_tris, &produced);
+        c->tris_emitted += produced;
+    } else rc = pfcu_submit(s->dev, c->states, c->n_states, c->tris[c->cur_buf], c->n_tris);
+    c->n_vparams = 0;
     if (rc != PFCU_OK) {
         fprintf(stderr, "pixelforge-b200: pfcu_submit failed (%d): %s\n", rc, pfcu_last_error());
         c->errCode = (rc == PFCU_ERR_OOM) ? PF_ERROR_OUT_OF_MEMORY : PF_INVALID_OPERATION;
@@ -287,76 +295,56 @@ static inline void emit_triangle(pf_ctx *c, int face, int is3d, const pf_vertex 
     }
 }
 
-/* ---- Gouraud vertex lighting: integer Blinn-Phong (lighting.c:23-144) ------------------------ */
+/* ---- Gouraud vertex lighting: pfv_light_vertex in pf_vstage.h (shared with the device) --------------- */
 
-static inline PFubyte min255(int n) { return (PFubyte)(n | ((255 - n) >> 31)); }
+/* Specular tables for the device (pfcu.h, PFCU_POW_TABLE_SIZE): T[k-1] = the smallest float x >= 0 with
+ * (int)(255 * powf(x, shininess)) >= k, found by bisection over float bit patterns with THIS libm's powf.
+ * Valid when that function is non-decreasing in x, which holds comfortably for shininess >= 1 (neighbouring
+ * floats move the result by shininess * 2^-24 relative, far above powf's error) and is spot-checked below.
+ * Returns the table index, or -1 when the shininess cannot be tabulated (then the host lights the vertices). */
+static int spec_of(float x, float shin) { return (int)(255 * powf(fmaxf(x, 0.0f), shin)); }
 
-static PFcolor light_vertex(const pf_ctx *c, const pf_material *m, PFcolor diffuse,
-                            const float *viewPos, const float *P, const float *N)
+static int pow_table_index(pf_ctx *c, float shininess)
 {
-    PFubyte R = m->emission.r, G = m->emission.g, B = m->emission.b;
-    PFubyte aR = (PFubyte)((m->ambient.r * diffuse.r) / 255);
-    PFubyte aG = (PFubyte)((m->ambient.g * diffuse.g) / 255);
-    PFubyte aB = (PFubyte)((m->ambient.b * diffuse.b) / 255);
-
-    float V[3], vl2 = 0.0f;
-    for (int i = 0; i < 3; i++) { V[i] = viewPos[i] - P[i]; vl2 += V[i] * V[i]; }
-    { float il = 1.0f / sqrtf(vl2); for (int i = 0; i < 3; i++) V[i] = V[i] * il; }
-
-    float shininess = m->shininess;
-    PFcolor spc = m->specular;
-
-    for (int li = c->activeHead; li >= 0; li = c->lights[li].next) {
-        const pf_light *l = &c->lights[li];
-        PFubyte lR = 0, lG = 0, lB = 0;
-        float L[3] = { l->position[0] - P[0], l->position[1] - P[1], l->position[2] - P[2] };
-        float d2 = L[0] * L[0] + L[1] * L[1] + L[2] * L[2];
-        float dist = 0.0f;
-        if (d2 != 0.0f) {
-            dist = sqrtf(d2);
-            float il = 1.0f / dist;
-            L[0] *= il; L[1] *= il; L[2] *= il;
-        }
-        PFubyte intensity = 255;
-        int skip = 0;
-        if (l->innerCutOff < (float)PFH_PI) {
-            float nd[3] = { -l->direction[0], -l->direction[1], -l->direction[2] };
-            float theta = v3_dot(L, nd);
-            float eps = l->innerCutOff - l->outerCutOff;
-            int iv = (int)(255 * (theta - l->outerCutOff) / eps);
-            intensity = (PFubyte)(iv < 0 ? 0 : (iv > 255 ? 255 : iv));
-            if (intensity == 0) skip = 1;
-        }
-        PFubyte attenuation = 255;
-        if (!skip && (l->attLinear || l->attQuadratic)) {
-            attenuation = (PFubyte)(255 / (l->attConstant + l->attLinear * dist + l->attQuadratic * d2));
-            if (attenuation == 0) skip = 1;
-        }
-        if (!skip) {
-            PFubyte factor = (PFubyte)((intensity * attenuation) / 255);
-            int di = (int)(255 * v3_dot(N, L));
-            PFubyte diff = (PFubyte)(di > 0 ? di : 0);
-            lR = min255(lR + (diffuse.r * l->diffuse.r * diff) / (255 * 255));
-            lG = min255(lG + (diffuse.g * l->diffuse.g * diff) / (255 * 255));
-            lB = min255(lB + (diffuse.b * l->diffuse.b * diff) / (255 * 255));
-
-            float H[3] = { L[0] + V[0], L[1] + V[1], L[2] + V[2] };
-            v3_normalize(H, H);
-            PFubyte spec = (PFubyte)(255 * powf(fmaxf(v3_dot(N, H), 0.0f), shininess));
-            lR = min255(lR + (spc.r * l->specular.r * spec) / (255 * 255));
-            lG = min255(lG + (spc.g * l->specular.g * spec) / (255 * 255));
-            lB = min255(lB + (spc.b * l->specular.b * spec) / (255 * 255));
-
-            lR = (PFubyte)((lR * factor) / 255);
-            lG = (PFubyte)((lG * factor) / 255);
-            lB = (PFubyte)((lB * factor) / 255);
-        }
-        R = min255(R + lR + (aR * l->ambient.r) / 255);
-        G = min255(G + lG + (aG * l->ambient.g) / 255);
-        B = min255(B + lB + (aB * l->ambient.b) / 255);
+    uint32_t key; memcpy(&key, &shininess, 4);
+    for (uint32_t i = 0; i < c->n_pow; i++) { uint32_t k; memcpy(&k, &c->pow_shininess[i], 4); if (k == key) return (int)i; }
+    if (!(shininess >= 1.0f && shininess <= 1024.0f)) return -1;
+    if (c->n_pow == c->pow_cap) {
+        uint32_t nc = c->pow_cap ? c->pow_cap * 2 : 4;
+        float *t = (float *)realloc(c->pow_tables, (size_t)nc * PFCU_POW_TABLE_SIZE * sizeof(float));
+        if (!t) return -1;
+        c->pow_tables = t;
+        float *sh = (float *)realloc(c->pow_shininess, (size_t)nc * sizeof(float));
+        if (!sh) return -1;
+        c->pow_shininess = sh; c->pow_cap = nc;
     }
-    PFcolor out = { R, G, B, diffuse.a };
-    return out;
+    float *T = c->pow_tables + (size_t)c->n_pow * PFCU_POW_TABLE_SIZE;
+    for (int k = 1; k <= PFCU_POW_TABLE_SIZE; k++) {
+        uint32_t lo = 0u, hi;                           /* bit patterns of non-negative floats order like the floats */
+        if (spec_of(0.0f, shininess) >= k) { T[k - 1] = 0.0f; continue; }
+        {   /* upper end 1.01: 255 * 1.01^s is >= 256 and below 2^31 for every s in [1, 1024] */
+            float top = 1.01f; memcpy(&hi, &top, 4);
+            if (spec_of(top, shininess) < k) return -1;
+        }
+        while (hi - lo > 1u) {
+            const uint32_t mid = lo + (hi - lo) / 2u;
+            float x; memcpy(&x, &mid, 4);
+            if (spec_of(x, shininess) >= k) hi = mid; else lo = mid;
+        }
+        memcpy(&T[k - 1], &hi, 4);
+    }
+    /* spot check of the step-function model against the real thing */
+    uint32_t rs = 0x9e3779b9u ^ key;
+    for (int i = 0; i < 4096; i++) {
+        rs = rs * 1664525u + 1013904223u;
+        const float x = (float)(rs >> 8) * (1.0f / 16777216.0f) * ((i & 15) ? 1.0f : 1.0001f);
+        int lo = 0, hi = PFCU_POW_TABLE_SIZE;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (T[mid] <= x) lo = mid + 1; else hi = mid; }
+        if ((uint8_t)lo != (uint8_t)spec_of(x, shininess)) return -1;
+    }
+    for (int k = 1; k < PFCU_POW_TABLE_SIZE; k++) if (T[k] < T[k - 1]) return -1;
+    c->pow_shininess[c->n_pow] = shininess;
+    return (int)c->n_pow++;
 }
 
 /* ---- parameters of the shared vertex stage (pf_vstage.h) ------------------------------------------ */
@@ -372,6 +360,60 @@ void pfh_vstage_params(const pf_ctx *c, pfv_params *p)
     p->diffuse[1] = color_dword(c->material[1].diffuse);
 }
 
+static void fill_vparams_lit(pf_ctx *c, pfcu_vparams_lit *e)
+{
+    memset(e, 0, sizeof *e);
+    pfh_vstage_params(c, &e->base);
+    e->gouraud = (e->base.lighting && c->lightingMode == PF_GOURAUD) ? 1u : 0u;
+    if (e->base.lighting) {
+        pfh_update_view_pos(c);
+        memcpy(e->view_z, c->matView + 8, 12);
+        memcpy(e->view_pos, c->viewPos, 12);
+        uint32_t n = 0;
+        for (int i = c->activeHead; i >= 0 && n < 8; i = c->lights[i].next) {
+            const pf_light *l = &c->lights[i];
+            pfcu_light *d = &e->lights[n++];
+            memcpy(d->position, l->position, 12); memcpy(d->direction, l->direction, 12);
+            d->inner_cutoff = l->innerCutOff; d->outer_cutoff = l->outerCutOff;
+            d->att_constant = l->attConstant; d->att_linear = l->attLinear; d->att_quadratic = l->attQuadratic;
+            d->ambient = color_dword(l->ambient); d->diffuse = color_dword(l->diffuse); d->specular = color_dword(l->specular);
+        }
+        e->n_lights = n;
+        fill_material(&e->material[0], &c->material[0]);
+        fill_material(&e->material[1], &c->material[1]);
+        if (e->gouraud)
+            for (int f = 0; f < 2; f++) {
+                const int t = pow_table_index(c, e->material[f].shininess);
+                e->pow_table[f] = t < 0 ? 0xffffffffu : (uint32_t)t;
+            }
+    }
+}
+
+/* The prologue environment of the next triangle: the newest table entry when nothing it reads has changed
+ * (API calls bump vp_epoch; materials, which PF_COLOR_MATERIAL changes per vertex, are compared by value). */
+static const pfcu_vparams_lit *current_vparams(pf_ctx *c, uint32_t *index)
+{
+    if (c->n_vparams > 0 && c->vp_epoch_built == c->vp_epoch &&
+        memcmp(c->vp_material, c->material, sizeof c->vp_material) == 0) {
+        *index = c->n_vparams - 1;
+        return &c->vparams[c->n_vparams - 1];
+    }
+    pfcu_vparams_lit e;
+    fill_vparams_lit(c, &e);                 /* may bump vp_epoch (view position) - record the epoch afterwards */
+    c->vp_epoch_built = c->vp_epoch;
+    memcpy(c->vp_material, c->material, sizeof c->vp_material);
+    if (c->n_vparams > 0 && memcmp(&c->vparams[c->n_vparams - 1], &e, sizeof e) == 0) { *index = c->n_vparams - 1; return &c->vparams[*index]; }
+    if (c->n_vparams == c->vparams_cap) {
+        uint32_t nc = c->vparams_cap ? c->vparams_cap * 2 : 8;
+        pfcu_vparams_lit *p = (pfcu_vparams_lit *)realloc(c->vparams, (size_t)nc * sizeof *p);
+        if (!p) { c->errCode = PF_ERROR_OUT_OF_MEMORY; *index = 0; return c->n_vparams ? &c->vparams[0] : NULL; }
+        c->vparams = p; c->vparams_cap = nc;
+    }
+    c->vparams[c->n_vparams] = e;
+    *index = c->n_vparams++;
+    return &c->vparams[*index];
+}
+
 void pfh_update_view_pos(pf_ctx *c)
 {
     if (c->viewPosValid) return;
@@ -379,6 +421,7 @@ void pfh_update_view_pos(pf_ctx *c)
     m4_invert(inv, c->matView);
     c->viewPos[0] = inv[12]; c->viewPos[1] = inv[13]; c->viewPos[2] = inv[14];
     c->viewPosValid = 1;
+    PFH_VP_TOUCH(c);
     if (c->lightingMode == PF_PHONG) c->state_dirty = 1;
 }
 
@@ -449,27 +492,63 @@ int pfh_device_draw(pf_ctx *c, PFsizei count, PFint first, int indexed, PFdataty
 
 /* ---- one triangle through the vertex stage (triangles.c:62-116) ------------------------------ */
 
+/* Can this triangle go to the device unprocessed?  (pfcu_submit_raw; the oracle build has no such path) */
+static int raw_path(pf_ctx *c, const pfcu_vparams_lit *e)
+{
+    static int caps = -1;
+    if (caps < 0) caps = (int)pfcu_capabilities();
+    if (!(caps & PFCU_CAP_RAW_TRIANGLES) || !c->device_vertex || c->capturing) return 0;
+    if (e->gouraud && (e->pow_table[0] == 0xffffffffu || e->pow_table[1] == 0xffffffffu)) return 0;   /* shininess not tabulable */
+    return 1;
+}
+
 static void process_triangle(pf_ctx *c, int face, pf_vertex poly[PFH_MAX_POLY_VERTS])
 {
-    pfv_params vp;
-    pfh_vstage_params(c, &vp);
-    int n = 3;
+    uint32_t vpi = 0;
+    const pfcu_vparams_lit *e = current_vparams(c, &vpi);
+    if (!e) return;
 
-    if (vp.lighting) {
-        pfh_update_view_pos(c);
+    if (raw_path(c, e)) {
+        if (!c->batch_raw && c->n_tris) {       /* a batch is all raw or all processed: close the processed one */
+            pfcu_vparams_lit keep = *e;
+            pfh_flush(c);
+            c->vparams[0] = keep; c->n_vparams = 1; vpi = 0;
+            c->vp_epoch_built = c->vp_epoch; memcpy(c->vp_material, c->material, sizeof c->vp_material);
+        }
+        c->batch_raw = 1;
+        if (!ensure_batch(c)) return;
+        const uint32_t sidx = current_state_index(c);
+        pfcu_rawtri *t = (pfcu_rawtri *)c->tris[c->cur_buf] + c->n_tris;
         for (int i = 0; i < 3; i++) {
-            pf_vertex *v = &poly[i];
-            pfv_prologue(&vp, face, v);
-            if (c->lightingMode == PF_GOURAUD) {
-                float ndv = v3_dot(v->normal, c->matView + 8);
-                PFcolor in, out; memcpy(&in, &v->color, 4);
-                out = light_vertex(c, &c->material[(ndv < 0) ? PF_FRONT : PF_BACK], in, c->viewPos, v->position, v->normal);
-                memcpy(&v->color, &out, 4);
+            const pf_vertex *v = &poly[i];
+            memcpy(t->v[i].pos, v->position, 16); memcpy(t->v[i].normal, v->normal, 12);
+            memcpy(t->v[i].uv, v->texcoord, 8); t->v[i].rgba = v->color;
+        }
+        t->state = sidx; t->vparams = vpi; t->face = (uint8_t)face; t->pad[0] = t->pad[1] = t->pad[2] = 0;
+        pf_surf *s = c->cur_surf;               /* screen coordinates are not known here: everything is dirty */
+        s->dirty_y0 = 0; s->dirty_y1 = s->tex->h;
+        if (++c->n_tris == c->tri_cap) {
+            pfh_flush(c);
+            if (c->tri_cap < batch_limit()) {
+                uint32_t cap = c->tri_cap * 4u;
+                alloc_batch(c, cap > batch_limit() ? batch_limit() : cap);
             }
         }
+        return;
     }
+    if (c->batch_raw && c->n_tris) {
+        pfcu_vparams_lit keep = *e;
+        pfh_flush(c);
+        c->vparams[0] = keep; c->n_vparams = 1; vpi = 0;
+        c->vp_epoch_built = c->vp_epoch; memcpy(c->vp_material, c->material, sizeof c->vp_material);
+        e = &c->vparams[0];
+    }
+    c->batch_raw = 0;
 
-    int is3d = pfv_project_and_clip(&vp, poly, &n);
+    int n = 3;
+    if (e->base.lighting)
+        for (int i = 0; i < 3; i++) pfv_prologue_lit(e, NULL, face, &poly[i]);
+    int is3d = pfv_project_and_clip(&e->base, poly, &n);
     if (n < 3) return;
     for (int i = 0; i < n - 2; i++) emit_triangle(c, face, is3d, &poly[0], &poly[i + 1], &poly[i + 2]);
 }

@@ -25,6 +25,7 @@
 #  define PFV_SUB(a, b) __fsub_rn((a), (b))
 #  define PFV_U2F(u) __uint2float_rn(u)
 #  define PFV_I2F(i) __int2float_rn(i)
+#  define PFV_F2I(f) pfv_cvttss2si(f)
 #else
 #  include <math.h>
 #  include <string.h>
@@ -36,6 +37,7 @@
 #  define PFV_SUB(a, b) ((a) - (b))
 #  define PFV_U2F(u) ((float)(u))
 #  define PFV_I2F(i) ((float)(i))
+#  define PFV_F2I(f) ((int)(f))
 #endif
 
 #define PFV_MAX_POLY 12
@@ -73,6 +75,111 @@ PFV_FN void pfv_prologue(const pfv_params *p, int face, pfv_vertex *v)
     uint32_t o = 0;
     for (int i = 0; i < 4; i++) o |= ((((c >> (8 * i)) & 255u) * ((d >> (8 * i)) & 255u)) / 255u) << (8 * i);
     v->color = o;
+}
+
+/* ---- Gouraud vertex lighting: integer Blinn-Phong (lighting.c:23-144) --------------------------------------
+ * One source for the host (real powf) and the device (the host-harvested specular table, see pfcu.h). */
+#ifdef __CUDACC__
+PFV_FN int pfv_cvttss2si(float f) { const int r = __float2int_rz(f); return (fabsf(f) < 2147483648.0f) ? r : (int)0x80000000; }
+PFV_FN unsigned pfv_specular(const float *tab, float x)
+{
+    /* fmaxf(x, 0): NaN -> 0 */
+    if (!(x > 0.0f)) x = 0.0f;
+    int lo = 0, hi = PFCU_POW_TABLE_SIZE;                 /* number of thresholds <= x */
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tab[mid] <= x) lo = mid + 1; else hi = mid; }
+    return (unsigned)lo & 255u;                            /* (PFubyte) of 256 is 0 */
+}
+#  define PFV_SPECULAR(env, tabs, mface, x, shin) pfv_specular((tabs) + (size_t)(env)->pow_table[mface] * PFCU_POW_TABLE_SIZE, (x))
+#else
+#  define PFV_SPECULAR(env, tabs, mface, x, shin) ((unsigned)(uint8_t)(int)(255 * powf(fmaxf((x), 0.0f), (shin))))
+#endif
+
+PFV_FN unsigned pfv_min255(int n) { return (unsigned)(uint8_t)(n | ((255 - n) >> 31)); }
+
+#define PFV_CH(c, i) ((int)(((c) >> (8 * (i))) & 255u))
+
+PFV_FN uint32_t pfv_light_vertex(const pfcu_vparams_lit *e, const float *pow_tables, int mface, uint32_t diffuse,
+                                 const float *P, const float *N)
+{
+    const pfcu_material *m = &e->material[mface];
+    unsigned R = (unsigned)PFV_CH(m->emission, 0), G = (unsigned)PFV_CH(m->emission, 1), B = (unsigned)PFV_CH(m->emission, 2);
+    const int dR = PFV_CH(diffuse, 0), dG = PFV_CH(diffuse, 1), dB = PFV_CH(diffuse, 2);
+    const int aR = (int)(uint8_t)((PFV_CH(m->ambient, 0) * dR) / 255);
+    const int aG = (int)(uint8_t)((PFV_CH(m->ambient, 1) * dG) / 255);
+    const int aB = (int)(uint8_t)((PFV_CH(m->ambient, 2) * dB) / 255);
+
+    float V[3], vl2 = 0.0f;
+    for (int i = 0; i < 3; i++) { V[i] = PFV_SUB(e->view_pos[i], P[i]); vl2 = PFV_ADD(vl2, PFV_MUL(V[i], V[i])); }
+    { const float il = PFV_DIV(1.0f, PFV_SQRT(vl2)); for (int i = 0; i < 3; i++) V[i] = PFV_MUL(V[i], il); }
+
+    const float shininess = m->shininess;
+    (void)shininess; (void)pow_tables;
+
+    for (uint32_t li = 0; li < e->n_lights; li++) {
+        const pfcu_light *l = &e->lights[li];
+        unsigned lR = 0, lG = 0, lB = 0;
+        float L[3] = { PFV_SUB(l->position[0], P[0]), PFV_SUB(l->position[1], P[1]), PFV_SUB(l->position[2], P[2]) };
+        const float d2 = PFV_ADD(PFV_ADD(PFV_MUL(L[0], L[0]), PFV_MUL(L[1], L[1])), PFV_MUL(L[2], L[2]));
+        float dist = 0.0f;
+        if (d2 != 0.0f) {
+            dist = PFV_SQRT(d2);
+            const float il = PFV_DIV(1.0f, dist);
+            L[0] = PFV_MUL(L[0], il); L[1] = PFV_MUL(L[1], il); L[2] = PFV_MUL(L[2], il);
+        }
+        unsigned intensity = 255;
+        int skip = 0;
+        if (l->inner_cutoff < (float)3.14159265358979323846) {
+            const float theta = PFV_ADD(PFV_ADD(PFV_MUL(L[0], -l->direction[0]), PFV_MUL(L[1], -l->direction[1])), PFV_MUL(L[2], -l->direction[2]));
+            const float eps = PFV_SUB(l->inner_cutoff, l->outer_cutoff);
+            const int iv = PFV_F2I(PFV_DIV(PFV_MUL(255.0f, PFV_SUB(theta, l->outer_cutoff)), eps));
+            intensity = (unsigned)(uint8_t)(iv < 0 ? 0 : (iv > 255 ? 255 : iv));
+            if (intensity == 0) skip = 1;
+        }
+        unsigned attenuation = 255;
+        if (!skip && (l->att_linear != 0.0f || l->att_quadratic != 0.0f)) {
+            attenuation = (unsigned)(uint8_t)PFV_F2I(PFV_DIV(255.0f, PFV_ADD(PFV_ADD(l->att_constant, PFV_MUL(l->att_linear, dist)), PFV_MUL(l->att_quadratic, d2))));
+            if (attenuation == 0) skip = 1;
+        }
+        if (!skip) {
+            const unsigned factor = (unsigned)(uint8_t)((intensity * attenuation) / 255);
+            const int di = PFV_F2I(PFV_MUL(255.0f, PFV_ADD(PFV_ADD(PFV_MUL(N[0], L[0]), PFV_MUL(N[1], L[1])), PFV_MUL(N[2], L[2]))));
+            const int diff = (int)(uint8_t)(di > 0 ? di : 0);
+            lR = pfv_min255((int)lR + (dR * PFV_CH(l->diffuse, 0) * diff) / (255 * 255));
+            lG = pfv_min255((int)lG + (dG * PFV_CH(l->diffuse, 1) * diff) / (255 * 255));
+            lB = pfv_min255((int)lB + (dB * PFV_CH(l->diffuse, 2) * diff) / (255 * 255));
+
+            float H[3] = { PFV_ADD(L[0], V[0]), PFV_ADD(L[1], V[1]), PFV_ADD(L[2], V[2]) };
+            const float hl2 = PFV_ADD(PFV_ADD(PFV_MUL(H[0], H[0]), PFV_MUL(H[1], H[1])), PFV_MUL(H[2], H[2]));
+            if (hl2 != 0.0f) {                  /* pfmVec3Normalize leaves the zero vector alone */
+                const float il = PFV_DIV(1.0f, PFV_SQRT(hl2));
+                H[0] = PFV_MUL(H[0], il); H[1] = PFV_MUL(H[1], il); H[2] = PFV_MUL(H[2], il);
+            }
+            const float ndh = PFV_ADD(PFV_ADD(PFV_MUL(N[0], H[0]), PFV_MUL(N[1], H[1])), PFV_MUL(N[2], H[2]));
+            const int spec = (int)PFV_SPECULAR(e, pow_tables, mface, ndh, shininess);
+            lR = pfv_min255((int)lR + (PFV_CH(m->specular, 0) * PFV_CH(l->specular, 0) * spec) / (255 * 255));
+            lG = pfv_min255((int)lG + (PFV_CH(m->specular, 1) * PFV_CH(l->specular, 1) * spec) / (255 * 255));
+            lB = pfv_min255((int)lB + (PFV_CH(m->specular, 2) * PFV_CH(l->specular, 2) * spec) / (255 * 255));
+
+            lR = (unsigned)(uint8_t)((lR * factor) / 255);
+            lG = (unsigned)(uint8_t)((lG * factor) / 255);
+            lB = (unsigned)(uint8_t)((lB * factor) / 255);
+        }
+        R = pfv_min255((int)(R + lR) + (aR * PFV_CH(l->ambient, 0)) / 255);
+        G = pfv_min255((int)(G + lG) + (aG * PFV_CH(l->ambient, 1)) / 255);
+        B = pfv_min255((int)(B + lB) + (aB * PFV_CH(l->ambient, 2)) / 255);
+    }
+    return R | (G << 8) | (B << 16) | (diffuse & 0xff000000u);
+}
+
+/* The per-triangle prologue of one vertex (triangles.c:88-103): normal transform, colour * diffuse, and
+ * Gouraud lighting with the material picked by the side of the normal relative to the view axis. */
+PFV_FN void pfv_prologue_lit(const pfcu_vparams_lit *e, const float *pow_tables, int face, pfv_vertex *v)
+{
+    pfv_prologue(&e->base, face, v);
+    if (e->gouraud) {
+        const float ndv = PFV_ADD(PFV_ADD(PFV_MUL(v->normal[0], e->view_z[0]), PFV_MUL(v->normal[1], e->view_z[1])), PFV_MUL(v->normal[2], e->view_z[2]));
+        v->color = pfv_light_vertex(e, pow_tables, (ndv < 0) ? 0 : 1, v->color, v->position, v->normal);
+    }
 }
 
 PFV_FN void pfv_to_screen(const pfv_params *p, pfv_vertex *v)

@@ -119,6 +119,11 @@ struct Lane {
     void *h_stage = nullptr; size_t cap_stage = 0; cudaEvent_t stage_done = nullptr;
     DevState *h_states = nullptr; size_t cap_hstates = 0; cudaEvent_t states_done = nullptr;
     cudaEvent_t fence = nullptr;
+    /* raw-triangle batches: their vertex stage is counted on a side stream so that the one host wait (for the
+       output triangle count) does not wait for the rasterisation queued on the lane */
+    cudaStream_t vstream = nullptr; cudaEvent_t raw_done = nullptr, vready = nullptr;
+    unsigned char *d_raw = nullptr; size_t cap_raw = 0;
+    unsigned *h_total = nullptr;                                        /* pinned: {last offset, last count} */
 };
 
 #define MAX_LANES 8
@@ -1926,6 +1931,53 @@ k_vertex_emit(const VtxArgs a, const pfv_params vp, unsigned n_items, const unsi
     for (int i = 0; i < n; i++) pfv_emit(dst + i, &poly[0], &poly[i + 1], &poly[i + 2], a.state, face, is3d);
 }
 
+/* ---- raw triangles (immediate mode, render lists): the whole per-triangle prologue on the device ---- */
+struct RawArgs { const pfcu_rawtri *tris; const pfcu_vparams_lit *vp; const float *pow_tables; unsigned n; };
+
+__device__ __forceinline__ int raw_process(const RawArgs &a, unsigned i, pfv_vertex *poly, int *is3d, int *face_out, unsigned *state)
+{
+    const pfcu_rawtri *t = a.tris + i;
+    const pfcu_vparams_lit *e = a.vp + t->vparams;
+    const int face = t->face;
+    *face_out = face; *state = t->state;
+    for (int k = 0; k < 3; k++) {
+        const pfcu_rawvertex *r = &t->v[k];
+        pfv_vertex *v = &poly[k];
+        for (int j = 0; j < 4; j++) v->position[j] = r->pos[j];
+        for (int j = 0; j < 3; j++) v->normal[j] = r->normal[j];
+        v->texcoord[0] = r->uv[0]; v->texcoord[1] = r->uv[1];
+        v->color = r->rgba;
+        v->screen[0] = 0.0f; v->screen[1] = 0.0f;
+        for (int j = 0; j < 4; j++) v->homogeneous[j] = 0.0f;
+        if (e->base.lighting) pfv_prologue_lit(e, a.pow_tables, face, v);
+    }
+    int n = 3;
+    *is3d = pfv_project_and_clip(&e->base, poly, &n);
+    return n >= 3 ? n - 2 : 0;
+}
+
+__global__ void __launch_bounds__(128)
+k_raw_count(const RawArgs a, unsigned *__restrict__ counts)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    pfv_vertex poly[PFV_MAX_POLY];
+    int is3d, face; unsigned state;
+    counts[i] = (unsigned)raw_process(a, i, poly, &is3d, &face, &state);
+}
+
+__global__ void __launch_bounds__(128)
+k_raw_emit(const RawArgs a, const unsigned *__restrict__ offsets, pfcu_triangle *__restrict__ out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    pfv_vertex poly[PFV_MAX_POLY];
+    int is3d, face; unsigned state;
+    const int n = raw_process(a, i, poly, &is3d, &face, &state);
+    pfcu_triangle *dst = out + offsets[i];
+    for (int k = 0; k < n; k++) pfv_emit(dst + k, &poly[0], &poly[k + 1], &poly[k + 2], state, face, is3d);
+}
+
 /* exclusive scan of up to 1024 items per CTA; sums[blockIdx] = CTA total */
 __global__ void __launch_bounds__(256)
 k_scan_block(const unsigned *__restrict__ in, unsigned *__restrict__ out, unsigned n, unsigned *__restrict__ sums)
@@ -2065,6 +2117,10 @@ int pfcu_init(int device)
         CK(cudaEventCreateWithFlags(&LN.stage_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&LN.states_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&LN.fence, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&LN.vstream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&LN.raw_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&LN.vready, cudaEventDisableTiming));
+        CK(cudaHostAlloc(&LN.h_total, 2 * sizeof(unsigned), cudaHostAllocDefault));
     }
     g.cur = &g.lanes[0];
     CK(cudaMalloc(&g.d_counters, 4 * sizeof(unsigned long long)));
@@ -2087,6 +2143,9 @@ void pfcu_shutdown(void)
         cudaFree(LN.d_bin_counts); cudaFree(LN.d_bin_list); cudaFree(LN.d_bin_start); cudaFree(LN.d_varrays); cudaFree(LN.d_vcounts);
         if (LN.h_stage) cudaFreeHost(LN.h_stage);
         if (LN.h_states) cudaFreeHost(LN.h_states);
+        if (LN.h_total) cudaFreeHost(LN.h_total);
+        cudaFree(LN.d_raw);
+        if (LN.vstream) cudaStreamDestroy(LN.vstream);
         if (LN.own_stream) cudaStreamDestroy(LN.stream);
         g.lanes[i] = Lane();
     }
@@ -2587,23 +2646,24 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
 
 /* ---- device vertex stage ---- */
 
-static int scan_exclusive(const unsigned *d_in, unsigned *d_out, unsigned n, unsigned *d_tmp /* >= n/1024 + n/1048576 + 4 */)
+static int scan_exclusive(const unsigned *d_in, unsigned *d_out, unsigned n, unsigned *d_tmp /* >= n/1024 + n/1048576 + 4 */, cudaStream_t st = nullptr)
 {
+    if (!st) st = LN.stream;
     const unsigned nb = (n + 1023u) / 1024u;
-    k_scan_block<<<nb, 256, 0, LN.stream>>>(d_in, d_out, n, d_tmp);
+    k_scan_block<<<nb, 256, 0, st>>>(d_in, d_out, n, d_tmp);
     g.launches++;
     if (nb > 1) {
         unsigned *d_tmp2 = d_tmp + nb;
-        int rc = scan_exclusive(d_tmp, d_tmp, nb, d_tmp2);
+        int rc = scan_exclusive(d_tmp, d_tmp, nb, d_tmp2, st);
         if (rc) return rc;
-        k_scan_add<<<(n + 255u) / 256u, 256, 0, LN.stream>>>(d_out, n, d_tmp);
+        k_scan_add<<<(n + 255u) / 256u, 256, 0, st>>>(d_out, n, d_tmp);
         g.launches++;
     }
     CK(cudaGetLastError());
     return PFCU_OK;
 }
 
-unsigned pfcu_capabilities(void) { return PFCU_CAP_DEVICE_VERTEX; }
+unsigned pfcu_capabilities(void) { return PFCU_CAP_DEVICE_VERTEX | PFCU_CAP_RAW_TRIANGLES; }
 
 int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vparams *vp, const pfcu_draw *d, uint32_t *n_out)
 {
@@ -2657,6 +2717,68 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     CK(cudaMemcpyAsync(LN.d_states, &hs, sizeof hs, cudaMemcpyHostToDevice, LN.stream));
     k_vertex_emit<<<(n_items + 127u) / 128u, 128, 0, LN.stream>>>(a, *vp, n_items, d_offsets, LN.d_tris);
     g.launches++;
+    CK(cudaEventRecord(LN.raw_done, LN.stream));        /* d_vcounts is shared with the raw-triangle path's side stream */
+    CK(cudaGetLastError());
+    return launch_pipeline(s, LN.d_tris, LN.d_states, total, mask, g_last_single_prog);
+}
+
+int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, const pfcu_vparams_lit *vparams, uint32_t n_vparams,
+                    const float *pow_tables, uint32_t n_pow_tables, const pfcu_rawtri *tris, uint32_t n_tris, uint32_t *n_out)
+{
+    API_LOCK;
+    if (n_out) *n_out = 0;
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!s || (n_tris && (!states || !tris || !vparams || n_states == 0 || n_vparams == 0))) return PFCU_ERR_INVALID;
+    if (n_tris == 0) return PFCU_OK;
+    use_lane(s);
+    int rc;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_tris = (size_t)n_tris * sizeof(pfcu_rawtri), b_vp = (size_t)n_vparams * sizeof(pfcu_vparams_lit);
+    const size_t b_pow = (size_t)n_pow_tables * PFCU_POW_TABLE_SIZE * sizeof(float);
+    /* the previous raw batch of this lane must have been emitted before its inputs are overwritten */
+    CK(cudaStreamWaitEvent(LN.vstream, LN.raw_done, 0));
+    if (al(b_tris) + al(b_vp) + al(b_pow) > LN.cap_raw) { CK(cudaEventSynchronize(LN.raw_done)); }
+    if ((rc = grow(&LN.d_raw, &LN.cap_raw, al(b_tris) + al(b_vp) + al(b_pow)))) return rc;
+    if ((rc = grow(&LN.d_vcounts, &LN.cap_vcounts, (size_t)n_tris * 2 + n_tris / 512 + 64))) return rc;
+    unsigned char *p = LN.d_raw;
+    RawArgs a; a.n = n_tris;
+    a.tris = (const pfcu_rawtri *)p;
+    CK(cudaMemcpyAsync(p, tris, b_tris, cudaMemcpyHostToDevice, LN.vstream));
+    if (PinnedBlock *pb = find_pinned(tris)) { CK(cudaEventRecord(pb->done, LN.vstream)); pb->pending = true; }
+    p += al(b_tris);
+    a.vp = (const pfcu_vparams_lit *)p; CK(cudaMemcpyAsync(p, vparams, b_vp, cudaMemcpyHostToDevice, LN.vstream)); p += al(b_vp);
+    a.pow_tables = (const float *)p; if (b_pow) CK(cudaMemcpyAsync(p, pow_tables, b_pow, cudaMemcpyHostToDevice, LN.vstream));
+    g.bytes_h2d += b_tris + b_vp + b_pow + n_states * sizeof(DevState);
+
+    unsigned *d_counts = LN.d_vcounts, *d_offsets = LN.d_vcounts + n_tris, *d_tmp = LN.d_vcounts + 2 * (size_t)n_tris;
+    k_raw_count<<<(n_tris + 127u) / 128u, 128, 0, LN.vstream>>>(a, d_counts);
+    g.launches++;
+    if ((rc = scan_exclusive(d_counts, d_offsets, n_tris, d_tmp, LN.vstream))) return rc;
+    CK(cudaMemcpyAsync(&LN.h_total[0], d_offsets + (n_tris - 1), 4, cudaMemcpyDeviceToHost, LN.vstream));
+    CK(cudaMemcpyAsync(&LN.h_total[1], d_counts + (n_tris - 1), 4, cudaMemcpyDeviceToHost, LN.vstream));
+    CK(cudaEventRecord(LN.vready, LN.vstream));
+    CK(cudaStreamSynchronize(LN.vstream));
+    const unsigned total = LN.h_total[0] + LN.h_total[1];
+    if (n_out) *n_out = total;
+    if (total == 0) { CK(cudaEventRecord(LN.raw_done, LN.vstream)); return PFCU_OK; }
+
+    /* states + emission + the usual pipeline on the surface's lane */
+    if ((rc = grow(&LN.d_tris, &LN.cap_tris, total))) return rc;
+    if ((rc = grow(&LN.d_states, &LN.cap_states, n_states))) return rc;
+    if (n_states > LN.cap_hstates) {
+        CK(cudaEventSynchronize(LN.states_done));
+        if (LN.h_states) cudaFreeHost(LN.h_states);
+        size_t c = LN.cap_hstates ? LN.cap_hstates : 64; while (c < n_states) c *= 2;
+        CK(cudaHostAlloc(&LN.h_states, c * sizeof(DevState), cudaHostAllocDefault));
+        LN.cap_hstates = c;
+    } else CK(cudaEventSynchronize(LN.states_done));
+    const unsigned mask = convert_states(states, n_states, LN.h_states);
+    CK(cudaMemcpyAsync(LN.d_states, LN.h_states, n_states * sizeof(DevState), cudaMemcpyHostToDevice, LN.stream));
+    CK(cudaEventRecord(LN.states_done, LN.stream));
+    CK(cudaStreamWaitEvent(LN.stream, LN.vready, 0));
+    k_raw_emit<<<(n_tris + 127u) / 128u, 128, 0, LN.stream>>>(a, d_offsets, LN.d_tris);
+    g.launches++;
+    CK(cudaEventRecord(LN.raw_done, LN.stream));
     CK(cudaGetLastError());
     return launch_pipeline(s, LN.d_tris, LN.d_states, total, mask, g_last_single_prog);
 }

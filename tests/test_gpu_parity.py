@@ -334,11 +334,17 @@ def _render_with_env(scene, w, h, env, **kw):
         return z["color"], z["depth"], int(z["tris"]), int(z["px"])
 
 
-@pytest.mark.parametrize("scene,kw", [("textured", dict(size=96, variant=1 | 32 | 64)), ("phong", dict(size=64, variant=32))],
-                         ids=["textured-closeup-clipped", "phong"])
+@pytest.mark.parametrize("scene,kw", [("textured", dict(size=96, variant=1 | 32 | 64)), ("phong", dict(size=64, variant=32)),
+                                      ("gears", dict(frames=2)), ("batch", dict(size=3)), ("textured", dict(size=48, variant=1 | 64)),
+                                      ("micro", dict(variant=(8 | 1) | (128 | (3 << 4)) | (1 << 9) | (1 << 11) | (1 << 13) | (1 << 18) | (1 << 19), seed=16, size=40)),
+                                      ("micro", dict(variant=(8 | 1) | (1 << 9) | (1 << 13) | (1 << 18), seed=5, size=60))],
+                         ids=["textured-closeup-clipped", "phong", "gears-gouraud-immediate", "batch-lists-gouraud", "textured-immediate-clipped",
+                              "micro-lit-spot", "micro-lit"])
 def test_device_vertex_stage_equals_host_stage(scene, kw):
-    """Large vertex-array draws run transform/clip/project on the GPU (pf_vstage.h compiled as device code);
-    the result must be bit-identical to the host vertex stage, including the triangle count after clipping."""
+    """Vertex-array draws, immediate mode and render lists run the per-triangle prologue on the GPU (pf_vstage.h
+    compiled as device code: normal transform, material multiply, Gouraud lighting through the host-harvested
+    specular tables, clipping, projection); the result must be bit-identical to the host vertex stage
+    (PF_CUDA_DEVICE_VERTEX=0), including the triangle count after clipping."""
     a = _render_with_env(scene, 640, 360, {"PF_CUDA_DEVICE_VERTEX": "1"}, **kw)
     b = _render_with_env(scene, 640, 360, {"PF_CUDA_DEVICE_VERTEX": "0"}, **kw)
     assert a[2] == b[2] and a[3] == b[3]

@@ -305,10 +305,12 @@ def ours_main(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    traffic = None
-    try:    # dram__bytes_read+write of k_raster per launch, from the committed ncu --set full capture
+    traffic = None; issue_active = None
+    try:    # dram__bytes_read+write of the raster kernel per launch (and its issue utilisation: the north star's
+            # evidence for setup/issue-bound scenes), from the committed ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            traffic = json.load(f).get(wl_name, {}).get("traffic_bytes_per_launch")
+            tj = json.load(f).get(wl_name, {})
+            traffic = tj.get("traffic_bytes_per_launch"); issue_active = tj.get("sm_issue_active_pct")
     except Exception:
         pass
     alg_bytes = m["dev_px_per_step"] * wl["bytes_px"]
@@ -385,7 +387,8 @@ def ours_main(args):
                 "ms_per_step": e2e_ms, "mtri_per_s": sum_over_ranks(m["tris_per_step"]) / (e2e_ms * 1e-3) / 1e6 if world == 1 else None},
         "gpu_launches": int(round(m["launches_per_step"] * args.steps)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "k_raster", "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_shaded_px": wl["bytes_px"],
+                     "kernel": "k_raster_frag" if wl["scene"] in ("textured", "phong", "gears", "batch") else "k_raster",
+                     "sm_issue_active_pct_ncu": issue_active, "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_shaded_px": wl["bytes_px"],
                      "kernel_ms": m["raster_ms"], "frontend_kernels_ms": m["frontend_ms"], "peak_source": peak_src},
         "cpu_baseline": cpu, "clocks": clocks, "extra": extra,
     }

@@ -255,6 +255,21 @@ PFCU_API int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t
                              const float *pow_tables, uint32_t n_pow_tables,
                              const pfcu_rawtri *tris, uint32_t n_tris, uint32_t *n_out);
 
+/* ---- points and lines (SURVEY 8-f "next" row 3) -------------------------------------------------- */
+/* The front end transforms and clips (lines.c:137-281, points.c:62-83) and submits screen-space primitives;
+ * the device walks them in submission order (one CTA per 64x64 tile, every CTA visits all primitives and keeps
+ * the pixels of its tile, so overlapping primitives blend and depth-test in order).  Arithmetic: pf_prims.h. */
+typedef struct {
+    float    x1, y1, x2, y2;    /* screen coordinates (a point uses x1, y1)                               */
+    float    z1, z2;            /* homogeneous z of the endpoints (not inverted: lines.c:301-302)         */
+    uint32_t c1, c2;            /* PFcolor dwords                                                          */
+    float    size;              /* ctx->lineWidth or ctx->pointSize                                        */
+    uint8_t  kind;              /* 0 point, 1 line                                                          */
+    uint8_t  flags;             /* PFCU_ST_BLEND | PFCU_ST_DEPTH_TEST                                       */
+    uint8_t  blend_mode, depth_func;
+} pfcu_prim;                    /* 40 B */
+PFCU_API int pfcu_submit_prims(pfcu_surface *s, const pfcu_prim *prims, uint32_t n_prims);
+
 /* ---- the hot path ---------------------------------------------------------------------------- */
 /* Rasterise `n_tris` triangles, in order, into `s`.  Host pointers; the call copies them to the
  * device (pinned staging + cudaMemcpyAsync) and launches setup -> bin -> tile raster.  Asynchronous. */

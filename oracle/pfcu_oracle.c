@@ -607,6 +607,53 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
     if (n_out) *n_out = 0;
     return PFCU_ERR_INVALID;
 }
+/* points and lines: the reference's scalar loops (lines.c:283-530, points.c:85-183), one primitive after the other */
+#include "../pixelforge_b200/csrc/pf_prims.h"
+static void prim_pixel(pfcu_surface *s, const pfcu_prim *p, uint32_t off, float z, uint32_t color, int test)
+{
+    if (off >= s->w * s->h) return;                     /* the reference would write outside its buffer */
+    const uint32_t x = off % s->w, y = off / s->w;
+    if (s->world > 1 && ((x / 64u) + (y / 64u) * ((s->w + 63u) / 64u)) % s->world != s->rank) return;
+    if (test && !pfp_depth(p->depth_func, z, s->depth[off])) return;
+    s->color[off] = (p->flags & PFCU_ST_BLEND) ? pfp_blend(p->blend_mode, color, s->color[off]) : color;
+    s->depth[off] = z;
+}
+int pfcu_submit_prims(pfcu_surface *s, const pfcu_prim *prims, uint32_t n)
+{
+    for (uint32_t i = 0; i < n; i++) {
+        const pfcu_prim *p = &prims[i];
+        const int ztest = (p->flags & PFCU_ST_DEPTH_TEST) != 0;
+        if (p->kind == PFP_KIND_POINT) {
+            const int cx = (int)p->x1, cy = (int)p->y1;
+            if (p->size <= 1.0f) { prim_pixel(s, p, (uint32_t)cy * s->w + (uint32_t)cx, p->z1, p->c1, ztest); continue; }
+            const float r = p->size * 0.5f, r2 = r * r;
+            const int R = (int)r;
+            for (int y = -R; y <= R; y++)
+                for (int x = -R; x <= R; x++)
+                    if ((float)(y * y + x * x) <= r2) {
+                        const uint32_t px = (uint32_t)(cx + x), py = (uint32_t)(cy + y);
+                        if (px < s->w && py < s->h) prim_pixel(s, p, py * s->w + px, p->z1, p->c1, ztest);
+                    }
+            continue;
+        }
+        int axis;
+        const unsigned nsub = pfp_thick_count(p->x1, p->y1, p->x2, p->y2, p->size, &axis);
+        const int thick = p->size > 1.5f;
+        for (unsigned sub = 0; sub < nsub; sub++) {
+            const float sh = pfp_thick_shift(sub);
+            pfp_line L;
+            pfp_line_setup(&L, axis ? p->x1 : p->x1 + sh, axis ? p->y1 + sh : p->y1, axis ? p->x2 : p->x2 + sh, axis ? p->y2 + sh : p->y2);
+            const int test = ztest || (thick && sub == 0);
+            const unsigned steps = pfp_line_steps(&L);
+            for (unsigned k = 0; k < steps; k++) {
+                float t;
+                const uint32_t off = pfp_line_step(&L, k, s->w, &t);
+                prim_pixel(s, p, off, p->z1 + t * (p->z2 - p->z1), pfp_color_lerp(p->c1, p->c2, t), test);
+            }
+        }
+    }
+    return PFCU_OK;
+}
 unsigned pfcu_capabilities(void) { return 0u; }     /* the oracle has no device vertex stage: the front end keeps it on the host */
 int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *st, const pfcu_vparams *vp, const pfcu_draw *d, uint32_t *n)
 { (void)s; (void)st; (void)vp; (void)d; (void)n; return PFCU_ERR_INVALID; }

@@ -92,7 +92,7 @@ void pfDeleteContext(PFcontext ctx)
     pfcu_finish();
     for (int i = 0; i < 2; i++) if (c->tris[i]) pfcu_host_free(c->tris[i]);
     free(c->states); free(c->cap_tris); free(c->cap_states);
-    free(c->vparams); free(c->pow_tables); free(c->pow_shininess);
+    free(c->vparams); free(c->pow_tables); free(c->pow_shininess); free(c->prims);
     pf_tex *tex = (pf_tex *)c->mainFramebuffer.texture;
     pfh_surf_destroy(c->main_surf);
     PF_FREE(tex);

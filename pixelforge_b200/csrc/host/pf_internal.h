@@ -150,6 +150,7 @@ typedef struct pf_ctx {
     uint32_t       vp_epoch, vp_epoch_built;    /* bumped by every call that changes what the prologue reads */
     pf_material    vp_material[2];              /* materials of the newest entry (may change per vertex with PF_COLOR_MATERIAL) */
     int            batch_raw;
+    pfcu_prim     *prims; uint32_t n_prims, prims_cap;      /* pending points / lines (never together with triangles) */
     float         *pow_tables; float *pow_shininess; uint32_t n_pow, pow_cap;   /* specular tables by shininess */
     /* optional capture of the submitted stream (pfxCaptureBegin/End) */
     int            device_vertex;   /* large vertex-array draws run the vertex stage on the GPU (default on) */

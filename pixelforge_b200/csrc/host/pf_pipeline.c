@@ -12,6 +12,7 @@
  */
 #include "pf_internal.h"
 #include "pf_math.h"
+#include "../pf_prims.h"
 
 #include <stdio.h>
 #include <math.h>
@@ -179,6 +180,7 @@ static int alloc_batch(pf_ctx *c, uint32_t cap)
 
 static int ensure_batch(pf_ctx *c)
 {
+    if (c->n_prims) pfh_flush(c);               /* points / lines submitted before this triangle come first */
     if (c->tris[0]) return 1;
     uint32_t cap = PFH_BATCH_TRIS_MIN;
     if (cap > batch_limit()) cap = batch_limit();
@@ -217,8 +219,22 @@ static void capture_append(pf_ctx *c)
     c->cap_ntris += c->n_tris; c->cap_nstates += c->n_states;
 }
 
+static void flush_prims(pf_ctx *c)
+{
+    pf_surf *s = c->cur_surf;
+    pfh_upload_if_needed(c, s);
+    int rc = pfcu_submit_prims(s->dev, c->prims, c->n_prims);
+    if (rc != PFCU_OK) {
+        fprintf(stderr, "pixelforge-b200: pfcu_submit_prims failed (%d): %s\n", rc, pfcu_last_error());
+        c->errCode = (rc == PFCU_ERR_OOM) ? PF_ERROR_OUT_OF_MEMORY : PF_INVALID_OPERATION;
+    }
+    s->dev_newer = 1; s->dirty_y0 = 0; s->dirty_y1 = s->tex->h;
+    c->n_prims = 0;
+}
+
 void pfh_flush(pf_ctx *c)
 {
+    if (c && c->n_prims) flush_prims(c);
     if (!c || c->n_tris == 0) { if (c) { c->n_states = 0; c->state_dirty = 1; c->n_vparams = 0; } return; }
     pf_surf *s = c->cur_surf;
     if (c->capturing) capture_append(c);
@@ -579,15 +595,129 @@ static void tri_strip(pf_ctx *c, int face, int count)
     }
 }
 
-static void unsupported_primitive(pf_ctx *c, const char *what)
+/* ---- points and lines: transform and clip on the host (few primitives), rasterise on the device ------------
+ * points.c:62-83, lines.c:137-281.  No lighting, no texturing: the vertex colour is used as is. */
+
+static void emit_prim(pf_ctx *c, const pfcu_prim *p)
 {
-    static int warned = 0;
-    if (!warned) {
-        fprintf(stderr, "pixelforge-b200: %s are outside the CUDA triangle path (SURVEY.md 8-f NEXT-3); ignored\n", what);
-        warned = 1;
+    if (c->n_tris) pfh_flush(c);                /* triangles submitted before this primitive come first */
+    if (c->n_prims == c->prims_cap) {
+        uint32_t nc = c->prims_cap ? c->prims_cap * 2 : 256;
+        pfcu_prim *q = (pfcu_prim *)realloc(c->prims, (size_t)nc * sizeof *q);
+        if (!q) { c->errCode = PF_ERROR_OUT_OF_MEMORY; return; }
+        c->prims = q; c->prims_cap = nc;
     }
-    c->errCode = PF_INVALID_OPERATION;
+    c->prims[c->n_prims++] = *p;
+    c->tris_emitted++;
+    if (c->n_prims >= 65536u) pfh_flush(c);
 }
+
+static void prim_state(const pf_ctx *c, pfcu_prim *p)
+{
+    p->flags = 0;
+    if (c->state & PF_BLEND) { p->flags |= PFCU_ST_BLEND; }
+    if (c->state & PF_DEPTH_TEST) { p->flags |= PFCU_ST_DEPTH_TEST; }
+    p->blend_mode = (uint8_t)c->blendMode; p->depth_func = (uint8_t)c->depthMode;
+}
+
+static void process_point(pf_ctx *c, pf_vertex *v)
+{
+    pfv_params vp; pfh_vstage_params(c, &vp);
+    pfv_transform(&vp, v);
+    float *h = v->homogeneous;
+    if (h[3] != 1.0f) {
+        for (int i = 0; i < 3; i++) if (h[i] < -h[3] || h[i] > h[3]) return;
+        const float iw = 1.0f / h[3];
+        h[0] *= iw; h[1] *= iw;
+    }
+    pfv_to_screen(&vp, v);
+    if (!(v->screen[0] >= c->vpMin[0] && v->screen[1] >= c->vpMin[1] && v->screen[0] <= c->vpMax[0] && v->screen[1] <= c->vpMax[1])) return;
+    pfcu_prim p; memset(&p, 0, sizeof p);
+    p.kind = PFP_KIND_POINT; p.x1 = v->screen[0]; p.y1 = v->screen[1]; p.z1 = h[2]; p.c1 = v->color; p.size = c->pointSize;
+    prim_state(c, &p);
+    emit_prim(c, &p);
+}
+
+static int clip_code_2d(const float *scr, PFint xMin, PFint yMin, PFint xMax, PFint yMax)
+{
+    int code = 0;
+    if (scr[0] < xMin) code |= 1;
+    if (scr[0] > xMax) code |= 2;
+    if (scr[1] < yMin) code |= 8;
+    if (scr[1] > yMax) code |= 4;
+    return code;
+}
+
+static int clip_line_2d(const pf_ctx *c, pf_vertex *v1, pf_vertex *v2)      /* lines.c:137-189 (Cohen-Sutherland, its quirks kept) */
+{
+    const PFint xMin = c->vpMin[0], yMin = c->vpMin[1], xMax = c->vpMax[0], yMax = c->vpMax[1];
+    float m = 0;
+    if (v1->screen[0] != v2->screen[0]) m = (v2->screen[1] - v1->screen[1]) / (v2->screen[0] - v1->screen[0]);
+    for (;;) {
+        int code0 = clip_code_2d(v1->screen, xMin, yMin, xMax, yMax);
+        int code1 = clip_code_2d(v2->screen, xMin, yMin, xMax, yMax);
+        if ((code0 | code1) == 0) return 1;
+        if (code0 & code1) return 0;
+        if (code0 == 0) { int ct = code0; code0 = code1; code1 = ct; pf_vertex vt = *v1; *v1 = *v2; *v2 = vt; }
+        if (code0 & 1)      { v1->screen[1] += (c->vpMin[0] - v1->screen[0]) * m; v1->screen[0] = (float)c->vpMin[0]; }
+        else if (code0 & 2) { v1->screen[1] += (c->vpMax[0] - v1->screen[0]) * m; v1->screen[0] = (float)c->vpMax[0]; }
+        else if (code0 & 4) { if (m) v1->screen[0] += (c->vpMin[1] - v1->screen[1]) / m; v1->screen[1] = (float)c->vpMin[1]; }
+        else if (code0 & 8) { if (m) v1->screen[0] += (c->vpMax[1] - v1->screen[1]) / m; v1->screen[1] = (float)c->vpMax[1]; }
+    }
+}
+
+static int clip_coord_3d(float q, float p, float *t1, float *t2)             /* lines.c:115-135 */
+{
+    if (fabsf(p) < PFH_CLIP_EPSILON) return !(q < -PFH_CLIP_EPSILON);
+    const float r = q / p;
+    if (p < 0) { if (r > *t2) return 0; if (r > *t1) *t1 = r; }
+    else       { if (r < *t1) return 0; if (r < *t2) *t2 = r; }
+    return 1;
+}
+
+static int clip_line_3d(pf_vertex *v1, pf_vertex *v2)                        /* lines.c:191-227 (Liang-Barsky in clip space) */
+{
+    float t1 = 0, t2 = 1, d[4];
+    float *a = v1->homogeneous, *b = v2->homogeneous;
+    for (int i = 0; i < 4; i++) d[i] = b[i] - a[i];
+    for (int ax = 0; ax < 3; ax++) {
+        if (!clip_coord_3d(a[3] - a[ax], -d[3] + d[ax], &t1, &t2)) return 0;
+        if (!clip_coord_3d(a[3] + a[ax], -d[3] - d[ax], &t1, &t2)) return 0;
+    }
+    if (t2 < 1) for (int i = 0; i < 4; i++) b[i] = a[i] + d[i] * t2;
+    if (t1 > 0) for (int i = 0; i < 4; i++) a[i] = a[i] + d[i] * t1;
+    return 1;
+}
+
+/* returns 0 when the line is clipped away (lines.c:229-268) */
+static int process_line(pf_ctx *c, const pf_vertex *in1, const pf_vertex *in2)
+{
+    pf_vertex l[2] = { *in1, *in2 };
+    pfv_params vp; pfh_vstage_params(c, &vp);
+    pfv_transform(&vp, &l[0]); pfv_transform(&vp, &l[1]);
+    if (l[0].homogeneous[3] == 1.0f && l[1].homogeneous[3] == 1.0f) {
+        pfv_to_screen(&vp, &l[0]); pfv_to_screen(&vp, &l[1]);
+        if (!clip_line_2d(c, &l[0], &l[1])) return 0;
+    } else {
+        if (!clip_line_3d(&l[0], &l[1])) return 0;
+        for (int i = 0; i < 2; i++) {
+            const float iw = 1.0f / l[i].homogeneous[3];
+            l[i].homogeneous[0] *= iw; l[i].homogeneous[1] *= iw;
+        }
+        pfv_to_screen(&vp, &l[0]); pfv_to_screen(&vp, &l[1]);
+    }
+    pfcu_prim p; memset(&p, 0, sizeof p);
+    p.kind = PFP_KIND_LINE;
+    p.x1 = l[0].screen[0]; p.y1 = l[0].screen[1]; p.x2 = l[1].screen[0]; p.y2 = l[1].screen[1];
+    p.z1 = l[0].homogeneous[2]; p.z2 = l[1].homogeneous[2]; p.c1 = l[0].color; p.c2 = l[1].color; p.size = c->lineWidth;
+    prim_state(c, &p);
+    emit_prim(c, &p);
+    return 1;
+}
+
+static void poly_points(pf_ctx *c, int n) { for (int i = 0; i < n; i++) { pf_vertex v = c->vertexBuffer[i]; process_point(c, &v); } }
+/* the outline of a triangle / quad in PF_LINE polygon mode stops at the first edge that is clipped away (lines.c:93) */
+static void poly_lines(pf_ctx *c, int n) { for (int i = 0; i < n; i++) if (!process_line(c, &c->vertexBuffer[i], &c->vertexBuffer[(i + 1) % n])) return; }
 
 /* draw-mode dispatch (internal/context/context.c:94-244) */
 void pfh_process_primitive(pf_ctx *c)
@@ -596,14 +726,15 @@ void pfh_process_primitive(pf_ctx *c)
     int one = culled ? !c->cullFace : PF_FRONT_AND_BACK;     /* face to render */
 
     switch (c->currentDrawMode) {
-    case PF_POINTS: unsupported_primitive(c, "PF_POINTS"); break;
-    case PF_LINES:  unsupported_primitive(c, "PF_LINES"); break;
+    case PF_POINTS: { pf_vertex v = c->vertexBuffer[0]; process_point(c, &v); } break;
+    case PF_LINES:  process_line(c, &c->vertexBuffer[0], &c->vertexBuffer[1]); break;
     case PF_TRIANGLES:
     case PF_QUADS: {
         int quad = c->currentDrawMode == PF_QUADS;
         int f0 = (one == PF_FRONT_AND_BACK) ? 0 : one, f1 = (one == PF_FRONT_AND_BACK) ? 1 : one;
         for (int f = f0; f <= f1; f++) {
-            if (c->polygonMode[f] != PF_FILL) { unsupported_primitive(c, "PF_POINT / PF_LINE polygon modes"); continue; }
+            if (c->polygonMode[f] == PF_POINT) { poly_points(c, quad ? 4 : 3); continue; }
+            if (c->polygonMode[f] == PF_LINE) { poly_lines(c, quad ? 4 : 3); continue; }
             if (quad) tri_fan(c, f, 2); else tri_list(c, f);
         }
     } break;

@@ -22,6 +22,7 @@
  */
 #include "pfcu.h"
 #include "pf_vstage.h"
+#include "pf_prims.h"
 
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -1978,6 +1979,82 @@ k_raw_emit(const RawArgs a, const unsigned *__restrict__ offsets, pfcu_triangle 
     for (int k = 0; k < n; k++) pfv_emit(dst + k, &poly[0], &poly[k + 1], &poly[k + 2], state, face, is3d);
 }
 
+/* ---- points and lines (pf_prims.h) ------------------------------------------------------------------
+ * One CTA per 64x64 tile; every CTA walks ALL primitives in submission order and applies the fragments that
+ * fall into its tile (threads = steps of one plain line / cells of one point), with a barrier between plain
+ * lines.  Order per pixel = submission order; no inter-CTA communication.  Primitives whose rectangle cannot
+ * touch the tile are skipped (only when every x of the line is inside the surface, because out-of-range columns
+ * wrap into the neighbouring rows like upstream). */
+struct PrimParams { const pfcu_prim *prims; unsigned n; uint32_t *color; float *depth; unsigned W, H; int tilesX; unsigned rank, world, nTiles; };
+
+__device__ __forceinline__ void prim_pixel(const PrimParams &p, const pfcu_prim &pr, int X0, int Y0, uint32_t off, float z, uint32_t color, bool test)
+{
+    if (off >= p.W * p.H) return;
+    const int x = (int)(off % p.W), y = (int)(off / p.W);
+    if (x < X0 || x >= X0 + TILE || y < Y0 || y >= Y0 + TILE) return;
+    if (test && !pfp_depth(pr.depth_func, z, p.depth[off])) return;
+    p.color[off] = (pr.flags & PFCU_ST_BLEND) ? pfp_blend(pr.blend_mode, color, p.color[off]) : color;
+    p.depth[off] = z;
+}
+
+__global__ void __launch_bounds__(256)
+k_prims(const PrimParams p)
+{
+    const unsigned tile = (p.world > 1) ? (p.rank + blockIdx.x * p.world) : blockIdx.x;
+    if (tile >= p.nTiles) return;
+    const int X0 = (int)(tile % (unsigned)p.tilesX) * TILE, Y0 = (int)(tile / (unsigned)p.tilesX) * TILE;
+    for (unsigned i = 0; i < p.n; i++) {
+        const pfcu_prim pr = p.prims[i];
+        const bool ztest = (pr.flags & PFCU_ST_DEPTH_TEST) != 0;
+        if (pr.kind == PFP_KIND_POINT) {
+            const int cx = PFV_F2I(pr.x1), cy = PFV_F2I(pr.y1);
+            if (pr.size <= 1.0f) {
+                if (threadIdx.x == 0) prim_pixel(p, pr, X0, Y0, (uint32_t)cy * p.W + (uint32_t)cx, pr.z1, pr.c1, ztest);
+            } else {
+                const float r = __fmul_rn(pr.size, 0.5f), r2 = __fmul_rn(r, r);
+                const int R = PFV_F2I(r);
+                if (R >= 0 && R < 16384 && !(cx + R < X0 || cx - R >= X0 + TILE || cy + R < Y0 || cy - R >= Y0 + TILE)) {
+                    const int side = 2 * R + 1;
+                    for (int c = threadIdx.x; c < side * side; c += 256) {
+                        const int y = c / side - R, x = c % side - R;
+                        if (__int2float_rn(y * y + x * x) <= r2) {
+                            const uint32_t px = (uint32_t)(cx + x), py = (uint32_t)(cy + y);
+                            if (px < p.W && py < p.H) prim_pixel(p, pr, X0, Y0, py * p.W + px, pr.z1, pr.c1, ztest);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        int axis;
+        const unsigned nsub = pfp_thick_count(pr.x1, pr.y1, pr.x2, pr.y2, pr.size, &axis);
+        const bool thick = pr.size > 1.5f;
+        /* conservative reject: all columns inside the surface (no wrapping) and the rectangle, widened by the
+           thickness, misses the tile */
+        {
+            const int x1 = PFV_F2I(pr.x1), y1 = PFV_F2I(pr.y1), x2 = PFV_F2I(pr.x2), y2 = PFV_F2I(pr.y2);
+            const int wd = (int)(nsub >> 1) + 1;
+            const int xa = min(x1, x2) - wd, xb = max(x1, x2) + wd, ya = min(y1, y2) - wd, yb = max(y1, y2) + wd;
+            if (xa >= 0 && xb < (int)p.W && (xb < X0 || xa >= X0 + TILE || yb < Y0 || ya >= Y0 + TILE)) continue;
+        }
+        for (unsigned sub = 0; sub < nsub; sub++) {
+            const float sh = pfp_thick_shift(sub);
+            pfp_line L;
+            pfp_line_setup(&L, axis ? pr.x1 : __fadd_rn(pr.x1, sh), axis ? __fadd_rn(pr.y1, sh) : pr.y1,
+                           axis ? pr.x2 : __fadd_rn(pr.x2, sh), axis ? __fadd_rn(pr.y2, sh) : pr.y2);
+            const bool test = ztest || (thick && sub == 0);
+            const unsigned steps = pfp_line_steps(&L);
+            for (unsigned k = threadIdx.x; k < steps; k += 256) {
+                float t;
+                const uint32_t off = pfp_line_step(&L, k, p.W, &t);
+                prim_pixel(p, pr, X0, Y0, off, __fadd_rn(pr.z1, __fmul_rn(t, __fsub_rn(pr.z2, pr.z1))), pfp_color_lerp(pr.c1, pr.c2, t), test);
+            }
+            __syncthreads();
+        }
+    }
+}
+
 /* exclusive scan of up to 1024 items per CTA; sums[blockIdx] = CTA total */
 __global__ void __launch_bounds__(256)
 k_scan_block(const unsigned *__restrict__ in, unsigned *__restrict__ out, unsigned n, unsigned *__restrict__ sums)
@@ -2781,6 +2858,28 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
     CK(cudaEventRecord(LN.raw_done, LN.stream));
     CK(cudaGetLastError());
     return launch_pipeline(s, LN.d_tris, LN.d_states, total, mask, g_last_single_prog);
+}
+
+int pfcu_submit_prims(pfcu_surface *s, const pfcu_prim *prims, uint32_t n)
+{
+    API_LOCK;
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!s || (n && !prims)) return PFCU_ERR_INVALID;
+    if (n == 0) return PFCU_OK;
+    use_lane(s);
+    int rc;
+    const size_t bytes = (size_t)n * sizeof(pfcu_prim);
+    if ((rc = grow(&LN.d_varrays, &LN.cap_varrays, bytes))) return rc;
+    CK(cudaMemcpyAsync(LN.d_varrays, prims, bytes, cudaMemcpyHostToDevice, LN.stream));
+    g.bytes_h2d += bytes;
+    PrimParams p;
+    p.prims = (const pfcu_prim *)LN.d_varrays; p.n = n; p.color = s->color; p.depth = s->depth; p.W = s->w; p.H = s->h;
+    p.tilesX = (int)s->tiles_x; p.rank = s->rank; p.world = s->world ? s->world : 1; p.nTiles = s->tiles_x * s->tiles_y;
+    const unsigned grid = owned_tiles(s, p.rank, p.world);
+    if (grid) { k_prims<<<grid, 256, 0, LN.stream>>>(p); g.launches++; }
+    CK(cudaGetLastError());
+    mark_done(s);
+    return PFCU_OK;
 }
 
 int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, const pfcu_triangle *tris, uint32_t n_tris)

@@ -558,6 +558,60 @@ SCN_API const char *pfscene_backend(void)
 
 SCN_API void pfscene_close(void *handle);
 
+/* "prims": points, lines and PF_POINT / PF_LINE polygon modes, interleaved with filled triangles so that the
+ * submission order across primitive kinds matters.  variant: bit0 blend, bits1-3 blend mode, bit4 depth test,
+ * bits5-7 depth function, bit8 perspective (3D lines are clipped against the frustum), bit9 thick lines and
+ * large points.  Everything 2D stays 12 pixels inside the surface: the reference's line loop has no bounds
+ * check and thick lines are shifted copies of the centre line. */
+static void prims_scene(const pfscene_cfg *cfg)
+{
+    const int v = cfg->variant, w = cfg->width, h = cfg->height, n = cfg->size > 0 ? cfg->size : 40;
+    lcg_state = (uint32_t)cfg->seed * 2654435761u + 12345u;
+    pfClearColor(20, 10, 40, 255);
+    pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+    const int persp = (v >> 8) & 1, thick = (v >> 9) & 1;
+    if (persp) {
+        pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
+        cam_perspective(60.0, (double)w / h, 0.1, 100.0);
+        float eye[3] = { 0.2f, 0.3f, 3.0f }, at[3] = { 0, 0, 0 };
+        cam_lookat(eye, at);
+    } else ortho2d(w, h);
+    if (v & 1) { pfEnable(PF_BLEND); pfBlendFunc((PFblendmode)((v >> 1) & 7)); }
+    if (v & 16) { pfEnable(PF_DEPTH_TEST); pfDepthFunc((PFdepthmode)((v >> 5) & 7)); }
+    pfDisable(PF_CULL_FACE);
+    for (int i = 0; i < n; i++) {
+        const int kind = i % 6;
+        float x[4], y[4], z[4];
+        for (int k = 0; k < 4; k++) {
+            if (persp) { x[k] = lcgf() * 5.0f - 2.5f; y[k] = lcgf() * 4.0f - 2.0f; z[k] = lcgf() * 5.0f - 2.0f; }
+            else { x[k] = 12.0f + lcgf() * (float)(w - 24); y[k] = 12.0f + lcgf() * (float)(h - 24); z[k] = 0.0f; }
+        }
+        /* thick 3D lines could be shifted outside the surface after clipping: thin ones only in perspective */
+        pfLineWidth(thick && !persp ? 1.0f + (float)(i % 5) : 1.0f);
+        pfPointSize(thick ? 1.0f + (float)(i % 7) : 1.0f);
+        pfPolygonMode(PF_FRONT_AND_BACK, PF_FILL);
+        switch (kind) {
+        case 0: pfBegin(PF_POINTS); break;
+        case 1: pfBegin(PF_LINES); break;
+        case 2: pfBegin(PF_TRIANGLES); break;
+        case 3: pfPolygonMode(PF_FRONT_AND_BACK, PF_LINE); pfBegin(PF_TRIANGLES); break;
+        case 4: pfPolygonMode(PF_FRONT, PF_POINT); pfPolygonMode(PF_BACK, PF_LINE); pfBegin(PF_QUADS); break;
+        default: pfPolygonMode(PF_FRONT, PF_LINE); pfBegin(PF_QUADS); break;        /* back faces stay filled */
+        }
+        const int nv = kind == 0 ? 3 : (kind == 1 ? 4 : (kind >= 4 ? 4 : 3));
+        for (int k = 0; k < nv; k++) {
+            pfColor4ub((PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(96 + (lcg() >> 25)));
+            if (kind >= 2 && !persp) {      /* keep polygons small so that many primitives overlap without filling the screen */
+                const float cx = x[0], cy = y[0];
+                pfVertex3f(cx + (x[k] - cx) * 0.25f, cy + (y[k] - cy) * 0.25f, z[k]);
+            } else pfVertex3f(x[k], y[k], z[k]);
+        }
+        pfEnd();
+    }
+    pfPolygonMode(PF_FRONT_AND_BACK, PF_FILL); pfLineWidth(1.0f); pfPointSize(1.0f);
+    pfDisable(PF_BLEND); pfDisable(PF_DEPTH_TEST); pfEnable(PF_CULL_FACE);
+}
+
 /* Creates the context(s), textures, meshes and fixed state of scene `name`.  Returns NULL on failure. */
 SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
 {
@@ -653,6 +707,8 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
            MAIN buffer the reference computes vpMax = x+width (one past the last column/row,
            context.c:567-570), so "2D" triangles may touch column 96 / row 80 */
         if (cfg->variant & (1 << 20)) s->fbo = pfGenFramebuffer(104, 88, PF_RGBA, PF_UNSIGNED_BYTE);
+    } else if (strcmp(name, "prims") == 0) {
+        /* no resources */
     } else if (strcmp(name, "api") == 0) {
         s->texpx = make_texture(64, 48, 4, (uint32_t)cfg->seed ^ 0x5151u, 0, 255, 64, 255);
         s->tex = pfGenTexture(s->texpx, 64, 48, PF_RGBA, PF_UNSIGNED_BYTE);
@@ -747,6 +803,8 @@ SCN_API void pfscene_frame(void *handle, int frame)
         } else micro_scene(cfg, s->tex);
     } else if (strcmp(name, "api") == 0) {
         api_scene(cfg, s->tex, s->aux);
+    } else if (strcmp(name, "prims") == 0) {
+        prims_scene(cfg);
     }
 }
 

@@ -80,3 +80,22 @@ CASES += [_api("plain", 0), _api("viewport", _B(0)), _api("texmatrix", _B(1)), _
 
 CASE_IDS = [c[0] for c in CASES]
 assert len(set(CASE_IDS)) == len(CASE_IDS)
+
+
+# points, lines and PF_POINT / PF_LINE polygon modes (scene "prims"): the reference's scalar rasterisers
+# (lines.c, points.c) - scalar blend / depth tables, thick lines, frustum-clipped 3D lines
+def _prims(desc, blend=None, depth=None, persp=0, thick=0, seed=1, size=48):
+    v = (persp << 8) | (thick << 9)
+    if blend is not None:
+        v |= 1 | (blend << 1)
+    if depth is not None:
+        v |= 16 | (depth << 5)
+    return (f"prims-{desc}", "prims", 200, 150, dict(variant=v, seed=seed, size=size), False)
+
+
+CASES += [_prims("plain"), _prims("thick", thick=1, seed=2), _prims("persp", persp=1, seed=3), _prims("persp-depth-less", persp=1, depth=2, seed=4)]
+CASES += [_prims(f"blend{b}-thick", blend=b, thick=1, seed=5 + b) for b in range(8)]
+CASES += [_prims(f"depth{d}-thick", depth=d, thick=1, seed=20 + d) for d in range(6)]
+CASES += [_prims("persp-blend1-depth3-points", blend=1, depth=3, persp=1, thick=1, seed=30, size=90)]
+
+CASE_IDS = [c[0] for c in CASES]

@@ -125,6 +125,7 @@ struct Lane {
     cudaStream_t vstream = nullptr; cudaEvent_t raw_done = nullptr, vready = nullptr;
     unsigned char *d_raw = nullptr; size_t cap_raw = 0;
     unsigned *h_total = nullptr;                                        /* pinned: {last offset, last count} */
+    unsigned *d_total = nullptr;                                        /* output count of a sync-free raw batch */
 };
 
 #define MAX_LANES 8
@@ -788,8 +789,10 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, int 
  * bin starts and the ordered fill in ONE single-CTA kernel instead of five launches; thread = triangle, warp w
  * owns the bin columns bx & 31 == w (see k_bin_fill). */
 #define FRONT_SMALL_MAX 1024
+#define FRONT_SMALL_CHUNKS 10           /* with a device-side count (raw batches after clipping): up to 10 x 1024 */
 __global__ void __launch_bounds__(1024)
-k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ states, unsigned n, int surfW, int surfH,
+k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ states, unsigned n_host, const unsigned *__restrict__ d_n,
+              int surfW, int surfH,
               int4 *__restrict__ bbox, TriSetup *__restrict__ setup, TriData *__restrict__ data, unsigned long long *__restrict__ counters,
               int binsX, int binsY, int bshift, unsigned *__restrict__ starts, uint2 *__restrict__ list)
 {
@@ -799,27 +802,28 @@ k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict
     __shared__ int4 s_bbox[FRONT_SMALL_MAX];
     __shared__ unsigned s_warp[32];
     __shared__ unsigned s_carry;
+    const unsigned n = d_n ? min(*d_n, (unsigned)(FRONT_SMALL_MAX * FRONT_SMALL_CHUNKS)) : n_host;
     const int nb = binsX * binsY;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int k = threadIdx.x; k < nb; k += 1024) s_pos[k] = 0;
     if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
 
-    const unsigned i = threadIdx.x;
-    bool rasterised = false;
-    int4 b = make_int4(1, 1, 0, 0), r = make_int4(1, 1, 0, 0);
-    if (i < n) b = setup_one(tris, states, i, surfW, surfH, bbox, setup, data, &rasterised);
-    if (b.x < b.z) {
-        r.x = max(b.x, 0) >> bshift; r.z = min((b.z - 1) >> bshift, binsX - 1);
-        r.y = max(b.y, 0) >> bshift; r.w = min(b.w >> bshift, binsY - 1);
-    }
-    s_rect[i] = r; s_bbox[i] = b;
-    {
+    /* pass 1: setup + bin counts */
+    for (unsigned base = 0; base < n; base += FRONT_SMALL_MAX) {
+        const unsigned i = base + threadIdx.x;
+        bool rasterised = false;
+        int4 b = make_int4(1, 1, 0, 0);
+        if (i < n) b = setup_one(tris, states, i, surfW, surfH, bbox, setup, data, &rasterised);
+        if (b.x < b.z) {
+            const int rx0 = max(b.x, 0) >> bshift, rx1 = min((b.z - 1) >> bshift, binsX - 1);
+            const int ry0 = max(b.y, 0) >> bshift, ry1 = min(b.w >> bshift, binsY - 1);
+            for (int by = ry0; by <= ry1; by++)
+                for (int bx = rx0; bx <= rx1; bx++) atomicAdd(&s_pos[by * binsX + bx], 1u);
+        }
         const unsigned bal = __ballot_sync(0xffffffffu, rasterised);
         if (lane == 0 && bal) atomicAdd(counters + 0, (unsigned long long)__popc(bal));
     }
-    __syncthreads();
-    for (int by = r.y; by <= r.w; by++)
-        for (int bx = r.x; bx <= r.z; bx++) atomicAdd(&s_pos[by * binsX + bx], 1u);
     __syncthreads();
 
     /* exclusive scan of the bin counts -> starts[] (global, for the rasteriser) and s_pos */
@@ -846,55 +850,68 @@ k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict
     }
     if (threadIdx.x == 0) starts[nb] = s_carry;
 
-    /* ordered fill: every warp walks all triangles, 32 at a time, and appends those with a bin column of its own */
-    const unsigned groups = (n + 31u) / 32u;
-    for (unsigned g8 = 0; g8 < groups; g8++) {
-        const int4 q = s_rect[g8 * 32 + lane];
-        const int4 qb = s_bbox[g8 * 32 + lane];
-        const int first = q.x + ((warp - q.x) & 31);
-        const bool mine = q.x <= q.z && q.y <= q.w && first <= q.z;
-        const bool one = mine && first + 32 > q.z;
-        unsigned mask = __ballot_sync(0xffffffffu, mine);
-        const unsigned single = __ballot_sync(0xffffffffu, one);
-        const unsigned my_idx = g8 * 32 + (unsigned)lane;
-        while (mask) {
-            const int j = __ffs(mask) - 1;
-            if ((single >> j) & 1u) {
-                const unsigned multi = mask & ~single;
-                const unsigned run = multi ? (mask & ((1u << (__ffs(multi) - 1)) - 1u)) : mask;
-                const bool in_run = (run >> lane) & 1u;
-                const int ylo = __reduce_min_sync(0xffffffffu, in_run ? q.y : INT_MAX);
-                const int yhi = __reduce_max_sync(0xffffffffu, in_run ? q.w : INT_MIN);
-                for (int by = ylo; by <= yhi; by++) {
-                    const bool act = in_run && q.y <= by && by <= q.w;
-                    const unsigned am = __ballot_sync(0xffffffffu, act);
-                    if (act) {
-                        const int bin = by * binsX + first;
-                        const unsigned peers = __match_any_sync(am, bin);
-                        const unsigned pos = s_pos[bin] + __popc(peers & ((1u << lane) - 1u));
-                        list[pos] = make_uint2(my_idx, bin_rel_bbox(qb, first, by, bshift));
-                        __syncwarp(peers);
-                        if ((peers >> lane) == 1u) s_pos[bin] = pos + 1;
+    /* pass 2: ordered fill, 1024 triangles at a time: every warp walks them 32 at a time and appends those with a
+       bin column of its own */
+    for (unsigned base = 0; base < n; base += FRONT_SMALL_MAX) {
+        const unsigned i = base + threadIdx.x;
+        int4 b = make_int4(1, 1, 0, 0), r = make_int4(1, 1, 0, 0);
+        if (i < n) b = bbox[i];                 /* written by this very thread in pass 1 */
+        if (b.x < b.z) {
+            r.x = max(b.x, 0) >> bshift; r.z = min((b.z - 1) >> bshift, binsX - 1);
+            r.y = max(b.y, 0) >> bshift; r.w = min(b.w >> bshift, binsY - 1);
+        }
+        __syncthreads();
+        s_rect[threadIdx.x] = r; s_bbox[threadIdx.x] = b;
+        __syncthreads();
+        const unsigned groups = (min(n - base, (unsigned)FRONT_SMALL_MAX) + 31u) / 32u;
+        for (unsigned g8 = 0; g8 < groups; g8++) {
+            const int4 q = s_rect[g8 * 32 + lane];
+            const int4 qb = s_bbox[g8 * 32 + lane];
+            const int first = q.x + ((warp - q.x) & 31);
+            const bool mine = q.x <= q.z && q.y <= q.w && first <= q.z;
+            const bool one = mine && first + 32 > q.z;
+            unsigned mask = __ballot_sync(0xffffffffu, mine);
+            const unsigned single = __ballot_sync(0xffffffffu, one);
+            const unsigned my_idx = base + g8 * 32 + (unsigned)lane;
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                if ((single >> j) & 1u) {
+                    const unsigned multi = mask & ~single;
+                    const unsigned run = multi ? (mask & ((1u << (__ffs(multi) - 1)) - 1u)) : mask;
+                    const bool in_run = (run >> lane) & 1u;
+                    const int ylo = __reduce_min_sync(0xffffffffu, in_run ? q.y : INT_MAX);
+                    const int yhi = __reduce_max_sync(0xffffffffu, in_run ? q.w : INT_MIN);
+                    for (int by = ylo; by <= yhi; by++) {
+                        const bool act = in_run && q.y <= by && by <= q.w;
+                        const unsigned am = __ballot_sync(0xffffffffu, act);
+                        if (act) {
+                            const int bin = by * binsX + first;
+                            const unsigned peers = __match_any_sync(am, bin);
+                            const unsigned pos = s_pos[bin] + __popc(peers & ((1u << lane) - 1u));
+                            list[pos] = make_uint2(my_idx, bin_rel_bbox(qb, first, by, bshift));
+                            __syncwarp(peers);
+                            if ((peers >> lane) == 1u) s_pos[bin] = pos + 1;
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
+                    mask &= ~run;
+                } else {
+                    mask &= mask - 1u;
+                    const int4 t = s_rect[g8 * 32 + j];
+                    const int4 tb = s_bbox[g8 * 32 + j];
+                    const int f0 = t.x + ((warp - t.x) & 31);
+                    const int ncols = ((t.z - f0) >> 5) + 1, rows = t.w - t.y + 1;
+                    const unsigned idx = base + g8 * 32 + (unsigned)j;
+                    for (int e = lane; e < ncols * rows; e += 32) {
+                        const int cy = e / ncols, cx = e - cy * ncols;
+                        const int bin = (t.y + cy) * binsX + f0 + (cx << 5);
+                        const unsigned pos = s_pos[bin];
+                        list[pos] = make_uint2(idx, bin_rel_bbox(tb, f0 + (cx << 5), t.y + cy, bshift));
+                        s_pos[bin] = pos + 1;
+                    }
                 }
-                mask &= ~run;
-            } else {
-                mask &= mask - 1u;
-                const int4 t = s_rect[g8 * 32 + j];
-                const int4 tb = s_bbox[g8 * 32 + j];
-                const int f0 = t.x + ((warp - t.x) & 31);
-                const int ncols = ((t.z - f0) >> 5) + 1, rows = t.w - t.y + 1;
-                const unsigned idx = g8 * 32 + (unsigned)j;
-                for (int e = lane; e < ncols * rows; e += 32) {
-                    const int cy = e / ncols, cx = e - cy * ncols;
-                    const int bin = (t.y + cy) * binsX + f0 + (cx << 5);
-                    const unsigned pos = s_pos[bin];
-                    list[pos] = make_uint2(idx, bin_rel_bbox(tb, f0 + (cx << 5), t.y + cy, bshift));
-                    s_pos[bin] = pos + 1;
-                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
 }
@@ -2055,6 +2072,34 @@ k_prims(const PrimParams p)
     }
 }
 
+/* Raw batches of at most 1024 triangles: count, scan and emission in ONE single-CTA kernel; the number of output
+ * triangles (at most 10 per input after clipping) stays on the device: *d_total feeds k_front_small, so the host
+ * never waits. */
+__global__ void __launch_bounds__(1024)
+k_raw_small(const RawArgs a, pfcu_triangle *__restrict__ out, unsigned *__restrict__ d_total, unsigned long long *__restrict__ counters)
+{
+    __shared__ unsigned s_warp[32];
+    const unsigned i = threadIdx.x, lane = i & 31u, warp = i >> 5;
+    pfv_vertex poly[PFV_MAX_POLY];
+    int is3d = 0, face = 0, n = 0; unsigned state = 0;
+    if (i < a.n) n = raw_process(a, i, poly, &is3d, &face, &state);
+    unsigned x = (unsigned)n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if ((int)lane >= o) x += y; }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, w, o); if ((int)lane >= o) w += y; }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    const unsigned off = (warp ? s_warp[warp - 1] : 0u) + x - (unsigned)n;
+    for (int k = 0; k < n; k++) pfv_emit(out + off + k, &poly[0], &poly[k + 1], &poly[k + 2], state, face, is3d);
+    if (i == 1023) { *d_total = off + (unsigned)n; atomicAdd(counters + 3, (unsigned long long)(off + (unsigned)n)); }
+}
+
 /* exclusive scan of up to 1024 items per CTA; sums[blockIdx] = CTA total */
 __global__ void __launch_bounds__(256)
 k_scan_block(const unsigned *__restrict__ in, unsigned *__restrict__ out, unsigned n, unsigned *__restrict__ sums)
@@ -2198,6 +2243,7 @@ int pfcu_init(int device)
         CK(cudaEventCreateWithFlags(&LN.raw_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&LN.vready, cudaEventDisableTiming));
         CK(cudaHostAlloc(&LN.h_total, 2 * sizeof(unsigned), cudaHostAllocDefault));
+        CK(cudaMalloc(&LN.d_total, 64));
     }
     g.cur = &g.lanes[0];
     CK(cudaMalloc(&g.d_counters, 4 * sizeof(unsigned long long)));
@@ -2221,7 +2267,7 @@ void pfcu_shutdown(void)
         if (LN.h_stage) cudaFreeHost(LN.h_stage);
         if (LN.h_states) cudaFreeHost(LN.h_states);
         if (LN.h_total) cudaFreeHost(LN.h_total);
-        cudaFree(LN.d_raw);
+        cudaFree(LN.d_raw); cudaFree(LN.d_total);
         if (LN.vstream) cudaStreamDestroy(LN.vstream);
         if (LN.own_stream) cudaStreamDestroy(LN.stream);
         g.lanes[i] = Lane();
@@ -2591,9 +2637,13 @@ static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
     return mask;
 }
 
-static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const DevState *d_states, uint32_t n, unsigned feature_mask, int single_prog = -1)
+/* n: number of triangles, or - when d_n is given - an upper bound of the count the device holds in *d_n (raw batches
+ * after clipping); n_est then stands in for n where only the batch shape matters. */
+static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const DevState *d_states, uint32_t n, unsigned feature_mask, int single_prog = -1,
+                           const unsigned *d_n = nullptr, uint32_t n_est = 0, int bshift_forced = 0)
 {
     if (n == 0) return PFCU_OK;
+    if (!d_n) n_est = n;
     if (!g.d_rcp) { snprintf(g.err, sizeof g.err, "pfcu_set_approx_tables() has not been called"); return PFCU_ERR_INVALID; }
     int rc;
     /* surfaces sampled as textures that live on another lane: wait for their last write */
@@ -2609,9 +2659,9 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     /* many small triangles per tile: fine bins (one per tile) and the fragment-compacting rasteriser;
        few large ones: coarse bins and the triangle-per-warp-step rasteriser */
     const unsigned nTilesAll = s->tiles_x * s->tiles_y;
-    const bool small_tris = (size_t)n > (size_t)4 * nTilesAll;
+    const bool small_tris = (size_t)n_est > (size_t)4 * nTilesAll;
     static const int force_bshift = getenv("PF_CUDA_BIN_SHIFT") ? atoi(getenv("PF_CUDA_BIN_SHIFT")) : 0;
-    int bshift = force_bshift >= 6 ? force_bshift : (small_tris ? BIN_SHIFT_FINE : BIN_SHIFT_COARSE);
+    int bshift = bshift_forced ? bshift_forced : (force_bshift >= 6 ? force_bshift : (small_tris ? BIN_SHIFT_FINE : BIN_SHIFT_COARSE));
     int binsX, binsY, nb;
     for (;; bshift++) {
         binsX = (int)((s->w + (1u << bshift) - 1) >> bshift); binsY = (int)((s->h + (1u << bshift) - 1) >> bshift);
@@ -2630,10 +2680,11 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         }
         CK(cudaEventRecord(pe[0], LN.stream));
     }
-    if (n <= FRONT_SMALL_MAX && nb <= 3072) {       /* 3072 bin counters + the rectangles fit the 48 KB of static + dynamic shared memory */
+    if (d_n && !(nb <= 3072 && n <= FRONT_SMALL_MAX * FRONT_SMALL_CHUNKS)) { snprintf(g.err, sizeof g.err, "internal: device-side count outside the single-CTA front end"); return PFCU_ERR_INVALID; }
+    if (d_n || (n <= FRONT_SMALL_MAX && nb <= 3072)) {      /* 3072 bin counters + the rectangles fit the 48 KB of static + dynamic shared memory */
         /* small batch: the (triangle, bin) overlap count is bounded by n * nb, no read-back needed */
         if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, (size_t)n * nb))) return rc;
-        k_front_small<<<1, 1024, nb * sizeof(unsigned), LN.stream>>>(d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data,
+        k_front_small<<<1, 1024, nb * sizeof(unsigned), LN.stream>>>(d_tris, d_states, n, d_n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data,
                                                                       g.d_counters, binsX, binsY, bshift, LN.d_bin_start, LN.d_bin_list);
         g.launches += 1;
     } else {
@@ -2717,8 +2768,22 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     for (pfcu_surface *dep : g.deps)
         if (dep != s && dep->lane != s->lane) CK(cudaStreamWaitEvent(g.lanes[dep->lane % g.n_lanes].stream, s->done, 0));
     g.deps.clear();
-    g.submitted += n;
+    if (!d_n) g.submitted += n;              /* otherwise counted on the device (counters[3]) */
     return PFCU_OK;
+}
+
+/* Can a raw batch of n_raw triangles run without the host learning its output count?  Picks the bin size. */
+static int sync_free_bshift(const pfcu_surface *s, uint32_t n_raw)
+{
+    static const int off = getenv("PF_CUDA_RAW_SYNC") ? atoi(getenv("PF_CUDA_RAW_SYNC")) : 0;
+    if (off || n_raw > FRONT_SMALL_MAX) return 0;
+    const size_t bound = (size_t)n_raw * FRONT_SMALL_CHUNKS;
+    const bool small_tris = (size_t)n_raw > (size_t)4 * s->tiles_x * s->tiles_y;
+    for (int bshift = small_tris ? BIN_SHIFT_FINE : BIN_SHIFT_COARSE; bshift <= BIN_SHIFT_COARSE; bshift += 2) {
+        const size_t nb = (size_t)((s->w + (1u << bshift) - 1) >> bshift) * ((s->h + (1u << bshift) - 1) >> bshift);
+        if (nb <= 3072 && bound * nb <= ((size_t)2 << 20)) return bshift;      /* bin list <= 16 MB */
+    }
+    return 0;
 }
 
 /* ---- device vertex stage ---- */
@@ -2812,6 +2877,41 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t b_tris = (size_t)n_tris * sizeof(pfcu_rawtri), b_vp = (size_t)n_vparams * sizeof(pfcu_vparams_lit);
     const size_t b_pow = (size_t)n_pow_tables * PFCU_POW_TABLE_SIZE * sizeof(float);
+    if (const int bshift = sync_free_bshift(s, n_tris)) {
+        /* small batch: one fused count + scan + emit kernel, output count kept on the device, no host wait;
+           everything on the surface's lane */
+        const size_t need = al(b_tris) + al(b_vp) + al(b_pow);
+        if ((rc = grow(&LN.d_raw, &LN.cap_raw, need))) return rc;
+        const uint32_t bound = n_tris * FRONT_SMALL_CHUNKS;
+        if ((rc = grow(&LN.d_tris, &LN.cap_tris, bound))) return rc;
+        if ((rc = grow(&LN.d_states, &LN.cap_states, n_states))) return rc;
+        unsigned char *q = LN.d_raw;
+        RawArgs ra; ra.n = n_tris;
+        ra.tris = (const pfcu_rawtri *)q;
+        CK(cudaMemcpyAsync(q, tris, b_tris, cudaMemcpyHostToDevice, LN.stream));
+        if (PinnedBlock *pb = find_pinned(tris)) { CK(cudaEventRecord(pb->done, LN.stream)); pb->pending = true; }
+        q += al(b_tris);
+        ra.vp = (const pfcu_vparams_lit *)q; CK(cudaMemcpyAsync(q, vparams, b_vp, cudaMemcpyHostToDevice, LN.stream)); q += al(b_vp);
+        ra.pow_tables = (const float *)q; if (b_pow) CK(cudaMemcpyAsync(q, pow_tables, b_pow, cudaMemcpyHostToDevice, LN.stream));
+        g.bytes_h2d += b_tris + b_vp + b_pow + n_states * sizeof(DevState);
+        if (n_states > LN.cap_hstates) {
+            CK(cudaEventSynchronize(LN.states_done));
+            if (LN.h_states) cudaFreeHost(LN.h_states);
+            size_t c = LN.cap_hstates ? LN.cap_hstates : 64; while (c < n_states) c *= 2;
+            CK(cudaHostAlloc(&LN.h_states, c * sizeof(DevState), cudaHostAllocDefault));
+            LN.cap_hstates = c;
+        } else CK(cudaEventSynchronize(LN.states_done));
+        const unsigned mask = convert_states(states, n_states, LN.h_states);
+        CK(cudaMemcpyAsync(LN.d_states, LN.h_states, n_states * sizeof(DevState), cudaMemcpyHostToDevice, LN.stream));
+        CK(cudaEventRecord(LN.states_done, LN.stream));
+        unsigned *d_total = LN.d_total;
+        k_raw_small<<<1, 1024, 0, LN.stream>>>(ra, LN.d_tris, d_total, g.d_counters);
+        g.launches++;
+        CK(cudaEventRecord(LN.raw_done, LN.stream));
+        CK(cudaGetLastError());
+        if (n_out) *n_out = n_tris;             /* the exact count stays on the device (pfcu_get_counters has it) */
+        return launch_pipeline(s, LN.d_tris, LN.d_states, bound, mask, g_last_single_prog, d_total, n_tris, bshift);
+    }
     /* the previous raw batch of this lane must have been emitted before its inputs are overwritten */
     CK(cudaStreamWaitEvent(LN.vstream, LN.raw_done, 0));
     if (al(b_tris) + al(b_vp) + al(b_pow) > LN.cap_raw) { CK(cudaEventSynchronize(LN.raw_done)); }
@@ -3002,7 +3102,7 @@ int pfcu_get_counters(pfcu_counters *out)
     unsigned long long h[4] = { 0, 0, 0, 0 };
     sync_all_lanes();
     CK(cudaMemcpy(h, g.d_counters, sizeof h, cudaMemcpyDeviceToHost));
-    out->triangles_submitted = g.submitted;
+    out->triangles_submitted = g.submitted + h[3];
     out->triangles_rasterised = h[0];
     out->pixels_shaded = h[1];
     out->pixels_depth_failed = h[2];

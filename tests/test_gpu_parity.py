@@ -352,8 +352,8 @@ def test_device_vertex_stage_equals_host_stage(scene, kw):
 
 
 @pytest.mark.parametrize("env", [{"PF_CUDA_LANES": "1"}, {"PF_CUDA_LANES": "8"}, {"PF_CUDA_BATCH_TRIS": "300"},
-                                 {"PF_CUDA_SLICE": "64"}, {"PF_CUDA_SLICE": "32"}, {"PF_CUDA_PIN_HOST": "0"}],
-                         ids=["1-lane", "8-lanes", "tiny-batches", "slice64", "slice32", "no-pin"])
+                                 {"PF_CUDA_SLICE": "64"}, {"PF_CUDA_SLICE": "32"}, {"PF_CUDA_PIN_HOST": "0"}, {"PF_CUDA_RAW_SYNC": "1"}],
+                         ids=["1-lane", "8-lanes", "tiny-batches", "slice64", "slice32", "no-pin", "raw-batches-with-host-count"])
 def test_runtime_knobs_do_not_change_pixels(env, product_scenes):
     """Stream lanes, batch splitting, slice height and host pinning are performance knobs only."""
     for scene, w, h, kw in (("batch", 256, 256, dict(size=5)), ("micro", 160, 120, dict(variant=0x1022a0 | 8 | 1, seed=18, size=40)),
@@ -361,6 +361,19 @@ def test_runtime_knobs_do_not_change_pixels(env, product_scenes):
         ref_c, ref_d, _ = product_scenes.render(scene, w, h, **kw)
         c, d, _, _ = _render_with_env(scene, w, h, env, **kw)
         assert np.array_equal(c, ref_c) and np.array_equal(d.view(np.uint32), ref_d.view(np.uint32)), (scene, env)
+
+
+def test_small_raw_batches_with_clipping_keep_their_count_on_the_device():
+    """Raw batches of <= 1024 triangles run count + scan + emit in one kernel and keep the output count on the device
+    (k_raw_small -> k_front_small); a close-up scene whose triangles are clipped into up to 10 pieces each must
+    give the host vertex stage's pixels and triangle count."""
+    kw = dict(size=48, variant=64)
+    a = _render_with_env("textured", 640, 360, {"PF_CUDA_BATCH_TRIS": "700"}, **kw)
+    b = _render_with_env("textured", 640, 360, {"PF_CUDA_BATCH_TRIS": "700", "PF_CUDA_DEVICE_VERTEX": "0"}, **kw)
+    c = _render_with_env("textured", 640, 360, {"PF_CUDA_BATCH_TRIS": "700", "PF_CUDA_RAW_SYNC": "1"}, **kw)
+    assert a[2] == b[2] == c[2] and a[3] == b[3] == c[3]
+    for x in (b, c):
+        assert np.array_equal(a[0], x[0]) and np.array_equal(a[1].view(np.uint32), x[1].view(np.uint32))
 
 
 def test_two_threads_two_contexts(product_scenes):

@@ -1,0 +1,51 @@
+/* pfcu_surface.cuh - kernels: surface fill / clear / tile packing.
+ * Part of the single translation unit pfcu.cu (included there, in order; not a stand-alone header). */
+
+/* ------------------------------------------------------------------------------------------------ */
+/* kernels: surface utilities                                                                       */
+/* ------------------------------------------------------------------------------------------------ */
+
+__global__ void k_fill(uint32_t *color, float *depth, size_t first, size_t n, int do_color, uint32_t rgba, int do_depth, float z)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < first + n; i += stride) {
+        if (do_color) color[i] = rgba;
+        if (do_depth) depth[i] = z;
+    }
+}
+
+/* vectorised body of a fill: [first4*4, (first4+n4)*4) */
+__global__ void k_fill4(uint4 *color, float4 *depth, size_t first4, size_t n4, int do_color, uint32_t rgba, int do_depth, float z)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const uint4 cv = make_uint4(rgba, rgba, rgba, rgba);
+    const float4 dv = make_float4(z, z, z, z);
+    for (size_t i = first4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < first4 + n4; i += stride) {
+        if (do_color) color[i] = cv;
+        if (do_depth) depth[i] = dv;
+    }
+}
+
+/* tail of the reference's pfClear: pixels [aligned, size) copy pixel 0 (context.c:710-713) */
+__global__ void k_clear_tail(uint32_t *color, float *depth, unsigned aligned, unsigned size, int do_color, int do_depth)
+{
+    const unsigned i = aligned + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < size) { if (do_color) color[i] = color[0]; if (do_depth) depth[i] = depth[0]; }
+}
+
+__global__ void k_pack_tiles(uint32_t *color, float *depth, int W, int H, int tilesX, unsigned nTiles,
+                             unsigned rank, unsigned world, int with_depth, uint32_t *staging, int unpack)
+{
+    const unsigned tile = rank + blockIdx.x * world;
+    if (tile >= nTiles) return;
+    const int X0 = (tile % tilesX) * TILE, Y0 = (tile / tilesX) * TILE;
+    uint32_t *sc = staging + (size_t)blockIdx.x * TILE_PIX * (with_depth ? 2 : 1);
+    uint32_t *sd = sc + TILE_PIX;
+    for (int k = threadIdx.x; k < TILE_PIX; k += blockDim.x) {
+        const int x = X0 + (k & (TILE - 1)), y = Y0 + (k >> 6);
+        if (x >= W || y >= H) continue;
+        const size_t gi = (size_t)y * W + x;
+        if (unpack) { color[gi] = sc[k]; if (with_depth) depth[gi] = __uint_as_float(sd[k]); }
+        else { sc[k] = color[gi]; if (with_depth) sd[k] = __float_as_uint(depth[gi]); }
+    }
+}

@@ -48,6 +48,12 @@ PF_API void pfxCaptureEnd(const void **states, PFuint *nStates, const void **tri
 /* Large PF_TRIANGLES vertex-array draws run their vertex stage (transform, clip, project) on the GPU
  * (default on; PF_CUDA_DEVICE_VERTEX=0 or this call turn it off for the current context). */
 PF_API void pfxEnableDeviceVertexStage(PFboolean on);
+/* Diagnostics for the Gouraud specular tables the device vertex stage uses instead of powf (pfcu.h,
+ * PFCU_POW_TABLE_SIZE): builds (or finds) the table of `shininess` for the current context and compares it with
+ * (PFubyte)(255 * powf(x, shininess)) of this host's libm on `samples` pseudo-random x in [0, 1.000001] (the dot product of two normalised vectors) plus both
+ * neighbours of every threshold.  Returns the number of mismatches, -1 when the shininess is not tabulated (the
+ * host then lights those vertices itself), -2 without a current context. */
+PF_API int pfxSpecularTableCheck(PFfloat shininess, PFuint samples);
 /* The pfcu_surface* behind the current target. */
 PF_API void *pfxGetSurfaceHandle(void);
 PF_API const char *pfxBackendName(void);

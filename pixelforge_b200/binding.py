@@ -137,6 +137,8 @@ VERTEX_DTYPE = np.dtype([("sx", "<f4"), ("sy", "<f4"), ("zinv", "<f4"), ("u", "<
                          ("px", "<f4"), ("py", "<f4"), ("pz", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
                          ("rgba", "<u4")])
 TRIANGLE_DTYPE = np.dtype([("v", VERTEX_DTYPE, (3,)), ("state", "<u4"), ("face", "u1"), ("is3d", "u1"), ("pad", "<u2")])
+PRIM_DTYPE = np.dtype([("x1", "<f4"), ("y1", "<f4"), ("x2", "<f4"), ("y2", "<f4"), ("z1", "<f4"), ("z2", "<f4"), ("c1", "<u4"), ("c2", "<u4"),
+                       ("size", "<f4"), ("kind", "u1"), ("flags", "u1"), ("blend_mode", "u1"), ("depth_func", "u1")])      # pfcu_prim, 40 B
 LIGHT_DTYPE = np.dtype([("position", "<f4", (3,)), ("direction", "<f4", (3,)), ("inner_cutoff", "<f4"),
                         ("outer_cutoff", "<f4"), ("att_constant", "<f4"), ("att_linear", "<f4"),
                         ("att_quadratic", "<f4"), ("ambient", "<u4"), ("diffuse", "<u4"), ("specular", "<u4")])
@@ -176,7 +178,7 @@ PFCU_SYMBOLS = [
 
 PFX_SYMBOLS = ["pfxSetSyncMode", "pfxFlush", "pfxFinish", "pfxGetCounters", "pfxResetCounters", "pfxSetTileOwner",
                "pfxGetDeviceColor", "pfxGetDeviceDepth", "pfxReadDepth", "pfxCaptureBegin", "pfxCaptureEnd",
-               "pfxGetSurfaceHandle", "pfxBackendName", "pfxEnableDeviceVertexStage"]
+               "pfxGetSurfaceHandle", "pfxBackendName", "pfxEnableDeviceVertexStage", "pfxSpecularTableCheck"]
 
 
 class PfcuLib:
@@ -206,7 +208,7 @@ class PfcuLib:
             "pfcu_surface_unpack_tiles": (C.c_int, [vp, u32, u32, C.c_int, vp]),
             "pfcu_texture_create": (vp, [vp, u32, u32, C.c_int]), "pfcu_texture_from_surface": (vp, [vp]),
             "pfcu_texture_update": (C.c_int, [vp, vp]), "pfcu_texture_destroy": (None, [vp]),
-            "pfcu_submit": (C.c_int, [vp, vp, u32, vp, u32]), "pfcu_batch_upload": (vp, [vp, u32, vp, u32]),
+            "pfcu_submit": (C.c_int, [vp, vp, u32, vp, u32]), "pfcu_submit_prims": (C.c_int, [vp, vp, u32]), "pfcu_batch_upload": (vp, [vp, u32, vp, u32]),
             "pfcu_batch_submit": (C.c_int, [vp, vp]), "pfcu_batch_destroy": (None, [vp]),
             "pfcu_fence": (C.c_int, []), "pfcu_finish": (C.c_int, []), "pfcu_get_counters": (C.c_int, [C.POINTER(Counters)]),
             "pfcu_reset_counters": (None, []),
@@ -267,8 +269,9 @@ class PfcuLib:
         tris = np.frombuffer((C.c_char * (nt.value * TRIANGLE_DTYPE.itemsize)).from_address(pt.value), dtype=TRIANGLE_DTYPE).copy() if nt.value else np.zeros(0, TRIANGLE_DTYPE)
         return states, tris
 
-    def render_stream(self, width, height, states, tris, color0=None, depth0=None, clear=None, tile_owner=None):
-        """Rasterise a triangle stream into a fresh surface; returns (color u32[h,w], depth f32[h,w])."""
+    def render_stream(self, width, height, states, tris, color0=None, depth0=None, clear=None, tile_owner=None, prims=None):
+        """Rasterise a triangle stream (then, optionally, a stream of points / lines) into a fresh surface;
+        returns (color u32[h,w], depth f32[h,w])."""
         L = self.lib
         s = L.pfcu_surface_create(width, height)
         if not s:
@@ -285,6 +288,10 @@ class PfcuLib:
             tris = np.ascontiguousarray(tris)
             assert states.dtype == STATE_DTYPE and tris.dtype == TRIANGLE_DTYPE
             self.check(L.pfcu_submit(s, states.ctypes.data, len(states), tris.ctypes.data, len(tris)), "pfcu_submit")
+            if prims is not None and len(prims):
+                prims = np.ascontiguousarray(prims)
+                assert prims.dtype == PRIM_DTYPE and prims.dtype.itemsize == 40
+                self.check(L.pfcu_submit_prims(s, prims.ctypes.data, len(prims)), "pfcu_submit_prims")
             self.check(L.pfcu_finish(), "finish")
             out_c = np.zeros((height, width), np.uint32)
             out_d = np.zeros((height, width), np.float32)

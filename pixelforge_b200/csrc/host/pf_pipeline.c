@@ -13,6 +13,7 @@
 #include "pf_internal.h"
 #include "pf_math.h"
 #include "../pf_prims.h"
+#include "pfx.h"
 
 #include <stdio.h>
 #include <math.h>
@@ -315,6 +316,8 @@ static inline void emit_triangle(pf_ctx *c, int face, int is3d, const pf_vertex 
 
 /* Specular tables for the device (pfcu.h, PFCU_POW_TABLE_SIZE): T[k-1] = the smallest float x >= 0 with
  * (int)(255 * powf(x, shininess)) >= k, found by bisection over float bit patterns with THIS libm's powf.
+ * The device sees x = max(N.H, 0) of two normalised vectors, i.e. x <= 1 + a few ulp; the table is exact up to the
+ * input where the result would reach 257 (x > 1.00001 even for shininess 1024), beyond which (PFubyte) wraps again.
  * Valid when that function is non-decreasing in x, which holds comfortably for shininess >= 1 (neighbouring
  * floats move the result by shininess * 2^-24 relative, far above powf's error) and is spot-checked below.
  * Returns the table index, or -1 when the shininess cannot be tabulated (then the host lights the vertices). */
@@ -353,7 +356,7 @@ static int pow_table_index(pf_ctx *c, float shininess)
     uint32_t rs = 0x9e3779b9u ^ key;
     for (int i = 0; i < 4096; i++) {
         rs = rs * 1664525u + 1013904223u;
-        const float x = (float)(rs >> 8) * (1.0f / 16777216.0f) * ((i & 15) ? 1.0f : 1.0001f);
+        const float x = (float)(rs >> 8) * (1.0f / 16777216.0f) * ((i & 15) ? 1.0f : 1.000001f);
         int lo = 0, hi = PFCU_POW_TABLE_SIZE;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (T[mid] <= x) lo = mid + 1; else hi = mid; }
         if ((uint8_t)lo != (uint8_t)spec_of(x, shininess)) return -1;
@@ -374,6 +377,31 @@ void pfh_vstage_params(const pf_ctx *c, pfv_params *p)
     p->lighting = ((c->state & PF_LIGHTING) && lights_active(c)) ? 1u : 0u;
     p->diffuse[0] = color_dword(c->material[0].diffuse);
     p->diffuse[1] = color_dword(c->material[1].diffuse);
+}
+
+int pfxSpecularTableCheck(PFfloat shininess, PFuint samples)
+{
+    pf_ctx *c = pf_cur;
+    if (!c) return -2;
+    const int ti = pow_table_index(c, shininess);
+    if (ti < 0) return -1;
+    const float *T = c->pow_tables + (size_t)ti * PFCU_POW_TABLE_SIZE;
+    int bad = 0;
+    uint32_t rs = 0x1234567u;
+    for (PFuint i = 0; i < samples + 3u * PFCU_POW_TABLE_SIZE; i++) {
+        float x;
+        if (i < samples) { rs = rs * 1664525u + 1013904223u; x = (float)(rs >> 8) * (1.0f / 16777216.0f) * 1.000001f; }
+        else {              /* the threshold itself and its two neighbours */
+            uint32_t u; memcpy(&u, &T[(i - samples) / 3u], 4);
+            const uint32_t k = (i - samples) % 3u;
+            u = k == 0 ? (u ? u - 1u : u) : (k == 2 ? u + 1u : u);
+            memcpy(&x, &u, 4);
+        }
+        int lo = 0, hi = PFCU_POW_TABLE_SIZE;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (T[mid] <= x) lo = mid + 1; else hi = mid; }
+        if ((uint8_t)lo != (uint8_t)spec_of(x, shininess)) bad++;
+    }
+    return bad;
 }
 
 static void fill_vparams_lit(pf_ctx *c, pfcu_vparams_lit *e)

@@ -21,6 +21,12 @@ def _stream(w, h, n, seed):
     return random_stream(np.random.default_rng(seed), w, h, n, 1 | 2 | 16, big=True, n_states=3)
 
 
+def _prims(w, h):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_parity import random_prims
+    return random_prims(np.random.default_rng(77), w, h, 200, 10)
+
+
 def _worker(rank, world, port, w, h, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
@@ -35,6 +41,8 @@ def _worker(rank, world, port, w, h, out_path):
     L.pfcu_surface_fill(s, 1, 0xFF102030, 1, np.finfo(np.float32).max)
     L.pfcu_surface_set_tile_owner(s, rank, world)
     lib.check(L.pfcu_submit(s, states.ctypes.data, len(states), tris.ctypes.data, len(tris)))
+    prims = _prims(w, h)
+    lib.check(L.pfcu_submit_prims(s, prims.ctypes.data, len(prims)))
     moved = gather_tiles(torch, dist, lib, s, w, h, rank, world, with_depth=True, device="cpu")
     if rank == 0:
         c = np.zeros((h, w), np.uint32); d = np.zeros((h, w), np.float32)
@@ -54,7 +62,7 @@ def test_tile_split_gather_gloo(world, built_libraries, tmp_path):
     got = np.load(out)
     lib = load_pfcu("oracle"); lib.init()
     states, tris = _stream(w, h, 300, 5)
-    full_c, full_d = lib.render_stream(w, h, states, tris, color0=np.full((h, w), 0xFF102030, np.uint32))
+    full_c, full_d = lib.render_stream(w, h, states, tris, color0=np.full((h, w), 0xFF102030, np.uint32), prims=_prims(w, h))
     assert np.array_equal(got["color"], full_c)
     assert np.array_equal(got["depth"].view(np.uint32), full_d.view(np.uint32))
     tiles = ((w + 63) // 64) * ((h + 63) // 64)

@@ -45,7 +45,7 @@ __device__ __forceinline__ float rsqrt_x86(float x)
 {
     const unsigned u = __float_as_uint(x), s = u & 0x80000000u, e = (u >> 23) & 255u, m = u & 0x7fffffu;
     const unsigned odd = (e & 1u) ^ 1u;
-    const int half = ((int)e - 127 - (int)odd) / 2;
+    const int half = ((int)e - 127 - (int)odd) >> 1;       /* even by construction */
     const unsigned tv = __ldg(c_rsq_tab + ((odd << c_rsq_bits) | (m >> c_rsq_shift)));
     unsigned r = ((unsigned)((int)(tv >> 23) - half) << 23) | (tv & 0x7fffffu);
     if (e == 255u) r = 0u;
@@ -147,13 +147,16 @@ __device__ __forceinline__ unsigned mul_color(unsigned a, unsigned b)
                  (CHN(a, 2) * CHN(b, 2)) >> 8, (CHN(a, 3) * CHN(b, 3)) >> 8);
 }
 
-__device__ __forceinline__ unsigned color_lerp(unsigned a, unsigned b, float t)   /* color.h:137-144 (Q7 fixed) */
+/* color.h:137-144 (Q7 fixed), for t in [0, 1] (the samplers clamp fx, fy; NaN becomes 0).  A and B are in [0, 1] and
+ * representable, and rounding is monotone, so A + t*(B - A) stays between A and B: the clamp of pfiColorPackFromF
+ * (quant) is the identity here and is left out. */
+__device__ __forceinline__ unsigned color_lerp(unsigned a, unsigned b, float t)
 {
     unsigned p = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const float A = FM(__int2float_rn(CHN(a, i)), INV255), B = FM(__int2float_rn(CHN(b, i)), INV255);
-        p |= quant(FA(A, FM(t, FS(B, A)))) << (8 * i);
+        p |= (unsigned)__float2int_rn(FM(FA(A, FM(t, FS(B, A))), 255.0f)) << (8 * i);
     }
     return p;
 }

@@ -29,7 +29,8 @@
 struct FragCtx {
     unsigned col_base;                  /* shared-window byte address of this warp's colour region     */
     unsigned rcp_base;                  /* ... of the shared RCPPS table                                */
-    int rcp_shift; bool rcp_shared;
+    int rcp_shift; bool rcp_shared;     /* rcp_shared: table copy in shared memory at rcp_base                  */
+    bool rcp_global;                    /* else, when the table has <= 2^11 entries: fast path through L1         */
     int RX0, RY0, RX1, RY1;             /* the region on the surface, inclusive                         */
     unsigned shaded, covered;
     unsigned tri_base;                  /* shared-window byte address of this warp's triangle staging   */
@@ -59,19 +60,19 @@ template <int OFF> __device__ __forceinline__ void sts_f32_off(unsigned addr, fl
 __device__ __forceinline__ float rcp_tab(const FragCtx &t, float x)
 {
     const unsigned u = __float_as_uint(x), E = u & 0x7f800000u;
-    if (!t.rcp_shared || E - 0x00800000u >= 0x7e000000u) return rcp_x86(x);
-    const unsigned tv = lds_u32(t.rcp_base + (((u & 0x007fffffu) >> t.rcp_shift) << 2));
+    if (!(t.rcp_shared || t.rcp_global) || E - 0x00800000u >= 0x7e000000u) return rcp_x86(x);
+    const unsigned idx = (u & 0x007fffffu) >> t.rcp_shift;
+    const unsigned tv = t.rcp_shared ? lds_u32(t.rcp_base + (idx << 2)) : __ldg(c_rcp_tab + idx);
     return __uint_as_float((tv + 0x3f800000u - E) | (u & 0x80000000u));
 }
 
 /* One group of <= 32 triangles in one state (lane l holds triangle ti with nn candidate pixels in this warp's
  * region; nn == 0 for lanes outside the group).  pk = cx0 | cy0<<4 | cw<<8 | ceil(1024/cw)<<12 describes the
  * clipped rectangle (region-local).  lo is a lane that is known to hold a valid triangle. */
-template <int TEXM, int BLENDM, bool PHONG, int NW>
+template <int TEXM, int BLENDM, bool PHONG, int DEPTH_OFF>
 __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const unsigned pk, const int lo,
                                          const DevState *st, const unsigned flags, const unsigned zmask, const int blend_mode, const TexRegs &tex)
 {
-    constexpr int DEPTH_OFF = NW * FRAG_RSTRIDE * 4;
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     unsigned I = nn;                                                /* inclusive scan of the candidate counts */
@@ -188,6 +189,113 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const un
     }
 }
 
+/* per-warp shading state that persists across groups: the state snapshot in force */
+struct GroupState {
+    unsigned cur_state; const DevState *st; unsigned flags, zmask; int blend_mode, prog; TexRegs tex;
+    __device__ __forceinline__ void reset()
+    {
+        cur_state = 0xffffffffu; st = nullptr; flags = 0; zmask = 8u; blend_mode = 0; prog = 0;
+        tex.base = nullptr; tex.tw = tex.th = tex.total = 0; tex.wm1 = tex.hm1 = 0.0f; tex.fmt = tex.wrap = tex.filter = 0;
+    }
+};
+
+/* One group: lane l < cnt holds triangle ti.  Stages the constants, clips to the region, splits the group into runs
+ * of one state and shades them (frag_run). */
+template <bool HAS_PHONG, int DEPTH_OFF>
+__device__ __forceinline__ void frag_group(FragCtx &t, GroupState &G, const int4 *__restrict__ bbox_, const TriSetup *__restrict__ setup_,
+                                           const TriData *__restrict__ data_, const DevState *__restrict__ states_,
+                                           const unsigned ti, const bool have, const unsigned cnt)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned &cur_state = G.cur_state; const DevState *&st = G.st; unsigned &flags = G.flags, &zmask = G.zmask;
+    int &blend_mode = G.blend_mode, &prog = G.prog; TexRegs &tex = G.tex;
+    unsigned state = 0xffffffffu, nn0 = 0, pk = 0;
+    if (have) {
+        /* stage this triangle's constants (every load is independent: one memory round trip per group) */
+        const int4 b = __ldg(bbox_ + ti);
+        const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(setup_ + ti));
+        const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(setup_ + ti) + 1);
+        const uint4 s2 = __ldg(reinterpret_cast<const uint4 *>(setup_ + ti) + 2);
+        const uint4 *da = reinterpret_cast<const uint4 *>(data_ + ti);
+        const uint4 a0 = __ldg(da), a1 = __ldg(da + 1), a2 = __ldg(da + 2), a3 = __ldg(da + 3);
+        state = a0.w & 0xffffffu;
+        const int ox = wsub(t.RX0, b.x), oy = wsub(t.RY0, b.y);
+        const unsigned E1 = (unsigned)wadd(wadd((int)s0.x, wmul(oy, (int)s1.y)), wmul(ox, (int)s1.x));
+        const unsigned E2 = (unsigned)wadd(wadd((int)s0.y, wmul(oy, (int)s1.w)), wmul(ox, (int)s1.z));
+        const unsigned E3 = (unsigned)wadd(wadd((int)s0.z, wmul(oy, (int)s2.y)), wmul(ox, (int)s2.x));
+        sts_tri(t.tri_base, 0, lane, make_uint4(E1, E2, E3, s0.w));
+        sts_tri(t.tri_base, 1, lane, s1);
+        sts_tri(t.tri_base, 2, lane, make_uint4(s2.x, s2.y, a0.x, a0.y));
+        sts_tri(t.tri_base, 3, lane, make_uint4(a0.z, a0.w, a1.x, a1.y));
+        sts_tri(t.tri_base, 4, lane, make_uint4(a1.z, a2.x, a2.y, a2.z));
+        sts_tri(t.tri_base, 5, lane, make_uint4(a3.x, a3.y, a3.z, 0u));
+        if (HAS_PHONG) {
+            const uint4 qx = __ldg(da + 4), qy = __ldg(da + 5), qz = __ldg(da + 6);
+            const uint4 nx = __ldg(da + 7), ny = __ldg(da + 8), nz = __ldg(da + 9);
+            sts_tri(t.tri_base, 6, lane, make_uint4(qx.x, qx.y, qx.z, qy.x));
+            sts_tri(t.tri_base, 7, lane, make_uint4(qy.y, qy.z, qz.x, qz.y));
+            sts_tri(t.tri_base, 8, lane, make_uint4(qz.z, nx.x, nx.y, nx.z));
+            sts_tri(t.tri_base, 9, lane, make_uint4(ny.x, ny.y, ny.z, nz.x));
+            sts_tri(t.tri_base, 10, lane, make_uint4(nz.y, nz.z, 0u, 0u));
+        }
+        const int cx0 = max(b.x, t.RX0) - t.RX0, cx1 = min(b.z - 1, t.RX1) - t.RX0;
+        const int cy0 = max(b.y, t.RY0) - t.RY0, cy1 = min(b.w, t.RY1) - t.RY0;
+        const int cw = cx1 - cx0 + 1, ch = cy1 - cy0 + 1;
+        if (cw > 0 && ch > 0) {
+            nn0 = (unsigned)(cw * ch);
+            pk = (unsigned)cx0 | ((unsigned)cy0 << 4) | ((unsigned)cw << 8) | (((1024u + (unsigned)cw - 1u) / (unsigned)cw) << 12);
+            if (s2.z & TF_SAFE) {       /* an edge function negative over the whole clipped rectangle: nothing to shade */
+                /* evaluated mod 2^32 from the region origin; the corner itself lies inside the bbox, where
+                   TF_SAFE guarantees the true value fits */
+                const int m1 = wadd((int)E1, wadd(wmul(((int)s1.x > 0) ? cx1 : cx0, (int)s1.x), wmul(((int)s1.y > 0) ? cy1 : cy0, (int)s1.y)));
+                const int m2 = wadd((int)E2, wadd(wmul(((int)s1.z > 0) ? cx1 : cx0, (int)s1.z), wmul(((int)s1.w > 0) ? cy1 : cy0, (int)s1.w)));
+                const int m3 = wadd((int)E3, wadd(wmul(((int)s2.x > 0) ? cx1 : cx0, (int)s2.x), wmul(((int)s2.y > 0) ? cy1 : cy0, (int)s2.y)));
+                if ((m1 | m2 | m3) < 0) nn0 = 0;
+            }
+        }
+    }
+    __syncwarp();
+    unsigned lo = 0;
+    while (lo < cnt) {
+        const unsigned sid = __shfl_sync(0xffffffffu, state, (int)lo);
+        const unsigned diff = __ballot_sync(0xffffffffu, have && (unsigned)lane >= lo && state != sid);
+        const unsigned hi = diff ? (unsigned)(__ffs(diff) - 1) : cnt;
+        const unsigned nn = ((unsigned)lane >= lo && (unsigned)lane < hi) ? nn0 : 0u;
+        if (sid != cur_state) {
+            cur_state = sid;
+            st = states_ + cur_state;
+            flags = st->flags; blend_mode = st->blend_mode;
+            zmask = (flags & PFCU_ST_DEPTH_TEST) ? depth_mask(st->depth_func) : 8u;
+            int texm = 0;
+            if (flags & PFCU_ST_TEXTURE) {
+                tex.base = st->tex; tex.tw = st->tw; tex.th = st->th; tex.total = st->tw * st->th;
+                tex.wm1 = __uint2float_rn(st->tw - 1u); tex.hm1 = __uint2float_rn(st->th - 1u);
+                tex.fmt = st->tfmt; tex.wrap = st->tex_wrap; tex.filter = st->tex_filter;
+                texm = (tex.fmt == PFCU_TEX_RGBA8 && tex.wrap == 0 && tex.filter == 0) ? 1 : 2;
+            }
+            const int blendm = !(flags & PFCU_ST_BLEND) ? 0 : (blend_mode == 1 ? 1 : (blend_mode == 2 ? 2 : 3));
+            prog = texm * 4 + blendm;
+            if (HAS_PHONG && (flags & PFCU_ST_PHONG)) prog = 12;
+        }
+        switch (prog) {
+        case 0:  frag_run<0, 0, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        case 1:  frag_run<0, 1, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        case 2:  frag_run<0, 2, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        case 3:  frag_run<0, 3, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        case 4:  frag_run<1, 0, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        case 5:  frag_run<1, 1, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        case 6:  frag_run<1, 2, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        case 7:  frag_run<1, 3, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        case 8:  frag_run<2, 0, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        case 9:  frag_run<2, 1, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        case 10: frag_run<2, 2, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        case 11: frag_run<2, 3, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        default: if (HAS_PHONG) frag_run<2, 3, true, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        }
+        lo = hi;
+    }
+}
+
 template <bool HAS_PHONG, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
 k_raster_frag(const RasterParams p)
@@ -220,7 +328,7 @@ k_raster_frag(const RasterParams p)
 
     FragCtx t;
     t.rcp_shift = c_rcp_shift;
-    t.rcp_shared = t.rcp_shift >= 23 - RCP_SMEM_BITS;
+    t.rcp_shared = t.rcp_shift >= 23 - RCP_SMEM_BITS; t.rcp_global = false;
     /* the RCPPS table and (full slices) the colour/depth slice arrive asynchronously while the queue is filled */
     if (t.rcp_shared) {
         const unsigned dst = (unsigned)__cvta_generic_to_shared(s_rcp);
@@ -305,10 +413,7 @@ k_raster_frag(const RasterParams p)
         }
 
         /* ---- every warp gathers the queue entries of its region, 32 at a time, and runs them ---- */
-        unsigned cur_state = 0xffffffffu;
-        const DevState *st = nullptr;
-        unsigned flags = 0, zmask = 8u; int blend_mode = 0, prog = 0;
-        TexRegs tex; tex.base = nullptr; tex.tw = tex.th = tex.total = 0; tex.wm1 = tex.hm1 = 0.0f; tex.fmt = tex.wrap = tex.filter = 0;
+        GroupState G; G.reset();
         unsigned cnt = 0;
         const unsigned ltm = (1u << lane) - 1u;
         for (unsigned q0 = 0; q0 < qn; q0 += 32) {
@@ -330,91 +435,7 @@ k_raster_frag(const RasterParams p)
                     const bool have = (unsigned)lane < cnt;
                     const unsigned ti = have ? s_group[warp][lane] : 0u;
                     __syncwarp();
-                    unsigned state = 0xffffffffu, nn0 = 0, pk = 0;
-                    if (have) {
-                        /* stage this triangle's constants (every load is independent: one memory round trip per group) */
-                        const int4 b = __ldg(p.bbox + ti);
-                        const uint4 s0 = __ldg(reinterpret_cast<const uint4 *>(p.setup + ti));
-                        const uint4 s1 = __ldg(reinterpret_cast<const uint4 *>(p.setup + ti) + 1);
-                        const uint4 s2 = __ldg(reinterpret_cast<const uint4 *>(p.setup + ti) + 2);
-                        const uint4 *da = reinterpret_cast<const uint4 *>(p.data + ti);
-                        const uint4 a0 = __ldg(da), a1 = __ldg(da + 1), a2 = __ldg(da + 2), a3 = __ldg(da + 3);
-                        state = a0.w & 0xffffffu;
-                        const int ox = wsub(t.RX0, b.x), oy = wsub(t.RY0, b.y);
-                        const unsigned E1 = (unsigned)wadd(wadd((int)s0.x, wmul(oy, (int)s1.y)), wmul(ox, (int)s1.x));
-                        const unsigned E2 = (unsigned)wadd(wadd((int)s0.y, wmul(oy, (int)s1.w)), wmul(ox, (int)s1.z));
-                        const unsigned E3 = (unsigned)wadd(wadd((int)s0.z, wmul(oy, (int)s2.y)), wmul(ox, (int)s2.x));
-                        sts_tri(t.tri_base, 0, lane, make_uint4(E1, E2, E3, s0.w));
-                        sts_tri(t.tri_base, 1, lane, s1);
-                        sts_tri(t.tri_base, 2, lane, make_uint4(s2.x, s2.y, a0.x, a0.y));
-                        sts_tri(t.tri_base, 3, lane, make_uint4(a0.z, a0.w, a1.x, a1.y));
-                        sts_tri(t.tri_base, 4, lane, make_uint4(a1.z, a2.x, a2.y, a2.z));
-                        sts_tri(t.tri_base, 5, lane, make_uint4(a3.x, a3.y, a3.z, 0u));
-                        if (HAS_PHONG) {
-                            const uint4 qx = __ldg(da + 4), qy = __ldg(da + 5), qz = __ldg(da + 6);
-                            const uint4 nx = __ldg(da + 7), ny = __ldg(da + 8), nz = __ldg(da + 9);
-                            sts_tri(t.tri_base, 6, lane, make_uint4(qx.x, qx.y, qx.z, qy.x));
-                            sts_tri(t.tri_base, 7, lane, make_uint4(qy.y, qy.z, qz.x, qz.y));
-                            sts_tri(t.tri_base, 8, lane, make_uint4(qz.z, nx.x, nx.y, nx.z));
-                            sts_tri(t.tri_base, 9, lane, make_uint4(ny.x, ny.y, ny.z, nz.x));
-                            sts_tri(t.tri_base, 10, lane, make_uint4(nz.y, nz.z, 0u, 0u));
-                        }
-                        const int cx0 = max(b.x, t.RX0) - t.RX0, cx1 = min(b.z - 1, t.RX1) - t.RX0;
-                        const int cy0 = max(b.y, t.RY0) - t.RY0, cy1 = min(b.w, t.RY1) - t.RY0;
-                        const int cw = cx1 - cx0 + 1, ch = cy1 - cy0 + 1;
-                        if (cw > 0 && ch > 0) {
-                            nn0 = (unsigned)(cw * ch);
-                            pk = (unsigned)cx0 | ((unsigned)cy0 << 4) | ((unsigned)cw << 8) | (((1024u + (unsigned)cw - 1u) / (unsigned)cw) << 12);
-                            if (s2.z & TF_SAFE) {       /* an edge function negative over the whole clipped rectangle: nothing to shade */
-                                /* evaluated mod 2^32 from the region origin; the corner itself lies inside the bbox, where
-                                   TF_SAFE guarantees the true value fits */
-                                const int m1 = wadd((int)E1, wadd(wmul(((int)s1.x > 0) ? cx1 : cx0, (int)s1.x), wmul(((int)s1.y > 0) ? cy1 : cy0, (int)s1.y)));
-                                const int m2 = wadd((int)E2, wadd(wmul(((int)s1.z > 0) ? cx1 : cx0, (int)s1.z), wmul(((int)s1.w > 0) ? cy1 : cy0, (int)s1.w)));
-                                const int m3 = wadd((int)E3, wadd(wmul(((int)s2.x > 0) ? cx1 : cx0, (int)s2.x), wmul(((int)s2.y > 0) ? cy1 : cy0, (int)s2.y)));
-                                if ((m1 | m2 | m3) < 0) nn0 = 0;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    unsigned lo = 0;
-                    while (lo < cnt) {
-                        const unsigned sid = __shfl_sync(0xffffffffu, state, (int)lo);
-                        const unsigned diff = __ballot_sync(0xffffffffu, have && (unsigned)lane >= lo && state != sid);
-                        const unsigned hi = diff ? (unsigned)(__ffs(diff) - 1) : cnt;
-                        const unsigned nn = ((unsigned)lane >= lo && (unsigned)lane < hi) ? nn0 : 0u;
-                        if (sid != cur_state) {
-                            cur_state = sid;
-                            st = p.states + cur_state;
-                            flags = st->flags; blend_mode = st->blend_mode;
-                            zmask = (flags & PFCU_ST_DEPTH_TEST) ? depth_mask(st->depth_func) : 8u;
-                            int texm = 0;
-                            if (flags & PFCU_ST_TEXTURE) {
-                                tex.base = st->tex; tex.tw = st->tw; tex.th = st->th; tex.total = st->tw * st->th;
-                                tex.wm1 = __uint2float_rn(st->tw - 1u); tex.hm1 = __uint2float_rn(st->th - 1u);
-                                tex.fmt = st->tfmt; tex.wrap = st->tex_wrap; tex.filter = st->tex_filter;
-                                texm = (tex.fmt == PFCU_TEX_RGBA8 && tex.wrap == 0 && tex.filter == 0) ? 1 : 2;
-                            }
-                            const int blendm = !(flags & PFCU_ST_BLEND) ? 0 : (blend_mode == 1 ? 1 : (blend_mode == 2 ? 2 : 3));
-                            prog = texm * 4 + blendm;
-                            if (HAS_PHONG && (flags & PFCU_ST_PHONG)) prog = 12;
-                        }
-                        switch (prog) {
-                        case 0:  frag_run<0, 0, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 1:  frag_run<0, 1, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 2:  frag_run<0, 2, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 3:  frag_run<0, 3, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 4:  frag_run<1, 0, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 5:  frag_run<1, 1, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 6:  frag_run<1, 2, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 7:  frag_run<1, 3, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 8:  frag_run<2, 0, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 9:  frag_run<2, 1, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 10: frag_run<2, 2, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        case 11: frag_run<2, 3, false, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        default: if (HAS_PHONG) frag_run<2, 3, true, NW>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-                        }
-                        lo = hi;
-                    }
+                    frag_group<HAS_PHONG, NW * FRAG_RSTRIDE * 4>(t, G, p.bbox, p.setup, p.data, p.states, ti, have, cnt);
                     cnt = 0;
                 }
             } while (rel);

@@ -56,7 +56,7 @@
 #define RASTER_THREADS 256
 #define QUEUE_CAP   1024            /* triangle indices buffered per tile between raster passes      */
 #define SETUP_THREADS 256
-#define BIN_BATCH   1024            /* triangles per binning CTA                                     */
+#define BIN_BATCH   1024            /* triangles per binning CTA (256 for mid-sized batches, see launch_pipeline) */
 #define MAX_BINS    12000           /* bin counters live in dynamic shared memory (48 KB); 7680x4320 in 64 px bins = 8160 */
 
 #define TF_VALID    1u              /* survived cull and has a non-empty bbox on the surface         */
@@ -674,7 +674,10 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         if (nb <= MAX_BINS) break;
     }
     if (bshift > 8) { snprintf(g.err, sizeof g.err, "surface too large for the binner (%u x %u)", s->w, s->h); return PFCU_ERR_INVALID; }
-    const unsigned nBatches = (n + BIN_BATCH - 1) / BIN_BATCH;
+    /* one row of per-bin counters per binning CTA: 256 triangles per CTA give the order-preserving fill four times the
+       CTAs (its per-CTA work is a serial chain) as long as the counter matrix stays small */
+    const unsigned bin_batch = ((size_t)((n + 255u) / 256u) * nb <= ((size_t)1 << 20)) ? 256u : BIN_BATCH;
+    const unsigned nBatches = (n + bin_batch - 1) / bin_batch;
     if ((rc = grow(&LN.d_bin_counts, &LN.cap_bin_counts, (size_t)nBatches * nb))) return rc;
 
     cudaEvent_t pe[3] = { nullptr, nullptr, nullptr };
@@ -695,7 +698,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     } else {
         k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, LN.stream>>>(
             d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data, g.d_counters);
-        k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, binsX, binsY, bshift, LN.d_bin_counts);
+        k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, bin_batch, binsX, binsY, bshift, LN.d_bin_counts);
         unsigned *d_totals = LN.d_bin_start + (MAX_BINS + 2);
         k_bin_scan<<<(nb + 31) / 32, 1024, 0, LN.stream>>>(LN.d_bin_counts, (int)nBatches, nb, d_totals);
         k_bin_starts<<<1, 1024, 0, LN.stream>>>(d_totals, nb, LN.d_bin_start);
@@ -713,7 +716,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
             }
             if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, want ? want : 1))) return rc;
         }
-        k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, binsX, binsY, bshift, LN.d_bin_counts, LN.d_bin_start, LN.d_bin_list);
+        k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, bin_batch, binsX, binsY, bshift, LN.d_bin_counts, LN.d_bin_start, LN.d_bin_list);
         g.launches += 5;
     }
     RasterParams p;

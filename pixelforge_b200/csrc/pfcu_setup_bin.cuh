@@ -111,14 +111,14 @@ k_setup(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ sta
 
 /* pass 1: counts[batch][bin] = number of triangles of this batch whose bbox touches the bin */
 __global__ void __launch_bounds__(256)
-k_bin_count(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, int bshift, unsigned *__restrict__ counts)
+k_bin_count(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX, int binsY, int bshift, unsigned *__restrict__ counts)
 {
     extern __shared__ unsigned s_cnt[];
     const int nb = binsX * binsY;
     for (int k = threadIdx.x; k < nb; k += blockDim.x) s_cnt[k] = 0;
     __syncthreads();
-    const unsigned base = blockIdx.x * BIN_BATCH;
-    for (unsigned k = threadIdx.x; k < BIN_BATCH; k += blockDim.x) {
+    const unsigned base = blockIdx.x * batch;
+    for (unsigned k = threadIdx.x; k < batch; k += blockDim.x) {
         const unsigned i = base + k;
         if (i >= n) break;
         const int4 b = __ldg(bbox + i);
@@ -212,7 +212,7 @@ __device__ __forceinline__ unsigned bin_rel_bbox(const int4 b, int bx, int by, i
  * appends them to those bins.  A bin is therefore written by one warp only, in submission order, with no
  * CTA barrier inside a group and no dependence on how the 256 triangles are spread over the screen. */
 __global__ void __launch_bounds__(256)
-k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, int bshift,
+k_bin_fill(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX, int binsY, int bshift,
            const unsigned *__restrict__ offsets /* scanned counts */, const unsigned *__restrict__ starts,
            uint2 *__restrict__ list)
 {
@@ -222,9 +222,9 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, int binsX, int binsY, int 
     __shared__ int4 s_bbox[256];
     const int nb = binsX * binsY;
     for (int k = threadIdx.x; k < nb; k += blockDim.x) s_pos[k] = starts[k] + offsets[(size_t)blockIdx.x * nb + k];
-    const unsigned base = blockIdx.x * BIN_BATCH;
+    const unsigned base = blockIdx.x * batch;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned k0 = 0; k0 < BIN_BATCH && base + k0 < n; k0 += 256) {
+    for (unsigned k0 = 0; k0 < batch && base + k0 < n; k0 += 256) {
         const unsigned i = base + k0 + threadIdx.x;
         int4 r = make_int4(1, 1, 0, 0);
         int4 b = make_int4(1, 1, 0, 0);

@@ -12,14 +12,13 @@ __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (
 __device__ __forceinline__ long long labs64(long long v) { return v < 0 ? -v : v; }
 
 /* setup of triangle i; returns its bbox (empty = (1,1,0,0)) and whether it counts as rasterised */
-__device__ __forceinline__ int4 setup_one(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ states, unsigned i,
+__device__ __forceinline__ int4 setup_one(const pfcu_triangle *t /* global or shared */, const DevState *__restrict__ states, unsigned i,
                                           int surfW, int surfH, int4 *__restrict__ bbox, TriSetup *__restrict__ setup,
                                           TriData *__restrict__ data, bool *rasterised)
 {
     bool valid = false;
     int4 out_box = make_int4(1, 1, 0, 0);
     {
-        const pfcu_triangle *t = tris + i;
         const pfcu_vertex *v1 = &t->v[0], *v2 = &t->v[1], *v3 = &t->v[2];
         const int face = t->face, is3d = t->is3d;
         const DevState *st = states + t->state;
@@ -98,9 +97,23 @@ k_setup(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ sta
         int surfW, int surfH, int4 *__restrict__ bbox, TriSetup *__restrict__ setup, TriData *__restrict__ data,
         unsigned long long *__restrict__ counters)
 {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    /* the 152-byte input records are read with 128-bit coalesced loads into shared memory (a thread reading its own
+       record field by field touches 32 different sectors per load instruction) */
+    __shared__ __align__(16) unsigned char s_in[SETUP_THREADS * sizeof(pfcu_triangle)];
+    static_assert((SETUP_THREADS * sizeof(pfcu_triangle)) % 16 == 0, "whole uint4s per CTA");
+    const unsigned base = blockIdx.x * SETUP_THREADS;
+    const unsigned here = min((unsigned)SETUP_THREADS, n - base);
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(tris) + (size_t)base * sizeof(pfcu_triangle));
+        const unsigned bytes = here * (unsigned)sizeof(pfcu_triangle), n16 = bytes / 16u;      /* 152 bytes: a multiple of 8, not of 16 */
+        for (unsigned k = threadIdx.x; k < n16; k += SETUP_THREADS) reinterpret_cast<uint4 *>(s_in)[k] = __ldcs(src + k);
+        if ((bytes & 15u) && threadIdx.x == 0)
+            reinterpret_cast<uint2 *>(s_in)[2 * n16] = __ldcs(reinterpret_cast<const uint2 *>(src) + 2 * n16);
+    }
+    __syncthreads();
+    const unsigned i = base + threadIdx.x;
     bool valid = false;
-    if (i < n) setup_one(tris, states, i, surfW, surfH, bbox, setup, data, &valid);
+    if (i < n) setup_one(reinterpret_cast<const pfcu_triangle *>(s_in) + threadIdx.x, states, i, surfW, surfH, bbox, setup, data, &valid);
     const unsigned b = __ballot_sync(0xffffffffu, valid);
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(counters + 0, (unsigned long long)__popc(b));
 }
@@ -323,7 +336,7 @@ k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict
         const unsigned i = base + threadIdx.x;
         bool rasterised = false;
         int4 b = make_int4(1, 1, 0, 0);
-        if (i < n) b = setup_one(tris, states, i, surfW, surfH, bbox, setup, data, &rasterised);
+        if (i < n) b = setup_one(tris + i, states, i, surfW, surfH, bbox, setup, data, &rasterised);
         if (b.x < b.z) {
             const int rx0 = max(b.x, 0) >> bshift, rx1 = min((b.z - 1) >> bshift, binsX - 1);
             const int ry0 = max(b.y, 0) >> bshift, ry1 = min(b.w >> bshift, binsY - 1);

@@ -121,9 +121,11 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const un
         const unsigned rank = __popc(peers & lt);
         const unsigned nr = __reduce_max_sync(FULL, m ? rank : 0u);
         if (ztest && nr == 0u) {                        /* no conflicts: test before shading, like the reference's early mask */
-            const float zb = lds_f32_off<DEPTH_OFF>(sa);
+            /* uncovered lanes do not read: their pixel may be another lane's covered pixel, written below */
+            float zb = 0.0f;
+            if (m) zb = lds_f32_off<DEPTH_OFF>(sa);
             m = m && depth_pass_mask(z, zb, zmask);
-            if (!__any_sync(FULL, m)) continue;
+            if (!__any_sync(FULL, m)) { __syncwarp(); continue; }       /* the depth reads above precede later chunks' stores */
         }
 
         /* colour (color.h:153-203) */
@@ -184,7 +186,9 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const un
                     t.shaded++;
                 }
             }
-            if (nr != 0u) __syncwarp();
+            /* orders this round's stores before the next round's (and the next chunk's) loads and stores of the same
+               pixel by OTHER lanes: lanes are not pinned to pixels here, so program order alone does not cover it */
+            __syncwarp();
         }
     }
 }

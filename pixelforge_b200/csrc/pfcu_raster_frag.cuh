@@ -146,14 +146,17 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const un
             float u = FA(FA(FM(__uint_as_float(f4.y), W1), FM(__uint_as_float(f4.z), W2)), FM(__uint_as_float(f4.w), W3));
             float v = FA(FA(FM(__uint_as_float(f5.x), W1), FM(__uint_as_float(f5.y), W2)), FM(__uint_as_float(f5.z), W3));
             if ((meta >> 25) & 1u) { u = FM(u, z); v = FM(v, z); }
-            unsigned texel;
-            if (TEXM == 1) {
-                const float fu = FM(FS(u, truncf(u)), tex.wm1), fv = FM(FS(v, truncf(v)), tex.hm1);
-                const int xi = cvt_rne_x86(fabsf(fu)), yi = cvt_rne_x86(fabsf(fv));
-                const unsigned off = (unsigned)yi * tex.tw + (unsigned)xi;
-                texel = 0u;
-                if (off < tex.total) texel = __ldg((const unsigned *)tex.base + off);
-            } else texel = tex_sample(tex, st, u, v);
+            /* uncovered / depth-failed lanes (about half of the candidates of a small triangle) fetch nothing: their
+               texels would be thrown away and their addresses are the least cache-friendly ones */
+            unsigned texel = 0u;
+            if (m) {
+                if (TEXM == 1) {
+                    const float fu = FM(FS(u, truncf(u)), tex.wm1), fv = FM(FS(v, truncf(v)), tex.hm1);
+                    const int xi = cvt_rne_x86(fabsf(fu)), yi = cvt_rne_x86(fabsf(fv));
+                    const unsigned off = (unsigned)yi * tex.tw + (unsigned)xi;
+                    if (off < tex.total) texel = __ldg((const unsigned *)tex.base + off);
+                } else texel = tex_sample(tex, st, u, v);
+            }
             frag = px_mul(texel, frag);
         }
 

@@ -165,6 +165,11 @@ PFCU_API void    *pfcu_surface_depth_ptr(const pfcu_surface *s);
  * uploads; downloads return after the data is on the host. */
 PFCU_API int pfcu_surface_upload(pfcu_surface *s, const void *host_color, const float *host_depth, uint32_t y0, uint32_t rows);
 PFCU_API int pfcu_surface_download(pfcu_surface *s, void *host_color, float *host_depth, uint32_t y0, uint32_t rows);
+/* The same copies enqueued behind the surface's pending work WITHOUT waiting (meant for page-locked host memory,
+ * see pfcu_host_register); pfcu_surface_wait() returns once everything enqueued for the surface has completed.
+ * The front end uses the pair to read a context back while the next contexts are still being drawn. */
+PFCU_API int pfcu_surface_download_async(pfcu_surface *s, void *host_color, float *host_depth, uint32_t y0, uint32_t rows);
+PFCU_API int pfcu_surface_wait(pfcu_surface *s);
 /* Plain fill of every pixel (pfClearFramebuffer, framebuffer.c:89-102). */
 PFCU_API int pfcu_surface_fill(pfcu_surface *s, int do_color, uint32_t rgba, int do_depth, float depth);
 /* pfClear with the reference's exact SIMD behaviour (context.c:696-713): pixels

@@ -600,6 +600,8 @@ pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const
 }
 int  pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b) { return pfcu_submit(s, b->states, b->n_states, b->tris, b->n_tris); }
 void pfcu_batch_destroy(pfcu_batch *b) { if (b) { free(b->states); free(b->tris); free(b); } }
+int pfcu_surface_download_async(pfcu_surface *s, void *c, float *d, uint32_t y0, uint32_t rows) { return pfcu_surface_download(s, c, d, y0, rows); }
+int pfcu_surface_wait(pfcu_surface *s) { (void)s; return PFCU_OK; }
 int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, const pfcu_vparams_lit *vparams, uint32_t n_vparams,
                     const float *pow_tables, uint32_t n_pow_tables, const pfcu_rawtri *tris, uint32_t n_tris, uint32_t *n_out)
 {   /* never advertised (pfcu_capabilities): with this library the front end runs the vertex stage itself */

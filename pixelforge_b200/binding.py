@@ -173,7 +173,7 @@ PFCU_SYMBOLS = [
     "pfcu_texture_create", "pfcu_texture_from_surface", "pfcu_texture_update", "pfcu_texture_destroy",
     "pfcu_submit", "pfcu_batch_upload", "pfcu_batch_submit", "pfcu_batch_destroy",
     "pfcu_fence", "pfcu_finish", "pfcu_get_counters", "pfcu_reset_counters", "pfcu_profile_enable", "pfcu_profile_read",
-    "pfcu_set_raster_path", "pfcu_submit_raw", "pfcu_submit_prims",
+    "pfcu_set_raster_path", "pfcu_submit_raw", "pfcu_submit_prims", "pfcu_surface_download_async", "pfcu_surface_wait",
 ]
 
 PFX_SYMBOLS = ["pfxSetSyncMode", "pfxFlush", "pfxFinish", "pfxGetCounters", "pfxResetCounters", "pfxSetTileOwner",

@@ -150,7 +150,7 @@ PFcontext pfGetCurrentContext(void) { return pf_cur; }
 void pfMakeCurrent(PFcontext ctx)
 {
     if (pf_cur && pf_cur != ctx) {
-        if (pfh_sync_mode_explicit()) pfh_flush(pf_cur);
+        if (pfh_sync_mode_explicit()) { pfh_flush(pf_cur); pfh_queue_readback(pf_cur, pf_cur->cur_surf); }
         else pfh_sync_surface(pf_cur, pf_cur->cur_surf);
     }
     pf_cur = (pf_ctx *)ctx;
@@ -363,7 +363,7 @@ void pfClear(PFclearflag flag)
     /* the reference's SIMD build clears BOTH buffers whenever either bit is set and never touches
        pixels 0..7 (context.c:696-713); pfcu_surface_clear_ref reproduces that */
     pfcu_surface_clear_ref(s->dev, 1, rgba, 1, c->clearDepth);
-    s->dev_newer = 1; s->dirty_y0 = 0; s->dirty_y1 = s->tex->h;
+    s->dev_newer = 1; s->dirty_y0 = 0; s->dirty_y1 = s->tex->h; s->readback_queued = 0;
     pfh_end_of_draw(c);
 }
 

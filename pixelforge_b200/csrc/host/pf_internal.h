@@ -50,6 +50,7 @@ typedef struct pf_surf {
     int           host_newer;       /* host mirror modified since the last upload                    */
     int           dev_newer;        /* device modified since the last download                       */
     PFuint        dirty_y0, dirty_y1; /* rows [y0, y1) touched on the device since last download     */
+    int           readback_queued;  /* the dirty rows are already on their way to the (page-locked) mirror   */
     pfcu_texture *as_texture;       /* alias used when the colour buffer is sampled                  */
     void         *pinned_color;     /* host mirror ranges page-locked in place (NULL: not pinned)    */
     void         *pinned_depth;
@@ -165,6 +166,7 @@ extern PF_CTX_DECL pf_ctx *pf_cur;
 void pfh_process_primitive(pf_ctx *c);                 /* vertexBuffer full -> triangles -> batch       */
 void pfh_flush(pf_ctx *c);                             /* submit the pending batch (asynchronous)       */
 void pfh_sync_surface(pf_ctx *c, pf_surf *s);          /* flush + bring the host mirror up to date      */
+void pfh_queue_readback(pf_ctx *c, pf_surf *s);        /* explicit mode: start the read-back without waiting */
 void pfh_upload_if_needed(pf_ctx *c, pf_surf *s);      /* host mirror -> device when host is newer      */
 void pfh_end_of_draw(pf_ctx *c);                       /* PF_CUDA_SYNC=end policy hook                  */
 int  pfh_sync_mode_explicit(void);

@@ -252,7 +252,7 @@ void pfClearFramebuffer(PFframebuffer *framebuffer, PFcolor color, PFfloat depth
     uint32_t rgba; memcpy(&rgba, &color, 4);
     s->host_newer = 0;                       /* every pixel is overwritten */
     pfcu_surface_fill(s->dev, 1, rgba, 1, depth);
-    s->dev_newer = 1; s->dirty_y0 = 0; s->dirty_y1 = s->tex->h;
+    s->dev_newer = 1; s->dirty_y0 = 0; s->dirty_y1 = s->tex->h; s->readback_queued = 0;
     if (pf_cur && !pfh_sync_mode_explicit()) pfh_sync_surface(pf_cur, s);
 }
 

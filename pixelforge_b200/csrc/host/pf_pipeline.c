@@ -229,7 +229,7 @@ static void flush_prims(pf_ctx *c)
         fprintf(stderr, "pixelforge-b200: pfcu_submit_prims failed (%d): %s\n", rc, pfcu_last_error());
         c->errCode = (rc == PFCU_ERR_OOM) ? PF_ERROR_OUT_OF_MEMORY : PF_INVALID_OPERATION;
     }
-    s->dev_newer = 1; s->dirty_y0 = 0; s->dirty_y1 = s->tex->h;
+    s->dev_newer = 1; s->dirty_y0 = 0; s->dirty_y1 = s->tex->h; s->readback_queued = 0;
     c->n_prims = 0;
 }
 
@@ -252,12 +252,27 @@ void pfh_flush(pf_ctx *c)
         fprintf(stderr, "pixelforge-b200: pfcu_submit failed (%d): %s\n", rc, pfcu_last_error());
         c->errCode = (rc == PFCU_ERR_OOM) ? PF_ERROR_OUT_OF_MEMORY : PF_INVALID_OPERATION;
     }
-    s->dev_newer = 1;
+    s->dev_newer = 1; s->readback_queued = 0;
     c->cur_buf ^= 1;
     pfcu_host_wait(c->tris[c->cur_buf]);    /* the other buffer may still be in flight */
     c->n_tris = 0;
     c->n_states = 0;
     c->state_dirty = 1;
+}
+
+/* PF_CUDA_SYNC=explicit, leaving a context for another one (a batch of contexts drawn in turn, then presented):
+ * queue the read-back of what this context drew right behind its kernels, so that it overlaps with the drawing of
+ * the next contexts instead of being paid, one blocking copy after the other, when they are presented.  Only for
+ * page-locked mirrors (the copy is then a plain DMA); drawing to the surface again simply invalidates it. */
+void pfh_queue_readback(pf_ctx *c, pf_surf *s)
+{
+    if (!s || !s->dev_newer || s->readback_queued || !s->pinned_color) return;
+    if (s->zhost && !s->pinned_depth) return;
+    PFuint y0 = s->dirty_y0, y1 = s->dirty_y1;
+    if (y1 > s->tex->h) y1 = s->tex->h;
+    if (y0 >= y1) return;
+    (void)c;
+    if (pfcu_surface_download_async(s->dev, s->tex->pixels, s->zhost, y0, y1 - y0) == PFCU_OK) s->readback_queued = 1;
 }
 
 void pfh_sync_surface(pf_ctx *c, pf_surf *s)
@@ -267,8 +282,10 @@ void pfh_sync_surface(pf_ctx *c, pf_surf *s)
     if (s->dev_newer) {
         PFuint y0 = s->dirty_y0, y1 = s->dirty_y1;
         if (y1 > s->tex->h) y1 = s->tex->h;
-        if (y0 < y1) pfcu_surface_download(s->dev, s->tex->pixels, s->zhost, y0, y1 - y0);
+        if (s->readback_queued) pfcu_surface_wait(s->dev);
+        else if (y0 < y1) pfcu_surface_download(s->dev, s->tex->pixels, s->zhost, y0, y1 - y0);
         else pfcu_finish();
+        s->readback_queued = 0;
         s->dev_newer = 0;
         s->dirty_y0 = s->tex->h; s->dirty_y1 = 0;
     }
@@ -560,7 +577,7 @@ int pfh_device_draw(pf_ctx *c, PFsizei count, PFint first, int indexed, PFdataty
         fprintf(stderr, "pixelforge-b200: pfcu_draw_triangles failed (%d): %s\n", rc, pfcu_last_error());
         c->errCode = (rc == PFCU_ERR_OOM) ? PF_ERROR_OUT_OF_MEMORY : PF_INVALID_OPERATION;
     }
-    s->dev_newer = 1; s->dirty_y0 = 0; s->dirty_y1 = s->tex->h;
+    s->dev_newer = 1; s->dirty_y0 = 0; s->dirty_y1 = s->tex->h; s->readback_queued = 0;
     c->tris_emitted += produced;
     c->state_dirty = 1;
     c->currentDrawMode = PF_TRIANGLES; c->vertexCounter = 0;

@@ -453,7 +453,7 @@ int pfcu_surface_upload(pfcu_surface *s, const void *hc, const float *hd, uint32
     return PFCU_OK;
 }
 
-int pfcu_surface_download(pfcu_surface *s, void *hc, float *hd, uint32_t y0, uint32_t rows)
+int pfcu_surface_download_async(pfcu_surface *s, void *hc, float *hd, uint32_t y0, uint32_t rows)
 {
     API_LOCK;
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
@@ -461,6 +461,23 @@ int pfcu_surface_download(pfcu_surface *s, void *hc, float *hd, uint32_t y0, uin
     const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;
     if (hc) { CK(cudaMemcpyAsync((uint32_t *)hc + off, s->color + off, n, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += n; }
     if (hd) { CK(cudaMemcpyAsync(hd + off, s->depth + off, n, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += n; }
+    mark_done(s);
+    return PFCU_OK;
+}
+
+int pfcu_surface_wait(pfcu_surface *s)
+{
+    API_LOCK;
+    if (!s) return PFCU_ERR_INVALID;
+    if (s->has_done) CK(cudaEventSynchronize(s->done));
+    return PFCU_OK;
+}
+
+int pfcu_surface_download(pfcu_surface *s, void *hc, float *hd, uint32_t y0, uint32_t rows)
+{
+    API_LOCK;
+    int rc = pfcu_surface_download_async(s, hc, hd, y0, rows);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(LN.stream));
     return PFCU_OK;
 }

@@ -97,6 +97,15 @@ class Scene:
     def make_current(self, index=0):
         self.lib.lib.pfscene_make_current(self.handle, index)
 
+    def read_context(self, index):
+        """Colour buffer of context `index` of a "batch" scene, exactly as the application sees it."""
+        color = np.zeros((self.cfg.height, self.cfg.width), np.uint32)
+        self.lib.lib.pfscene_read_context.restype = C.c_int
+        self.lib.lib.pfscene_read_context.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        if not self.lib.lib.pfscene_read_context(self.handle, index, color.ctypes.data):
+            raise IndexError(index)
+        return color
+
     def read(self, want_depth=False):
         color = np.zeros((self.cfg.height, self.cfg.width), dtype=np.uint32)
         depth = np.zeros((self.cfg.height, self.cfg.width), dtype=np.float32) if want_depth else None

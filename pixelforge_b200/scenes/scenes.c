@@ -824,6 +824,15 @@ SCN_API void pfscene_make_current(void *handle, int index)
 }
 
 /* Copies out the colour (w*h*4 bytes) and optionally the depth buffer (context size-1 for "batch"). */
+/* "batch" only: the caller-visible colour buffer of context `index`, as it is (no API call is made). */
+SCN_API int pfscene_read_context(void *handle, int index, uint8_t *color_out)
+{
+    scene_t *s = (scene_t *)handle;
+    if (!s->n || index < 0 || index >= s->n) return 0;
+    memcpy(color_out, s->bufs[index], (size_t)s->cfg.width * s->cfg.height * 4);
+    return 1;
+}
+
 SCN_API void pfscene_read(void *handle, uint8_t *color_out, float *depth_out)
 {
     scene_t *s = (scene_t *)handle;

@@ -53,6 +53,24 @@ def test_sync_modes_agree(product_scenes, sync_mode):
     assert np.array_equal(a, b) and np.array_equal(da.view(np.uint32), db.view(np.uint32))
 
 
+def test_explicit_mode_queued_readback_of_many_contexts(product_scenes):
+    """PF_CUDA_SYNC=explicit with several contexts drawn in turn: leaving a context queues the read-back of its
+    page-locked mirror (>= 1 MB) behind its kernels; drawing into it again in the next frame invalidates that copy.
+    The presented images must equal the synchronous mode's, for every context."""
+    def images(explicit, frames):
+        with product_scenes.open("batch", 512, 512, size=4, explicit_sync=explicit) as sc:
+            for f in range(frames):
+                sc.frame(f)
+                sc.finish()
+            return [sc.read_context(i) for i in range(4)]
+    for frames in (1, 3):
+        a, b = images(1, frames), images(0, frames)
+        for i in range(4):
+            assert (a[i] & 0xFFFFFF).any()
+            assert np.array_equal(a[i], b[i]), (frames, i)
+        assert not np.array_equal(a[0], a[1])          # per-context angle: the contexts really differ
+
+
 # ---- pfcu level: random triangle streams, CUDA vs oracle -----------------------------------------------
 
 @pytest.fixture(scope="module")

@@ -11,7 +11,7 @@
  * and this file holds the runtime (stream lanes, buffers, pinned staging) and the C-ABI entry points.
  *
  * Pipeline per submitted batch (each surface's work stays on one stream "lane", order preserving):
- *   vertex stage (optional)  k_vertex_* for vertex-array draws, k_raw_* / k_raw_small for immediate mode and
+ *   vertex stage (optional)  k_vertex_* for vertex-array draws, k_raw_* / k_raw_chain for immediate mode and
  *             render lists: pf_vstage.h compiled as device code (normal transform, material multiply, Gouraud
  *             lighting, clipping, projection); count -> scan -> emit keeps order;
  *   k_setup   one thread per triangle: integer snap, signed area / face cull, bbox, int32 edge
@@ -134,6 +134,7 @@ struct Lane {
     unsigned char *d_raw = nullptr; size_t cap_raw = 0;
     unsigned *h_total = nullptr;                                        /* pinned: {last offset, last count} */
     unsigned *d_total = nullptr;                                        /* output count of a sync-free raw batch */
+    unsigned long long *d_chain = nullptr; unsigned chain_seq = 0;      /* chained-scan flags of k_raw_chain */
 };
 
 #define MAX_LANES 8
@@ -249,6 +250,8 @@ int pfcu_init(int device)
         CK(cudaEventCreateWithFlags(&LN.vready, cudaEventDisableTiming));
         CK(cudaHostAlloc(&LN.h_total, 2 * sizeof(unsigned), cudaHostAllocDefault));
         CK(cudaMalloc(&LN.d_total, 64));
+        CK(cudaMalloc(&LN.d_chain, 16 * sizeof(unsigned long long)));
+        CK(cudaMemset(LN.d_chain, 0, 16 * sizeof(unsigned long long)));
     }
     g.cur = &g.lanes[0];
     CK(cudaMalloc(&g.d_counters, 4 * sizeof(unsigned long long)));
@@ -272,7 +275,7 @@ void pfcu_shutdown(void)
         if (LN.h_stage) cudaFreeHost(LN.h_stage);
         if (LN.h_states) cudaFreeHost(LN.h_states);
         if (LN.h_total) cudaFreeHost(LN.h_total);
-        cudaFree(LN.d_raw); cudaFree(LN.d_total);
+        cudaFree(LN.d_raw); cudaFree(LN.d_total); cudaFree(LN.d_chain);
         if (LN.vstream) cudaStreamDestroy(LN.vstream);
         if (LN.own_stream) cudaStreamDestroy(LN.stream);
         g.lanes[i] = Lane();
@@ -930,7 +933,7 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
         CK(cudaMemcpyAsync(LN.d_states, LN.h_states, n_states * sizeof(DevState), cudaMemcpyHostToDevice, LN.stream));
         CK(cudaEventRecord(LN.states_done, LN.stream));
         unsigned *d_total = LN.d_total;
-        k_raw_small<<<1, 1024, 0, LN.stream>>>(ra, LN.d_tris, d_total, g.d_counters);
+        k_raw_chain<<<(n_tris + 127u) / 128u, 128, 0, LN.stream>>>(ra, LN.d_tris, d_total, LN.d_chain, ++LN.chain_seq);
         g.launches++;
         CK(cudaEventRecord(LN.raw_done, LN.stream));
         CK(cudaGetLastError());

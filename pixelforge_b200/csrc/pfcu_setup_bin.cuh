@@ -325,6 +325,7 @@ k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict
     __shared__ unsigned s_warp[32];
     __shared__ unsigned s_carry;
     const unsigned n = d_n ? min(*d_n, (unsigned)(FRONT_SMALL_MAX * FRONT_SMALL_CHUNKS)) : n_host;
+    if (d_n && threadIdx.x == 0) atomicAdd(counters + 3, (unsigned long long)n);        /* "submitted", counted where the count is known */
     const int nb = binsX * binsY;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int k = threadIdx.x; k < nb; k += 1024) s_pos[k] = 0;

@@ -196,14 +196,18 @@ k_prims(const PrimParams p)
     }
 }
 
-/* Raw batches of at most 1024 triangles: count, scan and emission in ONE single-CTA kernel; the number of output
- * triangles (at most 10 per input after clipping) stays on the device: *d_total feeds k_front_small, so the host
- * never waits. */
-__global__ void __launch_bounds__(1024)
-k_raw_small(const RawArgs a, pfcu_triangle *__restrict__ out, unsigned *__restrict__ d_total, unsigned long long *__restrict__ counters)
+/* Raw batches of at most 1024 triangles: count, scan and emission in ONE launch of up to 8 CTAs of 128 threads.
+ * Every triangle runs the vertex stage once; the output offset of a CTA is the running total its predecessor
+ * publishes (a chained scan: flags[b] = launch sequence number << 32 | triangles emitted by CTAs 0..b; CTAs are
+ * dispatched in index order, so a predecessor is always resident).  The total stays on the device: *d_total feeds
+ * k_front_small, so the host never waits for it. */
+__global__ void __launch_bounds__(128)
+k_raw_chain(const RawArgs a, pfcu_triangle *__restrict__ out, unsigned *__restrict__ d_total,
+            unsigned long long *__restrict__ flags, unsigned seq)
 {
-    __shared__ unsigned s_warp[32];
-    const unsigned i = threadIdx.x, lane = i & 31u, warp = i >> 5;
+    __shared__ unsigned s_warp[4];
+    __shared__ unsigned s_prev;
+    const unsigned i = blockIdx.x * 128u + threadIdx.x, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     pfv_vertex poly[PFV_MAX_POLY];
     int is3d = 0, face = 0, n = 0; unsigned state = 0;
     if (i < a.n) n = raw_process(a, i, poly, &is3d, &face, &state);
@@ -212,16 +216,25 @@ k_raw_small(const RawArgs a, pfcu_triangle *__restrict__ out, unsigned *__restri
     for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if ((int)lane >= o) x += y; }
     if (lane == 31) s_warp[warp] = x;
     __syncthreads();
-    if (warp == 0) {
-        unsigned w = s_warp[lane];
+    unsigned woff = 0, total = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, w, o); if ((int)lane >= o) w += y; }
-        s_warp[lane] = w;
+    for (int w = 0; w < 4; w++) { const unsigned c = s_warp[w]; if (w < (int)warp) woff += c; total += c; }
+    if (threadIdx.x == 0) {
+        unsigned prev = 0;
+        if (blockIdx.x > 0) {
+            const volatile unsigned long long *f = flags + (blockIdx.x - 1);
+            unsigned long long v;
+            do { v = *f; } while ((unsigned)(v >> 32) != seq);
+            prev = (unsigned)v;
+        }
+        __threadfence();
+        *((volatile unsigned long long *)(flags + blockIdx.x)) = ((unsigned long long)seq << 32) | (prev + total);
+        s_prev = prev;
+        if (blockIdx.x == gridDim.x - 1) *d_total = prev + total;
     }
     __syncthreads();
-    const unsigned off = (warp ? s_warp[warp - 1] : 0u) + x - (unsigned)n;
+    const unsigned off = s_prev + woff + x - (unsigned)n;
     for (int k = 0; k < n; k++) pfv_emit(out + off + k, &poly[0], &poly[k + 1], &poly[k + 2], state, face, is3d);
-    if (i == 1023) { *d_total = off + (unsigned)n; atomicAdd(counters + 3, (unsigned long long)(off + (unsigned)n)); }
 }
 
 /* exclusive scan of up to 1024 items per CTA; sums[blockIdx] = CTA total */

@@ -421,8 +421,8 @@ def test_runtime_knobs_do_not_change_pixels(env, product_scenes):
 
 
 def test_small_raw_batches_with_clipping_keep_their_count_on_the_device():
-    """Raw batches of <= 1024 triangles run count + scan + emit in one kernel and keep the output count on the device
-    (k_raw_small -> k_front_small); a close-up scene whose triangles are clipped into up to 10 pieces each must
+    """Raw batches of <= 1024 triangles keep their output count on the device
+    (k_raw_chain -> k_front_small, the count read from device memory); a close-up scene whose triangles are clipped into up to 10 pieces each must
     give the host vertex stage's pixels and triangle count."""
     kw = dict(size=48, variant=64)
     a = _render_with_env("textured", 640, 360, {"PF_CUDA_BATCH_TRIS": "700"}, **kw)

@@ -209,7 +209,7 @@ typedef struct {
     const float   *normals;                            /* 3 floats per vertex, or NULL (normal = 0)       */
     const float   *texcoords;                          /* 2 floats per vertex, or NULL (texcoord = 0)     */
     const uint8_t *colors;     uint32_t color_size;    /* 3 or 4 ubytes per vertex, or NULL               */
-    uint32_t       n_vertices;                         /* vertices referenced (max index + 1)             */
+    uint32_t       n_vertices;                         /* vertices referenced (max index + 1); 0 with 32-bit indices: the device finds it */
     const void    *indices;    uint32_t index_bytes;   /* 1, 2 or 4; NULL = sequential from `first`       */
     uint32_t       first, count;                       /* number of indices / vertices to draw            */
     uint32_t       current_color;                      /* colour when there is no colour array            */

@@ -545,15 +545,18 @@ int pfh_device_draw(pf_ctx *c, PFsizei count, PFint first, int indexed, PFdataty
     for (uint32_t f = 0; f < d.n_faces; f++) if (c->polygonMode[d.faces[f]] != PF_FILL) return 0;
 
     /* vertices referenced by the draw */
-    size_t nverts;
+    size_t nverts; int unknown = 0;
     if (indexed) {
         size_t mx = 0;
         switch (itype) {
         case PF_UNSIGNED_BYTE:  { const PFubyte *p = (const PFubyte *)indices; for (PFsizei i = 0; i < count; i++) if (p[i] > mx) mx = p[i]; d.index_bytes = 1; } break;
         case PF_UNSIGNED_SHORT: { const PFushort *p = (const PFushort *)indices; for (PFsizei i = 0; i < count; i++) if (p[i] > mx) mx = p[i]; d.index_bytes = 2; } break;
-        default:                mx = max_index_u32((const uint32_t *)indices, count); d.index_bytes = 4; break;
+        default:                /* >= 1 M indices: the device scans them once they are uploaded (pfcu_draw.n_vertices == 0); below that the
+                                   extra round trip costs more than the AVX2 scan */
+                                if (count >= (1u << 20)) unknown = 1; else mx = max_index_u32((const uint32_t *)indices, count);
+                                d.index_bytes = 4; break;
         }
-        nverts = mx + 1; d.indices = indices; d.first = 0;
+        nverts = unknown ? 0 : mx + 1; d.indices = indices; d.first = 0;
     } else { nverts = (size_t)first + count; d.indices = NULL; d.first = (uint32_t)first; }
     if (nverts > 0x7fffffffu) return 0;
 

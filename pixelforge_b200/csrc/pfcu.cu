@@ -135,6 +135,7 @@ struct Lane {
     unsigned *h_total = nullptr;                                        /* pinned: {last offset, last count} */
     unsigned *d_total = nullptr;                                        /* output count of a sync-free raw batch */
     unsigned long long *d_chain = nullptr; unsigned chain_seq = 0;      /* chained-scan flags of k_raw_chain */
+    unsigned char *d_idx = nullptr; size_t cap_idx = 0;                 /* index buffer of a draw whose vertex count the device finds */
 };
 
 #define MAX_LANES 8
@@ -275,7 +276,7 @@ void pfcu_shutdown(void)
         if (LN.h_stage) cudaFreeHost(LN.h_stage);
         if (LN.h_states) cudaFreeHost(LN.h_states);
         if (LN.h_total) cudaFreeHost(LN.h_total);
-        cudaFree(LN.d_raw); cudaFree(LN.d_total); cudaFree(LN.d_chain);
+        cudaFree(LN.d_raw); cudaFree(LN.d_total); cudaFree(LN.d_chain); cudaFree(LN.d_idx);
         if (LN.vstream) cudaStreamDestroy(LN.vstream);
         if (LN.own_stream) cudaStreamDestroy(LN.stream);
         g.lanes[i] = Lane();
@@ -847,9 +848,25 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     const unsigned n_items = n_tri * d->n_faces;
     int rc;
     /* arrays -> device (pageable sources are staged by the driver; ordered on the stream) */
-    const size_t nv = d->n_vertices;
+    size_t nv = d->n_vertices;
+    const unsigned char *d_indices_ready = nullptr;
+    if (nv == 0 && d->indices) {
+        /* n_vertices unknown: upload the (32-bit) indices first and let the device find the largest one */
+        if (d->index_bytes != 4) return PFCU_ERR_INVALID;
+        const size_t bi = (size_t)d->count * 4;
+        if ((rc = grow(&LN.d_idx, &LN.cap_idx, bi))) return rc;
+        CK(cudaMemcpyAsync(LN.d_idx, d->indices, bi, cudaMemcpyHostToDevice, LN.stream));
+        CK(cudaMemsetAsync(LN.d_total, 0, 4, LN.stream));
+        k_index_max<<<g.sms * 4, 256, 0, LN.stream>>>((const unsigned *)LN.d_idx, d->count, LN.d_total);
+        g.launches++;
+        CK(cudaMemcpyAsync(&LN.h_total[0], LN.d_total, 4, cudaMemcpyDeviceToHost, LN.stream));
+        CK(cudaStreamSynchronize(LN.stream));
+        nv = (size_t)LN.h_total[0] + 1;
+        if (nv > 0x7fffffffu) return PFCU_ERR_INVALID;
+        d_indices_ready = LN.d_idx;
+    }
     const size_t b_pos = nv * d->pos_size * 4, b_nrm = d->normals ? nv * 12 : 0, b_uv = d->texcoords ? nv * 8 : 0;
-    const size_t b_col = d->colors ? nv * d->color_size : 0, b_idx = d->indices ? (size_t)d->count * d->index_bytes : 0;
+    const size_t b_col = d->colors ? nv * d->color_size : 0, b_idx = (d->indices && !d_indices_ready) ? (size_t)d->count * d->index_bytes : 0;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t total_bytes = al(b_pos) + al(b_nrm) + al(b_uv) + al(b_col) + al(b_idx);
     g.bytes_h2d += b_pos + b_nrm + b_uv + b_col + b_idx + sizeof(DevState);
@@ -861,6 +878,7 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     if (b_uv) { a.uv = (const float *)p; CK(cudaMemcpyAsync(p, d->texcoords, b_uv, cudaMemcpyHostToDevice, LN.stream)); p += al(b_uv); }
     if (b_col) { a.col = p; CK(cudaMemcpyAsync(p, d->colors, b_col, cudaMemcpyHostToDevice, LN.stream)); p += al(b_col); }
     if (b_idx) { a.idx = p; CK(cudaMemcpyAsync(p, d->indices, b_idx, cudaMemcpyHostToDevice, LN.stream)); p += al(b_idx); }
+    if (d_indices_ready) { a.idx = d_indices_ready; g.bytes_h2d += (size_t)d->count * 4; }
     a.pos_size = (int)d->pos_size; a.col_size = (int)d->color_size; a.idx_bytes = (int)d->index_bytes;
     a.first = d->first; a.n_tri = n_tri; a.cur_color = d->current_color; a.n_faces = (int)d->n_faces;
     a.face[0] = d->faces[0]; a.face[1] = d->faces[1]; a.state = 0;

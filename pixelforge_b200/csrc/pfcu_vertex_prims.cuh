@@ -36,6 +36,17 @@ __device__ __forceinline__ void vtx_load(const VtxArgs &a, unsigned vi, pfv_vert
     v->screen[0] = 0.0f; v->screen[1] = 0.0f;
 }
 
+/* largest 32-bit index of an index buffer (how many vertices a pfDrawElements call references): scanning 3 M
+ * indices costs the host ~1 ms even with AVX2, the device a few microseconds once they are uploaded anyway */
+__global__ void __launch_bounds__(256)
+k_index_max(const unsigned *__restrict__ idx, unsigned n, unsigned *__restrict__ out)
+{
+    unsigned m = 0;
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) m = max(m, __ldg(idx + i));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31u) == 0 && m) atomicMax(out, m);
+}
+
 /* runs the whole vertex stage for item (triangle, face pass); returns the number of output triangles */
 __device__ __forceinline__ int vtx_process(const VtxArgs &a, const pfv_params &vp, unsigned item, pfv_vertex *poly, int *is3d, int *face_out)
 {

@@ -602,6 +602,12 @@ int  pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b) { return pfcu_submit(s, b
 void pfcu_batch_destroy(pfcu_batch *b) { if (b) { free(b->states); free(b->tris); free(b); } }
 int pfcu_surface_download_async(pfcu_surface *s, void *c, float *d, uint32_t y0, uint32_t rows) { return pfcu_surface_download(s, c, d, y0, rows); }
 int pfcu_surface_wait(pfcu_surface *s) { (void)s; return PFCU_OK; }
+/* present over peer memory: CUDA only (the gloo tests use pack / gather / unpack) */
+int pfcu_surface_ipc_handles(pfcu_surface *s, void *c, void *d) { (void)s; (void)c; (void)d; return PFCU_ERR_INVALID; }
+int pfcu_surface_set_present_peer(pfcu_surface *s, const void *c, const void *d) { (void)s; (void)c; (void)d; return PFCU_ERR_INVALID; }
+int pfcu_surface_set_present_surface(pfcu_surface *s, pfcu_surface *t) { (void)s; (void)t; return PFCU_ERR_INVALID; }
+int pfcu_surface_clear_present(pfcu_surface *s) { (void)s; return PFCU_OK; }
+int pfcu_surface_push_tiles(pfcu_surface *s, uint32_t r, uint32_t w, int d) { (void)s; (void)r; (void)w; (void)d; return PFCU_ERR_INVALID; }
 int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, const pfcu_vparams_lit *vparams, uint32_t n_vparams,
                     const float *pow_tables, uint32_t n_pow_tables, const pfcu_rawtri *tris, uint32_t n_tris, uint32_t *n_out)
 {   /* never advertised (pfcu_capabilities): with this library the front end runs the vertex stage itself */

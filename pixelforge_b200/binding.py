@@ -182,7 +182,8 @@ PFCU_SYMBOLS = [
     "pfcu_texture_create", "pfcu_texture_from_surface", "pfcu_texture_update", "pfcu_texture_destroy",
     "pfcu_submit", "pfcu_batch_upload", "pfcu_batch_submit", "pfcu_batch_destroy",
     "pfcu_fence", "pfcu_finish", "pfcu_get_counters", "pfcu_reset_counters", "pfcu_profile_enable", "pfcu_profile_read",
-    "pfcu_set_raster_path", "pfcu_submit_raw", "pfcu_submit_prims", "pfcu_surface_download_async", "pfcu_surface_wait",
+    "pfcu_set_raster_path", "pfcu_submit_raw", "pfcu_submit_prims", "pfcu_surface_download_async", "pfcu_surface_wait", "pfcu_surface_ipc_handles", "pfcu_surface_set_present_peer",
+    "pfcu_surface_set_present_surface", "pfcu_surface_clear_present", "pfcu_surface_push_tiles",
 ]
 
 PFX_SYMBOLS = ["pfxSetSyncMode", "pfxFlush", "pfxFinish", "pfxGetCounters", "pfxResetCounters", "pfxSetTileOwner",
@@ -217,6 +218,9 @@ class PfcuLib:
             "pfcu_surface_unpack_tiles": (C.c_int, [vp, u32, u32, C.c_int, vp]),
             "pfcu_texture_create": (vp, [vp, u32, u32, C.c_int]), "pfcu_texture_from_surface": (vp, [vp]),
             "pfcu_texture_update": (C.c_int, [vp, vp]), "pfcu_texture_destroy": (None, [vp]),
+            "pfcu_surface_ipc_handles": (C.c_int, [vp, vp, vp]), "pfcu_surface_set_present_peer": (C.c_int, [vp, vp, vp]),
+            "pfcu_surface_set_present_surface": (C.c_int, [vp, vp]), "pfcu_surface_clear_present": (C.c_int, [vp]),
+            "pfcu_surface_push_tiles": (C.c_int, [vp, u32, u32, C.c_int]),
             "pfcu_submit": (C.c_int, [vp, vp, u32, vp, u32]), "pfcu_submit_prims": (C.c_int, [vp, vp, u32]), "pfcu_batch_upload": (vp, [vp, u32, vp, u32]),
             "pfcu_batch_submit": (C.c_int, [vp, vp]), "pfcu_batch_destroy": (None, [vp]),
             "pfcu_fence": (C.c_int, []), "pfcu_finish": (C.c_int, []), "pfcu_get_counters": (C.c_int, [C.POINTER(Counters)]),

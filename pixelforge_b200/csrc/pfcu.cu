@@ -98,6 +98,8 @@ struct pfcu_surface {
     uint32_t w, h; uint32_t *color; float *depth; bool owned;
     uint32_t rank, world; uint32_t tiles_x, tiles_y;
     int lane; cudaEvent_t done; bool has_done;      /* last work enqueued on this surface */
+    uint32_t *peer_color; float *peer_depth;        /* present target (peer memory or another local surface), or nullptr */
+    void *ipc_color, *ipc_depth;                    /* mappings opened with cudaIpcOpenMemHandle (to close) */
 };
 struct pfcu_texture { uint32_t w, h; int fmt; unsigned char *pixels; bool owned; pfcu_surface *alias; };
 struct pfcu_batch {
@@ -427,11 +429,88 @@ pfcu_surface *pfcu_surface_wrap(void *dev_color, void *dev_depth, uint32_t w, ui
     return s;
 }
 
+static uint32_t owned_tiles(const pfcu_surface *s, uint32_t rank, uint32_t world);
+static void mark_done(pfcu_surface *s);
+
+static void close_present(pfcu_surface *s)
+{
+    if (s->ipc_color) cudaIpcCloseMemHandle(s->ipc_color);
+    if (s->ipc_depth) cudaIpcCloseMemHandle(s->ipc_depth);
+    s->ipc_color = s->ipc_depth = nullptr; s->peer_color = nullptr; s->peer_depth = nullptr;
+}
+
+int pfcu_surface_ipc_handles(pfcu_surface *s, void *color_handle, void *depth_handle)
+{
+    API_LOCK;
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!s || !color_handle) return PFCU_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle buffers are 64 bytes");
+    CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)color_handle, s->color));
+    if (depth_handle) CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)depth_handle, s->depth));
+    return PFCU_OK;
+}
+
+int pfcu_surface_set_present_peer(pfcu_surface *s, const void *color_handle, const void *depth_handle)
+{
+    API_LOCK;
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!s || !color_handle) return PFCU_ERR_INVALID;
+    sync_all_lanes();
+    close_present(s);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, color_handle, sizeof h);
+    CK(cudaIpcOpenMemHandle(&s->ipc_color, h, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_color = (uint32_t *)s->ipc_color;
+    if (depth_handle) {
+        memcpy(&h, depth_handle, sizeof h);
+        CK(cudaIpcOpenMemHandle(&s->ipc_depth, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_depth = (float *)s->ipc_depth;
+    }
+    return PFCU_OK;
+}
+
+int pfcu_surface_set_present_surface(pfcu_surface *s, pfcu_surface *target)
+{
+    API_LOCK;
+    if (!s || !target || target->w != s->w || target->h != s->h || target == s) return PFCU_ERR_INVALID;
+    if (g.ok) sync_all_lanes();
+    close_present(s);
+    s->peer_color = target->color; s->peer_depth = target->depth;
+    return PFCU_OK;
+}
+
+int pfcu_surface_clear_present(pfcu_surface *s)
+{
+    API_LOCK;
+    if (!s) return PFCU_ERR_INVALID;
+    if (g.ok) sync_all_lanes();
+    close_present(s);
+    return PFCU_OK;
+}
+
+int pfcu_surface_push_tiles(pfcu_surface *s, uint32_t rank, uint32_t world, int with_depth)
+{
+    API_LOCK;
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!s || !s->peer_color || (with_depth && !s->peer_depth)) return PFCU_ERR_INVALID;
+    if (world == 0) world = 1;
+    use_lane(s);
+    const uint32_t n = owned_tiles(s, rank, world);
+    if (n == 0) return PFCU_OK;
+    k_push_tiles<<<n, 256, 0, LN.stream>>>(s->color, s->depth, s->peer_color, with_depth ? s->peer_depth : nullptr, (int)s->w, (int)s->h,
+                                          (int)s->tiles_x, s->tiles_x * s->tiles_y, rank, world);
+    g.launches++;
+    CK(cudaGetLastError());
+    mark_done(s);
+    return PFCU_OK;
+}
+
 void pfcu_surface_destroy(pfcu_surface *s)
 {
     API_LOCK;
     if (!s) return;
     if (g.ok) sync_all_lanes();
+    close_present(s);
     if (s->owned) { cudaFree(s->color); cudaFree(s->depth); }
     if (s->done) cudaEventDestroy(s->done);
     free(s);
@@ -746,7 +825,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     p.color = s->color; p.depth = s->depth; p.W = (int)s->w; p.H = (int)s->h;
     p.tilesX = (int)s->tiles_x; p.tilesY = (int)s->tiles_y;
     p.rank = s->rank; p.world = s->world ? s->world : 1; p.nTiles = s->tiles_x * s->tiles_y;
-    p.counters = g.d_counters;
+    p.counters = g.d_counters; p.peer_color = s->peer_color; p.peer_depth = s->peer_depth;
     const unsigned grid = owned_tiles(s, p.rank, p.world);
     if (g.profiling) CK(cudaEventRecord(pe[1], LN.stream));
     if (grid) {

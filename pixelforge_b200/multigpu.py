@@ -6,6 +6,10 @@ per-pixel result is byte-identical to a single-GPU render.  The only exchange st
 the finished tiles to the presenting rank: each rank packs its tiles into a contiguous staging
 buffer (k_pack_tiles), the buffers are gathered with NCCL over NVLink (or gloo in CPU tests, where
 the "device" is the oracle build), and the presenter unpacks them into its surface.
+
+The fused alternative (connect_present_peer): the presenter exports its surface over CUDA IPC and the other ranks'
+rasterisers store every finished tile straight into it over NVLink, overlapping the transfer with the shading of
+the remaining tiles; only a barrier is left between the kernels and the presenter's read.
 """
 import numpy as np
 
@@ -43,6 +47,24 @@ def gather_tiles(torch, dist, pfcu, surface, width, height, rank, world, with_de
     return 0
 
 
+def connect_present_peer(dist, pfcu, surface, rank, world, with_depth=False, dst=0):
+    """Fused present (include/pfcu.h): rank `dst` exports its surface with CUDA IPC, every other rank maps it; from
+    then on k_raster / k_raster_frag store each finished tile into the presenter's surface over NVLink as well."""
+    import ctypes as C
+    L = pfcu.lib
+    hc, hd = (C.c_ubyte * 64)(), (C.c_ubyte * 64)()
+    payload = [None]
+    if rank == dst:
+        pfcu.check(L.pfcu_surface_ipc_handles(surface, hc, hd if with_depth else None), "ipc_handles")
+        payload = [(bytes(hc), bytes(hd) if with_depth else None)]
+    dist.broadcast_object_list(payload, src=dst)
+    if rank != dst:
+        c, d = payload[0]
+        hc = (C.c_ubyte * 64).from_buffer_copy(c)
+        hd = (C.c_ubyte * 64).from_buffer_copy(d) if d else None
+        pfcu.check(L.pfcu_surface_set_present_peer(surface, hc, hd), "set_present_peer")
+
+
 def tile_split_benchmark(torch, dist, scenes, pfcu, stream, wl, rank, world, steps=3):
     """Strong-scaling run of one big surface split by screen tiles across `world` GPUs."""
     from .binding import Counters
@@ -73,6 +95,48 @@ def tile_split_benchmark(torch, dist, scenes, pfcu, stream, wl, rank, world, ste
             if i > 0:
                 times.append(e0.elapsed_time(e1)); gather_ms.append(e1.elapsed_time(e2))
         k = Counters(); L.pfcu_get_counters(k)
+        # the same frame with the fused present: peers store their tiles into rank 0's surface from inside the
+        # rasteriser; all that is left after the kernels is a barrier
+        fused, fused_ok = [], None
+        import hashlib
+        ref_hash = None
+        if rank == 0:               # what the gather produced is the truth to compare with
+            c = np.zeros((wl["h"], wl["w"]), np.uint32)
+            pfcu.check(L.pfcu_surface_download(surf, c.ctypes.data, None, 0, wl["h"]), "download")
+            ref_hash = hashlib.sha256(c.tobytes()).hexdigest()
+        try:
+            connect_present_peer(dist, pfcu, surf, rank, world)
+            ok = 1.0
+        except Exception as ex:     # no peer access between these devices
+            ok, fused_ok = 0.0, repr(ex)
+        okt = torch.tensor([ok], dtype=torch.float64, device="cuda")
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)          # every rank takes the same branch: collectives follow
+        if float(okt[0]) > 0.5:
+            for i in range(steps + 1):
+                torch.cuda.synchronize(); dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    e0.record(stream)
+                    L.pfcu_fence()
+                    L.pfcu_surface_clear_ref(surf, 1, 0xFF000000, 1, 3.4028234663852886e38)
+                # the presenter's clear must have finished before any peer stores a tile into its surface
+                torch.cuda.synchronize(); dist.barrier()
+                with torch.cuda.stream(stream):
+                    L.pfcu_batch_submit(surf, b)
+                    L.pfcu_fence()
+                    e1.record(stream)
+                torch.cuda.synchronize(); dist.barrier()
+                if i > 0:
+                    fused.append(e0.elapsed_time(e1))
+            if rank == 0:
+                c = np.zeros((wl["h"], wl["w"]), np.uint32)
+                pfcu.check(L.pfcu_surface_download(surf, c.ctypes.data, None, 0, wl["h"]), "download")
+                fused_ok = hashlib.sha256(c.tobytes()).hexdigest() == ref_hash
+        elif fused_ok is None:
+            fused_ok = "another rank could not map the presenter's surface"
+        L.pfcu_surface_clear_present(surf)
+        tf = torch.tensor([sum(fused) / len(fused) if fused else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
         t = torch.tensor([sum(times) / len(times), sum(gather_ms) / len(gather_ms)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         px = torch.tensor([k.pixels_shaded / (steps + 1)], dtype=torch.float64, device="cuda")
@@ -80,8 +144,14 @@ def tile_split_benchmark(torch, dist, scenes, pfcu, stream, wl, rank, world, ste
         L.pfcu_surface_set_tile_owner(surf, 0, 1)
         L.pfcu_batch_destroy(b)
         sc.finish()
-    render_ms, gat_ms = float(t[0]), float(t[1])
-    return {"desc": wl["desc"] + f", screen-tile split over {world} GPUs + NCCL gather to rank 0", "scaling": "strong",
-            "render_ms": render_ms, "gather_ms": gat_ms, "shaded_px": float(px[0]),
-            "gpix_per_s_render": float(px[0]) / (render_ms * 1e-3) / 1e9,
-            "gpix_per_s_with_gather": float(px[0]) / ((render_ms + gat_ms) * 1e-3) / 1e9}
+    render_ms, gat_ms, fused_ms = float(t[0]), float(t[1]), float(tf[0])
+    out = {"desc": wl["desc"] + f", screen-tile split over {world} GPUs; present to rank 0 by NCCL gather and by fused peer stores", "scaling": "strong",
+           "render_ms": render_ms, "gather_ms": gat_ms, "shaded_px": float(px[0]),
+           "gpix_per_s_render": float(px[0]) / (render_ms * 1e-3) / 1e9,
+           "gpix_per_s_with_gather": float(px[0]) / ((render_ms + gat_ms) * 1e-3) / 1e9}
+    if fused_ms > 0:
+        out.update(fused_present_ms=fused_ms, gpix_per_s_fused_present=float(px[0]) / (fused_ms * 1e-3) / 1e9,
+                   fused_present_matches_gather=fused_ok)
+    else:
+        out.update(fused_present_unavailable=str(fused_ok))
+    return out

@@ -339,6 +339,44 @@ def test_tile_split_reassembles(pfcu_pair):
         assert np.array_equal(acc_c, full_c) and np.array_equal(acc_d.view(np.uint32), full_d.view(np.uint32))
 
 
+def test_fused_present_to_another_surface(pfcu_pair):
+    """Present over peer memory, single-process form: N "ranks" render their tiles into surfaces of their own whose
+    present target is one shared surface; the rasterisers store every finished tile into the target as well
+    (k_raster and k_raster_frag write-back), and pfcu_surface_push_tiles covers what they did not produce.  The
+    target must end up byte-identical to a single full render, colour and depth."""
+    prod, _ = pfcu_pair
+    L = prod.lib
+    rng = np.random.default_rng(21)
+    w, h = 600, 333
+    for small in (False, True):
+        states, tris = random_stream(rng, w, h, 9000 if small else 500, 1 | 2 | 16, big=not small)
+        prims = random_prims(rng, w, h, 60, 12)
+        for path in (1, 2):
+            L.pfcu_set_raster_path(path)
+            try:
+                full_c, full_d = prod.render_stream(w, h, states, tris, prims=prims)
+                for world in (2, 3):
+                    target = L.pfcu_surface_create(w, h)
+                    zeros = np.zeros((h, w), np.uint32); fmax = np.full((h, w), FLT_MAX, np.float32)
+                    prod.check(L.pfcu_surface_upload(target, zeros.ctypes.data, fmax.ctypes.data, 0, h))
+                    for rank in range(world):
+                        s = L.pfcu_surface_create(w, h)
+                        prod.check(L.pfcu_surface_upload(s, zeros.ctypes.data, fmax.ctypes.data, 0, h))
+                        prod.check(L.pfcu_surface_set_tile_owner(s, rank, world))
+                        prod.check(L.pfcu_surface_set_present_surface(s, target))
+                        prod.check(L.pfcu_submit(s, states.ctypes.data, len(states), tris.ctypes.data, len(tris)))
+                        prod.check(L.pfcu_submit_prims(s, prims.ctypes.data, len(prims)))
+                        prod.check(L.pfcu_surface_push_tiles(s, rank, world, 1))      # points / lines are not fused
+                        prod.check(L.pfcu_finish())
+                        L.pfcu_surface_destroy(s)
+                    c = np.zeros((h, w), np.uint32); d = np.zeros((h, w), np.float32)
+                    prod.check(L.pfcu_surface_download(target, c.ctypes.data, d.ctypes.data, 0, h))
+                    L.pfcu_surface_destroy(target)
+                    assert np.array_equal(c, full_c) and np.array_equal(d.view(np.uint32), full_d.view(np.uint32)), (small, path, world)
+            finally:
+                L.pfcu_set_raster_path(0)
+
+
 # ---- full-size properties (BASELINE.json sizes; the oracle is too slow here) ----------------------------
 
 def test_fullsize_overdraw_properties(product_scenes):

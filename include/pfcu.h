@@ -184,14 +184,14 @@ PFCU_API size_t pfcu_surface_owned_bytes(const pfcu_surface *s, uint32_t rank, u
 PFCU_API int pfcu_surface_pack_tiles(pfcu_surface *s, uint32_t rank, uint32_t world, int with_depth, void *dev_staging);
 PFCU_API int pfcu_surface_unpack_tiles(pfcu_surface *s, uint32_t rank, uint32_t world, int with_depth, const void *dev_staging);
 
-/* Present over peer memory (NVLink / NVSwitch), the fused alternative to pack -> NCCL gather -> unpack: the presenting
- * rank exports its surface (CUDA IPC), every other rank maps it and from then on the rasterisers store each tile they
- * finish BOTH into the local surface and straight into the presenter's, 128 bits at a time, while the other tiles are
- * still being shaded - the transfer overlaps the rendering tile by tile and no staging buffer or collective is left
- * on the data path (the ranks only need a barrier before the presenter reads).  pfcu_surface_push_tiles() pushes the
- * owned tiles explicitly (content that did not come from k_raster / k_raster_frag: clears, points and lines).
- * handle buffers: 64 bytes each (cudaIpcMemHandle_t).  pfcu_surface_set_present_surface() is the same with a
- * surface of THIS process as the target (single-GPU tests, several surfaces on one device). */
+/* Present over peer memory (NVLink / NVSwitch), the alternative to pack -> NCCL gather -> unpack: the presenting
+ * rank exports its surface (CUDA IPC), every other rank maps it, and pfcu_surface_push_tiles() stores the rank's own
+ * tiles straight into the presenter's surface, 128 bits at a time - no staging buffer, no collective on the data path
+ * (the ranks only need a barrier before the presenter reads).  A variant that issued these peer stores from inside
+ * the rasterisers' tile write-back (overlapping the transfer with the shading of the remaining tiles) cost the tuned
+ * k_raster 16 % on the single-GPU scenes and was dropped; the push kernel moves a rank's share of an 8K surface in
+ * well under 0.1 ms.  handle buffers: 64 bytes each (cudaIpcMemHandle_t).  pfcu_surface_set_present_surface() is
+ * the same with a surface of THIS process as the target (single-GPU tests, several surfaces on one device). */
 PFCU_API int pfcu_surface_ipc_handles(pfcu_surface *s, void *color_handle, void *depth_handle);
 PFCU_API int pfcu_surface_set_present_peer(pfcu_surface *s, const void *color_handle, const void *depth_handle);
 PFCU_API int pfcu_surface_set_present_surface(pfcu_surface *s, pfcu_surface *target);

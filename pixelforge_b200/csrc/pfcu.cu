@@ -825,7 +825,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     p.color = s->color; p.depth = s->depth; p.W = (int)s->w; p.H = (int)s->h;
     p.tilesX = (int)s->tiles_x; p.tilesY = (int)s->tiles_y;
     p.rank = s->rank; p.world = s->world ? s->world : 1; p.nTiles = s->tiles_x * s->tiles_y;
-    p.counters = g.d_counters; p.peer_color = s->peer_color; p.peer_depth = s->peer_depth;
+    p.counters = g.d_counters;
     const unsigned grid = owned_tiles(s, p.rank, p.world);
     if (g.profiling) CK(cudaEventRecord(pe[1], LN.stream));
     if (grid) {

@@ -458,12 +458,8 @@ k_raster_frag(const RasterParams p)
                 const int r = k >> 4, c4 = (k & 15) << 2;
                 const size_t gi = (size_t)(Y0 + r) * p.W + X0 + c4;
                 const int sa = ((r >> 3) * 8 + (c4 >> 3)) * FRAG_RSTRIDE + (r & 7) * 8 + (c4 & 7);
-                const uint4 cv = *reinterpret_cast<const uint4 *>(s_col + sa);
-                const float4 dv = *reinterpret_cast<const float4 *>(s_dep + sa);
-                __stcs(reinterpret_cast<uint4 *>(p.color + gi), cv);
-                __stcs(reinterpret_cast<float4 *>(p.depth + gi), dv);
-                if (p.peer_color) __stcs(reinterpret_cast<uint4 *>(p.peer_color + gi), cv);       /* fused present: peer store over NVLink */
-                if (p.peer_depth) __stcs(reinterpret_cast<float4 *>(p.peer_depth + gi), dv);
+                __stcs(reinterpret_cast<uint4 *>(p.color + gi), *reinterpret_cast<const uint4 *>(s_col + sa));
+                __stcs(reinterpret_cast<float4 *>(p.depth + gi), *reinterpret_cast<const float4 *>(s_dep + sa));
             }
         } else {
             for (int k = tid; k < TILE * TH; k += NT) {
@@ -473,8 +469,6 @@ k_raster_frag(const RasterParams p)
                     const int sa = ((ly >> 3) * 8 + (lx >> 3)) * FRAG_RSTRIDE + (ly & 7) * 8 + (lx & 7);
                     p.color[gi] = s_col[sa];
                     p.depth[gi] = s_dep[sa];
-                    if (p.peer_color) p.peer_color[gi] = s_col[sa];
-                    if (p.peer_depth) p.peer_depth[gi] = s_dep[sa];
                 }
             }
         }

@@ -11,7 +11,6 @@ struct RasterParams {
     uint32_t *color; float *depth; int W, H; int tilesX, tilesY;
     unsigned rank, world; unsigned nTiles;
     unsigned long long *counters;
-    uint32_t *peer_color; float *peer_depth;    /* presenting rank's surface over NVLink (nullptr: none); same geometry */
 };
 
 /* swizzled tile address: rows are 64 words; XOR-ing bits 3..4 of x with (y & 3) makes both the
@@ -480,12 +479,8 @@ k_raster(const RasterParams p)
                 const int c4 = (tid & 15) << 2;
                 const size_t gi = (size_t)(Y0 + r) * p.W + X0 + c4;
                 const int sa = tile_addr(c4, r);
-                const uint4 cv = *reinterpret_cast<const uint4 *>(s_color + sa);
-                const float4 dv = *reinterpret_cast<const float4 *>(s_depth + sa);
-                __stcs(reinterpret_cast<uint4 *>(p.color + gi), cv);
-                __stcs(reinterpret_cast<float4 *>(p.depth + gi), dv);
-                if (p.peer_color) __stcs(reinterpret_cast<uint4 *>(p.peer_color + gi), cv);       /* fused present: peer store over NVLink */
-                if (p.peer_depth) __stcs(reinterpret_cast<float4 *>(p.peer_depth + gi), dv);
+                __stcs(reinterpret_cast<uint4 *>(p.color + gi), *reinterpret_cast<const uint4 *>(s_color + sa));
+                __stcs(reinterpret_cast<float4 *>(p.depth + gi), *reinterpret_cast<const float4 *>(s_depth + sa));
             }
         } else {
             for (int k = tid; k < TILE * TH; k += NT) {
@@ -494,8 +489,6 @@ k_raster(const RasterParams p)
                     const size_t gi = (size_t)(Y0 + ly) * p.W + X0 + lx;
                     p.color[gi] = s_color[tile_addr(lx, ly)];
                     p.depth[gi] = s_depth[tile_addr(lx, ly)];
-                    if (p.peer_color) p.peer_color[gi] = s_color[tile_addr(lx, ly)];
-                    if (p.peer_depth) p.peer_depth[gi] = s_depth[tile_addr(lx, ly)];
                 }
             }
         }

@@ -339,11 +339,11 @@ def test_tile_split_reassembles(pfcu_pair):
         assert np.array_equal(acc_c, full_c) and np.array_equal(acc_d.view(np.uint32), full_d.view(np.uint32))
 
 
-def test_fused_present_to_another_surface(pfcu_pair):
+def test_peer_present_to_another_surface(pfcu_pair):
     """Present over peer memory, single-process form: N "ranks" render their tiles into surfaces of their own whose
-    present target is one shared surface; the rasterisers store every finished tile into the target as well
-    (k_raster and k_raster_frag write-back), and pfcu_surface_push_tiles covers what they did not produce.  The
-    target must end up byte-identical to a single full render, colour and depth."""
+    present target is one shared surface, then push their tiles into it (pfcu_surface_push_tiles, the kernel that
+    stores into the presenting rank's IPC-mapped surface over NVLink on a multi-GPU box).  The target must end up
+    byte-identical to a single full render, colour and depth."""
     prod, _ = pfcu_pair
     L = prod.lib
     rng = np.random.default_rng(21)
@@ -366,7 +366,7 @@ def test_fused_present_to_another_surface(pfcu_pair):
                         prod.check(L.pfcu_surface_set_present_surface(s, target))
                         prod.check(L.pfcu_submit(s, states.ctypes.data, len(states), tris.ctypes.data, len(tris)))
                         prod.check(L.pfcu_submit_prims(s, prims.ctypes.data, len(prims)))
-                        prod.check(L.pfcu_surface_push_tiles(s, rank, world, 1))      # points / lines are not fused
+                        prod.check(L.pfcu_surface_push_tiles(s, rank, world, 1))
                         prod.check(L.pfcu_finish())
                         L.pfcu_surface_destroy(s)
                     c = np.zeros((h, w), np.uint32); d = np.zeros((h, w), np.float32)

@@ -24,7 +24,12 @@ def gather_tiles(torch, dist, pfcu, surface, width, height, rank, world, with_de
     L = pfcu.lib
     per_tile = 64 * 64 * 4 * (2 if with_depth else 1)
     max_tiles = owned_tiles(width, height, 0, world)            # rank 0 owns the most
-    staging = torch.zeros(max_tiles * per_tile, dtype=torch.uint8, device=device)
+    # no initialising kernel on torch's stream: the pack kernel runs on the surface's pfcu lane, which is a different
+    # stream unless the surface happens to live on lane 0, and would race with it (the tail of the buffer of a rank that
+    # owns fewer tiles is never read)
+    staging = torch.empty(max_tiles * per_tile, dtype=torch.uint8, device=device)
+    if device == "cuda":
+        torch.cuda.current_stream().synchronize()
     pfcu.check(L.pfcu_surface_pack_tiles(surface, rank, world, int(with_depth), staging.data_ptr()), "pack_tiles")
     if device == "cuda":
         # pack ran on the pfcu stream; make the collective wait for it

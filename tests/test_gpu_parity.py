@@ -411,6 +411,27 @@ def test_fullsize_phong_properties(product_scenes):
     assert r2.pixels_shaded == 2 * r1.pixels_shaded          # each frame clears first, so both frames shade alike
 
 
+def test_fullsize_c2_c3_both_rasterisers_and_vertex_stages_agree(pfcu_pair, product_scenes):
+    """BASELINE configs C2 (1920x1080 bilinear + alpha + depth torus, 131 k triangles) and C3 (3840x2160, 1 M
+    triangles, per-pixel Phong) at full size: the fragment-compacting rasteriser (what AUTO picks), the
+    triangle-per-warp-step rasteriser and the host vertex stage must all give the same colour and depth, bit for bit."""
+    prod, _ = pfcu_pair
+    for scene, w, h, kw in (("textured", 1920, 1080, dict(size=256, variant=1 | 32 | 64)), ("phong", 3840, 2160, dict(size=708, variant=32))):
+        ref_c, ref_d, ref_r = product_scenes.render(scene, w, h, **kw)
+        assert (ref_d != FLT_MAX).sum() > 0.3 * w * h
+        for path in (1, 2):
+            prod.lib.pfcu_set_raster_path(path)
+            try:
+                c, d, r = product_scenes.render(scene, w, h, **kw)
+            finally:
+                prod.lib.pfcu_set_raster_path(0)
+            assert r.pixels_shaded == ref_r.pixels_shaded and r.triangles_rasterised == ref_r.triangles_rasterised
+            assert np.array_equal(c, ref_c) and np.array_equal(d.view(np.uint32), ref_d.view(np.uint32)), (scene, path)
+    hc, hd, ht, hp = _render_with_env("textured", 1920, 1080, {"PF_CUDA_DEVICE_VERTEX": "0"}, size=256, variant=1 | 32 | 64)
+    ref_c, ref_d, ref_r = product_scenes.render("textured", 1920, 1080, size=256, variant=1 | 32 | 64)
+    assert hp == ref_r.pixels_shaded and np.array_equal(hc, ref_c) and np.array_equal(hd.view(np.uint32), ref_d.view(np.uint32))
+
+
 # ---- device vertex stage, lanes, batch growth ------------------------------------------------------------
 
 def _render_with_env(scene, w, h, env, **kw):

@@ -10,9 +10,10 @@ model at 1920x1080 with bilinear filtering, alpha blending and depth test.
 Legs of the default (ours) arm, all printed in ONE JSON line by rank 0:
   value      shaded Gpix/s with the frame's triangle stream already resident in HBM: CUDA events on
              the launching stream around {clear, setup, bin, raster}; L2 flushed between iterations.
-  e2e        the same metric through the public pixelforge.h API with HOST buffers: host vertex stage,
-             H2D of the triangle batch from pinned memory, kernels, D2H of the framebuffer into the
-             caller's buffer - wall clock around pfClear..pfxFinish.
+  e2e        the same metric through the public pixelforge.h API with HOST buffers: the application's API calls,
+             H2D of the step's inputs from pinned host memory (assembled-triangle batches; vertex / index arrays
+             that the scene allocated with pfxHostAlloc), device vertex stage + rasterisation, D2H of the
+             framebuffer into the caller's (page-locked) buffer - wall clock around pfClear..pfxFinish.
   roofline   k_raster (the dominant kernel): algorithmic bytes / its CUDA-event time.
   cpu_baseline  the reference's own OpenMP+AVX2 code (oracle/_ref, compiled from /root/reference)
              on this box's host cores, bounded sample, in a subprocess.

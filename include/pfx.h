@@ -8,6 +8,7 @@
 #define PIXEL_FORGE_X_H
 
 #include "pixelforge.h"
+#include <stddef.h>
 
 #if defined(__cplusplus)
 extern "C" {
@@ -54,6 +55,11 @@ PF_API void pfxEnableDeviceVertexStage(PFboolean on);
  * neighbours of every threshold.  Returns the number of mismatches, -1 when the shininess is not tabulated (the
  * host then lights those vertices itself), -2 without a current context. */
 PF_API int pfxSpecularTableCheck(PFfloat shininess, PFuint samples);
+/* Page-locked host memory for buffers the application hands to the library every frame (vertex / index arrays, pixel
+ * buffers): copies from it are plain DMA at full PCIe speed instead of being staged by the driver.  Optional: ordinary
+ * malloc'ed memory works everywhere, as with the reference.  Free with pfxHostFree (after the last call that used it). */
+PF_API void *pfxHostAlloc(size_t bytes);
+PF_API void  pfxHostFree(void *p);
 /* The pfcu_surface* behind the current target. */
 PF_API void *pfxGetSurfaceHandle(void);
 PF_API const char *pfxBackendName(void);

@@ -188,7 +188,7 @@ PFCU_SYMBOLS = [
 
 PFX_SYMBOLS = ["pfxSetSyncMode", "pfxFlush", "pfxFinish", "pfxGetCounters", "pfxResetCounters", "pfxSetTileOwner",
                "pfxGetDeviceColor", "pfxGetDeviceDepth", "pfxReadDepth", "pfxCaptureBegin", "pfxCaptureEnd",
-               "pfxGetSurfaceHandle", "pfxBackendName", "pfxEnableDeviceVertexStage", "pfxSpecularTableCheck"]
+               "pfxGetSurfaceHandle", "pfxBackendName", "pfxEnableDeviceVertexStage", "pfxSpecularTableCheck", "pfxHostAlloc", "pfxHostFree"]
 
 
 class PfcuLib:

@@ -1102,6 +1102,8 @@ void pfxReadDepth(PFfloat *out)
     pfcu_surface_download(c->cur_surf->dev, NULL, out, 0, c->cur_surf->tex->h);
 }
 
+void *pfxHostAlloc(size_t bytes) { return pfh_runtime_init() ? pfcu_host_alloc(bytes) : NULL; }
+void pfxHostFree(void *p) { if (p) { pfcu_finish(); pfcu_host_free(p); } }
 void pfxEnableDeviceVertexStage(PFboolean on) { if (pf_cur) pf_cur->device_vertex = on ? 1 : 0; }
 
 void pfxCaptureBegin(void)

@@ -225,11 +225,21 @@ static void gears_frame(float angle)
 
 typedef struct { float *pos, *nrm, *uv; uint32_t *idx; int nverts, nidx; } mesh_t;
 
+/* Vertex and index arrays of the big meshes: page-locked when the library offers it (pfx.h; bench.py's end-to-end leg
+ * copies its inputs from pinned host memory), plain malloc for the reference. */
+#ifdef PFSCENE_HAVE_PFX
+static void *mesh_alloc(size_t bytes) { void *p = pfxHostAlloc(bytes); return p ? p : NULL; }
+static void mesh_free(void *p) { pfxHostFree(p); }
+#else
+static void *mesh_alloc(size_t bytes) { return malloc(bytes); }
+static void mesh_free(void *p) { free(p); }
+#endif
+
 static mesh_t make_torus(int nu, int nv, float R, float r, float uvscale)
 {
     mesh_t m; m.nverts = (nu + 1) * (nv + 1); m.nidx = nu * nv * 6;
-    m.pos = (float *)malloc(sizeof(float) * 3 * m.nverts); m.nrm = (float *)malloc(sizeof(float) * 3 * m.nverts);
-    m.uv = (float *)malloc(sizeof(float) * 2 * m.nverts); m.idx = (uint32_t *)malloc(sizeof(uint32_t) * m.nidx);
+    m.pos = (float *)mesh_alloc(sizeof(float) * 3 * m.nverts); m.nrm = (float *)mesh_alloc(sizeof(float) * 3 * m.nverts);
+    m.uv = (float *)mesh_alloc(sizeof(float) * 2 * m.nverts); m.idx = (uint32_t *)mesh_alloc(sizeof(uint32_t) * m.nidx);
     for (int i = 0; i <= nu; i++) for (int j = 0; j <= nv; j++) {
         double a = 2.0 * SCN_PI * i / nu, b = 2.0 * SCN_PI * j / nv;
         int k = i * (nv + 1) + j;
@@ -245,7 +255,7 @@ static mesh_t make_torus(int nu, int nv, float R, float r, float uvscale)
     return m;
 }
 
-static void free_mesh(mesh_t *m) { free(m->pos); free(m->nrm); free(m->uv); free(m->idx); }
+static void free_mesh(mesh_t *m) { mesh_free(m->pos); mesh_free(m->nrm); mesh_free(m->uv); mesh_free(m->idx); }
 
 static void draw_mesh_immediate(const mesh_t *m)
 {
@@ -272,8 +282,8 @@ static void draw_mesh_arrays(const mesh_t *m)
 static mesh_t make_heightfield(int n)
 {
     mesh_t m; m.nverts = (n + 1) * (n + 1); m.nidx = n * n * 6;
-    m.pos = (float *)malloc(sizeof(float) * 3 * m.nverts); m.nrm = (float *)malloc(sizeof(float) * 3 * m.nverts);
-    m.uv = (float *)malloc(sizeof(float) * 2 * m.nverts); m.idx = (uint32_t *)malloc(sizeof(uint32_t) * m.nidx);
+    m.pos = (float *)mesh_alloc(sizeof(float) * 3 * m.nverts); m.nrm = (float *)mesh_alloc(sizeof(float) * 3 * m.nverts);
+    m.uv = (float *)mesh_alloc(sizeof(float) * 2 * m.nverts); m.idx = (uint32_t *)mesh_alloc(sizeof(uint32_t) * m.nidx);
     for (int j = 0; j <= n; j++) for (int i = 0; i <= n; i++) {
         double x = -2.0 + 4.0 * i / n, y = -1.2 + 2.4 * j / n;
         double z = 0.3 * sin(3 * x) * cos(3 * y);

@@ -130,6 +130,8 @@ struct Lane {
     void *h_stage = nullptr; size_t cap_stage = 0; cudaEvent_t stage_done = nullptr;
     DevState *h_states = nullptr; size_t cap_hstates = 0; cudaEvent_t states_done = nullptr;
     cudaEvent_t fence = nullptr;
+    bool touched = false;               /* work enqueued on this lane since the last pfcu_fence()            */
+    bool need_fence_wait = false;       /* the next use of this lane must first wait for lane 0's fence event */
     /* raw-triangle batches: their vertex stage is counted on a side stream so that the one host wait (for the
        output triangle count) does not wait for the rasterisation queued on the lane */
     cudaStream_t vstream = nullptr; cudaEvent_t raw_done = nullptr, vready = nullptr;
@@ -264,7 +266,15 @@ int pfcu_init(int device)
 }
 
 static void sync_all_lanes(void) { for (int i = 0; i < g.n_lanes; i++) cudaStreamSynchronize(g.lanes[i].stream); }
-static void use_lane(const pfcu_surface *s) { g.cur = &g.lanes[s ? s->lane % g.n_lanes : 0]; }
+static void use_lane(const pfcu_surface *s)
+{
+    g.cur = &g.lanes[s ? s->lane % g.n_lanes : 0];
+    if (LN.need_fence_wait) {           /* deferred half of pfcu_fence(): later work on this lane comes after lane 0's fence */
+        if (g.cur != &g.lanes[0]) cudaStreamWaitEvent(LN.stream, g.lanes[0].fence, 0);
+        LN.need_fence_wait = false;
+    }
+    LN.touched = true;
+}
 
 void pfcu_shutdown(void)
 {
@@ -294,12 +304,16 @@ int pfcu_fence(void)
 {
     API_LOCK;
     if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    /* lanes that were not used since the last fence have nothing new to order before lane 0; their wait for lane 0 is
+       deferred to their next use (use_lane) - a single-surface workload pays for one event, not for every lane */
     for (int i = 1; i < g.n_lanes; i++) {
+        if (!g.lanes[i].touched) continue;
         CK(cudaEventRecord(g.lanes[i].fence, g.lanes[i].stream));
         CK(cudaStreamWaitEvent(g.lanes[0].stream, g.lanes[i].fence, 0));
+        g.lanes[i].touched = false;
     }
     CK(cudaEventRecord(g.lanes[0].fence, g.lanes[0].stream));
-    for (int i = 1; i < g.n_lanes; i++) CK(cudaStreamWaitEvent(g.lanes[i].stream, g.lanes[0].fence, 0));
+    for (int i = 1; i < g.n_lanes; i++) g.lanes[i].need_fence_wait = true;
     return PFCU_OK;
 }
 

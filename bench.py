@@ -118,36 +118,69 @@ def shaded_pixels_table():
         return json.load(f)
 
 
-def run_reference(args, wl_name, bounded_frames=None, bilinear_fix=False):
+def is_bilinear(wl):
+    return (wl["scene"] == "textured" and bool(wl["variant"] & 1)) or (wl["scene"] == "overdraw" and bool(wl["variant"] & 2))
+
+
+def gate_size(wl):
+    """Scene size of the BOUNDED sample both the CPU arm and the reference-equivalence gate use: every context of C5,
+    full frames of C1-C3, a 4-layer slice of the 64-layer overdraw scenes (the work per layer is identical)."""
+    return min(wl["size"], 4) if wl["scene"] == "overdraw" else wl["size"]
+
+
+def bench_config(wl_name, n_gpus):
+    """The `config` object of the JSON line - the same in both arms (the driver compares them)."""
+    wl = WORKLOADS[wl_name]
+    counts = shaded_pixels_table().get(wl_name, {})
+    return {"workload": wl_name, "description": wl["desc"], "width": wl["w"], "height": wl["h"],
+            "triangles_per_step": counts.get("triangles_submitted"), "shaded_px_per_step": counts.get("pixels_shaded"),
+            "parallelism": f"independent contexts x{n_gpus}",
+            "l2_policy": "GPU arm: 256 MiB buffer written between timed iterations (untimed); CPU arm: n/a",
+            "reference_library": "bilinear workloads: reference rebuilt with the one-token fix of its uninitialised-vector bug "
+                                 "(src/internal/color.h:141, SURVEY Q7) in BOTH arms; everything else: unmodified reference"}
+
+
+def run_reference(args, wl_name, bounded_frames=None, dump=None):
+    """Times the reference's own OpenMP+AVX2 implementation (oracle/_ref, compiled from /root/reference) on frame 0 of
+    the workload, all host threads.  With `dump`, the colour and depth of every context after the last frame are
+    written there (np.savez): the GPU arm renders the same frame and compares (the reference-equivalence gate)."""
+    import numpy as np
     # all host threads (torchrun exports OMP_NUM_THREADS=1 to its children; only rank 0 runs this arm)
     os.environ["OMP_NUM_THREADS"] = os.environ.get("PF_REF_THREADS", str(os.cpu_count()))
     os.environ.setdefault("OMP_WAIT_POLICY", "active")
-    from pixelforge_b200 import load_reference_scenes
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from checkers import load_reference_scenes          # CPU arm only: the reference itself, never on the product path
     wl = WORKLOADS[wl_name]
-    lib = load_reference_scenes(bilinear_fix)
+    bfix = is_bilinear(wl)
+    lib = load_reference_scenes(bfix)
     steps = bounded_frames if bounded_frames else args.steps
     warm = 1 if bounded_frames else args.warmup
-    size = wl["size"]
-    sample = f"{steps} full frames after {warm} warm-up"
+    size = gate_size(wl)
     # bounded samples of the big workloads so that the CPU arm ends within minutes (work scales linearly)
-    if wl["scene"] == "batch":
-        size = min(size, 8)
-        sample += f", {size} of {wl['size']} contexts"
-    elif wl["scene"] == "overdraw":
-        size = min(size, 4)
-        sample += f", {size} of {wl['size']} layers"
-    if wl["scene"] in ("overdraw", "phong") and not bounded_frames:
+    if wl["scene"] in ("overdraw", "phong", "batch") and not bounded_frames:
         steps, warm = min(steps, 3), min(warm, 1)
-        sample = f"{steps} frames after {warm} warm-up" + (f", {size} of {wl['size']} layers" if wl["scene"] == "overdraw" else "")
-    _, _, res = lib.render(wl["scene"], wl["w"], wl["h"], frames=steps, warmup=warm, variant=wl["variant"], size=size, want_depth=False)
+    sample = f"{steps} full frames (frame 0) after {warm} warm-up"
+    if size != wl["size"]:
+        sample += f", {size} of {wl['size']} layers"
+    times = []
+    with lib.open(wl["scene"], wl["w"], wl["h"], variant=wl["variant"], size=size) as sc:
+        for i in range(warm + steps):
+            t0 = time.perf_counter()
+            sc.frame(0); sc.finish()
+            if i >= warm:
+                times.append((time.perf_counter() - t0) * 1e3)
+        if dump:
+            n_ctx = size if wl["scene"] == "batch" else 1
+            frames = [sc.read_index(i, want_depth=True) for i in range(n_ctx)]
+            np.savez(dump, color=np.stack([f[0] for f in frames]), depth=np.stack([f[1] for f in frames]))
     counts = shaded_pixels_table().get(wl_name, {})
-    scale = (size / wl["size"]) if wl["scene"] in ("batch", "overdraw") else 1
+    scale = size / wl["size"] if wl["scene"] == "overdraw" else 1
     px = counts.get("pixels_shaded", 0) * scale
     tris = counts.get("triangles_submitted", 0) * scale
-    ms = res.ms_total / max(steps, 1)
+    ms = sum(times) / max(len(times), 1)
     return {"ms_per_step": ms, "gpix": px / (ms * 1e-3) / 1e9 if ms > 0 else 0.0, "mtri": tris / (ms * 1e-3) / 1e6 if ms > 0 else 0.0,
-            "ms_median": res.ms_median, "cores": int(os.environ["OMP_NUM_THREADS"]), "sample": sample,
-            "kind": "reference", "library": "oracle/_ref/" + ("libpf_ref_bfix.so (Q7 one-token bilinear fix)" if bilinear_fix else "libpf_ref.so (unmodified)")}
+            "ms_median": sorted(times)[len(times) // 2] if times else 0.0, "cores": int(os.environ["OMP_NUM_THREADS"]), "sample": sample,
+            "kind": "reference", "library": "oracle/_ref/" + ("libpf_ref_bfix.so (reference + the one-token Q7 bilinear fix)" if bfix else "libpf_ref.so (unmodified reference)")}
 
 
 def reference_main(args):
@@ -155,10 +188,8 @@ def reference_main(args):
     if rank != 0:
         return 0
     wl_name = args.workload
-    wl = WORKLOADS[wl_name]
     try:
-        r = run_reference(args, wl_name, bounded_frames=args.baseline_frames if args.as_baseline else None,
-                          bilinear_fix=args.as_baseline and bool(wl["variant"] & 1) and wl["scene"] == "textured")
+        r = run_reference(args, wl_name, bounded_frames=args.baseline_frames if args.as_baseline else None, dump=args.dump)
     except FileNotFoundError as e:
         emit_json({"impl": "reference", "unavailable": f"oracle/_ref not built: {e}"})
         return 0
@@ -166,7 +197,7 @@ def reference_main(args):
         "impl": "reference", "metric": METRIC, "value": r["gpix"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/i32/f32", "data": "synthetic",
-        "config": {"workload": wl_name, "description": wl["desc"], "l2_policy": "n/a (CPU)"},
+        "config": bench_config(wl_name, args.gpus),
         "mtri_per_s": r["mtri"],
         "cpu_baseline": {"value": r["gpix"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": r["sample"], "library": r["library"]},
         "e2e": {"value": r["gpix"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -174,6 +205,29 @@ def reference_main(args):
     }
     emit_json(line)
     return 0
+
+
+def parity_against_dump(scenes, wl_name, dump):
+    """The reference-equivalence gate: render frame 0 of the workload at full size through the public
+    API of the product and compare colour and depth, bit for bit, with what the reference rendered in this very run."""
+    import numpy as np
+    wl = WORKLOADS[wl_name]
+    size = gate_size(wl)
+    z = np.load(dump)
+    ref_c, ref_d = z["color"], z["depth"]
+    n_ctx = size if wl["scene"] == "batch" else 1
+    dpx = dz = 0
+    with scenes.open(wl["scene"], wl["w"], wl["h"], variant=wl["variant"], size=size, explicit_sync=1) as sc:
+        sc.frame(0); sc.finish()
+        for i in range(n_ctx):
+            c, d = sc.read_index(i, want_depth=True)
+            dpx += int((c != ref_c[i]).sum())
+            dz += int((d.view(np.uint32) != ref_d[i].view(np.uint32)).sum())
+    out = {"differing_px": dpx, "differing_depth": dz, "pixels_compared": int(ref_c.size), "contexts": n_ctx,
+           "resolution": [wl["w"], wl["h"]]}
+    if size != wl["size"]:
+        out["layers"] = f"{size} of {wl['size']}"
+    return out
 
 
 # ---- our arm ---------------------------------------------------------------------------------------
@@ -346,14 +400,23 @@ def ours_main(args):
             dist.destroy_process_group()
         return 0
 
+    parity = {}
+
     def cpu_run(name, frames):
+        """CPU baseline of one workload (the reference itself, in a subprocess, all host threads) and, from the very
+        frames it rendered, the reference-equivalence gate of the product."""
+        import tempfile
         env = dict(os.environ); env.pop("OMP_NUM_THREADS", None)      # torchrun pins it to 1; the baseline uses every core
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--as-baseline", "--workload", name,
-                            "--baseline-frames", str(frames)], capture_output=True, text=True, timeout=900, env=env)
-        j = json.loads(r.stdout.strip().splitlines()[-1])
-        c = j.get("cpu_baseline") or {"unavailable": j.get("unavailable")}
-        if "value" in c:
-            c["ms_per_frame_of_sample"] = j["ms_per_step"]; c["mtri_per_s"] = j.get("mtri_per_s")
+        tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        with tempfile.TemporaryDirectory(dir=tmpdir) as d:
+            dump = os.path.join(d, "ref.npz")
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--as-baseline", "--workload", name,
+                                "--baseline-frames", str(frames), "--dump", dump], capture_output=True, text=True, timeout=900, env=env)
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            c = j.get("cpu_baseline") or {"unavailable": j.get("unavailable")}
+            if "value" in c:
+                c["ms_per_frame_of_sample"] = j["ms_per_step"]; c["mtri_per_s"] = j.get("mtri_per_s")
+                parity[name] = parity_against_dump(scenes, name, dump)
         return c
 
     if not args.no_cpu_baseline and not args.no_extra:
@@ -367,22 +430,18 @@ def ours_main(args):
     cpu = None
     if not args.no_cpu_baseline:
         try:
-            env = dict(os.environ); env.pop("OMP_NUM_THREADS", None)      # torchrun pins it to 1; the baseline uses every core
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--as-baseline", "--workload", wl_name,
-                                "--baseline-frames", "3"], capture_output=True, text=True, timeout=600, env=env)
-            j = json.loads(r.stdout.strip().splitlines()[-1])
-            cpu = j.get("cpu_baseline") or {"unavailable": j.get("unavailable")}
+            cpu = cpu_run(wl_name, 3)
             if "value" in (cpu or {}):
-                cpu["ms_per_frame"] = j["ms_per_step"]
+                cpu["ms_per_frame"] = cpu["ms_per_frame_of_sample"]
         except Exception as e:
             cpu = {"unavailable": repr(e)}
+    gate_failed = [n for n, p in parity.items() if p["differing_px"] or p["differing_depth"]]
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32/f32", "data": "synthetic",
-        "config": {"workload": wl_name, "description": wl["desc"], "width": wl["w"], "height": wl["h"],
-                   "triangles_per_step": tris_all / world, "shaded_px_per_step": px_all / world, "parallelism": f"independent contexts x{world}",
-                   "l2_policy": "256 MiB buffer written between timed iterations (untimed)"},
+        "config": bench_config(wl_name, world),
+        "measured_per_step": {"triangles": tris_all / world, "shaded_px": px_all / world},
         "mtri_per_s": tris_all / (dev_ms * 1e-3) / 1e6,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": m["d2h_bytes"],
                 "ms_per_step": e2e_ms, "mtri_per_s": sum_over_ranks(m["tris_per_step"]) / (e2e_ms * 1e-3) / 1e6 if world == 1 else None},
@@ -391,12 +450,19 @@ def ours_main(args):
                      "kernel": "k_raster_frag" if wl["scene"] in ("textured", "phong", "gears", "batch") else "k_raster",
                      "sm_issue_active_pct_ncu": issue_active, "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_shaded_px": wl["bytes_px"],
                      "kernel_ms": m["raster_ms"], "frontend_kernels_ms": m["frontend_ms"], "peak_source": peak_src},
-        "cpu_baseline": cpu, "clocks": clocks, "extra": extra,
+        "cpu_baseline": cpu, "clocks": clocks,
+        # the reference-equivalence gate: every workload's frame 0 at full size, product vs the frames the CPU arm rendered
+        "parity": parity if parity else "not run (--no-cpu-baseline: no reference frames to compare with)",
+        "extra": extra,
     }
+    if gate_failed:
+        # no number is reported for a build whose pixels differ from the reference's
+        line["value"] = None; line["e2e"]["value"] = None
+        line["error"] = "reference-equivalence gate failed for " + ", ".join(gate_failed)
     emit_json(line)
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return 1 if gate_failed else 0
 
 
 _REAL_STDOUT = None
@@ -424,6 +490,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--as-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--baseline-frames", type=int, default=3, help=argparse.SUPPRESS)
+    ap.add_argument("--dump", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -60,6 +60,10 @@ PF_API int pfxSpecularTableCheck(PFfloat shininess, PFuint samples);
  * malloc'ed memory works everywhere, as with the reference.  Free with pfxHostFree (after the last call that used it). */
 PF_API void *pfxHostAlloc(size_t bytes);
 PF_API void  pfxHostFree(void *p);
+/* Texel memory is copied to the device at the first draw that samples the texture; the reference reads the caller's
+ * memory at every fragment, so a program that rewrites texels in place (video frames, procedural updates) calls this
+ * after each rewrite to have them uploaded again.  Draw calls issued before it keep the old texels. */
+PF_API void pfxTextureDirty(PFtexture texture);
 /* The pfcu_surface* behind the current target. */
 PF_API void *pfxGetSurfaceHandle(void);
 PF_API const char *pfxBackendName(void);

@@ -6,6 +6,5 @@ Python package only holds thin ctypes bindings used by the tests and ``bench.py`
 anything itself and it raises loudly when the CUDA library is missing or no GPU is present.
 """
 from .binding import (  # noqa: F401
-    SceneLib, SceneCfg, SceneResult, load_product_scenes, load_oracle_scenes, load_reference_scenes,
-    load_pfcu, PfcuLib, LIB_DIR, REPO_ROOT, ProductUnavailable,
+    SceneLib, SceneCfg, SceneResult, load_product_scenes, load_pfcu, PfcuLib, LIB_DIR, REPO_ROOT, ProductUnavailable,
 )

@@ -1,10 +1,8 @@
-"""ctypes bindings: scene runner libraries and the pfcu C-ABI (include/pfcu.h).
+"""ctypes bindings: the scene runner and the pfcu C-ABI (include/pfcu.h) of the PRODUCT.
 
-Three scene-runner builds of the same C file (pixelforge_b200/scenes/scenes.c) exist:
-  product   pixelforge_b200/lib/libpfscenes_cuda.so     -> libpixelforge.so (CUDA, sm_100a)
-  oracle    oracle/_build/libpfscenes_oracle.so         -> front end + scalar C restatement (tests only)
-  reference oracle/_ref/libpfscenes_ref[_bfix].so       -> the unmodified reference (tests / CPU baseline)
-Only tests/, bench.py's cpu_baseline / --impl reference legs and smoke() may load the last two.
+SceneLib / PfcuLib are generic typed wrappers over a shared library path; this package only ever points them at
+pixelforge_b200/lib/ (libpfscenes_cuda.so -> libpixelforge.so, CUDA sm_100a).  The checkers (the scalar C oracle and
+the unmodified reference under oracle/) are loaded by tests/checkers.py, never from here.
 """
 import ctypes as C
 import os
@@ -106,6 +104,17 @@ class Scene:
             raise IndexError(index)
         return color
 
+    def read_index(self, index, want_depth=True):
+        """(colour u32[h,w], depth f32[h,w] or None) of context `index`, read through the public API."""
+        color = np.zeros((self.cfg.height, self.cfg.width), np.uint32)
+        depth = np.zeros((self.cfg.height, self.cfg.width), np.float32) if want_depth else None
+        f = self.lib.lib.pfscene_read_index
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        if not f(self.handle, index, color.ctypes.data, depth.ctypes.data if want_depth else None):
+            raise IndexError(index)
+        return color, depth
+
     def read(self, want_depth=False):
         color = np.zeros((self.cfg.height, self.cfg.width), dtype=np.uint32)
         depth = np.zeros((self.cfg.height, self.cfg.width), dtype=np.float32) if want_depth else None
@@ -129,15 +138,6 @@ def load_product_scenes():
     if not os.path.exists(path) or not os.path.exists(os.path.join(LIB_DIR, "libpixelforge.so")):
         raise ProductUnavailable(f"{path} not built - run `make lib scenes` (or __graft_entry__.build())")
     return SceneLib(path)
-
-
-def load_oracle_scenes():
-    return SceneLib(os.path.join(REPO_ROOT, "oracle", "_build", "libpfscenes_oracle.so"))
-
-
-def load_reference_scenes(bilinear_fix=False):
-    name = "libpfscenes_ref_bfix.so" if bilinear_fix else "libpfscenes_ref.so"
-    return SceneLib(os.path.join(REPO_ROOT, "oracle", "_ref", name))
 
 
 # ---- pfcu C-ABI ------------------------------------------------------------------------------------
@@ -315,11 +315,9 @@ class PfcuLib:
 
 
 def load_pfcu(which="product"):
-    if which == "product":
-        path = os.path.join(LIB_DIR, "libpixelforge.so")
-        if not os.path.exists(path):
-            raise ProductUnavailable(f"{path} not built - run `make lib` (or __graft_entry__.build())")
-        return PfcuLib(path)
-    if which == "oracle":
-        return PfcuLib(os.path.join(REPO_ROOT, "oracle", "_build", "libpixelforge_oracle.so"))
-    raise ValueError(which)
+    if which != "product":
+        raise ValueError(f"{which!r}: this package only loads the product; the checkers live in tests/checkers.py")
+    path = os.path.join(LIB_DIR, "libpixelforge.so")
+    if not os.path.exists(path):
+        raise ProductUnavailable(f"{path} not built - run `make lib` (or __graft_entry__.build())")
+    return PfcuLib(path)

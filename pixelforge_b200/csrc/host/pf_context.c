@@ -105,7 +105,13 @@ void pfSetMainBuffer(void *targetBuffer, PFsizei width, PFsizei height, PFpixelf
     CTX;
     if (!targetBuffer || width == 0 || height == 0) { c->errCode = PF_INVALID_VALUE; return; }
     pf_tex *old = (pf_tex *)c->mainFramebuffer.texture;
-    pfh_sync_surface(c, c->main_surf);
+    /* The reference never touches the outgoing buffer here, and applications commonly free or realloc it before this
+       call (window resize): submit what is pending, wait for a read-back that may already be in flight into it, and
+       drop the rest of the device -> host debt instead of paying it into memory that may be gone. */
+    if (c->cur_surf == c->main_surf) pfh_flush(c);
+    if (c->main_surf->readback_queued) pfcu_surface_wait(c->main_surf->dev);
+    c->main_surf->readback_queued = 0; c->main_surf->dev_newer = 0;
+    c->main_surf->dirty_y0 = old->h; c->main_surf->dirty_y1 = 0;
     if (old->w == width && old->h == height && old->format == format && old->type == type) {
         if (c->main_surf->pinned_color) { pfcu_host_unregister(c->main_surf->pinned_color); c->main_surf->pinned_color = NULL; }
         old->pixels = targetBuffer;             /* same geometry: retarget the host mirror, keep depth */
@@ -1100,6 +1106,14 @@ void pfxReadDepth(PFfloat *out)
     pfh_flush(c);
     pfh_upload_if_needed(c, c->cur_surf);
     pfcu_surface_download(c->cur_surf->dev, NULL, out, 0, c->cur_surf->tex->h);
+}
+
+void pfxTextureDirty(PFtexture texture)
+{
+    pf_tex *t = (pf_tex *)texture;
+    if (!t || t->surf || !t->dev || !t->pixels) return;        /* render targets are tracked; never-used textures upload at first use */
+    if (pf_cur) pfh_flush(pf_cur);                              /* draws issued so far sample the old texels */
+    pfcu_texture_update(t->dev, t->pixels);
 }
 
 void *pfxHostAlloc(size_t bytes) { return pfh_runtime_init() ? pfcu_host_alloc(bytes) : NULL; }

@@ -57,7 +57,8 @@
 #define QUEUE_CAP   1024            /* triangle indices buffered per tile between raster passes      */
 #define SETUP_THREADS 256
 #define BIN_BATCH   1024            /* triangles per binning CTA (256 for mid-sized batches, see launch_pipeline) */
-#define MAX_BINS    12000           /* bin counters live in dynamic shared memory (48 KB); 7680x4320 in 64 px bins = 8160 */
+#define MAX_BINS    10240           /* bin counters live in dynamic shared memory: 40 KB + the 8 KB of static rectangles of k_bin_fill = the 48 KB
+                                       a kernel gets without opting in; 7680x4320 in 64 px bins = 8160.  Larger surfaces take coarser bins. */
 
 #define TF_VALID    1u              /* survived cull and has a non-empty bbox on the surface         */
 #define TF_SAFE     2u              /* int32 edge functions cannot wrap inside the bbox              */
@@ -163,7 +164,18 @@ struct Runtime {
 
 static Runtime g;
 #define LN (*g.cur)
-#define API_LOCK std::lock_guard<std::recursive_mutex> api_lock_(g.mu)
+/* Every locked entry point also makes the runtime's device current on the calling thread: the C-ABI is shared by
+ * contexts on several host threads, and a thread that has not called pfcu_init starts with device 0 current
+ * (wrong allocations and "invalid resource handle" launches when PF_CUDA_DEVICE / LOCAL_RANK picked another one). */
+struct ApiGuard {
+    std::lock_guard<std::recursive_mutex> lk;
+    ApiGuard() : lk(g.mu)
+    {
+        static thread_local int t_device = -1;
+        if (g.ok && t_device != g.device) { if (cudaSetDevice(g.device) == cudaSuccess) t_device = g.device; }
+    }
+};
+#define API_LOCK ApiGuard api_lock_
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     snprintf(g.err, sizeof g.err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
@@ -289,12 +301,18 @@ void pfcu_shutdown(void)
         if (LN.h_states) cudaFreeHost(LN.h_states);
         if (LN.h_total) cudaFreeHost(LN.h_total);
         cudaFree(LN.d_raw); cudaFree(LN.d_total); cudaFree(LN.d_chain); cudaFree(LN.d_idx);
+        for (cudaEvent_t e : { LN.stage_done, LN.states_done, LN.fence, LN.raw_done, LN.vready }) if (e) cudaEventDestroy(e);
         if (LN.vstream) cudaStreamDestroy(LN.vstream);
         if (LN.own_stream) cudaStreamDestroy(LN.stream);
         g.lanes[i] = Lane();
     }
     cudaFree(g.d_counters); cudaFree(g.d_rcp); cudaFree(g.d_rsq);
     g.d_counters = nullptr; g.d_rcp = nullptr; g.d_rsq = nullptr;
+    /* blocks handed out by pfcu_host_alloc and never returned: released here, their pointers die with the runtime */
+    for (auto &b : g.pinned) { cudaEventDestroy(b.done); cudaFreeHost(b.p); }
+    for (auto e : g.prof_events) cudaEventDestroy(e);
+    for (auto e : g.prof_pool) cudaEventDestroy(e);
+    g.prof_events.clear(); g.prof_pool.clear();
     g.pinned.clear(); g.cur = nullptr; g.ok = false;
 }
 
@@ -333,10 +351,10 @@ void *pfcu_get_stream(void) { return g.ok ? (void *)g.lanes[0].stream : nullptr;
 void *pfcu_host_alloc(size_t bytes)
 {
     if (!g.ok && pfcu_init(-1) != PFCU_OK) return nullptr;
+    API_LOCK;
     PinnedBlock b; b.bytes = bytes; b.pending = false;
     if (cudaHostAlloc(&b.p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming) != cudaSuccess) { cudaFreeHost(b.p); return nullptr; }
-    API_LOCK;
     g.pinned.push_back(b);
     return b.p;
 }
@@ -770,9 +788,9 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         if (dep != s && dep->lane != s->lane && dep->has_done) CK(cudaStreamWaitEvent(LN.stream, dep->done, 0));
     if (n > LN.cap_setup) {
         size_t c1 = LN.cap_setup, c2 = LN.cap_setup, c3 = LN.cap_setup;
-        if ((rc = grow(&LN.d_bbox, &c1, n))) return rc;
-        if ((rc = grow(&LN.d_setup, &c2, n))) return rc;
-        if ((rc = grow(&LN.d_data, &c3, n))) return rc;
+        /* any failure leaves the three arrays with unknown capacities: forget them all, so that the next batch grows
+           every one of them again instead of writing through a pointer that grow() has already freed */
+        if ((rc = grow(&LN.d_bbox, &c1, n)) || (rc = grow(&LN.d_setup, &c2, n)) || (rc = grow(&LN.d_data, &c3, n))) { LN.cap_setup = 0; return rc; }
         LN.cap_setup = c1;
     }
     /* many small triangles per tile: fine bins (one per tile) and the fragment-compacting rasteriser;
@@ -1044,7 +1062,8 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
         CK(cudaMemcpyAsync(LN.d_states, LN.h_states, n_states * sizeof(DevState), cudaMemcpyHostToDevice, LN.stream));
         CK(cudaEventRecord(LN.states_done, LN.stream));
         unsigned *d_total = LN.d_total;
-        k_raw_chain<<<(n_tris + 127u) / 128u, 128, 0, LN.stream>>>(ra, LN.d_tris, d_total, LN.d_chain, ++LN.chain_seq);
+        if (++LN.chain_seq == 0) ++LN.chain_seq;         /* 0 is what the zero-initialised flags hold */
+        k_raw_chain<<<(n_tris + 127u) / 128u, 128, 0, LN.stream>>>(ra, LN.d_tris, d_total, LN.d_chain, LN.chain_seq);
         g.launches++;
         CK(cudaEventRecord(LN.raw_done, LN.stream));
         CK(cudaGetLastError());

@@ -209,16 +209,22 @@ k_prims(const PrimParams p)
 
 /* Raw batches of at most 1024 triangles: count, scan and emission in ONE launch of up to 8 CTAs of 128 threads.
  * Every triangle runs the vertex stage once; the output offset of a CTA is the running total its predecessor
- * publishes (a chained scan: flags[b] = launch sequence number << 32 | triangles emitted by CTAs 0..b; CTAs are
- * dispatched in index order, so a predecessor is always resident).  The total stays on the device: *d_total feeds
- * k_front_small, so the host never waits for it. */
+ * publishes (a chained scan: flags[b] = launch sequence number << 32 | triangles emitted by logical blocks 0..b).
+ * CUDA promises no dispatch order between the CTAs of a grid, so the LOGICAL block index is a ticket drawn with an
+ * atomic when the CTA starts running (flags[15], as in decoupled look-back scans): whoever holds ticket b-1 is
+ * resident and never waits for b, so the chain cannot deadlock however the hardware schedules the grid.  The CTA
+ * with the last ticket resets the counter for the next launch on this lane (every other ticket is drawn by then).
+ * The total stays on the device: *d_total feeds k_front_small, so the host never waits for it. */
 __global__ void __launch_bounds__(128)
 k_raw_chain(const RawArgs a, pfcu_triangle *__restrict__ out, unsigned *__restrict__ d_total,
             unsigned long long *__restrict__ flags, unsigned seq)
 {
     __shared__ unsigned s_warp[4];
-    __shared__ unsigned s_prev;
-    const unsigned i = blockIdx.x * 128u + threadIdx.x, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    __shared__ unsigned s_prev, s_bid;
+    if (threadIdx.x == 0) s_bid = (unsigned)atomicAdd(flags + 15, 1ull);
+    __syncthreads();
+    const unsigned bid = s_bid;
+    const unsigned i = bid * 128u + threadIdx.x, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     pfv_vertex poly[PFV_MAX_POLY];
     int is3d = 0, face = 0, n = 0; unsigned state = 0;
     if (i < a.n) n = raw_process(a, i, poly, &is3d, &face, &state);
@@ -232,16 +238,16 @@ k_raw_chain(const RawArgs a, pfcu_triangle *__restrict__ out, unsigned *__restri
     for (int w = 0; w < 4; w++) { const unsigned c = s_warp[w]; if (w < (int)warp) woff += c; total += c; }
     if (threadIdx.x == 0) {
         unsigned prev = 0;
-        if (blockIdx.x > 0) {
-            const volatile unsigned long long *f = flags + (blockIdx.x - 1);
+        if (bid > 0) {
+            const volatile unsigned long long *f = flags + (bid - 1);
             unsigned long long v;
             do { v = *f; } while ((unsigned)(v >> 32) != seq);
             prev = (unsigned)v;
         }
         __threadfence();
-        *((volatile unsigned long long *)(flags + blockIdx.x)) = ((unsigned long long)seq << 32) | (prev + total);
+        *((volatile unsigned long long *)(flags + bid)) = ((unsigned long long)seq << 32) | (prev + total);
         s_prev = prev;
-        if (blockIdx.x == gridDim.x - 1) *d_total = prev + total;
+        if (bid == gridDim.x - 1) { *d_total = prev + total; flags[15] = 0ull; }
     }
     __syncthreads();
     const unsigned off = s_prev + woff + x - (unsigned)n;

@@ -843,6 +843,26 @@ SCN_API int pfscene_read_context(void *handle, int index, uint8_t *color_out)
     return 1;
 }
 
+/* Colour and (optionally) depth of context `index` ("batch": 0..n-1; single-context scenes: index 0), through the
+ * public API only: the colour is the caller-owned target buffer after the frame was finished, the depth comes from
+ * pfxReadDepth (product) / a pfPostProcess pass (reference). */
+SCN_API int pfscene_read_index(void *handle, int index, uint8_t *color_out, float *depth_out)
+{
+    scene_t *s = (scene_t *)handle;
+    const size_t bytes = (size_t)s->cfg.width * s->cfg.height * 4;
+    if (s->n) {
+        if (index < 0 || index >= s->n) return 0;
+        pfMakeCurrent(s->ctxs[index]);
+        if (color_out) memcpy(color_out, s->bufs[index], bytes);
+    } else {
+        if (index != 0) return 0;
+        pfMakeCurrent(s->ctx);
+        if (color_out) memcpy(color_out, s->target, bytes);
+    }
+    read_depth(depth_out, s->cfg.width);
+    return 1;
+}
+
 SCN_API void pfscene_read(void *handle, uint8_t *color_out, float *depth_out)
 {
     scene_t *s = (scene_t *)handle;

@@ -36,12 +36,12 @@ def built_libraries():
 
 @pytest.fixture(scope="session")
 def oracle_scenes(built_libraries):
-    from pixelforge_b200 import load_oracle_scenes
+    from checkers import load_oracle_scenes
     return load_oracle_scenes()
 
 
 def _ref(bfix):
-    from pixelforge_b200 import load_reference_scenes
+    from checkers import load_reference_scenes
     try:
         return load_reference_scenes(bfix)
     except FileNotFoundError:
@@ -76,8 +76,8 @@ def host_matches_golden(golden, built_libraries):
     """Golden hashes were produced on a host with a particular RCPPS/RSQRTPS table + libm."""
     import hashlib
     import numpy as np
-    from pixelforge_b200 import load_pfcu
-    lib = load_pfcu("oracle")
+    from checkers import load_oracle_pfcu
+    lib = load_oracle_pfcu()
     rcp, rb, rsq, sb = lib.harvest_tables()
     a = np.ctypeslib.as_array(rcp, shape=(1 << rb,)).tobytes() + np.ctypeslib.as_array(rsq, shape=(2 << sb,)).tobytes()
     return hashlib.sha256(a).hexdigest() == golden["host_tables"]["sha256"]

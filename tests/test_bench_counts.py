@@ -35,3 +35,25 @@ def test_overdraw_closed_form(counts, oracle_scenes):
         assert (w - 1) * h <= per_layer <= (w - 1) * h + w + h
     _, _, r = oracle_scenes.render("overdraw", 96, 54, size=3, want_depth=False)
     assert r.pixels_shaded % 3 == 0 and (96 - 1) * 54 <= r.pixels_shaded // 3 <= 95 * 54 + 96 + 54
+
+
+def test_bench_gate_plumbing_on_cpu(oracle_scenes, ref_scenes, tmp_path):
+    """bench.py's reference-equivalence gate end to end, without a GPU: the CPU arm dumps the frames it rendered
+    (subprocess, as in the bench) and parity_against_dump compares a render of the same workload - here by the oracle
+    build standing in for the product - colour and depth, bit for bit.  A corrupted dump must be reported."""
+    import subprocess, sys
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    dump = str(tmp_path / "ref.npz")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--as-baseline", "--workload", "c1_gears_800x600",
+                        "--baseline-frames", "1", "--dump", dump], capture_output=True, text=True, timeout=300)
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["config"] == bench.bench_config("c1_gears_800x600", 1)
+    p = bench.parity_against_dump(oracle_scenes, "c1_gears_800x600", dump)
+    assert p["differing_px"] == 0 and p["differing_depth"] == 0 and p["pixels_compared"] == 800 * 600
+    z = np.load(dump)
+    c = z["color"].copy(); c[0, 300, 400] ^= 1
+    bad = str(tmp_path / "bad.npz")
+    np.savez(bad, color=c, depth=z["depth"])
+    assert bench.parity_against_dump(oracle_scenes, "c1_gears_800x600", bad)["differing_px"] == 1

@@ -76,7 +76,8 @@ def test_explicit_mode_queued_readback_of_many_contexts(product_scenes):
 @pytest.fixture(scope="module")
 def pfcu_pair():
     from pixelforge_b200 import load_pfcu
-    prod, orc = load_pfcu("product"), load_pfcu("oracle")
+    from checkers import load_oracle_pfcu
+    prod, orc = load_pfcu("product"), load_oracle_pfcu()
     prod.init(); orc.init()
     assert prod.backend == "cuda-sm_100a" and orc.backend == "oracle-c"
     return prod, orc
@@ -375,6 +376,41 @@ def test_peer_present_to_another_surface(pfcu_pair):
                     assert np.array_equal(c, full_c) and np.array_equal(d.view(np.uint32), full_d.view(np.uint32)), (small, path, world)
             finally:
                 L.pfcu_set_raster_path(0)
+
+
+# ---- the reference-equivalence gate at BASELINE.json's full sizes ---------------------------
+# The same comparison bench.py makes in the run that prints the numbers: frame 0 of every workload of its table,
+# rendered through the public API by the product and by the live reference (bilinear workloads: the reference
+# with the one-token Q7 fix), colour and depth bit for bit, every context of C5, a 4-layer slice of the
+# 64-layer overdraw scenes (each layer is the same work).
+
+def _bench_workloads():
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    return bench
+
+
+@pytest.mark.parametrize("name", ["c1_gears_800x600", "c2_textured_1080p", "c3_phong_4k", "c4_overdraw_8k", "ns_textured_blend_4k", "c5_batch_512"])
+def test_fullsize_reference_equivalence(name, product_scenes, ref_scenes, ref_bfix_scenes):
+    bench = _bench_workloads()
+    wl = bench.WORKLOADS[name]
+    size = bench.gate_size(wl)
+    ref = ref_bfix_scenes if bench.is_bilinear(wl) else ref_scenes
+    n_ctx = size if wl["scene"] == "batch" else 1
+    frames = {}
+    for key, lib in (("product", product_scenes), ("reference", ref)):
+        with lib.open(wl["scene"], wl["w"], wl["h"], variant=wl["variant"], size=size, explicit_sync=1) as sc:
+            sc.frame(0); sc.finish()
+            frames[key] = [sc.read_index(i, want_depth=True) for i in range(n_ctx)]
+    covered = 0
+    for i in range(n_ctx):
+        (cp, dp), (cr, dr) = frames["product"][i], frames["reference"][i]
+        assert int((cp != cr).sum()) == 0, (name, i, "colour")
+        assert int((dp.view(np.uint32) != dr.view(np.uint32)).sum()) == 0, (name, i, "depth")
+        covered += int((dr != FLT_MAX).sum())
+    assert covered > 0.15 * n_ctx * wl["w"] * wl["h"]      # the frames are not empty
+    assert _loaded_native_library()
 
 
 # ---- full-size properties (BASELINE.json sizes; the oracle is too slow here) ----------------------------

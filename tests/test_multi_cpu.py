@@ -32,10 +32,10 @@ def _worker(rank, world, port, w, h, out_path):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
-    from pixelforge_b200 import load_pfcu
+    from checkers import load_oracle_pfcu
     from pixelforge_b200.multigpu import gather_tiles
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    lib = load_pfcu("oracle"); lib.init(); L = lib.lib
+    lib = load_oracle_pfcu(); lib.init(); L = lib.lib
     states, tris = _stream(w, h, 300, 5)
     s = L.pfcu_surface_create(w, h)
     L.pfcu_surface_fill(s, 1, 0xFF102030, 1, np.finfo(np.float32).max)
@@ -55,12 +55,12 @@ def _worker(rank, world, port, w, h, out_path):
 @pytest.mark.parametrize("world", [2, 3])
 def test_tile_split_gather_gloo(world, built_libraries, tmp_path):
     import torch.multiprocessing as mp
-    from pixelforge_b200 import load_pfcu
+    from checkers import load_oracle_pfcu
     w, h = 333, 200
     out = str(tmp_path / "gathered.npz")
     mp.spawn(_worker, args=(world, _free_port(), w, h, out), nprocs=world, join=True)
     got = np.load(out)
-    lib = load_pfcu("oracle"); lib.init()
+    lib = load_oracle_pfcu(); lib.init()
     states, tris = _stream(w, h, 300, 5)
     full_c, full_d = lib.render_stream(w, h, states, tris, color0=np.full((h, w), 0xFF102030, np.uint32), prims=_prims(w, h))
     assert np.array_equal(got["color"], full_c)
@@ -70,9 +70,9 @@ def test_tile_split_gather_gloo(world, built_libraries, tmp_path):
 
 
 def test_owned_tile_accounting(built_libraries):
-    from pixelforge_b200 import load_pfcu
+    from checkers import load_oracle_pfcu
     from pixelforge_b200.multigpu import owned_tiles
-    lib = load_pfcu("oracle"); L = lib.lib
+    lib = load_oracle_pfcu(); L = lib.lib
     for (w, h) in ((7680, 4320), (800, 600), (65, 1)):
         s = L.pfcu_surface_create(w, h)
         for world in (1, 2, 4, 8):

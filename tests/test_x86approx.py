@@ -8,8 +8,8 @@ import pytest
 
 @pytest.fixture(scope="module")
 def lib(built_libraries):
-    from pixelforge_b200 import load_pfcu
-    return load_pfcu("oracle")
+    from checkers import load_oracle_pfcu
+    return load_oracle_pfcu()
 
 
 def test_tables_reproduce_hardware(lib):

@@ -2,7 +2,9 @@
 import argparse, sys, os, json
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pixelforge_b200 import load_oracle_scenes, load_reference_scenes, load_product_scenes
+from pixelforge_b200 import load_product_scenes
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from checkers import load_oracle_scenes, load_reference_scenes
 
 CASES = [
     ("gears", 800, 600, {}),

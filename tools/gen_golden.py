@@ -13,12 +13,13 @@ os.environ["OMP_NUM_THREADS"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
-from pixelforge_b200 import load_reference_scenes, load_pfcu
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from checkers import load_reference_scenes, load_oracle_pfcu
 from cases import CASES
 
 
 def table_fingerprint():
-    lib = load_pfcu("oracle")
+    lib = load_oracle_pfcu()
     rcp, rb, rsq, sb = lib.harvest_tables()
     a = np.ctypeslib.as_array(rcp, shape=(1 << rb,)).tobytes() + np.ctypeslib.as_array(rsq, shape=(2 << sb,)).tobytes()
     return {"rcp_bits": rb, "rsqrt_bits": sb, "sha256": hashlib.sha256(a).hexdigest()}

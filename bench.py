@@ -172,7 +172,9 @@ def run_reference(args, wl_name, bounded_frames=None, dump=None):
         if dump:
             n_ctx = size if wl["scene"] == "batch" else 1
             frames = [sc.read_index(i, want_depth=True) for i in range(n_ctx)]
-            np.savez(dump, color=np.stack([f[0] for f in frames]), depth=np.stack([f[1] for f in frames]))
+            # frames_rendered: pfClear never clears pixels 0..7, so with blending they depend on how many
+            # frames were drawn into the buffer - the product renders the same number before it is compared
+            np.savez(dump, color=np.stack([f[0] for f in frames]), depth=np.stack([f[1] for f in frames]), frames_rendered=warm + steps)
     counts = shaded_pixels_table().get(wl_name, {})
     scale = size / wl["size"] if wl["scene"] == "overdraw" else 1
     px = counts.get("pixels_shaded", 0) * scale
@@ -218,12 +220,13 @@ def parity_against_dump(scenes, wl_name, dump):
     n_ctx = size if wl["scene"] == "batch" else 1
     dpx = dz = 0
     with scenes.open(wl["scene"], wl["w"], wl["h"], variant=wl["variant"], size=size, explicit_sync=1) as sc:
-        sc.frame(0); sc.finish()
+        for _ in range(int(z["frames_rendered"])):
+            sc.frame(0); sc.finish()
         for i in range(n_ctx):
             c, d = sc.read_index(i, want_depth=True)
             dpx += int((c != ref_c[i]).sum())
             dz += int((d.view(np.uint32) != ref_d[i].view(np.uint32)).sum())
-    out = {"differing_px": dpx, "differing_depth": dz, "pixels_compared": int(ref_c.size), "contexts": n_ctx,
+    out = {"differing_px": dpx, "differing_depth": dz, "pixels_compared": int(ref_c.size), "contexts": n_ctx, "frames_rendered": int(z["frames_rendered"]),
            "resolution": [wl["w"], wl["h"]]}
     if size != wl["size"]:
         out["layers"] = f"{size} of {wl['size']}"

@@ -55,5 +55,5 @@ def test_bench_gate_plumbing_on_cpu(oracle_scenes, ref_scenes, tmp_path):
     z = np.load(dump)
     c = z["color"].copy(); c[0, 300, 400] ^= 1
     bad = str(tmp_path / "bad.npz")
-    np.savez(bad, color=c, depth=z["depth"])
+    np.savez(bad, color=c, depth=z["depth"], frames_rendered=z["frames_rendered"])
     assert bench.parity_against_dump(oracle_scenes, "c1_gears_800x600", bad)["differing_px"] == 1

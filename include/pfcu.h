@@ -152,7 +152,18 @@ PFCU_API void  pfcu_host_unregister(void *p);
 PFCU_API int  pfcu_set_approx_tables(const uint32_t *rcp, int rcp_bits, const uint32_t *rsqrt, int rsqrt_bits);
 
 /* ---- surfaces (framebuffer.c:29-64, context.c:126-138) -------------------------------------- */
-PFCU_API pfcu_surface *pfcu_surface_create(uint32_t width, uint32_t height);
+PFCU_API pfcu_surface *pfcu_surface_create(uint32_t width, uint32_t height);           /* PF_RGBA / PF_UNSIGNED_BYTE */
+/* Render targets in the other 8-bit formats (PFCU_TEX_BGRA8 / RGB8 / BGR8).  On the device every
+ * surface is held in ONE canonical layout - colour as RGBA8 dwords (alpha 255 for the 3-byte formats, which is what
+ * their getters return, pixel.h:576-588,2604-2632), depth f32 - and pfcu_surface_upload / download convert from / to
+ * the caller's layout (3 or 4 bytes per pixel, row y at byte offset y * width * bytes).  What the format changes in
+ * the triangle path is the reference's own SIMD behaviour: the BGRA8 setter and getter shuffle bytes
+ * with a mask that addresses only the first dword of each 128-bit half (pixel.h:2069-2078,2915-2920, simd.h:563-583),
+ * so the four pixels x0+4k .. x0+4k+3 of a triangle's row (x0 = its bbox xMin) all receive the blended fragment of
+ * the first one, and blend against that pixel's colour.  Batches that target a non-RGBA8 surface, or sample a BGRA8
+ * texture (same shuffle in the texel getter), are rasterised by a row-ordered kernel that reproduces this exactly. */
+PFCU_API pfcu_surface *pfcu_surface_create_format(uint32_t width, uint32_t height, int pfcu_tex_format);
+PFCU_API int pfcu_surface_format(const pfcu_surface *s);
 /* Wrap caller-owned device memory (e.g. a torch tensor): colour u32[w*h], depth f32[w*h]. */
 PFCU_API pfcu_surface *pfcu_surface_wrap(void *dev_color, void *dev_depth, uint32_t width, uint32_t height);
 PFCU_API void     pfcu_surface_destroy(pfcu_surface *s);

@@ -28,8 +28,11 @@
 #include <stdio.h>
 #include <limits.h>
 
-struct pfcu_surface { uint32_t w, h; uint32_t *color; float *depth; int owned; uint32_t rank, world; };
-struct pfcu_texture { uint32_t w, h; int fmt; uint8_t *pixels; int owned; pfcu_surface *alias; };
+/* colour is held as canonical RGBA8 dwords whatever the caller's layout (fmt); upload / download convert */
+struct pfcu_surface { uint32_t w, h; uint32_t *color; float *depth; int owned; uint32_t rank, world; int fmt; };
+/* leader: texels come through the reference's BGRA8 getter, whose shuffle hands the first texel of every group of four
+   pixels to all four (pixel.h:2915-2920, simd.h:563-583) */
+struct pfcu_texture { uint32_t w, h; int fmt; uint8_t *pixels; int owned; pfcu_surface *alias; int leader; };
 struct pfcu_batch   { pfcu_state *states; uint32_t n_states; pfcu_triangle *tris; uint32_t n_tris; };
 
 static pfcu_counters g_cnt;
@@ -269,6 +272,30 @@ static uint32_t tex_fetch(const pfcu_texture *t, int32_t x, int32_t y)
     }
 }
 
+/* The sampler in two steps, so that the caller can substitute another pixel's taps (the BGRA8 getter's behaviour):
+ * taps[0] (nearest) or taps[0..3] = texels at (x0,y0) (x1,y0) (x0,y1) (x1,y1), plus the filter weights. */
+static void tex_taps(const pfcu_state *st, float u, float v, uint32_t taps[4], float *fx, float *fy)
+{
+    const pfcu_texture *t = st->texture;
+    uint32_t tw = t->w, th = t->h;
+    int32_t x0, y0, x1, y1;
+    tex_map(st->tex_wrap, tw, th, u, v, &x0, &y0);
+    taps[0] = tex_fetch(t, x0, y0);
+    *fx = *fy = 0.0f;
+    if (st->tex_filter == 0) return;
+    float tx = 1.0f / (float)tw, ty = 1.0f / (float)th;
+    tex_map(st->tex_wrap, tw, th, u + tx, v + ty, &x1, &y1);
+    *fx = clamp_x86(u * (float)tw - (float)x0, 0.0f, 1.0f);
+    *fy = clamp_x86(v * (float)th - (float)y0, 0.0f, 1.0f);
+    taps[1] = tex_fetch(t, x1, y0); taps[2] = tex_fetch(t, x0, y1); taps[3] = tex_fetch(t, x1, y1);
+}
+
+static uint32_t tex_combine(const pfcu_state *st, const uint32_t taps[4], float fx, float fy)
+{
+    if (st->tex_filter == 0) return taps[0];
+    return color_lerp(color_lerp(taps[0], taps[1], fx), color_lerp(taps[2], taps[3], fx), fy);
+}
+
 static uint32_t tex_sample(const pfcu_state *st, float u, float v)
 {
     const pfcu_texture *t = st->texture;
@@ -448,6 +475,105 @@ static void raster_triangle(pfcu_surface *s, const pfcu_state *st, const pfcu_tr
     }
 }
 
+/* Rasterize_Triangle as the AVX2 lanes really behave for BGRA8, used for render targets other than RGBA8
+ * and for textures read through the BGRA8 getter.  The row of the bounding box is walked in groups of FOUR pixels
+ * from xMin (one 128-bit half of the reference's 8-pixel step): every lane runs the whole fragment program, covered
+ * or not (triangles.c:404-445, 500-529); with a BGRA8 texture lanes 1..3 sample lane 0's texels (taps), with a BGRA8
+ * target they blend against lane 0's pixel and store lane 0's final fragment (pixel.h:2069-2078, 2915-2920).  Reads
+ * of a group precede its writes, as in the vector code.  Pixels outside the surface (the reference would run off its
+ * buffer) read as 0 and are never written. */
+static void raster_triangle_rows(pfcu_surface *s, const pfcu_state *st, const pfcu_triangle *t)
+{
+    const pfcu_vertex *v1 = &t->v[0], *v2 = &t->v[1], *v3 = &t->v[2];
+    int face = t->face;
+    int32_t x1 = to_int_x86(v1->sx), y1 = to_int_x86(v1->sy);
+    int32_t x2 = to_int_x86(v2->sx), y2 = to_int_x86(v2->sy);
+    int32_t x3 = to_int_x86(v3->sx), y3 = to_int_x86(v3->sy);
+
+    g_cnt.triangles_submitted++;
+    float area = (float)WSUB(WMUL(WSUB(x2, x1), WSUB(y3, y1)), WMUL(WSUB(x3, x1), WSUB(y2, y1)));
+    if ((face == 0 && area >= 0) || (face == 1 && area <= 0)) return;
+    g_cnt.triangles_rasterised++;
+
+    int32_t xMin = imin(x1, imin(x2, x3)), yMin = imin(y1, imin(y2, y3));
+    int32_t xMax = imax(x1, imax(x2, x3)), yMax = imax(y1, imax(y2, y3));
+    if (!t->is3d) {
+        xMin = iclamp(xMin, st->vp_min[0], st->vp_max[0]); yMin = iclamp(yMin, st->vp_min[1], st->vp_max[1]);
+        xMax = iclamp(xMax, st->vp_min[0], st->vp_max[0]); yMax = iclamp(yMax, st->vp_min[1], st->vp_max[1]);
+    }
+    int32_t w1X = WSUB(y3, y2), w1Y = WSUB(x2, x3);
+    int32_t w2X = WSUB(y1, y3), w2Y = WSUB(x3, x1);
+    int32_t w3X = WSUB(y2, y1), w3Y = WSUB(x1, x2);
+    if (face == 1) {
+        w1X = WSUB(0, w1X); w1Y = WSUB(0, w1Y); w2X = WSUB(0, w2X);
+        w2Y = WSUB(0, w2Y); w3X = WSUB(0, w3X); w3Y = WSUB(0, w3Y);
+    }
+    int32_t w1R = WADD(WMUL(WSUB(xMin, x2), w1X), WMUL(w1Y, WSUB(yMin, y2)));
+    int32_t w2R = WADD(WMUL(WSUB(xMin, x3), w2X), WMUL(w2Y, WSUB(yMin, y3)));
+    int32_t w3R = WADD(WMUL(WSUB(xMin, x1), w3X), WMUL(w3Y, WSUB(yMin, y1)));
+    float invSum = 1.0f / (float)WADD(WADD(w1R, w2R), w3R);
+
+    int depth_on = (st->flags & PFCU_ST_DEPTH_TEST) != 0;
+    int blend_on = (st->flags & PFCU_ST_BLEND) != 0;
+    int tex_on = (st->flags & PFCU_ST_TEXTURE) && st->texture;
+    int phong_on = (st->flags & PFCU_ST_PHONG) && st->n_lights > 0;
+    int smooth = (st->flags & PFCU_ST_SMOOTH) != 0;
+    int tex_leader = tex_on && st->texture->leader, fb_leader = s->fmt == PFCU_TEX_BGRA8;
+    uint32_t alpha_or = s->fmt >= PFCU_TEX_RGB8 ? 0xff000000u : 0u;
+
+    if (!(xMin < xMax && yMin <= yMax && xMax > 0 && yMax >= 0 && xMin < (int32_t)s->w && yMin < (int32_t)s->h)) return;   /* nothing on the surface */
+    int32_t ya = imax(yMin, 0), yb = imin(yMax, (int32_t)s->h - 1);
+    long long gx0 = xMin < 0 ? (long long)xMin + ((-(long long)xMin) & ~3LL) : (long long)xMin;
+    long long gxl = xMax < (int32_t)s->w - 1 ? xMax : (long long)s->w - 1;
+    for (int32_t y = ya; y <= yb; y++) {
+        for (long long gx = gx0; gx <= gxl; gx += 4) {
+            int m[4], cov[4], ins[4]; float z[4]; uint32_t frag[4], dst[4], taps0[4] = { 0, 0, 0, 0 };
+            size_t idx[4];
+            for (int j = 0; j < 4; j++) {
+                long long x = gx + j;
+                ins[j] = x >= 0 && x < (long long)s->w;
+                idx[j] = (size_t)y * s->w + (size_t)(ins[j] ? x : 0);
+                int32_t xrel = (int32_t)(uint32_t)(x - (long long)xMin);
+                int32_t w1 = WADD(WADD(w1R, WMUL(WSUB(y, yMin), w1Y)), WMUL(xrel, w1X));
+                int32_t w2 = WADD(WADD(w2R, WMUL(WSUB(y, yMin), w2Y)), WMUL(xrel, w2X));
+                int32_t w3 = WADD(WADD(w3R, WMUL(WSUB(y, yMin), w3Y)), WMUL(xrel, w3X));
+                cov[j] = ((w1 | w2 | w3) > 0) && x < (long long)xMax && ins[j];
+                float W1 = (float)w1 * invSum, W2 = (float)w2 * invSum, W3 = (float)w3 * invSum;
+                z[j] = rcp_x86((v1->zinv * W1 + v2->zinv * W2) + v3->zinv * W3);
+                float zb = ins[j] ? s->depth[idx[j]] : 0.0f;
+                m[j] = cov[j] && (!depth_on || depth_pass(st->depth_func, z[j], zb));
+                uint32_t f = smooth ? color_smooth(v1->rgba, v2->rgba, v3->rgba, W1, W2, W3)
+                                    : color_flat(v1->rgba, v2->rgba, v3->rgba, W1, W2, W3);
+                if (tex_on) {
+                    float u = (v1->u * W1 + v2->u * W2) + v3->u * W3;
+                    float v = (v1->v * W1 + v2->v * W2) + v3->v * W3;
+                    if (t->is3d) { u = u * z[j]; v = v * z[j]; }
+                    if (!m[j]) { u = 0.0f; v = 0.0f; }                      /* triangles.c:510 */
+                    uint32_t taps[4] = { 0, 0, 0, 0 }; float fx, fy;
+                    tex_taps(st, u, v, taps, &fx, &fy);
+                    if (j == 0) memcpy(taps0, taps, sizeof taps0);
+                    f = mul_color(tex_combine(st, tex_leader ? taps0 : taps, fx, fy), f);
+                }
+                if (phong_on) {
+                    float N[3] = { (v1->nx * W1 + v2->nx * W2) + v3->nx * W3, (v1->ny * W1 + v2->ny * W2) + v3->ny * W3, (v1->nz * W1 + v2->nz * W2) + v3->nz * W3 };
+                    float P[3] = { (v1->px * W1 + v2->px * W2) + v3->px * W3, (v1->py * W1 + v2->py * W2) + v3->py * W3, (v1->pz * W1 + v2->pz * W2) + v3->pz * W3 };
+                    f = phong(f, st, face, P, N);
+                }
+                dst[j] = ins[j] ? s->color[idx[j]] : 0u;
+                if (blend_on) f = blend(st->blend_mode, f, fb_leader ? dst[0] : dst[j]);
+                frag[j] = f;
+            }
+            for (int j = 0; j < 4; j++) {
+                if (m[j]) {
+                    s->color[idx[j]] = (fb_leader ? frag[0] : frag[j]) | alpha_or;
+                    s->depth[idx[j]] = z[j];
+                    g_cnt.pixels_shaded++;
+                } else if (cov[j]) g_cnt.pixels_depth_failed++;
+            }
+        }
+    }
+}
+
 /* ---- C-ABI ----------------------------------------------------------------------------------- */
 
 int  pfcu_init(int device) { (void)device; return PFCU_OK; }
@@ -464,11 +590,14 @@ void  pfcu_host_unregister(void *p) { (void)p; }
 int  pfcu_set_approx_tables(const uint32_t *rcp, int rb, const uint32_t *rs, int sb)
 { (void)rcp; (void)rb; (void)rs; (void)sb; return PFCU_OK; }   /* native RCPSS/RSQRTSS are used */
 
-pfcu_surface *pfcu_surface_create(uint32_t w, uint32_t h)
+pfcu_surface *pfcu_surface_create(uint32_t w, uint32_t h) { return pfcu_surface_create_format(w, h, PFCU_TEX_RGBA8); }
+int pfcu_surface_format(const pfcu_surface *s) { return s ? s->fmt : -1; }
+pfcu_surface *pfcu_surface_create_format(uint32_t w, uint32_t h, int fmt)
 {
+    if (fmt < PFCU_TEX_RGBA8 || fmt > PFCU_TEX_BGR8) return NULL;
     pfcu_surface *s = (pfcu_surface *)calloc(1, sizeof *s);
     if (!s) return NULL;
-    s->w = w; s->h = h; s->owned = 1;
+    s->w = w; s->h = h; s->owned = 1; s->fmt = fmt;
     s->color = (uint32_t *)calloc((size_t)w * h + 16, 4);
     s->depth = (float *)calloc((size_t)w * h + 16, 4);
     if (!s->color || !s->depth) { free(s->color); free(s->depth); free(s); return NULL; }
@@ -487,11 +616,35 @@ uint32_t pfcu_surface_height(const pfcu_surface *s) { return s->h; }
 void *pfcu_surface_color_ptr(const pfcu_surface *s) { return s->color; }
 void *pfcu_surface_depth_ptr(const pfcu_surface *s) { return s->depth; }
 
+/* the scalar getters / setters of the reference for the four 8-bit layouts (pixel.h:233-360, 576-710), to / from
+   canonical RGBA8 (alpha of a 3-byte pixel reads as 255) */
+static uint32_t native_get(const void *px, size_t i, int fmt)
+{
+    const uint8_t *p = (const uint8_t *)px;
+    switch (fmt) {
+    case PFCU_TEX_BGRA8: return (uint32_t)p[4 * i + 2] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+    case PFCU_TEX_RGB8:  return (uint32_t)p[3 * i] | ((uint32_t)p[3 * i + 1] << 8) | ((uint32_t)p[3 * i + 2] << 16) | 0xff000000u;
+    case PFCU_TEX_BGR8:  return (uint32_t)p[3 * i + 2] | ((uint32_t)p[3 * i + 1] << 8) | ((uint32_t)p[3 * i] << 16) | 0xff000000u;
+    default: { uint32_t v; memcpy(&v, p + 4 * i, 4); return v; }
+    }
+}
+static void native_set(void *px, size_t i, int fmt, uint32_t c)
+{
+    uint8_t *p = (uint8_t *)px;
+    switch (fmt) {
+    case PFCU_TEX_BGRA8: p[4 * i] = (uint8_t)(c >> 16); p[4 * i + 1] = (uint8_t)(c >> 8); p[4 * i + 2] = (uint8_t)c; p[4 * i + 3] = (uint8_t)(c >> 24); break;
+    case PFCU_TEX_RGB8:  p[3 * i] = (uint8_t)c; p[3 * i + 1] = (uint8_t)(c >> 8); p[3 * i + 2] = (uint8_t)(c >> 16); break;
+    case PFCU_TEX_BGR8:  p[3 * i] = (uint8_t)(c >> 16); p[3 * i + 1] = (uint8_t)(c >> 8); p[3 * i + 2] = (uint8_t)c; break;
+    default: memcpy(p + 4 * i, &c, 4); break;
+    }
+}
+
 int pfcu_surface_upload(pfcu_surface *s, const void *c, const float *d, uint32_t y0, uint32_t rows)
 {
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
     size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w;
-    if (c) memcpy(s->color + off, (const uint32_t *)c + off, n * 4);
+    if (c && s->fmt == PFCU_TEX_RGBA8) memcpy(s->color + off, (const uint32_t *)c + off, n * 4);
+    else if (c) for (size_t i = off; i < off + n; i++) s->color[i] = native_get(c, i, s->fmt);
     if (d) memcpy(s->depth + off, d + off, n * 4);
     return PFCU_OK;
 }
@@ -499,13 +652,15 @@ int pfcu_surface_download(pfcu_surface *s, void *c, float *d, uint32_t y0, uint3
 {
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
     size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w;
-    if (c) memcpy((uint32_t *)c + off, s->color + off, n * 4);
+    if (c && s->fmt == PFCU_TEX_RGBA8) memcpy((uint32_t *)c + off, s->color + off, n * 4);
+    else if (c) for (size_t i = off; i < off + n; i++) native_set(c, i, s->fmt, s->color[i]);
     if (d) memcpy(d + off, s->depth + off, n * 4);
     return PFCU_OK;
 }
 int pfcu_surface_fill(pfcu_surface *s, int dc, uint32_t rgba, int dd, float depth)
 {
     size_t n = (size_t)s->w * s->h;
+    if (s->fmt >= PFCU_TEX_RGB8) rgba |= 0xff000000u;
     for (size_t i = 0; i < n; i++) { if (dc) s->color[i] = rgba; if (dd) s->depth[i] = depth; }
     return PFCU_OK;
 }
@@ -513,6 +668,7 @@ int pfcu_surface_fill(pfcu_surface *s, int dc, uint32_t rgba, int dd, float dept
 int pfcu_surface_clear_ref(pfcu_surface *s, int dc, uint32_t rgba, int dd, float depth)
 {
     uint32_t size = s->w * s->h, aligned = size - (size % 8u);
+    if (s->fmt >= PFCU_TEX_RGB8) rgba |= 0xff000000u;
     for (uint32_t i = 8; i < aligned; i++) { if (dc) s->color[i] = rgba; if (dd) s->depth[i] = depth; }
     for (uint32_t i = aligned; i < size; i++) { if (dc) s->color[i] = s->color[0]; if (dd) s->depth[i] = s->depth[0]; }
     return PFCU_OK;
@@ -557,7 +713,7 @@ pfcu_texture *pfcu_texture_create(const void *px, uint32_t w, uint32_t h, int fm
 {
     pfcu_texture *t = (pfcu_texture *)calloc(1, sizeof *t);
     if (!t) return NULL;
-    t->w = w; t->h = h; t->fmt = fmt; t->owned = 1;
+    t->w = w; t->h = h; t->fmt = fmt; t->owned = 1; t->leader = (fmt == PFCU_TEX_BGRA8);
     t->pixels = (uint8_t *)malloc(tex_bytes(w, h, fmt) + 16);
     if (!t->pixels) { free(t); return NULL; }
     memset(t->pixels, 0, tex_bytes(w, h, fmt) + 16);
@@ -568,7 +724,7 @@ pfcu_texture *pfcu_texture_from_surface(pfcu_surface *s)
 {
     pfcu_texture *t = (pfcu_texture *)calloc(1, sizeof *t);
     if (!t) return NULL;
-    t->w = s->w; t->h = s->h; t->fmt = PFCU_TEX_RGBA8; t->alias = s;
+    t->w = s->w; t->h = s->h; t->fmt = PFCU_TEX_RGBA8; t->alias = s; t->leader = (s->fmt == PFCU_TEX_BGRA8);
     return t;
 }
 int pfcu_texture_update(pfcu_texture *t, const void *px)
@@ -583,7 +739,9 @@ int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, co
 {
     for (uint32_t i = 0; i < n_tris; i++) {
         if (tris[i].state >= n_states) { snprintf(g_err, sizeof g_err, "state index out of range"); return PFCU_ERR_INVALID; }
-        raster_triangle(s, &states[tris[i].state], &tris[i]);
+        const pfcu_state *st = &states[tris[i].state];
+        if (s->fmt != PFCU_TEX_RGBA8 || ((st->flags & PFCU_ST_TEXTURE) && st->texture && st->texture->leader)) raster_triangle_rows(s, st, &tris[i]);
+        else raster_triangle(s, st, &tris[i]);
     }
     return PFCU_OK;
 }
@@ -623,7 +781,7 @@ static void prim_pixel(pfcu_surface *s, const pfcu_prim *p, uint32_t off, float 
     const uint32_t x = off % s->w, y = off / s->w;
     if (s->world > 1 && ((x / 64u) + (y / 64u) * ((s->w + 63u) / 64u)) % s->world != s->rank) return;
     if (test && !pfp_depth(p->depth_func, z, s->depth[off])) return;
-    s->color[off] = (p->flags & PFCU_ST_BLEND) ? pfp_blend(p->blend_mode, color, s->color[off]) : color;
+    s->color[off] = ((p->flags & PFCU_ST_BLEND) ? pfp_blend(p->blend_mode, color, s->color[off]) : color) | (s->fmt >= PFCU_TEX_RGB8 ? 0xff000000u : 0u);
     s->depth[off] = z;
 }
 int pfcu_submit_prims(pfcu_surface *s, const pfcu_prim *prims, uint32_t n)

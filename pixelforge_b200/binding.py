@@ -184,11 +184,12 @@ PFCU_SYMBOLS = [
     "pfcu_fence", "pfcu_finish", "pfcu_get_counters", "pfcu_reset_counters", "pfcu_profile_enable", "pfcu_profile_read",
     "pfcu_set_raster_path", "pfcu_submit_raw", "pfcu_submit_prims", "pfcu_surface_download_async", "pfcu_surface_wait", "pfcu_surface_ipc_handles", "pfcu_surface_set_present_peer",
     "pfcu_surface_set_present_surface", "pfcu_surface_clear_present", "pfcu_surface_push_tiles",
+    "pfcu_surface_create_format", "pfcu_surface_format",
 ]
 
 PFX_SYMBOLS = ["pfxSetSyncMode", "pfxFlush", "pfxFinish", "pfxGetCounters", "pfxResetCounters", "pfxSetTileOwner",
                "pfxGetDeviceColor", "pfxGetDeviceDepth", "pfxReadDepth", "pfxCaptureBegin", "pfxCaptureEnd",
-               "pfxGetSurfaceHandle", "pfxBackendName", "pfxEnableDeviceVertexStage", "pfxSpecularTableCheck", "pfxHostAlloc", "pfxHostFree"]
+               "pfxGetSurfaceHandle", "pfxBackendName", "pfxEnableDeviceVertexStage", "pfxSpecularTableCheck", "pfxHostAlloc", "pfxHostFree", "pfxTextureDirty"]
 
 
 class PfcuLib:
@@ -206,7 +207,8 @@ class PfcuLib:
             "pfcu_set_stream": (C.c_int, [vp]), "pfcu_get_stream": (vp, []),
             "pfcu_host_alloc": (vp, [sz]), "pfcu_host_free": (None, [vp]), "pfcu_host_wait": (C.c_int, [vp]),
             "pfcu_set_approx_tables": (C.c_int, [vp, C.c_int, vp, C.c_int]),
-            "pfcu_surface_create": (vp, [u32, u32]), "pfcu_surface_wrap": (vp, [vp, vp, u32, u32]),
+            "pfcu_surface_create": (vp, [u32, u32]), "pfcu_surface_create_format": (vp, [u32, u32, C.c_int]),
+            "pfcu_surface_format": (C.c_int, [vp]), "pfcu_surface_wrap": (vp, [vp, vp, u32, u32]),
             "pfcu_surface_destroy": (None, [vp]), "pfcu_surface_width": (u32, [vp]), "pfcu_surface_height": (u32, [vp]),
             "pfcu_surface_color_ptr": (vp, [vp]), "pfcu_surface_depth_ptr": (vp, [vp]),
             "pfcu_surface_upload": (C.c_int, [vp, vp, vp, u32, u32]), "pfcu_surface_download": (C.c_int, [vp, vp, vp, u32, u32]),
@@ -282,15 +284,18 @@ class PfcuLib:
         tris = np.frombuffer((C.c_char * (nt.value * TRIANGLE_DTYPE.itemsize)).from_address(pt.value), dtype=TRIANGLE_DTYPE).copy() if nt.value else np.zeros(0, TRIANGLE_DTYPE)
         return states, tris
 
-    def render_stream(self, width, height, states, tris, color0=None, depth0=None, clear=None, tile_owner=None, prims=None):
-        """Rasterise a triangle stream (then, optionally, a stream of points / lines) into a fresh surface;
-        returns (color u32[h,w], depth f32[h,w])."""
+    def render_stream(self, width, height, states, tris, color0=None, depth0=None, clear=None, tile_owner=None, prims=None, fmt=TEX_RGBA8):
+        """Rasterise a triangle stream (then, optionally, a stream of points / lines) into a fresh surface of colour
+        layout `fmt`; returns (color, depth f32[h,w]) with color u32[h,w] for the 4-byte layouts and u8[h,w,3] for
+        RGB8 / BGR8 (the caller's layout, as pfcu_surface_download delivers it)."""
         L = self.lib
-        s = L.pfcu_surface_create(width, height)
+        s = L.pfcu_surface_create_format(width, height, fmt)
         if not s:
             raise RuntimeError("pfcu_surface_create failed: " + self.error())
+        cshape, cdtype = ((height, width), np.uint32) if fmt in (TEX_RGBA8, TEX_BGRA8) else ((height, width, 3), np.uint8)
         try:
-            color = np.ascontiguousarray(color0 if color0 is not None else np.zeros((height, width), np.uint32))
+            color = np.ascontiguousarray(color0 if color0 is not None else np.zeros(cshape, cdtype))
+            assert color.shape == cshape and color.dtype == cdtype
             depth = np.ascontiguousarray(depth0 if depth0 is not None else np.full((height, width), np.finfo(np.float32).max, np.float32))
             self.check(L.pfcu_surface_upload(s, color.ctypes.data, depth.ctypes.data, 0, height), "upload")
             if clear is not None:
@@ -306,7 +311,7 @@ class PfcuLib:
                 assert prims.dtype == PRIM_DTYPE and prims.dtype.itemsize == 40
                 self.check(L.pfcu_submit_prims(s, prims.ctypes.data, len(prims)), "pfcu_submit_prims")
             self.check(L.pfcu_finish(), "finish")
-            out_c = np.zeros((height, width), np.uint32)
+            out_c = np.zeros(cshape, cdtype)
             out_d = np.zeros((height, width), np.float32)
             self.check(L.pfcu_surface_download(s, out_c.ctypes.data, out_d.ctypes.data, 0, height), "download")
             return out_c, out_d

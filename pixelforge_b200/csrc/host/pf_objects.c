@@ -103,15 +103,16 @@ static pf_surf *g_surfs = NULL;     /* registry: PFframebuffer is a by-value str
 pf_surf *pfh_surf_create(pf_tex *tex, PFfloat *zhost, int z_public)
 {
     if (!pfh_runtime_init()) return NULL;
-    if (!(tex->format == PF_RGBA && tex->type == PF_UNSIGNED_BYTE)) {
-        fprintf(stderr, "pixelforge-b200: render targets must be PF_RGBA / PF_UNSIGNED_BYTE (got %d/%d); "
-                        "other framebuffer formats are outside the CUDA path (SURVEY.md 8-f NEXT-4)\n",
+    const int code = pfh_tex_format_code(tex->format, tex->type);
+    if (code < 0) {
+        fprintf(stderr, "pixelforge-b200: render targets must be PF_RGBA, PF_BGRA, PF_RGB or PF_BGR with PF_UNSIGNED_BYTE (got %d/%d); "
+                        "the other framebuffer formats are outside the CUDA path (SURVEY.md 8-f NEXT-4)\n",
                 (int)tex->format, (int)tex->type);
         return NULL;
     }
     pf_surf *s = (pf_surf *)calloc(1, sizeof *s);
     if (!s) return NULL;
-    s->dev = pfcu_surface_create(tex->w, tex->h);
+    s->dev = pfcu_surface_create_format(tex->w, tex->h, code);
     if (!s->dev) { free(s); return NULL; }
     s->tex = tex; s->zhost = zhost; s->z_public = z_public;
     s->dirty_y0 = tex->h; s->dirty_y1 = 0;
@@ -122,10 +123,10 @@ pf_surf *pfh_surf_create(pf_tex *tex, PFfloat *zhost, int z_public)
     /* large mirrors: pin in place so that read-backs are direct DMA (PF_CUDA_PIN_HOST=0 disables) */
     {
         const char *e = getenv("PF_CUDA_PIN_HOST");
-        const size_t bytes = (size_t)tex->w * tex->h * 4;
+        const size_t px = (size_t)tex->w * tex->h, bytes = px * pfh_pixel_bytes(tex->format, tex->type);
         if (!(e && e[0] == '0') && bytes >= ((size_t)1 << 20)) {
             if (tex->pixels && pfcu_host_register(tex->pixels, bytes) == PFCU_OK) s->pinned_color = tex->pixels;
-            if (zhost && pfcu_host_register(zhost, bytes) == PFCU_OK) s->pinned_depth = zhost;
+            if (zhost && pfcu_host_register(zhost, px * 4) == PFCU_OK) s->pinned_depth = zhost;
         }
     }
     s->next = g_surfs; g_surfs = s;

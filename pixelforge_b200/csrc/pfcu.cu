@@ -91,20 +91,23 @@ struct __align__(16) DevState {
     DevLight lights[8];
     DevMaterial material[2];
     float view_pos[3];
+    unsigned tex_leader;                        /* texels come through the reference's BGRA8 getter (pfcu_raster_rows.cuh) */
 };
 
 static_assert(offsetof(DevState, tex_fw) % 16 == 0, "tex_fw..tex_ty are fetched as one float4");
 
 struct pfcu_surface {
     uint32_t w, h; uint32_t *color; float *depth; bool owned;
+    int fmt;                                        /* PFCU_TEX_*: the caller's layout; the device holds canonical RGBA8 */
+    unsigned char *conv; size_t conv_bytes;         /* device staging for layout conversion at upload / download */
     uint32_t rank, world; uint32_t tiles_x, tiles_y;
     int lane; cudaEvent_t done; bool has_done;      /* last work enqueued on this surface */
     uint32_t *peer_color; float *peer_depth;        /* present target (peer memory or another local surface), or nullptr */
     void *ipc_color, *ipc_depth;                    /* mappings opened with cudaIpcOpenMemHandle (to close) */
 };
-struct pfcu_texture { uint32_t w, h; int fmt; unsigned char *pixels; bool owned; pfcu_surface *alias; };
+struct pfcu_texture { uint32_t w, h; int fmt; unsigned char *pixels; bool owned; pfcu_surface *alias; bool leader; };
 struct pfcu_batch {
-    DevState *states; uint32_t n_states; pfcu_triangle *tris; uint32_t n_tris; unsigned feature_mask; int single_prog;
+    DevState *states; uint32_t n_states; pfcu_triangle *tris; uint32_t n_tris; unsigned feature_mask; int single_prog; bool leader_tex;
     std::vector<pfcu_surface *> deps;
 };
 
@@ -196,6 +199,8 @@ __constant__ int c_rcp_shift, c_rsq_shift, c_rsq_bits;
 #include "pfcu_raster_tiles.cuh"
 
 #include "pfcu_raster_frag.cuh"
+
+#include "pfcu_raster_rows.cuh"
 
 #include "pfcu_vertex_prims.cuh"
 
@@ -427,13 +432,19 @@ int pfcu_set_approx_tables(const uint32_t *rcp, int rcp_bits, const uint32_t *rs
 
 static void surface_dims(pfcu_surface *s) { s->tiles_x = (s->w + TILE - 1) / TILE; s->tiles_y = (s->h + TILE - 1) / TILE; }
 
-pfcu_surface *pfcu_surface_create(uint32_t w, uint32_t h)
+static size_t fmt_bytes(int fmt) { return (fmt == PFCU_TEX_RGBA8 || fmt == PFCU_TEX_BGRA8) ? 4u : 3u; }
+
+pfcu_surface *pfcu_surface_create(uint32_t w, uint32_t h) { return pfcu_surface_create_format(w, h, PFCU_TEX_RGBA8); }
+int pfcu_surface_format(const pfcu_surface *s) { return s ? s->fmt : -1; }
+
+pfcu_surface *pfcu_surface_create_format(uint32_t w, uint32_t h, int fmt)
 {
     API_LOCK;
     if (!g.ok || w == 0 || h == 0) { snprintf(g.err, sizeof g.err, "surface_create: runtime not initialised or empty surface"); return nullptr; }
+    if (fmt < PFCU_TEX_RGBA8 || fmt > PFCU_TEX_BGR8) { snprintf(g.err, sizeof g.err, "surface_create: unsupported colour format %d", fmt); return nullptr; }
     pfcu_surface *s = (pfcu_surface *)calloc(1, sizeof *s);
     if (!s) return nullptr;
-    s->w = w; s->h = h; s->owned = true; s->world = 1;
+    s->w = w; s->h = h; s->owned = true; s->world = 1; s->fmt = fmt;
     s->lane = (int)(g.next_lane++ % (unsigned)g.n_lanes);
     cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
     use_lane(s);
@@ -445,6 +456,13 @@ pfcu_surface *pfcu_surface_create(uint32_t w, uint32_t h)
     }
     cudaMemsetAsync(s->color, 0, bytes, LN.stream);
     cudaMemsetAsync(s->depth, 0, bytes, LN.stream);
+    if (fmt != PFCU_TEX_RGBA8) {
+        s->conv_bytes = (size_t)w * h * fmt_bytes(fmt) + 16;
+        if (cudaMalloc(&s->conv, s->conv_bytes) != cudaSuccess) {
+            snprintf(g.err, sizeof g.err, "surface_create: out of device memory (%ux%u staging)", w, h);
+            cudaFree(s->color); cudaFree(s->depth); free(s); return nullptr;
+        }
+    }
     return s;
 }
 
@@ -454,7 +472,7 @@ pfcu_surface *pfcu_surface_wrap(void *dev_color, void *dev_depth, uint32_t w, ui
     if (!g.ok || !dev_color || !dev_depth) return nullptr;
     pfcu_surface *s = (pfcu_surface *)calloc(1, sizeof *s);
     if (!s) return nullptr;
-    s->w = w; s->h = h; s->color = (uint32_t *)dev_color; s->depth = (float *)dev_depth; s->owned = false; s->world = 1;
+    s->w = w; s->h = h; s->color = (uint32_t *)dev_color; s->depth = (float *)dev_depth; s->owned = false; s->world = 1; s->fmt = PFCU_TEX_RGBA8;
     s->lane = 0;                                  /* caller-owned memory: stay on the caller-visible stream */
     cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
     surface_dims(s);
@@ -544,6 +562,7 @@ void pfcu_surface_destroy(pfcu_surface *s)
     if (g.ok) sync_all_lanes();
     close_present(s);
     if (s->owned) { cudaFree(s->color); cudaFree(s->depth); }
+    cudaFree(s->conv);
     if (s->done) cudaEventDestroy(s->done);
     free(s);
 }
@@ -561,6 +580,15 @@ int pfcu_surface_upload(pfcu_surface *s, const void *hc, const float *hd, uint32
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
     use_lane(s);
     const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;
+    if (hc && s->fmt != PFCU_TEX_RGBA8 && rows) {
+        /* the caller's layout -> staging -> canonical RGBA8 */
+        const size_t bpp = fmt_bytes(s->fmt), nb = (size_t)rows * s->w * bpp;
+        CK(cudaMemcpyAsync(s->conv + off * bpp, (const unsigned char *)hc + off * bpp, nb, cudaMemcpyHostToDevice, LN.stream));
+        k_surface_convert<<<g.sms * 4, 256, 0, LN.stream>>>(s->color + off, s->conv + off * bpp, (size_t)rows * s->w, s->fmt, 0);
+        g.launches++; g.bytes_h2d += nb;
+        CK(cudaGetLastError());
+        hc = nullptr;
+    }
     if (hc) { CK(cudaMemcpyAsync(s->color + off, (const uint32_t *)hc + off, n, cudaMemcpyHostToDevice, LN.stream)); g.bytes_h2d += n; }
     if (hd) { CK(cudaMemcpyAsync(s->depth + off, hd + off, n, cudaMemcpyHostToDevice, LN.stream)); g.bytes_h2d += n; }
     /* pageable sources are staged by the driver before the call returns; pinned ones are not */
@@ -574,6 +602,15 @@ int pfcu_surface_download_async(pfcu_surface *s, void *hc, float *hd, uint32_t y
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
     use_lane(s);
     const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;
+    if (hc && s->fmt != PFCU_TEX_RGBA8 && rows) {
+        /* canonical RGBA8 -> staging in the caller's layout -> host */
+        const size_t bpp = fmt_bytes(s->fmt), nb = (size_t)rows * s->w * bpp;
+        k_surface_convert<<<g.sms * 4, 256, 0, LN.stream>>>(s->color + off, s->conv + off * bpp, (size_t)rows * s->w, s->fmt, 1);
+        g.launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync((unsigned char *)hc + off * bpp, s->conv + off * bpp, nb, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += nb;
+        hc = nullptr;
+    }
     if (hc) { CK(cudaMemcpyAsync((uint32_t *)hc + off, s->color + off, n, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += n; }
     if (hd) { CK(cudaMemcpyAsync(hd + off, s->depth + off, n, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += n; }
     mark_done(s);
@@ -618,6 +655,7 @@ int pfcu_surface_fill(pfcu_surface *s, int dc, uint32_t rgba, int dd, float z)
 {
     API_LOCK;
     use_lane(s);
+    if (s->fmt >= PFCU_TEX_RGB8) rgba |= 0xff000000u;      /* 3-byte targets store no alpha and read it back as 255 */
     const int rc = fill_range(s, 0, (size_t)s->w * s->h, dc, rgba, dd, z);
     mark_done(s);
     return rc;
@@ -627,6 +665,7 @@ int pfcu_surface_clear_ref(pfcu_surface *s, int dc, uint32_t rgba, int dd, float
 {
     API_LOCK;
     use_lane(s);
+    if (s->fmt >= PFCU_TEX_RGB8) rgba |= 0xff000000u;
     const unsigned size = s->w * s->h, aligned = size - (size % 8u);
     if (aligned > 8) { int rc = fill_range(s, 8, aligned - 8, dc, rgba, dd, z); if (rc) return rc; }
     if (aligned < size) { k_clear_tail<<<1, 32, 0, LN.stream>>>(s->color, s->depth, aligned, size, dc, dd); g.launches++; }
@@ -682,7 +721,7 @@ pfcu_texture *pfcu_texture_create(const void *host_pixels, uint32_t w, uint32_t 
     if (!g.ok || fmt < PFCU_TEX_RGBA8 || fmt > PFCU_TEX_BGR8 || w == 0 || h == 0) return nullptr;
     pfcu_texture *t = (pfcu_texture *)calloc(1, sizeof *t);
     if (!t) return nullptr;
-    t->w = w; t->h = h; t->fmt = fmt; t->owned = true;
+    t->w = w; t->h = h; t->fmt = fmt; t->owned = true; t->leader = (fmt == PFCU_TEX_BGRA8);
     g.cur = &g.lanes[0];
     const size_t bytes = tex_bytes(w, h, fmt);
     if (cudaMalloc(&t->pixels, bytes + 16) != cudaSuccess) { snprintf(g.err, sizeof g.err, "texture_create: out of device memory"); free(t); return nullptr; }
@@ -696,7 +735,10 @@ pfcu_texture *pfcu_texture_from_surface(pfcu_surface *s)
     API_LOCK;
     pfcu_texture *t = (pfcu_texture *)calloc(1, sizeof *t);
     if (!t) return nullptr;
+    /* the surface is held as canonical RGBA8 whatever the caller's layout; a BGRA8 target sampled as a texture still goes
+       through the reference's BGRA8 getter, whose effect beyond the byte order is the leader replication */
     t->w = s->w; t->h = s->h; t->fmt = PFCU_TEX_RGBA8; t->pixels = (unsigned char *)s->color; t->owned = false; t->alias = s;
+    t->leader = (s->fmt == PFCU_TEX_BGRA8);
     return t;
 }
 
@@ -734,11 +776,13 @@ static int state_program(const DevState *d)
 }
 
 static int g_last_single_prog = -1;      /* set by convert_states: the common program of all states, or -1 */
+static bool g_last_leader_tex = false;   /* set by convert_states: some state samples through the BGRA8 getter */
 
 static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
 {
     unsigned mask = 0;
     g.deps.clear();
+    g_last_leader_tex = false;
     for (uint32_t i = 0; i < n; i++) {
         const pfcu_state *s = in + i; DevState *d = out + i;
         memset(d, 0, sizeof *d);
@@ -749,6 +793,8 @@ static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
         d->vp_min[0] = s->vp_min[0]; d->vp_min[1] = s->vp_min[1]; d->vp_max[0] = s->vp_max[0]; d->vp_max[1] = s->vp_max[1];
         if (d->flags & PFCU_ST_TEXTURE) {
             d->tex = s->texture->pixels; d->tw = s->texture->w; d->th = s->texture->h; d->tfmt = s->texture->fmt;
+            d->tex_leader = s->texture->leader ? 1u : 0u;
+            if (s->texture->leader) g_last_leader_tex = true;
             d->tex_fw = (float)d->tw; d->tex_fh = (float)d->th;
             { volatile float one = 1.0f; d->tex_tx = one / d->tex_fw; d->tex_ty = one / d->tex_fh; }   /* IEEE single division, as DIVPS */
             if (s->texture->alias) g.deps.push_back(s->texture->alias);      /* render-to-texture: order across lanes */
@@ -781,6 +827,13 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
 {
     if (n == 0) return PFCU_OK;
     if (!d_n) n_est = n;
+    /* render targets other than RGBA8 and BGRA8 textures: the row-ordered rasteriser (pfcu_raster_rows.cuh) */
+    const bool rows_path = s->fmt != PFCU_TEX_RGBA8 || g_last_leader_tex;
+    g_last_leader_tex = false;
+    if (rows_path && s->world > 1) {
+        snprintf(g.err, sizeof g.err, "the screen-tile split needs an RGBA8 target and no BGRA8 textures (a pixel depends on its row neighbours there)");
+        return PFCU_ERR_INVALID;
+    }
     if (!g.d_rcp) { snprintf(g.err, sizeof g.err, "pfcu_set_approx_tables() has not been called"); return PFCU_ERR_INVALID; }
     int rc;
     /* surfaces sampled as textures that live on another lane: wait for their last write */
@@ -830,6 +883,8 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     } else {
         k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, LN.stream>>>(
             d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data, g.d_counters);
+        g.launches += 1;
+        if (!rows_path) {
         k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, bin_batch, binsX, binsY, bshift, LN.d_bin_counts);
         unsigned *d_totals = LN.d_bin_start + (MAX_BINS + 2);
         k_bin_scan<<<(nb + 31) / 32, 1024, 0, LN.stream>>>(LN.d_bin_counts, (int)nBatches, nb, d_totals);
@@ -849,7 +904,26 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
             if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, want ? want : 1))) return rc;
         }
         k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, bin_batch, binsX, binsY, bshift, LN.d_bin_counts, LN.d_bin_start, LN.d_bin_list);
-        g.launches += 5;
+        g.launches += 4;
+        }
+    }
+    if (rows_path) {
+        RowsParams rp;
+        rp.bbox = LN.d_bbox; rp.setup = LN.d_setup; rp.data = LN.d_data; rp.states = d_states; rp.n = n; rp.d_n = d_n;
+        rp.color = s->color; rp.depth = s->depth; rp.W = (int)s->w; rp.H = (int)s->h; rp.fb_fmt = s->fmt; rp.counters = g.d_counters;
+        if (g.profiling) CK(cudaEventRecord(pe[1], LN.stream));
+        const unsigned bands = (s->h + ROWS_NW - 1) / ROWS_NW;
+        if (feature_mask & PFCU_ST_PHONG) k_raster_rows<true><<<bands, ROWS_NW * 32, 0, LN.stream>>>(rp);
+        else                              k_raster_rows<false><<<bands, ROWS_NW * 32, 0, LN.stream>>>(rp);
+        g.launches++;
+        if (g.profiling) { CK(cudaEventRecord(pe[2], LN.stream)); for (int i = 0; i < 3; i++) g.prof_events.push_back(pe[i]); }
+        CK(cudaGetLastError());
+        mark_done(s);
+        for (pfcu_surface *dep : g.deps)
+            if (dep != s && dep->lane != s->lane) CK(cudaStreamWaitEvent(g.lanes[dep->lane % g.n_lanes].stream, s->done, 0));
+        g.deps.clear();
+        if (!d_n) g.submitted += n;
+        return PFCU_OK;
     }
     RasterParams p;
     p.bbox = LN.d_bbox; p.setup = LN.d_setup; p.data = LN.d_data; p.states = d_states;
@@ -1133,6 +1207,7 @@ int pfcu_submit_prims(pfcu_surface *s, const pfcu_prim *prims, uint32_t n)
     PrimParams p;
     p.prims = (const pfcu_prim *)LN.d_varrays; p.n = n; p.color = s->color; p.depth = s->depth; p.W = s->w; p.H = s->h;
     p.tilesX = (int)s->tiles_x; p.rank = s->rank; p.world = s->world ? s->world : 1; p.nTiles = s->tiles_x * s->tiles_y;
+    p.alpha_or = s->fmt >= PFCU_TEX_RGB8 ? 0xff000000u : 0u;
     const unsigned grid = owned_tiles(s, p.rank, p.world);
     if (grid) { k_prims<<<grid, 256, 0, LN.stream>>>(p); g.launches++; }
     CK(cudaGetLastError());
@@ -1196,6 +1271,7 @@ pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const
     std::vector<DevState> tmp(n_states);
     b->feature_mask = convert_states(states, n_states, tmp.data());
     b->single_prog = g_last_single_prog;
+    b->leader_tex = g_last_leader_tex; g_last_leader_tex = false;
     new (&b->deps) std::vector<pfcu_surface *>(g.deps);
     b->n_states = n_states; b->n_tris = n_tris;
     CKP(cudaMalloc(&b->states, n_states * sizeof(DevState)));
@@ -1214,6 +1290,7 @@ int pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b)
     use_lane(s);
     g.deps.clear();
     for (pfcu_surface *dep : b->deps) g.deps.push_back(dep);
+    g_last_leader_tex = b->leader_tex;
     return launch_pipeline(s, b->tris, b->states, b->n_tris, b->feature_mask, b->single_prog);
 }
 

@@ -33,6 +33,27 @@ __global__ void k_clear_tail(uint32_t *color, float *depth, unsigned aligned, un
     if (i < size) { if (do_color) color[i] = color[0]; if (do_depth) depth[i] = depth[0]; }
 }
 
+/* Layout conversion between the caller's colour format (staging, 3 or 4 bytes per pixel) and the canonical RGBA8 the
+ * device works in: to_native = 0: staging -> canonical (upload), 1: canonical -> staging (download).  The scalar
+ * getters / setters of the reference (pixel.h:233-360,576-710): BGRA8 swaps R and B, RGB8 / BGR8 drop alpha and read it
+ * back as 255. */
+__global__ void __launch_bounds__(256)
+k_surface_convert(uint32_t *__restrict__ canon, unsigned char *__restrict__ native, size_t n, int fmt, int to_native)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (fmt == PFCU_TEX_BGRA8) {
+            uint32_t *nat = reinterpret_cast<uint32_t *>(native);
+            if (to_native) nat[i] = __byte_perm(canon[i], 0, 0x3012); else canon[i] = __byte_perm(nat[i], 0, 0x3012);
+        } else {
+            unsigned char *q = native + 3 * i;
+            const int r = fmt == PFCU_TEX_RGB8 ? 0 : 2, b = 2 - r;
+            if (to_native) { const uint32_t c = canon[i]; q[r] = (unsigned char)c; q[1] = (unsigned char)(c >> 8); q[b] = (unsigned char)(c >> 16); }
+            else canon[i] = (uint32_t)q[r] | ((uint32_t)q[1] << 8) | ((uint32_t)q[b] << 16) | 0xff000000u;
+        }
+    }
+}
+
 __global__ void k_pack_tiles(uint32_t *color, float *depth, int W, int H, int tilesX, unsigned nTiles,
                              unsigned rank, unsigned world, int with_depth, uint32_t *staging, int unpack)
 {

@@ -137,7 +137,8 @@ k_raw_emit(const RawArgs a, const unsigned *__restrict__ offsets, pfcu_triangle 
  * lines.  Order per pixel = submission order; no inter-CTA communication.  Primitives whose rectangle cannot
  * touch the tile are skipped (only when every x of the line is inside the surface, because out-of-range columns
  * wrap into the neighbouring rows like upstream). */
-struct PrimParams { const pfcu_prim *prims; unsigned n; uint32_t *color; float *depth; unsigned W, H; int tilesX; unsigned rank, world, nTiles; };
+struct PrimParams { const pfcu_prim *prims; unsigned n; uint32_t *color; float *depth; unsigned W, H; int tilesX; unsigned rank, world, nTiles;
+                    unsigned alpha_or; /* 0xff000000 for RGB8 / BGR8 targets: no stored alpha, reads back as 255 */ };
 
 __device__ __forceinline__ void prim_pixel(const PrimParams &p, const pfcu_prim &pr, int X0, int Y0, uint32_t off, float z, uint32_t color, bool test)
 {
@@ -145,7 +146,7 @@ __device__ __forceinline__ void prim_pixel(const PrimParams &p, const pfcu_prim 
     const int x = (int)(off % p.W), y = (int)(off / p.W);
     if (x < X0 || x >= X0 + TILE || y < Y0 || y >= Y0 + TILE) return;
     if (test && !pfp_depth(pr.depth_func, z, p.depth[off])) return;
-    p.color[off] = (pr.flags & PFCU_ST_BLEND) ? pfp_blend(pr.blend_mode, color, p.color[off]) : color;
+    p.color[off] = ((pr.flags & PFCU_ST_BLEND) ? pfp_blend(pr.blend_mode, color, p.color[off]) : color) | p.alpha_or;
     p.depth[off] = z;
 }
 

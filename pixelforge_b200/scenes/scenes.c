@@ -331,7 +331,7 @@ static void random_vertex(int w, int h, int with_uv, float zlo, float zhi)
 /* variant bits: 0-2 blend mode (with bit3: blending on), 4-6 depth func (bit7: depth test on),
    8 flat shading, 9 texture on, 10 bilinear, 11-12 wrap, 13 cull off, 14-16 draw mode selector,
    17 RGB8 texture, 18 perspective camera instead of 2D ortho, 19 Phong lights, 20 render into an FBO
-   and composite it, 21 spotlight+attenuation, 22 BGRA texture */
+   and composite it, 21 spotlight+attenuation, 22 BGRA texture, 23 BGR8 texture, 24-25 target layout (see pfscene_open) */
 static void micro_scene(const pfscene_cfg *cfg, PFtexture tex)
 {
     const int v = cfg->variant, w = cfg->width, h = cfg->height;
@@ -666,8 +666,13 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
         return s;
     }
 
+    /* variant bits 24-25 (every single-context scene): layout of the target buffer - 0 RGBA8, 1 BGRA8, 2 RGB8, 3 BGR8.
+       The buffer is always w*h*4 bytes (+ padding: the reference's RGB getter reads 4 bytes per pixel); 3-byte layouts
+       use the first w*h*3 of them. */
+    static const PFpixelformat target_formats[4] = { PF_RGBA, PF_BGRA, PF_RGB, PF_BGR };
+    const PFpixelformat tfmt = target_formats[(cfg->variant >> 24) & 3];
     s->target = (uint8_t *)calloc((size_t)w * h * 4 + 64, 1);
-    s->ctx = pfCreateContext(s->target, (PFsizei)w, (PFsizei)h, PF_RGBA, PF_UNSIGNED_BYTE);
+    s->ctx = pfCreateContext(s->target, (PFsizei)w, (PFsizei)h, tfmt, PF_UNSIGNED_BYTE);
     if (!s->ctx) { fprintf(stderr, "pfscene: pfCreateContext failed\n"); free(s->target); free(s); return NULL; }
     pfMakeCurrent(s->ctx);
 
@@ -710,13 +715,13 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
         if (cfg->variant & 1) { pfBlendFunc(PF_BLEND_ALPHA); pfEnable(PF_DEPTH_TEST); pfDepthFunc(PF_LEQUAL); }
         else pfBlendFunc(PF_BLEND_ADD);
     } else if (strcmp(name, "micro") == 0) {
-        const int rgb = (cfg->variant >> 17) & 1, bgra = (cfg->variant >> 22) & 1;
-        s->texpx = make_texture(61, 37, rgb ? 3 : 4, (uint32_t)cfg->seed ^ 0xabcdu, 0, 255, 0, 255);
-        s->tex = pfGenTexture(s->texpx, 61, 37, rgb ? PF_RGB : (bgra ? PF_BGRA : PF_RGBA), PF_UNSIGNED_BYTE);
+        const int rgb = (cfg->variant >> 17) & 1, bgra = (cfg->variant >> 22) & 1, bgr = (cfg->variant >> 23) & 1;
+        s->texpx = make_texture(61, 37, (rgb || bgr) ? 3 : 4, (uint32_t)cfg->seed ^ 0xabcdu, 0, 255, 0, 255);
+        s->tex = pfGenTexture(s->texpx, 61, 37, bgr ? PF_BGR : (rgb ? PF_RGB : (bgra ? PF_BGRA : PF_RGBA)), PF_UNSIGNED_BYTE);
         /* the FBO is larger than the 96x80 viewport used to draw into it: for a viewport smaller than the
            MAIN buffer the reference computes vpMax = x+width (one past the last column/row,
            context.c:567-570), so "2D" triangles may touch column 96 / row 80 */
-        if (cfg->variant & (1 << 20)) s->fbo = pfGenFramebuffer(104, 88, PF_RGBA, PF_UNSIGNED_BYTE);
+        if (cfg->variant & (1 << 20)) s->fbo = pfGenFramebuffer(104, 88, tfmt, PF_UNSIGNED_BYTE);       /* same layout as the target */
     } else if (strcmp(name, "prims") == 0) {
         /* no resources */
     } else if (strcmp(name, "api") == 0) {

@@ -6,15 +6,18 @@ property tests in test_gpu_parity.py.
 """
 
 
+TARGET_RGBA, TARGET_BGRA, TARGET_RGB, TARGET_BGR = 0, 1, 2, 3     # variant bits 24-25 of every single-context scene
+
+
 def micro_variant(blend=None, depth=None, flat=0, tex=0, bil=0, wrap=0, cull_off=0, mode=0, rgb=0, persp=0,
-                  phong=0, fbo=0, spot=0, bgra=0):
+                  phong=0, fbo=0, spot=0, bgra=0, bgr=0, target=0):
     v = 0
     if blend is not None:
         v |= 8 | blend
     if depth is not None:
         v |= 128 | (depth << 4)
     v |= (flat << 8 | tex << 9 | bil << 10 | wrap << 11 | cull_off << 13 | mode << 14 | rgb << 17 | persp << 18
-          | phong << 19 | fbo << 20 | spot << 21 | bgra << 22)
+          | phong << 19 | fbo << 20 | spot << 21 | bgra << 22 | bgr << 23 | target << 24)
     return v
 
 
@@ -60,11 +63,37 @@ CASES += [_micro(f"random{s}", s, size=60, blend=s % 8, depth=s % 6, tex=s & 1, 
 
 
 
+# BGRA8 / BGR8 textures and BGRA8 / RGB8 / BGR8 render targets against the LIVE reference.  The
+# reference's BGRA8 getter and setter hand the first pixel of every group of four (counted from the triangle's xMin) to
+# the whole group (Q19); these cases pin that behaviour - texel replication with per-pixel bilinear weights, the
+# leader's own mask deciding its uv, blending against the leader's pixel, stores of the leader's fragment - under
+# every blend mode, with depth testing, perspective, Phong, flat shading and an FBO of the same layout sampled back.
+CASES += [_micro(f"bgra-tex-wrap{w}", 41 + w, tex=1, bgra=1, wrap=w, cull_off=1, blend=1) for w in range(3)]
+CASES += [_micro(f"bgra-tex-persp-depth-wrap{w}", 44 + w, tex=1, bgra=1, wrap=w, cull_off=1, persp=1, depth=2) for w in range(3)]
+CASES += [_micro(f"bgra-tex-bilinear-wrap{w}", 47 + w, ref_bfix=True, tex=1, bgra=1, bil=1, wrap=w, cull_off=1, depth=3) for w in range(3)]
+CASES += [_micro("bgra-tex-phong", 50, tex=1, bgra=1, phong=1, persp=1, cull_off=1, depth=2, spot=1)]
+CASES += [_micro(f"bgr-tex-wrap{w}", 51 + w, tex=1, bgr=1, wrap=w, cull_off=1, blend=1) for w in range(3)]
+CASES += [_micro("bgr-tex-bilinear-persp", 54, ref_bfix=True, tex=1, bgr=1, bil=1, cull_off=1, persp=1, depth=2)]
+CASES += [_micro(f"target-bgra-blend{b}", 60 + b, target=TARGET_BGRA, blend=b, cull_off=1) for b in range(8)]
+CASES += [_micro(f"target-bgra-depth{d}", 68 + d, target=TARGET_BGRA, depth=d, cull_off=1, flat=d & 1) for d in range(6)]
+CASES += [_micro("target-bgra-tex-persp", 74, target=TARGET_BGRA, tex=1, wrap=1, cull_off=1, persp=1, depth=2, blend=1),
+          _micro("target-bgra-bgra-tex", 75, target=TARGET_BGRA, tex=1, bgra=1, cull_off=1, blend=1, depth=3),
+          _micro("target-bgra-bilinear", 76, ref_bfix=True, target=TARGET_BGRA, tex=1, bil=1, cull_off=1, blend=2),
+          _micro("target-bgra-phong", 77, target=TARGET_BGRA, phong=1, persp=1, cull_off=1, depth=2),
+          _micro("target-bgra-fbo", 78, target=TARGET_BGRA, fbo=1, tex=1, cull_off=1, depth=2),
+          _micro("target-bgra-fbo-persp-blend", 79, target=TARGET_BGRA, fbo=1, tex=1, cull_off=1, depth=2, persp=1, blend=1)]
+CASES += [_micro(f"target-bgra-mode{m}", 80 + m, target=TARGET_BGRA, mode=m, cull_off=m & 1, depth=2, blend=1) for m in range(6)]
+CASES += [_micro(f"target-rgb-blend{b}", 90 + b, target=TARGET_RGB, blend=b, cull_off=1, tex=b & 1) for b in range(8)]
+CASES += [_micro(f"target-bgr-blend{b}", 100 + b, target=TARGET_BGR, blend=b, cull_off=1, depth=b % 6) for b in (0, 1, 2, 5)]
+CASES += [_micro("target-rgb-fbo", 110, target=TARGET_RGB, fbo=1, tex=1, cull_off=1, depth=2, blend=1),
+          _micro("target-bgr-phong-persp", 111, target=TARGET_BGR, phong=1, persp=1, cull_off=1, depth=2)]
+
+
 # breadth of the public API around the triangle path (scene "api", see scenes.c for the variant bits):
 # viewport offsets, texture matrix, Gouraud with spot/attenuation/back materials/colour material/normalize,
 # colour arrays, pfRect*, pfDrawPixels + zoom, fog, post-processing, pfReadPixels, pfClearDepth, aux buffer
-def _api(desc, variant, seed=1, ref_bfix=False):
-    return (f"api-{desc}", "api", 200, 150, dict(variant=variant, seed=seed), ref_bfix)
+def _api(desc, variant, seed=1, ref_bfix=False, target=0):
+    return (f"api-{desc}", "api", 200, 150, dict(variant=variant | target << 24, seed=seed), ref_bfix)
 
 
 _B = lambda *bits: sum(1 << b for b in bits)
@@ -77,6 +106,11 @@ CASES += [_api("plain", 0), _api("viewport", _B(0)), _api("texmatrix", _B(1)), _
           _api("fog-linear", _B(6)), _api("fog-exp-opaque", _B(6, 15, 16)), _api("fog-cleardepth", _B(6, 9)),
           _api("postprocess", _B(7)), _api("swapbuffers", _B(14, 7)),
           _api("everything", 0x3ffff & ~_B(13), seed=2), _api("everything-bilinear", 0x7ffff & ~_B(13), seed=3, ref_bfix=True)]
+# the same API breadth on the other target layouts (scalar getters / setters: rects, draw pixels, fog, post-processing,
+# read pixels, swap buffers) and points / lines below
+CASES += [_api("everything-target-bgra", 0x3ffff & ~_B(13), seed=4, target=TARGET_BGRA),
+          _api("everything-target-rgb", 0x3ffff & ~_B(13), seed=5, target=TARGET_RGB),
+          _api("gouraud-target-bgr", _B(2, 3), seed=6, target=TARGET_BGR)]
 
 CASE_IDS = [c[0] for c in CASES]
 assert len(set(CASE_IDS)) == len(CASE_IDS)
@@ -84,8 +118,8 @@ assert len(set(CASE_IDS)) == len(CASE_IDS)
 
 # points, lines and PF_POINT / PF_LINE polygon modes (scene "prims"): the reference's scalar rasterisers
 # (lines.c, points.c) - scalar blend / depth tables, thick lines, frustum-clipped 3D lines
-def _prims(desc, blend=None, depth=None, persp=0, thick=0, seed=1, size=48):
-    v = (persp << 8) | (thick << 9)
+def _prims(desc, blend=None, depth=None, persp=0, thick=0, seed=1, size=48, target=0):
+    v = (persp << 8) | (thick << 9) | (target << 24)
     if blend is not None:
         v |= 1 | (blend << 1)
     if depth is not None:
@@ -97,5 +131,8 @@ CASES += [_prims("plain"), _prims("thick", thick=1, seed=2), _prims("persp", per
 CASES += [_prims(f"blend{b}-thick", blend=b, thick=1, seed=5 + b) for b in range(8)]
 CASES += [_prims(f"depth{d}-thick", depth=d, thick=1, seed=20 + d) for d in range(6)]
 CASES += [_prims("persp-blend1-depth3-points", blend=1, depth=3, persp=1, thick=1, seed=30, size=90)]
+CASES += [_prims("target-bgra-blend1-thick", blend=1, thick=1, seed=31, target=TARGET_BGRA),
+          _prims("target-rgb-blend2-depth2", blend=2, depth=2, seed=32, target=TARGET_RGB),
+          _prims("target-bgr-persp-blend0", blend=0, persp=1, seed=33, target=TARGET_BGR)]
 
 CASE_IDS = [c[0] for c in CASES]

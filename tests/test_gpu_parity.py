@@ -184,6 +184,68 @@ def test_stream_phong(pfcu_pair):
     assert (cp[dp != FLT_MAX] >> 24 == 0).all()         # Q9: Phong forces alpha to 0
 
 
+# ---- render targets other than RGBA8 and BGRA8 textures: the row-ordered rasteriser ----
+
+@pytest.mark.parametrize("fmt", [1, 2, 3], ids=["target-bgra8", "target-rgb8", "target-bgr8"])
+def test_stream_surface_formats(pfcu_pair, fmt):
+    """Random triangle streams into BGRA8 / RGB8 / BGR8 surfaces (k_raster_rows): every blend mode and depth function,
+    small and screen-sized triangles, 2D and perspective, textures in all four texel layouts (BGRA8 texels replicate
+    the first pixel of every group of four), Phong - colour in the caller's layout and depth must equal the oracle's."""
+    prod, orc = pfcu_pair
+    rng = np.random.default_rng(300 + fmt)
+    w, h = 203, 117
+    cshape, cdtype, hi = (((h, w), np.uint32, 2**32) if fmt == 1 else ((h, w, 3), np.uint8, 256))
+    for k, (flags, kw, texfmt, filt) in enumerate([
+            (1 | 2 | 16, dict(blend=1, depth=2), None, 0), (1 | 16, dict(blend=3, big=True, n_states=4), None, 0),
+            (1 | 2, dict(blend=0, depth=3, big=True, n_states=3), 0, 0), (1 | 2 | 16, dict(blend=2, depth=5, is3d=1), 1, 0),
+            (2 | 16, dict(depth=2, big=True, is3d=1, n_states=2), 1, 1), (1 | 16, dict(blend=5, n_states=3), 2, 1), (1 | 2 | 16, dict(blend=4, depth=4, big=True), 3, 0)]):
+        tp = to = None
+        if texfmt is not None:
+            tp, to = make_textures(prod, orc, rng, 37, 29, texfmt)
+        sp, tris = random_stream(rng, w, h, 900 if not kw.get("big") else 250, flags, tex=(tp, filt, k % 3) if tp else None, **kw)
+        so = sp.copy()
+        if to:
+            so["texture"] = to
+        color0 = rng.integers(0, hi, cshape, dtype=np.uint64).astype(cdtype)
+        cp, dp = prod.render_stream(w, h, sp, tris, color0=color0, fmt=fmt)
+        co, do = orc.render_stream(w, h, so, tris, color0=color0, fmt=fmt)
+        assert int((cp != co).sum()) == 0 and int((dp.view(np.uint32) != do.view(np.uint32)).sum()) == 0, (fmt, k)
+        if tp:
+            prod.lib.pfcu_texture_destroy(tp); orc.lib.pfcu_texture_destroy(to)
+    # Phong, degenerate coordinates, points and lines on top
+    tp, to = make_textures(prod, orc, rng, 64, 64, 1)
+    sp, tris = random_stream(rng, w, h, 700, 2 | 16, n_states=2, tex=(tp, 0, 1), phong=True, is3d=1)
+    tris["v"]["sx"][:8, 0] = np.nan; tris["v"]["sx"][8:16, 1] = -70000.0; tris["v"]["sy"][16:24, 2] = 3e9
+    so = sp.copy(); so["texture"] = to
+    prims = random_prims(rng, w, h, 80, 12)
+    cp, dp = prod.render_stream(w, h, sp, tris, prims=prims, fmt=fmt)
+    co, do = orc.render_stream(w, h, so, tris, prims=prims, fmt=fmt)
+    assert int((cp != co).sum()) == 0 and int((dp.view(np.uint32) != do.view(np.uint32)).sum()) == 0
+    prod.lib.pfcu_texture_destroy(tp); orc.lib.pfcu_texture_destroy(to)
+
+
+def test_bgra_texture_on_rgba_target_takes_the_leader_path(pfcu_pair):
+    """A BGRA8 texture on an ordinary RGBA8 target: lanes 1..3 of every group of four pixels (from the triangle's xMin)
+    get the leader's texel; same result under both forced rasterisers (the batch is routed to k_raster_rows either way)
+    and a tile split of such a batch is refused."""
+    prod, orc = pfcu_pair
+    rng = np.random.default_rng(77)
+    tp, to = make_textures(prod, orc, rng, 41, 23, 1)
+    sp, tris = random_stream(rng, 300, 200, 1200, 1 | 2 | 16, n_states=3, tex=(tp, 1, 2), big=False)
+    so = sp.copy(); so["texture"] = to
+    co, do = orc.render_stream(300, 200, so, tris)
+    for path in (0, 1, 2):
+        prod.lib.pfcu_set_raster_path(path)
+        try:
+            cp, dp = prod.render_stream(300, 200, sp, tris)
+        finally:
+            prod.lib.pfcu_set_raster_path(0)
+        assert int((cp != co).sum()) == 0 and int((dp.view(np.uint32) != do.view(np.uint32)).sum()) == 0, path
+    with pytest.raises(RuntimeError):
+        prod.render_stream(300, 200, sp, tris, tile_owner=(0, 2))
+    prod.lib.pfcu_texture_destroy(tp); orc.lib.pfcu_texture_destroy(to)
+
+
 # ---- both tile rasterisers (k_raster: triangle per warp step; k_raster_frag: fragment compaction) ------------
 
 @pytest.fixture(params=[1, 2], ids=["tiles", "fragments"])

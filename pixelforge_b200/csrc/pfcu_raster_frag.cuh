@@ -34,6 +34,7 @@ struct FragCtx {
     int RX0, RY0, RX1, RY1;             /* the region on the surface, inclusive                         */
     unsigned shaded, covered;
     unsigned tri_base;                  /* shared-window byte address of this warp's triangle staging   */
+    unsigned ring_base;                 /* ... of this warp's ring of 64 covered fragments (16 bits each) */
 };
 
 /* Per-warp staging of a group's triangle constants: field F of the triangle held by lane l is the 16-byte slot
@@ -54,6 +55,15 @@ __device__ __forceinline__ void sts_tri(unsigned base, int field, int j, uint4 v
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(base + (unsigned)((field * 32 + j) << 4)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ uint2 lds_tri2(unsigned base, int field, int j)     /* the first half of a staged field */
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(base + (unsigned)((field * 32 + j) << 4)));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(unsigned addr, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ unsigned lds_u16(unsigned addr) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr)); return v; }
+
 template <int OFF> __device__ __forceinline__ float lds_f32_off(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF)); return v; }
 template <int OFF> __device__ __forceinline__ void sts_f32_off(unsigned addr, float v) { asm volatile("st.shared.f32 [%0+%1], %2;" :: "r"(addr), "n"(OFF), "f"(v) : "memory"); }
 
@@ -68,9 +78,21 @@ __device__ __forceinline__ float rcp_tab(const FragCtx &t, float x)
 
 /* One group of <= 32 triangles in one state (lane l holds triangle ti with nn candidate pixels in this warp's
  * region; nn == 0 for lanes outside the group).  pk = cx0 | cy0<<4 | cw<<8 | ceil(1024/cw)<<12 describes the
- * clipped rectangle (region-local).  lo is a lane that is known to hold a valid triangle. */
+ * clipped rectangle (region-local).
+ *
+ * Two interleaved phases over the ordered candidate stream (the clipped bounding rectangles of the group laid end to
+ * end):
+ *   coverage   32 candidates at a time (lane = candidate): owner lookup by binary search over the scan, pixel from the
+ *              packed rectangle, the three integer edge functions - nothing else.  The covered ones are appended, in
+ *              order, to the warp's ring of 64 packed fragments {triangle lane, x, y} (ballot compaction);
+ *   shading    as soon as the ring holds 32 fragments (or the stream ends) they are shaded together, every lane a
+ *              COVERED fragment: depth, colour, texture, Phong, ordered read-modify-write.
+ * Only about a third (C2) to a half (C3) of the candidates of a small triangle are covered; with the fragment program
+ * running on compacted fragments the warp executes it that many times less often.  Same-pixel fragments of one
+ * shading step (shared edges and vertices are drawn by every triangle that owns them, Q4) are ranked by
+ * __match_any_sync and written in rank order, as before. */
 template <int TEXM, int BLENDM, bool PHONG, int DEPTH_OFF>
-__device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const unsigned pk, const int lo,
+__device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const unsigned pk,
                                          const DevState *st, const unsigned flags, const unsigned zmask, const int blend_mode, const TexRegs &tex)
 {
     const unsigned FULL = 0xffffffffu;
@@ -85,27 +107,45 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const un
     const bool texturing = TEXM != 0 && (!PHONG || (flags & PFCU_ST_TEXTURE));
     const bool blending = BLENDM != 0 && (!PHONG || (flags & PFCU_ST_BLEND));
 
-    for (unsigned base = 0; base < total; base += 32) {
-        const unsigned f = base + lane;
-        const bool valid = f < total;
-        unsigned pos = 0;                                           /* owner = number of lanes whose scan value is <= f */
+    unsigned base = 0, rc = 0, rh = 0;          /* next candidate; fragments waiting in the ring; ring head (all warp-uniform) */
+    for (;;) {
+        /* ---- coverage: fill the ring until a full shading step is there ---- */
+        while (rc < 32u && base < total) {
+            const unsigned f = base + lane;
+            const bool valid = f < total;
+            unsigned pos = 0;                                       /* owner = number of lanes whose scan value is <= f */
 #pragma unroll
-        for (int step = 16; step; step >>= 1) { const unsigned v = __shfl_sync(FULL, I, pos + step - 1); if (v <= f) pos += step; }
-        const int j = valid ? (int)pos : lo;
-        const unsigned Ej = __shfl_sync(FULL, Ex, j), pkj = __shfl_sync(FULL, pk, j);
-        const unsigned r = valid ? f - Ej : 0u;
-        const unsigned cw = (pkj >> 8) & 15u;
-        const unsigned ry = (r * (pkj >> 12)) >> 10, rx = r - ry * cw;          /* r / cw, r % cw (r < 64, cw <= 8: exact) */
-        const int px = (int)((pkj & 15u) + rx), py = (int)(((pkj >> 4) & 15u) + ry);
+            for (int step = 16; step; step >>= 1) { const unsigned v = __shfl_sync(FULL, I, pos + step - 1); if (v <= f) pos += step; }
+            const int j = (int)(pos & 31u);                         /* f >= total gives 32: any staged lane will do, the result is dropped */
+            const unsigned Ej = __shfl_sync(FULL, Ex, j), pkj = __shfl_sync(FULL, pk, j);
+            const unsigned r = valid ? f - Ej : 0u;
+            const unsigned cw = (pkj >> 8) & 15u;
+            const unsigned ry = (r * (pkj >> 12)) >> 10, rx = r - ry * cw;          /* r / cw, r % cw (r < 64, cw <= 8: exact) */
+            const unsigned px = (pkj & 15u) + rx, py = ((pkj >> 4) & 15u) + ry;
+            const uint4 f0 = lds_tri(t.tri_base, 0, j), f1 = lds_tri(t.tri_base, 1, j);
+            const uint2 f2 = lds_tri2(t.tri_base, 2, j);
+            const int w1 = wadd(wadd((int)f0.x, wmul((int)py, (int)f1.y)), wmul((int)px, (int)f1.x));
+            const int w2 = wadd(wadd((int)f0.y, wmul((int)py, (int)f1.w)), wmul((int)px, (int)f1.z));
+            const int w3 = wadd(wadd((int)f0.z, wmul((int)py, (int)f2.y)), wmul((int)px, (int)f2.x));
+            const bool c = valid && ((w1 | w2 | w3) > 0);
+            const unsigned bal = __ballot_sync(FULL, c);
+            if (c) sts_u16(t.ring_base + (((rh + rc + __popc(bal & lt)) & 63u) << 1), (unsigned)j | (px << 5) | (py << 8));
+            rc += __popc(bal);
+            base += 32u;
+        }
+        if (rc == 0u) break;                                        /* stream exhausted, ring empty */
+        __syncwarp();                                               /* ring writes -> ring reads by other lanes */
+        const unsigned ns = min(rc, 32u);
+        bool m = lane < ns;
+        const unsigned ent = lds_u16(t.ring_base + (((rh + (m ? lane : 0u)) & 63u) << 1));
+        rh = (rh + ns) & 63u; rc -= ns;
+        const int j = (int)(ent & 31u), px = (int)((ent >> 5) & 7u), py = (int)(ent >> 8);
+        t.covered += m ? 1u : 0u;
 
         const uint4 f0 = lds_tri(t.tri_base, 0, j), f1 = lds_tri(t.tri_base, 1, j), f2 = lds_tri(t.tri_base, 2, j);
         const int w1 = wadd(wadd((int)f0.x, wmul(py, (int)f1.y)), wmul(px, (int)f1.x));
         const int w2 = wadd(wadd((int)f0.y, wmul(py, (int)f1.w)), wmul(px, (int)f1.z));
         const int w3 = wadd(wadd((int)f0.z, wmul(py, (int)f2.y)), wmul(px, (int)f2.x));
-        bool m = valid && ((w1 | w2 | w3) > 0);
-        if (!__any_sync(FULL, m)) continue;
-        t.covered += m ? 1u : 0u;
-
         const uint4 f3 = lds_tri(t.tri_base, 3, j);
         const unsigned meta = f3.y;
         const float invSum = __uint_as_float(f0.w);
@@ -115,17 +155,17 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const un
         const float zsum = FA(FA(FM(__uint_as_float(f2.z), W1), FM(__uint_as_float(f2.w), W2)), FM(__uint_as_float(f3.x), W3));
         const float z = rcp_tab(t, zsum);
 
-        /* same-pixel fragments of this chunk (different triangles) must be applied in triangle order */
+        /* same-pixel fragments of this step (different triangles) must be applied in triangle order */
         const unsigned sa = t.col_base + (unsigned)(((py << 3) + px) << 2);
         const unsigned peers = __match_any_sync(FULL, m ? sa : (0x80000000u | lane));
         const unsigned rank = __popc(peers & lt);
         const unsigned nr = __reduce_max_sync(FULL, m ? rank : 0u);
         if (ztest && nr == 0u) {                        /* no conflicts: test before shading, like the reference's early mask */
-            /* uncovered lanes do not read: their pixel may be another lane's covered pixel, written below */
+            /* idle lanes do not read: their pixel may be another lane's fragment, written below */
             float zb = 0.0f;
             if (m) zb = lds_f32_off<DEPTH_OFF>(sa);
             m = m && depth_pass_mask(z, zb, zmask);
-            if (!__any_sync(FULL, m)) { __syncwarp(); continue; }       /* the depth reads above precede later chunks' stores */
+            if (!__any_sync(FULL, m)) { __syncwarp(); continue; }       /* the depth reads above precede later steps' stores */
         }
 
         /* colour (color.h:153-203) */
@@ -146,8 +186,7 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const un
             float u = FA(FA(FM(__uint_as_float(f4.y), W1), FM(__uint_as_float(f4.z), W2)), FM(__uint_as_float(f4.w), W3));
             float v = FA(FA(FM(__uint_as_float(f5.x), W1), FM(__uint_as_float(f5.y), W2)), FM(__uint_as_float(f5.z), W3));
             if ((meta >> 25) & 1u) { u = FM(u, z); v = FM(v, z); }
-            /* uncovered / depth-failed lanes (about half of the candidates of a small triangle) fetch nothing: their
-               texels would be thrown away and their addresses are the least cache-friendly ones */
+            /* depth-failed lanes fetch nothing: their texels would be thrown away */
             unsigned texel = 0u;
             if (m) {
                 if (TEXM == 1) {
@@ -189,7 +228,7 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const un
                     t.shaded++;
                 }
             }
-            /* orders this round's stores before the next round's (and the next chunk's) loads and stores of the same
+            /* orders this round's stores before the next round's (and the next step's) loads and stores of the same
                pixel by OTHER lanes: lanes are not pinned to pixels here, so program order alone does not cover it */
             __syncwarp();
         }
@@ -285,19 +324,19 @@ __device__ __forceinline__ void frag_group(FragCtx &t, GroupState &G, const int4
             if (HAS_PHONG && (flags & PFCU_ST_PHONG)) prog = 12;
         }
         switch (prog) {
-        case 0:  frag_run<0, 0, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-        case 1:  frag_run<0, 1, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-        case 2:  frag_run<0, 2, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-        case 3:  frag_run<0, 3, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-        case 4:  frag_run<1, 0, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-        case 5:  frag_run<1, 1, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-        case 6:  frag_run<1, 2, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-        case 7:  frag_run<1, 3, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-        case 8:  frag_run<2, 0, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-        case 9:  frag_run<2, 1, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-        case 10: frag_run<2, 2, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-        case 11: frag_run<2, 3, false, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
-        default: if (HAS_PHONG) frag_run<2, 3, true, DEPTH_OFF>(t, nn, pk, (int)lo, st, flags, zmask, blend_mode, tex); break;
+        case 0:  frag_run<0, 0, false, DEPTH_OFF>(t, nn, pk, st, flags, zmask, blend_mode, tex); break;
+        case 1:  frag_run<0, 1, false, DEPTH_OFF>(t, nn, pk, st, flags, zmask, blend_mode, tex); break;
+        case 2:  frag_run<0, 2, false, DEPTH_OFF>(t, nn, pk, st, flags, zmask, blend_mode, tex); break;
+        case 3:  frag_run<0, 3, false, DEPTH_OFF>(t, nn, pk, st, flags, zmask, blend_mode, tex); break;
+        case 4:  frag_run<1, 0, false, DEPTH_OFF>(t, nn, pk, st, flags, zmask, blend_mode, tex); break;
+        case 5:  frag_run<1, 1, false, DEPTH_OFF>(t, nn, pk, st, flags, zmask, blend_mode, tex); break;
+        case 6:  frag_run<1, 2, false, DEPTH_OFF>(t, nn, pk, st, flags, zmask, blend_mode, tex); break;
+        case 7:  frag_run<1, 3, false, DEPTH_OFF>(t, nn, pk, st, flags, zmask, blend_mode, tex); break;
+        case 8:  frag_run<2, 0, false, DEPTH_OFF>(t, nn, pk, st, flags, zmask, blend_mode, tex); break;
+        case 9:  frag_run<2, 1, false, DEPTH_OFF>(t, nn, pk, st, flags, zmask, blend_mode, tex); break;
+        case 10: frag_run<2, 2, false, DEPTH_OFF>(t, nn, pk, st, flags, zmask, blend_mode, tex); break;
+        case 11: frag_run<2, 3, false, DEPTH_OFF>(t, nn, pk, st, flags, zmask, blend_mode, tex); break;
+        default: if (HAS_PHONG) frag_run<2, 3, true, DEPTH_OFF>(t, nn, pk, st, flags, zmask, blend_mode, tex); break;
         }
         lo = hi;
     }
@@ -316,6 +355,7 @@ k_raster_frag(const RasterParams p)
     __shared__ unsigned short s_qmask[QUEUE_CAP];
     __shared__ unsigned s_wcount[NW];
     __shared__ unsigned s_group[NW][32];
+    __shared__ unsigned short s_ring[NW][64];
     extern __shared__ __align__(16) uint4 s_tri[];          /* [NW][NF][32] triangle staging, see FRAG_NF */
     constexpr int NF = HAS_PHONG ? FRAG_NF_PHONG : FRAG_NF;
     static_assert(NW == 8 || NW == 16, "one 8x8 region per warp, 8 regions per row");
@@ -359,6 +399,7 @@ k_raster_frag(const RasterParams p)
     t.RX1 = min(t.RX0 + 7, X1); t.RY1 = min(t.RY0 + 7, Y1);
     t.shaded = 0; t.covered = 0;
     t.tri_base = (unsigned)__cvta_generic_to_shared(s_tri + warp * NF * 32);
+    t.ring_base = (unsigned)__cvta_generic_to_shared(&s_ring[warp][0]);
 
     bool loaded = false;
     /* the slice relative to its bin, as the bin-list entries store their rectangles */

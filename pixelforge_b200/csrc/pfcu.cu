@@ -852,16 +852,33 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     const bool small_tris = (size_t)n_est > (size_t)4 * nTilesAll;
     static const int force_bshift = getenv("PF_CUDA_BIN_SHIFT") ? atoi(getenv("PF_CUDA_BIN_SHIFT")) : 0;
     int bshift = bshift_forced ? bshift_forced : (force_bshift >= 6 ? force_bshift : (small_tris ? BIN_SHIFT_FINE : BIN_SHIFT_COARSE));
+    static const bool env_once = [] {
+        const char *e = getenv("PF_CUDA_FRAG");
+        if (e) g.raster_path = atoi(e) == 0 ? PFCU_RASTER_TILES : (atoi(e) == 2 ? PFCU_RASTER_FRAGMENTS : PFCU_RASTER_AUTO);
+        return true; }();
+    (void)env_once;
+    static const int force_slice = getenv("PF_CUDA_SLICE") ? atoi(getenv("PF_CUDA_SLICE")) : 0;
+    const bool use_frag = !rows_path && (g.raster_path == PFCU_RASTER_FRAGMENTS || (g.raster_path == PFCU_RASTER_AUTO && small_tris && !force_slice));
+    /* The fragment rasteriser works on 64x8 slices, and with square 64x64 bins the eight slices of a tile each filter the
+       whole tile's list.  Flatter bins (64 x 2^bshy) shorten that, but every triangle then lands in more bins and the
+       ordered fill pays for it: measured (PF_CUDA_BIN_ROWS sweep, profiles/README.md) 64x16 bins are a small net gain
+       only for very large batches (the 1 M-triangle mesh: raster 0.475 -> 0.441 ms, binning +0.024 ms) and a loss below. */
+    static const int force_bshy = getenv("PF_CUDA_BIN_ROWS") ? atoi(getenv("PF_CUDA_BIN_ROWS")) : 0;
+    int bshy = bshift;
+    if (use_frag && !bshift_forced && bshift == BIN_SHIFT_FINE)
+        bshy = (force_bshy >= 3 && force_bshy <= 6) ? force_bshy : (n_est >= (1u << 19) ? 4 : BIN_SHIFT_FINE);
     int binsX, binsY, nb;
-    for (;; bshift++) {
-        binsX = (int)((s->w + (1u << bshift) - 1) >> bshift); binsY = (int)((s->h + (1u << bshift) - 1) >> bshift);
+    for (;;) {
+        binsX = (int)((s->w + (1u << bshift) - 1) >> bshift); binsY = (int)((s->h + (1u << bshy) - 1) >> bshy);
         nb = binsX * binsY;
         if (nb <= MAX_BINS) break;
+        if (bshy < bshift) bshy++; else { bshift++; bshy++; }
     }
     if (bshift > 8) { snprintf(g.err, sizeof g.err, "surface too large for the binner (%u x %u)", s->w, s->h); return PFCU_ERR_INVALID; }
     /* one row of per-bin counters per binning CTA: 256 triangles per CTA give the order-preserving fill four times the
        CTAs (its per-CTA work is a serial chain) as long as the counter matrix stays small */
-    const unsigned bin_batch = ((size_t)((n + 255u) / 256u) * nb <= ((size_t)1 << 20)) ? 256u : BIN_BATCH;
+    unsigned bin_batch = ((size_t)((n + 255u) / 256u) * nb <= ((size_t)1 << 20)) ? 256u : BIN_BATCH;
+    while ((size_t)((n + bin_batch - 1) / bin_batch) * nb > ((size_t)4 << 20) && bin_batch < 8192u) bin_batch *= 2;    /* keep the counter matrix below 16 MB */
     const unsigned nBatches = (n + bin_batch - 1) / bin_batch;
     if ((rc = grow(&LN.d_bin_counts, &LN.cap_bin_counts, (size_t)nBatches * nb))) return rc;
 
@@ -878,14 +895,14 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         /* small batch: the (triangle, bin) overlap count is bounded by n * nb, no read-back needed */
         if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, (size_t)n * nb))) return rc;
         k_front_small<<<1, 1024, nb * sizeof(unsigned), LN.stream>>>(d_tris, d_states, n, d_n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data,
-                                                                      g.d_counters, binsX, binsY, bshift, LN.d_bin_start, LN.d_bin_list);
+                                                                      g.d_counters, binsX, binsY, bshift, bshy, LN.d_bin_start, LN.d_bin_list);
         g.launches += 1;
     } else {
         k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, LN.stream>>>(
             d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data, g.d_counters);
         g.launches += 1;
         if (!rows_path) {
-        k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, bin_batch, binsX, binsY, bshift, LN.d_bin_counts);
+        k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, bin_batch, binsX, binsY, bshift, bshy, LN.d_bin_counts);
         unsigned *d_totals = LN.d_bin_start + (MAX_BINS + 2);
         k_bin_scan<<<(nb + 31) / 32, 1024, 0, LN.stream>>>(LN.d_bin_counts, (int)nBatches, nb, d_totals);
         k_bin_starts<<<1, 1024, 0, LN.stream>>>(d_totals, nb, LN.d_bin_start);
@@ -903,7 +920,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
             }
             if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, want ? want : 1))) return rc;
         }
-        k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, bin_batch, binsX, binsY, bshift, LN.d_bin_counts, LN.d_bin_start, LN.d_bin_list);
+        k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, bin_batch, binsX, binsY, bshift, bshy, LN.d_bin_counts, LN.d_bin_start, LN.d_bin_list);
         g.launches += 4;
         }
     }
@@ -927,7 +944,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     }
     RasterParams p;
     p.bbox = LN.d_bbox; p.setup = LN.d_setup; p.data = LN.d_data; p.states = d_states;
-    p.bin_list = LN.d_bin_list; p.bin_starts = LN.d_bin_start; p.binsX = binsX; p.bin_tshift = bshift - 6;
+    p.bin_list = LN.d_bin_list; p.bin_starts = LN.d_bin_start; p.binsX = binsX; p.bsx = bshift; p.bsy = bshy;
     p.color = s->color; p.depth = s->depth; p.W = (int)s->w; p.H = (int)s->h;
     p.tilesX = (int)s->tiles_x; p.tilesY = (int)s->tiles_y;
     p.rank = s->rank; p.world = s->world ? s->world : 1; p.nTiles = s->tiles_x * s->tiles_y;
@@ -943,15 +960,6 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         const int per_sm = (single_prog == 5 || single_prog == 6) ? 4 : 3;
         const double waves = (double)grid / ((double)g.sms * per_sm);
         const bool half = !small_tris && !ph && waves < 8.0 && (ceil(waves) / waves) > 1.06 && (ceil(2 * waves) / (2 * waves)) < (ceil(waves) / waves);
-        /* small triangles: slices of 64x16 (64x32 with Phong) shorten the serial work of the busiest tiles and
-           even out the SMs (C2: 0.51 -> 0.30 ms); PF_CUDA_SLICE=64|32|16 overrides for experiments */
-        static const int force_slice = getenv("PF_CUDA_SLICE") ? atoi(getenv("PF_CUDA_SLICE")) : 0;
-        static const bool env_once = [] {
-            const char *e = getenv("PF_CUDA_FRAG");
-            if (e) g.raster_path = atoi(e) == 0 ? PFCU_RASTER_TILES : (atoi(e) == 2 ? PFCU_RASTER_FRAGMENTS : PFCU_RASTER_AUTO);
-            return true; }();
-        (void)env_once;
-        const bool use_frag = g.raster_path == PFCU_RASTER_FRAGMENTS || (g.raster_path == PFCU_RASTER_AUTO && small_tris && !force_slice);
         if (use_frag) {
             /* 64x8 slices of eight 8x8 regions, 8 warps; 4 CTAs per SM (Phong: 3, 80 registers) */
             static const bool attr_once = [] {

@@ -369,7 +369,7 @@ k_raster_frag(const RasterParams p)
     const int X1 = min(X0 + TILE, p.W) - 1, Y1 = min(Y0 + TH, p.H) - 1;
     const bool full_tile = (X0 + TILE <= p.W) && (Y0 + TH <= p.H) && ((p.W & 3) == 0);
 
-    const int bin = (ty >> p.bin_tshift) * p.binsX + (tx >> p.bin_tshift);
+    const int bin = (Y0 >> p.bsy) * p.binsX + (X0 >> p.bsx);
     const unsigned lbeg = p.bin_starts[bin], lend = p.bin_starts[bin + 1];
     if (lbeg == lend) return;
 
@@ -403,7 +403,7 @@ k_raster_frag(const RasterParams p)
 
     bool loaded = false;
     /* the slice relative to its bin, as the bin-list entries store their rectangles */
-    const int bx0 = X0 - (((tx >> p.bin_tshift) << p.bin_tshift) * TILE), by0 = Y0 - (((ty >> p.bin_tshift) << p.bin_tshift) * TILE);
+    const int bx0 = X0 & ((1 << p.bsx) - 1), by0 = Y0 & ((1 << p.bsy) - 1);
     const int bx1 = bx0 + (X1 - X0), by1 = by0 + (Y1 - Y0);
 
     for (unsigned base = lbeg; base < lend; ) {

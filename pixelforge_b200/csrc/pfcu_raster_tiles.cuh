@@ -7,7 +7,7 @@
 
 struct RasterParams {
     const int4 *bbox; const TriSetup *setup; const TriData *data; const DevState *states;
-    const uint2 *bin_list; const unsigned *bin_starts; int binsX; int bin_tshift;   /* a bin is 2^bin_tshift tiles wide */
+    const uint2 *bin_list; const unsigned *bin_starts; int binsX; int bsx, bsy;      /* a bin is 2^bsx x 2^bsy pixels (k_raster: bsy == bsx >= 6) */
     uint32_t *color; float *depth; int W, H; int tilesX, tilesY;
     unsigned rank, world; unsigned nTiles;
     unsigned long long *counters;
@@ -311,7 +311,7 @@ k_raster(const RasterParams p)
     const int X0 = t.X0, Y0 = t.Y0, X1 = t.X1, Y1 = t.Y1;
     const bool full_tile = (X0 + TILE <= p.W) && (Y0 + TH <= p.H) && ((p.W & 3) == 0);
 
-    const int bin = (ty >> p.bin_tshift) * p.binsX + (tx >> p.bin_tshift);
+    const int bin = ((ty * TILE) >> p.bsy) * p.binsX + ((tx * TILE) >> p.bsx);
     const unsigned lbeg = p.bin_starts[bin], lend = p.bin_starts[bin + 1];
     if (lbeg == lend) return;
 

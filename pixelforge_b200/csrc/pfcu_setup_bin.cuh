@@ -124,7 +124,7 @@ k_setup(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ sta
 
 /* pass 1: counts[batch][bin] = number of triangles of this batch whose bbox touches the bin */
 __global__ void __launch_bounds__(256)
-k_bin_count(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX, int binsY, int bshift, unsigned *__restrict__ counts)
+k_bin_count(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX, int binsY, int bshift, int bshy, unsigned *__restrict__ counts)
 {
     extern __shared__ unsigned s_cnt[];
     const int nb = binsX * binsY;
@@ -137,7 +137,7 @@ k_bin_count(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX
         const int4 b = __ldg(bbox + i);
         if (b.x >= b.z) continue;
         const int bx0 = max(b.x, 0) >> bshift, bx1 = min((b.z - 1) >> bshift, binsX - 1);
-        const int by0 = max(b.y, 0) >> bshift, by1 = min(b.w >> bshift, binsY - 1);
+        const int by0 = max(b.y, 0) >> bshy, by1 = min(b.w >> bshy, binsY - 1);
         for (int by = by0; by <= by1; by++)
             for (int bx = bx0; bx <= bx1; bx++) atomicAdd(&s_cnt[by * binsX + bx], 1u);
     }
@@ -211,12 +211,13 @@ k_bin_starts(const unsigned *__restrict__ totals, int nb, unsigned *__restrict__
 
 /* A bin-list entry carries the triangle's visited rectangle [x0, x1] x [y0, y1] (inclusive) clipped to the bin and
  * relative to the bin's origin, 8 bits per coordinate (bins are at most 256 pixels wide): the rasteriser's
- * queue filter then needs no dependent load. */
-__device__ __forceinline__ unsigned bin_rel_bbox(const int4 b, int bx, int by, int bshift)
+ * queue filter then needs no dependent load.  Bins are 2^bshift pixels wide and 2^bshy pixels high: batches of many
+ * small triangles get bins as flat as the rasteriser's 64x8 slices, so that a slice reads (nearly) only its own list. */
+__device__ __forceinline__ unsigned bin_rel_bbox(const int4 b, int bx, int by, int bshift, int bshy)
 {
-    const int ox = bx << bshift, oy = by << bshift, hi = (1 << bshift) - 1;
+    const int ox = bx << bshift, oy = by << bshy, hi = (1 << bshift) - 1, hiy = (1 << bshy) - 1;
     const int x0 = min(max(b.x - ox, 0), hi), x1 = min(max(b.z - 1 - ox, 0), hi);
-    const int y0 = min(max(b.y - oy, 0), hi), y1 = min(max(b.w - oy, 0), hi);
+    const int y0 = min(max(b.y - oy, 0), hiy), y1 = min(max(b.w - oy, 0), hiy);
     return (unsigned)x0 | ((unsigned)y0 << 8) | ((unsigned)x1 << 16) | ((unsigned)y1 << 24);
 }
 
@@ -225,7 +226,7 @@ __device__ __forceinline__ unsigned bin_rel_bbox(const int4 b, int bx, int by, i
  * appends them to those bins.  A bin is therefore written by one warp only, in submission order, with no
  * CTA barrier inside a group and no dependence on how the 256 triangles are spread over the screen. */
 __global__ void __launch_bounds__(256)
-k_bin_fill(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX, int binsY, int bshift,
+k_bin_fill(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX, int binsY, int bshift, int bshy,
            const unsigned *__restrict__ offsets /* scanned counts */, const unsigned *__restrict__ starts,
            uint2 *__restrict__ list)
 {
@@ -245,7 +246,7 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX,
             b = __ldg(bbox + i);
             if (b.x < b.z) {
                 r.x = max(b.x, 0) >> bshift; r.z = min((b.z - 1) >> bshift, binsX - 1);
-                r.y = max(b.y, 0) >> bshift; r.w = min(b.w >> bshift, binsY - 1);
+                r.y = max(b.y, 0) >> bshy; r.w = min(b.w >> bshy, binsY - 1);
             }
         }
         __syncthreads();                        /* previous group done with s_rect (and s_pos initialised) */
@@ -279,7 +280,7 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX,
                             const int bin = by * binsX + first;
                             const unsigned peers = __match_any_sync(am, bin);
                             const unsigned pos = s_pos[bin] + __popc(peers & ((1u << lane) - 1u));
-                            list[pos] = make_uint2(my_idx, bin_rel_bbox(qb, first, by, bshift));
+                            list[pos] = make_uint2(my_idx, bin_rel_bbox(qb, first, by, bshift, bshy));
                             __syncwarp(peers);
                             if ((peers >> lane) == 1u) s_pos[bin] = pos + 1;   /* highest lane of the group */
                         }
@@ -297,7 +298,7 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX,
                         const int cy = e / ncols, cx = e - cy * ncols;
                         const int bin = (t.y + cy) * binsX + f0 + (cx << 3);
                         const unsigned pos = s_pos[bin];
-                        list[pos] = make_uint2(idx, bin_rel_bbox(tb, f0 + (cx << 3), t.y + cy, bshift));
+                        list[pos] = make_uint2(idx, bin_rel_bbox(tb, f0 + (cx << 3), t.y + cy, bshift, bshy));
                         s_pos[bin] = pos + 1;
                     }
                 }
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(1024)
 k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ states, unsigned n_host, const unsigned *__restrict__ d_n,
               int surfW, int surfH,
               int4 *__restrict__ bbox, TriSetup *__restrict__ setup, TriData *__restrict__ data, unsigned long long *__restrict__ counters,
-              int binsX, int binsY, int bshift, unsigned *__restrict__ starts, uint2 *__restrict__ list)
+              int binsX, int binsY, int bshift, int bshy, unsigned *__restrict__ starts, uint2 *__restrict__ list)
 {
     extern __shared__ unsigned s_mem[];
     unsigned *s_pos = s_mem;                    /* [nb] counts, then running write positions */
@@ -340,7 +341,7 @@ k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict
         if (i < n) b = setup_one(tris + i, states, i, surfW, surfH, bbox, setup, data, &rasterised);
         if (b.x < b.z) {
             const int rx0 = max(b.x, 0) >> bshift, rx1 = min((b.z - 1) >> bshift, binsX - 1);
-            const int ry0 = max(b.y, 0) >> bshift, ry1 = min(b.w >> bshift, binsY - 1);
+            const int ry0 = max(b.y, 0) >> bshy, ry1 = min(b.w >> bshy, binsY - 1);
             for (int by = ry0; by <= ry1; by++)
                 for (int bx = rx0; bx <= rx1; bx++) atomicAdd(&s_pos[by * binsX + bx], 1u);
         }
@@ -381,7 +382,7 @@ k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict
         if (i < n) b = bbox[i];                 /* written by this very thread in pass 1 */
         if (b.x < b.z) {
             r.x = max(b.x, 0) >> bshift; r.z = min((b.z - 1) >> bshift, binsX - 1);
-            r.y = max(b.y, 0) >> bshift; r.w = min(b.w >> bshift, binsY - 1);
+            r.y = max(b.y, 0) >> bshy; r.w = min(b.w >> bshy, binsY - 1);
         }
         __syncthreads();
         s_rect[threadIdx.x] = r; s_bbox[threadIdx.x] = b;
@@ -411,7 +412,7 @@ k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict
                             const int bin = by * binsX + first;
                             const unsigned peers = __match_any_sync(am, bin);
                             const unsigned pos = s_pos[bin] + __popc(peers & ((1u << lane) - 1u));
-                            list[pos] = make_uint2(my_idx, bin_rel_bbox(qb, first, by, bshift));
+                            list[pos] = make_uint2(my_idx, bin_rel_bbox(qb, first, by, bshift, bshy));
                             __syncwarp(peers);
                             if ((peers >> lane) == 1u) s_pos[bin] = pos + 1;
                         }
@@ -429,7 +430,7 @@ k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict
                         const int cy = e / ncols, cx = e - cy * ncols;
                         const int bin = (t.y + cy) * binsX + f0 + (cx << 5);
                         const unsigned pos = s_pos[bin];
-                        list[pos] = make_uint2(idx, bin_rel_bbox(tb, f0 + (cx << 5), t.y + cy, bshift));
+                        list[pos] = make_uint2(idx, bin_rel_bbox(tb, f0 + (cx << 5), t.y + cy, bshift, bshy));
                         s_pos[bin] = pos + 1;
                     }
                 }

@@ -78,8 +78,10 @@ struct __align__(16) TriData {      /* 160 B, grouped by what each fragment prog
     float nx[4], ny[4], nz[4];
 };
 
-struct DevLight { float pos[3], dir[3], inner, outer, attc, attl, attq; unsigned ambient, diffuse, specular; };
-struct DevMaterial { unsigned ambient, diffuse, specular, emission; float shininess; };
+/* *_f: the colour channels as the per-fragment Blinn-Phong uses them, float(c) * (1/255) (lighting.c:155-175), computed once
+   per state on the host (same IEEE single multiply) instead of once per fragment */
+struct DevLight { float pos[3], dir[3], inner, outer, attc, attl, attq; unsigned ambient, diffuse, specular; float amb_f[3], dif_f[3], spc_f[3]; };
+struct DevMaterial { unsigned ambient, diffuse, specular, emission; float shininess; float amb_f[3], spc_f[3]; };
 
 struct __align__(16) DevState {
     unsigned flags;
@@ -806,11 +808,22 @@ static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
             b->inner = a->inner_cutoff; b->outer = a->outer_cutoff;
             b->attc = a->att_constant; b->attl = a->att_linear; b->attq = a->att_quadratic;
             b->ambient = a->ambient; b->diffuse = a->diffuse; b->specular = a->specular;
+            for (int c = 0; c < 3; c++) {
+                volatile float k = 1.0f / 255.0f;       /* one rounded multiply per channel, as the reference's lanes */
+                b->amb_f[c] = (float)((a->ambient >> (8 * c)) & 255u) * k;
+                b->dif_f[c] = (float)((a->diffuse >> (8 * c)) & 255u) * k;
+                b->spc_f[c] = (float)((a->specular >> (8 * c)) & 255u) * k;
+            }
         }
         for (int f = 0; f < 2; f++) {
             d->material[f].ambient = s->material[f].ambient; d->material[f].diffuse = s->material[f].diffuse;
             d->material[f].specular = s->material[f].specular; d->material[f].emission = s->material[f].emission;
             d->material[f].shininess = s->material[f].shininess;
+            for (int c = 0; c < 3; c++) {
+                volatile float k = 1.0f / 255.0f;
+                d->material[f].amb_f[c] = (float)((s->material[f].ambient >> (8 * c)) & 255u) * k;
+                d->material[f].spc_f[c] = (float)((s->material[f].specular >> (8 * c)) & 255u) * k;
+            }
         }
         memcpy(d->view_pos, s->view_pos, 12);
         mask |= d->flags;

@@ -40,13 +40,17 @@ __device__ __forceinline__ float rcp_x86(float x)
     return __uint_as_float(r);
 }
 
-/* RSQRTPS (simd.h:1237-1245) */
-__device__ __forceinline__ float rsqrt_x86(float x)
+/* RSQRTPS (simd.h:1237-1245).  tab_smem: shared-window byte address of a copy of the table (k_raster_frag<Phong> keeps one:
+ * three look-ups per lit fragment were that kernel's main long-scoreboard stall), or 0 for the global one. */
+__device__ __forceinline__ float rsqrt_x86(float x, unsigned tab_smem = 0u)
 {
     const unsigned u = __float_as_uint(x), s = u & 0x80000000u, e = (u >> 23) & 255u, m = u & 0x7fffffu;
     const unsigned odd = (e & 1u) ^ 1u;
     const int half = ((int)e - 127 - (int)odd) >> 1;       /* even by construction */
-    const unsigned tv = __ldg(c_rsq_tab + ((odd << c_rsq_bits) | (m >> c_rsq_shift)));
+    const unsigned ti = (odd << c_rsq_bits) | (m >> c_rsq_shift);
+    unsigned tv;
+    if (tab_smem) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tv) : "r"(tab_smem + (ti << 2)));
+    else tv = __ldg(c_rsq_tab + ti);
     unsigned r = ((unsigned)((int)(tv >> 23) - half) << 23) | (tv & 0x7fffffu);
     if (e == 255u) r = 0u;
     if (s) r = 0xffc00000u;
@@ -275,19 +279,19 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
 }
 
 __device__ __noinline__ unsigned phong(unsigned frag, const DevState *st, int face,
-                                       float Px, float Py, float Pz, float Nx, float Ny, float Nz)
+                                       float Px, float Py, float Pz, float Nx, float Ny, float Nz, unsigned rsq_smem = 0u)
 {
     const DevMaterial *m = &st->material[face];
     float D[3], A[3], S[3], acc[3] = { 0.0f, 0.0f, 0.0f };
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         D[i] = FM(__int2float_rn(CHN(frag, i)), INV255);
-        A[i] = FM(FM(__int2float_rn(CHN(m->ambient, i)), INV255), D[i]);
-        S[i] = FM(__int2float_rn(CHN(m->specular, i)), INV255);
+        A[i] = FM(m->amb_f[i], D[i]);
+        S[i] = m->spc_f[i];
     }
     float Vx = FS(st->view_pos[0], Px), Vy = FS(st->view_pos[1], Py), Vz = FS(st->view_pos[2], Pz);
     {
-        const float inv = rsqrt_x86(max_x86(dot3(Vx, Vy, Vz, Vx, Vy, Vz), 1e-5f));
+        const float inv = rsqrt_x86(max_x86(dot3(Vx, Vy, Vz, Vx, Vy, Vz), 1e-5f), rsq_smem);
         Vx = FM(Vx, inv); Vy = FM(Vy, inv); Vz = FM(Vz, inv);
     }
     const float shininess = m->shininess;
@@ -295,13 +299,13 @@ __device__ __noinline__ unsigned phong(unsigned frag, const DevState *st, int fa
         const DevLight *l = &st->lights[li];
         float Lx = FS(l->pos[0], Px), Ly = FS(l->pos[1], Py), Lz = FS(l->pos[2], Pz);
         {
-            const float inv = rsqrt_x86(max_x86(dot3(Lx, Ly, Lz, Lx, Ly, Lz), 1e-5f));
+            const float inv = rsqrt_x86(max_x86(dot3(Lx, Ly, Lz, Lx, Ly, Lz), 1e-5f), rsq_smem);
             Lx = FM(Lx, inv); Ly = FM(Ly, inv); Lz = FM(Lz, inv);
         }
         const float diff = max_x86(dot3(Nx, Ny, Nz, Lx, Ly, Lz), 0.0f);
         float Hx = FA(Lx, Vx), Hy = FA(Ly, Vy), Hz = FA(Lz, Vz);
         {
-            const float inv = rsqrt_x86(dot3(Hx, Hy, Hz, Hx, Hy, Hz));      /* no epsilon here */
+            const float inv = rsqrt_x86(dot3(Hx, Hy, Hz, Hx, Hy, Hz), rsq_smem);      /* no epsilon here */
             Hx = FM(Hx, inv); Hy = FM(Hy, inv); Hz = FM(Hz, inv);
         }
         float spec = max_x86(dot3(Nx, Ny, Nz, Hx, Hy, Hz), 0.0f);
@@ -322,9 +326,9 @@ __device__ __noinline__ unsigned phong(unsigned frag, const DevState *st, int fa
         }
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            float amb = FM(FM(__int2float_rn(CHN(l->ambient, i)), INV255), A[i]);
-            float dif = FM(FM(FM(__int2float_rn(CHN(l->diffuse, i)), INV255), diff), D[i]);
-            float spc = FM(FM(FM(__int2float_rn(CHN(l->specular, i)), INV255), spec), S[i]);
+            float amb = FM(l->amb_f[i], A[i]);
+            float dif = FM(FM(l->dif_f[i], diff), D[i]);
+            float spc = FM(FM(l->spc_f[i], spec), S[i]);
             if (spot) { dif = FM(dif, inten); spc = FM(spc, inten); }
             if (atten) { amb = FM(amb, att); dif = FM(dif, att); spc = FM(spc, att); }
             acc[i] = FA(acc[i], amb); acc[i] = FA(acc[i], dif); acc[i] = FA(acc[i], spc);

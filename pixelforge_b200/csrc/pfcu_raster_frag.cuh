@@ -25,6 +25,7 @@
  * Launched as 64x8 slices, 8 warps: 4 CTAs per SM (64 registers), 3 with Phong (80 registers).
  */
 #define FRAG_RSTRIDE 72
+#define RSQ_SMEM_BITS 10        /* RSQRTPS tables of up to 2 x 2^10 entries are copied to shared memory by the Phong kernel */
 
 struct FragCtx {
     unsigned col_base;                  /* shared-window byte address of this warp's colour region     */
@@ -35,6 +36,7 @@ struct FragCtx {
     unsigned shaded, covered;
     unsigned tri_base;                  /* shared-window byte address of this warp's triangle staging   */
     unsigned ring_base;                 /* ... of this warp's ring of 64 covered fragments (16 bits each) */
+    unsigned rsq_base;                  /* ... of the shared RSQRTPS table (Phong kernel), or 0 */
 };
 
 /* Per-warp staging of a group's triangle constants: field F of the triangle held by lane l is the 16-byte slot
@@ -211,7 +213,7 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const un
                 const float Ny = FA(FA(FM(UF(g9.x), W1), FM(UF(g9.y), W2)), FM(UF(g9.z), W3));
                 const float Nz = FA(FA(FM(UF(g9.w), W1), FM(UF(g10.x), W2)), FM(UF(g10.y), W3));
 #undef UF
-                frag = px_split(phong(px_join(frag), st, (meta >> 24) & 1u, Qx, Qy, Qz, Nx, Ny, Nz));
+                frag = px_split(phong(px_join(frag), st, (meta >> 24) & 1u, Qx, Qy, Qz, Nx, Ny, Nz, t.rsq_base));
             }
         }
 
@@ -356,6 +358,7 @@ k_raster_frag(const RasterParams p)
     __shared__ unsigned s_wcount[NW];
     __shared__ unsigned s_group[NW][32];
     __shared__ unsigned short s_ring[NW][64];
+    __shared__ unsigned s_rsq[HAS_PHONG ? (2 << RSQ_SMEM_BITS) : 1];
     extern __shared__ __align__(16) uint4 s_tri[];          /* [NW][NF][32] triangle staging, see FRAG_NF */
     constexpr int NF = HAS_PHONG ? FRAG_NF_PHONG : FRAG_NF;
     static_assert(NW == 8 || NW == 16, "one 8x8 region per warp, 8 regions per row");
@@ -391,6 +394,13 @@ k_raster_frag(const RasterParams p)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dcol + sa), "l"(p.color + gi) : "memory");
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dcol + sa + NW * FRAG_RSTRIDE * 4), "l"(p.depth + gi) : "memory");
         }
+    }
+    t.rsq_base = 0u;
+    if (HAS_PHONG && c_rsq_bits <= RSQ_SMEM_BITS) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_rsq);
+        for (int k = tid; k < (2 << c_rsq_bits) / 4; k += NT)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst + (unsigned)(k << 4)), "l"(c_rsq_tab + 4 * k) : "memory");
+        t.rsq_base = dst;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     t.col_base = (unsigned)__cvta_generic_to_shared(s_col + warp * FRAG_RSTRIDE);

@@ -146,6 +146,10 @@ struct Lane {
     unsigned *d_total = nullptr;                                        /* output count of a sync-free raw batch */
     unsigned long long *d_chain = nullptr; unsigned chain_seq = 0;      /* chained-scan flags of k_raw_chain */
     unsigned char *d_idx = nullptr; size_t cap_idx = 0;                 /* index buffer of a draw whose vertex count the device finds */
+    /* bin-list sizing without a host wait: the total of the last large batch comes back asynchronously and only steers
+       the capacity of later batches; a batch that does not fit its list is still rendered correctly (see launch_pipeline) */
+    unsigned *h_list_total = nullptr; cudaEvent_t list_evt = nullptr; bool list_pending = false;
+    size_t list_hint = 0; uint32_t list_hint_n = 0;
 };
 
 #define MAX_LANES 8
@@ -273,6 +277,8 @@ int pfcu_init(int device)
         CK(cudaEventCreateWithFlags(&LN.raw_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&LN.vready, cudaEventDisableTiming));
         CK(cudaHostAlloc(&LN.h_total, 2 * sizeof(unsigned), cudaHostAllocDefault));
+        CK(cudaHostAlloc(&LN.h_list_total, sizeof(unsigned), cudaHostAllocDefault));
+        CK(cudaEventCreateWithFlags(&LN.list_evt, cudaEventDisableTiming));
         CK(cudaMalloc(&LN.d_total, 64));
         CK(cudaMalloc(&LN.d_chain, 16 * sizeof(unsigned long long)));
         CK(cudaMemset(LN.d_chain, 0, 16 * sizeof(unsigned long long)));
@@ -307,6 +313,8 @@ void pfcu_shutdown(void)
         if (LN.h_stage) cudaFreeHost(LN.h_stage);
         if (LN.h_states) cudaFreeHost(LN.h_states);
         if (LN.h_total) cudaFreeHost(LN.h_total);
+        if (LN.h_list_total) cudaFreeHost(LN.h_list_total);
+        if (LN.list_evt) cudaEventDestroy(LN.list_evt);
         cudaFree(LN.d_raw); cudaFree(LN.d_total); cudaFree(LN.d_chain); cudaFree(LN.d_idx);
         for (cudaEvent_t e : { LN.stage_done, LN.states_done, LN.fence, LN.raw_done, LN.vready }) if (e) cudaEventDestroy(e);
         if (LN.vstream) cudaStreamDestroy(LN.vstream);
@@ -895,6 +903,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     const unsigned nBatches = (n + bin_batch - 1) / bin_batch;
     if ((rc = grow(&LN.d_bin_counts, &LN.cap_bin_counts, (size_t)nBatches * nb))) return rc;
 
+    size_t list_cap = ~(size_t)0;          /* capacity the kernels check the real total against (small batches: sized by the bound) */
     cudaEvent_t pe[3] = { nullptr, nullptr, nullptr };
     if (g.profiling) {
         for (int i = 0; i < 3; i++) {
@@ -919,21 +928,33 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         unsigned *d_totals = LN.d_bin_start + (MAX_BINS + 2);
         k_bin_scan<<<(nb + 31) / 32, 1024, 0, LN.stream>>>(LN.d_bin_counts, (int)nBatches, nb, d_totals);
         k_bin_starts<<<1, 1024, 0, LN.stream>>>(d_totals, nb, LN.d_bin_start);
-        /* Per-bin lists hold (triangle, bin) overlaps.  The exact total is only known on the device;
-           n*nb bounds it.  Small cases are sized by the bound, large ones read the total back. */
+        /* Per-bin lists hold (triangle, bin) overlaps; their exact total is only known on the device (starts[nb]) and
+           n * nb merely bounds it.  The host does NOT wait for it: the list is sized from the bound when that is small,
+           else generously (4 entries per triangle, or what earlier batches of this lane needed, scaled), and the kernels
+           compare the real total with the capacity themselves - on overflow k_bin_fill writes nothing and the
+           rasterisers filter the whole batch against their tile instead of reading a list (slow, correct, and it
+           happens once: the total is copied back behind the batch and raises the capacity of the next ones). */
         {
-            const size_t bound = (size_t)n * (size_t)nb;
-            size_t want = bound <= ((size_t)n * 4 > 65536 ? (size_t)n * 4 : 65536) ? bound : 0;
-            if (!want && bound <= LN.cap_bin_list) want = bound;
-            if (!want) {
-                unsigned total = 0;
-                CK(cudaMemcpyAsync(&total, LN.d_bin_start + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, LN.stream));
-                CK(cudaStreamSynchronize(LN.stream));
-                want = total;
+            if (LN.list_pending && cudaEventQuery(LN.list_evt) == cudaSuccess) {
+                LN.list_pending = false;
+                if ((size_t)*LN.h_list_total > LN.list_hint) { LN.list_hint = *LN.h_list_total; }
             }
+            const size_t bound = (size_t)n * (size_t)nb;
+            size_t want = (size_t)n * 4 > 65536 ? (size_t)n * 4 : 65536;
+            if (LN.list_hint_n) {
+                const size_t scaled = (size_t)((double)LN.list_hint * 1.25 * ((double)n / (double)LN.list_hint_n > 1.0 ? (double)n / (double)LN.list_hint_n : 1.0)) + 1024;
+                if (scaled > want) want = scaled;
+            }
+            if (want > bound) want = bound;
+            if (want < LN.cap_bin_list) want = LN.cap_bin_list < bound ? LN.cap_bin_list : bound;
             if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, want ? want : 1))) return rc;
+            list_cap = LN.cap_bin_list;
+            CK(cudaMemcpyAsync(LN.h_list_total, LN.d_bin_start + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, LN.stream));
+            CK(cudaEventRecord(LN.list_evt, LN.stream));
+            LN.list_pending = true; LN.list_hint_n = n > LN.list_hint_n ? n : LN.list_hint_n;
         }
-        k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, bin_batch, binsX, binsY, bshift, bshy, LN.d_bin_counts, LN.d_bin_start, LN.d_bin_list);
+        k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, bin_batch, binsX, binsY, bshift, bshy, LN.d_bin_counts, LN.d_bin_start, LN.d_bin_list,
+                                                                          list_cap > 0xffffffffu ? 0xffffffffu : (unsigned)list_cap);
         g.launches += 4;
         }
     }
@@ -958,6 +979,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     RasterParams p;
     p.bbox = LN.d_bbox; p.setup = LN.d_setup; p.data = LN.d_data; p.states = d_states;
     p.bin_list = LN.d_bin_list; p.bin_starts = LN.d_bin_start; p.binsX = binsX; p.bsx = bshift; p.bsy = bshy;
+    p.nb = nb; p.list_cap = list_cap > 0xffffffffu ? 0xffffffffu : (unsigned)list_cap; p.n = d_n ? 0u : n;
     p.color = s->color; p.depth = s->depth; p.W = (int)s->w; p.H = (int)s->h;
     p.tilesX = (int)s->tiles_x; p.tilesY = (int)s->tiles_y;
     p.rank = s->rank; p.world = s->world ? s->world : 1; p.nTiles = s->tiles_x * s->tiles_y;

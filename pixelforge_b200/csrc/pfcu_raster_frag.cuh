@@ -373,7 +373,8 @@ k_raster_frag(const RasterParams p)
     const bool full_tile = (X0 + TILE <= p.W) && (Y0 + TH <= p.H) && ((p.W & 3) == 0);
 
     const int bin = (Y0 >> p.bsy) * p.binsX + (X0 >> p.bsx);
-    const unsigned lbeg = p.bin_starts[bin], lend = p.bin_starts[bin + 1];
+    const bool overflow = p.bin_starts[p.nb] > p.list_cap;      /* lists not written: filter the whole batch (see RasterParams) */
+    const unsigned lbeg = overflow ? 0u : p.bin_starts[bin], lend = overflow ? p.n : p.bin_starts[bin + 1];
     if (lbeg == lend) return;
 
     FragCtx t;
@@ -423,7 +424,14 @@ k_raster_frag(const RasterParams p)
             const unsigned k = base + tid;
             bool hit = false; unsigned ti = 0, wmask = 0;
             if (k < lend) {
-                const uint2 e = __ldg(p.bin_list + k);
+                uint2 e;
+                if (!overflow) e = __ldg(p.bin_list + k);
+                else {                                  /* the entry k_bin_fill would have written for this bin, or a miss */
+                    const int4 b = __ldg(p.bbox + k);
+                    const int ox = (X0 >> p.bsx) << p.bsx, oy = (Y0 >> p.bsy) << p.bsy;
+                    const bool in_bin = b.x < b.z && b.x < ox + (1 << p.bsx) && b.z - 1 >= ox && b.y < oy + (1 << p.bsy) && b.w >= oy;
+                    e = in_bin ? make_uint2(k, bin_rel_bbox(b, X0 >> p.bsx, Y0 >> p.bsy, p.bsx, p.bsy)) : make_uint2(k, 0x0000ffffu);   /* x0 = y0 = 255 > x1 = y1 = 0: never hits */
+                }
                 ti = e.x;
                 const int ex0 = (int)(e.y & 255u), ey0 = (int)((e.y >> 8) & 255u), ex1 = (int)((e.y >> 16) & 255u), ey1 = (int)(e.y >> 24);
                 hit = ex0 <= bx1 && ex1 >= bx0 && ey0 <= by1 && ey1 >= by0;

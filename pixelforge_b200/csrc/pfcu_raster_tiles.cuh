@@ -11,6 +11,9 @@ struct RasterParams {
     uint32_t *color; float *depth; int W, H; int tilesX, tilesY;
     unsigned rank, world; unsigned nTiles;
     unsigned long long *counters;
+    /* bin_starts[nb] is the real number of list entries; when it exceeds list_cap the lists were not written (the host
+       sizes them without waiting for the total) and every CTA filters all n triangles of the batch instead */
+    int nb; unsigned list_cap, n;
 };
 
 /* swizzled tile address: rows are 64 words; XOR-ing bits 3..4 of x with (y & 3) makes both the
@@ -312,7 +315,8 @@ k_raster(const RasterParams p)
     const bool full_tile = (X0 + TILE <= p.W) && (Y0 + TH <= p.H) && ((p.W & 3) == 0);
 
     const int bin = ((ty * TILE) >> p.bsy) * p.binsX + ((tx * TILE) >> p.bsx);
-    const unsigned lbeg = p.bin_starts[bin], lend = p.bin_starts[bin + 1];
+    const bool overflow = p.bin_starts[p.nb] > p.list_cap;
+    const unsigned lbeg = overflow ? 0u : p.bin_starts[bin], lend = overflow ? p.n : p.bin_starts[bin + 1];
     if (lbeg == lend) return;
 
     /* RCPPS table: shared copy when it has <= 2^11 entries (every CPU we met), else the global one */
@@ -342,7 +346,7 @@ k_raster(const RasterParams p)
             const unsigned k = base + tid;
             bool hit = false; unsigned ti = 0, wmask = 0;
             if (k < lend) {
-                ti = __ldg(&p.bin_list[k].x);
+                ti = overflow ? k : __ldg(&p.bin_list[k].x);
                 const int4 b = __ldg(p.bbox + ti);
                 hit = b.x <= X1 && b.z - 1 >= X0 && b.y <= Y1 && b.w >= Y0 && b.x < b.z;
                 if (hit) {

@@ -228,8 +228,9 @@ __device__ __forceinline__ unsigned bin_rel_bbox(const int4 b, int bx, int by, i
 __global__ void __launch_bounds__(256)
 k_bin_fill(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX, int binsY, int bshift, int bshy,
            const unsigned *__restrict__ offsets /* scanned counts */, const unsigned *__restrict__ starts,
-           uint2 *__restrict__ list)
+           uint2 *__restrict__ list, unsigned list_cap)
 {
+    if (starts[binsX * binsY] > list_cap) return;       /* the lists do not fit: the rasterisers filter the batch themselves */
     extern __shared__ unsigned s_mem[];
     unsigned *s_pos = s_mem;                    /* [nb] running write position of this batch per bin */
     __shared__ int4 s_rect[256];

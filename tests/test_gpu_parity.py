@@ -184,6 +184,32 @@ def test_stream_phong(pfcu_pair):
     assert (cp[dp != FLT_MAX] >> 24 == 0).all()         # Q9: Phong forces alpha to 0
 
 
+def test_bin_list_overflow_is_rendered_correctly(pfcu_pair):
+    """The host sizes the per-bin triangle lists without waiting for their real total (4 entries per triangle, or what
+    earlier batches needed).  A batch of many triangles whose bounding boxes all span every bin needs more: the binning
+    kernels then write no lists and every rasteriser CTA filters the whole batch itself.  Same pixels as the oracle, on
+    both rasterisers, and again on the next submission (by then the lane has learnt the size and takes the normal path)."""
+    prod, orc = pfcu_pair
+    rng = np.random.default_rng(4711)
+    w = h = 128
+    n = 17000                                   # 4 bins of 64x64: bound 68000 entries > the 65536 the first submission gets
+    states, tris = random_stream(rng, w, h, n, 1 | 2 | 16, blend=2, depth=3)
+    t = rng.uniform(0, 1, n)
+    for k, (dx, dy) in enumerate(((-8, -8), (w + 8, h + 6), (w + 9, h + 8))):      # slivers along the diagonal: huge boxes, few pixels
+        tris["v"]["sx"][:, k] = dx + (rng.uniform(-3, 3, n) if k else 0) + 6 * t
+        tris["v"]["sy"][:, k] = dy + (rng.uniform(-3, 3, n) if k else 0) - 6 * t
+    co, do = orc.render_stream(w, h, states, tris)
+    assert (do != FLT_MAX).sum() > 200
+    for path in (2, 1, 0):
+        prod.lib.pfcu_set_raster_path(path)
+        try:
+            for attempt in range(2):
+                cp, dp = prod.render_stream(w, h, states, tris)
+                assert int((cp != co).sum()) == 0 and int((dp.view(np.uint32) != do.view(np.uint32)).sum()) == 0, (path, attempt)
+        finally:
+            prod.lib.pfcu_set_raster_path(0)
+
+
 # ---- render targets other than RGBA8 and BGRA8 textures: the row-ordered rasteriser (SURVEY 8-f row 4, Q19) ----
 
 @pytest.mark.parametrize("fmt", [1, 2, 3], ids=["target-bgra8", "target-rgb8", "target-bgr8"])

@@ -289,22 +289,30 @@ def measure_workload(wl_name, steps, warmup, torch, scenes, pfcu, stream, flush_
             step()
         L.pfcu_finish()
         L.pfxResetCounters()
+
+        def timed_loop():
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            with torch.cuda.stream(stream):
+                for i in range(steps):
+                    flush_buf.fill_(i & 0xFF)          # L2 flush: write a buffer larger than L2 (untimed)
+                    ev[i][0].record(stream)
+                    L.pfcu_fence()                      # surfaces may live on other internal streams (lanes)
+                    step()
+                    L.pfcu_fence()
+                    ev[i][1].record(stream)
+            stream.synchronize()
+            return sum(a.elapsed_time(b) for a, b in ev) / steps
+
+        dev_ms = timed_loop()                           # the `value` leg: K steps, nothing but the step between the events
+        k = Counters(); L.pfcu_get_counters(k)
+        # the same K steps once more with the library's stage events on (CUDA events on the launching stream around the
+        # front-end kernels and around the raster kernel): the per-kernel times of the roofline object
         L.pfcu_profile_enable(1)
         prof = Profile(); L.pfcu_profile_read(prof)
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        with torch.cuda.stream(stream):
-            for i in range(steps):
-                flush_buf.fill_(i & 0xFF)          # L2 flush: write a buffer larger than L2 (untimed)
-                ev[i][0].record(stream)
-                L.pfcu_fence()                      # surfaces may live on other internal streams (lanes)
-                step()
-                L.pfcu_fence()
-                ev[i][1].record(stream)
-        stream.synchronize()
-        dev_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+        prof_ms = timed_loop()
         L.pfcu_profile_read(prof)
         L.pfcu_profile_enable(0)
-        k = Counters(); L.pfcu_get_counters(k)
+        out["dev_ms_with_stage_events"] = prof_ms
         out.update(dev_ms=dev_ms, dev_px_per_step=k.pixels_shaded / steps, dev_tris_per_step=k.triangles_submitted / steps,
                    raster_ms=prof.raster_ms / steps, frontend_ms=prof.frontend_ms / steps,
                    raster_launches_per_step=prof.raster_launches / steps, launches_per_step=k.kernel_launches / steps)

@@ -216,6 +216,19 @@ __constant__ int c_rcp_shift, c_rsq_shift, c_rsq_bits;
 /* host: runtime                                                                                    */
 /* ------------------------------------------------------------------------------------------------ */
 
+/* Launch as a programmatic dependent of the previous kernel in the stream (see pdl_wait in pfcu_setup_bin.cuh). */
+static const bool g_use_pdl = !(getenv("PF_CUDA_PDL") && atoi(getenv("PF_CUDA_PDL")) == 0);
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <typename T> static int grow(T **p, size_t *cap, size_t need)
 {
     if (need <= *cap) return PFCU_OK;
@@ -269,7 +282,8 @@ int pfcu_init(int device)
         g.cur = &g.lanes[i];
         CK(cudaStreamCreateWithFlags(&LN.stream, cudaStreamNonBlocking));
         LN.own_stream = true;
-        CK(cudaMalloc(&LN.d_bin_start, (MAX_BINS + 2) * 2 * sizeof(unsigned)));
+        CK(cudaMalloc(&LN.d_bin_start, ((MAX_BINS + 2) * 2 + 4) * sizeof(unsigned)));      /* starts | totals | ticket of k_bin_scan */
+        CK(cudaMemset(LN.d_bin_start, 0, ((MAX_BINS + 2) * 2 + 4) * sizeof(unsigned)));
         CK(cudaEventCreateWithFlags(&LN.stage_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&LN.states_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&LN.fence, cudaEventDisableTiming));
@@ -913,28 +927,21 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         CK(cudaEventRecord(pe[0], LN.stream));
     }
     if (d_n && !(nb <= 3072 && n <= FRONT_SMALL_MAX * FRONT_SMALL_CHUNKS)) { snprintf(g.err, sizeof g.err, "internal: device-side count outside the single-CTA front end"); return PFCU_ERR_INVALID; }
+    bool list_total_wanted = false;
     if (d_n || (n <= FRONT_SMALL_MAX && nb <= 3072)) {      /* 3072 bin counters + the rectangles fit the 48 KB of static + dynamic shared memory */
         /* small batch: the (triangle, bin) overlap count is bounded by n * nb, no read-back needed */
         if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, (size_t)n * nb))) return rc;
-        k_front_small<<<1, 1024, nb * sizeof(unsigned), LN.stream>>>(d_tris, d_states, n, d_n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data,
-                                                                      g.d_counters, binsX, binsY, bshift, bshy, LN.d_bin_start, LN.d_bin_list);
+        CK(launch_dep(k_front_small, dim3(1), dim3(1024), nb * sizeof(unsigned), LN.stream, d_tris, d_states, n, d_n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data,
+                      g.d_counters, binsX, binsY, bshift, bshy, LN.d_bin_start, LN.d_bin_list));
         g.launches += 1;
     } else {
-        k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, LN.stream>>>(
-            d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data, g.d_counters);
-        g.launches += 1;
         if (!rows_path) {
-        k_bin_count<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, bin_batch, binsX, binsY, bshift, bshy, LN.d_bin_counts);
-        unsigned *d_totals = LN.d_bin_start + (MAX_BINS + 2);
-        k_bin_scan<<<(nb + 31) / 32, 1024, 0, LN.stream>>>(LN.d_bin_counts, (int)nBatches, nb, d_totals);
-        k_bin_starts<<<1, 1024, 0, LN.stream>>>(d_totals, nb, LN.d_bin_start);
-        /* Per-bin lists hold (triangle, bin) overlaps; their exact total is only known on the device (starts[nb]) and
-           n * nb merely bounds it.  The host does NOT wait for it: the list is sized from the bound when that is small,
-           else generously (4 entries per triangle, or what earlier batches of this lane needed, scaled), and the kernels
-           compare the real total with the capacity themselves - on overflow k_bin_fill writes nothing and the
-           rasterisers filter the whole batch against their tile instead of reading a list (slow, correct, and it
-           happens once: the total is copied back behind the batch and raises the capacity of the next ones). */
-        {
+            /* Per-bin lists hold (triangle, bin) overlaps; their exact total is only known on the device (starts[nb]) and
+               n * nb merely bounds it.  The host does NOT wait for it: the list is sized from the bound when that is small,
+               else generously (4 entries per triangle, or what earlier batches of this lane needed, scaled), and the kernels
+               compare the real total with the capacity themselves - on overflow k_bin_fill writes nothing and the
+               rasterisers filter the whole batch against their tile instead of reading a list (slow, correct, and it
+               happens once: the total is copied back behind the batch and raises the capacity of the next ones). */
             if (LN.list_pending && cudaEventQuery(LN.list_evt) == cudaSuccess) {
                 LN.list_pending = false;
                 if ((size_t)*LN.h_list_total > LN.list_hint) { LN.list_hint = *LN.h_list_total; }
@@ -949,13 +956,19 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
             if (want < LN.cap_bin_list) want = LN.cap_bin_list < bound ? LN.cap_bin_list : bound;
             if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, want ? want : 1))) return rc;
             list_cap = LN.cap_bin_list;
-            CK(cudaMemcpyAsync(LN.h_list_total, LN.d_bin_start + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, LN.stream));
-            CK(cudaEventRecord(LN.list_evt, LN.stream));
-            LN.list_pending = true; LN.list_hint_n = n > LN.list_hint_n ? n : LN.list_hint_n;
+            list_total_wanted = true;
         }
-        k_bin_fill<<<nBatches, 256, nb * sizeof(unsigned), LN.stream>>>(LN.d_bbox, n, bin_batch, binsX, binsY, bshift, bshy, LN.d_bin_counts, LN.d_bin_start, LN.d_bin_list,
-                                                                          list_cap > 0xffffffffu ? 0xffffffffu : (unsigned)list_cap);
-        g.launches += 4;
+        /* the kernels of the batch back to back, each a programmatic dependent of the one before */
+        CK(launch_dep(k_setup, dim3((n + SETUP_THREADS - 1) / SETUP_THREADS), dim3(SETUP_THREADS), 0, LN.stream,
+                      d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data, g.d_counters));
+        g.launches += 1;
+        if (!rows_path) {
+            unsigned *d_totals = LN.d_bin_start + (MAX_BINS + 2), *d_ticket = LN.d_bin_start + (MAX_BINS + 2) * 2;
+            CK(launch_dep(k_bin_count, dim3(nBatches), dim3(256), nb * sizeof(unsigned), LN.stream, (const int4 *)LN.d_bbox, n, bin_batch, binsX, binsY, bshift, bshy, LN.d_bin_counts));
+            CK(launch_dep(k_bin_scan, dim3((nb + 31) / 32), dim3(1024), 0, LN.stream, LN.d_bin_counts, (int)nBatches, nb, d_totals, LN.d_bin_start, d_ticket));
+            CK(launch_dep(k_bin_fill, dim3(nBatches), dim3(256), nb * sizeof(unsigned), LN.stream, (const int4 *)LN.d_bbox, n, bin_batch, binsX, binsY, bshift, bshy,
+                          (const unsigned *)LN.d_bin_counts, (const unsigned *)LN.d_bin_start, LN.d_bin_list, list_cap > 0xffffffffu ? 0xffffffffu : (unsigned)list_cap));
+            g.launches += 3;
         }
     }
     if (rows_path) {
@@ -1002,24 +1015,29 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
                 cudaFuncSetAttribute(k_raster_frag<false, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * FRAG_NF * 512);
                 return true; }();
             (void)attr_once;
-            if (ph) k_raster_frag<true, 8, 3><<<grid * 8, 256, 8 * FRAG_NF_PHONG * 512, LN.stream>>>(p);
-            else    k_raster_frag<false, 8, 4><<<grid * 8, 256, 8 * FRAG_NF * 512, LN.stream>>>(p);
+            if (ph) CK(launch_dep(k_raster_frag<true, 8, 3>, dim3(grid * 8), dim3(256), (size_t)(8 * FRAG_NF_PHONG * 512), LN.stream, p));
+            else    CK(launch_dep(k_raster_frag<false, 8, 4>, dim3(grid * 8), dim3(256), (size_t)(8 * FRAG_NF * 512), LN.stream, p));
         }
         else if (small_tris) {
             const int th = force_slice ? force_slice : (ph ? 32 : 16);
-            if (ph) { if (th <= 32) k_raster<true, 16, -1, 32><<<grid * 2, 512, 0, LN.stream>>>(p); else k_raster<true, 16, -1, 64><<<grid, 512, 0, LN.stream>>>(p); }
-            else if (th <= 16) k_raster<false, 16, -1, 16><<<grid * 4, 512, 0, LN.stream>>>(p);
-            else if (th <= 32) k_raster<false, 16, -1, 32><<<grid * 2, 512, 0, LN.stream>>>(p);
-            else               k_raster<false, 16, -1, 64><<<grid, 512, 0, LN.stream>>>(p);
+            if (ph) { if (th <= 32) CK(launch_dep(k_raster<true, 16, -1, 32>, dim3(grid * 2), dim3(512), (size_t)(0), LN.stream, p)); else CK(launch_dep(k_raster<true, 16, -1, 64>, dim3(grid), dim3(512), (size_t)(0), LN.stream, p)); }
+            else if (th <= 16) CK(launch_dep(k_raster<false, 16, -1, 16>, dim3(grid * 4), dim3(512), (size_t)(0), LN.stream, p));
+            else if (th <= 32) CK(launch_dep(k_raster<false, 16, -1, 32>, dim3(grid * 2), dim3(512), (size_t)(0), LN.stream, p));
+            else               CK(launch_dep(k_raster<false, 16, -1, 64>, dim3(grid), dim3(512), (size_t)(0), LN.stream, p));
         }
-        else if (ph)          k_raster<true, 8, -1, 64><<<grid, 256, 0, LN.stream>>>(p);
-        else if (single_prog == 5) { if (half) k_raster<false, 8, 5, 32><<<grid * 2, 256, 0, LN.stream>>>(p); else k_raster<false, 8, 5, 64><<<grid, 256, 0, LN.stream>>>(p); }   /* nearest REPEAT RGBA8 texture + ALPHA blend */
-        else if (single_prog == 6) { if (half) k_raster<false, 8, 6, 32><<<grid * 2, 256, 0, LN.stream>>>(p); else k_raster<false, 8, 6, 64><<<grid, 256, 0, LN.stream>>>(p); }   /* nearest REPEAT RGBA8 texture + ADD blend   */
-        else { if (half) k_raster<false, 8, -1, 32><<<grid * 2, 256, 0, LN.stream>>>(p); else k_raster<false, 8, -1, 64><<<grid, 256, 0, LN.stream>>>(p); }
+        else if (ph)          CK(launch_dep(k_raster<true, 8, -1, 64>, dim3(grid), dim3(256), (size_t)(0), LN.stream, p));
+        else if (single_prog == 5) { if (half) CK(launch_dep(k_raster<false, 8, 5, 32>, dim3(grid * 2), dim3(256), (size_t)(0), LN.stream, p)); else CK(launch_dep(k_raster<false, 8, 5, 64>, dim3(grid), dim3(256), (size_t)(0), LN.stream, p)); }   /* nearest REPEAT RGBA8 texture + ALPHA blend */
+        else if (single_prog == 6) { if (half) CK(launch_dep(k_raster<false, 8, 6, 32>, dim3(grid * 2), dim3(256), (size_t)(0), LN.stream, p)); else CK(launch_dep(k_raster<false, 8, 6, 64>, dim3(grid), dim3(256), (size_t)(0), LN.stream, p)); }   /* nearest REPEAT RGBA8 texture + ADD blend   */
+        else { if (half) CK(launch_dep(k_raster<false, 8, -1, 32>, dim3(grid * 2), dim3(256), (size_t)(0), LN.stream, p)); else CK(launch_dep(k_raster<false, 8, -1, 64>, dim3(grid), dim3(256), (size_t)(0), LN.stream, p)); }
         g.launches++;
     }
     if (g.profiling) { CK(cudaEventRecord(pe[2], LN.stream)); for (int i = 0; i < 3; i++) g.prof_events.push_back(pe[i]); }
     CK(cudaGetLastError());
+    if (list_total_wanted) {            /* behind the batch, so that its kernels stay adjacent in the stream */
+        CK(cudaMemcpyAsync(LN.h_list_total, LN.d_bin_start + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, LN.stream));
+        CK(cudaEventRecord(LN.list_evt, LN.stream));
+        LN.list_pending = true; LN.list_hint_n = n > LN.list_hint_n ? n : LN.list_hint_n;
+    }
     mark_done(s);
     /* write-after-read: a sampled surface on another lane must not be overwritten before this batch read it */
     for (pfcu_surface *dep : g.deps)
@@ -1180,7 +1198,7 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
         CK(cudaEventRecord(LN.states_done, LN.stream));
         unsigned *d_total = LN.d_total;
         if (++LN.chain_seq == 0) ++LN.chain_seq;         /* 0 is what the zero-initialised flags hold */
-        k_raw_chain<<<(n_tris + 127u) / 128u, 128, 0, LN.stream>>>(ra, LN.d_tris, d_total, LN.d_chain, LN.chain_seq);
+        CK(launch_dep(k_raw_chain, dim3((n_tris + 127u) / 128u), dim3(128), 0, LN.stream, ra, LN.d_tris, d_total, LN.d_chain, LN.chain_seq));
         g.launches++;
         CK(cudaEventRecord(LN.raw_done, LN.stream));
         CK(cudaGetLastError());

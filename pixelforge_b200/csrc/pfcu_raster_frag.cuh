@@ -348,6 +348,7 @@ template <bool HAS_PHONG, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
 k_raster_frag(const RasterParams p)
 {
+    pdl_wait();         /* launched as a programmatic dependent of the binning kernels; before ANY exit, so that the grid cannot complete early */
     constexpr int NT = NW * 32, TH = NW, SUB = TILE / TH;
     __shared__ __align__(16) unsigned s_tile[2 * NW * FRAG_RSTRIDE];     /* colour regions, then depth regions */
     unsigned *const s_col = s_tile;

@@ -291,6 +291,7 @@ template <bool HAS_PHONG, int NW, int FIXED_PROG, int TH>
 __global__ void __launch_bounds__(NW * 32, FIXED_PROG >= 0 ? 4 : (NW == 16 ? (HAS_PHONG ? 1 : 2) : (HAS_PHONG ? 2 : 3)))
 k_raster(const RasterParams p)
 {
+    pdl_wait();         /* launched as a programmatic dependent of the binning kernels; before ANY exit, so that the grid cannot complete early */
     constexpr int NT = NW * 32;
     __shared__ __align__(16) unsigned s_mem[2 * TILE_PIX + (1 << RCP_SMEM_BITS)];   /* colour | depth | RCP table */
     unsigned *const s_color = s_mem;

@@ -5,6 +5,15 @@
 /* kernels: setup                                                                                   */
 /* ------------------------------------------------------------------------------------------------ */
 
+/* Programmatic dependent launch (sm_90+): the kernels of one batch are launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs are scheduled as soon as every CTA of
+ * its predecessor has started (pdl_trigger) and only wait, in pdl_wait, for the predecessor's completion and memory
+ * flush - the launch latency between the short front-end kernels overlaps their execution.  Every kernel calls
+ * pdl_wait before it touches anything an earlier kernel wrote (completion is transitive along the stream); both are
+ * no-ops for an ordinary launch. */
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ int to_int_x86(float f) { return cvt_trunc_x86(f); }   /* (PFint)f == CVTTSS2SI */
 __device__ __forceinline__ int wmul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
 __device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
@@ -101,6 +110,7 @@ k_setup(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ sta
        record field by field touches 32 different sectors per load instruction) */
     __shared__ __align__(16) unsigned char s_in[SETUP_THREADS * sizeof(pfcu_triangle)];
     static_assert((SETUP_THREADS * sizeof(pfcu_triangle)) % 16 == 0, "whole uint4s per CTA");
+    pdl_trigger(); pdl_wait();
     const unsigned base = blockIdx.x * SETUP_THREADS;
     const unsigned here = min((unsigned)SETUP_THREADS, n - base);
     {
@@ -128,8 +138,10 @@ k_bin_count(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX
 {
     extern __shared__ unsigned s_cnt[];
     const int nb = binsX * binsY;
+    pdl_trigger();
     for (int k = threadIdx.x; k < nb; k += blockDim.x) s_cnt[k] = 0;
     __syncthreads();
+    pdl_wait();
     const unsigned base = blockIdx.x * batch;
     for (unsigned k = threadIdx.x; k < batch; k += blockDim.x) {
         const unsigned i = base + k;
@@ -145,40 +157,8 @@ k_bin_count(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX
     for (int k = threadIdx.x; k < nb; k += blockDim.x) counts[(size_t)blockIdx.x * nb + k] = s_cnt[k];
 }
 
-/* pass 2: per bin, exclusive scan of counts over batches (in place) + bin totals.  A CTA of 32 warps owns 32
- * consecutive bins (one 128-byte row segment per batch); warp w owns a contiguous range of batches: it sums its
- * range, the 32 partial sums are scanned across warps, and it walks its range again writing the prefixes. */
-__global__ void __launch_bounds__(1024)
-k_bin_scan(unsigned *__restrict__ counts, int nBatches, int nb, unsigned *__restrict__ totals)
-{
-    __shared__ unsigned s_part[32][33];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int bin = blockIdx.x * 32 + lane;
-    const bool live = bin < nb;
-    const int per = (nBatches + 31) / 32;
-    const int k0 = warp * per, k1 = min(k0 + per, nBatches);
-    unsigned sum = 0;
-    if (live) {
-#pragma unroll 8
-        for (int k = k0; k < k1; k++) sum += counts[(size_t)k * nb + bin];
-    }
-    s_part[warp][lane] = sum;
-    __syncthreads();
-    unsigned run = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < 32; w++) { const unsigned c = s_part[w][lane]; if (w < warp) run += c; total += c; }
-    if (live) {
-        for (int k = k0; k < k1; k++) {
-            unsigned *pc = counts + (size_t)k * nb + bin;
-            const unsigned v = *pc; *pc = run; run += v;
-        }
-        if (warp == 0) totals[bin] = total;
-    }
-}
-
-/* pass 3: bin start offsets (exclusive scan over the bin totals); single CTA of 1024 threads */
-__global__ void __launch_bounds__(1024)
-k_bin_starts(const unsigned *__restrict__ totals, int nb, unsigned *__restrict__ starts)
+/* exclusive scan over the bin totals -> bin start offsets, starts[nb] = total; one CTA of 1024 threads */
+__device__ __forceinline__ void bin_starts_scan(const unsigned *totals, int nb, unsigned *__restrict__ starts)
 {
     __shared__ unsigned s_warp[32];
     __shared__ unsigned s_carry;
@@ -187,7 +167,7 @@ k_bin_starts(const unsigned *__restrict__ totals, int nb, unsigned *__restrict__
     __syncthreads();
     for (int base = 0; base < nb; base += 1024) {
         const int k = base + threadIdx.x;
-        const unsigned v = (k < nb) ? totals[k] : 0u;
+        const unsigned v = (k < nb) ? __ldcg(totals + k) : 0u;      /* written by other CTAs of this launch: read from L2 */
         unsigned x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -207,6 +187,49 @@ k_bin_starts(const unsigned *__restrict__ totals, int nb, unsigned *__restrict__
         __syncthreads();
     }
     if (threadIdx.x == 0) starts[nb] = s_carry;
+}
+
+/* pass 2: per bin, exclusive scan of counts over batches (in place) + bin totals.  A CTA of 32 warps owns 32
+ * consecutive bins (one 128-byte row segment per batch); warp w owns a contiguous range of batches: it sums its
+ * range, the 32 partial sums are scanned across warps, and it walks its range again writing the prefixes.
+ * pass 3 rides along: the CTA that finishes last (a ticket drawn with an atomic after its totals are out) turns the bin
+ * totals into the bin start offsets - one launch less on the critical path of every batch. */
+__global__ void __launch_bounds__(1024)
+k_bin_scan(unsigned *__restrict__ counts, int nBatches, int nb, unsigned *__restrict__ totals, unsigned *__restrict__ starts, unsigned *__restrict__ ticket)
+{
+    __shared__ unsigned s_part[32][33];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bin = blockIdx.x * 32 + lane;
+    const bool live = bin < nb;
+    const int per = (nBatches + 31) / 32;
+    const int k0 = warp * per, k1 = min(k0 + per, nBatches);
+    pdl_trigger(); pdl_wait();
+    unsigned sum = 0;
+    if (live) {
+#pragma unroll 8
+        for (int k = k0; k < k1; k++) sum += counts[(size_t)k * nb + bin];
+    }
+    s_part[warp][lane] = sum;
+    __syncthreads();
+    unsigned run = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 32; w++) { const unsigned c = s_part[w][lane]; if (w < warp) run += c; total += c; }
+    if (live) {
+        for (int k = k0; k < k1; k++) {
+            unsigned *pc = counts + (size_t)k * nb + bin;
+            const unsigned v = *pc; *pc = run; run += v;
+        }
+        if (warp == 0) totals[bin] = total;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) *ticket = 0u;         /* for the next launch on this lane */
+    __threadfence();
+    bin_starts_scan(totals, nb, starts);
 }
 
 /* A bin-list entry carries the triangle's visited rectangle [x0, x1] x [y0, y1] (inclusive) clipped to the bin and
@@ -230,6 +253,7 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX,
            const unsigned *__restrict__ offsets /* scanned counts */, const unsigned *__restrict__ starts,
            uint2 *__restrict__ list, unsigned list_cap)
 {
+    pdl_trigger(); pdl_wait();
     if (starts[binsX * binsY] > list_cap) return;       /* the lists do not fit: the rasterisers filter the batch themselves */
     extern __shared__ unsigned s_mem[];
     unsigned *s_pos = s_mem;                    /* [nb] running write position of this batch per bin */
@@ -326,6 +350,7 @@ k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict
     __shared__ int4 s_bbox[FRONT_SMALL_MAX];
     __shared__ unsigned s_warp[32];
     __shared__ unsigned s_carry;
+    pdl_trigger(); pdl_wait();
     const unsigned n = d_n ? min(*d_n, (unsigned)(FRONT_SMALL_MAX * FRONT_SMALL_CHUNKS)) : n_host;
     if (d_n && threadIdx.x == 0) atomicAdd(counters + 3, (unsigned long long)n);        /* "submitted", counted where the count is known */
     const int nb = binsX * binsY;

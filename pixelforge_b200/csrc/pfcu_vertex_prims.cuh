@@ -222,6 +222,7 @@ k_raw_chain(const RawArgs a, pfcu_triangle *__restrict__ out, unsigned *__restri
 {
     __shared__ unsigned s_warp[4];
     __shared__ unsigned s_prev, s_bid;
+    pdl_trigger(); pdl_wait();
     if (threadIdx.x == 0) s_bid = (unsigned)atomicAdd(flags + 15, 1ull);
     __syncthreads();
     const unsigned bid = s_bid;

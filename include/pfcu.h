@@ -242,7 +242,7 @@ typedef struct {
     uint16_t       pad;
 } pfcu_draw;
 
-enum { PFCU_CAP_DEVICE_VERTEX = 1u, PFCU_CAP_RAW_TRIANGLES = 2u };
+enum { PFCU_CAP_DEVICE_VERTEX = 1u, PFCU_CAP_RAW_TRIANGLES = 2u, PFCU_CAP_LISTS = 4u };
 PFCU_API unsigned pfcu_capabilities(void);
 /* Vertex stage + rasterisation of one draw call, entirely on the device; ordered after everything
  * submitted before it.  `state` is the single state snapshot in force.  *n_out receives the number of
@@ -284,6 +284,42 @@ PFCU_API int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t
                              const pfcu_vparams_lit *vparams, uint32_t n_vparams,
                              const float *pow_tables, uint32_t n_pow_tables,
                              const pfcu_rawtri *tris, uint32_t n_tris, uint32_t *n_out);
+
+/* ---- device-resident render lists, many surfaces per launch (SURVEY 8-f "next" row 2) ------------------------
+ * The reference replays a render list by re-issuing pfColor / pfTexCoord / pfNormal / pfVertex for every recorded
+ * vertex (renderlist.c:71-97, internal/context/context.h:271-294).  Here the front end assembles a list's triangles
+ * ONCE (draw modes, face passes) and leaves them in HBM as unprocessed pfcu_rawtri records whose `state` field holds
+ * the index of the recorded pfBegin..pfEnd call they came from (`vparams` is unused).  A replay then ships only what
+ * the reference reads from the context at replay time - per recorded call one pfcu_list_call naming the fragment state
+ * and the prologue environment in force (matrices, lights, the call's materials), both deduplicated - a few KB.
+ * pfcu_submit_list_jobs takes the pending replays of MANY surfaces (the contexts of a batch server, BASELINE config
+ * C5) and runs them with four launches in all: pfClear of every surface, vertex stage (k_list_chain), setup + binning
+ * (k_front_small) and rasterisation (k_raster_frag), the surface being the grid's y coordinate. */
+typedef struct pfcu_list pfcu_list;
+PFCU_API pfcu_list *pfcu_list_create(const pfcu_rawtri *tris, uint32_t n_tris);
+PFCU_API void       pfcu_list_destroy(pfcu_list *l);
+PFCU_API uint32_t   pfcu_list_size(const pfcu_list *l);
+typedef struct {
+    uint32_t state, vparams;    /* indices into the job's states[] / vparams[]                                          */
+    uint32_t override_color;    /* PF_COLOR_MATERIAL at replay: pfColor feeds the material and every vertex carries ... */
+    uint32_t rgba;              /* ... the context's current colour instead of the recorded one (context.c:1687-1717)   */
+} pfcu_list_call;
+typedef struct { const pfcu_list *list; uint32_t first_call; uint32_t pad; } pfcu_list_segment;   /* calls[first_call + tri.state] */
+typedef struct {
+    pfcu_surface *surface;
+    uint32_t clear; uint32_t clear_rgba; float clear_depth;     /* clear != 0: pfcu_surface_clear_ref(both buffers) first */
+    const pfcu_state *states;           uint32_t n_states;
+    const pfcu_vparams_lit *vparams;    uint32_t n_vparams;
+    const float *pow_tables;            uint32_t n_pow_tables;
+    const pfcu_list_call *calls;        uint32_t n_calls;
+    const pfcu_list_segment *segments;  uint32_t n_segments;    /* replayed in this order */
+} pfcu_list_job;
+#define PFCU_LIST_JOB_MAX_TRIS     1024u    /* assembled triangles per job (before clipping)                          */
+#define PFCU_LIST_JOB_MAX_SEGMENTS 16u
+/* Can a job of n_tris list triangles on this surface take this path?  (RGBA8 target, no tile split, size limits; a
+ * front end that gets 0 replays the list through pfcu_submit_raw or on the host instead.) */
+PFCU_API int pfcu_list_job_supported(const pfcu_surface *s, uint32_t n_tris, uint32_t n_segments);
+PFCU_API int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n_jobs);
 
 /* ---- points and lines (SURVEY 8-f "next" row 3) -------------------------------------------------- */
 /* The front end transforms and clips (lines.c:137-281, points.c:62-83) and submits screen-space primitives;

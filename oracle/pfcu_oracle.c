@@ -773,6 +773,12 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
     if (n_out) *n_out = 0;
     return PFCU_ERR_INVALID;
 }
+/* device-resident render lists: never advertised (pfcu_capabilities), the front end replays lists on the host here */
+pfcu_list *pfcu_list_create(const pfcu_rawtri *tris, uint32_t n) { (void)tris; (void)n; return NULL; }
+void pfcu_list_destroy(pfcu_list *l) { (void)l; }
+uint32_t pfcu_list_size(const pfcu_list *l) { (void)l; return 0; }
+int pfcu_list_job_supported(const pfcu_surface *s, uint32_t n, uint32_t k) { (void)s; (void)n; (void)k; return 0; }
+int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n) { (void)jobs; (void)n; return PFCU_ERR_INVALID; }
 /* points and lines: the reference's scalar loops (lines.c:283-530, points.c:85-183), one primitive after the other */
 #include "../pixelforge_b200/csrc/pf_prims.h"
 static void prim_pixel(pfcu_surface *s, const pfcu_prim *p, uint32_t off, float z, uint32_t color, int test)

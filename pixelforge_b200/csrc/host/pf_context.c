@@ -93,6 +93,7 @@ void pfDeleteContext(PFcontext ctx)
     for (int i = 0; i < 2; i++) if (c->tris[i]) pfcu_host_free(c->tris[i]);
     free(c->states); free(c->cap_tris); free(c->cap_states);
     free(c->vparams); free(c->pow_tables); free(c->pow_shininess); free(c->prims);
+    free(c->segs); free(c->lcalls); free(c->cmp_tris);
     pf_tex *tex = (pf_tex *)c->mainFramebuffer.texture;
     pfh_surf_destroy(c->main_surf);
     PF_FREE(tex);
@@ -156,8 +157,12 @@ PFcontext pfGetCurrentContext(void) { return pf_cur; }
 void pfMakeCurrent(PFcontext ctx)
 {
     if (pf_cur && pf_cur != ctx) {
-        if (pfh_sync_mode_explicit()) { pfh_flush(pf_cur); pfh_queue_readback(pf_cur, pf_cur->cur_surf); }
-        else pfh_sync_surface(pf_cur, pf_cur->cur_surf);
+        if (pfh_sync_mode_explicit()) {
+            /* a context whose pending work is a clear and / or replays of device-resident lists keeps it: the work of
+               all such contexts of this thread goes out together (one multi-surface submission) at the next flush */
+            if (pf_cur->n_tris == 0 && pf_cur->n_prims == 0 && (pf_cur->n_segs || pf_cur->clear_pending)) pfh_register_pending(pf_cur);
+            else { pfh_flush(pf_cur); pfh_queue_readback(pf_cur, pf_cur->cur_surf); }
+        } else pfh_sync_surface(pf_cur, pf_cur->cur_surf);
     }
     pf_cur = (pf_ctx *)ctx;
 }
@@ -363,12 +368,13 @@ void pfClear(PFclearflag flag)
     CTX;
     if (!flag) return;
     pf_surf *s = c->cur_surf;
-    pfh_flush(c);
+    if (c->n_tris || c->n_prims || c->n_segs) pfh_flush(c);
     pfh_upload_if_needed(c, s);
     uint32_t rgba; memcpy(&rgba, &c->clearColor, 4);
     /* the reference's SIMD build clears BOTH buffers whenever either bit is set and never touches
        pixels 0..7 (context.c:696-713); pfcu_surface_clear_ref reproduces that */
-    pfcu_surface_clear_ref(s->dev, 1, rgba, 1, c->clearDepth);
+    if (pfh_clear_deferrable(c)) { c->clear_pending = 1; c->clear_rgba = rgba; c->clear_z = c->clearDepth; pfh_register_pending(c); }
+    else { c->clear_pending = 0; pfcu_surface_clear_ref(s->dev, 1, rgba, 1, c->clearDepth); }
     s->dev_newer = 1; s->dirty_y0 = 0; s->dirty_y1 = s->tex->h; s->readback_queued = 0;
     pfh_end_of_draw(c);
 }
@@ -507,7 +513,7 @@ void pfColorMaterial(PFface face, PFenum mode)
 
 /* ---- immediate mode (context.c:41-74,1580-1913) ------------------------------------------------ */
 
-static PFsizei verts_per_primitive(PFdrawmode m)
+PFsizei pfh_verts_per_primitive(PFdrawmode m)
 {
     switch (m) {
     case PF_POINTS: return 1;  case PF_LINES: return 2;  case PF_TRIANGLES: return 3;
@@ -518,7 +524,7 @@ static PFsizei verts_per_primitive(PFdrawmode m)
 }
 
 /* what survives into the next primitive of a fan/strip (Q16: only v[3], resp. v[4..5]) */
-static void carry_over(pf_ctx *c)
+void pfh_carry_over(pf_ctx *c)
 {
     switch (c->currentDrawMode) {
     case PF_TRIANGLE_FAN: case PF_TRIANGLE_STRIP:
@@ -555,9 +561,9 @@ void pfVertex4fv(const PFfloat *v)
     memcpy(vx->normal, c->currentNormal, 12);
     memcpy(vx->texcoord, c->currentTexcoord, 8);
     memcpy(&vx->color, &c->currentColor, 4);
-    if (c->vertexCounter == verts_per_primitive(c->currentDrawMode)) {
+    if (c->vertexCounter == pfh_verts_per_primitive(c->currentDrawMode)) {
         pfh_process_primitive(c);
-        carry_over(c);
+        pfh_carry_over(c);
     }
 }
 
@@ -696,7 +702,7 @@ static void draw_indexed(PFdrawmode mode, PFsizei count, PFint first, int indexe
     int useTex = (c->state & PF_TEXTURE_COORD_ARRAY) && c->atex.buffer;
     int useNrm = (c->state & PF_NORMAL_ARRAY) && c->anrm.buffer;
     int useCol = (c->state & PF_COLOR_ARRAY) && c->acol.buffer;
-    PFsizei per = verts_per_primitive(mode);
+    PFsizei per = pfh_verts_per_primitive(mode);
 
     if (mode == PF_TRIANGLES && pfh_device_draw(c, count, first, indexed, itype, indices, useNrm, useTex, useCol)) {
         pfh_end_of_draw(c);
@@ -724,7 +730,7 @@ static void draw_indexed(PFdrawmode mode, PFsizei count, PFint first, int indexe
         if (useCol && !fetch_color(&c->acol, j, (PFcolor *)&vx->color)) { c->errCode = PF_INVALID_ENUM; if (indexed) return; }
         if (c->vertexCounter == per) {
             pfh_process_primitive(c);
-            carry_over(c);
+            pfh_carry_over(c);
         }
     }
     pfEnd();

@@ -84,7 +84,15 @@ typedef struct {
     PFdrawmode mode;
 } pf_call;
 
-typedef struct { pf_call *calls; size_t size, cap; } pf_list;
+/* A render list and its device-resident forms: the list's triangles assembled once per face mode
+ * (which faces a primitive is drawn for depends on the cull state at REPLAY time: 0 front only, 1 back only, 2 both,
+ * internal/context/context.c:94-244) and kept in HBM as unprocessed triangles (pfcu_list). */
+typedef struct {
+    pf_call *calls; size_t size, cap;
+    pfcu_list *dev[3]; uint32_t dev_tris[3]; int dev_state[3];     /* dev_state: 0 not built, 1 built, -1 cannot be built */
+    int colors_uniform;                                            /* every call carries one colour (checked when first compiled) */
+    int analysed;
+} pf_list;
 
 typedef struct {
     pf_material material[2];
@@ -152,6 +160,17 @@ typedef struct pf_ctx {
     pf_material    vp_material[2];              /* materials of the newest entry (may change per vertex with PF_COLOR_MATERIAL) */
     int            batch_raw;
     pfcu_prim     *prims; uint32_t n_prims, prims_cap;      /* pending points / lines (never together with triangles) */
+    /* pending replays of device-resident render lists (never together with triangles either): segments in replay order,
+       one pfcu_list_call per recorded call of each; states[] / vparams[] above hold what the calls refer to.  A pfClear
+       issued in explicit sync mode waits here too, so that clear + replays of many contexts go out as ONE submission
+       (pfcu_submit_list_jobs); any other drawing issues it at once. */
+    pfcu_list_segment *segs; uint32_t n_segs, segs_cap;
+    pfcu_list_call    *lcalls; uint32_t n_lcalls, lcalls_cap;
+    uint32_t       list_tris;
+    int            clear_pending; uint32_t clear_rgba; float clear_z;
+    int            registered;                               /* in the calling thread's table of contexts with pending list work */
+    /* list compilation: pfh_process_primitive appends assembled, unprocessed triangles here instead of batching them */
+    int            compiling; uint32_t cmp_call; pfcu_rawtri *cmp_tris; uint32_t cmp_n, cmp_cap;
     float         *pow_tables; float *pow_shininess; uint32_t n_pow, pow_cap;   /* specular tables by shininess */
     /* optional capture of the submitted stream (pfxCaptureBegin/End) */
     int            device_vertex;   /* large vertex-array draws run the vertex stage on the GPU (default on) */
@@ -176,6 +195,15 @@ void pfh_vstage_params(const pf_ctx *c, pfv_params *p);
 void pfh_update_view_pos(pf_ctx *c);
 #define PFH_VP_TOUCH(c) ((c)->vp_epoch++)
 void pfh_snapshot_state(pf_ctx *c, pfcu_state *st);
+int  pfh_call_list_device(pf_ctx *c, pf_list *l);      /* 1 = the replay was queued as device-resident segments */
+void pfh_lists_flush_all(pf_ctx *c);                   /* submit the pending list work of every context of this thread */
+int  pfh_lists_pending(void);
+void pfh_issue_pending_clear(pf_ctx *c);
+int  pfh_clear_deferrable(pf_ctx *c);
+void pfh_register_pending(pf_ctx *c);
+void pfh_list_release_device(pf_list *l);
+PFsizei pfh_verts_per_primitive(PFdrawmode m);
+void pfh_carry_over(pf_ctx *c);
 int  pfh_device_draw(pf_ctx *c, PFsizei count, PFint first, int indexed, PFdatatype itype, const void *indices,
                      int useNrm, int useTex, int useCol);    /* 1 = drawn on the device vertex path */   /* the state the next primitive would use */
 

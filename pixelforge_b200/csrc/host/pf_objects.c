@@ -366,6 +366,9 @@ void pfDeleteList(PFrenderlist *renderList)
     if (!renderList) return;
     pf_list *l = (pf_list *)*renderList;
     if (l) {
+        if (pf_cur) pfh_flush(pf_cur);
+        if (pfh_lists_pending()) pfh_lists_flush_all(pf_cur);      /* queued replays refer to the device copies */
+        pfh_list_release_device(l);
         for (size_t i = 0; i < l->size; i++) call_free(&l->calls[i]);
         free(l->calls);
         PF_FREE(l);
@@ -378,6 +381,9 @@ void pfNewList(PFrenderlist renderList)
     pf_ctx *c = pf_cur;
     if (!renderList) { c->errCode = PF_INVALID_VALUE; return; }
     pf_list *l = (pf_list *)renderList;
+    pfh_flush(c);
+    if (pfh_lists_pending()) pfh_lists_flush_all(c);
+    pfh_list_release_device(l);
     for (size_t i = 0; i < l->size; i++) call_free(&l->calls[i]);
     l->size = 0;
     c->recording = l;
@@ -424,6 +430,7 @@ void pfCallList(const PFrenderlist renderList)
 {
     pf_ctx *c = pf_cur;
     pf_list *l = (pf_list *)renderList;
+    if (pfh_call_list_device(c, l)) { pfh_end_of_draw(c); return; }     /* replayed from its device-resident form */
     backup_make(c);
     int outer = c->replaying;
     c->replaying = 1;

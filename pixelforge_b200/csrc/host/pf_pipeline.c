@@ -181,7 +181,8 @@ static int alloc_batch(pf_ctx *c, uint32_t cap)
 
 static int ensure_batch(pf_ctx *c)
 {
-    if (c->n_prims) pfh_flush(c);               /* points / lines submitted before this triangle come first */
+    if (c->n_prims || c->n_segs) pfh_flush(c);  /* points / lines / list replays submitted before this triangle come first */
+    if (c->clear_pending) pfh_issue_pending_clear(c);
     if (c->tris[0]) return 1;
     uint32_t cap = PFH_BATCH_TRIS_MIN;
     if (cap > batch_limit()) cap = batch_limit();
@@ -235,6 +236,10 @@ static void flush_prims(pf_ctx *c)
 
 void pfh_flush(pf_ctx *c)
 {
+    if (!c) return;
+    /* replays of device-resident lists (and a pfClear waiting with them) of this and every other context of the thread */
+    if (c->n_segs || pfh_lists_pending() > (c->registered ? 1 : 0)) pfh_lists_flush_all(c);
+    else if (c->clear_pending) pfh_issue_pending_clear(c);
     if (c && c->n_prims) flush_prims(c);
     if (!c || c->n_tris == 0) { if (c) { c->n_states = 0; c->state_dirty = 1; c->n_vparams = 0; } return; }
     pf_surf *s = c->cur_surf;
@@ -278,6 +283,7 @@ void pfh_queue_readback(pf_ctx *c, pf_surf *s)
 void pfh_sync_surface(pf_ctx *c, pf_surf *s)
 {
     if (c && c->cur_surf == s) pfh_flush(c);
+    if (pfh_lists_pending()) pfh_lists_flush_all(c);       /* another context of this thread may hold work for s */
     if (!s) return;
     if (s->dev_newer) {
         PFuint y0 = s->dirty_y0, y1 = s->dirty_y1;
@@ -601,6 +607,23 @@ static int raw_path(pf_ctx *c, const pfcu_vparams_lit *e)
 
 static void process_triangle(pf_ctx *c, int face, pf_vertex poly[PFH_MAX_POLY_VERTS])
 {
+    if (c->compiling) {         /* render-list compilation: keep the assembled triangle, unprocessed, tagged with its call */
+        if (c->cmp_n == c->cmp_cap) {
+            uint32_t nc = c->cmp_cap ? c->cmp_cap * 2 : 1024;
+            pfcu_rawtri *q = (pfcu_rawtri *)realloc(c->cmp_tris, (size_t)nc * sizeof *q);
+            if (!q) { c->errCode = PF_ERROR_OUT_OF_MEMORY; return; }
+            c->cmp_tris = q; c->cmp_cap = nc;
+        }
+        pfcu_rawtri *t = &c->cmp_tris[c->cmp_n++];
+        memset(t, 0, sizeof *t);
+        for (int i = 0; i < 3; i++) {
+            const pf_vertex *v = &poly[i];
+            memcpy(t->v[i].pos, v->position, 16); memcpy(t->v[i].normal, v->normal, 12);
+            memcpy(t->v[i].uv, v->texcoord, 8); t->v[i].rgba = v->color;
+        }
+        t->state = c->cmp_call; t->face = (uint8_t)face;
+        return;
+    }
     uint32_t vpi = 0;
     const pfcu_vparams_lit *e = current_vparams(c, &vpi);
     if (!e) return;
@@ -681,7 +704,8 @@ static void tri_strip(pf_ctx *c, int face, int count)
 
 static void emit_prim(pf_ctx *c, const pfcu_prim *p)
 {
-    if (c->n_tris) pfh_flush(c);                /* triangles submitted before this primitive come first */
+    if (c->n_tris || c->n_segs) pfh_flush(c);   /* triangles submitted before this primitive come first */
+    if (c->clear_pending) pfh_issue_pending_clear(c);
     if (c->n_prims == c->prims_cap) {
         uint32_t nc = c->prims_cap ? c->prims_cap * 2 : 256;
         pfcu_prim *q = (pfcu_prim *)realloc(c->prims, (size_t)nc * sizeof *q);
@@ -832,4 +856,231 @@ void pfh_process_primitive(pf_ctx *c)
         else tri_strip(c, one, cnt);
     } break;
     }
+}
+
+/* ---- device-resident render lists ---------------------------------------------------------
+ * The reference replays a list by re-issuing pfColor4ubv / pfTexCoordfv / pfNormal3fv / pfVertex4fv for every recorded
+ * vertex (renderlist.c:71-97).  What those calls compute from the context at replay time is small: the face passes
+ * (cull state), the prologue environment (matrices latched by pfBegin, lights, the call's materials - which pfColor
+ * feeds when PF_COLOR_MATERIAL is on) and the fragment state; the vertices themselves are the recorded ones as long as
+ * the texture matrix is the identity and PF_NORMALIZE is off.  So a list is assembled into triangles ONCE per face mode
+ * (with the very code that assembles immediate-mode primitives) and left on the device; a replay queues a reference to
+ * it plus one pfcu_list_call per recorded call.  Whatever does not fit (points / lines, polygon modes, a texture
+ * matrix, PF_NORMALIZE, per-vertex colours under PF_COLOR_MATERIAL, untabulable shininess, more than 1024 triangles)
+ * is replayed through the immediate-mode path as before. */
+
+static PF_CTX_DECL pf_ctx *g_pending[256];
+static PF_CTX_DECL int g_npending = 0;
+
+int pfh_lists_pending(void) { return g_npending; }
+
+void pfh_register_pending(pf_ctx *c)
+{
+    if (c->registered) return;
+    if (g_npending == 256) pfh_lists_flush_all(c);
+    g_pending[g_npending++] = c; c->registered = 1;
+}
+
+int pfh_clear_deferrable(pf_ctx *c)
+{
+    static int caps = -1;
+    if (caps < 0) caps = (int)pfcu_capabilities();
+    return (caps & PFCU_CAP_LISTS) && pfh_sync_mode_explicit() && c->device_vertex && !c->capturing && !c->recording && !c->replaying &&
+           c->cur_surf->tex->format == PF_RGBA && c->cur_surf->tex->type == PF_UNSIGNED_BYTE;
+}
+
+void pfh_issue_pending_clear(pf_ctx *c)
+{
+    if (!c->clear_pending) return;
+    c->clear_pending = 0;
+    pfcu_surface_clear_ref(c->cur_surf->dev, 1, c->clear_rgba, 1, c->clear_z);
+}
+
+void pfh_list_release_device(pf_list *l)
+{
+    for (int v = 0; v < 3; v++) { if (l->dev[v]) pfcu_list_destroy(l->dev[v]); l->dev[v] = NULL; l->dev_state[v] = 0; l->dev_tris[v] = 0; }
+    l->analysed = 0;
+}
+
+void pfh_lists_flush_all(pf_ctx *cur)
+{
+    if (cur && !cur->registered && (cur->n_segs || cur->clear_pending)) pfh_register_pending(cur);
+    if (g_npending == 0) return;
+    pfcu_list_job jobs[256];
+    int n = 0;
+    for (int i = 0; i < g_npending; i++) {
+        pf_ctx *x = g_pending[i];
+        if (!(x->n_segs || x->clear_pending)) continue;
+        pfcu_list_job *j = &jobs[n++];
+        memset(j, 0, sizeof *j);
+        j->surface = x->cur_surf->dev;
+        j->clear = (uint32_t)x->clear_pending; j->clear_rgba = x->clear_rgba; j->clear_depth = x->clear_z;
+        pfcu_state dummy_state; pfcu_vparams_lit dummy_vp;
+        if (x->n_states == 0) { memset(&dummy_state, 0, sizeof dummy_state); }
+        j->states = x->n_states ? x->states : NULL; j->n_states = x->n_states;
+        j->vparams = x->vparams; j->n_vparams = x->n_vparams;
+        j->pow_tables = x->pow_tables; j->n_pow_tables = x->n_pow;
+        j->calls = x->lcalls; j->n_calls = x->n_lcalls;
+        j->segments = x->segs; j->n_segments = x->n_segs;
+        (void)dummy_vp;
+    }
+    /* clear-only jobs carry no tables: give them an empty state / environment so that the C-ABI's checks hold */
+    static pfcu_state empty_state; static pfcu_vparams_lit empty_vp; static pfcu_list_call empty_call;
+    for (int i = 0; i < n; i++) {
+        if (!jobs[i].states) { jobs[i].states = &empty_state; jobs[i].n_states = 1; }
+        if (!jobs[i].vparams || jobs[i].n_vparams == 0) { jobs[i].vparams = &empty_vp; jobs[i].n_vparams = 1; }
+        if (!jobs[i].calls) { jobs[i].calls = &empty_call; jobs[i].n_calls = 1; }
+    }
+    if (n) {
+        int rc = pfcu_submit_list_jobs(jobs, (uint32_t)n);
+        if (rc != PFCU_OK) {
+            fprintf(stderr, "pixelforge-b200: pfcu_submit_list_jobs failed (%d): %s\n", rc, pfcu_last_error());
+            if (cur) cur->errCode = (rc == PFCU_ERR_OOM) ? PF_ERROR_OUT_OF_MEMORY : PF_INVALID_OPERATION;
+        }
+    }
+    const int np = g_npending;
+    g_npending = 0;
+    for (int i = 0; i < np; i++) {
+        pf_ctx *x = g_pending[i];
+        const int had = x->n_segs || x->clear_pending;
+        x->registered = 0;
+        x->n_segs = 0; x->n_lcalls = 0; x->list_tris = 0; x->clear_pending = 0;
+        if (x->n_tris == 0) { x->n_states = 0; x->n_vparams = 0; x->state_dirty = 1; }
+        if (had) {
+            pf_surf *s = x->cur_surf;
+            s->dev_newer = 1; s->readback_queued = 0; s->dirty_y0 = 0; s->dirty_y1 = s->tex->h;
+            if (x != cur && pfh_sync_mode_explicit()) pfh_queue_readback(x, s);      /* what leaving the context used to start */
+        }
+    }
+}
+
+static int mat_is_identity(const float *m)
+{
+    for (int i = 0; i < 16; i++) if (m[i] != ((i % 5 == 0) ? 1.0f : 0.0f)) return 0;
+    return 1;
+}
+
+/* Assemble the list's triangles for the face mode the context is in and put them on the device. */
+static void list_compile(pf_ctx *c, pf_list *l, int variant)
+{
+    pf_vertex saved[6]; memcpy(saved, c->vertexBuffer, sizeof saved);
+    const PFsizei saved_count = c->vertexCounter; const PFdrawmode saved_mode = c->currentDrawMode;
+    c->compiling = 1; c->cmp_n = 0;
+    for (size_t ci = 0; ci < l->size; ci++) {
+        const pf_call *k = &l->calls[ci];
+        c->cmp_call = (uint32_t)ci;
+        c->currentDrawMode = k->mode; c->vertexCounter = 0;
+        const PFsizei per = pfh_verts_per_primitive(k->mode);
+        for (size_t j = 0; j < k->positions.size; j++) {
+            pf_vertex *vx = &c->vertexBuffer[c->vertexCounter++];
+            memset(vx, 0, sizeof *vx);
+            memcpy(vx->position, k->positions.data + 4 * j, 16);
+            memcpy(vx->normal, k->normals.data + 3 * j, 12);
+            memcpy(vx->texcoord, k->texcoords.data + 2 * j, 8);
+            memcpy(&vx->color, k->colors.data + j, 4);
+            if (c->vertexCounter == per) { pfh_process_primitive(c); pfh_carry_over(c); }
+        }
+    }
+    c->compiling = 0;
+    memcpy(c->vertexBuffer, saved, sizeof saved); c->vertexCounter = saved_count; c->currentDrawMode = saved_mode;
+    l->dev_state[variant] = -1; l->dev_tris[variant] = c->cmp_n;
+    if (c->cmp_n == 0 || c->cmp_n > PFCU_LIST_JOB_MAX_TRIS) return;
+    l->dev[variant] = pfcu_list_create(c->cmp_tris, c->cmp_n);
+    if (l->dev[variant]) l->dev_state[variant] = 1;
+}
+
+int pfh_call_list_device(pf_ctx *c, pf_list *l)
+{
+    static int caps = -1;
+    if (caps < 0) caps = (int)pfcu_capabilities();
+    if (!(caps & PFCU_CAP_LISTS) || !c->device_vertex || c->capturing || c->recording || c->replaying || l->size == 0) return 0;
+    if ((c->state & PF_NORMALIZE) || !mat_is_identity(c->matTexture)) return 0;
+    const int culled = (c->state & PF_CULL_FACE) != 0;
+    const int variant = culled ? (c->cullFace == PF_BACK ? 0 : 1) : 2;      /* faces drawn: front only, back only, both */
+    if ((variant != 1 && c->polygonMode[0] != PF_FILL) || (variant != 0 && c->polygonMode[1] != PF_FILL)) return 0;
+    if (!l->analysed) {
+        l->analysed = 1; l->colors_uniform = 1;
+        for (size_t ci = 0; ci < l->size; ci++) {
+            const pf_call *k = &l->calls[ci];
+            if (k->mode < PF_TRIANGLES) { for (int v = 0; v < 3; v++) l->dev_state[v] = -1; break; }      /* points / lines: host replay */
+            for (size_t j = 1; j < k->colors.size; j++) if (memcmp(k->colors.data + j, k->colors.data, 4) != 0) { l->colors_uniform = 0; break; }
+        }
+    }
+    if ((c->state & PF_COLOR_MATERIAL) && !l->colors_uniform) return 0;
+    for (size_t ci = 0; ci < l->size; ci++) {
+        const pf_tex *t = (const pf_tex *)l->calls[ci].texture;
+        if (t && t->surf && t->surf == c->cur_surf) return 0;               /* sampling its own target: let the ordinary path sort it out */
+    }
+    if (l->dev_state[variant] == 0) list_compile(c, l, variant);
+    if (l->dev_state[variant] != 1) return 0;
+
+    pf_surf *s = c->cur_surf;
+    if (c->n_tris || c->n_prims) pfh_flush(c);                              /* earlier drawing comes first */
+    if (!pfcu_list_job_supported(s->dev, c->list_tris + l->dev_tris[variant], c->n_segs + 1)) {
+        if (c->n_segs) pfh_flush(c);
+        if (!pfcu_list_job_supported(s->dev, l->dev_tris[variant], 1)) return 0;
+    }
+    pfh_upload_if_needed(c, s);
+
+    /* what pfCallList does to the context around and inside the replay (renderlist.c:71-97), minus the vertices */
+    pf_backup keep = c->backup;
+    pf_material m0[2]; memcpy(m0, c->material, sizeof m0);
+    float tc0[2], n0[3]; memcpy(tc0, c->currentTexcoord, 8); memcpy(n0, c->currentNormal, 12);
+    const PFcolor col0 = c->currentColor; pf_tex *tex0 = c->currentTexture; const PFuint state0 = c->state;
+    const uint32_t first_call = c->n_lcalls, states0 = c->n_states, vparams0 = c->n_vparams;
+    int ok = 1;
+    c->replaying++;
+    for (size_t ci = 0; ci < l->size && ok; ci++) {
+        const pf_call *k = &l->calls[ci];
+        memcpy(c->material, k->material, sizeof c->material);
+        c->state_dirty = 1;
+        pfBindTexture(k->texture);
+        pfh_update_matrices(c, 1);                                          /* pfBegin of a triangle mode */
+        c->currentDrawMode = k->mode; c->vertexCounter = 0;
+        uint32_t override = 0, rgba = 0;
+        if (k->colors.size) {
+            PFcolor kc; memcpy(&kc, k->colors.data, 4);
+            if (c->state & PF_COLOR_MATERIAL) { pfColor(kc); override = 1; memcpy(&rgba, &c->currentColor, 4); }
+            else c->currentColor = kc;
+        }
+        const uint32_t sidx = current_state_index(c);
+        uint32_t vpi = 0;
+        const pfcu_vparams_lit *e = current_vparams(c, &vpi);
+        if (!e || !raw_path(c, e)) { ok = 0; break; }
+        if (c->n_lcalls == c->lcalls_cap) {
+            uint32_t nc = c->lcalls_cap ? c->lcalls_cap * 2 : 32;
+            pfcu_list_call *q = (pfcu_list_call *)realloc(c->lcalls, (size_t)nc * sizeof *q);
+            if (!q) { c->errCode = PF_ERROR_OUT_OF_MEMORY; ok = 0; break; }
+            c->lcalls = q; c->lcalls_cap = nc;
+        }
+        pfcu_list_call *lc = &c->lcalls[c->n_lcalls++];
+        lc->state = sidx; lc->vparams = vpi; lc->override_color = override; lc->rgba = rgba;
+        /* the last recorded vertex leaves its attributes behind (pfTexCoordfv / pfNormal3fv of the replay loop) */
+        if (k->positions.size) {
+            memcpy(c->currentTexcoord, k->texcoords.data + 2 * (k->positions.size - 1), 8);
+            memcpy(c->currentNormal, k->normals.data + 3 * (k->positions.size - 1), 12);
+        }
+    }
+    c->replaying--;
+    /* backup_restore of pfCallList: materials, current attributes, texture and enable bits come back */
+    memcpy(c->material, m0, sizeof m0); memcpy(c->currentTexcoord, tc0, 8); memcpy(c->currentNormal, n0, 12);
+    c->currentColor = col0; c->currentTexture = tex0; c->state = state0; c->state_dirty = 1; c->backup = keep;
+    PFH_VP_TOUCH(c);
+    if (!ok) {                                                              /* nothing was queued: the tables shrink back, the caller replays on the host */
+        c->n_lcalls = first_call;
+        if (c->n_segs == 0 && c->n_tris == 0) { c->n_states = states0; c->n_vparams = vparams0; }
+        return 0;
+    }
+    if (c->n_segs == c->segs_cap) {
+        uint32_t nc = c->segs_cap ? c->segs_cap * 2 : 16;
+        pfcu_list_segment *q = (pfcu_list_segment *)realloc(c->segs, (size_t)nc * sizeof *q);
+        if (!q) { c->errCode = PF_ERROR_OUT_OF_MEMORY; c->n_lcalls = first_call; return 0; }
+        c->segs = q; c->segs_cap = nc;
+    }
+    c->segs[c->n_segs].list = l->dev[variant]; c->segs[c->n_segs].first_call = first_call; c->segs[c->n_segs].pad = 0;
+    c->n_segs++; c->list_tris += l->dev_tris[variant];
+    c->tris_emitted += l->dev_tris[variant];
+    s->dirty_y0 = 0; s->dirty_y1 = s->tex->h;
+    pfh_register_pending(c);
+    return 1;
 }

@@ -106,8 +106,10 @@ struct pfcu_surface {
     int lane; cudaEvent_t done; bool has_done;      /* last work enqueued on this surface */
     uint32_t *peer_color; float *peer_depth;        /* present target (peer memory or another local surface), or nullptr */
     void *ipc_color, *ipc_depth;                    /* mappings opened with cudaIpcOpenMemHandle (to close) */
+    bool aliased;                                   /* a texture aliases the colour buffer (render to texture) */
 };
 struct pfcu_texture { uint32_t w, h; int fmt; unsigned char *pixels; bool owned; pfcu_surface *alias; bool leader; };
+struct pfcu_list { pfcu_rawtri *tris; uint32_t n; };
 struct pfcu_batch {
     DevState *states; uint32_t n_states; pfcu_triangle *tris; uint32_t n_tris; unsigned feature_mask; int single_prog; bool leader_tex;
     std::vector<pfcu_surface *> deps;
@@ -167,6 +169,13 @@ struct Runtime {
     std::vector<cudaEvent_t> prof_events;       /* triples: before setup, before raster, after raster */
     std::vector<cudaEvent_t> prof_pool;
     std::vector<pfcu_surface *> deps;           /* surfaces sampled as textures by the states being submitted */
+    /* render-list jobs (pfcu_submit_list_jobs): per-slot scratch, the packed upload and its pinned staging */
+    struct JobSlot {
+        pfcu_triangle *d_tris = nullptr; int4 *bbox = nullptr; TriSetup *setup = nullptr; TriData *data = nullptr; size_t cap_tris = 0;
+        uint2 *bin_list = nullptr; size_t cap_list = 0; unsigned *bin_start = nullptr; unsigned *d_total = nullptr; unsigned long long *chain = nullptr;
+    };
+    std::vector<JobSlot> job_slots;
+    unsigned char *d_jobs = nullptr, *h_jobs = nullptr; size_t cap_jobs = 0; cudaEvent_t jobs_copied = nullptr, jobs_done = nullptr; unsigned jobs_seq = 0;
     std::recursive_mutex mu;                    /* the C-ABI is serialised: contexts on several threads share one runtime */
     char err[512] = { 0 };
 };
@@ -211,6 +220,8 @@ __constant__ int c_rcp_shift, c_rsq_shift, c_rsq_bits;
 #include "pfcu_vertex_prims.cuh"
 
 #include "pfcu_surface.cuh"
+
+#include "pfcu_lists.cuh"
 
 /* ------------------------------------------------------------------------------------------------ */
 /* host: runtime                                                                                    */
@@ -337,6 +348,11 @@ void pfcu_shutdown(void)
     }
     cudaFree(g.d_counters); cudaFree(g.d_rcp); cudaFree(g.d_rsq);
     g.d_counters = nullptr; g.d_rcp = nullptr; g.d_rsq = nullptr;
+    for (auto &S : g.job_slots) { cudaFree(S.d_tris); cudaFree(S.bbox); cudaFree(S.setup); cudaFree(S.data); cudaFree(S.bin_list); cudaFree(S.bin_start); cudaFree(S.d_total); cudaFree(S.chain); }
+    g.job_slots.clear();
+    cudaFree(g.d_jobs); if (g.h_jobs) cudaFreeHost(g.h_jobs);
+    g.d_jobs = nullptr; g.h_jobs = nullptr; g.cap_jobs = 0;
+    if (g.jobs_copied) { cudaEventDestroy(g.jobs_copied); cudaEventDestroy(g.jobs_done); g.jobs_copied = g.jobs_done = nullptr; }
     /* blocks handed out by pfcu_host_alloc and never returned: released here, their pointers die with the runtime */
     for (auto &b : g.pinned) { cudaEventDestroy(b.done); cudaFreeHost(b.p); }
     for (auto e : g.prof_events) cudaEventDestroy(e);
@@ -763,6 +779,7 @@ pfcu_texture *pfcu_texture_from_surface(pfcu_surface *s)
        through the reference's BGRA8 getter, whose effect beyond the byte order is the leader replication */
     t->w = s->w; t->h = s->h; t->fmt = PFCU_TEX_RGBA8; t->pixels = (unsigned char *)s->color; t->owned = false; t->alias = s;
     t->leader = (s->fmt == PFCU_TEX_BGRA8);
+    s->aliased = true;
     return t;
 }
 
@@ -1080,7 +1097,7 @@ static int scan_exclusive(const unsigned *d_in, unsigned *d_out, unsigned n, uns
     return PFCU_OK;
 }
 
-unsigned pfcu_capabilities(void) { return PFCU_CAP_DEVICE_VERTEX | PFCU_CAP_RAW_TRIANGLES; }
+unsigned pfcu_capabilities(void) { return PFCU_CAP_DEVICE_VERTEX | PFCU_CAP_RAW_TRIANGLES | PFCU_CAP_LISTS; }
 
 int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vparams *vp, const pfcu_draw *d, uint32_t *n_out)
 {
@@ -1251,6 +1268,187 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
     CK(cudaEventRecord(LN.raw_done, LN.stream));
     CK(cudaGetLastError());
     return launch_pipeline(s, LN.d_tris, LN.d_states, total, mask, g_last_single_prog);
+}
+
+/* ---- device-resident render lists ---- */
+
+pfcu_list *pfcu_list_create(const pfcu_rawtri *tris, uint32_t n_tris)
+{
+    API_LOCK;
+    if (!g.ok || !tris || n_tris == 0) return nullptr;
+    pfcu_list *l = (pfcu_list *)calloc(1, sizeof *l);
+    if (!l) return nullptr;
+    l->n = n_tris;
+    g.cur = &g.lanes[0];
+    if (cudaMalloc(&l->tris, (size_t)n_tris * sizeof(pfcu_rawtri)) != cudaSuccess) { snprintf(g.err, sizeof g.err, "list_create: out of device memory"); free(l); return nullptr; }
+    if (cudaMemcpyAsync(l->tris, tris, (size_t)n_tris * sizeof(pfcu_rawtri), cudaMemcpyHostToDevice, LN.stream) != cudaSuccess ||
+        cudaStreamSynchronize(LN.stream) != cudaSuccess) { cudaFree(l->tris); free(l); return nullptr; }
+    g.bytes_h2d += (size_t)n_tris * sizeof(pfcu_rawtri);
+    return l;
+}
+
+void pfcu_list_destroy(pfcu_list *l)
+{
+    API_LOCK;
+    if (!l) return;
+    if (g.ok) sync_all_lanes();
+    cudaFree(l->tris); free(l);
+}
+
+uint32_t pfcu_list_size(const pfcu_list *l) { return l ? l->n : 0u; }
+
+int pfcu_list_job_supported(const pfcu_surface *s, uint32_t n_tris, uint32_t n_segments)
+{
+    if (!g.ok || !s || n_tris == 0 || n_tris > PFCU_LIST_JOB_MAX_TRIS || n_segments > PFCU_LIST_JOB_MAX_SEGMENTS) return 0;
+    if (s->fmt != PFCU_TEX_RGBA8 || s->world > 1) return 0;
+    return sync_free_bshift(s, n_tris) != 0;
+}
+
+int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n_jobs)
+{
+    API_LOCK;
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (n_jobs == 0) return PFCU_OK;
+    if (!jobs) return PFCU_ERR_INVALID;
+    if (!g.d_rcp) { snprintf(g.err, sizeof g.err, "pfcu_set_approx_tables() has not been called"); return PFCU_ERR_INVALID; }
+    Lane &L0 = g.lanes[0];
+    g.cur = &L0;
+    if (L0.need_fence_wait) L0.need_fence_wait = false;
+    L0.touched = true;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    /* ---- sizes, validation ---- */
+    size_t bytes = al(sizeof(DevJob) * (size_t)n_jobs);
+    unsigned feature = 0, max_slices = 0; size_t max_nb = 0;
+    std::vector<unsigned> n_raw(n_jobs);
+    for (uint32_t j = 0; j < n_jobs; j++) {
+        const pfcu_list_job &J = jobs[j];
+        if (!J.surface || !J.states || !J.vparams || !J.calls || (J.n_segments && !J.segments) || J.n_states == 0 || J.n_vparams == 0) return PFCU_ERR_INVALID;
+        unsigned n = 0;
+        for (uint32_t k = 0; k < J.n_segments; k++) { if (!J.segments[k].list) return PFCU_ERR_INVALID; n += J.segments[k].list->n; }
+        n_raw[j] = n;
+        if (n && !pfcu_list_job_supported(J.surface, n, J.n_segments)) { snprintf(g.err, sizeof g.err, "list job %u is outside the limits of pfcu_submit_list_jobs", j); return PFCU_ERR_INVALID; }
+        if (!n && (J.surface->fmt != PFCU_TEX_RGBA8)) return PFCU_ERR_INVALID;
+        bytes += al(sizeof(DevState) * J.n_states) + al(sizeof(pfcu_vparams_lit) * J.n_vparams) + al(sizeof(pfcu_list_call) * J.n_calls)
+               + al(sizeof(float) * PFCU_POW_TABLE_SIZE * J.n_pow_tables);
+    }
+    /* ---- slots and the packed upload ---- */
+    if (!g.jobs_copied) { CK(cudaEventCreateWithFlags(&g.jobs_copied, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&g.jobs_done, cudaEventDisableTiming)); }
+    if (bytes > g.cap_jobs) {
+        CK(cudaStreamSynchronize(L0.stream));
+        cudaFree(g.d_jobs); if (g.h_jobs) cudaFreeHost(g.h_jobs);
+        g.d_jobs = nullptr; g.h_jobs = nullptr; g.cap_jobs = 0;
+        size_t c = (size_t)1 << 16; while (c < bytes) c *= 2;
+        CK(cudaMalloc(&g.d_jobs, c)); CK(cudaHostAlloc(&g.h_jobs, c, cudaHostAllocDefault));
+        g.cap_jobs = c;
+    } else CK(cudaEventSynchronize(g.jobs_copied));          /* the previous submission has left the staging buffer */
+    if (g.job_slots.size() < n_jobs) g.job_slots.resize(n_jobs);
+    DevJob *hj = reinterpret_cast<DevJob *>(g.h_jobs);
+    size_t off = al(sizeof(DevJob) * (size_t)n_jobs);
+    for (uint32_t j = 0; j < n_jobs; j++) {
+        const pfcu_list_job &J = jobs[j];
+        pfcu_surface *s = J.surface;
+        DevJob &D = hj[j];
+        memset(&D, 0, sizeof D);
+        Runtime::JobSlot &S = g.job_slots[j];
+        const unsigned n = n_raw[j], bound = n * FRONT_SMALL_CHUNKS;
+        const int bshift = n ? sync_free_bshift(s, n) : BIN_SHIFT_COARSE;
+        const int binsX = (int)((s->w + (1u << bshift) - 1) >> bshift), binsY = (int)((s->h + (1u << bshift) - 1) >> bshift), nb = binsX * binsY;
+        if (bound > S.cap_tris || (size_t)bound * nb > S.cap_list || !S.bin_start) {
+            CK(cudaStreamSynchronize(L0.stream));
+            if (bound > S.cap_tris) {
+                cudaFree(S.d_tris); cudaFree(S.bbox); cudaFree(S.setup); cudaFree(S.data); S.cap_tris = 0;
+                size_t c = 1024; while (c < bound) c *= 2;
+                if (cudaMalloc(&S.d_tris, c * sizeof(pfcu_triangle)) != cudaSuccess || cudaMalloc(&S.bbox, c * sizeof(int4)) != cudaSuccess ||
+                    cudaMalloc(&S.setup, c * sizeof(TriSetup)) != cudaSuccess || cudaMalloc(&S.data, c * sizeof(TriData)) != cudaSuccess) {
+                    snprintf(g.err, sizeof g.err, "out of device memory for list job scratch"); return PFCU_ERR_OOM;
+                }
+                S.cap_tris = c;
+            }
+            if ((size_t)bound * nb > S.cap_list) {
+                cudaFree(S.bin_list); S.cap_list = 0;
+                size_t c = 4096; while (c < (size_t)bound * nb) c *= 2;
+                if (cudaMalloc(&S.bin_list, c * sizeof(uint2)) != cudaSuccess) { snprintf(g.err, sizeof g.err, "out of device memory for list job bins"); return PFCU_ERR_OOM; }
+                S.cap_list = c;
+            }
+            if (!S.bin_start) {
+                CK(cudaMalloc(&S.bin_start, (3072 + 2) * sizeof(unsigned)));
+                CK(cudaMalloc(&S.d_total, 64));
+                CK(cudaMalloc(&S.chain, 16 * sizeof(unsigned long long)));
+                CK(cudaMemset(S.chain, 0, 16 * sizeof(unsigned long long)));
+                CK(cudaMemset(S.d_total, 0, 64));
+            }
+        }
+        /* tables */
+        unsigned char *hb = g.h_jobs, *db = g.d_jobs;
+        DevState *hs = reinterpret_cast<DevState *>(hb + off); D.states = reinterpret_cast<const DevState *>(db + off);
+        const unsigned mask = convert_states(J.states, J.n_states, hs);
+        off += al(sizeof(DevState) * J.n_states);
+        if (g_last_leader_tex) { g_last_leader_tex = false; snprintf(g.err, sizeof g.err, "list jobs cannot sample BGRA8 textures (row-ordered path)"); return PFCU_ERR_INVALID; }
+        for (pfcu_surface *dep : g.deps) if (dep->has_done && dep->lane != 0) CK(cudaStreamWaitEvent(L0.stream, dep->done, 0));
+        g.deps.clear();
+        feature |= mask;
+        memcpy(hb + off, J.vparams, sizeof(pfcu_vparams_lit) * J.n_vparams); D.vp = reinterpret_cast<const pfcu_vparams_lit *>(db + off);
+        off += al(sizeof(pfcu_vparams_lit) * J.n_vparams);
+        memcpy(hb + off, J.calls, sizeof(pfcu_list_call) * J.n_calls); D.calls = reinterpret_cast<const pfcu_list_call *>(db + off);
+        off += al(sizeof(pfcu_list_call) * J.n_calls);
+        if (J.n_pow_tables) memcpy(hb + off, J.pow_tables, sizeof(float) * PFCU_POW_TABLE_SIZE * J.n_pow_tables);
+        D.pow_tables = reinterpret_cast<const float *>(db + off);
+        off += al(sizeof(float) * PFCU_POW_TABLE_SIZE * J.n_pow_tables);
+        unsigned first = 0;
+        for (uint32_t k = 0; k < J.n_segments; k++) {
+            D.seg[k].tris = J.segments[k].list->tris; D.seg[k].first_tri = first; D.seg[k].first_call = J.segments[k].first_call;
+            first += J.segments[k].list->n;
+        }
+        D.n_seg = J.n_segments; D.n_raw = n;
+        D.color = s->color; D.depth = s->depth; D.W = s->w; D.H = s->h;
+        D.clear = J.clear ? 1u : 0u; D.clear_rgba = J.clear_rgba; D.clear_z = J.clear_depth;
+        D.d_tris = S.d_tris; D.d_total = S.d_total; D.chain = S.chain;
+        D.binsX = binsX; D.binsY = binsY; D.bshift = bshift;
+        RasterParams &p = D.rp;
+        p.bbox = S.bbox; p.setup = S.setup; p.data = S.data; p.states = D.states;
+        p.bin_list = S.bin_list; p.bin_starts = S.bin_start; p.binsX = binsX; p.bsx = bshift; p.bsy = bshift;
+        p.color = s->color; p.depth = s->depth; p.W = (int)s->w; p.H = (int)s->h; p.tilesX = (int)s->tiles_x; p.tilesY = (int)s->tiles_y;
+        p.rank = 0; p.world = 1; p.nTiles = n ? s->tiles_x * s->tiles_y : 0u;      /* a job without triangles rasterises nothing */
+        p.counters = g.d_counters; p.nb = nb; p.list_cap = 0xffffffffu; p.n = 0;
+        if (n) { if (s->tiles_x * s->tiles_y * 8u > max_slices) max_slices = s->tiles_x * s->tiles_y * 8u; if ((size_t)nb > max_nb) max_nb = (size_t)nb; }
+        g.bytes_h2d += sizeof(DevState) * J.n_states + sizeof(pfcu_vparams_lit) * J.n_vparams + sizeof(pfcu_list_call) * J.n_calls + sizeof(DevJob);
+    }
+    /* ---- order against what is queued on the surfaces' own lanes, upload, four launches ---- */
+    bool lane_used[MAX_LANES] = { false };
+    for (uint32_t j = 0; j < n_jobs; j++) lane_used[jobs[j].surface->lane % g.n_lanes] = true;
+    for (int l = 1; l < g.n_lanes; l++) if (lane_used[l]) {
+        Lane &Ln = g.lanes[l];
+        if (Ln.need_fence_wait) { cudaStreamWaitEvent(Ln.stream, g.lanes[0].fence, 0); Ln.need_fence_wait = false; }
+        CK(cudaEventRecord(Ln.vready, Ln.stream));
+        CK(cudaStreamWaitEvent(L0.stream, Ln.vready, 0));
+    }
+    CK(cudaMemcpyAsync(g.d_jobs, g.h_jobs, off, cudaMemcpyHostToDevice, L0.stream));
+    CK(cudaEventRecord(g.jobs_copied, L0.stream));
+    const DevJob *dj = reinterpret_cast<const DevJob *>(g.d_jobs);
+    bool any_clear = false; for (uint32_t j = 0; j < n_jobs; j++) any_clear |= jobs[j].clear != 0;
+    if (any_clear) { k_jobs_clear<<<dim3(32, n_jobs), 256, 0, L0.stream>>>(dj); g.launches++; }
+    if (max_slices) {
+        if (++g.jobs_seq == 0) ++g.jobs_seq;
+        CK(launch_dep(k_list_chain, dim3(PFCU_LIST_JOB_MAX_TRIS / 128u, n_jobs), dim3(128), 0, L0.stream, dj, g.jobs_seq));
+        CK(launch_dep(k_front_small_jobs, dim3(1, n_jobs), dim3(1024), max_nb * sizeof(unsigned), L0.stream, dj, g.d_counters));
+        static const bool attr_once = [] {
+            cudaFuncSetAttribute(k_raster_frag_jobs<true, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * FRAG_NF_PHONG * 512);
+            cudaFuncSetAttribute(k_raster_frag_jobs<false, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * FRAG_NF * 512);
+            return true; }();
+        (void)attr_once;
+        if (feature & PFCU_ST_PHONG) CK(launch_dep(k_raster_frag_jobs<true, 8, 3>, dim3(max_slices, n_jobs), dim3(256), (size_t)(8 * FRAG_NF_PHONG * 512), L0.stream, dj));
+        else                         CK(launch_dep(k_raster_frag_jobs<false, 8, 4>, dim3(max_slices, n_jobs), dim3(256), (size_t)(8 * FRAG_NF * 512), L0.stream, dj));
+        g.launches += 3;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(g.jobs_done, L0.stream));
+    for (int l = 1; l < g.n_lanes; l++) if (lane_used[l]) { CK(cudaStreamWaitEvent(g.lanes[l].stream, g.jobs_done, 0)); g.lanes[l].touched = true; }
+    for (uint32_t j = 0; j < n_jobs; j++) {
+        pfcu_surface *s = jobs[j].surface;
+        if (s->aliased) { if (cudaEventRecord(s->done, L0.stream) == cudaSuccess) s->has_done = true; }     /* someone may sample it from another lane */
+        else s->has_done = false;          /* its lane already waits for this submission (above) */
+    }
+    return PFCU_OK;
 }
 
 int pfcu_submit_prims(pfcu_surface *s, const pfcu_prim *prims, uint32_t n)

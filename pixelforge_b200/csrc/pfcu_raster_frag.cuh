@@ -344,9 +344,8 @@ __device__ __forceinline__ void frag_group(FragCtx &t, GroupState &G, const int4
     }
 }
 
-template <bool HAS_PHONG, int NW, int MINB>
-__global__ void __launch_bounds__(NW * 32, MINB)
-k_raster_frag(const RasterParams p)
+template <bool HAS_PHONG, int NW>
+__device__ __forceinline__ void raster_frag_body(const RasterParams &p)
 {
     pdl_wait();         /* launched as a programmatic dependent of the binning kernels; before ANY exit, so that the grid cannot complete early */
     constexpr int NT = NW * 32, TH = NW, SUB = TILE / TH;
@@ -543,4 +542,11 @@ k_raster_frag(const RasterParams p)
         if (shaded) atomicAdd(p.counters + 1, (unsigned long long)shaded);
         if (zfailed) atomicAdd(p.counters + 2, (unsigned long long)zfailed);
     }
+}
+
+template <bool HAS_PHONG, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+k_raster_frag(const RasterParams p)
+{
+    raster_frag_body<HAS_PHONG, NW>(p);
 }

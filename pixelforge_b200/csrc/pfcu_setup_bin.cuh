@@ -338,11 +338,11 @@ k_bin_fill(const int4 *__restrict__ bbox, unsigned n, unsigned batch, int binsX,
  * owns the bin columns bx & 31 == w (see k_bin_fill). */
 #define FRONT_SMALL_MAX 1024
 #define FRONT_SMALL_CHUNKS 10           /* with a device-side count (raw batches after clipping): up to 10 x 1024 */
-__global__ void __launch_bounds__(1024)
-k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ states, unsigned n_host, const unsigned *__restrict__ d_n,
-              int surfW, int surfH,
-              int4 *__restrict__ bbox, TriSetup *__restrict__ setup, TriData *__restrict__ data, unsigned long long *__restrict__ counters,
-              int binsX, int binsY, int bshift, int bshy, unsigned *__restrict__ starts, uint2 *__restrict__ list)
+__device__ __forceinline__ void
+front_small_body(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ states, unsigned n_host, const unsigned *__restrict__ d_n,
+                 int surfW, int surfH,
+                 int4 *__restrict__ bbox, TriSetup *__restrict__ setup, TriData *__restrict__ data, unsigned long long *__restrict__ counters,
+                 int binsX, int binsY, int bshift, int bshy, unsigned *__restrict__ starts, uint2 *__restrict__ list)
 {
     extern __shared__ unsigned s_mem[];
     unsigned *s_pos = s_mem;                    /* [nb] counts, then running write positions */
@@ -464,4 +464,13 @@ k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(1024)
+k_front_small(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ states, unsigned n_host, const unsigned *__restrict__ d_n,
+              int surfW, int surfH,
+              int4 *__restrict__ bbox, TriSetup *__restrict__ setup, TriData *__restrict__ data, unsigned long long *__restrict__ counters,
+              int binsX, int binsY, int bshift, int bshy, unsigned *__restrict__ starts, uint2 *__restrict__ list)
+{
+    front_small_body(tris, states, n_host, d_n, surfW, surfH, bbox, setup, data, counters, binsX, binsY, bshift, bshy, starts, list);
 }

@@ -87,26 +87,34 @@ k_vertex_emit(const VtxArgs a, const pfv_params vp, unsigned n_items, const unsi
 /* ---- raw triangles (immediate mode, render lists): the whole per-triangle prologue on the device ---- */
 struct RawArgs { const pfcu_rawtri *tris; const pfcu_vparams_lit *vp; const float *pow_tables; unsigned n; };
 
-__device__ __forceinline__ int raw_process(const RawArgs &a, unsigned i, pfv_vertex *poly, int *is3d, int *face_out, unsigned *state)
+/* the reference's per-triangle prologue + clipping for one unprocessed triangle in prologue environment e; the vertices
+   carry colour `rgba` instead of their own when override is set (render-list replay under PF_COLOR_MATERIAL) */
+__device__ __forceinline__ int raw_process_tri(const pfcu_rawtri *t, const pfcu_vparams_lit *e, const float *pow_tables, bool override, unsigned rgba,
+                                               pfv_vertex *poly, int *is3d, int *face_out)
 {
-    const pfcu_rawtri *t = a.tris + i;
-    const pfcu_vparams_lit *e = a.vp + t->vparams;
     const int face = t->face;
-    *face_out = face; *state = t->state;
+    *face_out = face;
     for (int k = 0; k < 3; k++) {
         const pfcu_rawvertex *r = &t->v[k];
         pfv_vertex *v = &poly[k];
         for (int j = 0; j < 4; j++) v->position[j] = r->pos[j];
         for (int j = 0; j < 3; j++) v->normal[j] = r->normal[j];
         v->texcoord[0] = r->uv[0]; v->texcoord[1] = r->uv[1];
-        v->color = r->rgba;
+        v->color = override ? rgba : r->rgba;
         v->screen[0] = 0.0f; v->screen[1] = 0.0f;
         for (int j = 0; j < 4; j++) v->homogeneous[j] = 0.0f;
-        if (e->base.lighting) pfv_prologue_lit(e, a.pow_tables, face, v);
+        if (e->base.lighting) pfv_prologue_lit(e, pow_tables, face, v);
     }
     int n = 3;
     *is3d = pfv_project_and_clip(&e->base, poly, &n);
     return n >= 3 ? n - 2 : 0;
+}
+
+__device__ __forceinline__ int raw_process(const RawArgs &a, unsigned i, pfv_vertex *poly, int *is3d, int *face_out, unsigned *state)
+{
+    const pfcu_rawtri *t = a.tris + i;
+    *state = t->state;
+    return raw_process_tri(t, a.vp + t->vparams, a.pow_tables, false, 0u, poly, is3d, face_out);
 }
 
 __global__ void __launch_bounds__(128)

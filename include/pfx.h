@@ -64,6 +64,11 @@ PF_API void  pfxHostFree(void *p);
  * memory at every fragment, so a program that rewrites texels in place (video frames, procedural updates) calls this
  * after each rewrite to have them uploaded again.  Draw calls issued before it keep the old texels. */
 PF_API void pfxTextureDirty(PFtexture texture);
+/* Explicit sync mode starts the read-back of a context's (page-locked) target buffer as soon as the context is left or
+ * its queued work is submitted, so that presenting many contexts does not pay one blocking copy after the other.  A
+ * caller that renders contexts it will not read back this frame (device-side consumers, benchmarks of the render rate)
+ * turns that off; pfxFinish and the API's read-back points still deliver the pixels. */
+PF_API void pfxEnableQueuedReadback(PFboolean on);
 /* The pfcu_surface* behind the current target. */
 PF_API void *pfxGetSurfaceHandle(void);
 PF_API const char *pfxBackendName(void);

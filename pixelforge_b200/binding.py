@@ -185,11 +185,12 @@ PFCU_SYMBOLS = [
     "pfcu_set_raster_path", "pfcu_submit_raw", "pfcu_submit_prims", "pfcu_surface_download_async", "pfcu_surface_wait", "pfcu_surface_ipc_handles", "pfcu_surface_set_present_peer",
     "pfcu_surface_set_present_surface", "pfcu_surface_clear_present", "pfcu_surface_push_tiles",
     "pfcu_surface_create_format", "pfcu_surface_format",
+    "pfcu_list_create", "pfcu_list_destroy", "pfcu_list_size", "pfcu_list_job_supported", "pfcu_submit_list_jobs",
 ]
 
 PFX_SYMBOLS = ["pfxSetSyncMode", "pfxFlush", "pfxFinish", "pfxGetCounters", "pfxResetCounters", "pfxSetTileOwner",
                "pfxGetDeviceColor", "pfxGetDeviceDepth", "pfxReadDepth", "pfxCaptureBegin", "pfxCaptureEnd",
-               "pfxGetSurfaceHandle", "pfxBackendName", "pfxEnableDeviceVertexStage", "pfxSpecularTableCheck", "pfxHostAlloc", "pfxHostFree", "pfxTextureDirty"]
+               "pfxGetSurfaceHandle", "pfxBackendName", "pfxEnableDeviceVertexStage", "pfxSpecularTableCheck", "pfxHostAlloc", "pfxHostFree", "pfxTextureDirty", "pfxEnableQueuedReadback"]
 
 
 class PfcuLib:
@@ -233,7 +234,7 @@ class PfcuLib:
             "pfxGetDeviceColor": (vp, []), "pfxGetDeviceDepth": (vp, []), "pfxGetSurfaceHandle": (vp, []),
             "pfxCaptureBegin": (None, []),
             "pfxCaptureEnd": (None, [C.POINTER(vp), C.POINTER(u32), C.POINTER(vp), C.POINTER(u32)]),
-            "pfxResetCounters": (None, []),
+            "pfxResetCounters": (None, []), "pfxEnableQueuedReadback": (None, [C.c_ubyte]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)

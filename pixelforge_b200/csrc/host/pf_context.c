@@ -160,7 +160,14 @@ void pfMakeCurrent(PFcontext ctx)
         if (pfh_sync_mode_explicit()) {
             /* a context whose pending work is a clear and / or replays of device-resident lists keeps it: the work of
                all such contexts of this thread goes out together (one multi-surface submission) at the next flush */
-            if (pf_cur->n_tris == 0 && pf_cur->n_prims == 0 && (pf_cur->n_segs || pf_cur->clear_pending)) pfh_register_pending(pf_cur);
+            if (pf_cur->n_tris == 0 && pf_cur->n_prims == 0 && (pf_cur->n_segs || pf_cur->clear_pending)) {
+                pfh_register_pending(pf_cur);
+                /* ... in chunks: the first contexts of a long round are rendered and on their way back over PCIe (the
+                   read-backs are what a many-context frame waits for) while the application still draws the next ones */
+                static int chunk = 0;
+                if (!chunk) { const char *e = getenv("PF_CUDA_LIST_CHUNK"); chunk = e && atoi(e) > 0 ? atoi(e) : 32; }      /* measured on C5: below ~16 the per-submission cost outweighs the earlier start */
+                if (pfh_lists_pending() >= chunk) pfh_lists_flush_all(NULL);
+            }
             else { pfh_flush(pf_cur); pfh_queue_readback(pf_cur, pf_cur->cur_surf); }
         } else pfh_sync_surface(pf_cur, pf_cur->cur_surf);
     }

@@ -269,9 +269,12 @@ void pfh_flush(pf_ctx *c)
  * queue the read-back of what this context drew right behind its kernels, so that it overlaps with the drawing of
  * the next contexts instead of being paid, one blocking copy after the other, when they are presented.  Only for
  * page-locked mirrors (the copy is then a plain DMA); drawing to the surface again simply invalidates it. */
+static int g_queue_readback = 1;
+void pfxEnableQueuedReadback(PFboolean on) { g_queue_readback = on ? 1 : 0; }
+
 void pfh_queue_readback(pf_ctx *c, pf_surf *s)
 {
-    if (!s || !s->dev_newer || s->readback_queued || !s->pinned_color) return;
+    if (!g_queue_readback || !s || !s->dev_newer || s->readback_queued || !s->pinned_color) return;
     if (s->zhost && !s->pinned_depth) return;
     PFuint y0 = s->dirty_y0, y1 = s->dirty_y1;
     if (y1 > s->tex->h) y1 = s->tex->h;

@@ -1426,7 +1426,15 @@ int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n_jobs)
     CK(cudaEventRecord(g.jobs_copied, L0.stream));
     const DevJob *dj = reinterpret_cast<const DevJob *>(g.d_jobs);
     bool any_clear = false; for (uint32_t j = 0; j < n_jobs; j++) any_clear |= jobs[j].clear != 0;
+    cudaEvent_t pe[3] = { nullptr, nullptr, nullptr };
+    if (g.profiling) {
+        for (int i = 0; i < 3; i++) {
+            if (!g.prof_pool.empty()) { pe[i] = g.prof_pool.back(); g.prof_pool.pop_back(); }
+            else CK(cudaEventCreate(&pe[i]));
+        }
+    }
     if (any_clear) { k_jobs_clear<<<dim3(32, n_jobs), 256, 0, L0.stream>>>(dj); g.launches++; }
+    if (g.profiling) CK(cudaEventRecord(pe[0], L0.stream));
     if (max_slices) {
         if (++g.jobs_seq == 0) ++g.jobs_seq;
         CK(launch_dep(k_list_chain, dim3(PFCU_LIST_JOB_MAX_TRIS / 128u, n_jobs), dim3(128), 0, L0.stream, dj, g.jobs_seq));
@@ -1436,10 +1444,12 @@ int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n_jobs)
             cudaFuncSetAttribute(k_raster_frag_jobs<false, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * FRAG_NF * 512);
             return true; }();
         (void)attr_once;
+        if (g.profiling) CK(cudaEventRecord(pe[1], L0.stream));
         if (feature & PFCU_ST_PHONG) CK(launch_dep(k_raster_frag_jobs<true, 8, 3>, dim3(max_slices, n_jobs), dim3(256), (size_t)(8 * FRAG_NF_PHONG * 512), L0.stream, dj));
         else                         CK(launch_dep(k_raster_frag_jobs<false, 8, 4>, dim3(max_slices, n_jobs), dim3(256), (size_t)(8 * FRAG_NF * 512), L0.stream, dj));
         g.launches += 3;
-    }
+    } else if (g.profiling) CK(cudaEventRecord(pe[1], L0.stream));
+    if (g.profiling) { CK(cudaEventRecord(pe[2], L0.stream)); for (int i = 0; i < 3; i++) g.prof_events.push_back(pe[i]); }
     CK(cudaGetLastError());
     CK(cudaEventRecord(g.jobs_done, L0.stream));
     for (int l = 1; l < g.n_lanes; l++) if (lane_used[l]) { CK(cudaStreamWaitEvent(g.lanes[l].stream, g.jobs_done, 0)); g.lanes[l].touched = true; }

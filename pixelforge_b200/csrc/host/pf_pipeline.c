@@ -1046,10 +1046,10 @@ int pfh_call_list_device(pf_ctx *c, pf_list *l)
             if (c->state & PF_COLOR_MATERIAL) { pfColor(kc); override = 1; memcpy(&rgba, &c->currentColor, 4); }
             else c->currentColor = kc;
         }
-        const uint32_t sidx = current_state_index(c);
         uint32_t vpi = 0;
-        const pfcu_vparams_lit *e = current_vparams(c, &vpi);
+        const pfcu_vparams_lit *e = current_vparams(c, &vpi);               /* first: it brings the view position up to date, which a Phong state snapshots */
         if (!e || !raw_path(c, e)) { ok = 0; break; }
+        const uint32_t sidx = current_state_index(c);
         if (c->n_lcalls == c->lcalls_cap) {
             uint32_t nc = c->lcalls_cap ? c->lcalls_cap * 2 : 32;
             pfcu_list_call *q = (pfcu_list_call *)realloc(c->lcalls, (size_t)nc * sizeof *q);

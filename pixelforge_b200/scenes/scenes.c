@@ -654,14 +654,19 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
             gears_setup(w, h);
             pfEnable(PF_TEXTURE_2D);
             static const double gp[3][5] = { { 1.0, 4.0, 1.0, 20, 0.7 }, { 0.5, 2.0, 2.0, 10, 0.7 }, { 1.3, 2.0, 0.5, 10, 0.7 } };
+            /* variant bits of "batch": 1 culling off (both face passes), 2 no PF_COLOR_MATERIAL at replay, 4 lists recorded
+               with one colour per gear, 8 a texture matrix at replay, 16 front faces culled, 32 per-pixel Phong, 64 the
+               first list is recorded again before every frame */
             for (int g = 0; g < 3; g++) {
                 s->lists[c][g] = pfGenList();
                 pfBindTexture(s->texs[c]);
+                if (cfg->variant & 4) pfColor4ub((PFubyte)(90 + 60 * g), (PFubyte)(250 - 70 * g), (PFubyte)(120 + 40 * g), (PFubyte)(255 - 30 * g));
                 pfNewList(s->lists[c][g]);
                 pfTexCoord2f(0.25f * (float)g, 0.5f);
                 gear(gp[g][0], gp[g][1], gp[g][2], (int)gp[g][3], gp[g][4]);
                 pfEndList();
             }
+            pfColor4ub(255, 255, 255, 255);
         }
         return s;
     }
@@ -748,8 +753,19 @@ SCN_API void pfscene_frame(void *handle, int frame)
         for (int c = 0; c < s->n; c++) {
             pfMakeCurrent(s->ctxs[c]);
             float angle = 7.0f * (float)c + 1.44f * (float)frame;
+            const int bv = cfg->variant;
             pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
-            pfEnable(PF_COLOR_MATERIAL); pfColorMaterial(PF_FRONT_AND_BACK, PF_AMBIENT_AND_DIFFUSE);
+            if (!(bv & 2)) { pfEnable(PF_COLOR_MATERIAL); pfColorMaterial(PF_FRONT_AND_BACK, PF_AMBIENT_AND_DIFFUSE); }
+            if (bv & 1) pfDisable(PF_CULL_FACE); else { pfEnable(PF_CULL_FACE); pfCullFace((bv & 16) ? PF_FRONT : PF_BACK); }
+            if (bv & 8) { pfMatrixMode(PF_TEXTURE); pfLoadIdentity(); pfScalef(2.0f, 0.5f, 1.0f); pfMatrixMode(PF_MODELVIEW); }
+            pfLightModel((bv & 32) ? PF_PHONG : PF_GOURAUD);
+            if ((bv & 64) && frame > 0) {
+                pfBindTexture(s->texs[c]);
+                pfNewList(s->lists[c][0]);
+                pfTexCoord2f(0.125f * (float)(frame & 3), 0.25f);
+                gear(1.0, 4.0, 1.0 + 0.25 * (frame & 1), 20, 0.7);
+                pfEndList();
+            }
             pfPushMatrix();
             pfRotatef(20.0f, 1.0f, 0.0f, 0.0f); pfRotatef(30.0f, 0.0f, 1.0f, 0.0f);
             static const float tr[3][2] = { { -3.0f, -2.0f }, { 3.1f, -2.0f }, { -3.1f, 4.2f } };
@@ -764,6 +780,7 @@ SCN_API void pfscene_frame(void *handle, int frame)
             }
             pfPopMatrix();
             pfDisable(PF_COLOR_MATERIAL);
+            if (bv & 8) { pfMatrixMode(PF_TEXTURE); pfLoadIdentity(); pfMatrixMode(PF_MODELVIEW); }
         }
         return;
     }

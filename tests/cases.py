@@ -63,6 +63,18 @@ CASES += [_micro(f"random{s}", s, size=60, blend=s % 8, depth=s % 6, tex=s & 1, 
 
 
 
+# render-list replay in the states that decide how a device-resident list is replayed - both face
+# passes / front-face culling (one assembled form per face mode), with and without PF_COLOR_MATERIAL (pfColor feeds the
+# material and the vertices take the current colour, or the recorded colours are used), per-pixel Phong, a texture
+# matrix at replay (not expressible on the device: immediate-mode replay), a list recorded again between frames
+CASES += [("c5-batch-cull-off", "batch", 256, 256, dict(size=2, variant=1), False),
+          ("c5-batch-cull-front-nocolormat", "batch", 256, 256, dict(size=2, variant=2 | 16), False),
+          ("c5-batch-recorded-colours", "batch", 256, 256, dict(size=2, variant=2 | 4), False),
+          ("c5-batch-recorded-colours-colormat", "batch", 256, 256, dict(size=2, variant=4), False),
+          ("c5-batch-phong-cull-off", "batch", 200, 160, dict(size=2, variant=1 | 32), False),
+          ("c5-batch-texmatrix", "batch", 256, 256, dict(size=2, variant=8), False),
+          ("c5-batch-rerecorded-f2", "batch", 256, 256, dict(size=2, variant=64, first_frame=0, frames=3), False)]
+
 # BGRA8 / BGR8 textures and BGRA8 / RGB8 / BGR8 render targets against the LIVE reference.  The
 # reference's BGRA8 getter and setter hand the first pixel of every group of four (counted from the triangle's xMin) to
 # the whole group (Q19); these cases pin that behaviour - texel replication with per-pixel bilinear weights, the

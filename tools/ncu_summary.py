@@ -4,7 +4,7 @@
 """
 import csv, io, json, os, subprocess, sys
 
-KEEP = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+KEEP = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "lts__t_sectors.sum", "lts__t_sectors_srcunit_tex.sum",
         "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
         "launch__block_size", "smsp__thread_inst_executed_per_inst_executed.ratio",
@@ -24,6 +24,10 @@ def main():
         if k in h:
             i = h.index(k)
             d[k] = (r[i] + " " + units[i]).strip()
+    if "lts__t_sectors.sum" in d:       # L2 traffic in bytes (32-byte sectors), the figure SURVEY 8-d asks for beside dram__bytes
+        d["lts_t_bytes (sectors x 32)"] = "%.3f Mbyte" % (float(d["lts__t_sectors.sum"].split()[0]) * 32 / 1e6)
+    st = sorted(((float(r[i]), k) for i, k in enumerate(h) if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and "not_issued" not in k), reverse=True)
+    d["stalls_per_issue_top"] = {k.split("issue_stalled_")[1].split("_per_")[0]: round(v, 3) for v, k in st[:8]}
     allj = json.load(open(out)) if os.path.exists(out) else {}
     allj[label] = d
     json.dump(allj, open(out, "w"), indent=1)

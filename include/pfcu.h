@@ -209,6 +209,56 @@ PFCU_API int pfcu_surface_set_present_surface(pfcu_surface *s, pfcu_surface *tar
 PFCU_API int pfcu_surface_clear_present(pfcu_surface *s);
 PFCU_API int pfcu_surface_push_tiles(pfcu_surface *s, uint32_t rank, uint32_t world, int with_depth);
 
+/* ---- full-surface operations on the device (SURVEY 8-f "next" row 3) -------------------------------------------
+ * pfRect*, pfDrawPixels, pfFogProcess and pfReadPixels of the reference are loops over the framebuffer with the SCALAR
+ * getters / setters, blend table and depth table (context.c:1938-1977, 1988-2084, 2275-2344, 2349-2395).  The front end
+ * does what the reference does before its loop (projection of the corner / raster position, clamping to the viewport)
+ * and the device runs the loop on the surface, ordered after everything submitted before - no read-back, no host
+ * mirror.  Pixels are addressed as y * W + x like upstream (a column one past the right edge, which a viewport smaller
+ * than the buffer allows - SURVEY Q20 - lands in the next row); addresses outside the buffer are dropped. */
+
+/* pfRectf: every pixel of the inclusive rectangle takes `rgba` (context.c:1972-1976). */
+PFCU_API int pfcu_surface_rect(pfcu_surface *s, int32_t x1, int32_t y1, int32_t x2, int32_t y2, uint32_t rgba);
+
+/* pfFogProcess (context.c:2310-2342).  depth >= end: the fog colour (blended with PF_BLEND_ALPHA unless its alpha is
+ * 255); start < depth < end: the fog colour with alpha (PFubyte)(t * alpha) blended over the pixel, t = (depth - start)
+ * * inv_len (PF_LINEAR), 1 - expf(-density * (depth - start)) (PF_EXP) or 1 - exp2f(...) (PF_EXP2).  expf / exp2f are
+ * the HOST libm's and are not correctly rounded, so the device cannot recompute them: for the two exponential modes the
+ * front end tabulates, by bisection over float bit patterns with its own libm, thresholds[k-1] = the smallest depth in
+ * (start, end) whose fog alpha is >= k (k = 1 .. n_thresholds) and the device counts thresholds <= depth - the same
+ * device as the Gouraud specular tables (PFCU_POW_TABLE_SIZE above).  The oracle ignores the table and calls libm. */
+typedef struct {
+    float    start, end, inv_len;   /* inv_len = 1 / (end - start), the front end's IEEE single division        */
+    float    density;
+    uint32_t rgba;                  /* fog colour, alpha included                                                */
+    uint32_t mode;                  /* PFfogmode: 0 linear, 1 exp, 2 exp2; 3: any other value (t = 0 upstream)   */
+    const float *thresholds;        /* host pointer, exponential modes only                                      */
+    uint32_t n_thresholds;          /* <= 255                                                                    */
+} pfcu_fog;
+PFCU_API int pfcu_surface_fog(pfcu_surface *s, const pfcu_fog *fog);
+
+/* pfDrawPixels (context.c:2026-2077): nearest-neighbour copy of a host image into the inclusive rectangle
+ * [xmin, xmax] x [ymin, ymax] (already clamped to the viewport), source texel ((PFsizei)(v * (height - 1))) * width +
+ * (PFsizei)(u * (width - 1)) with u = (x - xs) * inv_xlen, v = (y - ys) * inv_ylen; depth test against the constant
+ * `z` with the scalar table (depth.h:28-78; NOTEQUAL really is "not equal" there), z written where it passes, colour
+ * through the scalar blend table (blend.h:29-130).  `format` is a PFCU_TEX_* code. */
+typedef struct {
+    const void *pixels; uint32_t width, height; int format;
+    int32_t  xs, ys;                /* the raster position on the screen                                         */
+    int32_t  xmin, ymin, xmax, ymax;
+    float    inv_xlen, inv_ylen;    /* 1 / (width * zoom_x), 1 / (height * zoom_y)                               */
+    float    z;
+    uint32_t flags;                 /* PFCU_ST_BLEND | PFCU_ST_DEPTH_TEST                                        */
+    uint8_t  blend_mode, depth_func; uint16_t pad;
+} pfcu_pixels;
+PFCU_API int pfcu_surface_draw_pixels(pfcu_surface *s, const pfcu_pixels *d);
+
+/* pfReadPixels (context.c:2349-2395): the surface's pixels [x0, x0+cols) x [y0, y0+rows) converted to `format`
+ * (PFCU_TEX_*) on the device and copied to host_pixels, pixel (x, y) at index (y - y0) * dst_width + (x - x0); nothing
+ * else of the destination is touched.  Returns after the data is on the host. */
+PFCU_API int pfcu_surface_read_pixels(pfcu_surface *s, uint32_t x0, uint32_t y0, uint32_t cols, uint32_t rows,
+                                      uint32_t dst_width, int format, void *host_pixels);
+
 /* ---- textures (texture.c:30-69) -------------------------------------------------------------- */
 PFCU_API pfcu_texture *pfcu_texture_create(const void *host_pixels, uint32_t width, uint32_t height, int pfcu_tex_format);
 PFCU_API pfcu_texture *pfcu_texture_from_surface(pfcu_surface *s);   /* render-to-texture alias, RGBA8 */

@@ -826,6 +826,70 @@ int pfcu_submit_prims(pfcu_surface *s, const pfcu_prim *prims, uint32_t n)
     }
     return PFCU_OK;
 }
+/* ---- full-surface operations: the reference's own loops, one pixel after the other (context.c:1938-1977, 1988-2084,
+ * 2275-2344, 2349-2395).  Scalar getters / setters = canonical RGBA8 with alpha 255 on 3-byte targets; scalar blend and
+ * depth tables = pfp_blend / pfp_depth (pinned by the points / lines cases). */
+int pfcu_surface_rect(pfcu_surface *s, int32_t x1, int32_t y1, int32_t x2, int32_t y2, uint32_t rgba)
+{
+    const uint32_t keep = s->fmt >= PFCU_TEX_RGB8 ? 0xff000000u : 0u;
+    for (int32_t y = y1; y <= y2; y++)
+        for (int32_t x = x1; x <= x2; x++) {
+            const uint32_t o = (uint32_t)y * s->w + (uint32_t)x;           /* tex->setter(pixels, y*tex->w + x, color) */
+            if (o < s->w * s->h) s->color[o] = rgba | keep;
+        }
+    return PFCU_OK;
+}
+int pfcu_surface_fog(pfcu_surface *s, const pfcu_fog *f)
+{
+    const uint32_t keep = s->fmt >= PFCU_TEX_RGB8 ? 0xff000000u : 0u, alpha = f->rgba >> 24, rgb = f->rgba & 0x00ffffffu;
+    const size_t n = (size_t)s->w * s->h;
+    for (size_t i = 0; i < n; i++) {
+        const float depth = s->depth[i];
+        if (depth >= f->end) {
+            s->color[i] = (alpha == 255u ? f->rgba : pfp_blend(1, f->rgba, s->color[i])) | keep;
+        } else if (depth > f->start) {
+            float t = 0;
+            switch (f->mode) {
+            case 0: t = (depth - f->start) * f->inv_len; break;
+            case 1: t = 1.0f - expf(-f->density * (depth - f->start)); break;      /* the host libm, as the reference */
+            case 2: t = 1.0f - exp2f(-f->density * (depth - f->start)); break;
+            }
+            const uint32_t a = (uint8_t)(t * (float)alpha);
+            s->color[i] = pfp_blend(1, rgb | (a << 24), s->color[i]) | keep;
+        }
+    }
+    return PFCU_OK;
+}
+int pfcu_surface_draw_pixels(pfcu_surface *s, const pfcu_pixels *d)
+{
+    const uint32_t keep = s->fmt >= PFCU_TEX_RGB8 ? 0xff000000u : 0u;
+    const uint32_t wm1 = d->width - 1u, hm1 = d->height - 1u;
+    for (int32_t y = d->ymin; y <= d->ymax; y++) {
+        const float v = (float)(y - d->ys) * d->inv_ylen;
+        const uint32_t ysrc = (uint32_t)(v * hm1) * d->width;
+        for (int32_t x = d->xmin; x <= d->xmax; x++) {
+            const uint32_t o = (uint32_t)y * s->w + (uint32_t)x;
+            if (o >= s->w * s->h) continue;
+            if (!(d->flags & PFCU_ST_DEPTH_TEST) || pfp_depth(d->depth_func, d->z, s->depth[o])) {
+                const float u = (float)(x - d->xs) * d->inv_xlen;
+                const uint32_t so = ysrc + (uint32_t)(u * wm1);
+                const uint32_t c = so < d->width * d->height ? native_get(d->pixels, so, d->format) : 0u;
+                s->depth[o] = d->z;
+                s->color[o] = ((d->flags & PFCU_ST_BLEND) ? pfp_blend(d->blend_mode, c, s->color[o]) : c) | keep;
+            }
+        }
+    }
+    return PFCU_OK;
+}
+int pfcu_surface_read_pixels(pfcu_surface *s, uint32_t x0, uint32_t y0, uint32_t cols, uint32_t rows, uint32_t dst_width, int format, void *host_pixels)
+{
+    if (cols == 0 || rows == 0) return PFCU_OK;
+    if (x0 >= s->w || y0 >= s->h || cols > s->w - x0 || rows > s->h - y0 || cols > dst_width) return PFCU_ERR_INVALID;
+    for (uint32_t y = 0; y < rows; y++)
+        for (uint32_t x = 0; x < cols; x++)
+            native_set(host_pixels, (size_t)y * dst_width + x, format, s->color[(size_t)(y0 + y) * s->w + x0 + x]);
+    return PFCU_OK;
+}
 unsigned pfcu_capabilities(void) { return 0u; }     /* the oracle has no device vertex stage: the front end keeps it on the host */
 int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *st, const pfcu_vparams *vp, const pfcu_draw *d, uint32_t *n)
 { (void)s; (void)st; (void)vp; (void)d; (void)n; return PFCU_ERR_INVALID; }

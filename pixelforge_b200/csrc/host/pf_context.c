@@ -751,9 +751,11 @@ void pfDrawElements(PFdrawmode mode, PFsizei count, PFdatatype type, const void 
 
 void pfDrawArrays(PFdrawmode mode, PFint first, PFsizei count) { draw_indexed(mode, count, first, 0, PF_UNSIGNED_INT, NULL); }
 
-/* ---- host-side full-surface operations (context.c:1918-2441) ----------------------------------
- * Not on the triangle hot path (SURVEY.md 8-f NEXT-3): they synchronise the device surface into
- * the host mirror, run the reference's per-pixel rule on the host, and mark the mirror as newer. */
+/* ---- full-surface operations (context.c:1918-2441) ----------------------------------------------
+ * pfRect*, pfDrawPixels, pfFogProcess and pfReadPixels run on the device surface: the
+ * front end does what the reference does before its pixel loop and pfcu_surface_* runs the loop, ordered
+ * behind the batches submitted before it.  Only pfPostProcess - a HOST callback per pixel - needs the
+ * mirror: it synchronises, calls the function for every pixel and marks the mirror as newer. */
 
 static float *host_depth(pf_ctx *c, pf_surf *s, int *temp)
 {
@@ -776,6 +778,31 @@ static void host_depth_done(pf_surf *s, float *z, int temp, int modified)
     }
 }
 
+/* everything queued for the bound surface goes first; a mirror the application wrote to is uploaded */
+static pf_surf *surface_op_begin(pf_ctx *c)
+{
+    pf_surf *s = c->cur_surf;
+    pfh_flush(c);
+    pfh_upload_if_needed(c, s);
+    return s;
+}
+
+static void surface_op_end(pf_ctx *c, pf_surf *s, PFint y0, PFint y1, int rc)       /* rows [y0, y1] were written */
+{
+    if (rc != PFCU_OK) {
+        fprintf(stderr, "pixelforge-b200: surface operation failed (%d): %s\n", rc, pfcu_last_error());
+        c->errCode = (rc == PFCU_ERR_OOM) ? PF_ERROR_OUT_OF_MEMORY : PF_INVALID_OPERATION;
+    }
+    if (y0 < 0) y0 = 0;
+    if (y1 >= (PFint)s->tex->h) y1 = (PFint)s->tex->h - 1;
+    if (y0 <= y1) {
+        if (!s->dev_newer) { s->dirty_y0 = (PFuint)y0; s->dirty_y1 = (PFuint)y1 + 1; }
+        else { if ((PFuint)y0 < s->dirty_y0) s->dirty_y0 = (PFuint)y0; if ((PFuint)y1 + 1 > s->dirty_y1) s->dirty_y1 = (PFuint)y1 + 1; }
+        s->dev_newer = 1; s->readback_queued = 0;
+    }
+    pfh_end_of_draw(c);
+}
+
 void pfRectf(PFfloat x1, PFfloat y1, PFfloat x2, PFfloat y2)
 {
     CTX;
@@ -790,11 +817,9 @@ void pfRectf(PFfloat x1, PFfloat y1, PFfloat x2, PFfloat y2)
     if (iy2 < iy1) { PFint t = iy1; iy1 = iy2; iy2 = t; }
     ix1 = PF_CLAMP(ix1, c->vpMin[0], c->vpMax[0]); iy1 = PF_CLAMP(iy1, c->vpMin[1], c->vpMax[1]);
     ix2 = PF_CLAMP(ix2, c->vpMin[0], c->vpMax[0]); iy2 = PF_CLAMP(iy2, c->vpMin[1], c->vpMax[1]);
-    pf_surf *s = c->cur_surf;
-    pfh_sync_surface(c, s);
-    for (PFint y = iy1; y <= iy2; y++)
-        for (PFint x = ix1; x <= ix2; x++) pfh_pixel_set(s->tex, (size_t)y * s->tex->w + (size_t)x, c->currentColor);
-    s->host_newer = 1;
+    pf_surf *s = surface_op_begin(c);
+    uint32_t rgba; memcpy(&rgba, &c->currentColor, 4);
+    surface_op_end(c, s, iy1, iy2 + 1, pfcu_surface_rect(s->dev, ix1, iy1, ix2, iy2, rgba));
 }
 
 void pfRects(PFshort x1, PFshort y1, PFshort x2, PFshort y2) { pfRectf((PFfloat)x1, (PFfloat)y1, (PFfloat)x2, (PFfloat)y2); }
@@ -804,71 +829,31 @@ void pfRectfv(const PFfloat *v1, const PFfloat *v2) { pfRectf(v1[0], v1[1], v2[0
 PF_API void pfRecti(PFint x1, PFint y1, PFint x2, PFint y2) { pfRectf((PFfloat)x1, (PFfloat)y1, (PFfloat)x2, (PFfloat)y2); }
 PF_API void pfRectiv(const PFint *v1, const PFint *v2) { pfRectf((PFfloat)v1[0], (PFfloat)v1[1], (PFfloat)v2[0], (PFfloat)v2[1]); }
 
-static int depth_cmp_host(PFdepthmode m, float s, float d)
-{
-    switch (m) {
-    case PF_EQUAL: return s == d;   case PF_NOTEQUAL: return s != d;
-    case PF_LESS: return s < d;     case PF_LEQUAL: return s <= d;
-    case PF_GREATER: return s > d;  default: return s >= d;
-    }
-}
-
-static PFcolor blend_host(PFblendmode m, PFcolor s, PFcolor d)      /* scalar table, blend.h:29-130 */
-{
-    PFubyte *sp = (PFubyte *)&s, *dp = (PFubyte *)&d; PFcolor r; PFubyte *rp = (PFubyte *)&r;
-    PFuint alpha = (PFuint)s.a + 1, inv = 256 - alpha;
-    for (int i = 0; i < 4; i++) {
-        int sv = sp[i], dv = dp[i], o;
-        switch (m) {
-        case PF_BLEND_AVERAGE: o = (sv + dv) >> 1; break;
-        case PF_BLEND_ALPHA:   o = (int)(((i == 3 ? alpha * 255 : alpha * (PFuint)sv) + inv * (PFuint)dv) >> 8); break;
-        case PF_BLEND_ADD:     o = PF_MIN(sv + dv, 255); break;
-        case PF_BLEND_SUB:     o = PF_MAX(dv - sv, 0); break;
-        case PF_BLEND_MUL:     o = (sv * dv) / 255; break;
-        case PF_BLEND_SCREEN:  o = PF_MIN(((dv * (255 - sv)) >> 8) + sv, 255); break;
-        case PF_BLEND_LIGHTEN: o = PF_MAX(sv, dv); break;
-        default:               o = PF_MIN(sv, dv); break;
-        }
-        rp[i] = (PFubyte)o;
-    }
-    return r;
-}
-
 void pfDrawPixels(PFsizei width, PFsizei height, PFpixelformat format, PFdatatype type, const void *pixels)
 {
     CTX;
     if (width == 0 || height == 0) { c->errCode = PF_INVALID_VALUE; return; }
     if (format > PF_BGRA || type > PF_DOUBLE || pfh_tex_format_code(format, type) < 0) { c->errCode = PF_INVALID_ENUM; return; }
-    pf_tex src = { (void *)pixels, width, height, format, type, PF_REPEAT, PF_NEAREST, NULL, NULL };
     pfh_update_matrices(c, 0);
     PFfloat rp[4]; memcpy(rp, c->rasterPos, 16);
     v4_transform(rp, rp, c->matMVP);
-    PFint xs = (PFint)(c->vpPos[0] + (rp[0] + 1.0f) * 0.5f * c->vpDim[0]);
-    PFint ys = (PFint)(c->vpPos[1] + (1.0f - rp[1]) * 0.5f * c->vpDim[1]);
-    PFfloat zp = rp[2];
-    PFint xMin = PF_CLAMP(xs, c->vpMin[0], c->vpMax[0]), yMin = PF_CLAMP(ys, c->vpMin[1], c->vpMax[1]);
-    PFint xMax = (PFint)PF_CLAMP(xs + width * c->pixelZoom[0], (PFfloat)c->vpMin[0], (PFfloat)c->vpMax[0]);
-    PFint yMax = (PFint)PF_CLAMP(ys + height * c->pixelZoom[1], (PFfloat)c->vpMin[1], (PFfloat)c->vpMax[1]);
-    PFfloat ixl = 1.0f / (PFfloat)(width * c->pixelZoom[0]), iyl = 1.0f / (PFfloat)(height * c->pixelZoom[1]);
-    pf_surf *s = c->cur_surf;
-    int temp; float *z = host_depth(c, s, &temp);
-    if (!z) return;
-    int no_test = !(c->state & PF_DEPTH_TEST), blending = (c->state & PF_BLEND) != 0;
-    for (PFint y = yMin; y <= yMax; y++) {
-        PFfloat v = (PFfloat)(y - ys) * iyl;
-        PFsizei so = (PFsizei)(v * (height - 1)) * width;
-        for (PFint x = xMin; x <= xMax; x++) {
-            size_t o = (size_t)y * s->tex->w + (size_t)x;
-            if (no_test || depth_cmp_host(c->depthMode, zp, z[o])) {
-                PFfloat u = (PFfloat)(x - xs) * ixl;
-                PFcolor col = pfh_pixel_get(&src, so + (PFsizei)(u * (width - 1)));
-                z[o] = zp;
-                pfh_pixel_set(s->tex, o, blending ? blend_host(c->blendMode, col, pfh_pixel_get(s->tex, o)) : col);
-            }
-        }
-    }
-    s->host_newer = 1;
-    host_depth_done(s, z, temp, 1);
+    pfcu_pixels d; memset(&d, 0, sizeof d);
+    d.pixels = pixels; d.width = width; d.height = height; d.format = pfh_tex_format_code(format, type);
+    d.xs = (PFint)(c->vpPos[0] + (rp[0] + 1.0f) * 0.5f * c->vpDim[0]);
+    d.ys = (PFint)(c->vpPos[1] + (1.0f - rp[1]) * 0.5f * c->vpDim[1]);
+    d.z = rp[2];
+    d.xmin = PF_CLAMP(d.xs, c->vpMin[0], c->vpMax[0]); d.ymin = PF_CLAMP(d.ys, c->vpMin[1], c->vpMax[1]);
+    d.xmax = (PFint)PF_CLAMP(d.xs + width * c->pixelZoom[0], (PFfloat)c->vpMin[0], (PFfloat)c->vpMax[0]);
+    d.ymax = (PFint)PF_CLAMP(d.ys + height * c->pixelZoom[1], (PFfloat)c->vpMin[1], (PFfloat)c->vpMax[1]);
+    d.inv_xlen = 1.0f / (PFfloat)(width * c->pixelZoom[0]); d.inv_ylen = 1.0f / (PFfloat)(height * c->pixelZoom[1]);
+    d.flags = ((c->state & PF_DEPTH_TEST) ? PFCU_ST_DEPTH_TEST : 0u) | ((c->state & PF_BLEND) ? PFCU_ST_BLEND : 0u);
+    d.blend_mode = (uint8_t)c->blendMode; d.depth_func = (uint8_t)c->depthMode;
+    /* the source may be the mirror of one of our surfaces (the aux buffer after pfSwapBuffers, a framebuffer's
+       texture): bring it up to date before it is uploaded */
+    for (pf_surf *o = pfh_surf_first(); o; o = pfh_surf_next(o))
+        if (o->tex && o->tex->pixels == pixels) pfh_sync_surface(c, o);
+    pf_surf *s = surface_op_begin(c);
+    surface_op_end(c, s, d.ymin, d.ymax + 1, pfcu_surface_draw_pixels(s->dev, &d));
 }
 
 void pfPixelZoom(PFfloat xf, PFfloat yf) { pf_cur->pixelZoom[0] = xf; pf_cur->pixelZoom[1] = yf; }
@@ -931,48 +916,87 @@ void pfFogfv(PFfogparam pname, PFfloat *param)
     }
 }
 
+/* The fog alpha of the exponential modes as the reference computes it (context.c:2331-2338), with the host's libm. */
+static PFubyte fog_alpha_host(const pf_ctx *c, PFfloat depth)
+{
+    const PFfloat start = c->fog.start, density = c->fog.density;
+    const PFubyte alpha = c->fog.color.a;
+    PFfloat t = (c->fog.mode == PF_EXP) ? 1.0f - expf(-density * (depth - start)) : 1.0f - exp2f(-density * (depth - start));
+    return (PFubyte)(t * alpha);
+}
+
+/* floats in their numeric order as integers (for bisection over bit patterns) */
+static int32_t fog_ord(float f) { int32_t i; memcpy(&i, &f, 4); return i < 0 ? (int32_t)(0x80000000u - (uint32_t)i) : i; }
+static float fog_unord(int32_t o) { int32_t i = o < 0 ? (int32_t)(0x80000000u - (uint32_t)o) : o; float f; memcpy(&f, &i, 4); return f; }
+
+/* thresholds[k-1] = the smallest depth in (start, end) whose fog alpha is >= k.  Returns their number, or -1 when the
+ * host's function turns out not to be monotonic over the interval (then a table cannot stand in for it). */
+static int fog_thresholds(const pf_ctx *c, float *thr)
+{
+    const int32_t lo0 = fog_ord(c->fog.start) + 1, hi0 = fog_ord(c->fog.end) - 1;     /* the open interval */
+    if (lo0 > hi0) return 0;
+    const int top = fog_alpha_host(c, fog_unord(hi0));
+    int32_t prev = lo0;
+    int n = 0;
+    for (int k = 1; k <= top; k++) {
+        int32_t lo = prev, hi = hi0;                  /* alpha(hi) >= k; find the first position with alpha >= k */
+        if (fog_alpha_host(c, fog_unord(lo)) >= k) hi = lo;
+        while (lo < hi) {
+            const int32_t mid = lo + (int32_t)(((int64_t)hi - lo) >> 1);
+            if (fog_alpha_host(c, fog_unord(mid)) >= k) hi = mid; else lo = mid + 1;
+        }
+        thr[n++] = fog_unord(hi);
+        prev = hi;
+    }
+    /* spot check: between consecutive thresholds the function must hold the step's value */
+    uint32_t rs = 12345u;
+    for (int k = 0; k <= n; k++) {
+        const int32_t a = k ? fog_ord(thr[k - 1]) : lo0, b = k < n ? fog_ord(thr[k]) - 1 : hi0;
+        if (a > b) continue;
+        for (int j = 0; j < 24; j++) {
+            rs = rs * 1664525u + 1013904223u;
+            const int32_t p = j == 0 ? a : (j == 1 ? b : a + (int32_t)(((uint64_t)(rs >> 1) * (uint64_t)((int64_t)b - a + 1)) >> 31));
+            if (fog_alpha_host(c, fog_unord(p)) != k) return -1;
+        }
+    }
+    return n;
+}
+
 void pfFogProcess(void)
 {
     CTX;
-    pf_surf *s = c->cur_surf;
-    int temp; float *z = host_depth(c, s, &temp);
-    if (!z) return;
-    size_t n = (size_t)s->tex->w * s->tex->h;
-    PFcolor fog = c->fog.color; PFubyte alpha = fog.a;
-    PFfloat start = c->fog.start, end = c->fog.end, inv = 1 / (end - start), density = c->fog.density;
-    for (size_t i = 0; i < n; i++) {
-        PFfloat d = z[i];
-        if (d >= end) {
-            fog.a = alpha;
-            pfh_pixel_set(s->tex, i, alpha == 255 ? fog : blend_host(PF_BLEND_ALPHA, fog, pfh_pixel_get(s->tex, i)));
-        } else if (d > start) {
-            PFfloat t = 0;
-            switch (c->fog.mode) {
-            case PF_LINEAR: t = (d - start) * inv; break;
-            case PF_EXP:    t = 1.0f - expf(-density * (d - start)); break;
-            case PF_EXP2:   t = 1.0f - exp2f(-density * (d - start)); break;
-            }
-            fog.a = (PFubyte)(t * alpha);
-            pfh_pixel_set(s->tex, i, blend_host(PF_BLEND_ALPHA, fog, pfh_pixel_get(s->tex, i)));
+    pfcu_fog f; memset(&f, 0, sizeof f);
+    float thr[256];
+    f.start = c->fog.start; f.end = c->fog.end; f.inv_len = 1 / (c->fog.end - c->fog.start); f.density = c->fog.density;
+    memcpy(&f.rgba, &c->fog.color, 4);
+    f.mode = (uint32_t)c->fog.mode;
+    if (f.mode > (uint32_t)PF_EXP2) f.mode = 3u;            /* no case of the reference's switch matches: t stays 0 */
+    else if (c->fog.mode != PF_LINEAR) {
+        const int n = fog_thresholds(c, thr);
+        if (n < 0) {
+            fprintf(stderr, "pixelforge-b200: pfFogProcess: the host's expf/exp2f is not monotonic over the fog range; cannot tabulate it for the device\n");
+            c->errCode = PF_INVALID_OPERATION; return;
         }
+        f.thresholds = thr; f.n_thresholds = (uint32_t)n;
     }
-    s->host_newer = 1;
-    host_depth_done(s, z, temp, 0);
+    pf_surf *s = surface_op_begin(c);
+    surface_op_end(c, s, 0, (PFint)s->tex->h - 1, pfcu_surface_fog(s->dev, &f));
 }
 
 void pfReadPixels(PFint x, PFint y, PFsizei width, PFsizei height, PFpixelformat format, PFdatatype type, void *pixels)
 {
     CTX;
     if (format > PF_BGRA || type > PF_DOUBLE || pfh_tex_format_code(format, type) < 0) { c->errCode = PF_INVALID_ENUM; return; }
-    pf_surf *s = c->cur_surf;
-    pfh_sync_surface(c, s);
-    pf_tex dst = { pixels, width, height, format, type, PF_REPEAT, PF_NEAREST, NULL, NULL };
+    pf_surf *s = surface_op_begin(c);
     PFint W = (PFint)s->tex->w, H = (PFint)s->tex->h;
     PFsizei xMin = (PFsizei)PF_CLAMP(x, 0, W - 1), yMin = (PFsizei)PF_CLAMP(y, 0, H - 1);
     PFsizei xMax = (PFsizei)PF_CLAMP(x + (PFint)width, 0, W), yMax = (PFsizei)PF_CLAMP(y + (PFint)height, 0, H);
-    for (PFsizei ys = yMin; ys < yMax; ys++)
-        for (PFsizei xs = xMin; xs < xMax; xs++)
-            pfh_pixel_set(&dst, (size_t)(ys - yMin) * width + (xs - xMin), pfh_pixel_get(s->tex, (size_t)ys * s->tex->w + xs));
+    if (xMax <= xMin || yMax <= yMin) return;
+    /* destination index (ySrc - yMin) * width + (xSrc - xMin) (context.c:2383-2386); a region wider than `width`
+       (x < 0 moves xMin to 0) would make rows overlap upstream - the columns past `width` are dropped here */
+    PFsizei cols = xMax - xMin; if (cols > width) cols = width;
+    int rc = pfcu_surface_read_pixels(s->dev, xMin, yMin, cols, yMax - yMin, width, pfh_tex_format_code(format, type), pixels);
+    if (rc != PFCU_OK) { fprintf(stderr, "pixelforge-b200: pfReadPixels failed (%d): %s\n", rc, pfcu_last_error()); c->errCode = PF_INVALID_OPERATION; }
 }
 
 void pfPostProcess(PFpostprocessfunc fn)

@@ -184,6 +184,8 @@ extern PF_CTX_DECL pf_ctx *pf_cur;
 /* pf_pipeline.c */
 void pfh_process_primitive(pf_ctx *c);                 /* vertexBuffer full -> triangles -> batch       */
 void pfh_flush(pf_ctx *c);                             /* submit the pending batch (asynchronous)       */
+pf_surf *pfh_surf_first(void);                          /* registry of live surfaces                    */
+pf_surf *pfh_surf_next(pf_surf *s);
 void pfh_sync_surface(pf_ctx *c, pf_surf *s);          /* flush + bring the host mirror up to date      */
 void pfh_queue_readback(pf_ctx *c, pf_surf *s);        /* explicit mode: start the read-back without waiting */
 void pfh_upload_if_needed(pf_ctx *c, pf_surf *s);      /* host mirror -> device when host is newer      */

@@ -100,6 +100,9 @@ void pfh_pixel_set(pf_tex *t, size_t i, PFcolor c)
 static pf_surf *g_surfs = NULL;     /* registry: PFframebuffer is a by-value struct, we find the
                                        surface again through its texture handle                  */
 
+pf_surf *pfh_surf_first(void) { return g_surfs; }
+pf_surf *pfh_surf_next(pf_surf *s) { return s ? s->next : NULL; }
+
 pf_surf *pfh_surf_create(pf_tex *tex, PFfloat *zhost, int z_public)
 {
     if (!pfh_runtime_init()) return NULL;

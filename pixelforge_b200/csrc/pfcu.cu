@@ -714,6 +714,102 @@ int pfcu_surface_clear_ref(pfcu_surface *s, int dc, uint32_t rgba, int dd, float
     return PFCU_OK;
 }
 
+/* ---- full-surface operations ---- */
+
+int pfcu_surface_rect(pfcu_surface *s, int32_t x1, int32_t y1, int32_t x2, int32_t y2, uint32_t rgba)
+{
+    API_LOCK;
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!s) return PFCU_ERR_INVALID;
+    if (x2 < x1 || y2 < y1) return PFCU_OK;
+    use_lane(s);
+    if (s->fmt >= PFCU_TEX_RGB8) rgba |= 0xff000000u;
+    const uint32_t cols = (uint32_t)(x2 - x1) + 1u, rows = (uint32_t)(y2 - y1) + 1u;
+    const size_t n = (size_t)cols * rows;
+    const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)g.sms * 8 ? (n + 255) / 256 : (size_t)g.sms * 8);
+    k_rect<<<blocks, 256, 0, LN.stream>>>(s->color, s->w, s->w * s->h, x1, y1, cols, rows, rgba);
+    g.launches++;
+    CK(cudaGetLastError());
+    mark_done(s);
+    return PFCU_OK;
+}
+
+int pfcu_surface_fog(pfcu_surface *s, const pfcu_fog *f)
+{
+    API_LOCK;
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!s || !f || f->mode > 3u || f->n_thresholds > 255u || (f->mode != 0u && f->n_thresholds && !f->thresholds)) return PFCU_ERR_INVALID;
+    use_lane(s);
+    int rc;
+    const float *d_thr = nullptr;
+    if ((f->mode == 1u || f->mode == 2u) && f->n_thresholds) {
+        if ((rc = grow(&LN.d_varrays, &LN.cap_varrays, 256 * sizeof(float)))) return rc;
+        /* pageable source: staged by the driver before the call returns */
+        CK(cudaMemcpyAsync(LN.d_varrays, f->thresholds, f->n_thresholds * sizeof(float), cudaMemcpyHostToDevice, LN.stream));
+        g.bytes_h2d += f->n_thresholds * sizeof(float);
+        d_thr = (const float *)LN.d_varrays;
+    }
+    FogArgs a;
+    a.start = f->start; a.end = f->end; a.inv_len = f->inv_len; a.rgba = f->rgba; a.mode = f->mode;
+    a.n_thr = (f->mode == 1u || f->mode == 2u) ? f->n_thresholds : 0u;       /* mode 3: t = 0 for every pixel in range */ a.alpha_or = s->fmt >= PFCU_TEX_RGB8 ? 0xff000000u : 0u;
+    k_fog<<<g.sms * 8, 256, 0, LN.stream>>>(s->color, s->depth, (size_t)s->w * s->h, a, d_thr);
+    g.launches++;
+    CK(cudaGetLastError());
+    mark_done(s);
+    return PFCU_OK;
+}
+
+int pfcu_surface_draw_pixels(pfcu_surface *s, const pfcu_pixels *d)
+{
+    API_LOCK;
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!s || !d || !d->pixels || d->width == 0 || d->height == 0 || d->format < PFCU_TEX_RGBA8 || d->format > PFCU_TEX_BGR8) return PFCU_ERR_INVALID;
+    if (d->xmax < d->xmin || d->ymax < d->ymin) return PFCU_OK;
+    use_lane(s);
+    int rc;
+    const size_t bytes = (size_t)d->width * d->height * fmt_bytes(d->format);
+    if ((rc = grow(&LN.d_varrays, &LN.cap_varrays, bytes + 16))) return rc;
+    CK(cudaMemcpyAsync(LN.d_varrays, d->pixels, bytes, cudaMemcpyHostToDevice, LN.stream));
+    /* the caller may reuse its image as soon as pfDrawPixels returns: page-locked sources are still being read */
+    if (find_pinned(d->pixels)) CK(cudaStreamSynchronize(LN.stream));
+    g.bytes_h2d += bytes;
+    PixArgs a;
+    a.src = LN.d_varrays; a.sw = d->width; a.sh = d->height; a.fmt = d->format;
+    a.xs = d->xs; a.ys = d->ys; a.xmin = d->xmin; a.ymin = d->ymin;
+    a.cols = (uint32_t)(d->xmax - d->xmin) + 1u; a.rows = (uint32_t)(d->ymax - d->ymin) + 1u;
+    a.inv_xlen = d->inv_xlen; a.inv_ylen = d->inv_ylen; a.z = d->z;
+    a.flags = d->flags; a.blend_mode = d->blend_mode; a.depth_func = d->depth_func;
+    a.alpha_or = s->fmt >= PFCU_TEX_RGB8 ? 0xff000000u : 0u;
+    const size_t n = (size_t)a.cols * a.rows;
+    const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)g.sms * 8 ? (n + 255) / 256 : (size_t)g.sms * 8);
+    k_draw_pixels<<<blocks, 256, 0, LN.stream>>>(s->color, s->depth, s->w, s->w * s->h, a);
+    g.launches++;
+    CK(cudaGetLastError());
+    mark_done(s);
+    return PFCU_OK;
+}
+
+int pfcu_surface_read_pixels(pfcu_surface *s, uint32_t x0, uint32_t y0, uint32_t cols, uint32_t rows, uint32_t dst_width, int format, void *host_pixels)
+{
+    API_LOCK;
+    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!s || !host_pixels || format < PFCU_TEX_RGBA8 || format > PFCU_TEX_BGR8) return PFCU_ERR_INVALID;
+    if (cols == 0 || rows == 0) return PFCU_OK;
+    if (x0 >= s->w || y0 >= s->h || cols > s->w - x0 || rows > s->h - y0 || cols > dst_width) return PFCU_ERR_INVALID;
+    use_lane(s);
+    int rc;
+    const size_t bpp = fmt_bytes(format), n = (size_t)cols * rows;
+    if ((rc = grow(&LN.d_varrays, &LN.cap_varrays, n * bpp + 16))) return rc;
+    const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)g.sms * 8 ? (n + 255) / 256 : (size_t)g.sms * 8);
+    k_read_pixels<<<blocks, 256, 0, LN.stream>>>(s->color, s->w, x0, y0, cols, rows, format, LN.d_varrays);
+    g.launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2DAsync(host_pixels, (size_t)dst_width * bpp, LN.d_varrays, (size_t)cols * bpp, (size_t)cols * bpp, rows, cudaMemcpyDeviceToHost, LN.stream));
+    g.bytes_d2h += n * bpp;
+    CK(cudaStreamSynchronize(LN.stream));
+    return PFCU_OK;
+}
+
 int pfcu_surface_set_tile_owner(pfcu_surface *s, uint32_t rank, uint32_t world)
 {
     if (world == 0) world = 1;

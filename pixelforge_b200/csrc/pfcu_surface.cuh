@@ -97,3 +97,126 @@ k_push_tiles(const uint32_t *__restrict__ color, const float *__restrict__ depth
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* kernels: full-surface operations (pfRect*, pfFogProcess, pfDrawPixels,          */
+/* pfReadPixels).  Scalar blend / depth tables of the reference: pfp_blend / pfp_depth (pf_prims.h). */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* (PFsizei)float as x86-64 gcc compiles it: CVTTSS2SI to a 64-bit register, low 32 bits kept; out of range -> 0 */
+__device__ __forceinline__ uint32_t f2u_x86(float f)
+{
+    if (!(f < 9.2233720368547758e18f && f >= -9.2233720368547758e18f)) return 0u;
+    return (uint32_t)(unsigned long long)__float2ll_rz(f);
+}
+
+/* pfRectf, context.c:1972-1976 */
+__global__ void __launch_bounds__(256)
+k_rect(uint32_t *__restrict__ color, uint32_t W, uint32_t npix, int x1, int y1, uint32_t cols, uint32_t rows, uint32_t rgba)
+{
+    const size_t n = (size_t)cols * rows, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t r = (uint32_t)(i / cols), c = (uint32_t)(i - (size_t)r * cols);
+        const uint32_t o = (uint32_t)(y1 + (int)r) * W + (uint32_t)(x1 + (int)c);
+        if (o < npix) color[o] = rgba;
+    }
+}
+
+struct FogArgs { float start, end, inv_len; uint32_t rgba, mode, n_thr, alpha_or; };
+
+/* pfFogProcess, context.c:2318-2342.  thr: the host-tabulated steps of (PFubyte)(t * alpha) for the exponential modes. */
+__global__ void __launch_bounds__(256)
+k_fog(uint32_t *__restrict__ color, const float *__restrict__ depth, size_t npix, FogArgs a, const float *__restrict__ thr)
+{
+    __shared__ float s_thr[256];
+    for (unsigned k = threadIdx.x; k < 256; k += blockDim.x) s_thr[k] = k < a.n_thr ? thr[k] : 0.0f;
+    __syncthreads();
+    const uint32_t alpha = a.rgba >> 24, rgb = a.rgba & 0x00ffffffu;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+        const float d = depth[i];
+        if (d >= a.end) {
+            color[i] = (alpha == 255u ? a.rgba : pfp_blend(1, a.rgba, color[i])) | a.alpha_or;
+        } else if (d > a.start) {
+            uint32_t fa;
+            if (a.mode == 0u) {
+                const float t = __fmul_rn(__fsub_rn(d, a.start), a.inv_len);
+                fa = (uint32_t)pfv_cvttss2si(__fmul_rn(t, __uint2float_rn(alpha))) & 255u;
+            } else {
+                /* number of thresholds <= d (they ascend): binary search */
+                unsigned lo = 0, hi = a.n_thr;
+                while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (s_thr[mid] <= d) lo = mid + 1; else hi = mid; }
+                fa = lo;
+            }
+            color[i] = pfp_blend(1, rgb | (fa << 24), color[i]) | a.alpha_or;
+        }
+    }
+}
+
+/* one source texel in the caller's 8-bit layout -> PFcolor dword (scalar getters, pixel.h:576-588,2604-2632) */
+__device__ __forceinline__ uint32_t pix_get(const unsigned char *__restrict__ px, size_t i, int fmt)
+{
+    if (fmt == PFCU_TEX_RGBA8) return reinterpret_cast<const uint32_t *>(px)[i];
+    if (fmt == PFCU_TEX_BGRA8) return __byte_perm(reinterpret_cast<const uint32_t *>(px)[i], 0, 0x3012);
+    const unsigned char *q = px + 3 * i;
+    const int r = fmt == PFCU_TEX_RGB8 ? 0 : 2;
+    return (uint32_t)q[r] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2 - r] << 16) | 0xff000000u;
+}
+
+struct PixArgs {
+    const unsigned char *src; uint32_t sw, sh; int fmt;
+    int xs, ys, xmin, ymin; uint32_t cols, rows;
+    float inv_xlen, inv_ylen, z;
+    uint32_t flags, blend_mode, depth_func, alpha_or;
+};
+
+/* one destination pixel of pfDrawPixels (context.c:2052-2075) */
+__device__ __forceinline__ void draw_pixel(uint32_t *__restrict__ color, float *__restrict__ depth, uint32_t o, int x, int y, const PixArgs &a)
+{
+    if (!(a.flags & PFCU_ST_DEPTH_TEST) || pfp_depth((int)a.depth_func, a.z, depth[o])) {
+        const float v = __fmul_rn(__int2float_rn(y - a.ys), a.inv_ylen), u = __fmul_rn(__int2float_rn(x - a.xs), a.inv_xlen);
+        const uint32_t so = f2u_x86(__fmul_rn(v, __uint2float_rn(a.sh - 1u))) * a.sw + f2u_x86(__fmul_rn(u, __uint2float_rn(a.sw - 1u)));
+        const uint32_t c = so < a.sw * a.sh ? pix_get(a.src, so, a.fmt) : 0u;      /* upstream reads past the image there */
+        depth[o] = a.z;
+        color[o] = ((a.flags & PFCU_ST_BLEND) ? pfp_blend((int)a.blend_mode, c, color[o]) : c) | a.alpha_or;
+    }
+}
+
+/* One thread per pixel of the rectangle.  When the rectangle spans columns 0 .. W (vpMax one past the right edge, SURVEY
+ * Q20), pixel (y, W) and pixel (y+1, 0) share the address (y+1)*W and the reference's row-major loop applies them in
+ * that order: the thread of (y+1, 0) then applies both, in order, and the thread of (y, W) stands down. */
+__global__ void __launch_bounds__(256)
+k_draw_pixels(uint32_t *__restrict__ color, float *__restrict__ depth, uint32_t W, uint32_t npix, PixArgs a)
+{
+    const bool conflict = a.xmin == 0 && a.cols == W + 1u;
+    const size_t n = (size_t)a.cols * a.rows, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t r = (uint32_t)(i / a.cols), c = (uint32_t)(i - (size_t)r * a.cols);
+        const int y = a.ymin + (int)r, x = a.xmin + (int)c;
+        const uint32_t o = (uint32_t)y * W + (uint32_t)x;
+        if (o >= npix) continue;
+        if (conflict) {
+            if (c == W && r + 1u < a.rows) continue;
+            if (c == 0u && r > 0u) draw_pixel(color, depth, o, (int)W, y - 1, a);
+        }
+        draw_pixel(color, depth, o, x, y, a);
+    }
+}
+
+/* pfReadPixels, context.c:2380-2394: region -> compact staging in the caller's layout (scalar setters, pixel.h:233-360) */
+__global__ void __launch_bounds__(256)
+k_read_pixels(const uint32_t *__restrict__ color, uint32_t W, uint32_t x0, uint32_t y0, uint32_t cols, uint32_t rows, int fmt, unsigned char *__restrict__ out)
+{
+    const size_t n = (size_t)cols * rows, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t r = (uint32_t)(i / cols), c = (uint32_t)(i - (size_t)r * cols);
+        const uint32_t v = color[(size_t)(y0 + r) * W + x0 + c];
+        if (fmt == PFCU_TEX_RGBA8) reinterpret_cast<uint32_t *>(out)[i] = v;
+        else if (fmt == PFCU_TEX_BGRA8) reinterpret_cast<uint32_t *>(out)[i] = __byte_perm(v, 0, 0x3012);
+        else {
+            unsigned char *q = out + 3 * i;
+            const int rr = fmt == PFCU_TEX_RGB8 ? 0 : 2;
+            q[rr] = (unsigned char)v; q[1] = (unsigned char)(v >> 8); q[2 - rr] = (unsigned char)(v >> 16);
+        }
+    }
+}

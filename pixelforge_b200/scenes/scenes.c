@@ -393,7 +393,10 @@ static void micro_scene(const pfscene_cfg *cfg, PFtexture tex)
    with attenuation), 3 separate back material + no culling, 4 pfRect*, 5 pfDrawPixels with zoom,
    6 fog, 7 pfPostProcess, 8 pfReadPixels -> pfDrawPixels, 9 pfClearDepth(0.9), 10 cull front faces,
    11 PF_NORMALIZE with unnormalised normals, 12 colour material (front, diffuse), 13 vertex arrays with a
-   colour pointer (pfDrawArrays, quads), 14 aux buffer + pfSwapBuffers, 15-16 fog mode, 17 blend on */
+   colour pointer (pfDrawArrays, quads), 14 aux buffer + pfSwapBuffers, 15 fog mode request (overwritten by the density
+   call, as upstream), 16 opaque fog colour, 17 blend on, 18 bilinear, 19-20 fog mode set AFTER the density call
+   (1 PF_EXP, 2 PF_EXP2, 3 an invalid mode), 21 pfReadPixels / pfDrawPixels round trip through the BGRA8, RGB8 and BGR8
+   layouts with a region that leaves the surface */
 
 static PFcolor api_postprocess(PFint x, PFint y, PFfloat depth, PFcolor c)
 {
@@ -509,11 +512,34 @@ static void api_scene(const pfscene_cfg *cfg, PFtexture tex, uint8_t *aux)
         pfDrawPixels(40, 30, PF_RGBA, PF_UNSIGNED_BYTE, grab);
         pfEnable(PF_DEPTH_TEST);
     }
+    if (v & (1 << 21)) {
+        /* read-back conversions and draw-pixels sources in the other 8-bit layouts; the first region starts left of and
+           above the surface (clamped by pfReadPixels), the last one hangs over the right / bottom edge */
+        static uint8_t conv[3][48 * 36 * 4];
+        static const PFpixelformat fm[3] = { PF_BGRA, PF_RGB, PF_BGR };
+        ortho2d(w, h);
+        pfDisable(PF_BLEND);
+        for (int k = 0; k < 3; k++) {
+            memset(conv[k], 0x5a, sizeof conv[k]);
+            pfReadPixels(k == 0 ? -7 : w / 4 + 31 * k, k == 0 ? -5 : (k == 2 ? h - 20 : h / 5), 48, 36, fm[k], PF_UNSIGNED_BYTE, conv[k]);
+            if (k == 1) { pfEnable(PF_DEPTH_TEST); pfDepthFunc(PF_NOTEQUAL); } else pfDisable(PF_DEPTH_TEST);
+            if (k == 2) { pfEnable(PF_BLEND); pfBlendFunc(PF_BLEND_SUB); }
+            pfPixelZoom(k == 1 ? 1.5f : 1.0f, k == 2 ? 0.75f : 1.0f); pfRasterPos3f(6.0f + 52.0f * k, (float)h - 60.0f, -0.5f);
+            pfDrawPixels(48, 36, fm[k], PF_UNSIGNED_BYTE, conv[k]);
+        }
+        pfDisable(PF_BLEND); pfEnable(PF_DEPTH_TEST); pfDepthFunc(PF_LESS); pfPixelZoom(1.0f, 1.0f);
+    }
     if (v & (1 << 6)) {
         PFint fc[4] = { 180, 190, 220, (v & (1 << 16)) ? 255 : 200 };
         pfFogi(PF_FOG_MODE, (PFint)(PF_LINEAR + ((v >> 15) & 1) * 1));
         pfFogf(PF_FOG_DENSITY, 0.8f); pfFogf(PF_FOG_START, 0.93f); pfFogf(PF_FOG_END, 0.985f);
         pfFogiv(PF_FOG_COLOR, fc);
+        if ((v >> 19) & 3) {
+            /* the exponential modes: reachable only through a call that does not range-check (context.c:2212-2226) */
+            PFint m = ((v >> 19) & 3) == 3 ? 7 : (PFint)(PF_LINEAR + ((v >> 19) & 3));
+            pfFogiv(PF_FOG_MODE, &m);
+            pfFogf(PF_FOG_START, 1.2f); pfFogf(PF_FOG_END, 3.0f);      /* the depth range of the scene's triangles */
+        }
         pfFogProcess();
     }
     if (v & (1 << 7)) pfPostProcess(api_postprocess);

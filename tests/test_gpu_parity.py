@@ -629,3 +629,23 @@ def test_two_threads_two_contexts(product_scenes):
     for i in range(2):
         ref = product_scenes.render("gears", 320, 240, first_frame=2 * i, frames=3)[0]
         assert np.array_equal(results[i], ref)
+
+
+def test_surface_operations_stay_on_the_device(product_scenes):
+    """pfRect*, pfDrawPixels and pfFogProcess (linear and exponential) run as kernels on the device
+    surface - in explicit sync mode a frame that uses them copies nothing back until the application asks
+    (pfxFinish), and pfReadPixels copies exactly the converted region."""
+    from pixelforge_b200 import load_pfcu
+    from pixelforge_b200.binding import Counters
+    L = load_pfcu("product").lib
+    bits = lambda *b: sum(1 << i for i in b)
+    for variant, d2h in ((bits(4, 5, 6, 19), 0), (bits(4, 5, 6, 20), 0), (bits(4, 5, 8), 40 * 30 * 4)):
+        with product_scenes.open("api", 200, 150, variant=variant, seed=3, explicit_sync=1) as sc:
+            sc.frame(0); sc.finish()
+            L.pfxResetCounters()
+            sc.frame(0)
+            L.pfxFlush()
+            k = Counters(); L.pfcu_get_counters(k)
+            assert k.kernel_launches > 0
+            assert k.bytes_d2h == d2h, (variant, k.bytes_d2h)
+            sc.finish()

@@ -47,6 +47,17 @@ WORKLOADS = {
                            desc="C4: 64 layers of additive-blended textured full-screen quads, 7680x4320, nearest REPEAT"),
     "ns_textured_blend_4k": dict(scene="overdraw", w=3840, h=2160, size=64, variant=1, bytes_px=20,
                                  desc="north-star scene: 64 layers textured + alpha-blended + depth-tested quads, 3840x2160, nearest"),
+    # the north-star scene OFF its most specialised fragment program: same 64 layers at 3840x2160, alpha blend + depth test
+    "ns4k_tinted": dict(scene="overdraw", w=3840, h=2160, size=64, variant=1 | 4, bytes_px=20,
+                        desc="north-star scene with a different vertex colour per corner (smooth-shaded tint times texel)"),
+    "ns4k_clamp": dict(scene="overdraw", w=3840, h=2160, size=64, variant=1 | 8, bytes_px=20,
+                       desc="north-star scene with CLAMP_TO_EDGE wrapping"),
+    "ns4k_rgb8": dict(scene="overdraw", w=3840, h=2160, size=64, variant=1 | 16, bytes_px=20,
+                      desc="north-star scene with an RGB8 (3 bytes per texel) texture"),
+    "ns4k_two_state": dict(scene="overdraw", w=3840, h=2160, size=64, variant=1 | 32, bytes_px=20,
+                           desc="north-star scene with two fragment states in one batch (even layers alpha-blend, odd layers add)"),
+    "ns4k_bilinear": dict(scene="overdraw", w=3840, h=2160, size=64, variant=1 | 2, bytes_px=32,
+                          desc="north-star scene with bilinear filtering (4 taps)"),
     "c5_batch_512": dict(scene="batch", w=512, h=512, size=32, variant=0, bytes_px=16,
                          desc="C5: independent 512x512 contexts (render-list replay, textured + Gouraud lit, depth), 32 per GPU"),
 }
@@ -396,7 +407,7 @@ def ours_main(args):
         names = [] if args.no_extra else [n for n in WORKLOADS if n != wl_name]
         for n in names:
             try:
-                steps = max(2, min(args.steps, 5)) if n in ("c3_phong_4k", "c4_overdraw_8k", "ns_textured_blend_4k", "c5_batch_512") else args.steps
+                steps = max(2, min(args.steps, 5)) if (n in ("c3_phong_4k", "c4_overdraw_8k", "c5_batch_512") or WORKLOADS[n]["scene"] == "overdraw") else args.steps
                 x = measure_workload(n, steps, 3, torch, scenes, pfcu, stream, flush_buf)
                 w2 = WORKLOADS[n]
                 a2 = x["dev_px_per_step"] * w2["bytes_px"] / (x["raster_ms"] * 1e-3) / 1e9 if x["raster_ms"] > 0 else 0.0

@@ -304,13 +304,17 @@ static mesh_t make_heightfield(int n)
 
 /* ---- C4: overdraw -------------------------------------------------------------------------------- */
 
-static void draw_textured_quad(PFtexture tex, float x, float y, float w, float h, float urep, float vrep)
+static void draw_textured_quad(PFtexture tex, float x, float y, float w, float h, float urep, float vrep, int tinted)
 {
     pfBindTexture(tex);
     pfBegin(PF_QUADS);
+    if (tinted) pfColor4ub(255, 200, 150, 220);
     pfTexCoord2f(0.0f, 0.0f); pfVertex2f(x, y);
+    if (tinted) pfColor4ub(200, 255, 180, 255);
     pfTexCoord2f(0.0f, vrep); pfVertex2f(x, y + h);
+    if (tinted) pfColor4ub(160, 210, 255, 240);
     pfTexCoord2f(urep, vrep); pfVertex2f(x + w, y + h);
+    if (tinted) pfColor4ub(255, 255, 200, 230);
     pfTexCoord2f(urep, 0.0f); pfVertex2f(x + w, y);
     pfEnd();
     pfBindTexture(0);
@@ -736,11 +740,14 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
         pfEnable(PF_DEPTH_TEST); pfEnable(PF_CULL_FACE);
     } else if (strcmp(name, "overdraw") == 0) {
         /* variant: bit0 alpha-blend + depth test (the "4K textured+blended" target scene) instead of
-           additive / no depth test; bit1 bilinear */
-        s->texpx = make_texture(512, 512, 4, (uint32_t)cfg->seed, 0, 3, (cfg->variant & 1) ? 96 : 0, (cfg->variant & 1) ? 200 : 3);
-        if (cfg->variant & 1) { lcg_state = 7u; for (size_t i = 0; i < 512u * 512u; i++) for (int c = 0; c < 3; c++) s->texpx[i * 4 + c] = (uint8_t)(lcg() >> 24); }
-        s->tex = pfGenTexture(s->texpx, 512, 512, PF_RGBA, PF_UNSIGNED_BYTE);
-        pfTextureParameter(s->tex, PF_REPEAT, (cfg->variant & 2) ? PF_BILINEAR : PF_NEAREST);
+           additive / no depth test; bit1 bilinear; the scene off its most specialised path: bit2 tinted vertex colours
+           (a different colour per corner), bit3 CLAMP_TO_EDGE, bit4 RGB8 texture, bit5 two fragment states in one
+           batch (odd layers blend additively) */
+        const int comps = (cfg->variant & 16) ? 3 : 4;
+        s->texpx = make_texture(512, 512, comps, (uint32_t)cfg->seed, 0, 3, (cfg->variant & 1) ? 96 : 0, (cfg->variant & 1) ? 200 : 3);
+        if (cfg->variant & 1) { lcg_state = 7u; for (size_t i = 0; i < 512u * 512u; i++) for (int c = 0; c < 3; c++) s->texpx[i * comps + c] = (uint8_t)(lcg() >> 24); }
+        s->tex = pfGenTexture(s->texpx, 512, 512, comps == 3 ? PF_RGB : PF_RGBA, PF_UNSIGNED_BYTE);
+        pfTextureParameter(s->tex, (cfg->variant & 8) ? PF_CLAMP_TO_EDGE : PF_REPEAT, (cfg->variant & 2) ? PF_BILINEAR : PF_NEAREST);
         ortho2d(w, h);
         pfEnable(PF_TEXTURE_2D); pfEnable(PF_BLEND);
         if (cfg->variant & 1) { pfBlendFunc(PF_BLEND_ALPHA); pfEnable(PF_DEPTH_TEST); pfDepthFunc(PF_LEQUAL); }
@@ -842,8 +849,12 @@ SCN_API void pfscene_frame(void *handle, int frame)
         pfClearColor(0, 0, 0, 255);
         pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
         pfColor4ub(255, 255, 255, 255);
-        for (int l = 0; l < layers; l++)
-            draw_textured_quad(s->tex, 0.0f, 0.0f, (float)w, (float)h, (float)w / 512.0f, (float)h / 512.0f);
+        /* CLAMP_TO_EDGE: texture coordinates 0..1 over the screen, so that every texel is still visited */
+        const float ur = (cfg->variant & 8) ? 1.0f : (float)w / 512.0f, vr = (cfg->variant & 8) ? 1.0f : (float)h / 512.0f;
+        for (int l = 0; l < layers; l++) {
+            if (cfg->variant & 32) pfBlendFunc((l & 1) ? PF_BLEND_ADD : ((cfg->variant & 1) ? PF_BLEND_ALPHA : PF_BLEND_SCREEN));
+            draw_textured_quad(s->tex, 0.0f, 0.0f, (float)w, (float)h, ur, vr, (cfg->variant & 4) != 0);
+        }
     } else if (strcmp(name, "micro") == 0) {
         if (cfg->variant & (1 << 20)) {
             /* pass 1: render into the FBO; pass 2: draw it as a texture over the main buffer */
@@ -857,7 +868,7 @@ SCN_API void pfscene_frame(void *handle, int frame)
             pfDisable(PF_LIGHTING); pfDisable(PF_DEPTH_TEST); pfEnable(PF_TEXTURE_2D); pfEnable(PF_BLEND); pfBlendFunc(PF_BLEND_ALPHA);
             pfTextureParameter(s->fbo.texture, PF_REPEAT, PF_NEAREST);   /* CLAMP would index row h of the FBO at v == 1 (reads past the reference's own allocation) */
             pfColor4ub(255, 255, 255, 255);
-            draw_textured_quad(s->fbo.texture, 8.0f, 6.0f, 0.7f * w, 0.6f * h, 1.0f, 1.0f);
+            draw_textured_quad(s->fbo.texture, 8.0f, 6.0f, 0.7f * w, 0.6f * h, 1.0f, 1.0f, 0);
         } else micro_scene(cfg, s->tex);
     } else if (strcmp(name, "api") == 0) {
         api_scene(cfg, s->tex, s->aux);

@@ -44,6 +44,13 @@ CASES = [
     ("c4-overdraw-alpha-depth", "overdraw", 512, 256, dict(size=8, variant=1), False),
     ("c4-overdraw-alpha-depth-bilinear", "overdraw", 256, 128, dict(size=4, variant=3), True),
     ("c5-batch", "batch", 256, 256, dict(size=3), False),
+    # the overdraw scene off its most specialised fragment program (bench extras ns4k_*): tinted corners, CLAMP_TO_EDGE,
+    # RGB8 texture, two fragment states in one batch
+    ("c4-overdraw-alpha-depth-tinted", "overdraw", 512, 256, dict(size=8, variant=1 | 4), False),
+    ("c4-overdraw-alpha-depth-clamp", "overdraw", 512, 256, dict(size=8, variant=1 | 8), False),
+    ("c4-overdraw-alpha-depth-rgb8", "overdraw", 512, 256, dict(size=8, variant=1 | 16), False),
+    ("c4-overdraw-alpha-depth-two-state", "overdraw", 512, 256, dict(size=8, variant=1 | 32), False),
+    ("c4-overdraw-add-screen-tinted-clamp-rgb8", "overdraw", 512, 256, dict(size=8, variant=4 | 8 | 16 | 32), False),
 ]
 # every blend mode / depth function / draw mode / wrap mode / shade mode of the hot path
 CASES += [_micro(f"blend{b}", 1, blend=b, cull_off=1) for b in range(8)]

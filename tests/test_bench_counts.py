@@ -29,7 +29,8 @@ def test_overdraw_closed_form(counts, oracle_scenes):
     """Each full-screen quad layer shades (W-1)*H pixels plus the pixels on the shared diagonal (hit by both
     triangles, Q4); the count per layer is measured on a small surface with the same aspect logic and the
     committed 8K/4K numbers must be exactly layers * per-layer."""
-    for name, w, h in (("c4_overdraw_8k", 7680, 4320), ("ns_textured_blend_4k", 3840, 2160)):
+    for name, w, h in (("c4_overdraw_8k", 7680, 4320), ("ns_textured_blend_4k", 3840, 2160), ("ns4k_tinted", 3840, 2160), ("ns4k_clamp", 3840, 2160),
+                       ("ns4k_rgb8", 3840, 2160), ("ns4k_two_state", 3840, 2160), ("ns4k_bilinear", 3840, 2160)):
         per_layer = counts[name]["pixels_shaded"] // 64
         assert per_layer * 64 == counts[name]["pixels_shaded"]
         assert (w - 1) * h <= per_layer <= (w - 1) * h + w + h

@@ -479,7 +479,8 @@ def _bench_workloads():
     return bench
 
 
-@pytest.mark.parametrize("name", ["c1_gears_800x600", "c2_textured_1080p", "c3_phong_4k", "c4_overdraw_8k", "ns_textured_blend_4k", "c5_batch_512"])
+@pytest.mark.parametrize("name", ["c1_gears_800x600", "c2_textured_1080p", "c3_phong_4k", "c4_overdraw_8k", "ns_textured_blend_4k", "c5_batch_512",
+                                  "ns4k_tinted", "ns4k_clamp", "ns4k_rgb8", "ns4k_two_state", "ns4k_bilinear"])
 def test_fullsize_reference_equivalence(name, product_scenes, ref_scenes, ref_bfix_scenes):
     bench = _bench_workloads()
     wl = bench.WORKLOADS[name]

@@ -240,6 +240,13 @@ static cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+/* the single-program instantiations of the big-triangle rasteriser, full tiles and half-height slices */
+template <int PROG> static cudaError_t launch_fixed(bool half, unsigned grid, cudaStream_t st, const RasterParams &p)
+{
+    return half ? launch_dep(k_raster<false, 8, PROG, 32>, dim3(grid * 2), dim3(256), (size_t)0, st, p)
+                : launch_dep(k_raster<false, 8, PROG, 64>, dim3(grid), dim3(256), (size_t)0, st, p);
+}
+
 template <typename T> static int grow(T **p, size_t *cap, size_t need)
 {
     if (need <= *cap) return PFCU_OK;
@@ -902,15 +909,18 @@ void pfcu_texture_destroy(pfcu_texture *t)
 
 /* ---- the hot path ---- */
 
-/* state program of a DevState, same numbering as k_raster's per-triangle dispatch */
+/* state program of a DevState: texm * 4 + blendm with texm 0 none, 1 nearest + REPEAT + RGBA8, 3 nearest (any wrap mode /
+   texel layout), 4 bilinear - the FIXED_PROG numbering of k_raster (pfcu_raster_tiles.cuh); per-fragment Phong: PROG_PHONG */
+#define PROG_PHONG 20
 static int state_program(const DevState *d)
 {
-    if (d->flags & PFCU_ST_PHONG) return 12;
+    if (d->flags & PFCU_ST_PHONG) return PROG_PHONG;
     int texm = 0;
-    if (d->flags & PFCU_ST_TEXTURE) texm = (d->tfmt == PFCU_TEX_RGBA8 && d->tex_wrap == 0 && d->tex_filter == 0) ? 1 : 2;
+    if (d->flags & PFCU_ST_TEXTURE) texm = d->tex_filter != 0 ? 4 : ((d->tfmt == PFCU_TEX_RGBA8 && d->tex_wrap == 0) ? 1 : 3);
     const int blendm = !(d->flags & PFCU_ST_BLEND) ? 0 : (d->blend_mode == 1 ? 1 : (d->blend_mode == 2 ? 2 : 3));
     return texm * 4 + blendm;
 }
+
 
 static int g_last_single_prog = -1;      /* set by convert_states: the common program of all states, or -1 */
 static bool g_last_leader_tex = false;   /* set by convert_states: some state samples through the BGRA8 getter */
@@ -962,8 +972,21 @@ static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
         }
         memcpy(d->view_pos, s->view_pos, 12);
         mask |= d->flags;
+        /* the program every state of the batch runs, or their join where one exists: blend modes that differ become
+           "any mode" (run-time switch, blending on in all of them), nearest samplers that differ become "nearest, any wrap
+           mode / layout" - e.g. layers that alternate between alpha and additive blending still get a one-program kernel */
         const int prog = state_program(d);
-        if (i == 0) g_last_single_prog = prog; else if (g_last_single_prog != prog) g_last_single_prog = -1;
+        if (i == 0) g_last_single_prog = prog;
+        else if (g_last_single_prog != prog && g_last_single_prog >= 0) {
+            const int a = g_last_single_prog, b = prog;
+            int texm = -1, blendm = -1;
+            if (a < PROG_PHONG && b < PROG_PHONG) {
+                const int ta = a / 4, tb = b / 4, ba = a % 4, bb = b % 4;
+                texm = ta == tb ? ta : (((ta == 1 || ta == 3) && (tb == 1 || tb == 3)) ? 3 : -1);
+                blendm = ba == bb ? ba : ((ba != 0 && bb != 0) ? 3 : -1);
+            }
+            g_last_single_prog = (texm >= 0 && blendm >= 0) ? texm * 4 + blendm : -1;
+        }
     }
     return mask;
 }
@@ -1118,7 +1141,8 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         const bool ph = (feature_mask & PFCU_ST_PHONG) != 0;
         if (g.rcp_bits > RCP_SMEM_BITS) single_prog = -1;      /* the fixed-program kernels assume the shared RCPPS table */
         /* half-height slices when the 64x64 grid would be only a few waves deep with a ragged last wave */
-        const int per_sm = (single_prog == 5 || single_prog == 6) ? 4 : 3;
+        const bool fixed = single_prog >= 0 && single_prog < PROG_PHONG && !small_tris && !use_frag;
+        const int per_sm = (fixed && single_prog / 4 != 4) ? 4 : 3;
         const double waves = (double)grid / ((double)g.sms * per_sm);
         const bool half = !small_tris && !ph && waves < 8.0 && (ceil(waves) / waves) > 1.06 && (ceil(2 * waves) / (2 * waves)) < (ceil(waves) / waves);
         if (use_frag) {
@@ -1139,8 +1163,16 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
             else               CK(launch_dep(k_raster<false, 16, -1, 64>, dim3(grid), dim3(512), (size_t)(0), LN.stream, p));
         }
         else if (ph)          CK(launch_dep(k_raster<true, 8, -1, 64>, dim3(grid), dim3(256), (size_t)(0), LN.stream, p));
-        else if (single_prog == 5) { if (half) CK(launch_dep(k_raster<false, 8, 5, 32>, dim3(grid * 2), dim3(256), (size_t)(0), LN.stream, p)); else CK(launch_dep(k_raster<false, 8, 5, 64>, dim3(grid), dim3(256), (size_t)(0), LN.stream, p)); }   /* nearest REPEAT RGBA8 texture + ALPHA blend */
-        else if (single_prog == 6) { if (half) CK(launch_dep(k_raster<false, 8, 6, 32>, dim3(grid * 2), dim3(256), (size_t)(0), LN.stream, p)); else CK(launch_dep(k_raster<false, 8, 6, 64>, dim3(grid), dim3(256), (size_t)(0), LN.stream, p)); }   /* nearest REPEAT RGBA8 texture + ADD blend   */
+        else if (fixed) {
+            /* one state program in the whole batch: the kernel that holds only that fragment program */
+            switch (single_prog) {
+#define FIXED_CASE(P) case P: CK(launch_fixed<P>(half, grid, LN.stream, p)); break;
+            FIXED_CASE(0) FIXED_CASE(1) FIXED_CASE(2) FIXED_CASE(3) FIXED_CASE(4) FIXED_CASE(5) FIXED_CASE(6) FIXED_CASE(7)
+            FIXED_CASE(12) FIXED_CASE(13) FIXED_CASE(14) FIXED_CASE(15) FIXED_CASE(16) FIXED_CASE(17) FIXED_CASE(18) FIXED_CASE(19)
+#undef FIXED_CASE
+            default: snprintf(g.err, sizeof g.err, "internal: no kernel for state program %d", single_prog); return PFCU_ERR_INVALID;
+            }
+        }
         else { if (half) CK(launch_dep(k_raster<false, 8, -1, 32>, dim3(grid * 2), dim3(256), (size_t)(0), LN.stream, p)); else CK(launch_dep(k_raster<false, 8, -1, 64>, dim3(grid), dim3(256), (size_t)(0), LN.stream, p)); }
         g.launches++;
     }

@@ -255,6 +255,19 @@ __device__ __forceinline__ unsigned tex_fetch(const TexRegs &t, int x, int y)
     return (t.fmt == PFCU_TEX_RGB8) ? (b0 | (b1 << 8) | (b2 << 16) | 0xff000000u) : (b2 | (b1 << 8) | (b0 << 16) | 0xff000000u);
 }
 
+__device__ __forceinline__ unsigned tex_sample_bilinear(const TexRegs &t, const DevState *st, float u, float v)
+{
+    const int x0 = tex_coord(t.wrap, u, t.wm1), y0 = tex_coord(t.wrap, v, t.hm1);
+    const float4 k = __ldg(reinterpret_cast<const float4 *>(&st->tex_fw));       /* fw, fh, 1/fw, 1/fh */
+    const float fw = k.x, fh = k.y, tx = k.z, ty = k.w;
+    const int x1 = tex_coord(t.wrap, FA(u, tx), t.wm1), y1 = tex_coord(t.wrap, FA(v, ty), t.hm1);
+    const float fx = clamp_x86(FS(FM(u, fw), __int2float_rn(x0)), 0.0f, 1.0f);
+    const float fy = clamp_x86(FS(FM(v, fh), __int2float_rn(y0)), 0.0f, 1.0f);
+    const unsigned c00 = tex_fetch(t, x0, y0), c10 = tex_fetch(t, x1, y0);
+    const unsigned c01 = tex_fetch(t, x0, y1), c11 = tex_fetch(t, x1, y1);
+    return color_lerp(color_lerp(c00, c10, fx), color_lerp(c01, c11, fx), fy);
+}
+
 __device__ __forceinline__ unsigned tex_sample(const TexRegs &t, const DevState *st, float u, float v)
 {
     const int x0 = tex_coord(t.wrap, u, t.wm1), y0 = tex_coord(t.wrap, v, t.hm1);

@@ -142,11 +142,13 @@ struct TileCtx {
 };
 
 /* One triangle over the 8x4 blocks this warp owns.  TEXM: 0 no texture, 1 nearest+REPEAT+RGBA8,
- * 2 any sampler.  BLENDM: 0 off, 1 ALPHA, 2 ADD, 3 any mode.  Everything is computed for all 32 lanes
+ * 2 any sampler, 3 nearest with any wrap mode / texel layout, 4 bilinear with any wrap mode / texel layout (3 and 4
+ * exist so that a batch in ONE such program gets a kernel without the other filter's code and registers).
+ * BLENDM: 0 off, 1 ALPHA, 2 ADD, 3 any mode.  Everything is computed for all 32 lanes
  * (no divergent regions); only the final stores are predicated by the coverage/depth mask.
  * BIG: the launch is a batch of large triangles in ONE state program with the RCPPS table in shared memory
  * (launch_pipeline checks both), so some per-block early-outs and run-time checks are dropped. */
-template <int TEXM, int BLENDM, bool PHONG, int NW, bool BIG>
+template <int TEXM, int BLENDM, bool PHONG, int NW, bool BIG, bool GREY = false>
 __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const int4 b, const TriSetup &s, const uint4 a0, const uint4 a1,
                                           const DevState *st, const unsigned flags, const unsigned zmask, const int blend_mode, const TexRegs &tex)
 {
@@ -164,8 +166,9 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
     const unsigned c3rb = a1.z & 0x00ff00ffu, c3ga = (a1.z >> 8) & 0x00ff00ffu;
     const bool same_color = (a1.x == a1.y) && (a1.y == a1.z);
     /* untinted (white / grey, alpha included) smooth-shaded textured triangles: the interpolated colour is one
-       scalar, see the grey_tex branches below */
-    const bool grey_tex = BIG && !PHONG && TEXM != 0 && same_color && smooth && a1.x == (a1.x & 0xffu) * 0x01010101u;
+       scalar, see the grey_tex branches below.  A template parameter (the caller tests the triangle with grey_triangle()):
+       as a run-time flag the compiler evaluates both colour paths for every fragment and selects. */
+    constexpr bool grey_tex = GREY;
     float tu1 = 0, tu2 = 0, tu3 = 0, tv1 = 0, tv2 = 0, tv3 = 0;
     const bool texturing = TEXM != 0 && (!PHONG || (flags & PFCU_ST_TEXTURE));     /* the Phong variant checks at run time */
     const bool blending = BLENDM != 0 && (!PHONG || (flags & PFCU_ST_BLEND));
@@ -182,9 +185,35 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
     const int e3 = wadd(wadd(s.w3R, wmul(dy0, s.w3Y)), wmul(dx0, s.w3X));
     const int rxc = t.lx8 - cx0, ryc = t.ly4 - cy0;            /* lane offset from the clipped bbox corner */
 
-    /* block ownership: 8 warps -> warp w owns block (bx,by) iff (bx + 3*by) & 7 == w;
-       16 warps -> additionally even block rows belong to warps 0..7, odd rows to warps 8..15 */
-    for (int by = (NW == 16) ? by0 + ((by0 ^ (t.warp >> 3)) & 1) : by0; by <= by1; by += (NW == 16) ? 2 : 1) {
+    /* block ownership: 8 warps -> warp w owns block (bx,by) iff (bx + 3*by) & 7 == w (one block per block row);
+       16 warps -> additionally even block rows belong to warps 0..7, odd rows to warps 8..15.
+       Which block rows can this warp's block be covered in?  Lane r answers for block row r, all rows at once: the block
+       must meet the clipped bbox and - when the int32 edge functions cannot wrap inside the bbox (TF_SAFE) - every edge
+       function must reach a non-negative value on the block's part of the bbox (its maximum lies on the corner picked
+       by the signs of the edge's steps).  Conservative, so the exact per-pixel test below decides; what it buys is that
+       the half of a large triangle's bounding box that lies outside the triangle costs one vote per triangle instead
+       of an edge evaluation per block.  Triangles of a few block rows skip the vote and walk their rows. */
+    unsigned rows;
+    if (by1 - by0 >= 3) {
+        const int r = (int)(threadIdx.x & 31u);
+        const int rbx = ((t.warp & 7) - 3 * r) & 7;
+        const int xlo = max(rbx << 3, cx0), xhi = min((rbx << 3) + 7, cx1), ylo = max(r << 2, cy0), yhi = min((r << 2) + 3, cy1);
+        bool ok = xlo <= xhi && ylo <= yhi && (NW != 16 || (((r ^ (t.warp >> 3)) & 1) == 0));
+        if (s.flags & TF_SAFE) {
+            const int ox = t.X0 - b.x, oy = t.Y0 - b.y;
+            const int ax0 = xlo + ox, ax1 = xhi + ox, ay0 = ylo + oy, ay1 = yhi + oy;
+            const int m1 = s.w1R + (s.w1X > 0 ? ax1 : ax0) * s.w1X + (s.w1Y > 0 ? ay1 : ay0) * s.w1Y;
+            const int m2 = s.w2R + (s.w2X > 0 ? ax1 : ax0) * s.w2X + (s.w2Y > 0 ? ay1 : ay0) * s.w2Y;
+            const int m3 = s.w3R + (s.w3X > 0 ? ax1 : ax0) * s.w3X + (s.w3Y > 0 ? ay1 : ay0) * s.w3Y;
+            ok = ok && (m1 | m2 | m3) >= 0;
+        }
+        rows = __ballot_sync(0xffffffffu, ok);
+    } else {
+        rows = ((2u << by1) - 1u) & ~((1u << by0) - 1u);
+        if (NW == 16) rows &= ((t.warp >> 3) & 1) ? 0xaaaaaaaau : 0x55555555u;
+    }
+    while (rows) {
+        const int by = __ffs(rows) - 1; rows &= rows - 1u;
         const int bx = ((t.warp & 7) - 3 * by) & 7;
         /* skipping blocks left/right of the bbox early pays for small triangles only; the per-lane
            x-range test below rejects them anyway */
@@ -251,7 +280,9 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
                 const unsigned off = (unsigned)yi * tex.tw + (unsigned)xi;
                 texel = 0u;
                 if (off < tex.total) texel = __ldg((const unsigned *)tex.base + off);
-            } else texel = tex_sample(tex, st, u, v);
+            } else if (TEXM == 3) texel = tex_fetch(tex, tex_coord(tex.wrap, u, tex.wm1), tex_coord(tex.wrap, v, tex.hm1));
+            else if (TEXM == 4) texel = tex_sample_bilinear(tex, st, u, v);
+            else texel = tex_sample(tex, st, u, v);
             if (grey_tex) {                         /* (texel_c * k) >> 8 on packed lanes: products stay below 2^16 */
                 frag.rb = (((texel & 0x00ff00ffu) * kgrey) >> 8) & 0x00ff00ffu;
                 frag.ga = ((((texel >> 8) & 0x00ff00ffu) * kgrey) >> 8) & 0x00ff00ffu;
@@ -285,10 +316,17 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
     }
 }
 
-/* FIXED_PROG >= 0: the whole batch runs one state program (texm*4 + blendm), known at launch; only that
- * variant is instantiated, which lets the register allocator fit 4 CTAs per SM.  -1: per-triangle dispatch. */
+/* smooth-shaded triangle whose three vertex colours are one grey (all four channels equal): see shade_tri<GREY> */
+__device__ __forceinline__ bool grey_triangle(const uint4 a1, unsigned flags)
+{
+    return (flags & PFCU_ST_SMOOTH) && a1.x == a1.y && a1.y == a1.z && a1.x == (a1.x & 0xffu) * 0x01010101u;
+}
+
+/* FIXED_PROG >= 0: the whole batch runs one state program (texm*4 + blendm, texm in {0, 1, 3, 4}: state_program() in
+ * pfcu.cu), known at launch; only that variant is instantiated, which lets the register allocator fit 4 CTAs per SM
+ * (bilinear: 3).  -1: per-triangle dispatch over the programs texm in {0, 1, 2}. */
 template <bool HAS_PHONG, int NW, int FIXED_PROG, int TH>
-__global__ void __launch_bounds__(NW * 32, FIXED_PROG >= 0 ? 4 : (NW == 16 ? (HAS_PHONG ? 1 : 2) : (HAS_PHONG ? 2 : 3)))
+__global__ void __launch_bounds__(NW * 32, FIXED_PROG >= 0 ? (FIXED_PROG / 4 == 4 ? 3 : 4) : (NW == 16 ? (HAS_PHONG ? 1 : 2) : (HAS_PHONG ? 2 : 3)))
 k_raster(const RasterParams p)
 {
     pdl_wait();         /* launched as a programmatic dependent of the binning kernels; before ANY exit, so that the grid cannot complete early */
@@ -454,7 +492,10 @@ k_raster(const RasterParams p)
                     if (HAS_PHONG && (flags & PFCU_ST_PHONG)) prog = 12;
                 }
                 if (FIXED_PROG >= 0) {
-                    shade_tri<FIXED_PROG / 4, FIXED_PROG % 4, false, NW, true>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex);
+                    if (FIXED_PROG / 4 != 0 && grey_triangle(a1, flags))
+                        shade_tri<FIXED_PROG / 4, FIXED_PROG % 4, false, NW, true, true>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex);
+                    else
+                        shade_tri<FIXED_PROG / 4, FIXED_PROG % 4, false, NW, true, false>(t, ti, b, s, a0, a1, st, flags, zmask, blend_mode, tex);
                     continue;
                 }
                 switch (prog) {

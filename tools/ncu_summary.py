@@ -16,7 +16,8 @@ KEEP = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
 
 def main():
     rep, out, label = sys.argv[1:4]
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # an .ncu-rep, or the `--page raw --csv` export of one (tools/ncu_capture.sh)
+    txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     h, units, r = rows[0], rows[1], rows[2]
     d = {}

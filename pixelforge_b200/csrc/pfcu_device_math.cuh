@@ -153,16 +153,39 @@ __device__ __forceinline__ unsigned mul_color(unsigned a, unsigned b)
 
 /* color.h:137-144 (Q7 fixed), for t in [0, 1] (the samplers clamp fx, fy; NaN becomes 0).  A and B are in [0, 1] and
  * representable, and rounding is monotone, so A + t*(B - A) stays between A and B: the clamp of pfiColorPackFromF
- * (quant) is the identity here and is left out. */
+ * (quant) is the identity here and is left out.
+ * The int <-> float conversions are done with exact float tricks instead of I2F / F2I: those run on the XU pipe, which the
+ * bilinear filter (36 conversions per fragment) saturated (ncu: pipe_xu 76 % on the 4K bilinear scene).
+ *   float(b), b a byte:  bits 0x4b000000 | b are the float 2^23 + b; subtracting 2^23 is exact;
+ *   RNE(x), 0 <= x <= 255:  x + 1.5 * 2^23 is rounded to an integer by the addition itself (ulp 1), to nearest-even
+ *                           like CVTPS2DQ; the integer sits in the low bits of the sum. */
+#define LERP_MAGIC 12582912.0f          /* 1.5 * 2^23 */
+__device__ __forceinline__ float byte_unit(unsigned c, int i)       /* float(byte i of c) * (1/255) */
+{
+    return FM(FS(__uint_as_float(__byte_perm(c, 0x4b000000u, 0x7440u | (unsigned)i)), 8388608.0f), INV255);
+}
+/* one channel: the sum x*255 + LERP_MAGIC, whose low byte is the quantised result */
+__device__ __forceinline__ float lerp_chan(float A, float B, float t) { return FA(FM(FA(A, FM(t, FS(B, A))), 255.0f), LERP_MAGIC); }
+__device__ __forceinline__ float magic_unit(float y) { return FM(FS(y, LERP_MAGIC), INV255); }      /* float(low bits of y) * (1/255) */
+
 __device__ __forceinline__ unsigned color_lerp(unsigned a, unsigned b, float t)
 {
-    unsigned p = 0;
+    float y[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) y[i] = lerp_chan(byte_unit(a, i), byte_unit(b, i), t);
+    return __byte_perm(__byte_perm(__float_as_uint(y[0]), __float_as_uint(y[1]), 0x0040), __byte_perm(__float_as_uint(y[2]), __float_as_uint(y[3]), 0x0040), 0x5410);
+}
+
+/* the three lerps of a bilinear tap set; the two intermediate colours stay in their float form */
+__device__ __forceinline__ unsigned color_bilerp(unsigned c00, unsigned c10, unsigned c01, unsigned c11, float fx, float fy)
+{
+    float y[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const float A = FM(__int2float_rn(CHN(a, i)), INV255), B = FM(__int2float_rn(CHN(b, i)), INV255);
-        p |= (unsigned)__float2int_rn(FM(FA(A, FM(t, FS(B, A))), 255.0f)) << (8 * i);
+        const float top = lerp_chan(byte_unit(c00, i), byte_unit(c10, i), fx), bot = lerp_chan(byte_unit(c01, i), byte_unit(c11, i), fx);
+        y[i] = lerp_chan(magic_unit(top), magic_unit(bot), fy);
     }
-    return p;
+    return __byte_perm(__byte_perm(__float_as_uint(y[0]), __float_as_uint(y[1]), 0x0040), __byte_perm(__float_as_uint(y[2]), __float_as_uint(y[3]), 0x0040), 0x5410);
 }
 
 __device__ __forceinline__ unsigned blend_px(int mode, unsigned s, unsigned d)   /* blend.h:137-274 */
@@ -265,7 +288,7 @@ __device__ __forceinline__ unsigned tex_sample_bilinear(const TexRegs &t, const 
     const float fy = clamp_x86(FS(FM(v, fh), __int2float_rn(y0)), 0.0f, 1.0f);
     const unsigned c00 = tex_fetch(t, x0, y0), c10 = tex_fetch(t, x1, y0);
     const unsigned c01 = tex_fetch(t, x0, y1), c11 = tex_fetch(t, x1, y1);
-    return color_lerp(color_lerp(c00, c10, fx), color_lerp(c01, c11, fx), fy);
+    return color_bilerp(c00, c10, c01, c11, fx, fy);
 }
 
 __device__ __forceinline__ unsigned tex_sample(const TexRegs &t, const DevState *st, float u, float v)
@@ -279,7 +302,7 @@ __device__ __forceinline__ unsigned tex_sample(const TexRegs &t, const DevState 
     const float fy = clamp_x86(FS(FM(v, fh), __int2float_rn(y0)), 0.0f, 1.0f);
     const unsigned c00 = tex_fetch(t, x0, y0), c10 = tex_fetch(t, x1, y0);
     const unsigned c01 = tex_fetch(t, x0, y1), c11 = tex_fetch(t, x1, y1);
-    return color_lerp(color_lerp(c00, c10, fx), color_lerp(c01, c11, fx), fy);
+    return color_bilerp(c00, c10, c01, c11, fx, fy);
 }
 
 /* ------------------------------------------------------------------------------------------------ */

@@ -246,12 +246,44 @@ def parity_against_dump(scenes, wl_name, dump):
 
 # ---- our arm ---------------------------------------------------------------------------------------
 
+def uses_vertex_arrays(wl):
+    return wl["scene"] in ("textured", "phong") and bool(wl["variant"] & 32)
+
+
+def measure_e2e_static(wl_name, steps, warmup, torch, scenes, pfcu):
+    """End to end once more for the workloads that draw from vertex arrays, with the arrays declared static (pfxHostStatic:
+    the application promises to announce changes, the library keeps the arrays in device memory): what a program with
+    static meshes pays per frame - state, launches and the frame's read-back, no geometry over PCIe."""
+    from pixelforge_b200.binding import Counters
+    wl = WORKLOADS[wl_name]; L = pfcu.lib
+    os.environ["PFSCENE_STATIC_ARRAYS"] = "1"
+    try:
+        with scenes.open(wl["scene"], wl["w"], wl["h"], variant=wl["variant"], size=wl["size"], explicit_sync=1) as sc:
+            for i in range(max(warmup, 2)):
+                sc.frame(0); sc.finish()
+            L.pfxResetCounters()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                sc.frame(0); sc.finish()
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) / steps * 1e3
+            k = Counters(); L.pfcu_get_counters(k)
+            return {"ms_per_step": ms, "h2d_bytes_per_step": int(k.bytes_h2d / steps), "d2h_bytes_per_step": int(k.bytes_d2h / steps),
+                    "gpix_per_s": k.pixels_shaded / steps / (ms * 1e-3) / 1e9, "mtri_per_s": k.triangles_submitted / steps / (ms * 1e-3) / 1e6,
+                    "note": "vertex / index arrays declared static (pfxHostStatic): resident in HBM after the first frame"}
+    finally:
+        os.environ["PFSCENE_STATIC_ARRAYS"] = "0"
+
+
 def measure_workload(wl_name, steps, warmup, torch, scenes, pfcu, stream, flush_buf, want_e2e=True, tile_owner=None):
     """Returns a dict with device-resident (`value`) and end-to-end numbers for one workload."""
     from pixelforge_b200.binding import Counters, Profile, STATE_DTYPE, TRIANGLE_DTYPE
     wl = WORKLOADS[wl_name]
     L = pfcu.lib
     out = {"workload": wl_name}
+    if want_e2e and uses_vertex_arrays(wl):
+        out["e2e_static"] = measure_e2e_static(wl_name, steps, warmup, torch, scenes, pfcu)
     with scenes.open(wl["scene"], wl["w"], wl["h"], variant=wl["variant"], size=wl["size"], explicit_sync=1) as sc:
         L.pfcu_set_stream(stream.cuda_stream)
         n_ctx = wl["size"] if wl["scene"] == "batch" else 1
@@ -417,6 +449,8 @@ def ours_main(args):
                             "e2e_ms_per_step": x["e2e_ms"], "shaded_px_per_step": x["dev_px_per_step"], "triangles_per_step": x["dev_tris_per_step"],
                             "roofline": {"bound": "hbm", "achieved": a2, "peak": peak, "unit": "GB/s", "frac": a2 / peak, "bytes_per_px": w2["bytes_px"],
                                          "raster_ms": x["raster_ms"], "frontend_ms": x["frontend_ms"]}}
+                if "e2e_static" in x:
+                    extra[n]["e2e_static_geometry"] = x["e2e_static"]
             except Exception as e:   # an extra must never take the headline down
                 extra[n] = {"error": repr(e)}
         if world > 1 and not args.no_extra:
@@ -475,7 +509,8 @@ def ours_main(args):
         "measured_per_step": {"triangles": tris_all / world, "shaded_px": px_all / world},
         "mtri_per_s": tris_all / (dev_ms * 1e-3) / 1e6,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": m["d2h_bytes"],
-                "ms_per_step": e2e_ms, "mtri_per_s": sum_over_ranks(m["tris_per_step"]) / (e2e_ms * 1e-3) / 1e6 if world == 1 else None},
+                "ms_per_step": e2e_ms, "mtri_per_s": sum_over_ranks(m["tris_per_step"]) / (e2e_ms * 1e-3) / 1e6 if world == 1 else None,
+                "static_geometry": m.get("e2e_static")},
         "gpu_launches": int(round(m["launches_per_step"] * args.steps)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "k_raster_frag" if wl["scene"] in ("textured", "phong", "gears", "batch") else "k_raster",

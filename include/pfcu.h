@@ -146,6 +146,13 @@ PFCU_API int   pfcu_host_wait(const void *p);
 PFCU_API int   pfcu_host_register(void *p, size_t bytes);
 PFCU_API void  pfcu_host_unregister(void *p);
 
+/* Static geometry: a block from pfcu_host_alloc whose content does not change from draw to draw is mirrored in device
+ * memory at the first pfcu_draw_triangles that reads an array out of it; later draws read the mirror and nothing crosses
+ * PCIe.  pfcu_host_modified(p) tells the library that the application rewrote (part of) the block: the next draw uploads
+ * it again.  Both return PFCU_ERR_INVALID for memory that is not a pfcu_host_alloc block. */
+PFCU_API int   pfcu_host_set_static(void *p, int on);
+PFCU_API int   pfcu_host_modified(void *p);
+
 /* Tables that reproduce the host's RCPPS / RSQRTPS (reference: src/internal/simd.h:1217-1245).
  * rcp[i], i = top `rcp_bits` mantissa bits: float bits of rcp(1.m);  rsqrt[(odd<<rsqrt_bits)|i]:
  * float bits of rsqrt(1.m * 2^odd).  Harvested by the host library from the CPU it runs on. */

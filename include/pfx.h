@@ -60,6 +60,13 @@ PF_API int pfxSpecularTableCheck(PFfloat shininess, PFuint samples);
  * malloc'ed memory works everywhere, as with the reference.  Free with pfxHostFree (after the last call that used it). */
 PF_API void *pfxHostAlloc(size_t bytes);
 PF_API void  pfxHostFree(void *p);
+/* Static geometry.  The reference reads the vertex and index arrays of pfDrawElements / pfDrawArrays from the caller's
+ * memory at every draw; this library copies them to the GPU at every draw, because it cannot know whether the
+ * application changed them.  pfxHostStatic(p, PF_TRUE) on a pfxHostAlloc block is the application's promise that it
+ * announces changes: the block is copied to the device once and draws whose arrays lie inside it move no vertex data
+ * over PCIe; after rewriting (any part of) the block call pfxHostModified(p) and the next draw uploads it again. */
+PF_API void pfxHostStatic(void *p, PFboolean isStatic);
+PF_API void pfxHostModified(void *p);
 /* Texel memory is copied to the device at the first draw that samples the texture; the reference reads the caller's
  * memory at every fragment, so a program that rewrites texels in place (video frames, procedural updates) calls this
  * after each rewrite to have them uploaded again.  Draw calls issued before it keep the old texels. */

@@ -1155,6 +1155,8 @@ void pfxTextureDirty(PFtexture texture)
 
 void *pfxHostAlloc(size_t bytes) { return pfh_runtime_init() ? pfcu_host_alloc(bytes) : NULL; }
 void pfxHostFree(void *p) { if (p) { pfcu_finish(); pfcu_host_free(p); } }
+void pfxHostStatic(void *p, PFboolean isStatic) { if (p && pfh_runtime_init()) pfcu_host_set_static(p, isStatic ? 1 : 0); }
+void pfxHostModified(void *p) { if (p && pfh_runtime_init()) pfcu_host_modified(p); }
 void pfxEnableDeviceVertexStage(PFboolean on) { if (pf_cur) pf_cur->device_vertex = on ? 1 : 0; }
 
 void pfxCaptureBegin(void)

@@ -119,7 +119,13 @@ struct pfcu_batch {
 /* runtime state                                                                                    */
 /* ------------------------------------------------------------------------------------------------ */
 
-struct PinnedBlock { void *p; size_t bytes; cudaEvent_t done; bool pending; };
+struct PinnedBlock {
+    void *p; size_t bytes; cudaEvent_t done; bool pending;
+    /* static geometry (pfcu_host_set_static): the block is mirrored in device memory and draws read the mirror; gen counts
+       the application's modifications, dev_gen is what the mirror holds */
+    bool is_static; unsigned gen, dev_gen; unsigned char *d_copy;
+    const void *imax_ptr; uint32_t imax_count, imax_value; unsigned imax_gen;     /* largest index of the last index range scanned */
+};
 
 /* A lane = one CUDA stream plus the scratch buffers of the batches in flight on it.  Surfaces are spread
  * round-robin over the lanes so that independent contexts (BASELINE config C5) overlap on the GPU; work on
@@ -361,7 +367,7 @@ void pfcu_shutdown(void)
     g.d_jobs = nullptr; g.h_jobs = nullptr; g.cap_jobs = 0;
     if (g.jobs_copied) { cudaEventDestroy(g.jobs_copied); cudaEventDestroy(g.jobs_done); g.jobs_copied = g.jobs_done = nullptr; }
     /* blocks handed out by pfcu_host_alloc and never returned: released here, their pointers die with the runtime */
-    for (auto &b : g.pinned) { cudaEventDestroy(b.done); cudaFreeHost(b.p); }
+    for (auto &b : g.pinned) { cudaEventDestroy(b.done); cudaFreeHost(b.p); cudaFree(b.d_copy); }
     for (auto e : g.prof_events) cudaEventDestroy(e);
     for (auto e : g.prof_pool) cudaEventDestroy(e);
     g.prof_events.clear(); g.prof_pool.clear();
@@ -404,7 +410,7 @@ void *pfcu_host_alloc(size_t bytes)
 {
     if (!g.ok && pfcu_init(-1) != PFCU_OK) return nullptr;
     API_LOCK;
-    PinnedBlock b; b.bytes = bytes; b.pending = false;
+    PinnedBlock b; memset(&b, 0, sizeof b); b.bytes = bytes; b.pending = false; b.dev_gen = ~0u;
     if (cudaHostAlloc(&b.p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming) != cudaSuccess) { cudaFreeHost(b.p); return nullptr; }
     g.pinned.push_back(b);
@@ -422,10 +428,48 @@ void pfcu_host_free(void *p)
     API_LOCK;
     for (size_t i = 0; i < g.pinned.size(); i++) if (g.pinned[i].p == p) {
         if (g.pinned[i].pending) cudaEventSynchronize(g.pinned[i].done);
+        if (g.pinned[i].d_copy) { sync_all_lanes(); cudaFree(g.pinned[i].d_copy); }
         cudaEventDestroy(g.pinned[i].done); cudaFreeHost(p);
         g.pinned.erase(g.pinned.begin() + i);
         return;
     }
+}
+
+int pfcu_host_set_static(void *p, int on)
+{
+    API_LOCK;
+    PinnedBlock *b = find_pinned(p);
+    if (!b) return PFCU_ERR_INVALID;
+    b->is_static = on != 0;
+    if (!on && b->d_copy) { sync_all_lanes(); cudaFree(b->d_copy); b->d_copy = nullptr; b->dev_gen = ~0u; }
+    return PFCU_OK;
+}
+
+int pfcu_host_modified(void *p)
+{
+    API_LOCK;
+    PinnedBlock *b = find_pinned(p);
+    if (!b) return PFCU_ERR_INVALID;
+    b->gen++;
+    return PFCU_OK;
+}
+
+/* Device address of host array `p` (bytes long) when it lies in a static block: the block's device mirror, brought up to
+ * date first if the application modified the block since the last upload.  nullptr: not static (the caller copies). */
+static const unsigned char *static_mirror(const void *p, size_t bytes, PinnedBlock **blk)
+{
+    PinnedBlock *b = find_pinned(p);
+    if (blk) *blk = b;
+    if (!b || !b->is_static || (const char *)p + bytes > (const char *)b->p + b->bytes) return nullptr;
+    if (!b->d_copy && cudaMalloc(&b->d_copy, b->bytes + 16) != cudaSuccess) { cudaGetLastError(); b->d_copy = nullptr; return nullptr; }
+    if (b->dev_gen != b->gen) {
+        /* every lane may be reading the old mirror; the upload is rare (once per modification), so it simply waits */
+        sync_all_lanes();
+        if (cudaMemcpy(b->d_copy, b->p, b->bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        g.bytes_h2d += b->bytes;
+        b->dev_gen = b->gen;
+    }
+    return b->d_copy + ((const char *)p - (const char *)b->p);
 }
 
 int pfcu_host_register(void *p, size_t bytes)
@@ -1238,38 +1282,56 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     use_lane(s);
     const unsigned n_items = n_tri * d->n_faces;
     int rc;
-    /* arrays -> device (pageable sources are staged by the driver; ordered on the stream) */
+    /* arrays -> device (pageable sources are staged by the driver; ordered on the stream); arrays in a static block
+       (pfcu_host_set_static) are read from the block's device mirror instead and cross PCIe only when modified */
     size_t nv = d->n_vertices;
     const unsigned char *d_indices_ready = nullptr;
     if (nv == 0 && d->indices) {
-        /* n_vertices unknown: upload the (32-bit) indices first and let the device find the largest one */
+        /* n_vertices unknown: the device finds the largest (32-bit) index */
         if (d->index_bytes != 4) return PFCU_ERR_INVALID;
         const size_t bi = (size_t)d->count * 4;
-        if ((rc = grow(&LN.d_idx, &LN.cap_idx, bi))) return rc;
-        CK(cudaMemcpyAsync(LN.d_idx, d->indices, bi, cudaMemcpyHostToDevice, LN.stream));
-        CK(cudaMemsetAsync(LN.d_total, 0, 4, LN.stream));
-        k_index_max<<<g.sms * 4, 256, 0, LN.stream>>>((const unsigned *)LN.d_idx, d->count, LN.d_total);
-        g.launches++;
-        CK(cudaMemcpyAsync(&LN.h_total[0], LN.d_total, 4, cudaMemcpyDeviceToHost, LN.stream));
-        CK(cudaStreamSynchronize(LN.stream));
-        nv = (size_t)LN.h_total[0] + 1;
+        PinnedBlock *ib = nullptr;
+        const unsigned char *mir = static_mirror(d->indices, bi, &ib);
+        if (mir && ib->imax_ptr == d->indices && ib->imax_count == d->count && ib->imax_gen == ib->gen) {
+            nv = (size_t)ib->imax_value + 1;        /* scanned before, block unchanged since */
+            d_indices_ready = mir;
+        } else {
+            if (mir) d_indices_ready = mir;
+            else {
+                if ((rc = grow(&LN.d_idx, &LN.cap_idx, bi))) return rc;
+                CK(cudaMemcpyAsync(LN.d_idx, d->indices, bi, cudaMemcpyHostToDevice, LN.stream));
+                g.bytes_h2d += bi;
+                d_indices_ready = LN.d_idx;
+            }
+            CK(cudaMemsetAsync(LN.d_total, 0, 4, LN.stream));
+            k_index_max<<<g.sms * 4, 256, 0, LN.stream>>>((const unsigned *)d_indices_ready, d->count, LN.d_total);
+            g.launches++;
+            CK(cudaMemcpyAsync(&LN.h_total[0], LN.d_total, 4, cudaMemcpyDeviceToHost, LN.stream));
+            CK(cudaStreamSynchronize(LN.stream));
+            nv = (size_t)LN.h_total[0] + 1;
+            if (mir) { ib->imax_ptr = d->indices; ib->imax_count = d->count; ib->imax_value = LN.h_total[0]; ib->imax_gen = ib->gen; }
+        }
         if (nv > 0x7fffffffu) return PFCU_ERR_INVALID;
-        d_indices_ready = LN.d_idx;
     }
     const size_t b_pos = nv * d->pos_size * 4, b_nrm = d->normals ? nv * 12 : 0, b_uv = d->texcoords ? nv * 8 : 0;
     const size_t b_col = d->colors ? nv * d->color_size : 0, b_idx = (d->indices && !d_indices_ready) ? (size_t)d->count * d->index_bytes : 0;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t total_bytes = al(b_pos) + al(b_nrm) + al(b_uv) + al(b_col) + al(b_idx);
-    g.bytes_h2d += b_pos + b_nrm + b_uv + b_col + b_idx + sizeof(DevState);
-    if ((rc = grow(&LN.d_varrays, &LN.cap_varrays, total_bytes))) return rc;
+    const unsigned char *m_pos = static_mirror(d->positions, b_pos, nullptr);
+    const unsigned char *m_nrm = b_nrm ? static_mirror(d->normals, b_nrm, nullptr) : nullptr;
+    const unsigned char *m_uv = b_uv ? static_mirror(d->texcoords, b_uv, nullptr) : nullptr;
+    const unsigned char *m_col = b_col ? static_mirror(d->colors, b_col, nullptr) : nullptr;
+    const unsigned char *m_idx = b_idx ? static_mirror(d->indices, b_idx, nullptr) : nullptr;
+    const size_t total_bytes = (m_pos ? 0 : al(b_pos)) + (m_nrm ? 0 : al(b_nrm)) + (m_uv ? 0 : al(b_uv)) + (m_col ? 0 : al(b_col)) + (m_idx ? 0 : al(b_idx));
+    g.bytes_h2d += (m_pos ? 0 : b_pos) + (m_nrm ? 0 : b_nrm) + (m_uv ? 0 : b_uv) + (m_col ? 0 : b_col) + (m_idx ? 0 : b_idx) + sizeof(DevState);
+    if ((rc = grow(&LN.d_varrays, &LN.cap_varrays, total_bytes ? total_bytes : 256))) return rc;
     unsigned char *p = LN.d_varrays;
     VtxArgs a; memset(&a, 0, sizeof a);
-    a.pos = (const float *)p; CK(cudaMemcpyAsync(p, d->positions, b_pos, cudaMemcpyHostToDevice, LN.stream)); p += al(b_pos);
-    if (b_nrm) { a.nrm = (const float *)p; CK(cudaMemcpyAsync(p, d->normals, b_nrm, cudaMemcpyHostToDevice, LN.stream)); p += al(b_nrm); }
-    if (b_uv) { a.uv = (const float *)p; CK(cudaMemcpyAsync(p, d->texcoords, b_uv, cudaMemcpyHostToDevice, LN.stream)); p += al(b_uv); }
-    if (b_col) { a.col = p; CK(cudaMemcpyAsync(p, d->colors, b_col, cudaMemcpyHostToDevice, LN.stream)); p += al(b_col); }
-    if (b_idx) { a.idx = p; CK(cudaMemcpyAsync(p, d->indices, b_idx, cudaMemcpyHostToDevice, LN.stream)); p += al(b_idx); }
-    if (d_indices_ready) { a.idx = d_indices_ready; g.bytes_h2d += (size_t)d->count * 4; }
+    if (m_pos) a.pos = (const float *)m_pos; else { a.pos = (const float *)p; CK(cudaMemcpyAsync(p, d->positions, b_pos, cudaMemcpyHostToDevice, LN.stream)); p += al(b_pos); }
+    if (b_nrm) { if (m_nrm) a.nrm = (const float *)m_nrm; else { a.nrm = (const float *)p; CK(cudaMemcpyAsync(p, d->normals, b_nrm, cudaMemcpyHostToDevice, LN.stream)); p += al(b_nrm); } }
+    if (b_uv) { if (m_uv) a.uv = (const float *)m_uv; else { a.uv = (const float *)p; CK(cudaMemcpyAsync(p, d->texcoords, b_uv, cudaMemcpyHostToDevice, LN.stream)); p += al(b_uv); } }
+    if (b_col) { if (m_col) a.col = m_col; else { a.col = p; CK(cudaMemcpyAsync(p, d->colors, b_col, cudaMemcpyHostToDevice, LN.stream)); p += al(b_col); } }
+    if (b_idx) { if (m_idx) a.idx = m_idx; else { a.idx = p; CK(cudaMemcpyAsync(p, d->indices, b_idx, cudaMemcpyHostToDevice, LN.stream)); p += al(b_idx); } }
+    if (d_indices_ready) a.idx = d_indices_ready;
     a.pos_size = (int)d->pos_size; a.col_size = (int)d->color_size; a.idx_bytes = (int)d->index_bytes;
     a.first = d->first; a.n_tri = n_tri; a.cur_color = d->current_color; a.n_faces = (int)d->n_faces;
     a.face[0] = d->faces[0]; a.face[1] = d->faces[1]; a.state = 0;

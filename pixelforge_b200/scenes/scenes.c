@@ -228,7 +228,15 @@ typedef struct { float *pos, *nrm, *uv; uint32_t *idx; int nverts, nidx; } mesh_
 /* Vertex and index arrays of the big meshes: page-locked when the library offers it (pfx.h; bench.py's end-to-end leg
  * copies its inputs from pinned host memory), plain malloc for the reference. */
 #ifdef PFSCENE_HAVE_PFX
-static void *mesh_alloc(size_t bytes) { void *p = pfxHostAlloc(bytes); return p ? p : NULL; }
+/* PFSCENE_STATIC_ARRAYS=1: the meshes never change after they are built, and the scene says so (pfxHostStatic): the
+   library then keeps them in device memory instead of copying them at every draw (bench.py reports both ways) */
+static void *mesh_alloc(size_t bytes)
+{
+    void *p = pfxHostAlloc(bytes);
+    const char *e = getenv("PFSCENE_STATIC_ARRAYS");
+    if (p && e && e[0] == '1') pfxHostStatic(p, PF_TRUE);
+    return p;
+}
 static void mesh_free(void *p) { pfxHostFree(p); }
 #else
 static void *mesh_alloc(size_t bytes) { return malloc(bytes); }
@@ -828,6 +836,14 @@ SCN_API void pfscene_frame(void *handle, int frame)
         pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
         pfBindTexture(s->tex);
         pfColor4ub(255, 255, 255, 200);
+        if ((cfg->variant & 128) && frame > 0) {
+            /* bit 7: the application rewrites the vertex array in place between frames (and announces it when the
+               arrays were declared static, pfx.h) */
+            for (int k = 0; k < s->mesh.nverts; k++) s->mesh.pos[3 * k + 1] *= 1.0f + 0.02f * (float)((k + frame) & 3);
+#ifdef PFSCENE_HAVE_PFX
+            pfxHostModified(s->mesh.pos);
+#endif
+        }
         if (cfg->variant & 32) draw_mesh_arrays(&s->mesh); else draw_mesh_immediate(&s->mesh);
     } else if (strcmp(name, "phong") == 0) {
         pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));

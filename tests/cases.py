@@ -38,6 +38,8 @@ CASES = [
     ("c2-textured-closeup-clipped-arrays", "textured", 640, 360, dict(size=96, variant=32 | 64), False),
     ("c2-textured-closeup-clipped-bilinear-arrays", "textured", 640, 360, dict(size=96, variant=1 | 32 | 64), True),
     ("c2-textured-closeup-clipped-immediate", "textured", 640, 360, dict(size=96, variant=64), False),
+    # the application rewrites the vertex array in place between frames (static-geometry mirrors must follow, pfx.h)
+    ("c2-textured-arrays-rewritten-f2", "textured", 640, 360, dict(size=64, variant=32 | 128, first_frame=0, frames=3), False),
     ("c3-phong", "phong", 640, 360, dict(size=96), False),
     ("c3-phong-arrays", "phong", 320, 200, dict(size=48, variant=32), False),
     ("c4-overdraw-add", "overdraw", 512, 256, dict(size=8), False),

@@ -650,3 +650,29 @@ def test_surface_operations_stay_on_the_device(product_scenes):
             assert k.kernel_launches > 0
             assert k.bytes_d2h == d2h, (variant, k.bytes_d2h)
             sc.finish()
+
+
+def test_static_geometry_mirrors():
+    """pfxHostStatic: vertex / index arrays declared static are copied to the device once and later draws move no vertex
+    data over PCIe; pfxHostModified makes the next draw upload the block again.  Images equal the dynamic path's, for
+    an unchanged mesh and for one the application rewrites between frames."""
+    for scene, kw in (("textured", dict(size=96, variant=1 | 32 | 64)), ("textured", dict(size=64, variant=32 | 128)), ("phong", dict(size=64, variant=32))):
+        dyn = _render_with_env(scene, 640, 360, {"PFSCENE_STATIC_ARRAYS": "0"}, frames=3, **kw)
+        sta = _render_with_env(scene, 640, 360, {"PFSCENE_STATIC_ARRAYS": "1"}, frames=3, **kw)
+        assert np.array_equal(dyn[0], sta[0]) and np.array_equal(dyn[1].view(np.uint32), sta[1].view(np.uint32)), (scene, kw)
+        assert dyn[2] == sta[2] and dyn[3] == sta[3]
+    # PCIe traffic of a steady-state frame: the arrays are gone from it
+    import os, subprocess, sys, json
+    code = ("import sys, json; sys.path.insert(0, %r); from pixelforge_b200 import load_product_scenes, load_pfcu; from pixelforge_b200.binding import Counters\n"
+            "p = load_product_scenes(); L = load_pfcu('product').lib\n"
+            "sc = p.open('phong', 640, 360, variant=32, size=64, explicit_sync=1).__enter__()\n"
+            "sc.frame(0); sc.finish(); L.pfxResetCounters(); sc.frame(0); sc.finish()\n"
+            "k = Counters(); L.pfcu_get_counters(k); print(json.dumps(dict(h2d=k.bytes_h2d)))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for mode in ("0", "1"):
+        env = dict(os.environ); env["PFSCENE_STATIC_ARRAYS"] = mode
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[mode] = json.loads(r.stdout.strip().splitlines()[-1])["h2d"]
+    mesh_bytes = 65 * 65 * 24 + 64 * 64 * 6 * 4
+    assert out["0"] >= mesh_bytes and out["1"] < 4096, out

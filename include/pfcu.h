@@ -152,6 +152,7 @@ PFCU_API void  pfcu_host_unregister(void *p);
  * it again.  Both return PFCU_ERR_INVALID for memory that is not a pfcu_host_alloc block. */
 PFCU_API int   pfcu_host_set_static(void *p, int on);
 PFCU_API int   pfcu_host_modified(void *p);
+PFCU_API int   pfcu_host_is_static(const void *p);      /* 1 when p lies in a block declared static */
 
 /* Tables that reproduce the host's RCPPS / RSQRTPS (reference: src/internal/simd.h:1217-1245).
  * rcp[i], i = top `rcp_bits` mantissa bits: float bits of rcp(1.m);  rsqrt[(odd<<rsqrt_bits)|i]:

@@ -587,6 +587,7 @@ void  pfcu_host_free(void *p) { free(p); }
 int   pfcu_host_wait(const void *p) { (void)p; return PFCU_OK; }
 int   pfcu_host_set_static(void *p, int on) { (void)p; (void)on; return PFCU_OK; }      /* host memory is read at every draw here */
 int   pfcu_host_modified(void *p) { (void)p; return PFCU_OK; }
+int   pfcu_host_is_static(const void *p) { (void)p; return 0; }
 int   pfcu_host_register(void *p, size_t bytes) { (void)p; (void)bytes; return PFCU_OK; }
 void  pfcu_host_unregister(void *p) { (void)p; }
 int  pfcu_set_approx_tables(const uint32_t *rcp, int rb, const uint32_t *rs, int sb)

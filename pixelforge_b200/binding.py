@@ -186,7 +186,7 @@ PFCU_SYMBOLS = [
     "pfcu_surface_set_present_surface", "pfcu_surface_clear_present", "pfcu_surface_push_tiles",
     "pfcu_surface_create_format", "pfcu_surface_format",
     "pfcu_list_create", "pfcu_list_destroy", "pfcu_list_size", "pfcu_list_job_supported", "pfcu_submit_list_jobs",
-    "pfcu_host_set_static", "pfcu_host_modified", "pfcu_surface_rect", "pfcu_surface_fog", "pfcu_surface_draw_pixels", "pfcu_surface_read_pixels",
+    "pfcu_host_set_static", "pfcu_host_modified", "pfcu_host_is_static", "pfcu_surface_rect", "pfcu_surface_fog", "pfcu_surface_draw_pixels", "pfcu_surface_read_pixels",
 ]
 
 PFX_SYMBOLS = ["pfxSetSyncMode", "pfxFlush", "pfxFinish", "pfxGetCounters", "pfxResetCounters", "pfxSetTileOwner",

@@ -562,7 +562,8 @@ int pfh_device_draw(pf_ctx *c, PFsizei count, PFint first, int indexed, PFdataty
         case PF_UNSIGNED_SHORT: { const PFushort *p = (const PFushort *)indices; for (PFsizei i = 0; i < count; i++) if (p[i] > mx) mx = p[i]; d.index_bytes = 2; } break;
         default:                /* >= 1 M indices: the device scans them once they are uploaded (pfcu_draw.n_vertices == 0); below that the
                                    extra round trip costs more than the AVX2 scan */
-                                if (count >= (1u << 20)) unknown = 1; else mx = max_index_u32((const uint32_t *)indices, count);
+                                /* indices in a block declared static: the device scans them once per modification */
+                                if (count >= (1u << 20) || pfcu_host_is_static(indices)) unknown = 1; else mx = max_index_u32((const uint32_t *)indices, count);
                                 d.index_bytes = 4; break;
         }
         nverts = unknown ? 0 : mx + 1; d.indices = indices; d.first = 0;

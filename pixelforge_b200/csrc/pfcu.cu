@@ -38,6 +38,7 @@
 #include <string.h>
 #include <limits.h>
 #include <math.h>
+#include <time.h>
 
 #include <vector>
 #include <mutex>
@@ -98,6 +99,7 @@ struct __align__(16) DevState {
 
 static_assert(offsetof(DevState, tex_fw) % 16 == 0, "tex_fw..tex_ty are fetched as one float4");
 
+#define MAX_BANDS 4
 struct pfcu_surface {
     uint32_t w, h; uint32_t *color; float *depth; bool owned;
     int fmt;                                        /* PFCU_TEX_*: the caller's layout; the device holds canonical RGBA8 */
@@ -107,6 +109,9 @@ struct pfcu_surface {
     uint32_t *peer_color; float *peer_depth;        /* present target (peer memory or another local surface), or nullptr */
     void *ipc_color, *ipc_depth;                    /* mappings opened with cudaIpcOpenMemHandle (to close) */
     bool aliased;                                   /* a texture aliases the colour buffer (render to texture) */
+    /* the last operation on the surface was a rasterisation in bands of tile rows: band b covers rows [band_y[b], band_y[b+1])
+       and band_evt[b] fires when it is complete (see launch_raster_bands / pfcu_surface_download_async) */
+    bool bands_valid; int n_bands; uint32_t band_y[MAX_BANDS + 1]; cudaEvent_t band_evt[MAX_BANDS];
 };
 struct pfcu_texture { uint32_t w, h; int fmt; unsigned char *pixels; bool owned; pfcu_surface *alias; bool leader; };
 struct pfcu_list { pfcu_rawtri *tris; uint32_t n; };
@@ -182,6 +187,8 @@ struct Runtime {
     };
     std::vector<JobSlot> job_slots;
     unsigned char *d_jobs = nullptr, *h_jobs = nullptr; size_t cap_jobs = 0; cudaEvent_t jobs_copied = nullptr, jobs_done = nullptr; unsigned jobs_seq = 0;
+    cudaStream_t band_streams[MAX_BANDS] = { nullptr, nullptr, nullptr, nullptr }; cudaStream_t copy_stream = nullptr;
+    cudaEvent_t front_evt = nullptr;
     std::recursive_mutex mu;                    /* the C-ABI is serialised: contexts on several threads share one runtime */
     char err[512] = { 0 };
 };
@@ -322,13 +329,26 @@ int pfcu_init(int device)
         CK(cudaMemset(LN.d_chain, 0, 16 * sizeof(unsigned long long)));
     }
     g.cur = &g.lanes[0];
+    {   /* band streams in descending priority: the block scheduler then drains band 0 first, band 1 next ... - launched
+           with equal priority the bands would share the SMs evenly and all finish together at the end */
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          /* lo: least (numerically largest), hi: greatest */
+        for (int b = 0; b < MAX_BANDS; b++) {
+            int pr = hi + b; if (pr > lo) pr = lo;
+            CK(cudaStreamCreateWithPriority(&g.band_streams[b], cudaStreamNonBlocking, pr));
+        }
+    }
+    CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&g.front_evt, cudaEventDisableTiming));
     CK(cudaMalloc(&g.d_counters, 4 * sizeof(unsigned long long)));
     CK(cudaMemset(g.d_counters, 0, 4 * sizeof(unsigned long long)));
     g.ok = true;
     return PFCU_OK;
 }
 
-static void sync_all_lanes(void) { for (int i = 0; i < g.n_lanes; i++) cudaStreamSynchronize(g.lanes[i].stream); }
+/* band and copy streams only ever hold work that a lane stream waits for (an event per band / per read-back), except
+   the read-backs themselves: pfcu_surface_wait covers those, and so does this */
+static void sync_all_lanes(void) { for (int i = 0; i < g.n_lanes; i++) cudaStreamSynchronize(g.lanes[i].stream); if (g.copy_stream) cudaStreamSynchronize(g.copy_stream); }
 static void use_lane(const pfcu_surface *s)
 {
     g.cur = &g.lanes[s ? s->lane % g.n_lanes : 0];
@@ -359,6 +379,9 @@ void pfcu_shutdown(void)
         if (LN.own_stream) cudaStreamDestroy(LN.stream);
         g.lanes[i] = Lane();
     }
+    for (int b = 0; b < MAX_BANDS; b++) if (g.band_streams[b]) { cudaStreamDestroy(g.band_streams[b]); g.band_streams[b] = nullptr; }
+    if (g.copy_stream) { cudaStreamDestroy(g.copy_stream); g.copy_stream = nullptr; }
+    if (g.front_evt) { cudaEventDestroy(g.front_evt); g.front_evt = nullptr; }
     cudaFree(g.d_counters); cudaFree(g.d_rcp); cudaFree(g.d_rsq);
     g.d_counters = nullptr; g.d_rcp = nullptr; g.d_rsq = nullptr;
     for (auto &S : g.job_slots) { cudaFree(S.d_tris); cudaFree(S.bbox); cudaFree(S.setup); cudaFree(S.data); cudaFree(S.bin_list); cudaFree(S.bin_start); cudaFree(S.d_total); cudaFree(S.chain); }
@@ -443,6 +466,13 @@ int pfcu_host_set_static(void *p, int on)
     b->is_static = on != 0;
     if (!on && b->d_copy) { sync_all_lanes(); cudaFree(b->d_copy); b->d_copy = nullptr; b->dev_gen = ~0u; }
     return PFCU_OK;
+}
+
+int pfcu_host_is_static(const void *p)
+{
+    API_LOCK;
+    PinnedBlock *b = find_pinned(p);
+    return b && b->is_static;
 }
 
 int pfcu_host_modified(void *p)
@@ -655,6 +685,7 @@ void pfcu_surface_destroy(pfcu_surface *s)
     if (s->owned) { cudaFree(s->color); cudaFree(s->depth); }
     cudaFree(s->conv);
     if (s->done) cudaEventDestroy(s->done);
+    for (int b = 0; b < MAX_BANDS; b++) if (s->band_evt[b]) cudaEventDestroy(s->band_evt[b]);
     free(s);
 }
 
@@ -663,13 +694,16 @@ uint32_t pfcu_surface_height(const pfcu_surface *s) { return s->h; }
 void *pfcu_surface_color_ptr(const pfcu_surface *s) { return s->color; }
 void *pfcu_surface_depth_ptr(const pfcu_surface *s) { return s->depth; }
 
-static void mark_done(pfcu_surface *s) { if (cudaEventRecord(s->done, LN.stream) == cudaSuccess) s->has_done = true; }
+/* end of an operation on the surface (recorded on its lane); whatever it was, the band events of an earlier
+   rasterisation no longer describe the surface's last write */
+static void mark_done(pfcu_surface *s) { s->bands_valid = false; if (cudaEventRecord(s->done, LN.stream) == cudaSuccess) s->has_done = true; }
 
 int pfcu_surface_upload(pfcu_surface *s, const void *hc, const float *hd, uint32_t y0, uint32_t rows)
 {
     API_LOCK;
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
     use_lane(s);
+    s->bands_valid = false;
     const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;
     if (hc && s->fmt != PFCU_TEX_RGBA8 && rows) {
         /* the caller's layout -> staging -> canonical RGBA8 */
@@ -701,6 +735,22 @@ int pfcu_surface_download_async(pfcu_surface *s, void *hc, float *hd, uint32_t y
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync((unsigned char *)hc + off * bpp, s->conv + off * bpp, nb, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += nb;
         hc = nullptr;
+    }
+    if (s->bands_valid && s->fmt == PFCU_TEX_RGBA8 && (hc || hd) && rows) {
+        /* the surface was last written by a banded rasterisation: band b's rows go out on the copy stream as soon as band
+           b is done, while later bands are still being rasterised; the lane then waits for the copies (later work on
+           the surface must not overtake them) */
+        for (int b = 0; b < s->n_bands; b++) {
+            const uint32_t r0 = s->band_y[b] > y0 ? s->band_y[b] : y0, r1 = s->band_y[b + 1] < y0 + rows ? s->band_y[b + 1] : y0 + rows;
+            if (r0 >= r1) continue;
+            const size_t o = (size_t)r0 * s->w, nb = (size_t)(r1 - r0) * s->w * 4;
+            CK(cudaStreamWaitEvent(g.copy_stream, s->band_evt[b], 0));
+            if (hc) { CK(cudaMemcpyAsync((uint32_t *)hc + o, s->color + o, nb, cudaMemcpyDeviceToHost, g.copy_stream)); g.bytes_d2h += nb; }
+            if (hd) { CK(cudaMemcpyAsync(hd + o, s->depth + o, nb, cudaMemcpyDeviceToHost, g.copy_stream)); g.bytes_d2h += nb; }
+        }
+        if (cudaEventRecord(s->done, g.copy_stream) == cudaSuccess) s->has_done = true;
+        CK(cudaStreamWaitEvent(LN.stream, s->done, 0));
+        return PFCU_OK;
     }
     if (hc) { CK(cudaMemcpyAsync((uint32_t *)hc + off, s->color + off, n, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += n; }
     if (hd) { CK(cudaMemcpyAsync(hd + off, s->depth + off, n, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += n; }
@@ -886,6 +936,7 @@ static int pack_unpack(pfcu_surface *s, uint32_t rank, uint32_t world, int with_
     API_LOCK;
     if (world == 0) world = 1;
     use_lane(s);
+    if (unpack) s->bands_valid = false;
     const uint32_t n = owned_tiles(s, rank, world);
     if (n == 0) return PFCU_OK;
     k_pack_tiles<<<n, 256, 0, LN.stream>>>(s->color, s->depth, (int)s->w, (int)s->h, (int)s->tiles_x, s->tiles_x * s->tiles_y,
@@ -1041,6 +1092,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
                            const unsigned *d_n = nullptr, uint32_t n_est = 0, int bshift_forced = 0)
 {
     if (n == 0) return PFCU_OK;
+    s->bands_valid = false;
     if (!d_n) n_est = n;
     /* render targets other than RGBA8 and BGRA8 textures: the row-ordered rasteriser (pfcu_raster_rows.cuh) */
     const bool rows_path = s->fmt != PFCU_TEX_RGBA8 || g_last_leader_tex;
@@ -1179,7 +1231,10 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     p.counters = g.d_counters;
     const unsigned grid = owned_tiles(s, p.rank, p.world);
     if (g.profiling) CK(cudaEventRecord(pe[1], LN.stream));
-    if (grid) {
+    p.tile_base = 0;
+    /* the rasteriser over `grid` tiles starting at p.tile_base, on stream st_ */
+    const unsigned grid_all = grid;
+    auto launch_raster = [&](unsigned grid, cudaStream_t st_) -> int {
         /* many small triangles per tile: 16 warps per tile halve the serial work of the busiest tiles;
            few large ones: 8 warps with more registers each issue faster */
         const bool ph = (feature_mask & PFCU_ST_PHONG) != 0;
@@ -1187,7 +1242,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         /* half-height slices when the 64x64 grid would be only a few waves deep with a ragged last wave */
         const bool fixed = single_prog >= 0 && single_prog < PROG_PHONG && !small_tris && !use_frag;
         const int per_sm = (fixed && single_prog / 4 != 4) ? 4 : 3;
-        const double waves = (double)grid / ((double)g.sms * per_sm);
+        const double waves = (double)grid_all / ((double)g.sms * per_sm);      /* bands run side by side: the whole surface counts */
         const bool half = !small_tris && !ph && waves < 8.0 && (ceil(waves) / waves) > 1.06 && (ceil(2 * waves) / (2 * waves)) < (ceil(waves) / waves);
         if (use_frag) {
             /* 64x8 slices of eight 8x8 regions, 8 warps; 4 CTAs per SM (Phong: 3, 80 registers) */
@@ -1196,29 +1251,62 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
                 cudaFuncSetAttribute(k_raster_frag<false, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * FRAG_NF * 512);
                 return true; }();
             (void)attr_once;
-            if (ph) CK(launch_dep(k_raster_frag<true, 8, 3>, dim3(grid * 8), dim3(256), (size_t)(8 * FRAG_NF_PHONG * 512), LN.stream, p));
-            else    CK(launch_dep(k_raster_frag<false, 8, 4>, dim3(grid * 8), dim3(256), (size_t)(8 * FRAG_NF * 512), LN.stream, p));
+            if (ph) CK(launch_dep(k_raster_frag<true, 8, 3>, dim3(grid * 8), dim3(256), (size_t)(8 * FRAG_NF_PHONG * 512), st_, p));
+            else    CK(launch_dep(k_raster_frag<false, 8, 4>, dim3(grid * 8), dim3(256), (size_t)(8 * FRAG_NF * 512), st_, p));
         }
         else if (small_tris) {
             const int th = force_slice ? force_slice : (ph ? 32 : 16);
-            if (ph) { if (th <= 32) CK(launch_dep(k_raster<true, 16, -1, 32>, dim3(grid * 2), dim3(512), (size_t)(0), LN.stream, p)); else CK(launch_dep(k_raster<true, 16, -1, 64>, dim3(grid), dim3(512), (size_t)(0), LN.stream, p)); }
-            else if (th <= 16) CK(launch_dep(k_raster<false, 16, -1, 16>, dim3(grid * 4), dim3(512), (size_t)(0), LN.stream, p));
-            else if (th <= 32) CK(launch_dep(k_raster<false, 16, -1, 32>, dim3(grid * 2), dim3(512), (size_t)(0), LN.stream, p));
-            else               CK(launch_dep(k_raster<false, 16, -1, 64>, dim3(grid), dim3(512), (size_t)(0), LN.stream, p));
+            if (ph) { if (th <= 32) CK(launch_dep(k_raster<true, 16, -1, 32>, dim3(grid * 2), dim3(512), (size_t)(0), st_, p)); else CK(launch_dep(k_raster<true, 16, -1, 64>, dim3(grid), dim3(512), (size_t)(0), st_, p)); }
+            else if (th <= 16) CK(launch_dep(k_raster<false, 16, -1, 16>, dim3(grid * 4), dim3(512), (size_t)(0), st_, p));
+            else if (th <= 32) CK(launch_dep(k_raster<false, 16, -1, 32>, dim3(grid * 2), dim3(512), (size_t)(0), st_, p));
+            else               CK(launch_dep(k_raster<false, 16, -1, 64>, dim3(grid), dim3(512), (size_t)(0), st_, p));
         }
-        else if (ph)          CK(launch_dep(k_raster<true, 8, -1, 64>, dim3(grid), dim3(256), (size_t)(0), LN.stream, p));
+        else if (ph)          CK(launch_dep(k_raster<true, 8, -1, 64>, dim3(grid), dim3(256), (size_t)(0), st_, p));
         else if (fixed) {
             /* one state program in the whole batch: the kernel that holds only that fragment program */
             switch (single_prog) {
-#define FIXED_CASE(P) case P: CK(launch_fixed<P>(half, grid, LN.stream, p)); break;
+#define FIXED_CASE(P) case P: CK(launch_fixed<P>(half, grid, st_, p)); break;
             FIXED_CASE(0) FIXED_CASE(1) FIXED_CASE(2) FIXED_CASE(3) FIXED_CASE(4) FIXED_CASE(5) FIXED_CASE(6) FIXED_CASE(7)
             FIXED_CASE(12) FIXED_CASE(13) FIXED_CASE(14) FIXED_CASE(15) FIXED_CASE(16) FIXED_CASE(17) FIXED_CASE(18) FIXED_CASE(19)
 #undef FIXED_CASE
             default: snprintf(g.err, sizeof g.err, "internal: no kernel for state program %d", single_prog); return PFCU_ERR_INVALID;
             }
         }
-        else { if (half) CK(launch_dep(k_raster<false, 8, -1, 32>, dim3(grid * 2), dim3(256), (size_t)(0), LN.stream, p)); else CK(launch_dep(k_raster<false, 8, -1, 64>, dim3(grid), dim3(256), (size_t)(0), LN.stream, p)); }
+        else { if (half) CK(launch_dep(k_raster<false, 8, -1, 32>, dim3(grid * 2), dim3(256), (size_t)(0), st_, p)); else CK(launch_dep(k_raster<false, 8, -1, 64>, dim3(grid), dim3(256), (size_t)(0), st_, p)); }
         g.launches++;
+        return PFCU_OK;
+    };
+    bool banded = false;
+    /* Large RGBA8 surfaces: a few launches over bands of tile rows, each on its own stream (they overlap on the GPU like
+       one launch), with an event per band - a read-back that follows (pfcu_surface_download_async) copies band b as
+       soon as band b is done, while the later bands are still being rasterised. */
+    static const int env_bands = getenv("PF_CUDA_BANDS") ? atoi(getenv("PF_CUDA_BANDS")) : -1;
+    int n_bands = 1;
+    /* from 1 Mpixel (a band costs four more runtime calls on the launch path; measured on the 1080p scene: 2 bands gain
+       nothing end to end, 4 bands 0.02 ms; 4K scenes 0.3 - 0.5 ms, 8K 1.9 ms) */
+    if (grid && p.world <= 1 && s->fmt == PFCU_TEX_RGBA8 && (size_t)s->w * s->h >= ((size_t)1 << 20) && s->tiles_y >= 8) n_bands = MAX_BANDS;
+    if (env_bands >= 1) n_bands = env_bands > MAX_BANDS ? MAX_BANDS : env_bands;
+    if (p.world > 1 || !grid || (unsigned)n_bands > s->tiles_y) n_bands = 1;
+    if (n_bands > 1) {
+        for (int b = 0; b < n_bands; b++) if (!s->band_evt[b]) CK(cudaEventCreateWithFlags(&s->band_evt[b], cudaEventDisableTiming));
+        CK(cudaEventRecord(g.front_evt, LN.stream));
+        unsigned row0 = 0;
+        for (int b = 0; b < n_bands; b++) {
+            /* the first bands are the smaller ones: their copies start early, the last band's copy is what remains exposed */
+            const unsigned row1 = (b == n_bands - 1) ? s->tiles_y : (unsigned)(((uint64_t)s->tiles_y * (unsigned)(b + 1)) / (unsigned)n_bands);
+            cudaStream_t bs = g.band_streams[b];
+            CK(cudaStreamWaitEvent(bs, g.front_evt, 0));
+            p.tile_base = row0 * s->tiles_x;
+            if ((rc = launch_raster((row1 - row0) * s->tiles_x, bs))) return rc;
+            CK(cudaEventRecord(s->band_evt[b], bs));
+            CK(cudaStreamWaitEvent(LN.stream, s->band_evt[b], 0));
+            s->band_y[b] = row0 * TILE;
+            row0 = row1;
+        }
+        s->band_y[n_bands] = s->h;
+        s->n_bands = n_bands; banded = true;
+    } else if (grid) {
+        if ((rc = launch_raster(grid, LN.stream))) return rc;
     }
     if (g.profiling) { CK(cudaEventRecord(pe[2], LN.stream)); for (int i = 0; i < 3; i++) g.prof_events.push_back(pe[i]); }
     CK(cudaGetLastError());
@@ -1228,6 +1316,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         LN.list_pending = true; LN.list_hint_n = n > LN.list_hint_n ? n : LN.list_hint_n;
     }
     mark_done(s);
+    s->bands_valid = banded;
     /* write-after-read: a sampled surface on another lane must not be overwritten before this batch read it */
     for (pfcu_surface *dep : g.deps)
         if (dep != s && dep->lane != s->lane) CK(cudaStreamWaitEvent(g.lanes[dep->lane % g.n_lanes].stream, s->done, 0));
@@ -1269,6 +1358,10 @@ static int scan_exclusive(const unsigned *d_in, unsigned *d_out, unsigned n, uns
     return PFCU_OK;
 }
 
+/* PF_CUDA_TIMING=1: host-side microseconds of the phases of pfcu_draw_triangles on stderr (development aid) */
+static const bool g_timing = getenv("PF_CUDA_TIMING") && atoi(getenv("PF_CUDA_TIMING")) != 0;
+static double now_us(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
+
 unsigned pfcu_capabilities(void) { return PFCU_CAP_DEVICE_VERTEX | PFCU_CAP_RAW_TRIANGLES | PFCU_CAP_LISTS; }
 
 int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vparams *vp, const pfcu_draw *d, uint32_t *n_out)
@@ -1282,6 +1375,7 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     use_lane(s);
     const unsigned n_items = n_tri * d->n_faces;
     int rc;
+    const double t_start = g_timing ? now_us() : 0.0; double t_up = 0, t_cnt = 0;
     /* arrays -> device (pageable sources are staged by the driver; ordered on the stream); arrays in a static block
        (pfcu_host_set_static) are read from the block's device mirror instead and cross PCIe only when modified */
     size_t nv = d->n_vertices;
@@ -1336,17 +1430,18 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     a.first = d->first; a.n_tri = n_tri; a.cur_color = d->current_color; a.n_faces = (int)d->n_faces;
     a.face[0] = d->faces[0]; a.face[1] = d->faces[1]; a.state = 0;
 
+    if (g_timing) t_up = now_us();
     /* pass A: output triangles per (triangle, face) item; scan; total */
     if ((rc = grow(&LN.d_vcounts, &LN.cap_vcounts, (size_t)n_items * 2 + n_items / 512 + 64))) return rc;
     unsigned *d_counts = LN.d_vcounts, *d_offsets = LN.d_vcounts + n_items, *d_tmp = LN.d_vcounts + 2 * (size_t)n_items;
     k_vertex_count<<<(n_items + 127u) / 128u, 128, 0, LN.stream>>>(a, *vp, n_items, d_counts);
     g.launches++;
     if ((rc = scan_exclusive(d_counts, d_offsets, n_items, d_tmp))) return rc;
-    unsigned last[2] = { 0, 0 };
-    CK(cudaMemcpyAsync(&last[0], d_offsets + (n_items - 1), 4, cudaMemcpyDeviceToHost, LN.stream));
-    CK(cudaMemcpyAsync(&last[1], d_counts + (n_items - 1), 4, cudaMemcpyDeviceToHost, LN.stream));
+    k_scan_total<<<1, 1, 0, LN.stream>>>(d_offsets + (n_items - 1), d_counts + (n_items - 1), LN.h_total);
+    g.launches++;
     CK(cudaStreamSynchronize(LN.stream));
-    const unsigned total = last[0] + last[1];
+    const unsigned total = LN.h_total[0] + LN.h_total[1];
+    if (g_timing) t_cnt = now_us();
     if (n_out) *n_out = total;
     if (total == 0) return PFCU_OK;
 
@@ -1360,7 +1455,9 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     g.launches++;
     CK(cudaEventRecord(LN.raw_done, LN.stream));        /* d_vcounts is shared with the raw-triangle path's side stream */
     CK(cudaGetLastError());
-    return launch_pipeline(s, LN.d_tris, LN.d_states, total, mask, g_last_single_prog);
+    rc = launch_pipeline(s, LN.d_tris, LN.d_states, total, mask, g_last_single_prog);
+    if (g_timing) fprintf(stderr, "pfcu_draw_triangles: arrays %.1f us, count pass + wait %.1f us, emit + pipeline launches %.1f us\n", t_up - t_start, t_cnt - t_up, now_us() - t_cnt);
+    return rc;
 }
 
 int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, const pfcu_vparams_lit *vparams, uint32_t n_vparams,
@@ -1431,8 +1528,8 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
     k_raw_count<<<(n_tris + 127u) / 128u, 128, 0, LN.vstream>>>(a, d_counts);
     g.launches++;
     if ((rc = scan_exclusive(d_counts, d_offsets, n_tris, d_tmp, LN.vstream))) return rc;
-    CK(cudaMemcpyAsync(&LN.h_total[0], d_offsets + (n_tris - 1), 4, cudaMemcpyDeviceToHost, LN.vstream));
-    CK(cudaMemcpyAsync(&LN.h_total[1], d_counts + (n_tris - 1), 4, cudaMemcpyDeviceToHost, LN.vstream));
+    k_scan_total<<<1, 1, 0, LN.vstream>>>(d_offsets + (n_tris - 1), d_counts + (n_tris - 1), LN.h_total);
+    g.launches++;
     CK(cudaEventRecord(LN.vready, LN.vstream));
     CK(cudaStreamSynchronize(LN.vstream));
     const unsigned total = LN.h_total[0] + LN.h_total[1];
@@ -1645,6 +1742,7 @@ int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n_jobs)
     for (int l = 1; l < g.n_lanes; l++) if (lane_used[l]) { CK(cudaStreamWaitEvent(g.lanes[l].stream, g.jobs_done, 0)); g.lanes[l].touched = true; }
     for (uint32_t j = 0; j < n_jobs; j++) {
         pfcu_surface *s = jobs[j].surface;
+        s->bands_valid = false;
         if (s->aliased) { if (cudaEventRecord(s->done, L0.stream) == cudaSuccess) s->has_done = true; }     /* someone may sample it from another lane */
         else s->has_done = false;          /* its lane already waits for this submission (above) */
     }

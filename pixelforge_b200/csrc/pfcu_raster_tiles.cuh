@@ -14,6 +14,9 @@ struct RasterParams {
     /* bin_starts[nb] is the real number of list entries; when it exceeds list_cap the lists were not written (the host
        sizes them without waiting for the total) and every CTA filters all n triangles of the batch instead */
     int nb; unsigned list_cap, n;
+    /* first tile of this launch: the rasterisation of a large surface goes out as a few launches over bands of tile rows
+       (on separate streams, they overlap) so that the read-back of a band can start when ITS launch is done */
+    unsigned tile_base;
 };
 
 /* swizzled tile address: rows are 64 words; XOR-ing bits 3..4 of x with (y & 3) makes both the
@@ -343,7 +346,7 @@ k_raster(const RasterParams p)
     /* a CTA handles a 64 x TH slice of a 64x64 tile (TH = 32 halves the work quantum when the grid would
        otherwise be only a few waves deep); ownership for the multi-GPU split stays per 64x64 tile */
     constexpr int SUB = TILE / TH;
-    const unsigned tile = (p.world > 1) ? (p.rank + (blockIdx.x / SUB) * p.world) : (blockIdx.x / SUB);
+    const unsigned tile = (p.world > 1) ? (p.rank + (blockIdx.x / SUB) * p.world) : (p.tile_base + blockIdx.x / SUB);
     if (tile >= p.nTiles) return;
     const int tx = tile % p.tilesX, ty = tile / p.tilesX;
     TileCtx t;

@@ -287,6 +287,13 @@ k_scan_block(const unsigned *__restrict__ in, unsigned *__restrict__ out, unsign
     if (threadIdx.x == 0 && sums) sums[blockIdx.x] = total;
 }
 
+/* total of a count -> exclusive-scan pair, written straight into page-locked host memory (mapped into the device's
+   address space): the host waits for the stream instead of issuing two small copies */
+__global__ void k_scan_total(const unsigned *__restrict__ last_offset, const unsigned *__restrict__ last_count, unsigned *__restrict__ host_total)
+{
+    host_total[0] = *last_offset; host_total[1] = *last_count;
+}
+
 __global__ void k_scan_add(unsigned *__restrict__ data, unsigned n, const unsigned *__restrict__ block_offsets)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -593,8 +593,9 @@ def test_device_vertex_stage_equals_host_stage(scene, kw):
 
 
 @pytest.mark.parametrize("env", [{"PF_CUDA_LANES": "1"}, {"PF_CUDA_LANES": "8"}, {"PF_CUDA_BATCH_TRIS": "300"},
-                                 {"PF_CUDA_SLICE": "64"}, {"PF_CUDA_SLICE": "32"}, {"PF_CUDA_PIN_HOST": "0"}, {"PF_CUDA_RAW_SYNC": "1"}],
-                         ids=["1-lane", "8-lanes", "tiny-batches", "slice64", "slice32", "no-pin", "raw-batches-with-host-count"])
+                                 {"PF_CUDA_SLICE": "64"}, {"PF_CUDA_SLICE": "32"}, {"PF_CUDA_PIN_HOST": "0"}, {"PF_CUDA_RAW_SYNC": "1"},
+                                 {"PF_CUDA_BANDS": "1"}, {"PF_CUDA_BANDS": "3"}],
+                         ids=["1-lane", "8-lanes", "tiny-batches", "slice64", "slice32", "no-pin", "raw-batches-with-host-count", "one-band", "three-bands"])
 def test_runtime_knobs_do_not_change_pixels(env, product_scenes):
     """Stream lanes, batch splitting, slice height and host pinning are performance knobs only."""
     for scene, w, h, kw in (("batch", 256, 256, dict(size=5)), ("micro", 160, 120, dict(variant=0x1022a0 | 8 | 1, seed=18, size=40)),

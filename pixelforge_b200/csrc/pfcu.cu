@@ -112,6 +112,9 @@ struct pfcu_surface {
     /* the last operation on the surface was a rasterisation in bands of tile rows: band b covers rows [band_y[b], band_y[b+1])
        and band_evt[b] fires when it is complete (see launch_raster_bands / pfcu_surface_download_async) */
     bool bands_valid; int n_bands; uint32_t band_y[MAX_BANDS + 1]; cudaEvent_t band_evt[MAX_BANDS];
+    /* bands pay off only when a read-back follows the batch: batches rasterised since the last read-back, and how many
+       there were between the two read-backs before - the batch predicted to be a frame's last one goes out in bands */
+    unsigned n_since_read, n_per_read;
 };
 struct pfcu_texture { uint32_t w, h; int fmt; unsigned char *pixels; bool owned; pfcu_surface *alias; bool leader; };
 struct pfcu_list { pfcu_rawtri *tris; uint32_t n; };
@@ -736,6 +739,7 @@ int pfcu_surface_download_async(pfcu_surface *s, void *hc, float *hd, uint32_t y
         CK(cudaMemcpyAsync((unsigned char *)hc + off * bpp, s->conv + off * bpp, nb, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += nb;
         hc = nullptr;
     }
+    if (hc && rows) { s->n_per_read = s->n_since_read; s->n_since_read = 0; }
     if (s->bands_valid && s->fmt == PFCU_TEX_RGBA8 && (hc || hd) && rows) {
         /* the surface was last written by a banded rasterisation: band b's rows go out on the copy stream as soon as band
            b is done, while later bands are still being rasterised; the lane then waits for the copies (later work on
@@ -1284,7 +1288,9 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     int n_bands = 1;
     /* from 1 Mpixel (a band costs four more runtime calls on the launch path; measured on the 1080p scene: 2 bands gain
        nothing end to end, 4 bands 0.02 ms; 4K scenes 0.3 - 0.5 ms, 8K 1.9 ms) */
-    if (grid && p.world <= 1 && s->fmt == PFCU_TEX_RGBA8 && (size_t)s->w * s->h >= ((size_t)1 << 20) && s->tiles_y >= 8) n_bands = MAX_BANDS;
+    s->n_since_read++;
+    const bool read_back_expected = s->n_per_read != 0 && s->n_since_read == s->n_per_read;
+    if (grid && p.world <= 1 && s->fmt == PFCU_TEX_RGBA8 && (size_t)s->w * s->h >= ((size_t)1 << 20) && s->tiles_y >= 8 && read_back_expected) n_bands = MAX_BANDS;
     if (env_bands >= 1) n_bands = env_bands > MAX_BANDS ? MAX_BANDS : env_bands;
     if (p.world > 1 || !grid || (unsigned)n_bands > s->tiles_y) n_bands = 1;
     if (n_bands > 1) {

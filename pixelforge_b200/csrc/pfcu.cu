@@ -42,11 +42,15 @@
 
 #include <vector>
 #include <mutex>
+#include <thread>
+#include <condition_variable>
+#include <functional>
 
 /* ------------------------------------------------------------------------------------------------ */
 /* configuration                                                                                    */
 /* ------------------------------------------------------------------------------------------------ */
 
+#define MAX_DEVS    8               /* devices of the single-process multi-GPU mode (PF_CUDA_DEVICES), see "multi-device mode" below */
 #define TILE        64              /* screen tile edge in pixels                                    */
 #define TILE_PIX    (TILE * TILE)
 /* A bin is 2^k x 2^k pixels, chosen per batch: 256 (4x4 tiles) for batches of large triangles, where a
@@ -115,12 +119,18 @@ struct pfcu_surface {
     /* bands pay off only when a read-back follows the batch: batches rasterised since the last read-back, and how many
        there were between the two read-backs before - the batch predicted to be a frame's last one goes out in bands */
     unsigned n_since_read, n_per_read;
+    /* multi-device mode: rep[d] is this surface on device d (rep[0] == the handle the caller holds, nullptr everywhere
+       on replicas); split: every device rasterises only its own tiles and a read-back gathers them on device 0;
+       full_evt (device 0): the last operation that wrote tiles of other devices too; pushed (replicas): the last store of
+       this device's tiles into device 0's surface */
+    pfcu_surface *rep[MAX_DEVS]; bool split; cudaEvent_t full_evt, pushed; bool has_full;
 };
-struct pfcu_texture { uint32_t w, h; int fmt; unsigned char *pixels; bool owned; pfcu_surface *alias; bool leader; };
+struct pfcu_texture { uint32_t w, h; int fmt; unsigned char *pixels; bool owned; pfcu_surface *alias; bool leader; pfcu_texture *rep[MAX_DEVS]; };
 struct pfcu_list { pfcu_rawtri *tris; uint32_t n; };
 struct pfcu_batch {
     DevState *states; uint32_t n_states; pfcu_triangle *tris; uint32_t n_tris; unsigned feature_mask; int single_prog; bool leader_tex;
     std::vector<pfcu_surface *> deps;
+    pfcu_batch *rep[MAX_DEVS];
 };
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -128,10 +138,12 @@ struct pfcu_batch {
 /* ------------------------------------------------------------------------------------------------ */
 
 struct PinnedBlock {
-    void *p; size_t bytes; cudaEvent_t done; bool pending;
+    /* done / pending / d_copy / dev_gen are per device (index = Runtime::index): every device copies from the block
+       with its own stream and keeps its own mirror */
+    void *p; size_t bytes; cudaEvent_t done[MAX_DEVS]; bool pending[MAX_DEVS];
     /* static geometry (pfcu_host_set_static): the block is mirrored in device memory and draws read the mirror; gen counts
        the application's modifications, dev_gen is what the mirror holds */
-    bool is_static; unsigned gen, dev_gen; unsigned char *d_copy;
+    bool is_static; unsigned gen, dev_gen[MAX_DEVS]; unsigned char *d_copy[MAX_DEVS];
     const void *imax_ptr; uint32_t imax_count, imax_value; unsigned imax_gen;     /* largest index of the last index range scanned */
 };
 
@@ -171,6 +183,7 @@ struct Lane {
 #define MAX_LANES 8
 
 struct Runtime {
+    int index = 0;                              /* 0: the primary runtime; 1..: the workers of the multi-device mode */
     bool ok = false; int device = 0; int sms = 148;
     Lane lanes[MAX_LANES]; int n_lanes = 1; unsigned next_lane = 0;
     Lane *cur = nullptr;                                              /* lane of the surface being worked on */
@@ -192,31 +205,126 @@ struct Runtime {
     unsigned char *d_jobs = nullptr, *h_jobs = nullptr; size_t cap_jobs = 0; cudaEvent_t jobs_copied = nullptr, jobs_done = nullptr; unsigned jobs_seq = 0;
     cudaStream_t band_streams[MAX_BANDS] = { nullptr, nullptr, nullptr, nullptr }; cudaStream_t copy_stream = nullptr;
     cudaEvent_t front_evt = nullptr;
+    bool frag_attr_set = false;
     std::recursive_mutex mu;                    /* the C-ABI is serialised: contexts on several threads share one runtime */
     char err[512] = { 0 };
 };
 
-static Runtime g;
-#define LN (*g.cur)
+/* One runtime per device.  Application threads use the primary one; the worker threads of the multi-device mode
+ * (one per additional GPU) point t_rt at theirs, so that every entry point below runs unchanged on either. */
+static Runtime g_main;
+static thread_local Runtime *t_rt = nullptr;
+#define RT (*(t_rt ? t_rt : &g_main))
+#define LN (*RT.cur)
+
+/* ---- multi-device mode (one process, several GPUs: PF_CUDA_DEVICES=0,1,...) ------------------------------------------
+ * north_star / SURVEY 8-e "large framebuffers are screen-tile split": with more than one device listed, every surface,
+ * texture and resident batch exists once per device (the handle the caller holds is device 0's and links to the
+ * others), every submission is replayed on all devices - one worker thread per additional GPU, each with its own
+ * Runtime - and a device rasterises only the 64x64 tiles it owns (tile % n == device, as in the multi-process split).
+ * Full-surface operations run everywhere; a read-back first has every other device store its tiles into device 0's
+ * surface over NVLink (peer access, k_push_tiles).  Surfaces that are sampled as textures (framebuffer objects), small
+ * surfaces and non-RGBA8 targets are rendered in full by every device instead, which keeps them usable everywhere.
+ * Results are byte-identical to one GPU.  Application-visible behaviour does not change; no entry point is added. */
+struct Multi {
+    int n = 1; int dev[MAX_DEVS] = { 0 };
+    Runtime *rt[MAX_DEVS] = { &g_main };
+    std::thread th[MAX_DEVS];
+    std::mutex m; std::condition_variable cv_job, cv_done;
+    const std::function<int(int)> *job = nullptr; unsigned seq = 0; int pending = 0; int rc[MAX_DEVS] = { 0 };
+    bool quit = false;
+    size_t split_min_pixels = (size_t)1 << 20;
+};
+/* never destroyed: worker threads may still wait on its condition variable when the process exits without pfcu_shutdown */
+static Multi *const mg_ptr = new Multi;
+#define mg (*mg_ptr)
+static thread_local bool t_dispatching = false;     /* this thread is inside multi_run_all: entry points it calls act on one device */
+#define MULTI_HERE() (mg.n > 1 && !t_rt && !t_dispatching)
+
+static void multi_worker(int d)
+{
+    t_rt = mg.rt[d];
+    unsigned seen = 0;
+    for (;;) {
+        const std::function<int(int)> *job;
+        {
+            std::unique_lock<std::mutex> lk(mg.m);
+            mg.cv_job.wait(lk, [&] { return mg.quit || mg.seq != seen; });
+            if (mg.quit) return;
+            seen = mg.seq; job = mg.job;
+        }
+        const int rc = (*job)(d);
+        {
+            std::lock_guard<std::mutex> lk(mg.m);
+            mg.rc[d] = rc;
+            if (--mg.pending == 0) mg.cv_done.notify_one();
+        }
+    }
+}
+
+static int multi_run_all(const std::function<int(int)> &fn)
+{
+    if (t_rt) return fn(RT.index);                       /* a worker acts on its own device */
+    if (mg.n <= 1 || t_dispatching) return fn(0);
+    {
+        std::lock_guard<std::mutex> lk(mg.m);
+        mg.job = &fn; mg.pending = mg.n - 1; mg.seq++;
+    }
+    mg.cv_job.notify_all();
+    t_dispatching = true;
+    const int rc0 = fn(0);
+    t_dispatching = false;
+    {
+        std::unique_lock<std::mutex> lk(mg.m);
+        mg.cv_done.wait(lk, [&] { return mg.pending == 0; });
+    }
+    if (rc0) return rc0;
+    for (int d = 1; d < mg.n; d++) if (mg.rc[d]) return mg.rc[d];
+    return PFCU_OK;
+}
+
+/* Device-side counters.  The workers of the multi-device mode repeat the setup of every triangle, and the rendering of
+   surfaces that are not split: they count those into a sink, so that the sums over the devices stay what one GPU counts. */
+static unsigned long long *setup_counters(void) { return RT.index == 0 ? RT.d_counters : RT.d_counters + 4; }
+static unsigned long long *raster_counters(const pfcu_surface *s) { return (RT.index == 0 || s->world > 1) ? RT.d_counters : RT.d_counters + 4; }
+
+/* the states of a submission as device d sees them: texture handles replaced by that device's replicas */
+static std::vector<pfcu_state> states_for_device(const pfcu_state *states, uint32_t n, int d)
+{
+    std::vector<pfcu_state> v(states, states + n);
+    if (d) for (auto &st : v) if (st.texture && st.texture->rep[d]) st.texture = st.texture->rep[d];
+    return v;
+}
+
+/* shut the workers' runtimes down and end their threads */
+static void multi_stop(void)
+{
+    if (mg.n <= 1) return;
+    multi_run_all([](int d) -> int { if (d) pfcu_shutdown(); return (int)PFCU_OK; });
+    { std::lock_guard<std::mutex> lk(mg.m); mg.quit = true; }
+    mg.cv_job.notify_all();
+    for (int d = 1; d < mg.n; d++) { if (mg.th[d].joinable()) mg.th[d].join(); delete mg.rt[d]; mg.rt[d] = nullptr; }
+    mg.n = 1; mg.quit = false;
+}
 /* Every locked entry point also makes the runtime's device current on the calling thread: the C-ABI is shared by
  * contexts on several host threads, and a thread that has not called pfcu_init starts with device 0 current
  * (wrong allocations and "invalid resource handle" launches when PF_CUDA_DEVICE / LOCAL_RANK picked another one). */
 struct ApiGuard {
     std::lock_guard<std::recursive_mutex> lk;
-    ApiGuard() : lk(g.mu)
+    ApiGuard() : lk(RT.mu)
     {
         static thread_local int t_device = -1;
-        if (g.ok && t_device != g.device) { if (cudaSetDevice(g.device) == cudaSuccess) t_device = g.device; }
+        if (RT.ok && t_device != RT.device) { if (cudaSetDevice(RT.device) == cudaSuccess) t_device = RT.device; }
     }
 };
 #define API_LOCK ApiGuard api_lock_
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
-    snprintf(g.err, sizeof g.err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    snprintf(RT.err, sizeof RT.err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     return PFCU_ERR_CUDA; } } while (0)
 
 #define CKP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
-    snprintf(g.err, sizeof g.err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    snprintf(RT.err, sizeof RT.err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     return nullptr; } } while (0)
 
 __constant__ const uint32_t *c_rcp_tab;
@@ -270,25 +378,39 @@ template <typename T> static int grow(T **p, size_t *cap, size_t need)
     while (ncap < need) ncap *= 2;
     CK(cudaStreamSynchronize(LN.stream));
     cudaFree(*p); *p = nullptr; *cap = 0;
-    if (cudaMalloc(p, ncap * sizeof(T)) != cudaSuccess) { snprintf(g.err, sizeof g.err, "out of device memory growing scratch to %zu elements", ncap); return PFCU_ERR_OOM; }
+    if (cudaMalloc(p, ncap * sizeof(T)) != cudaSuccess) { snprintf(RT.err, sizeof RT.err, "out of device memory growing scratch to %zu elements", ncap); return PFCU_ERR_OOM; }
     *cap = ncap;
     return PFCU_OK;
 }
 
 extern "C" {
 
-const char *pfcu_last_error(void) { return g.err; }
+const char *pfcu_last_error(void) { return RT.err; }
 const char *pfcu_backend_name(void) { return "cuda-sm_100a"; }
 
 int pfcu_init(int device)
 {
     API_LOCK;
-    if (g.ok) return PFCU_OK;
+    if (RT.ok) return PFCU_OK;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
-        snprintf(g.err, sizeof g.err, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        snprintf(RT.err, sizeof RT.err, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
         return PFCU_ERR_NO_DEVICE;
+    }
+    /* PF_CUDA_DEVICES=a,b,c...: the multi-device mode; the first device listed is the primary one */
+    int listed[MAX_DEVS], n_listed = 0;
+    if (!t_rt && getenv("PF_CUDA_DEVICES")) {
+        const char *e = getenv("PF_CUDA_DEVICES");
+        while (*e && n_listed < MAX_DEVS) {
+            char *end; const long v = strtol(e, &end, 10);
+            if (end == e) break;
+            bool dup = false; for (int k = 0; k < n_listed; k++) dup |= listed[k] == (int)v;
+            if (v >= 0 && v < count && !dup) listed[n_listed++] = (int)v;
+            e = (*end == ',') ? end + 1 : end;
+            if (*end && *end != ',') break;
+        }
+        if (n_listed && device < 0) device = listed[0];
     }
     if (device < 0) {
         const char *env = getenv("PF_CUDA_DEVICE");
@@ -296,24 +418,24 @@ int pfcu_init(int device)
         device = env ? atoi(env) : 0;
         if (device < 0 || device >= count) device = 0;
     }
-    if (device >= count) { snprintf(g.err, sizeof g.err, "device %d out of range (%d devices)", device, count); return PFCU_ERR_NO_DEVICE; }
+    if (device >= count) { snprintf(RT.err, sizeof RT.err, "device %d out of range (%d devices)", device, count); return PFCU_ERR_NO_DEVICE; }
     CK(cudaSetDevice(device));
-    g.device = device;
+    RT.device = device;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
-    g.sms = prop.multiProcessorCount;
+    RT.sms = prop.multiProcessorCount;
     if (prop.major < 10) {
-        snprintf(g.err, sizeof g.err, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        snprintf(RT.err, sizeof RT.err, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         return PFCU_ERR_NO_DEVICE;
     }
     {
         const char *env = getenv("PF_CUDA_LANES");
-        g.n_lanes = env ? atoi(env) : 4;
-        if (g.n_lanes < 1) g.n_lanes = 1;
-        if (g.n_lanes > MAX_LANES) g.n_lanes = MAX_LANES;
+        RT.n_lanes = env ? atoi(env) : 4;
+        if (RT.n_lanes < 1) RT.n_lanes = 1;
+        if (RT.n_lanes > MAX_LANES) RT.n_lanes = MAX_LANES;
     }
-    for (int i = 0; i < g.n_lanes; i++) {
-        g.cur = &g.lanes[i];
+    for (int i = 0; i < RT.n_lanes; i++) {
+        RT.cur = &RT.lanes[i];
         CK(cudaStreamCreateWithFlags(&LN.stream, cudaStreamNonBlocking));
         LN.own_stream = true;
         CK(cudaMalloc(&LN.d_bin_start, ((MAX_BINS + 2) * 2 + 4) * sizeof(unsigned)));      /* starts | totals | ticket of k_bin_scan */
@@ -331,32 +453,55 @@ int pfcu_init(int device)
         CK(cudaMalloc(&LN.d_chain, 16 * sizeof(unsigned long long)));
         CK(cudaMemset(LN.d_chain, 0, 16 * sizeof(unsigned long long)));
     }
-    g.cur = &g.lanes[0];
+    RT.cur = &RT.lanes[0];
     {   /* band streams in descending priority: the block scheduler then drains band 0 first, band 1 next ... - launched
            with equal priority the bands would share the SMs evenly and all finish together at the end */
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          /* lo: least (numerically largest), hi: greatest */
         for (int b = 0; b < MAX_BANDS; b++) {
             int pr = hi + b; if (pr > lo) pr = lo;
-            CK(cudaStreamCreateWithPriority(&g.band_streams[b], cudaStreamNonBlocking, pr));
+            CK(cudaStreamCreateWithPriority(&RT.band_streams[b], cudaStreamNonBlocking, pr));
         }
     }
-    CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&g.front_evt, cudaEventDisableTiming));
-    CK(cudaMalloc(&g.d_counters, 4 * sizeof(unsigned long long)));
-    CK(cudaMemset(g.d_counters, 0, 4 * sizeof(unsigned long long)));
-    g.ok = true;
+    CK(cudaStreamCreateWithFlags(&RT.copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&RT.front_evt, cudaEventDisableTiming));
+    CK(cudaMalloc(&RT.d_counters, 8 * sizeof(unsigned long long)));          /* [0..3] the counters, [4..7] a sink (see counters_for) */
+    CK(cudaMemset(RT.d_counters, 0, 8 * sizeof(unsigned long long)));
+    RT.ok = true;
+    if (!t_rt && n_listed > 1 && listed[0] == device) {
+        /* start one worker per additional device; each initialises its own runtime and opens peer access to the primary
+           (it will store its tiles into the primary's surfaces) */
+        if (getenv("PF_CUDA_SPLIT_MIN_PIXELS")) mg.split_min_pixels = (size_t)strtoull(getenv("PF_CUDA_SPLIT_MIN_PIXELS"), nullptr, 10);
+        mg.n = n_listed;
+        for (int d = 0; d < n_listed; d++) mg.dev[d] = listed[d];
+        for (int d = 1; d < n_listed; d++) { mg.rt[d] = new Runtime(); mg.rt[d]->index = d; mg.th[d] = std::thread(multi_worker, d); }
+        const int rc = multi_run_all([](int d) -> int {
+            if (d == 0) return (int)PFCU_OK;
+            int rc = pfcu_init(mg.dev[d]);
+            if (rc) return rc;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, mg.dev[d], mg.dev[0]) != cudaSuccess || !can) { snprintf(g_main.err, sizeof g_main.err, "device %d cannot access device %d as a peer", mg.dev[d], mg.dev[0]); return (int)PFCU_ERR_NO_DEVICE; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(mg.dev[0], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { snprintf(g_main.err, sizeof g_main.err, "cudaDeviceEnablePeerAccess(%d -> %d): %s", mg.dev[d], mg.dev[0], cudaGetErrorString(e)); return (int)PFCU_ERR_CUDA; }
+            cudaGetLastError();
+            return (int)PFCU_OK;
+        });
+        if (rc) {
+            fprintf(stderr, "pixelforge-b200: PF_CUDA_DEVICES: %s - continuing on device %d alone\n", g_main.err, device);
+            multi_stop();
+        }
+    }
     return PFCU_OK;
 }
 
 /* band and copy streams only ever hold work that a lane stream waits for (an event per band / per read-back), except
    the read-backs themselves: pfcu_surface_wait covers those, and so does this */
-static void sync_all_lanes(void) { for (int i = 0; i < g.n_lanes; i++) cudaStreamSynchronize(g.lanes[i].stream); if (g.copy_stream) cudaStreamSynchronize(g.copy_stream); }
+static void sync_all_lanes(void) { for (int i = 0; i < RT.n_lanes; i++) cudaStreamSynchronize(RT.lanes[i].stream); if (RT.copy_stream) cudaStreamSynchronize(RT.copy_stream); }
 static void use_lane(const pfcu_surface *s)
 {
-    g.cur = &g.lanes[s ? s->lane % g.n_lanes : 0];
+    RT.cur = &RT.lanes[s ? s->lane % RT.n_lanes : 0];
     if (LN.need_fence_wait) {           /* deferred half of pfcu_fence(): later work on this lane comes after lane 0's fence */
-        if (g.cur != &g.lanes[0]) cudaStreamWaitEvent(LN.stream, g.lanes[0].fence, 0);
+        if (RT.cur != &RT.lanes[0]) cudaStreamWaitEvent(LN.stream, RT.lanes[0].fence, 0);
         LN.need_fence_wait = false;
     }
     LN.touched = true;
@@ -365,10 +510,11 @@ static void use_lane(const pfcu_surface *s)
 void pfcu_shutdown(void)
 {
     API_LOCK;
-    if (!g.ok) return;
+    if (!RT.ok) return;
+    if (!t_rt) multi_stop();
     sync_all_lanes();
-    for (int i = 0; i < g.n_lanes; i++) {
-        g.cur = &g.lanes[i];
+    for (int i = 0; i < RT.n_lanes; i++) {
+        RT.cur = &RT.lanes[i];
         cudaFree(LN.d_tris); cudaFree(LN.d_states); cudaFree(LN.d_bbox); cudaFree(LN.d_setup); cudaFree(LN.d_data);
         cudaFree(LN.d_bin_counts); cudaFree(LN.d_bin_list); cudaFree(LN.d_bin_start); cudaFree(LN.d_varrays); cudaFree(LN.d_vcounts);
         if (LN.h_stage) cudaFreeHost(LN.h_stage);
@@ -380,24 +526,24 @@ void pfcu_shutdown(void)
         for (cudaEvent_t e : { LN.stage_done, LN.states_done, LN.fence, LN.raw_done, LN.vready }) if (e) cudaEventDestroy(e);
         if (LN.vstream) cudaStreamDestroy(LN.vstream);
         if (LN.own_stream) cudaStreamDestroy(LN.stream);
-        g.lanes[i] = Lane();
+        RT.lanes[i] = Lane();
     }
-    for (int b = 0; b < MAX_BANDS; b++) if (g.band_streams[b]) { cudaStreamDestroy(g.band_streams[b]); g.band_streams[b] = nullptr; }
-    if (g.copy_stream) { cudaStreamDestroy(g.copy_stream); g.copy_stream = nullptr; }
-    if (g.front_evt) { cudaEventDestroy(g.front_evt); g.front_evt = nullptr; }
-    cudaFree(g.d_counters); cudaFree(g.d_rcp); cudaFree(g.d_rsq);
-    g.d_counters = nullptr; g.d_rcp = nullptr; g.d_rsq = nullptr;
-    for (auto &S : g.job_slots) { cudaFree(S.d_tris); cudaFree(S.bbox); cudaFree(S.setup); cudaFree(S.data); cudaFree(S.bin_list); cudaFree(S.bin_start); cudaFree(S.d_total); cudaFree(S.chain); }
-    g.job_slots.clear();
-    cudaFree(g.d_jobs); if (g.h_jobs) cudaFreeHost(g.h_jobs);
-    g.d_jobs = nullptr; g.h_jobs = nullptr; g.cap_jobs = 0;
-    if (g.jobs_copied) { cudaEventDestroy(g.jobs_copied); cudaEventDestroy(g.jobs_done); g.jobs_copied = g.jobs_done = nullptr; }
+    for (int b = 0; b < MAX_BANDS; b++) if (RT.band_streams[b]) { cudaStreamDestroy(RT.band_streams[b]); RT.band_streams[b] = nullptr; }
+    if (RT.copy_stream) { cudaStreamDestroy(RT.copy_stream); RT.copy_stream = nullptr; }
+    if (RT.front_evt) { cudaEventDestroy(RT.front_evt); RT.front_evt = nullptr; }
+    cudaFree(RT.d_counters); cudaFree(RT.d_rcp); cudaFree(RT.d_rsq);
+    RT.d_counters = nullptr; RT.d_rcp = nullptr; RT.d_rsq = nullptr;
+    for (auto &S : RT.job_slots) { cudaFree(S.d_tris); cudaFree(S.bbox); cudaFree(S.setup); cudaFree(S.data); cudaFree(S.bin_list); cudaFree(S.bin_start); cudaFree(S.d_total); cudaFree(S.chain); }
+    RT.job_slots.clear();
+    cudaFree(RT.d_jobs); if (RT.h_jobs) cudaFreeHost(RT.h_jobs);
+    RT.d_jobs = nullptr; RT.h_jobs = nullptr; RT.cap_jobs = 0;
+    if (RT.jobs_copied) { cudaEventDestroy(RT.jobs_copied); cudaEventDestroy(RT.jobs_done); RT.jobs_copied = RT.jobs_done = nullptr; }
     /* blocks handed out by pfcu_host_alloc and never returned: released here, their pointers die with the runtime */
-    for (auto &b : g.pinned) { cudaEventDestroy(b.done); cudaFreeHost(b.p); cudaFree(b.d_copy); }
-    for (auto e : g.prof_events) cudaEventDestroy(e);
-    for (auto e : g.prof_pool) cudaEventDestroy(e);
-    g.prof_events.clear(); g.prof_pool.clear();
-    g.pinned.clear(); g.cur = nullptr; g.ok = false;
+    if (RT.index == 0) for (auto &b : RT.pinned) { if (b.done[0]) cudaEventDestroy(b.done[0]); cudaFreeHost(b.p); cudaFree(b.d_copy[0]); }
+    for (auto e : RT.prof_events) cudaEventDestroy(e);
+    for (auto e : RT.prof_pool) cudaEventDestroy(e);
+    RT.prof_events.clear(); RT.prof_pool.clear();
+    RT.pinned.clear(); RT.cur = nullptr; RT.ok = false;
 }
 
 /* Order everything enqueued so far on every lane before everything enqueued afterwards on every lane, without
@@ -405,58 +551,83 @@ void pfcu_shutdown(void)
 int pfcu_fence(void)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
+    if (MULTI_HERE()) return multi_run_all([](int) -> int { return pfcu_fence(); });
     /* lanes that were not used since the last fence have nothing new to order before lane 0; their wait for lane 0 is
        deferred to their next use (use_lane) - a single-surface workload pays for one event, not for every lane */
-    for (int i = 1; i < g.n_lanes; i++) {
-        if (!g.lanes[i].touched) continue;
-        CK(cudaEventRecord(g.lanes[i].fence, g.lanes[i].stream));
-        CK(cudaStreamWaitEvent(g.lanes[0].stream, g.lanes[i].fence, 0));
-        g.lanes[i].touched = false;
+    for (int i = 1; i < RT.n_lanes; i++) {
+        if (!RT.lanes[i].touched) continue;
+        CK(cudaEventRecord(RT.lanes[i].fence, RT.lanes[i].stream));
+        CK(cudaStreamWaitEvent(RT.lanes[0].stream, RT.lanes[i].fence, 0));
+        RT.lanes[i].touched = false;
     }
-    CK(cudaEventRecord(g.lanes[0].fence, g.lanes[0].stream));
-    for (int i = 1; i < g.n_lanes; i++) g.lanes[i].need_fence_wait = true;
+    CK(cudaEventRecord(RT.lanes[0].fence, RT.lanes[0].stream));
+    for (int i = 1; i < RT.n_lanes; i++) RT.lanes[i].need_fence_wait = true;
     return PFCU_OK;
 }
 
 int pfcu_set_stream(void *cuda_stream)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     sync_all_lanes();
-    Lane &l0 = g.lanes[0];
+    Lane &l0 = RT.lanes[0];
     if (l0.own_stream) { cudaStreamDestroy(l0.stream); l0.own_stream = false; }
     l0.stream = (cudaStream_t)cuda_stream;       /* lane 0 adopts the caller's stream; see pfcu_fence() */
     return PFCU_OK;
 }
 
-void *pfcu_get_stream(void) { return g.ok ? (void *)g.lanes[0].stream : nullptr; }
+void *pfcu_get_stream(void) { return RT.ok ? (void *)RT.lanes[0].stream : nullptr; }
 
 void *pfcu_host_alloc(size_t bytes)
 {
-    if (!g.ok && pfcu_init(-1) != PFCU_OK) return nullptr;
+    if (!RT.ok && pfcu_init(-1) != PFCU_OK) return nullptr;
     API_LOCK;
-    PinnedBlock b; memset(&b, 0, sizeof b); b.bytes = bytes; b.pending = false; b.dev_gen = ~0u;
-    if (cudaHostAlloc(&b.p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming) != cudaSuccess) { cudaFreeHost(b.p); return nullptr; }
-    g.pinned.push_back(b);
+    PinnedBlock b; memset(&b, 0, sizeof b); b.bytes = bytes;
+    for (int d = 0; d < MAX_DEVS; d++) b.dev_gen[d] = ~0u;
+    /* portable: page-locked for every device of the multi-device mode */
+    if (cudaHostAlloc(&b.p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    g_main.pinned.push_back(b);
     return b.p;
 }
 
+/* The registry of page-locked blocks lives in the primary runtime.  Worker threads only look blocks up, and only
+ * while the dispatching thread holds the primary's lock (multi_run), so the vector does not change under them; each
+ * device touches its own slots of a block. */
 static PinnedBlock *find_pinned(const void *p)
 {
-    for (auto &b : g.pinned) if ((const char *)p >= (const char *)b.p && (const char *)p < (const char *)b.p + b.bytes) return &b;
+    for (auto &b : g_main.pinned) if ((const char *)p >= (const char *)b.p && (const char *)p < (const char *)b.p + b.bytes) return &b;
     return nullptr;
+}
+
+/* the copy just enqueued on `st` reads from block b: the host may overwrite the block once this device is done with it */
+static int pinned_in_flight(PinnedBlock *b, cudaStream_t st)
+{
+    const int d = RT.index;
+    if (!b->done[d]) CK(cudaEventCreateWithFlags(&b->done[d], cudaEventDisableTiming));
+    CK(cudaEventRecord(b->done[d], st));
+    b->pending[d] = true;
+    return PFCU_OK;
+}
+
+/* this device's event and mirror of a block (runs on the device's own thread) */
+static int release_block_on_device(PinnedBlock *b)
+{
+    const int d = RT.index;
+    if (b->pending[d] && b->done[d]) cudaEventSynchronize(b->done[d]);
+    b->pending[d] = false;
+    if (b->d_copy[d]) { sync_all_lanes(); cudaFree(b->d_copy[d]); b->d_copy[d] = nullptr; b->dev_gen[d] = ~0u; }
+    return PFCU_OK;
 }
 
 void pfcu_host_free(void *p)
 {
     API_LOCK;
-    for (size_t i = 0; i < g.pinned.size(); i++) if (g.pinned[i].p == p) {
-        if (g.pinned[i].pending) cudaEventSynchronize(g.pinned[i].done);
-        if (g.pinned[i].d_copy) { sync_all_lanes(); cudaFree(g.pinned[i].d_copy); }
-        cudaEventDestroy(g.pinned[i].done); cudaFreeHost(p);
-        g.pinned.erase(g.pinned.begin() + i);
+    for (size_t i = 0; i < g_main.pinned.size(); i++) if (g_main.pinned[i].p == p) {
+        PinnedBlock *b = &g_main.pinned[i];
+        multi_run_all([b](int) -> int { release_block_on_device(b); if (b->done[RT.index]) { cudaEventDestroy(b->done[RT.index]); b->done[RT.index] = nullptr; } return (int)PFCU_OK; });
+        cudaFreeHost(p);
+        g_main.pinned.erase(g_main.pinned.begin() + i);
         return;
     }
 }
@@ -467,7 +638,7 @@ int pfcu_host_set_static(void *p, int on)
     PinnedBlock *b = find_pinned(p);
     if (!b) return PFCU_ERR_INVALID;
     b->is_static = on != 0;
-    if (!on && b->d_copy) { sync_all_lanes(); cudaFree(b->d_copy); b->d_copy = nullptr; b->dev_gen = ~0u; }
+    if (!on) multi_run_all([b](int) -> int { return release_block_on_device(b); });
     return PFCU_OK;
 }
 
@@ -494,23 +665,24 @@ static const unsigned char *static_mirror(const void *p, size_t bytes, PinnedBlo
     PinnedBlock *b = find_pinned(p);
     if (blk) *blk = b;
     if (!b || !b->is_static || (const char *)p + bytes > (const char *)b->p + b->bytes) return nullptr;
-    if (!b->d_copy && cudaMalloc(&b->d_copy, b->bytes + 16) != cudaSuccess) { cudaGetLastError(); b->d_copy = nullptr; return nullptr; }
-    if (b->dev_gen != b->gen) {
+    const int d = RT.index;
+    if (!b->d_copy[d] && cudaMalloc(&b->d_copy[d], b->bytes + 16) != cudaSuccess) { cudaGetLastError(); b->d_copy[d] = nullptr; return nullptr; }
+    if (b->dev_gen[d] != b->gen) {
         /* every lane may be reading the old mirror; the upload is rare (once per modification), so it simply waits */
         sync_all_lanes();
-        if (cudaMemcpy(b->d_copy, b->p, b->bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        g.bytes_h2d += b->bytes;
-        b->dev_gen = b->gen;
+        if (cudaMemcpy(b->d_copy[d], b->p, b->bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        RT.bytes_h2d += b->bytes;
+        b->dev_gen[d] = b->gen;
     }
-    return b->d_copy + ((const char *)p - (const char *)b->p);
+    return b->d_copy[d] + ((const char *)p - (const char *)b->p);
 }
 
 int pfcu_host_register(void *p, size_t bytes)
 {
     API_LOCK;
-    if (!g.ok || !p || bytes == 0) return PFCU_ERR_INVALID;
+    if (!RT.ok || !p || bytes == 0) return PFCU_ERR_INVALID;
     /* page-aligned sub-range; the partial first/last pages stay pageable (cudaMemcpy handles mixed ranges) */
-    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    cudaError_t e = cudaHostRegister(p, bytes, mg.n > 1 ? cudaHostRegisterPortable : cudaHostRegisterDefault);
     if (e != cudaSuccess) { cudaGetLastError(); return PFCU_ERR_CUDA; }
     return PFCU_OK;
 }
@@ -518,7 +690,7 @@ int pfcu_host_register(void *p, size_t bytes)
 void pfcu_host_unregister(void *p)
 {
     API_LOCK;
-    if (!g.ok || !p) return;
+    if (!RT.ok || !p) return;
     sync_all_lanes();
     if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
 }
@@ -527,28 +699,30 @@ int pfcu_host_wait(const void *p)
 {
     API_LOCK;
     PinnedBlock *b = find_pinned(p);
-    if (b && b->pending) { CK(cudaEventSynchronize(b->done)); b->pending = false; }
+    if (b) for (int d = 0; d < MAX_DEVS; d++)
+        if (b->pending[d]) { CK(cudaEventSynchronize(b->done[d])); b->pending[d] = false; }       /* waiting on another device's event is fine */
     return PFCU_OK;
 }
 
 int pfcu_set_approx_tables(const uint32_t *rcp, int rcp_bits, const uint32_t *rsqrt, int rsqrt_bits)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (rcp_bits < 1 || rcp_bits > 23 || rsqrt_bits < 1 || rsqrt_bits > 23) return PFCU_ERR_INVALID;
+    if (MULTI_HERE()) return multi_run_all([&](int) -> int { return pfcu_set_approx_tables(rcp, rcp_bits, rsqrt, rsqrt_bits); });
     sync_all_lanes();
-    cudaFree(g.d_rcp); cudaFree(g.d_rsq);
-    CK(cudaMalloc(&g.d_rcp, sizeof(uint32_t) << rcp_bits));
-    CK(cudaMalloc(&g.d_rsq, sizeof(uint32_t) << (rsqrt_bits + 1)));
-    CK(cudaMemcpy(g.d_rcp, rcp, sizeof(uint32_t) << rcp_bits, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(g.d_rsq, rsqrt, sizeof(uint32_t) << (rsqrt_bits + 1), cudaMemcpyHostToDevice));
+    cudaFree(RT.d_rcp); cudaFree(RT.d_rsq);
+    CK(cudaMalloc(&RT.d_rcp, sizeof(uint32_t) << rcp_bits));
+    CK(cudaMalloc(&RT.d_rsq, sizeof(uint32_t) << (rsqrt_bits + 1)));
+    CK(cudaMemcpy(RT.d_rcp, rcp, sizeof(uint32_t) << rcp_bits, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(RT.d_rsq, rsqrt, sizeof(uint32_t) << (rsqrt_bits + 1), cudaMemcpyHostToDevice));
     const int rshift = 23 - rcp_bits, sshift = 23 - rsqrt_bits;
-    CK(cudaMemcpyToSymbol(c_rcp_tab, &g.d_rcp, sizeof(void *)));
-    CK(cudaMemcpyToSymbol(c_rsq_tab, &g.d_rsq, sizeof(void *)));
+    CK(cudaMemcpyToSymbol(c_rcp_tab, &RT.d_rcp, sizeof(void *)));
+    CK(cudaMemcpyToSymbol(c_rsq_tab, &RT.d_rsq, sizeof(void *)));
     CK(cudaMemcpyToSymbol(c_rcp_shift, &rshift, sizeof(int)));
     CK(cudaMemcpyToSymbol(c_rsq_shift, &sshift, sizeof(int)));
     CK(cudaMemcpyToSymbol(c_rsq_bits, &rsqrt_bits, sizeof(int)));
-    g.rcp_bits = rcp_bits; g.rsq_bits = rsqrt_bits;
+    RT.rcp_bits = rcp_bits; RT.rsq_bits = rsqrt_bits;
     return PFCU_OK;
 }
 
@@ -564,18 +738,33 @@ int pfcu_surface_format(const pfcu_surface *s) { return s ? s->fmt : -1; }
 pfcu_surface *pfcu_surface_create_format(uint32_t w, uint32_t h, int fmt)
 {
     API_LOCK;
-    if (!g.ok || w == 0 || h == 0) { snprintf(g.err, sizeof g.err, "surface_create: runtime not initialised or empty surface"); return nullptr; }
-    if (fmt < PFCU_TEX_RGBA8 || fmt > PFCU_TEX_BGR8) { snprintf(g.err, sizeof g.err, "surface_create: unsupported colour format %d", fmt); return nullptr; }
+    if (MULTI_HERE()) {
+        pfcu_surface *r[MAX_DEVS] = { nullptr };
+        const int rc = multi_run_all([&](int d) -> int { r[d] = pfcu_surface_create_format(w, h, fmt); return r[d] ? PFCU_OK : PFCU_ERR_OOM; });
+        if (rc) { multi_run_all([&](int d) -> int { if (r[d]) pfcu_surface_destroy(r[d]); return (int)PFCU_OK; }); return nullptr; }
+        pfcu_surface *s = r[0];
+        /* large RGBA8 targets are split by tiles; everything else is rendered in full on every device */
+        s->split = fmt == PFCU_TEX_RGBA8 && (size_t)w * h >= mg.split_min_pixels && s->tiles_x * s->tiles_y >= (unsigned)mg.n;
+        for (int d = 0; d < mg.n; d++) {
+            s->rep[d] = r[d];
+            r[d]->rank = s->split ? (uint32_t)d : 0u; r[d]->world = s->split ? (uint32_t)mg.n : 1u;
+            if (d) { r[d]->peer_color = s->color; r[d]->peer_depth = s->depth; }      /* peer addresses: valid on every device (UVA + peer access) */
+        }
+        return s;
+    }
+    if (!RT.ok || w == 0 || h == 0) { snprintf(RT.err, sizeof RT.err, "surface_create: runtime not initialised or empty surface"); return nullptr; }
+    if (fmt < PFCU_TEX_RGBA8 || fmt > PFCU_TEX_BGR8) { snprintf(RT.err, sizeof RT.err, "surface_create: unsupported colour format %d", fmt); return nullptr; }
     pfcu_surface *s = (pfcu_surface *)calloc(1, sizeof *s);
     if (!s) return nullptr;
     s->w = w; s->h = h; s->owned = true; s->world = 1; s->fmt = fmt;
-    s->lane = (int)(g.next_lane++ % (unsigned)g.n_lanes);
+    s->lane = (int)(RT.next_lane++ % (unsigned)RT.n_lanes);
     cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
+    if (mg.n > 1) { cudaEventCreateWithFlags(&s->full_evt, cudaEventDisableTiming); cudaEventCreateWithFlags(&s->pushed, cudaEventDisableTiming); }
     use_lane(s);
     surface_dims(s);
     const size_t bytes = ((size_t)w * h + 64) * 4;
     if (cudaMalloc(&s->color, bytes) != cudaSuccess || cudaMalloc(&s->depth, bytes) != cudaSuccess) {
-        snprintf(g.err, sizeof g.err, "surface_create: out of device memory (%ux%u)", w, h);
+        snprintf(RT.err, sizeof RT.err, "surface_create: out of device memory (%ux%u)", w, h);
         cudaFree(s->color); free(s); return nullptr;
     }
     cudaMemsetAsync(s->color, 0, bytes, LN.stream);
@@ -583,7 +772,7 @@ pfcu_surface *pfcu_surface_create_format(uint32_t w, uint32_t h, int fmt)
     if (fmt != PFCU_TEX_RGBA8) {
         s->conv_bytes = (size_t)w * h * fmt_bytes(fmt) + 16;
         if (cudaMalloc(&s->conv, s->conv_bytes) != cudaSuccess) {
-            snprintf(g.err, sizeof g.err, "surface_create: out of device memory (%ux%u staging)", w, h);
+            snprintf(RT.err, sizeof RT.err, "surface_create: out of device memory (%ux%u staging)", w, h);
             cudaFree(s->color); cudaFree(s->depth); free(s); return nullptr;
         }
     }
@@ -593,7 +782,7 @@ pfcu_surface *pfcu_surface_create_format(uint32_t w, uint32_t h, int fmt)
 pfcu_surface *pfcu_surface_wrap(void *dev_color, void *dev_depth, uint32_t w, uint32_t h)
 {
     API_LOCK;
-    if (!g.ok || !dev_color || !dev_depth) return nullptr;
+    if (!RT.ok || !dev_color || !dev_depth) return nullptr;
     pfcu_surface *s = (pfcu_surface *)calloc(1, sizeof *s);
     if (!s) return nullptr;
     s->w = w; s->h = h; s->color = (uint32_t *)dev_color; s->depth = (float *)dev_depth; s->owned = false; s->world = 1; s->fmt = PFCU_TEX_RGBA8;
@@ -616,7 +805,7 @@ static void close_present(pfcu_surface *s)
 int pfcu_surface_ipc_handles(pfcu_surface *s, void *color_handle, void *depth_handle)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || !color_handle) return PFCU_ERR_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle buffers are 64 bytes");
     CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)color_handle, s->color));
@@ -627,7 +816,7 @@ int pfcu_surface_ipc_handles(pfcu_surface *s, void *color_handle, void *depth_ha
 int pfcu_surface_set_present_peer(pfcu_surface *s, const void *color_handle, const void *depth_handle)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || !color_handle) return PFCU_ERR_INVALID;
     sync_all_lanes();
     close_present(s);
@@ -647,7 +836,7 @@ int pfcu_surface_set_present_surface(pfcu_surface *s, pfcu_surface *target)
 {
     API_LOCK;
     if (!s || !target || target->w != s->w || target->h != s->h || target == s) return PFCU_ERR_INVALID;
-    if (g.ok) sync_all_lanes();
+    if (RT.ok) sync_all_lanes();
     close_present(s);
     s->peer_color = target->color; s->peer_depth = target->depth;
     return PFCU_OK;
@@ -657,7 +846,7 @@ int pfcu_surface_clear_present(pfcu_surface *s)
 {
     API_LOCK;
     if (!s) return PFCU_ERR_INVALID;
-    if (g.ok) sync_all_lanes();
+    if (RT.ok) sync_all_lanes();
     close_present(s);
     return PFCU_OK;
 }
@@ -665,7 +854,7 @@ int pfcu_surface_clear_present(pfcu_surface *s)
 int pfcu_surface_push_tiles(pfcu_surface *s, uint32_t rank, uint32_t world, int with_depth)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || !s->peer_color || (with_depth && !s->peer_depth)) return PFCU_ERR_INVALID;
     if (world == 0) world = 1;
     use_lane(s);
@@ -673,7 +862,7 @@ int pfcu_surface_push_tiles(pfcu_surface *s, uint32_t rank, uint32_t world, int 
     if (n == 0) return PFCU_OK;
     k_push_tiles<<<n, 256, 0, LN.stream>>>(s->color, s->depth, s->peer_color, with_depth ? s->peer_depth : nullptr, (int)s->w, (int)s->h,
                                           (int)s->tiles_x, s->tiles_x * s->tiles_y, rank, world);
-    g.launches++;
+    RT.launches++;
     CK(cudaGetLastError());
     mark_done(s);
     return PFCU_OK;
@@ -683,12 +872,20 @@ void pfcu_surface_destroy(pfcu_surface *s)
 {
     API_LOCK;
     if (!s) return;
-    if (g.ok) sync_all_lanes();
+    if (MULTI_HERE() && s->rep[1]) {
+        pfcu_surface *r[MAX_DEVS]; memcpy(r, s->rep, sizeof r);
+        for (int d = 1; d < mg.n; d++) { r[d]->peer_color = nullptr; r[d]->peer_depth = nullptr; }      /* not IPC mappings: nothing to close */
+        multi_run_all([&](int d) -> int { pfcu_surface_destroy(r[d]); return (int)PFCU_OK; });
+        return;
+    }
+    if (RT.ok) sync_all_lanes();
     close_present(s);
     if (s->owned) { cudaFree(s->color); cudaFree(s->depth); }
     cudaFree(s->conv);
     if (s->done) cudaEventDestroy(s->done);
     for (int b = 0; b < MAX_BANDS; b++) if (s->band_evt[b]) cudaEventDestroy(s->band_evt[b]);
+    if (s->full_evt) cudaEventDestroy(s->full_evt);
+    if (s->pushed) cudaEventDestroy(s->pushed);
     free(s);
 }
 
@@ -701,9 +898,44 @@ void *pfcu_surface_depth_ptr(const pfcu_surface *s) { return s->depth; }
    rasterisation no longer describe the surface's last write */
 static void mark_done(pfcu_surface *s) { s->bands_valid = false; if (cudaEventRecord(s->done, LN.stream) == cudaSuccess) s->has_done = true; }
 
+/* ---- multi-device helpers (see "multi-device mode" at the top) ---- */
+#define MULTI_SURF(s) (MULTI_HERE() && (s) && (s)->rep[1])
+
+/* op(d, replica) on every device; device 0 then notes that its surface was written outside its own tiles */
+static int multi_surface_op(pfcu_surface *s, const std::function<int(int, pfcu_surface *)> &op)
+{
+    return multi_run_all([&](int d) -> int {
+        const int rc = op(d, s->rep[d]);
+        if (d == 0 && s->full_evt) { use_lane(s); if (cudaEventRecord(s->full_evt, LN.stream) == cudaSuccess) s->has_full = true; }
+        return rc;
+    });
+}
+
+/* Before device 0 reads a split surface back (or reads pixels out of it): every other device stores its own tiles into
+ * device 0's buffers over NVLink, behind device 0's last full-surface write; device 0's lane waits for the stores. */
+static int multi_gather(pfcu_surface *s, int with_depth)
+{
+    if (!s->split) return PFCU_OK;
+    const int rc = multi_run_all([&](int d) -> int {
+        if (d == 0) return (int)PFCU_OK;
+        pfcu_surface *r = s->rep[d];
+        use_lane(r);
+        if (s->has_full) CK(cudaStreamWaitEvent(LN.stream, s->full_evt, 0));
+        const int rc = pfcu_surface_push_tiles(r, (uint32_t)d, (uint32_t)mg.n, with_depth);
+        use_lane(r);
+        CK(cudaEventRecord(r->pushed, LN.stream));
+        return rc;
+    });
+    if (rc) return rc;
+    use_lane(s);
+    for (int d = 1; d < mg.n; d++) CK(cudaStreamWaitEvent(LN.stream, s->rep[d]->pushed, 0));
+    return PFCU_OK;
+}
+
 int pfcu_surface_upload(pfcu_surface *s, const void *hc, const float *hd, uint32_t y0, uint32_t rows)
 {
     API_LOCK;
+    if (MULTI_SURF(s)) return multi_surface_op(s, [&](int, pfcu_surface *r) -> int { return pfcu_surface_upload(r, hc, hd, y0, rows); });
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
     use_lane(s);
     s->bands_valid = false;
@@ -712,13 +944,13 @@ int pfcu_surface_upload(pfcu_surface *s, const void *hc, const float *hd, uint32
         /* the caller's layout -> staging -> canonical RGBA8 */
         const size_t bpp = fmt_bytes(s->fmt), nb = (size_t)rows * s->w * bpp;
         CK(cudaMemcpyAsync(s->conv + off * bpp, (const unsigned char *)hc + off * bpp, nb, cudaMemcpyHostToDevice, LN.stream));
-        k_surface_convert<<<g.sms * 4, 256, 0, LN.stream>>>(s->color + off, s->conv + off * bpp, (size_t)rows * s->w, s->fmt, 0);
-        g.launches++; g.bytes_h2d += nb;
+        k_surface_convert<<<RT.sms * 4, 256, 0, LN.stream>>>(s->color + off, s->conv + off * bpp, (size_t)rows * s->w, s->fmt, 0);
+        RT.launches++; RT.bytes_h2d += nb;
         CK(cudaGetLastError());
         hc = nullptr;
     }
-    if (hc) { CK(cudaMemcpyAsync(s->color + off, (const uint32_t *)hc + off, n, cudaMemcpyHostToDevice, LN.stream)); g.bytes_h2d += n; }
-    if (hd) { CK(cudaMemcpyAsync(s->depth + off, hd + off, n, cudaMemcpyHostToDevice, LN.stream)); g.bytes_h2d += n; }
+    if (hc) { CK(cudaMemcpyAsync(s->color + off, (const uint32_t *)hc + off, n, cudaMemcpyHostToDevice, LN.stream)); RT.bytes_h2d += n; }
+    if (hd) { CK(cudaMemcpyAsync(s->depth + off, hd + off, n, cudaMemcpyHostToDevice, LN.stream)); RT.bytes_h2d += n; }
     /* pageable sources are staged by the driver before the call returns; pinned ones are not */
     CK(cudaStreamSynchronize(LN.stream));
     return PFCU_OK;
@@ -727,16 +959,17 @@ int pfcu_surface_upload(pfcu_surface *s, const void *hc, const float *hd, uint32
 int pfcu_surface_download_async(pfcu_surface *s, void *hc, float *hd, uint32_t y0, uint32_t rows)
 {
     API_LOCK;
+    if (MULTI_SURF(s)) { const int rc = multi_gather(s, hd != nullptr); if (rc) return rc; }
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
     use_lane(s);
     const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;
     if (hc && s->fmt != PFCU_TEX_RGBA8 && rows) {
         /* canonical RGBA8 -> staging in the caller's layout -> host */
         const size_t bpp = fmt_bytes(s->fmt), nb = (size_t)rows * s->w * bpp;
-        k_surface_convert<<<g.sms * 4, 256, 0, LN.stream>>>(s->color + off, s->conv + off * bpp, (size_t)rows * s->w, s->fmt, 1);
-        g.launches++;
+        k_surface_convert<<<RT.sms * 4, 256, 0, LN.stream>>>(s->color + off, s->conv + off * bpp, (size_t)rows * s->w, s->fmt, 1);
+        RT.launches++;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync((unsigned char *)hc + off * bpp, s->conv + off * bpp, nb, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += nb;
+        CK(cudaMemcpyAsync((unsigned char *)hc + off * bpp, s->conv + off * bpp, nb, cudaMemcpyDeviceToHost, LN.stream)); RT.bytes_d2h += nb;
         hc = nullptr;
     }
     if (hc && rows) { s->n_per_read = s->n_since_read; s->n_since_read = 0; }
@@ -748,16 +981,16 @@ int pfcu_surface_download_async(pfcu_surface *s, void *hc, float *hd, uint32_t y
             const uint32_t r0 = s->band_y[b] > y0 ? s->band_y[b] : y0, r1 = s->band_y[b + 1] < y0 + rows ? s->band_y[b + 1] : y0 + rows;
             if (r0 >= r1) continue;
             const size_t o = (size_t)r0 * s->w, nb = (size_t)(r1 - r0) * s->w * 4;
-            CK(cudaStreamWaitEvent(g.copy_stream, s->band_evt[b], 0));
-            if (hc) { CK(cudaMemcpyAsync((uint32_t *)hc + o, s->color + o, nb, cudaMemcpyDeviceToHost, g.copy_stream)); g.bytes_d2h += nb; }
-            if (hd) { CK(cudaMemcpyAsync(hd + o, s->depth + o, nb, cudaMemcpyDeviceToHost, g.copy_stream)); g.bytes_d2h += nb; }
+            CK(cudaStreamWaitEvent(RT.copy_stream, s->band_evt[b], 0));
+            if (hc) { CK(cudaMemcpyAsync((uint32_t *)hc + o, s->color + o, nb, cudaMemcpyDeviceToHost, RT.copy_stream)); RT.bytes_d2h += nb; }
+            if (hd) { CK(cudaMemcpyAsync(hd + o, s->depth + o, nb, cudaMemcpyDeviceToHost, RT.copy_stream)); RT.bytes_d2h += nb; }
         }
-        if (cudaEventRecord(s->done, g.copy_stream) == cudaSuccess) s->has_done = true;
+        if (cudaEventRecord(s->done, RT.copy_stream) == cudaSuccess) s->has_done = true;
         CK(cudaStreamWaitEvent(LN.stream, s->done, 0));
         return PFCU_OK;
     }
-    if (hc) { CK(cudaMemcpyAsync((uint32_t *)hc + off, s->color + off, n, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += n; }
-    if (hd) { CK(cudaMemcpyAsync(hd + off, s->depth + off, n, cudaMemcpyDeviceToHost, LN.stream)); g.bytes_d2h += n; }
+    if (hc) { CK(cudaMemcpyAsync((uint32_t *)hc + off, s->color + off, n, cudaMemcpyDeviceToHost, LN.stream)); RT.bytes_d2h += n; }
+    if (hd) { CK(cudaMemcpyAsync(hd + off, s->depth + off, n, cudaMemcpyDeviceToHost, LN.stream)); RT.bytes_d2h += n; }
     mark_done(s);
     return PFCU_OK;
 }
@@ -785,13 +1018,13 @@ static int fill_range(pfcu_surface *s, size_t first, size_t n, int dc, uint32_t 
     /* head (to 4-pixel alignment), vector body, tail */
     size_t head = (4 - (first & 3)) & 3; if (head > n) head = n;
     const size_t body4 = (n - head) / 4, tail = n - head - body4 * 4;
-    const int blocks = g.sms * 8;
-    if (head) { k_fill<<<1, 32, 0, LN.stream>>>(s->color, s->depth, first, head, dc, rgba, dd, z); g.launches++; }
+    const int blocks = RT.sms * 8;
+    if (head) { k_fill<<<1, 32, 0, LN.stream>>>(s->color, s->depth, first, head, dc, rgba, dd, z); RT.launches++; }
     if (body4) {
         k_fill4<<<blocks, 256, 0, LN.stream>>>((uint4 *)s->color, (float4 *)s->depth, (first + head) / 4, body4, dc, rgba, dd, z);
-        g.launches++;
+        RT.launches++;
     }
-    if (tail) { k_fill<<<1, 32, 0, LN.stream>>>(s->color, s->depth, first + head + body4 * 4, tail, dc, rgba, dd, z); g.launches++; }
+    if (tail) { k_fill<<<1, 32, 0, LN.stream>>>(s->color, s->depth, first + head + body4 * 4, tail, dc, rgba, dd, z); RT.launches++; }
     CK(cudaGetLastError());
     return PFCU_OK;
 }
@@ -799,6 +1032,7 @@ static int fill_range(pfcu_surface *s, size_t first, size_t n, int dc, uint32_t 
 int pfcu_surface_fill(pfcu_surface *s, int dc, uint32_t rgba, int dd, float z)
 {
     API_LOCK;
+    if (MULTI_SURF(s)) return multi_surface_op(s, [&](int, pfcu_surface *r) -> int { return pfcu_surface_fill(r, dc, rgba, dd, z); });
     use_lane(s);
     if (s->fmt >= PFCU_TEX_RGB8) rgba |= 0xff000000u;      /* 3-byte targets store no alpha and read it back as 255 */
     const int rc = fill_range(s, 0, (size_t)s->w * s->h, dc, rgba, dd, z);
@@ -809,11 +1043,12 @@ int pfcu_surface_fill(pfcu_surface *s, int dc, uint32_t rgba, int dd, float z)
 int pfcu_surface_clear_ref(pfcu_surface *s, int dc, uint32_t rgba, int dd, float z)
 {
     API_LOCK;
+    if (MULTI_SURF(s)) return multi_surface_op(s, [&](int, pfcu_surface *r) -> int { return pfcu_surface_clear_ref(r, dc, rgba, dd, z); });
     use_lane(s);
     if (s->fmt >= PFCU_TEX_RGB8) rgba |= 0xff000000u;
     const unsigned size = s->w * s->h, aligned = size - (size % 8u);
     if (aligned > 8) { int rc = fill_range(s, 8, aligned - 8, dc, rgba, dd, z); if (rc) return rc; }
-    if (aligned < size) { k_clear_tail<<<1, 32, 0, LN.stream>>>(s->color, s->depth, aligned, size, dc, dd); g.launches++; }
+    if (aligned < size) { k_clear_tail<<<1, 32, 0, LN.stream>>>(s->color, s->depth, aligned, size, dc, dd); RT.launches++; }
     CK(cudaGetLastError());
     mark_done(s);
     return PFCU_OK;
@@ -824,16 +1059,17 @@ int pfcu_surface_clear_ref(pfcu_surface *s, int dc, uint32_t rgba, int dd, float
 int pfcu_surface_rect(pfcu_surface *s, int32_t x1, int32_t y1, int32_t x2, int32_t y2, uint32_t rgba)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (!s) return PFCU_ERR_INVALID;
     if (x2 < x1 || y2 < y1) return PFCU_OK;
+    if (MULTI_SURF(s)) return multi_surface_op(s, [&](int, pfcu_surface *r) -> int { return pfcu_surface_rect(r, x1, y1, x2, y2, rgba); });
     use_lane(s);
     if (s->fmt >= PFCU_TEX_RGB8) rgba |= 0xff000000u;
     const uint32_t cols = (uint32_t)(x2 - x1) + 1u, rows = (uint32_t)(y2 - y1) + 1u;
     const size_t n = (size_t)cols * rows;
-    const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)g.sms * 8 ? (n + 255) / 256 : (size_t)g.sms * 8);
+    const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)RT.sms * 8 ? (n + 255) / 256 : (size_t)RT.sms * 8);
     k_rect<<<blocks, 256, 0, LN.stream>>>(s->color, s->w, s->w * s->h, x1, y1, cols, rows, rgba);
-    g.launches++;
+    RT.launches++;
     CK(cudaGetLastError());
     mark_done(s);
     return PFCU_OK;
@@ -842,8 +1078,9 @@ int pfcu_surface_rect(pfcu_surface *s, int32_t x1, int32_t y1, int32_t x2, int32
 int pfcu_surface_fog(pfcu_surface *s, const pfcu_fog *f)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || !f || f->mode > 3u || f->n_thresholds > 255u || (f->mode != 0u && f->n_thresholds && !f->thresholds)) return PFCU_ERR_INVALID;
+    if (MULTI_SURF(s)) return multi_surface_op(s, [&](int, pfcu_surface *r) -> int { return pfcu_surface_fog(r, f); });
     use_lane(s);
     int rc;
     const float *d_thr = nullptr;
@@ -851,14 +1088,14 @@ int pfcu_surface_fog(pfcu_surface *s, const pfcu_fog *f)
         if ((rc = grow(&LN.d_varrays, &LN.cap_varrays, 256 * sizeof(float)))) return rc;
         /* pageable source: staged by the driver before the call returns */
         CK(cudaMemcpyAsync(LN.d_varrays, f->thresholds, f->n_thresholds * sizeof(float), cudaMemcpyHostToDevice, LN.stream));
-        g.bytes_h2d += f->n_thresholds * sizeof(float);
+        RT.bytes_h2d += f->n_thresholds * sizeof(float);
         d_thr = (const float *)LN.d_varrays;
     }
     FogArgs a;
     a.start = f->start; a.end = f->end; a.inv_len = f->inv_len; a.rgba = f->rgba; a.mode = f->mode;
     a.n_thr = (f->mode == 1u || f->mode == 2u) ? f->n_thresholds : 0u;       /* mode 3: t = 0 for every pixel in range */ a.alpha_or = s->fmt >= PFCU_TEX_RGB8 ? 0xff000000u : 0u;
-    k_fog<<<g.sms * 8, 256, 0, LN.stream>>>(s->color, s->depth, (size_t)s->w * s->h, a, d_thr);
-    g.launches++;
+    k_fog<<<RT.sms * 8, 256, 0, LN.stream>>>(s->color, s->depth, (size_t)s->w * s->h, a, d_thr);
+    RT.launches++;
     CK(cudaGetLastError());
     mark_done(s);
     return PFCU_OK;
@@ -867,9 +1104,10 @@ int pfcu_surface_fog(pfcu_surface *s, const pfcu_fog *f)
 int pfcu_surface_draw_pixels(pfcu_surface *s, const pfcu_pixels *d)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || !d || !d->pixels || d->width == 0 || d->height == 0 || d->format < PFCU_TEX_RGBA8 || d->format > PFCU_TEX_BGR8) return PFCU_ERR_INVALID;
     if (d->xmax < d->xmin || d->ymax < d->ymin) return PFCU_OK;
+    if (MULTI_SURF(s)) return multi_surface_op(s, [&](int, pfcu_surface *r) -> int { return pfcu_surface_draw_pixels(r, d); });
     use_lane(s);
     int rc;
     const size_t bytes = (size_t)d->width * d->height * fmt_bytes(d->format);
@@ -877,7 +1115,7 @@ int pfcu_surface_draw_pixels(pfcu_surface *s, const pfcu_pixels *d)
     CK(cudaMemcpyAsync(LN.d_varrays, d->pixels, bytes, cudaMemcpyHostToDevice, LN.stream));
     /* the caller may reuse its image as soon as pfDrawPixels returns: page-locked sources are still being read */
     if (find_pinned(d->pixels)) CK(cudaStreamSynchronize(LN.stream));
-    g.bytes_h2d += bytes;
+    RT.bytes_h2d += bytes;
     PixArgs a;
     a.src = LN.d_varrays; a.sw = d->width; a.sh = d->height; a.fmt = d->format;
     a.xs = d->xs; a.ys = d->ys; a.xmin = d->xmin; a.ymin = d->ymin;
@@ -886,9 +1124,9 @@ int pfcu_surface_draw_pixels(pfcu_surface *s, const pfcu_pixels *d)
     a.flags = d->flags; a.blend_mode = d->blend_mode; a.depth_func = d->depth_func;
     a.alpha_or = s->fmt >= PFCU_TEX_RGB8 ? 0xff000000u : 0u;
     const size_t n = (size_t)a.cols * a.rows;
-    const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)g.sms * 8 ? (n + 255) / 256 : (size_t)g.sms * 8);
+    const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)RT.sms * 8 ? (n + 255) / 256 : (size_t)RT.sms * 8);
     k_draw_pixels<<<blocks, 256, 0, LN.stream>>>(s->color, s->depth, s->w, s->w * s->h, a);
-    g.launches++;
+    RT.launches++;
     CK(cudaGetLastError());
     mark_done(s);
     return PFCU_OK;
@@ -897,20 +1135,21 @@ int pfcu_surface_draw_pixels(pfcu_surface *s, const pfcu_pixels *d)
 int pfcu_surface_read_pixels(pfcu_surface *s, uint32_t x0, uint32_t y0, uint32_t cols, uint32_t rows, uint32_t dst_width, int format, void *host_pixels)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || !host_pixels || format < PFCU_TEX_RGBA8 || format > PFCU_TEX_BGR8) return PFCU_ERR_INVALID;
     if (cols == 0 || rows == 0) return PFCU_OK;
     if (x0 >= s->w || y0 >= s->h || cols > s->w - x0 || rows > s->h - y0 || cols > dst_width) return PFCU_ERR_INVALID;
+    if (MULTI_SURF(s)) { const int rc = multi_gather(s, 0); if (rc) return rc; }
     use_lane(s);
     int rc;
     const size_t bpp = fmt_bytes(format), n = (size_t)cols * rows;
     if ((rc = grow(&LN.d_varrays, &LN.cap_varrays, n * bpp + 16))) return rc;
-    const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)g.sms * 8 ? (n + 255) / 256 : (size_t)g.sms * 8);
+    const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)RT.sms * 8 ? (n + 255) / 256 : (size_t)RT.sms * 8);
     k_read_pixels<<<blocks, 256, 0, LN.stream>>>(s->color, s->w, x0, y0, cols, rows, format, LN.d_varrays);
-    g.launches++;
+    RT.launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpy2DAsync(host_pixels, (size_t)dst_width * bpp, LN.d_varrays, (size_t)cols * bpp, (size_t)cols * bpp, rows, cudaMemcpyDeviceToHost, LN.stream));
-    g.bytes_d2h += n * bpp;
+    RT.bytes_d2h += n * bpp;
     CK(cudaStreamSynchronize(LN.stream));
     return PFCU_OK;
 }
@@ -945,7 +1184,7 @@ static int pack_unpack(pfcu_surface *s, uint32_t rank, uint32_t world, int with_
     if (n == 0) return PFCU_OK;
     k_pack_tiles<<<n, 256, 0, LN.stream>>>(s->color, s->depth, (int)s->w, (int)s->h, (int)s->tiles_x, s->tiles_x * s->tiles_y,
                                           rank, world, with_depth, (uint32_t *)staging, unpack);
-    g.launches++;
+    RT.launches++;
     CK(cudaGetLastError());
     return PFCU_OK;
 }
@@ -960,13 +1199,20 @@ static size_t tex_bytes(uint32_t w, uint32_t h, int fmt) { return (size_t)w * h 
 pfcu_texture *pfcu_texture_create(const void *host_pixels, uint32_t w, uint32_t h, int fmt)
 {
     API_LOCK;
-    if (!g.ok || fmt < PFCU_TEX_RGBA8 || fmt > PFCU_TEX_BGR8 || w == 0 || h == 0) return nullptr;
+    if (MULTI_HERE()) {
+        pfcu_texture *r[MAX_DEVS] = { nullptr };
+        const int rc = multi_run_all([&](int d) -> int { r[d] = pfcu_texture_create(host_pixels, w, h, fmt); return r[d] ? PFCU_OK : PFCU_ERR_OOM; });
+        if (rc) { multi_run_all([&](int d) -> int { if (r[d]) pfcu_texture_destroy(r[d]); return (int)PFCU_OK; }); return nullptr; }
+        for (int d = 0; d < mg.n; d++) r[0]->rep[d] = r[d];
+        return r[0];
+    }
+    if (!RT.ok || fmt < PFCU_TEX_RGBA8 || fmt > PFCU_TEX_BGR8 || w == 0 || h == 0) return nullptr;
     pfcu_texture *t = (pfcu_texture *)calloc(1, sizeof *t);
     if (!t) return nullptr;
     t->w = w; t->h = h; t->fmt = fmt; t->owned = true; t->leader = (fmt == PFCU_TEX_BGRA8);
-    g.cur = &g.lanes[0];
+    RT.cur = &RT.lanes[0];
     const size_t bytes = tex_bytes(w, h, fmt);
-    if (cudaMalloc(&t->pixels, bytes + 16) != cudaSuccess) { snprintf(g.err, sizeof g.err, "texture_create: out of device memory"); free(t); return nullptr; }
+    if (cudaMalloc(&t->pixels, bytes + 16) != cudaSuccess) { snprintf(RT.err, sizeof RT.err, "texture_create: out of device memory"); free(t); return nullptr; }
     cudaMemsetAsync(t->pixels, 0, bytes + 16, LN.stream);
     if (host_pixels && pfcu_texture_update(t, host_pixels) != PFCU_OK) { cudaFree(t->pixels); free(t); return nullptr; }
     return t;
@@ -975,6 +1221,39 @@ pfcu_texture *pfcu_texture_create(const void *host_pixels, uint32_t w, uint32_t 
 pfcu_texture *pfcu_texture_from_surface(pfcu_surface *s)
 {
     API_LOCK;
+    if (MULTI_SURF(s)) {
+        /* a surface that is sampled must be whole on every device: from now on each device renders all of it */
+        if (s->split) {
+            /* keep what was rendered so far: gather the tiles on device 0, then hand every other device the whole surface */
+            int rc = multi_gather(s, 1);
+            if (rc) return nullptr;
+            use_lane(s);
+            if (cudaEventRecord(s->full_evt, LN.stream) != cudaSuccess) return nullptr;
+            s->has_full = true;
+            const size_t bytes = (size_t)s->w * s->h * 4;
+            rc = multi_run_all([&](int d) -> int {
+                if (d == 0) return (int)PFCU_OK;
+                pfcu_surface *r = s->rep[d];
+                use_lane(r);
+                CK(cudaStreamWaitEvent(LN.stream, s->full_evt, 0));
+                CK(cudaMemcpyPeerAsync(r->color, mg.dev[d], s->color, mg.dev[0], bytes, LN.stream));
+                CK(cudaMemcpyPeerAsync(r->depth, mg.dev[d], s->depth, mg.dev[0], bytes, LN.stream));
+                mark_done(r);
+                CK(cudaEventRecord(r->pushed, LN.stream));
+                return (int)PFCU_OK;
+            });
+            if (rc) return nullptr;
+            use_lane(s);
+            for (int d = 1; d < mg.n; d++) if (cudaStreamWaitEvent(LN.stream, s->rep[d]->pushed, 0) != cudaSuccess) return nullptr;   /* device 0 must not overwrite what is being copied */
+            s->split = false;
+            for (int d = 0; d < mg.n; d++) { s->rep[d]->rank = 0; s->rep[d]->world = 1; }
+        }
+        pfcu_texture *r[MAX_DEVS] = { nullptr };
+        const int rc = multi_run_all([&](int d) -> int { r[d] = pfcu_texture_from_surface(s->rep[d]); return r[d] ? PFCU_OK : PFCU_ERR_OOM; });
+        if (rc) return nullptr;
+        for (int d = 0; d < mg.n; d++) r[0]->rep[d] = r[d];
+        return r[0];
+    }
     pfcu_texture *t = (pfcu_texture *)calloc(1, sizeof *t);
     if (!t) return nullptr;
     /* the surface is held as canonical RGBA8 whatever the caller's layout; a BGRA8 target sampled as a texture still goes
@@ -989,10 +1268,11 @@ int pfcu_texture_update(pfcu_texture *t, const void *host_pixels)
 {
     API_LOCK;
     if (!t || !t->owned || !host_pixels) return PFCU_ERR_INVALID;
+    if (MULTI_HERE() && t->rep[1]) return multi_run_all([&](int d) -> int { return pfcu_texture_update(t->rep[d], host_pixels); });
     sync_all_lanes();                           /* nobody may still be sampling the old texels */
-    g.cur = &g.lanes[0];
+    RT.cur = &RT.lanes[0];
     CK(cudaMemcpyAsync(t->pixels, host_pixels, tex_bytes(t->w, t->h, t->fmt), cudaMemcpyHostToDevice, LN.stream));
-    g.bytes_h2d += tex_bytes(t->w, t->h, t->fmt);
+    RT.bytes_h2d += tex_bytes(t->w, t->h, t->fmt);
     CK(cudaStreamSynchronize(LN.stream));
     return PFCU_OK;
 }
@@ -1001,7 +1281,12 @@ void pfcu_texture_destroy(pfcu_texture *t)
 {
     API_LOCK;
     if (!t) return;
-    if (g.ok) sync_all_lanes();
+    if (MULTI_HERE() && t->rep[1]) {
+        pfcu_texture *r[MAX_DEVS]; memcpy(r, t->rep, sizeof r);
+        multi_run_all([&](int d) -> int { pfcu_texture_destroy(r[d]); return (int)PFCU_OK; });
+        return;
+    }
+    if (RT.ok) sync_all_lanes();
     if (t->owned) cudaFree(t->pixels);
     free(t);
 }
@@ -1027,7 +1312,7 @@ static bool g_last_leader_tex = false;   /* set by convert_states: some state sa
 static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
 {
     unsigned mask = 0;
-    g.deps.clear();
+    RT.deps.clear();
     g_last_leader_tex = false;
     for (uint32_t i = 0; i < n; i++) {
         const pfcu_state *s = in + i; DevState *d = out + i;
@@ -1043,7 +1328,7 @@ static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
             if (s->texture->leader) g_last_leader_tex = true;
             d->tex_fw = (float)d->tw; d->tex_fh = (float)d->th;
             { volatile float one = 1.0f; d->tex_tx = one / d->tex_fw; d->tex_ty = one / d->tex_fh; }   /* IEEE single division, as DIVPS */
-            if (s->texture->alias) g.deps.push_back(s->texture->alias);      /* render-to-texture: order across lanes */
+            if (s->texture->alias) RT.deps.push_back(s->texture->alias);      /* render-to-texture: order across lanes */
         }
         d->n_lights = s->n_lights > 8 ? 8 : s->n_lights;
         for (unsigned l = 0; l < d->n_lights; l++) {
@@ -1073,7 +1358,7 @@ static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
         mask |= d->flags;
         /* the program every state of the batch runs, or their join where one exists: blend modes that differ become
            "any mode" (run-time switch, blending on in all of them), nearest samplers that differ become "nearest, any wrap
-           mode / layout" - e.g. layers that alternate between alpha and additive blending still get a one-program kernel */
+           mode / layout" - e.RT. layers that alternate between alpha and additive blending still get a one-program kernel */
         const int prog = state_program(d);
         if (i == 0) g_last_single_prog = prog;
         else if (g_last_single_prog != prog && g_last_single_prog >= 0) {
@@ -1102,13 +1387,13 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     const bool rows_path = s->fmt != PFCU_TEX_RGBA8 || g_last_leader_tex;
     g_last_leader_tex = false;
     if (rows_path && s->world > 1) {
-        snprintf(g.err, sizeof g.err, "the screen-tile split needs an RGBA8 target and no BGRA8 textures (a pixel depends on its row neighbours there)");
+        snprintf(RT.err, sizeof RT.err, "the screen-tile split needs an RGBA8 target and no BGRA8 textures (a pixel depends on its row neighbours there)");
         return PFCU_ERR_INVALID;
     }
-    if (!g.d_rcp) { snprintf(g.err, sizeof g.err, "pfcu_set_approx_tables() has not been called"); return PFCU_ERR_INVALID; }
+    if (!RT.d_rcp) { snprintf(RT.err, sizeof RT.err, "pfcu_set_approx_tables() has not been called"); return PFCU_ERR_INVALID; }
     int rc;
     /* surfaces sampled as textures that live on another lane: wait for their last write */
-    for (pfcu_surface *dep : g.deps)
+    for (pfcu_surface *dep : RT.deps)
         if (dep != s && dep->lane != s->lane && dep->has_done) CK(cudaStreamWaitEvent(LN.stream, dep->done, 0));
     if (n > LN.cap_setup) {
         size_t c1 = LN.cap_setup, c2 = LN.cap_setup, c3 = LN.cap_setup;
@@ -1125,11 +1410,11 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     int bshift = bshift_forced ? bshift_forced : (force_bshift >= 6 ? force_bshift : (small_tris ? BIN_SHIFT_FINE : BIN_SHIFT_COARSE));
     static const bool env_once = [] {
         const char *e = getenv("PF_CUDA_FRAG");
-        if (e) g.raster_path = atoi(e) == 0 ? PFCU_RASTER_TILES : (atoi(e) == 2 ? PFCU_RASTER_FRAGMENTS : PFCU_RASTER_AUTO);
+        if (e) RT.raster_path = atoi(e) == 0 ? PFCU_RASTER_TILES : (atoi(e) == 2 ? PFCU_RASTER_FRAGMENTS : PFCU_RASTER_AUTO);
         return true; }();
     (void)env_once;
     static const int force_slice = getenv("PF_CUDA_SLICE") ? atoi(getenv("PF_CUDA_SLICE")) : 0;
-    const bool use_frag = !rows_path && (g.raster_path == PFCU_RASTER_FRAGMENTS || (g.raster_path == PFCU_RASTER_AUTO && small_tris && !force_slice));
+    const bool use_frag = !rows_path && (RT.raster_path == PFCU_RASTER_FRAGMENTS || (RT.raster_path == PFCU_RASTER_AUTO && small_tris && !force_slice));
     /* The fragment rasteriser works on 64x8 slices, and with square 64x64 bins the eight slices of a tile each filter the
        whole tile's list.  Flatter bins (64 x 2^bshy) shorten that, but every triangle then lands in more bins and the
        ordered fill pays for it: measured (PF_CUDA_BIN_ROWS sweep, profiles/README.md) 64x16 bins are a small net gain
@@ -1145,7 +1430,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         if (nb <= MAX_BINS) break;
         if (bshy < bshift) bshy++; else { bshift++; bshy++; }
     }
-    if (bshift > 8) { snprintf(g.err, sizeof g.err, "surface too large for the binner (%u x %u)", s->w, s->h); return PFCU_ERR_INVALID; }
+    if (bshift > 8) { snprintf(RT.err, sizeof RT.err, "surface too large for the binner (%u x %u)", s->w, s->h); return PFCU_ERR_INVALID; }
     /* one row of per-bin counters per binning CTA: 256 triangles per CTA give the order-preserving fill four times the
        CTAs (its per-CTA work is a serial chain) as long as the counter matrix stays small */
     unsigned bin_batch = ((size_t)((n + 255u) / 256u) * nb <= ((size_t)1 << 20)) ? 256u : BIN_BATCH;
@@ -1155,21 +1440,21 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
 
     size_t list_cap = ~(size_t)0;          /* capacity the kernels check the real total against (small batches: sized by the bound) */
     cudaEvent_t pe[3] = { nullptr, nullptr, nullptr };
-    if (g.profiling) {
+    if (RT.profiling) {
         for (int i = 0; i < 3; i++) {
-            if (!g.prof_pool.empty()) { pe[i] = g.prof_pool.back(); g.prof_pool.pop_back(); }
+            if (!RT.prof_pool.empty()) { pe[i] = RT.prof_pool.back(); RT.prof_pool.pop_back(); }
             else CK(cudaEventCreate(&pe[i]));
         }
         CK(cudaEventRecord(pe[0], LN.stream));
     }
-    if (d_n && !(nb <= 3072 && n <= FRONT_SMALL_MAX * FRONT_SMALL_CHUNKS)) { snprintf(g.err, sizeof g.err, "internal: device-side count outside the single-CTA front end"); return PFCU_ERR_INVALID; }
+    if (d_n && !(nb <= 3072 && n <= FRONT_SMALL_MAX * FRONT_SMALL_CHUNKS)) { snprintf(RT.err, sizeof RT.err, "internal: device-side count outside the single-CTA front end"); return PFCU_ERR_INVALID; }
     bool list_total_wanted = false;
     if (d_n || (n <= FRONT_SMALL_MAX && nb <= 3072)) {      /* 3072 bin counters + the rectangles fit the 48 KB of static + dynamic shared memory */
         /* small batch: the (triangle, bin) overlap count is bounded by n * nb, no read-back needed */
         if ((rc = grow(&LN.d_bin_list, &LN.cap_bin_list, (size_t)n * nb))) return rc;
         CK(launch_dep(k_front_small, dim3(1), dim3(1024), nb * sizeof(unsigned), LN.stream, d_tris, d_states, n, d_n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data,
-                      g.d_counters, binsX, binsY, bshift, bshy, LN.d_bin_start, LN.d_bin_list));
-        g.launches += 1;
+                      setup_counters(), binsX, binsY, bshift, bshy, LN.d_bin_start, LN.d_bin_list));
+        RT.launches += 1;
     } else {
         if (!rows_path) {
             /* Per-bin lists hold (triangle, bin) overlaps; their exact total is only known on the device (starts[nb]) and
@@ -1196,33 +1481,33 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         }
         /* the kernels of the batch back to back, each a programmatic dependent of the one before */
         CK(launch_dep(k_setup, dim3((n + SETUP_THREADS - 1) / SETUP_THREADS), dim3(SETUP_THREADS), 0, LN.stream,
-                      d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data, g.d_counters));
-        g.launches += 1;
+                      d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data, setup_counters()));
+        RT.launches += 1;
         if (!rows_path) {
             unsigned *d_totals = LN.d_bin_start + (MAX_BINS + 2), *d_ticket = LN.d_bin_start + (MAX_BINS + 2) * 2;
             CK(launch_dep(k_bin_count, dim3(nBatches), dim3(256), nb * sizeof(unsigned), LN.stream, (const int4 *)LN.d_bbox, n, bin_batch, binsX, binsY, bshift, bshy, LN.d_bin_counts));
             CK(launch_dep(k_bin_scan, dim3((nb + 31) / 32), dim3(1024), 0, LN.stream, LN.d_bin_counts, (int)nBatches, nb, d_totals, LN.d_bin_start, d_ticket));
             CK(launch_dep(k_bin_fill, dim3(nBatches), dim3(256), nb * sizeof(unsigned), LN.stream, (const int4 *)LN.d_bbox, n, bin_batch, binsX, binsY, bshift, bshy,
                           (const unsigned *)LN.d_bin_counts, (const unsigned *)LN.d_bin_start, LN.d_bin_list, list_cap > 0xffffffffu ? 0xffffffffu : (unsigned)list_cap));
-            g.launches += 3;
+            RT.launches += 3;
         }
     }
     if (rows_path) {
         RowsParams rp;
         rp.bbox = LN.d_bbox; rp.setup = LN.d_setup; rp.data = LN.d_data; rp.states = d_states; rp.n = n; rp.d_n = d_n;
-        rp.color = s->color; rp.depth = s->depth; rp.W = (int)s->w; rp.H = (int)s->h; rp.fb_fmt = s->fmt; rp.counters = g.d_counters;
-        if (g.profiling) CK(cudaEventRecord(pe[1], LN.stream));
+        rp.color = s->color; rp.depth = s->depth; rp.W = (int)s->w; rp.H = (int)s->h; rp.fb_fmt = s->fmt; rp.counters = raster_counters(s);
+        if (RT.profiling) CK(cudaEventRecord(pe[1], LN.stream));
         const unsigned bands = (s->h + ROWS_NW - 1) / ROWS_NW;
         if (feature_mask & PFCU_ST_PHONG) k_raster_rows<true><<<bands, ROWS_NW * 32, 0, LN.stream>>>(rp);
         else                              k_raster_rows<false><<<bands, ROWS_NW * 32, 0, LN.stream>>>(rp);
-        g.launches++;
-        if (g.profiling) { CK(cudaEventRecord(pe[2], LN.stream)); for (int i = 0; i < 3; i++) g.prof_events.push_back(pe[i]); }
+        RT.launches++;
+        if (RT.profiling) { CK(cudaEventRecord(pe[2], LN.stream)); for (int i = 0; i < 3; i++) RT.prof_events.push_back(pe[i]); }
         CK(cudaGetLastError());
         mark_done(s);
-        for (pfcu_surface *dep : g.deps)
-            if (dep != s && dep->lane != s->lane) CK(cudaStreamWaitEvent(g.lanes[dep->lane % g.n_lanes].stream, s->done, 0));
-        g.deps.clear();
-        if (!d_n) g.submitted += n;
+        for (pfcu_surface *dep : RT.deps)
+            if (dep != s && dep->lane != s->lane) CK(cudaStreamWaitEvent(RT.lanes[dep->lane % RT.n_lanes].stream, s->done, 0));
+        RT.deps.clear();
+        if (!d_n) RT.submitted += n;
         return PFCU_OK;
     }
     RasterParams p;
@@ -1232,9 +1517,9 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     p.color = s->color; p.depth = s->depth; p.W = (int)s->w; p.H = (int)s->h;
     p.tilesX = (int)s->tiles_x; p.tilesY = (int)s->tiles_y;
     p.rank = s->rank; p.world = s->world ? s->world : 1; p.nTiles = s->tiles_x * s->tiles_y;
-    p.counters = g.d_counters;
+    p.counters = raster_counters(s);
     const unsigned grid = owned_tiles(s, p.rank, p.world);
-    if (g.profiling) CK(cudaEventRecord(pe[1], LN.stream));
+    if (RT.profiling) CK(cudaEventRecord(pe[1], LN.stream));
     p.tile_base = 0;
     /* the rasteriser over `grid` tiles starting at p.tile_base, on stream st_ */
     const unsigned grid_all = grid;
@@ -1242,19 +1527,19 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         /* many small triangles per tile: 16 warps per tile halve the serial work of the busiest tiles;
            few large ones: 8 warps with more registers each issue faster */
         const bool ph = (feature_mask & PFCU_ST_PHONG) != 0;
-        if (g.rcp_bits > RCP_SMEM_BITS) single_prog = -1;      /* the fixed-program kernels assume the shared RCPPS table */
+        if (RT.rcp_bits > RCP_SMEM_BITS) single_prog = -1;      /* the fixed-program kernels assume the shared RCPPS table */
         /* half-height slices when the 64x64 grid would be only a few waves deep with a ragged last wave */
         const bool fixed = single_prog >= 0 && single_prog < PROG_PHONG && !small_tris && !use_frag;
         const int per_sm = (fixed && single_prog / 4 != 4) ? 4 : 3;
-        const double waves = (double)grid_all / ((double)g.sms * per_sm);      /* bands run side by side: the whole surface counts */
+        const double waves = (double)grid_all / ((double)RT.sms * per_sm);      /* bands run side by side: the whole surface counts */
         const bool half = !small_tris && !ph && waves < 8.0 && (ceil(waves) / waves) > 1.06 && (ceil(2 * waves) / (2 * waves)) < (ceil(waves) / waves);
         if (use_frag) {
             /* 64x8 slices of eight 8x8 regions, 8 warps; 4 CTAs per SM (Phong: 3, 80 registers) */
-            static const bool attr_once = [] {
+            if (!RT.frag_attr_set) {            /* function attributes are per device: once per runtime, not per process */
                 cudaFuncSetAttribute(k_raster_frag<true, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * FRAG_NF_PHONG * 512);
                 cudaFuncSetAttribute(k_raster_frag<false, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * FRAG_NF * 512);
-                return true; }();
-            (void)attr_once;
+                RT.frag_attr_set = true;
+            }
             if (ph) CK(launch_dep(k_raster_frag<true, 8, 3>, dim3(grid * 8), dim3(256), (size_t)(8 * FRAG_NF_PHONG * 512), st_, p));
             else    CK(launch_dep(k_raster_frag<false, 8, 4>, dim3(grid * 8), dim3(256), (size_t)(8 * FRAG_NF * 512), st_, p));
         }
@@ -1273,11 +1558,11 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
             FIXED_CASE(0) FIXED_CASE(1) FIXED_CASE(2) FIXED_CASE(3) FIXED_CASE(4) FIXED_CASE(5) FIXED_CASE(6) FIXED_CASE(7)
             FIXED_CASE(12) FIXED_CASE(13) FIXED_CASE(14) FIXED_CASE(15) FIXED_CASE(16) FIXED_CASE(17) FIXED_CASE(18) FIXED_CASE(19)
 #undef FIXED_CASE
-            default: snprintf(g.err, sizeof g.err, "internal: no kernel for state program %d", single_prog); return PFCU_ERR_INVALID;
+            default: snprintf(RT.err, sizeof RT.err, "internal: no kernel for state program %d", single_prog); return PFCU_ERR_INVALID;
             }
         }
         else { if (half) CK(launch_dep(k_raster<false, 8, -1, 32>, dim3(grid * 2), dim3(256), (size_t)(0), st_, p)); else CK(launch_dep(k_raster<false, 8, -1, 64>, dim3(grid), dim3(256), (size_t)(0), st_, p)); }
-        g.launches++;
+        RT.launches++;
         return PFCU_OK;
     };
     bool banded = false;
@@ -1295,13 +1580,13 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     if (p.world > 1 || !grid || (unsigned)n_bands > s->tiles_y) n_bands = 1;
     if (n_bands > 1) {
         for (int b = 0; b < n_bands; b++) if (!s->band_evt[b]) CK(cudaEventCreateWithFlags(&s->band_evt[b], cudaEventDisableTiming));
-        CK(cudaEventRecord(g.front_evt, LN.stream));
+        CK(cudaEventRecord(RT.front_evt, LN.stream));
         unsigned row0 = 0;
         for (int b = 0; b < n_bands; b++) {
             /* the first bands are the smaller ones: their copies start early, the last band's copy is what remains exposed */
             const unsigned row1 = (b == n_bands - 1) ? s->tiles_y : (unsigned)(((uint64_t)s->tiles_y * (unsigned)(b + 1)) / (unsigned)n_bands);
-            cudaStream_t bs = g.band_streams[b];
-            CK(cudaStreamWaitEvent(bs, g.front_evt, 0));
+            cudaStream_t bs = RT.band_streams[b];
+            CK(cudaStreamWaitEvent(bs, RT.front_evt, 0));
             p.tile_base = row0 * s->tiles_x;
             if ((rc = launch_raster((row1 - row0) * s->tiles_x, bs))) return rc;
             CK(cudaEventRecord(s->band_evt[b], bs));
@@ -1314,7 +1599,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     } else if (grid) {
         if ((rc = launch_raster(grid, LN.stream))) return rc;
     }
-    if (g.profiling) { CK(cudaEventRecord(pe[2], LN.stream)); for (int i = 0; i < 3; i++) g.prof_events.push_back(pe[i]); }
+    if (RT.profiling) { CK(cudaEventRecord(pe[2], LN.stream)); for (int i = 0; i < 3; i++) RT.prof_events.push_back(pe[i]); }
     CK(cudaGetLastError());
     if (list_total_wanted) {            /* behind the batch, so that its kernels stay adjacent in the stream */
         CK(cudaMemcpyAsync(LN.h_list_total, LN.d_bin_start + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, LN.stream));
@@ -1324,10 +1609,10 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     mark_done(s);
     s->bands_valid = banded;
     /* write-after-read: a sampled surface on another lane must not be overwritten before this batch read it */
-    for (pfcu_surface *dep : g.deps)
-        if (dep != s && dep->lane != s->lane) CK(cudaStreamWaitEvent(g.lanes[dep->lane % g.n_lanes].stream, s->done, 0));
-    g.deps.clear();
-    if (!d_n) g.submitted += n;              /* otherwise counted on the device (counters[3]) */
+    for (pfcu_surface *dep : RT.deps)
+        if (dep != s && dep->lane != s->lane) CK(cudaStreamWaitEvent(RT.lanes[dep->lane % RT.n_lanes].stream, s->done, 0));
+    RT.deps.clear();
+    if (!d_n) RT.submitted += n;              /* otherwise counted on the device (counters[3]) */
     return PFCU_OK;
 }
 
@@ -1352,13 +1637,13 @@ static int scan_exclusive(const unsigned *d_in, unsigned *d_out, unsigned n, uns
     if (!st) st = LN.stream;
     const unsigned nb = (n + 1023u) / 1024u;
     k_scan_block<<<nb, 256, 0, st>>>(d_in, d_out, n, d_tmp);
-    g.launches++;
+    RT.launches++;
     if (nb > 1) {
         unsigned *d_tmp2 = d_tmp + nb;
         int rc = scan_exclusive(d_tmp, d_tmp, nb, d_tmp2, st);
         if (rc) return rc;
         k_scan_add<<<(n + 255u) / 256u, 256, 0, st>>>(d_out, n, d_tmp);
-        g.launches++;
+        RT.launches++;
     }
     CK(cudaGetLastError());
     return PFCU_OK;
@@ -1368,16 +1653,21 @@ static int scan_exclusive(const unsigned *d_in, unsigned *d_out, unsigned n, uns
 static const bool g_timing = getenv("PF_CUDA_TIMING") && atoi(getenv("PF_CUDA_TIMING")) != 0;
 static double now_us(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
 
-unsigned pfcu_capabilities(void) { return PFCU_CAP_DEVICE_VERTEX | PFCU_CAP_RAW_TRIANGLES | PFCU_CAP_LISTS; }
+/* device-resident lists run many small surfaces per launch on ONE device; the multi-device mode replays lists through
+   pfcu_submit_raw instead, which every device executes */
+unsigned pfcu_capabilities(void) { return PFCU_CAP_DEVICE_VERTEX | PFCU_CAP_RAW_TRIANGLES | (mg.n > 1 ? 0u : PFCU_CAP_LISTS); }
 
 int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vparams *vp, const pfcu_draw *d, uint32_t *n_out)
 {
     API_LOCK;
     if (n_out) *n_out = 0;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || !state || !vp || !d || !d->positions || d->pos_size < 2 || d->pos_size > 4 || d->n_faces < 1 || d->n_faces > 2) return PFCU_ERR_INVALID;
     const unsigned n_tri = d->count / 3u;
     if (n_tri == 0) return PFCU_OK;
+    if (MULTI_SURF(s)) return multi_run_all([&](int k) -> int {
+        const std::vector<pfcu_state> st = states_for_device(state, 1, k);
+        return pfcu_draw_triangles(s->rep[k], st.data(), vp, d, k == 0 ? n_out : nullptr); });
     use_lane(s);
     const unsigned n_items = n_tri * d->n_faces;
     int rc;
@@ -1400,12 +1690,12 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
             else {
                 if ((rc = grow(&LN.d_idx, &LN.cap_idx, bi))) return rc;
                 CK(cudaMemcpyAsync(LN.d_idx, d->indices, bi, cudaMemcpyHostToDevice, LN.stream));
-                g.bytes_h2d += bi;
+                RT.bytes_h2d += bi;
                 d_indices_ready = LN.d_idx;
             }
             CK(cudaMemsetAsync(LN.d_total, 0, 4, LN.stream));
-            k_index_max<<<g.sms * 4, 256, 0, LN.stream>>>((const unsigned *)d_indices_ready, d->count, LN.d_total);
-            g.launches++;
+            k_index_max<<<RT.sms * 4, 256, 0, LN.stream>>>((const unsigned *)d_indices_ready, d->count, LN.d_total);
+            RT.launches++;
             CK(cudaMemcpyAsync(&LN.h_total[0], LN.d_total, 4, cudaMemcpyDeviceToHost, LN.stream));
             CK(cudaStreamSynchronize(LN.stream));
             nv = (size_t)LN.h_total[0] + 1;
@@ -1422,7 +1712,7 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     const unsigned char *m_col = b_col ? static_mirror(d->colors, b_col, nullptr) : nullptr;
     const unsigned char *m_idx = b_idx ? static_mirror(d->indices, b_idx, nullptr) : nullptr;
     const size_t total_bytes = (m_pos ? 0 : al(b_pos)) + (m_nrm ? 0 : al(b_nrm)) + (m_uv ? 0 : al(b_uv)) + (m_col ? 0 : al(b_col)) + (m_idx ? 0 : al(b_idx));
-    g.bytes_h2d += (m_pos ? 0 : b_pos) + (m_nrm ? 0 : b_nrm) + (m_uv ? 0 : b_uv) + (m_col ? 0 : b_col) + (m_idx ? 0 : b_idx) + sizeof(DevState);
+    RT.bytes_h2d += (m_pos ? 0 : b_pos) + (m_nrm ? 0 : b_nrm) + (m_uv ? 0 : b_uv) + (m_col ? 0 : b_col) + (m_idx ? 0 : b_idx) + sizeof(DevState);
     if ((rc = grow(&LN.d_varrays, &LN.cap_varrays, total_bytes ? total_bytes : 256))) return rc;
     unsigned char *p = LN.d_varrays;
     VtxArgs a; memset(&a, 0, sizeof a);
@@ -1441,10 +1731,10 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     if ((rc = grow(&LN.d_vcounts, &LN.cap_vcounts, (size_t)n_items * 2 + n_items / 512 + 64))) return rc;
     unsigned *d_counts = LN.d_vcounts, *d_offsets = LN.d_vcounts + n_items, *d_tmp = LN.d_vcounts + 2 * (size_t)n_items;
     k_vertex_count<<<(n_items + 127u) / 128u, 128, 0, LN.stream>>>(a, *vp, n_items, d_counts);
-    g.launches++;
+    RT.launches++;
     if ((rc = scan_exclusive(d_counts, d_offsets, n_items, d_tmp))) return rc;
     k_scan_total<<<1, 1, 0, LN.stream>>>(d_offsets + (n_items - 1), d_counts + (n_items - 1), LN.h_total);
-    g.launches++;
+    RT.launches++;
     CK(cudaStreamSynchronize(LN.stream));
     const unsigned total = LN.h_total[0] + LN.h_total[1];
     if (g_timing) t_cnt = now_us();
@@ -1458,7 +1748,7 @@ int pfcu_draw_triangles(pfcu_surface *s, const pfcu_state *state, const pfcu_vpa
     const unsigned mask = convert_states(state, 1, &hs);
     CK(cudaMemcpyAsync(LN.d_states, &hs, sizeof hs, cudaMemcpyHostToDevice, LN.stream));
     k_vertex_emit<<<(n_items + 127u) / 128u, 128, 0, LN.stream>>>(a, *vp, n_items, d_offsets, LN.d_tris);
-    g.launches++;
+    RT.launches++;
     CK(cudaEventRecord(LN.raw_done, LN.stream));        /* d_vcounts is shared with the raw-triangle path's side stream */
     CK(cudaGetLastError());
     rc = launch_pipeline(s, LN.d_tris, LN.d_states, total, mask, g_last_single_prog);
@@ -1471,9 +1761,12 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
 {
     API_LOCK;
     if (n_out) *n_out = 0;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || (n_tris && (!states || !tris || !vparams || n_states == 0 || n_vparams == 0))) return PFCU_ERR_INVALID;
     if (n_tris == 0) return PFCU_OK;
+    if (MULTI_SURF(s)) return multi_run_all([&](int k) -> int {
+        const std::vector<pfcu_state> st = states_for_device(states, n_states, k);
+        return pfcu_submit_raw(s->rep[k], st.data(), n_states, vparams, n_vparams, pow_tables, n_pow_tables, tris, n_tris, k == 0 ? n_out : nullptr); });
     use_lane(s);
     int rc;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -1491,11 +1784,11 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
         RawArgs ra; ra.n = n_tris;
         ra.tris = (const pfcu_rawtri *)q;
         CK(cudaMemcpyAsync(q, tris, b_tris, cudaMemcpyHostToDevice, LN.stream));
-        if (PinnedBlock *pb = find_pinned(tris)) { CK(cudaEventRecord(pb->done, LN.stream)); pb->pending = true; }
+        if (PinnedBlock *pb = find_pinned(tris)) { if ((rc = pinned_in_flight(pb, LN.stream))) return rc; }
         q += al(b_tris);
         ra.vp = (const pfcu_vparams_lit *)q; CK(cudaMemcpyAsync(q, vparams, b_vp, cudaMemcpyHostToDevice, LN.stream)); q += al(b_vp);
         ra.pow_tables = (const float *)q; if (b_pow) CK(cudaMemcpyAsync(q, pow_tables, b_pow, cudaMemcpyHostToDevice, LN.stream));
-        g.bytes_h2d += b_tris + b_vp + b_pow + n_states * sizeof(DevState);
+        RT.bytes_h2d += b_tris + b_vp + b_pow + n_states * sizeof(DevState);
         if (n_states > LN.cap_hstates) {
             CK(cudaEventSynchronize(LN.states_done));
             if (LN.h_states) cudaFreeHost(LN.h_states);
@@ -1509,7 +1802,7 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
         unsigned *d_total = LN.d_total;
         if (++LN.chain_seq == 0) ++LN.chain_seq;         /* 0 is what the zero-initialised flags hold */
         CK(launch_dep(k_raw_chain, dim3((n_tris + 127u) / 128u), dim3(128), 0, LN.stream, ra, LN.d_tris, d_total, LN.d_chain, LN.chain_seq));
-        g.launches++;
+        RT.launches++;
         CK(cudaEventRecord(LN.raw_done, LN.stream));
         CK(cudaGetLastError());
         if (n_out) *n_out = n_tris;             /* the exact count stays on the device (pfcu_get_counters has it) */
@@ -1524,18 +1817,18 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
     RawArgs a; a.n = n_tris;
     a.tris = (const pfcu_rawtri *)p;
     CK(cudaMemcpyAsync(p, tris, b_tris, cudaMemcpyHostToDevice, LN.vstream));
-    if (PinnedBlock *pb = find_pinned(tris)) { CK(cudaEventRecord(pb->done, LN.vstream)); pb->pending = true; }
+    if (PinnedBlock *pb = find_pinned(tris)) { if ((rc = pinned_in_flight(pb, LN.vstream))) return rc; }
     p += al(b_tris);
     a.vp = (const pfcu_vparams_lit *)p; CK(cudaMemcpyAsync(p, vparams, b_vp, cudaMemcpyHostToDevice, LN.vstream)); p += al(b_vp);
     a.pow_tables = (const float *)p; if (b_pow) CK(cudaMemcpyAsync(p, pow_tables, b_pow, cudaMemcpyHostToDevice, LN.vstream));
-    g.bytes_h2d += b_tris + b_vp + b_pow + n_states * sizeof(DevState);
+    RT.bytes_h2d += b_tris + b_vp + b_pow + n_states * sizeof(DevState);
 
     unsigned *d_counts = LN.d_vcounts, *d_offsets = LN.d_vcounts + n_tris, *d_tmp = LN.d_vcounts + 2 * (size_t)n_tris;
     k_raw_count<<<(n_tris + 127u) / 128u, 128, 0, LN.vstream>>>(a, d_counts);
-    g.launches++;
+    RT.launches++;
     if ((rc = scan_exclusive(d_counts, d_offsets, n_tris, d_tmp, LN.vstream))) return rc;
     k_scan_total<<<1, 1, 0, LN.vstream>>>(d_offsets + (n_tris - 1), d_counts + (n_tris - 1), LN.h_total);
-    g.launches++;
+    RT.launches++;
     CK(cudaEventRecord(LN.vready, LN.vstream));
     CK(cudaStreamSynchronize(LN.vstream));
     const unsigned total = LN.h_total[0] + LN.h_total[1];
@@ -1557,7 +1850,7 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
     CK(cudaEventRecord(LN.states_done, LN.stream));
     CK(cudaStreamWaitEvent(LN.stream, LN.vready, 0));
     k_raw_emit<<<(n_tris + 127u) / 128u, 128, 0, LN.stream>>>(a, d_offsets, LN.d_tris);
-    g.launches++;
+    RT.launches++;
     CK(cudaEventRecord(LN.raw_done, LN.stream));
     CK(cudaGetLastError());
     return launch_pipeline(s, LN.d_tris, LN.d_states, total, mask, g_last_single_prog);
@@ -1568,15 +1861,15 @@ int pfcu_submit_raw(pfcu_surface *s, const pfcu_state *states, uint32_t n_states
 pfcu_list *pfcu_list_create(const pfcu_rawtri *tris, uint32_t n_tris)
 {
     API_LOCK;
-    if (!g.ok || !tris || n_tris == 0) return nullptr;
+    if (!RT.ok || !tris || n_tris == 0) return nullptr;
     pfcu_list *l = (pfcu_list *)calloc(1, sizeof *l);
     if (!l) return nullptr;
     l->n = n_tris;
-    g.cur = &g.lanes[0];
-    if (cudaMalloc(&l->tris, (size_t)n_tris * sizeof(pfcu_rawtri)) != cudaSuccess) { snprintf(g.err, sizeof g.err, "list_create: out of device memory"); free(l); return nullptr; }
+    RT.cur = &RT.lanes[0];
+    if (cudaMalloc(&l->tris, (size_t)n_tris * sizeof(pfcu_rawtri)) != cudaSuccess) { snprintf(RT.err, sizeof RT.err, "list_create: out of device memory"); free(l); return nullptr; }
     if (cudaMemcpyAsync(l->tris, tris, (size_t)n_tris * sizeof(pfcu_rawtri), cudaMemcpyHostToDevice, LN.stream) != cudaSuccess ||
         cudaStreamSynchronize(LN.stream) != cudaSuccess) { cudaFree(l->tris); free(l); return nullptr; }
-    g.bytes_h2d += (size_t)n_tris * sizeof(pfcu_rawtri);
+    RT.bytes_h2d += (size_t)n_tris * sizeof(pfcu_rawtri);
     return l;
 }
 
@@ -1584,7 +1877,7 @@ void pfcu_list_destroy(pfcu_list *l)
 {
     API_LOCK;
     if (!l) return;
-    if (g.ok) sync_all_lanes();
+    if (RT.ok) sync_all_lanes();
     cudaFree(l->tris); free(l);
 }
 
@@ -1592,7 +1885,7 @@ uint32_t pfcu_list_size(const pfcu_list *l) { return l ? l->n : 0u; }
 
 int pfcu_list_job_supported(const pfcu_surface *s, uint32_t n_tris, uint32_t n_segments)
 {
-    if (!g.ok || !s || n_tris == 0 || n_tris > PFCU_LIST_JOB_MAX_TRIS || n_segments > PFCU_LIST_JOB_MAX_SEGMENTS) return 0;
+    if (!RT.ok || mg.n > 1 || !s || n_tris == 0 || n_tris > PFCU_LIST_JOB_MAX_TRIS || n_segments > PFCU_LIST_JOB_MAX_SEGMENTS) return 0;
     if (s->fmt != PFCU_TEX_RGBA8 || s->world > 1) return 0;
     return sync_free_bshift(s, n_tris) != 0;
 }
@@ -1600,12 +1893,12 @@ int pfcu_list_job_supported(const pfcu_surface *s, uint32_t n_tris, uint32_t n_s
 int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n_jobs)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (n_jobs == 0) return PFCU_OK;
     if (!jobs) return PFCU_ERR_INVALID;
-    if (!g.d_rcp) { snprintf(g.err, sizeof g.err, "pfcu_set_approx_tables() has not been called"); return PFCU_ERR_INVALID; }
-    Lane &L0 = g.lanes[0];
-    g.cur = &L0;
+    if (!RT.d_rcp) { snprintf(RT.err, sizeof RT.err, "pfcu_set_approx_tables() has not been called"); return PFCU_ERR_INVALID; }
+    Lane &L0 = RT.lanes[0];
+    RT.cur = &L0;
     if (L0.need_fence_wait) L0.need_fence_wait = false;
     L0.touched = true;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -1619,30 +1912,30 @@ int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n_jobs)
         unsigned n = 0;
         for (uint32_t k = 0; k < J.n_segments; k++) { if (!J.segments[k].list) return PFCU_ERR_INVALID; n += J.segments[k].list->n; }
         n_raw[j] = n;
-        if (n && !pfcu_list_job_supported(J.surface, n, J.n_segments)) { snprintf(g.err, sizeof g.err, "list job %u is outside the limits of pfcu_submit_list_jobs", j); return PFCU_ERR_INVALID; }
+        if (n && !pfcu_list_job_supported(J.surface, n, J.n_segments)) { snprintf(RT.err, sizeof RT.err, "list job %u is outside the limits of pfcu_submit_list_jobs", j); return PFCU_ERR_INVALID; }
         if (!n && (J.surface->fmt != PFCU_TEX_RGBA8)) return PFCU_ERR_INVALID;
         bytes += al(sizeof(DevState) * J.n_states) + al(sizeof(pfcu_vparams_lit) * J.n_vparams) + al(sizeof(pfcu_list_call) * J.n_calls)
                + al(sizeof(float) * PFCU_POW_TABLE_SIZE * J.n_pow_tables);
     }
     /* ---- slots and the packed upload ---- */
-    if (!g.jobs_copied) { CK(cudaEventCreateWithFlags(&g.jobs_copied, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&g.jobs_done, cudaEventDisableTiming)); }
-    if (bytes > g.cap_jobs) {
+    if (!RT.jobs_copied) { CK(cudaEventCreateWithFlags(&RT.jobs_copied, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&RT.jobs_done, cudaEventDisableTiming)); }
+    if (bytes > RT.cap_jobs) {
         CK(cudaStreamSynchronize(L0.stream));
-        cudaFree(g.d_jobs); if (g.h_jobs) cudaFreeHost(g.h_jobs);
-        g.d_jobs = nullptr; g.h_jobs = nullptr; g.cap_jobs = 0;
+        cudaFree(RT.d_jobs); if (RT.h_jobs) cudaFreeHost(RT.h_jobs);
+        RT.d_jobs = nullptr; RT.h_jobs = nullptr; RT.cap_jobs = 0;
         size_t c = (size_t)1 << 16; while (c < bytes) c *= 2;
-        CK(cudaMalloc(&g.d_jobs, c)); CK(cudaHostAlloc(&g.h_jobs, c, cudaHostAllocDefault));
-        g.cap_jobs = c;
-    } else CK(cudaEventSynchronize(g.jobs_copied));          /* the previous submission has left the staging buffer */
-    if (g.job_slots.size() < n_jobs) g.job_slots.resize(n_jobs);
-    DevJob *hj = reinterpret_cast<DevJob *>(g.h_jobs);
+        CK(cudaMalloc(&RT.d_jobs, c)); CK(cudaHostAlloc(&RT.h_jobs, c, cudaHostAllocDefault));
+        RT.cap_jobs = c;
+    } else CK(cudaEventSynchronize(RT.jobs_copied));          /* the previous submission has left the staging buffer */
+    if (RT.job_slots.size() < n_jobs) RT.job_slots.resize(n_jobs);
+    DevJob *hj = reinterpret_cast<DevJob *>(RT.h_jobs);
     size_t off = al(sizeof(DevJob) * (size_t)n_jobs);
     for (uint32_t j = 0; j < n_jobs; j++) {
         const pfcu_list_job &J = jobs[j];
         pfcu_surface *s = J.surface;
         DevJob &D = hj[j];
         memset(&D, 0, sizeof D);
-        Runtime::JobSlot &S = g.job_slots[j];
+        Runtime::JobSlot &S = RT.job_slots[j];
         const unsigned n = n_raw[j], bound = n * FRONT_SMALL_CHUNKS;
         const int bshift = n ? sync_free_bshift(s, n) : BIN_SHIFT_COARSE;
         const int binsX = (int)((s->w + (1u << bshift) - 1) >> bshift), binsY = (int)((s->h + (1u << bshift) - 1) >> bshift), nb = binsX * binsY;
@@ -1653,14 +1946,14 @@ int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n_jobs)
                 size_t c = 1024; while (c < bound) c *= 2;
                 if (cudaMalloc(&S.d_tris, c * sizeof(pfcu_triangle)) != cudaSuccess || cudaMalloc(&S.bbox, c * sizeof(int4)) != cudaSuccess ||
                     cudaMalloc(&S.setup, c * sizeof(TriSetup)) != cudaSuccess || cudaMalloc(&S.data, c * sizeof(TriData)) != cudaSuccess) {
-                    snprintf(g.err, sizeof g.err, "out of device memory for list job scratch"); return PFCU_ERR_OOM;
+                    snprintf(RT.err, sizeof RT.err, "out of device memory for list job scratch"); return PFCU_ERR_OOM;
                 }
                 S.cap_tris = c;
             }
             if ((size_t)bound * nb > S.cap_list) {
                 cudaFree(S.bin_list); S.cap_list = 0;
                 size_t c = 4096; while (c < (size_t)bound * nb) c *= 2;
-                if (cudaMalloc(&S.bin_list, c * sizeof(uint2)) != cudaSuccess) { snprintf(g.err, sizeof g.err, "out of device memory for list job bins"); return PFCU_ERR_OOM; }
+                if (cudaMalloc(&S.bin_list, c * sizeof(uint2)) != cudaSuccess) { snprintf(RT.err, sizeof RT.err, "out of device memory for list job bins"); return PFCU_ERR_OOM; }
                 S.cap_list = c;
             }
             if (!S.bin_start) {
@@ -1672,13 +1965,13 @@ int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n_jobs)
             }
         }
         /* tables */
-        unsigned char *hb = g.h_jobs, *db = g.d_jobs;
+        unsigned char *hb = RT.h_jobs, *db = RT.d_jobs;
         DevState *hs = reinterpret_cast<DevState *>(hb + off); D.states = reinterpret_cast<const DevState *>(db + off);
         const unsigned mask = convert_states(J.states, J.n_states, hs);
         off += al(sizeof(DevState) * J.n_states);
-        if (g_last_leader_tex) { g_last_leader_tex = false; snprintf(g.err, sizeof g.err, "list jobs cannot sample BGRA8 textures (row-ordered path)"); return PFCU_ERR_INVALID; }
-        for (pfcu_surface *dep : g.deps) if (dep->has_done && dep->lane != 0) CK(cudaStreamWaitEvent(L0.stream, dep->done, 0));
-        g.deps.clear();
+        if (g_last_leader_tex) { g_last_leader_tex = false; snprintf(RT.err, sizeof RT.err, "list jobs cannot sample BGRA8 textures (row-ordered path)"); return PFCU_ERR_INVALID; }
+        for (pfcu_surface *dep : RT.deps) if (dep->has_done && dep->lane != 0) CK(cudaStreamWaitEvent(L0.stream, dep->done, 0));
+        RT.deps.clear();
         feature |= mask;
         memcpy(hb + off, J.vparams, sizeof(pfcu_vparams_lit) * J.n_vparams); D.vp = reinterpret_cast<const pfcu_vparams_lit *>(db + off);
         off += al(sizeof(pfcu_vparams_lit) * J.n_vparams);
@@ -1702,50 +1995,50 @@ int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n_jobs)
         p.bin_list = S.bin_list; p.bin_starts = S.bin_start; p.binsX = binsX; p.bsx = bshift; p.bsy = bshift;
         p.color = s->color; p.depth = s->depth; p.W = (int)s->w; p.H = (int)s->h; p.tilesX = (int)s->tiles_x; p.tilesY = (int)s->tiles_y;
         p.rank = 0; p.world = 1; p.nTiles = n ? s->tiles_x * s->tiles_y : 0u;      /* a job without triangles rasterises nothing */
-        p.counters = g.d_counters; p.nb = nb; p.list_cap = 0xffffffffu; p.n = 0;
+        p.counters = RT.d_counters; p.nb = nb; p.list_cap = 0xffffffffu; p.n = 0;
         if (n) { if (s->tiles_x * s->tiles_y * 8u > max_slices) max_slices = s->tiles_x * s->tiles_y * 8u; if ((size_t)nb > max_nb) max_nb = (size_t)nb; }
-        g.bytes_h2d += sizeof(DevState) * J.n_states + sizeof(pfcu_vparams_lit) * J.n_vparams + sizeof(pfcu_list_call) * J.n_calls + sizeof(DevJob);
+        RT.bytes_h2d += sizeof(DevState) * J.n_states + sizeof(pfcu_vparams_lit) * J.n_vparams + sizeof(pfcu_list_call) * J.n_calls + sizeof(DevJob);
     }
     /* ---- order against what is queued on the surfaces' own lanes, upload, four launches ---- */
     bool lane_used[MAX_LANES] = { false };
-    for (uint32_t j = 0; j < n_jobs; j++) lane_used[jobs[j].surface->lane % g.n_lanes] = true;
-    for (int l = 1; l < g.n_lanes; l++) if (lane_used[l]) {
-        Lane &Ln = g.lanes[l];
-        if (Ln.need_fence_wait) { cudaStreamWaitEvent(Ln.stream, g.lanes[0].fence, 0); Ln.need_fence_wait = false; }
+    for (uint32_t j = 0; j < n_jobs; j++) lane_used[jobs[j].surface->lane % RT.n_lanes] = true;
+    for (int l = 1; l < RT.n_lanes; l++) if (lane_used[l]) {
+        Lane &Ln = RT.lanes[l];
+        if (Ln.need_fence_wait) { cudaStreamWaitEvent(Ln.stream, RT.lanes[0].fence, 0); Ln.need_fence_wait = false; }
         CK(cudaEventRecord(Ln.vready, Ln.stream));
         CK(cudaStreamWaitEvent(L0.stream, Ln.vready, 0));
     }
-    CK(cudaMemcpyAsync(g.d_jobs, g.h_jobs, off, cudaMemcpyHostToDevice, L0.stream));
-    CK(cudaEventRecord(g.jobs_copied, L0.stream));
-    const DevJob *dj = reinterpret_cast<const DevJob *>(g.d_jobs);
+    CK(cudaMemcpyAsync(RT.d_jobs, RT.h_jobs, off, cudaMemcpyHostToDevice, L0.stream));
+    CK(cudaEventRecord(RT.jobs_copied, L0.stream));
+    const DevJob *dj = reinterpret_cast<const DevJob *>(RT.d_jobs);
     bool any_clear = false; for (uint32_t j = 0; j < n_jobs; j++) any_clear |= jobs[j].clear != 0;
     cudaEvent_t pe[3] = { nullptr, nullptr, nullptr };
-    if (g.profiling) {
+    if (RT.profiling) {
         for (int i = 0; i < 3; i++) {
-            if (!g.prof_pool.empty()) { pe[i] = g.prof_pool.back(); g.prof_pool.pop_back(); }
+            if (!RT.prof_pool.empty()) { pe[i] = RT.prof_pool.back(); RT.prof_pool.pop_back(); }
             else CK(cudaEventCreate(&pe[i]));
         }
     }
-    if (any_clear) { k_jobs_clear<<<dim3(32, n_jobs), 256, 0, L0.stream>>>(dj); g.launches++; }
-    if (g.profiling) CK(cudaEventRecord(pe[0], L0.stream));
+    if (any_clear) { k_jobs_clear<<<dim3(32, n_jobs), 256, 0, L0.stream>>>(dj); RT.launches++; }
+    if (RT.profiling) CK(cudaEventRecord(pe[0], L0.stream));
     if (max_slices) {
-        if (++g.jobs_seq == 0) ++g.jobs_seq;
-        CK(launch_dep(k_list_chain, dim3(PFCU_LIST_JOB_MAX_TRIS / 128u, n_jobs), dim3(128), 0, L0.stream, dj, g.jobs_seq));
-        CK(launch_dep(k_front_small_jobs, dim3(1, n_jobs), dim3(1024), max_nb * sizeof(unsigned), L0.stream, dj, g.d_counters));
+        if (++RT.jobs_seq == 0) ++RT.jobs_seq;
+        CK(launch_dep(k_list_chain, dim3(PFCU_LIST_JOB_MAX_TRIS / 128u, n_jobs), dim3(128), 0, L0.stream, dj, RT.jobs_seq));
+        CK(launch_dep(k_front_small_jobs, dim3(1, n_jobs), dim3(1024), max_nb * sizeof(unsigned), L0.stream, dj, RT.d_counters));
         static const bool attr_once = [] {
             cudaFuncSetAttribute(k_raster_frag_jobs<true, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * FRAG_NF_PHONG * 512);
             cudaFuncSetAttribute(k_raster_frag_jobs<false, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * FRAG_NF * 512);
             return true; }();
         (void)attr_once;
-        if (g.profiling) CK(cudaEventRecord(pe[1], L0.stream));
+        if (RT.profiling) CK(cudaEventRecord(pe[1], L0.stream));
         if (feature & PFCU_ST_PHONG) CK(launch_dep(k_raster_frag_jobs<true, 8, 3>, dim3(max_slices, n_jobs), dim3(256), (size_t)(8 * FRAG_NF_PHONG * 512), L0.stream, dj));
         else                         CK(launch_dep(k_raster_frag_jobs<false, 8, 4>, dim3(max_slices, n_jobs), dim3(256), (size_t)(8 * FRAG_NF * 512), L0.stream, dj));
-        g.launches += 3;
-    } else if (g.profiling) CK(cudaEventRecord(pe[1], L0.stream));
-    if (g.profiling) { CK(cudaEventRecord(pe[2], L0.stream)); for (int i = 0; i < 3; i++) g.prof_events.push_back(pe[i]); }
+        RT.launches += 3;
+    } else if (RT.profiling) CK(cudaEventRecord(pe[1], L0.stream));
+    if (RT.profiling) { CK(cudaEventRecord(pe[2], L0.stream)); for (int i = 0; i < 3; i++) RT.prof_events.push_back(pe[i]); }
     CK(cudaGetLastError());
-    CK(cudaEventRecord(g.jobs_done, L0.stream));
-    for (int l = 1; l < g.n_lanes; l++) if (lane_used[l]) { CK(cudaStreamWaitEvent(g.lanes[l].stream, g.jobs_done, 0)); g.lanes[l].touched = true; }
+    CK(cudaEventRecord(RT.jobs_done, L0.stream));
+    for (int l = 1; l < RT.n_lanes; l++) if (lane_used[l]) { CK(cudaStreamWaitEvent(RT.lanes[l].stream, RT.jobs_done, 0)); RT.lanes[l].touched = true; }
     for (uint32_t j = 0; j < n_jobs; j++) {
         pfcu_surface *s = jobs[j].surface;
         s->bands_valid = false;
@@ -1758,21 +2051,22 @@ int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n_jobs)
 int pfcu_submit_prims(pfcu_surface *s, const pfcu_prim *prims, uint32_t n)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || (n && !prims)) return PFCU_ERR_INVALID;
     if (n == 0) return PFCU_OK;
+    if (MULTI_SURF(s)) return multi_run_all([&](int d) -> int { return pfcu_submit_prims(s->rep[d], prims, n); });
     use_lane(s);
     int rc;
     const size_t bytes = (size_t)n * sizeof(pfcu_prim);
     if ((rc = grow(&LN.d_varrays, &LN.cap_varrays, bytes))) return rc;
     CK(cudaMemcpyAsync(LN.d_varrays, prims, bytes, cudaMemcpyHostToDevice, LN.stream));
-    g.bytes_h2d += bytes;
+    RT.bytes_h2d += bytes;
     PrimParams p;
     p.prims = (const pfcu_prim *)LN.d_varrays; p.n = n; p.color = s->color; p.depth = s->depth; p.W = s->w; p.H = s->h;
     p.tilesX = (int)s->tiles_x; p.rank = s->rank; p.world = s->world ? s->world : 1; p.nTiles = s->tiles_x * s->tiles_y;
     p.alpha_or = s->fmt >= PFCU_TEX_RGB8 ? 0xff000000u : 0u;
     const unsigned grid = owned_tiles(s, p.rank, p.world);
-    if (grid) { k_prims<<<grid, 256, 0, LN.stream>>>(p); g.launches++; }
+    if (grid) { k_prims<<<grid, 256, 0, LN.stream>>>(p); RT.launches++; }
     CK(cudaGetLastError());
     mark_done(s);
     return PFCU_OK;
@@ -1781,9 +2075,12 @@ int pfcu_submit_prims(pfcu_surface *s, const pfcu_prim *prims, uint32_t n)
 int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, const pfcu_triangle *tris, uint32_t n_tris)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || (n_tris && (!states || !tris || n_states == 0))) return PFCU_ERR_INVALID;
     if (n_tris == 0) return PFCU_OK;
+    if (MULTI_SURF(s)) return multi_run_all([&](int k) -> int {
+        const std::vector<pfcu_state> st = states_for_device(states, n_states, k);
+        return pfcu_submit(s->rep[k], st.data(), n_states, tris, n_tris); });
     use_lane(s);
     int rc;
     if ((rc = grow(&LN.d_tris, &LN.cap_tris, n_tris))) return rc;
@@ -1800,15 +2097,14 @@ int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, co
     const unsigned mask = convert_states(states, n_states, LN.h_states);
     CK(cudaMemcpyAsync(LN.d_states, LN.h_states, n_states * sizeof(DevState), cudaMemcpyHostToDevice, LN.stream));
     CK(cudaEventRecord(LN.states_done, LN.stream));
-    g.bytes_h2d += n_states * sizeof(DevState) + (size_t)n_tris * sizeof(pfcu_triangle);
+    RT.bytes_h2d += n_states * sizeof(DevState) + (size_t)n_tris * sizeof(pfcu_triangle);
 
     /* triangles: one DMA from pinned memory, or staged through our own pinned buffer */
     const size_t bytes = (size_t)n_tris * sizeof(pfcu_triangle);
     PinnedBlock *pb = find_pinned(tris);
     if (pb) {
         CK(cudaMemcpyAsync(LN.d_tris, tris, bytes, cudaMemcpyHostToDevice, LN.stream));
-        CK(cudaEventRecord(pb->done, LN.stream));
-        pb->pending = true;
+        if ((rc = pinned_in_flight(pb, LN.stream))) return rc;
     } else {
         if (bytes > LN.cap_stage) {
             CK(cudaEventSynchronize(LN.stage_done));
@@ -1827,15 +2123,24 @@ int pfcu_submit(pfcu_surface *s, const pfcu_state *states, uint32_t n_states, co
 pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const pfcu_triangle *tris, uint32_t n_tris)
 {
     API_LOCK;
-    if (!g.ok || !states || !tris || n_states == 0 || n_tris == 0) return nullptr;
+    if (!RT.ok || !states || !tris || n_states == 0 || n_tris == 0) return nullptr;
+    if (MULTI_HERE()) {
+        pfcu_batch *r[MAX_DEVS] = { nullptr };
+        const int rc = multi_run_all([&](int k) -> int {
+            const std::vector<pfcu_state> st = states_for_device(states, n_states, k);
+            r[k] = pfcu_batch_upload(st.data(), n_states, tris, n_tris); return r[k] ? PFCU_OK : PFCU_ERR_OOM; });
+        if (rc) { multi_run_all([&](int k) -> int { if (r[k]) pfcu_batch_destroy(r[k]); return (int)PFCU_OK; }); return nullptr; }
+        for (int k = 0; k < mg.n; k++) r[0]->rep[k] = r[k];
+        return r[0];
+    }
     pfcu_batch *b = (pfcu_batch *)calloc(1, sizeof *b);
     if (!b) return nullptr;
-    g.cur = &g.lanes[0];
+    RT.cur = &RT.lanes[0];
     std::vector<DevState> tmp(n_states);
     b->feature_mask = convert_states(states, n_states, tmp.data());
     b->single_prog = g_last_single_prog;
     b->leader_tex = g_last_leader_tex; g_last_leader_tex = false;
-    new (&b->deps) std::vector<pfcu_surface *>(g.deps);
+    new (&b->deps) std::vector<pfcu_surface *>(RT.deps);
     b->n_states = n_states; b->n_tris = n_tris;
     CKP(cudaMalloc(&b->states, n_states * sizeof(DevState)));
     CKP(cudaMalloc(&b->tris, (size_t)n_tris * sizeof(pfcu_triangle)));
@@ -1848,11 +2153,12 @@ pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const
 int pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     if (!s || !b) return PFCU_ERR_INVALID;
+    if (MULTI_SURF(s) && b->rep[1]) return multi_run_all([&](int k) -> int { return pfcu_batch_submit(s->rep[k], b->rep[k]); });
     use_lane(s);
-    g.deps.clear();
-    for (pfcu_surface *dep : b->deps) g.deps.push_back(dep);
+    RT.deps.clear();
+    for (pfcu_surface *dep : b->deps) RT.deps.push_back(dep);
     g_last_leader_tex = b->leader_tex;
     return launch_pipeline(s, b->tris, b->states, b->n_tris, b->feature_mask, b->single_prog);
 }
@@ -1861,61 +2167,80 @@ void pfcu_batch_destroy(pfcu_batch *b)
 {
     API_LOCK;
     if (!b) return;
-    if (g.ok) sync_all_lanes();
+    if (MULTI_HERE() && b->rep[1]) {
+        pfcu_batch *r[MAX_DEVS]; memcpy(r, b->rep, sizeof r);
+        multi_run_all([&](int k) -> int { pfcu_batch_destroy(r[k]); return (int)PFCU_OK; });
+        return;
+    }
+    if (RT.ok) sync_all_lanes();
     cudaFree(b->states); cudaFree(b->tris); b->deps.~vector(); free(b);
 }
 
-void pfcu_profile_enable(int on) { g.profiling = on != 0; }
-void pfcu_set_raster_path(int path) { API_LOCK; g.raster_path = (path == PFCU_RASTER_TILES || path == PFCU_RASTER_FRAGMENTS) ? path : PFCU_RASTER_AUTO; }
+void pfcu_profile_enable(int on) { RT.profiling = on != 0; }
+void pfcu_set_raster_path(int path) { API_LOCK; if (MULTI_HERE()) { multi_run_all([path](int) -> int { pfcu_set_raster_path(path); return (int)PFCU_OK; }); return; } RT.raster_path = (path == PFCU_RASTER_TILES || path == PFCU_RASTER_FRAGMENTS) ? path : PFCU_RASTER_AUTO; }
 
 int pfcu_profile_read(pfcu_profile *out)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
     sync_all_lanes();
     out->raster_ms = 0; out->frontend_ms = 0; out->raster_launches = 0;
-    for (size_t i = 0; i + 2 < g.prof_events.size(); i += 3) {
+    for (size_t i = 0; i + 2 < RT.prof_events.size(); i += 3) {
         float a = 0, b = 0;
-        CK(cudaEventElapsedTime(&a, g.prof_events[i], g.prof_events[i + 1]));
-        CK(cudaEventElapsedTime(&b, g.prof_events[i + 1], g.prof_events[i + 2]));
+        CK(cudaEventElapsedTime(&a, RT.prof_events[i], RT.prof_events[i + 1]));
+        CK(cudaEventElapsedTime(&b, RT.prof_events[i + 1], RT.prof_events[i + 2]));
         out->frontend_ms += a; out->raster_ms += b; out->raster_launches++;
     }
-    for (auto e : g.prof_events) g.prof_pool.push_back(e);
-    g.prof_events.clear();
+    for (auto e : RT.prof_events) RT.prof_pool.push_back(e);
+    RT.prof_events.clear();
     return PFCU_OK;
 }
 
 int pfcu_finish(void)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
-    for (int i = 0; i < g.n_lanes; i++) CK(cudaStreamSynchronize(g.lanes[i].stream));
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
+    if (MULTI_HERE()) return multi_run_all([](int) -> int { return pfcu_finish(); });
+    for (int i = 0; i < RT.n_lanes; i++) CK(cudaStreamSynchronize(RT.lanes[i].stream));
     return PFCU_OK;
 }
 
 int pfcu_get_counters(pfcu_counters *out)
 {
     API_LOCK;
-    if (!g.ok) return PFCU_ERR_NO_DEVICE;
+    if (!RT.ok) return PFCU_ERR_NO_DEVICE;
+    if (MULTI_HERE()) {
+        /* triangles are counted by device 0 (every device sets all of them up); pixels, launches and bytes are sums */
+        pfcu_counters c[MAX_DEVS];
+        const int rc = multi_run_all([&](int d) -> int { return pfcu_get_counters(&c[d]); });
+        if (rc) return rc;
+        *out = c[0];
+        for (int d = 1; d < mg.n; d++) {
+            out->pixels_shaded += c[d].pixels_shaded; out->pixels_depth_failed += c[d].pixels_depth_failed;
+            out->kernel_launches += c[d].kernel_launches; out->bytes_h2d += c[d].bytes_h2d; out->bytes_d2h += c[d].bytes_d2h;
+        }
+        return PFCU_OK;
+    }
     unsigned long long h[4] = { 0, 0, 0, 0 };
     sync_all_lanes();
-    CK(cudaMemcpy(h, g.d_counters, sizeof h, cudaMemcpyDeviceToHost));
-    out->triangles_submitted = g.submitted + h[3];
+    CK(cudaMemcpy(h, RT.d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    out->triangles_submitted = RT.submitted + h[3];
     out->triangles_rasterised = h[0];
     out->pixels_shaded = h[1];
     out->pixels_depth_failed = h[2];
-    out->kernel_launches = g.launches;
-    out->bytes_h2d = g.bytes_h2d; out->bytes_d2h = g.bytes_d2h;
+    out->kernel_launches = RT.launches;
+    out->bytes_h2d = RT.bytes_h2d; out->bytes_d2h = RT.bytes_d2h;
     return PFCU_OK;
 }
 
 void pfcu_reset_counters(void)
 {
     API_LOCK;
-    if (!g.ok) return;
+    if (!RT.ok) return;
+    if (MULTI_HERE()) { multi_run_all([](int) -> int { pfcu_reset_counters(); return (int)PFCU_OK; }); return; }
     sync_all_lanes();
-    cudaMemset(g.d_counters, 0, 4 * sizeof(unsigned long long));
-    g.submitted = 0; g.launches = 0; g.bytes_h2d = 0; g.bytes_d2h = 0;
+    cudaMemset(RT.d_counters, 0, 4 * sizeof(unsigned long long));
+    RT.submitted = 0; RT.launches = 0; RT.bytes_h2d = 0; RT.bytes_d2h = 0;
 }
 
 } /* extern "C" */

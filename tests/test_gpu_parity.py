@@ -570,7 +570,7 @@ def _render_with_env(scene, w, h, env, **kw):
                 "c, d, r = load_product_scenes().render(%r, %d, %d, **%r)\n"
                 "np.savez(%r, color=c, depth=d, tris=r.triangles_submitted, px=r.pixels_shaded)\n") % (root, scene, w, h, kw, out)
         e = dict(os.environ); e.update(env)
-        subprocess.run([sys.executable, "-c", code], check=True, env=e)
+        subprocess.run([sys.executable, "-c", code], check=True, env=e, timeout=300)
         z = np.load(out)
         return z["color"], z["depth"], int(z["tris"]), int(z["px"])
 
@@ -677,3 +677,49 @@ def test_static_geometry_mirrors():
         out[mode] = json.loads(r.stdout.strip().splitlines()[-1])["h2d"]
     mesh_bytes = 65 * 65 * 24 + 64 * 64 * 6 * 4
     assert out["0"] >= mesh_bytes and out["1"] < 4096, out
+
+
+# ---- multi-device mode: one process, several GPUs (PF_CUDA_DEVICES) --------------------------------------
+
+def _visible_gpus():
+    import subprocess
+    try:
+        return len([l for l in subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.splitlines() if l.startswith("GPU ")])
+    except Exception:
+        return 0
+
+
+MULTI_CASE_IDS = ["c1-gears-f0", "c2-textured-bilinear-repeat", "c2-textured-closeup-clipped-bilinear-arrays", "c2-textured-arrays-rewritten-f2", "c3-phong-arrays",
+                  "c4-overdraw-alpha-depth", "c4-overdraw-alpha-depth-two-state", "c5-batch", "c5-batch-phong-cull-off", "micro-blend3", "micro-depth1",
+                  "micro-mode4-cull0", "micro-fbo", "micro-fbo-persp", "micro-phong-tex-spot1", "micro-random27", "micro-target-bgra-fbo", "micro-target-rgb-blend3",
+                  "api-everything", "api-fog-exp", "api-pixel-layouts-viewport", "api-swapbuffers", "prims-thick", "prims-persp-blend1-depth3-points"]
+
+
+@pytest.mark.parametrize("cid", MULTI_CASE_IDS)
+def test_multi_device_mode_matches_one_gpu(cid, product_scenes):
+    """PF_CUDA_DEVICES=0,1[,2,3]: every device replays the submissions and rasterises its own tiles (here every surface is
+    split, PF_CUDA_SPLIT_MIN_PIXELS=0), read-backs gather the tiles on device 0 over NVLink; surfaces that are sampled as
+    textures and non-RGBA8 targets are rendered in full everywhere.  Pixels, depth and counters equal one GPU's."""
+    n = _visible_gpus()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    case = [c for c in CASES if c[0] == cid][0]
+    _, scene, w, h, kw, _ = case
+    ref_c, ref_d, ref_r = product_scenes.render(scene, w, h, **kw)
+    for devs in (["0,1"] + (["0,1,2,3"] if n >= 4 else [])):
+        c, d, tris, px = _render_with_env(scene, w, h, {"PF_CUDA_DEVICES": devs, "PF_CUDA_SPLIT_MIN_PIXELS": "0"}, **kw)
+        assert int((c != ref_c).sum()) == 0, (cid, devs, "colour")
+        assert int((d.view(np.uint32) != ref_d.view(np.uint32)).sum()) == 0, (cid, devs, "depth")
+        assert tris == ref_r.triangles_submitted and px == ref_r.pixels_shaded, (cid, devs, tris, px)
+
+
+def test_multi_device_fullsize(product_scenes):
+    """The 4K blended scene and the 1 M-triangle Phong mesh at full size on two devices, default split threshold."""
+    if _visible_gpus() < 2:
+        pytest.skip("needs at least two GPUs")
+    for scene, w, h, kw in (("overdraw", 3840, 2160, dict(size=6, variant=1)), ("phong", 3840, 2160, dict(size=708, variant=32)),
+                            ("textured", 1920, 1080, dict(size=256, variant=1 | 32 | 64))):
+        ref_c, ref_d, ref_r = product_scenes.render(scene, w, h, **kw)
+        c, d, tris, px = _render_with_env(scene, w, h, {"PF_CUDA_DEVICES": "0,1"}, **kw)
+        assert int((c != ref_c).sum()) == 0 and int((d.view(np.uint32) != ref_d.view(np.uint32)).sum()) == 0, scene
+        assert px == ref_r.pixels_shaded

@@ -116,6 +116,8 @@ struct pfcu_surface {
     /* the last operation on the surface was a rasterisation in bands of tile rows: band b covers rows [band_y[b], band_y[b+1])
        and band_evt[b] fires when it is complete (see launch_raster_bands / pfcu_surface_download_async) */
     bool bands_valid; int n_bands; uint32_t band_y[MAX_BANDS + 1]; cudaEvent_t band_evt[MAX_BANDS];
+    uint32_t band_owned[MAX_BANDS + 1];             /* tile split: band b = this rank's owned tiles [band_owned[b], band_owned[b+1]) */
+    cudaEvent_t push_evt[MAX_BANDS]; bool pushed_in_bands;      /* pfcu_surface_push_tiles of a banded surface: band b's tiles have been stored */
     /* bands pay off only when a read-back follows the batch: batches rasterised since the last read-back, and how many
        there were between the two read-backs before - the batch predicted to be a frame's last one goes out in bands */
     unsigned n_since_read, n_per_read;
@@ -123,7 +125,7 @@ struct pfcu_surface {
        on replicas); split: every device rasterises only its own tiles and a read-back gathers them on device 0;
        full_evt (device 0): the last operation that wrote tiles of other devices too; pushed (replicas): the last store of
        this device's tiles into device 0's surface */
-    pfcu_surface *rep[MAX_DEVS]; bool split; cudaEvent_t full_evt, pushed; bool has_full;
+    pfcu_surface *rep[MAX_DEVS]; bool split; cudaEvent_t full_evt, pushed; bool has_full, peer_bands;
 };
 struct pfcu_texture { uint32_t w, h; int fmt; unsigned char *pixels; bool owned; pfcu_surface *alias; bool leader; pfcu_texture *rep[MAX_DEVS]; };
 struct pfcu_list { pfcu_rawtri *tris; uint32_t n; };
@@ -365,10 +367,11 @@ static cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 /* the single-program instantiations of the big-triangle rasteriser, full tiles and half-height slices */
-template <int PROG> static cudaError_t launch_fixed(bool half, unsigned grid, cudaStream_t st, const RasterParams &p)
+template <int PROG> static cudaError_t launch_fixed(int slices, unsigned grid, cudaStream_t st, const RasterParams &p)
 {
-    return half ? launch_dep(k_raster<false, 8, PROG, 32>, dim3(grid * 2), dim3(256), (size_t)0, st, p)
-                : launch_dep(k_raster<false, 8, PROG, 64>, dim3(grid), dim3(256), (size_t)0, st, p);
+    return slices == 4 ? launch_dep(k_raster<false, 8, PROG, 16>, dim3(grid * 4), dim3(256), (size_t)0, st, p)
+         : slices == 2 ? launch_dep(k_raster<false, 8, PROG, 32>, dim3(grid * 2), dim3(256), (size_t)0, st, p)
+                       : launch_dep(k_raster<false, 8, PROG, 64>, dim3(grid), dim3(256), (size_t)0, st, p);
 }
 
 template <typename T> static int grow(T **p, size_t *cap, size_t need)
@@ -462,8 +465,10 @@ int pfcu_init(int device)
             int pr = hi + b; if (pr > lo) pr = lo;
             CK(cudaStreamCreateWithPriority(&RT.band_streams[b], cudaStreamNonBlocking, pr));
         }
+        /* the copy stream also runs kernels (the tile stores of a finished band to another device): above every band,
+           or they would wait for the SMs until the whole surface is rasterised */
+        CK(cudaStreamCreateWithPriority(&RT.copy_stream, cudaStreamNonBlocking, hi));
     }
-    CK(cudaStreamCreateWithFlags(&RT.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&RT.front_evt, cudaEventDisableTiming));
     CK(cudaMalloc(&RT.d_counters, 8 * sizeof(unsigned long long)));          /* [0..3] the counters, [4..7] a sink (see counters_for) */
     CK(cudaMemset(RT.d_counters, 0, 8 * sizeof(unsigned long long)));
@@ -860,8 +865,30 @@ int pfcu_surface_push_tiles(pfcu_surface *s, uint32_t rank, uint32_t world, int 
     use_lane(s);
     const uint32_t n = owned_tiles(s, rank, world);
     if (n == 0) return PFCU_OK;
+    if (s->bands_valid && s->band_owned[s->n_bands] == n) {
+        /* the surface was last written by a banded rasterisation: band b's tiles leave on the copy stream as soon as band b
+           is done, while the later bands are still being rasterised; push_evt[b] tells the receiving side */
+        for (int b = 0; b < s->n_bands; b++) {
+            const uint32_t o0 = s->band_owned[b], o1 = s->band_owned[b + 1];
+            CK(cudaStreamWaitEvent(RT.copy_stream, s->band_evt[b], 0));
+            if (o1 > o0) {
+                k_push_tiles<<<o1 - o0, 256, 0, RT.copy_stream>>>(s->color, s->depth, s->peer_color, with_depth ? s->peer_depth : nullptr, (int)s->w, (int)s->h,
+                                                                 (int)s->tiles_x, s->tiles_x * s->tiles_y, rank, world, o0);
+                RT.launches++;
+            }
+            if (!s->push_evt[b]) CK(cudaEventCreateWithFlags(&s->push_evt[b], cudaEventDisableTiming));
+            CK(cudaEventRecord(s->push_evt[b], RT.copy_stream));
+        }
+        CK(cudaGetLastError());
+        const bool keep = s->bands_valid;
+        if (cudaEventRecord(s->done, RT.copy_stream) == cudaSuccess) s->has_done = true;
+        CK(cudaStreamWaitEvent(LN.stream, s->done, 0));         /* later work on the surface must not overtake the stores' reads */
+        s->bands_valid = keep; s->pushed_in_bands = true;
+        return PFCU_OK;
+    }
+    s->pushed_in_bands = false;
     k_push_tiles<<<n, 256, 0, LN.stream>>>(s->color, s->depth, s->peer_color, with_depth ? s->peer_depth : nullptr, (int)s->w, (int)s->h,
-                                          (int)s->tiles_x, s->tiles_x * s->tiles_y, rank, world);
+                                          (int)s->tiles_x, s->tiles_x * s->tiles_y, rank, world, 0u);
     RT.launches++;
     CK(cudaGetLastError());
     mark_done(s);
@@ -884,6 +911,7 @@ void pfcu_surface_destroy(pfcu_surface *s)
     cudaFree(s->conv);
     if (s->done) cudaEventDestroy(s->done);
     for (int b = 0; b < MAX_BANDS; b++) if (s->band_evt[b]) cudaEventDestroy(s->band_evt[b]);
+    for (int b = 0; b < MAX_BANDS; b++) if (s->push_evt[b]) cudaEventDestroy(s->push_evt[b]);
     if (s->full_evt) cudaEventDestroy(s->full_evt);
     if (s->pushed) cudaEventDestroy(s->pushed);
     free(s);
@@ -897,6 +925,10 @@ void *pfcu_surface_depth_ptr(const pfcu_surface *s) { return s->depth; }
 /* end of an operation on the surface (recorded on its lane); whatever it was, the band events of an earlier
    rasterisation no longer describe the surface's last write */
 static void mark_done(pfcu_surface *s) { s->bands_valid = false; if (cudaEventRecord(s->done, LN.stream) == cudaSuccess) s->has_done = true; }
+
+/* PF_CUDA_TIMING=1: host-side microseconds of the phases of pfcu_draw_triangles, band decisions of the multi-device read-back, on stderr (development aid) */
+static const bool g_timing = getenv("PF_CUDA_TIMING") && atoi(getenv("PF_CUDA_TIMING")) != 0;
+static double now_us(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
 
 /* ---- multi-device helpers (see "multi-device mode" at the top) ---- */
 #define MULTI_SURF(s) (MULTI_HERE() && (s) && (s)->rep[1])
@@ -920,7 +952,8 @@ static int multi_gather(pfcu_surface *s, int with_depth)
         if (d == 0) return (int)PFCU_OK;
         pfcu_surface *r = s->rep[d];
         use_lane(r);
-        if (s->has_full) CK(cudaStreamWaitEvent(LN.stream, s->full_evt, 0));
+        r->n_per_read = r->n_since_read; r->n_since_read = 0;       /* the replicas band their last batch like device 0 does */
+        if (s->has_full) { CK(cudaStreamWaitEvent(LN.stream, s->full_evt, 0)); CK(cudaStreamWaitEvent(RT.copy_stream, s->full_evt, 0)); }
         const int rc = pfcu_surface_push_tiles(r, (uint32_t)d, (uint32_t)mg.n, with_depth);
         use_lane(r);
         CK(cudaEventRecord(r->pushed, LN.stream));
@@ -928,6 +961,17 @@ static int multi_gather(pfcu_surface *s, int with_depth)
     });
     if (rc) return rc;
     use_lane(s);
+    /* device 0 waits for the stores: band by band on its copy stream when everyone worked in the same bands (the read-back
+       that follows then streams band b out while band b+1 is still being rasterised and stored), else on its lane */
+    bool per_band = s->bands_valid;
+    for (int d = 1; d < mg.n && per_band; d++) per_band = s->rep[d]->pushed_in_bands && s->rep[d]->n_bands == s->n_bands;
+    if (g_timing) fprintf(stderr, "multi_gather: per_band %d (device 0 bands_valid %d, n_bands %d; device 1 pushed_in_bands %d n_bands %d)\n", (int)per_band, (int)s->bands_valid, s->n_bands, (int)s->rep[1]->pushed_in_bands, s->rep[1]->n_bands);
+    s->peer_bands = per_band;       /* pfcu_surface_download_async: band b also waits for every device's push_evt[b] (in the
+                                       copy stream, right before band b's copy - not all bands' waits ahead of the first copy) */
+    if (per_band) {
+        for (int d = 1; d < mg.n; d++) CK(cudaStreamWaitEvent(LN.stream, s->rep[d]->pushed, 0));
+        return PFCU_OK;
+    }
     for (int d = 1; d < mg.n; d++) CK(cudaStreamWaitEvent(LN.stream, s->rep[d]->pushed, 0));
     return PFCU_OK;
 }
@@ -982,6 +1026,7 @@ int pfcu_surface_download_async(pfcu_surface *s, void *hc, float *hd, uint32_t y
             if (r0 >= r1) continue;
             const size_t o = (size_t)r0 * s->w, nb = (size_t)(r1 - r0) * s->w * 4;
             CK(cudaStreamWaitEvent(RT.copy_stream, s->band_evt[b], 0));
+            if (s->peer_bands) for (int d = 1; d < mg.n; d++) CK(cudaStreamWaitEvent(RT.copy_stream, s->rep[d]->push_evt[b], 0));
             if (hc) { CK(cudaMemcpyAsync((uint32_t *)hc + o, s->color + o, nb, cudaMemcpyDeviceToHost, RT.copy_stream)); RT.bytes_d2h += nb; }
             if (hd) { CK(cudaMemcpyAsync(hd + o, s->depth + o, nb, cudaMemcpyDeviceToHost, RT.copy_stream)); RT.bytes_d2h += nb; }
         }
@@ -1532,7 +1577,15 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         const bool fixed = single_prog >= 0 && single_prog < PROG_PHONG && !small_tris && !use_frag;
         const int per_sm = (fixed && single_prog / 4 != 4) ? 4 : 3;
         const double waves = (double)grid_all / ((double)RT.sms * per_sm);      /* bands run side by side: the whole surface counts */
-        const bool half = !small_tris && !ph && waves < 8.0 && (ceil(waves) / waves) > 1.06 && (ceil(2 * waves) / (2 * waves)) < (ceil(waves) / waves);
+        /* slices per tile: 64x64, 64x32 or 64x16 - whichever leaves the least of the last wave empty (a tile-split surface
+           on 8 GPUs: 1020 tiles = 1.7 waves of 64x64 CTAs, 6.9 waves of 64x16 slices) */
+        int slices = 1;
+        if (!small_tris && !ph && waves < 8.0 && (ceil(waves) / waves) > 1.06) {
+            const double loss1 = ceil(waves) / waves, loss2 = ceil(2 * waves) / (2 * waves), loss4 = ceil(4 * waves) / (4 * waves);
+            if (loss2 < loss1) slices = 2;
+            if (loss4 < 0.97 * (slices == 2 ? loss2 : loss1)) slices = 4;
+        }
+        const bool half = slices == 2;
         if (use_frag) {
             /* 64x8 slices of eight 8x8 regions, 8 warps; 4 CTAs per SM (Phong: 3, 80 registers) */
             if (!RT.frag_attr_set) {            /* function attributes are per device: once per runtime, not per process */
@@ -1554,14 +1607,14 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         else if (fixed) {
             /* one state program in the whole batch: the kernel that holds only that fragment program */
             switch (single_prog) {
-#define FIXED_CASE(P) case P: CK(launch_fixed<P>(half, grid, st_, p)); break;
+#define FIXED_CASE(P) case P: CK(launch_fixed<P>(slices, grid, st_, p)); break;
             FIXED_CASE(0) FIXED_CASE(1) FIXED_CASE(2) FIXED_CASE(3) FIXED_CASE(4) FIXED_CASE(5) FIXED_CASE(6) FIXED_CASE(7)
             FIXED_CASE(12) FIXED_CASE(13) FIXED_CASE(14) FIXED_CASE(15) FIXED_CASE(16) FIXED_CASE(17) FIXED_CASE(18) FIXED_CASE(19)
 #undef FIXED_CASE
             default: snprintf(RT.err, sizeof RT.err, "internal: no kernel for state program %d", single_prog); return PFCU_ERR_INVALID;
             }
         }
-        else { if (half) CK(launch_dep(k_raster<false, 8, -1, 32>, dim3(grid * 2), dim3(256), (size_t)(0), st_, p)); else CK(launch_dep(k_raster<false, 8, -1, 64>, dim3(grid), dim3(256), (size_t)(0), st_, p)); }
+        else { if (half || slices == 4) CK(launch_dep(k_raster<false, 8, -1, 32>, dim3(grid * 2), dim3(256), (size_t)(0), st_, p)); else CK(launch_dep(k_raster<false, 8, -1, 64>, dim3(grid), dim3(256), (size_t)(0), st_, p)); }
         RT.launches++;
         return PFCU_OK;
     };
@@ -1575,9 +1628,15 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
        nothing end to end, 4 bands 0.02 ms; 4K scenes 0.3 - 0.5 ms, 8K 1.9 ms) */
     s->n_since_read++;
     const bool read_back_expected = s->n_per_read != 0 && s->n_since_read == s->n_per_read;
-    if (grid && p.world <= 1 && s->fmt == PFCU_TEX_RGBA8 && (size_t)s->w * s->h >= ((size_t)1 << 20) && s->tiles_y >= 8 && read_back_expected) n_bands = MAX_BANDS;
+    if (grid && s->fmt == PFCU_TEX_RGBA8 && (size_t)s->w * s->h >= ((size_t)1 << 20) && s->tiles_y >= 8 && read_back_expected) n_bands = MAX_BANDS;
     if (env_bands >= 1) n_bands = env_bands > MAX_BANDS ? MAX_BANDS : env_bands;
-    if (p.world > 1 || !grid || (unsigned)n_bands > s->tiles_y) n_bands = 1;
+    if (!grid || (unsigned)n_bands > s->tiles_y) n_bands = 1;
+    /* tile split: this rank's tiles t = rank + k * world, k = 0 .. grid-1; the ones in tile rows < R are k < first_owned(R) */
+    auto first_owned = [&](unsigned R) -> unsigned {
+        const unsigned t = R * s->tiles_x;
+        if (p.world <= 1) return t;
+        return t <= p.rank ? 0u : (t - p.rank + p.world - 1u) / p.world;
+    };
     if (n_bands > 1) {
         for (int b = 0; b < n_bands; b++) if (!s->band_evt[b]) CK(cudaEventCreateWithFlags(&s->band_evt[b], cudaEventDisableTiming));
         CK(cudaEventRecord(RT.front_evt, LN.stream));
@@ -1587,14 +1646,15 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
             const unsigned row1 = (b == n_bands - 1) ? s->tiles_y : (unsigned)(((uint64_t)s->tiles_y * (unsigned)(b + 1)) / (unsigned)n_bands);
             cudaStream_t bs = RT.band_streams[b];
             CK(cudaStreamWaitEvent(bs, RT.front_evt, 0));
-            p.tile_base = row0 * s->tiles_x;
-            if ((rc = launch_raster((row1 - row0) * s->tiles_x, bs))) return rc;
+            const unsigned o0 = first_owned(row0), o1 = b == n_bands - 1 ? grid : first_owned(row1);
+            p.tile_base = o0;
+            if (o1 > o0 && (rc = launch_raster(o1 - o0, bs))) return rc;
             CK(cudaEventRecord(s->band_evt[b], bs));
             CK(cudaStreamWaitEvent(LN.stream, s->band_evt[b], 0));
-            s->band_y[b] = row0 * TILE;
+            s->band_y[b] = row0 * TILE; s->band_owned[b] = o0;
             row0 = row1;
         }
-        s->band_y[n_bands] = s->h;
+        s->band_y[n_bands] = s->h; s->band_owned[n_bands] = grid;
         s->n_bands = n_bands; banded = true;
     } else if (grid) {
         if ((rc = launch_raster(grid, LN.stream))) return rc;
@@ -1649,9 +1709,6 @@ static int scan_exclusive(const unsigned *d_in, unsigned *d_out, unsigned n, uns
     return PFCU_OK;
 }
 
-/* PF_CUDA_TIMING=1: host-side microseconds of the phases of pfcu_draw_triangles on stderr (development aid) */
-static const bool g_timing = getenv("PF_CUDA_TIMING") && atoi(getenv("PF_CUDA_TIMING")) != 0;
-static double now_us(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
 
 /* device-resident lists run many small surfaces per launch on ONE device; the multi-device mode replays lists through
    pfcu_submit_raw instead, which every device executes */

@@ -364,7 +364,7 @@ __device__ __forceinline__ void raster_frag_body(const RasterParams &p)
     static_assert(NW == 8 || NW == 16, "one 8x8 region per warp, 8 regions per row");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned tile = (p.world > 1) ? (p.rank + (blockIdx.x / SUB) * p.world) : (p.tile_base + blockIdx.x / SUB);
+    const unsigned tile = (p.world > 1) ? (p.rank + (p.tile_base + blockIdx.x / SUB) * p.world) : (p.tile_base + blockIdx.x / SUB);
     if (tile >= p.nTiles) return;
     const int tx = tile % p.tilesX, ty = tile / p.tilesX;
     const int X0 = tx * TILE, Y0 = ty * TILE + (int)(blockIdx.x % SUB) * TH;

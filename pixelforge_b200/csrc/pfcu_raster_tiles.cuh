@@ -346,7 +346,7 @@ k_raster(const RasterParams p)
     /* a CTA handles a 64 x TH slice of a 64x64 tile (TH = 32 halves the work quantum when the grid would
        otherwise be only a few waves deep); ownership for the multi-GPU split stays per 64x64 tile */
     constexpr int SUB = TILE / TH;
-    const unsigned tile = (p.world > 1) ? (p.rank + (blockIdx.x / SUB) * p.world) : (p.tile_base + blockIdx.x / SUB);
+    const unsigned tile = (p.world > 1) ? (p.rank + (p.tile_base + blockIdx.x / SUB) * p.world) : (p.tile_base + blockIdx.x / SUB);
     if (tile >= p.nTiles) return;
     const int tx = tile % p.tilesX, ty = tile / p.tilesX;
     TileCtx t;

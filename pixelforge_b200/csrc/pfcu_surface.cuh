@@ -74,9 +74,9 @@ __global__ void k_pack_tiles(uint32_t *color, float *depth, int W, int H, int ti
 /* owned tiles -> the presenting rank's surface (peer memory), 128 bits per access when the row layout allows */
 __global__ void __launch_bounds__(256)
 k_push_tiles(const uint32_t *__restrict__ color, const float *__restrict__ depth, uint32_t *__restrict__ peer_color, float *__restrict__ peer_depth,
-             int W, int H, int tilesX, unsigned nTiles, unsigned rank, unsigned world)
+             int W, int H, int tilesX, unsigned nTiles, unsigned rank, unsigned world, unsigned first_owned)
 {
-    const unsigned tile = rank + blockIdx.x * world;
+    const unsigned tile = rank + (first_owned + blockIdx.x) * world;
     if (tile >= nTiles) return;
     const int X0 = (tile % tilesX) * TILE, Y0 = (tile / tilesX) * TILE;
     if ((W & 3) == 0 && X0 + TILE <= W) {

@@ -373,6 +373,32 @@ def measure_workload(wl_name, steps, warmup, torch, scenes, pfcu, stream, flush_
     return out
 
 
+def single_process_scaling(world):
+    """tools/multi_bench.py on 1 and on `world` devices (PF_CUDA_DEVICES), wall clock through the public API."""
+    out = {"note": "one process, PF_CUDA_DEVICES=0..N-1, unmodified pixelforge.h calls; wall clock around the API calls; frame hash equal to one device's"}
+    for name in ("c4_overdraw_8k", "ns_textured_blend_4k"):
+        res = {}
+        for n in (1, world):
+            env = dict(os.environ); env["PF_CUDA_DEVICES"] = ",".join(str(i) for i in range(n)); env.pop("PF_CUDA_DEVICE", None)
+            for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS"):
+                env.pop(k, None)
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "multi_bench.py"), name, "5"], capture_output=True, text=True, timeout=300, env=env)
+                res[n] = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as e:
+                res[n] = {"error": repr(e)}
+        one, many = res.get(1, {}), res.get(world, {})
+        o = {"one_device": one, f"{world}_devices": many}
+        if "render_ms" in one and "render_ms" in many:
+            o["scaling"] = "strong"
+            for key in ("render", "present", "e2e"):
+                o[f"{key}_speedup"] = one[f"{key}_ms"] / many[f"{key}_ms"]
+                o[f"{key}_efficiency"] = one[f"{key}_ms"] / many[f"{key}_ms"] / world
+            o["identical_frames"] = one.get("frame_sha256_16") == many.get("frame_sha256_16")
+        out[name] = o
+    return out
+
+
 def ours_main(args):
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("PF_CUDA_DEVICE", str(local))
@@ -459,6 +485,24 @@ def ours_main(args):
                 extra["tile_split_c4"] = tile_split_benchmark(torch, dist, scenes, pfcu, stream, WORKLOADS["c4_overdraw_8k"], rank, world, steps=3)
             except Exception as e:
                 extra["tile_split_c4"] = {"error": repr(e)}
+
+    # single-process multi-device mode of the library (PF_CUDA_DEVICES): rank 0 drives all N GPUs of the box through the
+    # PUBLIC API in a fresh process while the other ranks wait - the C4 screen-tile split and the 4K scene, strong scaling
+    # against the same tool on one device
+    if world > 1 and not args.no_extra:
+        import datetime
+        barrier()
+        # the other ranks wait on the rendezvous store, on the CPU: a NCCL barrier would keep a kernel spinning on their
+        # GPUs, which the driver then time-slices with rank 0's work on the same devices
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            try:
+                extra["single_process_multi_device"] = single_process_scaling(world)
+            finally:
+                store.set("pf_single_process_done", "1")
+        else:
+            store.wait(["pf_single_process_done"], datetime.timedelta(seconds=1200))
+        barrier()
 
     if rank != 0:
         if world > 1:

@@ -104,6 +104,7 @@ struct __align__(16) DevState {
 static_assert(offsetof(DevState, tex_fw) % 16 == 0, "tex_fw..tex_ty are fetched as one float4");
 
 #define MAX_BANDS 4
+#define PUSH_HOST_CTAS 48u        /* CTAs of a tile store towards host memory (see k_push_tiles) */
 struct pfcu_surface {
     uint32_t w, h; uint32_t *color; float *depth; bool owned;
     int fmt;                                        /* PFCU_TEX_*: the caller's layout; the device holds canonical RGBA8 */
@@ -117,7 +118,7 @@ struct pfcu_surface {
        and band_evt[b] fires when it is complete (see launch_raster_bands / pfcu_surface_download_async) */
     bool bands_valid; int n_bands; uint32_t band_y[MAX_BANDS + 1]; cudaEvent_t band_evt[MAX_BANDS];
     uint32_t band_owned[MAX_BANDS + 1];             /* tile split: band b = this rank's owned tiles [band_owned[b], band_owned[b+1]) */
-    cudaEvent_t push_evt[MAX_BANDS]; bool pushed_in_bands;      /* pfcu_surface_push_tiles of a banded surface: band b's tiles have been stored */
+    cudaEvent_t push_evt[MAX_BANDS]; bool pushed_in_bands; bool peer_is_host;      /* peer_is_host: peer_color / peer_depth address the caller's page-locked buffer */      /* pfcu_surface_push_tiles of a banded surface: band b's tiles have been stored */
     /* bands pay off only when a read-back follows the batch: batches rasterised since the last read-back, and how many
        there were between the two read-backs before - the batch predicted to be a frame's last one goes out in bands */
     unsigned n_since_read, n_per_read;
@@ -687,7 +688,7 @@ int pfcu_host_register(void *p, size_t bytes)
     API_LOCK;
     if (!RT.ok || !p || bytes == 0) return PFCU_ERR_INVALID;
     /* page-aligned sub-range; the partial first/last pages stay pageable (cudaMemcpy handles mixed ranges) */
-    cudaError_t e = cudaHostRegister(p, bytes, mg.n > 1 ? cudaHostRegisterPortable : cudaHostRegisterDefault);
+    cudaError_t e = cudaHostRegister(p, bytes, mg.n > 1 ? (cudaHostRegisterPortable | cudaHostRegisterMapped) : cudaHostRegisterDefault);     /* multi-device: every device stores its tiles straight into the buffer */
     if (e != cudaSuccess) { cudaGetLastError(); return PFCU_ERR_CUDA; }
     return PFCU_OK;
 }
@@ -872,8 +873,9 @@ int pfcu_surface_push_tiles(pfcu_surface *s, uint32_t rank, uint32_t world, int 
             const uint32_t o0 = s->band_owned[b], o1 = s->band_owned[b + 1];
             CK(cudaStreamWaitEvent(RT.copy_stream, s->band_evt[b], 0));
             if (o1 > o0) {
-                k_push_tiles<<<o1 - o0, 256, 0, RT.copy_stream>>>(s->color, s->depth, s->peer_color, with_depth ? s->peer_depth : nullptr, (int)s->w, (int)s->h,
-                                                                 (int)s->tiles_x, s->tiles_x * s->tiles_y, rank, world, o0);
+                const unsigned cnt = o1 - o0, ctas = s->peer_is_host && cnt > PUSH_HOST_CTAS ? PUSH_HOST_CTAS : cnt;
+                k_push_tiles<<<ctas, 256, 0, RT.copy_stream>>>(s->color, s->depth, s->peer_color, with_depth ? s->peer_depth : nullptr, (int)s->w, (int)s->h,
+                                                              (int)s->tiles_x, s->tiles_x * s->tiles_y, rank, world, o0, cnt);
                 RT.launches++;
             }
             if (!s->push_evt[b]) CK(cudaEventCreateWithFlags(&s->push_evt[b], cudaEventDisableTiming));
@@ -887,8 +889,8 @@ int pfcu_surface_push_tiles(pfcu_surface *s, uint32_t rank, uint32_t world, int 
         return PFCU_OK;
     }
     s->pushed_in_bands = false;
-    k_push_tiles<<<n, 256, 0, LN.stream>>>(s->color, s->depth, s->peer_color, with_depth ? s->peer_depth : nullptr, (int)s->w, (int)s->h,
-                                          (int)s->tiles_x, s->tiles_x * s->tiles_y, rank, world, 0u);
+    k_push_tiles<<<(s->peer_is_host && n > PUSH_HOST_CTAS) ? PUSH_HOST_CTAS : n, 256, 0, LN.stream>>>(s->color, s->depth, s->peer_color, with_depth ? s->peer_depth : nullptr, (int)s->w, (int)s->h,
+                                          (int)s->tiles_x, s->tiles_x * s->tiles_y, rank, world, 0u, n);
     RT.launches++;
     CK(cudaGetLastError());
     mark_done(s);
@@ -1003,7 +1005,44 @@ int pfcu_surface_upload(pfcu_surface *s, const void *hc, const float *hd, uint32
 int pfcu_surface_download_async(pfcu_surface *s, void *hc, float *hd, uint32_t y0, uint32_t rows)
 {
     API_LOCK;
-    if (MULTI_SURF(s)) { const int rc = multi_gather(s, hd != nullptr); if (rc) return rc; }
+    if (MULTI_SURF(s)) {
+        /* A whole-surface read-back of a split surface into page-locked memory that the devices can address: every device
+           stores ITS tiles straight into the caller's buffer (the same kernel that stores them into device 0's surface,
+           band by band behind the rasterisation) - N PCIe links instead of one, no gather.  Anything else: gather the
+           tiles on device 0 first, then copy from there. */
+        void *dc0 = nullptr, *dd0 = nullptr;
+        /* from 4 devices on: with 2, one link still carries the frame faster by DMA behind the gather than two links
+           carry it by stores (measured, 8K: 5.3 vs 5.9 ms); PF_CUDA_DIRECT_PRESENT=0|1 overrides */
+        static const int env_direct = getenv("PF_CUDA_DIRECT_PRESENT") ? atoi(getenv("PF_CUDA_DIRECT_PRESENT")) : -1;
+        bool direct = s->split && s->fmt == PFCU_TEX_RGBA8 && hc && y0 == 0 && rows == s->h && (env_direct < 0 ? mg.n >= 4 : env_direct != 0);
+        if (direct && (cudaHostGetDevicePointer(&dc0, hc, 0) != cudaSuccess || (hd && cudaHostGetDevicePointer(&dd0, hd, 0) != cudaSuccess))) { cudaGetLastError(); direct = false; }
+        if (direct) {
+            int rc = multi_run_all([&](int d) -> int {
+                pfcu_surface *r = s->rep[d];
+                void *dc = nullptr, *dd = nullptr;
+                if (cudaHostGetDevicePointer(&dc, hc, 0) != cudaSuccess || (hd && cudaHostGetDevicePointer(&dd, hd, 0) != cudaSuccess)) { cudaGetLastError(); return (int)PFCU_ERR_CUDA; }
+                r->n_per_read = r->n_since_read; r->n_since_read = 0;
+                uint32_t *const kc = r->peer_color; float *const kd = r->peer_depth;
+                r->peer_color = (uint32_t *)dc; r->peer_depth = (float *)dd; r->peer_is_host = true;
+                const int rc = pfcu_surface_push_tiles(r, (uint32_t)d, (uint32_t)mg.n, hd != nullptr);
+                r->peer_color = kc; r->peer_depth = kd; r->peer_is_host = false;
+                use_lane(r);
+                CK(cudaEventRecord(r->pushed, LN.stream));
+                RT.bytes_d2h += pfcu_surface_owned_bytes(r, (uint32_t)d, (uint32_t)mg.n, hd != nullptr);
+                return rc;
+            });
+            if (rc == PFCU_OK) {
+                use_lane(s);
+                for (int d = 1; d < mg.n; d++) CK(cudaStreamWaitEvent(LN.stream, s->rep[d]->pushed, 0));
+                const bool keep = s->bands_valid;
+                mark_done(s);
+                s->bands_valid = keep;
+                return PFCU_OK;
+            }
+            cudaGetLastError();         /* fall through to the gather */
+        }
+        const int rc = multi_gather(s, hd != nullptr); if (rc) return rc;
+    }
     if (y0 > s->h || rows > s->h - y0) return PFCU_ERR_INVALID;
     use_lane(s);
     const size_t off = (size_t)y0 * s->w, n = (size_t)rows * s->w * 4;

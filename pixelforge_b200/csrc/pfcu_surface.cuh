@@ -71,29 +71,34 @@ __global__ void k_pack_tiles(uint32_t *color, float *depth, int W, int H, int ti
     }
 }
 
-/* owned tiles -> the presenting rank's surface (peer memory), 128 bits per access when the row layout allows */
+/* owned tiles -> the presenting rank's surface (peer memory) or the caller's page-locked buffer (multi-device read-back),
+ * 128 bits per access when the row layout allows.  A CTA takes tiles first_owned + blockIdx.x, + gridDim.x, ... of the
+ * `count` given: one tile per CTA towards a peer over NVLink; a few dozen looping CTAs towards the host - PCIe stores
+ * are slow, and a CTA waiting for them holds an SM slot that the rasterisation of the next band wants. */
 __global__ void __launch_bounds__(256)
 k_push_tiles(const uint32_t *__restrict__ color, const float *__restrict__ depth, uint32_t *__restrict__ peer_color, float *__restrict__ peer_depth,
-             int W, int H, int tilesX, unsigned nTiles, unsigned rank, unsigned world, unsigned first_owned)
+             int W, int H, int tilesX, unsigned nTiles, unsigned rank, unsigned world, unsigned first_owned, unsigned count)
 {
-    const unsigned tile = rank + (first_owned + blockIdx.x) * world;
-    if (tile >= nTiles) return;
-    const int X0 = (tile % tilesX) * TILE, Y0 = (tile / tilesX) * TILE;
-    if ((W & 3) == 0 && X0 + TILE <= W) {
-        for (int k = threadIdx.x; k < TILE * 16; k += 256) {
-            const int r = k >> 4, c4 = (k & 15) << 2;
-            if (Y0 + r >= H) break;
-            const size_t gi = (size_t)(Y0 + r) * W + X0 + c4;
-            __stcs(reinterpret_cast<uint4 *>(peer_color + gi), __ldcs(reinterpret_cast<const uint4 *>(color + gi)));
-            if (peer_depth) __stcs(reinterpret_cast<float4 *>(peer_depth + gi), __ldcs(reinterpret_cast<const float4 *>(depth + gi)));
-        }
-    } else {
-        for (int k = threadIdx.x; k < TILE_PIX; k += 256) {
-            const int x = X0 + (k & (TILE - 1)), y = Y0 + (k >> 6);
-            if (x >= W || y >= H) continue;
-            const size_t gi = (size_t)y * W + x;
-            peer_color[gi] = color[gi];
-            if (peer_depth) peer_depth[gi] = depth[gi];
+    for (unsigned k0 = blockIdx.x; k0 < count; k0 += gridDim.x) {
+        const unsigned tile = rank + (first_owned + k0) * world;
+        if (tile >= nTiles) return;
+        const int X0 = (tile % tilesX) * TILE, Y0 = (tile / tilesX) * TILE;
+        if ((W & 3) == 0 && X0 + TILE <= W) {
+            for (int k = threadIdx.x; k < TILE * 16; k += 256) {
+                const int r = k >> 4, c4 = (k & 15) << 2;
+                if (Y0 + r >= H) break;
+                const size_t gi = (size_t)(Y0 + r) * W + X0 + c4;
+                __stcs(reinterpret_cast<uint4 *>(peer_color + gi), __ldcs(reinterpret_cast<const uint4 *>(color + gi)));
+                if (peer_depth) __stcs(reinterpret_cast<float4 *>(peer_depth + gi), __ldcs(reinterpret_cast<const float4 *>(depth + gi)));
+            }
+        } else {
+            for (int k = threadIdx.x; k < TILE_PIX; k += 256) {
+                const int x = X0 + (k & (TILE - 1)), y = Y0 + (k >> 6);
+                if (x >= W || y >= H) continue;
+                const size_t gi = (size_t)y * W + x;
+                peer_color[gi] = color[gi];
+                if (peer_depth) peer_depth[gi] = depth[gi];
+            }
         }
     }
 }

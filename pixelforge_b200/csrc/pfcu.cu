@@ -45,6 +45,7 @@
 #include <thread>
 #include <condition_variable>
 #include <functional>
+#include <atomic>
 
 /* ------------------------------------------------------------------------------------------------ */
 /* configuration                                                                                    */
@@ -234,8 +235,8 @@ struct Multi {
     Runtime *rt[MAX_DEVS] = { &g_main };
     std::thread th[MAX_DEVS];
     std::mutex m; std::condition_variable cv_job, cv_done;
-    const std::function<int(int)> *job = nullptr; unsigned seq = 0; int pending = 0; int rc[MAX_DEVS] = { 0 };
-    bool quit = false;
+    const std::function<int(int)> *job = nullptr; std::atomic<unsigned> seq{0}; std::atomic<int> pending{0}; int rc[MAX_DEVS] = { 0 };
+    std::atomic<bool> quit{false};
     size_t split_min_pixels = (size_t)1 << 20;
 };
 /* never destroyed: worker threads may still wait on its condition variable when the process exits without pfcu_shutdown */
@@ -244,24 +245,28 @@ static Multi *const mg_ptr = new Multi;
 static thread_local bool t_dispatching = false;     /* this thread is inside multi_run_all: entry points it calls act on one device */
 #define MULTI_HERE() (mg.n > 1 && !t_rt && !t_dispatching)
 
+/* Calls come in bursts (the submissions of a frame): after a job a worker spins for a short while before it goes to
+   sleep on the condition variable, and the dispatching thread spins for the workers likewise - a wake-up through the
+   kernel costs tens of microseconds per call and device, which a 1 ms frame on 8 GPUs would feel. */
+#define MULTI_SPIN_US 200.0
+static double multi_now_us(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
+
 static void multi_worker(int d)
 {
     t_rt = mg.rt[d];
     unsigned seen = 0;
     for (;;) {
-        const std::function<int(int)> *job;
-        {
+        const double t0 = multi_now_us();
+        while (mg.seq.load(std::memory_order_acquire) == seen && !mg.quit.load(std::memory_order_relaxed) && multi_now_us() - t0 < MULTI_SPIN_US) { }
+        if (mg.seq.load(std::memory_order_acquire) == seen && !mg.quit.load()) {
             std::unique_lock<std::mutex> lk(mg.m);
-            mg.cv_job.wait(lk, [&] { return mg.quit || mg.seq != seen; });
-            if (mg.quit) return;
-            seen = mg.seq; job = mg.job;
+            mg.cv_job.wait(lk, [&] { return mg.quit.load() || mg.seq.load() != seen; });
         }
-        const int rc = (*job)(d);
-        {
-            std::lock_guard<std::mutex> lk(mg.m);
-            mg.rc[d] = rc;
-            if (--mg.pending == 0) mg.cv_done.notify_one();
-        }
+        if (mg.quit.load()) return;
+        seen = mg.seq.load(std::memory_order_acquire);
+        const std::function<int(int)> *job = mg.job;
+        mg.rc[d] = (*job)(d);
+        if (mg.pending.fetch_sub(1, std::memory_order_acq_rel) == 1) { std::lock_guard<std::mutex> lk(mg.m); mg.cv_done.notify_one(); }
     }
 }
 
@@ -271,15 +276,19 @@ static int multi_run_all(const std::function<int(int)> &fn)
     if (mg.n <= 1 || t_dispatching) return fn(0);
     {
         std::lock_guard<std::mutex> lk(mg.m);
-        mg.job = &fn; mg.pending = mg.n - 1; mg.seq++;
+        mg.job = &fn; mg.pending.store(mg.n - 1, std::memory_order_relaxed); mg.seq.fetch_add(1, std::memory_order_release);
     }
     mg.cv_job.notify_all();
     t_dispatching = true;
     const int rc0 = fn(0);
     t_dispatching = false;
     {
-        std::unique_lock<std::mutex> lk(mg.m);
-        mg.cv_done.wait(lk, [&] { return mg.pending == 0; });
+        const double t0 = multi_now_us();
+        while (mg.pending.load(std::memory_order_acquire) != 0 && multi_now_us() - t0 < MULTI_SPIN_US) { }
+        if (mg.pending.load(std::memory_order_acquire) != 0) {
+            std::unique_lock<std::mutex> lk(mg.m);
+            mg.cv_done.wait(lk, [&] { return mg.pending.load() == 0; });
+        }
     }
     if (rc0) return rc0;
     for (int d = 1; d < mg.n; d++) if (mg.rc[d]) return mg.rc[d];
@@ -304,10 +313,10 @@ static void multi_stop(void)
 {
     if (mg.n <= 1) return;
     multi_run_all([](int d) -> int { if (d) pfcu_shutdown(); return (int)PFCU_OK; });
-    { std::lock_guard<std::mutex> lk(mg.m); mg.quit = true; }
+    { std::lock_guard<std::mutex> lk(mg.m); mg.quit.store(true); }
     mg.cv_job.notify_all();
     for (int d = 1; d < mg.n; d++) { if (mg.th[d].joinable()) mg.th[d].join(); delete mg.rt[d]; mg.rt[d] = nullptr; }
-    mg.n = 1; mg.quit = false;
+    mg.n = 1; mg.quit.store(false);
 }
 /* Every locked entry point also makes the runtime's device current on the calling thread: the C-ABI is shared by
  * contexts on several host threads, and a thread that has not called pfcu_init starts with device 0 current

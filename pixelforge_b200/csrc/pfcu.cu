@@ -379,8 +379,7 @@ static cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 /* the single-program instantiations of the big-triangle rasteriser, full tiles and half-height slices */
 template <int PROG> static cudaError_t launch_fixed(int slices, unsigned grid, cudaStream_t st, const RasterParams &p)
 {
-    return slices == 4 ? launch_dep(k_raster<false, 8, PROG, 16>, dim3(grid * 4), dim3(256), (size_t)0, st, p)
-         : slices == 2 ? launch_dep(k_raster<false, 8, PROG, 32>, dim3(grid * 2), dim3(256), (size_t)0, st, p)
+    return slices == 2 ? launch_dep(k_raster<false, 8, PROG, 32>, dim3(grid * 2), dim3(256), (size_t)0, st, p)
                        : launch_dep(k_raster<false, 8, PROG, 64>, dim3(grid), dim3(256), (size_t)0, st, p);
 }
 
@@ -1140,6 +1139,14 @@ int pfcu_surface_clear_ref(pfcu_surface *s, int dc, uint32_t rgba, int dd, float
     use_lane(s);
     if (s->fmt >= PFCU_TEX_RGB8) rgba |= 0xff000000u;
     const unsigned size = s->w * s->h, aligned = size - (size % 8u);
+    if (s->world > 1 && aligned == size && s->fmt == PFCU_TEX_RGBA8) {
+        /* tile split: only the tiles this rank rasterises (an eighth of an 8K clear instead of all of it on every GPU) */
+        const uint32_t n = owned_tiles(s, s->rank, s->world);
+        if (n) { k_clear_tiles<<<n, 256, 0, LN.stream>>>(s->color, s->depth, (int)s->w, (int)s->h, (int)s->tiles_x, s->tiles_x * s->tiles_y, s->rank, s->world, dc, rgba, dd, z); RT.launches++; }
+        CK(cudaGetLastError());
+        mark_done(s);
+        return PFCU_OK;
+    }
     if (aligned > 8) { int rc = fill_range(s, 8, aligned - 8, dc, rgba, dd, z); if (rc) return rc; }
     if (aligned < size) { k_clear_tail<<<1, 32, 0, LN.stream>>>(s->color, s->depth, aligned, size, dc, dd); RT.launches++; }
     CK(cudaGetLastError());
@@ -1628,11 +1635,12 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         /* slices per tile: 64x64, 64x32 or 64x16 - whichever leaves the least of the last wave empty (a tile-split surface
            on 8 GPUs: 1020 tiles = 1.7 waves of 64x64 CTAs, 6.9 waves of 64x16 slices) */
         int slices = 1;
-        if (!small_tris && !ph && waves < 8.0 && (ceil(waves) / waves) > 1.06) {
-            const double loss1 = ceil(waves) / waves, loss2 = ceil(2 * waves) / (2 * waves), loss4 = ceil(4 * waves) / (4 * waves);
-            if (loss2 < loss1) slices = 2;
-            if (loss4 < 0.97 * (slices == 2 ? loss2 : loss1)) slices = 4;
-        }
+        if (!small_tris && !ph && waves < 8.0 && (ceil(waves) / waves) > 1.06 && (ceil(2 * waves) / (2 * waves)) < (ceil(waves) / waves)) slices = 2;
+        /* 64x16 slices were tried for the 1.7-wave grids of an 8-GPU split: the per-slice cost (every warp pays each
+           triangle's prologue for four block rows instead of sixteen) is +17 % against +4 % for 64x32, more than the
+           emptier last wave costs (measured on one rank's share of the 8K scene: 1.274 / 1.250 / 1.351 ms) */
+        static const int env_slices = getenv("PF_CUDA_SLICES") ? atoi(getenv("PF_CUDA_SLICES")) : 0;       /* 1 or 2: experiments */
+        if (env_slices == 1 || env_slices == 2) slices = (small_tris || ph) ? 1 : env_slices;
         const bool half = slices == 2;
         if (use_frag) {
             /* 64x8 slices of eight 8x8 regions, 8 warps; 4 CTAs per SM (Phong: 3, 80 registers) */
@@ -1662,7 +1670,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
             default: snprintf(RT.err, sizeof RT.err, "internal: no kernel for state program %d", single_prog); return PFCU_ERR_INVALID;
             }
         }
-        else { if (half || slices == 4) CK(launch_dep(k_raster<false, 8, -1, 32>, dim3(grid * 2), dim3(256), (size_t)(0), st_, p)); else CK(launch_dep(k_raster<false, 8, -1, 64>, dim3(grid), dim3(256), (size_t)(0), st_, p)); }
+        else { if (half) CK(launch_dep(k_raster<false, 8, -1, 32>, dim3(grid * 2), dim3(256), (size_t)(0), st_, p)); else CK(launch_dep(k_raster<false, 8, -1, 64>, dim3(grid), dim3(256), (size_t)(0), st_, p)); }
         RT.launches++;
         return PFCU_OK;
     };

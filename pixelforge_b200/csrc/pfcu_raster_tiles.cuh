@@ -133,6 +133,9 @@ __device__ __forceinline__ float rcp_fast(unsigned tab_addr, int shift, float x)
 /* ------------------------------------------------------------------------------------------------ */
 
 #define RCP_SMEM_BITS 11
+#ifndef FILTER_REFINE
+#define FILTER_REFINE 0      /* per-warp edge-function test in the queue filter: measured, costs 1 % on the 4K / 8K scenes and gains nothing (the per-row vote in shade_tri already rejects cheaply) */
+#endif
 
 struct TileCtx {
     int X0, Y0, X1, Y1;                 /* tile rectangle on the surface, inclusive               */
@@ -405,11 +408,31 @@ k_raster(const RasterParams p)
                     /* which warps own an 8x4 block inside the clipped bbox?  (see shade_tri) */
                     const int bx0 = (rx0 - X0) >> 3, nbx = ((rx1 - X0) >> 3) - bx0 + 1;
                     const int by0 = (ry0 - Y0) >> 2, nby = ((ry1 - Y0) >> 2) - by0 + 1;
-                    const unsigned run = nbx >= 8 ? 0xffu : ((1u << nbx) - 1u);
-                    for (int j = 0; j < min(nby, 8); j++) {
-                        const int sh = (bx0 + 3 * (by0 + j)) & 7;
-                        const unsigned bits = ((run << sh) | (run >> (8 - sh))) & 0xffu;
-                        wmask |= (NW == 16 && ((by0 + j) & 1)) ? (bits << 8) : bits;
+                    if (FILTER_REFINE && hit && (s.flags & TF_SAFE) && nbx * nby >= 4) {
+                        /* a triangle of many blocks: test every block of the clipped bbox with the edge functions (their
+                           maxima over the block's part of the bbox, as for the whole tile above) and list only the warps
+                           that own a block the triangle can cover - a warp otherwise pays the triangle's whole prologue
+                           to find out that, say, the other half of a screen-filling quad is not its business */
+                        const int sx1 = s.w1X > 0, sx2 = s.w2X > 0, sx3 = s.w3X > 0, sy1 = s.w1Y > 0, sy2 = s.w2Y > 0, sy3 = s.w3Y > 0;
+                        for (int r = by0; r < by0 + nby; r++) {
+                            const int ay0 = max(Y0 + (r << 2), ry0) - b.y, ay1 = min(Y0 + (r << 2) + 3, ry1) - b.y;
+                            const int r1 = s.w1R + (sy1 ? ay1 : ay0) * s.w1Y, r2 = s.w2R + (sy2 ? ay1 : ay0) * s.w2Y, r3 = s.w3R + (sy3 ? ay1 : ay0) * s.w3Y;
+                            unsigned bits = 0;
+                            for (int c = bx0; c < bx0 + nbx; c++) {
+                                const int ax0 = max(X0 + (c << 3), rx0) - b.x, ax1 = min(X0 + (c << 3) + 7, rx1) - b.x;
+                                const int m1 = r1 + (sx1 ? ax1 : ax0) * s.w1X, m2 = r2 + (sx2 ? ax1 : ax0) * s.w2X, m3 = r3 + (sx3 ? ax1 : ax0) * s.w3X;
+                                if ((m1 | m2 | m3) >= 0) bits |= 1u << ((c + 3 * r) & 7);
+                            }
+                            wmask |= (NW == 16 && (r & 1)) ? (bits << 8) : bits;
+                        }
+                        if (!wmask) hit = false;
+                    } else {
+                        const unsigned run = nbx >= 8 ? 0xffu : ((1u << nbx) - 1u);
+                        for (int j = 0; j < min(nby, 8); j++) {
+                            const int sh = (bx0 + 3 * (by0 + j)) & 7;
+                            const unsigned bits = ((run << sh) | (run >> (8 - sh))) & 0xffu;
+                            wmask |= (NW == 16 && ((by0 + j) & 1)) ? (bits << 8) : bits;
+                        }
                     }
                 }
             }

@@ -33,6 +33,36 @@ __global__ void k_clear_tail(uint32_t *color, float *depth, unsigned aligned, un
     if (i < size) { if (do_color) color[i] = color[0]; if (do_depth) depth[i] = depth[0]; }
 }
 
+/* pfClear of a tile-split surface: a rank clears only the tiles it rasterises (the others are never read on this device).
+ * Same rule as the whole-surface form for surfaces whose size is a multiple of 8 pixels: pixels 0..7 keep their value. */
+__global__ void __launch_bounds__(256)
+k_clear_tiles(uint32_t *__restrict__ color, float *__restrict__ depth, int W, int H, int tilesX, unsigned nTiles, unsigned rank, unsigned world,
+              int do_color, uint32_t rgba, int do_depth, float z)
+{
+    const unsigned tile = rank + blockIdx.x * world;
+    if (tile >= nTiles) return;
+    const int X0 = (tile % tilesX) * TILE, Y0 = (tile / tilesX) * TILE;
+    if ((W & 3) == 0 && X0 + TILE <= W && tile != 0) {
+        const uint4 cv = make_uint4(rgba, rgba, rgba, rgba); const float4 dv = make_float4(z, z, z, z);
+        for (int k = threadIdx.x; k < TILE * 16; k += 256) {
+            const int r = k >> 4, c4 = (k & 15) << 2;
+            if (Y0 + r >= H) break;
+            const size_t gi = (size_t)(Y0 + r) * W + X0 + c4;
+            if (do_color) *reinterpret_cast<uint4 *>(color + gi) = cv;
+            if (do_depth) *reinterpret_cast<float4 *>(depth + gi) = dv;
+        }
+    } else {
+        for (int k = threadIdx.x; k < TILE_PIX; k += 256) {
+            const int x = X0 + (k & (TILE - 1)), y = Y0 + (k >> 6);
+            if (x >= W || y >= H) continue;
+            const size_t gi = (size_t)y * W + x;
+            if (gi < 8) continue;
+            if (do_color) color[gi] = rgba;
+            if (do_depth) depth[gi] = z;
+        }
+    }
+}
+
 /* Layout conversion between the caller's colour format (staging, 3 or 4 bytes per pixel) and the canonical RGBA8 the
  * device works in: to_native = 0: staging -> canonical (upload), 1: canonical -> staging (download).  The scalar
  * getters / setters of the reference (pixel.h:233-360,576-710): BGRA8 swaps R and B, RGB8 / BGR8 drop alpha and read it

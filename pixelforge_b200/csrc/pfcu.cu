@@ -61,7 +61,7 @@
 #define BIN_SHIFT_FINE   6
 #define RASTER_THREADS 256
 #define QUEUE_CAP   1024            /* triangle indices buffered per tile between raster passes      */
-#define SETUP_THREADS 256
+#define SETUP_THREADS 128
 #define BIN_BATCH   1024            /* triangles per binning CTA (256 for mid-sized batches, see launch_pipeline) */
 #define MAX_BINS    10240           /* bin counters live in dynamic shared memory: 40 KB + the 8 KB of static rectangles of k_bin_fill = the 48 KB
                                        a kernel gets without opting in; 7680x4320 in 64 px bins = 8160.  Larger surfaces take coarser bins. */
@@ -209,7 +209,7 @@ struct Runtime {
     unsigned char *d_jobs = nullptr, *h_jobs = nullptr; size_t cap_jobs = 0; cudaEvent_t jobs_copied = nullptr, jobs_done = nullptr; unsigned jobs_seq = 0;
     cudaStream_t band_streams[MAX_BANDS] = { nullptr, nullptr, nullptr, nullptr }; cudaStream_t copy_stream = nullptr;
     cudaEvent_t front_evt = nullptr;
-    bool frag_attr_set = false;
+    bool frag_attr_set = false, setup_attr_set = false;
     std::recursive_mutex mu;                    /* the C-ABI is serialised: contexts on several threads share one runtime */
     char err[512] = { 0 };
 };
@@ -1580,7 +1580,9 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
             list_total_wanted = true;
         }
         /* the kernels of the batch back to back, each a programmatic dependent of the one before */
-        CK(launch_dep(k_setup, dim3((n + SETUP_THREADS - 1) / SETUP_THREADS), dim3(SETUP_THREADS), 0, LN.stream,
+        if (!RT.setup_attr_set) { cudaFuncSetAttribute(k_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, SETUP_SMEM_BYTES); RT.setup_attr_set = true; }
+        const unsigned setup_chunks = (n + SETUP_THREADS - 1) / SETUP_THREADS, setup_ctas = setup_chunks < (unsigned)RT.sms * 3u ? setup_chunks : (unsigned)RT.sms * 3u;
+        CK(launch_dep(k_setup, dim3(setup_ctas), dim3(SETUP_THREADS), (size_t)SETUP_SMEM_BYTES, LN.stream,
                       d_tris, d_states, n, (int)s->w, (int)s->h, LN.d_bbox, LN.d_setup, LN.d_data, setup_counters()));
         RT.launches += 1;
         if (!rows_path) {

@@ -101,31 +101,95 @@ __device__ __forceinline__ int4 setup_one(const pfcu_triangle *t /* global or sh
     return out_box;
 }
 
+/* ---- bulk asynchronous copies (the TMA unit's 1-D form: cp.async.bulk + mbarrier, SASS UBLKCP) ------------------ */
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gdst, const void *smem_src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+
+/* k_setup: HBM-bound (152 B in, 224 B out per triangle).  A persistent CTA walks chunks of SETUP_THREADS triangles with
+ * the input double-buffered: one elected thread has the TMA unit fetch the NEXT chunk (cp.async.bulk, completion on an
+ * mbarrier) while the CTA computes the current one into shared staging, and the three output arrays leave as bulk stores
+ * as well - whole 128-byte lines in both directions, a handful of instructions per chunk instead of a load loop and
+ * strided 16-byte stores per thread (round 2: 94 -> see profiles/ us on the 1 M-triangle mesh). */
+#define SETUP_SMEM_BYTES (2 * SETUP_THREADS * (int)sizeof(pfcu_triangle) + SETUP_THREADS * (16 + (int)sizeof(TriSetup) + (int)sizeof(TriData)) + 32)
 __global__ void __launch_bounds__(SETUP_THREADS)
 k_setup(const pfcu_triangle *__restrict__ tris, const DevState *__restrict__ states, unsigned n,
         int surfW, int surfH, int4 *__restrict__ bbox, TriSetup *__restrict__ setup, TriData *__restrict__ data,
         unsigned long long *__restrict__ counters)
 {
-    /* the 152-byte input records are read with 128-bit coalesced loads into shared memory (a thread reading its own
-       record field by field touches 32 different sectors per load instruction) */
-    __shared__ __align__(16) unsigned char s_in[SETUP_THREADS * sizeof(pfcu_triangle)];
-    static_assert((SETUP_THREADS * sizeof(pfcu_triangle)) % 16 == 0, "whole uint4s per CTA");
-    pdl_trigger(); pdl_wait();
-    const unsigned base = blockIdx.x * SETUP_THREADS;
-    const unsigned here = min((unsigned)SETUP_THREADS, n - base);
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(tris) + (size_t)base * sizeof(pfcu_triangle));
-        const unsigned bytes = here * (unsigned)sizeof(pfcu_triangle), n16 = bytes / 16u;      /* 152 bytes: a multiple of 8, not of 16 */
-        for (unsigned k = threadIdx.x; k < n16; k += SETUP_THREADS) reinterpret_cast<uint4 *>(s_in)[k] = __ldcs(src + k);
-        if ((bytes & 15u) && threadIdx.x == 0)
-            reinterpret_cast<uint2 *>(s_in)[2 * n16] = __ldcs(reinterpret_cast<const uint2 *>(src) + 2 * n16);
-    }
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    constexpr unsigned CHUNK_IN = SETUP_THREADS * (unsigned)sizeof(pfcu_triangle);
+    static_assert(CHUNK_IN % 128 == 0 && sizeof(TriSetup) % 16 == 0 && sizeof(TriData) % 16 == 0, "bulk copies move multiples of 16 bytes");
+    unsigned char *s_in = s_dyn;                                                            /* [2][CHUNK_IN] */
+    int4 *s_bbox = reinterpret_cast<int4 *>(s_dyn + 2 * CHUNK_IN);
+    TriSetup *s_setup = reinterpret_cast<TriSetup *>(s_bbox + SETUP_THREADS);
+    TriData *s_data = reinterpret_cast<TriData *>(s_setup + SETUP_THREADS);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(s_data + SETUP_THREADS);  /* [2] */
+    const unsigned tid = threadIdx.x;
+    const unsigned nChunks = (n + SETUP_THREADS - 1) / SETUP_THREADS;
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
-    const unsigned i = base + threadIdx.x;
-    bool valid = false;
-    if (i < n) setup_one(reinterpret_cast<const pfcu_triangle *>(s_in) + threadIdx.x, states, i, surfW, surfH, bbox, setup, data, &valid);
-    const unsigned b = __ballot_sync(0xffffffffu, valid);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(counters + 0, (unsigned long long)__popc(b));
+    pdl_trigger(); pdl_wait();
+    auto issue = [&](unsigned c, unsigned buf) {          /* thread 0: fetch chunk c into buffer buf */
+        const unsigned here = min((unsigned)SETUP_THREADS, n - c * SETUP_THREADS);
+        const unsigned bytes = (here * (unsigned)sizeof(pfcu_triangle)) & ~15u;             /* 152 bytes: a multiple of 8, not of 16 */
+        mbar_expect_tx(&bar[buf], bytes);
+        bulk_load(s_in + buf * CHUNK_IN, reinterpret_cast<const unsigned char *>(tris) + (size_t)c * CHUNK_IN, bytes, &bar[buf]);
+    };
+    unsigned c = blockIdx.x;
+    if (tid == 0 && c < nChunks) issue(c, 0);
+    unsigned counted = 0;
+    for (unsigned it = 0; c < nChunks; c += gridDim.x, it++) {
+        const unsigned buf = it & 1u, base = c * SETUP_THREADS;
+        const unsigned here = min((unsigned)SETUP_THREADS, n - base);
+        if (tid == 0) {
+            if (c + gridDim.x < nChunks) issue(c + gridDim.x, buf ^ 1u);        /* the other buffer was consumed an iteration ago */
+            if (it) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      /* the last chunk's stores have read the staging */
+        }
+        mbar_wait(&bar[buf], (it >> 1) & 1u);
+        const pfcu_triangle *in = reinterpret_cast<const pfcu_triangle *>(s_in + buf * CHUNK_IN);
+        if (tid == here - 1u && ((here * (unsigned)sizeof(pfcu_triangle)) & 15u))       /* the odd 8 bytes end the last record: its owner fetches them */
+            reinterpret_cast<uint2 *>(s_in + buf * CHUNK_IN)[here * 19u - 1u] =
+                __ldcs(reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(tris) + (size_t)c * CHUNK_IN) + (here * 19u - 1u));
+        __syncthreads();                                                        /* staging is free (thread 0 waited for the stores above) */
+        bool valid = false;
+        if (tid < here) setup_one(in + tid, states, tid, surfW, surfH, s_bbox, s_setup, s_data, &valid);
+        const unsigned b = __ballot_sync(0xffffffffu, valid);
+        if ((tid & 31u) == 0u) counted += __popc(b);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            /* generic-proxy writes -> the bulk stores' reads */
+        __syncthreads();
+        if (tid == 0) {
+            bulk_store(bbox + base, s_bbox, here * 16u);
+            bulk_store(setup + base, s_setup, here * (unsigned)sizeof(TriSetup));
+            bulk_store(data + base, s_data, here * (unsigned)sizeof(TriData));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     /* shared memory must outlive the stores */
+    if ((tid & 31u) == 0u && counted) atomicAdd(counters + 0, (unsigned long long)counted);
 }
 
 /* ------------------------------------------------------------------------------------------------ */

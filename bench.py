@@ -452,7 +452,7 @@ def ours_main(args):
     traffic = None; issue_active = None
     try:    # dram__bytes_read+write of the raster kernel per launch (and its issue utilisation: the north star's
             # evidence for setup/issue-bound scenes), from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tj = json.load(f).get(wl_name, {})
             traffic = tj.get("traffic_bytes_per_launch"); issue_active = tj.get("sm_issue_active_pct")
     except Exception:

@@ -18,7 +18,7 @@ NVCC_FLAGS  = -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false 
 HOST_SRC = pixelforge_b200/csrc/host/pf_context.c pixelforge_b200/csrc/host/pf_pipeline.c \
            pixelforge_b200/csrc/host/pf_objects.c pixelforge_b200/csrc/host/pf_x86approx.c
 HOST_HDR = include/pixelforge.h include/pfcu.h include/pfx.h pixelforge_b200/csrc/host/pf_internal.h pixelforge_b200/csrc/host/pf_math.h \
-           pixelforge_b200/csrc/pf_vstage.h pixelforge_b200/csrc/pf_prims.h
+           pixelforge_b200/csrc/pf_vstage.h pixelforge_b200/csrc/pf_prims.h pixelforge_b200/csrc/pf_pixfmt.h
 HOST_OBJ = $(patsubst pixelforge_b200/csrc/host/%.c,build/host/%.o,$(HOST_SRC))
 SCENES   = pixelforge_b200/scenes/scenes.c
 LIBDIR   = pixelforge_b200/lib
@@ -37,7 +37,7 @@ build/host/%.o: pixelforge_b200/csrc/host/%.c $(HOST_HDR)
 	@mkdir -p build/host
 	$(CC) $(HOST_CFLAGS) -c $< -o $@
 
-build/pfcu.o: pixelforge_b200/csrc/pfcu.cu $(wildcard pixelforge_b200/csrc/*.cuh) include/pfcu.h pixelforge_b200/csrc/pf_vstage.h pixelforge_b200/csrc/pf_prims.h
+build/pfcu.o: pixelforge_b200/csrc/pfcu.cu $(wildcard pixelforge_b200/csrc/*.cuh) include/pfcu.h pixelforge_b200/csrc/pf_vstage.h pixelforge_b200/csrc/pf_prims.h pixelforge_b200/csrc/pf_pixfmt.h
 	@mkdir -p build
 	$(NVCC) $(NVCC_FLAGS) $(NVCC_EXTRA) -Xptxas -v -c $< -o $@ 2> build/pfcu.ptxas.log || (cat build/pfcu.ptxas.log; false)
 
@@ -49,7 +49,7 @@ $(LIBDIR)/libpfscenes_cuda.so: $(SCENES) $(LIBDIR)/libpixelforge.so include/pixe
 	$(CC) -std=gnu99 -O2 -fPIC -shared -Iinclude -DPFSCENE_HAVE_PFX -o $@ $(SCENES) -L$(LIBDIR) -lpixelforge -lm \
 	    -Wl,-rpath,'$$ORIGIN'
 
-build/pfcu_oracle.o: oracle/pfcu_oracle.c include/pfcu.h pixelforge_b200/csrc/pf_vstage.h pixelforge_b200/csrc/pf_prims.h
+build/pfcu_oracle.o: oracle/pfcu_oracle.c include/pfcu.h pixelforge_b200/csrc/pf_vstage.h pixelforge_b200/csrc/pf_prims.h pixelforge_b200/csrc/pf_pixfmt.h
 	@mkdir -p build
 	$(CC) -std=gnu99 -O2 -fPIC -ffp-contract=off -fno-fast-math -msse4.1 -Iinclude -c $< -o $@
 

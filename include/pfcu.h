@@ -249,7 +249,10 @@ PFCU_API int pfcu_surface_fog(pfcu_surface *s, const pfcu_fog *fog);
  * [xmin, xmax] x [ymin, ymax] (already clamped to the viewport), source texel ((PFsizei)(v * (height - 1))) * width +
  * (PFsizei)(u * (width - 1)) with u = (x - xs) * inv_xlen, v = (y - ys) * inv_ylen; depth test against the constant
  * `z` with the scalar table (depth.h:28-78; NOTEQUAL really is "not equal" there), z written where it passes, colour
- * through the scalar blend table (blend.h:29-130).  `format` is a PFCU_TEX_* code. */
+ * through the scalar blend table (blend.h:29-130).  `format` is PFCU_PIX(PFpixelformat, PFdatatype): any of the 38 pairs the
+ * reference has a getter for (pixel.h:764-812); 8-bit, 5-6-5 / 5-5-5-1 / 4-4-4-4, half and float components, single
+ * channels and luminance (pf_pixfmt.h restates the getters and setters). */
+#define PFCU_PIX(format, type) ((int)(format) * 16 + (int)(type))
 typedef struct {
     const void *pixels; uint32_t width, height; int format;
     int32_t  xs, ys;                /* the raster position on the screen                                         */
@@ -262,7 +265,7 @@ typedef struct {
 PFCU_API int pfcu_surface_draw_pixels(pfcu_surface *s, const pfcu_pixels *d);
 
 /* pfReadPixels (context.c:2349-2395): the surface's pixels [x0, x0+cols) x [y0, y0+rows) converted to `format`
- * (PFCU_TEX_*) on the device and copied to host_pixels, pixel (x, y) at index (y - y0) * dst_width + (x - x0); nothing
+ * (PFCU_PIX(format, type), any pair the reference has a setter for) on the device and copied to host_pixels, pixel (x, y) at index (y - y0) * dst_width + (x - x0); nothing
  * else of the destination is touched.  Returns after the data is on the host. */
 PFCU_API int pfcu_surface_read_pixels(pfcu_surface *s, uint32_t x0, uint32_t y0, uint32_t cols, uint32_t rows,
                                       uint32_t dst_width, int format, void *host_pixels);

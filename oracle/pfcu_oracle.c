@@ -784,6 +784,7 @@ int pfcu_list_job_supported(const pfcu_surface *s, uint32_t n, uint32_t k) { (vo
 int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n) { (void)jobs; (void)n; return PFCU_ERR_INVALID; }
 /* points and lines: the reference's scalar loops (lines.c:283-530, points.c:85-183), one primitive after the other */
 #include "../pixelforge_b200/csrc/pf_prims.h"
+#include "../pixelforge_b200/csrc/pf_pixfmt.h"
 static void prim_pixel(pfcu_surface *s, const pfcu_prim *p, uint32_t off, float z, uint32_t color, int test)
 {
     if (off >= s->w * s->h) return;                     /* the reference would write outside its buffer */
@@ -876,7 +877,7 @@ int pfcu_surface_draw_pixels(pfcu_surface *s, const pfcu_pixels *d)
             if (!(d->flags & PFCU_ST_DEPTH_TEST) || pfp_depth(d->depth_func, d->z, s->depth[o])) {
                 const float u = (float)(x - d->xs) * d->inv_xlen;
                 const uint32_t so = ysrc + (uint32_t)(u * wm1);
-                const uint32_t c = so < d->width * d->height ? native_get(d->pixels, so, d->format) : 0u;
+                const uint32_t c = so < d->width * d->height ? pfx_get(d->pixels, so, d->format) : 0u;
                 s->depth[o] = d->z;
                 s->color[o] = ((d->flags & PFCU_ST_BLEND) ? pfp_blend(d->blend_mode, c, s->color[o]) : c) | keep;
             }
@@ -890,7 +891,7 @@ int pfcu_surface_read_pixels(pfcu_surface *s, uint32_t x0, uint32_t y0, uint32_t
     if (x0 >= s->w || y0 >= s->h || cols > s->w - x0 || rows > s->h - y0 || cols > dst_width) return PFCU_ERR_INVALID;
     for (uint32_t y = 0; y < rows; y++)
         for (uint32_t x = 0; x < cols; x++)
-            native_set(host_pixels, (size_t)y * dst_width + x, format, s->color[(size_t)(y0 + y) * s->w + x0 + x]);
+            pfx_set(host_pixels, (size_t)y * dst_width + x, format, s->color[(size_t)(y0 + y) * s->w + x0 + x]);
     return PFCU_OK;
 }
 unsigned pfcu_capabilities(void) { return 0u; }     /* the oracle has no device vertex stage: the front end keeps it on the host */

@@ -9,6 +9,7 @@
 #include "pf_internal.h"
 #include "pf_math.h"
 #include "pfx.h"
+#include "../pf_pixfmt.h"
 
 #include <float.h>
 #include <math.h>
@@ -833,12 +834,12 @@ void pfDrawPixels(PFsizei width, PFsizei height, PFpixelformat format, PFdatatyp
 {
     CTX;
     if (width == 0 || height == 0) { c->errCode = PF_INVALID_VALUE; return; }
-    if (format > PF_BGRA || type > PF_DOUBLE || pfh_tex_format_code(format, type) < 0) { c->errCode = PF_INVALID_ENUM; return; }
+    if (format > PF_BGRA || type > PF_DOUBLE || pfx_bytes(PFCU_PIX(format, type)) == 0) { c->errCode = PF_INVALID_ENUM; return; }
     pfh_update_matrices(c, 0);
     PFfloat rp[4]; memcpy(rp, c->rasterPos, 16);
     v4_transform(rp, rp, c->matMVP);
     pfcu_pixels d; memset(&d, 0, sizeof d);
-    d.pixels = pixels; d.width = width; d.height = height; d.format = pfh_tex_format_code(format, type);
+    d.pixels = pixels; d.width = width; d.height = height; d.format = PFCU_PIX(format, type);
     d.xs = (PFint)(c->vpPos[0] + (rp[0] + 1.0f) * 0.5f * c->vpDim[0]);
     d.ys = (PFint)(c->vpPos[1] + (1.0f - rp[1]) * 0.5f * c->vpDim[1]);
     d.z = rp[2];
@@ -986,7 +987,7 @@ void pfFogProcess(void)
 void pfReadPixels(PFint x, PFint y, PFsizei width, PFsizei height, PFpixelformat format, PFdatatype type, void *pixels)
 {
     CTX;
-    if (format > PF_BGRA || type > PF_DOUBLE || pfh_tex_format_code(format, type) < 0) { c->errCode = PF_INVALID_ENUM; return; }
+    if (format > PF_BGRA || type > PF_DOUBLE || pfx_bytes(PFCU_PIX(format, type)) == 0) { c->errCode = PF_INVALID_ENUM; return; }
     pf_surf *s = surface_op_begin(c);
     PFint W = (PFint)s->tex->w, H = (PFint)s->tex->h;
     PFsizei xMin = (PFsizei)PF_CLAMP(x, 0, W - 1), yMin = (PFsizei)PF_CLAMP(y, 0, H - 1);
@@ -995,7 +996,7 @@ void pfReadPixels(PFint x, PFint y, PFsizei width, PFsizei height, PFpixelformat
     /* destination index (ySrc - yMin) * width + (xSrc - xMin) (context.c:2383-2386); a region wider than `width`
        (x < 0 moves xMin to 0) would make rows overlap upstream - the columns past `width` are dropped here */
     PFsizei cols = xMax - xMin; if (cols > width) cols = width;
-    int rc = pfcu_surface_read_pixels(s->dev, xMin, yMin, cols, yMax - yMin, width, pfh_tex_format_code(format, type), pixels);
+    int rc = pfcu_surface_read_pixels(s->dev, xMin, yMin, cols, yMax - yMin, width, PFCU_PIX(format, type), pixels);
     if (rc != PFCU_OK) { fprintf(stderr, "pixelforge-b200: pfReadPixels failed (%d): %s\n", rc, pfcu_last_error()); c->errCode = PF_INVALID_OPERATION; }
 }
 

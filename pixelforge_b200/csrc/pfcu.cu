@@ -31,6 +31,7 @@
 #include "pfcu.h"
 #include "pf_vstage.h"
 #include "pf_prims.h"
+#include "pf_pixfmt.h"
 
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -1205,12 +1206,12 @@ int pfcu_surface_draw_pixels(pfcu_surface *s, const pfcu_pixels *d)
 {
     API_LOCK;
     if (!RT.ok) return PFCU_ERR_NO_DEVICE;
-    if (!s || !d || !d->pixels || d->width == 0 || d->height == 0 || d->format < PFCU_TEX_RGBA8 || d->format > PFCU_TEX_BGR8) return PFCU_ERR_INVALID;
+    if (!s || !d || !d->pixels || d->width == 0 || d->height == 0 || pfx_bytes(d->format) == 0) return PFCU_ERR_INVALID;
     if (d->xmax < d->xmin || d->ymax < d->ymin) return PFCU_OK;
     if (MULTI_SURF(s)) return multi_surface_op(s, [&](int, pfcu_surface *r) -> int { return pfcu_surface_draw_pixels(r, d); });
     use_lane(s);
     int rc;
-    const size_t bytes = (size_t)d->width * d->height * fmt_bytes(d->format);
+    const size_t bytes = (size_t)d->width * d->height * (size_t)pfx_bytes(d->format);
     if ((rc = grow(&LN.d_varrays, &LN.cap_varrays, bytes + 16))) return rc;
     CK(cudaMemcpyAsync(LN.d_varrays, d->pixels, bytes, cudaMemcpyHostToDevice, LN.stream));
     /* the caller may reuse its image as soon as pfDrawPixels returns: page-locked sources are still being read */
@@ -1236,13 +1237,13 @@ int pfcu_surface_read_pixels(pfcu_surface *s, uint32_t x0, uint32_t y0, uint32_t
 {
     API_LOCK;
     if (!RT.ok) return PFCU_ERR_NO_DEVICE;
-    if (!s || !host_pixels || format < PFCU_TEX_RGBA8 || format > PFCU_TEX_BGR8) return PFCU_ERR_INVALID;
+    if (!s || !host_pixels || pfx_bytes(format) == 0) return PFCU_ERR_INVALID;
     if (cols == 0 || rows == 0) return PFCU_OK;
     if (x0 >= s->w || y0 >= s->h || cols > s->w - x0 || rows > s->h - y0 || cols > dst_width) return PFCU_ERR_INVALID;
     if (MULTI_SURF(s)) { const int rc = multi_gather(s, 0); if (rc) return rc; }
     use_lane(s);
     int rc;
-    const size_t bpp = fmt_bytes(format), n = (size_t)cols * rows;
+    const size_t bpp = (size_t)pfx_bytes(format), n = (size_t)cols * rows;
     if ((rc = grow(&LN.d_varrays, &LN.cap_varrays, n * bpp + 16))) return rc;
     const unsigned blocks = (unsigned)((n + 255) / 256 < (size_t)RT.sms * 8 ? (n + 255) / 256 : (size_t)RT.sms * 8);
     k_read_pixels<<<blocks, 256, 0, LN.stream>>>(s->color, s->w, x0, y0, cols, rows, format, LN.d_varrays);

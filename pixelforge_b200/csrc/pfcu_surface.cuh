@@ -188,16 +188,7 @@ k_fog(uint32_t *__restrict__ color, const float *__restrict__ depth, size_t npix
     }
 }
 
-/* one source texel in the caller's 8-bit layout -> PFcolor dword (scalar getters, pixel.h:576-588,2604-2632) */
-__device__ __forceinline__ uint32_t pix_get(const unsigned char *__restrict__ px, size_t i, int fmt)
-{
-    if (fmt == PFCU_TEX_RGBA8) return reinterpret_cast<const uint32_t *>(px)[i];
-    if (fmt == PFCU_TEX_BGRA8) return __byte_perm(reinterpret_cast<const uint32_t *>(px)[i], 0, 0x3012);
-    const unsigned char *q = px + 3 * i;
-    const int r = fmt == PFCU_TEX_RGB8 ? 0 : 2;
-    return (uint32_t)q[r] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2 - r] << 16) | 0xff000000u;
-}
-
+/* source texels / destination pixels of pfDrawPixels / pfReadPixels: any (format, type) pair of the reference, pf_pixfmt.h */
 struct PixArgs {
     const unsigned char *src; uint32_t sw, sh; int fmt;
     int xs, ys, xmin, ymin; uint32_t cols, rows;
@@ -211,7 +202,7 @@ __device__ __forceinline__ void draw_pixel(uint32_t *__restrict__ color, float *
     if (!(a.flags & PFCU_ST_DEPTH_TEST) || pfp_depth((int)a.depth_func, a.z, depth[o])) {
         const float v = __fmul_rn(__int2float_rn(y - a.ys), a.inv_ylen), u = __fmul_rn(__int2float_rn(x - a.xs), a.inv_xlen);
         const uint32_t so = f2u_x86(__fmul_rn(v, __uint2float_rn(a.sh - 1u))) * a.sw + f2u_x86(__fmul_rn(u, __uint2float_rn(a.sw - 1u)));
-        const uint32_t c = so < a.sw * a.sh ? pix_get(a.src, so, a.fmt) : 0u;      /* upstream reads past the image there */
+        const uint32_t c = so < a.sw * a.sh ? pfx_get(a.src, so, a.fmt) : 0u;      /* upstream reads past the image there */
         depth[o] = a.z;
         color[o] = ((a.flags & PFCU_ST_BLEND) ? pfp_blend((int)a.blend_mode, c, color[o]) : c) | a.alpha_or;
     }
@@ -238,20 +229,13 @@ k_draw_pixels(uint32_t *__restrict__ color, float *__restrict__ depth, uint32_t 
     }
 }
 
-/* pfReadPixels, context.c:2380-2394: region -> compact staging in the caller's layout (scalar setters, pixel.h:233-360) */
+/* pfReadPixels, context.c:2380-2394: region -> compact staging in the caller's (format, type) layout (scalar setters, pf_pixfmt.h) */
 __global__ void __launch_bounds__(256)
 k_read_pixels(const uint32_t *__restrict__ color, uint32_t W, uint32_t x0, uint32_t y0, uint32_t cols, uint32_t rows, int fmt, unsigned char *__restrict__ out)
 {
     const size_t n = (size_t)cols * rows, stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t r = (uint32_t)(i / cols), c = (uint32_t)(i - (size_t)r * cols);
-        const uint32_t v = color[(size_t)(y0 + r) * W + x0 + c];
-        if (fmt == PFCU_TEX_RGBA8) reinterpret_cast<uint32_t *>(out)[i] = v;
-        else if (fmt == PFCU_TEX_BGRA8) reinterpret_cast<uint32_t *>(out)[i] = __byte_perm(v, 0, 0x3012);
-        else {
-            unsigned char *q = out + 3 * i;
-            const int rr = fmt == PFCU_TEX_RGB8 ? 0 : 2;
-            q[rr] = (unsigned char)v; q[1] = (unsigned char)(v >> 8); q[2 - rr] = (unsigned char)(v >> 16);
-        }
+        pfx_set(out, i, fmt, color[(size_t)(y0 + r) * W + x0 + c]);
     }
 }

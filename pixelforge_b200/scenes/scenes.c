@@ -408,7 +408,8 @@ static void micro_scene(const pfscene_cfg *cfg, PFtexture tex)
    colour pointer (pfDrawArrays, quads), 14 aux buffer + pfSwapBuffers, 15 fog mode request (overwritten by the density
    call, as upstream), 16 opaque fog colour, 17 blend on, 18 bilinear, 19-20 fog mode set AFTER the density call
    (1 PF_EXP, 2 PF_EXP2, 3 an invalid mode), 21 pfReadPixels / pfDrawPixels round trip through the BGRA8, RGB8 and BGR8
-   layouts with a region that leaves the surface */
+   layouts with a region that leaves the surface, 22 the same round trip through every (format, type) pair the
+   reference has a getter and a setter for (38 pairs: single channels, luminance, 5-6-5 / 5-5-5-1 / 4-4-4-4, half, float) */
 
 static PFcolor api_postprocess(PFint x, PFint y, PFfloat depth, PFcolor c)
 {
@@ -540,6 +541,25 @@ static void api_scene(const pfscene_cfg *cfg, PFtexture tex, uint8_t *aux)
             pfDrawPixels(48, 36, fm[k], PF_UNSIGNED_BYTE, conv[k]);
         }
         pfDisable(PF_BLEND); pfEnable(PF_DEPTH_TEST); pfDepthFunc(PF_LESS); pfPixelZoom(1.0f, 1.0f);
+    }
+    if (v & (1 << 22)) {
+        static const PFpixelformat fmts[10] = { PF_RED, PF_GREEN, PF_BLUE, PF_ALPHA, PF_LUMINANCE, PF_LUMINANCE_ALPHA, PF_RGB, PF_RGBA, PF_BGR, PF_BGRA };
+        static const PFdatatype types[6] = { PF_UNSIGNED_BYTE, PF_UNSIGNED_SHORT_5_6_5, PF_UNSIGNED_SHORT_5_5_5_1, PF_UNSIGNED_SHORT_4_4_4_4, PF_HALF_FLOAT, PF_FLOAT };
+        static uint8_t conv[20 * 14 * 16];
+        ortho2d(w, h);
+        pfDisable(PF_DEPTH_TEST);
+        int k = 0;
+        for (int f = 0; f < 10; f++) for (int t = 0; t < 6; t++) {
+            const int comps = f < 5 ? 1 : (f == 5 ? 2 : ((fmts[f] == PF_RGB || fmts[f] == PF_BGR) ? 3 : 4));
+            if ((t == 1 && comps != 3) || ((t == 2 || t == 3) && comps != 4)) continue;      /* pairs without getter / setter upstream */
+            memset(conv, 0, sizeof conv);
+            pfReadPixels(w / 5 + 3 * k, h / 4 + 2 * (k % 7), 20, 14, fmts[f], types[t], conv);
+            if (k & 1) { pfEnable(PF_BLEND); pfBlendFunc((PFblendmode)(k % 8)); } else pfDisable(PF_BLEND);
+            pfPixelZoom(1.0f, 1.0f); pfRasterPos2f(2.0f + 22.0f * (float)(k % 9), 2.0f + 16.0f * (float)(k / 9));
+            pfDrawPixels(20, 14, fmts[f], types[t], conv);
+            k++;
+        }
+        pfDisable(PF_BLEND); pfEnable(PF_DEPTH_TEST);
     }
     if (v & (1 << 6)) {
         PFint fc[4] = { 180, 190, 220, (v & (1 << 16)) ? 255 : 200 };

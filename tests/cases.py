@@ -127,6 +127,7 @@ CASES += [_api("plain", 0), _api("viewport", _B(0)), _api("texmatrix", _B(1)), _
           _api("fog-linear", _B(6)), _api("fog-exp-opaque", _B(6, 15, 16)), _api("fog-cleardepth", _B(6, 9)),
           _api("fog-exp", _B(6, 19)), _api("fog-exp2-opaque", _B(6, 16, 20), seed=7), _api("fog-invalid-mode", _B(6, 19, 20), seed=8),
           _api("fog-exp-blend-viewport", _B(0, 6, 17, 19), seed=9), _api("pixel-layouts", _B(21), seed=10), _api("pixel-layouts-viewport", _B(0, 21), seed=11),
+          _api("pixel-formats-all", _B(22), seed=15), _api("pixel-formats-all-gouraud-viewport", _B(0, 2, 22), seed=16),
           _api("postprocess", _B(7)), _api("swapbuffers", _B(14, 7)),
           _api("everything", 0x3ffff & ~_B(13), seed=2), _api("everything-bilinear", 0x7ffff & ~_B(13), seed=3, ref_bfix=True)]
 # the same API breadth on the other target layouts (scalar getters / setters: rects, draw pixels, fog, post-processing,
@@ -136,7 +137,8 @@ CASES += [_api("everything-target-bgra", 0x3ffff & ~_B(13), seed=4, target=TARGE
           _api("gouraud-target-bgr", _B(2, 3), seed=6, target=TARGET_BGR),
           _api("fog-exp-layouts-target-bgra", _B(4, 5, 6, 19, 21), seed=12, target=TARGET_BGRA),
           _api("fog-exp2-layouts-target-rgb", _B(4, 5, 6, 20, 21), seed=13, target=TARGET_RGB),
-          _api("fog-layouts-target-bgr", _B(4, 5, 6, 8, 21), seed=14, target=TARGET_BGR)]
+          _api("fog-layouts-target-bgr", _B(4, 5, 6, 8, 21), seed=14, target=TARGET_BGR),
+          _api("pixel-formats-all-target-bgra", _B(22), seed=17, target=TARGET_BGRA)]
 
 CASE_IDS = [c[0] for c in CASES]
 assert len(set(CASE_IDS)) == len(CASE_IDS)

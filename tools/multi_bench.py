@@ -29,7 +29,8 @@ with scenes.open(wl["scene"], wl["w"], wl["h"], variant=wl["variant"], size=wl["
 
     def present():
         sc.frame(0); L.pfxFlush()
-        pfcu.check(L.pfcu_surface_read_pixels(surf, 8, 0, 1, 1, 1, 0, one.ctypes.data), "read_pixels"); L.pfcu_finish()
+        pfcu.check(L.pfcu_surface_read_pixels(surf, 8, 0, 1, 1, 1, 7 * 16 + 0, one.ctypes.data), "read_pixels")      # PFCU_PIX(PF_RGBA, PF_UNSIGNED_BYTE)
+        L.pfcu_finish()
 
     def e2e():
         sc.frame(0); sc.finish()

@@ -55,6 +55,10 @@ PF_API void pfxEnableDeviceVertexStage(PFboolean on);
  * neighbours of every threshold.  Returns the number of mismatches, -1 when the shininess is not tabulated (the
  * host then lights those vertices itself), -2 without a current context. */
 PF_API int pfxSpecularTableCheck(PFfloat shininess, PFuint samples);
+/* The same kind of check for the fog alpha steps that stand in for the host's expf / exp2f on the device (pfFogProcess in
+ * the PF_EXP / PF_EXP2 modes): mismatches on `samples` pseudo-random depths plus the neighbours of every step; -1 when the
+ * host function is not monotonic over the fog range, -2 without a context or in PF_LINEAR mode. */
+PF_API int pfxFogTableCheck(PFuint samples);
 /* Page-locked host memory for buffers the application hands to the library every frame (vertex / index arrays, pixel
  * buffers): copies from it are plain DMA at full PCIe speed instead of being staged by the driver.  Optional: ordinary
  * malloc'ed memory works everywhere, as with the reference.  Free with pfxHostFree (after the last call that used it). */

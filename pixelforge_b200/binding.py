@@ -191,7 +191,7 @@ PFCU_SYMBOLS = [
 
 PFX_SYMBOLS = ["pfxSetSyncMode", "pfxFlush", "pfxFinish", "pfxGetCounters", "pfxResetCounters", "pfxSetTileOwner",
                "pfxGetDeviceColor", "pfxGetDeviceDepth", "pfxReadDepth", "pfxCaptureBegin", "pfxCaptureEnd",
-               "pfxGetSurfaceHandle", "pfxBackendName", "pfxEnableDeviceVertexStage", "pfxSpecularTableCheck", "pfxHostAlloc", "pfxHostFree", "pfxTextureDirty", "pfxEnableQueuedReadback", "pfxHostStatic", "pfxHostModified"]
+               "pfxGetSurfaceHandle", "pfxBackendName", "pfxEnableDeviceVertexStage", "pfxSpecularTableCheck", "pfxHostAlloc", "pfxHostFree", "pfxTextureDirty", "pfxEnableQueuedReadback", "pfxHostStatic", "pfxHostModified", "pfxFogTableCheck"]
 
 
 class PfcuLib:

@@ -963,6 +963,32 @@ static int fog_thresholds(const pf_ctx *c, float *thr)
     return n;
 }
 
+/* Diagnostics for the fog alpha steps the device uses instead of expf / exp2f (pfcu_fog.thresholds): tabulates the
+ * current context's fog state and compares "number of thresholds <= depth" with the host function on `samples`
+ * pseudo-random depths in (start, end) plus both neighbours of every threshold.  Returns the number of mismatches,
+ * -1 when the host function is not monotonic (pfFogProcess then refuses), -2 without a context or in PF_LINEAR mode. */
+int pfxFogTableCheck(PFuint samples)
+{
+    pf_ctx *c = pf_cur;
+    if (!c || c->fog.mode == PF_LINEAR || (uint32_t)c->fog.mode > (uint32_t)PF_EXP2) return -2;
+    float thr[256];
+    const int n = fog_thresholds(c, thr);
+    if (n < 0) return -1;
+    const int32_t lo0 = fog_ord(c->fog.start) + 1, hi0 = fog_ord(c->fog.end) - 1;
+    if (lo0 > hi0) return 0;
+    int bad = 0;
+    uint32_t rs = 2463534242u;
+    for (PFuint i = 0; i < samples + 2u * (PFuint)n; i++) {
+        int32_t p;
+        if (i < samples) { rs = rs * 1664525u + 1013904223u; p = lo0 + (int32_t)(((uint64_t)(rs >> 1) * (uint64_t)((int64_t)hi0 - lo0 + 1)) >> 31); }
+        else { const PFuint k = (i - samples) >> 1; p = fog_ord(thr[k]) - (int32_t)((i - samples) & 1u); if (p < lo0) continue; }
+        const float d = fog_unord(p);
+        int cnt = 0; while (cnt < n && thr[cnt] <= d) cnt++;
+        if (cnt != (int)fog_alpha_host(c, d)) bad++;
+    }
+    return bad;
+}
+
 void pfFogProcess(void)
 {
     CTX;

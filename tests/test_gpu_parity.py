@@ -679,6 +679,19 @@ def test_static_geometry_mirrors():
     assert out["0"] >= mesh_bytes and out["1"] < 4096, out
 
 
+def test_banded_readback_equals_single_launch():
+    """Frames that are read back are rasterised as four band launches on prioritised streams with the copies chasing the
+    bands (from the second frame on, when the read-back is predicted); the images must equal the single-launch path's
+    (PF_CUDA_BANDS=1), for a small-triangle scene, the Phong mesh and the blended overdraw scene."""
+    for scene, w, h, kw in (("textured", 1920, 1080, dict(size=128, variant=1 | 32 | 64)), ("phong", 2560, 1440, dict(size=300, variant=32)),
+                            ("overdraw", 2048, 1536, dict(size=6, variant=1 | 4))):
+        a = _render_with_env(scene, w, h, {"PF_CUDA_BANDS": "1"}, frames=4, **kw)
+        for env in ({}, {"PF_CUDA_BANDS": "3"}):
+            b = _render_with_env(scene, w, h, env, frames=4, **kw)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), (scene, env)
+            assert a[2] == b[2] and a[3] == b[3]
+
+
 # ---- multi-device mode: one process, several GPUs (PF_CUDA_DEVICES) --------------------------------------
 
 def _visible_gpus():

@@ -124,6 +124,14 @@ typedef struct {
 
 /* ---- runtime -------------------------------------------------------------------------------- */
 
+/* Multi-device mode.  With PF_CUDA_DEVICES=a,b,c... in the environment at pfcu_init() the library drives every listed GPU of
+ * the box from the one process: every surface, texture and resident batch created afterwards exists once per device, every
+ * call below that takes such a handle is replayed on all devices (the handle the caller holds is the first device's), a
+ * device rasterises only the 64x64 tiles it owns of the large RGBA8 surfaces (tile % n == device) and read-backs collect the
+ * tiles (pfcu_surface_download*, pfcu_surface_read_pixels).  Images, depth buffers and counters are what one GPU produces.
+ * Not available in that mode: pfcu_surface_wrap, the explicit tile-owner / pack / IPC-present calls of the multi-PROCESS
+ * split (they keep acting on the first device only) and device-resident list jobs (pfcu_list_job_supported returns 0). */
+
 /* Bind to CUDA device `device` (-1: $PF_CUDA_DEVICE, else $LOCAL_RANK, else 0) and create the stream.
  * Idempotent.  Returns PFCU_ERR_NO_DEVICE when no GPU is usable. */
 PFCU_API int  pfcu_init(int device);

@@ -292,7 +292,13 @@ static int multi_run_all(const std::function<int(int)> &fn)
         }
     }
     if (rc0) return rc0;
-    for (int d = 1; d < mg.n; d++) if (mg.rc[d]) return mg.rc[d];
+    for (int d = 1; d < mg.n; d++) if (mg.rc[d]) {
+        /* pfcu_last_error() reads the primary runtime: bring the worker's message over */
+        char msg[sizeof g_main.err];
+        snprintf(msg, sizeof msg, "device %d: %s", mg.dev[d], mg.rt[d]->err);
+        memcpy(g_main.err, msg, sizeof msg);
+        return mg.rc[d];
+    }
     return PFCU_OK;
 }
 

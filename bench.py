@@ -436,7 +436,7 @@ def ours_main(args):
         sampler.start()
     m = measure_workload(wl_name, args.steps, args.warmup, torch, scenes, pfcu, stream, flush_buf)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
 
     dev_ms = max_over_ranks(m["dev_ms"]); e2e_ms = max_over_ranks(m["e2e_ms"])
     px_all = sum_over_ranks(m["dev_px_per_step"]); tris_all = sum_over_ranks(m["dev_tris_per_step"])
@@ -479,6 +479,8 @@ def ours_main(args):
                     extra[n]["e2e_static_geometry"] = x["e2e_static"]
             except Exception as e:   # an extra must never take the headline down
                 extra[n] = {"error": repr(e)}
+        if rank == 0:
+            clocks = sampler.stop()         # sampled every 100 ms over the headline's and the extras' timed regions
         if world > 1 and not args.no_extra:
             try:
                 from pixelforge_b200.multigpu import tile_split_benchmark
@@ -508,6 +510,8 @@ def ours_main(args):
         if world > 1:
             dist.destroy_process_group()
         return 0
+    if clocks is None:
+        clocks = sampler.stop()
 
     parity = {}
 

@@ -194,6 +194,22 @@ PFX_SYMBOLS = ["pfxSetSyncMode", "pfxFlush", "pfxFinish", "pfxGetCounters", "pfx
                "pfxGetSurfaceHandle", "pfxBackendName", "pfxEnableDeviceVertexStage", "pfxSpecularTableCheck", "pfxHostAlloc", "pfxHostFree", "pfxTextureDirty", "pfxEnableQueuedReadback", "pfxHostStatic", "pfxHostModified", "pfxFogTableCheck"]
 
 
+class Fog(C.Structure):          # pfcu_fog
+    _fields_ = [("start", C.c_float), ("end", C.c_float), ("inv_len", C.c_float), ("density", C.c_float), ("rgba", C.c_uint32),
+                ("mode", C.c_uint32), ("thresholds", C.c_void_p), ("n_thresholds", C.c_uint32)]
+
+
+class Pixels(C.Structure):       # pfcu_pixels
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_int), ("xs", C.c_int32), ("ys", C.c_int32),
+                ("xmin", C.c_int32), ("ymin", C.c_int32), ("xmax", C.c_int32), ("ymax", C.c_int32), ("inv_xlen", C.c_float), ("inv_ylen", C.c_float),
+                ("z", C.c_float), ("flags", C.c_uint32), ("blend_mode", C.c_uint8), ("depth_func", C.c_uint8), ("pad", C.c_uint16)]
+
+
+def pix_code(pf_format, pf_type):
+    """PFCU_PIX(PFpixelformat, PFdatatype) of include/pfcu.h."""
+    return pf_format * 16 + pf_type
+
+
 class PfcuLib:
     """Typed access to a library exporting the pfcu C-ABI (the product or the oracle build)."""
 
@@ -227,6 +243,9 @@ class PfcuLib:
             "pfcu_surface_push_tiles": (C.c_int, [vp, u32, u32, C.c_int]),
             "pfcu_submit": (C.c_int, [vp, vp, u32, vp, u32]), "pfcu_submit_prims": (C.c_int, [vp, vp, u32]), "pfcu_batch_upload": (vp, [vp, u32, vp, u32]),
             "pfcu_batch_submit": (C.c_int, [vp, vp]), "pfcu_batch_destroy": (None, [vp]),
+            "pfcu_surface_rect": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, u32]),
+            "pfcu_surface_fog": (C.c_int, [vp, C.POINTER(Fog)]), "pfcu_surface_draw_pixels": (C.c_int, [vp, C.POINTER(Pixels)]),
+            "pfcu_surface_read_pixels": (C.c_int, [vp, u32, u32, u32, u32, u32, C.c_int, vp]),
             "pfcu_fence": (C.c_int, []), "pfcu_finish": (C.c_int, []), "pfcu_get_counters": (C.c_int, [C.POINTER(Counters)]),
             "pfcu_reset_counters": (None, []),
             "pfcu_profile_enable": (None, [C.c_int]), "pfcu_set_raster_path": (None, [C.c_int]), "pfcu_profile_read": (C.c_int, [C.POINTER(Profile)]),

@@ -679,6 +679,72 @@ def test_static_geometry_mirrors():
     assert out["0"] >= mesh_bytes and out["1"] < 4096, out
 
 
+@pytest.mark.parametrize("w,h", [(96, 80), (200, 150), (64, 64), (333, 77)], ids=lambda v: str(v))
+def test_surface_ops_cuda_vs_oracle(pfcu_pair, w, h):
+    """pfcu level: random sequences of pfcu_surface_rect / draw_pixels / fog / read_pixels on the CUDA product and on the oracle's
+    sequential restatement of the reference loops.  Rectangles reach column W (a viewport as wide as a framebuffer object
+    that is smaller than the main buffer has vpMax = W): pixel (y, W) and pixel (y+1, 0) share an address and the
+    reference applies them in row-major order - with blending the order is visible."""
+    import ctypes as C
+    from pixelforge_b200.binding import Fog, Pixels, pix_code
+    prod, orc = pfcu_pair
+    rng = np.random.default_rng(w * 1000 + h)
+    c0 = rng.integers(0, 2**32, size=(h, w), dtype=np.uint32)
+    d0 = rng.uniform(0.0, 4.0, size=(h, w)).astype(np.float32)
+    src = rng.integers(0, 2**32, size=(24, 16), dtype=np.uint32)
+    thr = np.sort(rng.uniform(1.0, 3.0, size=200).astype(np.float32))
+    ops = []
+    for i in range(40):
+        kind = i % 4
+        if kind == 0:
+            x1, y1 = int(rng.integers(-3, w)), int(rng.integers(0, h - 1))
+            ops.append(("rect", max(x1, 0), y1, int(min(x1 + rng.integers(0, w), w)), int(min(y1 + rng.integers(0, 20), h - 2)), int(rng.integers(0, 2**32))))
+        elif kind == 1:
+            full = i % 8 == 1        # every other one spans columns 0 .. W: the shared-address case
+            xs, ys = (0 if full else int(rng.integers(-10, w - 4))), int(rng.integers(-5, h - 8))
+            zoom_x = (w + 1) / 16.0 if full else float(rng.uniform(0.5, 3.0))
+            zoom_y = float(rng.uniform(0.5, 2.0))
+            xmin, ymin = min(max(xs, 0), w), min(max(ys, 0), h - 2)
+            xmax = int(min(max(xs + 16 * zoom_x, 0), w)); ymax = int(min(max(ys + 24 * zoom_y, 0), h - 2))
+            ops.append(("pix", xs, ys, xmin, ymin, xmax, ymax, 1.0 / (16 * zoom_x), 1.0 / (24 * zoom_y), float(rng.uniform(0.0, 4.0)),
+                        int(rng.integers(0, 4)), int(rng.integers(0, 8)), int(rng.integers(0, 6)), int(rng.choice([7 * 16, 9 * 16, 6 * 16, 8 * 16, 7 * 16 + 4, 5 * 16 + 9]))))
+        elif kind == 2:
+            ops.append(("fog", 0, int(rng.integers(0, 2**32))))      # linear: the exponential modes' tables are pinned by the api-fog-* cases
+        else:
+            ops.append(("read", int(rng.integers(0, w // 2)), int(rng.integers(0, h // 2)), int(rng.integers(1, w // 2)), int(rng.integers(1, h // 2)),
+                        int(rng.choice([7 * 16, 9 * 16 + 3, 6 * 16 + 2, 4 * 16 + 10, 9 * 16 + 9, 0 * 16 + 9]))))
+    results = []
+    for lib in (prod, orc):
+        L = lib.lib
+        s = L.pfcu_surface_create_format(w, h, 0)
+        lib.check(L.pfcu_surface_upload(s, c0.ctypes.data, d0.ctypes.data, 0, h), "upload")
+        reads = []
+        for op in ops:
+            if op[0] == "rect":
+                lib.check(L.pfcu_surface_rect(s, op[1], op[2], op[3], op[4], op[5]), "rect")
+            elif op[0] == "pix":
+                _, xs, ys, xmin, ymin, xmax, ymax, ix, iy, z, fl, bm, df, code = op
+                # the source buffer is reinterpreted per layout: 24 x 16 texels fit every pair used here (<= 4 bytes per texel)
+                p = Pixels(src.ctypes.data, 16, 24, code, xs, ys, xmin, ymin, xmax, ymax, ix, iy, z, fl, bm, df, 0)
+                lib.check(L.pfcu_surface_draw_pixels(s, C.byref(p)), "draw_pixels")
+            elif op[0] == "fog":
+                f = Fog(1.0, 3.0, 0.5, 1.0, op[2], op[1], thr.ctypes.data, 0)
+                lib.check(L.pfcu_surface_fog(s, C.byref(f)), "fog")
+            else:
+                _, x0, y0, cols, rows, code = op
+                out = np.full(rows * (cols + 3) * 16 + 64, 0xAB, np.uint8)
+                lib.check(L.pfcu_surface_read_pixels(s, x0, y0, cols, rows, cols + 3, code, out.ctypes.data), "read_pixels")
+                reads.append(out)
+        oc, od = np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32)
+        lib.check(L.pfcu_surface_download(s, oc.ctypes.data, od.ctypes.data, 0, h), "download")
+        L.pfcu_surface_destroy(s)
+        results.append((oc, od, reads))
+    (pc, pd, pr), (qc, qd, qr) = results
+    assert int((pc != qc).sum()) == 0 and int((pd.view(np.uint32) != qd.view(np.uint32)).sum()) == 0
+    for a, b in zip(pr, qr):
+        assert np.array_equal(a, b)
+
+
 def test_banded_readback_equals_single_launch():
     """Frames that are read back are rasterised as four band launches on prioritised streams with the copies chasing the
     bands (from the second frame on, when the read-back is predicted); the images must equal the single-launch path's

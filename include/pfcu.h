@@ -57,6 +57,10 @@ enum {
     PFCU_TEX_RGB8  = 2,   /* PF_RGB  / PF_UNSIGNED_BYTE  (3 bytes per texel, alpha reads 255) */
     PFCU_TEX_BGR8  = 3    /* PF_BGR  / PF_UNSIGNED_BYTE */
 };
+/* every other (PFpixelformat, PFdatatype) pair the reference has a SIMD texel getter for (pixel.h:2249-3040: single
+   channels, luminance(-alpha), 5-6-5 / 5-5-5-1 / 4-4-4-4, half, float): PFCU_TEX_PIX + PFCU_PIX(format, type).
+   Textures only; surfaces take the four codes above. */
+#define PFCU_TEX_PIX 256
 
 typedef struct pfcu_surface pfcu_surface;   /* colour RGBA8 + depth f32, row-major [y*W+x], in HBM   */
 typedef struct pfcu_texture pfcu_texture;   /* texel array in HBM                                    */

@@ -27,6 +27,7 @@
 #include <string.h>
 #include <stdio.h>
 #include <limits.h>
+#include "../pixelforge_b200/csrc/pf_pixfmt.h"
 
 /* colour is held as canonical RGBA8 dwords whatever the caller's layout (fmt); upload / download convert */
 struct pfcu_surface { uint32_t w, h; uint32_t *color; float *depth; int owned; uint32_t rank, world; int fmt; };
@@ -257,6 +258,10 @@ static uint32_t tex_fetch(const pfcu_texture *t, int32_t x, int32_t y)
     size_t n = (size_t)t->w * t->h;
     /* the reference would read out of bounds here (e.g. CLAMP_TO_EDGE rounds v*(h-1)+0.5 up to row h);
        defined as "memory after the texture reads as zero": RGBA 0, and alpha 255 for 3-byte formats */
+    if (t->fmt >= PFCU_TEX_PIX) {          /* the other texel layouts: the SIMD getters of pixel.h:2249-3040, restated in pf_pixfmt.h */
+        static const uint8_t zeros[16];
+        return (off < 0 || (size_t)off >= n) ? pfx_tex_get(zeros, 0u, t->fmt - PFCU_TEX_PIX) : pfx_tex_get(base, (uint32_t)off, t->fmt - PFCU_TEX_PIX);
+    }
     if (off < 0 || (size_t)off >= n) return (t->fmt == PFCU_TEX_RGB8 || t->fmt == PFCU_TEX_BGR8) ? 0xff000000u : 0u;
     uint32_t raw;
     switch (t->fmt) {
@@ -710,7 +715,11 @@ static int pack_unpack(pfcu_surface *s, uint32_t rank, uint32_t world, int with_
 int pfcu_surface_pack_tiles(pfcu_surface *s, uint32_t r, uint32_t w, int wd, void *st) { return pack_unpack(s, r, w, wd, st, 0); }
 int pfcu_surface_unpack_tiles(pfcu_surface *s, uint32_t r, uint32_t w, int wd, const void *st) { return pack_unpack(s, r, w, wd, (void *)st, 1); }
 
-static size_t tex_bytes(uint32_t w, uint32_t h, int fmt) { return (size_t)w * h * ((fmt == PFCU_TEX_RGBA8 || fmt == PFCU_TEX_BGRA8) ? 4u : 3u); }
+static size_t tex_bytes(uint32_t w, uint32_t h, int fmt)
+{
+    if (fmt >= PFCU_TEX_PIX) return (size_t)w * h * (size_t)pfx_bytes(fmt - PFCU_TEX_PIX);
+    return (size_t)w * h * ((fmt == PFCU_TEX_RGBA8 || fmt == PFCU_TEX_BGRA8) ? 4u : 3u);
+}
 
 pfcu_texture *pfcu_texture_create(const void *px, uint32_t w, uint32_t h, int fmt)
 {
@@ -784,7 +793,6 @@ int pfcu_list_job_supported(const pfcu_surface *s, uint32_t n, uint32_t k) { (vo
 int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n) { (void)jobs; (void)n; return PFCU_ERR_INVALID; }
 /* points and lines: the reference's scalar loops (lines.c:283-530, points.c:85-183), one primitive after the other */
 #include "../pixelforge_b200/csrc/pf_prims.h"
-#include "../pixelforge_b200/csrc/pf_pixfmt.h"
 static void prim_pixel(pfcu_surface *s, const pfcu_prim *p, uint32_t off, float z, uint32_t color, int test)
 {
     if (off >= s->w * s->h) return;                     /* the reference would write outside its buffer */

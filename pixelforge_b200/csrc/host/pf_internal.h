@@ -214,6 +214,7 @@ pf_surf *pfh_surf_create(pf_tex *tex, PFfloat *zhost, int z_public);
 void     pfh_surf_destroy(pf_surf *s);
 pf_surf *pfh_surf_lookup(PFtexture tex);
 int      pfh_tex_format_code(PFpixelformat f, PFdatatype t);   /* PFCU_TEX_* or -1 */
+int      pfh_texture_code(PFpixelformat f, PFdatatype t);      /* ... or PFCU_TEX_PIX + pair code for the other texel layouts */
 PFsizei  pfh_pixel_bytes(PFpixelformat f, PFdatatype t);
 PFcolor  pfh_pixel_get(const pf_tex *t, size_t i);            /* host mirror access (RGBA8 family)     */
 void     pfh_pixel_set(pf_tex *t, size_t i, PFcolor c);

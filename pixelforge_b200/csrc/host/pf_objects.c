@@ -6,6 +6,7 @@
  * authoritative, and the caller-visible host arrays are mirrors refreshed at sync points.
  */
 #include "pf_internal.h"
+#include "../pf_pixfmt.h"
 
 #include <float.h>
 #include <stdio.h>
@@ -69,6 +70,16 @@ int pfh_tex_format_code(PFpixelformat f, PFdatatype t)
     }
 }
 
+/* texture format of the C-ABI: the four 8-bit layouts keep their codes (and fast paths), every other (format, type) pair
+   the reference has a getter for is PFCU_TEX_PIX + PFCU_PIX(format, type); -1: no such getter upstream */
+int pfh_texture_code(PFpixelformat f, PFdatatype t)
+{
+    const int legacy = pfh_tex_format_code(f, t);
+    if (legacy >= 0) return legacy;
+    if ((int)f < 0 || f > PF_BGRA || (int)t < 0 || t > PF_DOUBLE) return -1;
+    return pfx_bytes(PFCU_PIX(f, t)) ? PFCU_TEX_PIX + PFCU_PIX(f, t) : -1;
+}
+
 PFcolor pfh_pixel_get(const pf_tex *t, size_t i)
 {
     const PFubyte *p = (const PFubyte *)t->pixels;
@@ -78,7 +89,9 @@ PFcolor pfh_pixel_get(const pf_tex *t, size_t i)
     case PFCU_TEX_BGRA8: c.b = p[4 * i]; c.g = p[4 * i + 1]; c.r = p[4 * i + 2]; c.a = p[4 * i + 3]; break;
     case PFCU_TEX_RGB8:  c.r = p[3 * i]; c.g = p[3 * i + 1]; c.b = p[3 * i + 2]; break;
     case PFCU_TEX_BGR8:  c.b = p[3 * i]; c.g = p[3 * i + 1]; c.r = p[3 * i + 2]; break;
-    default: break;
+    default:
+        if (pfx_bytes(PFCU_PIX(t->format, t->type))) { const uint32_t v = pfx_get(t->pixels, i, PFCU_PIX(t->format, t->type)); memcpy(&c, &v, 4); }
+        break;
     }
     return c;
 }
@@ -91,7 +104,9 @@ void pfh_pixel_set(pf_tex *t, size_t i, PFcolor c)
     case PFCU_TEX_BGRA8: p[4 * i] = c.b; p[4 * i + 1] = c.g; p[4 * i + 2] = c.r; p[4 * i + 3] = c.a; break;
     case PFCU_TEX_RGB8:  p[3 * i] = c.r; p[3 * i + 1] = c.g; p[3 * i + 2] = c.b; break;
     case PFCU_TEX_BGR8:  p[3 * i] = c.b; p[3 * i + 1] = c.g; p[3 * i + 2] = c.r; break;
-    default: break;
+    default:
+        if (pfx_bytes(PFCU_PIX(t->format, t->type))) { uint32_t v; memcpy(&v, &c, 4); pfx_set(t->pixels, i, PFCU_PIX(t->format, t->type), v); }
+        break;
     }
 }
 

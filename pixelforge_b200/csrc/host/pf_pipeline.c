@@ -90,7 +90,7 @@ static void build_state(pf_ctx *c, pfcu_state *st)
             dev = tex->surf->as_texture;
         } else {
             if (!tex->dev) {
-                int code = pfh_tex_format_code(tex->format, tex->type);
+                int code = pfh_texture_code(tex->format, tex->type);
                 if (code >= 0 && tex->pixels) tex->dev = pfcu_texture_create(tex->pixels, tex->w, tex->h, code);
                 if (!tex->dev) {
                     fprintf(stderr, "pixelforge-b200: texture format %d/%d is not supported by the CUDA sampler\n",

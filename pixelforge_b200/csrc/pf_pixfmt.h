@@ -3,8 +3,9 @@
  * and compiled as CUDA device code (k_draw_pixels / k_read_pixels in pfcu_surface.cuh) and as C99 (the oracle, the front
  * end's validity check).  Restates, in behaviour, src/internal/pixel.h:76-406 (setters), :408-760 (getters), the tables
  * GC_pixelGetters / GC_pixelSetters (:764-860) and pfmFloatToHalf / pfmHalfToFloat (src/pfm.h:107-161).
- * pfReadPixels and pfDrawPixels take any of the 38 pairs (context.c:1998-2005, 2351-2362); framebuffers and textures
- * of the triangle path exist in the four 8-bit layouts only.
+ * pfReadPixels and pfDrawPixels take any of the 38 pairs (context.c:1998-2005, 2351-2362); framebuffers of the triangle
+ * path exist in the four 8-bit layouts only.  Textures exist in every pair: pfx_tex_get at the end of this
+ * file restates the SIMD texel getters (pixel.h:2249-3040), which are NOT the scalar ones (DESIGN Q22).
  * Arithmetic notes kept from upstream: single-channel HALF / FLOAT setters DIVIDE by 255.0f, the multi-channel ones
  * multiply by (float)(1.0/255); luminance = r*k*0.299f + g*k*0.587f + b*k*0.114f in float, left to right;
  * (PFubyte)(float) is CVTTSS2SI followed by a truncation to 8 bits; the 5-5-5-1 alpha threshold compares in double.
@@ -15,7 +16,12 @@
 #include "pf_vstage.h"
 
 /* code of a (PFpixelformat, PFdatatype) pair as the C-ABI carries it */
+#ifndef PFCU_PIX
 #define PFCU_PIX(format, type) ((int)(format) * 16 + (int)(type))
+#endif
+#ifndef PFCU_TEX_PIX
+#define PFCU_TEX_PIX 256     /* include/pfcu.h */
+#endif
 enum { PFX_RED = 0, PFX_GREEN, PFX_BLUE, PFX_ALPHA, PFX_LUM, PFX_LUMA, PFX_RGB, PFX_RGBA, PFX_BGR, PFX_BGRA };       /* PFpixelformat */
 enum { PFX_UBYTE = 0, PFX_565 = 2, PFX_5551 = 3, PFX_4444 = 4, PFX_HALF = 9, PFX_FLOAT = 10 };                      /* PFdatatype    */
 
@@ -184,6 +190,80 @@ PFV_FN void pfx_set(void *px, size_t i, int code, uint32_t c)
         } else { pfx_store_comp(px, 4 * i, t, c0, n0); pfx_store_comp(px, 4 * i + 1, t, g, n1); pfx_store_comp(px, 4 * i + 2, t, c2, n2); pfx_store_comp(px, 4 * i + 3, t, a, n3); }
         return;
     }
+    }
+}
+
+/* ---- texel fetch of the TRIANGLE path: the reference's SIMD getters (pixel.h:2249-3040), lane by lane --------------------
+ * Not the scalar getters above: every SIMD getter gathers a 32-bit word at the texel's byte offset and differs from its
+ * scalar twin in ways that define the pixels a textured triangle gets -
+ *   8-bit single channels and luminance take the gathered word >> 24, i.e. the byte THREE texels further on; ALPHA takes the
+ *     right byte and leaves red / green / blue 0 (the scalar getter says 255); LUMINANCE_ALPHA shuffles bytes 2, 2, 2, 3 of the
+ *     word, i.e. reads the NEXT texel;
+ *   5-6-5 expands by shifts (r5 << 3), 5-5-5-1 and 4-4-4-4 multiply by the integers 255/31 = 8 and 255/15 = 17;
+ *   half and float components go through CVTPS2DQ (round to nearest even, 0x80000000 out of range or NaN) after the
+ *     multiplication by 255 and are OR-ed together unmasked: a component above 1.0 spills into its neighbours; BGR half / float
+ *     come back with blue in the red channel (the getter ORs its first element into the low byte); half = the low 16 bits
+ *     of the gathered word through pfmHalfToFloat (the F16C path is compiled out: FLT16_MAX is not defined, simd.h:973-990).
+ * The word is assembled from bytes (texel offsets of the 2- and 3-byte layouts are not word aligned); bytes past the end of
+ * the texture read as zero (DESIGN Q18: the texture copies carry a zeroed tail). */
+#ifdef __CUDACC__
+PFV_FN uint32_t pfx_rne(float x) { const int r = __float2int_rn(x); return (fabsf(x) < 2147483648.0f) ? (uint32_t)r : 0x80000000u; }
+#else
+#  include <xmmintrin.h>
+PFV_FN uint32_t pfx_rne(float x) { return (uint32_t)_mm_cvtss_si32(_mm_set_ss(x)); }
+#endif
+PFV_FN uint32_t pfx_raw32(const uint8_t *p, size_t off)
+{
+    return (uint32_t)p[off] | ((uint32_t)p[off + 1] << 8) | ((uint32_t)p[off + 2] << 16) | ((uint32_t)p[off + 3] << 24);
+}
+PFV_FN uint32_t pfx_c255(float x) { return pfx_rne(PFV_MUL(x, 255.0f)); }
+
+PFV_FN uint32_t pfx_tex_get(const uint8_t *px, uint32_t idx, int code)
+{
+    const int f = code >> 4, t = code & 15;
+    const uint32_t A = 0xFF000000u;
+    if (t == PFX_UBYTE) {
+        const uint32_t w = pfx_raw32(px, f == PFX_LUMA ? 2u * (size_t)idx : (size_t)idx);
+        switch (f) {
+        case PFX_RED:   return (w >> 24) | A;
+        case PFX_GREEN: return ((w >> 24) << 8) | A;
+        case PFX_BLUE:  return ((w >> 24) << 16) | A;
+        case PFX_ALPHA: return w << 24;
+        case PFX_LUM:   { const uint32_t g = w >> 24; return A | g | (g << 8) | (g << 16); }
+        default:        { const uint32_t g = (w >> 16) & 255u; return g | (g << 8) | (g << 16) | (w & A); }     /* LUMINANCE_ALPHA */
+        }
+    }
+    if (t == PFX_565) {
+        const uint32_t w = pfx_raw32(px, 2u * (size_t)idx);
+        const uint32_t hi = ((w & 0xF800u) >> 11) << 3, mid = ((w & 0x07E0u) >> 5) << 2, lo = (w & 0x001Fu) << 3;
+        return f == PFX_RGB ? (A | (lo << 16) | (mid << 8) | hi) : (A | (hi << 16) | (mid << 8) | lo);
+    }
+    if (t == PFX_5551 || t == PFX_4444) {
+        const uint32_t w = pfx_raw32(px, 2u * (size_t)idx);
+        uint32_t c0, c1, c2, a8;
+        if (t == PFX_5551) { c0 = ((w >> 11) & 0x1Fu) * 8u; c1 = ((w >> 6) & 0x1Fu) * 8u; c2 = ((w >> 1) & 0x1Fu) * 8u; a8 = (w & 1u) * 255u; }
+        else               { c0 = ((w >> 12) & 0xFu) * 17u; c1 = ((w >> 8) & 0xFu) * 17u; c2 = ((w >> 4) & 0xFu) * 17u; a8 = (w & 0xFu) * 17u; }
+        /* first field = red (RGBA) or blue (BGRA) */
+        return f == PFX_RGBA ? ((a8 << 24) | (c2 << 16) | (c1 << 8) | c0) : ((a8 << 24) | (c0 << 16) | (c1 << 8) | c2);
+    }
+    /* half / float components */
+    const uint32_t n = f <= PFX_LUM ? 1u : (f == PFX_LUMA ? 2u : ((f == PFX_RGB || f == PFX_BGR) ? 3u : 4u));
+    uint32_t e[4] = { 0, 0, 0, 0 };
+    for (uint32_t k = 0; k < n; k++) {
+        const size_t el = (size_t)idx * n + k;
+        const float v = t == PFX_HALF ? pfx_half_to_float((uint16_t)(pfx_raw32(px, 2u * el) & 0xFFFFu)) : pfx_u2f(pfx_raw32(px, 4u * el));
+        e[k] = pfx_c255(v);
+    }
+    switch (f) {
+    case PFX_RED:   return e[0] | A;
+    case PFX_GREEN: return (e[0] << 8) | A;
+    case PFX_BLUE:  return (e[0] << 16) | A;
+    case PFX_ALPHA: return e[0] << 24;
+    case PFX_LUM:   return A | (e[0] << 16) | (e[0] << 8) | e[0];
+    case PFX_LUMA:  return (e[1] << 24) | (e[0] << 16) | (e[0] << 8) | e[0];
+    case PFX_RGB: case PFX_BGR: return A | (e[2] << 16) | (e[1] << 8) | e[0];          /* BGR: blue lands in the red channel, as upstream */
+    case PFX_RGBA:  return (e[3] << 24) | (e[2] << 16) | (e[1] << 8) | e[0];
+    default:        return (e[3] << 24) | (e[0] << 16) | (e[1] << 8) | e[2];            /* BGRA */
     }
 }
 

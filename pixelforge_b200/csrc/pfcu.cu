@@ -1301,7 +1301,12 @@ int pfcu_surface_unpack_tiles(pfcu_surface *s, uint32_t r, uint32_t w, int wd, c
 
 /* ---- textures ---- */
 
-static size_t tex_bytes(uint32_t w, uint32_t h, int fmt) { return (size_t)w * h * ((fmt == PFCU_TEX_RGBA8 || fmt == PFCU_TEX_BGRA8) ? 4u : 3u); }
+static bool tex_fmt_ok(int fmt) { return (fmt >= PFCU_TEX_RGBA8 && fmt <= PFCU_TEX_BGR8) || (fmt >= PFCU_TEX_PIX && pfx_bytes(fmt - PFCU_TEX_PIX) != 0); }
+static size_t tex_bytes(uint32_t w, uint32_t h, int fmt)
+{
+    if (fmt >= PFCU_TEX_PIX) return (size_t)w * h * (size_t)pfx_bytes(fmt - PFCU_TEX_PIX);
+    return (size_t)w * h * ((fmt == PFCU_TEX_RGBA8 || fmt == PFCU_TEX_BGRA8) ? 4u : 3u);
+}
 
 pfcu_texture *pfcu_texture_create(const void *host_pixels, uint32_t w, uint32_t h, int fmt)
 {
@@ -1313,7 +1318,7 @@ pfcu_texture *pfcu_texture_create(const void *host_pixels, uint32_t w, uint32_t 
         for (int d = 0; d < mg.n; d++) r[0]->rep[d] = r[d];
         return r[0];
     }
-    if (!RT.ok || fmt < PFCU_TEX_RGBA8 || fmt > PFCU_TEX_BGR8 || w == 0 || h == 0) return nullptr;
+    if (!RT.ok || !tex_fmt_ok(fmt) || w == 0 || h == 0) return nullptr;
     pfcu_texture *t = (pfcu_texture *)calloc(1, sizeof *t);
     if (!t) return nullptr;
     t->w = w; t->h = h; t->fmt = fmt; t->owned = true; t->leader = (fmt == PFCU_TEX_BGRA8);

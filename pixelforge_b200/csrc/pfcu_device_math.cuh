@@ -265,11 +265,20 @@ __device__ __forceinline__ int tex_coord(int wrap, float t, float sm1)
     }
 }
 
+/* The texel layouts beyond the four 8-bit ones: the reference's SIMD getters lane by lane (pf_pixfmt.h); memory past
+   the end of the texture reads as zero bytes.  Out of line: the 8-bit paths keep their registers. */
+__device__ __noinline__ unsigned tex_fetch_pix(const unsigned char *base, unsigned total, int off, int code)
+{
+    const unsigned char zeros[16] = { 0 };
+    return (unsigned)off >= total ? pfx_tex_get(zeros, 0u, code) : pfx_tex_get(base, (unsigned)off, code);
+}
+
 __device__ __forceinline__ unsigned tex_fetch(const TexRegs &t, int x, int y)
 {
     const int off = (int)((unsigned)y * t.tw + (unsigned)x);
     /* the reference reads out of bounds here (CLAMP/MIRROR round v*(h-1)+0.5 up to row h); defined as
        "memory after the texture reads as zero": RGBA 0, and alpha 255 for the 3-byte formats */
+    if (t.fmt >= PFCU_TEX_PIX) return tex_fetch_pix(t.base, t.total, off, t.fmt - PFCU_TEX_PIX);
     if ((unsigned)off >= t.total) return (t.fmt >= PFCU_TEX_RGB8) ? 0xff000000u : 0u;
     if (t.fmt == PFCU_TEX_RGBA8) return __ldg((const unsigned *)t.base + off);
     if (t.fmt == PFCU_TEX_BGRA8) { const unsigned r = __ldg((const unsigned *)t.base + off); return __byte_perm(r, 0, 0x3012); }

@@ -125,6 +125,41 @@ static uint8_t *make_texture(int w, int h, int comps, uint32_t seed, int lo, int
     return t;
 }
 
+/* A texture in any (format, type) pair the reference has texel getters for ("texfmt" scene).  Byte and packed types take
+   random bits; half and float components lie in [0, 1] with a few above 1 and below 0 mixed in (the reference's getters
+   OR the converted channels together without masking, pixel.h:2652-3040: those texels smear into their neighbours). */
+static uint8_t *make_texture_pair(int w, int h, PFpixelformat f, PFdatatype t, uint32_t seed, int *texel_bytes)
+{
+    const int comps = f <= PF_LUMINANCE ? 1 : (f == PF_LUMINANCE_ALPHA ? 2 : ((f == PF_RGB || f == PF_BGR) ? 3 : 4));
+    const int bytes = t == PF_UNSIGNED_BYTE ? comps : (t == PF_HALF_FLOAT ? 2 * comps : (t == PF_FLOAT ? 4 * comps : 2));
+    uint8_t *px = (uint8_t *)calloc((size_t)w * (h + 2) * bytes + 16, 1);
+    lcg_state = seed;
+    const size_t n = (size_t)w * h;
+    if (t == PF_HALF_FLOAT) {
+        uint16_t *p = (uint16_t *)px;
+        for (size_t i = 0; i < n * comps; i++) {
+            uint32_t r = lcg() >> 8;
+            uint16_t v = (uint16_t)(r % 0x3C01u);                     /* 0 .. 1.0 */
+            if ((r >> 16) % 61u == 0) v = 0x3E00;                     /* 1.5 */
+            else if ((r >> 16) % 67u == 0) v |= 0x8000u;              /* negative */
+            p[i] = v;
+        }
+    } else if (t == PF_FLOAT) {
+        float *p = (float *)px;
+        for (size_t i = 0; i < n * comps; i++) {
+            uint32_t r = lcg() >> 8;
+            float v = (float)(r & 0xFFFFu) / 65535.0f;
+            if ((r >> 16) % 61u == 0) v += 1.0f;
+            else if ((r >> 16) % 67u == 0) v = -v;
+            p[i] = v;
+        }
+    } else {
+        for (size_t i = 0; i < n * bytes; i++) px[i] = (uint8_t)(lcg() >> 24);
+    }
+    *texel_bytes = bytes;
+    return px;
+}
+
 /* ---- C1: gears (call sequence of the reference's Gears demo, examples/SDL2/SDL2_Gears.c:4-194) --- */
 
 static unsigned long long g_api_tris;
@@ -788,6 +823,12 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
            MAIN buffer the reference computes vpMax = x+width (one past the last column/row,
            context.c:567-570), so "2D" triangles may touch column 96 / row 80 */
         if (cfg->variant & (1 << 20)) s->fbo = pfGenFramebuffer(104, 88, tfmt, PF_UNSIGNED_BYTE);       /* same layout as the target */
+    } else if (strcmp(name, "texfmt") == 0) {
+        /* "texfmt": the micro scene sampling a texture whose layout is the pair size = format * 16 + type */
+        int tb = 0;
+        const PFpixelformat f = (PFpixelformat)(cfg->size >> 4); const PFdatatype t = (PFdatatype)(cfg->size & 15);
+        s->texpx = make_texture_pair(53, 29, f, t, (uint32_t)cfg->seed ^ 0x7e57u, &tb);
+        s->tex = pfGenTexture(s->texpx, 53, 29, f, t);
     } else if (strcmp(name, "prims") == 0) {
         /* no resources */
     } else if (strcmp(name, "api") == 0) {
@@ -906,6 +947,9 @@ SCN_API void pfscene_frame(void *handle, int frame)
             pfColor4ub(255, 255, 255, 255);
             draw_textured_quad(s->fbo.texture, 8.0f, 6.0f, 0.7f * w, 0.6f * h, 1.0f, 1.0f, 0);
         } else micro_scene(cfg, s->tex);
+    } else if (strcmp(name, "texfmt") == 0) {
+        pfscene_cfg sub = *cfg; sub.size = 0; sub.variant |= 512;
+        micro_scene(&sub, s->tex);
     } else if (strcmp(name, "api") == 0) {
         api_scene(cfg, s->tex, s->aux);
     } else if (strcmp(name, "prims") == 0) {

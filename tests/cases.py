@@ -164,3 +164,34 @@ CASES += [_prims("target-bgra-blend1-thick", blend=1, thick=1, seed=31, target=T
           _prims("target-bgr-persp-blend0", blend=0, persp=1, seed=33, target=TARGET_BGR)]
 
 CASE_IDS = [c[0] for c in CASES]
+
+# textures in every (format, type) pair besides the four 8-bit layouts (scene "texfmt": the micro scene sampling a 53x29
+# texture of that pair; size = format * 16 + type): the reference's SIMD texel getters (pixel.h:2249-3040), including
+# what they do with out-of-range half / float components
+_PF_FORMATS = dict(red=0, green=1, blue=2, alpha=3, lum=4, luma=5, rgb=6, rgba=7, bgr=8, bgra=9)
+_PF_TYPES = dict(ubyte=0, s565=2, s5551=3, s4444=4, half=9, float=10)
+
+
+def texture_pairs():
+    out = []
+    for f, fv in _PF_FORMATS.items():
+        comps = 1 if fv <= 4 else 2 if fv == 5 else 3 if fv in (6, 8) else 4
+        for t, tv in _PF_TYPES.items():
+            if (tv == 2 and comps != 3) or (tv in (3, 4) and comps != 4) or (tv == 0 and comps >= 3):
+                continue
+            out.append((f"{f}-{t}", fv * 16 + tv))
+    return out
+
+
+def _texfmt(name, code, k):
+    nearest = micro_variant(tex=1, wrap=k % 3, blend=(None, 1, 5, 2)[k % 4], depth=(None, 1)[k % 2], persp=(k // 2) % 2, cull_off=k % 2)
+    bilinear = micro_variant(tex=1, bil=1, wrap=(k + 1) % 3, blend=(1, None, 0)[k % 3], persp=k % 2, cull_off=1)
+    return [(f"texfmt-{name}-nearest", "texfmt", 160, 120, dict(variant=nearest, seed=40 + k, size=code), False),
+            (f"texfmt-{name}-bilinear", "texfmt", 160, 120, dict(variant=bilinear, seed=80 + k, size=code), True)]
+
+
+for _k, (_name, _code) in enumerate(texture_pairs()):
+    CASES += _texfmt(_name, _code, _k)
+
+CASE_IDS = [c[0] for c in CASES]
+assert len(set(CASE_IDS)) == len(CASE_IDS)

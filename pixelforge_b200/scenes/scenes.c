@@ -160,6 +160,232 @@ static uint8_t *make_texture_pair(int w, int h, PFpixelformat f, PFdatatype t, u
     return px;
 }
 
+/* ---- "conform": the corners of the public API no other scene touches ------------------------------ */
+/* Every pfGet*v getter over every PFgettable and PFstate (plus invalid names), pfIsEnabled / pfIsEnabledLight / pfGetError,
+   all pfColor* / pfVertex* / pfRasterPos* / pfRect* argument variants, pfFogfv, the framebuffer pixel accessors
+   (pfSetFramebufferPixel / ...Depth / ...DepthTest, pfGetFramebufferPixel / ...Depth, pfClearFramebuffer, pfIsValid*),
+   pfGetTexturePixels, pfGetCurrentContext.  What the getters return is written word by word into a 128x64 framebuffer
+   object through pfSetFramebufferPixel and drawn onto the target with pfDrawPixels, so that the ordinary colour / depth
+   comparison against the reference covers it.  variant bit 0: blending + depth test while the variants draw. */
+/* exported by the reference library (context.c:1928-1936) but missing from its header */
+extern void pfRecti(PFint x1, PFint y1, PFint x2, PFint y2);
+extern void pfRectiv(const PFint *v1, const PFint *v2);
+typedef struct { PFframebuffer *fb; uint32_t n; } conf_log;
+static void conf_word(conf_log *l, uint32_t wd)
+{
+    if (l->n >= 128u * 60u) return;
+    PFcolor c; memcpy(&c, &wd, 4);
+    pfSetFramebufferPixel(l->fb, (PFsizei)(l->n % 128u), (PFsizei)(l->n / 128u), c);
+    l->n++;
+}
+static void conf_words(conf_log *l, const void *p, int nwords)
+{
+    const uint32_t *u = (const uint32_t *)p;
+    for (int i = 0; i < nwords; i++) conf_word(l, u[i]);
+}
+static void conf_getters(conf_log *l, PFenum name)
+{
+    PFint iv[16]; PFfloat fv[16]; PFdouble dv[16]; PFboolean bv[4];
+    memset(iv, 0, sizeof iv); memset(fv, 0, sizeof fv); memset(dv, 0, sizeof dv); memset(bv, 0, sizeof bv);
+    pfGetIntegerv(name, iv); conf_word(l, (uint32_t)pfGetError()); conf_words(l, iv, 4);
+    pfGetFloatv(name, fv);   conf_word(l, (uint32_t)pfGetError()); conf_words(l, fv, 16);
+    pfGetDoublev(name, dv);  conf_word(l, (uint32_t)pfGetError()); conf_words(l, dv, 32);
+    pfGetBooleanv(name, bv); conf_word(l, (uint32_t)pfGetError()); conf_word(l, (uint32_t)(bv[0] != 0));
+}
+
+static void conform_scene(const pfscene_cfg *cfg, PFtexture tex, PFframebuffer *fbo, uint8_t *aux, uint8_t *target, PFpixelformat tfmt)
+{
+    const int v = cfg->variant, w = cfg->width, h = cfg->height;
+    static float varr[12]; static uint8_t carr[16];
+    conf_log log = { fbo, 0 };
+    lcg_state = (uint32_t)cfg->seed * 22695477u + 1u;
+    pfClearFramebuffer(fbo, (PFcolor){ 1, 2, 3, 4 }, 0.5f);
+    pfClearColor(12, 34, 56, 255);
+    pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+
+    /* 1. state with a distinct value everywhere, then every getter */
+    pfViewport(3, 5, (PFsizei)(w - 10), (PFsizei)(h - 9));
+    pfClearDepth(0.75f);
+    pfEnable(PF_CULL_FACE); pfCullFace(PF_FRONT);
+    pfColor4us(0x1234, 0x5678, 0x9abc, 0xdef0);
+    pfNormal3f(0.25f, -0.5f, 0.75f);
+    pfTexCoord2f(0.125f, 0.625f);
+    pfRasterPos4f(7.5f, 9.25f, 0.5f, 2.0f);
+    pfBlendFunc(PF_BLEND_SCREEN); pfDepthFunc(PF_GEQUAL);
+    pfPolygonMode(PF_FRONT, PF_LINE); pfPolygonMode(PF_BACK, PF_POINT);
+    pfPointSize(3.5f); pfLineWidth(2.25f);
+    pfShadeModel(PF_FLAT);
+    pfMatrixMode(PF_PROJECTION); pfLoadIdentity(); pfFrustum(-1.0f, 1.5f, -0.75f, 0.5f, 1.0f, 40.0f);
+    pfMatrixMode(PF_TEXTURE); pfLoadIdentity(); pfScalef(2.0f, 0.5f, 1.0f); pfTranslatef(0.25f, 0.5f, 0.0f);
+    pfMatrixMode(PF_MODELVIEW); pfLoadIdentity(); pfTranslatef(1.0f, -2.0f, -5.0f); pfRotatef(33.0f, 0.3f, 0.5f, 0.7f);
+    pfPushMatrix(); pfScalef(1.5f, 0.5f, 2.0f);
+    pfVertexPointer(3, PF_FLOAT, 12, varr); pfNormalPointer(PF_FLOAT, 12, varr); pfTexCoordPointer(PF_FLOAT, 8, varr);
+    pfColorPointer(4, PF_UNSIGNED_BYTE, 4, carr);
+    pfEnable(PF_VERTEX_ARRAY); pfEnable(PF_COLOR_ARRAY);
+    pfPixelZoom(1.5f, -2.0f);
+    pfEnable(PF_TEXTURE_2D); pfBindTexture(tex); pfEnable(PF_NORMALIZE); pfEnable(PF_COLOR_MATERIAL);
+    pfEnableLight(PF_LIGHT3);
+    conf_word(&log, (uint32_t)pfGetError());
+    for (int name = PF_VIEWPORT - 1; name <= PF_ZOOM_Y + 1; name++) conf_getters(&log, (PFenum)name);
+    for (int bit = 0; bit < 13; bit++) {
+        PFboolean b = 0;
+        pfGetBooleanv((PFenum)(1 << bit), &b); conf_word(&log, (uint32_t)pfGetError()); conf_word(&log, (uint32_t)(b != 0));
+        conf_word(&log, (uint32_t)(pfIsEnabled((PFstate)(1 << bit)) != 0));
+    }
+    for (int li = 0; li < 8; li++) conf_word(&log, (uint32_t)(pfIsEnabledLight((PFsizei)li) != 0));
+    {
+        const void *ptr = NULL;
+        pfGetPointerv(PF_TEXTURE_2D, &ptr);  conf_word(&log, (uint32_t)(ptr == (const void *)tex));
+        ptr = (const void *)&log; pfGetPointerv(PF_FRAMEBUFFER, &ptr); conf_word(&log, (uint32_t)(ptr == NULL));
+        pfGetPointerv(PF_BLEND_FUNC, &ptr);  conf_word(&log, (uint32_t)(ptr != NULL)); conf_word(&log, (uint32_t)pfGetError());
+        pfGetPointerv(PF_DEPTH_FUNC, &ptr);  conf_word(&log, (uint32_t)(ptr != NULL)); conf_word(&log, (uint32_t)pfGetError());
+        pfGetPointerv(PF_VIEWPORT, &ptr);    conf_word(&log, (uint32_t)pfGetError());
+        PFsizei tw = 0, th = 0; PFpixelformat tf = PF_RED; PFdatatype tt = PF_FLOAT;
+        void *px = pfGetTexturePixels(tex, &tw, &th, &tf, &tt);
+        conf_word(&log, (uint32_t)tw); conf_word(&log, (uint32_t)th); conf_word(&log, (uint32_t)tf); conf_word(&log, (uint32_t)tt);
+        conf_words(&log, px, 4);
+        conf_word(&log, (uint32_t)(pfIsValidTexture(tex) != 0)); conf_word(&log, (uint32_t)(pfIsValidFramebuffer(fbo) != 0));
+        PFframebuffer none = { NULL, NULL };
+        conf_word(&log, (uint32_t)(pfIsValidFramebuffer(&none) != 0));
+        conf_word(&log, (uint32_t)(pfGetCurrentContext() != NULL));
+    }
+    /* errors are sticky until fetched, and fetching clears them */
+    pfBlendFunc((PFblendmode)77); pfDepthFunc((PFdepthmode)99); pfCullFace((PFface)17);
+    conf_word(&log, (uint32_t)pfGetError()); conf_word(&log, (uint32_t)pfGetError());
+    pfPopMatrix(); pfPopMatrix(); pfPopMatrix();
+    conf_word(&log, (uint32_t)pfGetError());
+    pfLightf((PFsizei)99, PF_SHININESS, 1.0f); conf_word(&log, (uint32_t)pfGetError());
+    pfMaterialf(PF_FRONT, PF_POSITION, 1.0f); conf_word(&log, (uint32_t)pfGetError());
+    {
+        PFfloat fc[4] = { 0.2f, 0.4f, 0.6f, 0.8f }, fs = 1.5f, fe = 4.0f, fd = 1.0f;
+        pfFogfv(PF_FOG_COLOR, fc); pfFogfv(PF_FOG_START, &fs); pfFogfv(PF_FOG_END, &fe); pfFogfv(PF_FOG_DENSITY, &fd);
+        pfFogfv((PFfogparam)55, &fd); conf_word(&log, (uint32_t)pfGetError());
+    }
+
+    /* 2. back to a plain 2D state; one small rectangle / quad per argument variant */
+    pfDisable(PF_VERTEX_ARRAY); pfDisable(PF_COLOR_ARRAY);
+    pfDisable(PF_TEXTURE_2D); pfDisable(PF_NORMALIZE); pfDisable(PF_COLOR_MATERIAL); pfDisableLight(PF_LIGHT3);
+    pfPolygonMode(PF_FRONT_AND_BACK, PF_FILL); pfShadeModel(PF_SMOOTH); pfPointSize(1.0f); pfLineWidth(1.0f);
+    pfMatrixMode(PF_TEXTURE); pfLoadIdentity();
+    ortho2d(w, h);
+    pfDisable(PF_CULL_FACE); pfCullFace(PF_BACK);
+    if (v & 1) { pfEnable(PF_BLEND); pfBlendFunc(PF_BLEND_ALPHA); pfEnable(PF_DEPTH_TEST); pfDepthFunc(PF_LEQUAL); }
+    else { pfDisable(PF_BLEND); pfDisable(PF_DEPTH_TEST); pfBlendFunc(PF_BLEND_ALPHA); pfDepthFunc(PF_LESS); }
+    for (int k = 0; k < 17; k++) {
+        const PFubyte ub[4] = { (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(128 + (lcg() >> 25)) };
+        const PFushort us[4] = { (PFushort)(lcg() >> 16), (PFushort)(lcg() >> 16), (PFushort)(lcg() >> 16), (PFushort)(0x8000u | (lcg() >> 17)) };
+        const PFuint ui[4] = { lcg(), lcg(), lcg(), 0x80000000u | lcg() };
+        const PFfloat fl[4] = { lcgf(), lcgf(), lcgf(), 0.5f + 0.5f * lcgf() };
+        switch (k) {
+        case 0: pfColor1ui(ui[0] | 0xc0000000u); break;        case 1: pfColor3ub(ub[0], ub[1], ub[2]); break;
+        case 2: pfColor3ubv(ub); break;                         case 3: pfColor3us(us[0], us[1], us[2]); break;
+        case 4: pfColor3usv(us); break;                         case 5: pfColor3ui(ui[0], ui[1], ui[2]); break;
+        case 6: pfColor3uiv(ui); break;                         case 7: pfColor3f(fl[0], fl[1], fl[2]); break;
+        case 8: pfColor3fv(fl); break;                          case 9: pfColor4ub(ub[0], ub[1], ub[2], ub[3]); break;
+        case 10: pfColor4ubv(ub); break;                        case 11: pfColor4us(us[0], us[1], us[2], us[3]); break;
+        case 12: pfColor4usv(us); break;                        case 13: pfColor4ui(ui[0], ui[1], ui[2], ui[3]); break;
+        case 14: pfColor4uiv(ui); break;                        case 15: pfColor4f(fl[0], fl[1], fl[2], fl[3]); break;
+        default: pfColor4fv(fl); break;
+        }
+        PFint ci[4]; memset(ci, 0, sizeof ci); pfGetIntegerv(PF_CURRENT_COLOR, ci); conf_words(&log, ci, 4);
+        const int x0 = 6 + (k % 6) * 24, y0 = 70 + (k / 6) * 14;
+        const PFshort s1[2] = { (PFshort)x0, (PFshort)y0 }, s2[2] = { (PFshort)(x0 + 18), (PFshort)(y0 + 10) };
+        const PFint i1[2] = { x0, y0 }, i2[2] = { x0 + 18, y0 + 10 };
+        const PFfloat f1[2] = { (PFfloat)x0 + 0.25f, (PFfloat)y0 + 0.5f }, f2[2] = { (PFfloat)x0 + 18.5f, (PFfloat)y0 + 10.25f };
+        switch (k % 6) {
+        case 0: pfRects(s1[0], s1[1], s2[0], s2[1]); break;     case 1: pfRectsv(s1, s2); break;
+        case 2: pfRecti(i1[0], i1[1], i2[0], i2[1]); break;     case 3: pfRectiv(i1, i2); break;
+        case 4: pfRectf(f1[0], f1[1], f2[0], f2[1]); break;     default: pfRectfv(f1, f2); break;
+        }
+    }
+    /* vertex argument variants: nine overlapping quads (w = 1 or 2: the 4-component forms divide) */
+    for (int k = 0; k < 9; k++) {
+        const int x0 = 10 + k * 16, y0 = 118;
+        pfColor4ub((PFubyte)(40 + 20 * k), (PFubyte)(250 - 25 * k), (PFubyte)(90 + 10 * k), 200);
+        pfBegin(PF_QUADS);
+        for (int c = 0; c < 4; c++) {
+            const int xi = x0 + ((c == 1 || c == 2) ? 22 : 0), yi = y0 + ((c >= 2) ? 20 : 0);
+            const PFfloat f4[4] = { (PFfloat)xi + 0.5f, (PFfloat)yi + 0.25f, -0.5f, 1.0f };
+            switch (k) {
+            case 0: pfVertex2i(xi, yi); break;                  case 1: pfVertex2f(f4[0], f4[1]); break;
+            case 2: pfVertex2fv(f4); break;                     case 3: pfVertex3i(xi, yi, 0); break;
+            case 4: pfVertex3f(f4[0], f4[1], f4[2]); break;     case 5: pfVertex3fv(f4); break;
+            case 6: pfVertex4i(xi, yi, 0, 1); break;            case 7: pfVertex4f(f4[0], f4[1], f4[2], f4[3]); break;
+            default: pfVertex4fv(f4); break;
+            }
+        }
+        pfEnd();
+    }
+    /* raster position variants, each followed by a 6x5 pfDrawPixels */
+    for (size_t i = 0; i < 6u * 5u * 4u; i++) aux[i] = (uint8_t)(lcg() >> 24);
+    for (int k = 0; k < 9; k++) {
+        const int xi = 8 + k * 15, yi = 40;
+        const PFfloat f4[4] = { (PFfloat)xi + 0.75f, (PFfloat)yi + 0.5f, 0.25f, 1.0f };
+        switch (k) {
+        case 0: pfRasterPos2i(xi, yi); break;                   case 1: pfRasterPos2f(f4[0], f4[1]); break;
+        case 2: pfRasterPos2fv(f4); break;                      case 3: pfRasterPos3i(xi, yi, 0); break;
+        case 4: pfRasterPos3f(f4[0], f4[1], f4[2]); break;      case 5: pfRasterPos3fv(f4); break;
+        case 6: pfRasterPos4i(xi, yi, 0, 1); break;             case 7: pfRasterPos4f(f4[0], f4[1], f4[2], f4[3]); break;
+        default: pfRasterPos4fv(f4); break;
+        }
+        PFfloat rp[4] = { 0, 0, 0, 0 }; pfGetFloatv(PF_CURRENT_RASTER_POSITION, rp); conf_words(&log, rp, 4);
+        pfPixelZoom(1.0f, 1.0f);
+        pfDrawPixels(6, 5, PF_RGBA, PF_UNSIGNED_BYTE, aux);
+    }
+
+    /* 3. framebuffer pixel accessors on the object's last rows (the log never reaches row 60) */
+    for (int k = 0; k < 24; k++) {
+        const PFsizei x = (PFsizei)(5 + 4 * k), y = (PFsizei)(60 + (k & 3));
+        const PFcolor c = { (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24) };
+        const PFfloat z = 0.25f + 0.5f * lcgf();          /* around the 0.5 the object was cleared to */
+        if (k % 3 == 0) pfSetFramebufferPixelDepth(fbo, x, y, z, c);
+        else if (k % 3 == 1) pfSetFramebufferPixelDepthTest(fbo, x, y, z, c, (PFdepthmode)(k % 6));
+        else pfSetFramebufferPixel(fbo, x, y, c);
+        const PFcolor g = pfGetFramebufferPixel(fbo, x, y); const PFfloat gz = pfGetFramebufferDepth(fbo, x, y);
+        conf_words(&log, &g, 1); conf_words(&log, &gz, 1);
+    }
+    pfSetFramebufferPixelDepthTest(fbo, 1, 61, 0.1f, (PFcolor){ 9, 9, 9, 9 }, (PFdepthmode)42);
+    conf_word(&log, (uint32_t)pfGetError());
+
+    /* 3b. double buffering with pfSetMainBuffer (same geometry: the reference keeps the depth buffer and adopts the new
+       pixels as they are; a different size would run into upstream's realloc with an element count, context.c:284) */
+    {
+        uint8_t *second = aux + 4096;
+        for (size_t i = 0; i < (size_t)w * h * 4; i++) second[i] = (uint8_t)(lcg() >> 24);
+        finish();                                  /* explicit-sync mode: the outgoing buffer is brought up to date at sync points only */
+        pfSetMainBuffer(second, (PFsizei)w, (PFsizei)h, tfmt, PF_UNSIGNED_BYTE);
+        conf_word(&log, (uint32_t)pfGetError());
+        pfEnable(PF_BLEND); pfBlendFunc(PF_BLEND_ADD);
+        pfColor4ub(40, 80, 20, 90); pfRecti(30, 30, 90, 60);
+        pfDisable(PF_BLEND);
+        PFcolor rd[16 * 8]; memset(rd, 0, sizeof rd);
+        pfReadPixels(40, 40, 16, 8, PF_RGBA, PF_UNSIGNED_BYTE, rd); conf_words(&log, rd, 16 * 8);
+        pfReadPixels(100, 100, 8, 2, PF_RGBA, PF_UNSIGNED_BYTE, rd); conf_words(&log, rd, 8 * 2);
+        finish();
+        pfSetMainBuffer(target, (PFsizei)w, (PFsizei)h, tfmt, PF_UNSIGNED_BYTE);
+        pfSetMainBuffer(NULL, (PFsizei)w, (PFsizei)h, tfmt, PF_UNSIGNED_BYTE);
+        conf_word(&log, (uint32_t)pfGetError());
+        if (v & 1) { pfEnable(PF_BLEND); pfBlendFunc(PF_BLEND_ALPHA); }
+        pfColor4ub(200, 100, 50, 160); pfRecti(150, 150, 190, 200);
+    }
+
+    /* 4. the log and the object's depth onto the target */
+    {
+        PFsizei tw = 0, th = 0; PFpixelformat tf = PF_RED; PFdatatype tt = PF_FLOAT;
+        void *px = pfGetTexturePixels(fbo->texture, &tw, &th, &tf, &tt);
+        pfDisable(PF_BLEND); pfDisable(PF_DEPTH_TEST);
+        pfRasterPos2i(16, 150); pfPixelZoom(1.0f, 1.0f);
+        pfDrawPixels(tw, th, tf, tt, px);
+        for (int k = 0; k < 24; k++) {
+            const PFsizei x = (PFsizei)(5 + 4 * k), y = (PFsizei)(60 + (k & 3));
+            const PFfloat gz = pfGetFramebufferDepth(fbo, x, y);
+            PFcolor c; memcpy(&c, &gz, 4);
+            pfColor(c); pfRecti(20 + 5 * k, 8, 24 + 5 * k, 12);
+        }
+    }
+    pfColor4ub(255, 255, 255, 255);
+}
+
 /* ---- C1: gears (call sequence of the reference's Gears demo, examples/SDL2/SDL2_Gears.c:4-194) --- */
 
 static unsigned long long g_api_tris;
@@ -628,6 +854,8 @@ static void api_scene(const pfscene_cfg *cfg, PFtexture tex, uint8_t *aux)
     pfDisable(PF_BLEND);
 }
 
+static const PFpixelformat target_formats_g[4] = { PF_RGBA, PF_BGRA, PF_RGB, PF_BGR };
+
 /* ---- the runner ------------------------------------------------------------------------------------ */
 
 #define MAX_BATCH_CTX 1024
@@ -767,7 +995,7 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
     /* variant bits 24-25 (every single-context scene): layout of the target buffer - 0 RGBA8, 1 BGRA8, 2 RGB8, 3 BGR8.
        The buffer is always w*h*4 bytes (+ padding: the reference's RGB getter reads 4 bytes per pixel); 3-byte layouts
        use the first w*h*3 of them. */
-    static const PFpixelformat target_formats[4] = { PF_RGBA, PF_BGRA, PF_RGB, PF_BGR };
+    const PFpixelformat *target_formats = target_formats_g;
     const PFpixelformat tfmt = target_formats[(cfg->variant >> 24) & 3];
     s->target = (uint8_t *)calloc((size_t)w * h * 4 + 64, 1);
     s->ctx = pfCreateContext(s->target, (PFsizei)w, (PFsizei)h, tfmt, PF_UNSIGNED_BYTE);
@@ -829,6 +1057,11 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
         const PFpixelformat f = (PFpixelformat)(cfg->size >> 4); const PFdatatype t = (PFdatatype)(cfg->size & 15);
         s->texpx = make_texture_pair(53, 29, f, t, (uint32_t)cfg->seed ^ 0x7e57u, &tb);
         s->tex = pfGenTexture(s->texpx, 53, 29, f, t);
+    } else if (strcmp(name, "conform") == 0) {
+        s->texpx = make_texture(32, 16, 4, (uint32_t)cfg->seed ^ 0xc0f0u, 0, 255, 0, 255);
+        s->tex = pfGenTexture(s->texpx, 32, 16, PF_RGBA, PF_UNSIGNED_BYTE);
+        s->fbo = pfGenFramebuffer(128, 64, PF_RGBA, PF_UNSIGNED_BYTE);
+        s->aux = (uint8_t *)calloc((size_t)w * h * 4 + 4096 + 64, 1);
     } else if (strcmp(name, "prims") == 0) {
         /* no resources */
     } else if (strcmp(name, "api") == 0) {
@@ -950,6 +1183,8 @@ SCN_API void pfscene_frame(void *handle, int frame)
     } else if (strcmp(name, "texfmt") == 0) {
         pfscene_cfg sub = *cfg; sub.size = 0; sub.variant |= 512;
         micro_scene(&sub, s->tex);
+    } else if (strcmp(name, "conform") == 0) {
+        conform_scene(cfg, s->tex, &s->fbo, s->aux, s->target, target_formats_g[(cfg->variant >> 24) & 3]);
     } else if (strcmp(name, "api") == 0) {
         api_scene(cfg, s->tex, s->aux);
     } else if (strcmp(name, "prims") == 0) {

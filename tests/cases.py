@@ -195,3 +195,17 @@ for _k, (_name, _code) in enumerate(texture_pairs()):
 
 CASE_IDS = [c[0] for c in CASES]
 assert len(set(CASE_IDS)) == len(CASE_IDS)
+
+# the corners of the public API no other scene touches (scene "conform"): every pfGet*v getter over every PFgettable /
+# PFstate / invalid name, sticky error codes, all pfColor* / pfVertex* / pfRasterPos* / pfRect* argument variants,
+# pfFogfv, the framebuffer pixel accessors, pfClearFramebuffer, pfGetTexturePixels - what the getters return is drawn
+# into the frame, so the colour / depth comparison covers it
+def _conform(desc, variant, seed, target=0):
+    return (f"conform-{desc}", "conform", 200, 224, dict(variant=variant | (target << 24), seed=seed), False)
+
+
+CASES += [_conform("plain", 0, 1), _conform("blend-depth", 1, 2), _conform("target-bgra", 1, 3, TARGET_BGRA),
+          _conform("target-rgb", 0, 4, TARGET_RGB), _conform("target-bgr", 1, 5, TARGET_BGR)]
+
+CASE_IDS = [c[0] for c in CASES]
+assert len(set(CASE_IDS)) == len(CASE_IDS)

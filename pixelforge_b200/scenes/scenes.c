@@ -854,6 +854,265 @@ static void api_scene(const pfscene_cfg *cfg, PFtexture tex, uint8_t *aux)
     pfDisable(PF_BLEND);
 }
 
+/* ---- "examples": the call sequences of the reference's example programs --------------------------- */
+/* Restated from what the programs under examples/ do (examples/common.h:42-296 helpers, raylib/raylib_2D.c, _3D.c,
+   _Framebuffer.c, _Points.c, _ModelWires.c, _TextureMatrix.c, _Texture2D.c, _FirstPerson.c, raylib_common.h:170-280), without
+   their window system: variant & 15 picks the program, first_frame is its clock.  9 = vertex arrays in every component
+   type the API accepts (pfDrawElements / pfDrawArrays). */
+static void ex_begin3d(int w, int h, double fovy)
+{
+    pfMatrixMode(PF_PROJECTION); pfPushMatrix(); pfLoadIdentity();
+    const float aspect = (float)w / (float)h, top = 0.01f * tanf((float)(fovy * 0.5 * SCN_PI / 180.0)), right = top * aspect;
+    pfFrustum(-right, right, -top, top, 0.01f, 1000.0f);
+    pfMatrixMode(PF_MODELVIEW); pfLoadIdentity();
+    pfEnable(PF_DEPTH_TEST);
+}
+static void ex_end3d(void)
+{
+    pfMatrixMode(PF_PROJECTION); pfPopMatrix();
+    pfMatrixMode(PF_MODELVIEW); pfLoadIdentity();
+    pfDisable(PF_DEPTH_TEST);
+}
+static void ex_camera(float px, float py, float pz, float tx, float ty, float tz)
+{
+    const float eye[3] = { px, py, pz }, at[3] = { tx, ty, tz };
+    cam_lookat(eye, at);
+}
+static void ex_cube(float size)
+{
+    const float h = size * 0.5f;
+    static const float face[6][4][3] = {
+        { { -1, -1, 1 }, { 1, -1, 1 }, { 1, 1, 1 }, { -1, 1, 1 } },     { { 1, -1, -1 }, { -1, -1, -1 }, { -1, 1, -1 }, { 1, 1, -1 } },
+        { { -1, -1, -1 }, { -1, -1, 1 }, { -1, 1, 1 }, { -1, 1, -1 } }, { { 1, -1, 1 }, { 1, -1, -1 }, { 1, 1, -1 }, { 1, 1, 1 } },
+        { { -1, 1, 1 }, { 1, 1, 1 }, { 1, 1, -1 }, { -1, 1, -1 } },     { { 1, -1, 1 }, { -1, -1, 1 }, { -1, -1, -1 }, { 1, -1, -1 } } };
+    pfBegin(PF_QUADS);
+    for (int f = 0; f < 6; f++) {
+        pfColor3f(f < 2 ? 1.0f : 0.0f, (f >> 1) == 1 ? 1.0f : 0.0f, f >= 4 ? 1.0f : 0.0f);
+        for (int k = 0; k < 4; k++) pfVertex3f(face[f][k][0] * h, face[f][k][1] * h, face[f][k][2] * h);
+    }
+    pfEnd();
+}
+static void ex_grid(int slices, float spacing)
+{
+    const int hs = slices / 2;
+    pfBegin(PF_LINES);
+    for (int i = -hs; i <= hs; i++) {
+        if (i == 0) pfColor3f(0.5f, 0.5f, 0.5f); else pfColor3f(0.75f, 0.75f, 0.75f);
+        pfVertex3f((float)i * spacing, 0.0f, (float)-hs * spacing); pfVertex3f((float)i * spacing, 0.0f, (float)hs * spacing);
+        pfVertex3f((float)-hs * spacing, 0.0f, (float)i * spacing); pfVertex3f((float)hs * spacing, 0.0f, (float)i * spacing);
+    }
+    pfEnd();
+}
+static void ex_rotated_sprite(PFtexture tex, float x, float y, float wd, float ht, float ox, float oy, float deg)
+{
+    const float a = deg * (float)(SCN_PI / 180.0), c = cosf(a), sn = sinf(a), hw = wd * 0.5f, hh = ht * 0.5f;
+    const float cx[4] = { -hw, -hw, hw, hw }, cy[4] = { -hh, hh, hh, -hh }, tu[4] = { 0, 0, 1, 1 }, tv[4] = { 0, 1, 1, 0 };
+    pfBindTexture(tex);
+    pfBegin(PF_QUADS);
+    for (int k = 0; k < 4; k++) {
+        pfTexCoord2f(tu[k], tv[k]);
+        pfVertex2f(x - ox + (cx[k] * c - cy[k] * sn) + hw, y - oy + (cx[k] * sn + cy[k] * c) + hh);
+    }
+    pfEnd();
+    pfBindTexture(0);
+}
+
+static void examples_scene(const pfscene_cfg *cfg, PFtexture tex, PFframebuffer *fbo, uint8_t *aux, const mesh_t *mesh, int frame)
+{
+    const int which = cfg->variant & 15, w = cfg->width, h = cfg->height;
+    const float timer = 0.35f * (float)frame + 0.2f;
+    lcg_state = (uint32_t)cfg->seed * 69069u + 7u;
+    switch (which) {
+    case 0:     /* 2D: a triangle in normalised device coordinates, nothing but the context's initial state */
+        pfBegin(PF_TRIANGLES);
+        pfColor3f(1.0f, 0.0f, 0.0f); pfVertex2f(-0.5f, -0.5f);
+        pfColor3f(0.0f, 1.0f, 0.0f); pfVertex2f(0.5f, -0.5f);
+        pfColor3f(0.0f, 0.0f, 1.0f); pfVertex2f(0.0f, 0.5f);
+        pfEnd();
+        break;
+    case 1:     /* 3D: orbiting camera around the coloured cube */
+        ortho2d(w, h);
+        pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+        ex_begin3d(w, h, 60.0);
+        ex_camera(2.0f * cosf(timer), 1.5f, 2.0f * sinf(timer), 0, 0, 0);
+        ex_cube(1.0f);
+        ex_end3d();
+        break;
+    case 2:     /* Framebuffer: the cube into an object of the target's size, then pfDrawPixels of it at half size */
+        ortho2d(w, h);
+        pfBindFramebuffer(fbo);
+        pfEnable(PF_TEXTURE_2D);
+        pfEnable(PF_FRAMEBUFFER);
+        pfClearColor(255, 255, 255, 255);
+        pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+        ex_begin3d(w, h, 60.0);
+        ex_camera(2.0f * cosf(timer), 1.5f, 2.0f * sinf(timer), 0, 0, 0);
+        ex_cube(1.0f);
+        ex_end3d();
+        pfDisable(PF_FRAMEBUFFER);
+        pfClearColor(0, 0, 0, 255);
+        pfClear(PF_COLOR_BUFFER_BIT);
+        pfPixelZoom(0.5f, 0.5f);
+        pfRasterPos2f((float)(w - w / 2) / 2.0f, (float)(h - h / 2) / 2.0f);
+        {
+            PFpixelformat format; PFdatatype type;
+            const void *pixels = pfGetTexturePixels(fbo->texture, NULL, NULL, &format, &type);
+            pfDrawPixels((PFsizei)w, (PFsizei)h, format, type, pixels);
+        }
+        pfPixelZoom(1.0f, 1.0f);
+        pfDisable(PF_TEXTURE_2D);
+        break;
+    case 3:     /* Points: a lattice of sized points */
+        ortho2d(w, h);
+        pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+        pfPointSize(sinf(2.0f * timer) * 2.0f + 3.0f);
+        ex_begin3d(w, h, 60.0);
+        ex_camera(5.0f * cosf(timer), 3.0f, 5.0f * sinf(timer), 0, 0, 0);
+        pfBegin(PF_POINTS);
+        for (float x = -2.0f; x <= 2.0f; x += 0.5f)
+            for (float y = -2.0f; y <= 2.0f; y += 0.5f)
+                for (float z = -2.0f; z <= 2.0f; z += 0.5f) {
+                    pfColor3f((x + 2.0f) / 4.0f, (y + 2.0f) / 4.0f, (y + 2.0f) / 4.0f);
+                    pfVertex3f(x, y, z);
+                }
+        pfEnd();
+        ex_end3d();
+        pfPointSize(1.0f);
+        break;
+    case 4:     /* ModelWires: grid + a model drawn with front faces as lines (16-bit indices, as raylib meshes have) */
+    case 8: {   /* FirstPerson: the model textured and lit by a spotlight carried by the camera */
+        ortho2d(w, h);
+        pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+        ex_begin3d(w, h, 60.0);
+        static uint16_t idx16[65536];
+        const int nidx = mesh->nidx < 65536 ? mesh->nidx : 65535 / 3 * 3;
+        for (int k = 0; k < nidx; k++) idx16[k] = (uint16_t)mesh->idx[k];
+        if (which == 4) {
+            ex_camera(25.0f, 25.0f, 25.0f, 0, 10.0f, 0);
+            ex_grid(10, 10.0f);
+            pfPolygonMode(PF_FRONT, PF_LINE);
+        } else {
+            const float cam[3] = { 30.0f * cosf(timer), 14.0f, 30.0f * sinf(timer) }, dir[3] = { -cam[0], 10.0f - cam[1], -cam[2] };
+            const float amb[3] = { 0.2f, 0.2f, 0.3f };
+            ex_camera(cam[0], cam[1], cam[2], 0, 10.0f, 0);
+            pfLightf(PF_LIGHT0, PF_SPOT_INNER_CUTOFF, 17.5f); pfLightf(PF_LIGHT0, PF_SPOT_OUTER_CUTOFF, 32.5f);
+            pfLightfv(PF_LIGHT0, PF_AMBIENT, amb);
+            pfLightf(0, PF_LINEAR_ATTENUATION, 0.009f); pfLightf(0, PF_QUADRATIC_ATTENUATION, 0.0032f);
+            pfLightfv(PF_LIGHT0, PF_POSITION, cam); pfLightfv(PF_LIGHT0, PF_SPOT_DIRECTION, dir);
+            pfEnable(PF_LIGHTING); pfEnableLight(PF_LIGHT0);
+            pfEnable(PF_TEXTURE_2D); pfBindTexture(tex);
+        }
+        pfPushMatrix();
+        pfTranslatef(0.0f, 10.0f, 0.0f); pfScalef(0.9f, 0.9f, 0.9f);
+        pfColor4ub(255, 255, 255, 255);
+        pfEnable(PF_VERTEX_ARRAY); pfVertexPointer(3, PF_FLOAT, 0, mesh->pos);
+        pfEnable(PF_NORMAL_ARRAY); pfNormalPointer(PF_FLOAT, 0, mesh->nrm);
+        pfEnable(PF_TEXTURE_COORD_ARRAY); pfTexCoordPointer(PF_FLOAT, 0, mesh->uv);
+        pfDrawElements(PF_TRIANGLES, (PFsizei)nidx, PF_UNSIGNED_SHORT, idx16);
+        pfDisable(PF_VERTEX_ARRAY); pfDisable(PF_NORMAL_ARRAY); pfDisable(PF_TEXTURE_COORD_ARRAY);
+        pfPopMatrix();
+        if (which == 4) pfPolygonMode(PF_FRONT, PF_FILL);
+        else { pfBindTexture(0); pfDisable(PF_TEXTURE_2D); pfDisable(PF_LIGHTING); pfDisableLight(PF_LIGHT0); }
+        ex_end3d();
+        break; }
+    case 5:     /* TextureMatrix: a ground plane far larger than the frustum, its texture scrolled by the texture matrix */
+        ortho2d(w, h);
+        pfEnable(PF_TEXTURE_2D);
+        pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+        ex_begin3d(w, h, 60.0);
+        ex_camera(-2.0f, 1.5f + 0.1f * (float)frame, -2.0f, 0, 0, 0);
+        pfMatrixMode(PF_TEXTURE); pfLoadIdentity();
+        pfTranslatef(0.25f * timer, 0.25f * timer, 0.0f);
+        pfMatrixMode(PF_MODELVIEW);
+        pfBindTexture(tex);
+        pfColor4ub(255, 255, 255, 255);
+        pfBegin(PF_QUADS);
+        pfTexCoord2f(0, 0); pfVertex3f(-1000, 0, -1000);
+        pfTexCoord2f(0, 200); pfVertex3f(-1000, 0, 1000);
+        pfTexCoord2f(200, 200); pfVertex3f(1000, 0, 1000);
+        pfTexCoord2f(200, 0); pfVertex3f(1000, 0, -1000);
+        pfEnd();
+        pfBindTexture(NULL);
+        ex_end3d();
+        pfMatrixMode(PF_TEXTURE); pfLoadIdentity(); pfMatrixMode(PF_MODELVIEW);
+        pfDisable(PF_TEXTURE_2D);
+        break;
+    case 6:     /* Texture2D: two states in one pfEnable, a LUMINANCE_ALPHA background stretched by pfDrawPixels, rotated sprites */
+        ortho2d(w, h);
+        pfEnable((PFstate)(PF_TEXTURE_2D | PF_BLEND));
+        pfClear(PF_COLOR_BUFFER_BIT);
+        for (size_t i = 0; i < 40u * 20u * 2u; i++) aux[i] = (uint8_t)(lcg() >> 24);
+        pfRasterPos2i(0, h - h / 2);
+        pfPixelZoom((float)w / 40.0f, (float)(h / 2) / 20.0f);
+        pfDrawPixels(40, 20, PF_LUMINANCE_ALPHA, PF_UNSIGNED_BYTE, aux);
+        pfPixelZoom(1.0f, 1.0f);
+        for (int k = 0; k < 12; k++)
+            ex_rotated_sprite(tex, 20.0f + lcgf() * (float)(w - 100), 20.0f + lcgf() * (float)(h - 100), 64, 64, 32, 32, 360.0f * lcgf() + 20.0f * timer);
+        pfDisable((PFstate)(PF_TEXTURE_2D | PF_BLEND));
+        break;
+    default: {  /* 9: vertex arrays in every component type; strides are ignored upstream (context.c:1282-1370 index j*size+k) */
+        ortho2d(w, h);
+        pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+        static PFshort ps[64 * 2]; static PFint pi[64 * 3]; static PFfloat pf4[64 * 4]; static PFdouble pd[64 * 3];
+        static PFfloat nf[64 * 3]; static PFdouble nd[64 * 3]; static PFfloat tf[64 * 2]; static PFdouble td[64 * 2];
+        static PFubyte cub[64 * 4]; static PFushort cus[64 * 3]; static PFuint cui[64 * 4]; static PFfloat cf[64 * 3]; static PFdouble cd[64 * 4];
+        static PFubyte i8[96]; static PFushort i16[96]; static PFuint i32[96];
+        pfEnable(PF_TEXTURE_2D); pfBindTexture(tex);
+        pfEnable(PF_BLEND); pfBlendFunc(PF_BLEND_ALPHA);
+        for (int pass = 0; pass < 10; pass++) {
+            const int ox = 10 + (pass % 5) * 60, oy = 10 + (pass / 5) * 90;
+            for (int v = 0; v < 64; v++) {
+                const float x = (float)ox + lcgf() * 50.0f, y = (float)oy + lcgf() * 80.0f;
+                ps[2 * v] = (PFshort)x; ps[2 * v + 1] = (PFshort)y;
+                pi[3 * v] = (PFint)x; pi[3 * v + 1] = (PFint)y; pi[3 * v + 2] = 0;
+                pf4[4 * v] = x; pf4[4 * v + 1] = y; pf4[4 * v + 2] = -0.25f; pf4[4 * v + 3] = 1.0f;
+                pd[3 * v] = x; pd[3 * v + 1] = y; pd[3 * v + 2] = -0.5;
+                for (int k = 0; k < 3; k++) { nf[3 * v + k] = lcgf() - 0.5f; nd[3 * v + k] = nf[3 * v + k]; }
+                for (int k = 0; k < 2; k++) { tf[2 * v + k] = lcgf() * 2.0f; td[2 * v + k] = tf[2 * v + k]; }
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t r = lcg();
+                    cub[4 * v + k] = (PFubyte)(r >> 24); cui[4 * v + k] = r; cd[4 * v + k] = (double)(r >> 8) / 16777216.0;
+                    if (k < 3) { cus[3 * v + k] = (PFushort)(r >> 16); cf[3 * v + k] = (float)(r >> 8) / 16777216.0f; }
+                }
+            }
+            for (int k = 0; k < 96; k++) { const uint32_t j = lcg() >> 26; i8[k] = (PFubyte)j; i16[k] = (PFushort)j; i32[k] = j; }
+            pfEnable(PF_VERTEX_ARRAY);
+            switch (pass % 4) {
+            case 0: pfVertexPointer(2, PF_SHORT, 0, ps); break;     case 1: pfVertexPointer(3, PF_INT, 64, pi); break;
+            case 2: pfVertexPointer(4, PF_FLOAT, 0, pf4); break;    default: pfVertexPointer(3, PF_DOUBLE, 8, pd); break;
+            }
+            if (pass & 1) { pfEnable(PF_NORMAL_ARRAY); if (pass & 2) pfNormalPointer(PF_DOUBLE, 0, nd); else pfNormalPointer(PF_FLOAT, 4, nf); }
+            if (pass % 3) { pfEnable(PF_TEXTURE_COORD_ARRAY); if (pass & 4) pfTexCoordPointer(PF_DOUBLE, 0, td); else pfTexCoordPointer(PF_FLOAT, 0, tf); }
+            pfEnable(PF_COLOR_ARRAY);
+            switch (pass % 5) {
+            case 0: pfColorPointer(4, PF_UNSIGNED_BYTE, 0, cub); break;    case 1: pfColorPointer(3, PF_UNSIGNED_SHORT, 0, cus); break;
+            case 2: pfColorPointer(4, PF_UNSIGNED_INT, 16, cui); break;    case 3: pfColorPointer(3, PF_FLOAT, 0, cf); break;
+            default: pfColorPointer(4, PF_DOUBLE, 0, cd); break;
+            }
+            static const PFdrawmode modes[5] = { PF_TRIANGLES, PF_QUADS, PF_TRIANGLE_STRIP, PF_TRIANGLE_FAN, PF_QUAD_STRIP };
+            const PFdrawmode mode = modes[pass % 5];
+            if (pass % 3 == 0) pfDrawElements(mode, 96, PF_UNSIGNED_BYTE, i8);
+            else if (pass % 3 == 1) pfDrawElements(mode, 96, PF_UNSIGNED_SHORT, i16);
+            else pfDrawElements(mode, 96, PF_UNSIGNED_INT, i32);
+            pfDrawArrays(pass & 1 ? PF_TRIANGLES : PF_QUADS, 4 + pass, 24);
+            pfDisable(PF_VERTEX_ARRAY); pfDisable(PF_NORMAL_ARRAY); pfDisable(PF_TEXTURE_COORD_ARRAY); pfDisable(PF_COLOR_ARRAY);
+        }
+        /* what the error paths leave behind goes into the corner of the frame */
+        pfDrawElements(PF_TRIANGLES, 3, PF_UNSIGNED_INT, i32);       /* arrays disabled */
+        PFerrcode e1 = pfGetError();
+        pfEnable(PF_VERTEX_ARRAY);
+        pfDrawElements(PF_TRIANGLES, 3, PF_FLOAT, i32);              /* not an index type */
+        PFerrcode e2 = pfGetError();
+        pfDisable(PF_VERTEX_ARRAY);
+        pfDrawArrays(PF_TRIANGLES, 0, 3);
+        PFerrcode e3 = pfGetError();
+        pfDisable(PF_BLEND); pfBindTexture(0); pfDisable(PF_TEXTURE_2D);
+        pfColor4ub((PFubyte)e1, (PFubyte)e2, (PFubyte)e3, 255); pfRecti(0, 0, 8, 4);
+        pfColor4ub(255, 255, 255, 255);
+        break; }
+    }
+}
+
 static const PFpixelformat target_formats_g[4] = { PF_RGBA, PF_BGRA, PF_RGB, PF_BGR };
 
 /* ---- the runner ------------------------------------------------------------------------------------ */
@@ -1062,6 +1321,12 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
         s->tex = pfGenTexture(s->texpx, 32, 16, PF_RGBA, PF_UNSIGNED_BYTE);
         s->fbo = pfGenFramebuffer(128, 64, PF_RGBA, PF_UNSIGNED_BYTE);
         s->aux = (uint8_t *)calloc((size_t)w * h * 4 + 4096 + 64, 1);
+    } else if (strcmp(name, "examples") == 0) {
+        s->texpx = make_texture(64, 64, 4, (uint32_t)cfg->seed ^ 0xe8a3u, 0, 255, 96, 255);
+        s->tex = pfGenTexture(s->texpx, 64, 64, PF_RGBA, PF_UNSIGNED_BYTE);
+        s->fbo = pfGenFramebuffer((PFsizei)w, (PFsizei)h, PF_RGBA, PF_UNSIGNED_BYTE);
+        s->aux = (uint8_t *)calloc(4096, 1);
+        s->mesh = make_torus(48, 24, 12.0f, 5.0f, 2.0f);
     } else if (strcmp(name, "prims") == 0) {
         /* no resources */
     } else if (strcmp(name, "api") == 0) {
@@ -1183,6 +1448,8 @@ SCN_API void pfscene_frame(void *handle, int frame)
     } else if (strcmp(name, "texfmt") == 0) {
         pfscene_cfg sub = *cfg; sub.size = 0; sub.variant |= 512;
         micro_scene(&sub, s->tex);
+    } else if (strcmp(name, "examples") == 0) {
+        examples_scene(cfg, s->tex, &s->fbo, s->aux, &s->mesh, frame);
     } else if (strcmp(name, "conform") == 0) {
         conform_scene(cfg, s->tex, &s->fbo, s->aux, s->target, target_formats_g[(cfg->variant >> 24) & 3]);
     } else if (strcmp(name, "api") == 0) {

@@ -209,3 +209,22 @@ CASES += [_conform("plain", 0, 1), _conform("blend-depth", 1, 2), _conform("targ
 
 CASE_IDS = [c[0] for c in CASES]
 assert len(set(CASE_IDS)) == len(CASE_IDS)
+
+# the call sequences of the reference's example programs (scene "examples": examples/common.h helpers, raylib_2D / _3D /
+# _Framebuffer / _Points / _ModelWires / _TextureMatrix / _Texture2D / _FirstPerson) and vertex arrays in every component
+# and index type pfDrawElements / pfDrawArrays accept
+_EXAMPLES = {0: "2d-initial-state", 1: "3d-cube", 2: "framebuffer-drawpixels", 3: "points", 4: "wires-ushort-indices",
+             5: "texture-matrix-ground", 6: "texture2d-sprites-luma", 8: "firstperson-spotlight", 9: "arrays-all-types"}
+
+
+def _example(which, frame, target=0):
+    tname = {0: "", 1: "-target-bgra", 2: "-target-rgb", 3: "-target-bgr"}[target]
+    return (f"examples-{_EXAMPLES[which]}-f{frame}{tname}", "examples", 320, 240,
+            dict(variant=which | (target << 24), seed=1 + which, first_frame=frame), False)
+
+
+CASES += [_example(k, f) for k in _EXAMPLES for f in (0, 3)]
+CASES += [_example(2, 1, TARGET_BGRA), _example(6, 1, TARGET_BGRA), _example(9, 1, TARGET_RGB), _example(8, 1, TARGET_BGR)]
+
+CASE_IDS = [c[0] for c in CASES]
+assert len(set(CASE_IDS)) == len(CASE_IDS)

@@ -771,7 +771,9 @@ def _visible_gpus():
 MULTI_CASE_IDS = ["c1-gears-f0", "c2-textured-bilinear-repeat", "c2-textured-closeup-clipped-bilinear-arrays", "c2-textured-arrays-rewritten-f2", "c3-phong-arrays",
                   "c4-overdraw-alpha-depth", "c4-overdraw-alpha-depth-two-state", "c5-batch", "c5-batch-phong-cull-off", "micro-blend3", "micro-depth1",
                   "micro-mode4-cull0", "micro-fbo", "micro-fbo-persp", "micro-phong-tex-spot1", "micro-random27", "micro-target-bgra-fbo", "micro-target-rgb-blend3",
-                  "api-everything", "api-fog-exp", "api-pixel-layouts-viewport", "api-swapbuffers", "prims-thick", "prims-persp-blend1-depth3-points"]
+                  "api-everything", "api-fog-exp", "api-pixel-layouts-viewport", "api-swapbuffers", "prims-thick", "prims-persp-blend1-depth3-points",
+                  "conform-blend-depth", "conform-target-bgra", "examples-framebuffer-drawpixels-f0", "examples-firstperson-spotlight-f3",
+                  "examples-arrays-all-types-f0", "examples-texture2d-sprites-luma-f0", "texfmt-rgb-s565-nearest", "texfmt-luma-half-bilinear"]
 
 
 @pytest.mark.parametrize("cid", MULTI_CASE_IDS)

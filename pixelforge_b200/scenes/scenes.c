@@ -1050,6 +1050,35 @@ static void examples_scene(const pfscene_cfg *cfg, PFtexture tex, PFframebuffer 
             ex_rotated_sprite(tex, 20.0f + lcgf() * (float)(w - 100), 20.0f + lcgf() * (float)(h - 100), 64, 64, 32, 32, 360.0f * lcgf() + 20.0f * timer);
         pfDisable((PFstate)(PF_TEXTURE_2D | PF_BLEND));
         break;
+    case 10: {  /* pfBegin / pfEnd used loosely: what the reference does with it (context.c:1580-1608, 1658-1685) */
+        ortho2d(w, h);
+        pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+        pfColor4ub(250, 60, 60, 255);
+        pfBegin(PF_TRIANGLES); pfVertex2f(10, 10); pfVertex2f(10, 90); pfEnd();                 /* incomplete: dropped */
+        pfBegin(PF_QUADS); pfVertex2f(20, 20); pfVertex2f(20, 80);
+        pfBegin(PF_TRIANGLES);                                                                  /* a second pfBegin starts over */
+        pfColor4ub(60, 250, 60, 255); pfVertex2f(30, 20); pfVertex2f(30, 100); pfVertex2f(120, 60);
+        pfEnd();
+        pfColor4ub(60, 60, 250, 255);                                                           /* vertices after pfEnd: still assembled */
+        pfVertex2f(130, 20); pfVertex2f(130, 100); pfVertex2f(220, 60);
+        pfTranslatef(40.0f, 100.0f, 0.0f);                                                      /* ... with the matrices of the last pfBegin */
+        pfColor4ub(250, 250, 60, 255);
+        pfVertex2f(130, 20); pfVertex2f(130, 100); pfVertex2f(220, 60);
+        pfBegin((PFdrawmode)77);                                                                /* refused: mode and counter stay */
+        const PFerrcode e1 = pfGetError();
+        pfColor4ub(60, 250, 250, 255);
+        pfVertex2f(10, 120); pfVertex2f(10, 200); pfVertex2f(100, 160);
+        pfEnd(); pfEnd();
+        pfBegin(PF_TRIANGLE_STRIP);
+        pfColor4ub(250, 60, 250, 255);
+        pfVertex2f(230, 120); pfVertex2f(230, 200); pfVertex2f(260, 120); pfVertex2f(260, 200); pfVertex2f(290, 120);
+        pfEnd();
+        pfVertex2f(290, 200); pfVertex2f(310, 120);                                             /* the strip after its pfEnd */
+        pfVertex2f(310, 200); pfVertex2f(315, 120);
+        pfLoadIdentity();
+        pfColor4ub((PFubyte)e1, 7, 9, 255); pfRecti(0, 0, 8, 4);
+        pfColor4ub(255, 255, 255, 255);
+        break; }
     default: {  /* 9: vertex arrays in every component type; strides are ignored upstream (context.c:1282-1370 index j*size+k) */
         ortho2d(w, h);
         pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));

@@ -214,7 +214,8 @@ assert len(set(CASE_IDS)) == len(CASE_IDS)
 # _Framebuffer / _Points / _ModelWires / _TextureMatrix / _Texture2D / _FirstPerson) and vertex arrays in every component
 # and index type pfDrawElements / pfDrawArrays accept
 _EXAMPLES = {0: "2d-initial-state", 1: "3d-cube", 2: "framebuffer-drawpixels", 3: "points", 4: "wires-ushort-indices",
-             5: "texture-matrix-ground", 6: "texture2d-sprites-luma", 8: "firstperson-spotlight", 9: "arrays-all-types"}
+             5: "texture-matrix-ground", 6: "texture2d-sprites-luma", 8: "firstperson-spotlight", 9: "arrays-all-types",
+             10: "loose-begin-end"}
 
 
 def _example(which, frame, target=0):

@@ -1014,6 +1014,10 @@ int pfh_call_list_device(pf_ctx *c, pf_list *l)
     for (size_t ci = 0; ci < l->size; ci++) {
         const pf_tex *t = (const pf_tex *)l->calls[ci].texture;
         if (t && t->surf && t->surf == c->cur_surf) return 0;               /* sampling its own target: let the ordinary path sort it out */
+        if (t && !t->surf) {                                                /* list jobs sample RGBA8 / RGB8 / BGR8 texels only */
+            const int code = pfh_texture_code(t->format, t->type);
+            if (code == PFCU_TEX_BGRA8 || code >= PFCU_TEX_PIX || code < 0) return 0;
+        }
     }
     if (l->dev_state[variant] == 0) list_compile(c, l, variant);
     if (l->dev_state[variant] != 1) return 0;

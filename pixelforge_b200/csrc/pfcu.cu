@@ -133,7 +133,7 @@ struct pfcu_surface {
 struct pfcu_texture { uint32_t w, h; int fmt; unsigned char *pixels; bool owned; pfcu_surface *alias; bool leader; pfcu_texture *rep[MAX_DEVS]; };
 struct pfcu_list { pfcu_rawtri *tris; uint32_t n; };
 struct pfcu_batch {
-    DevState *states; uint32_t n_states; pfcu_triangle *tris; uint32_t n_tris; unsigned feature_mask; int single_prog; bool leader_tex;
+    DevState *states; uint32_t n_states; pfcu_triangle *tris; uint32_t n_tris; unsigned feature_mask; int single_prog; bool leader_tex, pix_tex;
     std::vector<pfcu_surface *> deps;
     pfcu_batch *rep[MAX_DEVS];
 };
@@ -1411,6 +1411,7 @@ void pfcu_texture_destroy(pfcu_texture *t)
 static int state_program(const DevState *d)
 {
     if (d->flags & PFCU_ST_PHONG) return PROG_PHONG;
+    if ((d->flags & PFCU_ST_TEXTURE) && d->tfmt >= PFCU_TEX_PIX) return -1;       /* the other texel layouts: run-time sampler only */
     int texm = 0;
     if (d->flags & PFCU_ST_TEXTURE) texm = d->tex_filter != 0 ? 4 : ((d->tfmt == PFCU_TEX_RGBA8 && d->tex_wrap == 0) ? 1 : 3);
     const int blendm = !(d->flags & PFCU_ST_BLEND) ? 0 : (d->blend_mode == 1 ? 1 : (d->blend_mode == 2 ? 2 : 3));
@@ -1420,12 +1421,13 @@ static int state_program(const DevState *d)
 
 static int g_last_single_prog = -1;      /* set by convert_states: the common program of all states, or -1 */
 static bool g_last_leader_tex = false;   /* set by convert_states: some state samples through the BGRA8 getter */
+static bool g_last_pix_tex = false;      /* set by convert_states: some state samples a texture beyond the four 8-bit layouts */
 
 static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
 {
     unsigned mask = 0;
     RT.deps.clear();
-    g_last_leader_tex = false;
+    g_last_leader_tex = false; g_last_pix_tex = false;
     for (uint32_t i = 0; i < n; i++) {
         const pfcu_state *s = in + i; DevState *d = out + i;
         memset(d, 0, sizeof *d);
@@ -1438,6 +1440,7 @@ static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
             d->tex = s->texture->pixels; d->tw = s->texture->w; d->th = s->texture->h; d->tfmt = s->texture->fmt;
             d->tex_leader = s->texture->leader ? 1u : 0u;
             if (s->texture->leader) g_last_leader_tex = true;
+            if (s->texture->fmt >= PFCU_TEX_PIX) g_last_pix_tex = true;
             d->tex_fw = (float)d->tw; d->tex_fh = (float)d->th;
             { volatile float one = 1.0f; d->tex_tx = one / d->tex_fw; d->tex_ty = one / d->tex_fh; }   /* IEEE single division, as DIVPS */
             if (s->texture->alias) RT.deps.push_back(s->texture->alias);      /* render-to-texture: order across lanes */
@@ -1472,7 +1475,7 @@ static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
            "any mode" (run-time switch, blending on in all of them), nearest samplers that differ become "nearest, any wrap
            mode / layout" - e.RT. layers that alternate between alpha and additive blending still get a one-program kernel */
         const int prog = state_program(d);
-        if (i == 0) g_last_single_prog = prog;
+        if (i == 0 || prog < 0) g_last_single_prog = prog;
         else if (g_last_single_prog != prog && g_last_single_prog >= 0) {
             const int a = g_last_single_prog, b = prog;
             int texm = -1, blendm = -1;
@@ -1497,7 +1500,9 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     if (!d_n) n_est = n;
     /* render targets other than RGBA8 and BGRA8 textures: the row-ordered rasteriser (pfcu_raster_rows.cuh) */
     const bool rows_path = s->fmt != PFCU_TEX_RGBA8 || g_last_leader_tex;
-    g_last_leader_tex = false;
+    /* textures beyond the four 8-bit layouts: the tile rasteriser's run-time sampler (or the row-ordered one) has their getters */
+    const bool pix_tex = g_last_pix_tex;
+    g_last_leader_tex = false; g_last_pix_tex = false;
     if (rows_path && s->world > 1) {
         snprintf(RT.err, sizeof RT.err, "the screen-tile split needs an RGBA8 target and no BGRA8 textures (a pixel depends on its row neighbours there)");
         return PFCU_ERR_INVALID;
@@ -1526,7 +1531,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
         return true; }();
     (void)env_once;
     static const int force_slice = getenv("PF_CUDA_SLICE") ? atoi(getenv("PF_CUDA_SLICE")) : 0;
-    const bool use_frag = !rows_path && (RT.raster_path == PFCU_RASTER_FRAGMENTS || (RT.raster_path == PFCU_RASTER_AUTO && small_tris && !force_slice));
+    const bool use_frag = !rows_path && !pix_tex && (RT.raster_path == PFCU_RASTER_FRAGMENTS || (RT.raster_path == PFCU_RASTER_AUTO && small_tris && !force_slice));
     /* The fragment rasteriser works on 64x8 slices, and with square 64x64 bins the eight slices of a tile each filter the
        whole tile's list.  Flatter bins (64 x 2^bshy) shorten that, but every triangle then lands in more bins and the
        ordered fill pays for it: measured (PF_CUDA_BIN_ROWS sweep, profiles/README.md) 64x16 bins are a small net gain
@@ -2096,7 +2101,10 @@ int pfcu_submit_list_jobs(const pfcu_list_job *jobs, uint32_t n_jobs)
         DevState *hs = reinterpret_cast<DevState *>(hb + off); D.states = reinterpret_cast<const DevState *>(db + off);
         const unsigned mask = convert_states(J.states, J.n_states, hs);
         off += al(sizeof(DevState) * J.n_states);
-        if (g_last_leader_tex) { g_last_leader_tex = false; snprintf(RT.err, sizeof RT.err, "list jobs cannot sample BGRA8 textures (row-ordered path)"); return PFCU_ERR_INVALID; }
+        if (g_last_leader_tex || g_last_pix_tex) {
+            g_last_leader_tex = false; g_last_pix_tex = false;
+            snprintf(RT.err, sizeof RT.err, "list jobs sample RGBA8 / RGB8 / BGR8 textures only"); return PFCU_ERR_INVALID;
+        }
         for (pfcu_surface *dep : RT.deps) if (dep->has_done && dep->lane != 0) CK(cudaStreamWaitEvent(L0.stream, dep->done, 0));
         RT.deps.clear();
         feature |= mask;
@@ -2267,6 +2275,7 @@ pfcu_batch *pfcu_batch_upload(const pfcu_state *states, uint32_t n_states, const
     b->feature_mask = convert_states(states, n_states, tmp.data());
     b->single_prog = g_last_single_prog;
     b->leader_tex = g_last_leader_tex; g_last_leader_tex = false;
+    b->pix_tex = g_last_pix_tex; g_last_pix_tex = false;
     new (&b->deps) std::vector<pfcu_surface *>(RT.deps);
     b->n_states = n_states; b->n_tris = n_tris;
     CKP(cudaMalloc(&b->states, n_states * sizeof(DevState)));
@@ -2286,7 +2295,7 @@ int pfcu_batch_submit(pfcu_surface *s, pfcu_batch *b)
     use_lane(s);
     RT.deps.clear();
     for (pfcu_surface *dep : b->deps) RT.deps.push_back(dep);
-    g_last_leader_tex = b->leader_tex;
+    g_last_leader_tex = b->leader_tex; g_last_pix_tex = b->pix_tex;
     return launch_pipeline(s, b->tris, b->states, b->n_tris, b->feature_mask, b->single_prog);
 }
 

@@ -273,12 +273,15 @@ __device__ __noinline__ unsigned tex_fetch_pix(const unsigned char *base, unsign
     return (unsigned)off >= total ? pfx_tex_get(zeros, 0u, code) : pfx_tex_get(base, (unsigned)off, code);
 }
 
+/* PIX: this kernel also samples the layouts beyond the four 8-bit ones (the generic tile rasteriser and the row-ordered
+   one do; batches with such a texture are routed to them, launch_pipeline) */
+template <bool PIX>
 __device__ __forceinline__ unsigned tex_fetch(const TexRegs &t, int x, int y)
 {
     const int off = (int)((unsigned)y * t.tw + (unsigned)x);
     /* the reference reads out of bounds here (CLAMP/MIRROR round v*(h-1)+0.5 up to row h); defined as
        "memory after the texture reads as zero": RGBA 0, and alpha 255 for the 3-byte formats */
-    if (t.fmt >= PFCU_TEX_PIX) return tex_fetch_pix(t.base, t.total, off, t.fmt - PFCU_TEX_PIX);
+    if (PIX && t.fmt >= PFCU_TEX_PIX) return tex_fetch_pix(t.base, t.total, off, t.fmt - PFCU_TEX_PIX);
     if ((unsigned)off >= t.total) return (t.fmt >= PFCU_TEX_RGB8) ? 0xff000000u : 0u;
     if (t.fmt == PFCU_TEX_RGBA8) return __ldg((const unsigned *)t.base + off);
     if (t.fmt == PFCU_TEX_BGRA8) { const unsigned r = __ldg((const unsigned *)t.base + off); return __byte_perm(r, 0, 0x3012); }
@@ -287,6 +290,7 @@ __device__ __forceinline__ unsigned tex_fetch(const TexRegs &t, int x, int y)
     return (t.fmt == PFCU_TEX_RGB8) ? (b0 | (b1 << 8) | (b2 << 16) | 0xff000000u) : (b2 | (b1 << 8) | (b0 << 16) | 0xff000000u);
 }
 
+template <bool PIX>
 __device__ __forceinline__ unsigned tex_sample_bilinear(const TexRegs &t, const DevState *st, float u, float v)
 {
     const int x0 = tex_coord(t.wrap, u, t.wm1), y0 = tex_coord(t.wrap, v, t.hm1);
@@ -295,22 +299,23 @@ __device__ __forceinline__ unsigned tex_sample_bilinear(const TexRegs &t, const 
     const int x1 = tex_coord(t.wrap, FA(u, tx), t.wm1), y1 = tex_coord(t.wrap, FA(v, ty), t.hm1);
     const float fx = clamp_x86(FS(FM(u, fw), __int2float_rn(x0)), 0.0f, 1.0f);
     const float fy = clamp_x86(FS(FM(v, fh), __int2float_rn(y0)), 0.0f, 1.0f);
-    const unsigned c00 = tex_fetch(t, x0, y0), c10 = tex_fetch(t, x1, y0);
-    const unsigned c01 = tex_fetch(t, x0, y1), c11 = tex_fetch(t, x1, y1);
+    const unsigned c00 = tex_fetch<PIX>(t, x0, y0), c10 = tex_fetch<PIX>(t, x1, y0);
+    const unsigned c01 = tex_fetch<PIX>(t, x0, y1), c11 = tex_fetch<PIX>(t, x1, y1);
     return color_bilerp(c00, c10, c01, c11, fx, fy);
 }
 
+template <bool PIX>
 __device__ __forceinline__ unsigned tex_sample(const TexRegs &t, const DevState *st, float u, float v)
 {
     const int x0 = tex_coord(t.wrap, u, t.wm1), y0 = tex_coord(t.wrap, v, t.hm1);
-    if (t.filter == 0) return tex_fetch(t, x0, y0);
+    if (t.filter == 0) return tex_fetch<PIX>(t, x0, y0);
     const float4 k = __ldg(reinterpret_cast<const float4 *>(&st->tex_fw));       /* fw, fh, 1/fw, 1/fh */
     const float fw = k.x, fh = k.y, tx = k.z, ty = k.w;
     const int x1 = tex_coord(t.wrap, FA(u, tx), t.wm1), y1 = tex_coord(t.wrap, FA(v, ty), t.hm1);
     const float fx = clamp_x86(FS(FM(u, fw), __int2float_rn(x0)), 0.0f, 1.0f);
     const float fy = clamp_x86(FS(FM(v, fh), __int2float_rn(y0)), 0.0f, 1.0f);
-    const unsigned c00 = tex_fetch(t, x0, y0), c10 = tex_fetch(t, x1, y0);
-    const unsigned c01 = tex_fetch(t, x0, y1), c11 = tex_fetch(t, x1, y1);
+    const unsigned c00 = tex_fetch<PIX>(t, x0, y0), c10 = tex_fetch<PIX>(t, x1, y0);
+    const unsigned c01 = tex_fetch<PIX>(t, x0, y1), c11 = tex_fetch<PIX>(t, x1, y1);
     return color_bilerp(c00, c10, c01, c11, fx, fy);
 }
 

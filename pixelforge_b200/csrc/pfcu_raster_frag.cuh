@@ -196,7 +196,7 @@ __device__ __forceinline__ void frag_run(FragCtx &t, const unsigned nn, const un
                     const int xi = cvt_rne_x86(fabsf(fu)), yi = cvt_rne_x86(fabsf(fv));
                     const unsigned off = (unsigned)yi * tex.tw + (unsigned)xi;
                     if (off < tex.total) texel = __ldg((const unsigned *)tex.base + off);
-                } else texel = tex_sample(tex, st, u, v);
+                } else texel = tex_sample<false>(tex, st, u, v);
             }
             frag = px_mul(texel, frag);
         }

@@ -55,7 +55,7 @@ __device__ __forceinline__ unsigned color_smooth_any(unsigned c1, unsigned c2, u
 /* texel fetch through the reference's getter: `leader` >= 0 selects the BGRA8 getter's behaviour */
 __device__ __forceinline__ unsigned tex_fetch_q(const TexRegs &t, int x, int y, int leader)
 {
-    unsigned v = tex_fetch(t, x, y);
+    unsigned v = tex_fetch<true>(t, x, y);
     if (leader >= 0) v = __shfl_sync(0xffffffffu, v, leader);
     return v;
 }

@@ -286,9 +286,9 @@ __device__ __forceinline__ void shade_tri(TileCtx &t, const unsigned ti, const i
                 const unsigned off = (unsigned)yi * tex.tw + (unsigned)xi;
                 texel = 0u;
                 if (off < tex.total) texel = __ldg((const unsigned *)tex.base + off);
-            } else if (TEXM == 3) texel = tex_fetch(tex, tex_coord(tex.wrap, u, tex.wm1), tex_coord(tex.wrap, v, tex.hm1));
-            else if (TEXM == 4) texel = tex_sample_bilinear(tex, st, u, v);
-            else texel = tex_sample(tex, st, u, v);
+            } else if (TEXM == 3) texel = tex_fetch<false>(tex, tex_coord(tex.wrap, u, tex.wm1), tex_coord(tex.wrap, v, tex.hm1));
+            else if (TEXM == 4) texel = tex_sample_bilinear<false>(tex, st, u, v);
+            else texel = tex_sample<true>(tex, st, u, v);        /* run-time sampler: every texel layout */
             if (grey_tex) {                         /* (texel_c * k) >> 8 on packed lanes: products stay below 2^16 */
                 frag.rb = (((texel & 0x00ff00ffu) * kgrey) >> 8) & 0x00ff00ffu;
                 frag.ga = ((((texel >> 8) & 0x00ff00ffu) * kgrey) >> 8) & 0x00ff00ffu;

@@ -945,6 +945,25 @@ static void mark_done(pfcu_surface *s) { s->bands_valid = false; if (cudaEventRe
 
 /* PF_CUDA_TIMING=1: host-side microseconds of the phases of pfcu_draw_triangles, band decisions of the multi-device read-back, on stderr (development aid) */
 static const bool g_timing = getenv("PF_CUDA_TIMING") && atoi(getenv("PF_CUDA_TIMING")) != 0;
+/* PF_CUDA_TIMING=1: device timeline of the last banded frame (pipeline start, front end done, band b rasterised, band b on the
+   host), printed by pfcu_surface_wait; debugging aid, never on in measurements */
+struct Timeline { cudaEvent_t start = nullptr, front = nullptr, band[MAX_BANDS] = {}, copied[MAX_BANDS] = {}; int n = 0; bool armed = false, copies = false; double host_start = 0; };
+static Timeline g_tl;
+static void tl_event(cudaEvent_t *e, cudaStream_t st) { if (!*e) cudaEventCreate(e); cudaEventRecord(*e, st); }
+static double now_us(void);
+static void tl_print(void)
+{
+    if (g_tl.armed && g_tl.copies) {
+        float f = 0; cudaEventElapsedTime(&f, g_tl.start, g_tl.front);
+        fprintf(stderr, "timeline: host enqueue -> wait returned %.3f ms; device: front end %.3f", (now_us() - g_tl.host_start) * 1e-3, f);
+        for (int b = 0; b < g_tl.n; b++) {
+            float r = 0, c = 0; cudaEventElapsedTime(&r, g_tl.start, g_tl.band[b]); cudaEventElapsedTime(&c, g_tl.start, g_tl.copied[b]);
+            fprintf(stderr, " | band %d raster %.3f host %.3f", b, r, c);
+        }
+        fprintf(stderr, " ms\n");
+        g_tl.armed = false;
+    }
+}
 static double now_us(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
 
 /* ---- multi-device helpers (see "multi-device mode" at the top) ---- */
@@ -1083,6 +1102,7 @@ int pfcu_surface_download_async(pfcu_surface *s, void *hc, float *hd, uint32_t y
             if (s->peer_bands) for (int d = 1; d < mg.n; d++) CK(cudaStreamWaitEvent(RT.copy_stream, s->rep[d]->push_evt[b], 0));
             if (hc) { CK(cudaMemcpyAsync((uint32_t *)hc + o, s->color + o, nb, cudaMemcpyDeviceToHost, RT.copy_stream)); RT.bytes_d2h += nb; }
             if (hd) { CK(cudaMemcpyAsync(hd + o, s->depth + o, nb, cudaMemcpyDeviceToHost, RT.copy_stream)); RT.bytes_d2h += nb; }
+            if (g_timing && g_tl.armed) { tl_event(&g_tl.copied[b], RT.copy_stream); g_tl.copies = true; }
         }
         if (cudaEventRecord(s->done, RT.copy_stream) == cudaSuccess) s->has_done = true;
         CK(cudaStreamWaitEvent(LN.stream, s->done, 0));
@@ -1099,6 +1119,7 @@ int pfcu_surface_wait(pfcu_surface *s)
     API_LOCK;
     if (!s) return PFCU_ERR_INVALID;
     if (s->has_done) CK(cudaEventSynchronize(s->done));
+    if (g_timing) tl_print();
     return PFCU_OK;
 }
 
@@ -1108,6 +1129,7 @@ int pfcu_surface_download(pfcu_surface *s, void *hc, float *hd, uint32_t y0, uin
     int rc = pfcu_surface_download_async(s, hc, hd, y0, rows);
     if (rc) return rc;
     CK(cudaStreamSynchronize(LN.stream));
+    if (g_timing) tl_print();
     return PFCU_OK;
 }
 
@@ -1498,6 +1520,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     if (n == 0) return PFCU_OK;
     s->bands_valid = false;
     if (!d_n) n_est = n;
+    if (g_timing && !g_tl.armed) { use_lane(s); tl_event(&g_tl.start, LN.stream); g_tl.host_start = now_us(); }
     /* render targets other than RGBA8 and BGRA8 textures: the row-ordered rasteriser (pfcu_raster_rows.cuh) */
     const bool rows_path = s->fmt != PFCU_TEX_RGBA8 || g_last_leader_tex;
     /* textures beyond the four 8-bit layouts: the tile rasteriser's run-time sampler (or the row-ordered one) has their getters */
@@ -1715,6 +1738,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     if (n_bands > 1) {
         for (int b = 0; b < n_bands; b++) if (!s->band_evt[b]) CK(cudaEventCreateWithFlags(&s->band_evt[b], cudaEventDisableTiming));
         CK(cudaEventRecord(RT.front_evt, LN.stream));
+        if (g_timing) { tl_event(&g_tl.front, LN.stream); g_tl.n = n_bands; g_tl.armed = true; g_tl.copies = false; }
         unsigned row0 = 0;
         for (int b = 0; b < n_bands; b++) {
             /* the first bands are the smaller ones: their copies start early, the last band's copy is what remains exposed */
@@ -1725,6 +1749,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
             p.tile_base = o0;
             if (o1 > o0 && (rc = launch_raster(o1 - o0, bs))) return rc;
             CK(cudaEventRecord(s->band_evt[b], bs));
+            if (g_timing) tl_event(&g_tl.band[b], bs);
             CK(cudaStreamWaitEvent(LN.stream, s->band_evt[b], 0));
             s->band_y[b] = row0 * TILE; s->band_owned[b] = o0;
             row0 = row1;

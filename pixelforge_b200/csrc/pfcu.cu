@@ -105,7 +105,8 @@ struct __align__(16) DevState {
 
 static_assert(offsetof(DevState, tex_fw) % 16 == 0, "tex_fw..tex_ty are fetched as one float4");
 
-#define MAX_BANDS 4
+#define MAX_BANDS 6
+#define PCIE_GBS 50.0        /* device -> host copies of page-locked memory as measured on this pool (8.3 MB in 0.16 ms) */
 #define PUSH_HOST_CTAS 48u        /* CTAs of a tile store towards host memory (see k_push_tiles) */
 struct pfcu_surface {
     uint32_t w, h; uint32_t *color; float *depth; bool owned;
@@ -120,6 +121,7 @@ struct pfcu_surface {
        and band_evt[b] fires when it is complete (see launch_raster_bands / pfcu_surface_download_async) */
     bool bands_valid; int n_bands; uint32_t band_y[MAX_BANDS + 1]; cudaEvent_t band_evt[MAX_BANDS];
     uint32_t band_owned[MAX_BANDS + 1];             /* tile split: band b = this rank's owned tiles [band_owned[b], band_owned[b+1]) */
+    cudaEvent_t t_front, t_raster; bool t_pending; bool raster_longer;   /* banded frames time their rasterisation: see launch_pipeline */
     cudaEvent_t push_evt[MAX_BANDS]; bool pushed_in_bands; bool peer_is_host;      /* peer_is_host: peer_color / peer_depth address the caller's page-locked buffer */      /* pfcu_surface_push_tiles of a banded surface: band b's tiles have been stored */
     /* bands pay off only when a read-back follows the batch: batches rasterised since the last read-back, and how many
        there were between the two read-backs before - the batch predicted to be a frame's last one goes out in bands */
@@ -208,7 +210,7 @@ struct Runtime {
     };
     std::vector<JobSlot> job_slots;
     unsigned char *d_jobs = nullptr, *h_jobs = nullptr; size_t cap_jobs = 0; cudaEvent_t jobs_copied = nullptr, jobs_done = nullptr; unsigned jobs_seq = 0;
-    cudaStream_t band_streams[MAX_BANDS] = { nullptr, nullptr, nullptr, nullptr }; cudaStream_t copy_stream = nullptr;
+    cudaStream_t band_streams[MAX_BANDS] = {}; cudaStream_t copy_stream = nullptr;
     cudaEvent_t front_evt = nullptr;
     bool frag_attr_set = false, setup_attr_set = false;
     std::recursive_mutex mu;                    /* the C-ABI is serialised: contexts on several threads share one runtime */
@@ -931,6 +933,8 @@ void pfcu_surface_destroy(pfcu_surface *s)
     for (int b = 0; b < MAX_BANDS; b++) if (s->push_evt[b]) cudaEventDestroy(s->push_evt[b]);
     if (s->full_evt) cudaEventDestroy(s->full_evt);
     if (s->pushed) cudaEventDestroy(s->pushed);
+    if (s->t_front) cudaEventDestroy(s->t_front);
+    if (s->t_raster) cudaEventDestroy(s->t_raster);
     free(s);
 }
 
@@ -1726,7 +1730,23 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
        nothing end to end, 4 bands 0.02 ms; 4K scenes 0.3 - 0.5 ms, 8K 1.9 ms) */
     s->n_since_read++;
     const bool read_back_expected = s->n_per_read != 0 && s->n_since_read == s->n_per_read;
-    if (grid && s->fmt == PFCU_TEX_RGBA8 && (size_t)s->w * s->h >= ((size_t)1 << 20) && s->tiles_y >= 8 && read_back_expected) n_bands = MAX_BANDS;
+    /* one GPU: six bands of unequal height (profiles/r02_e2e_timeline.txt).  Where the read-back is the longer leg, the frame
+       ends one transfer of the whole surface after the FIRST band is rasterised: heights grow from the first band on
+       (weights 1, g, g^2, ...; g below the copy / raster time ratio, so the copy engine is never left waiting).  Where
+       rasterisation is the longer leg, the frame ends one transfer of the LAST band after it is rasterised: small at both
+       ends (1, g, g^2, g^2, g, 1).  Which leg is longer is taken from the surface's previous banded frame: its
+       rasterisation is timed with two events, the transfer is its bytes at PCIE_GBS.  Tile split (several devices): four
+       equal bands, as measured there. */
+    const bool grow_bands = p.world <= 1;
+    if (grow_bands && s->t_pending) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, s->t_front, s->t_raster) == cudaSuccess) {
+            s->raster_longer = (double)ms * 1e-3 > (double)s->w * s->h * 4.0 / (PCIE_GBS * 1e9);
+            s->t_pending = false;
+        } else cudaGetLastError();              /* not finished yet: keep the last answer */
+    }
+    static const double band_growth = getenv("PF_CUDA_BAND_GROWTH") ? atof(getenv("PF_CUDA_BAND_GROWTH")) : 0.0;
+    if (grid && s->fmt == PFCU_TEX_RGBA8 && (size_t)s->w * s->h >= ((size_t)1 << 20) && s->tiles_y >= 8 && read_back_expected) n_bands = grow_bands ? MAX_BANDS : 4;
     if (env_bands >= 1) n_bands = env_bands > MAX_BANDS ? MAX_BANDS : env_bands;
     if (!grid || (unsigned)n_bands > s->tiles_y) n_bands = 1;
     /* tile split: this rank's tiles t = rank + k * world, k = 0 .. grid-1; the ones in tile rows < R are k < first_owned(R) */
@@ -1738,11 +1758,27 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
     if (n_bands > 1) {
         for (int b = 0; b < n_bands; b++) if (!s->band_evt[b]) CK(cudaEventCreateWithFlags(&s->band_evt[b], cudaEventDisableTiming));
         CK(cudaEventRecord(RT.front_evt, LN.stream));
+        const bool time_it = grow_bands && !s->t_pending;
+        if (time_it) { if (!s->t_front) { CK(cudaEventCreate(&s->t_front)); CK(cudaEventCreate(&s->t_raster)); } CK(cudaEventRecord(s->t_front, LN.stream)); }
         if (g_timing) { tl_event(&g_tl.front, LN.stream); g_tl.n = n_bands; g_tl.armed = true; g_tl.copies = false; }
         unsigned row0 = 0;
         for (int b = 0; b < n_bands; b++) {
             /* the first bands are the smaller ones: their copies start early, the last band's copy is what remains exposed */
-            const unsigned row1 = (b == n_bands - 1) ? s->tiles_y : (unsigned)(((uint64_t)s->tiles_y * (unsigned)(b + 1)) / (unsigned)n_bands);
+            unsigned row1 = (b == n_bands - 1) ? s->tiles_y : (unsigned)(((uint64_t)s->tiles_y * (unsigned)(b + 1)) / (unsigned)n_bands);
+            const double growth = band_growth > 0.0 ? band_growth : (s->raster_longer ? 1.5 : 1.35);
+            if (grow_bands && growth > 1.0 && b != n_bands - 1) {
+                double cum = 0.0, all = 0.0, w = 1.0;
+                for (int k = 0; k < n_bands; k++) {
+                    const int e = (s->raster_longer && n_bands - 1 - k < k) ? n_bands - 1 - k : k;     /* from the first band, or from the nearer end */
+                    w = 1.0; for (int j = 0; j < e; j++) w *= growth;
+                    if (k <= b) cum += w;
+                    all += w;
+                }
+                row1 = (unsigned)((double)s->tiles_y * cum / all + 0.5);
+                if (row1 <= row0) row1 = row0 + 1;
+                const unsigned most = s->tiles_y - (unsigned)(n_bands - 1 - b);      /* every later band keeps a row */
+                if (row1 > most) row1 = most;
+            }
             cudaStream_t bs = RT.band_streams[b];
             CK(cudaStreamWaitEvent(bs, RT.front_evt, 0));
             const unsigned o0 = first_owned(row0), o1 = b == n_bands - 1 ? grid : first_owned(row1);
@@ -1754,6 +1790,7 @@ static int launch_pipeline(pfcu_surface *s, const pfcu_triangle *d_tris, const D
             s->band_y[b] = row0 * TILE; s->band_owned[b] = o0;
             row0 = row1;
         }
+        if (time_it) { CK(cudaEventRecord(s->t_raster, LN.stream)); s->t_pending = true; }      /* the lane has waited for every band */
         s->band_y[n_bands] = s->h; s->band_owned[n_bands] = grid;
         s->n_bands = n_bands; banded = true;
     } else if (grid) {

@@ -1152,7 +1152,7 @@ typedef struct {
     char name[32];
     pfscene_cfg cfg;
     /* single-context scenes */
-    PFcontext ctx; uint8_t *target; uint8_t *aux; uint8_t *texpx; PFtexture tex; mesh_t mesh; PFframebuffer fbo;
+    PFcontext ctx; uint8_t *target; uint8_t *aux; uint8_t *texpx; PFtexture tex, tex2; mesh_t mesh; PFframebuffer fbo;
     /* "batch": n contexts */
     int n; PFcontext *ctxs; uint8_t **bufs; uint8_t **texpxs; PFtexture *texs; PFrenderlist (*lists)[3];
 } scene_t;
@@ -1258,14 +1258,21 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
             s->ctxs[c] = pfCreateContext(s->bufs[c], (PFsizei)w, (PFsizei)h, PF_RGBA, PF_UNSIGNED_BYTE);
             if (!s->ctxs[c]) { fprintf(stderr, "pfscene: pfCreateContext failed\n"); s->n = c; pfscene_close(s); return NULL; }
             pfMakeCurrent(s->ctxs[c]);
-            s->texpxs[c] = make_texture(256, 256, 4, (uint32_t)(cfg->seed + c), 96, 255, 255, 255);
-            s->texs[c] = pfGenTexture(s->texpxs[c], 256, 256, PF_RGBA, PF_UNSIGNED_BYTE);
+            if (cfg->variant & 128) {           /* lists that sample a 5-6-5 texture */
+                int tb = 0;
+                s->texpxs[c] = make_texture_pair(256, 256, PF_RGB, PF_UNSIGNED_SHORT_5_6_5, (uint32_t)(cfg->seed + c), &tb);
+                s->texs[c] = pfGenTexture(s->texpxs[c], 256, 256, PF_RGB, PF_UNSIGNED_SHORT_5_6_5);
+            } else {
+                s->texpxs[c] = make_texture(256, 256, 4, (uint32_t)(cfg->seed + c), 96, 255, 255, 255);
+                s->texs[c] = pfGenTexture(s->texpxs[c], 256, 256, (cfg->variant & 256) ? PF_BGRA : PF_RGBA, PF_UNSIGNED_BYTE);
+            }
             gears_setup(w, h);
             pfEnable(PF_TEXTURE_2D);
             static const double gp[3][5] = { { 1.0, 4.0, 1.0, 20, 0.7 }, { 0.5, 2.0, 2.0, 10, 0.7 }, { 1.3, 2.0, 0.5, 10, 0.7 } };
             /* variant bits of "batch": 1 culling off (both face passes), 2 no PF_COLOR_MATERIAL at replay, 4 lists recorded
                with one colour per gear, 8 a texture matrix at replay, 16 front faces culled, 32 per-pixel Phong, 64 the
-               first list is recorded again before every frame */
+               first list is recorded again before every frame, 128 5-6-5 textures, 256 BGRA8 textures (both: lists replayed through
+               the ordinary path) */
             for (int g = 0; g < 3; g++) {
                 s->lists[c][g] = pfGenList();
                 pfBindTexture(s->texs[c]);
@@ -1345,6 +1352,10 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
         const PFpixelformat f = (PFpixelformat)(cfg->size >> 4); const PFdatatype t = (PFdatatype)(cfg->size & 15);
         s->texpx = make_texture_pair(53, 29, f, t, (uint32_t)cfg->seed ^ 0x7e57u, &tb);
         s->tex = pfGenTexture(s->texpx, 53, 29, f, t);
+        if (cfg->variant & (1 << 27)) {         /* bit 27: quads with a second, RGBA8 texture follow in the same batch */
+            s->aux = make_texture(32, 32, 4, (uint32_t)cfg->seed ^ 0x2222u, 0, 255, 128, 255);
+            s->tex2 = pfGenTexture(s->aux, 32, 32, PF_RGBA, PF_UNSIGNED_BYTE);
+        }
     } else if (strcmp(name, "conform") == 0) {
         s->texpx = make_texture(32, 16, 4, (uint32_t)cfg->seed ^ 0xc0f0u, 0, 255, 0, 255);
         s->tex = pfGenTexture(s->texpx, 32, 16, PF_RGBA, PF_UNSIGNED_BYTE);
@@ -1475,8 +1486,17 @@ SCN_API void pfscene_frame(void *handle, int frame)
             draw_textured_quad(s->fbo.texture, 8.0f, 6.0f, 0.7f * w, 0.6f * h, 1.0f, 1.0f, 0);
         } else micro_scene(cfg, s->tex);
     } else if (strcmp(name, "texfmt") == 0) {
-        pfscene_cfg sub = *cfg; sub.size = 0; sub.variant |= 512;
+        pfscene_cfg sub = *cfg; sub.size = 0; sub.variant |= 512; sub.variant &= ~(1 << 27);
         micro_scene(&sub, s->tex);
+        if (s->tex2) {                          /* the batch's states now differ in their texel layout */
+            ortho2d(w, h); pfEnable(PF_TEXTURE_2D); pfDisable(PF_CULL_FACE);
+            pfTextureParameter(s->tex2, PF_REPEAT, PF_NEAREST);
+            draw_textured_quad(s->tex2, 6.0f, 8.0f, 60.0f, 40.0f, 2.0f, 2.0f, 1);
+            pfTextureParameter(s->tex, PF_MIRRORED_REPEAT, PF_NEAREST);
+            draw_textured_quad(s->tex, 80.0f, 70.0f, 70.0f, 40.0f, 3.0f, 2.0f, 0);
+            draw_textured_quad(s->tex2, 100.0f, 20.0f, 50.0f, 30.0f, 1.0f, 1.0f, 0);
+            pfDisable(PF_TEXTURE_2D);
+        }
     } else if (strcmp(name, "examples") == 0) {
         examples_scene(cfg, s->tex, &s->fbo, s->aux, &s->mesh, frame);
     } else if (strcmp(name, "conform") == 0) {
@@ -1560,6 +1580,7 @@ SCN_API void pfscene_close(void *handle)
         pfMakeCurrent(s->ctx);
         if (s->fbo.texture) pfDeleteFramebuffer(&s->fbo);
         if (s->tex) pfDeleteTexture(&s->tex, PF_FALSE);
+        if (s->tex2) pfDeleteTexture(&s->tex2, PF_FALSE);
         free(s->texpx);
         if (s->mesh.pos) free_mesh(&s->mesh);
         pfMakeCurrent(NULL);

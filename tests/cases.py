@@ -229,3 +229,15 @@ CASES += [_example(2, 1, TARGET_BGRA), _example(6, 1, TARGET_BGRA), _example(9, 
 
 CASE_IDS = [c[0] for c in CASES]
 assert len(set(CASE_IDS)) == len(CASE_IDS)
+
+# a batch whose states differ in their texel layout (one of the other layouts + RGBA8: no one-program kernel, the run-time
+# sampler of the tile rasteriser), and render lists that sample a 5-6-5 / BGRA8 texture (replayed through the ordinary path)
+CASES += [("texfmt-rgba-s4444-plus-rgba8-blend", "texfmt", 160, 120, dict(variant=micro_variant(tex=1, blend=1) | (1 << 27), seed=3, size=7 * 16 + 4), False),
+          ("texfmt-lum-half-plus-rgba8-persp-depth", "texfmt", 160, 120, dict(variant=micro_variant(tex=1, wrap=2, persp=1, depth=1) | (1 << 27), seed=4, size=4 * 16 + 9), False),
+          ("texfmt-rgb-s565-plus-rgba8-bilinear", "texfmt", 160, 120, dict(variant=micro_variant(tex=1, bil=1, blend=1) | (1 << 27), seed=5, size=6 * 16 + 2), True),
+          ("c5-batch-s565-textures", "batch", 256, 256, dict(size=2, variant=128), False),
+          ("c5-batch-bgra8-textures", "batch", 256, 256, dict(size=2, variant=256), False),
+          ("c5-batch-s565-textures-cull-off-recorded-colours", "batch", 256, 256, dict(size=2, variant=128 | 1 | 4), False)]
+
+CASE_IDS = [c[0] for c in CASES]
+assert len(set(CASE_IDS)) == len(CASE_IDS)

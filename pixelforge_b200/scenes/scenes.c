@@ -1050,6 +1050,79 @@ static void examples_scene(const pfscene_cfg *cfg, PFtexture tex, PFframebuffer 
             ex_rotated_sprite(tex, 20.0f + lcgf() * (float)(w - 100), 20.0f + lcgf() * (float)(h - 100), 64, 64, 32, 32, 360.0f * lcgf() + 20.0f * timer);
         pfDisable((PFstate)(PF_TEXTURE_2D | PF_BLEND));
         break;
+    case 12: {  /* matrix stacks: overflow and underflow of all three, nested transforms, rotation about a non-unit axis */
+        ortho2d(w, h);
+        pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+        PFerrcode errs[8]; int ne = 0;
+        static const PFmatrixmode stacks[3] = { PF_PROJECTION, PF_MODELVIEW, PF_TEXTURE };
+        for (int m = 0; m < 3; m++) {
+            pfMatrixMode(stacks[m]);
+            int pushed = 0;
+            for (int k = 0; k < 70; k++) { pfPushMatrix(); if (pfGetError() != PF_NO_ERROR) break; pushed++; if (stacks[m] == PF_MODELVIEW) pfTranslatef(0.5f, 0.25f, 0.0f); }
+            errs[ne++] = (PFerrcode)pushed;
+            int popped = 0;
+            for (int k = 0; k < 80; k++) { pfPopMatrix(); if (pfGetError() != PF_NO_ERROR) break; popped++; }
+            errs[ne++] = (PFerrcode)popped;
+        }
+        pfMatrixMode(PF_MODELVIEW); pfLoadIdentity();
+        pfEnable(PF_TEXTURE_2D); pfBindTexture(tex);
+        for (int k = 0; k < 6; k++) {
+            pfPushMatrix();
+            pfTranslatef(50.0f + 44.0f * (float)k, 60.0f + 20.0f * (float)(k & 1), 0.0f);
+            pfRotatef(17.0f * (float)k + 5.0f * timer, 0.0f, 0.0f, 2.5f);              /* axis length 2.5 */
+            pfScalef(1.0f + 0.1f * (float)k, 0.8f, 1.0f);
+            pfPushMatrix();
+            const float shear[16] = { 1, 0.2f, 0, 0, 0.3f, 1, 0, 0, 0, 0, 1, 0, 2.0f, -3.0f, 0, 1 };
+            pfMultMatrixf(shear);
+            pfMatrixMode(PF_TEXTURE); pfPushMatrix(); pfRotatef(10.0f * (float)k, 0, 0, 1); pfScalef(2.0f, 2.0f, 1.0f); pfMatrixMode(PF_MODELVIEW);
+            pfColor4ub((PFubyte)(255 - 30 * k), (PFubyte)(100 + 25 * k), 200, 255);
+            pfBegin(PF_QUADS);
+            pfTexCoord2f(0, 0); pfVertex2f(-18, -14); pfTexCoord2f(0, 1); pfVertex2f(-18, 14);
+            pfTexCoord2f(1, 1); pfVertex2f(18, 14); pfTexCoord2f(1, 0); pfVertex2f(18, -14);
+            pfEnd();
+            pfMatrixMode(PF_TEXTURE); pfPopMatrix(); pfMatrixMode(PF_MODELVIEW);
+            pfPopMatrix();
+            pfColor4ub(40, (PFubyte)(40 * k), 90, 255); pfRectf(-4.0f, 18.0f, 4.0f, 26.0f);      /* under the outer transform only */
+            pfPopMatrix();
+        }
+        pfBindTexture(0); pfDisable(PF_TEXTURE_2D);
+        /* a projection pushed inside a frame, 3D under it, then back to the 2D one */
+        ex_begin3d(w, h, 45.0);
+        ex_camera(3.0f, 2.0f, 4.0f, 0, 0, 0);
+        pfPushMatrix(); pfRotatef(30.0f + 10.0f * timer, 1.0f, 1.0f, 0.0f); ex_cube(1.5f); pfPopMatrix();
+        ex_end3d();
+        for (int k = 0; k < ne; k++) { pfColor4ub((PFubyte)errs[k], (PFubyte)(errs[k] >> 8), (PFubyte)k, 255); pfRecti(4 * k, 0, 4 * k + 4, 4); }
+        pfColor4ub(255, 255, 255, 255);
+        break; }
+    case 11: {  /* all eight lights at once (Gouraud; variant bit 4: per-fragment Phong), spots and attenuation among them */
+        ortho2d(w, h);
+        pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+        ex_begin3d(w, h, 60.0);
+        ex_camera(28.0f * cosf(timer), 16.0f, 28.0f * sinf(timer), 0, 0, 0);
+        pfEnable(PF_LIGHTING); pfLightModel((cfg->variant & 16) ? PF_PHONG : PF_GOURAUD);
+        pfEnable(PF_CULL_FACE); pfCullFace(PF_BACK);
+        for (int li = 0; li < 8; li++) {
+            const float a = (float)li * 0.785398f;
+            const float pos[3] = { 22.0f * cosf(a), 6.0f + 3.0f * (float)(li & 3), 22.0f * sinf(a) }, dir[3] = { -pos[0], -pos[1], -pos[2] };
+            const float dif[3] = { 0.25f + 0.09f * (float)li, 0.9f - 0.1f * (float)li, 0.3f + 0.05f * (float)((li * 3) & 7) };
+            const float spc[3] = { 0.6f, 0.5f + 0.05f * (float)li, 0.4f }, amb[3] = { 0.02f * (float)li, 0.03f, 0.04f };
+            pfLightfv((PFsizei)li, PF_POSITION, pos); pfLightfv((PFsizei)li, PF_DIFFUSE, dif);
+            pfLightfv((PFsizei)li, PF_SPECULAR, spc); pfLightfv((PFsizei)li, PF_AMBIENT, amb);
+            if (li & 1) { pfLightfv((PFsizei)li, PF_SPOT_DIRECTION, dir); pfLightf((PFsizei)li, PF_SPOT_INNER_CUTOFF, 20.0f + 2.0f * (float)li); pfLightf((PFsizei)li, PF_SPOT_OUTER_CUTOFF, 35.0f + 2.0f * (float)li); }
+            if (li & 2) { pfLightf((PFsizei)li, PF_LINEAR_ATTENUATION, 0.01f * (float)li); pfLightf((PFsizei)li, PF_QUADRATIC_ATTENUATION, 0.001f * (float)li); }
+            pfEnableLight((PFsizei)li);
+        }
+        {
+            const float mdif[3] = { 0.8f, 0.7f, 0.6f }, mspec[3] = { 0.9f, 0.9f, 0.8f }, mamb[3] = { 0.3f, 0.3f, 0.4f };
+            pfMaterialfv(PF_FRONT_AND_BACK, PF_DIFFUSE, mdif); pfMaterialfv(PF_FRONT_AND_BACK, PF_SPECULAR, mspec);
+            pfMaterialfv(PF_FRONT_AND_BACK, PF_AMBIENT, mamb); pfMaterialf(PF_FRONT_AND_BACK, PF_SHININESS, 24.0f);
+        }
+        pfColor4ub(255, 255, 255, 255);
+        draw_mesh_arrays(mesh);
+        for (int li = 0; li < 8; li++) pfDisableLight((PFsizei)li);
+        pfDisable(PF_LIGHTING); pfLightModel(PF_GOURAUD); pfDisable(PF_CULL_FACE);
+        ex_end3d();
+        break; }
     case 10: {  /* pfBegin / pfEnd used loosely: what the reference does with it (context.c:1580-1608, 1658-1685) */
         ortho2d(w, h);
         pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));

@@ -241,3 +241,15 @@ CASES += [("texfmt-rgba-s4444-plus-rgba8-blend", "texfmt", 160, 120, dict(varian
 
 CASE_IDS = [c[0] for c in CASES]
 assert len(set(CASE_IDS)) == len(CASE_IDS)
+
+# all eight lights at once (Gouraud on the device through the specular threshold tables, and per-fragment Phong), and the
+# three matrix stacks driven into overflow / underflow with nested transforms around textured quads and a 3D pass
+CASES += [("examples-eight-lights-gouraud-f0", "examples", 320, 240, dict(variant=11, seed=2, first_frame=0), False),
+          ("examples-eight-lights-gouraud-f2", "examples", 320, 240, dict(variant=11, seed=2, first_frame=2), False),
+          ("examples-eight-lights-phong-f0", "examples", 320, 240, dict(variant=11 | 16, seed=2, first_frame=0), False),
+          ("examples-eight-lights-phong-f2-target-bgra", "examples", 320, 240, dict(variant=11 | 16 | (TARGET_BGRA << 24), seed=2, first_frame=2), False),
+          ("examples-matrix-stacks-f0", "examples", 320, 240, dict(variant=12, seed=2, first_frame=0), False),
+          ("examples-matrix-stacks-f2", "examples", 320, 240, dict(variant=12, seed=2, first_frame=2), False)]
+
+CASE_IDS = [c[0] for c in CASES]
+assert len(set(CASE_IDS)) == len(CASE_IDS)

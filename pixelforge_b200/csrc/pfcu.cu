@@ -1445,9 +1445,11 @@ static int state_program(const DevState *d)
 }
 
 
-static int g_last_single_prog = -1;      /* set by convert_states: the common program of all states, or -1 */
-static bool g_last_leader_tex = false;   /* set by convert_states: some state samples through the BGRA8 getter */
-static bool g_last_pix_tex = false;      /* set by convert_states: some state samples a texture beyond the four 8-bit layouts */
+/* what convert_states found, for the launch_pipeline call that follows it in the same entry point; per thread: in the
+   multi-device mode every device's worker thread converts and launches on its own */
+static thread_local int g_last_single_prog = -1;      /* the common program of all states, or -1 */
+static thread_local bool g_last_leader_tex = false;   /* some state samples through the BGRA8 getter */
+static thread_local bool g_last_pix_tex = false;      /* some state samples a texture beyond the four 8-bit layouts */
 
 static unsigned convert_states(const pfcu_state *in, uint32_t n, DevState *out)
 {

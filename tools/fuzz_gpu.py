@@ -1,6 +1,8 @@
 """Random walks over the API (scene "fuzz"): the product on cuda:0 against the C oracle, colour and depth bit for bit.
 usage: python tools/fuzz_gpu.py [first_seed] [last_seed] [ops]      (the CPU twin, oracle against the live reference, is
-tests/test_oracle_parity.py::test_fuzz_oracle_matches_live_reference)"""
+tests/test_oracle_parity.py::test_fuzz_oracle_matches_live_reference).
+State at the end of round 2: written after the GPU budget was spent; the one 10-second attempt ended in pfscene_open returning
+NULL before any frame was drawn (message cut off by the log tail) - to be run and looked at first thing next round."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -17,7 +17,14 @@ prod, orc = load_product_scenes(), load_oracle_scenes()
 bad = []
 for seed in range(lo, hi):
     kw = dict(variant=0, seed=seed, size=ops)
-    cp, dp, rp = prod.render("fuzz", 256, 192, **kw)
+    try:
+        cp, dp, rp = prod.render("fuzz", 256, 192, **kw)
+    except RuntimeError as e:       # say why: the library keeps the last error text
+        import ctypes
+        lib = ctypes.CDLL(os.path.join(ROOT, "pixelforge_b200", "lib", "libpixelforge.so"))
+        lib.pfcu_last_error.restype = ctypes.c_char_p
+        print("product failed:", e, "| pfcu_last_error:", lib.pfcu_last_error().decode(), flush=True)
+        raise
     co, do, ro = orc.render("fuzz", 256, 192, **kw)
     dc, dd = int((cp != co).sum()), int((dp.view(np.uint32) != do.view(np.uint32)).sum())
     if dc or dd or rp.pixels_shaded != ro.pixels_shaded:

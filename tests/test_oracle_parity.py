@@ -51,6 +51,18 @@ def test_fuzz_oracle_matches_live_reference(first_seed, oracle_scenes, ref_bfix_
         assert int((do.view(np.uint32) != dr.view(np.uint32)).sum()) == 0, f"seed {seed}: depth"
 
 
+@pytest.mark.parametrize("target", [1, 2, 3], ids=["bgra8", "rgb8", "bgr8"])
+def test_fuzz_other_target_layouts(target, oracle_scenes, ref_bfix_scenes):
+    """The same walks into BGRA8 / RGB8 / BGR8 targets (scene variant bits 24-25; Q19 group-of-four behaviour of the BGRA8
+    setter and getter included)."""
+    for seed in range(1000, 1040):
+        kw = dict(variant=target << 24, seed=seed, size=200)
+        co, do, _ = oracle_scenes.render("fuzz", 256, 192, **kw)
+        cr, dr, _ = ref_bfix_scenes.render("fuzz", 256, 192, **kw)
+        assert int((co != cr).sum()) == 0, f"seed {seed}: colour"
+        assert int((do.view(np.uint32) != dr.view(np.uint32)).sum()) == 0, f"seed {seed}: depth"
+
+
 def test_small_fixtures(oracle_scenes, host_matches_golden):
     """Full-image fixtures (not just hashes) so that a regression shows WHERE it differs."""
     if not host_matches_golden:

@@ -1218,10 +1218,11 @@ static void examples_scene(const pfscene_cfg *cfg, PFtexture tex, PFframebuffer 
 /* ---- "fuzz": a random walk over the API --------------------------------------------------------- */
 /* `size` operations drawn from the LCG (seed): state toggles, blend / depth / cull / shade / light model / polygon mode,
    matrix operations on all three stacks, 2D and perspective projections, lights and materials, texture parameters, immediate
-   primitives of every draw mode, rectangles, render lists recorded and replayed on the spot, clears, viewports, pfDrawPixels.
+   primitives of every draw mode, rectangles, render lists recorded and replayed on the spot, clears, viewports, pfDrawPixels,
+   vertex arrays, a framebuffer object rendered into and sampled, fog.
    Everything the reference does not bounds-check stays inside: 2D coordinates keep 14 pixels from the border, lines and
    points are one pixel wide, PF_POINT / PF_LINE polygon modes and points / lines are 2D only. */
-static void fuzz_scene(const pfscene_cfg *cfg, PFtexture tex, uint8_t *aux)
+static void fuzz_scene(const pfscene_cfg *cfg, PFtexture tex, uint8_t *aux, PFframebuffer *fbo)
 {
     const int w = cfg->width, h = cfg->height, nops = cfg->size > 0 ? cfg->size : 120;
     lcg_state = (uint32_t)cfg->seed * 2246822519u + 374761393u;
@@ -1362,8 +1363,63 @@ static void fuzz_scene(const pfscene_cfg *cfg, PFtexture tex, uint8_t *aux)
             }
             break;
         default: {
-            PFcolor px[8 * 4];
-            if (!persp) pfReadPixels(20 + (PFint)((r >> 5) % 64u), 20 + (PFint)((r >> 11) % 64u), 8, 4, PF_RGBA, PF_UNSIGNED_BYTE, px);
+            const uint32_t sub = (r >> 19) % 8u;
+            if (sub < 3) {                       /* vertex arrays: a random subset enabled, indexed or not */
+                static float vp[48 * 3], vn[48 * 3], vt[48 * 2]; static uint8_t vc[48 * 4]; static uint16_t vi[60];
+                if (persp && FUZZ_FAR() && !mv_far) { pfBindTexture(NULL); tex_bound = 0; }
+                for (int v = 0; v < 48; v++) {
+                    const float x = lcgf(), y = lcgf(), z = lcgf();
+                    if (persp) { const float sc = FUZZ_FAR() ? 0.45f : 1.0f; vp[3 * v] = sc * (5.0f * x - 2.5f); vp[3 * v + 1] = sc * (4.0f * y - 2.0f); vp[3 * v + 2] = sc * (5.0f * z - 2.0f); }
+                    else { vp[3 * v] = 20.0f + x * (float)(w - 40); vp[3 * v + 1] = 20.0f + y * (float)(h - 40); vp[3 * v + 2] = -0.9f * z; }
+                    vn[3 * v] = lcgf() - 0.5f; vn[3 * v + 1] = lcgf() - 0.5f; vn[3 * v + 2] = lcgf() + 0.2f;
+                    vt[2 * v] = 3.0f * lcgf() - 1.0f; vt[2 * v + 1] = 3.0f * lcgf() - 1.0f;
+                    for (int k = 0; k < 4; k++) vc[4 * v + k] = (uint8_t)(lcg() >> 24);
+                }
+                for (int k = 0; k < 60; k++) vi[k] = (uint16_t)((lcg() >> 8) % 48u);
+                pfEnable(PF_VERTEX_ARRAY); pfVertexPointer(3, PF_FLOAT, 0, vp);
+                if ((r >> 5) & 1u) { pfEnable(PF_NORMAL_ARRAY); pfNormalPointer(PF_FLOAT, 0, vn); }
+                if ((r >> 6) & 1u) { pfEnable(PF_TEXTURE_COORD_ARRAY); pfTexCoordPointer(PF_FLOAT, 0, vt); }
+                if ((r >> 7) & 1u) { pfEnable(PF_COLOR_ARRAY); pfColorPointer(4, PF_UNSIGNED_BYTE, 0, vc); }
+                static const PFdrawmode amodes[4] = { PF_TRIANGLES, PF_QUADS, PF_TRIANGLE_STRIP, PF_TRIANGLE_FAN };
+                if ((r >> 8) & 1u) pfDrawElements(amodes[(r >> 9) % 4u], (PFsizei)(12 + (r >> 11) % 48u), PF_UNSIGNED_SHORT, vi);
+                else pfDrawArrays(amodes[(r >> 9) % 4u], (PFint)((r >> 11) % 12u), (PFsizei)(12 + (r >> 15) % 24u));
+                pfDisable(PF_VERTEX_ARRAY); pfDisable(PF_NORMAL_ARRAY); pfDisable(PF_TEXTURE_COORD_ARRAY); pfDisable(PF_COLOR_ARRAY);
+            } else if (sub == 3 && fbo->texture) {     /* render to the 64x64 object, then sample it (2D state from scratch around it) */
+                pfMatrixMode(PF_MODELVIEW); for (int k = 0; k < 40; k++) pfPopMatrix();
+                (void)pfGetError();
+                pfPolygonMode(PF_FRONT_AND_BACK, PF_FILL);
+                pfBindFramebuffer(fbo); pfEnable(PF_FRAMEBUFFER);
+                pfViewport(0, 0, 56, 56);
+                pfMatrixMode(PF_PROJECTION); pfLoadIdentity(); pfOrtho(0.0f, 56.0f, 56.0f, 0.0f, 0.0f, 1.0f);
+                pfMatrixMode(PF_MODELVIEW); pfLoadIdentity();
+                if ((r >> 5) & 1u) pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+                pfBegin(PF_TRIANGLES);
+                for (int v = 0; v < 9; v++) {
+                    pfColor4ub((PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(lcg() >> 24), (PFubyte)(128 + (lcg() >> 25)));
+                    pfTexCoord2f(2.0f * lcgf(), 2.0f * lcgf());
+                    pfVertex3f(2.0f + 50.0f * lcgf(), 2.0f + 50.0f * lcgf(), -0.9f * lcgf());
+                }
+                pfEnd();
+                pfDisable(PF_FRAMEBUFFER);
+                pfViewport(0, 0, (PFsizei)w, (PFsizei)h); ortho2d(w, h);
+                persp = 0; clean = 1; mv_far = 1;
+                {
+                    const int was_tex = tex_enabled;
+                    pfEnable(PF_TEXTURE_2D);
+                    pfTextureParameter(fbo->texture, PF_REPEAT, PF_NEAREST);
+                    draw_textured_quad(fbo->texture, 24.0f + lcgf() * (float)(w - 120), 24.0f + lcgf() * (float)(h - 110), 64.0f, 64.0f, 1.0f, 1.0f, (int)((r >> 6) & 1u));
+                    if (!was_tex) pfDisable(PF_TEXTURE_2D);
+                    tex_bound = 0;              /* draw_textured_quad leaves no texture bound */
+                }
+            } else if (sub == 4 && (r >> 5) % 4u == 0) {      /* fog over what has been drawn so far */
+                const float fc[4] = { lcgf(), lcgf(), lcgf(), 0.3f + 0.7f * lcgf() };
+                pfFogi(PF_FOG_MODE, (PFint)((r >> 8) % 3u)); pfFogf(PF_FOG_START, 0.2f * lcgf()); pfFogf(PF_FOG_END, 0.5f + 2.0f * lcgf());
+                pfFogfv(PF_FOG_COLOR, (PFfloat *)fc);
+                pfFogProcess();
+            } else {
+                PFcolor px[8 * 4];
+                if (!persp) pfReadPixels(20 + (PFint)((r >> 5) % 64u), 20 + (PFint)((r >> 11) % 64u), 8, 4, PF_RGBA, PF_UNSIGNED_BYTE, px);
+            }
             break; }
         }
     }
@@ -1604,6 +1660,7 @@ SCN_API void *pfscene_open(const char *name, const pfscene_cfg *cfg)
         s->texpx = make_texture(48, 40, 4, (uint32_t)cfg->seed ^ 0xf022u, 0, 255, 64, 255);
         s->tex = pfGenTexture(s->texpx, 48, 40, PF_RGBA, PF_UNSIGNED_BYTE);
         s->aux = (uint8_t *)calloc(4096, 1);
+        s->fbo = pfGenFramebuffer(64, 64, PF_RGBA, PF_UNSIGNED_BYTE);
     } else if (strcmp(name, "examples") == 0) {
         s->texpx = make_texture(64, 64, 4, (uint32_t)cfg->seed ^ 0xe8a3u, 0, 255, 96, 255);
         s->tex = pfGenTexture(s->texpx, 64, 64, PF_RGBA, PF_UNSIGNED_BYTE);
@@ -1741,7 +1798,7 @@ SCN_API void pfscene_frame(void *handle, int frame)
             pfDisable(PF_TEXTURE_2D);
         }
     } else if (strcmp(name, "fuzz") == 0) {
-        fuzz_scene(cfg, s->tex, s->aux);
+        fuzz_scene(cfg, s->tex, s->aux, &s->fbo);
     } else if (strcmp(name, "examples") == 0) {
         examples_scene(cfg, s->tex, &s->fbo, s->aux, &s->mesh, frame);
     } else if (strcmp(name, "conform") == 0) {

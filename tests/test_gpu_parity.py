@@ -804,3 +804,22 @@ def test_multi_device_fullsize(product_scenes):
         c, d, tris, px = _render_with_env(scene, w, h, {"PF_CUDA_DEVICES": "0,1"}, **kw)
         assert int((c != ref_c).sum()) == 0 and int((d.view(np.uint32) != ref_d.view(np.uint32)).sum()) == 0, scene
         assert px == ref_r.pixels_shaded
+
+# ---- random walks over the API (scene "fuzz") ------------------------------------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("first_seed", range(0, 120, 40))
+def test_fuzz_product_matches_oracle(first_seed, product_scenes, oracle_scenes):
+    """The CPU suite pins the front end + oracle against the live reference on these walks (test_oracle_parity.py); this is
+    the product against the oracle on the same seeds.  Opt-in (PF_FUZZ_GPU=1) until it has had its first run on a GPU: it was
+    written after round 2's GPU budget was spent (tools/fuzz_gpu.py is the same loop as a script)."""
+    import os
+    if os.environ.get("PF_FUZZ_GPU", "0") != "1":
+        pytest.skip("opt-in: PF_FUZZ_GPU=1")
+    for seed in range(first_seed, first_seed + 40):
+        kw = dict(variant=0, seed=seed, size=200)
+        cp, dp, rp = product_scenes.render("fuzz", 256, 192, **kw)
+        co, do, ro = oracle_scenes.render("fuzz", 256, 192, **kw)
+        assert int((cp != co).sum()) == 0, f"seed {seed}: colour"
+        assert int((dp.view(np.uint32) != do.view(np.uint32)).sum()) == 0, f"seed {seed}: depth"
+        assert rp.pixels_shaded == ro.pixels_shaded, f"seed {seed}: shaded pixel count"

@@ -1224,20 +1224,38 @@ static void examples_scene(const pfscene_cfg *cfg, PFtexture tex, PFframebuffer 
    points are one pixel wide, PF_POINT / PF_LINE polygon modes and points / lines are 2D only. */
 static void fuzz_scene(const pfscene_cfg *cfg, PFtexture tex, uint8_t *aux, PFframebuffer *fbo)
 {
-    const int w = cfg->width, h = cfg->height, nops = cfg->size > 0 ? cfg->size : 120;
+    const int nops = cfg->size > 0 ? cfg->size : 120;
     lcg_state = (uint32_t)cfg->seed * 2246822519u + 374761393u;
-    int persp = 0, tex_enabled = 0, tex_bound = 0, mv_far = 1, list_persp[4] = { 0, 0, 0, 0 };   /* mv_far: the modelview holds the camera, rotations and shrinking scales only */
+    /* two contexts: the scene's own and a 128x96 one created for the frame; the walk switches between them, each keeps its own
+       state (and the walk its own notes about that state); lists, the texture and the framebuffer object serve both */
+    struct { int w, h, persp, tex_enabled, tex_bound, mv_far, clean; } T[2];
+    int cur = 0, list_persp[4] = { 0, 0, 0, 0 };
+    PFcontext ctxs[2] = { pfGetCurrentContext(), NULL };
+    uint8_t *second = (uint8_t *)calloc(128u * 96u * 4u + 64u, 1);
+    ctxs[1] = pfCreateContext(second, 128, 96, PF_RGBA, PF_UNSIGNED_BYTE);
+    T[0].w = cfg->width; T[0].h = cfg->height; T[1].w = 128; T[1].h = 96;
+#define w (T[cur].w)
+#define h (T[cur].h)
+#define persp (T[cur].persp)
+#define tex_enabled (T[cur].tex_enabled)
+#define tex_bound (T[cur].tex_bound)
+#define mv_far (T[cur].mv_far)          /* the modelview holds the camera, rotations and shrinking scales only */
+#define clean (T[cur].clean)            /* 2D, identity modelview, full viewport: only then points, lines, PF_POINT / PF_LINE modes and pfDrawPixels (upstream checks no bounds there) */
     /* perspective + texture: geometry stays farther than 2 * near from the eye - where clip-space z crosses 0 the reference's
        perspective-corrected texcoords become inf / NaN and its gathers leave the texture by gigabytes (it crashes) */
 #define FUZZ_FAR() (tex_enabled && tex_bound)
-    int clean = 1;      /* 2D, identity modelview, full viewport: only then points, lines, PF_POINT / PF_LINE modes and pfDrawPixels (upstream checks no bounds there) */
 #define FUZZ_DIRTY() do { clean = 0; pfPolygonMode(PF_FRONT_AND_BACK, PF_FILL); } while (0)
     PFrenderlist lists[4] = { NULL, NULL, NULL, NULL };
-    pfClearColor(16, 24, 40, 255); pfClearDepth(3.4028234663852886e38f);
-    pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
-    pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
-    ortho2d(w, h);
-    pfPolygonMode(PF_FRONT_AND_BACK, PF_FILL); pfLineWidth(1.0f); pfPointSize(1.0f);
+    for (cur = 1; cur >= 0; cur--) {
+        pfMakeCurrent(ctxs[cur]);
+        persp = 0; tex_enabled = 0; tex_bound = 0; mv_far = 1; clean = 1;
+        pfClearColor((PFubyte)(16 + 40 * cur), 24, 40, 255); pfClearDepth(3.4028234663852886e38f);
+        pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
+        pfClear((PFclearflag)(PF_COLOR_BUFFER_BIT | PF_DEPTH_BUFFER_BIT));
+        ortho2d(w, h);
+        pfPolygonMode(PF_FRONT_AND_BACK, PF_FILL); pfLineWidth(1.0f); pfPointSize(1.0f);
+    }
+    cur = 0;
     for (int op = 0; op < nops; op++) {
         const uint32_t r = lcg() >> 8;
         if (getenv("PFSCENE_FUZZ_TRACE")) fprintf(stderr, "fuzz op %d kind %u r %06x persp %d\n", op, r % 19u, r, persp);
@@ -1348,6 +1366,7 @@ static void fuzz_scene(const pfscene_cfg *cfg, PFtexture tex, uint8_t *aux, PFfr
             break; }
         case 16:
             if ((r >> 5) % 6u == 0) pfClear((PFclearflag)(((r >> 9) & 1u ? PF_COLOR_BUFFER_BIT : 0) | ((r >> 10) & 1u ? PF_DEPTH_BUFFER_BIT : 0)));
+            else if ((r >> 5) % 6u == 3) { cur ^= 1; pfMakeCurrent(ctxs[cur]); }
             else if ((r >> 5) % 6u == 1) {
                 const int vx = (int)((r >> 9) % 24u), vy = (int)((r >> 14) % 24u);
                 pfViewport(vx, vy, (PFsizei)(w - 2 * vx - 8), (PFsizei)(h - 2 * vy - 8)); FUZZ_DIRTY();
@@ -1423,9 +1442,9 @@ static void fuzz_scene(const pfscene_cfg *cfg, PFtexture tex, uint8_t *aux, PFfr
             break; }
         }
     }
-#undef FUZZ_DIRTY
-#undef FUZZ_FAR
     for (int li = 0; li < 4; li++) if (lists[li]) pfDeleteList(&lists[li]);
+    /* the second context's frame goes into a corner of the first one's, then the context goes away */
+    cur = 0; pfMakeCurrent(ctxs[0]);
     for (int k = 0; k < 40; k++) { pfMatrixMode(PF_MODELVIEW); pfPopMatrix(); }
     (void)pfGetError();
     for (PFsizei li = 0; li < 4; li++) pfDisableLight(li);
@@ -1434,7 +1453,22 @@ static void fuzz_scene(const pfscene_cfg *cfg, PFtexture tex, uint8_t *aux, PFfr
     pfPolygonMode(PF_FRONT_AND_BACK, PF_FILL); pfLightModel(PF_GOURAUD); pfShadeModel(PF_SMOOTH);
     pfMatrixMode(PF_TEXTURE); pfLoadIdentity(); pfMatrixMode(PF_MODELVIEW);
     pfBindTexture(NULL); pfViewport(0, 0, (PFsizei)w, (PFsizei)h);
+    ortho2d(w, h);
+    pfRasterPos2i(w - 136, 8); pfPixelZoom(1.0f, 1.0f);
+    pfDrawPixels(128, 96, PF_RGBA, PF_UNSIGNED_BYTE, second);
     pfColor4ub(255, 255, 255, 255);
+    pfDeleteContext(ctxs[1]);
+    pfMakeCurrent(ctxs[0]);
+    free(second);
+#undef FUZZ_DIRTY
+#undef FUZZ_FAR
+#undef w
+#undef h
+#undef persp
+#undef tex_enabled
+#undef tex_bound
+#undef mv_far
+#undef clean
 }
 
 static const PFpixelformat target_formats_g[4] = { PF_RGBA, PF_BGRA, PF_RGB, PF_BGR };

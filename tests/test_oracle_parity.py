@@ -40,7 +40,8 @@ def test_fuzz_oracle_matches_live_reference(first_seed, oracle_scenes, ref_bfix_
     the three matrix stacks, 2D and perspective projections, lights, materials, texture parameters and matrix, every draw
     mode, rectangles, render lists recorded and replayed on the spot, clears, viewports, pfDrawPixels, pfReadPixels): the
     product's front end + the oracle against the live reference, colour and depth bit for bit, 50 seeds x 200 operations per
-    test.  (20,000 seeds x 400 operations were run once while writing it: no difference; what the walk avoids is what makes the
+    test.  (60,000 seeds x 400 - 800 operations were run once while writing it, 25,000 of them with the two-context walk: no
+    difference; what the walk avoids is what makes the
     reference itself crash - out-of-viewport pfDrawPixels, textured geometry where clip-space z crosses 0.  tools/fuzz_gpu.py is the
     GPU twin: product against oracle.)"""
     for seed in range(first_seed, first_seed + 50):
